@@ -1,0 +1,78 @@
+"""ctypes binding of the C-ABI library `csrc/libgraphnet_b200.so` (see include/graphnet_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing or a launch fails the
+operators raise `RuntimeError`.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libgraphnet_b200.so")
+
+_p = ctypes.c_void_p
+_i32 = ctypes.c_int32
+_i64 = ctypes.c_int64
+
+# name -> argument types (return type is always int status); mirrors include/graphnet_b200.h
+SIGNATURES: Dict[str, list] = {
+    "gnb_batch_to_ptr": [_p, _i64, _i64, _p, _p],
+    "gnb_knn_table": [_p, _i64, _p, _i32, _p, _i64, _i64, _i32, _p, _p, _p],
+    "gnb_table_to_edge_index": [_p, _p, _p, _i64, _i32, _i64, _p, _p],
+    "gnb_global_vars": [_p, _i64, _i32, _p, _p, _i32, _p, _i64, _p, _p, _p, _i64, _p],
+    "gnb_edge_hidden_fwd": [_p, _i64, _i32, _p, _p, _i32, _i64, _i32, _p, _i64, _p],
+    "gnb_edge_hidden_bwd": [_p, _i64, _p, _i64, _i32, _p, _p, _i32, _i64, _i32, _p, _i64, _p],
+    "gnb_edge_cat_fwd": [_p, _i64, _i32, _p, _p, _i32, _i64, _p, _i64, _p],
+    "gnb_edge_cat_bwd": [_p, _i64, _i32, _p, _p, _i32, _i64, _p, _i64, _p],
+    "gnb_edge_aggregate_fwd": [_p, _i64, _i32, _p, _i32, _i64, _i32, _p, _i64, _p, _p],
+    "gnb_edge_aggregate_bwd": [_p, _i64, _i32, _p, _i32, _i64, _i32, _p, _p, _i64, _p],
+    "gnb_segment_pool_fwd": [_p, _i64, _i32, _p, _i64, _p, _i32, _p, _p, _p],
+    "gnb_segment_pool_bwd": [_p, _p, _i32, _p, _i64, _i64, _p, _i32, _p, _i64, _p],
+    "gnb_relu_bwd": [_p, _i64, _p, _i64, _i64, _i32, _p, _i64, _p],
+    "gnb_colsum": [_p, _i64, _i64, _i32, _p, _p],
+    "gnb_linear_fwd_f32": [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p],
+    "gnb_linear_bwd_data_f32": [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i32, _p],
+    "gnb_linear_bwd_weight_f32": [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _p],
+}
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def library_path() -> str:
+    return LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Load the CUDA library; raise loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"graphnet_b200: CUDA library {LIB_PATH} is missing. Build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+            "There is no CPU fallback for the DynEdge hot path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError here = header / library mismatch
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status == 0:
+        return
+    if status > 0:
+        try:
+            import torch
+            msg = torch.cuda.cudart().cudaGetErrorString(status)  # type: ignore[attr-defined]
+        except Exception:  # pragma: no cover
+            msg = "cudaError"
+        raise RuntimeError(f"graphnet_b200::{what}: CUDA error {status} ({msg})")
+    reason = {-1: "invalid argument (shape/alignment/size)", -2: "unsupported configuration"}.get(status, "error")
+    raise RuntimeError(f"graphnet_b200::{what}: {reason} [{status}]")

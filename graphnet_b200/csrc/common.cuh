@@ -1,0 +1,40 @@
+// Shared helpers for the graphnet_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define GNB_OK 0
+#define GNB_ERR_ARG (-1)          // bad argument (shape / alignment / unsupported size)
+#define GNB_ERR_UNSUPPORTED (-2)  // valid request this build does not implement
+
+#define GNB_EXPORT extern "C" __attribute__((visibility("default")))
+
+// Launch-error check: returns the cudaError_t (>0) to the C-ABI caller; never throws.
+#define GNB_RETURN_LAUNCH()                          \
+    do {                                             \
+        cudaError_t e__ = cudaGetLastError();        \
+        return e__ == cudaSuccess ? GNB_OK : (int)e__; \
+    } while (0)
+
+#define GNB_CHECK(call)                                  \
+    do {                                                 \
+        cudaError_t e__ = (call);                        \
+        if (e__ != cudaSuccess) return (int)e__;         \
+    } while (0)
+
+static inline int gnb_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float gnb_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// activation codes shared by every epilogue
+enum : int { GNB_ACT_NONE = 0, GNB_ACT_RELU = 1 };
+
+// aggregation codes
+enum : int { GNB_AGGR_ADD = 0, GNB_AGGR_MEAN = 1, GNB_AGGR_MAX = 2 };
+
+// pooling scheme codes
+enum : int { GNB_POOL_MIN = 0, GNB_POOL_MAX = 1, GNB_POOL_SUM = 2, GNB_POOL_MEAN = 3 };

@@ -1,0 +1,473 @@
+// HBM-bound graph operators of the DynEdge path: global variables, neighbour gathers, k-neighbour
+// aggregation, global pooling and their backward passes. All are single-pass, coalesced (a warp
+// always walks consecutive channels of one row) and use the fixed-width neighbour table
+// nbr[N, W] / deg[N] written by knn.cu.
+//
+// Reference call sites replaced (paths relative to /root/reference):
+//   global variables  src/graphnet/models/gnn/dynedge.py:266-293, 300-319 + models/utils.py:13-29
+//   EdgeConv gather / aggregate  models/components/layers.py:60 (PyG EdgeConv.propagate)
+//   global pooling    src/graphnet/models/gnn/dynedge.py:251-264 (torch_scatter.scatter_*)
+#include "common.cuh"
+#include <float.h>
+
+namespace {
+
+constexpr int GV_THREADS = 128;
+constexpr int GV_MAX_F = 32;
+
+// One CTA per event: feature means, x/y/z/t homophily over the event's edges, log10(n_pulses);
+// then the same CTA writes x0 = [x | g[event]] (zero padded to ld0) for the event's nodes, which
+// replaces the reference's dense [N,B] "distribute" mask (dynedge.py:308-319) by a gather.
+__global__ void __launch_bounds__(GV_THREADS)
+global_vars_kernel(const float* __restrict__ x, int64_t ldx, int nf, const int* __restrict__ nbr,
+                   const int* __restrict__ deg, int width, const int64_t* __restrict__ ptr,
+                   const float* __restrict__ n_pulses, float* __restrict__ g, float* __restrict__ x0,
+                   int64_t ld0, int x0_cols) {
+    const int b = blockIdx.x;
+    const int64_t lo = ptr[b], hi = ptr[b + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = GV_THREADS / 32;
+    __shared__ float s_part[NW][GV_MAX_F + 5];
+    __shared__ float s_g[GV_MAX_F + 5];
+    float acc[GV_MAX_F];
+#pragma unroll
+    for (int f = 0; f < GV_MAX_F; ++f) acc[f] = 0.f;
+    float same[4] = {0.f, 0.f, 0.f, 0.f};
+    float edges = 0.f;
+    for (int64_t i = lo + tid; i < hi; i += GV_THREADS) {
+        const float* xi = x + i * ldx;
+#pragma unroll
+        for (int f = 0; f < GV_MAX_F; ++f)
+            if (f < nf) acc[f] += xi[f];
+        const int dg = deg[i];
+        for (int s = 0; s < dg; ++s) {
+            const float* xj = x + (int64_t)nbr[i * width + s] * ldx;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) same[c] += (xj[c] == xi[c]) ? 1.f : 0.f;
+        }
+        edges += (float)dg;
+    }
+    // block reduction: warp shuffles then one smem row per warp
+#pragma unroll
+    for (int f = 0; f < GV_MAX_F; ++f) {
+        if (f < nf) {
+            const float v = gnb_warp_sum(acc[f]);
+            if (lane == 0) s_part[warp][f] = v;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float v = gnb_warp_sum(same[c]);
+        if (lane == 0) s_part[warp][GV_MAX_F + c] = v;
+    }
+    {
+        const float v = gnb_warp_sum(edges);
+        if (lane == 0) s_part[warp][GV_MAX_F + 4] = v;
+    }
+    __syncthreads();
+    const int ng = nf + 5;
+    if (tid < nf) {
+        float v = 0.f;
+        for (int w = 0; w < NW; ++w) v += s_part[w][tid];
+        const float cnt = (float)(hi - lo);
+        s_g[tid] = v / (cnt < 1.f ? 1.f : cnt);
+    } else if (tid < nf + 4) {
+        const int c = tid - nf;
+        float v = 0.f, e = 0.f;
+        for (int w = 0; w < NW; ++w) { v += s_part[w][GV_MAX_F + c]; e += s_part[w][GV_MAX_F + 4]; }
+        s_g[tid] = v / (e < 1.f ? 1.f : e);
+    } else if (tid == nf + 4) {
+        s_g[tid] = log10f(n_pulses[b]);
+    }
+    __syncthreads();
+    if (tid < ng) g[(int64_t)b * ng + tid] = s_g[tid];
+    if (x0 != nullptr) {
+        const int64_t total = (hi - lo) * ld0;
+        for (int64_t t = tid; t < total; t += GV_THREADS) {
+            const int64_t i = lo + t / ld0;
+            const int c = (int)(t % ld0);
+            float v = 0.f;
+            if (c < nf) v = x[i * ldx + c];
+            else if (c < x0_cols) v = s_g[c - nf];
+            x0[i * ld0 + c] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// hoisted EdgeConv hidden layer: row r = (i, s) of the padded edge list,
+//   h[r, :] = act(P[i, :] + Q[nbr[i,s], :])   (zero row when s >= deg[i])
+// PQ is [N, 2H]: P = columns [0,H) (already includes the bias), Q = columns [H, 2H).
+// One warp per row, float4 along the channel dimension.
+__global__ void edge_hidden_fwd_kernel(const float* __restrict__ pq, int64_t ldpq, int hdim,
+                                       const int* __restrict__ nbr, const int* __restrict__ deg, int width,
+                                       int64_t n, int act, float* __restrict__ h, int64_t ldh) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n * width) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t i = r / width;
+    const int s = (int)(r - i * width);
+    float4* out = reinterpret_cast<float4*>(h + r * ldh);
+    const int h4 = hdim >> 2;
+    if (s >= deg[i]) {
+        for (int c = lane; c < h4; c += 32) out[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const int64_t j = nbr[i * width + s];
+    const float4* p = reinterpret_cast<const float4*>(pq + i * ldpq);
+    const float4* q = reinterpret_cast<const float4*>(pq + j * ldpq + hdim);
+    for (int c = lane; c < h4; c += 32) {
+        const float4 a = p[c], b = q[c];
+        float4 v = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        if (act == GNB_ACT_RELU) {
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        }
+        out[c] = v;
+    }
+}
+
+// backward of the above: da1 = gh * act'(h); dPQ[i, 0:H] = sum_s da1[(i,s)] (own rows, no atomics);
+// dPQ[j, H:2H] += da1[(i,s)] (scatter to the source node: vector atomics, 32 consecutive channels
+// per warp instruction). dPQ's Q half must be zero on entry. One warp per target node.
+__global__ void edge_hidden_bwd_kernel(const float* __restrict__ gh, int64_t ldg, const float* __restrict__ h,
+                                       int64_t ldh, int hdim, const int* __restrict__ nbr,
+                                       const int* __restrict__ deg, int width, int64_t n, int act,
+                                       float* __restrict__ dpq, int64_t ldpq) {
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int lane = threadIdx.x & 31;
+    const int dg = deg[i];
+    const int h4 = hdim >> 2;
+    float4* dp = reinterpret_cast<float4*>(dpq + i * ldpq);
+    for (int c = lane; c < h4; c += 32) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < dg; ++s) {
+            const int64_t r = i * width + s;
+            float4 g = reinterpret_cast<const float4*>(gh + r * ldg)[c];
+            if (act == GNB_ACT_RELU) {
+                const float4 hv = reinterpret_cast<const float4*>(h + r * ldh)[c];
+                g.x = hv.x > 0.f ? g.x : 0.f; g.y = hv.y > 0.f ? g.y : 0.f;
+                g.z = hv.z > 0.f ? g.z : 0.f; g.w = hv.w > 0.f ? g.w : 0.f;
+            }
+            acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+            const int64_t j = nbr[r];
+            atomicAdd(reinterpret_cast<float4*>(dpq + j * ldpq + hdim) + c, g);
+        }
+        dp[c] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic EdgeConv message input: u[(i,s), :] = [x_i | x_j - x_i]  (zero row when s >= deg[i])
+__global__ void edge_cat_fwd_kernel(const float* __restrict__ x, int64_t ldx, int c_in,
+                                    const int* __restrict__ nbr, const int* __restrict__ deg, int width,
+                                    int64_t n, float* __restrict__ u, int64_t ldu) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n * width) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t i = r / width;
+    const int s = (int)(r - i * width);
+    float* out = u + r * ldu;
+    if (s >= deg[i]) {
+        for (int c = lane; c < 2 * c_in; c += 32) out[c] = 0.f;
+        return;
+    }
+    const int64_t j = nbr[i * width + s];
+    for (int c = lane; c < c_in; c += 32) {
+        const float a = x[i * ldx + c], b = x[j * ldx + c];
+        out[c] = a;
+        out[c_in + c] = b - a;
+    }
+}
+
+// backward: dx[i] += sum_s (du_a - du_b); dx[j] += du_b.  dx must be zero on entry.
+__global__ void edge_cat_bwd_kernel(const float* __restrict__ du, int64_t ldu, int c_in,
+                                    const int* __restrict__ nbr, const int* __restrict__ deg, int width,
+                                    int64_t n, float* __restrict__ dx, int64_t ldx) {
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int lane = threadIdx.x & 31;
+    const int dg = deg[i];
+    for (int c = lane; c < c_in; c += 32) {
+        float acc = 0.f;
+        for (int s = 0; s < dg; ++s) {
+            const int64_t r = i * width + s;
+            const float ga = du[r * ldu + c], gb = du[r * ldu + c_in + c];
+            acc += ga - gb;
+            atomicAdd(dx + (int64_t)nbr[r] * ldx + c, gb);
+        }
+        if (dg > 0) atomicAdd(dx + i * ldx + c, acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k-neighbour aggregation over the padded edge list: y[i,:] = AGG_{s<deg[i]} m[(i,s),:]
+// add / mean / max (max also writes the arg slot, first occurrence; empty neighbourhood -> 0).
+__global__ void edge_aggregate_fwd_kernel(const float* __restrict__ m, int64_t ldm, int c_out,
+                                          const int* __restrict__ deg, int width, int64_t n, int aggr,
+                                          float* __restrict__ y, int64_t ldy, int8_t* __restrict__ arg) {
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int lane = threadIdx.x & 31;
+    const int dg = deg[i];
+    for (int c = lane; c < c_out; c += 32) {
+        float acc = 0.f;
+        int best = -1;
+        if (aggr == GNB_AGGR_MAX) {
+            if (dg > 0) { acc = m[(i * width) * ldm + c]; best = 0; }
+            for (int s = 1; s < dg; ++s) {
+                const float v = m[(i * width + s) * ldm + c];
+                if (v > acc) { acc = v; best = s; }
+            }
+            if (arg) arg[i * c_out + c] = (int8_t)best;
+        } else {
+            for (int s = 0; s < dg; ++s) acc += m[(i * width + s) * ldm + c];
+            if (aggr == GNB_AGGR_MEAN && dg > 0) acc = acc / (float)dg;
+        }
+        y[i * ldy + c] = acc;
+    }
+}
+
+__global__ void edge_aggregate_bwd_kernel(const float* __restrict__ gy, int64_t ldy, int c_out,
+                                          const int* __restrict__ deg, int width, int64_t n, int aggr,
+                                          const int8_t* __restrict__ arg, float* __restrict__ gm, int64_t ldm) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n * width) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t i = r / width;
+    const int s = (int)(r - i * width);
+    const int dg = deg[i];
+    for (int c = lane; c < c_out; c += 32) {
+        float v = 0.f;
+        if (s < dg) {
+            const float g = gy[i * ldy + c];
+            if (aggr == GNB_AGGR_ADD) v = g;
+            else if (aggr == GNB_AGGR_MEAN) v = g / (float)dg;
+            else v = (arg[i * c_out + c] == s) ? g : 0.f;
+        }
+        gm[r * ldm + c] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// global pooling: [N, C] -> [B, P*C] for up to 4 schemes in caller order, single read of x.
+// CTA = (64 channels) x (4 row lanes); grid = (B, C/64). arg (int32 node index, -1 for sum/mean or an
+// empty event) is kept for the min/max backward; ties resolve to the lowest node index.
+constexpr int POOL_CX = 64, POOL_RY = 4;
+
+__global__ void __launch_bounds__(POOL_CX * POOL_RY)
+segment_pool_fwd_kernel(const float* __restrict__ x, int64_t ldx, int c_tot, const int64_t* __restrict__ ptr,
+                        int np, int s0, int s1, int s2, int s3, float* __restrict__ out,
+                        int* __restrict__ arg) {
+    const int b = blockIdx.x;
+    const int c = blockIdx.y * POOL_CX + threadIdx.x;
+    const int ty = threadIdx.y;
+    const int64_t lo = ptr[b], hi = ptr[b + 1];
+    __shared__ float s_min[POOL_RY][POOL_CX], s_max[POOL_RY][POOL_CX], s_sum[POOL_RY][POOL_CX];
+    __shared__ int s_amin[POOL_RY][POOL_CX], s_amax[POOL_RY][POOL_CX];
+    float vmin = FLT_MAX, vmax = -FLT_MAX, vsum = 0.f;
+    int amin = -1, amax = -1;
+    if (c < c_tot) {
+        for (int64_t i = lo + ty; i < hi; i += POOL_RY) {
+            const float v = x[i * ldx + c];
+            vsum += v;
+            if (amin < 0 || v < vmin) { vmin = v; amin = (int)i; }
+            if (amax < 0 || v > vmax) { vmax = v; amax = (int)i; }
+        }
+    }
+    s_min[ty][threadIdx.x] = vmin; s_max[ty][threadIdx.x] = vmax; s_sum[ty][threadIdx.x] = vsum;
+    s_amin[ty][threadIdx.x] = amin; s_amax[ty][threadIdx.x] = amax;
+    __syncthreads();
+    if (ty != 0 || c >= c_tot) return;
+    for (int t = 1; t < POOL_RY; ++t) {
+        const int a1 = s_amin[t][threadIdx.x], a2 = s_amax[t][threadIdx.x];
+        const float m1 = s_min[t][threadIdx.x], m2 = s_max[t][threadIdx.x];
+        if (a1 >= 0 && (amin < 0 || m1 < vmin || (m1 == vmin && a1 < amin))) { vmin = m1; amin = a1; }
+        if (a2 >= 0 && (amax < 0 || m2 > vmax || (m2 == vmax && a2 < amax))) { vmax = m2; amax = a2; }
+        vsum += s_sum[t][threadIdx.x];
+    }
+    const int schemes[4] = {s0, s1, s2, s3};
+    const float cnt = (float)(hi - lo);
+    for (int p = 0; p < np; ++p) {
+        float v; int a = -1;
+        switch (schemes[p]) {
+            case GNB_POOL_MIN: v = amin < 0 ? 0.f : vmin; a = amin; break;
+            case GNB_POOL_MAX: v = amax < 0 ? 0.f : vmax; a = amax; break;
+            case GNB_POOL_SUM: v = vsum; break;
+            default: v = vsum / (cnt < 1.f ? 1.f : cnt); break;
+        }
+        const int64_t o = (int64_t)b * np * c_tot + (int64_t)p * c_tot + c;
+        out[o] = v;
+        if (arg) arg[o] = a;
+    }
+}
+
+// backward: one thread per (node, channel)
+__global__ void segment_pool_bwd_kernel(const float* __restrict__ gout, const int* __restrict__ arg, int c_tot,
+                                        const int64_t* __restrict__ ptr, int nseg, int64_t n, int np, int s0,
+                                        int s1, int s2, int s3, float* __restrict__ gx, int64_t ldx) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * c_tot) return;
+    const int64_t i = t / c_tot;
+    const int c = (int)(t - i * c_tot);
+    int lo = 0, hi = nseg;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ptr[mid] <= i) lo = mid; else hi = mid; }
+    const int b = lo;
+    const float cnt = (float)(ptr[b + 1] - ptr[b]);
+    const int schemes[4] = {s0, s1, s2, s3};
+    float acc = 0.f;
+    for (int p = 0; p < np; ++p) {
+        const int64_t o = (int64_t)b * np * c_tot + (int64_t)p * c_tot + c;
+        const float g = gout[o];
+        switch (schemes[p]) {
+            case GNB_POOL_SUM: acc += g; break;
+            case GNB_POOL_MEAN: acc += g / cnt; break;
+            default: acc += (arg[o] == (int)i) ? g : 0.f; break;
+        }
+    }
+    gx[i * ldx + c] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small dense helpers
+__global__ void relu_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ y, int64_t ldy,
+                                int64_t rows, int cols, float* __restrict__ dz, int64_t ldz) {
+    const int c4 = cols >> 2;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * c4) return;
+    const int64_t r = t / c4;
+    const int c = (int)(t - r * c4);
+    float4 gv = reinterpret_cast<const float4*>(g + r * ldg)[c];
+    const float4 yv = reinterpret_cast<const float4*>(y + r * ldy)[c];
+    gv.x = yv.x > 0.f ? gv.x : 0.f; gv.y = yv.y > 0.f ? gv.y : 0.f;
+    gv.z = yv.z > 0.f ? gv.z : 0.f; gv.w = yv.w > 0.f ? gv.w : 0.f;
+    reinterpret_cast<float4*>(dz + r * ldz)[c] = gv;
+}
+
+// out[c] += sum_r a[r, c]; out must be zero on entry. CTA = 32 x 8, 256 rows per CTA.
+__global__ void colsum_kernel(const float* __restrict__ a, int64_t lda, int64_t rows, int cols,
+                              float* __restrict__ out) {
+    __shared__ float s[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * 256;
+    float acc = 0.f;
+    if (c < cols)
+        for (int64_t r = r0 + threadIdx.y; r < r0 + 256 && r < rows; r += 8) acc += a[r * lda + c];
+    s[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+        for (int t = 1; t < 8; ++t) acc += s[t][threadIdx.x];
+        atomicAdd(out + c, acc);
+    }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+GNB_EXPORT int gnb_global_vars(const float* x, int64_t ldx, int32_t nf, const int32_t* nbr, const int32_t* deg,
+                               int32_t width, const int64_t* ptr, int64_t nseg, const float* n_pulses, float* g,
+                               float* x0, int64_t ld0, void* stream) {
+    if (nf < 4 || nf > GV_MAX_F || nseg < 0) return GNB_ERR_ARG;
+    if (x0 != nullptr && ld0 < 2 * nf + 5) return GNB_ERR_ARG;
+    if (nseg == 0) return GNB_OK;
+    global_vars_kernel<<<(unsigned)nseg, GV_THREADS, 0, (cudaStream_t)stream>>>(
+        x, ldx, nf, nbr, deg, width, ptr, n_pulses, g, x0, ld0, 2 * nf + 5);
+    GNB_RETURN_LAUNCH();
+}
+
+GNB_EXPORT int gnb_edge_hidden_fwd(const float* pq, int64_t ldpq, int32_t hdim, const int32_t* nbr,
+                                   const int32_t* deg, int32_t width, int64_t n, int32_t act, float* h, int64_t ldh,
+                                   void* stream) {
+    if ((hdim & 3) || (ldpq & 3) || (ldh & 3) || !aligned16(pq) || !aligned16(h)) return GNB_ERR_ARG;
+    if (n == 0) return GNB_OK;
+    edge_hidden_fwd_kernel<<<gnb_div_up(n * width, 8), 256, 0, (cudaStream_t)stream>>>(pq, ldpq, hdim, nbr, deg, width,
+                                                                                       n, act, h, ldh);
+    GNB_RETURN_LAUNCH();
+}
+
+GNB_EXPORT int gnb_edge_hidden_bwd(const float* gh, int64_t ldg, const float* h, int64_t ldh, int32_t hdim,
+                                   const int32_t* nbr, const int32_t* deg, int32_t width, int64_t n, int32_t act,
+                                   float* dpq, int64_t ldpq, void* stream) {
+    if ((hdim & 3) || (ldpq & 3) || (ldh & 3) || (ldg & 3) || !aligned16(gh) || !aligned16(h) || !aligned16(dpq))
+        return GNB_ERR_ARG;
+    if (n == 0) return GNB_OK;
+    edge_hidden_bwd_kernel<<<gnb_div_up(n, 8), 256, 0, (cudaStream_t)stream>>>(gh, ldg, h, ldh, hdim, nbr, deg, width,
+                                                                               n, act, dpq, ldpq);
+    GNB_RETURN_LAUNCH();
+}
+
+GNB_EXPORT int gnb_edge_cat_fwd(const float* x, int64_t ldx, int32_t c_in, const int32_t* nbr, const int32_t* deg,
+                                int32_t width, int64_t n, float* u, int64_t ldu, void* stream) {
+    if (n == 0) return GNB_OK;
+    edge_cat_fwd_kernel<<<gnb_div_up(n * width, 8), 256, 0, (cudaStream_t)stream>>>(x, ldx, c_in, nbr, deg, width, n, u,
+                                                                                    ldu);
+    GNB_RETURN_LAUNCH();
+}
+
+GNB_EXPORT int gnb_edge_cat_bwd(const float* du, int64_t ldu, int32_t c_in, const int32_t* nbr, const int32_t* deg,
+                                int32_t width, int64_t n, float* dx, int64_t ldx, void* stream) {
+    if (n == 0) return GNB_OK;
+    edge_cat_bwd_kernel<<<gnb_div_up(n, 8), 256, 0, (cudaStream_t)stream>>>(du, ldu, c_in, nbr, deg, width, n, dx, ldx);
+    GNB_RETURN_LAUNCH();
+}
+
+GNB_EXPORT int gnb_edge_aggregate_fwd(const float* m, int64_t ldm, int32_t c_out, const int32_t* deg, int32_t width,
+                                      int64_t n, int32_t aggr, float* y, int64_t ldy, int8_t* arg, void* stream) {
+    if (aggr < 0 || aggr > 2 || width > 127) return GNB_ERR_ARG;
+    if (n == 0) return GNB_OK;
+    edge_aggregate_fwd_kernel<<<gnb_div_up(n, 8), 256, 0, (cudaStream_t)stream>>>(m, ldm, c_out, deg, width, n, aggr, y,
+                                                                                  ldy, arg);
+    GNB_RETURN_LAUNCH();
+}
+
+GNB_EXPORT int gnb_edge_aggregate_bwd(const float* gy, int64_t ldy, int32_t c_out, const int32_t* deg, int32_t width,
+                                      int64_t n, int32_t aggr, const int8_t* arg, float* gm, int64_t ldm, void* stream) {
+    if (aggr < 0 || aggr > 2 || (aggr == GNB_AGGR_MAX && arg == nullptr)) return GNB_ERR_ARG;
+    if (n == 0) return GNB_OK;
+    edge_aggregate_bwd_kernel<<<gnb_div_up(n * width, 8), 256, 0, (cudaStream_t)stream>>>(gy, ldy, c_out, deg, width, n,
+                                                                                          aggr, arg, gm, ldm);
+    GNB_RETURN_LAUNCH();
+}
+
+GNB_EXPORT int gnb_segment_pool_fwd(const float* x, int64_t ldx, int32_t c, const int64_t* ptr, int64_t nseg,
+                                    const int32_t* schemes, int32_t np, float* out, int32_t* arg, void* stream) {
+    if (np < 1 || np > 4 || c < 1) return GNB_ERR_ARG;
+    for (int p = 0; p < np; ++p) if (schemes[p] < 0 || schemes[p] > 3) return GNB_ERR_ARG;
+    if (nseg == 0) return GNB_OK;
+    int s[4] = {0, 0, 0, 0};
+    for (int p = 0; p < np; ++p) s[p] = schemes[p];
+    dim3 grid((unsigned)nseg, (unsigned)gnb_div_up(c, POOL_CX)), block(POOL_CX, POOL_RY);
+    segment_pool_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, ldx, c, ptr, np, s[0], s[1], s[2], s[3], out,
+                                                                      arg);
+    GNB_RETURN_LAUNCH();
+}
+
+GNB_EXPORT int gnb_segment_pool_bwd(const float* gout, const int32_t* arg, int32_t c, const int64_t* ptr, int64_t nseg,
+                                    int64_t n, const int32_t* schemes, int32_t np, float* gx, int64_t ldx,
+                                    void* stream) {
+    if (np < 1 || np > 4 || c < 1) return GNB_ERR_ARG;
+    if (n == 0) return GNB_OK;
+    int s[4] = {0, 0, 0, 0};
+    for (int p = 0; p < np; ++p) s[p] = schemes[p];
+    segment_pool_bwd_kernel<<<gnb_div_up(n * c, 256), 256, 0, (cudaStream_t)stream>>>(gout, arg, c, ptr, (int)nseg, n, np,
+                                                                                      s[0], s[1], s[2], s[3], gx, ldx);
+    GNB_RETURN_LAUNCH();
+}
+
+GNB_EXPORT int gnb_relu_bwd(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows, int32_t cols,
+                            float* dz, int64_t ldz, void* stream) {
+    if ((cols & 3) || (ldg & 3) || (ldy & 3) || (ldz & 3) || !aligned16(g) || !aligned16(y) || !aligned16(dz))
+        return GNB_ERR_ARG;
+    if (rows == 0) return GNB_OK;
+    relu_bwd_kernel<<<gnb_div_up(rows * (cols >> 2), 256), 256, 0, (cudaStream_t)stream>>>(g, ldg, y, ldy, rows, cols,
+                                                                                           dz, ldz);
+    GNB_RETURN_LAUNCH();
+}
+
+GNB_EXPORT int gnb_colsum(const float* a, int64_t lda, int64_t rows, int32_t cols, float* out, void* stream) {
+    if (rows == 0) return GNB_OK;
+    dim3 grid((unsigned)gnb_div_up(cols, 32), (unsigned)gnb_div_up(rows, 256)), block(32, 8);
+    colsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a, lda, rows, cols, out);
+    GNB_RETURN_LAUNCH();
+}

@@ -1,0 +1,384 @@
+"""Torch-facing operators of the B200 DynEdge path.
+
+Every function here hands raw device pointers, sizes and the current CUDA
+stream to the C-ABI library (`include/graphnet_b200.h`); PyTorch only owns the
+memory and the autograd graph. Nothing in this module computes on the CPU: a
+non-CUDA tensor raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+ACT_NONE, ACT_RELU = 0, 1
+AGGR = {"add": 0, "sum": 0, "mean": 1, "max": 2}
+POOL = {"min": 0, "max": 1, "sum": 2, "mean": 3}
+
+# number of kernels launched through this module (bench.py reports it as `gpu_launches`)
+LAUNCHES = 0
+
+
+def _call(name: str, *args) -> None:
+    global LAUNCHES
+    LAUNCHES += 1
+    _lib.check(getattr(_lib.load(), name)(*args), name)
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _cuda(*tensors: Optional[Tensor]) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("graphnet_b200 operators run on CUDA tensors only (no CPU fallback)")
+
+
+def _rowmajor(t: Tensor) -> Tensor:
+    """2-D tensor with unit inner stride (row pitch may exceed the width)."""
+    if t.dim() != 2:
+        raise RuntimeError("expected a 2-D tensor")
+    if t.stride(1) != 1 and t.shape[1] > 1:
+        t = t.contiguous()
+    if t.shape[1] == 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def _ld(t: Tensor) -> int:
+    return int(t.stride(0)) if t.shape[0] > 1 else int(max(t.stride(0), t.shape[1]))
+
+
+# --------------------------------------------------------------------------- #
+# graph container
+# --------------------------------------------------------------------------- #
+class KnnGraph:
+    """Fixed-width neighbour table: `nbr[N, W]` int32 (-1 padded), `deg[N]` int32.
+
+    Row `i` lists the sources `j` of the edges `j -> i` in ascending distance;
+    this is `edge_index` grouped by target, so it doubles as a CSR by target.
+    """
+
+    def __init__(self, nbr: Tensor, deg: Tensor, k: int):
+        self.nbr, self.deg, self.k = nbr, deg, k
+        self.n, self.width = int(nbr.shape[0]), int(nbr.shape[1])
+        self._edge_index: Optional[Tensor] = None
+
+    def to(self, device) -> "KnnGraph":
+        return KnnGraph(self.nbr.to(device), self.deg.to(device), self.k)
+
+    def edge_index(self) -> Tensor:
+        """Materialise the PyG `[2, E]` int64 tensor (one host sync for E)."""
+        if self._edge_index is None:
+            _cuda(self.nbr)
+            rowptr = torch.zeros(self.n + 1, dtype=torch.int64, device=self.nbr.device)
+            torch.cumsum(self.deg, 0, out=rowptr[1:])
+            e = int(rowptr[-1].item())
+            ei = torch.empty(2, e, dtype=torch.int64, device=self.nbr.device)
+            _call("gnb_table_to_edge_index", _ptr(self.nbr), _ptr(self.deg), _ptr(rowptr), self.n, self.width,
+                  e, _ptr(ei), _stream())
+            self._edge_index = ei
+        return self._edge_index
+
+    @staticmethod
+    def from_edge_index(edge_index: Tensor, n: int, k: int = 0) -> "KnnGraph":
+        """Foreign `edge_index` -> table (not on the hot path; syncs once for the max degree)."""
+        _cuda(edge_index)
+        src, dst = edge_index[0], edge_index[1]
+        if src.numel() and not bool((dst[1:] >= dst[:-1]).all()):
+            order = torch.argsort(dst, stable=True)
+            src, dst = src[order], dst[order]
+        rowptr = torch.searchsorted(dst.contiguous(), torch.arange(n + 1, device=dst.device))
+        deg = (rowptr[1:] - rowptr[:-1])
+        width = max(int(deg.max().item()) if n else 1, 1)
+        nbr = torch.full((n, width), -1, dtype=torch.int32, device=dst.device)
+        slot = torch.arange(src.numel(), device=dst.device) - rowptr[dst]
+        nbr[dst, slot] = src.to(torch.int32)
+        g = KnnGraph(nbr, deg.to(torch.int32), k or width)
+        g._edge_index = torch.stack([src, dst])
+        return g
+
+
+# --------------------------------------------------------------------------- #
+# graph building
+# --------------------------------------------------------------------------- #
+def batch_to_ptr(batch: Tensor, num_graphs: int) -> Tensor:
+    _cuda(batch)
+    batch = batch.contiguous()
+    ptr = torch.empty(num_graphs + 1, dtype=torch.int64, device=batch.device)
+    _call("gnb_batch_to_ptr", _ptr(batch), batch.numel(), num_graphs, _ptr(ptr), _stream())
+    return ptr
+
+
+_COLS_CACHE = {}
+
+
+def _cols_tensor(cols: Sequence[int], device) -> Tensor:
+    key = (tuple(cols), str(device))
+    if key not in _COLS_CACHE:
+        _COLS_CACHE[key] = torch.tensor(list(cols), dtype=torch.int32, device=device)
+    return _COLS_CACHE[key]
+
+
+def resolve_columns(features_subset, width: int) -> List[int]:
+    if isinstance(features_subset, slice):
+        return list(range(width))[features_subset]
+    return [int(c) for c in features_subset]
+
+
+def knn_table(x: Tensor, cols: Sequence[int], ptr: Tensor, k: int) -> KnnGraph:
+    """Batched per-event kNN on columns `cols` of `x` (replaces `knn_graph`, layers.py:63-67)."""
+    _cuda(x, ptr)
+    x = _rowmajor(x.detach())
+    if x.dtype != torch.float32:
+        x = x.float()
+    n = x.shape[0]
+    nbr = torch.empty(n, k + 1, dtype=torch.int32, device=x.device)
+    deg = torch.empty(n, dtype=torch.int32, device=x.device)
+    _call("gnb_knn_table", _ptr(x), _ld(x), _ptr(_cols_tensor(cols, x.device)), len(cols), _ptr(ptr),
+          ptr.numel() - 1, n, k, _ptr(nbr), _ptr(deg), _stream())
+    return KnnGraph(nbr, deg, k)
+
+
+def global_variables(x: Tensor, graph: KnnGraph, ptr: Tensor, n_pulses: Tensor,
+                     x0_width: Optional[int] = None) -> Tuple[Tensor, Optional[Tensor]]:
+    """[mean(x) | h_x h_y h_z h_t | log10 n_pulses] per event (dynedge.py:266-293) and, optionally,
+    x0 = [x | g[batch] | 0-pad] per node (dynedge.py:308-319)."""
+    _cuda(x, ptr, n_pulses)
+    x = _rowmajor(x.detach().float())
+    nseg = ptr.numel() - 1
+    nf = x.shape[1]
+    g = torch.empty(nseg, nf + 5, dtype=torch.float32, device=x.device)
+    x0 = None
+    if x0_width is not None:
+        x0 = torch.empty(x.shape[0], x0_width, dtype=torch.float32, device=x.device)
+    npf = n_pulses.to(torch.float32).contiguous()
+    _call("gnb_global_vars", _ptr(x), _ld(x), nf, _ptr(graph.nbr), _ptr(graph.deg), graph.width, _ptr(ptr), nseg,
+          _ptr(npf), _ptr(g), _ptr(x0), 0 if x0 is None else x0_width, _stream())
+    return g, x0
+
+
+# --------------------------------------------------------------------------- #
+# dense layers (fp32 SIMT backend; tensor-core backends hook in through `linear_*`)
+# --------------------------------------------------------------------------- #
+def _gemm_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], y: Tensor, k: int, act: int, accumulate: bool) -> None:
+    _call("gnb_linear_fwd_f32", _ptr(x), _ld(x), _ptr(w), _ld(w), _ptr(b), _ptr(y), _ld(y), x.shape[0], y.shape[1],
+          k, act, 1 if accumulate else 0, _stream())
+
+
+def _gemm_bwd_data(dz: Tensor, w: Tensor, dx: Tensor, k: int, accumulate: bool = False) -> None:
+    _call("gnb_linear_bwd_data_f32", _ptr(dz), _ld(dz), _ptr(w), _ld(w), _ptr(dx), _ld(dx), dz.shape[0], dz.shape[1],
+          k, 1 if accumulate else 0, _stream())
+
+
+def _gemm_bwd_weight(dz: Tensor, x: Tensor, dw: Tensor, k: int) -> None:
+    _call("gnb_linear_bwd_weight_f32", _ptr(dz), _ld(dz), _ptr(x), _ld(x), _ptr(dw), _ld(dw), dz.shape[0],
+          dz.shape[1], k, _stream())
+
+
+def _act_bwd(g: Tensor, y: Tensor, act: int) -> Tensor:
+    g = _rowmajor(g)
+    if act == ACT_NONE:
+        return g
+    dz = torch.empty(g.shape, dtype=torch.float32, device=g.device)
+    if g.shape[1] % 4 == 0 and _ld(g) % 4 == 0 and _ld(y) % 4 == 0 and g.data_ptr() % 16 == 0:
+        _call("gnb_relu_bwd", _ptr(g), _ld(g), _ptr(y), _ld(y), g.shape[0], g.shape[1], _ptr(dz), _ld(dz), _stream())
+    else:   # odd widths only occur on tiny read-out tensors
+        dz = g * (y > 0)
+    return dz
+
+
+def _colsum(a: Tensor) -> Tensor:
+    out = torch.zeros(a.shape[1], dtype=torch.float32, device=a.device)
+    _call("gnb_colsum", _ptr(a), _ld(a), a.shape[0], a.shape[1], _ptr(out), _stream())
+    return out
+
+
+class _MultiLinearAct(torch.autograd.Function):
+    """y = act(sum_p parts[p] @ W[:, off_p : off_p + K_p]^T + b): a K-split Linear over several
+    inputs, so the skip-concatenation of dynedge.py:328 is never materialised."""
+
+    @staticmethod
+    def forward(ctx, w: Tensor, b: Optional[Tensor], act: int, offsets: Tuple[int, ...], *parts: Tensor):
+        _cuda(w, b, *parts)
+        w = _rowmajor(w)
+        parts = tuple(_rowmajor(p) for p in parts)
+        rows, n_out = parts[0].shape[0], w.shape[0]
+        y = torch.empty(rows, n_out, dtype=torch.float32, device=w.device)
+        last = len(parts) - 1
+        for i, (p, off) in enumerate(zip(parts, offsets)):
+            _gemm_fwd(p, w[:, off:], b if i == last else None, y, p.shape[1],
+                      act if i == last else ACT_NONE, accumulate=i > 0)
+        ctx.act, ctx.offsets = act, offsets
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(w, y, *parts)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy: Tensor):
+        w, y, *parts = ctx.saved_tensors
+        dz = _act_bwd(gy.contiguous(), y, ctx.act)
+        dw = torch.zeros_like(w) if ctx.needs_input_grad[0] else None
+        db = _colsum(dz) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
+        dparts: List[Optional[Tensor]] = []
+        for i, (p, off) in enumerate(zip(parts, ctx.offsets)):
+            kp = p.shape[1]
+            if dw is not None:
+                _gemm_bwd_weight(dz, p, dw[:, off:], kp)
+            if ctx.needs_input_grad[4 + i]:
+                dx = torch.empty(p.shape, dtype=torch.float32, device=p.device)
+                _gemm_bwd_data(dz, w[:, off:], dx, kp)
+                dparts.append(dx)
+            else:
+                dparts.append(None)
+        return (dw, db, None, None, *dparts)
+
+
+def linear_act(x: Tensor, w: Tensor, b: Optional[Tensor], act: int = ACT_NONE) -> Tensor:
+    """act(x @ w^T + b) (torch.nn.Linear + activation of dynedge.py:200-247)."""
+    return _MultiLinearAct.apply(w, b, act, (0,), x)
+
+
+def multi_linear_act(parts: Sequence[Tensor], w: Tensor, b: Optional[Tensor], offsets: Sequence[int],
+                     act: int = ACT_NONE) -> Tensor:
+    return _MultiLinearAct.apply(w, b, act, tuple(int(o) for o in offsets), *parts)
+
+
+# --------------------------------------------------------------------------- #
+# EdgeConv pieces
+# --------------------------------------------------------------------------- #
+class _EdgeHidden(torch.autograd.Function):
+    """h[(i,s)] = act(P[i] + Q[nbr[i,s]]), the first Linear of the EdgeConv MLP hoisted to nodes:
+    W1 [x_i ; x_j - x_i] + b1 = (W1a - W1b) x_i + b1 + W1b x_j."""
+
+    @staticmethod
+    def forward(ctx, pq: Tensor, graph: KnnGraph, act: int):
+        _cuda(pq)
+        pq = _rowmajor(pq)
+        hdim = pq.shape[1] // 2
+        h = torch.empty(graph.n * graph.width, hdim, dtype=torch.float32, device=pq.device)
+        _call("gnb_edge_hidden_fwd", _ptr(pq), _ld(pq), hdim, _ptr(graph.nbr), _ptr(graph.deg), graph.width, graph.n,
+              act, _ptr(h), _ld(h), _stream())
+        ctx.graph, ctx.act = graph, act
+        ctx.save_for_backward(h)
+        return h
+
+    @staticmethod
+    def backward(ctx, gh: Tensor):
+        (h,) = ctx.saved_tensors
+        graph = ctx.graph
+        gh = _rowmajor(gh.contiguous())
+        hdim = h.shape[1]
+        dpq = torch.zeros(graph.n, 2 * hdim, dtype=torch.float32, device=h.device)
+        _call("gnb_edge_hidden_bwd", _ptr(gh), _ld(gh), _ptr(h), _ld(h), hdim, _ptr(graph.nbr), _ptr(graph.deg),
+              graph.width, graph.n, ctx.act, _ptr(dpq), _ld(dpq), _stream())
+        return dpq, None, None
+
+
+def edge_hidden(pq: Tensor, graph: KnnGraph, act: int = ACT_RELU) -> Tensor:
+    return _EdgeHidden.apply(pq, graph, act)
+
+
+class _EdgeCat(torch.autograd.Function):
+    """u[(i,s)] = [x_i | x_j - x_i] (PyG EdgeConv.message input), padded-edge-list rows."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, graph: KnnGraph):
+        _cuda(x)
+        x = _rowmajor(x)
+        c = x.shape[1]
+        u = torch.empty(graph.n * graph.width, 2 * c, dtype=torch.float32, device=x.device)
+        _call("gnb_edge_cat_fwd", _ptr(x), _ld(x), c, _ptr(graph.nbr), _ptr(graph.deg), graph.width, graph.n,
+              _ptr(u), _ld(u), _stream())
+        ctx.graph, ctx.c = graph, c
+        return u
+
+    @staticmethod
+    def backward(ctx, du: Tensor):
+        graph = ctx.graph
+        du = _rowmajor(du.contiguous())
+        dx = torch.zeros(graph.n, ctx.c, dtype=torch.float32, device=du.device)
+        _call("gnb_edge_cat_bwd", _ptr(du), _ld(du), ctx.c, _ptr(graph.nbr), _ptr(graph.deg), graph.width, graph.n,
+              _ptr(dx), _ld(dx), _stream())
+        return dx, None
+
+
+def edge_cat(x: Tensor, graph: KnnGraph) -> Tensor:
+    return _EdgeCat.apply(x, graph)
+
+
+class _EdgeAggregate(torch.autograd.Function):
+    """y[i] = AGG_{s < deg[i]} m[(i,s)] with AGG in add / mean / max (arg-routed backward)."""
+
+    @staticmethod
+    def forward(ctx, m: Tensor, graph: KnnGraph, aggr: int):
+        _cuda(m)
+        m = _rowmajor(m)
+        c = m.shape[1]
+        y = torch.empty(graph.n, c, dtype=torch.float32, device=m.device)
+        arg = torch.empty(graph.n, c, dtype=torch.int8, device=m.device) if aggr == 2 else None
+        _call("gnb_edge_aggregate_fwd", _ptr(m), _ld(m), c, _ptr(graph.deg), graph.width, graph.n, aggr, _ptr(y),
+              _ld(y), _ptr(arg), _stream())
+        ctx.graph, ctx.aggr, ctx.c = graph, aggr, c
+        ctx.save_for_backward(arg) if arg is not None else None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy: Tensor):
+        graph = ctx.graph
+        arg = ctx.saved_tensors[0] if ctx.aggr == 2 else None
+        gy = _rowmajor(gy.contiguous())
+        gm = torch.empty(graph.n * graph.width, ctx.c, dtype=torch.float32, device=gy.device)
+        _call("gnb_edge_aggregate_bwd", _ptr(gy), _ld(gy), ctx.c, _ptr(graph.deg), graph.width, graph.n, ctx.aggr,
+              _ptr(arg), _ptr(gm), _ld(gm), _stream())
+        return gm, None, None
+
+
+def edge_aggregate(m: Tensor, graph: KnnGraph, aggr: str = "add") -> Tensor:
+    return _EdgeAggregate.apply(m, graph, AGGR[aggr])
+
+
+# --------------------------------------------------------------------------- #
+# global pooling (dynedge.py:251-264)
+# --------------------------------------------------------------------------- #
+class _SegmentPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, ptr: Tensor, schemes: Tuple[int, ...]):
+        _cuda(x, ptr)
+        x = _rowmajor(x)
+        nseg, c, npool = ptr.numel() - 1, x.shape[1], len(schemes)
+        out = torch.empty(nseg, npool * c, dtype=torch.float32, device=x.device)
+        arg = torch.empty(nseg, npool * c, dtype=torch.int32, device=x.device)
+        sch = (ctypes.c_int32 * npool)(*schemes)
+        _call("gnb_segment_pool_fwd", _ptr(x), _ld(x), c, _ptr(ptr), nseg, sch, npool, _ptr(out), _ptr(arg), _stream())
+        ctx.schemes, ctx.n, ctx.c = schemes, x.shape[0], c
+        ctx.save_for_backward(arg, ptr)
+        ctx.mark_non_differentiable(arg)
+        return out, arg
+
+    @staticmethod
+    def backward(ctx, gout: Tensor, _garg):
+        arg, ptr = ctx.saved_tensors
+        gout = gout.contiguous()
+        npool = len(ctx.schemes)
+        gx = torch.empty(ctx.n, ctx.c, dtype=torch.float32, device=gout.device)
+        sch = (ctypes.c_int32 * npool)(*ctx.schemes)
+        _call("gnb_segment_pool_bwd", _ptr(gout), _ptr(arg), ctx.c, _ptr(ptr), ptr.numel() - 1, ctx.n, sch, npool,
+              _ptr(gx), _ld(gx), _stream())
+        return gx, None, None
+
+
+def segment_pool(x: Tensor, ptr: Tensor, schemes: Sequence[str], return_arg: bool = False):
+    """cat_p scatter_<p>(x, batch) -> [B, P*C] in the caller's scheme order."""
+    out, arg = _SegmentPool.apply(x, ptr, tuple(POOL[s] for s in schemes))
+    return (out, arg) if return_arg else out

@@ -1,0 +1,112 @@
+/* graphnet_b200 -- C ABI of the B200 (sm_100a) DynEdge hot path.
+ *
+ * The reference (ArturoLlorente/graphnet) has no FFI of its own: its hot path calls third-party
+ * torch operators from Python. The entry points below are the operator boundary a binding would
+ * target; each comment names the reference call site (path:line relative to the reference tree) and
+ * the third-party operator it replaces. INTEGRATION.md shows the ctypes / torch-extension stub.
+ *
+ * Conventions
+ *   - plain pointers + sizes; all pointers are DEVICE pointers unless marked (host);
+ *   - fp32 data, row-major, `ld*` = row pitch in elements; int32 neighbour tables; int64 ptr/batch;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised;
+ *   - return value: 0 = OK, >0 = cudaError_t of the failed launch, -1 = invalid argument,
+ *     -2 = unsupported configuration. Nothing throws; inputs are never modified.
+ *
+ * Graph format: `nbr[N, W]` (int32, -1 padded) holds for node i the sources j of the edges j->i in
+ * ascending (distance, index) order, `deg[N]` their count. For kNN graphs W = k+1 (a node with more
+ * than k exact duplicates at lower index keeps k+1 edges, as torch_cluster does). Row r = i*W + s of
+ * a "padded edge list" tensor belongs to edge slot s of node i.
+ */
+#ifndef GRAPHNET_B200_H
+#define GRAPHNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- graph construction ------------------------------------------------------------------ */
+
+/* ptr[b] = first i with batch[i] >= b, b in [0, nseg]; batch sorted ascending.
+ * Replaces torch_cluster.knn's `ptr = bucketize(arange(B+1), batch)`. */
+int gnb_batch_to_ptr(const int64_t* batch, int64_t n, int64_t nseg, int64_t* ptr, void* stream);
+
+/* Batched per-event k-nearest-neighbour table on columns cols[0..d) of x[n, ldx].
+ * Replaces torch_geometric.nn.pool.knn_graph(x[:, cols], k, batch) at
+ *   src/graphnet/models/components/layers.py:63-67 and src/graphnet/models/graphs/edges/edges.py:74-78.
+ * Bit-exact total order (L2^2 in fp32 without FMA, index). k <= 100, d <= 512. */
+int gnb_knn_table(const float* x, int64_t ldx, const int32_t* cols, int32_t d, const int64_t* ptr, int64_t nseg,
+                  int64_t n, int32_t k, int32_t* nbr, int32_t* deg, void* stream);
+
+/* Expand a table into the PyG edge_index[2, n_edges] (row 0 = source/neighbour, row 1 = target);
+ * rowptr = exclusive prefix sum of deg (n+1 entries). */
+int gnb_table_to_edge_index(const int32_t* nbr, const int32_t* deg, const int64_t* rowptr, int64_t n, int32_t width,
+                            int64_t n_edges, int64_t* edge_index, void* stream);
+
+/* ---- DynEdge global variables ------------------------------------------------------------ */
+
+/* g[nseg, nf+5] = [scatter_mean(x) | homophily of columns 0..3 | log10(n_pulses)] and, when x0 != NULL,
+ * x0[n, ld0] = [x | g[event of node] | 0...]. 4 <= nf <= 32; n_pulses is fp32[nseg].
+ * Replaces DynEdge._calculate_global_variables + the dense distribute/concat at
+ *   src/graphnet/models/gnn/dynedge.py:266-293, 300-319 and src/graphnet/models/utils.py:13-29. */
+int gnb_global_vars(const float* x, int64_t ldx, int32_t nf, const int32_t* nbr, const int32_t* deg, int32_t width,
+                    const int64_t* ptr, int64_t nseg, const float* n_pulses, float* g, float* x0, int64_t ld0,
+                    void* stream);
+
+/* ---- EdgeConv pieces (PyG EdgeConv.propagate at models/components/layers.py:60) ----------- */
+
+/* h[(i,s), 0:hdim] = act(P[i] + Q[nbr[i,s]]) with pq[n, 2*hdim] = [P | Q]; zero row for s >= deg[i].
+ * First Linear of the edge MLP hoisted to nodes. hdim % 4 == 0, 16-byte aligned rows. */
+int gnb_edge_hidden_fwd(const float* pq, int64_t ldpq, int32_t hdim, const int32_t* nbr, const int32_t* deg,
+                        int32_t width, int64_t n, int32_t act, float* h, int64_t ldh, void* stream);
+/* dpq[n, 2*hdim] (Q half zero on entry) from gh = dL/dh. */
+int gnb_edge_hidden_bwd(const float* gh, int64_t ldg, const float* h, int64_t ldh, int32_t hdim, const int32_t* nbr,
+                        const int32_t* deg, int32_t width, int64_t n, int32_t act, float* dpq, int64_t ldpq,
+                        void* stream);
+
+/* Generic message input u[(i,s)] = [x_i | x_j - x_i] and its backward (dx zero on entry). */
+int gnb_edge_cat_fwd(const float* x, int64_t ldx, int32_t c_in, const int32_t* nbr, const int32_t* deg, int32_t width,
+                     int64_t n, float* u, int64_t ldu, void* stream);
+int gnb_edge_cat_bwd(const float* du, int64_t ldu, int32_t c_in, const int32_t* nbr, const int32_t* deg, int32_t width,
+                     int64_t n, float* dx, int64_t ldx, void* stream);
+
+/* y[i] = AGG_{s<deg[i]} m[(i,s)], aggr: 0 add, 1 mean, 2 max (arg = winning slot, int8[n, c_out]).
+ * Replaces the scatter in MessagePassing.aggregate; max routes the gradient to one arg (torch_scatter). */
+int gnb_edge_aggregate_fwd(const float* m, int64_t ldm, int32_t c_out, const int32_t* deg, int32_t width, int64_t n,
+                           int32_t aggr, float* y, int64_t ldy, int8_t* arg, void* stream);
+int gnb_edge_aggregate_bwd(const float* gy, int64_t ldy, int32_t c_out, const int32_t* deg, int32_t width, int64_t n,
+                           int32_t aggr, const int8_t* arg, float* gm, int64_t ldm, void* stream);
+
+/* ---- global pooling ----------------------------------------------------------------------- */
+
+/* out[nseg, np*c] = cat_p scatter_<schemes[p]>(x, batch); schemes (host) in {0 min, 1 max, 2 sum, 3 mean};
+ * arg[nseg, np*c] = node index of the min/max (lowest index on ties), -1 otherwise.
+ * Replaces DynEdge._global_pooling, src/graphnet/models/gnn/dynedge.py:251-264 (torch_scatter). */
+int gnb_segment_pool_fwd(const float* x, int64_t ldx, int32_t c, const int64_t* ptr, int64_t nseg,
+                         const int32_t* schemes, int32_t np, float* out, int32_t* arg, void* stream);
+int gnb_segment_pool_bwd(const float* gout, const int32_t* arg, int32_t c, const int64_t* ptr, int64_t nseg, int64_t n,
+                         const int32_t* schemes, int32_t np, float* gx, int64_t ldx, void* stream);
+
+/* ---- dense layers (torch.nn.Linear + ReLU at dynedge.py:200-203, 226-229, 246-247) -------- */
+
+/* dz = g * (y > 0), all [rows, cols], cols % 4 == 0. */
+int gnb_relu_bwd(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows, int32_t cols, float* dz,
+                 int64_t ldz, void* stream);
+/* out[c] += sum_r a[r, c]. */
+int gnb_colsum(const float* a, int64_t lda, int64_t rows, int32_t cols, float* out, void* stream);
+
+/* fp32 SIMT backend: y[m,n] = act(x[m,k] w[n,k]^T + bias (+ y if accumulate)); act: 0 none, 1 relu. */
+int gnb_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,
+                       int64_t ldy, int64_t m, int64_t n, int64_t k, int32_t act, int32_t accumulate, void* stream);
+/* dx[m,k] = dz[m,n] w[n,k] (+ dx if accumulate). */
+int gnb_linear_bwd_data_f32(const float* dz, int64_t lddz, const float* w, int64_t ldw, float* dx, int64_t lddx,
+                            int64_t m, int64_t n, int64_t k, int32_t accumulate, void* stream);
+/* dw[n,k] += dz[m,n]^T x[m,k]. */
+int gnb_linear_bwd_weight_f32(const float* dz, int64_t lddz, const float* x, int64_t ldx, float* dw, int64_t lddw,
+                              int64_t m, int64_t n, int64_t k, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPHNET_B200_H */

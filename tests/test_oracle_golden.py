@@ -1,0 +1,49 @@
+"""The oracle against the golden vectors produced by the reference's own DynEdge code
+(tests/golden/make_golden.py runs /root/reference/src/graphnet/models/gnn/dynedge.py with shims for the
+absent third-party operators). CPU only."""
+
+import pytest
+import torch
+
+from helpers import golden_files, load_golden, namespace, rel_err, seeded_state_dict
+from oracle.dynedge_oracle import DynEdgeRef, knn_graph_ref
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1][:-3])
+@pytest.mark.parametrize("literal", [False, True], ids=["gather", "dense_distribute"])
+def test_oracle_matches_reference_golden(path, literal):
+    fx = load_golden(path)
+    model = DynEdgeRef(fx["nb_inputs"], literal_distribute=literal, **fx["kwargs"])
+    model.load_state_dict(fx.get("state_dict") or seeded_state_dict(model, fx["weight_seed"]))
+    k = fx["kwargs"].get("nb_neighbours", 8)
+    edge_index = knn_graph_ref(fx["x"][:, [0, 1, 2]], k, batch=fx["batch"])
+    assert torch.equal(edge_index, fx["edge_index"])          # integer work: bit-exact
+    data = namespace(x=fx["x"], edge_index=edge_index, batch=fx["batch"], n_pulses=fx["n_pulses"])
+    y = model(data)
+    w = torch.linspace(0.5, 1.5, y.numel()).reshape(y.shape)
+    (y * w).sum().backward()
+    assert rel_err(y, fx["out_f32"]) < 1e-6                   # same fp32 op order as the reference
+    assert rel_err(y, fx["out_f64"]) < 1e-5
+    for key, p in model.named_parameters():
+        if p.grad is None:
+            assert key not in fx["grads_f32"]
+            continue
+        g = fx["grads_f32"][key]
+        if g.shape == p.grad.shape:
+            assert rel_err(p.grad, g) < 1e-5, key
+        else:   # compact fixture: [norm, max|.|, first element]
+            mine = torch.stack([p.grad.norm(), p.grad.abs().max()])
+            assert rel_err(mine, g[:2]) < 1e-5, key
+
+
+def test_state_dict_keys_match_reference_layout():
+    model = DynEdgeRef(7, global_pooling_schemes=["min", "max", "mean", "sum"])
+    keys = list(model.state_dict().keys())
+    assert "_conv_layers.0.nn.0.weight" in keys and "_conv_layers.3.nn.2.bias" in keys
+    assert "_post_processing.0.weight" in keys and "_post_processing.2.bias" in keys and "_readout.0.weight" in keys
+    sd = model.state_dict()
+    assert tuple(sd["_conv_layers.0.nn.0.weight"].shape) == (128, 38)
+    assert tuple(sd["_conv_layers.1.nn.0.weight"].shape) == (336, 512)
+    assert tuple(sd["_post_processing.0.weight"].shape) == (336, 1043)
+    assert tuple(sd["_readout.0.weight"].shape) == (128, 1024)
+    assert sum(p.numel() for p in model.parameters()) == 1382192
