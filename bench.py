@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 DynEdge hot path (BASELINE.json metric: DynEdge events/sec, fwd+bwd and inference).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU cores
+
+One "step" = one pass of the hot path over one batch of synthetic IceCube-like events:
+  headline `value`  : training step of BASELINE configs[2] -- device-resident x/batch/n_pulses (no edge_index)
+                      -> kNN graph -> DynEdge fwd -> direction(vMF)+energy(LogCosh) heads and loss -> bwd ->
+                      (NCCL mean all-reduce of the flat gradient buffer when N > 1) -> fused Adam step;
+                      512 events per GPU (weak scaling), events/s summed over all ranks.
+  `inference`       : BASELINE configs[1] -- forward + energy head on 1024 events per GPU, no collective.
+  `e2e`             : the training step driven from pinned HOST buffers through the public API
+                      (H2D copy of the batch and D2H read of the loss inside the timed region).
+Rank 0 prints ONE JSON line.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+METRIC = "dynedge_train_events_per_sec"
+UNIT = "events/s"
+POOLS = ["min", "max", "mean", "sum"]
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--events", type=int, default=512, help="training events per GPU (configs[2])")
+    ap.add_argument("--infer-events", type=int, default=1024, help="inference events per GPU (configs[1])")
+    ap.add_argument("--precision", default=os.environ.get("GNB_PRECISION", "fp32"))
+    ap.add_argument("--cpu-events", type=int, default=48, help="events of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inference", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# --------------------------------------------------------------------------------------------- #
+# clocks sampling (B200_PROFILING.md)
+# --------------------------------------------------------------------------------------------- #
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        # under load = samples above 70 % of the busiest clock seen
+        load = [v for v in sm if sm and v >= 0.7 * max(sm)]
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- #
+# workload
+# --------------------------------------------------------------------------------------------- #
+def host_batches(num_events: int, count: int, seed0: int):
+    from graphnet_b200.synthetic import make_batch
+    out = []
+    for i in range(count):
+        raw = make_batch(num_events, seed=seed0 + i)
+        out.append({k: torch.from_numpy(raw[k]).pin_memory() if torch.cuda.is_available() else torch.from_numpy(raw[k])
+                    for k in ("x", "batch", "n_pulses", "energy", "direction")})
+    return out
+
+
+def to_device(hb, dev):
+    return {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+
+
+class Trainer:
+    """The public-API training step: KNNEdges -> DynEdge -> heads/loss -> backward -> all-reduce -> Adam."""
+
+    def __init__(self, dev, world: int):
+        from graphnet_b200.distributed import FlatGradAllReduce
+        from graphnet_b200.models.gnn import DynEdge
+        from graphnet_b200.models.graphs.edges import KNNEdges
+        from graphnet_b200.tasks import DirectionReconstructionWithKappa, EnergyReconstruction
+        torch.manual_seed(0)
+        self.backbone = DynEdge(7, global_pooling_schemes=POOLS).to(dev)
+        self.energy = EnergyReconstruction(128).to(dev)
+        self.direction = DirectionReconstructionWithKappa(128).to(dev)
+        self.edges = KNNEdges(8)
+        self.params = list(self.backbone.parameters()) + list(self.energy.parameters()) + \
+            list(self.direction.parameters())
+        self.reducer = FlatGradAllReduce(self.params)
+        self.opt = torch.optim.Adam(self.params, lr=1e-3, eps=1e-3, fused=True)
+        self.world = world
+
+    def make_data(self, db):
+        from graphnet_b200 import Data
+        return Data(x=db["x"], batch=db["batch"], n_pulses=db["n_pulses"])
+
+    def train_step(self, db):
+        self.reducer.zero()
+        data = self.edges(self.make_data(db))
+        h = self.backbone(data)
+        loss = self.energy.compute_loss(self.energy(h), db["energy"]) + \
+            self.direction.compute_loss(self.direction(h), db["direction"])
+        loss.backward()
+        self.reducer.all_reduce_mean()
+        self.opt.step()
+        return loss
+
+    @torch.no_grad()
+    def infer_step(self, db):
+        data = self.edges(self.make_data(db))
+        return self.energy(self.backbone(data))
+
+
+def timed_loop(fn, batches, steps, warmup, flush, e2e_host=None, dev=None):
+    """Per-step CUDA-event timing with an (untimed) L2 flush between steps. Returns seconds."""
+    for i in range(warmup):
+        fn(batches[i % len(batches)] if e2e_host is None else to_device(e2e_host[i % len(e2e_host)], dev))
+    torch.cuda.synchronize()
+    if dist.is_initialized():
+        dist.barrier()
+    torch.cuda.synchronize()
+    from graphnet_b200 import ops as _ops
+    total_ms, wall, launches0 = 0.0, 0.0, _ops.LAUNCHES
+    for i in range(steps):
+        flush.fill_(float(i))                       # 256 MiB write: evicts L2 between timed steps
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        beg.record()
+        if e2e_host is None:
+            out = fn(batches[i % len(batches)])
+        else:
+            out = fn(to_device(e2e_host[i % len(e2e_host)], dev))
+            _ = float(out.detach().float().sum().item()) if out.numel() > 1 else float(out.item())   # D2H read
+        end.record()
+        torch.cuda.synchronize()
+        wall += time.perf_counter() - t0
+        total_ms += beg.elapsed_time(end)
+    if dist.is_initialized():
+        dist.barrier()
+    torch.cuda.synchronize()
+    timed_loop.last_launches = _ops.LAUNCHES - launches0
+    return (wall if e2e_host is not None else total_ms / 1e3)
+
+
+def max_over_ranks(seconds: float, dev) -> float:
+    if not dist.is_initialized():
+        return seconds
+    t = torch.tensor([seconds], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, dev) -> float:
+    if not dist.is_initialized():
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+# --------------------------------------------------------------------------------------------- #
+# roofline of the dominant kernel, timed live with CUDA events on the launching stream
+# --------------------------------------------------------------------------------------------- #
+def roofline_top_kernel(trainer, db, pk):
+    """Dominant kernel = the per-edge Linear(336->256)+ReLU GEMM of a DynEdgeConv layer (E rows).
+    Algorithmic FLOPs per launch = 2 * E * 336 * 256 with E = actual edge count (deg * 2 * in * out
+    per node), tensor-core bound."""
+    from graphnet_b200 import ops
+    data = trainer.edges(trainer.make_data(db))
+    graph = data.knn_graph()
+    rows = graph.n * graph.width
+    e_real = int(graph.deg.sum().item())
+    lin = trainer.backbone._conv_layers[1].nn[2]
+    h = torch.rand(rows, lin.in_features, device=db["x"].device)
+    w, b = lin.weight.detach(), lin.bias.detach()
+    for _ in range(3):
+        ops.linear_act(h, w, b, ops.ACT_RELU)
+    torch.cuda.synchronize()
+    reps = 10
+    beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    beg.record()
+    for _ in range(reps):
+        ops.linear_act(h, w, b, ops.ACT_RELU)
+    end.record()
+    torch.cuda.synchronize()
+    sec = beg.elapsed_time(end) / 1e3 / reps
+    flops = 2.0 * e_real * lin.in_features * lin.out_features
+    achieved = flops / sec / 1e12
+    peak = pk["bf16_tflops_sustained"]
+    return {"bound": "tensor", "kernel": "gemm_f32_kernel<0,0,1> (edge MLP Linear 336->256 + ReLU)",
+            "achieved": round(achieved, 3), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 5),
+            "traffic": None, "peak_source": pk["source"] + " bf16 dense sustained",
+            "launch_ms": round(sec * 1e3, 4), "rows": rows, "edges": e_real}
+
+
+# --------------------------------------------------------------------------------------------- #
+# CPU baseline / reference arm: the oracle (pure-torch restatement of the reference algorithm)
+# --------------------------------------------------------------------------------------------- #
+def cpu_reference_events_per_sec(num_events: int, steps: int, warmup: int, train: bool = True):
+    from types import SimpleNamespace
+    from graphnet_b200.synthetic import make_batch
+    from graphnet_b200.tasks import DirectionReconstructionWithKappa, EnergyReconstruction
+    from oracle.dynedge_oracle import DynEdgeRef, knn_graph_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = DynEdgeRef(7, global_pooling_schemes=POOLS)
+    energy, direction = EnergyReconstruction(128), DirectionReconstructionWithKappa(128)
+    params = list(model.parameters()) + list(energy.parameters()) + list(direction.parameters())
+    opt = torch.optim.Adam(params, lr=1e-3, eps=1e-3)
+    raw = make_batch(num_events, seed=20240607)
+    x, batch, n_pulses = (torch.from_numpy(raw[k]) for k in ("x", "batch", "n_pulses"))
+    e, d = torch.from_numpy(raw["energy"]), torch.from_numpy(raw["direction"])
+
+    def step():
+        ei = knn_graph_ref(x[:, :3], 8, batch=batch)
+        data = SimpleNamespace(x=x, edge_index=ei, batch=batch, n_pulses=n_pulses)
+        if train:
+            opt.zero_grad()
+            h = model(data)
+            loss = energy.compute_loss(energy(h), e) + direction.compute_loss(direction(h), d)
+            loss.backward()
+            opt.step()
+        else:
+            with torch.no_grad():
+                energy(model(data))
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    sec = (time.perf_counter() - t0) / steps
+    return num_events / sec, sec, cores, int(x.shape[0])
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    evs, sec, cores, nodes = cpu_reference_events_per_sec(args.cpu_events, steps, warm, train=True)
+    sample = (f"{args.cpu_events} synthetic events ({nodes} pulses), {warm} warm-up + {steps} timed training steps of "
+              "the pure-torch oracle (reference's own PyG stack is not installable here)")
+    line = {"impl": "reference", "metric": METRIC, "value": round(evs, 3), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": round(evs, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": round(evs, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "BASELINE configs[2]: DynEdge (nb_inputs=7, k=8, pooling min/max/mean/sum) direction(vMF)+energy"
+                        "(LogCosh) training step fwd+bwd+Adam, 512 events/GPU, synthetic IceCube86 pulse maps "
+                        "(lognormal pulses/event, median 100, max 5000); configs[1] inference B=1024 under 'inference'",
+            "events_per_gpu": args.events, "global_events": args.events * world, "parallelism": f"dp{world}",
+            "precision": args.precision, "inputs": "x/batch/n_pulses resident in HBM; kNN graph built inside the step",
+            "l2": "256 MiB buffer rewritten between timed steps; 4 rotating batches"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as entry
+    if rank == 0 and not os.path.exists(os.path.join(ROOT, "graphnet_b200", "csrc", "libgraphnet_b200.so")):
+        entry.build()
+    if world > 1:
+        dist.barrier()
+    from graphnet_b200 import ops
+    pk = peaks()
+    trainer = Trainer(dev, world)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+
+    train_host = host_batches(args.events, 4, seed0=20240607 + 1000 * rank)
+    train_dev = [to_device(hb, dev) for hb in train_host]
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    sec = timed_loop(trainer.train_step, train_dev, args.steps, args.warmup, flush)
+    launches = timed_loop.last_launches        # kernels of libgraphnet_b200.so launched inside the timed steps
+    sec = max_over_ranks(sec, dev)
+    events_total = sum_over_ranks(float(args.events * args.steps), dev)
+    value = events_total / sec
+
+    # end-to-end through the public API from pinned host buffers
+    sec_e2e = timed_loop(trainer.train_step, None, args.steps, min(args.warmup, 1), flush, e2e_host=train_host, dev=dev)
+    sec_e2e = max_over_ranks(sec_e2e, dev)
+    h2d = sum(int(v.numel() * v.element_size()) for v in train_host[0].values())
+    e2e = {"value": round(events_total / sec_e2e, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+
+    inference = None
+    if not args.no_inference:
+        inf_host = host_batches(args.infer_events, 2, seed0=777 + 1000 * rank)
+        inf_dev = [to_device(hb, dev) for hb in inf_host]
+        sec_inf = max_over_ranks(timed_loop(trainer.infer_step, inf_dev, args.steps, args.warmup, flush), dev)
+        inference = {"value": round(sum_over_ranks(float(args.infer_events * args.steps), dev) / sec_inf, 2), "unit": UNIT,
+                     "workload": "BASELINE configs[1]: energy-regression inference, 1024 events/GPU, no collective",
+                     "ms_per_step": round(sec_inf / args.steps * 1e3, 3)}
+    clocks = sampler.stop() if rank == 0 else None
+
+    roof = roofline_top_kernel(trainer, train_dev[0], pk) if rank == 0 else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        evs, csec, cores, nodes = cpu_reference_events_per_sec(args.cpu_events, 2, 1, train=True)
+        cpu = {"value": round(evs, 3), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_events} of the same synthetic events ({nodes} pulses), 1 warm-up + 2 timed "
+                         f"training steps of the pure-torch oracle on {cores} host threads"}
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(sec / args.steps * 1e3, 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else args.precision,
+                "data": "synthetic", "config": workload_config(args, world), "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "inference": inference,
+                "nodes_per_step_rank0": int(train_host[0]["x"].shape[0])}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,57 @@
+"""Task heads and losses used by the training benchmark (BASELINE config #3): the O(B) step right
+after the hot path. Plain torch ops on the device -- listed as a "next" row in SURVEY.md section 8f.
+
+Reference: `EnergyReconstruction` (src/graphnet/models/task/reconstruction.py:101-112) with
+`LogCoshLoss` (src/graphnet/training/loss_functions.py:93-112) on log10(energy) as in
+examples/04_training/01_train_dynedge.py:113-124; `DirectionReconstructionWithKappa`
+(reconstruction.py:49-70) with `VonMisesFisher3DLoss` (loss_functions.py:281-353, 424-447). log C_3(kappa)
+is evaluated in closed form (kappa / (4 pi sinh kappa)), which is what the reference's scipy-Bessel
+`LogCMK` computes for m = 3 (tests/training/test_loss_functions.py:81-83) without the host round trip.
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import Tensor
+
+
+def _eps_like(x: Tensor) -> float:
+    return torch.finfo(x.dtype).eps
+
+
+class EnergyReconstruction(torch.nn.Module):
+    def __init__(self, hidden_size: int):
+        super().__init__()
+        self._affine = torch.nn.Linear(hidden_size, 1)
+
+    def forward(self, x: Tensor) -> Tensor:
+        z = self._affine(x)
+        return torch.nn.functional.softplus(z, beta=0.05) + _eps_like(z)
+
+    def compute_loss(self, pred: Tensor, energy: Tensor) -> Tensor:
+        diff = torch.log10(pred.squeeze(1)) - torch.log10(energy)
+        return torch.mean(diff + torch.nn.functional.softplus(-2.0 * diff) - math.log(2.0))
+
+
+class DirectionReconstructionWithKappa(torch.nn.Module):
+    def __init__(self, hidden_size: int):
+        super().__init__()
+        self._affine = torch.nn.Linear(hidden_size, 3)
+
+    def forward(self, x: Tensor) -> Tensor:
+        z = self._affine(x)
+        kappa = torch.linalg.vector_norm(z, dim=1) + _eps_like(z)
+        return torch.cat([z / kappa.unsqueeze(1), kappa.unsqueeze(1)], dim=1)
+
+    @staticmethod
+    def log_c3(kappa: Tensor) -> Tensor:
+        # log(kappa / (4 pi sinh kappa)) = log k - log(2 pi) - k - log(1 - exp(-2k))
+        return torch.log(kappa) - math.log(2.0 * math.pi) - kappa - torch.log1p(-torch.exp(-2.0 * kappa))
+
+    def compute_loss(self, pred: Tensor, direction: Tensor) -> Tensor:
+        kappa = pred[:, 3]
+        p = kappa.unsqueeze(1) * pred[:, :3]
+        k = torch.norm(p, dim=1)
+        return torch.mean(-self.log_c3(k) - torch.sum(p * direction.reshape(-1, 3), dim=1))

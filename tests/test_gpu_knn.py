@@ -1,0 +1,90 @@
+"""Bit-exact parity of the batched kNN kernel against the oracle (through the C ABI)."""
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import tie_heavy_events
+from oracle import c_oracle
+from oracle.dynedge_oracle import batch_to_ptr, knn_graph_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _kernel_graph(x, cols, ptr, k):
+    from graphnet_b200 import ops
+    return ops.knn_table(x.cuda(), cols, ptr.cuda(), k)
+
+
+@pytest.mark.parametrize("k", [1, 4, 8, 16, 23])
+def test_knn_bit_exact_tie_heavy(built_library, k):
+    sizes = [1, 2, 3, 9, 10, 50, 300, 7, 12, 40, 129, 128, 127, 1]
+    x, batch, _ = tie_heavy_events(sizes, 7, seed=k)
+    ptr = batch_to_ptr(batch)
+    g = _kernel_graph(x, [0, 1, 2], ptr, k)
+    ei_ref = knn_graph_ref(x[:, :3], k, ptr=ptr)
+    assert torch.equal(g.edge_index().cpu(), ei_ref)
+    nbr_c, deg_c = c_oracle.knn_table(x.numpy(), [0, 1, 2], ptr.numpy(), k)
+    assert np.array_equal(g.nbr.cpu().numpy(), nbr_c) and np.array_equal(g.deg.cpu().numpy(), deg_c)
+
+
+def test_knn_duplicate_quirk_and_empty_segments(built_library):
+    x = torch.zeros(30, 3)
+    x[12:] = torch.rand(18, 3)
+    ptr = torch.tensor([0, 12, 12, 13, 30, 30])
+    g = _kernel_graph(x, [0, 1, 2], ptr, 8)
+    assert g.deg.cpu().tolist()[:13] == [8] * 9 + [9] * 3 + [0]
+    assert torch.equal(g.edge_index().cpu(), knn_graph_ref(x, 8, ptr=ptr))
+
+
+@pytest.mark.parametrize("cols", [[3], [4, 0, 5, 2], list(range(40))])
+def test_knn_generic_columns_and_strided_rows(built_library, cols):
+    rng = np.random.default_rng(len(cols))
+    wide = torch.from_numpy(rng.integers(-2, 3, size=(150, 64)).astype(np.float32) * 0.5)
+    x = wide[:, :48]                                        # row pitch 64, width 48
+    ptr = torch.tensor([0, 20, 90, 150])
+    g = _kernel_graph(wide.cuda()[:, :48], cols, ptr, 5)
+    assert torch.equal(g.edge_index().cpu(), knn_graph_ref(x[:, cols], 5, ptr=ptr))
+
+
+def test_knn_latent_layout_large_events(built_library):
+    # columns 0..2 of a 256-wide latent tensor, events up to 5000 nodes (C oracle as checker)
+    rng = np.random.default_rng(7)
+    sizes = [5000, 3, 1200, 64, 2500]
+    n = sum(sizes)
+    feat = torch.from_numpy(rng.normal(size=(n, 256)).astype(np.float32))
+    feat[:, :3] = torch.round(feat[:, :3] * 8) / 8            # force ties
+    ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(sizes)]))
+    g = _kernel_graph(feat, [0, 1, 2], ptr, 8)
+    nbr_c, deg_c = c_oracle.knn_table(feat.numpy(), [0, 1, 2], ptr.numpy(), 8, threads=8)
+    assert np.array_equal(g.nbr.cpu().numpy(), nbr_c) and np.array_equal(g.deg.cpu().numpy(), deg_c)
+
+
+def test_knn_full_size_properties(built_library):
+    # BASELINE config #2 size (B=1024): properties that do not need the oracle at full size
+    from graphnet_b200 import ops
+    from graphnet_b200.synthetic import make_batch
+    raw = make_batch(1024, seed=20240607)
+    x = torch.from_numpy(raw["x"]).cuda()
+    ptr = torch.from_numpy(raw["ptr"]).cuda()
+    batch = torch.from_numpy(raw["batch"]).cuda()
+    g = ops.knn_table(x, [0, 1, 2], ptr, 8)
+    ei = g.edge_index()
+    assert torch.equal(batch[ei[0]], batch[ei[1]])                      # never crosses events
+    assert not bool((ei[0] == ei[1]).any())                            # no self loops
+    n_b = (ptr[1:] - ptr[:-1])[batch]
+    deg = g.deg.long()
+    assert bool(((deg == torch.clamp(n_b - 1, max=8)) | (deg == 9)).all())
+    d = ((x[ei[0], :3] - x[ei[1], :3]) ** 2).sum(1)
+    same_q = ei[1][1:] == ei[1][:-1]
+    assert bool((d[1:][same_q] >= d[:-1][same_q] - 1e-6).all())          # ascending distance per query
+    # idempotence / determinism
+    g2 = ops.knn_table(x, [0, 1, 2], ptr, 8)
+    assert torch.equal(g.nbr, g2.nbr)
+    # a sample of events against the C oracle
+    sel = [0, 1, 2, 3, 500, 1023]
+    for b in sel:
+        lo, hi = int(raw["ptr"][b]), int(raw["ptr"][b + 1])
+        nbr_c, deg_c = c_oracle.knn_table(raw["x"][lo:hi], [0, 1, 2], np.array([0, hi - lo]), 8)
+        got = g.nbr[lo:hi].cpu().numpy()
+        assert np.array_equal(np.where(got >= 0, got - lo, -1), nbr_c)
