@@ -247,7 +247,8 @@ def roofline_top_kernel(trainer, db, pk):
     flops = 2.0 * e_real * lin.in_features * lin.out_features
     achieved = flops / sec / 1e12
     peak = pk["bf16_tflops_sustained"]
-    return {"bound": "tensor", "kernel": "gemm_f32_kernel<0,0,1> (edge MLP Linear 336->256 + ReLU)",
+    kname = ("gemm_tc_linear_kernel (tcgen05 kind::tf32)" if ops.PRECISION == "tf32" else "gemm_f32_kernel<0,0,1> (fp32 SIMT)")
+    return {"bound": "tensor", "kernel": kname + ": edge MLP Linear 336->256 + ReLU over the padded edge list",
             "achieved": round(achieved, 3), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 5),
             "traffic": None, "peak_source": pk["source"] + " bf16 dense sustained",
             "launch_ms": round(sec * 1e3, 4), "rows": rows, "edges": e_real}
@@ -341,6 +342,7 @@ def main():
     if world > 1:
         dist.barrier()
     from graphnet_b200 import ops
+    ops.set_precision(args.precision)
     pk = peaks()
     trainer = Trainer(dev, world)
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)

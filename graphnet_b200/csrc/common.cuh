@@ -32,6 +32,15 @@ __device__ __forceinline__ float gnb_warp_sum(float v) {
 
 // activation codes shared by every epilogue
 enum : int { GNB_ACT_NONE = 0, GNB_ACT_RELU = 1 };
+// OR-ed into an `act` / `aggr` argument: round the stored result to tf32 (cvt.rna) so that a following
+// tcgen05 kind::tf32 GEMM, which truncates its fp32 operands, sees exactly representable values.
+enum : int { GNB_FLAG_ROUND_TF32 = 0x100 };
+
+__device__ __forceinline__ float gnb_round_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
 
 // aggregation codes
 enum : int { GNB_AGGR_ADD = 0, GNB_AGGR_MEAN = 1, GNB_AGGR_MAX = 2 };

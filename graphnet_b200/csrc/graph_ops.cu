@@ -116,11 +116,15 @@ __global__ void edge_hidden_fwd_kernel(const float* __restrict__ pq, int64_t ldp
     const int64_t j = nbr[i * width + s];
     const float4* p = reinterpret_cast<const float4*>(pq + i * ldpq);
     const float4* q = reinterpret_cast<const float4*>(pq + j * ldpq + hdim);
+    const bool relu = (act & 0xff) == GNB_ACT_RELU, rnd = (act & GNB_FLAG_ROUND_TF32) != 0;
     for (int c = lane; c < h4; c += 32) {
         const float4 a = p[c], b = q[c];
         float4 v = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-        if (act == GNB_ACT_RELU) {
+        if (relu) {
             v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        }
+        if (rnd) {
+            v.x = gnb_round_tf32(v.x); v.y = gnb_round_tf32(v.y); v.z = gnb_round_tf32(v.z); v.w = gnb_round_tf32(v.w);
         }
         out[c] = v;
     }
@@ -144,7 +148,7 @@ __global__ void edge_hidden_bwd_kernel(const float* __restrict__ gh, int64_t ldg
         for (int s = 0; s < dg; ++s) {
             const int64_t r = i * width + s;
             float4 g = reinterpret_cast<const float4*>(gh + r * ldg)[c];
-            if (act == GNB_ACT_RELU) {
+            if ((act & 0xff) == GNB_ACT_RELU) {
                 const float4 hv = reinterpret_cast<const float4*>(h + r * ldh)[c];
                 g.x = hv.x > 0.f ? g.x : 0.f; g.y = hv.y > 0.f ? g.y : 0.f;
                 g.z = hv.z > 0.f ? g.z : 0.f; g.w = hv.w > 0.f ? g.w : 0.f;
@@ -210,6 +214,8 @@ __global__ void edge_aggregate_fwd_kernel(const float* __restrict__ m, int64_t l
     if (i >= n) return;
     const int lane = threadIdx.x & 31;
     const int dg = deg[i];
+    const bool rnd = (aggr & GNB_FLAG_ROUND_TF32) != 0;
+    aggr &= 0xff;
     for (int c = lane; c < c_out; c += 32) {
         float acc = 0.f;
         int best = -1;
@@ -224,7 +230,7 @@ __global__ void edge_aggregate_fwd_kernel(const float* __restrict__ m, int64_t l
             for (int s = 0; s < dg; ++s) acc += m[(i * width + s) * ldm + c];
             if (aggr == GNB_AGGR_MEAN && dg > 0) acc = acc / (float)dg;
         }
-        y[i * ldy + c] = acc;
+        y[i * ldy + c] = rnd ? gnb_round_tf32(acc) : acc;
     }
 }
 
@@ -331,7 +337,7 @@ __global__ void segment_pool_bwd_kernel(const float* __restrict__ gout, const in
 // ---------------------------------------------------------------------------------------------
 // small dense helpers
 __global__ void relu_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ y, int64_t ldy,
-                                int64_t rows, int cols, float* __restrict__ dz, int64_t ldz) {
+                                int64_t rows, int cols, float* __restrict__ dz, int64_t ldz, int flags) {
     const int c4 = cols >> 2;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rows * c4) return;
@@ -341,6 +347,9 @@ __global__ void relu_bwd_kernel(const float* __restrict__ g, int64_t ldg, const 
     const float4 yv = reinterpret_cast<const float4*>(y + r * ldy)[c];
     gv.x = yv.x > 0.f ? gv.x : 0.f; gv.y = yv.y > 0.f ? gv.y : 0.f;
     gv.z = yv.z > 0.f ? gv.z : 0.f; gv.w = yv.w > 0.f ? gv.w : 0.f;
+    if (flags & GNB_FLAG_ROUND_TF32) {
+        gv.x = gnb_round_tf32(gv.x); gv.y = gnb_round_tf32(gv.y); gv.z = gnb_round_tf32(gv.z); gv.w = gnb_round_tf32(gv.w);
+    }
     reinterpret_cast<float4*>(dz + r * ldz)[c] = gv;
 }
 
@@ -414,7 +423,7 @@ GNB_EXPORT int gnb_edge_cat_bwd(const float* du, int64_t ldu, int32_t c_in, cons
 
 GNB_EXPORT int gnb_edge_aggregate_fwd(const float* m, int64_t ldm, int32_t c_out, const int32_t* deg, int32_t width,
                                       int64_t n, int32_t aggr, float* y, int64_t ldy, int8_t* arg, void* stream) {
-    if (aggr < 0 || aggr > 2 || width > 127) return GNB_ERR_ARG;
+    if ((aggr & 0xff) > 2 || width > 127) return GNB_ERR_ARG;
     if (n == 0) return GNB_OK;
     edge_aggregate_fwd_kernel<<<gnb_div_up(n, 8), 256, 0, (cudaStream_t)stream>>>(m, ldm, c_out, deg, width, n, aggr, y,
                                                                                   ldy, arg);
@@ -456,12 +465,12 @@ GNB_EXPORT int gnb_segment_pool_bwd(const float* gout, const int32_t* arg, int32
 }
 
 GNB_EXPORT int gnb_relu_bwd(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows, int32_t cols,
-                            float* dz, int64_t ldz, void* stream) {
+                            float* dz, int64_t ldz, int32_t flags, void* stream) {
     if ((cols & 3) || (ldg & 3) || (ldy & 3) || (ldz & 3) || !aligned16(g) || !aligned16(y) || !aligned16(dz))
         return GNB_ERR_ARG;
     if (rows == 0) return GNB_OK;
     relu_bwd_kernel<<<gnb_div_up(rows * (cols >> 2), 256), 256, 0, (cudaStream_t)stream>>>(g, ldg, y, ldy, rows, cols,
-                                                                                           dz, ldz);
+                                                                                           dz, ldz, flags);
     GNB_RETURN_LAUNCH();
 }
 

@@ -9,6 +9,7 @@ non-CUDA tensor raises.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -17,8 +18,34 @@ from torch import Tensor
 from . import _lib
 
 ACT_NONE, ACT_RELU = 0, 1
+FLAG_ROUND_TF32 = 0x100
 AGGR = {"add": 0, "sum": 0, "mean": 1, "max": 2}
 POOL = {"min": 0, "max": 1, "sum": 2, "mean": 3}
+
+# Precision of the dense contractions:
+#   "fp32": fp32 SIMT GEMMs (exact fp32 products, ~1e-6 from the oracle)
+#   "tf32": tcgen05 kind::tf32 GEMMs (operands rounded to tf32 with cvt.rna, fp32 accumulation in TMEM)
+PRECISION = os.environ.get("GNB_PRECISION", "fp32")
+
+
+def set_precision(mode: str) -> None:
+    global PRECISION
+    if mode not in ("fp32", "tf32"):
+        raise ValueError(f"unknown precision {mode!r}")
+    PRECISION = mode
+
+
+def _tf32() -> bool:
+    return PRECISION == "tf32"
+
+
+def _mark_rounded(t: Tensor) -> Tensor:
+    t._gnb_tf32 = True          # values are exactly representable in tf32
+    return t
+
+
+def _is_rounded(t: Tensor) -> bool:
+    return bool(getattr(t, "_gnb_tf32", False))
 
 # number of kernels launched through this module (bench.py reports it as `gpu_launches`)
 LAUNCHES = 0
@@ -192,10 +219,59 @@ def _act_bwd(g: Tensor, y: Tensor, act: int) -> Tensor:
         return g
     dz = torch.empty(g.shape, dtype=torch.float32, device=g.device)
     if g.shape[1] % 4 == 0 and _ld(g) % 4 == 0 and _ld(y) % 4 == 0 and g.data_ptr() % 16 == 0:
-        _call("gnb_relu_bwd", _ptr(g), _ld(g), _ptr(y), _ld(y), g.shape[0], g.shape[1], _ptr(dz), _ld(dz), _stream())
+        _call("gnb_relu_bwd", _ptr(g), _ld(g), _ptr(y), _ld(y), g.shape[0], g.shape[1], _ptr(dz), _ld(dz),
+              FLAG_ROUND_TF32 if _tf32() else 0, _stream())
+        if _tf32():
+            _mark_rounded(dz)
     else:   # odd widths only occur on tiny read-out tensors
         dz = g * (y > 0)
     return dz
+
+
+def _round_pad(src: Tensor, dst_cols: Optional[int] = None) -> Tensor:
+    """Fresh [rows, dst_cols] copy of `src` rounded to tf32 (cvt.rna), zero padded on the right."""
+    src = _rowmajor(src)
+    cols = src.shape[1]
+    dst_cols = ((cols + 3) // 4) * 4 if dst_cols is None else dst_cols
+    dst = torch.empty(src.shape[0], dst_cols, dtype=torch.float32, device=src.device)
+    _call("gnb_round_pad_tf32", _ptr(src), _ld(src), src.shape[0], cols, _ptr(dst), dst_cols, dst_cols, _stream())
+    return _mark_rounded(dst if dst_cols == cols else dst[:, :cols])    # logical width kept, pitch padded
+
+
+def _tma_ok(t: Tensor) -> bool:
+    return t.data_ptr() % 16 == 0 and _ld(t) % 4 == 0 and t.stride(1) == 1
+
+
+def _tc_operand(t: Tensor) -> Tensor:
+    """tf32-exact, TMA-addressable version of an activation matrix."""
+    if _is_rounded(t) and _tma_ok(t):
+        return t
+    return _round_pad(t)
+
+
+def _tc_pack_weight(w: Tensor, offsets: Sequence[int], ks: Sequence[int]) -> Tensor:
+    """[n_out, sum ceil(k_p/32)*32]: part p's columns, rounded to tf32, at the 32-aligned running offset."""
+    kbs = [(k + 31) // 32 * 32 for k in ks]
+    packed = torch.empty(w.shape[0], sum(kbs), dtype=torch.float32, device=w.device)
+    ldp, koff = packed.shape[1], 0
+    for off, k, kb in zip(offsets, ks, kbs):
+        src = w[:, off:off + k]
+        _call("gnb_round_pad_tf32", _ptr(src), _ld(w), w.shape[0], k, ctypes.c_void_p(packed.data_ptr() + 4 * koff),
+              ldp, kb, _stream())
+        koff += kb
+    return packed
+
+
+def _tc_linear(parts: Sequence[Tensor], packed_w: Tensor, bias: Optional[Tensor], n_out: int, act: int,
+               round_out: bool) -> Tensor:
+    rows, nparts = parts[0].shape[0], len(parts)
+    y = torch.empty(rows, n_out, dtype=torch.float32, device=packed_w.device)
+    xs = (ctypes.c_void_p * nparts)(*[p.data_ptr() for p in parts])
+    lds = (ctypes.c_int64 * nparts)(*[_ld(p) for p in parts])
+    ks = (ctypes.c_int32 * nparts)(*[p.shape[1] for p in parts])
+    _call("gnb_linear_fwd_tf32", xs, lds, ks, nparts, _ptr(packed_w), packed_w.shape[1], _ptr(bias), _ptr(y), n_out,
+          rows, n_out, act, 1 if round_out else 0, _stream())
+    return _mark_rounded(y) if round_out else y
 
 
 def _colsum(a: Tensor) -> Tensor:
@@ -214,11 +290,17 @@ class _MultiLinearAct(torch.autograd.Function):
         w = _rowmajor(w)
         parts = tuple(_rowmajor(p) for p in parts)
         rows, n_out = parts[0].shape[0], w.shape[0]
-        y = torch.empty(rows, n_out, dtype=torch.float32, device=w.device)
-        last = len(parts) - 1
-        for i, (p, off) in enumerate(zip(parts, offsets)):
-            _gemm_fwd(p, w[:, off:], b if i == last else None, y, p.shape[1],
-                      act if i == last else ACT_NONE, accumulate=i > 0)
+        ctx.tc = _tf32() and len(parts) <= 6 and rows > 0
+        if ctx.tc:
+            parts = tuple(_tc_operand(p) for p in parts)
+            packed = _tc_pack_weight(w, offsets, [p.shape[1] for p in parts])
+            y = _tc_linear(parts, packed, b, n_out, act, round_out=True)
+        else:
+            y = torch.empty(rows, n_out, dtype=torch.float32, device=w.device)
+            last = len(parts) - 1
+            for i, (p, off) in enumerate(zip(parts, offsets)):
+                _gemm_fwd(p, w[:, off:], b if i == last else None, y, p.shape[1],
+                          act if i == last else ACT_NONE, accumulate=i > 0)
         ctx.act, ctx.offsets = act, offsets
         ctx.has_bias = b is not None
         ctx.save_for_backward(w, y, *parts)
@@ -236,8 +318,14 @@ class _MultiLinearAct(torch.autograd.Function):
             if dw is not None:
                 _gemm_bwd_weight(dz, p, dw[:, off:], kp)
             if ctx.needs_input_grad[4 + i]:
-                dx = torch.empty(p.shape, dtype=torch.float32, device=p.device)
-                _gemm_bwd_data(dz, w[:, off:], dx, kp)
+                if ctx.tc:    # dx = dz W on the tensor cores: same kernel, W^T as the weight operand
+                    dzr = _tc_operand(dz)
+                    wt = w[:, off:off + kp].t().contiguous()                 # [kp, n_out]
+                    dx = _tc_linear((dzr,), _tc_pack_weight(wt, (0,), (wt.shape[1],)), None, kp, ACT_NONE,
+                                    round_out=False)
+                else:
+                    dx = torch.empty(p.shape, dtype=torch.float32, device=p.device)
+                    _gemm_bwd_data(dz, w[:, off:], dx, kp)
                 dparts.append(dx)
             else:
                 dparts.append(None)
@@ -246,12 +334,14 @@ class _MultiLinearAct(torch.autograd.Function):
 
 def linear_act(x: Tensor, w: Tensor, b: Optional[Tensor], act: int = ACT_NONE) -> Tensor:
     """act(x @ w^T + b) (torch.nn.Linear + activation of dynedge.py:200-247)."""
-    return _MultiLinearAct.apply(w, b, act, (0,), x)
+    y = _MultiLinearAct.apply(w, b, act, (0,), x)
+    return _mark_rounded(y) if _tf32() else y
 
 
 def multi_linear_act(parts: Sequence[Tensor], w: Tensor, b: Optional[Tensor], offsets: Sequence[int],
                      act: int = ACT_NONE) -> Tensor:
-    return _MultiLinearAct.apply(w, b, act, tuple(int(o) for o in offsets), *parts)
+    y = _MultiLinearAct.apply(w, b, act, tuple(int(o) for o in offsets), *parts)
+    return _mark_rounded(y) if _tf32() else y
 
 
 # --------------------------------------------------------------------------- #
@@ -268,10 +358,10 @@ class _EdgeHidden(torch.autograd.Function):
         hdim = pq.shape[1] // 2
         h = torch.empty(graph.n * graph.width, hdim, dtype=torch.float32, device=pq.device)
         _call("gnb_edge_hidden_fwd", _ptr(pq), _ld(pq), hdim, _ptr(graph.nbr), _ptr(graph.deg), graph.width, graph.n,
-              act, _ptr(h), _ld(h), _stream())
+              act | (FLAG_ROUND_TF32 if _tf32() else 0), _ptr(h), _ld(h), _stream())
         ctx.graph, ctx.act = graph, act
         ctx.save_for_backward(h)
-        return h
+        return _mark_rounded(h) if _tf32() else h
 
     @staticmethod
     def backward(ctx, gh: Tensor):
@@ -286,7 +376,8 @@ class _EdgeHidden(torch.autograd.Function):
 
 
 def edge_hidden(pq: Tensor, graph: KnnGraph, act: int = ACT_RELU) -> Tensor:
-    return _EdgeHidden.apply(pq, graph, act)
+    h = _EdgeHidden.apply(pq, graph, act)
+    return _mark_rounded(h) if _tf32() else h
 
 
 class _EdgeCat(torch.autograd.Function):
@@ -327,11 +418,11 @@ class _EdgeAggregate(torch.autograd.Function):
         c = m.shape[1]
         y = torch.empty(graph.n, c, dtype=torch.float32, device=m.device)
         arg = torch.empty(graph.n, c, dtype=torch.int8, device=m.device) if aggr == 2 else None
-        _call("gnb_edge_aggregate_fwd", _ptr(m), _ld(m), c, _ptr(graph.deg), graph.width, graph.n, aggr, _ptr(y),
-              _ld(y), _ptr(arg), _stream())
+        _call("gnb_edge_aggregate_fwd", _ptr(m), _ld(m), c, _ptr(graph.deg), graph.width, graph.n,
+              aggr | (FLAG_ROUND_TF32 if _tf32() else 0), _ptr(y), _ld(y), _ptr(arg), _stream())
         ctx.graph, ctx.aggr, ctx.c = graph, aggr, c
         ctx.save_for_backward(arg) if arg is not None else None
-        return y
+        return _mark_rounded(y) if _tf32() else y
 
     @staticmethod
     def backward(ctx, gy: Tensor):
@@ -345,7 +436,8 @@ class _EdgeAggregate(torch.autograd.Function):
 
 
 def edge_aggregate(m: Tensor, graph: KnnGraph, aggr: str = "add") -> Tensor:
-    return _EdgeAggregate.apply(m, graph, AGGR[aggr])
+    y = _EdgeAggregate.apply(m, graph, AGGR[aggr])
+    return _mark_rounded(y) if _tf32() else y
 
 
 # --------------------------------------------------------------------------- #

@@ -57,7 +57,8 @@ int gnb_global_vars(const float* x, int64_t ldx, int32_t nf, const int32_t* nbr,
 /* ---- EdgeConv pieces (PyG EdgeConv.propagate at models/components/layers.py:60) ----------- */
 
 /* h[(i,s), 0:hdim] = act(P[i] + Q[nbr[i,s]]) with pq[n, 2*hdim] = [P | Q]; zero row for s >= deg[i].
- * First Linear of the edge MLP hoisted to nodes. hdim % 4 == 0, 16-byte aligned rows. */
+ * First Linear of the edge MLP hoisted to nodes. hdim % 4 == 0, 16-byte aligned rows.
+ * act: 0 none, 1 relu, | 0x100 round h to tf32. */
 int gnb_edge_hidden_fwd(const float* pq, int64_t ldpq, int32_t hdim, const int32_t* nbr, const int32_t* deg,
                         int32_t width, int64_t n, int32_t act, float* h, int64_t ldh, void* stream);
 /* dpq[n, 2*hdim] (Q half zero on entry) from gh = dL/dh. */
@@ -71,7 +72,8 @@ int gnb_edge_cat_fwd(const float* x, int64_t ldx, int32_t c_in, const int32_t* n
 int gnb_edge_cat_bwd(const float* du, int64_t ldu, int32_t c_in, const int32_t* nbr, const int32_t* deg, int32_t width,
                      int64_t n, float* dx, int64_t ldx, void* stream);
 
-/* y[i] = AGG_{s<deg[i]} m[(i,s)], aggr: 0 add, 1 mean, 2 max (arg = winning slot, int8[n, c_out]).
+/* y[i] = AGG_{s<deg[i]} m[(i,s)], aggr: 0 add, 1 mean, 2 max (arg = winning slot, int8[n, c_out]), | 0x100 round y
+ * to tf32.
  * Replaces the scatter in MessagePassing.aggregate; max routes the gradient to one arg (torch_scatter). */
 int gnb_edge_aggregate_fwd(const float* m, int64_t ldm, int32_t c_out, const int32_t* deg, int32_t width, int64_t n,
                            int32_t aggr, float* y, int64_t ldy, int8_t* arg, void* stream);
@@ -90,11 +92,23 @@ int gnb_segment_pool_bwd(const float* gout, const int32_t* arg, int32_t c, const
 
 /* ---- dense layers (torch.nn.Linear + ReLU at dynedge.py:200-203, 226-229, 246-247) -------- */
 
-/* dz = g * (y > 0), all [rows, cols], cols % 4 == 0. */
+/* dz = g * (y > 0), all [rows, cols], cols % 4 == 0; flags & 0x100: round dz to tf32. */
 int gnb_relu_bwd(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows, int32_t cols, float* dz,
-                 int64_t ldz, void* stream);
+                 int64_t ldz, int32_t flags, void* stream);
 /* out[c] += sum_r a[r, c]. */
 int gnb_colsum(const float* a, int64_t lda, int64_t rows, int32_t cols, float* out, void* stream);
+
+/* tcgen05 (kind::tf32, fp32 accumulate in TMEM, TMA-fed) backend of the same Linear:
+ * y[rows, n_out] = act(sum_p xs[p][rows, ks[p]] w[:, koff_p : koff_p + ks[p]]^T + bias), koff_p = running sum of
+ * ceil(ks[p]/32)*32. xs / ldxs / ks are HOST arrays (nparts <= 6); pointers 16-byte aligned, pitches % 4 == 0.
+ * Operands are expected pre-rounded to tf32 (gnb_round_pad_tf32 or a producer's 0x100 flag); round_out rounds y.
+ * With nparts > 1 this is the skip-concatenation + first post-processing Linear of dynedge.py:328-331. */
+int gnb_linear_fwd_tf32(const float* const* xs, const int64_t* ldxs, const int32_t* ks, int32_t nparts, const float* w,
+                        int64_t ldw, const float* bias, float* y, int64_t ldy, int64_t rows, int32_t n_out, int32_t act,
+                        int32_t round_out, void* stream);
+/* dst[rows, dst_cols] = [rna_tf32(src[rows, cols]) | 0]. */
+int gnb_round_pad_tf32(const float* src, int64_t lds, int64_t rows, int32_t cols, float* dst, int64_t ldd,
+                       int32_t dst_cols, void* stream);
 
 /* fp32 SIMT backend: y[m,n] = act(x[m,k] w[n,k]^T + bias (+ y if accumulate)); act: 0 none, 1 relu. */
 int gnb_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,
