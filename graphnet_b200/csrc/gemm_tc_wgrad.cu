@@ -1,0 +1,180 @@
+// tcgen05 weight-gradient GEMM of the "tf32" mode:  dW[n_out, k_in] += dz[rows, n_out]^T x[rows, k_in]
+// (backward of torch.nn.Linear at src/graphnet/models/gnn/dynedge.py:200-247; reduction over the rows, i.e. over
+// all edges / nodes of the batch).
+//
+// Both operands are row-major with the reduction index (row) as the SLOW dimension, i.e. "MN-major" in UMMA
+// terms. TMA drops [32 rows x 32 columns] boxes (128-byte swizzle) straight into the canonical MN-major layout
+// (atom = 8 rows x 128 B; LBO = distance between 32-column blocks, SBO = distance between 8-row groups), so no
+// thread ever touches the operands:
+//     A = x tile   : M = 128 k_in columns  x K = 32 rows     (4 boxes,  16 KiB)
+//     B = dz tile  : N <= 256 n_out columns x K = 32 rows    (<= 8 boxes, 32 KiB)
+//     D[k_in, n_out] in TMEM (lane = k_in, column = n_out)
+// Lane = k_in makes the epilogue's reductions into dW[n_out, k_in] coalesced: for a fixed n_out the 32 lanes of a
+// warp hit 32 consecutive floats. The row range is split over gridDim.y CTAs (split-K); partial sums are
+// combined with fp32 `red.global.add`. 4-stage TMA/mbarrier pipeline, 1 CTA per SM.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int WG_BM = 128, WG_BN = 256, WG_BK = 32, WG_STAGES = 4, WG_THREADS = 192;
+constexpr uint32_t WG_BOX_BYTES = 32 * 32 * 4;                       // one [32 x 32] fp32 box
+constexpr uint32_t WG_A_BYTES = (WG_BM / 32) * WG_BOX_BYTES;         // 16 KiB
+constexpr uint32_t WG_B_BYTES = (WG_BN / 32) * WG_BOX_BYTES;         // 32 KiB
+constexpr uint32_t WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;
+constexpr uint32_t WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+
+// MN-major operand, 128-byte swizzle: lbo/sbo in bytes
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_z,
+                     float* __restrict__ dw, int64_t lddw, int64_t rows, int n_out, int k_in, int n_tiles_n,
+                     int64_t rows_per_split, int swap_lbo_sbo) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+    uint64_t* empty = full + WG_STAGES;
+    uint64_t* tmem_full = empty + WG_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_m = blockIdx.x / n_tiles_n, tile_n = blockIdx.x % n_tiles_n;
+    const int kin0 = tile_m * WG_BM;
+    const int out0 = tile_n * WG_BN;
+    int n_cols = n_out - out0;                       // columns of this N tile, rounded up to 16 for the MMA
+    if (n_cols > WG_BN) n_cols = WG_BN;
+    const int n_mma = (n_cols + 15) & ~15;
+    const int n_boxes_b = (n_cols + 31) >> 5;
+    const int64_t r_lo = (int64_t)blockIdx.y * rows_per_split;
+    int64_t r_hi = r_lo + rows_per_split;
+    if (r_hi > rows) r_hi = rows;
+    const int num_kb = r_hi > r_lo ? (int)((r_hi - r_lo + WG_BK - 1) / WG_BK) : 0;
+
+    if (warp == 0 && lane == 0) { tc::tma_prefetch_desc(&tm_x); tc::tma_prefetch_desc(&tm_z); }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < WG_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+            tc::mbar_init(tmem_full, 1);
+            tc::fence_barrier_init();
+            tc::fence_proxy_async();
+        }
+        __syncwarp();
+        tc::tmem_alloc<WG_BN>(tmem_slot);
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (num_kb > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                for (int it = 0; it < num_kb; ++it) {
+                    const int s = it % WG_STAGES;
+                    const uint32_t ph = (it / WG_STAGES) & 1;
+                    tc::mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* sa = smem + s * WG_STAGE_BYTES;
+                    uint8_t* sb = sa + WG_A_BYTES;
+                    const int r = (int)(r_lo + (int64_t)it * WG_BK);
+                    tc::mbar_arrive_expect_tx(&full[s], (WG_BM / 32 + n_boxes_b) * WG_BOX_BYTES);
+#pragma unroll
+                    for (int b = 0; b < WG_BM / 32; ++b) tc::tma_load_2d(sa + b * WG_BOX_BYTES, &tm_x, &full[s], kin0 + 32 * b, r);
+                    for (int b = 0; b < n_boxes_b; ++b) tc::tma_load_2d(sb + b * WG_BOX_BYTES, &tm_z, &full[s], out0 + 32 * b, r);
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                // kind::tf32, fp32 accumulate, A and B MN-major (bits 15, 16)
+                const uint32_t idesc = tc::umma_idesc_tf32(WG_BM, (uint32_t)n_mma) | (1u << 15) | (1u << 16);
+                const uint32_t lbo = swap_lbo_sbo ? 1024u : WG_BOX_BYTES;
+                const uint32_t sbo = swap_lbo_sbo ? WG_BOX_BYTES : 1024u;
+                for (int it = 0; it < num_kb; ++it) {
+                    const int s = it % WG_STAGES;
+                    const uint32_t ph = (it / WG_STAGES) & 1;
+                    tc::mbar_wait(&full[s], ph);
+                    tc::tcgen05_fence_after();
+                    const uint32_t sa = tc::smem_u32(smem + s * WG_STAGE_BYTES);
+                    const uint64_t adesc = umma_desc_sw128_mnmajor(sa, lbo, sbo);
+                    const uint64_t bdesc = umma_desc_sw128_mnmajor(sa + WG_A_BYTES, lbo, sbo);
+#pragma unroll
+                    for (int k = 0; k < WG_BK / 8; ++k)   // 8 rows = one 1024-byte swizzle atom per 32-column block
+                        tc::umma_tf32(tmem_base, adesc + (uint64_t)(k * (1024 >> 4)), bdesc + (uint64_t)(k * (1024 >> 4)),
+                                      idesc, (it | k) != 0 ? 1u : 0u);
+                    tc::umma_commit(&empty[s]);
+                }
+                tc::umma_commit(tmem_full);
+            }
+        } else {
+            tc::mbar_wait(tmem_full, 0);
+            tc::tcgen05_fence_after();
+            const int q = warp & 3;
+            const int kin = kin0 + q * 32 + lane;
+            const bool ok = kin < k_in;
+            for (int c = 0; c * 32 < n_cols; ++c) {
+                uint32_t r[32];
+                tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+                tc::tmem_ld_wait();
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int o = out0 + c * 32 + j;
+                        if (o < n_out) atomicAdd(dw + (int64_t)o * lddw + kin, __uint_as_float(r[j]));
+                    }
+                }
+            }
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<WG_BN>(tmem_base);
+}
+
+// [rows, cols] fp32 row-major, box = 32 columns x 32 rows, 128-byte swizzle, OOB -> 0
+static int make_tmap_box32(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld) {
+    return gnb_make_tmap_f32(map, base, rows, cols, ld, 32u);
+}
+
+}  // namespace
+
+// dw[n_out, k_in] += dz[rows, n_out]^T x[rows, k_in]; operands pre-rounded to tf32, 16-byte aligned, pitches % 4 == 0.
+// debug_swap != 0 exchanges the LBO/SBO descriptor fields (bring-up aid; production passes 0).
+GNB_EXPORT int gnb_linear_bwd_weight_tf32(const float* dz, int64_t lddz, const float* x, int64_t ldx, float* dw,
+                                          int64_t lddw, int64_t rows, int32_t n_out, int32_t k_in, int32_t debug_swap,
+                                          void* stream) {
+    if (rows < 0 || n_out < 1 || k_in < 1) return GNB_ERR_ARG;
+    if (rows == 0) return GNB_OK;
+    if (rows >= (int64_t)1 << 31) return GNB_ERR_ARG;
+    CUtensorMap tx, tz;
+    int rc = make_tmap_box32(&tx, x, rows, k_in, ldx);
+    if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    rc = make_tmap_box32(&tz, dz, rows, n_out, lddz);
+    if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GNB_CHECK(cudaFuncSetAttribute(gemm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)WG_SMEM_BYTES));
+        attr_set = true;
+    }
+    const int tiles_m = gnb_div_up(k_in, WG_BM), tiles_n = gnb_div_up(n_out, WG_BN);
+    const int tiles = tiles_m * tiles_n;
+    int splits = (2 * 148 + tiles - 1) / tiles;
+    const int64_t max_splits = (rows + 8 * WG_BK - 1) / (8 * WG_BK);     // at least 8 K-blocks per CTA
+    if (splits > max_splits) splits = (int)max_splits;
+    if (splits < 1) splits = 1;
+    int64_t rps = (rows + splits - 1) / splits;
+    rps = ((rps + WG_BK - 1) / WG_BK) * WG_BK;
+    splits = (int)((rows + rps - 1) / rps);
+    dim3 grid((unsigned)tiles, (unsigned)splits);
+    gemm_tc_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, (cudaStream_t)stream>>>(tx, tz, dw, lddw, rows, n_out, k_in,
+                                                                                    tiles_n, rps, debug_swap);
+    GNB_RETURN_LAUNCH();
+}

@@ -213,6 +213,15 @@ def _gemm_bwd_weight(dz: Tensor, x: Tensor, dw: Tensor, k: int) -> None:
           dz.shape[1], k, _stream())
 
 
+WGRAD_TC = os.environ.get("GNB_WGRAD_TC", "1") == "1"      # tcgen05 weight gradients in tf32 mode
+WGRAD_SWAP = int(os.environ.get("GNB_WGRAD_SWAP", "0"))     # bring-up aid: swap LBO/SBO in the MN-major descriptors
+
+
+def _gemm_bwd_weight_tc(dz: Tensor, x: Tensor, dw: Tensor, k: int) -> None:
+    _call("gnb_linear_bwd_weight_tf32", _ptr(dz), _ld(dz), _ptr(x), _ld(x), _ptr(dw), _ld(dw), dz.shape[0],
+          dz.shape[1], k, WGRAD_SWAP, _stream())
+
+
 def _act_bwd(g: Tensor, y: Tensor, act: int) -> Tensor:
     g = _rowmajor(g)
     if act == ACT_NONE:
@@ -316,7 +325,10 @@ class _MultiLinearAct(torch.autograd.Function):
         for i, (p, off) in enumerate(zip(parts, ctx.offsets)):
             kp = p.shape[1]
             if dw is not None:
-                _gemm_bwd_weight(dz, p, dw[:, off:], kp)
+                if ctx.tc and WGRAD_TC:
+                    _gemm_bwd_weight_tc(_tc_operand(dz), _tc_operand(p), dw[:, off:], kp)
+                else:
+                    _gemm_bwd_weight(dz, p, dw[:, off:], kp)
             if ctx.needs_input_grad[4 + i]:
                 if ctx.tc:    # dx = dz W on the tensor cores: same kernel, W^T as the weight operand
                     dzr = _tc_operand(dz)

@@ -106,6 +106,10 @@ int gnb_colsum(const float* a, int64_t lda, int64_t rows, int32_t cols, float* o
 int gnb_linear_fwd_tf32(const float* const* xs, const int64_t* ldxs, const int32_t* ks, int32_t nparts, const float* w,
                         int64_t ldw, const float* bias, float* y, int64_t ldy, int64_t rows, int32_t n_out, int32_t act,
                         int32_t round_out, void* stream);
+/* dw[n_out, k_in] += dz[rows, n_out]^T x[rows, k_in] on tcgen05 (split over rows, fp32 red.add into dw).
+ * TMA-fed MN-major operands; same alignment rules as gnb_linear_fwd_tf32. debug_swap: 0 in production. */
+int gnb_linear_bwd_weight_tf32(const float* dz, int64_t lddz, const float* x, int64_t ldx, float* dw, int64_t lddw,
+                               int64_t rows, int32_t n_out, int32_t k_in, int32_t debug_swap, void* stream);
 /* dst[rows, dst_cols] = [rna_tf32(src[rows, cols]) | 0]. */
 int gnb_round_pad_tf32(const float* src, int64_t lds, int64_t rows, int32_t cols, float* dst, int64_t ldd,
                        int32_t dst_cols, void* stream);
