@@ -3,9 +3,11 @@
 // all edges / nodes of the batch).
 //
 // Both operands are row-major with the reduction index (row) as the SLOW dimension, i.e. "MN-major" in UMMA
-// terms. TMA drops [32 rows x 32 columns] boxes (128-byte swizzle) straight into the canonical MN-major layout
-// (atom = 8 rows x 128 B; LBO = distance between 32-column blocks, SBO = distance between 8-row groups), so no
-// thread ever touches the operands:
+// terms. For 32-bit MN-major operands the only UMMA layout is "128-byte swizzle with 32-byte atomicity"
+// (Swizzle<2,5,2>: atom = 4 rows x 128 B, 32-byte chunks XOR-ed with row & 3; descriptor layout type 1), which
+// TMA produces with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B. TMA drops [32 rows x 32 columns] boxes straight into
+// that layout (LBO = distance between 32-column blocks = 4096 B, SBO = distance between 4-row groups = 512 B),
+// so no thread ever touches the operands:
 //     A = x tile   : M = 128 k_in columns  x K = 32 rows     (4 boxes,  16 KiB)
 //     B = dz tile  : N <= 256 n_out columns x K = 32 rows    (<= 8 boxes, 32 KiB)
 //     D[k_in, n_out] in TMEM (lane = k_in, column = n_out)
@@ -24,14 +26,14 @@ constexpr uint32_t WG_B_BYTES = (WG_BN / 32) * WG_BOX_BYTES;         // 32 KiB
 constexpr uint32_t WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;
 constexpr uint32_t WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
 
-// MN-major operand, 128-byte swizzle: lbo/sbo in bytes
+// MN-major 32-bit operand, 128-byte swizzle with 32-byte atomicity (layout type 1): lbo/sbo in bytes
 __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
     d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16;
     d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32;
-    d |= static_cast<uint64_t>(1) << 46;
-    d |= static_cast<uint64_t>(2) << 61;
+    d |= static_cast<uint64_t>(1) << 46;          // descriptor version (sm_100)
+    d |= static_cast<uint64_t>(1) << 61;          // SWIZZLE_128B_BASE32B
     return d;
 }
 
@@ -95,8 +97,10 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             if (lane == 0) {
                 // kind::tf32, fp32 accumulate, A and B MN-major (bits 15, 16)
                 const uint32_t idesc = tc::umma_idesc_tf32(WG_BM, (uint32_t)n_mma) | (1u << 15) | (1u << 16);
-                const uint32_t lbo = swap_lbo_sbo ? 1024u : WG_BOX_BYTES;
-                const uint32_t sbo = swap_lbo_sbo ? WG_BOX_BYTES : 1024u;
+                // bring-up variants (production: 0): bit0 swaps LBO/SBO, bit1 uses an 8-row K group stride
+                const uint32_t kgrp = (swap_lbo_sbo & 2) ? 1024u : 512u;
+                const uint32_t lbo = (swap_lbo_sbo & 1) ? kgrp : WG_BOX_BYTES;
+                const uint32_t sbo = (swap_lbo_sbo & 1) ? WG_BOX_BYTES : kgrp;
                 for (int it = 0; it < num_kb; ++it) {
                     const int s = it % WG_STAGES;
                     const uint32_t ph = (it / WG_STAGES) & 1;
@@ -138,9 +142,9 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     if (warp == 1) tc::tmem_dealloc<WG_BN>(tmem_base);
 }
 
-// [rows, cols] fp32 row-major, box = 32 columns x 32 rows, 128-byte swizzle, OOB -> 0
+// [rows, cols] fp32 row-major, box = 32 columns x 32 rows, 128-byte swizzle with 32-byte atoms, OOB -> 0
 static int make_tmap_box32(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld) {
-    return gnb_make_tmap_f32(map, base, rows, cols, ld, 32u);
+    return gnb_make_tmap_f32(map, base, rows, cols, ld, 32u, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
 }
 
 }  // namespace

@@ -353,6 +353,73 @@ __global__ void relu_bwd_kernel(const float* __restrict__ g, int64_t ldg, const 
     reinterpret_cast<float4*>(dz + r * ldz)[c] = gv;
 }
 
+
+// Fused backward of "activation + bias" for a Linear output, optionally combined with the backward of the
+// k-neighbour aggregation in front of it:
+//   dz[r, :] = g_row(r) * act'(y[r, :])       db[:] += sum_r dz[r, :]
+// with g_row(r) = g[r] (plain) or, when deg != nullptr, the broadcast of the aggregated gradient
+// g[i] (add) / g[i]/deg[i] (mean) to the valid slots of node i = r / width (zero for padding slots).
+// One pass over the E x C tensors instead of three (aggregate-bwd, relu-bwd, colsum).
+// CTA = 64 float4 columns x 4 rows, ACT_ROWS rows per CTA, grid.y over 256-column chunks.
+constexpr int ACT_ROWS = 256;
+
+__global__ void __launch_bounds__(256)
+act_bwd_colsum_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ y, int64_t ldy,
+                      int64_t rows, int cols4, float* __restrict__ dz, int64_t ldz, float* __restrict__ db, int flags,
+                      const int* __restrict__ deg, int width, int aggr) {
+    const int c4 = blockIdx.y * 64 + threadIdx.x;
+    const int ty = threadIdx.y;
+    const bool col_ok = c4 < cols4;
+    const bool relu = (flags & 0xff) == GNB_ACT_RELU, rnd = (flags & GNB_FLAG_ROUND_TF32) != 0;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t r0 = (int64_t)blockIdx.x * ACT_ROWS;
+    const int64_t r1 = r0 + ACT_ROWS < rows ? r0 + ACT_ROWS : rows;
+    if (col_ok) {
+        for (int64_t r = r0 + ty; r < r1; r += 4) {
+            float4 gv;
+            if (deg != nullptr) {
+                const int64_t i = r / width;
+                const int s = (int)(r - i * width);
+                const int dg = deg[i];
+                if (s < dg) {
+                    gv = reinterpret_cast<const float4*>(g + i * ldg)[c4];
+                    if (aggr == GNB_AGGR_MEAN) {
+                        const float sc = 1.f / (float)dg;
+                        gv.x *= sc; gv.y *= sc; gv.z *= sc; gv.w *= sc;
+                    }
+                } else {
+                    gv = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+                gv = reinterpret_cast<const float4*>(g + r * ldg)[c4];
+            }
+            if (relu) {
+                const float4 yv = reinterpret_cast<const float4*>(y + r * ldy)[c4];
+                gv.x = yv.x > 0.f ? gv.x : 0.f; gv.y = yv.y > 0.f ? gv.y : 0.f;
+                gv.z = yv.z > 0.f ? gv.z : 0.f; gv.w = yv.w > 0.f ? gv.w : 0.f;
+            }
+            if (rnd) {
+                gv.x = gnb_round_tf32(gv.x); gv.y = gnb_round_tf32(gv.y);
+                gv.z = gnb_round_tf32(gv.z); gv.w = gnb_round_tf32(gv.w);
+            }
+            reinterpret_cast<float4*>(dz + r * ldz)[c4] = gv;
+            acc.x += gv.x; acc.y += gv.y; acc.z += gv.z; acc.w += gv.w;
+        }
+    }
+    if (db == nullptr) return;
+    __shared__ float4 s_acc[4][64];
+    s_acc[ty][threadIdx.x] = acc;
+    __syncthreads();
+    if (ty == 0 && col_ok) {
+        for (int t = 1; t < 4; ++t) {
+            const float4 o = s_acc[t][threadIdx.x];
+            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        atomicAdd(db + 4 * c4 + 0, acc.x); atomicAdd(db + 4 * c4 + 1, acc.y);
+        atomicAdd(db + 4 * c4 + 2, acc.z); atomicAdd(db + 4 * c4 + 3, acc.w);
+    }
+}
+
 // out[c] += sum_r a[r, c]; out must be zero on entry. CTA = 32 x 8, 256 rows per CTA.
 __global__ void colsum_kernel(const float* __restrict__ a, int64_t lda, int64_t rows, int cols,
                               float* __restrict__ out) {
@@ -471,6 +538,20 @@ GNB_EXPORT int gnb_relu_bwd(const float* g, int64_t ldg, const float* y, int64_t
     if (rows == 0) return GNB_OK;
     relu_bwd_kernel<<<gnb_div_up(rows * (cols >> 2), 256), 256, 0, (cudaStream_t)stream>>>(g, ldg, y, ldy, rows, cols,
                                                                                            dz, ldz, flags);
+    GNB_RETURN_LAUNCH();
+}
+
+
+GNB_EXPORT int gnb_act_bwd_colsum(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows, int32_t cols,
+                                  float* dz, int64_t ldz, float* db, int32_t flags, const int32_t* deg, int32_t width,
+                                  int32_t aggr, void* stream) {
+    if ((cols & 3) || (ldg & 3) || (ldz & 3) || !aligned16(g) || !aligned16(dz)) return GNB_ERR_ARG;
+    if ((flags & 0xff) == GNB_ACT_RELU && ((ldy & 3) || !aligned16(y))) return GNB_ERR_ARG;
+    if (deg != nullptr && (width < 1 || aggr < 0 || aggr > 1)) return GNB_ERR_ARG;
+    if (rows == 0) return GNB_OK;
+    dim3 grid((unsigned)gnb_div_up(rows, ACT_ROWS), (unsigned)gnb_div_up(cols >> 2, 64)), block(64, 4);
+    act_bwd_colsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(g, ldg, y, ldy, rows, cols >> 2, dz, ldz, db, flags,
+                                                                    deg, width, aggr);
     GNB_RETURN_LAUNCH();
 }
 

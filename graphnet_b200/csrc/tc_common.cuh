@@ -156,7 +156,7 @@ static inline gnb_encode_tiled_fn gnb_get_encode_tiled() {
 // fp32 row-major matrix [rows, cols] with row pitch ld (elements): box = [32 cols (=128 B), box_rows],
 // 128-byte swizzle, out-of-bounds elements read as zero.
 static inline int gnb_make_tmap_f32(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld,
-                                    uint32_t box_rows) {
+                                    uint32_t box_rows, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     gnb_encode_tiled_fn enc = gnb_get_encode_tiled();
     if (enc == nullptr) return -2;
     if ((reinterpret_cast<uintptr_t>(base) & 15u) || ((ld * 4) & 15)) return -1;
@@ -165,7 +165,7 @@ static inline int gnb_make_tmap_f32(CUtensorMap* map, const float* base, int64_t
     cuuint32_t box[2] = {32u, box_rows};
     cuuint32_t estr[2] = {1u, 1u};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -1;
 }

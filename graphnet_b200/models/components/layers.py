@@ -79,6 +79,8 @@ class DynEdgeConv(Model):
             if lin1.bias is not None:
                 bcat = torch.cat([lin1.bias, torch.zeros_like(lin1.bias)])
             pq = ops.linear_act(x, wcat, bcat, ops.ACT_NONE)             # [N, 2H] = [P | Q]
+            if lin1.out_features % 4 == 0 and lin2.out_features % 4 == 0 and self.aggr in ("add", "sum", "mean"):
+                return ops.edgeconv_hoisted(pq, lin2.weight, lin2.bias, graph, self.aggr)
             if lin1.out_features % 4 == 0:
                 h = ops.edge_hidden(pq, graph, ops.ACT_RELU)             # [N*W, H]
                 m = ops.linear_act(h, lin2.weight, lin2.bias, ops.ACT_RELU)

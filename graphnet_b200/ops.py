@@ -222,19 +222,30 @@ def _gemm_bwd_weight_tc(dz: Tensor, x: Tensor, dw: Tensor, k: int) -> None:
           dz.shape[1], k, WGRAD_SWAP, _stream())
 
 
-def _act_bwd(g: Tensor, y: Tensor, act: int) -> Tensor:
+def _bias_act_backward(g: Tensor, y: Optional[Tensor], act: int, want_db: bool,
+                       graph: Optional["KnnGraph"] = None, aggr: int = 0) -> Tuple[Tensor, Optional[Tensor]]:
+    """dz = grow * act'(y) and db = colsum(dz) in ONE pass (gnb_act_bwd_colsum). With `graph`, `g` is the
+    gradient of the aggregated node tensor and is broadcast to the node's valid edge slots first."""
     g = _rowmajor(g)
-    if act == ACT_NONE:
-        return g
-    dz = torch.empty(g.shape, dtype=torch.float32, device=g.device)
-    if g.shape[1] % 4 == 0 and _ld(g) % 4 == 0 and _ld(y) % 4 == 0 and g.data_ptr() % 16 == 0:
-        _call("gnb_relu_bwd", _ptr(g), _ld(g), _ptr(y), _ld(y), g.shape[0], g.shape[1], _ptr(dz), _ld(dz),
-              FLAG_ROUND_TF32 if _tf32() else 0, _stream())
-        if _tf32():
-            _mark_rounded(dz)
-    else:   # odd widths only occur on tiny read-out tensors
-        dz = g * (y > 0)
-    return dz
+    cols = g.shape[1]
+    rows = g.shape[0] if graph is None else graph.n * graph.width
+    fast = cols % 4 == 0 and _ld(g) % 4 == 0 and g.data_ptr() % 16 == 0 and (y is None or (_ld(y) % 4 == 0 and
+                                                                                     y.data_ptr() % 16 == 0))
+    if not fast:   # odd widths only occur on tiny read-out tensors
+        assert graph is None
+        dz = g if act == ACT_NONE else g * (y > 0)
+        return dz, (dz.sum(0) if want_db else None)
+    if act == ACT_NONE and graph is None and not _tf32():
+        return g, (_colsum(g) if want_db else None)
+    dz = torch.empty(rows, cols, dtype=torch.float32, device=g.device)
+    db = torch.zeros(cols, dtype=torch.float32, device=g.device) if want_db else None
+    flags = act | (FLAG_ROUND_TF32 if _tf32() else 0)
+    _call("gnb_act_bwd_colsum", _ptr(g), _ld(g), _ptr(y), 0 if y is None else _ld(y), rows, cols, _ptr(dz), _ld(dz),
+          _ptr(db), flags, _ptr(None if graph is None else graph.deg), 1 if graph is None else graph.width, aggr,
+          _stream())
+    if _tf32():
+        _mark_rounded(dz)
+    return dz, db
 
 
 def _round_pad(src: Tensor, dst_cols: Optional[int] = None) -> Tensor:
@@ -289,6 +300,49 @@ def _colsum(a: Tensor) -> Tensor:
     return out
 
 
+def _dense_forward(parts: Sequence[Tensor], w: Tensor, b: Optional[Tensor], offsets: Sequence[int], act: int):
+    """y = act(sum_p parts[p] @ w[:, off_p : off_p + K_p]^T + b). Returns (y, parts as consumed, used_tc)."""
+    rows, n_out = parts[0].shape[0], w.shape[0]
+    tc = _tf32() and len(parts) <= 6 and rows > 0
+    if tc:
+        parts = tuple(_tc_operand(p) for p in parts)
+        packed = _tc_pack_weight(w, offsets, [p.shape[1] for p in parts])
+        y = _tc_linear(parts, packed, b, n_out, act, round_out=True)
+    else:
+        y = torch.empty(rows, n_out, dtype=torch.float32, device=w.device)
+        last = len(parts) - 1
+        for i, (p, off) in enumerate(zip(parts, offsets)):
+            _gemm_fwd(p, w[:, off:], b if i == last else None, y, p.shape[1],
+                      act if i == last else ACT_NONE, accumulate=i > 0)
+    return y, tuple(parts), tc
+
+
+def _dense_backward(dz: Tensor, w: Tensor, parts: Sequence[Tensor], offsets: Sequence[int], need_dw: bool,
+                    need_dparts: Sequence[bool], tc: bool):
+    """dW = dz^T [parts] (into the packed column layout of w) and dparts[p] = dz @ w[:, off_p : off_p + K_p]."""
+    dw = torch.zeros_like(w) if need_dw else None
+    dzr = _tc_operand(dz) if tc else dz
+    dparts: List[Optional[Tensor]] = []
+    for p, off, need in zip(parts, offsets, need_dparts):
+        kp = p.shape[1]
+        if dw is not None:
+            if tc and WGRAD_TC:
+                _gemm_bwd_weight_tc(dzr, _tc_operand(p), dw[:, off:], kp)
+            else:
+                _gemm_bwd_weight(dz, p, dw[:, off:], kp)
+        if not need:
+            dparts.append(None)
+        elif tc:      # dx = dz W on the tensor cores: same kernel, W^T as the weight operand
+            wt = w[:, off:off + kp].t().contiguous()                      # [kp, n_out]
+            dparts.append(_tc_linear((dzr,), _tc_pack_weight(wt, (0,), (wt.shape[1],)), None, kp, ACT_NONE,
+                                     round_out=False))
+        else:
+            dx = torch.empty(p.shape, dtype=torch.float32, device=p.device)
+            _gemm_bwd_data(dz, w[:, off:], dx, kp)
+            dparts.append(dx)
+    return dw, dparts
+
+
 class _MultiLinearAct(torch.autograd.Function):
     """y = act(sum_p parts[p] @ W[:, off_p : off_p + K_p]^T + b): a K-split Linear over several
     inputs, so the skip-concatenation of dynedge.py:328 is never materialised."""
@@ -297,19 +351,7 @@ class _MultiLinearAct(torch.autograd.Function):
     def forward(ctx, w: Tensor, b: Optional[Tensor], act: int, offsets: Tuple[int, ...], *parts: Tensor):
         _cuda(w, b, *parts)
         w = _rowmajor(w)
-        parts = tuple(_rowmajor(p) for p in parts)
-        rows, n_out = parts[0].shape[0], w.shape[0]
-        ctx.tc = _tf32() and len(parts) <= 6 and rows > 0
-        if ctx.tc:
-            parts = tuple(_tc_operand(p) for p in parts)
-            packed = _tc_pack_weight(w, offsets, [p.shape[1] for p in parts])
-            y = _tc_linear(parts, packed, b, n_out, act, round_out=True)
-        else:
-            y = torch.empty(rows, n_out, dtype=torch.float32, device=w.device)
-            last = len(parts) - 1
-            for i, (p, off) in enumerate(zip(parts, offsets)):
-                _gemm_fwd(p, w[:, off:], b if i == last else None, y, p.shape[1],
-                          act if i == last else ACT_NONE, accumulate=i > 0)
+        y, parts, ctx.tc = _dense_forward(tuple(_rowmajor(p) for p in parts), w, b, offsets, act)
         ctx.act, ctx.offsets = act, offsets
         ctx.has_bias = b is not None
         ctx.save_for_backward(w, y, *parts)
@@ -318,29 +360,9 @@ class _MultiLinearAct(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy: Tensor):
         w, y, *parts = ctx.saved_tensors
-        dz = _act_bwd(gy.contiguous(), y, ctx.act)
-        dw = torch.zeros_like(w) if ctx.needs_input_grad[0] else None
-        db = _colsum(dz) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
-        dparts: List[Optional[Tensor]] = []
-        for i, (p, off) in enumerate(zip(parts, ctx.offsets)):
-            kp = p.shape[1]
-            if dw is not None:
-                if ctx.tc and WGRAD_TC:
-                    _gemm_bwd_weight_tc(_tc_operand(dz), _tc_operand(p), dw[:, off:], kp)
-                else:
-                    _gemm_bwd_weight(dz, p, dw[:, off:], kp)
-            if ctx.needs_input_grad[4 + i]:
-                if ctx.tc:    # dx = dz W on the tensor cores: same kernel, W^T as the weight operand
-                    dzr = _tc_operand(dz)
-                    wt = w[:, off:off + kp].t().contiguous()                 # [kp, n_out]
-                    dx = _tc_linear((dzr,), _tc_pack_weight(wt, (0,), (wt.shape[1],)), None, kp, ACT_NONE,
-                                    round_out=False)
-                else:
-                    dx = torch.empty(p.shape, dtype=torch.float32, device=p.device)
-                    _gemm_bwd_data(dz, w[:, off:], dx, kp)
-                dparts.append(dx)
-            else:
-                dparts.append(None)
+        dz, db = _bias_act_backward(gy.contiguous(), y, ctx.act, ctx.has_bias and ctx.needs_input_grad[1])
+        dw, dparts = _dense_backward(dz, w, parts, ctx.offsets, ctx.needs_input_grad[0],
+                                     [ctx.needs_input_grad[4 + i] for i in range(len(parts))], ctx.tc)
         return (dw, db, None, None, *dparts)
 
 
@@ -449,6 +471,54 @@ class _EdgeAggregate(torch.autograd.Function):
 
 def edge_aggregate(m: Tensor, graph: KnnGraph, aggr: str = "add") -> Tensor:
     y = _EdgeAggregate.apply(m, graph, AGGR[aggr])
+    return _mark_rounded(y) if _tf32() else y
+
+
+class _EdgeConvHoisted(torch.autograd.Function):
+    """y_i = AGG_s act(W2 act(P_i + Q_{nbr[i,s]}) + b2): the whole per-edge part of a DynEdge EdgeConv as one
+    autograd node, so its backward runs as fused kernels: (aggregate-bwd + ReLU-bwd + bias-grad) in one pass,
+    dW2 and dh on the tensor cores, (ReLU-bwd + dP segment-sum + dQ scatter) in one pass."""
+
+    @staticmethod
+    def forward(ctx, pq: Tensor, w2: Tensor, b2: Optional[Tensor], graph: KnnGraph, aggr: int):
+        _cuda(pq, w2, b2)
+        pq, w2 = _rowmajor(pq), _rowmajor(w2)
+        hdim = pq.shape[1] // 2
+        rnd = FLAG_ROUND_TF32 if _tf32() else 0
+        h = torch.empty(graph.n * graph.width, hdim, dtype=torch.float32, device=pq.device)
+        _call("gnb_edge_hidden_fwd", _ptr(pq), _ld(pq), hdim, _ptr(graph.nbr), _ptr(graph.deg), graph.width, graph.n,
+              ACT_RELU | rnd, _ptr(h), _ld(h), _stream())
+        if _tf32():
+            _mark_rounded(h)
+        m, (h,), ctx.tc = _dense_forward((h,), w2, b2, (0,), ACT_RELU)
+        c = m.shape[1]
+        y = torch.empty(graph.n, c, dtype=torch.float32, device=pq.device)
+        _call("gnb_edge_aggregate_fwd", _ptr(m), _ld(m), c, _ptr(graph.deg), graph.width, graph.n, aggr | rnd, _ptr(y),
+              _ld(y), _ptr(None), _stream())
+        ctx.graph, ctx.aggr, ctx.has_bias = graph, aggr, b2 is not None
+        ctx.save_for_backward(h, m, w2)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy: Tensor):
+        h, m, w2 = ctx.saved_tensors
+        graph = ctx.graph
+        dz, db2 = _bias_act_backward(gy.contiguous(), m, ACT_RELU, ctx.has_bias and ctx.needs_input_grad[2], graph,
+                                     ctx.aggr)
+        dw2, (dh,) = _dense_backward(dz, w2, (h,), (0,), ctx.needs_input_grad[1], (ctx.needs_input_grad[0],), ctx.tc)
+        dpq = None
+        if dh is not None:
+            hdim = h.shape[1]
+            dpq = torch.zeros(graph.n, 2 * hdim, dtype=torch.float32, device=h.device)
+            _call("gnb_edge_hidden_bwd", _ptr(dh), _ld(dh), _ptr(h), _ld(h), hdim, _ptr(graph.nbr), _ptr(graph.deg),
+                  graph.width, graph.n, ACT_RELU, _ptr(dpq), _ld(dpq), _stream())
+        return dpq, dw2, db2, None, None
+
+
+def edgeconv_hoisted(pq: Tensor, w2: Tensor, b2: Optional[Tensor], graph: KnnGraph, aggr: str = "add") -> Tensor:
+    """Per-edge half of EdgeConv for an MLP `Linear, ReLU, Linear, ReLU` whose first Linear was hoisted to nodes
+    (pq = [P | Q]); aggr in add / mean. (max keeps the unfused route: it needs the arg-routed backward.)"""
+    y = _EdgeConvHoisted.apply(pq, w2, b2, graph, AGGR[aggr])
     return _mark_rounded(y) if _tf32() else y
 
 

@@ -95,6 +95,12 @@ int gnb_segment_pool_bwd(const float* gout, const int32_t* arg, int32_t c, const
 /* dz = g * (y > 0), all [rows, cols], cols % 4 == 0; flags & 0x100: round dz to tf32. */
 int gnb_relu_bwd(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows, int32_t cols, float* dz,
                  int64_t ldz, int32_t flags, void* stream);
+/* Fused backward of bias+activation (and optionally of the k-neighbour aggregation in front of it):
+ * dz[r] = grow(r) * act'(y[r]), db += colsum(dz); grow(r) = g[r] or, with deg != NULL, g[r / width] (add) or
+ * g[r / width] / deg (mean) for valid slots and 0 for padding slots. flags: act | 0x100 (round dz to tf32). */
+int gnb_act_bwd_colsum(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows, int32_t cols, float* dz,
+                       int64_t ldz, float* db, int32_t flags, const int32_t* deg, int32_t width, int32_t aggr,
+                       void* stream);
 /* out[c] += sum_r a[r, c]. */
 int gnb_colsum(const float* a, int64_t lda, int64_t rows, int32_t cols, float* out, void* stream);
 
