@@ -25,12 +25,13 @@ SIGNATURES: Dict[str, list] = {
     "gnb_global_vars": [_p, _i64, _i32, _p, _p, _i32, _p, _i64, _p, _p, _p, _i64, _p],
     "gnb_edge_hidden_fwd": [_p, _i64, _i32, _p, _p, _i32, _i64, _i32, _p, _i64, _p],
     "gnb_edge_hidden_bwd": [_p, _i64, _p, _i64, _i32, _p, _p, _i32, _i64, _i32, _p, _i64, _p],
+    "gnb_edgeconv_fused_fwd_tf32": [_p, _i64, _i32, _p, _p, _i32, _i64, _p, _i64, _p, _i32, _i32, _i32, _p, _i64, _p],
     "gnb_edge_cat_fwd": [_p, _i64, _i32, _p, _p, _i32, _i64, _p, _i64, _p],
     "gnb_edge_cat_bwd": [_p, _i64, _i32, _p, _p, _i32, _i64, _p, _i64, _p],
     "gnb_edge_aggregate_fwd": [_p, _i64, _i32, _p, _i32, _i64, _i32, _p, _i64, _p, _p],
     "gnb_edge_aggregate_bwd": [_p, _i64, _i32, _p, _i32, _i64, _i32, _p, _p, _i64, _p],
     "gnb_segment_pool_fwd": [_p, _i64, _i32, _p, _i64, _p, _i32, _p, _p, _p],
-    "gnb_segment_pool_bwd": [_p, _p, _i32, _p, _i64, _i64, _p, _i32, _p, _i64, _p],
+    "gnb_segment_pool_bwd": [_p, _i64, _p, _i32, _p, _i64, _i64, _p, _i32, _p, _i64, _p],
     "gnb_relu_bwd": [_p, _i64, _p, _i64, _i64, _i32, _p, _i64, _i32, _p],
     "gnb_linear_fwd_tf32": [_p, _p, _p, _i32, _p, _i64, _p, _p, _i64, _i64, _i32, _i32, _i32, _p],
     "gnb_linear_bwd_weight_tf32": [_p, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _p],
@@ -41,6 +42,28 @@ SIGNATURES: Dict[str, list] = {
     "gnb_linear_bwd_data_f32": [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i32, _p],
     "gnb_linear_bwd_weight_f32": [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _p],
 }
+
+
+
+class DynEdgeConfig(ctypes.Structure):
+    """Mirror of `gnb_dynedge_config` (include/graphnet_b200.h)."""
+    _fields_ = [("nb_inputs", _i32), ("k", _i32), ("precision", _i32),
+                ("n_conv", _i32), ("conv_hidden", _i32 * 8), ("conv_out", _i32 * 8),
+                ("n_post", _i32), ("post_out", _i32 * 8),
+                ("n_readout", _i32), ("readout_out", _i32 * 8),
+                ("n_pool", _i32), ("pool", _i32 * 4),
+                ("globals_after_pooling", _i32), ("skip_readout", _i32),
+                ("n_knn_cols", _i32), ("knn_cols", _i32 * 16)]
+
+
+SIGNATURES.update({
+    "gnb_launch_count": [],
+    "gnb_dynedge_workspace_bytes": [_p, _i64, _i64, _i32, _i32],
+    "gnb_dynedge_layout": [_p, _i64, _i64, _i32, _i32, _p],
+    "gnb_dynedge_forward": [_p, _p, _p, _i64, _p, _p, _p, _p, _i32, _p, _i64, _i64, _p, _i64, _p, _i32, _p],
+    "gnb_dynedge_backward": [_p, _p, _p, _p, _p, _i32, _i64, _i64, _p, _i64, _p, _p],
+})
+RESTYPES = {"gnb_dynedge_workspace_bytes": ctypes.c_int64, "gnb_launch_count": ctypes.c_int64}
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -63,7 +86,7 @@ def load() -> ctypes.CDLL:
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)   # AttributeError here = header / library mismatch
         fn.argtypes = argtypes
-        fn.restype = ctypes.c_int
+        fn.restype = RESTYPES.get(name, ctypes.c_int)
     _lib = lib
     return lib
 

@@ -9,9 +9,13 @@
 
 #define GNB_EXPORT extern "C" __attribute__((visibility("default")))
 
+// Number of kernels this library has launched (bench.py reports the per-step delta as `gpu_launches`).
+extern "C" long long gnb_launch_counter;
+
 // Launch-error check: returns the cudaError_t (>0) to the C-ABI caller; never throws.
 #define GNB_RETURN_LAUNCH()                          \
     do {                                             \
+        ++gnb_launch_counter;                        \
         cudaError_t e__ = cudaGetLastError();        \
         return e__ == cudaSuccess ? GNB_OK : (int)e__; \
     } while (0)

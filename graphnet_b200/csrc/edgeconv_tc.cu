@@ -1,0 +1,333 @@
+// Fused dynamic EdgeConv forward on tcgen05 (tf32 mode, inference path):
+//
+//     y[i, :] = AGG_{s < deg[i]}  relu( W2 relu(P[i] + Q[nbr[i,s]]) + b2 )
+//
+// i.e. the per-edge half of PyG EdgeConv.propagate at src/graphnet/models/components/layers.py:60 for the DynEdge
+// MLP (dynedge.py:192-210) after the first Linear has been hoisted to nodes (pq = [P | Q] = x [W1a-W1b ; W1b]^T).
+// The gather, the hidden activation, the E x H x C contraction, bias + ReLU and the k-neighbour aggregation run
+// in ONE kernel: neither the [E, H] hidden tensor nor the [E, C] message tensor ever exists in HBM.
+//
+// Mapping. Orientation is "weights are A": D[channel, edge] = W2_half[128 ch x H] * Hid[edges x H]^T, so a TMEM
+// lane is an output channel and a TMEM column is an edge; an epilogue thread then sums its channel over the
+// consecutive columns of a node entirely in registers (no shuffles, any degree) and writes y[node, ch]
+// with 32 consecutive channels per warp store.
+//   * a CTA owns one 128-channel half of W2 for its whole life: the half (<= 11 K-blocks of 128 x 32 tf32 =
+//     176 KiB) is TMA-loaded ONCE into shared memory; no weight streaming in the main loop;
+//   * persistent loop over tiles of `npt` consecutive nodes (npt * width <= 128 edges);
+//   * warp 0 prepares per-tile edge lists (source / target node per row, node boundaries) up to two tiles ahead;
+//   * 8 builder warps gather P[i] + Q[j] from L2/HBM (fully coalesced 128-byte row segments, loads issued two
+//     K-blocks ahead), apply ReLU, round to tf32 and write the B operand tile (<= 128 edges x 32) straight into the 128-byte-
+//     swizzled K-major layout (2-stage ring, mbarrier + proxy fence);
+//   * 1 thread issues tcgen05.mma (kind::tf32, M = 128, N = edges rounded up to 16);
+//   * accumulators double-buffered in TMEM (2 x 128 columns): 4 epilogue warps drain tile t while tile t+1 is
+//     being built and multiplied.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int EF_THREADS = 448;                 // 14 warps: 0 TMA/setup, 1 MMA, 2-5 epilogue, 6-13 builders
+constexpr int EF_BUILDERS = 256;
+constexpr int EF_MAX_KB = 11;                   // hidden width <= 352
+constexpr int EF_STAGES = 2;
+constexpr uint32_t EF_TILE_BYTES = 128 * 32 * 4;   // 16 KiB: 128 rows x 32 tf32
+
+struct TileMeta {
+    int src[128];          // source node j of each edge row
+    int node[128];         // target node i of each edge row
+    unsigned last[4];      // bit e set: edge row e is the last edge of its node
+    int flush_node[32];    // target node of the f-th flush
+    float flush_scale[32]; // 1 (add) or 1/deg (mean)
+    int n_edges, n_mma;
+};
+
+struct EfParams {
+    const float* pq; int64_t ldpq; int hdim; int kblocks;
+    const int* nbr; const int* deg; int width; int64_t n;
+    const float* b2; int c_out; int aggr; int round_out;
+    float* y; int64_t ldy; int num_tiles; int npt;
+};
+
+__global__ void __launch_bounds__(EF_THREADS, 1)
+edgeconv_fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_a = smem;                                            // [kblocks][16 KiB] resident weights
+    uint8_t* s_b = smem + EF_MAX_KB * EF_TILE_BYTES;                // [2][16 KiB] hidden tiles
+    TileMeta* meta = reinterpret_cast<TileMeta*>(s_b + EF_STAGES * EF_TILE_BYTES);   // [2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 2);
+    uint64_t* a_full = bars;
+    uint64_t* b_full = bars + 1;      // [2]
+    uint64_t* b_empty = bars + 3;     // [2]
+    uint64_t* tmem_full = bars + 5;   // [2]
+    uint64_t* tmem_empty = bars + 7;  // [2]
+    uint64_t* meta_full = bars + 9;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int half = blockIdx.y;                    // 128-channel block of W2 owned by this CTA
+    const int ch_base = half * 128;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            tc::mbar_init(a_full, 1);
+            for (int s = 0; s < 2; ++s) {
+                tc::mbar_init(&b_full[s], EF_BUILDERS / 32);
+                tc::mbar_init(&b_empty[s], 1);
+                tc::mbar_init(&tmem_full[s], 1);
+                tc::mbar_init(&tmem_empty[s], 4);
+                tc::mbar_init(&meta_full[s], 1);
+            }
+            tc::fence_barrier_init();
+            tc::fence_proxy_async();
+        }
+        __syncwarp();
+        tc::tmem_alloc<256>(tmem_slot);
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {   // resident weights: one TMA box per K-block, a single transaction barrier
+            tc::tma_prefetch_desc(&tm_w2);
+            tc::mbar_arrive_expect_tx(a_full, (uint32_t)p.kblocks * EF_TILE_BYTES);
+            for (int kb = 0; kb < p.kblocks; ++kb) tc::tma_load_2d(s_a + kb * EF_TILE_BYTES, &tm_w2, a_full, kb * 32, ch_base);
+        }
+        __syncwarp();
+        // ---- tile metadata producer: runs up to two tiles ahead of the builders ---------------------------
+        uint32_t ti = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++ti) {
+            const uint32_t buf = ti & 1;
+            tc::mbar_wait<200>(&tmem_empty[buf], ((ti >> 1) & 1) ^ 1); // epilogue of tile ti-2 has released meta[buf]
+            TileMeta& m = meta[buf];
+            const int64_t node0 = (int64_t)t * p.npt;
+            const int nn = (int)((p.n - node0) < p.npt ? (p.n - node0) : p.npt);
+            const int d = lane < nn ? p.deg[node0 + lane] : 0;
+            int incl = d;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int off = incl - d;
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (lane < 4) m.last[lane] = 0u;
+            __syncwarp();
+            const unsigned has = __ballot_sync(0xffffffffu, d > 0);
+            if (d > 0) {
+                const int pos = __popc(has & ((1u << lane) - 1u));
+                m.flush_node[pos] = (int)(node0 + lane);
+                m.flush_scale[pos] = p.aggr == GNB_AGGR_MEAN ? 1.f / (float)d : 1.f;
+                for (int s = 0; s < d; ++s) {
+                    m.src[off + s] = p.nbr[(node0 + lane) * p.width + s];
+                    m.node[off + s] = (int)(node0 + lane);
+                }
+                const int e = off + d - 1;
+                atomicOr(&m.last[e >> 5], 1u << (e & 31));
+            }
+            if (lane == 0) {
+                m.n_edges = total;
+                const int nm = (total + 15) & ~15;
+                m.n_mma = nm < 16 ? 16 : nm;
+            }
+            // nodes without in-edges aggregate to 0 (PyG: empty neighbourhood -> 0)
+            for (int l = 0; l < nn; ++l) {
+                const int dl = __shfl_sync(0xffffffffu, d, l);
+                if (dl == 0)
+                    for (int c = lane; c < 128; c += 32)
+                        if (ch_base + c < p.c_out) p.y[(node0 + l) * p.ldy + ch_base + c] = 0.f;
+            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&meta_full[buf]);
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            tc::mbar_wait(a_full, 0);
+            uint32_t it = 0, ti = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++ti) {
+                const uint32_t buf = ti & 1;
+                tc::mbar_wait(&tmem_empty[buf], ((ti >> 1) & 1) ^ 1);
+                tc::tcgen05_fence_after();
+                const uint32_t acc = tmem_base + buf * 128;
+                for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+                    const uint32_t s = it & 1, ph = (it >> 1) & 1;
+                    tc::mbar_wait<20>(&b_full[s], ph);
+                    tc::tcgen05_fence_after();
+                    const uint32_t idesc = tc::umma_idesc_tf32(128, (uint32_t)meta[buf].n_mma);
+                    const uint64_t adesc = tc::umma_desc_sw128_kmajor(tc::smem_u32(s_a + kb * EF_TILE_BYTES));
+                    const uint64_t bdesc = tc::umma_desc_sw128_kmajor(tc::smem_u32(s_b + s * EF_TILE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::umma_tf32(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc::umma_commit(&b_empty[s]);
+                }
+                tc::umma_commit(&tmem_full[buf]);
+            }
+        }
+    } else if (warp < 6) {
+        // ---- epilogue: bias + ReLU + k-neighbour aggregation in registers, coalesced stores ----------------
+        const int q = warp & 3;
+        const int ch = ch_base + q * 32 + lane;
+        const bool ch_ok = ch < p.c_out;
+        const float bv = (ch_ok && p.b2 != nullptr) ? p.b2[ch] : 0.f;
+        uint32_t ti = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++ti) {
+            const uint32_t buf = ti & 1;
+            tc::mbar_wait<100>(&tmem_full[buf], (ti >> 1) & 1);
+            tc::tcgen05_fence_after();
+            const TileMeta& m = meta[buf];
+            const int n_edges = m.n_edges;
+            float acc = 0.f;
+            int fl = 0;
+            for (int c = 0; c * 32 < n_edges; ++c) {
+                uint32_t r[32];
+                tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + c * 32), r);
+                tc::tmem_ld_wait();
+                const unsigned lastbits = m.last[c];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    acc += fmaxf(__uint_as_float(r[j]) + bv, 0.f);
+                    if ((lastbits >> j) & 1u) {
+                        float o = acc * m.flush_scale[fl];
+                        if (p.round_out) o = tc::round_tf32(o);
+                        if (ch_ok) p.y[(int64_t)m.flush_node[fl] * p.ldy + ch] = o;
+                        ++fl;
+                        acc = 0.f;
+                    }
+                }
+            }
+            tc::tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tmem_empty[buf]);
+        }
+    } else {
+        // ---- builders: gather P[i] + Q[j], ReLU, tf32 rounding, swizzled K-major store -------------------
+        // 8 consecutive lanes cover the 128 bytes (one K-block) of ONE edge row, so every warp load touches 4 rows x
+        // 128 B (full sectors); a thread owns 16-byte chunk `chunk` of rows 4*rg + {0,1,2,3}. Global loads run two
+        // K-blocks ahead of the shared-memory stores (register ring of three, statically unrolled).
+        const int bt = threadIdx.x - 192;            // 0..255
+        const int chunk = bt & 7, rg = bt >> 3;
+        const int kbs = p.kblocks;
+        const float* __restrict__ pq = p.pq;
+        const int tiles_cta = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const bool tail_chunk = (kbs - 1) * 32 + chunk * 4 >= p.hdim;      // this chunk is K padding in the last block
+        uint32_t g = 0;                                                     // flat (tile, K-block) step counter
+
+        struct Regs { float4 pv[4], qv[4]; };
+        for (int tl = 0; tl < tiles_cta; ++tl) {
+            const int b = tl & 1;
+            tc::mbar_wait<50>(&meta_full[b], (tl >> 1) & 1);
+            const TileMeta& m = meta[b];
+            const int n_edges = m.n_edges;
+            int offp[4], offq[4];
+            bool ok[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int row = 4 * rg + j;
+                ok[j] = row < n_edges;
+                // rows past the edge list read a valid dummy location (row 0 of the tile); they are never stored
+                const int rr = ok[j] ? row : 0;
+                offp[j] = m.node[rr] * (int)p.ldpq + chunk * 4;
+                offq[j] = m.src[rr] * (int)p.ldpq + p.hdim + chunk * 4;
+            }
+            if (n_edges == 0) { offp[0] = offp[1] = offp[2] = offp[3] = 0; offq[0] = offq[1] = offq[2] = offq[3] = 0; }
+
+            auto load = [&](int kb, Regs& r) {
+                if (kb >= kbs) return;
+                if (kb == kbs - 1 && tail_chunk) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { r.pv[j] = make_float4(0.f, 0.f, 0.f, 0.f); r.qv[j] = r.pv[j]; }
+                    return;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    r.pv[j] = __ldg(reinterpret_cast<const float4*>(pq + offp[j] + kb * 32));
+                    r.qv[j] = __ldg(reinterpret_cast<const float4*>(pq + offq[j] + kb * 32));
+                }
+            };
+            auto emit = [&](int kb, const Regs& r) {
+                if (kb >= kbs) return;
+                const uint32_t st = g & 1, ph = (g >> 1) & 1;
+                ++g;
+                tc::mbar_wait<20>(&b_empty[st], ph ^ 1);             // MMA has consumed this stage
+                uint8_t* base = s_b + st * EF_TILE_BYTES;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (ok[j]) {
+                        const int row = 4 * rg + j;
+                        // relu, then round-to-nearest tf32: +half ulp (0x1000) on the bits; the MMA truncates the rest
+                        uint4 v;
+                        v.x = __float_as_uint(fmaxf(r.pv[j].x + r.qv[j].x, 0.f)) + 0x1000u;
+                        v.y = __float_as_uint(fmaxf(r.pv[j].y + r.qv[j].y, 0.f)) + 0x1000u;
+                        v.z = __float_as_uint(fmaxf(r.pv[j].z + r.qv[j].z, 0.f)) + 0x1000u;
+                        v.w = __float_as_uint(fmaxf(r.pv[j].w + r.qv[j].w, 0.f)) + 0x1000u;
+                        *reinterpret_cast<uint4*>(base + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
+                    }
+                }
+                tc::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&b_full[st]);
+            };
+
+            Regs ra, rb, rc;
+            load(0, ra);
+            load(1, rb);
+            for (int kb = 0; kb < kbs; kb += 3) {
+                load(kb + 2, rc);
+                emit(kb, ra);
+                load(kb + 3, ra);
+                emit(kb + 1, rb);
+                load(kb + 4, rb);
+                emit(kb + 2, rc);
+            }
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<256>(tmem_base);
+}
+
+constexpr uint32_t EF_SMEM_BYTES = EF_MAX_KB * EF_TILE_BYTES + EF_STAGES * EF_TILE_BYTES + 2 * sizeof(TileMeta) + 128 + 1024;
+int g_ef_sms = 0;
+
+}  // namespace
+
+// w2p: [c_out, ceil(hdim/32)*32] fp32, tf32-rounded, zero padded columns. pq: [n, 2*hdim] (tf32-rounded P | Q).
+// aggr: 0 add, 1 mean. hdim % 4 == 0, hdim <= 352, width <= 32.
+GNB_EXPORT int gnb_edgeconv_fused_fwd_tf32(const float* pq, int64_t ldpq, int32_t hdim, const int32_t* nbr,
+                                           const int32_t* deg, int32_t width, int64_t n, const float* w2p, int64_t ldw,
+                                           const float* b2, int32_t c_out, int32_t aggr, int32_t round_out, float* y,
+                                           int64_t ldy, void* stream) {
+    const int kblocks = (hdim + 31) / 32;
+    if ((hdim & 3) || hdim < 4 || kblocks > EF_MAX_KB || width < 1 || width > 32 || c_out < 1 || aggr < 0 || aggr > 1 ||
+        (ldpq & 3) || (reinterpret_cast<uintptr_t>(pq) & 15u) || ldw < kblocks * 32)
+        return hdim > EF_MAX_KB * 32 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    if (n == 0) return GNB_OK;
+    CUtensorMap tw;
+    int rc = gnb_make_tmap_f32(&tw, w2p, c_out, (int64_t)kblocks * 32, ldw, 128);
+    if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    if (g_ef_sms == 0) {
+        int dev = 0;
+        GNB_CHECK(cudaGetDevice(&dev));
+        GNB_CHECK(cudaDeviceGetAttribute(&g_ef_sms, cudaDevAttrMultiProcessorCount, dev));
+        GNB_CHECK(cudaFuncSetAttribute(edgeconv_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)EF_SMEM_BYTES));
+    }
+    EfParams p;
+    p.pq = pq; p.ldpq = ldpq; p.hdim = hdim; p.kblocks = kblocks;
+    p.nbr = nbr; p.deg = deg; p.width = width; p.n = n;
+    p.b2 = b2; p.c_out = c_out; p.aggr = aggr; p.round_out = round_out;
+    p.y = y; p.ldy = ldy;
+    p.npt = 128 / width;
+    if (p.npt > 32) p.npt = 32;
+    p.num_tiles = gnb_div_up(n, p.npt);
+    const int halves = gnb_div_up(c_out, 128);
+    int ctas = g_ef_sms / halves;
+    if (ctas < 1) ctas = 1;
+    if (ctas > p.num_tiles) ctas = p.num_tiles;
+    dim3 grid((unsigned)ctas, (unsigned)halves);
+    edgeconv_fused_fwd_kernel<<<grid, EF_THREADS, EF_SMEM_BYTES, (cudaStream_t)stream>>>(tw, p);
+    GNB_RETURN_LAUNCH();
+}

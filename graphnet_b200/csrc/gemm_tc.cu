@@ -11,10 +11,11 @@
 // TMEM lane = output channel and column = row. An epilogue warp then writes, per row, 32 consecutive
 // channels = one coalesced 128-byte store straight from registers; no shared-memory staging of the output.
 //
-// CTA = 128 channels x 128 rows, K in blocks of 32 tf32 (= one 128-byte swizzle atom). 3-stage TMA ->
-// mbarrier -> tcgen05.mma pipeline, accumulator in 128 TMEM columns, 2 CTAs resident per SM so one CTA's
-// epilogue overlaps the other's main loop. Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc),
-// 2..5 = epilogue (one TMEM lane quarter each).
+// Persistent CTAs (one per SM) loop over 128-row tiles; each tile computes up to TWO 128-channel tiles from
+// the same activation tile (the big operand is read once), K in blocks of 32 tf32 (one 128-byte swizzle
+// atom). 4-stage TMA -> mbarrier -> tcgen05.mma pipeline; the fp32 accumulators (2 x 128 columns) are
+// double-buffered in TMEM (512 columns) so the epilogue of tile t overlaps the main loop of tile t+1.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..9 = epilogue (lane quarter x column half).
 // Operands are fp32 in HBM; weights and activations are expected pre-rounded to tf32 (cvt.rna) by their
 // producers so that the tensor core's truncation is exact (unbiased rounding overall).
 #include "common.cuh"
@@ -22,28 +23,32 @@
 
 namespace {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3, TC_THREADS = 192;
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_MT = 2, TC_STAGES = 4, TC_THREADS = 320;
 constexpr int TC_MAX_PARTS = 6;
-constexpr uint32_t TC_STAGE_BYTES = (TC_BM + TC_BN) * TC_BK * 4;   // 32 KiB
+constexpr uint32_t TC_TILE_BYTES = TC_BM * TC_BK * 4;                           // 16 KiB: one 128 x 32 fp32 tile
+constexpr uint32_t TC_STAGE_BYTES = (TC_MT + 1) * TC_TILE_BYTES;                // 2 weight tiles + 1 activation tile
 constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t TC_TMEM_COLS = 2 * TC_MT * TC_BN;                            // 512: two accumulator buffers
 
 struct TmapArray { CUtensorMap m[TC_MAX_PARTS]; };
 struct PartInfo { int nparts; int kblocks[TC_MAX_PARTS]; };
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ TmapArray tm_x,
                       const PartInfo parts, const float* __restrict__ bias, float* __restrict__ y, int64_t ldy,
-                      int64_t rows, int n_out, int act, int round_out) {
+                      int64_t rows, int n_out, int act, int round_out, int num_row_tiles) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
     uint64_t* empty = full + TC_STAGES;
-    uint64_t* tmem_full = empty + TC_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_full = empty + TC_STAGES;      // [2]
+    uint64_t* tmem_empty = tmem_full + 2;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t row0 = (int64_t)blockIdx.x * TC_BN;
-    const int ch0 = blockIdx.y * TC_BM;
+    const int ch0 = blockIdx.y * (TC_MT * TC_BM);
+    int mt = (n_out - ch0 + TC_BM - 1) / TC_BM;   // valid channel tiles of this CTA (1 or 2)
+    if (mt > TC_MT) mt = TC_MT;
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tm_w);
@@ -52,12 +57,12 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < TC_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
-            tc::mbar_init(tmem_full, 1);
+            for (int b = 0; b < 2; ++b) { tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], 8); }
             tc::fence_barrier_init();
             tc::fence_proxy_async();
         }
         __syncwarp();
-        tc::tmem_alloc<TC_BN>(tmem_slot);
+        tc::tmem_alloc<TC_TMEM_COLS>(tmem_slot);
     }
     tc::tcgen05_fence_before();
     __syncthreads();
@@ -69,67 +74,92 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
 
     if (warp == 0) {
         if (lane == 0) {
-            int it = 0;
-            for (int p = 0; p < parts.nparts; ++p) {
-                for (int kb = 0; kb < parts.kblocks[p]; ++kb, ++it) {
-                    const int s = it % TC_STAGES;
-                    const uint32_t ph = (it / TC_STAGES) & 1;
-                    tc::mbar_wait(&empty[s], ph ^ 1);
-                    uint8_t* sa = smem + s * TC_STAGE_BYTES;
-                    uint8_t* sb = sa + TC_BM * TC_BK * 4;
-                    tc::mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
-                    tc::tma_load_2d(sa, &tm_w, &full[s], it * TC_BK, ch0);
-                    tc::tma_load_2d(sb, &tm_x.m[p], &full[s], kb * TC_BK, (int)row0);
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < num_row_tiles; t += gridDim.x) {
+                const int row0 = t * TC_BN;
+                int kb_w = 0;
+                for (int p = 0; p < parts.nparts; ++p) {
+                    for (int kb = 0; kb < parts.kblocks[p]; ++kb, ++kb_w, ++it) {
+                        const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                        tc::mbar_wait(&empty[s], ph ^ 1);
+                        uint8_t* st = smem + s * TC_STAGE_BYTES;
+                        tc::mbar_arrive_expect_tx(&full[s], (uint32_t)(mt + 1) * TC_TILE_BYTES);
+                        for (int m = 0; m < mt; ++m)
+                            tc::tma_load_2d(st + m * TC_TILE_BYTES, &tm_w, &full[s], kb_w * TC_BK, ch0 + m * TC_BM);
+                        tc::tma_load_2d(st + TC_MT * TC_TILE_BYTES, &tm_x.m[p], &full[s], kb * TC_BK, row0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = tc::umma_idesc_tf32(TC_BM, TC_BN);
-            for (int it = 0; it < total_kb; ++it) {
-                const int s = it % TC_STAGES;
-                const uint32_t ph = (it / TC_STAGES) & 1;
-                tc::mbar_wait(&full[s], ph);
+            uint32_t it = 0, tile_i = 0;
+            for (int t = blockIdx.x; t < num_row_tiles; t += gridDim.x, ++tile_i) {
+                const uint32_t buf = tile_i & 1;
+                tc::mbar_wait(&tmem_empty[buf], ((tile_i >> 1) & 1) ^ 1);      // epilogue drained this buffer
                 tc::tcgen05_fence_after();
-                const uint32_t sa = tc::smem_u32(smem + s * TC_STAGE_BYTES);
-                const uint64_t adesc = tc::umma_desc_sw128_kmajor(sa);
-                const uint64_t bdesc = tc::umma_desc_sw128_kmajor(sa + TC_BM * TC_BK * 4);
+                const uint32_t acc = tmem_base + buf * (TC_MT * TC_BN);
+                for (int kbi = 0; kbi < total_kb; ++kbi, ++it) {
+                    const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                    tc::mbar_wait(&full[s], ph);
+                    tc::tcgen05_fence_after();
+                    const uint32_t st = tc::smem_u32(smem + s * TC_STAGE_BYTES);
+                    const uint64_t bdesc = tc::umma_desc_sw128_kmajor(st + TC_MT * TC_TILE_BYTES);
+                    for (int m = 0; m < mt; ++m) {
+                        const uint64_t adesc = tc::umma_desc_sw128_kmajor(st + m * TC_TILE_BYTES);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k)   // UMMA_K = 8 tf32 = 32 bytes -> +2 in the 16-byte address field
-                    tc::umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
-                tc::umma_commit(&empty[s]);
+                        for (int k = 0; k < TC_BK / 8; ++k)   // UMMA_K = 8 tf32 = 32 B -> +2 in the 16-byte address field
+                            tc::umma_tf32(acc + m * TC_BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kbi | k) != 0 ? 1u : 0u);
+                    }
+                    tc::umma_commit(&empty[s]);
+                }
+                tc::umma_commit(&tmem_full[buf]);
             }
-            tc::umma_commit(tmem_full);
         }
     } else {
-        tc::mbar_wait(tmem_full, 0);
-        tc::tcgen05_fence_after();
-        const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int ch = ch0 + q * 32 + lane;
-        const bool ch_ok = ch < n_out;
-        const float bv = (bias != nullptr && ch_ok) ? bias[ch] : 0.f;
+        const int ew = warp - 2;                    // 0..7
+        const int q = warp & 3;                     // TMEM lane quarter this warp may access
+        const int half = ew >> 2;                   // column half: rows [64*half, 64*half + 64) of the tile
+        uint32_t tile_i = 0;
+        for (int t = blockIdx.x; t < num_row_tiles; t += gridDim.x, ++tile_i) {
+            const uint32_t buf = tile_i & 1;
+            const int64_t row0 = (int64_t)t * TC_BN;
+            tc::mbar_wait<100>(&tmem_full[buf], (tile_i >> 1) & 1);
+            tc::tcgen05_fence_after();
+            for (int m = 0; m < mt; ++m) {
+                const int ch = ch0 + m * TC_BM + q * 32 + lane;
+                const bool ch_ok = ch < n_out;
+                const float bv = (bias != nullptr && ch_ok) ? bias[ch] : 0.f;
 #pragma unroll 1
-        for (int c = 0; c < TC_BN / 32; ++c) {
-            uint32_t r[32];
-            tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-            tc::tmem_ld_wait();
-            if (ch_ok) {
+                for (int c = 0; c < 2; ++c) {
+                    const int col0 = half * 64 + c * 32;
+                    uint32_t r[32];
+                    tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) +
+                                               (uint32_t)(buf * (TC_MT * TC_BN) + m * TC_BN + col0), r);
+                    tc::tmem_ld_wait();
+                    if (ch_ok) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int64_t row = row0 + c * 32 + j;
-                    if (row < rows) {
-                        float v = __uint_as_float(r[j]) + bv;
-                        if (act == GNB_ACT_RELU) v = fmaxf(v, 0.f);
-                        if (round_out) v = tc::round_tf32(v);
-                        y[row * ldy + ch] = v;
+                        for (int j = 0; j < 32; ++j) {
+                            const int64_t row = row0 + col0 + j;
+                            if (row < rows) {
+                                float v = __uint_as_float(r[j]) + bv;
+                                if (act == GNB_ACT_RELU) v = fmaxf(v, 0.f);
+                                if (round_out) v = tc::round_tf32(v);
+                                y[row * ldy + ch] = v;
+                            }
+                        }
                     }
                 }
             }
+            tc::tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tmem_empty[buf]);
         }
     }
     tc::tcgen05_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc<TC_BN>(tmem_base);
+    if (warp == 1) tc::tmem_dealloc<TC_TMEM_COLS>(tmem_base);
 }
 
 // dst[r, c] = rna_tf32(src[r, c]) for c < cols, 0 for cols <= c < dst_cols
@@ -141,6 +171,8 @@ __global__ void round_pad_tf32_kernel(const float* __restrict__ src, int64_t lds
     const int c = (int)(t - r * dst_cols);
     dst[r * ldd + c] = c < cols ? tc::round_tf32(src[r * lds + c]) : 0.f;
 }
+
+int g_num_sms = 0;
 
 }  // namespace
 
@@ -169,15 +201,21 @@ GNB_EXPORT int gnb_linear_fwd_tf32(const float* const* xs, const int64_t* ldxs, 
     CUtensorMap tw;
     int rc = gnb_make_tmap_f32(&tw, w, n_out, ktot, ldw, TC_BM);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        GNB_CHECK(cudaGetDevice(&dev));
+        GNB_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
         GNB_CHECK(cudaFuncSetAttribute(gemm_tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)TC_SMEM_BYTES));
-        attr_set = true;
     }
-    dim3 grid((unsigned)gnb_div_up(rows, TC_BN), (unsigned)gnb_div_up(n_out, TC_BM));
+    const int row_tiles = gnb_div_up(rows, TC_BN);
+    const int groups = gnb_div_up(n_out, TC_MT * TC_BM);
+    int ctas_x = g_num_sms / groups;                 // persistent: about one CTA per SM in total
+    if (ctas_x < 1) ctas_x = 1;
+    if (ctas_x > row_tiles) ctas_x = row_tiles;
+    dim3 grid((unsigned)ctas_x, (unsigned)groups);
     gemm_tc_linear_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(tw, tx, pi, bias, y, ldy, rows,
-                                                                                     n_out, act, round_out);
+                                                                                     n_out, act, round_out, row_tiles);
     GNB_RETURN_LAUNCH();
 }
 

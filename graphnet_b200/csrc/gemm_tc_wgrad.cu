@@ -118,7 +118,7 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                 tc::umma_commit(tmem_full);
             }
         } else {
-            tc::mbar_wait(tmem_full, 0);
+            tc::mbar_wait<200>(tmem_full, 0);
             tc::tcgen05_fence_after();
             const int q = warp & 3;
             const int kin = kin0 + q * 32 + lane;

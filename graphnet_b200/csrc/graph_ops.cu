@@ -309,7 +309,7 @@ segment_pool_fwd_kernel(const float* __restrict__ x, int64_t ldx, int c_tot, con
 }
 
 // backward: one thread per (node, channel)
-__global__ void segment_pool_bwd_kernel(const float* __restrict__ gout, const int* __restrict__ arg, int c_tot,
+__global__ void segment_pool_bwd_kernel(const float* __restrict__ gout, int64_t ldg, const int* __restrict__ arg, int c_tot,
                                         const int64_t* __restrict__ ptr, int nseg, int64_t n, int np, int s0,
                                         int s1, int s2, int s3, float* __restrict__ gx, int64_t ldx) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -324,7 +324,7 @@ __global__ void segment_pool_bwd_kernel(const float* __restrict__ gout, const in
     float acc = 0.f;
     for (int p = 0; p < np; ++p) {
         const int64_t o = (int64_t)b * np * c_tot + (int64_t)p * c_tot + c;
-        const float g = gout[o];
+        const float g = gout[(int64_t)b * ldg + (int64_t)p * c_tot + c];
         switch (schemes[p]) {
             case GNB_POOL_SUM: acc += g; break;
             case GNB_POOL_MEAN: acc += g / cnt; break;
@@ -519,14 +519,14 @@ GNB_EXPORT int gnb_segment_pool_fwd(const float* x, int64_t ldx, int32_t c, cons
     GNB_RETURN_LAUNCH();
 }
 
-GNB_EXPORT int gnb_segment_pool_bwd(const float* gout, const int32_t* arg, int32_t c, const int64_t* ptr, int64_t nseg,
+GNB_EXPORT int gnb_segment_pool_bwd(const float* gout, int64_t ldg, const int32_t* arg, int32_t c, const int64_t* ptr, int64_t nseg,
                                     int64_t n, const int32_t* schemes, int32_t np, float* gx, int64_t ldx,
                                     void* stream) {
     if (np < 1 || np > 4 || c < 1) return GNB_ERR_ARG;
     if (n == 0) return GNB_OK;
     int s[4] = {0, 0, 0, 0};
     for (int p = 0; p < np; ++p) s[p] = schemes[p];
-    segment_pool_bwd_kernel<<<gnb_div_up(n * c, 256), 256, 0, (cudaStream_t)stream>>>(gout, arg, c, ptr, (int)nseg, n, np,
+    segment_pool_bwd_kernel<<<gnb_div_up(n * c, 256), 256, 0, (cudaStream_t)stream>>>(gout, ldg, arg, c, ptr, (int)nseg, n, np,
                                                                                       s[0], s[1], s[2], s[3], gx, ldx);
     GNB_RETURN_LAUNCH();
 }

@@ -28,20 +28,29 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return done;
+}
 // Bounded wait: a lost arrival traps (reported as a launch error) instead of hanging the GPU.
+// SLEEP_NS > 0 backs off between polls so that long waits (epilogue / metadata warps) do not steal issue slots
+// from the warps doing the work.
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    uint32_t done = 0;
+    if (mbar_try_wait(addr, parity)) return;
     long long t0 = 0;
-    for (uint32_t it = 0; !done; ++it) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (!done && (it & 1023u) == 1023u) {
+    for (uint32_t it = 1;; ++it) {
+        if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+        if (mbar_try_wait(addr, parity)) return;
+        if ((it & 4095u) == 0u) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
             else if (now - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz

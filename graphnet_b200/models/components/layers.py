@@ -78,7 +78,7 @@ class DynEdgeConv(Model):
             bcat = None
             if lin1.bias is not None:
                 bcat = torch.cat([lin1.bias, torch.zeros_like(lin1.bias)])
-            pq = ops.linear_act(x, wcat, bcat, ops.ACT_NONE)             # [N, 2H] = [P | Q]
+            pq = ops.linear_act(x, wcat, bcat, ops.ACT_NONE, round_out=False)   # [N, 2H] = [P | Q], added in fp32
             if lin1.out_features % 4 == 0 and lin2.out_features % 4 == 0 and self.aggr in ("add", "sum", "mean"):
                 return ops.edgeconv_hoisted(pq, lin2.weight, lin2.bias, graph, self.aggr)
             if lin1.out_features % 4 == 0:

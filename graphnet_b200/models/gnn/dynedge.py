@@ -173,6 +173,66 @@ class DynEdge(GNN):
         rest = torch.nn.Sequential(*list(self._post_processing)[2:])
         return self._linear_chain(rest, x) if len(rest) else x
 
+    # -- native executor --------------------------------------------------------------------------
+    def _executor_config(self):
+        """`gnb_dynedge_config` for the fast-path family, or None when this model needs the per-operator route."""
+        cached = getattr(self, "_exec_cfg", None)
+        if cached is not None:
+            return cached if cached != "unsupported" else None
+        from graphnet_b200._lib import DynEdgeConfig
+        ok = (_is_linear_relu_chain(self._post_processing) and _is_linear_relu_chain(self._readout)
+              and all(_hoistable(c.nn) and c.aggr in ("add", "sum") for c in self._conv_layers)
+              and len(self._conv_layers) <= 8 and len(self._post_processing) <= 16 and len(self._readout) <= 16
+              and 4 <= self._nb_inputs <= 32)
+        cols: List[int] = []
+        if ok:
+            widths = [w for c in self._conv_layers for w in (c.nn[0].out_features, c.nn[2].out_features)]
+            widths += [m.out_features for m in self._post_processing if isinstance(m, torch.nn.Linear)]
+            widths += [m.out_features for m in self._readout if isinstance(m, torch.nn.Linear)]
+            cols = ops.resolve_columns(self._features_subset, min(c.nn[2].out_features for c in self._conv_layers))
+            ok = all(w % 4 == 0 for w in widths) and 1 <= len(cols) <= 16
+        if not ok:
+            object.__setattr__(self, "_exec_cfg", "unsupported")
+            return None
+        cfg = DynEdgeConfig()
+        cfg.nb_inputs, cfg.k, cfg.precision = self._nb_inputs, self._nb_neighbours, 0
+        cfg.n_conv = len(self._conv_layers)
+        for i, c in enumerate(self._conv_layers):
+            cfg.conv_hidden[i], cfg.conv_out[i] = c.nn[0].out_features, c.nn[2].out_features
+        posts = [m for m in self._post_processing if isinstance(m, torch.nn.Linear)]
+        cfg.n_post = len(posts)
+        for i, m in enumerate(posts):
+            cfg.post_out[i] = m.out_features
+        ros = [m for m in self._readout if isinstance(m, torch.nn.Linear)]
+        cfg.n_readout = len(ros)
+        for i, m in enumerate(ros):
+            cfg.readout_out[i] = m.out_features
+        schemes = self._global_pooling_schemes or []
+        cfg.n_pool = len(schemes)
+        for i, s in enumerate(schemes):
+            cfg.pool[i] = ops.POOL[s]
+        cfg.globals_after_pooling = int(self._add_global_variables_after_pooling)
+        cfg.skip_readout = int(self._skip_readout)
+        cfg.n_knn_cols = len(cols)
+        for i, c in enumerate(cols):
+            cfg.knn_cols[i] = c
+        object.__setattr__(self, "_exec_cfg", cfg)
+        object.__setattr__(self, "_exec_cols", cols)
+        return cfg
+
+    def _executor_params(self) -> List[Tensor]:
+        out: List[Tensor] = []
+        for c in self._conv_layers:
+            out += [c.nn[0].weight, c.nn[0].bias, c.nn[2].weight, c.nn[2].bias]
+        for m in self._post_processing:
+            if isinstance(m, torch.nn.Linear):
+                out += [m.weight, m.bias]
+        if not self._skip_readout:
+            for m in self._readout:
+                if isinstance(m, torch.nn.Linear):
+                    out += [m.weight, m.bias]
+        return out
+
     def forward(self, data) -> Tensor:
         """Apply learnable forward pass (dynedge.py:295-349)."""
         x, batch = data.x, data.batch
@@ -186,6 +246,20 @@ class DynEdge(GNN):
         graph = data.knn_graph() if hasattr(data, "knn_graph") else None
         if graph is None:
             graph = ops.KnnGraph.from_edge_index(data.edge_index, x.shape[0], self._nb_neighbours)
+
+        cfg = self._executor_config() if ops.USE_EXECUTOR else None
+        if cfg is not None:
+            record = {} if getattr(self, "_debug_record", False) else None
+            if self._skip_readout:
+                out_cols, per_event = self._post_processing_layer_sizes[-1], False
+            else:
+                out_cols, per_event = self._readout_layer_sizes[-1], bool(self._global_pooling_schemes)
+            y = ops.dynedge_execute(cfg, graph, ptr, n_pulses, x, self._exec_cols, out_cols, per_event,
+                                    self._executor_params(), record)
+            if record is not None:
+                self._debug = {"graphs": record["graphs"], "skips": [record["x0"]] + record["ys"],
+                               "global_variables": record["g"]}
+            return y
 
         distribute = not self._add_global_variables_after_pooling
         node_width = self._nb_inputs + (self._nb_global_variables if distribute else 0)

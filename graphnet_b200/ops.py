@@ -57,6 +57,11 @@ def _call(name: str, *args) -> None:
     _lib.check(getattr(_lib.load(), name)(*args), name)
 
 
+def kernel_launch_count() -> int:
+    """Kernels launched by libgraphnet_b200.so so far (counted inside the library, executor included)."""
+    return int(_lib.load().gnb_launch_count())
+
+
 def _stream() -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -300,14 +305,16 @@ def _colsum(a: Tensor) -> Tensor:
     return out
 
 
-def _dense_forward(parts: Sequence[Tensor], w: Tensor, b: Optional[Tensor], offsets: Sequence[int], act: int):
-    """y = act(sum_p parts[p] @ w[:, off_p : off_p + K_p]^T + b). Returns (y, parts as consumed, used_tc)."""
+def _dense_forward(parts: Sequence[Tensor], w: Tensor, b: Optional[Tensor], offsets: Sequence[int], act: int,
+                   round_out: bool = True):
+    """y = act(sum_p parts[p] @ w[:, off_p : off_p + K_p]^T + b). Returns (y, parts as consumed, used_tc).
+    round_out: round y to tf32 (only needed when y itself feeds a tensor-core GEMM)."""
     rows, n_out = parts[0].shape[0], w.shape[0]
     tc = _tf32() and len(parts) <= 6 and rows > 0
     if tc:
         parts = tuple(_tc_operand(p) for p in parts)
         packed = _tc_pack_weight(w, offsets, [p.shape[1] for p in parts])
-        y = _tc_linear(parts, packed, b, n_out, act, round_out=True)
+        y = _tc_linear(parts, packed, b, n_out, act, round_out=round_out)
     else:
         y = torch.empty(rows, n_out, dtype=torch.float32, device=w.device)
         last = len(parts) - 1
@@ -348,10 +355,10 @@ class _MultiLinearAct(torch.autograd.Function):
     inputs, so the skip-concatenation of dynedge.py:328 is never materialised."""
 
     @staticmethod
-    def forward(ctx, w: Tensor, b: Optional[Tensor], act: int, offsets: Tuple[int, ...], *parts: Tensor):
+    def forward(ctx, w: Tensor, b: Optional[Tensor], act: int, offsets: Tuple[int, ...], round_out: bool, *parts: Tensor):
         _cuda(w, b, *parts)
         w = _rowmajor(w)
-        y, parts, ctx.tc = _dense_forward(tuple(_rowmajor(p) for p in parts), w, b, offsets, act)
+        y, parts, ctx.tc = _dense_forward(tuple(_rowmajor(p) for p in parts), w, b, offsets, act, round_out)
         ctx.act, ctx.offsets = act, offsets
         ctx.has_bias = b is not None
         ctx.save_for_backward(w, y, *parts)
@@ -362,19 +369,19 @@ class _MultiLinearAct(torch.autograd.Function):
         w, y, *parts = ctx.saved_tensors
         dz, db = _bias_act_backward(gy.contiguous(), y, ctx.act, ctx.has_bias and ctx.needs_input_grad[1])
         dw, dparts = _dense_backward(dz, w, parts, ctx.offsets, ctx.needs_input_grad[0],
-                                     [ctx.needs_input_grad[4 + i] for i in range(len(parts))], ctx.tc)
-        return (dw, db, None, None, *dparts)
+                                     [ctx.needs_input_grad[5 + i] for i in range(len(parts))], ctx.tc)
+        return (dw, db, None, None, None, *dparts)
 
 
-def linear_act(x: Tensor, w: Tensor, b: Optional[Tensor], act: int = ACT_NONE) -> Tensor:
+def linear_act(x: Tensor, w: Tensor, b: Optional[Tensor], act: int = ACT_NONE, round_out: bool = True) -> Tensor:
     """act(x @ w^T + b) (torch.nn.Linear + activation of dynedge.py:200-247)."""
-    y = _MultiLinearAct.apply(w, b, act, (0,), x)
-    return _mark_rounded(y) if _tf32() else y
+    y = _MultiLinearAct.apply(w, b, act, (0,), round_out, x)
+    return _mark_rounded(y) if (_tf32() and round_out) else y
 
 
 def multi_linear_act(parts: Sequence[Tensor], w: Tensor, b: Optional[Tensor], offsets: Sequence[int],
                      act: int = ACT_NONE) -> Tensor:
-    y = _MultiLinearAct.apply(w, b, act, tuple(int(o) for o in offsets), *parts)
+    y = _MultiLinearAct.apply(w, b, act, tuple(int(o) for o in offsets), True, *parts)
     return _mark_rounded(y) if _tf32() else y
 
 
@@ -490,7 +497,7 @@ class _EdgeConvHoisted(torch.autograd.Function):
               ACT_RELU | rnd, _ptr(h), _ld(h), _stream())
         if _tf32():
             _mark_rounded(h)
-        m, (h,), ctx.tc = _dense_forward((h,), w2, b2, (0,), ACT_RELU)
+        m, (h,), ctx.tc = _dense_forward((h,), w2, b2, (0,), ACT_RELU, round_out=False)    # summed in fp32
         c = m.shape[1]
         y = torch.empty(graph.n, c, dtype=torch.float32, device=pq.device)
         _call("gnb_edge_aggregate_fwd", _ptr(m), _ld(m), c, _ptr(graph.deg), graph.width, graph.n, aggr | rnd, _ptr(y),
@@ -515,9 +522,29 @@ class _EdgeConvHoisted(torch.autograd.Function):
         return dpq, dw2, db2, None, None
 
 
+FUSED_EDGECONV = os.environ.get("GNB_FUSED_EDGECONV", "1") == "1"
+
+
+def edgeconv_fused_forward(pq: Tensor, w2: Tensor, b2: Optional[Tensor], graph: KnnGraph, aggr: str = "add") -> Tensor:
+    """Inference-only fused EdgeConv (gather + hidden ReLU + contraction + bias/ReLU + aggregation in ONE tcgen05
+    kernel; no [E, H] / [E, C] tensors in HBM). tf32 mode."""
+    _cuda(pq, w2, b2)
+    pq = _rowmajor(pq.detach())
+    w2 = _rowmajor(w2.detach())
+    hdim, c_out = w2.shape[1], w2.shape[0]
+    w2p = _tc_pack_weight(w2, (0,), (hdim,))
+    y = torch.empty(graph.n, c_out, dtype=torch.float32, device=pq.device)
+    _call("gnb_edgeconv_fused_fwd_tf32", _ptr(pq), _ld(pq), hdim, _ptr(graph.nbr), _ptr(graph.deg), graph.width, graph.n,
+          _ptr(w2p), w2p.shape[1], _ptr(None if b2 is None else b2.detach()), c_out, AGGR[aggr], 1, _ptr(y), c_out, _stream())
+    return _mark_rounded(y)
+
+
 def edgeconv_hoisted(pq: Tensor, w2: Tensor, b2: Optional[Tensor], graph: KnnGraph, aggr: str = "add") -> Tensor:
     """Per-edge half of EdgeConv for an MLP `Linear, ReLU, Linear, ReLU` whose first Linear was hoisted to nodes
     (pq = [P | Q]); aggr in add / mean. (max keeps the unfused route: it needs the arg-routed backward.)"""
+    needs_grad = torch.is_grad_enabled() and (pq.requires_grad or w2.requires_grad or (b2 is not None and b2.requires_grad))
+    if _tf32() and FUSED_EDGECONV and not needs_grad and w2.shape[1] <= 352 and w2.shape[1] % 4 == 0 and graph.width <= 32:
+        return edgeconv_fused_forward(pq, w2, b2, graph, aggr)
     y = _EdgeConvHoisted.apply(pq, w2, b2, graph, AGGR[aggr])
     return _mark_rounded(y) if _tf32() else y
 
@@ -547,7 +574,7 @@ class _SegmentPool(torch.autograd.Function):
         npool = len(ctx.schemes)
         gx = torch.empty(ctx.n, ctx.c, dtype=torch.float32, device=gout.device)
         sch = (ctypes.c_int32 * npool)(*ctx.schemes)
-        _call("gnb_segment_pool_bwd", _ptr(gout), _ptr(arg), ctx.c, _ptr(ptr), ptr.numel() - 1, ctx.n, sch, npool,
+        _call("gnb_segment_pool_bwd", _ptr(gout), gout.shape[1], _ptr(arg), ctx.c, _ptr(ptr), ptr.numel() - 1, ctx.n, sch, npool,
               _ptr(gx), _ld(gx), _stream())
         return gx, None, None
 
@@ -556,3 +583,73 @@ def segment_pool(x: Tensor, ptr: Tensor, schemes: Sequence[str], return_arg: boo
     """cat_p scatter_<p>(x, batch) -> [B, P*C] in the caller's scheme order."""
     out, arg = _SegmentPool.apply(x, ptr, tuple(POOL[s] for s in schemes))
     return (out, arg) if return_arg else out
+
+
+# --------------------------------------------------------------------------- #
+# native step executor (csrc/dynedge_exec.cu): DynEdge.forward / backward from one C call each
+# --------------------------------------------------------------------------- #
+USE_EXECUTOR = os.environ.get("GNB_EXECUTOR", "1") == "1"
+
+
+class _DynEdgeExec(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg, graph: KnnGraph, ptr: Tensor, n_pulses: Tensor, x: Tensor, cols_dev: Tensor, out_cols: int,
+                out_per_event: bool, record: Optional[dict], training: int, *params: Tensor):
+        _cuda(x, ptr, n_pulses, *params)
+        lib = _lib.load()
+        x = _rowmajor(x.detach().float())
+        n, nseg = x.shape[0], ptr.numel() - 1
+        cfg.precision = 1 if _tf32() else 0
+        nbytes = lib.gnb_dynedge_workspace_bytes(ctypes.byref(cfg), n, nseg, graph.width, training)
+        if nbytes < 0:
+            raise RuntimeError(f"gnb_dynedge_workspace_bytes: unsupported configuration [{nbytes}]")
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=x.device)
+        out = torch.empty(nseg if out_per_event else n, out_cols, dtype=torch.float32, device=x.device)
+        npf = n_pulses.to(torch.float32).contiguous()
+        plist = [p.detach().contiguous() for p in params]
+        parr = (ctypes.c_void_p * len(plist))(*[p.data_ptr() for p in plist])
+        _call("gnb_dynedge_forward", ctypes.byref(cfg), parr, _ptr(x), _ld(x), _ptr(ptr), _ptr(npf), _ptr(graph.nbr),
+              _ptr(graph.deg), graph.width, _ptr(cols_dev), n, nseg, _ptr(ws), int(nbytes), _ptr(out),
+              training | (0 if FUSED_EDGECONV else 2), _stream())
+        if record is not None:       # test hook: views of the per-layer outputs / recomputed graphs inside `ws`
+            offs = (ctypes.c_int64 * (3 * cfg.n_conv))()
+            _lib.check(lib.gnb_dynedge_layout(ctypes.byref(cfg), n, nseg, graph.width, training, offs), "layout")
+            ys, graphs = [], [graph]
+            for li in range(cfg.n_conv):
+                c = cfg.conv_out[li]
+                ys.append(ws[offs[3 * li]: offs[3 * li] + 4 * n * c].view(torch.float32).view(n, c))
+                if offs[3 * li + 1] >= 0:
+                    w = cfg.k + 1
+                    nbr = ws[offs[3 * li + 1]: offs[3 * li + 1] + 4 * n * w].view(torch.int32).view(n, w)
+                    deg = ws[offs[3 * li + 2]: offs[3 * li + 2] + 4 * n].view(torch.int32)
+                    graphs.append(KnnGraph(nbr, deg, cfg.k))
+            record["ys"], record["graphs"] = ys, graphs
+            ng = cfg.nb_inputs + 5
+            record["g"] = ws[: 4 * nseg * ng].view(torch.float32).view(nseg, ng)
+            node_w = cfg.nb_inputs + (0 if cfg.globals_after_pooling else ng)
+            x0_ld = (node_w + 31) // 32 * 32
+            x0_off = (4 * nseg * ng + 255) // 256 * 256
+            record["x0"] = ws[x0_off: x0_off + 4 * n * x0_ld].view(torch.float32).view(n, x0_ld)[:, :node_w]
+        ctx.cfg, ctx.graph, ctx.nbytes, ctx.n, ctx.nseg, ctx.training = cfg, graph, int(nbytes), n, nseg, training
+        ctx.save_for_backward(ws, ptr, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout: Tensor):
+        ws, ptr, *params = ctx.saved_tensors
+        if not ctx.training:
+            raise RuntimeError("DynEdge executor: backward requested after an inference-mode forward")
+        gout = gout.contiguous().float()
+        grads = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in params]
+        garr = (ctypes.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
+        graph = ctx.graph
+        _call("gnb_dynedge_backward", ctypes.byref(ctx.cfg), garr, _ptr(ptr), _ptr(graph.nbr), _ptr(graph.deg), graph.width,
+              ctx.n, ctx.nseg, _ptr(ws), ctx.nbytes, _ptr(gout), _stream())
+        return (None,) * 10 + tuple(grads)
+
+
+def dynedge_execute(cfg, graph: KnnGraph, ptr: Tensor, n_pulses: Tensor, x: Tensor, cols: Sequence[int], out_cols: int,
+                    out_per_event: bool, params: Sequence[Tensor], record: Optional[dict] = None) -> Tensor:
+    training = 1 if (torch.is_grad_enabled() and any(p.requires_grad for p in params)) else 0
+    return _DynEdgeExec.apply(cfg, graph, ptr, n_pulses, x, _cols_tensor(cols, x.device), out_cols, out_per_event,
+                              record, training, *params)

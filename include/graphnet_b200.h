@@ -66,6 +66,13 @@ int gnb_edge_hidden_bwd(const float* gh, int64_t ldg, const float* h, int64_t ld
                         const int32_t* deg, int32_t width, int64_t n, int32_t act, float* dpq, int64_t ldpq,
                         void* stream);
 
+/* Fused EdgeConv forward on tcgen05 (tf32, no autograd state): y[i] = AGG_s relu(W2 relu(P[i] + Q[nbr[i,s]]) + b2)
+ * without materialising the [E, hdim] / [E, c_out] per-edge tensors. w2p: [c_out, ceil(hdim/32)*32] tf32-rounded,
+ * zero padded; pq tf32-rounded; aggr 0 add / 1 mean; hdim % 4 == 0, hdim <= 352, width <= 32. */
+int gnb_edgeconv_fused_fwd_tf32(const float* pq, int64_t ldpq, int32_t hdim, const int32_t* nbr, const int32_t* deg,
+                                int32_t width, int64_t n, const float* w2p, int64_t ldw, const float* b2, int32_t c_out,
+                                int32_t aggr, int32_t round_out, float* y, int64_t ldy, void* stream);
+
 /* Generic message input u[(i,s)] = [x_i | x_j - x_i] and its backward (dx zero on entry). */
 int gnb_edge_cat_fwd(const float* x, int64_t ldx, int32_t c_in, const int32_t* nbr, const int32_t* deg, int32_t width,
                      int64_t n, float* u, int64_t ldu, void* stream);
@@ -87,7 +94,7 @@ int gnb_edge_aggregate_bwd(const float* gy, int64_t ldy, int32_t c_out, const in
  * Replaces DynEdge._global_pooling, src/graphnet/models/gnn/dynedge.py:251-264 (torch_scatter). */
 int gnb_segment_pool_fwd(const float* x, int64_t ldx, int32_t c, const int64_t* ptr, int64_t nseg,
                          const int32_t* schemes, int32_t np, float* out, int32_t* arg, void* stream);
-int gnb_segment_pool_bwd(const float* gout, const int32_t* arg, int32_t c, const int64_t* ptr, int64_t nseg, int64_t n,
+int gnb_segment_pool_bwd(const float* gout, int64_t ldg, const int32_t* arg, int32_t c, const int64_t* ptr, int64_t nseg, int64_t n,
                          const int32_t* schemes, int32_t np, float* gx, int64_t ldx, void* stream);
 
 /* ---- dense layers (torch.nn.Linear + ReLU at dynedge.py:200-203, 226-229, 246-247) -------- */
@@ -129,6 +136,43 @@ int gnb_linear_bwd_data_f32(const float* dz, int64_t lddz, const float* w, int64
 /* dw[n,k] += dz[m,n]^T x[m,k]. */
 int gnb_linear_bwd_weight_f32(const float* dz, int64_t lddz, const float* x, int64_t ldx, float* dw, int64_t lddw,
                               int64_t m, int64_t n, int64_t k, void* stream);
+
+/* Number of kernels launched by this library so far (monotonic; bench.py reports per-step deltas). */
+int64_t gnb_launch_count(void);
+
+/* ---- native step executor (whole DynEdge.forward / backward from one call) ------------------- */
+
+#define GNB_MAX_LAYERS 8
+#define GNB_MAX_KNN_COLS 16
+/* Mirrors the constructor arguments of DynEdge (src/graphnet/models/gnn/dynedge.py:24-38) for the fast-path
+ * family: ReLU, no norm layers, 2-Linear conv MLPs with aggr=add, Linear-ReLU post-processing / read-out chains. */
+typedef struct {
+    int32_t nb_inputs, k, precision;                 /* precision: 0 fp32 SIMT GEMMs, 1 tf32 tcgen05 GEMMs */
+    int32_t n_conv, conv_hidden[GNB_MAX_LAYERS], conv_out[GNB_MAX_LAYERS];
+    int32_t n_post, post_out[GNB_MAX_LAYERS];
+    int32_t n_readout, readout_out[GNB_MAX_LAYERS];
+    int32_t n_pool, pool[4];                         /* 0 min, 1 max, 2 sum, 3 mean, caller order */
+    int32_t globals_after_pooling, skip_readout;
+    int32_t n_knn_cols, knn_cols[GNB_MAX_KNN_COLS];  /* features_subset */
+} gnb_dynedge_config;
+
+/* Bytes of workspace for a batch of n nodes / nseg events whose initial graph has table width w0; < 0: error. */
+int64_t gnb_dynedge_workspace_bytes(const gnb_dynedge_config* cfg, int64_t n, int64_t nseg, int32_t w0, int32_t training);
+/* Byte offsets into the workspace of, per conv layer l: its output y_l [n, conv_out[l]], and the graph recomputed
+ * from it (nbr [n, k+1], deg [n]; -1 for the last layer): offsets[3*l + {0,1,2}]. Test / debug aid. */
+int gnb_dynedge_layout(const gnb_dynedge_config* cfg, int64_t n, int64_t nseg, int32_t w0, int32_t training,
+                       int64_t* offsets);
+/* DynEdge.forward(data) (dynedge.py:295-349). params: HOST array of device pointers in state_dict order
+ * ({W1,b1,W2,b2} per conv, {W,b} per post layer, {W,b} per read-out layer). out: [nseg or n, last width]. */
+int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* const* params, const float* x, int64_t ldx,
+                        const int64_t* ptr, const float* n_pulses, const int32_t* nbr0, const int32_t* deg0, int32_t w0,
+                        const int32_t* knn_cols_dev, int64_t n, int64_t nseg, void* workspace, int64_t workspace_bytes,
+                        float* out, int32_t training, void* stream);
+/* Backward of the above (after a forward with training = 1 on the same workspace); gradients are accumulated
+ * onto grads[] (HOST array of device pointers parallel to params). */
+int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const* grads, const int64_t* ptr, const int32_t* nbr0,
+                         const int32_t* deg0, int32_t w0, int64_t n, int64_t nseg, void* workspace,
+                         int64_t workspace_bytes, const float* gout, void* stream);
 
 #ifdef __cplusplus
 }

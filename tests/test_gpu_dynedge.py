@@ -109,3 +109,41 @@ def test_dynedge_accepts_foreign_edge_index_and_pulse_level_output(built_library
 def test_smoke_entry(built_library):
     import __graft_entry__ as entry
     entry.smoke()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_executor_matches_per_operator_route(built_library, precision):
+    """The native step executor (one C call) and the per-operator autograd route run the same kernels: outputs and
+    all gradients must agree to fp32 round-off (atomics change summation order only)."""
+    from graphnet_b200 import Data, ops
+    from graphnet_b200.models.gnn import DynEdge
+    from graphnet_b200.models.graphs.edges import KNNEdges
+    from graphnet_b200.synthetic import make_batch
+    raw = make_batch(16, seed=8, n_max=300)
+    x, batch, n_pulses = (torch.from_numpy(raw[k]).cuda() for k in ("x", "batch", "n_pulses"))
+    old_p, old_e = ops.PRECISION, ops.USE_EXECUTOR
+    try:
+        ops.set_precision(precision)
+        for kwargs in (dict(global_pooling_schemes=["min", "max", "mean", "sum"]),
+                       dict(global_pooling_schemes=["max", "sum"], add_global_variables_after_pooling=True,
+                            dynedge_layer_sizes=[(64, 96), (80, 96)], post_processing_layer_sizes=[80], readout_layer_sizes=[32, 16]),
+                       dict(global_pooling_schemes=None, dynedge_layer_sizes=[(32, 48)], readout_layer_sizes=[8]),
+                       dict(skip_readout=True, dynedge_layer_sizes=[(32, 48), (32, 48)], post_processing_layer_sizes=[64, 32])):
+            torch.manual_seed(1)
+            model = DynEdge(7, **kwargs).cuda()
+            results = []
+            for use_exec in (False, True):
+                ops.USE_EXECUTOR = use_exec
+                model.zero_grad()
+                data = KNNEdges(8)(Data(x=x, batch=batch, n_pulses=n_pulses))
+                y = model(data)
+                y.square().sum().backward()
+                results.append((y.detach().clone(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}))
+            (y0, g0), (y1, g1) = results
+            assert y0.shape == y1.shape and rel_err(y1, y0) < 1e-5, kwargs
+            assert g0.keys() == g1.keys()
+            for k in g0:
+                assert rel_err(g1[k], g0[k]) < 2e-4, (k, kwargs)
+    finally:
+        ops.set_precision(old_p)
+        ops.USE_EXECUTOR = old_e

@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_header_symbols_are_exported(built_library):
     header = open(os.path.join(ROOT, "include", "graphnet_b200.h")).read()
-    declared = set(re.findall(r"\bint\s+(gnb_\w+)\s*\(", header))
+    declared = set(re.findall(r"\b(?:int|int64_t)\s+(gnb_\w+)\s*\(", header))
     assert len(declared) >= 15
     assert declared == set(_lib.SIGNATURES.keys())            # python binding covers exactly the header
     lib = ctypes.CDLL(built_library)
