@@ -26,11 +26,22 @@
 
 namespace {
 
-constexpr int EF_THREADS = 448;                 // 14 warps: 0 TMA/setup, 1 MMA, 2-5 epilogue, 6-13 builders
+constexpr int EF_THREADS = 480;                 // 15 warps: 0 TMA/meta, 1 MMA, 2-5 epilogue, 6-13 builders, 14 signal
 constexpr int EF_BUILDERS = 256;
 constexpr int EF_MAX_KB = 11;                   // hidden width <= 352
 constexpr int EF_STAGES = 2;
 constexpr uint32_t EF_TILE_BYTES = 128 * 32 * 4;   // 16 KiB: 128 rows x 32 tf32
+
+// Builders publish a finished B stage with a non-blocking named-barrier arrive; a dedicated signal warp (no global
+// loads in flight) joins that named barrier and performs the mbarrier arrive. A release-arrive issued by a builder
+// itself compiles to MEMBAR + ERRBAR and would wait for the builder's prefetched global loads every K step.
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+constexpr int EF_SIGNAL_COUNT = EF_BUILDERS + 32;
 
 struct TileMeta {
     int src[128];          // source node j of each edge row
@@ -39,6 +50,8 @@ struct TileMeta {
     int flush_node[32];    // target node of the f-th flush
     float flush_scale[32]; // 1 (add) or 1/deg (mean)
     int n_edges, n_mma;
+    int regular;           // every node of the tile has exactly 8 in-edges: node f owns edge rows [8f, 8f+8)
+    int n_nodes;
 };
 
 struct EfParams {
@@ -47,6 +60,54 @@ struct EfParams {
     const float* b2; int c_out; int aggr; int round_out;
     float* y; int64_t ldy; int num_tiles; int npt;
 };
+
+
+// Epilogue of one tile for one thread (= one output channel): bias + ReLU on every edge column of the TMEM
+// accumulator, k-neighbour sum in registers, one coalesced store per node. Fast path for tiles whose nodes all
+// have 8 in-edges (the common case for k = 8): fixed groups of 8 columns, no per-element control flow.
+__device__ __forceinline__ void ef_epilogue_tile(const TileMeta& m, uint32_t taddr, int64_t node0, int ch, bool ch_ok,
+                                                 float bv, const EfParams& p) {
+    const int n_edges = m.n_edges;
+    if (m.regular) {
+        const int nn = m.n_nodes;
+        const float sc = p.aggr == GNB_AGGR_MEAN ? 0.125f : 1.f;
+        for (int c = 0; c * 32 < n_edges; ++c) {
+            uint32_t r[32];
+            tc::tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                float a = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a += fmaxf(__uint_as_float(r[8 * f + i]) + bv, 0.f);
+                a *= sc;
+                if (p.round_out) a = tc::round_tf32(a);
+                const int node = 4 * c + f;
+                if (ch_ok && node < nn) p.y[(node0 + node) * p.ldy + ch] = a;
+            }
+        }
+        return;
+    }
+    float acc = 0.f;
+    int fl = 0;
+    for (int c = 0; c * 32 < n_edges; ++c) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
+        tc::tmem_ld_wait();
+        const unsigned lastbits = m.last[c];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            acc += fmaxf(__uint_as_float(r[j]) + bv, 0.f);
+            if ((lastbits >> j) & 1u) {
+                float o = acc * m.flush_scale[fl];
+                if (p.round_out) o = tc::round_tf32(o);
+                if (ch_ok) p.y[(int64_t)m.flush_node[fl] * p.ldy + ch] = o;
+                ++fl;
+                acc = 0.f;
+            }
+        }
+    }
+}
 
 __global__ void __launch_bounds__(EF_THREADS, 1)
 edgeconv_fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfParams p) {
@@ -72,7 +133,7 @@ edgeconv_fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPar
         if (lane == 0) {
             tc::mbar_init(a_full, 1);
             for (int s = 0; s < 2; ++s) {
-                tc::mbar_init(&b_full[s], EF_BUILDERS / 32);
+                tc::mbar_init(&b_full[s], 1);
                 tc::mbar_init(&b_empty[s], 1);
                 tc::mbar_init(&tmem_full[s], 1);
                 tc::mbar_init(&tmem_empty[s], 4);
@@ -127,10 +188,13 @@ edgeconv_fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPar
                 const int e = off + d - 1;
                 atomicOr(&m.last[e >> 5], 1u << (e & 31));
             }
+            const unsigned all8 = __ballot_sync(0xffffffffu, lane >= nn || d == 8);
             if (lane == 0) {
                 m.n_edges = total;
                 const int nm = (total + 15) & ~15;
                 m.n_mma = nm < 16 ? 16 : nm;
+                m.regular = (all8 == 0xffffffffu) ? 1 : 0;
+                m.n_nodes = nn;
             }
             // nodes without in-edges aggregate to 0 (PyG: empty neighbourhood -> 0)
             for (int l = 0; l < nn; ++l) {
@@ -177,32 +241,13 @@ edgeconv_fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPar
             const uint32_t buf = ti & 1;
             tc::mbar_wait<100>(&tmem_full[buf], (ti >> 1) & 1);
             tc::tcgen05_fence_after();
-            const TileMeta& m = meta[buf];
-            const int n_edges = m.n_edges;
-            float acc = 0.f;
-            int fl = 0;
-            for (int c = 0; c * 32 < n_edges; ++c) {
-                uint32_t r[32];
-                tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + c * 32), r);
-                tc::tmem_ld_wait();
-                const unsigned lastbits = m.last[c];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    acc += fmaxf(__uint_as_float(r[j]) + bv, 0.f);
-                    if ((lastbits >> j) & 1u) {
-                        float o = acc * m.flush_scale[fl];
-                        if (p.round_out) o = tc::round_tf32(o);
-                        if (ch_ok) p.y[(int64_t)m.flush_node[fl] * p.ldy + ch] = o;
-                        ++fl;
-                        acc = 0.f;
-                    }
-                }
-            }
+            ef_epilogue_tile(meta[buf], tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128), (int64_t)t * p.npt, ch,
+                             ch_ok, bv, p);
             tc::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tmem_empty[buf]);
         }
-    } else {
+    } else if (warp < 14) {
         // ---- builders: gather P[i] + Q[j], ReLU, tf32 rounding, swizzled K-major store -------------------
         // 8 consecutive lanes cover the 128 bytes (one K-block) of ONE edge row, so every warp load touches 4 rows x
         // 128 B (full sectors); a thread owns 16-byte chunk `chunk` of rows 4*rg + {0,1,2,3}. Global loads run two
@@ -267,8 +312,7 @@ edgeconv_fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPar
                     }
                 }
                 tc::fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&b_full[st]);
+                named_bar_arrive(1 + (int)st, EF_SIGNAL_COUNT);
             };
 
             Regs ra, rb, rc;
@@ -283,16 +327,266 @@ edgeconv_fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPar
                 emit(kb + 2, rc);
             }
         }
+    } else {
+        // ---- signal warp: forwards "stage built" from the builders' named barrier to the MMA's mbarrier --------
+        const int tiles_cta = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const uint32_t total = (uint32_t)tiles_cta * (uint32_t)p.kblocks;
+        for (uint32_t g = 0; g < total; ++g) {
+            const uint32_t st = g & 1;
+            named_bar_sync(1 + (int)st, EF_SIGNAL_COUNT);
+            if (lane == 0) tc::mbar_arrive(&b_full[st]);
+        }
     }
     tc::tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) tc::tmem_dealloc<256>(tmem_base);
 }
 
+
+// =====================================================================================================
+// CTA-pair variant (cta_group::2) for c_out in (128, 256]: the two CTAs of a cluster own the two 128-channel
+// halves of W2 (each resident in its own shared memory) and SHARE the gathered hidden tile: every CTA builds
+// only 64 of the tile's 128 edge rows (half the gather / ALU work and half the B bytes per SM, 4 x 8 KiB
+// stages instead of 2 x 16 KiB), the leader CTA issues one M = 256, N = 128 tcgen05.mma per K step, and each
+// CTA's TMEM receives its own 128 channels x 128 edges.
+// Cross-CTA signalling: builders of both CTAs arrive on the LEADER's b_full[s] (remote mbarrier arrive through
+// mapa), the MMA commits are multicast to both CTAs' b_empty / tmem_full, epilogues of both CTAs arrive on the
+// leader's tmem_empty.
+constexpr int EP_STAGES = 4;
+constexpr uint32_t EP_BTILE_BYTES = 64 * 32 * 4;    // 8 KiB: 64 rows x 32 tf32 per CTA
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EF_THREADS, 1)
+edgeconv_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_a = smem;                                            // [kblocks][16 KiB] resident weights (this CTA's half)
+    uint8_t* s_b = smem + EF_MAX_KB * EF_TILE_BYTES;                // [4][8 KiB] this CTA's 64 rows of the hidden tile
+    TileMeta* meta = reinterpret_cast<TileMeta*>(s_b + EP_STAGES * EP_BTILE_BYTES);   // [2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 2);
+    uint64_t* a_full = bars;            // [1]
+    uint64_t* b_full = bars + 1;        // [4]  (used on the leader: 16 warp arrivals)
+    uint64_t* b_empty = bars + 5;       // [4]  (multicast commit)
+    uint64_t* tmem_full = bars + 9;     // [2]  (multicast commit)
+    uint64_t* tmem_empty = bars + 11;   // [2]  (used on the leader: 8 warp arrivals)
+    uint64_t* epi_done = bars + 13;     // [2]  local: 4 epilogue warps (metadata slot reuse)
+    uint64_t* meta_full = bars + 15;    // [2]  local
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();       // 0 = leader
+    const int ch_base = (int)rank * 128;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            tc::mbar_init(a_full, 1);
+            for (int s = 0; s < EP_STAGES; ++s) { tc::mbar_init(&b_full[s], 2); tc::mbar_init(&b_empty[s], 1); }
+            for (int s = 0; s < 2; ++s) {
+                tc::mbar_init(&tmem_full[s], 1);
+                tc::mbar_init(&tmem_empty[s], 8);
+                tc::mbar_init(&epi_done[s], 4);
+                tc::mbar_init(&meta_full[s], 1);
+            }
+            tc::fence_barrier_init();
+            tc::fence_proxy_async();
+        }
+        __syncwarp();
+        tc::tmem_alloc_2cta<256>(tmem_slot);
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();                                          // barriers are initialised from here on
+    if (threadIdx.x == 0) {   // this CTA's resident half of W2
+        tc::tma_prefetch_desc(&tm_w2);
+        tc::mbar_arrive_expect_tx(a_full, (uint32_t)p.kblocks * EF_TILE_BYTES);
+        for (int kb = 0; kb < p.kblocks; ++kb) tc::tma_load_2d(s_a + kb * EF_TILE_BYTES, &tm_w2, a_full, kb * 32, ch_base);
+        tc::mbar_wait<100>(a_full, 0);                        // weights landed in THIS CTA
+    }
+    __syncthreads();
+    tc::cluster_sync_all();                                   // barriers initialised + weights resident in BOTH CTAs
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---- tile metadata producer (both CTAs compute the same edge list; each zero-fills its channel half) ----
+        uint32_t ti = 0;
+        for (int t = cluster_id; t < p.num_tiles; t += num_clusters, ++ti) {
+            const uint32_t buf = ti & 1;
+            tc::mbar_wait<200>(&epi_done[buf], ((ti >> 1) & 1) ^ 1);
+            TileMeta& m = meta[buf];
+            const int64_t node0 = (int64_t)t * p.npt;
+            const int nn = (int)((p.n - node0) < p.npt ? (p.n - node0) : p.npt);
+            const int d = lane < nn ? p.deg[node0 + lane] : 0;
+            int incl = d;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int off = incl - d;
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (lane < 4) m.last[lane] = 0u;
+            __syncwarp();
+            const unsigned has = __ballot_sync(0xffffffffu, d > 0);
+            if (d > 0) {
+                const int pos = __popc(has & ((1u << lane) - 1u));
+                m.flush_node[pos] = (int)(node0 + lane);
+                m.flush_scale[pos] = p.aggr == GNB_AGGR_MEAN ? 1.f / (float)d : 1.f;
+                for (int s = 0; s < d; ++s) {
+                    m.src[off + s] = p.nbr[(node0 + lane) * p.width + s];
+                    m.node[off + s] = (int)(node0 + lane);
+                }
+                const int e = off + d - 1;
+                atomicOr(&m.last[e >> 5], 1u << (e & 31));
+            }
+            const unsigned all8 = __ballot_sync(0xffffffffu, lane >= nn || d == 8);
+            if (lane == 0) { m.n_edges = total; m.n_mma = 128; m.regular = (all8 == 0xffffffffu) ? 1 : 0; m.n_nodes = nn; }
+            for (int l = 0; l < nn; ++l) {
+                const int dl = __shfl_sync(0xffffffffu, d, l);
+                if (dl == 0)
+                    for (int c = lane; c < 128; c += 32)
+                        if (ch_base + c < p.c_out) p.y[(node0 + l) * p.ldy + ch_base + c] = 0.f;
+            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&meta_full[buf]);
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && lane == 0) {
+            // ---- MMA issuer (leader CTA only): M = 256 over both CTAs, N = 128 edges ------------------------
+            const uint32_t idesc = tc::umma_idesc_tf32(256, 128);
+            uint32_t it = 0, ti = 0;
+            for (int t = cluster_id; t < p.num_tiles; t += num_clusters, ++ti) {
+                const uint32_t buf = ti & 1;
+                tc::mbar_wait<20>(&tmem_empty[buf], ((ti >> 1) & 1) ^ 1);
+                tc::tcgen05_fence_after();
+                const uint32_t acc = tmem_base + buf * 128;
+                for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+                    const uint32_t s = it % EP_STAGES, ph = (it / EP_STAGES) & 1;
+                    tc::mbar_wait<20>(&b_full[s], ph);
+                    tc::tcgen05_fence_after();
+                    const uint64_t adesc = tc::umma_desc_sw128_kmajor(tc::smem_u32(s_a + kb * EF_TILE_BYTES));
+                    const uint64_t bdesc = tc::umma_desc_sw128_kmajor(tc::smem_u32(s_b + s * EP_BTILE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::umma_tf32_2cta(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc::umma_commit_2cta(&b_empty[s], 3);
+                }
+                tc::umma_commit_2cta(&tmem_full[buf], 3);
+            }
+        }
+    } else if (warp < 6) {
+        // ---- epilogue (each CTA: its own 128 channels) ------------------------------------------------------
+        const int q = warp & 3;
+        const int ch = ch_base + q * 32 + lane;
+        const bool ch_ok = ch < p.c_out;
+        const float bv = (ch_ok && p.b2 != nullptr) ? p.b2[ch] : 0.f;
+        uint32_t ti = 0;
+        for (int t = cluster_id; t < p.num_tiles; t += num_clusters, ++ti) {
+            const uint32_t buf = ti & 1;
+            tc::mbar_wait<100>(&tmem_full[buf], (ti >> 1) & 1);
+            tc::tcgen05_fence_after();
+            ef_epilogue_tile(meta[buf], tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128), (int64_t)t * p.npt, ch,
+                             ch_ok, bv, p);
+            tc::tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                tc::mbar_arrive(&epi_done[buf]);                  // local: metadata slot may be rewritten
+                tc::mbar_arrive_cluster(&tmem_empty[buf], 0);     // leader: accumulator buffer may be overwritten
+            }
+        }
+    } else if (warp < 14) {
+        // ---- builders: this CTA's 64 edge rows (tile rows 64*rank + [0, 64)) --------------------------------
+        const int bt = threadIdx.x - 192;            // 0..255
+        const int chunk = bt & 7, rg = bt >> 3;      // local rows 2*rg + {0,1}
+        const int kbs = p.kblocks;
+        const float* __restrict__ pq = p.pq;
+        const bool tail_chunk = (kbs - 1) * 32 + chunk * 4 >= p.hdim;
+        uint32_t g = 0;
+        struct Regs { float4 pv[2], qv[2]; };
+        uint32_t tl = 0;
+        for (int t = cluster_id; t < p.num_tiles; t += num_clusters, ++tl) {
+            const int b = tl & 1;
+            tc::mbar_wait<50>(&meta_full[b], (tl >> 1) & 1);
+            const TileMeta& m = meta[b];
+            const int n_edges = m.n_edges;
+            int offp[2], offq[2];
+            bool ok[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int row = 64 * (int)rank + 2 * rg + j;     // row of the 128-row tile
+                ok[j] = row < n_edges;
+                const int rr = (ok[j] && n_edges > 0) ? row : 0;
+                offp[j] = n_edges > 0 ? m.node[rr] * (int)p.ldpq + chunk * 4 : 0;
+                offq[j] = n_edges > 0 ? m.src[rr] * (int)p.ldpq + p.hdim + chunk * 4 : 0;
+            }
+            auto load = [&](int kb, Regs& r) {
+                if (kb >= kbs) return;
+                if (kb == kbs - 1 && tail_chunk) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) { r.pv[j] = make_float4(0.f, 0.f, 0.f, 0.f); r.qv[j] = r.pv[j]; }
+                    return;
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    r.pv[j] = __ldg(reinterpret_cast<const float4*>(pq + offp[j] + kb * 32));
+                    r.qv[j] = __ldg(reinterpret_cast<const float4*>(pq + offq[j] + kb * 32));
+                }
+            };
+            auto emit = [&](int kb, const Regs& r) {
+                if (kb >= kbs) return;
+                const uint32_t st = g % EP_STAGES, ph = (g / EP_STAGES) & 1;
+                ++g;
+                tc::mbar_wait<20>(&b_empty[st], ph ^ 1);
+                uint8_t* base = s_b + st * EP_BTILE_BYTES;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (ok[j]) {
+                        const int lrow = 2 * rg + j;             // row inside this CTA's 64-row B tile
+                        uint4 v;
+                        v.x = __float_as_uint(fmaxf(r.pv[j].x + r.qv[j].x, 0.f)) + 0x1000u;
+                        v.y = __float_as_uint(fmaxf(r.pv[j].y + r.qv[j].y, 0.f)) + 0x1000u;
+                        v.z = __float_as_uint(fmaxf(r.pv[j].z + r.qv[j].z, 0.f)) + 0x1000u;
+                        v.w = __float_as_uint(fmaxf(r.pv[j].w + r.qv[j].w, 0.f)) + 0x1000u;
+                        *reinterpret_cast<uint4*>(base + lrow * 128 + ((chunk ^ (lrow & 7)) << 4)) = v;
+                    }
+                }
+                tc::fence_proxy_async();
+                named_bar_arrive(1 + (int)st, EF_SIGNAL_COUNT);
+            };
+            Regs r0, r1, r2, r3;
+            load(0, r0); load(1, r1); load(2, r2);
+            for (int kb = 0; kb < kbs; kb += 4) {
+                load(kb + 3, r3); emit(kb, r0);
+                load(kb + 4, r0); emit(kb + 1, r1);
+                load(kb + 5, r1); emit(kb + 2, r2);
+                load(kb + 6, r2); emit(kb + 3, r3);
+            }
+        }
+    } else {
+        // ---- signal warp: this CTA's 64 rows of stage st are built -> arrive on the LEADER's b_full[st] ----------
+        const int tiles_cl = (p.num_tiles - cluster_id + num_clusters - 1) / num_clusters;
+        const uint32_t total = (uint32_t)tiles_cl * (uint32_t)p.kblocks;
+        for (uint32_t g = 0; g < total; ++g) {
+            const uint32_t st = g % EP_STAGES;
+            named_bar_sync(1 + (int)st, EF_SIGNAL_COUNT);
+            if (lane == 0) tc::mbar_arrive_cluster(&b_full[st], 0);
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();            // no CTA may exit while its peer can still signal it
+    if (warp == 1) tc::tmem_dealloc_2cta<256>(tmem_base);
+}
+
+constexpr uint32_t EP_SMEM_BYTES = EF_MAX_KB * EF_TILE_BYTES + EP_STAGES * EP_BTILE_BYTES + 2 * sizeof(TileMeta) + 256 + 1024;
+int g_ef_variant = 0;      // 0 auto, 1 single-CTA kernel, 2 CTA-pair kernel
+
 constexpr uint32_t EF_SMEM_BYTES = EF_MAX_KB * EF_TILE_BYTES + EF_STAGES * EF_TILE_BYTES + 2 * sizeof(TileMeta) + 128 + 1024;
 int g_ef_sms = 0;
 
 }  // namespace
+
+// bring-up / A-B testing: 0 auto (CTA-pair kernel when c_out needs exactly two 128-channel halves), 1 single-CTA, 2 pair
+GNB_EXPORT int gnb_edgeconv_set_variant(int32_t v) { g_ef_variant = v; return GNB_OK; }
 
 // w2p: [c_out, ceil(hdim/32)*32] fp32, tf32-rounded, zero padded columns. pq: [n, 2*hdim] (tf32-rounded P | Q).
 // aggr: 0 add, 1 mean. hdim % 4 == 0, hdim <= 352, width <= 32.
@@ -324,6 +618,18 @@ GNB_EXPORT int gnb_edgeconv_fused_fwd_tf32(const float* pq, int64_t ldpq, int32_
     if (p.npt > 32) p.npt = 32;
     p.num_tiles = gnb_div_up(n, p.npt);
     const int halves = gnb_div_up(c_out, 128);
+    if (halves == 2 && g_ef_variant != 1) {   // CTA-pair kernel
+        static bool pair_attr = false;
+        if (!pair_attr) {
+            GNB_CHECK(cudaFuncSetAttribute(edgeconv_fused_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)EP_SMEM_BYTES));
+            pair_attr = true;
+        }
+        int clusters = g_ef_sms / 2;
+        if (clusters > p.num_tiles) clusters = p.num_tiles;
+        edgeconv_fused_pair_kernel<<<dim3((unsigned)(2 * clusters)), EF_THREADS, EP_SMEM_BYTES, (cudaStream_t)stream>>>(tw, p);
+        GNB_RETURN_LAUNCH();
+    }
     int ctas = g_ef_sms / halves;
     if (ctas < 1) ctas = 1;
     if (ctas > p.num_tiles) ctas = p.num_tiles;

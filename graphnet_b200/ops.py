@@ -525,6 +525,11 @@ class _EdgeConvHoisted(torch.autograd.Function):
 FUSED_EDGECONV = os.environ.get("GNB_FUSED_EDGECONV", "1") == "1"
 
 
+def set_edgeconv_variant(v: int) -> None:
+    """0 auto, 1 single-CTA fused EdgeConv kernel, 2 CTA-pair (cta_group::2) kernel."""
+    _lib.check(_lib.load().gnb_edgeconv_set_variant(v), "gnb_edgeconv_set_variant")
+
+
 def edgeconv_fused_forward(pq: Tensor, w2: Tensor, b2: Optional[Tensor], graph: KnnGraph, aggr: str = "add") -> Tensor:
     """Inference-only fused EdgeConv (gather + hidden ReLU + contraction + bias/ReLU + aggregation in ONE tcgen05
     kernel; no [E, H] / [E, C] tensors in HBM). tf32 mode."""

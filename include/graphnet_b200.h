@@ -73,6 +73,10 @@ int gnb_edgeconv_fused_fwd_tf32(const float* pq, int64_t ldpq, int32_t hdim, con
                                 int32_t width, int64_t n, const float* w2p, int64_t ldw, const float* b2, int32_t c_out,
                                 int32_t aggr, int32_t round_out, float* y, int64_t ldy, void* stream);
 
+/* Kernel selection for gnb_edgeconv_fused_fwd_tf32: 0 auto (CTA-pair cta_group::2 kernel when 128 < c_out <= 256),
+ * 1 single-CTA kernel, 2 CTA-pair kernel. */
+int gnb_edgeconv_set_variant(int32_t v);
+
 /* Generic message input u[(i,s)] = [x_i | x_j - x_i] and its backward (dx zero on entry). */
 int gnb_edge_cat_fwd(const float* x, int64_t ldx, int32_t c_in, const int32_t* nbr, const int32_t* deg, int32_t width,
                      int64_t n, float* u, int64_t ldu, void* stream);

@@ -152,7 +152,8 @@ def _edgeconv_reference(pq, w2, b2, nbr, deg, aggr):
 
 @pytest.mark.parametrize("hdim,c_out,k", [(336, 256, 8), (128, 256, 8), (32, 48, 4), (352, 128, 16), (64, 300, 8)])
 @pytest.mark.parametrize("aggr", ["add", "mean"])
-def test_fused_edgeconv_bit_exact_on_integers(built_library, tf32_mode, hdim, c_out, k, aggr):
+@pytest.mark.parametrize("variant", [1, 2], ids=["single_cta", "cta_pair"])
+def test_fused_edgeconv_bit_exact_on_integers(built_library, tf32_mode, hdim, c_out, k, aggr, variant):
     """Fused gather + hidden ReLU + tcgen05 contraction + bias/ReLU + aggregation: exact on small integers
     (sum aggregation; mean compared to 1e-6) including degree-0, short and k+1-degree nodes."""
     ops = tf32_mode
@@ -169,8 +170,13 @@ def test_fused_edgeconv_bit_exact_on_integers(built_library, tf32_mode, hdim, c_
     w2 = torch.randint(-1, 2, (c_out, hdim), generator=g).float()
     b2 = torch.randint(-3, 4, (c_out,), generator=g).float()
     ref = _edgeconv_reference(pq, w2, b2, graph.nbr.cpu(), graph.deg.cpu(), aggr)
-    with torch.no_grad():
-        y = ops.edgeconv_fused_forward(pq.cuda(), w2.cuda(), b2.cuda(), graph, aggr)
+    ops.set_edgeconv_variant(variant)      # the pair kernel only applies to 128 < c_out <= 256
+    try:
+        with torch.no_grad():
+            y = ops.edgeconv_fused_forward(pq.cuda(), w2.cuda(), b2.cuda(), graph, aggr)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_edgeconv_variant(0)
     if aggr == "add":
         assert torch.equal(y.cpu().double(), ref)
     else:
