@@ -59,6 +59,8 @@ struct EfParams {
     const int* nbr; const int* deg; int width; int64_t n;
     const float* b2; int c_out; int aggr; int round_out;
     float* y; int64_t ldy; int num_tiles; int npt;
+    unsigned long long* prof;   // optional [16] cycle counters written by cluster 0 (tuning aid)
+    int debug;                  // tuning experiments: bit0 Q rows := own node (no gather), bit1 no global loads, bit2 no epilogue, bit3 no MMA
 };
 
 
@@ -353,9 +355,10 @@ edgeconv_fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPar
 // mapa), the MMA commits are multicast to both CTAs' b_empty / tmem_full, epilogues of both CTAs arrive on the
 // leader's tmem_empty.
 constexpr int EP_STAGES = 4;
+constexpr int EP_THREADS = EF_THREADS + 32;      // + a second signal warp (warps 14, 15 alternate K steps)
 constexpr uint32_t EP_BTILE_BYTES = 64 * 32 * 4;    // 8 KiB: 64 rows x 32 tf32 per CTA
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EF_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EP_THREADS, 1)
 edgeconv_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -376,6 +379,10 @@ edgeconv_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPa
     const uint32_t rank = tc::cluster_ctarank();       // 0 = leader
     const int ch_base = (int)rank * 128;
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const bool prof_on = p.prof != nullptr && blockIdx.x == 0;
+    long long pw0 = 0, pw1 = 0;                       // cycles this thread spent in its two kinds of waits
+    const long long pt0 = clock64();
+#define EF_TIMED(acc, stmt) do { const long long c0__ = clock64(); stmt; acc += clock64() - c0__; } while (0)
 
     if (warp == 1) {
         if (lane == 0) {
@@ -411,7 +418,7 @@ edgeconv_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPa
         uint32_t ti = 0;
         for (int t = cluster_id; t < p.num_tiles; t += num_clusters, ++ti) {
             const uint32_t buf = ti & 1;
-            tc::mbar_wait<200>(&epi_done[buf], ((ti >> 1) & 1) ^ 1);
+            EF_TIMED(pw0, tc::mbar_wait<200>(&epi_done[buf], ((ti >> 1) & 1) ^ 1));
             TileMeta& m = meta[buf];
             const int64_t node0 = (int64_t)t * p.npt;
             const int nn = (int)((p.n - node0) < p.npt ? (p.n - node0) : p.npt);
@@ -456,18 +463,20 @@ edgeconv_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPa
             uint32_t it = 0, ti = 0;
             for (int t = cluster_id; t < p.num_tiles; t += num_clusters, ++ti) {
                 const uint32_t buf = ti & 1;
-                tc::mbar_wait<20>(&tmem_empty[buf], ((ti >> 1) & 1) ^ 1);
+                EF_TIMED(pw1, tc::mbar_wait<20>(&tmem_empty[buf], ((ti >> 1) & 1) ^ 1));
                 tc::tcgen05_fence_after();
                 const uint32_t acc = tmem_base + buf * 128;
                 for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
                     const uint32_t s = it % EP_STAGES, ph = (it / EP_STAGES) & 1;
-                    tc::mbar_wait<20>(&b_full[s], ph);
+                    EF_TIMED(pw0, tc::mbar_wait<20>(&b_full[s], ph));
                     tc::tcgen05_fence_after();
                     const uint64_t adesc = tc::umma_desc_sw128_kmajor(tc::smem_u32(s_a + kb * EF_TILE_BYTES));
                     const uint64_t bdesc = tc::umma_desc_sw128_kmajor(tc::smem_u32(s_b + s * EP_BTILE_BYTES));
+                    if (!(p.debug & 8)) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         tc::umma_tf32_2cta(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
                     tc::umma_commit_2cta(&b_empty[s], 3);
                 }
                 tc::umma_commit_2cta(&tmem_full[buf], 3);
@@ -482,16 +491,17 @@ edgeconv_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPa
         uint32_t ti = 0;
         for (int t = cluster_id; t < p.num_tiles; t += num_clusters, ++ti) {
             const uint32_t buf = ti & 1;
-            tc::mbar_wait<100>(&tmem_full[buf], (ti >> 1) & 1);
+            EF_TIMED(pw0, tc::mbar_wait<100>(&tmem_full[buf], (ti >> 1) & 1));
             tc::tcgen05_fence_after();
+            if (!(p.debug & 4))
             ef_epilogue_tile(meta[buf], tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128), (int64_t)t * p.npt, ch,
                              ch_ok, bv, p);
             tc::tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) {
+            EF_TIMED(pw1, if (lane == 0) {
                 tc::mbar_arrive(&epi_done[buf]);                  // local: metadata slot may be rewritten
                 tc::mbar_arrive_cluster(&tmem_empty[buf], 0);     // leader: accumulator buffer may be overwritten
-            }
+            } __syncwarp());
         }
     } else if (warp < 14) {
         // ---- builders: this CTA's 64 edge rows (tile rows 64*rank + [0, 64)) --------------------------------
@@ -505,7 +515,7 @@ edgeconv_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPa
         uint32_t tl = 0;
         for (int t = cluster_id; t < p.num_tiles; t += num_clusters, ++tl) {
             const int b = tl & 1;
-            tc::mbar_wait<50>(&meta_full[b], (tl >> 1) & 1);
+            EF_TIMED(pw0, tc::mbar_wait<50>(&meta_full[b], (tl >> 1) & 1));
             const TileMeta& m = meta[b];
             const int n_edges = m.n_edges;
             int offp[2], offq[2];
@@ -516,11 +526,11 @@ edgeconv_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPa
                 ok[j] = row < n_edges;
                 const int rr = (ok[j] && n_edges > 0) ? row : 0;
                 offp[j] = n_edges > 0 ? m.node[rr] * (int)p.ldpq + chunk * 4 : 0;
-                offq[j] = n_edges > 0 ? m.src[rr] * (int)p.ldpq + p.hdim + chunk * 4 : 0;
+                offq[j] = n_edges > 0 ? ((p.debug & 1) ? m.node[rr] : m.src[rr]) * (int)p.ldpq + p.hdim + chunk * 4 : 0;
             }
             auto load = [&](int kb, Regs& r) {
                 if (kb >= kbs) return;
-                if (kb == kbs - 1 && tail_chunk) {
+                if ((kb == kbs - 1 && tail_chunk) || (p.debug & 2)) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) { r.pv[j] = make_float4(0.f, 0.f, 0.f, 0.f); r.qv[j] = r.pv[j]; }
                     return;
@@ -535,7 +545,7 @@ edgeconv_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPa
                 if (kb >= kbs) return;
                 const uint32_t st = g % EP_STAGES, ph = (g / EP_STAGES) & 1;
                 ++g;
-                tc::mbar_wait<20>(&b_empty[st], ph ^ 1);
+                EF_TIMED(pw1, tc::mbar_wait<20>(&b_empty[st], ph ^ 1));
                 uint8_t* base = s_b + st * EP_BTILE_BYTES;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
@@ -549,7 +559,8 @@ edgeconv_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPa
                         *reinterpret_cast<uint4*>(base + lrow * 128 + ((chunk ^ (lrow & 7)) << 4)) = v;
                     }
                 }
-                tc::fence_proxy_async();
+                // no per-thread proxy fence here: the named barrier orders these stores before the signal warp, which
+                // issues ONE fence.proxy.async per stage (a fence in every builder warp costs ~400 cycles per K step)
                 named_bar_arrive(1 + (int)st, EF_SIGNAL_COUNT);
             };
             Regs r0, r1, r2, r3;
@@ -565,12 +576,20 @@ edgeconv_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPa
         // ---- signal warp: this CTA's 64 rows of stage st are built -> arrive on the LEADER's b_full[st] ----------
         const int tiles_cl = (p.num_tiles - cluster_id + num_clusters - 1) / num_clusters;
         const uint32_t total = (uint32_t)tiles_cl * (uint32_t)p.kblocks;
-        for (uint32_t g = 0; g < total; ++g) {
+        for (uint32_t g = (uint32_t)(warp - 14); g < total; g += 2) {      // warp 14: even steps, warp 15: odd steps
             const uint32_t st = g % EP_STAGES;
-            named_bar_sync(1 + (int)st, EF_SIGNAL_COUNT);
-            if (lane == 0) tc::mbar_arrive_cluster(&b_full[st], 0);
+            EF_TIMED(pw0, named_bar_sync(1 + (int)st, EF_SIGNAL_COUNT));
+            tc::fence_proxy_async();          // builders' generic-proxy stores -> visible to the tensor core (async proxy)
+            EF_TIMED(pw1, if (lane == 0) tc::mbar_arrive_cluster_relaxed(&b_full[st], 0); __syncwarp());
         }
     }
+    if (prof_on && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 6 || warp == 14)) {
+        const int slot = warp == 0 ? 0 : warp == 1 ? 3 : warp == 2 ? 6 : warp == 6 ? 9 : 12;
+        p.prof[slot] = (unsigned long long)pw0;
+        p.prof[slot + 1] = (unsigned long long)pw1;
+        p.prof[slot + 2] = (unsigned long long)(clock64() - pt0);
+    }
+#undef EF_TIMED
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::cluster_sync_all();            // no CTA may exit while its peer can still signal it
@@ -579,6 +598,8 @@ edgeconv_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPa
 
 constexpr uint32_t EP_SMEM_BYTES = EF_MAX_KB * EF_TILE_BYTES + EP_STAGES * EP_BTILE_BYTES + 2 * sizeof(TileMeta) + 256 + 1024;
 int g_ef_variant = 0;      // 0 auto, 1 single-CTA kernel, 2 CTA-pair kernel
+unsigned long long* g_ef_prof = nullptr;
+int g_ef_debug = 0;
 
 constexpr uint32_t EF_SMEM_BYTES = EF_MAX_KB * EF_TILE_BYTES + EF_STAGES * EF_TILE_BYTES + 2 * sizeof(TileMeta) + 128 + 1024;
 int g_ef_sms = 0;
@@ -586,7 +607,9 @@ int g_ef_sms = 0;
 }  // namespace
 
 // bring-up / A-B testing: 0 auto (CTA-pair kernel when c_out needs exactly two 128-channel halves), 1 single-CTA, 2 pair
-GNB_EXPORT int gnb_edgeconv_set_variant(int32_t v) { g_ef_variant = v; return GNB_OK; }
+GNB_EXPORT int gnb_edgeconv_set_variant(int32_t v) { g_ef_variant = v & 0xff; g_ef_debug = (v >> 8) & 0xff; return GNB_OK; }
+// device buffer of 16 uint64 receiving per-role wait / total cycle counters of cluster 0 (nullptr = off)
+GNB_EXPORT int gnb_edgeconv_set_profile_buffer(void* buf) { g_ef_prof = (unsigned long long*)buf; return GNB_OK; }
 
 // w2p: [c_out, ceil(hdim/32)*32] fp32, tf32-rounded, zero padded columns. pq: [n, 2*hdim] (tf32-rounded P | Q).
 // aggr: 0 add, 1 mean. hdim % 4 == 0, hdim <= 352, width <= 32.
@@ -613,7 +636,7 @@ GNB_EXPORT int gnb_edgeconv_fused_fwd_tf32(const float* pq, int64_t ldpq, int32_
     p.pq = pq; p.ldpq = ldpq; p.hdim = hdim; p.kblocks = kblocks;
     p.nbr = nbr; p.deg = deg; p.width = width; p.n = n;
     p.b2 = b2; p.c_out = c_out; p.aggr = aggr; p.round_out = round_out;
-    p.y = y; p.ldy = ldy;
+    p.y = y; p.ldy = ldy; p.prof = g_ef_prof; p.debug = g_ef_debug;
     p.npt = 128 / width;
     if (p.npt > 32) p.npt = 32;
     p.num_tiles = gnb_div_up(n, p.npt);
@@ -627,7 +650,7 @@ GNB_EXPORT int gnb_edgeconv_fused_fwd_tf32(const float* pq, int64_t ldpq, int32_
         }
         int clusters = g_ef_sms / 2;
         if (clusters > p.num_tiles) clusters = p.num_tiles;
-        edgeconv_fused_pair_kernel<<<dim3((unsigned)(2 * clusters)), EF_THREADS, EP_SMEM_BYTES, (cudaStream_t)stream>>>(tw, p);
+        edgeconv_fused_pair_kernel<<<dim3((unsigned)(2 * clusters)), EP_THREADS, EP_SMEM_BYTES, (cudaStream_t)stream>>>(tw, p);
         GNB_RETURN_LAUNCH();
     }
     int ctas = g_ef_sms / halves;

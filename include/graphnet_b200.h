@@ -76,6 +76,9 @@ int gnb_edgeconv_fused_fwd_tf32(const float* pq, int64_t ldpq, int32_t hdim, con
 /* Kernel selection for gnb_edgeconv_fused_fwd_tf32: 0 auto (CTA-pair cta_group::2 kernel when 128 < c_out <= 256),
  * 1 single-CTA kernel, 2 CTA-pair kernel. */
 int gnb_edgeconv_set_variant(int32_t v);
+/* Tuning aid: device buffer of 16 uint64 that cluster 0 of the CTA-pair kernel fills with per-role wait / total cycle
+ * counters {meta, mma, epilogue, builder, signal} x {wait0, wait1, total}; NULL switches it off. */
+int gnb_edgeconv_set_profile_buffer(void* buf);
 
 /* Generic message input u[(i,s)] = [x_i | x_j - x_i] and its backward (dx zero on entry). */
 int gnb_edge_cat_fwd(const float* x, int64_t ldx, int32_t c_in, const int32_t* nbr, const int32_t* deg, int32_t width,
