@@ -99,7 +99,28 @@ knn_table_kernel(const float* __restrict__ x, int64_t ld, const int* __restrict_
         if (active) {
             const int a = (int)((lo > c0 ? lo : c0) - c0);
             const int b = (int)((hi < c0 + cnt ? hi : c0 + cnt) - c0);
-            for (int jj = a; jj < b; ++jj) {
+            int jj = a;
+            if (D && K1) {
+                // 4 candidates per iteration: the distance evaluations are independent (shared-memory latency
+                // overlaps), the insertions stay in ascending candidate order so ties keep the lower index
+                for (; jj + 4 <= b; jj += 4) {
+                    float acc4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float d0 = s_c[jj + u] - qf[0];
+                        float acc = __fmul_rn(d0, d0);
+#pragma unroll
+                        for (int j = 1; j < (D ? D : 1); ++j) {
+                            const float dj = s_c[j * chunk + jj + u] - qf[j];
+                            acc = __fadd_rn(acc, __fmul_rn(dj, dj));
+                        }
+                        acc4[u] = acc;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) insert_static<KA>(bd, bi, acc4[u], (int)(c0 + jj + u));
+                }
+            }
+            for (; jj < b; ++jj) {
                 float acc;
                 if (D) {
                     const float d0 = s_c[jj] - qf[0];

@@ -594,6 +594,36 @@ def segment_pool(x: Tensor, ptr: Tensor, schemes: Sequence[str], return_arg: boo
 # native step executor (csrc/dynedge_exec.cu): DynEdge.forward / backward from one C call each
 # --------------------------------------------------------------------------- #
 USE_EXECUTOR = os.environ.get("GNB_EXECUTOR", "1") == "1"
+# When True and every parameter already owns a contiguous fp32 `.grad` (e.g. the views of
+# `distributed.FlatGradAllReduce`), the executor's backward accumulates straight into those buffers and hands
+# autograd `None`, saving one zero-fill and one add kernel per parameter tensor. Off by default because autograd
+# hooks on the parameters would not observe these gradients.
+ACCUMULATE_INTO_GRAD = False
+
+
+# Workspace pool: the executor needs one multi-GB scratch buffer per step. Allocating it through the caching
+# allocator every call makes step time depend on allocator state (a 150 ms cudaMalloc hiccup was measured);
+# buffers are therefore recycled here (grow-only, same-stream use assumed, at most 4 kept per device).
+_WS_POOL: dict = {}
+
+
+def _ws_acquire(nbytes: int, device) -> Tensor:
+    pool = _WS_POOL.setdefault(str(device), [])
+    best = -1
+    for i, t in enumerate(pool):
+        if t.numel() >= nbytes and (best < 0 or t.numel() < pool[best].numel()):
+            best = i
+    if best >= 0:
+        return pool.pop(best)
+    return torch.empty(int(nbytes * 1.2) + 256, dtype=torch.uint8, device=device)
+
+
+def _ws_release(t: Tensor) -> None:
+    pool = _WS_POOL.setdefault(str(t.device), [])
+    pool.append(t)
+    if len(pool) > 4:
+        pool.sort(key=lambda b: b.numel())
+        pool.pop(0)
 
 
 class _DynEdgeExec(torch.autograd.Function):
@@ -608,7 +638,7 @@ class _DynEdgeExec(torch.autograd.Function):
         nbytes = lib.gnb_dynedge_workspace_bytes(ctypes.byref(cfg), n, nseg, graph.width, training)
         if nbytes < 0:
             raise RuntimeError(f"gnb_dynedge_workspace_bytes: unsupported configuration [{nbytes}]")
-        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=x.device)
+        ws = _ws_acquire(int(nbytes), x.device)
         out = torch.empty(nseg if out_per_event else n, out_cols, dtype=torch.float32, device=x.device)
         npf = n_pulses.to(torch.float32).contiguous()
         plist = [p.detach().contiguous() for p in params]
@@ -636,20 +666,30 @@ class _DynEdgeExec(torch.autograd.Function):
             x0_off = (4 * nseg * ng + 255) // 256 * 256
             record["x0"] = ws[x0_off: x0_off + 4 * n * x0_ld].view(torch.float32).view(n, x0_ld)[:, :node_w]
         ctx.cfg, ctx.graph, ctx.nbytes, ctx.n, ctx.nseg, ctx.training = cfg, graph, int(nbytes), n, nseg, training
-        ctx.save_for_backward(ws, ptr, *params)
+        if training:
+            ctx.save_for_backward(ws, ptr, *params)
+        elif record is None:
+            _ws_release(ws)          # inference: nothing is kept, the buffer can serve the next call right away
         return out
 
     @staticmethod
     def backward(ctx, gout: Tensor):
-        ws, ptr, *params = ctx.saved_tensors
         if not ctx.training:
             raise RuntimeError("DynEdge executor: backward requested after an inference-mode forward")
+        ws, ptr, *params = ctx.saved_tensors
         gout = gout.contiguous().float()
-        grads = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in params]
+        direct = ACCUMULATE_INTO_GRAD and all(
+            p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32 and p.grad.shape == p.shape
+            for p in params)
+        grads = [p.grad for p in params] if direct else \
+            [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in params]
         garr = (ctypes.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
         graph = ctx.graph
         _call("gnb_dynedge_backward", ctypes.byref(ctx.cfg), garr, _ptr(ptr), _ptr(graph.nbr), _ptr(graph.deg), graph.width,
               ctx.n, ctx.nseg, _ptr(ws), ctx.nbytes, _ptr(gout), _stream())
+        _ws_release(ws)
+        if direct:
+            return (None,) * (10 + len(params))
         return (None,) * 10 + tuple(grads)
 
 

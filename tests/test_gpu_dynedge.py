@@ -147,3 +147,65 @@ def test_executor_matches_per_operator_route(built_library, precision):
     finally:
         ops.set_precision(old_p)
         ops.USE_EXECUTOR = old_e
+
+
+def test_executor_direct_grad_accumulation(built_library):
+    """`ops.ACCUMULATE_INTO_GRAD`: the executor's backward adds straight into the flat gradient buffer."""
+    from graphnet_b200 import Data, ops
+    from graphnet_b200.distributed import FlatGradAllReduce
+    from graphnet_b200.models.gnn import DynEdge
+    from graphnet_b200.models.graphs.edges import KNNEdges
+    from graphnet_b200.synthetic import make_batch
+    raw = make_batch(8, seed=4, n_max=200)
+    x, batch, n_pulses = (torch.from_numpy(raw[k]).cuda() for k in ("x", "batch", "n_pulses"))
+    torch.manual_seed(3)
+    model = DynEdge(7, global_pooling_schemes=["min", "max", "mean", "sum"]).cuda()
+    data = KNNEdges(8)(Data(x=x, batch=batch, n_pulses=n_pulses))
+    model(data).square().sum().backward()
+    expect = torch.cat([p.grad.flatten() for p in model.parameters()])
+    model.zero_grad(set_to_none=True)
+    reducer = FlatGradAllReduce(model.parameters())
+    old = ops.ACCUMULATE_INTO_GRAD
+    try:
+        ops.ACCUMULATE_INTO_GRAD = True
+        for _ in range(2):                      # two passes accumulate
+            model(data).square().sum().backward()
+    finally:
+        ops.ACCUMULATE_INTO_GRAD = old
+    assert rel_err(reducer.flat, 2 * expect) < 2e-4
+
+
+def test_high_multiplicity_event_and_layer_sweep(built_library):
+    """BASELINE configs #4/#5: one 20 000-pulse event (kNN bit-exact vs the C oracle, pooling vs oracle) and an
+    EdgeConv sweep over k in {4, 16} and latent widths {128, 336} against the literal oracle (fp32 mode)."""
+    import copy
+    from graphnet_b200 import ops
+    from graphnet_b200.models.components.layers import DynEdgeConv
+    from oracle import c_oracle
+    from oracle.dynedge_oracle import edgeconv_ref, segment_pool_ref
+    rng = np.random.default_rng(42)
+    sizes = [20000, 17, 3000]
+    n = sum(sizes)
+    feat = torch.from_numpy(rng.normal(size=(n, 8)).astype(np.float32))
+    feat[:, :3] = torch.round(feat[:, :3] * 16) / 16
+    ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(sizes)]))
+    g = ops.knn_table(feat.cuda(), [0, 1, 2], ptr.cuda(), 8)
+    nbr_c, deg_c = c_oracle.knn_table(feat.numpy(), [0, 1, 2], ptr.numpy(), 8, threads=8)
+    assert np.array_equal(g.nbr.cpu().numpy(), nbr_c) and np.array_equal(g.deg.cpu().numpy(), deg_c)
+    pooled = ops.segment_pool(feat.cuda(), ptr.cuda(), ["min", "max", "mean", "sum"])
+    ref = torch.cat([segment_pool_ref(feat, ptr, s) for s in ("min", "max", "mean", "sum")], dim=1)
+    assert rel_err(pooled, ref) < 1e-5
+    # layer sweep on a smaller graph
+    x = torch.from_numpy(rng.normal(size=(400, 24)).astype(np.float32))
+    ptr2 = torch.tensor([0, 150, 163, 400])
+    for k in (4, 16):
+        ei = knn_graph_ref(x[:, :3], k, ptr=ptr2)
+        graph = ops.knn_table(x.cuda(), [0, 1, 2], ptr2.cuda(), k)
+        assert torch.equal(graph.edge_index().cpu(), ei)
+        for width in (128, 336):
+            torch.manual_seed(width + k)
+            nn = torch.nn.Sequential(torch.nn.Linear(48, width), torch.nn.ReLU(), torch.nn.Linear(width, 256), torch.nn.ReLU())
+            ref_out = edgeconv_ref(x, ei, nn, "add")
+            conv = DynEdgeConv(copy.deepcopy(nn), aggr="add", nb_neighbors=k, features_subset=slice(0, 3)).cuda()
+            out, _ = conv.forward_table(x.cuda(), graph, ptr2.cuda())
+            assert rel_err(out, ref_out) < 1e-5, (k, width)
