@@ -387,7 +387,7 @@ def run_reference(args):
             "config": workload_config(args, args.gpus),
             "cpu_baseline": {"value": round(evs, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": round(evs, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(args, world):
@@ -401,8 +401,26 @@ def workload_config(args, world):
             "repeats": f"{args.repeats} repetitions of the K timed steps, fastest reported"}
 
 
+def _emit(line):
+    """Write the result line to the process's ORIGINAL stdout (see `_quiet_stdout`)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def _quiet_stdout():
+    """Point fd 1 at stderr for the rest of the run: native libraries (NCCL's version banner, for one) print to
+    stdout, and the driver expects exactly one JSON line there."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
     args = parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -471,7 +489,7 @@ def main():
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "inference": inference,
                 "nodes_per_step_rank0": int(train_host[0]["x"].shape[0]),
                 "host_enqueue_ms_per_step": round(host_ms, 3)}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 

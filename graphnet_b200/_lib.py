@@ -37,6 +37,8 @@ SIGNATURES: Dict[str, list] = {
     "gnb_relu_bwd": [_p, _i64, _p, _i64, _i64, _i32, _p, _i64, _i32, _p],
     "gnb_linear_fwd_tf32": [_p, _p, _p, _i32, _p, _i64, _p, _p, _i64, _i64, _i32, _i32, _i32, _p],
     "gnb_linear_bwd_weight_tf32": [_p, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _p],
+    "gnb_edge_linear_agg_fwd_tf32": [_p, _i64, _i32, _p, _i64, _p, _p, _i64, _i32, _i32, _p, _i64, _p, _p],
+    "gnb_edge_mask_bwd_colsum": [_p, _i64, _p, _i64, _i32, _p, _p, _i64, _p, _i32, _p],
     "gnb_round_pad_tf32": [_p, _i64, _i64, _i32, _p, _i64, _i32, _p],
     "gnb_act_bwd_colsum": [_p, _i64, _p, _i64, _i64, _i32, _p, _i64, _p, _i32, _p, _i32, _i32, _p],
     "gnb_colsum": [_p, _i64, _i64, _i32, _p, _p],
@@ -55,7 +57,7 @@ class DynEdgeConfig(ctypes.Structure):
                 ("n_readout", _i32), ("readout_out", _i32 * 8),
                 ("n_pool", _i32), ("pool", _i32 * 4),
                 ("globals_after_pooling", _i32), ("skip_readout", _i32),
-                ("n_knn_cols", _i32), ("knn_cols", _i32 * 16)]
+                ("n_knn_cols", _i32), ("knn_cols", _i32 * 16), ("flags", _i32)]
 
 
 SIGNATURES.update({

@@ -29,6 +29,10 @@ int gnb_segment_pool_fwd(const float*, int64_t, int32_t, const int64_t*, int64_t
                          int32_t*, void*);
 int gnb_edgeconv_fused_fwd_tf32(const float*, int64_t, int32_t, const int32_t*, const int32_t*, int32_t, int64_t,
                                 const float*, int64_t, const float*, int32_t, int32_t, int32_t, float*, int64_t, void*);
+int gnb_edge_linear_agg_fwd_tf32(const float*, int64_t, int32_t, const float*, int64_t, const float*, const int32_t*, int64_t,
+                                 int32_t, int32_t, float*, int64_t, uint32_t*, void*);
+int gnb_edge_mask_bwd_colsum(const float*, int64_t, const uint32_t*, int64_t, int32_t, const int32_t*, float*, int64_t, float*,
+                             int32_t, void*);
 int gnb_segment_pool_bwd(const float*, int64_t, const int32_t*, int32_t, const int64_t*, int64_t, int64_t, const int32_t*,
                          int32_t, float*, int64_t, void*);
 int gnb_act_bwd_colsum(const float*, int64_t, const float*, int64_t, int64_t, int32_t, float*, int64_t, float*, int32_t,
@@ -56,6 +60,7 @@ struct gnb_dynedge_config {
     int32_t n_pool, pool[4];
     int32_t globals_after_pooling, skip_readout;
     int32_t n_knn_cols, knn_cols[GNB_MAX_KNN_COLS];
+    int32_t flags;                                 // bit 0: do not use the fused tcgen05 EdgeConv kernels
 };
 
 extern "C" __attribute__((visibility("default"))) long long gnb_launch_counter = 0;
@@ -144,12 +149,13 @@ struct Arena {
     }
 };
 
-struct ConvBuf { float *wcat, *bcat, *w2p, *pq, *h, *m, *y; int32_t *nbr, *deg; int cin, cin_ld, kld, hid, hld, cout; };
+struct ConvBuf { float *wcat, *bcat, *w2p, *pq, *h, *m, *y; int32_t *nbr, *deg; uint32_t* mask; int cin, cin_ld, kld, hid, hld, cout; };
 struct DenseBuf { float *wp, *z; int k_total, kld, n_out; };
 
 struct Plan {
     int64_t n, nseg;
     int w0, width;                       // width = k + 1
+    bool agg;                            // training: second EdgeConv Linear fused with ReLU + k-sum (mask bits instead of m)
     int node_width, x0_ld;
     float *g, *x0;
     ConvBuf conv[GNB_MAX_LAYERS];
@@ -171,6 +177,7 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
     if (c.globals_after_pooling && c.n_pool == 0) return GNB_ERR_ARG;
     Arena a(ws, cap);
     p.n = n; p.nseg = nseg; p.w0 = w0; p.width = c.k + 1;
+    p.agg = training && c.precision == 1 && c.k == 8 && w0 == 9 && !(c.flags & 1);
     const int f = c.nb_inputs, ng = f + 5;
     const bool distribute = !c.globals_after_pooling;
     p.node_width = f + (distribute ? ng : 0);
@@ -202,7 +209,8 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
         b.w2p = a.get<float>((int64_t)b.cout * b.hld);
         b.pq = training ? a.get<float>(n * 2 * b.hid) : pq_shared;
         b.h = training ? a.get<float>(n * wl * b.hid) : h_shared;
-        b.m = training ? a.get<float>(n * wl * b.cout) : m_shared;
+        b.m = training ? (p.agg ? nullptr : a.get<float>(n * wl * b.cout)) : m_shared;
+        b.mask = p.agg ? a.get<uint32_t>((n + 13) / 14 * (int64_t)b.cout * 4) : nullptr;
         b.y = a.get<float>(n * b.cout);
         b.nbr = (l + 1 < c.n_conv) ? a.get<int32_t>(n * p.width) : nullptr;
         b.deg = (l + 1 < c.n_conv) ? a.get<int32_t>(n) : nullptr;
@@ -375,7 +383,7 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
     Exec e(c, stream);
     const int f = c.nb_inputs;
     const bool distribute = !c.globals_after_pooling;
-    const bool fused_edge = (training & 2) == 0;      // bit 1 of `training` disables the fused EdgeConv kernel
+    const bool fused_edge = (training & 2) == 0 && !(c.flags & 1);   // fused inference EdgeConv kernel
     training &= 1;
     // global variables (+ x0 = [x | g[batch] | 0])
     EX(gnb_global_vars(x, ldx, f, nbr0, deg0, w0, ptr, nseg, n_pulses, p.g, distribute ? p.x0 : nullptr, p.x0_ld, stream));
@@ -401,6 +409,11 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
             // inference: gather + hidden ReLU + E x H x C contraction + bias/ReLU + aggregation in one tcgen05 kernel
             EX(gnb_edgeconv_fused_fwd_tf32(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, b.w2p, b.hld, b2, b.cout, GNB_AGGR_ADD, 1,
                                            b.y, b.cout, stream));
+        } else if (p.agg) {
+            // training: h is kept for the backward pass; the second Linear, ReLU and the k-sum run in one tcgen05 kernel
+            // whose epilogue writes y and one ReLU bit per (slot, channel) -- the [E, C] message tensor is never stored
+            EX(gnb_edge_hidden_fwd(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, GNB_ACT_RELU | e.rnd, b.h, b.hid, stream));
+            EX(gnb_edge_linear_agg_fwd_tf32(b.h, b.hid, b.hid, b.w2p, b.hld, b2, deg, n, b.cout, 1, b.y, b.cout, b.mask, stream));
         } else {
             EX(gnb_edge_hidden_fwd(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, GNB_ACT_RELU | e.rnd, b.h, b.hid, stream));
             {   // m = relu(h W2^T + b2)
@@ -550,8 +563,11 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
         const int64_t rows = n * wl;
         const float* gy = p.gnode[l + 1];
         // (aggregate-bwd + ReLU-bwd + bias grad) in one pass
-        EX(gnb_act_bwd_colsum(gy, b.cout, b.m, b.cout, rows, b.cout, p.dz_big, b.cout, gb2, GNB_ACT_RELU | e.rnd, deg, wl,
-                              GNB_AGGR_ADD, stream));
+        if (p.agg)
+            EX(gnb_edge_mask_bwd_colsum(gy, b.cout, b.mask, n, b.cout, deg, p.dz_big, b.cout, gb2, e.rnd, stream));
+        else
+            EX(gnb_act_bwd_colsum(gy, b.cout, b.m, b.cout, rows, b.cout, p.dz_big, b.cout, gb2, GNB_ACT_RELU | e.rnd, deg, wl,
+                                  GNB_AGGR_ADD, stream));
         GNB_CHECK(cudaMemsetAsync(p.dwp, 0, (size_t)b.cout * b.hld * 4, e.st));
         EX(e.lin_bwd_weight(p.dz_big, b.cout, b.h, b.hid, p.dwp, b.hld, 0, b.hid, b.cout, rows));
         EX(e.add2d(p.dwp, b.hld, b.cout, b.hid, gw2, b.hid));

@@ -32,11 +32,16 @@ constexpr uint32_t TC_TMEM_COLS = 2 * TC_MT * TC_BN;                            
 
 struct TmapArray { CUtensorMap m[TC_MAX_PARTS]; };
 struct PartInfo { int nparts; int kblocks[TC_MAX_PARTS]; };
+// Aggregating epilogue (EdgeConv second Linear): rows are padded edge slots (node i, slot s) = i * 9 + s; a tile is
+// 14 nodes = 126 rows; the epilogue sums relu(acc + b) over the valid slots of every node, writes y[node, ch] and one
+// bit per (slot, channel) = "pre-activation > 0" for the backward pass. The [E, C] message tensor is never stored.
+struct AggInfo { const int* deg; int64_t n_nodes; unsigned* maskbits; int enabled; };
+constexpr int AGG_W = 9, AGG_NPT = 14, AGG_ROWS = AGG_W * AGG_NPT;   // k = 8 neighbour tables
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ TmapArray tm_x,
                       const PartInfo parts, const float* __restrict__ bias, float* __restrict__ y, int64_t ldy,
-                      int64_t rows, int n_out, int act, int round_out, int num_row_tiles) {
+                      int64_t rows, int n_out, int act, int round_out, int num_row_tiles, const AggInfo agg) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
@@ -71,19 +76,20 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
 
     int total_kb = 0;
     for (int p = 0; p < parts.nparts; ++p) total_kb += parts.kblocks[p];
+    const int tile_rows = agg.enabled ? AGG_ROWS : TC_BN;                 // rows of the activation tile (TMA box rows)
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
             for (int t = blockIdx.x; t < num_row_tiles; t += gridDim.x) {
-                const int row0 = t * TC_BN;
+                const int row0 = t * tile_rows;
                 int kb_w = 0;
                 for (int p = 0; p < parts.nparts; ++p) {
                     for (int kb = 0; kb < parts.kblocks[p]; ++kb, ++kb_w, ++it) {
                         const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
                         tc::mbar_wait(&empty[s], ph ^ 1);
                         uint8_t* st = smem + s * TC_STAGE_BYTES;
-                        tc::mbar_arrive_expect_tx(&full[s], (uint32_t)(mt + 1) * TC_TILE_BYTES);
+                        tc::mbar_arrive_expect_tx(&full[s], (uint32_t)mt * TC_TILE_BYTES + (uint32_t)tile_rows * TC_BK * 4);
                         for (int m = 0; m < mt; ++m)
                             tc::tma_load_2d(st + m * TC_TILE_BYTES, &tm_w, &full[s], kb_w * TC_BK, ch0 + m * TC_BM);
                         tc::tma_load_2d(st + TC_MT * TC_TILE_BYTES, &tm_x.m[p], &full[s], kb * TC_BK, row0);
@@ -127,6 +133,49 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
             const int64_t row0 = (int64_t)t * TC_BN;
             tc::mbar_wait<100>(&tmem_full[buf], (tile_i >> 1) & 1);
             tc::tcgen05_fence_after();
+            if (agg.enabled) {
+                // warps 2-5 own channel tile 0, warps 6-9 channel tile 1; every thread walks all 126 slot columns
+                const int m = half;
+                if (m < mt) {
+                    const int ch = ch0 + m * TC_BM + q * 32 + lane;
+                    const bool ch_ok = ch < n_out;
+                    const float bv = (bias != nullptr && ch_ok) ? bias[ch] : 0.f;
+                    const int64_t node0 = (int64_t)t * AGG_NPT;
+                    int dg[AGG_NPT];
+#pragma unroll
+                    for (int f = 0; f < AGG_NPT; ++f) dg[f] = (node0 + f < agg.n_nodes) ? agg.deg[node0 + f] : 0;
+                    float acc = 0.f;
+                    unsigned bits[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t r[32];
+                        tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) +
+                                                   (uint32_t)(buf * (TC_MT * TC_BN) + m * TC_BN + c * 32), r);
+                        tc::tmem_ld_wait();
+                        unsigned w = 0u;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = c * 32 + j;
+                            if (col < AGG_ROWS) {
+                                const int f = col / AGG_W, sl = col % AGG_W;       // compile-time after unrolling
+                                const float pre = __uint_as_float(r[j]) + bv;
+                                const bool on = (sl < dg[f]) && (pre > 0.f);
+                                acc += on ? pre : 0.f;
+                                w |= on ? (1u << j) : 0u;
+                                if (sl == AGG_W - 1) {
+                                    float o = acc;
+                                    if (round_out) o = tc::round_tf32(o);
+                                    if (ch_ok && node0 + f < agg.n_nodes) y[(node0 + f) * ldy + ch] = o;
+                                    acc = 0.f;
+                                }
+                            }
+                        }
+                        bits[c] = w;
+                    }
+                    if (ch_ok && agg.maskbits != nullptr)
+                        reinterpret_cast<uint4*>(agg.maskbits)[(int64_t)t * n_out + ch] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+                }
+            } else
             for (int m = 0; m < mt; ++m) {
                 const int ch = ch0 + m * TC_BM + q * 32 + lane;
                 const bool ch_ok = ch < n_out;
@@ -214,8 +263,50 @@ GNB_EXPORT int gnb_linear_fwd_tf32(const float* const* xs, const int64_t* ldxs, 
     if (ctas_x < 1) ctas_x = 1;
     if (ctas_x > row_tiles) ctas_x = row_tiles;
     dim3 grid((unsigned)ctas_x, (unsigned)groups);
+    AggInfo agg{nullptr, 0, nullptr, 0};
     gemm_tc_linear_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(tw, tx, pi, bias, y, ldy, rows,
-                                                                                     n_out, act, round_out, row_tiles);
+                                                                                     n_out, act, round_out, row_tiles, agg);
+    GNB_RETURN_LAUNCH();
+}
+
+// Second Linear of the EdgeConv MLP fused with ReLU and the k-neighbour SUM (k = 8 tables, width 9):
+//   y[i, :] = sum_{s < deg[i]} relu(h[i*9 + s, :] w^T + bias),   maskbits[tile = i / 14][ch][4 x u32] = (pre-activation > 0)
+// h: [n*9, k] tf32-rounded padded edge list, w: [n_out, ceil(k/32)*32] packed. n_out <= 512. maskbits may be NULL.
+GNB_EXPORT int gnb_edge_linear_agg_fwd_tf32(const float* h, int64_t ldh, int32_t k, const float* w, int64_t ldw,
+                                            const float* bias, const int32_t* deg, int64_t n, int32_t n_out,
+                                            int32_t round_out, float* y, int64_t ldy, uint32_t* maskbits, void* stream) {
+    if (n < 0 || n_out < 1 || k < 1) return GNB_ERR_ARG;
+    if (n == 0) return GNB_OK;
+    const int64_t rows = n * AGG_W;
+    if (rows >= (int64_t)1 << 31) return GNB_ERR_ARG;
+    PartInfo pi;
+    TmapArray tx;
+    pi.nparts = 1;
+    pi.kblocks[0] = (k + TC_BK - 1) / TC_BK;
+    const int64_t ktot = (int64_t)pi.kblocks[0] * TC_BK;
+    int rc = gnb_make_tmap_f32(&tx.m[0], h, rows, k, ldh, AGG_ROWS);
+    if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    for (int p = 1; p < TC_MAX_PARTS; ++p) { pi.kblocks[p] = 0; tx.m[p] = tx.m[0]; }
+    if (ldw < ktot) return GNB_ERR_ARG;
+    CUtensorMap tw;
+    rc = gnb_make_tmap_f32(&tw, w, n_out, ktot, ldw, TC_BM);
+    if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    if (g_num_sms == 0) {
+        int dev = 0;
+        GNB_CHECK(cudaGetDevice(&dev));
+        GNB_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+        GNB_CHECK(cudaFuncSetAttribute(gemm_tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)TC_SMEM_BYTES));
+    }
+    const int row_tiles = gnb_div_up(n, AGG_NPT);
+    const int groups = gnb_div_up(n_out, TC_MT * TC_BM);
+    int ctas_x = g_num_sms / groups;
+    if (ctas_x < 1) ctas_x = 1;
+    if (ctas_x > row_tiles) ctas_x = row_tiles;
+    dim3 grid((unsigned)ctas_x, (unsigned)groups);
+    AggInfo agg{deg, n, maskbits, 1};
+    gemm_tc_linear_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(tw, tx, pi, bias, y, ldy, rows, n_out,
+                                                                                     GNB_ACT_RELU, round_out, row_tiles, agg);
     GNB_RETURN_LAUNCH();
 }
 

@@ -635,6 +635,7 @@ class _DynEdgeExec(torch.autograd.Function):
         x = _rowmajor(x.detach().float())
         n, nseg = x.shape[0], ptr.numel() - 1
         cfg.precision = 1 if _tf32() else 0
+        cfg.flags = 0 if FUSED_EDGECONV else 1
         nbytes = lib.gnb_dynedge_workspace_bytes(ctypes.byref(cfg), n, nseg, graph.width, training)
         if nbytes < 0:
             raise RuntimeError(f"gnb_dynedge_workspace_bytes: unsupported configuration [{nbytes}]")
@@ -645,7 +646,7 @@ class _DynEdgeExec(torch.autograd.Function):
         parr = (ctypes.c_void_p * len(plist))(*[p.data_ptr() for p in plist])
         _call("gnb_dynedge_forward", ctypes.byref(cfg), parr, _ptr(x), _ld(x), _ptr(ptr), _ptr(npf), _ptr(graph.nbr),
               _ptr(graph.deg), graph.width, _ptr(cols_dev), n, nseg, _ptr(ws), int(nbytes), _ptr(out),
-              training | (0 if FUSED_EDGECONV else 2), _stream())
+              training, _stream())
         if record is not None:       # test hook: views of the per-layer outputs / recomputed graphs inside `ws`
             offs = (ctypes.c_int64 * (3 * cfg.n_conv))()
             _lib.check(lib.gnb_dynedge_layout(ctypes.byref(cfg), n, nseg, graph.width, training, offs), "layout")

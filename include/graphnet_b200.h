@@ -130,6 +130,15 @@ int gnb_linear_fwd_tf32(const float* const* xs, const int64_t* ldxs, const int32
  * TMA-fed MN-major operands; same alignment rules as gnb_linear_fwd_tf32. debug_swap: 0 in production. */
 int gnb_linear_bwd_weight_tf32(const float* dz, int64_t lddz, const float* x, int64_t ldx, float* dw, int64_t lddw,
                                int64_t rows, int32_t n_out, int32_t k_in, int32_t debug_swap, void* stream);
+/* Second EdgeConv Linear + ReLU + k-neighbour SUM in one tcgen05 kernel (k = 8 tables: width 9, tiles of 14 nodes):
+ * y[i] = sum_{s<deg[i]} relu(h[i*9+s] w^T + bias); maskbits[(i/14) * n_out + ch][4 x u32]: bit (i%14)*9+s = pre-act > 0.
+ * The [E, n_out] message tensor is never stored. h / w as for gnb_linear_fwd_tf32 (single part). */
+int gnb_edge_linear_agg_fwd_tf32(const float* h, int64_t ldh, int32_t k, const float* w, int64_t ldw, const float* bias,
+                                 const int32_t* deg, int64_t n, int32_t n_out, int32_t round_out, float* y, int64_t ldy,
+                                 uint32_t* maskbits, void* stream);
+/* Backward of the above up to the pre-activation: dz[i*9+s] = g[i] * maskbit, db += colsum(dz); flags & 0x100 rounds dz. */
+int gnb_edge_mask_bwd_colsum(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols,
+                             const int32_t* deg, float* dz, int64_t ldz, float* db, int32_t flags, void* stream);
 /* dst[rows, dst_cols] = [rna_tf32(src[rows, cols]) | 0]. */
 int gnb_round_pad_tf32(const float* src, int64_t lds, int64_t rows, int32_t cols, float* dst, int64_t ldd,
                        int32_t dst_cols, void* stream);
@@ -161,6 +170,7 @@ typedef struct {
     int32_t n_pool, pool[4];                         /* 0 min, 1 max, 2 sum, 3 mean, caller order */
     int32_t globals_after_pooling, skip_readout;
     int32_t n_knn_cols, knn_cols[GNB_MAX_KNN_COLS];  /* features_subset */
+    int32_t flags;                                   /* bit 0: do not use the fused tcgen05 EdgeConv kernels */
 } gnb_dynedge_config;
 
 /* Bytes of workspace for a batch of n nodes / nseg events whose initial graph has table width w0; < 0: error. */
