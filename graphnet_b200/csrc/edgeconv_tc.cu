@@ -209,7 +209,7 @@ edgeconv_fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPar
             if (lane == 0) tc::mbar_arrive(&meta_full[buf]);
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp in uniform control flow, one elected lane issues (see tc::elect_one)
             tc::mbar_wait(a_full, 0);
             uint32_t it = 0, ti = 0;
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++ti) {
@@ -226,10 +226,12 @@ edgeconv_fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPar
                     const uint64_t bdesc = tc::umma_desc_sw128_kmajor(tc::smem_u32(s_b + s * EF_TILE_BYTES));
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        tc::umma_tf32(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    tc::umma_commit(&b_empty[s]);
+                        if (tc::elect_one()) tc::umma_tf32(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    if (tc::elect_one()) tc::umma_commit(&b_empty[s]);
+                    __syncwarp();
                 }
-                tc::umma_commit(&tmem_full[buf]);
+                if (tc::elect_one()) tc::umma_commit(&tmem_full[buf]);
+                __syncwarp();
             }
         }
     } else if (warp < 6) {
@@ -457,7 +459,7 @@ edgeconv_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPa
             if (lane == 0) tc::mbar_arrive(&meta_full[buf]);
         }
     } else if (warp == 1) {
-        if (rank == 0 && lane == 0) {
+        if (rank == 0) {   // whole warp in uniform control flow, one elected lane issues (see tc::elect_one)
             // ---- MMA issuer (leader CTA only): M = 256 over both CTAs, N = 128 edges ------------------------
             const uint32_t idesc = tc::umma_idesc_tf32(256, 128);
             uint32_t it = 0, ti = 0;
@@ -475,11 +477,14 @@ edgeconv_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPa
                     if (!(p.debug & 8)) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        tc::umma_tf32_2cta(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (tc::elect_one())
+                            tc::umma_tf32_2cta(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    tc::umma_commit_2cta(&b_empty[s], 3);
+                    if (tc::elect_one()) tc::umma_commit_2cta(&b_empty[s], 3);
+                    __syncwarp();
                 }
-                tc::umma_commit_2cta(&tmem_full[buf], 3);
+                if (tc::elect_one()) tc::umma_commit_2cta(&tmem_full[buf], 3);
+                __syncwarp();
             }
         }
     } else if (warp < 6) {

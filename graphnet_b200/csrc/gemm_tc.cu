@@ -35,8 +35,34 @@ struct PartInfo { int nparts; int kblocks[TC_MAX_PARTS]; };
 // Aggregating epilogue (EdgeConv second Linear): rows are padded edge slots (node i, slot s) = i * 9 + s; a tile is
 // 14 nodes = 126 rows; the epilogue sums relu(acc + b) over the valid slots of every node, writes y[node, ch] and one
 // bit per (slot, channel) = "pre-activation > 0" for the backward pass. The [E, C] message tensor is never stored.
-struct AggInfo { const int* deg; int64_t n_nodes; unsigned* maskbits; int enabled; };
+struct AggInfo { const int* deg; int64_t n_nodes; unsigned* maskbits; int enabled; int dbg; unsigned long long* prof; };
 constexpr int AGG_W = 9, AGG_NPT = 14, AGG_ROWS = AGG_W * AGG_NPT;   // k = 8 neighbour tables
+
+// Epilogue store of one 32-row chunk: lane = output channel, r[j] = row j. One coalesced 128-byte store per row; the
+// address is a running pointer and activation / rounding are resolved outside the unrolled loop (the naive per-element
+// form compiled to ~30 instructions per store and made the epilogue warps the bottleneck of the kernel).
+template <bool ROUND>
+__device__ __forceinline__ void epi_store32(const uint32_t (&r)[32], float bv, float lo, float* __restrict__ yp, int64_t ldy) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        float v = fmaxf(__uint_as_float(r[j]) + bv, lo);
+        if (ROUND) v = tc::round_tf32(v);
+        *yp = v;
+        yp += ldy;
+    }
+}
+__device__ __noinline__ void epi_store_partial(const uint32_t (&r)[32], float bv, float lo, bool round, float* __restrict__ yp,
+                                               int64_t ldy, int nvalid) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (j < nvalid) {
+            float v = fmaxf(__uint_as_float(r[j]) + bv, lo);
+            if (round) v = tc::round_tf32(v);
+            *yp = v;
+            yp += ldy;
+        }
+    }
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ TmapArray tm_x,
@@ -77,9 +103,12 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     int total_kb = 0;
     for (int p = 0; p < parts.nparts; ++p) total_kb += parts.kblocks[p];
     const int tile_rows = agg.enabled ? AGG_ROWS : TC_BN;                 // rows of the activation tile (TMA box rows)
+    const bool prof_on = agg.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+    long long pw0 = 0, pw1 = 0;
+    const long long pt0 = clock64();
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // whole warp walks the pipeline (uniform control flow); one elected lane issues
             uint32_t it = 0;
             for (int t = blockIdx.x; t < num_row_tiles; t += gridDim.x) {
                 const int row0 = t * tile_rows;
@@ -87,51 +116,69 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
                 for (int p = 0; p < parts.nparts; ++p) {
                     for (int kb = 0; kb < parts.kblocks[p]; ++kb, ++kb_w, ++it) {
                         const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                        const long long c0 = prof_on ? clock64() : 0;
                         tc::mbar_wait(&empty[s], ph ^ 1);
+                        if (prof_on) pw0 += clock64() - c0;
                         uint8_t* st = smem + s * TC_STAGE_BYTES;
-                        tc::mbar_arrive_expect_tx(&full[s], (uint32_t)mt * TC_TILE_BYTES + (uint32_t)tile_rows * TC_BK * 4);
-                        for (int m = 0; m < mt; ++m)
-                            tc::tma_load_2d(st + m * TC_TILE_BYTES, &tm_w, &full[s], kb_w * TC_BK, ch0 + m * TC_BM);
-                        tc::tma_load_2d(st + TC_MT * TC_TILE_BYTES, &tm_x.m[p], &full[s], kb * TC_BK, row0);
+                        const bool ld_w = !(agg.dbg & 4), ld_x = !(agg.dbg & 8);
+                        if (tc::elect_one()) {
+                            tc::mbar_arrive_expect_tx(&full[s], (ld_w ? (uint32_t)mt * TC_TILE_BYTES : 0u) +
+                                                                    (ld_x ? (uint32_t)tile_rows * TC_BK * 4 : 0u));
+                            if (ld_w)
+                                for (int m = 0; m < mt; ++m)
+                                    tc::tma_load_2d(st + m * TC_TILE_BYTES, &tm_w, &full[s], kb_w * TC_BK, ch0 + m * TC_BM);
+                            if (ld_x) tc::tma_load_2d(st + TC_MT * TC_TILE_BYTES, &tm_x.m[p], &full[s], kb * TC_BK, row0);
+                        }
+                        __syncwarp();
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp, uniform control flow; tcgen05.mma / commit issued by one elected lane
             constexpr uint32_t idesc = tc::umma_idesc_tf32(TC_BM, TC_BN);
             uint32_t it = 0, tile_i = 0;
             for (int t = blockIdx.x; t < num_row_tiles; t += gridDim.x, ++tile_i) {
                 const uint32_t buf = tile_i & 1;
+                const long long c1 = prof_on ? clock64() : 0;
                 tc::mbar_wait(&tmem_empty[buf], ((tile_i >> 1) & 1) ^ 1);      // epilogue drained this buffer
+                if (prof_on) pw1 += clock64() - c1;
                 tc::tcgen05_fence_after();
                 const uint32_t acc = tmem_base + buf * (TC_MT * TC_BN);
                 for (int kbi = 0; kbi < total_kb; ++kbi, ++it) {
                     const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                    const long long c0 = prof_on ? clock64() : 0;
                     tc::mbar_wait(&full[s], ph);
+                    if (prof_on) pw0 += clock64() - c0;
                     tc::tcgen05_fence_after();
                     const uint32_t st = tc::smem_u32(smem + s * TC_STAGE_BYTES);
                     const uint64_t bdesc = tc::umma_desc_sw128_kmajor(st + TC_MT * TC_TILE_BYTES);
-                    for (int m = 0; m < mt; ++m) {
+                    for (int m = 0; m < ((agg.dbg & 2) ? 0 : mt); ++m) {
                         const uint64_t adesc = tc::umma_desc_sw128_kmajor(st + m * TC_TILE_BYTES);
 #pragma unroll
                         for (int k = 0; k < TC_BK / 8; ++k)   // UMMA_K = 8 tf32 = 32 B -> +2 in the 16-byte address field
-                            tc::umma_tf32(acc + m * TC_BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kbi | k) != 0 ? 1u : 0u);
+                            if (tc::elect_one())
+                                tc::umma_tf32(acc + m * TC_BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kbi | k) != 0 ? 1u : 0u);
                     }
-                    tc::umma_commit(&empty[s]);
+                    if (tc::elect_one()) tc::umma_commit(&empty[s]);
+                    __syncwarp();
                 }
-                tc::umma_commit(&tmem_full[buf]);
+                if (tc::elect_one()) tc::umma_commit(&tmem_full[buf]);
+                __syncwarp();
             }
         }
     } else {
         const int ew = warp - 2;                    // 0..7
         const int q = warp & 3;                     // TMEM lane quarter this warp may access
         const int half = ew >> 2;                   // column half: rows [64*half, 64*half + 64) of the tile
+        const float relu_lo = act == GNB_ACT_RELU ? 0.f : -INFINITY;
         uint32_t tile_i = 0;
         for (int t = blockIdx.x; t < num_row_tiles; t += gridDim.x, ++tile_i) {
             const uint32_t buf = tile_i & 1;
             const int64_t row0 = (int64_t)t * TC_BN;
+            const long long c0 = prof_on ? clock64() : 0;
             tc::mbar_wait<100>(&tmem_full[buf], (tile_i >> 1) & 1);
+            if (prof_on) pw0 += clock64() - c0;
             tc::tcgen05_fence_after();
             if (agg.enabled) {
                 // warps 2-5 own channel tile 0, warps 6-9 channel tile 1; every thread walks all 126 slot columns
@@ -184,19 +231,19 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
                 for (int c = 0; c < 2; ++c) {
                     const int col0 = half * 64 + c * 32;
                     uint32_t r[32];
+                    const long long c1 = prof_on ? clock64() : 0;
                     tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) +
                                                (uint32_t)(buf * (TC_MT * TC_BN) + m * TC_BN + col0), r);
                     tc::tmem_ld_wait();
-                    if (ch_ok) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int64_t row = row0 + col0 + j;
-                            if (row < rows) {
-                                float v = __uint_as_float(r[j]) + bv;
-                                if (act == GNB_ACT_RELU) v = fmaxf(v, 0.f);
-                                if (round_out) v = tc::round_tf32(v);
-                                y[row * ldy + ch] = v;
-                            }
+                    if (prof_on) pw1 += clock64() - c1;
+                    const int64_t left = rows - (row0 + col0);          // valid rows of this 32-row chunk
+                    if (ch_ok && left > 0 && !(agg.dbg & 1)) {
+                        float* yp = y + (row0 + col0) * ldy + ch;
+                        if (left >= 32) {
+                            if (round_out) epi_store32<true>(r, bv, relu_lo, yp, ldy);
+                            else epi_store32<false>(r, bv, relu_lo, yp, ldy);
+                        } else {
+                            epi_store_partial(r, bv, relu_lo, round_out != 0, yp, ldy, (int)left);
                         }
                     }
                 }
@@ -205,6 +252,12 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tmem_empty[buf]);
         }
+    }
+    __syncwarp();
+    if (prof_on && lane == 0 && warp <= 2) {
+        agg.prof[warp * 3] = (unsigned long long)pw0;
+        agg.prof[warp * 3 + 1] = (unsigned long long)pw1;
+        agg.prof[warp * 3 + 2] = (unsigned long long)(clock64() - pt0);
     }
     tc::tcgen05_fence_before();
     __syncthreads();
@@ -222,8 +275,18 @@ __global__ void round_pad_tf32_kernel(const float* __restrict__ src, int64_t lds
 }
 
 int g_num_sms = 0;
+unsigned long long* g_linear_prof = nullptr;
+int g_linear_dbg = 0;   // tuning hook: see gnb_linear_set_debug
 
 }  // namespace
+
+// Tuning hook (profiling only): bit0 epilogue skips its global stores, bit1 no MMAs, bit2 no weight loads, bit3 no
+// activation loads. Results are garbage with any bit set.
+GNB_EXPORT int gnb_linear_set_debug(int32_t flags) { g_linear_dbg = flags; return GNB_OK; }
+
+// Tuning aid: device buffer of 16 uint64 that CTA (0,0) fills with cycle counters
+// {producer: wait-empty, total, -} {mma: wait-full, wait-tmem-empty, total} {epilogue warp 2: wait-tmem-full, tmem-ld, total}.
+GNB_EXPORT int gnb_linear_set_profile_buffer(void* buf) { g_linear_prof = (unsigned long long*)buf; return GNB_OK; }
 
 // xs / ldxs / ks: HOST arrays with one entry per part (device pointer, row pitch, width).
 // w: [n_out, sum_p ceil(k_p/32)*32] fp32, part p's columns start at the 32-aligned running offset and are
@@ -263,7 +326,7 @@ GNB_EXPORT int gnb_linear_fwd_tf32(const float* const* xs, const int64_t* ldxs, 
     if (ctas_x < 1) ctas_x = 1;
     if (ctas_x > row_tiles) ctas_x = row_tiles;
     dim3 grid((unsigned)ctas_x, (unsigned)groups);
-    AggInfo agg{nullptr, 0, nullptr, 0};
+    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof};
     gemm_tc_linear_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(tw, tx, pi, bias, y, ldy, rows,
                                                                                      n_out, act, round_out, row_tiles, agg);
     GNB_RETURN_LAUNCH();
@@ -304,7 +367,7 @@ GNB_EXPORT int gnb_edge_linear_agg_fwd_tf32(const float* h, int64_t ldh, int32_t
     if (ctas_x < 1) ctas_x = 1;
     if (ctas_x > row_tiles) ctas_x = row_tiles;
     dim3 grid((unsigned)ctas_x, (unsigned)groups);
-    AggInfo agg{deg, n, maskbits, 1};
+    AggInfo agg{deg, n, maskbits, 1, g_linear_dbg, g_linear_prof};
     gemm_tc_linear_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(tw, tx, pi, bias, y, ldy, rows, n_out,
                                                                                      GNB_ACT_RELU, round_out, row_tiles, agg);
     GNB_RETURN_LAUNCH();

@@ -79,7 +79,7 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 
     if (num_kb > 0) {
         if (warp == 0) {
-            if (lane == 0) {
+            {   // whole warp walks the ring (uniform control flow, see tc::elect_one); one elected lane issues
                 for (int it = 0; it < num_kb; ++it) {
                     const int s = it % WG_STAGES;
                     const uint32_t ph = (it / WG_STAGES) & 1;
@@ -87,14 +87,19 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                     uint8_t* sa = smem + s * WG_STAGE_BYTES;
                     uint8_t* sb = sa + WG_A_BYTES;
                     const int r = (int)(r_lo + (int64_t)it * WG_BK);
-                    tc::mbar_arrive_expect_tx(&full[s], (WG_BM / 32 + n_boxes_b) * WG_BOX_BYTES);
+                    if (tc::elect_one()) {
+                        tc::mbar_arrive_expect_tx(&full[s], (WG_BM / 32 + n_boxes_b) * WG_BOX_BYTES);
 #pragma unroll
-                    for (int b = 0; b < WG_BM / 32; ++b) tc::tma_load_2d(sa + b * WG_BOX_BYTES, &tm_x, &full[s], kin0 + 32 * b, r);
-                    for (int b = 0; b < n_boxes_b; ++b) tc::tma_load_2d(sb + b * WG_BOX_BYTES, &tm_z, &full[s], out0 + 32 * b, r);
+                        for (int b = 0; b < WG_BM / 32; ++b)
+                            tc::tma_load_2d(sa + b * WG_BOX_BYTES, &tm_x, &full[s], kin0 + 32 * b, r);
+                        for (int b = 0; b < n_boxes_b; ++b)
+                            tc::tma_load_2d(sb + b * WG_BOX_BYTES, &tm_z, &full[s], out0 + 32 * b, r);
+                    }
+                    __syncwarp();
                 }
             }
         } else if (warp == 1) {
-            if (lane == 0) {
+            {   // whole warp, uniform control flow; one elected lane issues the MMAs and commits
                 // kind::tf32, fp32 accumulate, A and B MN-major (bits 15, 16)
                 const uint32_t idesc = tc::umma_idesc_tf32(WG_BM, (uint32_t)n_mma) | (1u << 15) | (1u << 16);
                 // bring-up variants (production: 0): bit0 swaps LBO/SBO, bit1 uses an 8-row K group stride
@@ -111,11 +116,14 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                     const uint64_t bdesc = umma_desc_sw128_mnmajor(sa + WG_A_BYTES, lbo, sbo);
 #pragma unroll
                     for (int k = 0; k < WG_BK / 8; ++k)   // 8 rows = one 1024-byte swizzle atom per 32-column block
-                        tc::umma_tf32(tmem_base, adesc + (uint64_t)(k * (1024 >> 4)), bdesc + (uint64_t)(k * (1024 >> 4)),
-                                      idesc, (it | k) != 0 ? 1u : 0u);
-                    tc::umma_commit(&empty[s]);
+                        if (tc::elect_one())
+                            tc::umma_tf32(tmem_base, adesc + (uint64_t)(k * (1024 >> 4)), bdesc + (uint64_t)(k * (1024 >> 4)),
+                                          idesc, (it | k) != 0 ? 1u : 0u);
+                    if (tc::elect_one()) tc::umma_commit(&empty[s]);
+                    __syncwarp();
                 }
-                tc::umma_commit(tmem_full);
+                if (tc::elect_one()) tc::umma_commit(tmem_full);
+                __syncwarp();
             }
         } else {
             tc::mbar_wait<200>(tmem_full, 0);
@@ -170,7 +178,7 @@ GNB_EXPORT int gnb_linear_bwd_weight_tf32(const float* dz, int64_t lddz, const f
     }
     const int tiles_m = gnb_div_up(k_in, WG_BM), tiles_n = gnb_div_up(n_out, WG_BN);
     const int tiles = tiles_m * tiles_n;
-    int splits = (2 * 148 + tiles - 1) / tiles;
+    int splits = (2 * 148) / tiles;                                       // <= 2 full waves of 148 CTAs
     const int64_t max_splits = (rows + 8 * WG_BK - 1) / (8 * WG_BK);     // at least 8 K-blocks per CTA
     if (splits > max_splits) splits = (int)max_splits;
     if (splits < 1) splits = 1;

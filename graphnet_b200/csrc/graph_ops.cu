@@ -429,6 +429,70 @@ act_bwd_colsum_kernel(const float* __restrict__ g, int64_t ldg, const float* __r
     }
 }
 
+// Backward of "ReLU + k-sum" from the bit mask of the aggregating GEMM epilogue (gemm_tc.cu: one uint4 = 126 bits per
+// (14-node tile, channel); bit = slot valid && pre-activation > 0):  dz[(i, s), c] = bit ? g[i, c] : 0, db[c] += sum.
+// One CTA pass per tile: the tile's 14 gradient rows and its mask words are staged in shared memory (coalesced),
+// then 126 rows x 256 channels are written as coalesced float4 stores. CTA = 64 float4 columns x 4 row lanes.
+constexpr int EM_W = 9, EM_NPT = 14, EM_ROWS = EM_W * EM_NPT;
+
+__global__ void __launch_bounds__(256)
+edge_mask_bwd_kernel(const float* __restrict__ g, int64_t ldg, const uint4* __restrict__ mask4, int64_t n, int cols,
+                     float* __restrict__ dz, int64_t ldz, float* __restrict__ db, int rnd, int64_t n_tiles) {
+    __shared__ float4 s_g[EM_NPT][64];
+    __shared__ __align__(16) unsigned s_m[4][256];
+    __shared__ float4 s_acc[4][64];
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 64 + tx;
+    const int cols4 = cols >> 2;
+    const int c4 = blockIdx.y * 64 + tx;
+    const bool col_ok = c4 < cols4;
+    const int64_t rows = n * EM_W;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        __syncthreads();
+        for (int e = tid; e < EM_NPT * 64; e += 256) {
+            const int f = e >> 6, cc = blockIdx.y * 64 + (e & 63);
+            const int64_t node = tile * EM_NPT + f;
+            s_g[f][e & 63] = (node < n && cc < cols4) ? reinterpret_cast<const float4*>(g + node * ldg)[cc]
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        {
+            const int ch = blockIdx.y * 256 + tid;
+            const uint4 m = ch < cols ? mask4[tile * cols + ch] : make_uint4(0u, 0u, 0u, 0u);
+            s_m[0][tid] = m.x; s_m[1][tid] = m.y; s_m[2][tid] = m.z; s_m[3][tid] = m.w;
+        }
+        __syncthreads();
+        if (col_ok) {
+            const int64_t row_base = tile * EM_ROWS;
+            const int r_end = rows - row_base < EM_ROWS ? (int)(rows - row_base) : EM_ROWS;
+#pragma unroll 4
+            for (int r = ty; r < r_end; r += 4) {
+                float4 gv = s_g[r / EM_W][tx];
+                const uint4 w = reinterpret_cast<const uint4*>(s_m[r >> 5])[tx];
+                const unsigned sh = r & 31;
+                gv.x = ((w.x >> sh) & 1u) ? gv.x : 0.f; gv.y = ((w.y >> sh) & 1u) ? gv.y : 0.f;
+                gv.z = ((w.z >> sh) & 1u) ? gv.z : 0.f; gv.w = ((w.w >> sh) & 1u) ? gv.w : 0.f;
+                if (rnd) {
+                    gv.x = gnb_round_tf32(gv.x); gv.y = gnb_round_tf32(gv.y);
+                    gv.z = gnb_round_tf32(gv.z); gv.w = gnb_round_tf32(gv.w);
+                }
+                reinterpret_cast<float4*>(dz + (row_base + r) * ldz)[c4] = gv;
+                acc.x += gv.x; acc.y += gv.y; acc.z += gv.z; acc.w += gv.w;
+            }
+        }
+    }
+    if (db == nullptr) return;
+    s_acc[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && col_ok) {
+        for (int t = 1; t < 4; ++t) {
+            const float4 o = s_acc[t][tx];
+            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        atomicAdd(db + 4 * c4 + 0, acc.x); atomicAdd(db + 4 * c4 + 1, acc.y);
+        atomicAdd(db + 4 * c4 + 2, acc.z); atomicAdd(db + 4 * c4 + 3, acc.w);
+    }
+}
+
 // out[c] += sum_r a[r, c]; out must be zero on entry. CTA = 32 x 8, 256 rows per CTA.
 __global__ void colsum_kernel(const float* __restrict__ a, int64_t lda, int64_t rows, int cols,
                               float* __restrict__ out) {
@@ -566,8 +630,15 @@ GNB_EXPORT int gnb_act_bwd_colsum(const float* g, int64_t ldg, const float* y, i
 GNB_EXPORT int gnb_edge_mask_bwd_colsum(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols,
                                         const int32_t* deg, float* dz, int64_t ldz, float* db, int32_t flags, void* stream) {
     if (maskbits == nullptr || deg == nullptr) return GNB_ERR_ARG;
-    return act_bwd_launch(g, ldg, nullptr, 0, n * 9, cols, dz, ldz, db, (flags & ~0xff) | GNB_ACT_NONE, deg, 9, GNB_AGGR_ADD,
-                          maskbits, 14, stream);
+    if ((cols & 3) || (ldg & 3) || (ldz & 3) || !aligned16(g) || !aligned16(dz) || !aligned16(maskbits)) return GNB_ERR_ARG;
+    if (n == 0) return GNB_OK;
+    const int64_t n_tiles = (n + EM_NPT - 1) / EM_NPT;
+    const int64_t max_ctas = 148 * 8;
+    dim3 grid((unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas), (unsigned)gnb_div_up(cols >> 2, 64)), block(64, 4);
+    edge_mask_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(g, ldg, reinterpret_cast<const uint4*>(maskbits), n, cols,
+                                                                    dz, ldz, db, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0,
+                                                                    n_tiles);
+    GNB_RETURN_LAUNCH();
 }
 
 static int act_bwd_launch(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows, int32_t cols, float* dz,

@@ -63,6 +63,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// One lane of a CONVERGED warp. Single-thread roles (TMA producer, MMA issuer) run their loops with the whole warp
+// and elect only around the issuing instructions: inside an `if (lane == 0)` region the compiler cannot prove that
+// descriptors / addresses are warp-uniform and wraps every tcgen05.mma in an ELECT + R2UR.BROADCAST + BRA.U.ANY
+// loop (~110 cycles per MMA measured, against a 64-cycle tensor-pipe floor for 128x128x8 tf32).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- TMA -----------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

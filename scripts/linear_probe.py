@@ -1,0 +1,85 @@
+"""Time the tcgen05 Linear kernel alone on the EdgeConv shapes of the training step, with the profiling switches of
+gnb_linear_set_debug (which role bounds the kernel?). Run on a GPU box: python scripts/linear_probe.py"""
+import ctypes
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from graphnet_b200 import ops, _lib  # noqa: E402
+
+ops.set_precision("tf32")
+lib = _lib.load()
+dev = torch.device("cuda", 0)
+N = 79261
+ROWS = N * 9
+
+
+def timed(fn, reps=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    ev[0].record()
+    for i in range(reps):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ts = sorted(ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(reps))
+    return ts[len(ts) // 2]
+
+
+def linear_case(rows, k, n_out, label):
+    x = ops._mark_rounded(torch.randn(rows, k, device=dev).round_())
+    w = torch.randn(n_out, k, device=dev).round_()
+    b = torch.randn(n_out, device=dev)
+    pw = ops._tc_pack_weight(w, [0], [k])
+    out = []
+    for dbg in (0, 1, 2, 3, 4, 8, 12, 14, 15):
+        lib.gnb_linear_set_debug(dbg)
+        t = timed(lambda: ops._tc_linear([x], pw, b, n_out, 1, True))
+        out.append(f"dbg{dbg}={t:.0f}")
+    lib.gnb_linear_set_debug(0)
+    prof = torch.zeros(16, dtype=torch.int64, device=dev)
+    for dbg in (0, 1, 15):
+        lib.gnb_linear_set_debug(dbg)
+        lib.gnb_linear_set_profile_buffer(ctypes.c_void_p(prof.data_ptr()))
+        ops._tc_linear([x], pw, b, n_out, 1, True)
+        torch.cuda.synchronize()
+        lib.gnb_linear_set_profile_buffer(None)
+        v = prof.tolist()
+        print(f"   dbg{dbg} cycles: producer wait-empty {v[0]} total {v[2]} | mma wait-full {v[3]} wait-tmem-empty {v[4]} "
+              f"total {v[5]} | epilogue wait-tmem-full {v[6]} tmem-ld {v[7]} total {v[8]}", flush=True)
+    lib.gnb_linear_set_debug(0)
+    gf = 2.0 * rows * k * n_out
+    print(f"{label}: rows={rows} k={k} n_out={n_out} us: " + " ".join(out) +
+          f" | {gf / 1e6 / float(out[0].split('=')[1]):.0f} TFLOP/s", flush=True)
+
+
+def agg_case(n, k, n_out, label):
+    rows = n * 9
+    h = torch.randn(rows, k, device=dev).round_()
+    w = torch.randn(n_out, k, device=dev).round_()
+    b = torch.randn(n_out, device=dev)
+    pw = ops._tc_pack_weight(w, [0], [k])
+    deg = torch.full((n,), 8, dtype=torch.int32, device=dev)
+    y = torch.empty(n, n_out, device=dev)
+    ntile = (n + 13) // 14
+    mask = torch.empty(ntile * n_out * 4, dtype=torch.int32, device=dev)
+    out = []
+    for dbg in (0, 2, 4, 8, 12, 14):
+        lib.gnb_linear_set_debug(dbg)
+
+        def run():
+            ops._call("gnb_edge_linear_agg_fwd_tf32", ops._ptr(h), k, k, ops._ptr(pw), pw.shape[1], ops._ptr(b),
+                      ops._ptr(deg), n, n_out, 1, ops._ptr(y), n_out, ops._ptr(mask), ops._stream())
+        out.append(f"dbg{dbg}={timed(run):.0f}")
+    lib.gnb_linear_set_debug(0)
+    print(f"{label}: n={n} k={k} n_out={n_out} us: " + " ".join(out), flush=True)
+
+
+linear_case(ROWS, 336, 256, "edge GEMM2 fwd (plain)")
+linear_case(ROWS, 256, 336, "edge GEMM2 dgrad")
+linear_case(ROWS, 256, 128, "layer-1 dgrad")
+linear_case(N, 256, 672, "PQ linear")
+agg_case(N, 336, 256, "edge GEMM2 fwd (aggregating)")
