@@ -33,6 +33,10 @@ int gnb_edge_linear_agg_fwd_tf32(const float*, int64_t, int32_t, const float*, i
                                  int32_t, int32_t, float*, int64_t, uint32_t*, void*);
 int gnb_edge_mask_bwd_colsum(const float*, int64_t, const uint32_t*, int64_t, int32_t, const int32_t*, float*, int64_t, float*,
                              int32_t, void*);
+int gnb_edge_hidden_dgrad_scatter_tf32(const float*, int64_t, int32_t, const float*, int64_t, const uint32_t*, int32_t, int32_t,
+                                       const int32_t*, int64_t, float*, int64_t, void*);
+int gnb_edge_hidden_fwd_mask(const float*, int64_t, int32_t, const int32_t*, const int32_t*, int32_t, int64_t, int32_t, float*,
+                             int64_t, uint32_t*, int32_t, void*);
 int gnb_segment_pool_bwd(const float*, int64_t, const int32_t*, int32_t, const int64_t*, int64_t, int64_t, const int32_t*,
                          int32_t, float*, int64_t, void*);
 int gnb_act_bwd_colsum(const float*, int64_t, const float*, int64_t, int64_t, int32_t, float*, int64_t, float*, int32_t,
@@ -149,7 +153,7 @@ struct Arena {
     }
 };
 
-struct ConvBuf { float *wcat, *bcat, *w2p, *pq, *h, *m, *y; int32_t *nbr, *deg; uint32_t* mask; int cin, cin_ld, kld, hid, hld, cout; };
+struct ConvBuf { float *wcat, *bcat, *w2p, *pq, *h, *m, *y; int32_t *nbr, *deg; uint32_t *mask, *hmask; int cin, cin_ld, kld, hid, hld, cout, mld; };
 struct DenseBuf { float *wp, *z; int k_total, kld, n_out; };
 
 struct Plan {
@@ -211,6 +215,10 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
         b.h = training ? a.get<float>(n * wl * b.hid) : h_shared;
         b.m = training ? (p.agg ? nullptr : a.get<float>(n * wl * b.cout)) : m_shared;
         b.mask = p.agg ? a.get<uint32_t>((n + 13) / 14 * (int64_t)b.cout * 4) : nullptr;
+        // activation bits of h for the scattering data-gradient epilogue (whole 14-node tiles, mld words per slot row)
+        b.mld = 4 * ((b.hid + 127) / 128);
+        const bool scat = p.agg && b.hid <= 512 && n * 2 * b.hid < ((int64_t)1 << 31);
+        b.hmask = scat ? a.get<uint32_t>((n + 13) / 14 * 126 * (int64_t)b.mld) : nullptr;
         b.y = a.get<float>(n * b.cout);
         b.nbr = (l + 1 < c.n_conv) ? a.get<int32_t>(n * p.width) : nullptr;
         b.deg = (l + 1 < c.n_conv) ? a.get<int32_t>(n) : nullptr;
@@ -412,7 +420,11 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
         } else if (p.agg) {
             // training: h is kept for the backward pass; the second Linear, ReLU and the k-sum run in one tcgen05 kernel
             // whose epilogue writes y and one ReLU bit per (slot, channel) -- the [E, C] message tensor is never stored
-            EX(gnb_edge_hidden_fwd(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, GNB_ACT_RELU | e.rnd, b.h, b.hid, stream));
+            if (b.hmask != nullptr)
+                EX(gnb_edge_hidden_fwd_mask(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, GNB_ACT_RELU | e.rnd, b.h, b.hid, b.hmask,
+                                            b.mld, stream));
+            else
+                EX(gnb_edge_hidden_fwd(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, GNB_ACT_RELU | e.rnd, b.h, b.hid, stream));
             EX(gnb_edge_linear_agg_fwd_tf32(b.h, b.hid, b.hid, b.w2p, b.hld, b2, deg, n, b.cout, 1, b.y, b.cout, b.mask, stream));
         } else {
             EX(gnb_edge_hidden_fwd(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, GNB_ACT_RELU | e.rnd, b.h, b.hid, stream));
@@ -571,9 +583,17 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
         GNB_CHECK(cudaMemsetAsync(p.dwp, 0, (size_t)b.cout * b.hld * 4, e.st));
         EX(e.lin_bwd_weight(p.dz_big, b.cout, b.h, b.hid, p.dwp, b.hld, 0, b.hid, b.cout, rows));
         EX(e.add2d(p.dwp, b.hld, b.cout, b.hid, gw2, b.hid));
-        EX(e.lin_bwd_data(p.dz_big, b.cout, b.w2p, b.hld, 0, b.hid, b.cout, p.dh_big, b.hid, rows, false, p.wt, nullptr));
         GNB_CHECK(cudaMemsetAsync(p.dpq, 0, (size_t)n * 2 * b.hid * 4, e.st));
-        EX(gnb_edge_hidden_bwd(p.dh_big, b.hid, b.h, b.hid, b.hid, nbr, deg, wl, n, GNB_ACT_RELU, p.dpq, 2 * b.hid, stream));
+        if (b.hmask != nullptr) {
+            // data gradient + ReLU mask + scatter into dPQ in one kernel: dh [E, hid] is never materialised
+            const int nld = (int)up(b.cout, 32);
+            EX(e.transpose_pad(b.w2p, b.hld, b.cout, b.hid, p.wt, nld, nld));
+            EX(gnb_edge_hidden_dgrad_scatter_tf32(p.dz_big, b.cout, b.cout, p.wt, nld, b.hmask, b.mld, b.hid, nbr, n, p.dpq,
+                                                  2 * b.hid, stream));
+        } else {
+            EX(e.lin_bwd_data(p.dz_big, b.cout, b.w2p, b.hld, 0, b.hid, b.cout, p.dh_big, b.hid, rows, false, p.wt, nullptr));
+            EX(gnb_edge_hidden_bwd(p.dh_big, b.hid, b.h, b.hid, b.hid, nbr, deg, wl, n, GNB_ACT_RELU, p.dpq, 2 * b.hid, stream));
+        }
         // PQ = xin Wcat^T + bcat
         GNB_CHECK(cudaMemsetAsync(p.dbtmp, 0, (size_t)2 * b.hid * 4, e.st));
         const float* dzq = p.dpq;

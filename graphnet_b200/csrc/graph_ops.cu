@@ -101,7 +101,8 @@ global_vars_kernel(const float* __restrict__ x, int64_t ldx, int nf, const int* 
 // One warp per row, float4 along the channel dimension.
 __global__ void edge_hidden_fwd_kernel(const float* __restrict__ pq, int64_t ldpq, int hdim,
                                        const int* __restrict__ nbr, const int* __restrict__ deg, int width,
-                                       int64_t n, int act, float* __restrict__ h, int64_t ldh) {
+                                       int64_t n, int act, float* __restrict__ h, int64_t ldh,
+                                       unsigned* __restrict__ hmask, int mask_ld) {
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n * width) return;
     const int lane = threadIdx.x & 31;
@@ -109,24 +110,54 @@ __global__ void edge_hidden_fwd_kernel(const float* __restrict__ pq, int64_t ldp
     const int s = (int)(r - i * width);
     float4* out = reinterpret_cast<float4*>(h + r * ldh);
     const int h4 = hdim >> 2;
+    // optional bit mask of the activation (bit c of row r = h[r, c] > 0), mask_ld words per row: lanes 8g..8g+7 of
+    // iteration `it` own the 8 float4 chunks = 32 channels of word 4*it + g
+    unsigned* mrow = hmask != nullptr ? hmask + r * mask_ld : nullptr;
     if (s >= deg[i]) {
         for (int c = lane; c < h4; c += 32) out[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mrow != nullptr)
+            for (int w = lane; w < mask_ld; w += 32) mrow[w] = 0u;
         return;
     }
     const int64_t j = nbr[i * width + s];
     const float4* p = reinterpret_cast<const float4*>(pq + i * ldpq);
     const float4* q = reinterpret_cast<const float4*>(pq + j * ldpq + hdim);
     const bool relu = (act & 0xff) == GNB_ACT_RELU, rnd = (act & GNB_FLAG_ROUND_TF32) != 0;
-    for (int c = lane; c < h4; c += 32) {
-        const float4 a = p[c], b = q[c];
-        float4 v = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-        if (relu) {
-            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    if (mrow == nullptr) {
+        for (int c = lane; c < h4; c += 32) {
+            const float4 a = p[c], b = q[c];
+            float4 v = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+            if (relu) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+            if (rnd) {
+                v.x = gnb_round_tf32(v.x); v.y = gnb_round_tf32(v.y); v.z = gnb_round_tf32(v.z); v.w = gnb_round_tf32(v.w);
+            }
+            out[c] = v;
         }
-        if (rnd) {
-            v.x = gnb_round_tf32(v.x); v.y = gnb_round_tf32(v.y); v.z = gnb_round_tf32(v.z); v.w = gnb_round_tf32(v.w);
+        return;
+    }
+    for (int c0 = 0; c0 < 8 * mask_ld; c0 += 32) {          // whole warp iterates (shuffles below)
+        const int c = c0 + lane;
+        unsigned nib = 0u;
+        if (c < h4) {
+            const float4 a = p[c], b = q[c];
+            float4 v = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+            if (relu) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+            if (rnd) {
+                v.x = gnb_round_tf32(v.x); v.y = gnb_round_tf32(v.y); v.z = gnb_round_tf32(v.z); v.w = gnb_round_tf32(v.w);
+            }
+            out[c] = v;
+            nib = (v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u);
         }
-        out[c] = v;
+        unsigned wv = nib << (4 * (lane & 7));
+        wv |= __shfl_xor_sync(0xffffffffu, wv, 1);
+        wv |= __shfl_xor_sync(0xffffffffu, wv, 2);
+        wv |= __shfl_xor_sync(0xffffffffu, wv, 4);
+        const int w = (c0 >> 3) + (lane >> 3);
+        if ((lane & 7) == 0 && w < mask_ld) mrow[w] = wv;
     }
 }
 
@@ -531,7 +562,20 @@ GNB_EXPORT int gnb_edge_hidden_fwd(const float* pq, int64_t ldpq, int32_t hdim, 
     if ((hdim & 3) || (ldpq & 3) || (ldh & 3) || !aligned16(pq) || !aligned16(h)) return GNB_ERR_ARG;
     if (n == 0) return GNB_OK;
     edge_hidden_fwd_kernel<<<gnb_div_up(n * width, 8), 256, 0, (cudaStream_t)stream>>>(pq, ldpq, hdim, nbr, deg, width,
-                                                                                       n, act, h, ldh);
+                                                                                       n, act, h, ldh, nullptr, 0);
+    GNB_RETURN_LAUNCH();
+}
+
+// Same, additionally writing the activation bit mask hmask[r, mask_ld] (bit c of row r = h[r, c] > 0; mask_ld words per
+// row, mask_ld * 32 >= hdim, bits beyond hdim zero) consumed by gnb_edge_hidden_dgrad_scatter_tf32.
+GNB_EXPORT int gnb_edge_hidden_fwd_mask(const float* pq, int64_t ldpq, int32_t hdim, const int32_t* nbr,
+                                        const int32_t* deg, int32_t width, int64_t n, int32_t act, float* h, int64_t ldh,
+                                        uint32_t* hmask, int32_t mask_ld, void* stream) {
+    if ((hdim & 3) || (ldpq & 3) || (ldh & 3) || !aligned16(pq) || !aligned16(h)) return GNB_ERR_ARG;
+    if (hmask == nullptr || (int64_t)mask_ld * 32 < hdim) return GNB_ERR_ARG;
+    if (n == 0) return GNB_OK;
+    edge_hidden_fwd_kernel<<<gnb_div_up(n * width, 8), 256, 0, (cudaStream_t)stream>>>(pq, ldpq, hdim, nbr, deg, width,
+                                                                                       n, act, h, ldh, hmask, mask_ld);
     GNB_RETURN_LAUNCH();
 }
 

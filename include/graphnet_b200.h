@@ -146,6 +146,19 @@ int gnb_edge_linear_agg_fwd_tf32(const float* h, int64_t ldh, int32_t k, const f
 /* Backward of the above up to the pre-activation: dz[i*9+s] = g[i] * maskbit, db += colsum(dz); flags & 0x100 rounds dz. */
 int gnb_edge_mask_bwd_colsum(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols,
                              const int32_t* deg, float* dz, int64_t ldz, float* db, int32_t flags, void* stream);
+/* Data gradient of the EdgeConv second Linear fused with the backward of the hoisted hidden layer (autograd of
+ * torch.nn.Linear + ReLU + the x_i / x_j gather at dynedge.py:200-203 / PyG EdgeConv.message), k = 8 tables (width 9):
+ *   dh = dz wt^T, da = dh * (h > 0), dpq[i, 0:hdim] = sum_s da[(i,s)], dpq[nbr[i,s], hdim:2*hdim] += da[(i,s)].
+ * wt = W2^T [hdim, ceil(c_out/32)*32] tf32-rounded, zero padded; dz [n*9, c_out] tf32-rounded; hmask = activation bits
+ * written by gnb_edge_hidden_fwd_mask, [ceil(n/14)*126, mask_ld] words (mask_ld % 4 == 0, >= 4*ceil(hdim/128), 16-byte
+ * aligned); nbr [n, 9] (-1 padded); dpq [n, ldpq >= 2*hdim], Q half zero on entry; n*ldpq < 2^31. dh is never stored. */
+int gnb_edge_hidden_dgrad_scatter_tf32(const float* dz, int64_t lddz, int32_t c_out, const float* wt, int64_t ldw,
+                                       const uint32_t* hmask, int32_t mask_ld, int32_t hdim, const int32_t* nbr, int64_t n,
+                                       float* dpq, int64_t ldpq, void* stream);
+/* gnb_edge_hidden_fwd that also writes hmask[r, mask_ld]: bit c of row r = (h[r, c] > 0), zero beyond hdim. */
+int gnb_edge_hidden_fwd_mask(const float* pq, int64_t ldpq, int32_t hdim, const int32_t* nbr, const int32_t* deg,
+                             int32_t width, int64_t n, int32_t act, float* h, int64_t ldh, uint32_t* hmask,
+                             int32_t mask_ld, void* stream);
 /* dst[rows, dst_cols] = [rna_tf32(src[rows, cols]) | 0]. */
 int gnb_round_pad_tf32(const float* src, int64_t lds, int64_t rows, int32_t cols, float* dst, int64_t ldd,
                        int32_t dst_cols, void* stream);

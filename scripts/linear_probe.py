@@ -78,6 +78,34 @@ def agg_case(n, k, n_out, label):
     print(f"{label}: n={n} k={k} n_out={n_out} us: " + " ".join(out), flush=True)
 
 
+def scatter_case(n, c_out, hdim, label):
+    rows = n * 9
+    dz = torch.randn(rows, c_out, device=dev).round_()
+    kpad = (c_out + 31) // 32 * 32
+    wt = torch.randn(hdim, kpad, device=dev).round_()
+    mld = 4 * ((hdim + 127) // 128)
+    hmask = torch.randint(-2**31, 2**31 - 1, ((n + 13) // 14 * 126, mld), device=dev, dtype=torch.int32)
+    # neighbours: random nodes within +-64 of the target (kNN-like locality), degree 8
+    base = torch.arange(n, device=dev).unsqueeze(1)
+    nbr = (base + torch.randint(-64, 65, (n, 9), device=dev)).clamp_(0, n - 1).int()
+    nbr[:, 8] = -1
+    dpq = torch.zeros(n, 2 * hdim, device=dev)
+    out = []
+    for dbg in (0, 16, 2, 18):
+        lib.gnb_linear_set_debug(dbg)
+
+        def run():
+            ops._call("gnb_edge_hidden_dgrad_scatter_tf32", ops._ptr(dz), c_out, c_out, ops._ptr(wt), kpad, ops._ptr(hmask), mld,
+                      hdim, ops._ptr(nbr), n, ops._ptr(dpq), 2 * hdim, ops._stream())
+        out.append(f"dbg{dbg}={timed(run):.0f}")
+    lib.gnb_linear_set_debug(0)
+    print(f"{label}: n={n} c_out={c_out} hdim={hdim} us: " + " ".join(out), flush=True)
+
+
+scatter_case(N, 256, 336, "dgrad + scatter epilogue")
+import sys as _s
+if len(_s.argv) > 1 and _s.argv[1] == "scatter":
+    _s.exit(0)
 linear_case(ROWS, 336, 256, "edge GEMM2 fwd (plain)")
 linear_case(ROWS, 256, 336, "edge GEMM2 dgrad")
 linear_case(ROWS, 256, 128, "layer-1 dgrad")

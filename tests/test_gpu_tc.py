@@ -237,3 +237,61 @@ def test_dynedge_tf32_fused_inference_vs_oracle(built_library, tf32_mode):
     err = rel_err(y, y_ref)
     print("tf32 fused inference rel error:", f"{err:.2e}")
     assert err < 1e-3
+
+
+@pytest.mark.parametrize("hdim,c_out", [(336, 256), (128, 256), (64, 40), (512, 96)])
+def test_edge_hidden_dgrad_scatter_bit_exact_on_integers(built_library, tf32_mode, hdim, c_out):
+    """Hidden layer forward with activation bit mask, then dgrad GEMM + ReLU mask + scatter epilogue: dP = sum over
+    slots, dQ scattered to the neighbours. Integer operands make every product and (order-independent) sum exact, so
+    the result must equal the fp64 reference."""
+    ops = tf32_mode
+    from helpers import tie_heavy_events
+    sizes = [1, 2, 5, 9, 10, 64, 130, 12, 300]
+    x, batch, _ = tie_heavy_events(sizes, 5, seed=hdim)
+    x[-12:] = x[-12]                                   # duplicates: degree k + 1
+    ptr = batch_to_ptr(batch)
+    graph = ops.knn_table(x.cuda(), [0, 1, 2], ptr.cuda(), 8)
+    n = x.shape[0]
+    nbr, deg = graph.nbr.cpu().long(), graph.deg.cpu()
+    assert nbr.shape[1] == 9
+    g = torch.Generator().manual_seed(c_out)
+    pq = torch.randint(-2, 3, (n, 2 * hdim), generator=g).float()
+    dz = torch.randint(-2, 3, (n * 9, c_out), generator=g).float()
+    w2 = torch.randint(-1, 2, (c_out, hdim), generator=g).float()
+    # reference: h[(i,s)] = relu(P_i + Q_j); dh = (dz W2) * (h > 0); scatter
+    h_ref = torch.zeros(n * 9, hdim, dtype=torch.float64)
+    for i in range(n):
+        for s_ in range(int(deg[i])):
+            h_ref[i * 9 + s_] = torch.relu(pq[i, :hdim] + pq[nbr[i, s_], hdim:]).double()
+    dh = (dz.double() @ w2.double()) * (h_ref > 0).double()
+    dpq_ref = torch.zeros(n, 2 * hdim, dtype=torch.float64)
+    for i in range(n):
+        for s_ in range(int(deg[i])):
+            r = i * 9 + s_
+            dpq_ref[i, :hdim] += dh[r]
+            dpq_ref[nbr[i, s_], hdim:] += dh[r]
+    # device
+    mld = 4 * ((hdim + 127) // 128)
+    ntile = (n + 13) // 14
+    hmask = torch.full((ntile * 126, mld), -1, dtype=torch.int32, device="cuda")     # garbage in the padding rows
+    hdev = torch.empty(n * 9, hdim, device="cuda")
+    pqc = pq.cuda()
+    ops._call("gnb_edge_hidden_fwd_mask", ops._ptr(pqc), 2 * hdim, hdim, ops._ptr(graph.nbr), ops._ptr(graph.deg), 9, n,
+              1 | 0x100, ops._ptr(hdev), hdim, ops._ptr(hmask), mld, ops._stream())
+    assert torch.equal(hdev.cpu().double(), h_ref)
+    bits = hmask[: n * 9].cpu().numpy().view(np.uint32)
+    expect = np.zeros((n * 9, mld), dtype=np.uint32)
+    hpos = (h_ref > 0).numpy()
+    for c in range(hdim):
+        expect[:, c // 32] |= hpos[:, c].astype(np.uint32) << np.uint32(c % 32)
+    assert np.array_equal(bits, expect)
+    kpad = (c_out + 31) // 32 * 32
+    wt = torch.zeros(hdim, kpad)
+    wt[:, :c_out] = w2.t()
+    dzc, wtc = dz.cuda(), wt.cuda()
+    dpq = torch.zeros(n, 2 * hdim, device="cuda")
+    dpq[:, :hdim] = 7.0                                # the P half is overwritten, not accumulated
+    ops._call("gnb_edge_hidden_dgrad_scatter_tf32", ops._ptr(dzc), c_out, c_out, ops._ptr(wtc), kpad, ops._ptr(hmask), mld,
+              hdim, ops._ptr(graph.nbr), n, ops._ptr(dpq), 2 * hdim, ops._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(dpq.cpu().double(), dpq_ref)
