@@ -210,14 +210,14 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
             for (int t = blockIdx.x; t < num_row_tiles; t += gridDim.x, ++tile_i) {
                 const uint32_t buf = tile_i & 1;
                 const long long c1 = prof_on ? clock64() : 0;
-                tc::mbar_wait(&tmem_empty[buf], ((tile_i >> 1) & 1) ^ 1);      // epilogue drained this buffer
+                tc::mbar_wait_warp(&tmem_empty[buf], ((tile_i >> 1) & 1) ^ 1);      // epilogue drained this buffer
                 if (prof_on) pw1 += clock64() - c1;
                 tc::tcgen05_fence_after();
-                const uint32_t acc = tmem_base + buf * (TC_MT * TC_BN);
+                const uint32_t acc = __shfl_sync(0xffffffffu, tmem_base, 0) + buf * (TC_MT * TC_BN);
                 for (int kbi = 0; kbi < total_kb; ++kbi, ++it) {
                     const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
                     const long long c0 = prof_on ? clock64() : 0;
-                    tc::mbar_wait(&full[s], ph);
+                    tc::mbar_wait_warp(&full[s], ph);
                     if (prof_on) pw0 += clock64() - c0;
                     tc::tcgen05_fence_after();
                     const uint32_t st = tc::smem_u32(smem + s * TC_STAGE_BYTES);

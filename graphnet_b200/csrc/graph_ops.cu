@@ -137,27 +137,35 @@ __global__ void edge_hidden_fwd_kernel(const float* __restrict__ pq, int64_t ldp
         }
         return;
     }
-    for (int c0 = 0; c0 < 8 * mask_ld; c0 += 32) {          // whole warp iterates (shuffles below)
-        const int c = c0 + lane;
-        unsigned nib = 0u;
-        if (c < h4) {
-            const float4 a = p[c], b = q[c];
-            float4 v = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-            if (relu) {
-                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    // all loads first (independent), then the arithmetic, the stores and the nibble -> word shuffles
+    float4 va[4], vb[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int c = it * 32 + lane;
+        if (it * 4 < mask_ld && c < h4) { va[it] = p[c]; vb[it] = q[c]; }
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        if (it * 4 < mask_ld) {                               // warp-uniform
+            const int c = it * 32 + lane;
+            unsigned nib = 0u;
+            if (c < h4) {
+                float4 v = make_float4(va[it].x + vb[it].x, va[it].y + vb[it].y, va[it].z + vb[it].z, va[it].w + vb[it].w);
+                if (relu) {
+                    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                }
+                if (rnd) {
+                    v.x = gnb_round_tf32(v.x); v.y = gnb_round_tf32(v.y); v.z = gnb_round_tf32(v.z); v.w = gnb_round_tf32(v.w);
+                }
+                out[c] = v;
+                nib = (v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u);
             }
-            if (rnd) {
-                v.x = gnb_round_tf32(v.x); v.y = gnb_round_tf32(v.y); v.z = gnb_round_tf32(v.z); v.w = gnb_round_tf32(v.w);
-            }
-            out[c] = v;
-            nib = (v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u);
+            unsigned wv = nib << (4 * (lane & 7));
+            wv |= __shfl_xor_sync(0xffffffffu, wv, 1);
+            wv |= __shfl_xor_sync(0xffffffffu, wv, 2);
+            wv |= __shfl_xor_sync(0xffffffffu, wv, 4);
+            if ((lane & 7) == 0) mrow[it * 4 + (lane >> 3)] = wv;
         }
-        unsigned wv = nib << (4 * (lane & 7));
-        wv |= __shfl_xor_sync(0xffffffffu, wv, 1);
-        wv |= __shfl_xor_sync(0xffffffffu, wv, 2);
-        wv |= __shfl_xor_sync(0xffffffffu, wv, 4);
-        const int w = (c0 >> 3) + (lane >> 3);
-        if ((lane & 7) == 0 && w < mask_ld) mrow[w] = wv;
     }
 }
 
@@ -572,7 +580,7 @@ GNB_EXPORT int gnb_edge_hidden_fwd_mask(const float* pq, int64_t ldpq, int32_t h
                                         const int32_t* deg, int32_t width, int64_t n, int32_t act, float* h, int64_t ldh,
                                         uint32_t* hmask, int32_t mask_ld, void* stream) {
     if ((hdim & 3) || (ldpq & 3) || (ldh & 3) || !aligned16(pq) || !aligned16(h)) return GNB_ERR_ARG;
-    if (hmask == nullptr || (int64_t)mask_ld * 32 < hdim) return GNB_ERR_ARG;
+    if (hmask == nullptr || (int64_t)mask_ld * 32 < hdim || (mask_ld & 3) || mask_ld > 16) return GNB_ERR_ARG;
     if (n == 0) return GNB_OK;
     edge_hidden_fwd_kernel<<<gnb_div_up(n * width, 8), 256, 0, (cudaStream_t)stream>>>(pq, ldpq, hdim, nbr, deg, width,
                                                                                        n, act, h, ldh, hmask, mask_ld);

@@ -73,6 +73,27 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// Wait executed by a CONVERGED warp with a warp-uniform exit (vote): unlike the per-thread spin of mbar_wait, the
+// compiler can prove that control flow stays convergent, so loop counters / descriptors computed afterwards live in
+// uniform registers and the tcgen05.mma / TMA operands need no R2UR broadcasts.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    long long t0 = 0;
+    for (uint32_t it = 1;; ++it) {
+        if (__all_sync(0xffffffffu, mbar_try_wait(addr, parity))) return;
+        if ((it & 4095u) == 0u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) {
+                if ((threadIdx.x & 31) == 0)
+                    printf("gnb mbar_wait_warp timeout: block %d warp %d barrier smem 0x%x parity %u\n", (int)blockIdx.x,
+                           (int)(threadIdx.x >> 5), addr, parity);
+                __trap();
+            }
+        }
+    }
+}
+
 // ---- TMA -----------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

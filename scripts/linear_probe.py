@@ -75,6 +75,14 @@ def agg_case(n, k, n_out, label):
                       ops._ptr(deg), n, n_out, 1, ops._ptr(y), n_out, ops._ptr(mask), ops._stream())
         out.append(f"dbg{dbg}={timed(run):.0f}")
     lib.gnb_linear_set_debug(0)
+    prof = torch.zeros(16, dtype=torch.int64, device=dev)
+    lib.gnb_linear_set_profile_buffer(ctypes.c_void_p(prof.data_ptr()))
+    run()
+    torch.cuda.synchronize()
+    lib.gnb_linear_set_profile_buffer(None)
+    v = prof.tolist()
+    print(f"   agg cycles: producer wait-empty {v[0]} total {v[2]} | mma wait-full {v[3]} wait-tmem-empty {v[4]} "
+          f"total {v[5]} | epilogue wait-tmem-full {v[6]} total {v[8]}", flush=True)
     print(f"{label}: n={n} k={k} n_out={n_out} us: " + " ".join(out), flush=True)
 
 
@@ -103,6 +111,7 @@ def scatter_case(n, c_out, hdim, label):
 
 
 scatter_case(N, 256, 336, "dgrad + scatter epilogue")
+agg_case(N, 336, 256, "edge GEMM2 fwd (aggregating)")
 import sys as _s
 if len(_s.argv) > 1 and _s.argv[1] == "scatter":
     _s.exit(0)
