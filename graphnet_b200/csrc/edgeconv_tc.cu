@@ -505,7 +505,7 @@ edgeconv_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPa
             __syncwarp();
             EF_TIMED(pw1, if (lane == 0) {
                 tc::mbar_arrive(&epi_done[buf]);                  // local: metadata slot may be rewritten
-                tc::mbar_arrive_cluster(&tmem_empty[buf], 0);     // leader: accumulator buffer may be overwritten
+                tc::mbar_arrive_cluster_relaxed(&tmem_empty[buf], 0);     // leader: accumulator buffer may be overwritten (reads done: wait::ld)
             } __syncwarp());
         }
     } else if (warp < 14) {

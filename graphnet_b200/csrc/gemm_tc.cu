@@ -51,16 +51,19 @@ struct ScatInfo { const int* nbr; const unsigned* hmask; int mask_ld; float* dpq
 // Scatter epilogue for NN consecutive nodes whose 9 slot columns sit in r[J0 ...]; col0 = first column in the tile.
 template <int NN, int J0>
 __device__ __forceinline__ void scat_nodes(const uint32_t (&r)[32], int col0, const int* __restrict__ s_off,
-                                           const unsigned* __restrict__ s_msk, int mask_ld, int lane, float* __restrict__ dq,
-                                           float* __restrict__ dp, int64_t ldpq, int64_t nodes_left, bool ch_ok, int off_kill) {
-    // metadata first (independent broadcast LDS, issued back to back), then a branch-free body: the reduction is a
-    // predicated `red` (a C++ `if` around atomicAdd compiles to a divergence region per element that serialises the
-    // shared-memory loads behind it: 90 cycles per element measured)
+                                           const unsigned* __restrict__ s_msk, int mask_ld, unsigned lanebit,
+                                           float* __restrict__ dq, float* __restrict__ dp, int64_t ldpq, int64_t nodes_left,
+                                           bool ch_ok, int own_off, bool no_atomics) {
+    // Branch-free body: a conditional reduction compiles to a divergence region (BSSY / BRA / BSYNC, ~60 cycles per
+    // element measured), so EVERY slot issues its `red`: padding slots (offset < 0; their mask bits are zero, so the
+    // value is 0) are redirected to the Q row of the tile's first node, lanes beyond the last channel carry a zero lane
+    // bit and a wrapped (valid) channel. Metadata first: independent broadcast LDS issued back to back.
     int offr[NN * AGG_W];
     unsigned mwr[NN * AGG_W];
 #pragma unroll
     for (int e = 0; e < NN * AGG_W; ++e) {
-        offr[e] = s_off[col0 + e] | off_kill;            // negative = no reduction (padding slot / channel out of range)
+        const int o = s_off[col0 + e];
+        offr[e] = o >= 0 ? o : own_off;
         mwr[e] = s_msk[(col0 + e) * mask_ld];
     }
 #pragma unroll
@@ -69,10 +72,9 @@ __device__ __forceinline__ void scat_nodes(const uint32_t (&r)[32], int col0, co
 #pragma unroll
         for (int sl = 0; sl < AGG_W; ++sl) {
             const int e = f * AGG_W + sl;
-            const float v = ((mwr[e] >> lane) & 1u) ? __uint_as_float(r[J0 + e]) : 0.f;
+            const float v = (mwr[e] & lanebit) ? __uint_as_float(r[J0 + e]) : 0.f;
             accp += v;
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %2, 0;\n\t@p red.global.add.f32 [%0], %1;\n\t}"
-                         ::"l"(dq + offr[e]), "f"(v), "r"(offr[e]) : "memory");
+            if (!no_atomics) atomicAdd(dq + offr[e], v);
         }
         if (ch_ok && f < nodes_left) dp[(int64_t)f * ldpq] = accp;
     }
@@ -252,31 +254,33 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
             if (sc.enabled) {
                 tc::mbar_wait<100>(&meta_full[buf], (tile_i >> 1) & 1);
                 const int m = half;
-                if (m < mt) {
+                if (m < mt && ch0 + m * TC_BM + q * 32 < n_out) {      // warps without a valid channel skip the tile
                     const int ch = ch0 + m * TC_BM + q * 32 + lane;
                     const bool ch_ok = ch < n_out;
                     const int64_t node0 = (int64_t)t * AGG_NPT;
                     const uint8_t* mb = meta + buf * SC_META_BYTES;
                     const int* s_off = reinterpret_cast<const int*>(mb + 8192);
                     const unsigned* s_msk = reinterpret_cast<const unsigned*>(mb) + ((ch0 + m * TC_BM + q * 32) >> 5);
-                    float* dq = sc.dpq + sc.hdim + ch;
+                    float* dq = sc.dpq + sc.hdim + (ch_ok ? ch : ch % sc.hdim);
                     float* dp = sc.dpq + node0 * sc.ldpq + ch;
                     const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * (TC_MT * TC_BN) + m * TC_BN);
-                    const int no_at = (!ch_ok || (agg.dbg & 16)) ? (int)0x80000000 : 0;
+                    const unsigned lanebit = ch_ok ? (1u << lane) : 0u;
+                    const int own_off = (int)node0 * (int)sc.ldpq;
+                    const bool no_at = (agg.dbg & 16) != 0;
 #pragma unroll 1
                     for (int c = 0; c < 4; ++c) {          // columns [27 c, 27 c + 27): three nodes
                         uint32_t r[32];
                         tc::tmem_ld_32x32b_x32(tcol + (uint32_t)(27 * c), r);
                         tc::tmem_ld_wait();
-                        scat_nodes<3, 0>(r, 27 * c, s_off, s_msk, sc.mask_ld, lane, dq, dp + (int64_t)(3 * c) * sc.ldpq, sc.ldpq,
-                                         sc.n_nodes - node0 - 3 * c, ch_ok, no_at);
+                        if (!(agg.dbg & 64)) scat_nodes<3, 0>(r, 27 * c, s_off, s_msk, sc.mask_ld, lanebit, dq, dp + (int64_t)(3 * c) * sc.ldpq, sc.ldpq,
+                                         sc.n_nodes - node0 - 3 * c, ch_ok, own_off, no_at);
                     }
                     {                                       // columns [108, 126): the last two nodes, registers 12..29
                         uint32_t r[32];
                         tc::tmem_ld_32x32b_x32(tcol + 96u, r);
                         tc::tmem_ld_wait();
-                        scat_nodes<2, 12>(r, 108, s_off, s_msk, sc.mask_ld, lane, dq, dp + (int64_t)12 * sc.ldpq, sc.ldpq,
-                                          sc.n_nodes - node0 - 12, ch_ok, no_at);
+                        if (!(agg.dbg & 64)) scat_nodes<2, 12>(r, 108, s_off, s_msk, sc.mask_ld, lanebit, dq, dp + (int64_t)12 * sc.ldpq, sc.ldpq,
+                                          sc.n_nodes - node0 - 12, ch_ok, own_off, no_at);
                     }
                 }
             } else if (agg.enabled) {
@@ -363,6 +367,293 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     if (warp == 1) tc::tmem_dealloc<TC_TMEM_COLS>(tmem_base);
 }
 
+
+// =====================================================================================================================
+// CTA-pair variant (cta_group::2): one tcgen05.mma covers M = 256 output channels (128 per CTA) x N = 256 rows x K = 8.
+// Measured on B200 (scripts/probes): a tcgen05.mma costs ~125 cycles of issue time whatever its shape, so the
+// single-CTA kernel above (8 MMAs of 128 x 128 x 8 per K block) is issue-bound at ~1/3 of the tensor pipe, while
+// 4 MMAs of 256 x 256 x 8 per K block run at the pipe's 128-cycle floor. Per CTA and K block the pair also moves only
+// 32 KiB through TMA (its 128 weight rows + its half of the 256 activation rows) for twice the work of the 48 KiB
+// single-CTA stage. CTA r of a pair owns channels [ch0 + 128 r, +128) and loads rows [row0 + half r, + half) of the tile;
+// every CTA's epilogue drains its own 128 TMEM lanes x 256 columns. Row tile = 256 rows (plain) or 2 x 126 rows =
+// 28 nodes (aggregating / scattering epilogues; sub-tile h of tile t is the 14-node tile 2 t + h of the layouts above).
+// Barriers: full[s] lives in the leader (both CTAs' TMA loads credit it), empty[s] / tmem_full[b] are multicast by the
+// leader's tcgen05.commit to both CTAs, tmem_empty[b] of the leader collects the 16 epilogue warps of the pair.
+constexpr int PL_STAGES = 6, PL_STAGES_SCAT = 5, PL_THREADS = 320;
+constexpr uint32_t PL_STAGE_BYTES = 2 * TC_TILE_BYTES;                         // A (128 ch) + B half (128 rows)
+constexpr uint32_t PL_SMEM_BYTES = PL_STAGES * PL_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t PL_SMEM_BYTES_SCAT = PL_STAGES_SCAT * PL_STAGE_BYTES + 1024 + 256 + 4 * SC_META_BYTES;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PL_THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ TmapArray tm_x,
+                    const PartInfo parts, const float* __restrict__ bias, float* __restrict__ y, int64_t ldy,
+                    int64_t rows, int n_out, int act, int round_out, int num_tiles, const AggInfo agg, const ScatInfo sc) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int nstages = sc.enabled ? PL_STAGES_SCAT : PL_STAGES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + nstages * PL_STAGE_BYTES);
+    uint64_t* empty = full + PL_STAGES;
+    uint64_t* tmem_full = empty + PL_STAGES;      // [2]
+    uint64_t* tmem_empty = tmem_full + 2;         // [2] (leader's copy is the one waited on)
+    uint64_t* meta_full = tmem_empty + 2;         // [2]
+    uint64_t* meta_empty = meta_full + 2;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(meta_empty + 2);
+    uint8_t* meta = smem + nstages * PL_STAGE_BYTES + 256;        // [2 buffers][2 sub-tiles] x SC_META_BYTES
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int ch0 = blockIdx.y * 256 + (int)rank * 128;        // first channel of this CTA
+    const bool sub = agg.enabled || sc.enabled;                // 2 x 126-row sub-tiles instead of 256 rows
+    const int half_rows = sub ? AGG_ROWS : 128;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tm_w);
+        for (int p = 0; p < parts.nparts; ++p) tc::tma_prefetch_desc(&tm_x.m[p]);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < PL_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+            for (int b = 0; b < 2; ++b) {
+                tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], 16);
+                tc::mbar_init(&meta_full[b], 1); tc::mbar_init(&meta_empty[b], 8);
+            }
+            tc::fence_barrier_init();
+            tc::fence_proxy_async();
+        }
+        __syncwarp();
+        tc::tmem_alloc_2cta<512>(tmem_slot);
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();                       // both CTAs' barriers are initialised before any remote arrive / TMA
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    int total_kb = 0;
+    for (int p = 0; p < parts.nparts; ++p) total_kb += parts.kblocks[p];
+    const bool prof_on = agg.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+    long long pw0 = 0, pw1 = 0;
+    const long long pt0 = clock64();
+
+    if (warp == 0) {
+        // ---- TMA producer (both CTAs): own weight rows + own half of the activation rows ------------------------
+        uint32_t it = 0, tile_i = 0;
+        const uint32_t stage_tx = 2u * (TC_TILE_BYTES + (uint32_t)half_rows * TC_BK * 4);   // both CTAs' loads
+        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++tile_i) {
+            const int64_t row0 = (int64_t)t * (2 * half_rows) + (int64_t)rank * half_rows;
+            int offv[2][4];
+            if (sc.enabled) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const int col = lane + 32 * q4;
+                        const int64_t r = ((int64_t)t * 2 + h) * AGG_ROWS + col;
+                        const int nb = (col < AGG_ROWS && r < rows) ? sc.nbr[r] : -1;
+                        offv[h][q4] = nb >= 0 ? nb * (int)sc.ldpq : -1;
+                    }
+            }
+            int kb_w = 0;
+            for (int p = 0; p < parts.nparts; ++p) {
+                for (int kb = 0; kb < parts.kblocks[p]; ++kb, ++kb_w, ++it) {
+                    const uint32_t s = it % (uint32_t)nstages, ph = (it / (uint32_t)nstages) & 1;
+                    const long long c0 = prof_on ? clock64() : 0;
+                    tc::mbar_wait_warp(&empty[s], ph ^ 1);
+                    if (prof_on) pw0 += clock64() - c0;
+                    uint8_t* st = smem + s * PL_STAGE_BYTES;
+                    if (tc::elect_one()) {
+                        if (rank == 0) tc::mbar_arrive_expect_tx(&full[s], stage_tx);
+                        tc::tma_load_2d_2sm(st, &tm_w, &full[s], kb_w * TC_BK, ch0);
+                        tc::tma_load_2d_2sm(st + TC_TILE_BYTES, &tm_x.m[p], &full[s], kb * TC_BK, (int)row0);
+                    }
+                    __syncwarp();
+                }
+            }
+            if (sc.enabled) {
+                const uint32_t buf = tile_i & 1;
+                tc::mbar_wait_warp(&meta_empty[buf], ((tile_i >> 1) & 1) ^ 1);   // local epilogue of tile_i - 2 is done
+                uint32_t bytes = 0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    int* so = reinterpret_cast<int*>(meta + (buf * 2 + h) * SC_META_BYTES + 8192);
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) so[lane + 32 * q4] = offv[h][q4];
+                    if (((int64_t)t * 2 + h) * AGG_NPT < sc.n_nodes) bytes += (uint32_t)(AGG_ROWS * sc.mask_ld * 4);
+                }
+                __syncwarp();
+                if (tc::elect_one()) {
+                    tc::mbar_arrive_expect_tx(&meta_full[buf], bytes);
+                    const uint32_t one = (uint32_t)(AGG_ROWS * sc.mask_ld * 4);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        if (((int64_t)t * 2 + h) * AGG_NPT < sc.n_nodes)
+                            tc::bulk_load(meta + (buf * 2 + h) * SC_META_BYTES,
+                                          sc.hmask + ((int64_t)t * 2 + h) * AGG_ROWS * sc.mask_ld, one, &meta_full[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ---- MMA issuer (leader CTA): M = 256 over both CTAs, N = 256 rows (128 from each CTA's stage) -----------
+            constexpr uint32_t idesc = tc::umma_idesc_tf32(256, 256);
+            uint32_t it = 0, tile_i = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters, ++tile_i) {
+                const uint32_t buf = tile_i & 1;
+                const long long c1 = prof_on ? clock64() : 0;
+                tc::mbar_wait_warp(&tmem_empty[buf], ((tile_i >> 1) & 1) ^ 1);
+                if (prof_on) pw1 += clock64() - c1;
+                tc::tcgen05_fence_after();
+                const uint32_t acc = tmem_base + buf * 256;
+                for (int kbi = 0; kbi < total_kb; ++kbi, ++it) {
+                    const uint32_t s = it % (uint32_t)nstages, ph = (it / (uint32_t)nstages) & 1;
+                    const long long c0 = prof_on ? clock64() : 0;
+                    tc::mbar_wait_warp(&full[s], ph);
+                    if (prof_on) pw0 += clock64() - c0;
+                    tc::tcgen05_fence_after();
+                    const uint32_t st = tc::smem_u32(smem + s * PL_STAGE_BYTES);
+                    const uint64_t adesc = tc::umma_desc_sw128_kmajor(st);
+                    const uint64_t bdesc = tc::umma_desc_sw128_kmajor(st + TC_TILE_BYTES);
+                    if (!(agg.dbg & 2)) {
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 8; ++k)
+                            if (tc::elect_one())
+                                tc::umma_tf32_2cta(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kbi | k) != 0 ? 1u : 0u);
+                    }
+                    if (tc::elect_one()) tc::umma_commit_2cta(&empty[s], 3);
+                    __syncwarp();
+                }
+                if (tc::elect_one()) tc::umma_commit_2cta(&tmem_full[buf], 3);
+                __syncwarp();
+            }
+        }
+    } else {
+        // ---- epilogue (each CTA: its own 128 channels, all 256 columns) ---------------------------------------------
+        const int q = warp & 3;                     // TMEM lane quarter
+        const int half = (warp - 2) >> 2;           // column half = sub-tile
+        const int ch = ch0 + q * 32 + lane;
+        const bool ch_ok = ch < n_out;
+        const float bv = (bias != nullptr && ch_ok) ? bias[ch] : 0.f;
+        const float relu_lo = act == GNB_ACT_RELU ? 0.f : -INFINITY;
+        uint32_t tile_i = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++tile_i) {
+            const uint32_t buf = tile_i & 1;
+            const long long c0 = prof_on ? clock64() : 0;
+            tc::mbar_wait<100>(&tmem_full[buf], (tile_i >> 1) & 1);
+            if (prof_on) pw0 += clock64() - c0;
+            tc::tcgen05_fence_after();
+            const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + half * 128);
+            if (sc.enabled) {
+                tc::mbar_wait<100>(&meta_full[buf], (tile_i >> 1) & 1);
+                const int64_t node0 = ((int64_t)t * 2 + half) * AGG_NPT;
+                if (node0 < sc.n_nodes && ch0 + q * 32 < n_out) {
+                    const uint8_t* mb = meta + (buf * 2 + half) * SC_META_BYTES;
+                    const int* s_off = reinterpret_cast<const int*>(mb + 8192);
+                    const unsigned* s_msk = reinterpret_cast<const unsigned*>(mb) + ((ch0 + q * 32) >> 5);
+                    float* dq = sc.dpq + sc.hdim + (ch_ok ? ch : ch % sc.hdim);
+                    float* dp = sc.dpq + node0 * sc.ldpq + ch;
+                    const unsigned lanebit = ch_ok ? (1u << lane) : 0u;
+                    const int own_off = (int)node0 * (int)sc.ldpq;
+                    const bool no_at = (agg.dbg & 16) != 0;
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t r[32];
+                        tc::tmem_ld_32x32b_x32(tcol + (uint32_t)(27 * c), r);
+                        tc::tmem_ld_wait();
+                        if (!(agg.dbg & 64)) scat_nodes<3, 0>(r, 27 * c, s_off, s_msk, sc.mask_ld, lanebit, dq, dp + (int64_t)(3 * c) * sc.ldpq, sc.ldpq,
+                                         sc.n_nodes - node0 - 3 * c, ch_ok, own_off, no_at);
+                    }
+                    {
+                        uint32_t r[32];
+                        tc::tmem_ld_32x32b_x32(tcol + 96u, r);
+                        tc::tmem_ld_wait();
+                        if (!(agg.dbg & 64)) scat_nodes<2, 12>(r, 108, s_off, s_msk, sc.mask_ld, lanebit, dq, dp + (int64_t)12 * sc.ldpq, sc.ldpq,
+                                          sc.n_nodes - node0 - 12, ch_ok, own_off, no_at);
+                    }
+                }
+            } else if (agg.enabled) {
+                const int64_t st14 = (int64_t)t * 2 + half;            // 14-node tile index of the mask layout
+                const int64_t node0 = st14 * AGG_NPT;
+                if (node0 < agg.n_nodes) {
+                    int dg[AGG_NPT];
+#pragma unroll
+                    for (int f = 0; f < AGG_NPT; ++f) dg[f] = (node0 + f < agg.n_nodes) ? agg.deg[node0 + f] : 0;
+                    float acc = 0.f;
+                    unsigned bits[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t r[32];
+                        tc::tmem_ld_32x32b_x32(tcol + (uint32_t)(c * 32), r);
+                        tc::tmem_ld_wait();
+                        unsigned w = 0u;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = c * 32 + j;
+                            if (col < AGG_ROWS) {
+                                const int f = col / AGG_W, sl = col % AGG_W;       // compile-time after unrolling
+                                const float pre = __uint_as_float(r[j]) + bv;
+                                const bool on = (sl < dg[f]) && (pre > 0.f);
+                                acc += on ? pre : 0.f;
+                                w |= on ? (1u << j) : 0u;
+                                if (sl == AGG_W - 1) {
+                                    float o = acc;
+                                    if (round_out) o = tc::round_tf32(o);
+                                    if (ch_ok && node0 + f < agg.n_nodes) y[(node0 + f) * ldy + ch] = o;
+                                    acc = 0.f;
+                                }
+                            }
+                        }
+                        bits[c] = w;
+                    }
+                    if (ch_ok && agg.maskbits != nullptr)
+                        reinterpret_cast<uint4*>(agg.maskbits)[st14 * n_out + ch] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+                }
+            } else {
+                const int64_t rbase = (int64_t)t * 256 + half * 128;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[32];
+                    tc::tmem_ld_32x32b_x32(tcol + (uint32_t)(c * 32), r);
+                    tc::tmem_ld_wait();
+                    const int64_t left = rows - (rbase + c * 32);
+                    if (ch_ok && left > 0 && !(agg.dbg & 1)) {
+                        float* yp = y + (rbase + c * 32) * ldy + ch;
+                        if (left >= 32) {
+                            if (round_out) epi_store32<true>(r, bv, relu_lo, yp, ldy);
+                            else epi_store32<false>(r, bv, relu_lo, yp, ldy);
+                        } else {
+                            epi_store_partial(r, bv, relu_lo, round_out != 0, yp, ldy, (int)left);
+                        }
+                    }
+                }
+            }
+            const long long c1 = prof_on ? clock64() : 0;
+            tc::tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                // the leader's MMA warp waits for all 16 epilogue warps. Relaxed: the accumulator reads are already complete
+                // (tcgen05.wait::ld + fence::before_thread_sync); a release at cluster scope would also wait for this warp's
+                // outstanding global stores to drain (~4000 cycles per tile measured)
+                tc::mbar_arrive_cluster_relaxed(&tmem_empty[buf], 0);
+                if (sc.enabled) tc::mbar_arrive(&meta_empty[buf]);
+            }
+            __syncwarp();
+            if (prof_on) pw1 += clock64() - c1;
+        }
+    }
+    __syncwarp();
+    if (prof_on && lane == 0 && warp <= 2) {
+        agg.prof[warp * 3] = (unsigned long long)pw0;
+        agg.prof[warp * 3 + 1] = (unsigned long long)pw1;
+        agg.prof[warp * 3 + 2] = (unsigned long long)(clock64() - pt0);
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();                       // no CTA exits (or frees TMEM) while its peer may still signal it
+    if (warp == 1) tc::tmem_dealloc_2cta<512>(tmem_base);
+}
+
 // dst[r, c] = rna_tf32(src[r, c]) for c < cols, 0 for cols <= c < dst_cols
 __global__ void round_pad_tf32_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
                                       float* __restrict__ dst, int64_t ldd, int dst_cols) {
@@ -376,12 +667,57 @@ __global__ void round_pad_tf32_kernel(const float* __restrict__ src, int64_t lds
 int g_num_sms = 0;
 unsigned long long* g_linear_prof = nullptr;
 int g_linear_dbg = 0;   // tuning hook: see gnb_linear_set_debug
+int g_linear_variant = 0;   // 0 auto, 1 single-CTA kernel, 2 CTA-pair kernel
+
+// row_tiles = number of 128-row (plain) or 126-row (aggregating / scattering) tiles
+int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi, const float* bias, float* y, int64_t ldy,
+                  int64_t rows, int n_out, int act, int round_out, int row_tiles, const AggInfo& agg, const ScatInfo& sc,
+                  cudaStream_t stream) {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        GNB_CHECK(cudaGetDevice(&dev));
+        GNB_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+        GNB_CHECK(cudaFuncSetAttribute(gemm_tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)TC_SMEM_BYTES));
+        GNB_CHECK(cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(PL_SMEM_BYTES > PL_SMEM_BYTES_SCAT ? PL_SMEM_BYTES : PL_SMEM_BYTES_SCAT)));
+    }
+    // measured (scripts/linear_probe.py): the pair kernel wins from two ch-tiles up; a single 128-channel tile is
+    // faster on the single-CTA kernel (half of the pair's M = 256 would be padding)
+    const bool pair = g_linear_variant == 2 || (g_linear_variant == 0 && row_tiles >= 2 * 148 && n_out > 128);
+    if (pair) {
+        const int tiles = (row_tiles + 1) / 2;
+        const int groups = gnb_div_up(n_out, 256);
+        int clusters = (g_num_sms / 2) / groups;
+        if (clusters < 1) clusters = 1;
+        if (clusters > tiles) clusters = tiles;
+        dim3 grid((unsigned)(2 * clusters), (unsigned)groups);
+        gemm_tc_pair_kernel<<<grid, PL_THREADS, sc.enabled ? PL_SMEM_BYTES_SCAT : PL_SMEM_BYTES, stream>>>(
+            tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out, tiles, agg, sc);
+        GNB_RETURN_LAUNCH();
+    }
+    const int groups = gnb_div_up(n_out, TC_MT * TC_BM);
+    int ctas_x = g_num_sms / groups;                 // persistent: about one CTA per SM in total
+    if (ctas_x < 1) ctas_x = 1;
+    if (ctas_x > row_tiles) ctas_x = row_tiles;
+    dim3 grid((unsigned)ctas_x, (unsigned)groups);
+    gemm_tc_linear_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out,
+                                                                       row_tiles, agg, sc);
+    GNB_RETURN_LAUNCH();
+}
 
 }  // namespace
 
 // Tuning hook (profiling only): bit0 epilogue skips its global stores, bit1 no MMAs, bit2 no weight loads, bit3 no
 // activation loads. Results are garbage with any bit set.
 GNB_EXPORT int gnb_linear_set_debug(int32_t flags) { g_linear_dbg = flags; return GNB_OK; }
+// Kernel selection for the tf32 Linear entry points: 0 auto (CTA-pair cta_group::2 kernel from 296 row tiles up),
+// 1 single-CTA kernel, 2 CTA-pair kernel.
+GNB_EXPORT int gnb_linear_set_variant(int32_t v) {
+    if (v < 0 || v > 2) return GNB_ERR_ARG;
+    g_linear_variant = v;
+    return GNB_OK;
+}
 
 // Tuning aid: device buffer of 16 uint64 that CTA (0,0) fills with cycle counters
 // {producer: wait-empty, total, -} {mma: wait-full, wait-tmem-empty, total} {epilogue warp 2: wait-tmem-full, tmem-ld, total}.
@@ -412,24 +748,10 @@ GNB_EXPORT int gnb_linear_fwd_tf32(const float* const* xs, const int64_t* ldxs, 
     CUtensorMap tw;
     int rc = gnb_make_tmap_f32(&tw, w, n_out, ktot, ldw, TC_BM);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
-    if (g_num_sms == 0) {
-        int dev = 0;
-        GNB_CHECK(cudaGetDevice(&dev));
-        GNB_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-        GNB_CHECK(cudaFuncSetAttribute(gemm_tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)TC_SMEM_BYTES));
-    }
-    const int row_tiles = gnb_div_up(rows, TC_BN);
-    const int groups = gnb_div_up(n_out, TC_MT * TC_BM);
-    int ctas_x = g_num_sms / groups;                 // persistent: about one CTA per SM in total
-    if (ctas_x < 1) ctas_x = 1;
-    if (ctas_x > row_tiles) ctas_x = row_tiles;
-    dim3 grid((unsigned)ctas_x, (unsigned)groups);
     AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof};
     ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0};
-    gemm_tc_linear_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(tw, tx, pi, bias, y, ldy, rows,
-                                                                                     n_out, act, round_out, row_tiles, agg, sc);
-    GNB_RETURN_LAUNCH();
+    return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out, gnb_div_up(rows, TC_BN), agg, sc,
+                         (cudaStream_t)stream);
 }
 
 // Second Linear of the EdgeConv MLP fused with ReLU and the k-neighbour SUM (k = 8 tables, width 9):
@@ -454,24 +776,10 @@ GNB_EXPORT int gnb_edge_linear_agg_fwd_tf32(const float* h, int64_t ldh, int32_t
     CUtensorMap tw;
     rc = gnb_make_tmap_f32(&tw, w, n_out, ktot, ldw, TC_BM);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
-    if (g_num_sms == 0) {
-        int dev = 0;
-        GNB_CHECK(cudaGetDevice(&dev));
-        GNB_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-        GNB_CHECK(cudaFuncSetAttribute(gemm_tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)TC_SMEM_BYTES));
-    }
-    const int row_tiles = gnb_div_up(n, AGG_NPT);
-    const int groups = gnb_div_up(n_out, TC_MT * TC_BM);
-    int ctas_x = g_num_sms / groups;
-    if (ctas_x < 1) ctas_x = 1;
-    if (ctas_x > row_tiles) ctas_x = row_tiles;
-    dim3 grid((unsigned)ctas_x, (unsigned)groups);
     AggInfo agg{deg, n, maskbits, 1, g_linear_dbg, g_linear_prof};
     ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0};
-    gemm_tc_linear_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(tw, tx, pi, bias, y, ldy, rows, n_out,
-                                                                                     GNB_ACT_RELU, round_out, row_tiles, agg, sc);
-    GNB_RETURN_LAUNCH();
+    return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, GNB_ACT_RELU, round_out, gnb_div_up(n, AGG_NPT), agg, sc,
+                         (cudaStream_t)stream);
 }
 
 // Data gradient of the EdgeConv second Linear fused with the backward of the hoisted hidden layer (k = 8 tables, width 9):
@@ -501,24 +809,10 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_tf32(const float* dz, int64_t lddz,
     CUtensorMap tw;
     rc = gnb_make_tmap_f32(&tw, wt, hdim, ktot, ldw, TC_BM);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
-    if (g_num_sms == 0) {
-        int dev = 0;
-        GNB_CHECK(cudaGetDevice(&dev));
-        GNB_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-        GNB_CHECK(cudaFuncSetAttribute(gemm_tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)TC_SMEM_BYTES));
-    }
-    const int row_tiles = gnb_div_up(n, AGG_NPT);
-    const int groups = gnb_div_up(hdim, TC_MT * TC_BM);
-    int ctas_x = g_num_sms / groups;
-    if (ctas_x < 1) ctas_x = 1;
-    if (ctas_x > row_tiles) ctas_x = row_tiles;
-    dim3 grid((unsigned)ctas_x, (unsigned)groups);
     AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof};
     ScatInfo sc{nbr, hmask, mask_ld, dpq, ldpq, hdim, n, 1};
-    gemm_tc_linear_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(tw, tx, pi, nullptr, nullptr, 0, rows, hdim,
-                                                                                     GNB_ACT_NONE, 0, row_tiles, agg, sc);
-    GNB_RETURN_LAUNCH();
+    return launch_linear(tw, tx, pi, nullptr, nullptr, 0, rows, hdim, GNB_ACT_NONE, 0, gnb_div_up(n, AGG_NPT), agg, sc,
+                         (cudaStream_t)stream);
 }
 
 // dst[rows, dst_cols] = [rna_tf32(src[rows, cols]) | 0]; used to pack weights / round activations.

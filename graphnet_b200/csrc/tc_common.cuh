@@ -237,6 +237,15 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t mask) {
                  : "memory");
 }
 
+// 2-D tiled load issued by either CTA of a pair; the transaction bytes are credited to the barrier at the same offset
+// in the EVEN (leader) CTA: the CTA rank of a shared::cluster address is bit 24, cleared here.
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+
 __device__ __forceinline__ float round_tf32(float v) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));

@@ -76,6 +76,9 @@ int gnb_edgeconv_fused_fwd_tf32(const float* pq, int64_t ldpq, int32_t hdim, con
 /* Tuning aid for gnb_linear_fwd_tf32 / gnb_edge_linear_agg_fwd_tf32 (results are garbage with any bit set): bit0 the
  * epilogue skips its global stores, bit1 no MMAs, bit2 no weight loads, bit3 no activation loads. 0 = normal. */
 int gnb_linear_set_debug(int32_t flags);
+/* Kernel selection for gnb_linear_fwd_tf32 / gnb_edge_linear_agg_fwd_tf32 / gnb_edge_hidden_dgrad_scatter_tf32: 0 auto
+ * (CTA-pair cta_group::2 kernel for >= 296 row tiles), 1 single-CTA kernel, 2 CTA-pair kernel. */
+int gnb_linear_set_variant(int32_t v);
 /* Tuning aid: device buffer of 16 uint64 that CTA (0,0) of the Linear kernel fills with cycle counters {producer:
  * wait-empty, -, total} {mma: wait-full, wait-tmem-empty, total} {epilogue warp 2: wait-tmem-full, tmem-ld, total}. */
 int gnb_linear_set_profile_buffer(void* buf);

@@ -99,7 +99,7 @@ def scatter_case(n, c_out, hdim, label):
     nbr[:, 8] = -1
     dpq = torch.zeros(n, 2 * hdim, device=dev)
     out = []
-    for dbg in (0, 16, 2, 18):
+    for dbg in (0, 16, 18, 82, 66):
         lib.gnb_linear_set_debug(dbg)
 
         def run():
@@ -110,9 +110,15 @@ def scatter_case(n, c_out, hdim, label):
     print(f"{label}: n={n} c_out={c_out} hdim={hdim} us: " + " ".join(out), flush=True)
 
 
-scatter_case(N, 256, 336, "dgrad + scatter epilogue")
-agg_case(N, 336, 256, "edge GEMM2 fwd (aggregating)")
 import sys as _s
+for variant in (1, 2):
+    lib.gnb_linear_set_variant(variant)
+    print("== variant", variant, "(1 single-CTA, 2 CTA pair)", flush=True)
+    scatter_case(N, 256, 336, "dgrad + scatter epilogue")
+    scatter_case(N, 256, 128, "layer-1 dgrad + scatter")
+    agg_case(N, 336, 256, "edge GEMM2 fwd (aggregating)")
+    linear_case(ROWS, 336, 256, "edge GEMM2 fwd (plain)")
+lib.gnb_linear_set_variant(0)
 if len(_s.argv) > 1 and _s.argv[1] == "scatter":
     _s.exit(0)
 linear_case(ROWS, 336, 256, "edge GEMM2 fwd (plain)")

@@ -23,6 +23,16 @@ def tf32_mode():
     ops.set_precision(old)
 
 
+@pytest.fixture(params=[1, 2], ids=["single_cta", "cta_pair"])
+def linear_variant(request, built_library):
+    """Run the tf32 Linear entry points on the single-CTA kernel and on the cta_group::2 CTA-pair kernel."""
+    from graphnet_b200 import _lib
+    lib = _lib.load()
+    assert lib.gnb_linear_set_variant(request.param) == 0
+    yield request.param
+    lib.gnb_linear_set_variant(0)
+
+
 SHAPES = [  # rows, n_out, part widths
     (128, 128, [32]), (1, 1, [4]), (300, 336, [256]), (1000, 672, [32]), (515, 256, [336]),
     (777, 336, [32, 256, 256, 256, 256]), (129, 19, [20, 7]), (4099, 128, [1024]), (64, 700, [96, 40]),
@@ -30,7 +40,7 @@ SHAPES = [  # rows, n_out, part widths
 
 
 @pytest.mark.parametrize("rows,n_out,widths", SHAPES)
-def test_tc_linear_bit_exact_on_integers(built_library, tf32_mode, rows, n_out, widths):
+def test_tc_linear_bit_exact_on_integers(built_library, tf32_mode, linear_variant, rows, n_out, widths):
     ops = tf32_mode
     g = torch.Generator().manual_seed(rows + n_out)
     parts = [torch.randint(-2, 3, (rows, w), generator=g).float() for w in widths]
@@ -240,7 +250,7 @@ def test_dynedge_tf32_fused_inference_vs_oracle(built_library, tf32_mode):
 
 
 @pytest.mark.parametrize("hdim,c_out", [(336, 256), (128, 256), (64, 40), (512, 96)])
-def test_edge_hidden_dgrad_scatter_bit_exact_on_integers(built_library, tf32_mode, hdim, c_out):
+def test_edge_hidden_dgrad_scatter_bit_exact_on_integers(built_library, tf32_mode, linear_variant, hdim, c_out):
     """Hidden layer forward with activation bit mask, then dgrad GEMM + ReLU mask + scatter epilogue: dP = sum over
     slots, dQ scattered to the neighbours. Integer operands make every product and (order-independent) sum exact, so
     the result must equal the fp64 reference."""
@@ -295,3 +305,47 @@ def test_edge_hidden_dgrad_scatter_bit_exact_on_integers(built_library, tf32_mod
               hdim, ops._ptr(graph.nbr), n, ops._ptr(dpq), 2 * hdim, ops._stream())
     torch.cuda.synchronize()
     assert torch.equal(dpq.cpu().double(), dpq_ref)
+
+
+@pytest.mark.parametrize("k,n_out", [(336, 256), (128, 256), (40, 100), (352, 336)])
+def test_edge_linear_agg_bit_exact_on_integers(built_library, tf32_mode, linear_variant, k, n_out):
+    """Second EdgeConv Linear + ReLU + k-sum + mask bits in the GEMM epilogue, and the mask-bit backward kernel."""
+    ops = tf32_mode
+    from helpers import tie_heavy_events
+    sizes = [1, 2, 5, 9, 10, 64, 130, 12, 300, 3]
+    x, batch, _ = tie_heavy_events(sizes, 5, seed=k)
+    x[-15:-3] = x[-15]
+    ptr = batch_to_ptr(batch)
+    graph = ops.knn_table(x.cuda(), [0, 1, 2], ptr.cuda(), 8)
+    n = x.shape[0]
+    deg = graph.deg.cpu()
+    g = torch.Generator().manual_seed(n_out)
+    h = torch.randint(-1, 3, (n * 9, k), generator=g).float()
+    w = torch.randint(-1, 2, (n_out, k), generator=g).float()
+    b = torch.randint(-3, 4, (n_out,), generator=g).float()
+    pre = h.double() @ w.double().t() + b.double()
+    valid = (torch.arange(9).unsqueeze(0) < deg.unsqueeze(1)).reshape(-1)            # [n*9]
+    on = (pre > 0) & valid.unsqueeze(1)
+    y_ref = (pre * on).reshape(n, 9, n_out).sum(1)
+    kpad = (k + 31) // 32 * 32
+    wp = torch.zeros(n_out, kpad)
+    wp[:, :k] = w
+    hc, wpc, bc = h.cuda(), wp.cuda(), b.cuda()
+    y = torch.empty(n, n_out, device="cuda")
+    ntile = (n + 13) // 14
+    mask = torch.zeros(ntile * n_out * 4, dtype=torch.int32, device="cuda")
+    ops._call("gnb_edge_linear_agg_fwd_tf32", ops._ptr(hc), k, k, ops._ptr(wpc), kpad, ops._ptr(bc), ops._ptr(graph.deg), n,
+              n_out, 1, ops._ptr(y), n_out, ops._ptr(mask), ops._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(y.cpu().double(), y_ref)
+    # backward from the mask bits: dz[(i,s)] = g[i] * bit
+    gy = torch.randint(-2, 3, (n, n_out), generator=g).float()
+    dz = torch.full((n * 9, n_out), 7.0, device="cuda")
+    db = torch.zeros(n_out, device="cuda")
+    gyc = gy.cuda()
+    ops._call("gnb_edge_mask_bwd_colsum", ops._ptr(gyc), n_out, ops._ptr(mask), n, n_out, ops._ptr(graph.deg), ops._ptr(dz),
+              n_out, ops._ptr(db), 0x100, ops._stream())
+    torch.cuda.synchronize()
+    dz_ref = gy.double().repeat_interleave(9, dim=0) * on
+    assert torch.equal(dz.cpu().double(), dz_ref)
+    assert torch.equal(db.cpu().double(), dz_ref.sum(0))
