@@ -260,11 +260,12 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
                     const int64_t node0 = (int64_t)t * AGG_NPT;
                     const uint8_t* mb = meta + buf * SC_META_BYTES;
                     const int* s_off = reinterpret_cast<const int*>(mb + 8192);
-                    const unsigned* s_msk = reinterpret_cast<const unsigned*>(mb) + ((ch0 + m * TC_BM + q * 32) >> 5);
+                    // mask layout of gnb_edge_hidden_fwd_mask: channel c is bit (c % 128) / 4 of word 4 (c / 128) + c % 4
+                    const unsigned* s_msk = reinterpret_cast<const unsigned*>(mb) + 4 * ((ch0 + m * TC_BM) >> 7) + (lane & 3);
                     float* dq = sc.dpq + sc.hdim + (ch_ok ? ch : ch % sc.hdim);
                     float* dp = sc.dpq + node0 * sc.ldpq + ch;
                     const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * (TC_MT * TC_BN) + m * TC_BN);
-                    const unsigned lanebit = ch_ok ? (1u << lane) : 0u;
+                    const unsigned lanebit = ch_ok ? (1u << (q * 8 + (lane >> 2))) : 0u;
                     const int own_off = (int)node0 * (int)sc.ldpq;
                     const bool no_at = (agg.dbg & 16) != 0;
 #pragma unroll 1
@@ -550,10 +551,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                 if (node0 < sc.n_nodes && ch0 + q * 32 < n_out) {
                     const uint8_t* mb = meta + (buf * 2 + half) * SC_META_BYTES;
                     const int* s_off = reinterpret_cast<const int*>(mb + 8192);
-                    const unsigned* s_msk = reinterpret_cast<const unsigned*>(mb) + ((ch0 + q * 32) >> 5);
+                    const unsigned* s_msk = reinterpret_cast<const unsigned*>(mb) + 4 * (ch0 >> 7) + (lane & 3);
                     float* dq = sc.dpq + sc.hdim + (ch_ok ? ch : ch % sc.hdim);
                     float* dp = sc.dpq + node0 * sc.ldpq + ch;
-                    const unsigned lanebit = ch_ok ? (1u << lane) : 0u;
+                    const unsigned lanebit = ch_ok ? (1u << (q * 8 + (lane >> 2))) : 0u;
                     const int own_off = (int)node0 * (int)sc.ldpq;
                     const bool no_at = (agg.dbg & 16) != 0;
 #pragma unroll 1

@@ -110,8 +110,8 @@ __global__ void edge_hidden_fwd_kernel(const float* __restrict__ pq, int64_t ldp
     const int s = (int)(r - i * width);
     float4* out = reinterpret_cast<float4*>(h + r * ldh);
     const int h4 = hdim >> 2;
-    // optional bit mask of the activation (bit c of row r = h[r, c] > 0), mask_ld words per row: lanes 8g..8g+7 of
-    // iteration `it` own the 8 float4 chunks = 32 channels of word 4*it + g
+    // optional bit mask of the activation, mask_ld words per row: channel c = 128 it + 4 L + k (float4 chunk L of
+    // iteration it, component k) is bit L of word 4 it + k -- one __ballot_sync per component, no shuffles
     unsigned* mrow = hmask != nullptr ? hmask + r * mask_ld : nullptr;
     if (s >= deg[i]) {
         for (int c = lane; c < h4; c += 32) out[c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -148,7 +148,7 @@ __global__ void edge_hidden_fwd_kernel(const float* __restrict__ pq, int64_t ldp
     for (int it = 0; it < 4; ++it) {
         if (it * 4 < mask_ld) {                               // warp-uniform
             const int c = it * 32 + lane;
-            unsigned nib = 0u;
+            bool px = false, py = false, pz = false, pw = false;
             if (c < h4) {
                 float4 v = make_float4(va[it].x + vb[it].x, va[it].y + vb[it].y, va[it].z + vb[it].z, va[it].w + vb[it].w);
                 if (relu) {
@@ -158,13 +158,11 @@ __global__ void edge_hidden_fwd_kernel(const float* __restrict__ pq, int64_t ldp
                     v.x = gnb_round_tf32(v.x); v.y = gnb_round_tf32(v.y); v.z = gnb_round_tf32(v.z); v.w = gnb_round_tf32(v.w);
                 }
                 out[c] = v;
-                nib = (v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u);
+                px = v.x > 0.f; py = v.y > 0.f; pz = v.z > 0.f; pw = v.w > 0.f;
             }
-            unsigned wv = nib << (4 * (lane & 7));
-            wv |= __shfl_xor_sync(0xffffffffu, wv, 1);
-            wv |= __shfl_xor_sync(0xffffffffu, wv, 2);
-            wv |= __shfl_xor_sync(0xffffffffu, wv, 4);
-            if ((lane & 7) == 0) mrow[it * 4 + (lane >> 3)] = wv;
+            const unsigned bx = __ballot_sync(0xffffffffu, px), by = __ballot_sync(0xffffffffu, py);
+            const unsigned bz = __ballot_sync(0xffffffffu, pz), bw = __ballot_sync(0xffffffffu, pw);
+            if (lane == 0) *reinterpret_cast<uint4*>(mrow + it * 4) = make_uint4(bx, by, bz, bw);
         }
     }
 }
@@ -580,7 +578,7 @@ GNB_EXPORT int gnb_edge_hidden_fwd_mask(const float* pq, int64_t ldpq, int32_t h
                                         const int32_t* deg, int32_t width, int64_t n, int32_t act, float* h, int64_t ldh,
                                         uint32_t* hmask, int32_t mask_ld, void* stream) {
     if ((hdim & 3) || (ldpq & 3) || (ldh & 3) || !aligned16(pq) || !aligned16(h)) return GNB_ERR_ARG;
-    if (hmask == nullptr || (int64_t)mask_ld * 32 < hdim || (mask_ld & 3) || mask_ld > 16) return GNB_ERR_ARG;
+    if (hmask == nullptr || (int64_t)mask_ld * 32 < hdim || (mask_ld & 3) || mask_ld > 16 || !aligned16(hmask)) return GNB_ERR_ARG;
     if (n == 0) return GNB_OK;
     edge_hidden_fwd_kernel<<<gnb_div_up(n * width, 8), 256, 0, (cudaStream_t)stream>>>(pq, ldpq, hdim, nbr, deg, width,
                                                                                        n, act, h, ldh, hmask, mask_ld);

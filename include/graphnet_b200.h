@@ -158,7 +158,8 @@ int gnb_edge_mask_bwd_colsum(const float* g, int64_t ldg, const uint32_t* maskbi
 int gnb_edge_hidden_dgrad_scatter_tf32(const float* dz, int64_t lddz, int32_t c_out, const float* wt, int64_t ldw,
                                        const uint32_t* hmask, int32_t mask_ld, int32_t hdim, const int32_t* nbr, int64_t n,
                                        float* dpq, int64_t ldpq, void* stream);
-/* gnb_edge_hidden_fwd that also writes hmask[r, mask_ld]: bit c of row r = (h[r, c] > 0), zero beyond hdim. */
+/* gnb_edge_hidden_fwd that also writes the activation bits hmask[r, mask_ld] (mask_ld % 4 == 0, mask_ld * 32 >= hdim):
+ * (h[r, c] > 0) is bit (c % 128) / 4 of word 4 * (c / 128) + c % 4; bits beyond hdim are zero. */
 int gnb_edge_hidden_fwd_mask(const float* pq, int64_t ldpq, int32_t hdim, const int32_t* nbr, const int32_t* deg,
                              int32_t width, int64_t n, int32_t act, float* h, int64_t ldh, uint32_t* hmask,
                              int32_t mask_ld, void* stream);

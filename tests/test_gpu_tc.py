@@ -292,8 +292,8 @@ def test_edge_hidden_dgrad_scatter_bit_exact_on_integers(built_library, tf32_mod
     bits = hmask[: n * 9].cpu().numpy().view(np.uint32)
     expect = np.zeros((n * 9, mld), dtype=np.uint32)
     hpos = (h_ref > 0).numpy()
-    for c in range(hdim):
-        expect[:, c // 32] |= hpos[:, c].astype(np.uint32) << np.uint32(c % 32)
+    for c in range(hdim):      # layout: channel c = bit (c % 128) / 4 of word 4 (c / 128) + c % 4
+        expect[:, 4 * (c // 128) + c % 4] |= hpos[:, c].astype(np.uint32) << np.uint32((c % 128) // 4)
     assert np.array_equal(bits, expect)
     kpad = (c_out + 31) // 32 * 32
     wt = torch.zeros(hdim, kpad)
