@@ -167,6 +167,92 @@ __global__ void edge_hidden_fwd_kernel(const float* __restrict__ pq, int64_t ldp
     }
 }
 
+// Same operation, one warp per TARGET NODE: P_i, deg and the neighbour row are read once, the Q gathers of three slots
+// are in flight together, and every slot row is written with 512-byte warp stores. NIT = ceil(hdim / 128) float4
+// iterations per row. MASK adds the activation bits (layout above).
+template <int NIT, bool MASK>
+__global__ void __launch_bounds__(256)
+edge_hidden_fwd_node_kernel(const float* __restrict__ pq, int64_t ldpq, int hdim, const int* __restrict__ nbr,
+                            const int* __restrict__ deg, int width, int64_t n, int act, float* __restrict__ h, int64_t ldh,
+                            unsigned* __restrict__ hmask, int mask_ld) {
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int lane = threadIdx.x & 31;
+    const int h4 = hdim >> 2;
+    const int dg = deg[i];
+    const int nb = lane < width ? nbr[i * width + lane] : -1;
+    const bool relu = (act & 0xff) == GNB_ACT_RELU, rnd = (act & GNB_FLAG_ROUND_TF32) != 0;
+    const float4* p = reinterpret_cast<const float4*>(pq + i * ldpq);
+    float4 pa[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int c = it * 32 + lane;
+        pa[it] = c < h4 ? p[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int s0 = 0; s0 < width; s0 += 3) {
+        float4 qv[3][NIT];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int s = s0 + u;
+            const int j = __shfl_sync(0xffffffffu, nb, s < 32 ? s : 0);
+            const bool valid = s < width && s < dg && j >= 0;
+            const float4* q = reinterpret_cast<const float4*>(pq + (int64_t)(valid ? j : 0) * ldpq + hdim);
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int c = it * 32 + lane;
+                qv[u][it] = (valid && c < h4) ? q[c] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int s = s0 + u;
+            if (s < width) {                                  // warp-uniform
+                const int64_t r = i * width + s;
+                float4* out = reinterpret_cast<float4*>(h + r * ldh);
+                const bool valid = s < dg && __shfl_sync(0xffffffffu, nb, s < 32 ? s : 0) >= 0;
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    const int c = it * 32 + lane;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid) {
+                        v = make_float4(pa[it].x + qv[u][it].x, pa[it].y + qv[u][it].y, pa[it].z + qv[u][it].z,
+                                        pa[it].w + qv[u][it].w);
+                        if (relu) {
+                            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                        }
+                        if (rnd) {
+                            v.x = gnb_round_tf32(v.x); v.y = gnb_round_tf32(v.y);
+                            v.z = gnb_round_tf32(v.z); v.w = gnb_round_tf32(v.w);
+                        }
+                    }
+                    if (c < h4) out[c] = v;
+                    if (MASK) {
+                        const bool in = c < h4;
+                        const unsigned bx = __ballot_sync(0xffffffffu, in && v.x > 0.f), by = __ballot_sync(0xffffffffu, in && v.y > 0.f);
+                        const unsigned bz = __ballot_sync(0xffffffffu, in && v.z > 0.f), bw = __ballot_sync(0xffffffffu, in && v.w > 0.f);
+                        if (lane == 0 && it * 4 < mask_ld)
+                            *reinterpret_cast<uint4*>(hmask + r * mask_ld + it * 4) = make_uint4(bx, by, bz, bw);
+                    }
+                }
+                if (MASK)                                     // words beyond the last iteration (mask_ld > 4 NIT never happens
+                    for (int w = 4 * NIT + lane; w < mask_ld; w += 32) hmask[r * mask_ld + w] = 0u;   // for mask_ld = 4 ceil(hdim/128))
+            }
+        }
+    }
+}
+
+template <bool MASK>
+static void launch_hidden_node(int nit, dim3 grid, cudaStream_t st, const float* pq, int64_t ldpq, int hdim, const int* nbr,
+                               const int* deg, int width, int64_t n, int act, float* h, int64_t ldh, unsigned* hmask,
+                               int mask_ld) {
+    switch (nit) {
+        case 1: edge_hidden_fwd_node_kernel<1, MASK><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, act, h, ldh, hmask, mask_ld); break;
+        case 2: edge_hidden_fwd_node_kernel<2, MASK><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, act, h, ldh, hmask, mask_ld); break;
+        case 3: edge_hidden_fwd_node_kernel<3, MASK><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, act, h, ldh, hmask, mask_ld); break;
+        default: edge_hidden_fwd_node_kernel<4, MASK><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, act, h, ldh, hmask, mask_ld); break;
+    }
+}
+
 // backward of the above: da1 = gh * act'(h); dPQ[i, 0:H] = sum_s da1[(i,s)] (own rows, no atomics);
 // dPQ[j, H:2H] += da1[(i,s)] (scatter to the source node: vector atomics, 32 consecutive channels
 // per warp instruction). dPQ's Q half must be zero on entry. One warp per target node.
@@ -567,6 +653,11 @@ GNB_EXPORT int gnb_edge_hidden_fwd(const float* pq, int64_t ldpq, int32_t hdim, 
                                    void* stream) {
     if ((hdim & 3) || (ldpq & 3) || (ldh & 3) || !aligned16(pq) || !aligned16(h)) return GNB_ERR_ARG;
     if (n == 0) return GNB_OK;
+    if (hdim <= 512 && width <= 32) {
+        launch_hidden_node<false>((hdim + 127) / 128, dim3((unsigned)gnb_div_up(n, 8)), (cudaStream_t)stream, pq, ldpq, hdim, nbr,
+                                  deg, width, n, act, h, ldh, nullptr, 0);
+        GNB_RETURN_LAUNCH();
+    }
     edge_hidden_fwd_kernel<<<gnb_div_up(n * width, 8), 256, 0, (cudaStream_t)stream>>>(pq, ldpq, hdim, nbr, deg, width,
                                                                                        n, act, h, ldh, nullptr, 0);
     GNB_RETURN_LAUNCH();
@@ -580,6 +671,11 @@ GNB_EXPORT int gnb_edge_hidden_fwd_mask(const float* pq, int64_t ldpq, int32_t h
     if ((hdim & 3) || (ldpq & 3) || (ldh & 3) || !aligned16(pq) || !aligned16(h)) return GNB_ERR_ARG;
     if (hmask == nullptr || (int64_t)mask_ld * 32 < hdim || (mask_ld & 3) || mask_ld > 16 || !aligned16(hmask)) return GNB_ERR_ARG;
     if (n == 0) return GNB_OK;
+    if (hdim <= 512 && width <= 32 && mask_ld == 4 * ((hdim + 127) / 128)) {
+        launch_hidden_node<true>((hdim + 127) / 128, dim3((unsigned)gnb_div_up(n, 8)), (cudaStream_t)stream, pq, ldpq, hdim, nbr,
+                                 deg, width, n, act, h, ldh, hmask, mask_ld);
+        GNB_RETURN_LAUNCH();
+    }
     edge_hidden_fwd_kernel<<<gnb_div_up(n * width, 8), 256, 0, (cudaStream_t)stream>>>(pq, ldpq, hdim, nbr, deg, width,
                                                                                        n, act, h, ldh, hmask, mask_ld);
     GNB_RETURN_LAUNCH();
