@@ -280,12 +280,112 @@ def sum_over_ranks(value: float, dev) -> float:
 # --------------------------------------------------------------------------------------------- #
 # roofline of the dominant kernel, timed live with CUDA events on the launching stream
 # --------------------------------------------------------------------------------------------- #
+def dominant_launches(trainer, db):
+    """The two heaviest launches of the training step (profiles/r01 launch lists), set up on real graph metadata of
+    one batch with random operand values, each as a zero-argument callable through the C-ABI:
+
+      dgrad_scatter: gemm_tc_pair_kernel, backward of an EdgeConv layer: dh = dz W2 (rows = N*9 padded edge slots,
+                     K = 256, 336 output channels) with the ReLU-mask + dP/dQ scatter epilogue (dh never stored)
+      agg_fwd:       gemm_tc_pair_kernel, forward m = relu(h W2^T + b2) (K = 336, 256 channels) with the k-sum
+                     + mask-bit epilogue (m never stored)
+    """
+    import ctypes
+    from graphnet_b200 import ops
+    dev = db["x"].device
+    data = trainer.edges(trainer.make_data(db))
+    graph = data.knn_graph()
+    n, width = graph.n, graph.width
+    assert width == 9
+    rows = n * width
+    lin = trainer.backbone._conv_layers[1].nn[2]          # Linear(336, 256)
+    hid, cout = lin.in_features, lin.out_features
+    ntile = (n + 13) // 14
+    w2 = lin.weight.detach()
+    # forward operands
+    h = ops._round_pad(torch.rand(rows, hid, device=dev))
+    w2p = ops._tc_pack_weight(w2, (0,), (hid,))
+    b2 = lin.bias.detach()
+    y = torch.empty(n, cout, device=dev)
+    maskbits = torch.empty(ntile * cout * 4, dtype=torch.int32, device=dev)
+    # backward operands
+    dz = ops._round_pad(torch.randn(rows, cout, device=dev))
+    wt = ops._tc_pack_weight(w2.t().contiguous(), (0,), (cout,))
+    mld = 4 * ((hid + 127) // 128)
+    hmask = torch.randint(-2 ** 31, 2 ** 31 - 1, (ntile * 126, mld), dtype=torch.int32, device=dev)
+    dpq = torch.zeros(n, 2 * hid, device=dev)
+
+    def agg_fwd():
+        ops._call("gnb_edge_linear_agg_fwd_tf32", ops._ptr(h), hid, hid, ops._ptr(w2p), w2p.shape[1], ops._ptr(b2),
+                  ops._ptr(graph.deg), n, cout, 1, ops._ptr(y), cout, ops._ptr(maskbits), ops._stream())
+
+    def dgrad_scatter():
+        ops._call("gnb_edge_hidden_dgrad_scatter_tf32", ops._ptr(dz), cout, cout, ops._ptr(wt), wt.shape[1], ops._ptr(hmask),
+                  mld, hid, ops._ptr(graph.nbr), n, ops._ptr(dpq), 2 * hid, ops._stream())
+
+    keep = (h, w2p, b2, y, maskbits, dz, wt, hmask, dpq, graph)
+    e_real = int(graph.deg.sum().item())
+    return {"agg_fwd": agg_fwd, "dgrad_scatter": dgrad_scatter, "rows": rows, "n": n, "edges": e_real, "hid": hid,
+            "cout": cout, "mld": mld, "keep": keep}
+
+
+def _time_launch(fn, reps=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    beg.record()
+    for _ in range(reps):
+        fn()
+    end.record()
+    torch.cuda.synchronize()
+    return beg.elapsed_time(end) / 1e3 / reps
+
+
 def roofline_top_kernel(trainer, db, pk):
-    """Dominant kernel of the training step (largest share of device time in profiles/r01): the tcgen05 Linear
-    `gemm_tc_linear_kernel` on the per-edge GEMM  m = relu(h W2^T + b2)  of a DynEdgeConv layer, rows = N*(k+1)
-    padded edge slots. Algorithmic FLOPs per launch = 2 * E * 336 * 256 with E = actual edge count (SURVEY 8d:
-    deg * 2 * in * out per node). Timed alone with CUDA events on the launching stream, operands pre-rounded so
-    only the kernel runs."""
+    """Dominant kernel of the training step (largest share of device time in profiles/r01): `gemm_tc_pair_kernel`, the
+    cta_group::2 tcgen05 (kind::tf32) GEMM over the padded edge list of a DynEdgeConv layer. Its heaviest launch is
+    the backward data-gradient GEMM with the scattering epilogue; the forward launch with the aggregating epilogue is
+    reported beside it. Algorithmic FLOPs per launch = 2 * E * 336 * 256 with E = actual edge count (SURVEY 8d:
+    deg * 2 * in * out per node). Timed alone with CUDA events on the launching stream (operands pre-rounded, so only
+    the kernel runs); operands (> 0.7 GB per launch) exceed the 126 MB L2."""
+    from graphnet_b200 import ops
+    if ops.PRECISION != "tf32":
+        return roofline_fp32_kernel(trainer, db, pk)
+    d = dominant_launches(trainer, db)
+    rows, n, e_real, hid, cout = d["rows"], d["n"], d["edges"], d["hid"], d["cout"]
+    flops = 2.0 * e_real * hid * cout
+    peak = pk["bf16_tflops"]            # kernel timed alone -> burst figure
+    sec_b = _time_launch(d["dgrad_scatter"])
+    sec_f = _time_launch(d["agg_fwd"])
+    tpath = os.path.join(ROOT, "profiles", "r01", "roofline_traffic.json")
+    traffic = None
+    if os.path.exists(tpath):
+        t = json.load(open(tpath))
+        traffic = {"dram_bytes_per_launch": t.get("dram_bytes_per_launch"), "rows": t.get("rows"), "source": t.get("source")}
+    # HBM view. backward: reads dz [rows, 256] + mask rows, reduces into dPQ [n, 672] (one fp32 per (edge slot, channel)
+    # through L2 atomics, counted once as written bytes); forward: reads h [rows, 336], writes y [n, 256] + mask bits
+    bytes_b = 4.0 * rows * cout + 4.0 * rows * d["mld"] + 4.0 * n * 2 * hid
+    bytes_f = 4.0 * rows * hid + 4.0 * n * cout + 16.0 * ((n + 13) // 14) * cout
+    fwd = {"kernel": "gemm_tc_pair_kernel, aggregating epilogue: m = relu(h W2^T + b2) summed over the k slots, 336 -> 256",
+           "launch_ms": round(sec_f * 1e3, 4), "achieved": round(flops / sec_f / 1e12, 3), "unit": "TFLOP/s",
+           "frac": round(flops / sec_f / 1e12 / peak, 5),
+           "hbm_view": {"algorithmic_bytes": bytes_f, "achieved_gbs": round(bytes_f / sec_f / 1e9, 1),
+                        "frac": round(bytes_f / sec_f / 1e9 / pk["hbm_gbs"], 4)}}
+    achieved = flops / sec_b / 1e12
+    return {"bound": "tensor",
+            "kernel": "gemm_tc_pair_kernel (tcgen05 cta_group::2 kind::tf32 M256xN256xK8, TMA, TMEM double-buffered), scattering "
+                      "epilogue: dh = dz W2 (256 -> 336), ReLU mask, dP/dQ reduction over the padded edge list",
+            "achieved": round(achieved, 3), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 5),
+            "traffic": traffic, "peak_source": pk["source"] + " bf16 dense burst (tf32 tensor peak is half of it)",
+            "launch_ms": round(sec_b * 1e3, 4), "rows": rows, "edges": e_real,
+            "hbm_view": {"algorithmic_bytes": bytes_b, "achieved_gbs": round(bytes_b / sec_b / 1e9, 1),
+                         "peak_gbs": pk["hbm_gbs"], "frac": round(bytes_b / sec_b / 1e9 / pk["hbm_gbs"], 4),
+                         "note": "plus one fp32 L2 reduction per (edge slot, channel): 4 * rows * 336 bytes of atomic traffic"},
+            "forward_launch": fwd}
+
+
+def roofline_fp32_kernel(trainer, db, pk):
+    """fp32 precision mode: the SIMT GEMM on the per-edge Linear 336 -> 256."""
     from graphnet_b200 import ops
     data = trainer.edges(trainer.make_data(db))
     graph = data.knn_graph()
@@ -294,41 +394,17 @@ def roofline_top_kernel(trainer, db, pk):
     lin = trainer.backbone._conv_layers[1].nn[2]
     h = torch.rand(rows, lin.in_features, device=db["x"].device)
     w, b = lin.weight.detach(), lin.bias.detach()
-    if ops.PRECISION == "tf32":
-        h = ops._round_pad(h)
-        packed = ops._tc_pack_weight(w, (0,), (lin.in_features,))
-        run = lambda: ops._tc_linear((h,), packed, b, lin.out_features, ops.ACT_RELU, round_out=False)
-        kname = "gemm_tc_linear_kernel (tcgen05 kind::tf32, TMA, TMEM double-buffered)"
-    else:
-        run = lambda: ops.linear_act(h, w, b, ops.ACT_RELU)
-        kname = "gemm_f32_kernel<0,0,1> (fp32 SIMT)"
-    for _ in range(3):
-        run()
-    torch.cuda.synchronize()
-    reps = 10
-    beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    beg.record()
-    for _ in range(reps):
-        run()
-    end.record()
-    torch.cuda.synchronize()
-    sec = beg.elapsed_time(end) / 1e3 / reps
+    sec = _time_launch(lambda: ops.linear_act(h, w, b, ops.ACT_RELU))
     flops = 2.0 * e_real * lin.in_features * lin.out_features
     achieved = flops / sec / 1e12
-    peak = pk["bf16_tflops"]            # kernel timed alone -> burst figure
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01", "roofline_traffic.json")
-    if os.path.exists(tpath):
-        t = json.load(open(tpath))
-        traffic = {"dram_bytes_per_launch": t.get("dram_bytes_per_launch"), "rows": t.get("rows"), "source": t.get("source")}
+    peak = pk["bf16_tflops"]
     hbm_bytes = 4.0 * rows * (lin.in_features + lin.out_features)
-    return {"bound": "tensor", "kernel": kname + ": edge MLP Linear 336->256 + ReLU over the padded edge list",
+    return {"bound": "tensor", "kernel": "gemm_f32_kernel<0,0,1> (fp32 SIMT): edge MLP Linear 336->256 + ReLU over the padded edge list",
             "achieved": round(achieved, 3), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 5),
-            "traffic": traffic, "peak_source": pk["source"] + " bf16 dense burst (tf32 tensor peak is half of it)",
-            "launch_ms": round(sec * 1e3, 4), "rows": rows, "edges": e_real,
+            "traffic": None, "peak_source": pk["source"] + " bf16 dense burst", "launch_ms": round(sec * 1e3, 4),
+            "rows": rows, "edges": e_real,
             "hbm_view": {"algorithmic_bytes": hbm_bytes, "achieved_gbs": round(hbm_bytes / sec / 1e9, 1),
-                         "peak_gbs": pk["hbm_gbs"], "frac": round(hbm_bytes / sec / 1e9 / pk["hbm_gbs"], 4),
-                         "note": "unfused per-edge GEMM reads h and writes m once: 73 FLOP/B, i.e. HBM-bound on B200"}}
+                         "peak_gbs": pk["hbm_gbs"], "frac": round(hbm_bytes / sec / 1e9 / pk["hbm_gbs"], 4)}}
 
 
 # --------------------------------------------------------------------------------------------- #

@@ -1,4 +1,5 @@
-"""Runs only the dominant kernel (tcgen05 Linear on the [E_rows, 336] x [336, 256] edge GEMM) for ncu --set full."""
+"""Runs only the two dominant launches of the training step (gemm_tc_pair_kernel: scattering data-gradient GEMM and
+aggregating forward GEMM of an EdgeConv layer) for `ncu --set full`:  python scripts/profile_top_kernel.py"""
 import sys, torch
 sys.path.insert(0, '.')
 import bench
@@ -7,13 +8,9 @@ ops.set_precision('tf32')
 dev = torch.device('cuda', 0)
 tr = bench.Trainer(dev, 1)
 db = bench.to_device(bench.host_batches(512, 1, 20240607)[0], dev)
-data = tr.edges(tr.make_data(db))
-graph = data.knn_graph()
-rows = graph.n * graph.width
-lin = tr.backbone._conv_layers[1].nn[2]
-h = ops._round_pad(torch.rand(rows, lin.in_features, device=dev))
-packed = ops._tc_pack_weight(lin.weight.detach(), (0,), (lin.in_features,))
-for _ in range(4):
-    ops._tc_linear((h,), packed, lin.bias.detach(), lin.out_features, ops.ACT_RELU, round_out=False)
+d = bench.dominant_launches(tr, db)
+for _ in range(3):
+    d["dgrad_scatter"]()
+    d["agg_fwd"]()
 torch.cuda.synchronize()
-print("rows", rows)
+print("rows", d["rows"], "n", d["n"], "edges", d["edges"])
