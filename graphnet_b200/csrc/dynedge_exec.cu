@@ -181,7 +181,7 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
     if (c.globals_after_pooling && c.n_pool == 0) return GNB_ERR_ARG;
     Arena a(ws, cap);
     p.n = n; p.nseg = nseg; p.w0 = w0; p.width = c.k + 1;
-    p.agg = training && c.precision == 1 && c.k == 8 && w0 == 9 && !(c.flags & 1);
+    p.agg = c.precision == 1 && c.k == 8 && w0 == 9 && !(c.flags & 1) && (training || (c.flags & 2));
     const int f = c.nb_inputs, ng = f + 5;
     const bool distribute = !c.globals_after_pooling;
     p.node_width = f + (distribute ? ng : 0);
@@ -214,10 +214,10 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
         b.pq = training ? a.get<float>(n * 2 * b.hid) : pq_shared;
         b.h = training ? a.get<float>(n * wl * b.hid) : h_shared;
         b.m = training ? (p.agg ? nullptr : a.get<float>(n * wl * b.cout)) : m_shared;
-        b.mask = p.agg ? a.get<uint32_t>((n + 13) / 14 * (int64_t)b.cout * 4) : nullptr;
+        b.mask = (p.agg && training) ? a.get<uint32_t>((n + 13) / 14 * (int64_t)b.cout * 4) : nullptr;
         // activation bits of h for the scattering data-gradient epilogue (whole 14-node tiles, mld words per slot row)
         b.mld = 4 * ((b.hid + 127) / 128);
-        const bool scat = p.agg && b.hid <= 512 && n * 2 * b.hid < ((int64_t)1 << 31);
+        const bool scat = p.agg && training && b.hid <= 512 && n * 2 * b.hid < ((int64_t)1 << 31);
         b.hmask = scat ? a.get<uint32_t>((n + 13) / 14 * 126 * (int64_t)b.mld) : nullptr;
         b.y = a.get<float>(n * b.cout);
         b.nbr = (l + 1 < c.n_conv) ? a.get<int32_t>(n * p.width) : nullptr;
@@ -413,12 +413,12 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
             const float* xs[1] = {xin}; const int64_t lds[1] = {b.cin_ld}; const int32_t ks[1] = {b.cin_ld}; const int offs[1] = {0};
             EX(e.lin_fwd(1, xs, lds, ks, offs, b.wcat, b.kld, b.bcat, b.pq, n, 2 * b.hid, GNB_ACT_NONE, 0));   // P+Q is added in fp32
         }
-        if (!training && e.tf32 && fused_edge && b.hid <= 352 && wl <= 32) {
+        if (!training && e.tf32 && fused_edge && !p.agg && b.hid <= 352 && wl <= 32) {
             // inference: gather + hidden ReLU + E x H x C contraction + bias/ReLU + aggregation in one tcgen05 kernel
             EX(gnb_edgeconv_fused_fwd_tf32(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, b.w2p, b.hld, b2, b.cout, GNB_AGGR_ADD, 1,
                                            b.y, b.cout, stream));
         } else if (p.agg) {
-            // training: h is kept for the backward pass; the second Linear, ReLU and the k-sum run in one tcgen05 kernel
+            // training (and inference with flags bit 1): the second Linear, ReLU and the k-sum run in one tcgen05 kernel; h is kept for the backward pass;
             // whose epilogue writes y and one ReLU bit per (slot, channel) -- the [E, C] message tensor is never stored
             if (b.hmask != nullptr)
                 EX(gnb_edge_hidden_fwd_mask(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, GNB_ACT_RELU | e.rnd, b.h, b.hid, b.hmask,

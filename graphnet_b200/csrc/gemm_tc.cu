@@ -381,6 +381,9 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
 // Barriers: full[s] lives in the leader (both CTAs' TMA loads credit it), empty[s] / tmem_full[b] are multicast by the
 // leader's tcgen05.commit to both CTAs, tmem_empty[b] of the leader collects the 16 epilogue warps of the pair.
 constexpr int PL_STAGES = 6, PL_STAGES_SCAT = 5, PL_THREADS = 320;
+// Clusters are split UNEVENLY over the 256-channel groups (336 channels = 256 + 80: the second group has a third of the
+// epilogue work): clusters [start[g], start[g+1]) walk the row tiles of channel group g.
+struct GroupSplit { int ngroups; int start[5]; };
 constexpr uint32_t PL_STAGE_BYTES = 2 * TC_TILE_BYTES;                         // A (128 ch) + B half (128 rows)
 constexpr uint32_t PL_SMEM_BYTES = PL_STAGES * PL_STAGE_BYTES + 1024 + 256;
 constexpr uint32_t PL_SMEM_BYTES_SCAT = PL_STAGES_SCAT * PL_STAGE_BYTES + 1024 + 256 + 4 * SC_META_BYTES;
@@ -388,7 +391,8 @@ constexpr uint32_t PL_SMEM_BYTES_SCAT = PL_STAGES_SCAT * PL_STAGE_BYTES + 1024 +
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PL_THREADS, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ TmapArray tm_x,
                     const PartInfo parts, const float* __restrict__ bias, float* __restrict__ y, int64_t ldy,
-                    int64_t rows, int n_out, int act, int round_out, int num_tiles, const AggInfo agg, const ScatInfo sc) {
+                    int64_t rows, int n_out, int act, int round_out, int num_tiles, const AggInfo agg, const ScatInfo sc,
+                    const GroupSplit gs) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int nstages = sc.enabled ? PL_STAGES_SCAT : PL_STAGES;
@@ -403,8 +407,11 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = tc::cluster_ctarank();
-    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-    const int ch0 = blockIdx.y * 256 + (int)rank * 128;        // first channel of this CTA
+    int group = 0;
+    for (int g = 1; g < gs.ngroups; ++g) group = ((int)(blockIdx.x >> 1) >= gs.start[g]) ? g : group;
+    const int cluster_id = (int)(blockIdx.x >> 1) - gs.start[group];
+    const int num_clusters = gs.start[group + 1] - gs.start[group];
+    const int ch0 = group * 256 + (int)rank * 128;             // first channel of this CTA
     const bool sub = agg.enabled || sc.enabled;                // 2 x 126-row sub-tiles instead of 256 rows
     const int half_rows = sub ? AGG_ROWS : 128;
 
@@ -433,7 +440,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
 
     int total_kb = 0;
     for (int p = 0; p < parts.nparts; ++p) total_kb += parts.kblocks[p];
-    const bool prof_on = agg.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+    const bool prof_on = agg.prof != nullptr && blockIdx.x == 0;
     long long pw0 = 0, pw1 = 0;
     const long long pt0 = clock64();
 
@@ -685,16 +692,31 @@ int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi
     }
     // measured (scripts/linear_probe.py): the pair kernel wins from two ch-tiles up; a single 128-channel tile is
     // faster on the single-CTA kernel (half of the pair's M = 256 would be padding)
-    const bool pair = g_linear_variant == 2 || (g_linear_variant == 0 && row_tiles >= 2 * 148 && n_out > 128);
+    const bool pair = (g_linear_variant == 2 || (g_linear_variant == 0 && row_tiles >= 2 * 148 && n_out > 128)) && n_out <= 1024;
     if (pair) {
         const int tiles = (row_tiles + 1) / 2;
         const int groups = gnb_div_up(n_out, 256);
-        int clusters = (g_num_sms / 2) / groups;
-        if (clusters < 1) clusters = 1;
-        if (clusters > tiles) clusters = tiles;
-        dim3 grid((unsigned)(2 * clusters), (unsigned)groups);
+        if (groups > 4) return GNB_ERR_UNSUPPORTED;
+        GroupSplit gs;
+        gs.ngroups = groups;
+        int total = g_num_sms / 2, wsum = 0, w[4];
+        if (total < groups) total = groups;
+        // equal weights: every group streams ALL activation rows, so a group with few valid channels (336 = 256 + 80)
+        // still needs its share of the TMA bandwidth (a 49 / 25 split measured 20 % slower than 37 / 37)
+        for (int g = 0; g < groups; ++g) { w[g] = 1; wsum += w[g]; }
+        int used = 0;
+        gs.start[0] = 0;
+        for (int g = 0; g < groups; ++g) {
+            int c = g + 1 < groups ? (total * w[g] + wsum / 2) / wsum : total - used;
+            if (c < 1) c = 1;
+            if (c > tiles) c = tiles;
+            used += c;
+            gs.start[g + 1] = used;
+        }
+        for (int g = groups + 1; g < 5; ++g) gs.start[g] = used;
+        dim3 grid((unsigned)(2 * used));
         gemm_tc_pair_kernel<<<grid, PL_THREADS, sc.enabled ? PL_SMEM_BYTES_SCAT : PL_SMEM_BYTES, stream>>>(
-            tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out, tiles, agg, sc);
+            tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out, tiles, agg, sc, gs);
         GNB_RETURN_LAUNCH();
     }
     const int groups = gnb_div_up(n_out, TC_MT * TC_BM);

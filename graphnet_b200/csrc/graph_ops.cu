@@ -431,30 +431,37 @@ segment_pool_fwd_kernel(const float* __restrict__ x, int64_t ldx, int c_tot, con
     }
 }
 
-// backward: one thread per (node, channel)
-__global__ void segment_pool_bwd_kernel(const float* __restrict__ gout, int64_t ldg, const int* __restrict__ arg, int c_tot,
-                                        const int64_t* __restrict__ ptr, int nseg, int64_t n, int np, int s0,
-                                        int s1, int s2, int s3, float* __restrict__ gx, int64_t ldx) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * c_tot) return;
-    const int64_t i = t / c_tot;
-    const int c = (int)(t - i * c_tot);
+// backward: one warp per node (the event is found once per warp: binary search over ptr, all lanes on the same
+// cached addresses), lanes stride over the channels; the pooled gradients / arg tables (B x P x C) stay L2-resident
+__global__ void __launch_bounds__(256)
+segment_pool_bwd_kernel(const float* __restrict__ gout, int64_t ldg, const int* __restrict__ arg, int c_tot,
+                        const int64_t* __restrict__ ptr, int nseg, int64_t n, int np, int s0,
+                        int s1, int s2, int s3, float* __restrict__ gx, int64_t ldx) {
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int lane = threadIdx.x & 31;
     int lo = 0, hi = nseg;
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ptr[mid] <= i) lo = mid; else hi = mid; }
     const int b = lo;
     const float cnt = (float)(ptr[b + 1] - ptr[b]);
-    const int schemes[4] = {s0, s1, s2, s3};
-    float acc = 0.f;
-    for (int p = 0; p < np; ++p) {
-        const int64_t o = (int64_t)b * np * c_tot + (int64_t)p * c_tot + c;
-        const float g = gout[(int64_t)b * ldg + (int64_t)p * c_tot + c];
-        switch (schemes[p]) {
-            case GNB_POOL_SUM: acc += g; break;
-            case GNB_POOL_MEAN: acc += g / cnt; break;
-            default: acc += (arg[o] == (int)i) ? g : 0.f; break;
-        }
+    const float* gb = gout + (int64_t)b * ldg;
+    const int* ab = arg != nullptr ? arg + (int64_t)b * np * c_tot : nullptr;
+    const int ii = (int)i;
+    auto term = [&](int scheme, int p, int c) -> float {
+        if (p >= np) return 0.f;
+        const float g = gb[(int64_t)p * c_tot + c];
+        if (scheme == GNB_POOL_SUM) return g;
+        if (scheme == GNB_POOL_MEAN) return g / cnt;
+        return ab[(int64_t)p * c_tot + c] == ii ? g : 0.f;
+    };
+    for (int c = lane; c < c_tot; c += 32) {
+        // same summation order as the schemes are listed
+        float acc = term(s0, 0, c);
+        acc += term(s1, 1, c);
+        acc += term(s2, 2, c);
+        acc += term(s3, 3, c);
+        gx[i * ldx + c] = acc;
     }
-    gx[i * ldx + c] = acc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -745,7 +752,7 @@ GNB_EXPORT int gnb_segment_pool_bwd(const float* gout, int64_t ldg, const int32_
     if (n == 0) return GNB_OK;
     int s[4] = {0, 0, 0, 0};
     for (int p = 0; p < np; ++p) s[p] = schemes[p];
-    segment_pool_bwd_kernel<<<gnb_div_up(n * c, 256), 256, 0, (cudaStream_t)stream>>>(gout, ldg, arg, c, ptr, (int)nseg, n, np,
+    segment_pool_bwd_kernel<<<gnb_div_up(n, 8), 256, 0, (cudaStream_t)stream>>>(gout, ldg, arg, c, ptr, (int)nseg, n, np,
                                                                                       s[0], s[1], s[2], s[3], gx, ldx);
     GNB_RETURN_LAUNCH();
 }

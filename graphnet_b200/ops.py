@@ -523,6 +523,9 @@ class _EdgeConvHoisted(torch.autograd.Function):
 
 
 FUSED_EDGECONV = os.environ.get("GNB_FUSED_EDGECONV", "1") == "1"
+# inference route of the executor for k = 8 graphs: "split" = hidden-layer kernel + aggregating CTA-pair GEMM (measured
+# faster on B200), "fused" = the single fused EdgeConv kernel (gather + MLP + aggregation, nothing per-edge in HBM)
+INFERENCE_ROUTE = os.environ.get("GNB_INFERENCE_ROUTE", "split")
 
 
 def set_edgeconv_variant(v: int) -> None:
@@ -635,7 +638,7 @@ class _DynEdgeExec(torch.autograd.Function):
         x = _rowmajor(x.detach().float())
         n, nseg = x.shape[0], ptr.numel() - 1
         cfg.precision = 1 if _tf32() else 0
-        cfg.flags = 0 if FUSED_EDGECONV else 1
+        cfg.flags = (0 if FUSED_EDGECONV else 1) | (2 if INFERENCE_ROUTE == "split" else 0)
         nbytes = lib.gnb_dynedge_workspace_bytes(ctypes.byref(cfg), n, nseg, graph.width, training)
         if nbytes < 0:
             raise RuntimeError(f"gnb_dynedge_workspace_bytes: unsupported configuration [{nbytes}]")

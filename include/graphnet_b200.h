@@ -194,7 +194,9 @@ typedef struct {
     int32_t n_pool, pool[4];                         /* 0 min, 1 max, 2 sum, 3 mean, caller order */
     int32_t globals_after_pooling, skip_readout;
     int32_t n_knn_cols, knn_cols[GNB_MAX_KNN_COLS];  /* features_subset */
-    int32_t flags;                                   /* bit 0: do not use the fused tcgen05 EdgeConv kernels */
+    int32_t flags;                                   /* bit 0: do not use the fused tcgen05 EdgeConv kernels / epilogues;
+                                                        bit 1: inference runs hidden layer + aggregating GEMM (two kernels per
+                                                        layer, faster at k = 8) instead of the single fused EdgeConv kernel */
 } gnb_dynedge_config;
 
 /* Bytes of workspace for a batch of n nodes / nseg events whose initial graph has table width w0; < 0: error. */

@@ -204,22 +204,27 @@ def test_fused_edgeconv_matches_unfused_route_and_executor(built_library, tf32_m
     torch.manual_seed(2)
     model = DynEdge(7, global_pooling_schemes=["min", "max", "mean", "sum"]).cuda()
     outs = {}
-    old = ops.FUSED_EDGECONV
+    old, old_route = ops.FUSED_EDGECONV, ops.INFERENCE_ROUTE
     try:
-        for fused in (False, True):
-            ops.FUSED_EDGECONV = fused
+        # per-kernel route, hidden layer + aggregating GEMM epilogue ("split"), single fused EdgeConv kernel ("fused")
+        for name, fused, route in (("unfused", False, "split"), ("split", True, "split"), ("fused", True, "fused")):
+            ops.FUSED_EDGECONV, ops.INFERENCE_ROUTE = fused, route
             with torch.no_grad():
-                outs[fused] = model(KNNEdges(8)(Data(x=x, batch=batch, n_pulses=n_pulses))).clone()
+                outs[name] = model(KNNEdges(8)(Data(x=x, batch=batch, n_pulses=n_pulses))).clone()
     finally:
-        ops.FUSED_EDGECONV = old
-    # same rounding points except the per-edge message (not rounded to tf32 before the k-sum in the fused kernel);
-    # the latent kNN graphs of the two runs may differ where rounding flips a near-tie, hence the looser bound
-    assert rel_err(outs[True], outs[False]) < 5e-3
+        ops.FUSED_EDGECONV, ops.INFERENCE_ROUTE = old, old_route
+    # same rounding points except the per-edge message (not rounded to tf32 before the k-sum in the fused kernels);
+    # the latent kNN graphs of the runs may differ where rounding flips a near-tie, hence the looser bound
+    assert rel_err(outs["split"], outs["unfused"]) < 5e-3
+    assert rel_err(outs["fused"], outs["unfused"]) < 5e-3
 
 
-def test_dynedge_tf32_fused_inference_vs_oracle(built_library, tf32_mode):
-    """Inference path (fused tcgen05 EdgeConv) against the fp32 oracle fed the kernel's own graphs: rel 1e-3."""
+@pytest.mark.parametrize("route", ["split", "fused"])
+def test_dynedge_tf32_fused_inference_vs_oracle(built_library, tf32_mode, route, monkeypatch):
+    """Inference paths (hidden layer + aggregating tcgen05 GEMM; single fused tcgen05 EdgeConv kernel) against the fp32
+    oracle fed the kernel's own graphs: rel 1e-3."""
     from graphnet_b200 import Data
+    monkeypatch.setattr(tf32_mode, "INFERENCE_ROUTE", route)
     from graphnet_b200.models.gnn import DynEdge
     from graphnet_b200.models.graphs.edges import KNNEdges
     from graphnet_b200.synthetic import make_batch
