@@ -343,9 +343,9 @@ struct Exec {
         const int nld = (int)up(n_out, 32);
         EX(transpose_pad(wp + off, ldw, n_out, k, wt, nld, nld));
         const float* xs[1] = {dz}; const int64_t l1[1] = {lddz}; const int32_t k1[1] = {n_out};
-        if (!accumulate) return gnb_linear_fwd_tf32(xs, l1, k1, 1, wt, nld, nullptr, dx, lddx, rows, k, GNB_ACT_NONE, 0, st);
-        EX(gnb_linear_fwd_tf32(xs, l1, k1, 1, wt, nld, nullptr, tmp, k, rows, k, GNB_ACT_NONE, 0, st));
-        return add2d(tmp, k, rows, k, dx, lddx);
+        (void)tmp;   // dx += dz W is accumulated in the GEMM epilogue (flag 0x200), no temporary
+        return gnb_linear_fwd_tf32(xs, l1, k1, 1, wt, nld, nullptr, dx, lddx, rows, k,
+                                   GNB_ACT_NONE | (accumulate ? GNB_FLAG_ACCUMULATE : 0), 0, st);
     }
     // dwp[:, off : off + k] += dz^T x     (dwp zeroed by the caller)
     int lin_bwd_weight(const float* dz, int64_t lddz, const float* x, int64_t ldx, float* dwp, int64_t ldw, int off, int k,

@@ -93,13 +93,22 @@ __device__ __forceinline__ void epi_store32(const uint32_t (&r)[32], float bv, f
         yp += ldy;
     }
 }
-__device__ __noinline__ void epi_store_partial(const uint32_t (&r)[32], float bv, float lo, bool round, float* __restrict__ yp,
-                                               int64_t ldy, int nvalid) {
+// y += result (gradient accumulation onto an existing tensor): loads issued together, then the stores
+__device__ __forceinline__ void epi_accum32(const uint32_t (&r)[32], float bv, float lo, float* __restrict__ yp, int64_t ldy) {
+    float old[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) old[j] = yp[(int64_t)j * ldy];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) yp[(int64_t)j * ldy] = old[j] + fmaxf(__uint_as_float(r[j]) + bv, lo);
+}
+__device__ __noinline__ void epi_store_partial(const uint32_t (&r)[32], float bv, float lo, bool round, bool accum,
+                                               float* __restrict__ yp, int64_t ldy, int nvalid) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         if (j < nvalid) {
             float v = fmaxf(__uint_as_float(r[j]) + bv, lo);
             if (round) v = tc::round_tf32(v);
+            if (accum) v += *yp;
             *yp = v;
             yp += ldy;
         }
@@ -242,7 +251,8 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
         const int ew = warp - 2;                    // 0..7
         const int q = warp & 3;                     // TMEM lane quarter this warp may access
         const int half = ew >> 2;                   // column half: rows [64*half, 64*half + 64) of the tile
-        const float relu_lo = act == GNB_ACT_RELU ? 0.f : -INFINITY;
+        const float relu_lo = (act & 0xff) == GNB_ACT_RELU ? 0.f : -INFINITY;
+        const bool accum = (act & GNB_FLAG_ACCUMULATE) != 0;
         uint32_t tile_i = 0;
         for (int t = blockIdx.x; t < num_row_tiles; t += gridDim.x, ++tile_i) {
             const uint32_t buf = tile_i & 1;
@@ -344,10 +354,11 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
                     if (ch_ok && left > 0 && !(agg.dbg & 1)) {
                         float* yp = y + (row0 + col0) * ldy + ch;
                         if (left >= 32) {
-                            if (round_out) epi_store32<true>(r, bv, relu_lo, yp, ldy);
+                            if (accum) epi_accum32(r, bv, relu_lo, yp, ldy);
+                            else if (round_out) epi_store32<true>(r, bv, relu_lo, yp, ldy);
                             else epi_store32<false>(r, bv, relu_lo, yp, ldy);
                         } else {
-                            epi_store_partial(r, bv, relu_lo, round_out != 0, yp, ldy, (int)left);
+                            epi_store_partial(r, bv, relu_lo, round_out != 0 && !accum, accum, yp, ldy, (int)left);
                         }
                     }
                 }
@@ -543,7 +554,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
         const int ch = ch0 + q * 32 + lane;
         const bool ch_ok = ch < n_out;
         const float bv = (bias != nullptr && ch_ok) ? bias[ch] : 0.f;
-        const float relu_lo = act == GNB_ACT_RELU ? 0.f : -INFINITY;
+        const float relu_lo = (act & 0xff) == GNB_ACT_RELU ? 0.f : -INFINITY;
+        const bool accum = (act & GNB_FLAG_ACCUMULATE) != 0;
         uint32_t tile_i = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters, ++tile_i) {
             const uint32_t buf = tile_i & 1;
@@ -628,10 +640,11 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                     if (ch_ok && left > 0 && !(agg.dbg & 1)) {
                         float* yp = y + (rbase + c * 32) * ldy + ch;
                         if (left >= 32) {
-                            if (round_out) epi_store32<true>(r, bv, relu_lo, yp, ldy);
+                            if (accum) epi_accum32(r, bv, relu_lo, yp, ldy);
+                            else if (round_out) epi_store32<true>(r, bv, relu_lo, yp, ldy);
                             else epi_store32<false>(r, bv, relu_lo, yp, ldy);
                         } else {
-                            epi_store_partial(r, bv, relu_lo, round_out != 0, yp, ldy, (int)left);
+                            epi_store_partial(r, bv, relu_lo, round_out != 0 && !accum, accum, yp, ldy, (int)left);
                         }
                     }
                 }

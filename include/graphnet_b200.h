@@ -132,7 +132,8 @@ int gnb_colsum(const float* a, int64_t lda, int64_t rows, int32_t cols, float* o
  * y[rows, n_out] = act(sum_p xs[p][rows, ks[p]] w[:, koff_p : koff_p + ks[p]]^T + bias), koff_p = running sum of
  * ceil(ks[p]/32)*32. xs / ldxs / ks are HOST arrays (nparts <= 6); pointers 16-byte aligned, pitches % 4 == 0.
  * Operands are expected pre-rounded to tf32 (gnb_round_pad_tf32 or a producer's 0x100 flag); round_out rounds y.
- * With nparts > 1 this is the skip-concatenation + first post-processing Linear of dynedge.py:328-331. */
+ * With nparts > 1 this is the skip-concatenation + first post-processing Linear of dynedge.py:328-331.
+ * act = GNB_ACT_* | 0x200: with bit 0x200 the result is ADDED to y (gradient accumulation; round_out ignored). */
 int gnb_linear_fwd_tf32(const float* const* xs, const int64_t* ldxs, const int32_t* ks, int32_t nparts, const float* w,
                         int64_t ldw, const float* bias, float* y, int64_t ldy, int64_t rows, int32_t n_out, int32_t act,
                         int32_t round_out, void* stream);

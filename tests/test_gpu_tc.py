@@ -354,3 +354,26 @@ def test_edge_linear_agg_bit_exact_on_integers(built_library, tf32_mode, linear_
     dz_ref = gy.double().repeat_interleave(9, dim=0) * on
     assert torch.equal(dz.cpu().double(), dz_ref)
     assert torch.equal(db.cpu().double(), dz_ref.sum(0))
+
+
+@pytest.mark.parametrize("rows,n_out,k", [(70000, 256, 336), (515, 336, 256), (129, 19, 40)])
+def test_tc_linear_accumulate_flag(built_library, tf32_mode, linear_variant, rows, n_out, k):
+    """act | 0x200: y += x W^T (the data-gradient accumulation onto the skip path), bit-exact on integers."""
+    import ctypes
+    ops = tf32_mode
+    g = torch.Generator().manual_seed(rows)
+    x = torch.randint(-2, 3, (rows, k), generator=g).float()
+    w = torch.randint(-2, 3, (n_out, k), generator=g).float()
+    y0 = torch.randint(-5, 6, (rows, n_out), generator=g).float()
+    ref = y0.double() + x.double() @ w.double().t()
+    kp = (k + 3) // 4 * 4
+    xc = torch.nn.functional.pad(x, (0, kp - k)).cuda()
+    packed = ops._tc_pack_weight(torch.nn.functional.pad(w, (0, kp - k)).cuda(), (0,), (kp,))
+    y = y0.cuda()
+    xs = (ctypes.c_void_p * 1)(xc.data_ptr())
+    lds = (ctypes.c_int64 * 1)(kp)
+    ks = (ctypes.c_int32 * 1)(kp)
+    ops._call("gnb_linear_fwd_tf32", xs, lds, ks, 1, ops._ptr(packed), packed.shape[1], ops._ptr(None), ops._ptr(y), n_out,
+              rows, n_out, 0x200, 0, ops._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(y.cpu().double(), ref)
