@@ -29,6 +29,7 @@ SIGNATURES: Dict[str, list] = {
     "gnb_edgeconv_set_variant": [_i32],
     "gnb_linear_set_debug": [_i32],
     "gnb_linear_set_variant": [_i32],
+    "gnb_knn_set_variant": [_i32],
     "gnb_linear_set_profile_buffer": [_p],
     "gnb_edgeconv_set_profile_buffer": [_p],
     "gnb_edge_cat_fwd": [_p, _i64, _i32, _p, _p, _i32, _i64, _p, _i64, _p],

@@ -170,6 +170,120 @@ knn_table_kernel(const float* __restrict__ x, int64_t ld, const int* __restrict_
     }
 }
 
+// Split variant for the k = 8, 3-column graphs of DynEdge: S consecutive lanes share one query, lane s scans the
+// candidates a + s, a + s + S, ... of the query's event (ascending, strict '>' insertion: every partial list is the
+// exact top-9 of its subset under the total order (distance, index)), then the S sorted lists are merged with S-lane
+// shuffle minima under the same total order. The kernel's time is set by the largest event of the batch (one thread
+// used to walk all of its 5 000 pulses); with S = 8 that tail is 8 x shorter. Result is identical bit for bit.
+template <int K1, int D, int S>
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_table_split_kernel(const float* __restrict__ x, int64_t ld, const int* __restrict__ cols,
+                       const int64_t* __restrict__ ptr, int nseg, int64_t n, int chunk,
+                       int* __restrict__ nbr, int* __restrict__ deg) {
+    extern __shared__ float s_c[];            // [D][chunk]
+    __shared__ int s_cols[D];
+    __shared__ long long s_range[2];
+    constexpr int QPC = KNN_THREADS / S;      // queries per CTA
+    const int tid = threadIdx.x;
+    const int sub = tid % S;
+    const int64_t q0 = (int64_t)blockIdx.x * QPC;
+    const int64_t q = q0 + tid / S;
+    const bool active = q < n;
+    if (tid < D) s_cols[tid] = cols[tid];
+
+    int64_t lo = 0, hi = 0;
+    if (active) {
+        const int b = find_segment(ptr, nseg, q);
+        lo = ptr[b];
+        hi = ptr[b + 1];
+    }
+    if (tid == 0) s_range[0] = lo;
+    const int64_t q_last = (q0 + QPC < n ? q0 + QPC : n) - 1;
+    if (q == q_last && sub == 0) s_range[1] = hi;
+    __syncthreads();
+    const int64_t r_lo = s_range[0], r_hi = s_range[1];
+
+    float qf[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) qf[j] = active ? x[q * ld + s_cols[j]] : 0.f;
+
+    float bd[K1];
+    int bi[K1];
+#pragma unroll
+    for (int e = 0; e < K1; ++e) { bd[e] = 1e10f; bi[e] = -1; }
+
+    for (int64_t c0 = r_lo; c0 < r_hi; c0 += chunk) {
+        const int cnt = (int)((r_hi - c0) < chunk ? (r_hi - c0) : chunk);
+        __syncthreads();   // previous chunk fully consumed
+        for (int idx = tid; idx < cnt * D; idx += KNN_THREADS) {
+            const int j = idx / cnt, c = idx - j * cnt;
+            s_c[j * chunk + c] = x[(c0 + c) * ld + s_cols[j]];
+        }
+        __syncthreads();
+        if (active) {
+            const int a = (int)((lo > c0 ? lo : c0) - c0);
+            const int b = (int)((hi < c0 + cnt ? hi : c0 + cnt) - c0);
+            int jj = a + sub;
+            for (; jj + 3 * S < b; jj += 4 * S) {       // 4 independent distance evaluations, inserted in ascending order
+                float acc4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float d0 = s_c[jj + u * S] - qf[0];
+                    float acc = __fmul_rn(d0, d0);
+#pragma unroll
+                    for (int j = 1; j < D; ++j) {
+                        const float dj = s_c[j * chunk + jj + u * S] - qf[j];
+                        acc = __fadd_rn(acc, __fmul_rn(dj, dj));
+                    }
+                    acc4[u] = acc;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) insert_static<K1>(bd, bi, acc4[u], (int)(c0 + jj + u * S));
+            }
+            for (; jj < b; jj += S) {
+                const float d0 = s_c[jj] - qf[0];
+                float acc = __fmul_rn(d0, d0);
+#pragma unroll
+                for (int j = 1; j < D; ++j) {
+                    const float dj = s_c[j * chunk + jj] - qf[j];
+                    acc = __fadd_rn(acc, __fmul_rn(dj, dj));
+                }
+                insert_static<K1>(bd, bi, acc, (int)(c0 + jj));
+            }
+        }
+    }
+    // merge the S sorted partial lists: K1 rounds of "smallest head under (distance, index)"; the owner pops its head
+    int res[K1];
+#pragma unroll
+    for (int r = 0; r < K1; ++r) {
+        float md = bd[0];
+        int mi = bi[0];
+#pragma unroll
+        for (int off = 1; off < S; off <<= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, md, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, mi, off);
+            // empty entries are (1e10, -1): as unsigned, -1 loses every index tie
+            if (od < md || (od == md && (unsigned)oi < (unsigned)mi)) { md = od; mi = oi; }
+        }
+        res[r] = mi;
+        if (mi >= 0 && bi[0] == mi) {
+#pragma unroll
+            for (int e = 0; e + 1 < K1; ++e) { bd[e] = bd[e + 1]; bi[e] = bi[e + 1]; }
+            bd[K1 - 1] = 1e10f;
+            bi[K1 - 1] = -1;
+        }
+    }
+    if (active && sub == 0) {
+        int cntd = 0;
+        int* row = nbr + q * K1;
+#pragma unroll
+        for (int e = 0; e < K1; ++e)
+            if (res[e] >= 0 && res[e] != (int)q) row[cntd++] = res[e];
+        for (int e = cntd; e < K1; ++e) row[e] = -1;
+        deg[q] = cntd;
+    }
+}
+
 // ptr[b] = first i with batch[i] >= b  (batch sorted ascending; ptr has nseg+1 entries)
 __global__ void batch_to_ptr_kernel(const int64_t* __restrict__ batch, int64_t n, int64_t nseg,
                                     int64_t* __restrict__ ptr) {
@@ -206,7 +320,26 @@ int launch_knn(const float* x, int64_t ld, const int* cols, int d, const int64_t
     GNB_RETURN_LAUNCH();
 }
 
+template <int K1, int D, int S>
+int launch_knn_split(const float* x, int64_t ld, const int* cols, const int64_t* ptr, int nseg, int64_t n, int* nbr, int* deg,
+                     cudaStream_t st) {
+    const int chunk = 1024;
+    const size_t smem = (size_t)chunk * D * sizeof(float);
+    knn_table_split_kernel<K1, D, S><<<gnb_div_up(n, KNN_THREADS / S), KNN_THREADS, smem, st>>>(x, ld, cols, ptr, nseg, n, chunk,
+                                                                                                  nbr, deg);
+    GNB_RETURN_LAUNCH();
+}
+
+int g_knn_variant = 0;   // 0 auto (split kernel for k = 8, 3 columns), 1 one thread per query
+
 }  // namespace
+
+// Kernel selection for gnb_knn_table (tests pin both): 0 auto, 1 one thread per query, 2 split (k = 8, 3 columns only).
+GNB_EXPORT int gnb_knn_set_variant(int32_t v) {
+    if (v < 0 || v > 2) return GNB_ERR_ARG;
+    g_knn_variant = v;
+    return GNB_OK;
+}
 
 GNB_EXPORT int gnb_batch_to_ptr(const int64_t* batch, int64_t n, int64_t nseg, int64_t* ptr, void* stream) {
     if (n < 0 || nseg < 0) return GNB_ERR_ARG;
@@ -222,6 +355,7 @@ GNB_EXPORT int gnb_knn_table(const float* x, int64_t ld, const int32_t* cols, in
     cudaStream_t st = (cudaStream_t)stream;
     const int k1 = k + 1;
     if (d == 3) {
+        if (k1 == 9 && g_knn_variant != 1) return launch_knn_split<9, 3, 8>(x, ld, cols, ptr, (int)nseg, n, nbr, deg, st);
         if (k1 == 9) return launch_knn<9, 3>(x, ld, cols, d, ptr, (int)nseg, n, k1, nbr, deg, st);
         if (k1 == 5) return launch_knn<5, 3>(x, ld, cols, d, ptr, (int)nseg, n, k1, nbr, deg, st);
         if (k1 == 17) return launch_knn<17, 3>(x, ld, cols, d, ptr, (int)nseg, n, k1, nbr, deg, st);

@@ -38,6 +38,9 @@ int gnb_batch_to_ptr(const int64_t* batch, int64_t n, int64_t nseg, int64_t* ptr
  * Bit-exact total order (L2^2 in fp32 without FMA, index). k <= 100, d <= 512. */
 int gnb_knn_table(const float* x, int64_t ldx, const int32_t* cols, int32_t d, const int64_t* ptr, int64_t nseg,
                   int64_t n, int32_t k, int32_t* nbr, int32_t* deg, void* stream);
+/* Kernel selection for gnb_knn_table: 0 auto (8 lanes per query for k = 8 on 3 columns), 1 one thread per query,
+ * 2 split. Both produce the same table bit for bit. */
+int gnb_knn_set_variant(int32_t v);
 
 /* Expand a table into the PyG edge_index[2, n_edges] (row 0 = source/neighbour, row 1 = target);
  * rowptr = exclusive prefix sum of deg (n+1 entries). */

@@ -11,6 +11,17 @@ from oracle.dynedge_oracle import batch_to_ptr, knn_graph_ref
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=[1, 0], ids=["thread_per_query", "auto_split8"])
+def knn_variant(request, built_library):
+    """Every test runs on the one-thread-per-query kernel and on the default selection (8 lanes per query + merge for
+    k = 8 on 3 columns): both must reproduce the oracle's table bit for bit."""
+    from graphnet_b200 import _lib
+    lib = _lib.load()
+    assert lib.gnb_knn_set_variant(request.param) == 0
+    yield request.param
+    lib.gnb_knn_set_variant(0)
+
+
 def _kernel_graph(x, cols, ptr, k):
     from graphnet_b200 import ops
     return ops.knn_table(x.cuda(), cols, ptr.cuda(), k)
