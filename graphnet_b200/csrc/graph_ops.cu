@@ -12,7 +12,7 @@
 
 namespace {
 
-constexpr int GV_THREADS = 128;
+constexpr int GV_THREADS = 512;
 constexpr int GV_MAX_F = 32;
 
 // One CTA per event: feature means, x/y/z/t homophily over the event's edges, log10(n_pulses);
@@ -380,9 +380,9 @@ __global__ void edge_aggregate_bwd_kernel(const float* __restrict__ gy, int64_t 
 
 // ---------------------------------------------------------------------------------------------
 // global pooling: [N, C] -> [B, P*C] for up to 4 schemes in caller order, single read of x.
-// CTA = (64 channels) x (4 row lanes); grid = (B, C/64). arg (int32 node index, -1 for sum/mean or an
+// CTA = (64 channels) x (16 row lanes); grid = (B, C/64). arg (int32 node index, -1 for sum/mean or an
 // empty event) is kept for the min/max backward; ties resolve to the lowest node index.
-constexpr int POOL_CX = 64, POOL_RY = 4;
+constexpr int POOL_CX = 64, POOL_RY = 16;   // 16 row lanes: the kernel's time is the largest event's row count / POOL_RY
 
 __global__ void __launch_bounds__(POOL_CX * POOL_RY)
 segment_pool_fwd_kernel(const float* __restrict__ x, int64_t ldx, int c_tot, const int64_t* __restrict__ ptr,
@@ -436,7 +436,7 @@ segment_pool_fwd_kernel(const float* __restrict__ x, int64_t ldx, int c_tot, con
 __global__ void __launch_bounds__(256)
 segment_pool_bwd_kernel(const float* __restrict__ gout, int64_t ldg, const int* __restrict__ arg, int c_tot,
                         const int64_t* __restrict__ ptr, int nseg, int64_t n, int np, int s0,
-                        int s1, int s2, int s3, float* __restrict__ gx, int64_t ldx) {
+                        int s1, int s2, int s3, float* __restrict__ gx, int64_t ldx, int vec4) {
     const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
     const int lane = threadIdx.x & 31;
@@ -454,6 +454,26 @@ segment_pool_bwd_kernel(const float* __restrict__ gout, int64_t ldg, const int* 
         if (scheme == GNB_POOL_MEAN) return g / cnt;
         return ab[(int64_t)p * c_tot + c] == ii ? g : 0.f;
     };
+    if (vec4) {   // c_tot % 4 == 0, 16-byte aligned rows: four channels per lane, 512-byte warp stores
+        const int c4n = c_tot >> 2;
+        auto term4 = [&](int scheme, int p, int c4) -> float4 {
+            if (p >= np) return make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 g = reinterpret_cast<const float4*>(gb + (int64_t)p * c_tot)[c4];
+            if (scheme == GNB_POOL_SUM) return g;
+            if (scheme == GNB_POOL_MEAN) return make_float4(g.x / cnt, g.y / cnt, g.z / cnt, g.w / cnt);
+            const int4 a = reinterpret_cast<const int4*>(ab + (int64_t)p * c_tot)[c4];
+            return make_float4(a.x == ii ? g.x : 0.f, a.y == ii ? g.y : 0.f, a.z == ii ? g.z : 0.f, a.w == ii ? g.w : 0.f);
+        };
+        for (int c4 = lane; c4 < c4n; c4 += 32) {
+            float4 acc = term4(s0, 0, c4);
+            const float4 t1 = term4(s1, 1, c4), t2 = term4(s2, 2, c4), t3 = term4(s3, 3, c4);
+            acc.x += t1.x; acc.y += t1.y; acc.z += t1.z; acc.w += t1.w;
+            acc.x += t2.x; acc.y += t2.y; acc.z += t2.z; acc.w += t2.w;
+            acc.x += t3.x; acc.y += t3.y; acc.z += t3.z; acc.w += t3.w;
+            reinterpret_cast<float4*>(gx + i * ldx)[c4] = acc;
+        }
+        return;
+    }
     for (int c = lane; c < c_tot; c += 32) {
         // same summation order as the schemes are listed
         float acc = term(s0, 0, c);
@@ -752,8 +772,9 @@ GNB_EXPORT int gnb_segment_pool_bwd(const float* gout, int64_t ldg, const int32_
     if (n == 0) return GNB_OK;
     int s[4] = {0, 0, 0, 0};
     for (int p = 0; p < np; ++p) s[p] = schemes[p];
+    const int vec4 = !(c & 3) && !(ldg & 3) && !(ldx & 3) && aligned16(gout) && aligned16(gx) && (arg == nullptr || aligned16(arg));
     segment_pool_bwd_kernel<<<gnb_div_up(n, 8), 256, 0, (cudaStream_t)stream>>>(gout, ldg, arg, c, ptr, (int)nseg, n, np,
-                                                                                      s[0], s[1], s[2], s[3], gx, ldx);
+                                                                                      s[0], s[1], s[2], s[3], gx, ldx, vec4);
     GNB_RETURN_LAUNCH();
 }
 
