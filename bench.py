@@ -172,11 +172,11 @@ class Trainer:
         from graphnet_b200.distributed import FlatGradAllReduce
         from graphnet_b200.models.gnn import DynEdge
         from graphnet_b200.models.graphs.edges import KNNEdges
-        from graphnet_b200.tasks import DirectionReconstructionWithKappa, EnergyReconstruction
+        from graphnet_b200.tasks import FusedEnergyDirectionTask
         torch.manual_seed(0)
         self.backbone = DynEdge(7, global_pooling_schemes=POOLS).to(dev)
-        self.energy = EnergyReconstruction(128).to(dev)
-        self.direction = DirectionReconstructionWithKappa(128).to(dev)
+        self.tasks = FusedEnergyDirectionTask(128).to(dev)      # both heads + both losses in two CUDA kernels
+        self.energy, self.direction = self.tasks.energy, self.tasks.direction
         self.edges = KNNEdges(8)
         self.params = list(self.backbone.parameters()) + list(self.energy.parameters()) + \
             list(self.direction.parameters())
@@ -194,8 +194,7 @@ class Trainer:
         self.reducer.zero()
         data = self.edges(self.make_data(db))
         h = self.backbone(data)
-        loss = self.energy.compute_loss(self.energy(h), db["energy"]) + \
-            self.direction.compute_loss(self.direction(h), db["direction"])
+        loss, _, _ = self.tasks(h, db["energy"], db["direction"])
         loss.backward()
         self.reducer.all_reduce_mean()
         self.opt.step()

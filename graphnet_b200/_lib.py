@@ -30,6 +30,8 @@ SIGNATURES: Dict[str, list] = {
     "gnb_linear_set_debug": [_i32],
     "gnb_linear_set_variant": [_i32],
     "gnb_knn_set_variant": [_i32],
+    "gnb_task_heads_fwd": [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p],
+    "gnb_task_heads_bwd": [_p, _i64, _i32, _p, _p, _p, _p, _i64, _p, _i64, _p, _p, _p, _p, _p],
     "gnb_linear_set_profile_buffer": [_p],
     "gnb_edgeconv_set_profile_buffer": [_p],
     "gnb_edge_cat_fwd": [_p, _i64, _i32, _p, _p, _i32, _i64, _p, _i64, _p],

@@ -702,3 +702,57 @@ def dynedge_execute(cfg, graph: KnnGraph, ptr: Tensor, n_pulses: Tensor, x: Tens
     training = 1 if (torch.is_grad_enabled() and any(p.requires_grad for p in params)) else 0
     return _DynEdgeExec.apply(cfg, graph, ptr, n_pulses, x, _cols_tensor(cols, x.device), out_cols, out_per_event,
                               record, training, *params)
+
+
+# --------------------------------------------------------------------------- #
+# fused task heads + losses (csrc/task_heads.cu): energy (log-cosh on log10) + direction (vMF-3D) in two kernels
+# --------------------------------------------------------------------------- #
+class _TaskHeadsLoss(torch.autograd.Function):
+    """loss[2] = (mean log-cosh(log10 E_pred - log10 E), mean vMF-3D NLL); also returns the predictions (detached)."""
+
+    @staticmethod
+    def forward(ctx, feat: Tensor, we: Tensor, be: Tensor, wd: Tensor, bd: Tensor, energy: Tensor, direction: Tensor):
+        _cuda(feat, we, be, wd, bd, energy, direction)
+        feat = _rowmajor(feat.detach().float())
+        we_, be_, wd_, bd_ = (t.detach().float().contiguous() for t in (we, be, wd, bd))
+        energy = energy.detach().float().contiguous()
+        direction = direction.detach().float().reshape(-1, 3).contiguous()
+        nev, hdim = feat.shape
+        pred_e = torch.empty(nev, device=feat.device)
+        pred_d = torch.empty(nev, 4, device=feat.device)
+        dz = torch.empty(nev, 4, device=feat.device)
+        loss = torch.zeros(2, device=feat.device)
+        _call("gnb_task_heads_fwd", _ptr(feat), _ld(feat), hdim, _ptr(we_), _ptr(be_), _ptr(wd_), _ptr(bd_), _ptr(energy),
+              _ptr(direction), nev, _ptr(pred_e), _ptr(pred_d), _ptr(dz), _ptr(loss), _stream())
+        ctx.save_for_backward(feat, we_, wd_, dz)
+        ctx.params = (we, be, wd, bd)
+        ctx.mark_non_differentiable(pred_e, pred_d)
+        return loss, pred_e, pred_d
+
+    @staticmethod
+    def backward(ctx, gloss: Tensor, _ge, _gd):
+        feat, we_, wd_, dz = ctx.saved_tensors
+        nev, hdim = feat.shape
+        we, be, wd, bd = ctx.params
+        # d(sum of both losses): the two loss terms share one upstream scale only if their gradients are equal, which
+        # is the case for loss.sum() / loss[0] + loss[1]; general weights are applied per head below
+        g = gloss.contiguous().float()
+        if not bool(ctx.needs_input_grad[0]) and not any(ctx.needs_input_grad[1:5]):
+            return (None,) * 7
+        dzs = dz * torch.stack([g[0], g[1], g[1], g[1]]).unsqueeze(0)      # per-head upstream gradient
+        dfeat = torch.empty_like(feat) if ctx.needs_input_grad[0] else None
+        direct = ACCUMULATE_INTO_GRAD and all(
+            p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32 and p.grad.shape == p.shape
+            for p in (we, be, wd, bd))
+        grads = [p.grad for p in (we, be, wd, bd)] if direct else \
+            [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in (we, be, wd, bd)]
+        _call("gnb_task_heads_bwd", _ptr(feat), _ld(feat), hdim, _ptr(we_), _ptr(wd_), _ptr(dzs), _ptr(None), nev,
+              _ptr(dfeat), hdim, _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2]), _ptr(grads[3]), _stream())
+        if direct:
+            return (dfeat, None, None, None, None, None, None)
+        return (dfeat, grads[0], grads[1], grads[2], grads[3], None, None)
+
+
+def task_heads_loss(feat: Tensor, we: Tensor, be: Tensor, wd: Tensor, bd: Tensor, energy: Tensor, direction: Tensor):
+    """(loss[2], pred_energy[B], pred_direction[B, 4]) of the fused energy + direction heads."""
+    return _TaskHeadsLoss.apply(feat, we, be, wd, bd, energy, direction)

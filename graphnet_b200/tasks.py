@@ -55,3 +55,24 @@ class DirectionReconstructionWithKappa(torch.nn.Module):
         p = kappa.unsqueeze(1) * pred[:, :3]
         k = torch.norm(p, dim=1)
         return torch.mean(-self.log_c3(k) - torch.sum(p * direction.reshape(-1, 3), dim=1))
+
+
+class FusedEnergyDirectionTask(torch.nn.Module):
+    """Both heads and both losses of BASELINE config #3 in two CUDA kernels (csrc/task_heads.cu): the same arithmetic as
+    `EnergyReconstruction` + log-cosh and `DirectionReconstructionWithKappa` + vMF-3D above, one warp per event, no
+    intermediate tensors. `forward(h, energy, direction)` returns `(loss_energy + loss_direction, pred_energy[B, 1],
+    pred_direction[B, 4])`. The two plain-torch heads are held as submodules so `state_dict()` keys stay those of the
+    separate tasks (`energy._affine.*`, `direction._affine.*`)."""
+
+    def __init__(self, hidden_size: int):
+        super().__init__()
+        self.energy = EnergyReconstruction(hidden_size)
+        self.direction = DirectionReconstructionWithKappa(hidden_size)
+
+    def forward(self, h: Tensor, energy: Tensor, direction: Tensor):
+        from graphnet_b200 import ops
+        if not h.is_cuda:
+            raise RuntimeError("FusedEnergyDirectionTask needs CUDA tensors (no CPU fallback)")
+        loss, pe, pd = ops.task_heads_loss(h, self.energy._affine.weight, self.energy._affine.bias,
+                                           self.direction._affine.weight, self.direction._affine.bias, energy, direction)
+        return loss.sum(), pe.unsqueeze(1), pd

@@ -221,6 +221,21 @@ int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const* grads, con
                          const int32_t* deg0, int32_t w0, int64_t n, int64_t nseg, void* workspace,
                          int64_t workspace_bytes, const float* gout, void* stream);
 
+/* ---- task heads + losses (the O(B) step right after the path) -------------------------------------
+ * EnergyReconstruction (task/reconstruction.py:101-112) + LogCoshLoss on log10 (training/loss_functions.py:93-112) and
+ * DirectionReconstructionWithKappa (reconstruction.py:49-70) + VonMisesFisher3DLoss (loss_functions.py:281-353, 424-447;
+ * log C_3 in closed form, no host round trip). feat [nev, hdim]; we [hdim], be [1]; wd [3, hdim], bd [3]; energy [nev];
+ * direction [nev, 3]. pred_e [nev], pred_d [nev, 4] = (unit vector, kappa); dz [nev, 4] = d(loss_e + loss_d) / d(affine
+ * outputs), already divided by nev; loss[2] += (mean log-cosh, mean vMF NLL), zero on entry. */
+int gnb_task_heads_fwd(const float* feat, int64_t ldf, int32_t hdim, const float* we, const float* be, const float* wd,
+                       const float* bd, const float* energy, const float* direction, int64_t nev, float* pred_e,
+                       float* pred_d, float* dz, float* loss, void* stream);
+/* Backward for an upstream scalar gradient gout[0] (NULL = 1): dfeat [nev, hdim] written (may be NULL); dwe [hdim],
+ * dbe [1], dwd [3, hdim], dbd [3] ACCUMULATED (+=). hdim <= 2048. */
+int gnb_task_heads_bwd(const float* feat, int64_t ldf, int32_t hdim, const float* we, const float* wd, const float* dz,
+                       const float* gout, int64_t nev, float* dfeat, int64_t lddf, float* dwe, float* dbe, float* dwd,
+                       float* dbd, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

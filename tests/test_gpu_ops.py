@@ -126,3 +126,31 @@ def test_multi_linear_is_linear_on_concatenation(built_library):
     ref = torch.relu(torch.cat(parts, 1).double() @ w.double().t() + b.double())
     out = ops.multi_linear_act([p.cuda() for p in parts], w.cuda(), b.cuda(), [0, 32, 288], ops.ACT_RELU)
     assert rel_err(out, ref) < TOL
+
+
+def test_fused_task_heads_match_torch_heads(built_library):
+    """csrc/task_heads.cu against the plain-torch heads / losses of graphnet_b200.tasks evaluated in fp64 (those are
+    pinned on the reference's own loss functions by tests/test_tasks.py): loss, predictions and all gradients."""
+    from graphnet_b200.tasks import DirectionReconstructionWithKappa, EnergyReconstruction, FusedEnergyDirectionTask
+    torch.manual_seed(3)
+    nev, hdim = 517, 128
+    fused = FusedEnergyDirectionTask(hdim).cuda()
+    h = (torch.randn(nev, hdim) * torch.logspace(-2, 0.5, nev).unsqueeze(1)).cuda().requires_grad_(True)
+    energy = (10 ** (torch.rand(nev) * 4)).cuda()
+    direction = torch.nn.functional.normalize(torch.randn(nev, 3), dim=1).cuda()
+    loss, pe, pd = fused(h, energy, direction)
+    loss.backward()
+    # fp64 reference with the same weights
+    e64, d64 = EnergyReconstruction(hdim).double(), DirectionReconstructionWithKappa(hdim).double()
+    e64.load_state_dict({k: v.double().cpu() for k, v in fused.energy.state_dict().items()})
+    d64.load_state_dict({k: v.double().cpu() for k, v in fused.direction.state_dict().items()})
+    h64 = h.detach().double().cpu().requires_grad_(True)
+    pe64, pd64 = e64(h64), d64(h64)
+    loss64 = e64.compute_loss(pe64, energy.double().cpu()) + d64.compute_loss(pd64, direction.double().cpu())
+    loss64.backward()
+    assert abs(float(loss) - float(loss64)) < 1e-5 * max(1.0, abs(float(loss64)))
+    assert rel_err(pe, pe64) < 1e-5 and rel_err(pd, pd64) < 1e-5
+    assert rel_err(h.grad, h64.grad) < 2e-4
+    for pf, pr in zip(list(fused.energy.parameters()) + list(fused.direction.parameters()),
+                      list(e64.parameters()) + list(d64.parameters())):
+        assert rel_err(pf.grad, pr.grad) < 2e-4, pf.shape
