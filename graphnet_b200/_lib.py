@@ -29,6 +29,7 @@ SIGNATURES: Dict[str, list] = {
     "gnb_edgeconv_set_variant": [_i32],
     "gnb_linear_set_debug": [_i32],
     "gnb_linear_set_variant": [_i32],
+    "gnb_linear_set_pair_resident": [_i32],
     "gnb_knn_set_variant": [_i32],
     "gnb_task_heads_fwd": [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p],
     "gnb_task_heads_bwd": [_p, _i64, _i32, _p, _p, _p, _p, _i64, _p, _i64, _p, _p, _p, _p, _p],

@@ -391,30 +391,39 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
 // 28 nodes (aggregating / scattering epilogues; sub-tile h of tile t is the 14-node tile 2 t + h of the layouts above).
 // Barriers: full[s] lives in the leader (both CTAs' TMA loads credit it), empty[s] / tmem_full[b] are multicast by the
 // leader's tcgen05.commit to both CTAs, tmem_empty[b] of the leader collects the 16 epilogue warps of the pair.
-constexpr int PL_STAGES = 6, PL_STAGES_SCAT = 5, PL_THREADS = 320;
+constexpr int PL_MAX_STAGES = 8, PL_THREADS = 320;
+constexpr uint32_t PL_MAX_DYN_SMEM = 231424;          // 226 KiB of dynamic shared memory per CTA
 // Clusters are split UNEVENLY over the 256-channel groups (336 channels = 256 + 80: the second group has a third of the
 // epilogue work): clusters [start[g], start[g+1]) walk the row tiles of channel group g.
 struct GroupSplit { int ngroups; int start[5]; };
-constexpr uint32_t PL_STAGE_BYTES = 2 * TC_TILE_BYTES;                         // A (128 ch) + B half (128 rows)
-constexpr uint32_t PL_SMEM_BYTES = PL_STAGES * PL_STAGE_BYTES + 1024 + 256;
-constexpr uint32_t PL_SMEM_BYTES_SCAT = PL_STAGES_SCAT * PL_STAGE_BYTES + 1024 + 256 + 4 * SC_META_BYTES;
+// Shared memory: [resident weights: total_kb x 16 KiB, only in `resident` mode][ring: nstages x stage bytes][barriers]
+// [scatter metadata]. Streaming mode: a stage = this CTA's weight tile + its half of the activation rows (32 KiB);
+// resident mode (single-part K that fits): the CTA's 128 weight rows stay in shared memory for the kernel's lifetime
+// (one TMA pass), a stage is the activation half only (16 KiB) and the L2->SM traffic per launch halves.
+struct PairCfg { int resident; int nstages; };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PL_THREADS, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ TmapArray tm_x,
                     const PartInfo parts, const float* __restrict__ bias, float* __restrict__ y, int64_t ldy,
                     int64_t rows, int n_out, int act, int round_out, int num_tiles, const AggInfo agg, const ScatInfo sc,
-                    const GroupSplit gs) {
+                    const GroupSplit gs, const PairCfg pc) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int nstages = sc.enabled ? PL_STAGES_SCAT : PL_STAGES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + nstages * PL_STAGE_BYTES);
-    uint64_t* empty = full + PL_STAGES;
-    uint64_t* tmem_full = empty + PL_STAGES;      // [2]
+    int total_kb = 0;
+    for (int p = 0; p < parts.nparts; ++p) total_kb += parts.kblocks[p];
+    const int nstages = pc.nstages;
+    const uint32_t stage_bytes = pc.resident ? TC_TILE_BYTES : 2 * TC_TILE_BYTES;
+    uint8_t* s_a = smem;                                                     // resident weights (resident mode)
+    uint8_t* ring = smem + (pc.resident ? (uint32_t)total_kb * TC_TILE_BYTES : 0u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + nstages * stage_bytes);
+    uint64_t* empty = full + PL_MAX_STAGES;
+    uint64_t* tmem_full = empty + PL_MAX_STAGES;      // [2]
     uint64_t* tmem_empty = tmem_full + 2;         // [2] (leader's copy is the one waited on)
     uint64_t* meta_full = tmem_empty + 2;         // [2]
     uint64_t* meta_empty = meta_full + 2;         // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(meta_empty + 2);
-    uint8_t* meta = smem + nstages * PL_STAGE_BYTES + 256;        // [2 buffers][2 sub-tiles] x SC_META_BYTES
+    uint64_t* a_full = meta_empty + 2;            // [1] resident weights landed (leader's copy is waited on)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
+    uint8_t* meta = ring + nstages * stage_bytes + 256;           // [2 buffers][2 sub-tiles] x SC_META_BYTES
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = tc::cluster_ctarank();
@@ -432,7 +441,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < PL_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+            for (int s = 0; s < PL_MAX_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+            tc::mbar_init(a_full, 1);
             for (int b = 0; b < 2; ++b) {
                 tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], 16);
                 tc::mbar_init(&meta_full[b], 1); tc::mbar_init(&meta_empty[b], 8);
@@ -449,8 +459,6 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     tc::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    int total_kb = 0;
-    for (int p = 0; p < parts.nparts; ++p) total_kb += parts.kblocks[p];
     const bool prof_on = agg.prof != nullptr && blockIdx.x == 0;
     long long pw0 = 0, pw1 = 0;
     const long long pt0 = clock64();
@@ -458,7 +466,12 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     if (warp == 0) {
         // ---- TMA producer (both CTAs): own weight rows + own half of the activation rows ------------------------
         uint32_t it = 0, tile_i = 0;
-        const uint32_t stage_tx = 2u * (TC_TILE_BYTES + (uint32_t)half_rows * TC_BK * 4);   // both CTAs' loads
+        const uint32_t stage_tx = 2u * ((pc.resident ? 0u : TC_TILE_BYTES) + (uint32_t)half_rows * TC_BK * 4);   // both CTAs
+        if (pc.resident && tc::elect_one()) {      // the CTA's 128 weight rows, all K blocks, once
+            if (rank == 0) tc::mbar_arrive_expect_tx(a_full, 2u * (uint32_t)total_kb * TC_TILE_BYTES);
+            for (int kb = 0; kb < total_kb; ++kb) tc::tma_load_2d_2sm(s_a + kb * TC_TILE_BYTES, &tm_w, a_full, kb * TC_BK, ch0);
+        }
+        __syncwarp();
         for (int t = cluster_id; t < num_tiles; t += num_clusters, ++tile_i) {
             const int64_t row0 = (int64_t)t * (2 * half_rows) + (int64_t)rank * half_rows;
             int offv[2][4];
@@ -480,11 +493,11 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                     const long long c0 = prof_on ? clock64() : 0;
                     tc::mbar_wait_warp(&empty[s], ph ^ 1);
                     if (prof_on) pw0 += clock64() - c0;
-                    uint8_t* st = smem + s * PL_STAGE_BYTES;
+                    uint8_t* st = ring + s * stage_bytes;
                     if (tc::elect_one()) {
                         if (rank == 0) tc::mbar_arrive_expect_tx(&full[s], stage_tx);
-                        tc::tma_load_2d_2sm(st, &tm_w, &full[s], kb_w * TC_BK, ch0);
-                        tc::tma_load_2d_2sm(st + TC_TILE_BYTES, &tm_x.m[p], &full[s], kb * TC_BK, (int)row0);
+                        if (!pc.resident) tc::tma_load_2d_2sm(st, &tm_w, &full[s], kb_w * TC_BK, ch0);
+                        tc::tma_load_2d_2sm(st + (pc.resident ? 0u : TC_TILE_BYTES), &tm_x.m[p], &full[s], kb * TC_BK, (int)row0);
                     }
                     __syncwarp();
                 }
@@ -518,6 +531,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
             // ---- MMA issuer (leader CTA): M = 256 over both CTAs, N = 256 rows (128 from each CTA's stage) -----------
             constexpr uint32_t idesc = tc::umma_idesc_tf32(256, 256);
             uint32_t it = 0, tile_i = 0;
+            if (pc.resident) { tc::mbar_wait_warp(a_full, 0); tc::tcgen05_fence_after(); }
             for (int t = cluster_id; t < num_tiles; t += num_clusters, ++tile_i) {
                 const uint32_t buf = tile_i & 1;
                 const long long c1 = prof_on ? clock64() : 0;
@@ -531,9 +545,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                     tc::mbar_wait_warp(&full[s], ph);
                     if (prof_on) pw0 += clock64() - c0;
                     tc::tcgen05_fence_after();
-                    const uint32_t st = tc::smem_u32(smem + s * PL_STAGE_BYTES);
-                    const uint64_t adesc = tc::umma_desc_sw128_kmajor(st);
-                    const uint64_t bdesc = tc::umma_desc_sw128_kmajor(st + TC_TILE_BYTES);
+                    const uint32_t st = tc::smem_u32(ring + s * stage_bytes);
+                    const uint64_t adesc = tc::umma_desc_sw128_kmajor(pc.resident ? tc::smem_u32(s_a + kbi * TC_TILE_BYTES) : st);
+                    const uint64_t bdesc = tc::umma_desc_sw128_kmajor(pc.resident ? st : st + TC_TILE_BYTES);
                     if (!(agg.dbg & 2)) {
 #pragma unroll
                         for (int k = 0; k < TC_BK / 8; ++k)
@@ -689,6 +703,7 @@ int g_num_sms = 0;
 unsigned long long* g_linear_prof = nullptr;
 int g_linear_dbg = 0;   // tuning hook: see gnb_linear_set_debug
 int g_linear_variant = 0;   // 0 auto, 1 single-CTA kernel, 2 CTA-pair kernel
+int g_pair_resident = 0;    // 0: pair kernel streams the weights; n > 0: keep them resident when >= n activation stages fit
 
 // row_tiles = number of 128-row (plain) or 126-row (aggregating / scattering) tiles
 int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi, const float* bias, float* y, int64_t ldy,
@@ -700,8 +715,7 @@ int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi
         GNB_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
         GNB_CHECK(cudaFuncSetAttribute(gemm_tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)TC_SMEM_BYTES));
-        GNB_CHECK(cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(PL_SMEM_BYTES > PL_SMEM_BYTES_SCAT ? PL_SMEM_BYTES : PL_SMEM_BYTES_SCAT)));
+        GNB_CHECK(cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM));
     }
     // measured (scripts/linear_probe.py): the pair kernel wins from two ch-tiles up; a single 128-channel tile is
     // faster on the single-CTA kernel (half of the pair's M = 256 would be padding)
@@ -728,8 +742,25 @@ int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi
         }
         for (int g = groups + 1; g < 5; ++g) gs.start[g] = used;
         dim3 grid((unsigned)(2 * used));
-        gemm_tc_pair_kernel<<<grid, PL_THREADS, sc.enabled ? PL_SMEM_BYTES_SCAT : PL_SMEM_BYTES, stream>>>(
-            tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out, tiles, agg, sc, gs);
+        // shared-memory plan: resident weights when a single-part K leaves at least `min_res_stages` activation stages
+        int total_kb = 0;
+        for (int p = 0; p < pi.nparts; ++p) total_kb += pi.kblocks[p];
+        const uint32_t fixed = 1024 + 256 + (sc.enabled ? 4 * SC_META_BYTES : 0);
+        PairCfg pc;
+        const int64_t res_left = (int64_t)PL_MAX_DYN_SMEM - fixed - (int64_t)total_kb * TC_TILE_BYTES;
+        int res_stages = res_left > 0 ? (int)(res_left / TC_TILE_BYTES) : 0;
+        if (res_stages > PL_MAX_STAGES) res_stages = PL_MAX_STAGES;
+        pc.resident = (g_pair_resident != 0 && pi.nparts == 1 && res_stages >= g_pair_resident) ? 1 : 0;
+        if (pc.resident) {
+            pc.nstages = res_stages;
+        } else {
+            pc.nstages = (int)((PL_MAX_DYN_SMEM - fixed) / (2 * TC_TILE_BYTES));
+            if (pc.nstages > 6) pc.nstages = 6;
+        }
+        const uint32_t smem = fixed + (pc.resident ? (uint32_t)total_kb * TC_TILE_BYTES + pc.nstages * TC_TILE_BYTES
+                                                   : pc.nstages * 2 * TC_TILE_BYTES);
+        gemm_tc_pair_kernel<<<grid, PL_THREADS, smem, stream>>>(tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out, tiles,
+                                                               agg, sc, gs, pc);
         GNB_RETURN_LAUNCH();
     }
     const int groups = gnb_div_up(n_out, TC_MT * TC_BM);
@@ -752,6 +783,13 @@ GNB_EXPORT int gnb_linear_set_debug(int32_t flags) { g_linear_dbg = flags; retur
 GNB_EXPORT int gnb_linear_set_variant(int32_t v) {
     if (v < 0 || v > 2) return GNB_ERR_ARG;
     g_linear_variant = v;
+    return GNB_OK;
+}
+// CTA-pair kernel: 0 = always stream the weight tiles with the activations; n > 0 = keep the CTA's weight rows
+// resident in shared memory whenever a single-part K leaves at least n (>= 2) activation stages.
+GNB_EXPORT int gnb_linear_set_pair_resident(int32_t min_stages) {
+    if (min_stages < 0 || min_stages == 1 || min_stages > 8) return GNB_ERR_ARG;
+    g_pair_resident = min_stages;
     return GNB_OK;
 }
 

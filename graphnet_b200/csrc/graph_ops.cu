@@ -516,7 +516,7 @@ constexpr int ACT_ROWS = 256;
 __global__ void __launch_bounds__(256)
 act_bwd_colsum_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ y, int64_t ldy,
                       int64_t rows, int cols4, float* __restrict__ dz, int64_t ldz, float* __restrict__ db, int flags,
-                      const int* __restrict__ deg, int width, int aggr, const unsigned* __restrict__ maskbits, int npt) {
+                      const int* __restrict__ deg, int width, int aggr) {
     const int c4 = blockIdx.y * 64 + threadIdx.x;
     const int ty = threadIdx.y;
     const bool col_ok = c4 < cols4;
@@ -543,16 +543,7 @@ act_bwd_colsum_kernel(const float* __restrict__ g, int64_t ldg, const float* __r
             } else {
                 gv = reinterpret_cast<const float4*>(g + r * ldg)[c4];
             }
-            if (maskbits != nullptr) {
-                // ReLU mask saved by the aggregating GEMM epilogue: one bit per (slot column, channel) of a 14-node tile
-                const int64_t i = r / width;
-                const int64_t tile = i / npt;
-                const int col = (int)(i - tile * npt) * width + (int)(r - i * width);
-                const unsigned* w = maskbits + ((tile * (int64_t)(cols4 * 4) + 4 * c4) * 4 + (col >> 5));
-                const unsigned sh = col & 31;
-                gv.x = ((w[0] >> sh) & 1u) ? gv.x : 0.f; gv.y = ((w[4] >> sh) & 1u) ? gv.y : 0.f;
-                gv.z = ((w[8] >> sh) & 1u) ? gv.z : 0.f; gv.w = ((w[12] >> sh) & 1u) ? gv.w : 0.f;
-            } else if (relu) {
+            if (relu) {
                 const float4 yv = reinterpret_cast<const float4*>(y + r * ldy)[c4];
                 gv.x = yv.x > 0.f ? gv.x : 0.f; gv.y = yv.y > 0.f ? gv.y : 0.f;
                 gv.z = yv.z > 0.f ? gv.z : 0.f; gv.w = yv.w > 0.f ? gv.w : 0.f;
@@ -789,14 +780,17 @@ GNB_EXPORT int gnb_relu_bwd(const float* g, int64_t ldg, const float* y, int64_t
 }
 
 
-static int act_bwd_launch(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows, int32_t cols, float* dz,
-                          int64_t ldz, float* db, int32_t flags, const int32_t* deg, int32_t width, int32_t aggr,
-                          const unsigned* maskbits, int npt, void* stream);
-
 GNB_EXPORT int gnb_act_bwd_colsum(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows, int32_t cols,
                                   float* dz, int64_t ldz, float* db, int32_t flags, const int32_t* deg, int32_t width,
                                   int32_t aggr, void* stream) {
-    return act_bwd_launch(g, ldg, y, ldy, rows, cols, dz, ldz, db, flags, deg, width, aggr, nullptr, 1, stream);
+    if ((cols & 3) || (ldg & 3) || (ldz & 3) || !aligned16(g) || !aligned16(dz)) return GNB_ERR_ARG;
+    if ((flags & 0xff) == GNB_ACT_RELU && ((ldy & 3) || !aligned16(y))) return GNB_ERR_ARG;
+    if (deg != nullptr && (width < 1 || aggr < 0 || aggr > 1)) return GNB_ERR_ARG;
+    if (rows == 0) return GNB_OK;
+    dim3 grid((unsigned)gnb_div_up(rows, ACT_ROWS), (unsigned)gnb_div_up(cols >> 2, 64)), block(64, 4);
+    act_bwd_colsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(g, ldg, y, ldy, rows, cols >> 2, dz, ldz, db, flags,
+                                                                    deg, width, aggr);
+    GNB_RETURN_LAUNCH();
 }
 
 // Same, with the ReLU mask taken from the bit mask written by gnb_edge_linear_agg_fwd_tf32 (k = 8 tables: width 9,
@@ -812,19 +806,6 @@ GNB_EXPORT int gnb_edge_mask_bwd_colsum(const float* g, int64_t ldg, const uint3
     edge_mask_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(g, ldg, reinterpret_cast<const uint4*>(maskbits), n, cols,
                                                                     dz, ldz, db, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0,
                                                                     n_tiles);
-    GNB_RETURN_LAUNCH();
-}
-
-static int act_bwd_launch(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows, int32_t cols, float* dz,
-                          int64_t ldz, float* db, int32_t flags, const int32_t* deg, int32_t width, int32_t aggr,
-                          const unsigned* maskbits, int npt, void* stream) {
-    if ((cols & 3) || (ldg & 3) || (ldz & 3) || !aligned16(g) || !aligned16(dz)) return GNB_ERR_ARG;
-    if ((flags & 0xff) == GNB_ACT_RELU && ((ldy & 3) || !aligned16(y))) return GNB_ERR_ARG;
-    if (deg != nullptr && (width < 1 || aggr < 0 || aggr > 1)) return GNB_ERR_ARG;
-    if (rows == 0) return GNB_OK;
-    dim3 grid((unsigned)gnb_div_up(rows, ACT_ROWS), (unsigned)gnb_div_up(cols >> 2, 64)), block(64, 4);
-    act_bwd_colsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(g, ldg, y, ldy, rows, cols >> 2, dz, ldz, db, flags,
-                                                                    deg, width, aggr, maskbits, npt);
     GNB_RETURN_LAUNCH();
 }
 

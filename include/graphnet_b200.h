@@ -82,6 +82,9 @@ int gnb_linear_set_debug(int32_t flags);
 /* Kernel selection for gnb_linear_fwd_tf32 / gnb_edge_linear_agg_fwd_tf32 / gnb_edge_hidden_dgrad_scatter_tf32: 0 auto
  * (CTA-pair cta_group::2 kernel for >= 296 row tiles), 1 single-CTA kernel, 2 CTA-pair kernel. */
 int gnb_linear_set_variant(int32_t v);
+/* CTA-pair kernel shared-memory plan: 0 = stream the weight tiles with the activations; n >= 2 = keep the CTA's 128
+ * weight rows resident whenever a single-part K leaves at least n activation stages (halves the L2->SM traffic). */
+int gnb_linear_set_pair_resident(int32_t min_stages);
 /* Tuning aid: device buffer of 16 uint64 that CTA (0,0) of the Linear kernel fills with cycle counters {producer:
  * wait-empty, -, total} {mma: wait-full, wait-tmem-empty, total} {epilogue warp 2: wait-tmem-full, tmem-ld, total}. */
 int gnb_linear_set_profile_buffer(void* buf);

@@ -111,14 +111,16 @@ def scatter_case(n, c_out, hdim, label):
 
 
 import sys as _s
-for variant in (1, 2):
+for variant, resident in ((2, 0), (2, 2), (2, 3)):
     lib.gnb_linear_set_variant(variant)
-    print("== variant", variant, "(1 single-CTA, 2 CTA pair)", flush=True)
+    lib.gnb_linear_set_pair_resident(resident)
+    print("== variant", variant, "(1 single-CTA, 2 CTA pair), resident weights from", resident, "stages", flush=True)
     scatter_case(N, 256, 336, "dgrad + scatter epilogue")
     scatter_case(N, 256, 128, "layer-1 dgrad + scatter")
     agg_case(N, 336, 256, "edge GEMM2 fwd (aggregating)")
     linear_case(ROWS, 336, 256, "edge GEMM2 fwd (plain)")
 lib.gnb_linear_set_variant(0)
+lib.gnb_linear_set_pair_resident(0)
 if len(_s.argv) > 1 and _s.argv[1] == "scatter":
     _s.exit(0)
 linear_case(ROWS, 336, 256, "edge GEMM2 fwd (plain)")

@@ -23,14 +23,18 @@ def tf32_mode():
     ops.set_precision(old)
 
 
-@pytest.fixture(params=[1, 2], ids=["single_cta", "cta_pair"])
+@pytest.fixture(params=[(1, 0), (2, 0), (2, 2)], ids=["single_cta", "cta_pair", "cta_pair_resident_weights"])
 def linear_variant(request, built_library):
-    """Run the tf32 Linear entry points on the single-CTA kernel and on the cta_group::2 CTA-pair kernel."""
+    """Run the tf32 Linear entry points on the single-CTA kernel and on the cta_group::2 CTA-pair kernel (weights
+    streamed / resident in shared memory)."""
     from graphnet_b200 import _lib
     lib = _lib.load()
-    assert lib.gnb_linear_set_variant(request.param) == 0
+    variant, resident = request.param
+    assert lib.gnb_linear_set_variant(variant) == 0
+    assert lib.gnb_linear_set_pair_resident(resident) == 0
     yield request.param
     lib.gnb_linear_set_variant(0)
+    lib.gnb_linear_set_pair_resident(0)
 
 
 SHAPES = [  # rows, n_out, part widths
