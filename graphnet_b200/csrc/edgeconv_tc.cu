@@ -224,10 +224,11 @@ edgeconv_fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPar
                     const uint32_t idesc = tc::umma_idesc_tf32(128, (uint32_t)meta[buf].n_mma);
                     const uint64_t adesc = tc::umma_desc_sw128_kmajor(tc::smem_u32(s_a + kb * EF_TILE_BYTES));
                     const uint64_t bdesc = tc::umma_desc_sw128_kmajor(tc::smem_u32(s_b + s * EF_TILE_BYTES));
+                    const bool lead = tc::elect_one();      // one election per K block: MMAs + commit issued back to back
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        if (tc::elect_one()) tc::umma_tf32(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    if (tc::elect_one()) tc::umma_commit(&b_empty[s]);
+                        if (lead) tc::umma_tf32(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    if (lead) tc::umma_commit(&b_empty[s]);
                     __syncwarp();
                 }
                 if (tc::elect_one()) tc::umma_commit(&tmem_full[buf]);
@@ -474,13 +475,14 @@ edgeconv_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfPa
                     tc::tcgen05_fence_after();
                     const uint64_t adesc = tc::umma_desc_sw128_kmajor(tc::smem_u32(s_a + kb * EF_TILE_BYTES));
                     const uint64_t bdesc = tc::umma_desc_sw128_kmajor(tc::smem_u32(s_b + s * EP_BTILE_BYTES));
+                    const bool lead = tc::elect_one();      // one election per K block: MMAs + commit issued back to back
                     if (!(p.debug & 8)) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        if (tc::elect_one())
+                        if (lead)
                             tc::umma_tf32_2cta(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    if (tc::elect_one()) tc::umma_commit_2cta(&b_empty[s], 3);
+                    if (lead) tc::umma_commit_2cta(&b_empty[s], 3);
                     __syncwarp();
                 }
                 if (tc::elect_one()) tc::umma_commit_2cta(&tmem_full[buf], 3);

@@ -233,14 +233,18 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
                     tc::tcgen05_fence_after();
                     const uint32_t st = tc::smem_u32(smem + s * TC_STAGE_BYTES);
                     const uint64_t bdesc = tc::umma_desc_sw128_kmajor(st + TC_MT * TC_TILE_BYTES);
-                    for (int m = 0; m < ((agg.dbg & 2) ? 0 : mt); ++m) {
-                        const uint64_t adesc = tc::umma_desc_sw128_kmajor(st + m * TC_TILE_BYTES);
+                    // ONE election per K block: the elected lane issues all MMAs and the commit back to back (an election
+                    // per MMA costs ~125 cycles of issue each, one per K block ~60: scripts/probes/pair_mma_probe.cu)
+                    const int mt_eff = (agg.dbg & 2) ? 0 : mt;
+                    if (tc::elect_one()) {
+                        for (int m = 0; m < mt_eff; ++m) {
+                            const uint64_t adesc = tc::umma_desc_sw128_kmajor(st + m * TC_TILE_BYTES);
 #pragma unroll
-                        for (int k = 0; k < TC_BK / 8; ++k)   // UMMA_K = 8 tf32 = 32 B -> +2 in the 16-byte address field
-                            if (tc::elect_one())
+                            for (int k = 0; k < TC_BK / 8; ++k)   // UMMA_K = 8 tf32 = 32 B -> +2 in the 16-byte address field
                                 tc::umma_tf32(acc + m * TC_BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kbi | k) != 0 ? 1u : 0u);
+                        }
+                        tc::umma_commit(&empty[s]);
                     }
-                    if (tc::elect_one()) tc::umma_commit(&empty[s]);
                     __syncwarp();
                 }
                 if (tc::elect_one()) tc::umma_commit(&tmem_full[buf]);
@@ -460,7 +464,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     const uint32_t tmem_base = *tmem_slot;
 
     const bool prof_on = agg.prof != nullptr && blockIdx.x == 0;
-    long long pw0 = 0, pw1 = 0;
+    long long pw0 = 0, pw1 = 0, pe0 = 0, pe1 = 0;
     const long long pt0 = clock64();
 
     if (warp == 0) {
@@ -548,13 +552,14 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                     const uint32_t st = tc::smem_u32(ring + s * stage_bytes);
                     const uint64_t adesc = tc::umma_desc_sw128_kmajor(pc.resident ? tc::smem_u32(s_a + kbi * TC_TILE_BYTES) : st);
                     const uint64_t bdesc = tc::umma_desc_sw128_kmajor(pc.resident ? st : st + TC_TILE_BYTES);
-                    if (!(agg.dbg & 2)) {
+                    if (tc::elect_one()) {          // one election per K block (see the single-CTA kernel)
+                        if (!(agg.dbg & 2)) {
 #pragma unroll
-                        for (int k = 0; k < TC_BK / 8; ++k)
-                            if (tc::elect_one())
+                            for (int k = 0; k < TC_BK / 8; ++k)
                                 tc::umma_tf32_2cta(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kbi | k) != 0 ? 1u : 0u);
+                        }
+                        tc::umma_commit_2cta(&empty[s], 3);
                     }
-                    if (tc::elect_one()) tc::umma_commit_2cta(&empty[s], 3);
                     __syncwarp();
                 }
                 if (tc::elect_one()) tc::umma_commit_2cta(&tmem_full[buf], 3);
@@ -611,15 +616,58 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                 const int64_t node0 = st14 * AGG_NPT;
                 if (node0 < agg.n_nodes) {
                     int dg[AGG_NPT];
+                    const long long e0 = prof_on ? clock64() : 0;
 #pragma unroll
                     for (int f = 0; f < AGG_NPT; ++f) dg[f] = (node0 + f < agg.n_nodes) ? agg.deg[node0 + f] : 0;
+                    if (prof_on) {
+                        int sdg = 0;
+#pragma unroll
+                        for (int f = 0; f < AGG_NPT; ++f) sdg += dg[f];
+                        asm volatile("" ::"r"(sdg));
+                        pe0 += clock64() - e0;
+                    }
                     float acc = 0.f;
                     unsigned bits[4];
+                    bool regular = true;                       // every node of the sub-tile has exactly k = 8 neighbours
+#pragma unroll
+                    for (int f = 0; f < AGG_NPT; ++f) regular = regular && dg[f] == AGG_W - 1;
+                    if (regular && !(agg.dbg & 256)) {
+                        // fast path: slot validity is compile-time (slots 0..7 valid, slot 8 padding), relu = fmaxf, and the
+                        // mask word is built in four independent partial words (no 126-long dependency chain)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            uint32_t r[32];
+                            tc::tmem_ld_32x32b_x32(tcol + (uint32_t)(c * 32), r);
+                            tc::tmem_ld_wait();
+                            unsigned w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int col = c * 32 + j;
+                                if (col < AGG_ROWS) {
+                                    const int f = col / AGG_W, sl = col % AGG_W;
+                                    if (sl < AGG_W - 1) {
+                                        const float pre = __uint_as_float(r[j]) + bv;
+                                        acc += fmaxf(pre, 0.f);
+                                        const unsigned b = pre > 0.f ? (1u << j) : 0u;
+                                        if ((j & 3) == 0) w0 |= b; else if ((j & 3) == 1) w1 |= b; else if ((j & 3) == 2) w2 |= b; else w3 |= b;
+                                    } else {
+                                        float o = acc;
+                                        if (round_out) o = tc::round_tf32(o);
+                                        if (ch_ok && !(agg.dbg & 128)) y[(node0 + f) * ldy + ch] = o;
+                                        acc = 0.f;
+                                    }
+                                }
+                            }
+                            bits[c] = (w0 | w1) | (w2 | w3);
+                        }
+                    } else
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         uint32_t r[32];
+                        const long long e1 = prof_on ? clock64() : 0;
                         tc::tmem_ld_32x32b_x32(tcol + (uint32_t)(c * 32), r);
                         tc::tmem_ld_wait();
+                        if (prof_on) pe1 += clock64() - e1;
                         unsigned w = 0u;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -633,7 +681,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                                 if (sl == AGG_W - 1) {
                                     float o = acc;
                                     if (round_out) o = tc::round_tf32(o);
-                                    if (ch_ok && node0 + f < agg.n_nodes) y[(node0 + f) * ldy + ch] = o;
+                                    if (ch_ok && node0 + f < agg.n_nodes && !(agg.dbg & 128)) y[(node0 + f) * ldy + ch] = o;
                                     acc = 0.f;
                                 }
                             }
@@ -682,6 +730,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
         agg.prof[warp * 3] = (unsigned long long)pw0;
         agg.prof[warp * 3 + 1] = (unsigned long long)pw1;
         agg.prof[warp * 3 + 2] = (unsigned long long)(clock64() - pt0);
+        if (warp == 2) { agg.prof[9] = (unsigned long long)pe0; agg.prof[10] = (unsigned long long)pe1; }
     }
     tc::tcgen05_fence_before();
     __syncthreads();

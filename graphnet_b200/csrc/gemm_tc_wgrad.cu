@@ -114,12 +114,13 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                     const uint32_t sa = tc::smem_u32(smem + s * WG_STAGE_BYTES);
                     const uint64_t adesc = umma_desc_sw128_mnmajor(sa, lbo, sbo);
                     const uint64_t bdesc = umma_desc_sw128_mnmajor(sa + WG_A_BYTES, lbo, sbo);
+                    if (tc::elect_one()) {                // one election per K block: MMAs + commit issued back to back
 #pragma unroll
-                    for (int k = 0; k < WG_BK / 8; ++k)   // 8 rows = one 1024-byte swizzle atom per 32-column block
-                        if (tc::elect_one())
+                        for (int k = 0; k < WG_BK / 8; ++k)   // 8 rows = one 1024-byte swizzle atom per 32-column block
                             tc::umma_tf32(tmem_base, adesc + (uint64_t)(k * (1024 >> 4)), bdesc + (uint64_t)(k * (1024 >> 4)),
                                           idesc, (it | k) != 0 ? 1u : 0u);
-                    if (tc::elect_one()) tc::umma_commit(&empty[s]);
+                        tc::umma_commit(&empty[s]);
+                    }
                     __syncwarp();
                 }
                 if (tc::elect_one()) tc::umma_commit(tmem_full);

@@ -67,7 +67,7 @@ def agg_case(n, k, n_out, label):
     ntile = (n + 13) // 14
     mask = torch.empty(ntile * n_out * 4, dtype=torch.int32, device=dev)
     out = []
-    for dbg in (0, 2, 4, 8, 12, 14):
+    for dbg in (0, 2):
         lib.gnb_linear_set_debug(dbg)
 
         def run():
@@ -82,7 +82,7 @@ def agg_case(n, k, n_out, label):
     lib.gnb_linear_set_profile_buffer(None)
     v = prof.tolist()
     print(f"   agg cycles: producer wait-empty {v[0]} total {v[2]} | mma wait-full {v[3]} wait-tmem-empty {v[4]} "
-          f"total {v[5]} | epilogue wait-tmem-full {v[6]} total {v[8]}", flush=True)
+          f"total {v[5]} | epilogue wait-tmem-full {v[6]} arrive {v[7]} total {v[8]} deg-loads {v[9]} tmem-ld {v[10]}", flush=True)
     print(f"{label}: n={n} k={k} n_out={n_out} us: " + " ".join(out), flush=True)
 
 
@@ -111,7 +111,7 @@ def scatter_case(n, c_out, hdim, label):
 
 
 import sys as _s
-for variant, resident in ((2, 0), (2, 2), (2, 3)):
+for variant, resident in ((1, 0), (2, 0)):
     lib.gnb_linear_set_variant(variant)
     lib.gnb_linear_set_pair_resident(resident)
     print("== variant", variant, "(1 single-CTA, 2 CTA pair), resident weights from", resident, "stages", flush=True)

@@ -6,7 +6,7 @@
 #include <cuda_runtime.h>
 #include "tc_common.cuh"
 
-__global__ void __cluster_dims__(2, 1, 1) probe(int n, int iters, long long* out) {
+__global__ void __cluster_dims__(2, 1, 1) probe(int n, int iters, long long* out, int mode) {
     extern __shared__ uint8_t dyn[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dyn) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t bar[2];
@@ -26,9 +26,16 @@ __global__ void __cluster_dims__(2, 1, 1) probe(int n, int iters, long long* out
             const uint32_t st = tc::smem_u32(sm + (i & 1) * 65536);
             const uint64_t adesc = tc::umma_desc_sw128_kmajor(st);
             const uint64_t bdesc = tc::umma_desc_sw128_kmajor(st + 16384);
+            if (mode == 0) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (tc::elect_one()) tc::umma_tf32_2cta(slot, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+                for (int k = 0; k < 4; ++k)
+                    if (tc::elect_one()) tc::umma_tf32_2cta(slot, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+            } else {          // one election per K block: the four MMAs issued back to back by the elected lane
+                if (tc::elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tc::umma_tf32_2cta(slot, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+                }
+            }
             __syncwarp();
         }
         if (tc::elect_one()) tc::umma_commit_2cta(&bar[0], 3);
@@ -48,12 +55,13 @@ int main() {
     cudaMalloc(&d, 16);
     const int iters = 2000;
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536 + 1024);
-    for (int n : {256, 128, 64}) {
-        probe<<<2, 64, 2 * 65536 + 1024>>>(n, iters, d);
+    for (int mode = 0; mode < 2; ++mode)
+    for (int n : {256, 64}) {
+        probe<<<2, 64, 2 * 65536 + 1024>>>(n, iters, d, mode);
         cudaError_t e = cudaDeviceSynchronize();
         long long h[2] = {0, 0};
         cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-        printf("cta_group::2 M256 x N%d x K8: %s  %.1f cycles per 4 MMAs (leader), %.1f (peer)\n", n, cudaGetErrorString(e),
+        printf("mode %d cta_group::2 M256 x N%d x K8: %s  %.1f cycles per 4 MMAs (leader), %.1f (peer)\n", mode, n, cudaGetErrorString(e),
                (double)h[0] / iters, (double)h[1] / iters);
     }
     return 0;
