@@ -253,7 +253,7 @@ def timed_loop(fn, batches, steps, warmup, flush, e2e_host=None, dev=None, sampl
     if dist.is_initialized():
         dist.barrier()
     torch.cuda.synchronize()
-    timed_loop.last_launches = (_ops.kernel_launch_count() - launches0) // max(steps, 1)
+    timed_loop.last_launches = _ops.kernel_launch_count() - launches0      # over all `steps` timed steps
     timed_loop.last_host_ms = host / max(steps, 1) * 1e3
     return (wall if e2e_host is not None else total_ms / 1e3)
 
@@ -572,7 +572,7 @@ def main():
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(sec / args.steps * 1e3, 3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else args.precision,
-                "data": "synthetic", "config": workload_config(args, world), "e2e": e2e, "gpu_launches": int(launches),
+                "data": "synthetic", "config": workload_config(args, world), "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_per_step": int(launches) // max(args.steps, 1),
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "inference": inference,
                 "nodes_per_step_rank0": int(train_host[0]["x"].shape[0]),
                 "host_enqueue_ms_per_step": round(host_ms, 3)}
