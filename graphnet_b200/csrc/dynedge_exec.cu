@@ -583,7 +583,10 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
         GNB_CHECK(cudaMemsetAsync(p.dwp, 0, (size_t)b.cout * b.hld * 4, e.st));
         EX(e.lin_bwd_weight(p.dz_big, b.cout, b.h, b.hid, p.dwp, b.hld, 0, b.hid, b.cout, rows));
         EX(e.add2d(p.dwp, b.hld, b.cout, b.hid, gw2, b.hid));
-        GNB_CHECK(cudaMemsetAsync(p.dpq, 0, (size_t)n * 2 * b.hid * 4, e.st));
+        if (b.hmask != nullptr)   // the scattering epilogue overwrites the P half: only the Q half (atomics) needs zeroing
+            GNB_CHECK(cudaMemset2DAsync(p.dpq + b.hid, (size_t)2 * b.hid * 4, 0, (size_t)b.hid * 4, (size_t)n, e.st));
+        else
+            GNB_CHECK(cudaMemsetAsync(p.dpq, 0, (size_t)n * 2 * b.hid * 4, e.st));
         if (b.hmask != nullptr) {
             // data gradient + ReLU mask + scatter into dPQ in one kernel: dh [E, hid] is never materialised
             const int nld = (int)up(b.cout, 32);
