@@ -519,9 +519,8 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
             float* dx = (dz == gz) ? gz2 : gz;
             EX(gnb_act_bwd_colsum(gcur, gcur_ld, d.z, d.n_out, p.out_rows, d.n_out, dz, d.n_out, gb, GNB_ACT_RELU | e.rnd,
                                   nullptr, 1, 0, stream));
-            GNB_CHECK(cudaMemsetAsync(p.dwp, 0, (size_t)d.n_out * d.kld * 4, e.st));
-            EX(e.lin_bwd_weight(dz, d.n_out, xin, xin_ld, p.dwp, d.kld, 0, d.k_total, d.n_out, p.out_rows));
-            EX(e.add2d(p.dwp, d.kld, d.n_out, d.k_total, gw, d.k_total));
+            // weight gradients accumulate straight into the caller's gradient buffer (both GEMM back ends add)
+            EX(e.lin_bwd_weight(dz, d.n_out, xin, xin_ld, gw, d.k_total, 0, d.k_total, d.n_out, p.out_rows));
             const int64_t dx_ld = up(d.k_total, 4);
             EX(e.lin_bwd_data(dz, d.n_out, d.wp, d.kld, 0, d.k_total, d.n_out, dx, dx_ld, p.out_rows, false, p.wt, nullptr));
             gcur = dx; gcur_ld = dx_ld;
@@ -541,10 +540,8 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
         float *gw = grads[pi], *gb = grads[pi + 1];
         float* dz = (gcur == gz) ? gz2 : gz;      // a buffer that is not the current gradient
         EX(gnb_act_bwd_colsum(gcur, gcur_ld, d.z, d.n_out, n, d.n_out, dz, d.n_out, gb, GNB_ACT_RELU | e.rnd, nullptr, 1, 0, stream));
-        GNB_CHECK(cudaMemsetAsync(p.dwp, 0, (size_t)d.n_out * d.kld * 4, e.st));
         if (j > 0) {
-            EX(e.lin_bwd_weight(dz, d.n_out, p.post[j - 1].z, p.post[j - 1].n_out, p.dwp, d.kld, 0, d.k_total, d.n_out, n));
-            EX(e.add2d(p.dwp, d.kld, d.n_out, d.k_total, gw, d.k_total));
+            EX(e.lin_bwd_weight(dz, d.n_out, p.post[j - 1].z, p.post[j - 1].n_out, gw, d.k_total, 0, d.k_total, d.n_out, n));
             float* dx = (dz == gz) ? gz2 : gz;
             EX(e.lin_bwd_data(dz, d.n_out, d.wp, d.kld, 0, d.k_total, d.n_out, dx, d.k_total, n, false, p.wt, nullptr));
             gcur = dx; gcur_ld = d.k_total;
@@ -555,8 +552,7 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
             for (int q = 0; q < p.post_parts; ++q) {
                 const int valid = q == 0 ? p.node_width : c.conv_out[q - 1];
                 const float* xq = q == 0 ? p.x0 : p.conv[q - 1].y;
-                EX(e.lin_bwd_weight(dz, d.n_out, xq, p.part_k[q], p.dwp, d.kld, p.part_off[q], p.part_k[q], d.n_out, n));
-                EX(e.add2d(p.dwp + p.part_off[q], d.kld, d.n_out, valid, gw + dst_col, dst_ld));
+                EX(e.lin_bwd_weight(dz, d.n_out, xq, p.part_k[q], gw, dst_ld, dst_col, valid, d.n_out, n));
                 dst_col += valid;
                 if (q > 0)   // gradient w.r.t. the output of conv q-1 (x0 carries none)
                     EX(e.lin_bwd_data(dz, d.n_out, d.wp, d.kld, p.part_off[q], p.part_k[q], d.n_out, p.gnode[q], p.part_k[q], n,
@@ -580,9 +576,7 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
         else
             EX(gnb_act_bwd_colsum(gy, b.cout, b.m, b.cout, rows, b.cout, p.dz_big, b.cout, gb2, GNB_ACT_RELU | e.rnd, deg, wl,
                                   GNB_AGGR_ADD, stream));
-        GNB_CHECK(cudaMemsetAsync(p.dwp, 0, (size_t)b.cout * b.hld * 4, e.st));
-        EX(e.lin_bwd_weight(p.dz_big, b.cout, b.h, b.hid, p.dwp, b.hld, 0, b.hid, b.cout, rows));
-        EX(e.add2d(p.dwp, b.hld, b.cout, b.hid, gw2, b.hid));
+        EX(e.lin_bwd_weight(p.dz_big, b.cout, b.h, b.hid, gw2, b.hid, 0, b.hid, b.cout, rows));
         if (b.hmask != nullptr)   // the scattering epilogue overwrites the P half: only the Q half (atomics) needs zeroing
             GNB_CHECK(cudaMemset2DAsync(p.dpq + b.hid, (size_t)2 * b.hid * 4, 0, (size_t)b.hid * 4, (size_t)n, e.st));
         else
