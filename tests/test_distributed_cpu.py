@@ -56,3 +56,28 @@ def test_flat_grad_allreduce_matches_single_process(tmp_path):
     total.backward()
     expect = torch.cat([p.grad.flatten() for p in model.parameters()])
     assert torch.allclose(outs[0]["flat"], expect, rtol=1e-5, atol=1e-6)
+
+
+def test_bench_global_batch_sharding_covers_every_event_once():
+    """bench.host_batches(world > 1): the ranks' shards are the contiguous, pulse-balanced ranges of ONE global batch --
+    concatenated they reproduce it exactly (events, pulses, labels), with `batch` renumbered from 0 on every rank."""
+    import os
+    import sys
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    world, per_gpu = 3, 16
+    full = bench.host_batches(per_gpu * world, 1, seed0=5)[0]
+    shards = [bench.host_batches(per_gpu, 1, seed0=5, rank=r, world=world)[0] for r in range(world)]
+    assert sum(int(s["n_pulses"].numel()) for s in shards) == per_gpu * world
+    assert torch.equal(torch.cat([s["x"] for s in shards]), full["x"])
+    assert torch.equal(torch.cat([s["n_pulses"] for s in shards]), full["n_pulses"])
+    assert torch.equal(torch.cat([s["energy"] for s in shards]), full["energy"])
+    assert torch.equal(torch.cat([s["direction"] for s in shards]), full["direction"])
+    pulses = [int(s["x"].shape[0]) for s in shards]
+    assert max(pulses) - min(pulses) <= int(full["n_pulses"].max())          # balanced to within one event
+    for s in shards:
+        b = s["batch"]
+        assert int(b.min()) == 0 and int(b.max()) == s["n_pulses"].numel() - 1
+        assert torch.equal(torch.bincount(b), s["n_pulses"].long())
