@@ -48,40 +48,97 @@ constexpr int AGG_W = 9, AGG_NPT = 14, AGG_ROWS = AGG_W * AGG_NPT;   // k = 8 ne
 // the 126 scatter offsets nbr * ldpq in shared memory, so the epilogue touches no global metadata.
 struct ScatInfo { const int* nbr; const unsigned* hmask; int mask_ld; float* dpq; int64_t ldpq; int hdim; int64_t n_nodes; int enabled; };
 
-// Scatter epilogue for NN consecutive nodes whose 9 slot columns sit in r[J0 ...]; col0 = first column in the tile.
-template <int NN, int J0>
-__device__ __forceinline__ void scat_nodes(const uint32_t (&r)[32], int col0, const int* __restrict__ s_off,
-                                           const unsigned* __restrict__ s_msk, int mask_ld, unsigned lanebit,
-                                           float* __restrict__ dq, float* __restrict__ dp, int64_t ldpq, int64_t nodes_left,
-                                           bool ch_ok, int own_off, bool no_atomics) {
-    // Branch-free body: a conditional reduction compiles to a divergence region (BSSY / BRA / BSYNC, ~60 cycles per
-    // element measured), so EVERY slot issues its `red`: padding slots (offset < 0; their mask bits are zero, so the
-    // value is 0) are redirected to the Q row of the tile's first node, lanes beyond the last channel carry a zero lane
-    // bit and a wrapped (valid) channel. Metadata first: independent broadcast LDS issued back to back.
+// Producer side of the scattering epilogue: per 126-slot sub-tile (first node `node0`) every lane resolves 4 of the 128
+// offsets `nbr * ldpq` (floats; padding slots and slots beyond the tensor are redirected to the Q row of the sub-tile's
+// first node, where they add 0) and the warp builds `lastv`: bit f = "slot 8 of node f holds an edge" (the duplicate
+// quirk). The epilogue therefore runs no comparison / select on the offsets.
+__device__ __forceinline__ void scat_meta(const ScatInfo& sc, int64_t node0, int64_t rows, int lane, int (&offv)[4], unsigned& lastv) {
+    unsigned vb[4];
+    const int own_off = (int)node0 * (int)sc.ldpq;
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+        const int col = lane + 32 * q4;
+        const int64_t r = node0 * AGG_W + col;
+        const int nb = (col < AGG_ROWS && r < rows) ? sc.nbr[r] : -1;
+        vb[q4] = __ballot_sync(0xffffffffu, nb >= 0);
+        offv[q4] = nb >= 0 ? nb * (int)sc.ldpq : own_off;
+    }
+    lastv = 0u;
+#pragma unroll
+    for (int f = 0; f < AGG_NPT; ++f) {
+        const int col = f * AGG_W + AGG_W - 1;
+        lastv |= ((vb[col >> 5] >> (col & 31)) & 1u) << f;
+    }
+}
+constexpr uint32_t SC_META_OFF = 8192;   // single-CTA kernel: byte offset of the 128 scatter offsets in a metadata block
+// metadata block of one sub-tile: {126 mask rows of mask_ld words | lastv (4 B) | pad to 16 | 128 offsets}
+__host__ __device__ constexpr uint32_t sc_meta_stride(int mask_ld) {
+    return (((uint32_t)AGG_ROWS * (uint32_t)mask_ld * 4u + 4u + 15u) & ~15u) + 512u;
+}
+
+// Scatter epilogue for NN consecutive nodes whose 9 slot columns sit in r[J0 ...] once the TMEM load issued here lands.
+// off_a / msk_a: shared-memory addresses of the first column's offset and of this lane's mask word; MLD = mask words per
+// row when known at compile time (constant LDS offsets), 0 = runtime stride `mstride` (bytes).
+// Branch-free body: a conditional reduction compiles to a divergence region (BSSY / BRA / BSYNC, ~60 cycles per
+// element measured), so EVERY slot 0..7 issues its `red` (padding slots carry 0 to a harmless row, lanes beyond the
+// last channel carry a zero lane bit and a wrapped, valid channel); slot 8 is skipped with a WARP-UNIFORM branch when
+// it is padding (1/9 of all reductions; a per-lane `v != 0` test would halve the reductions but costs a divergence
+// region per element: 461 -> 673 us). Per element: 2 LDS + LOP3 + FSEL + FADD + IMAD.WIDE + RED (the first version,
+// with generic-pointer metadata loads and offset selects, ran 17 and made the epilogue warps the kernel's bound).
+template <int NN, int J0, int MLD>
+__device__ __forceinline__ void scat_nodes(uint32_t taddr, uint32_t off_a, uint32_t msk_a, uint32_t mstride, unsigned lanebit,
+                                           unsigned lastv, float* __restrict__ dq, float* __restrict__ dp, int64_t ldpq,
+                                           int64_t nodes_left, bool ch_ok, bool skip) {
+    uint32_t r[32];
+    tc::tmem_ld_32x32b_x32(taddr, r);
     int offr[NN * AGG_W];
     unsigned mwr[NN * AGG_W];
-    bool last_valid[NN];                                 // slot k (the 9th) is padding unless the duplicate quirk filled it
+    const uint32_t ms = MLD ? (uint32_t)MLD * 4u : mstride;
 #pragma unroll
-    for (int e = 0; e < NN * AGG_W; ++e) {
-        const int o = s_off[col0 + e];
-        offr[e] = o >= 0 ? o : own_off;
-        mwr[e] = s_msk[(col0 + e) * mask_ld];
-        if (e % AGG_W == AGG_W - 1) last_valid[e / AGG_W] = o >= 0;
+    for (int e = 0; e < NN * AGG_W; ++e) {               // metadata loads overlap the TMEM load
+        offr[e] = (int)tc::lds_u32(off_a + 4u * e);
+        mwr[e] = tc::lds_u32(msk_a + (uint32_t)e * ms);
     }
+    tc::tmem_ld_wait();
+    if (skip) return;
 #pragma unroll
     for (int f = 0; f < NN; ++f) {
         float accp = 0.f;
+        const bool last_valid = (lastv >> f) & 1u;
 #pragma unroll
         for (int sl = 0; sl < AGG_W; ++sl) {
             const int e = f * AGG_W + sl;
             const float v = (mwr[e] & lanebit) ? __uint_as_float(r[J0 + e]) : 0.f;
             accp += v;
-            // the last slot is skipped with a WARP-UNIFORM branch when it is padding (1/9 of all reductions)
-            // (a per-lane `v != 0` test would halve the reductions but costs a divergence region per element: 461 -> 673 us)
-            if (!no_atomics && (sl < AGG_W - 1 || last_valid[f])) atomicAdd(dq + offr[e], v);
+            if (sl < AGG_W - 1 || last_valid) tc::red_add_f32(dq + offr[e], v);
         }
         if (ch_ok && f < nodes_left) dp[(int64_t)f * ldpq] = accp;
     }
+}
+// One 126-slot sub-tile = 14 nodes: columns [27 c, 27 c + 27) for c = 0..3, then [108, 126) out of a load at column 96.
+template <int MLD>
+__device__ __forceinline__ void scat_tile(uint32_t tcol, uint32_t mb_a, uint32_t off_a, uint32_t mword, uint32_t mstride,
+                                          unsigned lanebit, float* dq, float* dp, int64_t ldpq, int64_t nodes_left, bool ch_ok,
+                                          bool skip) {
+    const uint32_t ms = MLD ? (uint32_t)MLD * 4u : mstride;
+    const uint32_t msk_a = mb_a + 4u * mword;
+    const unsigned lastv = tc::lds_u32(mb_a + (uint32_t)AGG_ROWS * ms);     // right behind the 126 mask rows
+    asm volatile("" : "+l"(dq));      // keep the row base opaque: `dq + off` stays one IMAD.WIDE per reduction
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c)
+        scat_nodes<3, 0, MLD>(tcol + (uint32_t)(27 * c), off_a + 108u * c, msk_a + 27u * c * ms, ms, lanebit, lastv >> (3 * c), dq,
+                              dp + (int64_t)(3 * c) * ldpq, ldpq, nodes_left - 3 * c, ch_ok, skip);
+    scat_nodes<2, 12, MLD>(tcol + 96u, off_a + 432u, msk_a + 108u * ms, ms, lanebit, lastv >> 12, dq, dp + (int64_t)12 * ldpq, ldpq,
+                           nodes_left - 12, ch_ok, skip);
+}
+// mb_a: shared address of the sub-tile's metadata block {126 mask rows | lastv | ... | 128 offsets at off_a}
+__device__ __forceinline__ void scat_tile_any(int mask_ld, uint32_t tcol, uint32_t mb_a, uint32_t off_a, uint32_t mword,
+                                              unsigned lanebit, float* dq, float* dp, int64_t ldpq, int64_t nodes_left, bool ch_ok,
+                                              bool skip) {
+    // 4 / 12 words per row = hidden widths up to 128 / 257..384 (DynEdge: 128 and 336)
+    if (mask_ld == 12) scat_tile<12>(tcol, mb_a, off_a, mword, 48u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip);
+    else if (mask_ld == 4) scat_tile<4>(tcol, mb_a, off_a, mword, 16u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip);
+    else scat_tile<0>(tcol, mb_a, off_a, mword, (uint32_t)mask_ld * 4u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip);
 }
 
 // Epilogue store of one 32-row chunk: lane = output channel, r[j] = row j. One coalesced 128-byte store per row; the
@@ -172,15 +229,10 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
             uint32_t it = 0, tile_i = 0;
             for (int t = blockIdx.x; t < num_row_tiles; t += gridDim.x, ++tile_i) {
                 const int row0 = t * tile_rows;
-                int offv[4] = {-1, -1, -1, -1};
-                if (sc.enabled) {        // scatter offsets of the tile's 126 slots (consumed after the K loop: latency hidden)
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        const int col = lane + 32 * q4;
-                        const int nb = (col < AGG_ROWS && (int64_t)row0 + col < rows) ? sc.nbr[(int64_t)row0 + col] : -1;
-                        offv[q4] = nb >= 0 ? nb * (int)sc.ldpq : -1;
-                    }
-                }
+                int offv[4] = {0, 0, 0, 0};
+                unsigned lastv = 0u;
+                // scatter offsets of the tile's 126 slots (consumed after the K loop: latency hidden)
+                if (sc.enabled) scat_meta(sc, (int64_t)t * AGG_NPT, rows, lane, offv, lastv);
                 int kb_w = 0;
                 for (int p = 0; p < parts.nparts; ++p) {
                     for (int kb = 0; kb < parts.kblocks[p]; ++kb, ++kb_w, ++it) {
@@ -205,9 +257,10 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
                     const uint32_t buf = tile_i & 1;
                     tc::mbar_wait(&tmem_empty[buf], ((tile_i >> 1) & 1) ^ 1);   // epilogue of tile_i - 2 is done with meta[buf]
                     uint8_t* mb = meta + buf * SC_META_BYTES;
-                    int* so = reinterpret_cast<int*>(mb + 8192);
+                    int* so = reinterpret_cast<int*>(mb + SC_META_OFF);
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) so[lane + 32 * q4] = offv[q4];
+                    if (lane == 0) *reinterpret_cast<unsigned*>(mb + AGG_ROWS * sc.mask_ld * 4) = lastv;
                     __syncwarp();
                     if (tc::elect_one()) {
                         const uint32_t bytes = (uint32_t)(AGG_ROWS * sc.mask_ld * 4);
@@ -276,31 +329,15 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
                     const int ch = ch0 + m * TC_BM + q * 32 + lane;
                     const bool ch_ok = ch < n_out;
                     const int64_t node0 = (int64_t)t * AGG_NPT;
-                    const uint8_t* mb = meta + buf * SC_META_BYTES;
-                    const int* s_off = reinterpret_cast<const int*>(mb + 8192);
+                    const uint32_t mb_a = tc::smem_u32(meta + buf * SC_META_BYTES);
                     // mask layout of gnb_edge_hidden_fwd_mask: channel c is bit (c % 128) / 4 of word 4 (c / 128) + c % 4
-                    const unsigned* s_msk = reinterpret_cast<const unsigned*>(mb) + 4 * ((ch0 + m * TC_BM) >> 7) + (lane & 3);
+                    const uint32_t mword = 4u * (uint32_t)((ch0 + m * TC_BM) >> 7) + (uint32_t)(lane & 3);
                     float* dq = sc.dpq + sc.hdim + (ch_ok ? ch : ch % sc.hdim);
                     float* dp = sc.dpq + node0 * sc.ldpq + ch;
                     const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * (TC_MT * TC_BN) + m * TC_BN);
                     const unsigned lanebit = ch_ok ? (1u << (q * 8 + (lane >> 2))) : 0u;
-                    const int own_off = (int)node0 * (int)sc.ldpq;
-                    const bool no_at = (agg.dbg & 16) != 0;
-#pragma unroll 1
-                    for (int c = 0; c < 4; ++c) {          // columns [27 c, 27 c + 27): three nodes
-                        uint32_t r[32];
-                        tc::tmem_ld_32x32b_x32(tcol + (uint32_t)(27 * c), r);
-                        tc::tmem_ld_wait();
-                        if (!(agg.dbg & 64)) scat_nodes<3, 0>(r, 27 * c, s_off, s_msk, sc.mask_ld, lanebit, dq, dp + (int64_t)(3 * c) * sc.ldpq, sc.ldpq,
-                                         sc.n_nodes - node0 - 3 * c, ch_ok, own_off, no_at);
-                    }
-                    {                                       // columns [108, 126): the last two nodes, registers 12..29
-                        uint32_t r[32];
-                        tc::tmem_ld_32x32b_x32(tcol + 96u, r);
-                        tc::tmem_ld_wait();
-                        if (!(agg.dbg & 64)) scat_nodes<2, 12>(r, 108, s_off, s_msk, sc.mask_ld, lanebit, dq, dp + (int64_t)12 * sc.ldpq, sc.ldpq,
-                                          sc.n_nodes - node0 - 12, ch_ok, own_off, no_at);
-                    }
+                    scat_tile_any(sc.mask_ld, tcol, mb_a, mb_a + SC_META_OFF, mword, lanebit, dq, dp, sc.ldpq, sc.n_nodes - node0,
+                                  ch_ok, (agg.dbg & 64) != 0);
                 }
             } else if (agg.enabled) {
                 // warps 2-5 own channel tile 0, warps 6-9 channel tile 1; every thread walks all 126 slot columns
@@ -408,7 +445,7 @@ struct GroupSplit { int ngroups; int start[5]; };
 // [scatter metadata]. Streaming mode: a stage = this CTA's weight tile + its half of the activation rows (32 KiB);
 // resident mode (single-part K that fits): the CTA's 128 weight rows stay in shared memory for the kernel's lifetime
 // (one TMA pass), a stage is the activation half only (16 KiB) and the L2->SM traffic per launch halves.
-struct PairCfg { int resident; int nstages; };
+struct PairCfg { int resident; int nstages; uint32_t meta_stride; };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PL_THREADS, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ TmapArray tm_x,
@@ -431,7 +468,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     uint64_t* meta_empty = meta_full + 2;         // [2]
     uint64_t* a_full = meta_empty + 2;            // [1] resident weights landed (leader's copy is waited on)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
-    uint8_t* meta = ring + nstages * stage_bytes + 256;           // [2 buffers][2 sub-tiles] x SC_META_BYTES
+    uint8_t* meta = ring + nstages * stage_bytes + 256;           // [2 buffers][2 sub-tiles] x pc.meta_stride
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = tc::cluster_ctarank();
@@ -483,16 +520,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
         for (int t = cluster_id; t < num_tiles; t += num_clusters, ++tile_i) {
             const int64_t row0 = (int64_t)t * (2 * half_rows) + (int64_t)rank * half_rows;
             int offv[2][4];
+            unsigned lastv[2] = {0u, 0u};
             if (sc.enabled) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        const int col = lane + 32 * q4;
-                        const int64_t r = ((int64_t)t * 2 + h) * AGG_ROWS + col;
-                        const int nb = (col < AGG_ROWS && r < rows) ? sc.nbr[r] : -1;
-                        offv[h][q4] = nb >= 0 ? nb * (int)sc.ldpq : -1;
-                    }
+                for (int h = 0; h < 2; ++h) scat_meta(sc, ((int64_t)t * 2 + h) * AGG_NPT, rows, lane, offv[h], lastv[h]);
             }
             int kb_w = 0;
             for (int p = 0; p < parts.nparts; ++p) {
@@ -516,9 +547,11 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                 uint32_t bytes = 0;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    int* so = reinterpret_cast<int*>(meta + (buf * 2 + h) * SC_META_BYTES + 8192);
+                    uint8_t* mbh = meta + (buf * 2 + h) * pc.meta_stride;
+                    int* so = reinterpret_cast<int*>(mbh + pc.meta_stride - 512);
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) so[lane + 32 * q4] = offv[h][q4];
+                    if (lane == 0) *reinterpret_cast<unsigned*>(mbh + AGG_ROWS * sc.mask_ld * 4) = lastv[h];
                     if (((int64_t)t * 2 + h) * AGG_NPT < sc.n_nodes) bytes += (uint32_t)(AGG_ROWS * sc.mask_ld * 4);
                 }
                 __syncwarp();
@@ -528,7 +561,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
 #pragma unroll
                     for (int h = 0; h < 2; ++h)
                         if (((int64_t)t * 2 + h) * AGG_NPT < sc.n_nodes)
-                            tc::bulk_load(meta + (buf * 2 + h) * SC_META_BYTES,
+                            tc::bulk_load(meta + (buf * 2 + h) * pc.meta_stride,
                                           sc.hmask + ((int64_t)t * 2 + h) * AGG_ROWS * sc.mask_ld, one, &meta_full[buf]);
                 }
                 __syncwarp();
@@ -591,29 +624,13 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                 tc::mbar_wait<100>(&meta_full[buf], (tile_i >> 1) & 1);
                 const int64_t node0 = ((int64_t)t * 2 + half) * AGG_NPT;
                 if (node0 < sc.n_nodes && ch0 + q * 32 < n_out) {
-                    const uint8_t* mb = meta + (buf * 2 + half) * SC_META_BYTES;
-                    const int* s_off = reinterpret_cast<const int*>(mb + 8192);
-                    const unsigned* s_msk = reinterpret_cast<const unsigned*>(mb) + 4 * (ch0 >> 7) + (lane & 3);
+                    const uint32_t mb_a = tc::smem_u32(meta + (buf * 2 + half) * pc.meta_stride);
+                    const uint32_t mword = 4u * (uint32_t)(ch0 >> 7) + (uint32_t)(lane & 3);
                     float* dq = sc.dpq + sc.hdim + (ch_ok ? ch : ch % sc.hdim);
                     float* dp = sc.dpq + node0 * sc.ldpq + ch;
                     const unsigned lanebit = ch_ok ? (1u << (q * 8 + (lane >> 2))) : 0u;
-                    const int own_off = (int)node0 * (int)sc.ldpq;
-                    const bool no_at = (agg.dbg & 16) != 0;
-#pragma unroll 1
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t r[32];
-                        tc::tmem_ld_32x32b_x32(tcol + (uint32_t)(27 * c), r);
-                        tc::tmem_ld_wait();
-                        if (!(agg.dbg & 64)) scat_nodes<3, 0>(r, 27 * c, s_off, s_msk, sc.mask_ld, lanebit, dq, dp + (int64_t)(3 * c) * sc.ldpq, sc.ldpq,
-                                         sc.n_nodes - node0 - 3 * c, ch_ok, own_off, no_at);
-                    }
-                    {
-                        uint32_t r[32];
-                        tc::tmem_ld_32x32b_x32(tcol + 96u, r);
-                        tc::tmem_ld_wait();
-                        if (!(agg.dbg & 64)) scat_nodes<2, 12>(r, 108, s_off, s_msk, sc.mask_ld, lanebit, dq, dp + (int64_t)12 * sc.ldpq, sc.ldpq,
-                                          sc.n_nodes - node0 - 12, ch_ok, own_off, no_at);
-                    }
+                    scat_tile_any(sc.mask_ld, tcol, mb_a, mb_a + pc.meta_stride - 512u, mword, lanebit, dq, dp, sc.ldpq,
+                                  sc.n_nodes - node0, ch_ok, (agg.dbg & 64) != 0);
                 }
             } else if (agg.enabled) {
                 const int64_t st14 = (int64_t)t * 2 + half;            // 14-node tile index of the mask layout
@@ -638,31 +655,48 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                     if (regular && !(agg.dbg & 256)) {
                         // fast path: slot validity is compile-time (slots 0..7 valid, slot 8 padding), relu = fmaxf, and the
                         // mask word is built in four independent partial words (no 126-long dependency chain)
+                        float nodeacc[AGG_NPT];
+#pragma unroll
+                        for (int f = 0; f < AGG_NPT; ++f) nodeacc[f] = 0.f;
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             uint32_t r[32];
                             tc::tmem_ld_32x32b_x32(tcol + (uint32_t)(c * 32), r);
                             tc::tmem_ld_wait();
-                            unsigned w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
+                            // phase 1: 32 independent elements (bias, ReLU, mask bit); padding columns contribute nothing
+                            float rl[32];
+                            unsigned bt[32];
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
                                 const int col = c * 32 + j;
-                                if (col < AGG_ROWS) {
-                                    const int f = col / AGG_W, sl = col % AGG_W;
-                                    if (sl < AGG_W - 1) {
-                                        const float pre = __uint_as_float(r[j]) + bv;
-                                        acc += fmaxf(pre, 0.f);
-                                        const unsigned b = pre > 0.f ? (1u << j) : 0u;
-                                        if ((j & 3) == 0) w0 |= b; else if ((j & 3) == 1) w1 |= b; else if ((j & 3) == 2) w2 |= b; else w3 |= b;
-                                    } else {
-                                        float o = acc;
+                                const bool slot_ok = col < AGG_ROWS && (col % AGG_W) < AGG_W - 1;     // compile-time
+                                const float pre = __uint_as_float(r[j]) + bv;
+                                rl[j] = slot_ok ? fmaxf(pre, 0.f) : 0.f;
+                                bt[j] = (slot_ok && pre > 0.f) ? (1u << j) : 0u;
+                            }
+                            // phase 2: mask word by a log-depth OR tree
+#pragma unroll
+                            for (int st = 16; st > 0; st >>= 1)
+#pragma unroll
+                                for (int j = 0; j < st; ++j) bt[j] |= bt[j + st];
+                            bits[c] = bt[0];
+                            // phase 3: per-node sums as pairwise trees over the node's slots inside this chunk
+#pragma unroll
+                            for (int f = 0; f < AGG_NPT; ++f) {
+                                const int c_lo = c * 32, c_hi = c * 32 + 32;
+                                const int n_lo = f * AGG_W, n_hi = f * AGG_W + AGG_W - 1;            // valid slots [n_lo, n_hi)
+                                if (n_lo < c_hi && n_hi > c_lo) {                                     // compile-time
+                                    auto g = [&](int col) -> float { return (col >= c_lo && col < c_hi) ? rl[col - c_lo] : 0.f; };
+                                    const float s8 = ((g(n_lo) + g(n_lo + 1)) + (g(n_lo + 2) + g(n_lo + 3))) +
+                                                     ((g(n_lo + 4) + g(n_lo + 5)) + (g(n_lo + 6) + g(n_lo + 7)));
+                                    nodeacc[f] += s8;
+                                    if (n_hi <= c_hi) {                                               // node complete in this chunk
+                                        float o = nodeacc[f];
                                         if (round_out) o = tc::round_tf32(o);
                                         if (ch_ok && !(agg.dbg & 128)) y[(node0 + f) * ldy + ch] = o;
-                                        acc = 0.f;
                                     }
                                 }
                             }
-                            bits[c] = (w0 | w1) | (w2 | w3);
                         }
                     } else
 #pragma unroll
@@ -798,8 +832,9 @@ int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi
         // shared-memory plan: resident weights when a single-part K leaves at least `min_res_stages` activation stages
         int total_kb = 0;
         for (int p = 0; p < pi.nparts; ++p) total_kb += pi.kblocks[p];
-        const uint32_t fixed = 1024 + 256 + (sc.enabled ? 4 * SC_META_BYTES : 0);
         PairCfg pc;
+        pc.meta_stride = sc.enabled ? sc_meta_stride(sc.mask_ld) : 0u;
+        const uint32_t fixed = 1024 + 256 + 4 * pc.meta_stride;
         const int64_t res_left = (int64_t)PL_MAX_DYN_SMEM - fixed - (int64_t)total_kb * TC_TILE_BYTES;
         int res_stages = res_left > 0 ? (int)(res_left / TC_TILE_BYTES) : 0;
         if (res_stages > PL_MAX_STAGES) res_stages = PL_MAX_STAGES;
@@ -829,7 +864,7 @@ int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi
 }  // namespace
 
 // Tuning hook (profiling only): bit0 epilogue skips its global stores, bit1 no MMAs, bit2 no weight loads, bit3 no
-// activation loads. Results are garbage with any bit set.
+// activation loads, bit6 no scatter epilogue math. Results are garbage with any bit set.
 GNB_EXPORT int gnb_linear_set_debug(int32_t flags) { g_linear_dbg = flags; return GNB_OK; }
 // Kernel selection for the tf32 Linear entry points: 0 auto (CTA-pair cta_group::2 kernel from 296 row tiles up),
 // 1 single-CTA kernel, 2 CTA-pair kernel.

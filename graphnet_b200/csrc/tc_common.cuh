@@ -13,6 +13,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// 32-bit shared-memory loads / fire-and-forget global reductions for the metadata-driven epilogues. A `const T*` into
+// dynamic shared memory that crossed a function boundary compiles to generic LD.E with 64-bit address arithmetic
+// (4 integer instructions per load); these take the 32-bit shared address, so constant offsets fold into the LDS.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
 // ---- mbarrier ------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -44,3 +44,6 @@ for variant in (0, 1):
     t = timed(lambda: ops.knn_table(x, [0, 1, 2], ptr, 8))
     print(f"kNN variant {variant}: {t:.0f} us", flush=True)
 lib.gnb_knn_set_variant(0)
+xl = torch.randn(n, 256, device=dev)
+t = timed(lambda: ops.knn_table(xl, [0, 1, 2], ptr, 8))
+print(f"kNN on a 256-wide latent tensor (random normal): {t:.0f} us", flush=True)

@@ -35,7 +35,7 @@ def linear_case(rows, k, n_out, label):
     b = torch.randn(n_out, device=dev)
     pw = ops._tc_pack_weight(w, [0], [k])
     out = []
-    for dbg in (0, 1, 2, 3, 4, 8, 12, 14, 15):
+    for dbg in (0, 1, 2, 3, 15):
         lib.gnb_linear_set_debug(dbg)
         t = timed(lambda: ops._tc_linear([x], pw, b, n_out, 1, True))
         out.append(f"dbg{dbg}={t:.0f}")
@@ -86,9 +86,10 @@ def agg_case(n, k, n_out, label):
     print(f"{label}: n={n} k={k} n_out={n_out} us: " + " ".join(out), flush=True)
 
 
-def scatter_case(n, c_out, hdim, label):
+def scatter_case(n, c_out, hdim, label, pitch=None):
     rows = n * 9
-    dz = torch.randn(rows, c_out, device=dev).round_()
+    pitch = pitch or c_out
+    dz = torch.randn(rows, pitch, device=dev).round_()[:, :c_out]
     kpad = (c_out + 31) // 32 * 32
     wt = torch.randn(hdim, kpad, device=dev).round_()
     mld = 4 * ((hdim + 127) // 128)
@@ -99,19 +100,27 @@ def scatter_case(n, c_out, hdim, label):
     nbr[:, 8] = -1
     dpq = torch.zeros(n, 2 * hdim, device=dev)
     out = []
-    for dbg in (0, 16, 18, 82, 66):
+    for dbg in (0, 2, 64, 66):
         lib.gnb_linear_set_debug(dbg)
 
         def run():
-            ops._call("gnb_edge_hidden_dgrad_scatter_tf32", ops._ptr(dz), c_out, c_out, ops._ptr(wt), kpad, ops._ptr(hmask), mld,
+            ops._call("gnb_edge_hidden_dgrad_scatter_tf32", ops._ptr(dz), pitch, c_out, ops._ptr(wt), kpad, ops._ptr(hmask), mld,
                       hdim, ops._ptr(nbr), n, ops._ptr(dpq), 2 * hdim, ops._stream())
         out.append(f"dbg{dbg}={timed(run):.0f}")
     lib.gnb_linear_set_debug(0)
+    prof = torch.zeros(16, dtype=torch.int64, device=dev)
+    lib.gnb_linear_set_profile_buffer(ctypes.c_void_p(prof.data_ptr()))
+    run()
+    torch.cuda.synchronize()
+    lib.gnb_linear_set_profile_buffer(None)
+    v = prof.tolist()
+    print(f"   scatter cycles (cluster 0): producer wait-empty {v[0]} total {v[2]} | mma wait-full {v[3]} wait-tmem-empty {v[4]} "
+          f"total {v[5]} | epilogue wait-tmem-full {v[6]} arrive {v[7]} total {v[8]}", flush=True)
     print(f"{label}: n={n} c_out={c_out} hdim={hdim} us: " + " ".join(out), flush=True)
 
 
 import sys as _s
-for variant, resident in ((1, 0), (2, 0)):
+for variant, resident in (((1, 0), (2, 0)) if not (len(_s.argv) > 1 and _s.argv[1] in ("resident", "pitch")) else ()):
     lib.gnb_linear_set_variant(variant)
     lib.gnb_linear_set_pair_resident(resident)
     print("== variant", variant, "(1 single-CTA, 2 CTA pair), resident weights from", resident, "stages", flush=True)
@@ -122,6 +131,26 @@ for variant, resident in ((1, 0), (2, 0)):
 lib.gnb_linear_set_variant(0)
 lib.gnb_linear_set_pair_resident(0)
 if len(_s.argv) > 1 and _s.argv[1] == "scatter":
+    _s.exit(0)
+if len(_s.argv) > 1 and _s.argv[1] == "pitch":
+    lib.gnb_linear_set_variant(2)
+    for pitch in (256, 272, 288, 320, 336):
+        scatter_case(N, 256, 336, f"dgrad + scatter, dz pitch {pitch}", pitch=pitch)
+    for pitch in (256, 272):
+        scatter_case(N, 256, 128, f"layer-1 dgrad + scatter, dz pitch {pitch}", pitch=pitch)
+    lib.gnb_linear_set_variant(0)
+    _s.exit(0)
+if len(_s.argv) > 1 and _s.argv[1] == "resident":
+    for resident in (0, 3, 2):
+        lib.gnb_linear_set_variant(2)
+        lib.gnb_linear_set_pair_resident(resident)
+        print("== CTA pair, resident weights from", resident, "stages", flush=True)
+        scatter_case(N, 256, 336, "dgrad + scatter epilogue")
+        scatter_case(N, 256, 128, "layer-1 dgrad + scatter")
+        agg_case(N, 336, 256, "edge GEMM2 fwd (aggregating)")
+        linear_case(N, 256, 672, "PQ linear")
+    lib.gnb_linear_set_variant(0)
+    lib.gnb_linear_set_pair_resident(0)
     _s.exit(0)
 linear_case(ROWS, 336, 256, "edge GEMM2 fwd (plain)")
 linear_case(ROWS, 256, 336, "edge GEMM2 dgrad")
