@@ -46,6 +46,8 @@ SIGNATURES: Dict[str, list] = {
     "gnb_linear_bwd_weight_tf32": [_p, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _p],
     "gnb_edge_linear_agg_fwd_tf32": [_p, _i64, _i32, _p, _i64, _p, _p, _i64, _i32, _i32, _p, _i64, _p, _p],
     "gnb_edge_hidden_dgrad_scatter_tf32": [_p, _i64, _i32, _p, _i64, _p, _i32, _i32, _p, _i64, _p, _i64, _p],
+    "gnb_edge_hidden_dgrad_scatter_split_tf32": [_p, _i64, _i32, _p, _i64, _p, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _p,
+                                                 _i32, _p],
     "gnb_edge_hidden_fwd_mask": [_p, _i64, _i32, _p, _p, _i32, _i64, _i32, _p, _i64, _p, _i32, _p],
     "gnb_edge_mask_bwd_colsum": [_p, _i64, _p, _i64, _i32, _p, _p, _i64, _p, _i32, _p],
     "gnb_round_pad_tf32": [_p, _i64, _i64, _i32, _p, _i64, _i32, _p],

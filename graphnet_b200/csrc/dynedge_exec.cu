@@ -35,6 +35,8 @@ int gnb_edge_mask_bwd_colsum(const float*, int64_t, const uint32_t*, int64_t, in
                              int32_t, void*);
 int gnb_edge_hidden_dgrad_scatter_tf32(const float*, int64_t, int32_t, const float*, int64_t, const uint32_t*, int32_t, int32_t,
                                        const int32_t*, int64_t, float*, int64_t, void*);
+int gnb_edge_hidden_dgrad_scatter_split_tf32(const float*, int64_t, int32_t, const float*, int64_t, const uint32_t*, int32_t, int32_t,
+                                             const int32_t*, int64_t, float*, int64_t, float*, int64_t, float*, int32_t, void*);
 int gnb_edge_hidden_fwd_mask(const float*, int64_t, int32_t, const int32_t*, const int32_t*, int32_t, int64_t, int32_t, float*,
                              int64_t, uint32_t*, int32_t, void*);
 int gnb_segment_pool_bwd(const float*, int64_t, const int32_t*, int32_t, const int64_t*, int64_t, int64_t, const int32_t*,
@@ -561,6 +563,7 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
         }
     }
     // ---- DynEdgeConv layers, last to first -------------------------------------------------------
+    int dq_zeroed_hid = -1;     // width for which the Q half of p.dpq is known to be all zero
     for (int l = c.n_conv - 1; l >= 0; --l) {
         ConvBuf& b = p.conv[l];
         pi -= 4;
@@ -577,31 +580,31 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
             EX(gnb_act_bwd_colsum(gy, b.cout, b.m, b.cout, rows, b.cout, p.dz_big, b.cout, gb2, GNB_ACT_RELU | e.rnd, deg, wl,
                                   GNB_AGGR_ADD, stream));
         EX(e.lin_bwd_weight(p.dz_big, b.cout, b.h, b.hid, gw2, b.hid, 0, b.hid, b.cout, rows));
-        if (b.hmask != nullptr)   // the scattering epilogue overwrites the P half: only the Q half (atomics) needs zeroing
-            GNB_CHECK(cudaMemset2DAsync(p.dpq + b.hid, (size_t)2 * b.hid * 4, 0, (size_t)b.hid * 4, (size_t)n, e.st));
-        else
-            GNB_CHECK(cudaMemsetAsync(p.dpq, 0, (size_t)n * 2 * b.hid * 4, e.st));
+        GNB_CHECK(cudaMemsetAsync(p.dbtmp, 0, (size_t)2 * b.hid * 4, e.st));
+        const float* dzq = p.dzq;
         if (b.hmask != nullptr) {
-            // data gradient + ReLU mask + scatter into dPQ in one kernel: dh [E, hid] is never materialised
+            // data gradient + ReLU mask + scatter in one kernel (dh [E, hid] is never materialised). The P half (slot sums,
+            // plain stores) goes straight into dzq, rounded for the tensor cores, with its column sums (bias gradient)
+            // accumulated by the epilogue; only the Q half (fp32 reductions from all over the event) needs the dPQ
+            // accumulation buffer and a rounding pass, which also leaves that half zeroed for the next layer of the same
+            // width (so it is memset only when the layout changes).
+            if (dq_zeroed_hid != b.hid)
+                GNB_CHECK(cudaMemset2DAsync(p.dpq + b.hid, (size_t)2 * b.hid * 4, 0, (size_t)b.hid * 4, (size_t)n, e.st));
             const int nld = (int)up(b.cout, 32);
             EX(e.transpose_pad(b.w2p, b.hld, b.cout, b.hid, p.wt, nld, nld));
-            EX(gnb_edge_hidden_dgrad_scatter_tf32(p.dz_big, b.cout, b.cout, p.wt, nld, b.hmask, b.mld, b.hid, nbr, n, p.dpq,
-                                                  2 * b.hid, stream));
+            EX(gnb_edge_hidden_dgrad_scatter_split_tf32(p.dz_big, b.cout, b.cout, p.wt, nld, b.hmask, b.mld, b.hid, nbr, n,
+                                                        p.dpq + b.hid, 2 * b.hid, p.dzq, 2 * b.hid, p.dbtmp, e.rnd, stream));
+            EX(gnb_act_bwd_colsum(p.dpq + b.hid, 2 * b.hid, nullptr, 0, n, b.hid, p.dzq + b.hid, 2 * b.hid, nullptr,
+                                  GNB_ACT_NONE | e.rnd | GNB_FLAG_ZERO_SRC, nullptr, 1, 0, stream));
+            dq_zeroed_hid = b.hid;
         } else {
+            GNB_CHECK(cudaMemsetAsync(p.dpq, 0, (size_t)n * 2 * b.hid * 4, e.st));
+            dq_zeroed_hid = -1;
             EX(e.lin_bwd_data(p.dz_big, b.cout, b.w2p, b.hld, 0, b.hid, b.cout, p.dh_big, b.hid, rows, false, p.wt, nullptr));
             EX(gnb_edge_hidden_bwd(p.dh_big, b.hid, b.h, b.hid, b.hid, nbr, deg, wl, n, GNB_ACT_RELU, p.dpq, 2 * b.hid, stream));
-        }
-        // PQ = xin Wcat^T + bcat
-        GNB_CHECK(cudaMemsetAsync(p.dbtmp, 0, (size_t)2 * b.hid * 4, e.st));
-        const float* dzq = p.dpq;
-        if (e.tf32) {   // rounded copy for the tensor cores + bias gradient in the same pass
+            // PQ = xin Wcat^T + bcat: rounded copy for the tensor cores (tf32 mode) + bias gradient in the same pass
             EX(gnb_act_bwd_colsum(p.dpq, 2 * b.hid, nullptr, 0, n, 2 * b.hid, p.dzq, 2 * b.hid, p.dbtmp, GNB_ACT_NONE | e.rnd,
                                   nullptr, 1, 0, stream));
-            dzq = p.dzq;
-        } else {
-            EX(gnb_act_bwd_colsum(p.dpq, 2 * b.hid, nullptr, 0, n, 2 * b.hid, p.dzq, 2 * b.hid, p.dbtmp, GNB_ACT_NONE, nullptr, 1,
-                                  0, stream));
-            dzq = p.dzq;
         }
         const float* xin = l == 0 ? p.x0 : p.conv[l - 1].y;
         GNB_CHECK(cudaMemsetAsync(p.dwp, 0, (size_t)2 * b.hid * b.kld * 4, e.st));

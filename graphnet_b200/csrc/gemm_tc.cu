@@ -46,22 +46,25 @@ constexpr int AGG_W = 9, AGG_NPT = 14, AGG_ROWS = AGG_W * AGG_NPT;   // k = 8 ne
 // adds each slot into dPQ[nbr[i,s], hdim + c] (Q half, fp32 `red.global.add`, 32 consecutive channels per warp
 // instruction). dh [E, hdim] is never stored. Per tile the producer warp stages the 126 mask rows (one bulk copy) and
 // the 126 scatter offsets nbr * ldpq in shared memory, so the epilogue touches no global metadata.
-struct ScatInfo { const int* nbr; const unsigned* hmask; int mask_ld; float* dpq; int64_t ldpq; int hdim; int64_t n_nodes; int enabled; };
+// dq: [n, >= hdim] rows of pitch lddq (fp32 reductions; zero on entry); dp: [n, >= hdim] rows of pitch lddp (overwritten,
+// rounded to tf32 when round_p); dbias (optional): [hdim] += column sums of dp (the bias gradient of the hoisted Linear).
+struct ScatInfo { const int* nbr; const unsigned* hmask; int mask_ld; float* dq; int64_t lddq; int hdim; int64_t n_nodes; int enabled;
+                  float* dp; int64_t lddp; float* dbias; int round_p; };
 
 // Producer side of the scattering epilogue: per 126-slot sub-tile (first node `node0`) every lane resolves 4 of the 128
-// offsets `nbr * ldpq` (floats; padding slots and slots beyond the tensor are redirected to the Q row of the sub-tile's
+// offsets `nbr * lddq` (floats; padding slots and slots beyond the tensor are redirected to the Q row of the sub-tile's
 // first node, where they add 0) and the warp builds `lastv`: bit f = "slot 8 of node f holds an edge" (the duplicate
 // quirk). The epilogue therefore runs no comparison / select on the offsets.
 __device__ __forceinline__ void scat_meta(const ScatInfo& sc, int64_t node0, int64_t rows, int lane, int (&offv)[4], unsigned& lastv) {
     unsigned vb[4];
-    const int own_off = (int)node0 * (int)sc.ldpq;
+    const int own_off = (int)node0 * (int)sc.lddq;
 #pragma unroll
     for (int q4 = 0; q4 < 4; ++q4) {
         const int col = lane + 32 * q4;
         const int64_t r = node0 * AGG_W + col;
         const int nb = (col < AGG_ROWS && r < rows) ? sc.nbr[r] : -1;
         vb[q4] = __ballot_sync(0xffffffffu, nb >= 0);
-        offv[q4] = nb >= 0 ? nb * (int)sc.ldpq : own_off;
+        offv[q4] = nb >= 0 ? nb * (int)sc.lddq : own_off;
     }
     lastv = 0u;
 #pragma unroll
@@ -87,8 +90,8 @@ __host__ __device__ constexpr uint32_t sc_meta_stride(int mask_ld) {
 // with generic-pointer metadata loads and offset selects, ran 17 and made the epilogue warps the kernel's bound).
 template <int NN, int J0, int MLD>
 __device__ __forceinline__ void scat_nodes(uint32_t taddr, uint32_t off_a, uint32_t msk_a, uint32_t mstride, unsigned lanebit,
-                                           unsigned lastv, float* __restrict__ dq, float* __restrict__ dp, int64_t ldpq,
-                                           int64_t nodes_left, bool ch_ok, bool skip) {
+                                           unsigned lastv, float* __restrict__ dq, float* __restrict__ dp, int64_t lddp,
+                                           int64_t nodes_left, bool ch_ok, bool skip, bool round_p, float& colacc) {
     uint32_t r[32];
     tc::tmem_ld_32x32b_x32(taddr, r);
     int offr[NN * AGG_W];
@@ -112,14 +115,15 @@ __device__ __forceinline__ void scat_nodes(uint32_t taddr, uint32_t off_a, uint3
             accp += v;
             if (sl < AGG_W - 1 || last_valid) tc::red_add_f32(dq + offr[e], v);
         }
-        if (ch_ok && f < nodes_left) dp[(int64_t)f * ldpq] = accp;
+        colacc += accp;                                   // nodes beyond n / channels beyond hdim contribute exact zeros
+        if (ch_ok && f < nodes_left) dp[(int64_t)f * lddp] = round_p ? tc::round_tf32(accp) : accp;
     }
 }
 // One 126-slot sub-tile = 14 nodes: columns [27 c, 27 c + 27) for c = 0..3, then [108, 126) out of a load at column 96.
 template <int MLD>
 __device__ __forceinline__ void scat_tile(uint32_t tcol, uint32_t mb_a, uint32_t off_a, uint32_t mword, uint32_t mstride,
                                           unsigned lanebit, float* dq, float* dp, int64_t ldpq, int64_t nodes_left, bool ch_ok,
-                                          bool skip) {
+                                          bool skip, bool round_p, float& colacc) {
     const uint32_t ms = MLD ? (uint32_t)MLD * 4u : mstride;
     const uint32_t msk_a = mb_a + 4u * mword;
     const unsigned lastv = tc::lds_u32(mb_a + (uint32_t)AGG_ROWS * ms);     // right behind the 126 mask rows
@@ -127,18 +131,18 @@ __device__ __forceinline__ void scat_tile(uint32_t tcol, uint32_t mb_a, uint32_t
 #pragma unroll 1
     for (int c = 0; c < 4; ++c)
         scat_nodes<3, 0, MLD>(tcol + (uint32_t)(27 * c), off_a + 108u * c, msk_a + 27u * c * ms, ms, lanebit, lastv >> (3 * c), dq,
-                              dp + (int64_t)(3 * c) * ldpq, ldpq, nodes_left - 3 * c, ch_ok, skip);
+                              dp + (int64_t)(3 * c) * ldpq, ldpq, nodes_left - 3 * c, ch_ok, skip, round_p, colacc);
     scat_nodes<2, 12, MLD>(tcol + 96u, off_a + 432u, msk_a + 108u * ms, ms, lanebit, lastv >> 12, dq, dp + (int64_t)12 * ldpq, ldpq,
-                           nodes_left - 12, ch_ok, skip);
+                           nodes_left - 12, ch_ok, skip, round_p, colacc);
 }
 // mb_a: shared address of the sub-tile's metadata block {126 mask rows | lastv | ... | 128 offsets at off_a}
 __device__ __forceinline__ void scat_tile_any(int mask_ld, uint32_t tcol, uint32_t mb_a, uint32_t off_a, uint32_t mword,
                                               unsigned lanebit, float* dq, float* dp, int64_t ldpq, int64_t nodes_left, bool ch_ok,
-                                              bool skip) {
+                                              bool skip, bool round_p, float& colacc) {
     // 4 / 12 words per row = hidden widths up to 128 / 257..384 (DynEdge: 128 and 336)
-    if (mask_ld == 12) scat_tile<12>(tcol, mb_a, off_a, mword, 48u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip);
-    else if (mask_ld == 4) scat_tile<4>(tcol, mb_a, off_a, mword, 16u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip);
-    else scat_tile<0>(tcol, mb_a, off_a, mword, (uint32_t)mask_ld * 4u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip);
+    if (mask_ld == 12) scat_tile<12>(tcol, mb_a, off_a, mword, 48u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip, round_p, colacc);
+    else if (mask_ld == 4) scat_tile<4>(tcol, mb_a, off_a, mword, 16u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip, round_p, colacc);
+    else scat_tile<0>(tcol, mb_a, off_a, mword, (uint32_t)mask_ld * 4u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip, round_p, colacc);
 }
 
 // Epilogue store of one 32-row chunk: lane = output channel, r[j] = row j. One coalesced 128-byte store per row; the
@@ -314,6 +318,7 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
         const int half = ew >> 2;                   // column half: rows [64*half, 64*half + 64) of the tile
         const float relu_lo = (act & 0xff) == GNB_ACT_RELU ? 0.f : -INFINITY;
         const bool accum = (act & GNB_FLAG_ACCUMULATE) != 0;
+        float colacc = 0.f;                         // scattering epilogue: this lane's column sum of dP over all its tiles
         uint32_t tile_i = 0;
         for (int t = blockIdx.x; t < num_row_tiles; t += gridDim.x, ++tile_i) {
             const uint32_t buf = tile_i & 1;
@@ -332,12 +337,12 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
                     const uint32_t mb_a = tc::smem_u32(meta + buf * SC_META_BYTES);
                     // mask layout of gnb_edge_hidden_fwd_mask: channel c is bit (c % 128) / 4 of word 4 (c / 128) + c % 4
                     const uint32_t mword = 4u * (uint32_t)((ch0 + m * TC_BM) >> 7) + (uint32_t)(lane & 3);
-                    float* dq = sc.dpq + sc.hdim + (ch_ok ? ch : ch % sc.hdim);
-                    float* dp = sc.dpq + node0 * sc.ldpq + ch;
+                    float* dq = sc.dq + (ch_ok ? ch : ch % sc.hdim);
+                    float* dp = sc.dp + node0 * sc.lddp + ch;
                     const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * (TC_MT * TC_BN) + m * TC_BN);
                     const unsigned lanebit = ch_ok ? (1u << (q * 8 + (lane >> 2))) : 0u;
-                    scat_tile_any(sc.mask_ld, tcol, mb_a, mb_a + SC_META_OFF, mword, lanebit, dq, dp, sc.ldpq, sc.n_nodes - node0,
-                                  ch_ok, (agg.dbg & 64) != 0);
+                    scat_tile_any(sc.mask_ld, tcol, mb_a, mb_a + SC_META_OFF, mword, lanebit, dq, dp, sc.lddp, sc.n_nodes - node0,
+                                  ch_ok, (agg.dbg & 64) != 0, sc.round_p != 0, colacc);
                 }
             } else if (agg.enabled) {
                 // warps 2-5 own channel tile 0, warps 6-9 channel tile 1; every thread walks all 126 slot columns
@@ -411,6 +416,10 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
             tc::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tmem_empty[buf]);
+        }
+        if (sc.enabled && sc.dbias != nullptr) {
+            const int chs = ch0 + half * TC_BM + q * 32 + lane;
+            if (half < mt && chs < n_out) atomicAdd(sc.dbias + chs, colacc);
         }
     }
     __syncwarp();
@@ -612,6 +621,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
         const float bv = (bias != nullptr && ch_ok) ? bias[ch] : 0.f;
         const float relu_lo = (act & 0xff) == GNB_ACT_RELU ? 0.f : -INFINITY;
         const bool accum = (act & GNB_FLAG_ACCUMULATE) != 0;
+        float colacc = 0.f;                         // scattering epilogue: this lane's column sum of dP over all its tiles
         uint32_t tile_i = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters, ++tile_i) {
             const uint32_t buf = tile_i & 1;
@@ -626,11 +636,11 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                 if (node0 < sc.n_nodes && ch0 + q * 32 < n_out) {
                     const uint32_t mb_a = tc::smem_u32(meta + (buf * 2 + half) * pc.meta_stride);
                     const uint32_t mword = 4u * (uint32_t)(ch0 >> 7) + (uint32_t)(lane & 3);
-                    float* dq = sc.dpq + sc.hdim + (ch_ok ? ch : ch % sc.hdim);
-                    float* dp = sc.dpq + node0 * sc.ldpq + ch;
+                    float* dq = sc.dq + (ch_ok ? ch : ch % sc.hdim);
+                    float* dp = sc.dp + node0 * sc.lddp + ch;
                     const unsigned lanebit = ch_ok ? (1u << (q * 8 + (lane >> 2))) : 0u;
-                    scat_tile_any(sc.mask_ld, tcol, mb_a, mb_a + pc.meta_stride - 512u, mword, lanebit, dq, dp, sc.ldpq,
-                                  sc.n_nodes - node0, ch_ok, (agg.dbg & 64) != 0);
+                    scat_tile_any(sc.mask_ld, tcol, mb_a, mb_a + pc.meta_stride - 512u, mword, lanebit, dq, dp, sc.lddp,
+                                  sc.n_nodes - node0, ch_ok, (agg.dbg & 64) != 0, sc.round_p != 0, colacc);
                 }
             } else if (agg.enabled) {
                 const int64_t st14 = (int64_t)t * 2 + half;            // 14-node tile index of the mask layout
@@ -762,6 +772,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
             __syncwarp();
             if (prof_on) pw1 += clock64() - c1;
         }
+        if (sc.enabled && sc.dbias != nullptr && ch_ok) atomicAdd(sc.dbias + ch, colacc);
     }
     __syncwarp();
     if (prof_on && lane == 0 && warp <= 2) {
@@ -911,7 +922,7 @@ GNB_EXPORT int gnb_linear_fwd_tf32(const float* const* xs, const int64_t* ldxs, 
     int rc = gnb_make_tmap_f32(&tw, w, n_out, ktot, ldw, TC_BM);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof};
-    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0};
+    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0};
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out, gnb_div_up(rows, TC_BN), agg, sc,
                          (cudaStream_t)stream);
 }
@@ -939,23 +950,27 @@ GNB_EXPORT int gnb_edge_linear_agg_fwd_tf32(const float* h, int64_t ldh, int32_t
     rc = gnb_make_tmap_f32(&tw, w, n_out, ktot, ldw, TC_BM);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     AggInfo agg{deg, n, maskbits, 1, g_linear_dbg, g_linear_prof};
-    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0};
+    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0};
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, GNB_ACT_RELU, round_out, gnb_div_up(n, AGG_NPT), agg, sc,
                          (cudaStream_t)stream);
 }
 
 // Data gradient of the EdgeConv second Linear fused with the backward of the hoisted hidden layer (k = 8 tables, width 9):
 //   dh[(i,s), :] = dz[(i,s), :] wt^T          (wt = W2^T: [hdim, ceil(c_out/32)*32] tf32-rounded, zero padded)
-//   da = dh * (h > 0);   dpq[i, 0:hdim] = sum_s da[(i,s)];   dpq[nbr[i,s], hdim:2 hdim] += da[(i,s)]
+//   da = dh * (h > 0);   dp[i, 0:hdim] = sum_s da[(i,s)];   dq[nbr[i,s], 0:hdim] += da[(i,s)]
 // dz: [n*9, c_out] tf32-rounded; hmask: [ceil(n/14)*126, mask_ld] activation bits from gnb_edge_hidden_fwd_mask (rows
 // beyond n*9 are read but ignored; mask_ld % 4 == 0, mask_ld >= 4*ceil(hdim/128)); nbr: [n, 9] (-1 padded).
-// dpq: [n, >= 2 hdim]; its Q half must be zero on entry (the P half is overwritten). hdim <= 512, n * ldpq < 2^31.
-GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_tf32(const float* dz, int64_t lddz, int32_t c_out, const float* wt, int64_t ldw,
-                                                  const uint32_t* hmask, int32_t mask_ld, int32_t hdim, const int32_t* nbr,
-                                                  int64_t n, float* dpq, int64_t ldpq, void* stream) {
-    if (n < 0 || hdim < 1 || hdim > 512 || c_out < 1 || ldpq < 2 * (int64_t)hdim) return GNB_ERR_ARG;
+// dq: [n, >= hdim] (pitch lddq) must be zero on entry (fp32 reductions); dp: [n, >= hdim] (pitch lddp) is overwritten,
+// rounded to tf32 with flags & 0x100; dbias (may be NULL): [hdim] += column sums of the unrounded dp = the bias gradient of
+// the hoisted first Linear. hdim <= 512, n * lddq < 2^31.
+GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_split_tf32(const float* dz, int64_t lddz, int32_t c_out, const float* wt,
+                                                        int64_t ldw, const uint32_t* hmask, int32_t mask_ld, int32_t hdim,
+                                                        const int32_t* nbr, int64_t n, float* dq, int64_t lddq, float* dp,
+                                                        int64_t lddp, float* dbias, int32_t flags, void* stream) {
+    if (n < 0 || hdim < 1 || hdim > 512 || c_out < 1 || lddq < hdim || lddp < hdim || dq == nullptr || dp == nullptr)
+        return GNB_ERR_ARG;
     if ((mask_ld & 3) || mask_ld > SC_MAX_MASK_LD || mask_ld < 4 * ((hdim + 127) / 128)) return GNB_ERR_ARG;
-    if ((reinterpret_cast<uintptr_t>(hmask) & 15u) || n * ldpq >= ((int64_t)1 << 31)) return GNB_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(hmask) & 15u) || n * lddq >= ((int64_t)1 << 31)) return GNB_ERR_ARG;
     if (n == 0) return GNB_OK;
     const int64_t rows = n * AGG_W;
     if (rows >= (int64_t)1 << 31) return GNB_ERR_ARG;
@@ -972,9 +987,18 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_tf32(const float* dz, int64_t lddz,
     rc = gnb_make_tmap_f32(&tw, wt, hdim, ktot, ldw, TC_BM);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof};
-    ScatInfo sc{nbr, hmask, mask_ld, dpq, ldpq, hdim, n, 1};
+    ScatInfo sc{nbr, hmask, mask_ld, dq, lddq, hdim, n, 1, dp, lddp, dbias, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0};
     return launch_linear(tw, tx, pi, nullptr, nullptr, 0, rows, hdim, GNB_ACT_NONE, 0, gnb_div_up(n, AGG_NPT), agg, sc,
                          (cudaStream_t)stream);
+}
+// Same with both halves in one [n, >= 2 hdim] tensor: dpq[:, 0:hdim] = dp (overwritten, unrounded), dpq[:, hdim:2 hdim] = dq
+// (must be zero on entry).
+GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_tf32(const float* dz, int64_t lddz, int32_t c_out, const float* wt, int64_t ldw,
+                                                  const uint32_t* hmask, int32_t mask_ld, int32_t hdim, const int32_t* nbr,
+                                                  int64_t n, float* dpq, int64_t ldpq, void* stream) {
+    if (hdim < 1 || ldpq < 2 * (int64_t)hdim || dpq == nullptr) return GNB_ERR_ARG;
+    return gnb_edge_hidden_dgrad_scatter_split_tf32(dz, lddz, c_out, wt, ldw, hmask, mask_ld, hdim, nbr, n, dpq + hdim, ldpq, dpq,
+                                                    ldpq, nullptr, 0, stream);
 }
 
 // dst[rows, dst_cols] = [rna_tf32(src[rows, cols]) | 0]; used to pack weights / round activations.

@@ -780,6 +780,31 @@ GNB_EXPORT int gnb_relu_bwd(const float* g, int64_t ldg, const float* y, int64_t
 }
 
 
+// GNB_FLAG_ZERO_SRC form (no activation, no aggregation, no column sums): dz = maybe_round(g), then g = 0. `g` is an
+// accumulation buffer that its next user expects empty; it is read and written through the same non-restrict pointer,
+// four independent rows per thread and step so that the loads still overlap.
+__global__ void __launch_bounds__(256)
+round_move_zero_kernel(float* g, int64_t ldg, int64_t rows, int cols4, float* __restrict__ dz, int64_t ldz, int rnd) {
+    const int c4 = blockIdx.y * 64 + threadIdx.x;
+    if (c4 >= cols4) return;
+    const int64_t r0 = (int64_t)blockIdx.x * ACT_ROWS;
+    const int64_t r1 = r0 + ACT_ROWS < rows ? r0 + ACT_ROWS : rows;
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 16) {
+        float4 gv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (r + 4 * u < r1) gv[u] = reinterpret_cast<const float4*>(g + (r + 4 * u) * ldg)[c4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (r + 4 * u < r1) {
+                reinterpret_cast<float4*>(g + (r + 4 * u) * ldg)[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 v = gv[u];
+                if (rnd) { v.x = gnb_round_tf32(v.x); v.y = gnb_round_tf32(v.y); v.z = gnb_round_tf32(v.z); v.w = gnb_round_tf32(v.w); }
+                reinterpret_cast<float4*>(dz + (r + 4 * u) * ldz)[c4] = v;
+            }
+    }
+}
+
 GNB_EXPORT int gnb_act_bwd_colsum(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows, int32_t cols,
                                   float* dz, int64_t ldz, float* db, int32_t flags, const int32_t* deg, int32_t width,
                                   int32_t aggr, void* stream) {
@@ -788,6 +813,12 @@ GNB_EXPORT int gnb_act_bwd_colsum(const float* g, int64_t ldg, const float* y, i
     if (deg != nullptr && (width < 1 || aggr < 0 || aggr > 1)) return GNB_ERR_ARG;
     if (rows == 0) return GNB_OK;
     dim3 grid((unsigned)gnb_div_up(rows, ACT_ROWS), (unsigned)gnb_div_up(cols >> 2, 64)), block(64, 4);
+    if (flags & GNB_FLAG_ZERO_SRC) {
+        if ((flags & 0xff) != GNB_ACT_NONE || deg != nullptr || db != nullptr) return GNB_ERR_ARG;
+        round_move_zero_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(const_cast<float*>(g), ldg, rows, cols >> 2, dz, ldz,
+                                                                         (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0);
+        GNB_RETURN_LAUNCH();
+    }
     act_bwd_colsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(g, ldg, y, ldy, rows, cols >> 2, dz, ldz, db, flags,
                                                                     deg, width, aggr);
     GNB_RETURN_LAUNCH();

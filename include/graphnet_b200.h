@@ -127,7 +127,8 @@ int gnb_relu_bwd(const float* g, int64_t ldg, const float* y, int64_t ldy, int64
                  int64_t ldz, int32_t flags, void* stream);
 /* Fused backward of bias+activation (and optionally of the k-neighbour aggregation in front of it):
  * dz[r] = grow(r) * act'(y[r]), db += colsum(dz); grow(r) = g[r] or, with deg != NULL, g[r / width] (add) or
- * g[r / width] / deg (mean) for valid slots and 0 for padding slots. flags: act | 0x100 (round dz to tf32). */
+ * g[r / width] / deg (mean) for valid slots and 0 for padding slots. flags: act | 0x100 (round dz to tf32) | 0x400 (only with
+ * act = none, deg = NULL, db = NULL: g is zeroed behind the read -- an accumulation buffer its next user expects empty). */
 int gnb_act_bwd_colsum(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows, int32_t cols, float* dz,
                        int64_t ldz, float* db, int32_t flags, const int32_t* deg, int32_t width, int32_t aggr,
                        void* stream);
@@ -165,6 +166,14 @@ int gnb_edge_mask_bwd_colsum(const float* g, int64_t ldg, const uint32_t* maskbi
 int gnb_edge_hidden_dgrad_scatter_tf32(const float* dz, int64_t lddz, int32_t c_out, const float* wt, int64_t ldw,
                                        const uint32_t* hmask, int32_t mask_ld, int32_t hdim, const int32_t* nbr, int64_t n,
                                        float* dpq, int64_t ldpq, void* stream);
+/* Same kernel with the two halves in separate tensors: dq [n, lddq >= hdim] receives the reductions (zero on entry,
+ * n*lddq < 2^31), dp [n, lddp >= hdim] is overwritten with the slot sums (rounded to tf32 with flags & 0x100, i.e. ready
+ * to feed the next tensor-core GEMM) and, if dbias != NULL, dbias[0:hdim] += column sums of the unrounded dp (= gradient
+ * of the hoisted Linear's bias; torch.nn.Linear autograd at dynedge.py:200-203). */
+int gnb_edge_hidden_dgrad_scatter_split_tf32(const float* dz, int64_t lddz, int32_t c_out, const float* wt, int64_t ldw,
+                                             const uint32_t* hmask, int32_t mask_ld, int32_t hdim, const int32_t* nbr,
+                                             int64_t n, float* dq, int64_t lddq, float* dp, int64_t lddp, float* dbias,
+                                             int32_t flags, void* stream);
 /* gnb_edge_hidden_fwd that also writes the activation bits hmask[r, mask_ld] (mask_ld % 4 == 0, mask_ld * 32 >= hdim):
  * (h[r, c] > 0) is bit (c % 128) / 4 of word 4 * (c / 128) + c % 4; bits beyond hdim are zero. */
 int gnb_edge_hidden_fwd_mask(const float* pq, int64_t ldpq, int32_t hdim, const int32_t* nbr, const int32_t* deg,

@@ -314,6 +314,39 @@ def test_edge_hidden_dgrad_scatter_bit_exact_on_integers(built_library, tf32_mod
               hdim, ops._ptr(graph.nbr), n, ops._ptr(dpq), 2 * hdim, ops._stream())
     torch.cuda.synchronize()
     assert torch.equal(dpq.cpu().double(), dpq_ref)
+    # split form used by the step executor: Q half reduced into its own tensor (odd pitch), P half written to a second
+    # tensor (tf32 rounding is exact on these integers) and the P half's column sums added onto a bias-gradient vector
+    dq = torch.zeros(n, hdim + 8, device="cuda")
+    dp = torch.full((n, hdim + 4), 7.0, device="cuda")
+    dbias = torch.full((hdim,), 3.0, device="cuda")
+    ops._call("gnb_edge_hidden_dgrad_scatter_split_tf32", ops._ptr(dzc), c_out, c_out, ops._ptr(wtc), kpad, ops._ptr(hmask), mld,
+              hdim, ops._ptr(graph.nbr), n, ops._ptr(dq), hdim + 8, ops._ptr(dp), hdim + 4, ops._ptr(dbias), 0x100, ops._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(dq[:, :hdim].cpu().double(), dpq_ref[:, hdim:])
+    assert torch.equal(dq[:, hdim:].cpu(), torch.zeros(n, 8))
+    assert torch.equal(dp[:, :hdim].cpu().double(), dpq_ref[:, :hdim])
+    assert torch.equal(dp[:, hdim:].cpu(), torch.full((n, 4), 7.0))
+    assert torch.equal(dbias.cpu().double(), dpq_ref[:, :hdim].sum(0) + 3.0)
+
+
+def test_act_bwd_colsum_zero_source_flag(built_library, tf32_mode):
+    """gnb_act_bwd_colsum with flag 0x400 on a strided half of an accumulation buffer: the rounded copy is written, the
+    source half is left zeroed and the other half untouched (how the executor recycles the dQ accumulation buffer)."""
+    ops = tf32_mode
+    g = torch.Generator().manual_seed(5)
+    n, hdim = 1000, 336
+    acc = torch.randn(n, 2 * hdim, generator=g).cuda()
+    keep = acc.clone()
+    out = torch.full((n, 2 * hdim), -1.0, device="cuda")
+    ops._call("gnb_act_bwd_colsum", acc.data_ptr() + 4 * hdim, 2 * hdim, None, 0, n, hdim, out.data_ptr() + 4 * hdim, 2 * hdim,
+              None, 0x100 | 0x400, None, 1, 0, ops._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(acc[:, :hdim], keep[:, :hdim]) and torch.equal(acc[:, hdim:], torch.zeros_like(acc[:, hdim:]))
+    assert torch.equal(out[:, :hdim], torch.full_like(out[:, :hdim], -1.0))
+    # cvt.rna.tf32.f32: nearest, ties away from zero, 10 mantissa bits = add half an ulp to the magnitude bits, truncate
+    bits = keep[:, hdim:].cpu().numpy().view(np.uint32)
+    expect = ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+    assert np.array_equal(out[:, hdim:].cpu().numpy(), expect)
 
 
 @pytest.mark.parametrize("k,n_out", [(336, 256), (128, 256), (40, 100), (352, 336)])
