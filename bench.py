@@ -7,7 +7,7 @@
 One "step" = one pass of the hot path over one batch of synthetic IceCube-like events:
   headline `value`  : training step of BASELINE configs[2] -- device-resident x/batch/n_pulses (no edge_index)
                       -> kNN graph -> DynEdge fwd -> direction(vMF)+energy(LogCosh) heads and loss -> bwd ->
-                      (NCCL mean all-reduce of the flat gradient buffer when N > 1) -> fused Adam step;
+                      (NCCL mean all-reduce of the flat gradient buffer when N > 1) -> Adam step (one launch on the flat buffers);
                       512 events per GPU (weak scaling), events/s summed over all ranks.
   `inference`       : BASELINE configs[1] -- forward + energy head on 1024 events per GPU, no collective.
   `e2e`             : the training step driven from pinned HOST buffers through the public API
@@ -183,7 +183,8 @@ class Trainer:
         self.reducer = FlatGradAllReduce(self.params)
         from graphnet_b200 import ops as _ops
         _ops.ACCUMULATE_INTO_GRAD = True      # gradients land directly in the flat all-reduce buffer
-        self.opt = torch.optim.Adam(self.params, lr=1e-3, eps=1e-3, fused=True)
+        from graphnet_b200.distributed import FlatAdam
+        self.opt = FlatAdam(self.reducer, lr=1e-3, eps=1e-3)     # torch.optim.Adam semantics, one launch on the flat buffers
         self.world = world
 
     def make_data(self, db):
@@ -191,13 +192,13 @@ class Trainer:
         return Data(x=db["x"], batch=db["batch"], n_pulses=db["n_pulses"])
 
     def train_step(self, db):
-        self.reducer.zero()
+        # the flat gradient buffer is zero here: allocated zeroed, then zeroed again by every Adam step behind its read
         data = self.edges(self.make_data(db))
         h = self.backbone(data)
         loss, _, _ = self.tasks(h, db["energy"], db["direction"])
         loss.backward()
         self.reducer.all_reduce_mean()
-        self.opt.step()
+        self.opt.step(zero_grad=True)
         return loss
 
     @torch.no_grad()

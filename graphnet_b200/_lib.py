@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libgraphnet_b200.so")
 _p = ctypes.c_void_p
 _i32 = ctypes.c_int32
 _i64 = ctypes.c_int64
+_f32 = ctypes.c_float
 
 # name -> argument types (return type is always int status); mirrors include/graphnet_b200.h
 SIGNATURES: Dict[str, list] = {
@@ -31,6 +32,7 @@ SIGNATURES: Dict[str, list] = {
     "gnb_linear_set_variant": [_i32],
     "gnb_linear_set_pair_resident": [_i32],
     "gnb_knn_set_variant": [_i32],
+    "gnb_adam_flat": [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _i32, _p],
     "gnb_task_heads_fwd": [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p],
     "gnb_task_heads_bwd": [_p, _i64, _i32, _p, _p, _p, _p, _i64, _p, _i64, _p, _p, _p, _p, _p],
     "gnb_linear_set_profile_buffer": [_p],

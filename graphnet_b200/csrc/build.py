@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["knn.cu", "graph_ops.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc_wgrad.cu", "dynedge_exec.cu", "edgeconv_tc.cu",
-           "task_heads.cu"]
+           "task_heads.cu", "optim.cu"]
 LIB = os.path.join(HERE, "libgraphnet_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -63,3 +63,45 @@ class FlatGradAllReduce:
         self.rebind()
         self.flat.div_(dist.get_world_size())
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
+
+
+class FlatAdam:
+    """`torch.optim.Adam` (no amsgrad) over ONE flat fp32 parameter buffer, one CUDA launch per step.
+
+    The reference trains with `optimizer_class=Adam, optimizer_kwargs={"lr": 1e-3, "eps": 1e-3}`
+    (examples/04_training/01_train_dynedge.py:128-129, instantiated at models/easy_model.py:215-219). Here every
+    parameter becomes a view into `flat_p` (same order as `FlatGradAllReduce.flat`, which holds the gradients), the
+    moments live in two more flat buffers and `csrc/optim.cu::gnb_adam_flat` updates all 1.38 M values in one launch
+    (torch's fused multi-tensor Adam needs ~80 us for the 26 small tensors of DynEdge; this takes < 10 us) and can
+    zero the gradient buffer behind the read. CUDA only: there is no CPU fallback.
+    """
+
+    def __init__(self, reducer: FlatGradAllReduce, lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.999),
+                 eps: float = 1e-8, weight_decay: float = 0.0):
+        if not reducer.flat.is_cuda:
+            raise RuntimeError("graphnet_b200.FlatAdam: parameters must live on a CUDA device (no CPU fallback)")
+        self.reducer = reducer
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        self.flat_p = torch.empty_like(reducer.flat)
+        off = 0
+        with torch.no_grad():
+            for p in reducer.params:
+                view = self.flat_p[off:off + p.numel()].view_as(p)
+                view.copy_(p)
+                p.data = view                     # the module's parameters now alias the flat buffer
+                off += p.numel()
+        self.exp_avg = torch.zeros_like(self.flat_p)
+        self.exp_avg_sq = torch.zeros_like(self.flat_p)
+        self.step_count = 0
+
+    def step(self, zero_grad: bool = False) -> None:
+        from . import ops
+        self.reducer.rebind()
+        self.step_count += 1
+        b1, b2 = self.betas
+        step_size = self.lr / (1.0 - b1 ** self.step_count)
+        inv_sqrt_bc2 = 1.0 / float(np.sqrt(1.0 - b2 ** self.step_count))
+        n = self.flat_p.numel()
+        ops._call("gnb_adam_flat", ops._ptr(self.flat_p), ops._ptr(self.reducer.flat), ops._ptr(self.exp_avg),
+                  ops._ptr(self.exp_avg_sq), n, step_size, b1, b2, self.eps, inv_sqrt_bc2, self.weight_decay,
+                  1 if zero_grad else 0, ops._stream())

@@ -233,6 +233,12 @@ int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const* grads, con
                          const int32_t* deg0, int32_t w0, int64_t n, int64_t nseg, void* workspace,
                          int64_t workspace_bytes, const float* gout, void* stream);
 
+/* Adam step over one flat fp32 parameter buffer (torch.optim.Adam semantics as configured by the reference:
+ * easy_model.py:215-219, examples/04_training/01_train_dynedge.py:128-129): g' = g + weight_decay p, m += (1-beta1)(g'-m),
+ * v = beta2 v + (1-beta2) g'^2, p -= step_size m / (sqrt(v) inv_sqrt_bc2 + eps) with step_size = lr / (1 - beta1^t) and
+ * inv_sqrt_bc2 = 1 / sqrt(1 - beta2^t) computed by the caller. p, g, m, v: [n], 16-byte aligned; zero_grad != 0 leaves g = 0. */
+int gnb_adam_flat(float* p, float* g, float* m, float* v, int64_t n, float step_size, float beta1, float beta2, float eps,
+                  float inv_sqrt_bc2, float weight_decay, int32_t zero_grad, void* stream);
 /* ---- task heads + losses (the O(B) step right after the path) -------------------------------------
  * EnergyReconstruction (task/reconstruction.py:101-112) + LogCoshLoss on log10 (training/loss_functions.py:93-112) and
  * DirectionReconstructionWithKappa (reconstruction.py:49-70) + VonMisesFisher3DLoss (loss_functions.py:281-353, 424-447;

@@ -154,3 +154,33 @@ def test_fused_task_heads_match_torch_heads(built_library):
     for pf, pr in zip(list(fused.energy.parameters()) + list(fused.direction.parameters()),
                       list(e64.parameters()) + list(d64.parameters())):
         assert rel_err(pf.grad, pr.grad) < 2e-4, pf.shape
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("eps,wd", [(1e-3, 0.0), (1e-8, 0.01)])
+def test_flat_adam_matches_torch_adam(built_library, eps, wd):
+    """FlatAdam (one launch over the flat parameter / gradient buffers) follows torch.optim.Adam, the optimizer the
+    reference configures (easy_model.py:215-219; lr = 1e-3, eps = 1e-3 in examples/04_training/01_train_dynedge.py)."""
+    import copy
+    from graphnet_b200.distributed import FlatAdam, FlatGradAllReduce
+    torch.manual_seed(0)
+    mod = torch.nn.Sequential(torch.nn.Linear(7, 13), torch.nn.ReLU(), torch.nn.Linear(13, 5)).cuda()   # 174 values: tail of 2
+    ref = copy.deepcopy(mod)
+    red = FlatGradAllReduce(mod.parameters())
+    opt = FlatAdam(red, lr=1e-3, eps=eps, weight_decay=wd)
+    ref_opt = torch.optim.Adam(ref.parameters(), lr=1e-3, eps=eps, weight_decay=wd)
+    for p, q in zip(mod.parameters(), ref.parameters()):
+        assert torch.equal(p, q) and p.data_ptr() >= opt.flat_p.data_ptr()      # parameters alias the flat buffer
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for step in range(6):
+        gflat = torch.randn(red.flat.numel(), device="cuda", generator=g) * (10.0 ** (step - 3))   # identical gradients
+        red.flat.copy_(gflat)
+        off = 0
+        for q in ref.parameters():
+            q.grad = gflat[off:off + q.numel()].view_as(q).clone()
+            off += q.numel()
+        opt.step(zero_grad=True)
+        ref_opt.step()
+        assert float(red.flat.abs().max()) == 0.0                              # zeroed behind the read
+        for p, q in zip(mod.parameters(), ref.parameters()):
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-7), (step, float((p - q).abs().max()))
