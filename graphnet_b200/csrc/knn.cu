@@ -215,9 +215,10 @@ knn_table_split_kernel(const float* __restrict__ x, int64_t ld, const int* __res
     for (int64_t c0 = r_lo; c0 < r_hi; c0 += chunk) {
         const int cnt = (int)((r_hi - c0) < chunk ? (r_hi - c0) : chunk);
         __syncthreads();   // previous chunk fully consumed
-        for (int idx = tid; idx < cnt * D; idx += KNN_THREADS) {
-            const int j = idx / cnt, c = idx - j * cnt;
-            s_c[j * chunk + c] = x[(c0 + c) * ld + s_cols[j]];
+        for (int c = tid; c < cnt; c += KNN_THREADS) {       // one node per thread: its D coordinates share a sector
+            const float* row = x + (c0 + c) * ld;
+#pragma unroll
+            for (int j = 0; j < D; ++j) s_c[j * chunk + c] = row[s_cols[j]];
         }
         __syncthreads();
         if (active) {
