@@ -32,6 +32,8 @@ SIGNATURES: Dict[str, list] = {
     "gnb_linear_set_variant": [_i32],
     "gnb_linear_set_pair_resident": [_i32],
     "gnb_knn_set_variant": [_i32],
+    "gnb_standardize": [_p, _i64, _i64, _i32, _p, _p, _p, _p, _i64, _p],
+    "gnb_ptr_to_batch": [_p, _i64, _i64, _p, _p],
     "gnb_adam_flat": [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _i32, _p],
     "gnb_task_heads_fwd": [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p],
     "gnb_task_heads_bwd": [_p, _i64, _i32, _p, _p, _p, _p, _i64, _p, _i64, _p, _p, _p, _p, _p],

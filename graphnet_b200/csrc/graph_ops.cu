@@ -485,6 +485,37 @@ segment_pool_bwd_kernel(const float* __restrict__ gout, int64_t ldg, const int* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Device-side graph definition: detector standardisation of a raw pulse batch and the
+// collate arithmetic, so that raw [N, F] pulse arrays become the DynEdge input on the GPU.
+// Reference: Detector._standardize (src/graphnet/models/detector/detector.py:63-77) applies one callable per named
+// column; for IceCube86 (detector/icecube.py:21-48) these are x / 500, (t - 1e4) / 3e4, log10(q), (rde - 1.25) / 0.25,
+// area / 0.05, identity -- i.e. every column is one of {identity, (x - a) / b, log10(x)}. Same fp32 operations in the
+// same order (IEEE subtraction and division, log10f), one pass over the tensor.
+struct StdTable { int kind[GNB_STD_MAX_F]; float sub[GNB_STD_MAX_F]; float div[GNB_STD_MAX_F]; };
+
+__global__ void standardize_kernel(const float* __restrict__ x, int64_t ldx, int64_t n, int f, const StdTable t,
+                                   float* __restrict__ out, int64_t ldo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * f) return;
+    const int64_t r = i / f;
+    const int c = (int)(i - r * f);
+    const float v = x[r * ldx + c];
+    float o = v;
+    if (t.kind[c] == 1) o = __fdiv_rn(__fsub_rn(v, t.sub[c]), t.div[c]);
+    else if (t.kind[c] == 2) o = log10f(v);
+    out[r * ldo + c] = o;
+}
+
+// batch[i] = b for ptr[b] <= i < ptr[b+1] (the `batch` vector Batch.from_data_list builds, dataloader.py:12-18)
+__global__ void ptr_to_batch_kernel(const int64_t* __restrict__ ptr, int nseg, int64_t n, int64_t* __restrict__ batch) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lo = 0, hi = nseg;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ptr[mid] <= i) lo = mid; else hi = mid; }
+    batch[i] = lo;
+}
+
+// ---------------------------------------------------------------------------------------------
 // small dense helpers
 __global__ void relu_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ y, int64_t ldy,
                                 int64_t rows, int cols, float* __restrict__ dz, int64_t ldz, int flags) {
@@ -844,5 +875,28 @@ GNB_EXPORT int gnb_colsum(const float* a, int64_t lda, int64_t rows, int32_t col
     if (rows == 0) return GNB_OK;
     dim3 grid((unsigned)gnb_div_up(cols, 32), (unsigned)gnb_div_up(rows, 256)), block(32, 8);
     colsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a, lda, rows, cols, out);
+    GNB_RETURN_LAUNCH();
+}
+
+// out[r, c] = kind[c] == 0 ? x : kind[c] == 1 ? (x - sub[c]) / div[c] : log10(x); kind / sub / div are HOST arrays (f <= 32).
+GNB_EXPORT int gnb_standardize(const float* x, int64_t ldx, int64_t n, int32_t f, const int32_t* kind, const float* sub,
+                               const float* div, float* out, int64_t ldo, void* stream) {
+    if (n < 0 || f < 1 || f > GNB_STD_MAX_F || ldx < f || ldo < f || kind == nullptr || sub == nullptr || div == nullptr)
+        return GNB_ERR_ARG;
+    StdTable t;
+    for (int c = 0; c < GNB_STD_MAX_F; ++c) { t.kind[c] = 0; t.sub[c] = 0.f; t.div[c] = 1.f; }
+    for (int c = 0; c < f; ++c) {
+        if (kind[c] < 0 || kind[c] > 2) return GNB_ERR_ARG;
+        t.kind[c] = kind[c]; t.sub[c] = sub[c]; t.div[c] = div[c];
+    }
+    if (n == 0) return GNB_OK;
+    standardize_kernel<<<gnb_div_up(n * f, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, n, f, t, out, ldo);
+    GNB_RETURN_LAUNCH();
+}
+
+GNB_EXPORT int gnb_ptr_to_batch(const int64_t* ptr, int64_t nseg, int64_t n, int64_t* batch, void* stream) {
+    if (n < 0 || nseg < 1 || nseg >= ((int64_t)1 << 31)) return GNB_ERR_ARG;
+    if (n == 0) return GNB_OK;
+    ptr_to_batch_kernel<<<gnb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(ptr, (int)nseg, n, batch);
     GNB_RETURN_LAUNCH();
 }

@@ -233,6 +233,13 @@ int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const* grads, con
                          const int32_t* deg0, int32_t w0, int64_t n, int64_t nseg, void* workspace,
                          int64_t workspace_bytes, const float* gout, void* stream);
 
+/* Device-side graph definition (raw pulses -> DynEdge input). gnb_standardize replaces Detector._standardize
+ * (models/detector/detector.py:63-77; IceCube86 table at detector/icecube.py:21-48): out[r, c] = x (kind 0),
+ * (x - sub[c]) / div[c] (kind 1) or log10(x) (kind 2), fp32, same operation order. kind / sub / div: HOST arrays of f <= 32
+ * entries. gnb_ptr_to_batch builds the `batch` vector of a collated Batch (data/dataloader.py:12-18) from ptr[nseg + 1]. */
+int gnb_standardize(const float* x, int64_t ldx, int64_t n, int32_t f, const int32_t* kind, const float* sub, const float* div,
+                    float* out, int64_t ldo, void* stream);
+int gnb_ptr_to_batch(const int64_t* ptr, int64_t nseg, int64_t n, int64_t* batch, void* stream);
 /* Adam step over one flat fp32 parameter buffer (torch.optim.Adam semantics as configured by the reference:
  * easy_model.py:215-219, examples/04_training/01_train_dynedge.py:128-129): g' = g + weight_decay p, m += (1-beta1)(g'-m),
  * v = beta2 v + (1-beta2) g'^2, p -= step_size m / (sqrt(v) inv_sqrt_bc2 + eps) with step_size = lr / (1 - beta1^t) and

@@ -338,3 +338,32 @@ class DynEdgeRef(torch.nn.Module):
         if return_intermediates:
             return x, {"global_variables": g, "skips": skips, "graphs": graphs, "post": post}
         return x
+
+
+# --------------------------------------------------------------------------------------------- #
+# graph definition in front of the path -- checker for models/graphs/device.py
+# --------------------------------------------------------------------------------------------- #
+def standardize_icecube86_ref(raw: torch.Tensor, feature_names) -> torch.Tensor:
+    """`Detector._standardize` (reference detector/detector.py:63-77) with the IceCube86 map (detector/icecube.py:21-48):
+    one callable per named column, fp32, an unknown column is a KeyError. Pinned bit-for-bit on
+    tests/golden/detector_icecube86.pt (the reference's own two files run here)."""
+    fmap = {
+        "dom_x": lambda x: x / 500.0, "dom_y": lambda x: x / 500.0, "dom_z": lambda x: x / 500.0,       # icecube.py:35-36
+        "dom_time": lambda x: (x - 1.0e04) / 3.0e4,                                                       # :38-39
+        "charge": lambda x: torch.log10(x),                                                               # :41-42
+        "rde": lambda x: (x - 1.25) / 0.25,                                                               # :44-45
+        "pmt_area": lambda x: x / 0.05,                                                                   # :47-48
+        "hlc": lambda x: x,                                                                               # detector.py:79-81
+    }
+    out = raw.clone()
+    for idx, name in enumerate(feature_names):
+        out[:, idx] = fmap[name](raw[:, idx])
+    return out
+
+
+def collate_ref(n_pulses: torch.Tensor):
+    """`batch` and `ptr` of `Batch.from_data_list` (reference data/dataloader.py:12-18) for events of the given sizes."""
+    sizes = n_pulses.to(torch.int64)
+    ptr = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(sizes, 0)])
+    batch = torch.repeat_interleave(torch.arange(sizes.numel(), dtype=torch.int64), sizes)
+    return batch, ptr

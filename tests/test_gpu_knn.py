@@ -99,3 +99,49 @@ def test_knn_full_size_properties(built_library):
         nbr_c, deg_c = c_oracle.knn_table(raw["x"][lo:hi], [0, 1, 2], np.array([0, hi - lo]), 8)
         got = g.nbr[lo:hi].cpu().numpy()
         assert np.array_equal(np.where(got >= 0, got - lo, -1), nbr_c)
+
+
+@pytest.mark.gpu
+def test_device_graph_definition_from_raw_pulses(built_library):
+    """raw pulse batch on the GPU -> standardised nodes, batch / ptr / n_pulses, kNN table in three
+    launches. x is checked against the golden output of the reference's own detector/icecube.py (CPU fp32): affine
+    columns bit-exact (IEEE subtract / divide), log10(charge) within 2 ulp (CUDA log10f vs the CPU libm the reference's
+    dataloader workers use; tolerance rel 2.4e-7 + the value's own ulp); batch / ptr equal the collate restatement and the
+    host path (per-event KNNGraph.forward + Batch.from_data_list); the graph equals the oracle kNN on the device's x."""
+    import os
+    from helpers import GOLDEN_DIR
+    from graphnet_b200.data import Batch
+    from graphnet_b200.models.detector import IceCube86
+    from graphnet_b200.models.graphs import DeviceKNNGraph, KNNGraph
+    from oracle.dynedge_oracle import collate_ref
+    gold = torch.load(os.path.join(GOLDEN_DIR, "detector_icecube86.pt"))
+    raw, want, names = gold["raw"], gold["standardized"], gold["features"]
+    sizes = torch.tensor([1, 2, 9, 10, 300, 64, 700, 0, 1500, 1510], dtype=torch.int32)   # sums to 4096; one empty event
+    assert int(sizes.sum()) == raw.shape[0]
+    definition = KNNGraph(detector=IceCube86(), input_feature_names=names, nb_nearest_neighbours=8, columns=[0, 1, 2])
+    graph = DeviceKNNGraph(definition)(raw.cuda(), sizes.cuda())
+    x = graph.x.cpu()
+    for c, name in enumerate(names):
+        if name == "charge":
+            assert torch.allclose(x[:, c], want[:, c], rtol=2.4e-7, atol=1e-9), name
+        else:
+            assert torch.equal(x[:, c], want[:, c]), name
+        assert torch.equal(graph[name].cpu(), x[:, c])                # per-feature attributes, graph_definition.py:243-247
+    batch_ref, ptr_ref = collate_ref(sizes)
+    assert torch.equal(graph.batch.cpu(), batch_ref) and torch.equal(graph.ptr.cpu(), ptr_ref)
+    assert torch.equal(graph.n_pulses.cpu(), sizes) and graph.n_pulses.dtype == torch.int32
+    assert torch.equal(graph.edge_index.cpu(), knn_graph_ref(x[:, :3], 8, ptr=ptr_ref))
+    # host path of the reference's dataloader: one Data per (non-empty) event, collated
+    off, parts = 0, []
+    for s_ in sizes.tolist():
+        if s_ > 0:
+            parts.append(definition(raw[off:off + s_].numpy(), names))
+        off += s_
+    host = Batch.from_data_list(parts)
+    keep = sizes > 0
+    assert torch.equal(host.n_pulses, sizes[keep])
+    for c, name in enumerate(names):
+        if name != "charge":
+            assert torch.equal(host.x[:, c], x[:, c])
+    with pytest.raises(RuntimeError):                                   # no CPU fallback
+        DeviceKNNGraph(definition)(raw, sizes)

@@ -2,10 +2,12 @@
 (tests/golden/make_golden.py runs /root/reference/src/graphnet/models/gnn/dynedge.py with shims for the
 absent third-party operators). CPU only."""
 
+import os
+
 import pytest
 import torch
 
-from helpers import golden_files, load_golden, namespace, rel_err, seeded_state_dict
+from helpers import GOLDEN_DIR, golden_files, load_golden, namespace, rel_err, seeded_state_dict
 from oracle.dynedge_oracle import DynEdgeRef, knn_graph_ref
 
 
@@ -47,3 +49,28 @@ def test_state_dict_keys_match_reference_layout():
     assert tuple(sd["_post_processing.0.weight"].shape) == (336, 1043)
     assert tuple(sd["_readout.0.weight"].shape) == (128, 1024)
     assert sum(p.numel() for p in model.parameters()) == 1382192
+
+
+def test_detector_standardisation_pinned_on_reference_icecube86():
+    """Oracle restatement, the host-side `IceCube86` mirror and its (kind, subtract, divide) table all reproduce the
+    reference's own detector/icecube.py + detector.py:_standardize output bit for bit (tests/golden/make_golden_detector.py)."""
+    import numpy as np
+    from graphnet_b200.models.detector import IceCube86
+    from oracle.dynedge_oracle import standardize_icecube86_ref
+    gold = torch.load(os.path.join(GOLDEN_DIR, "detector_icecube86.pt"))
+    raw, want, names = gold["raw"], gold["standardized"], gold["features"]
+    assert torch.equal(standardize_icecube86_ref(raw, names), want)
+    det = IceCube86()
+    assert torch.equal(det(raw, names), want)
+    kinds, subs, divs = det.standardisation_table(names)
+    got = raw.clone()
+    for c, (k, a, b) in enumerate(zip(kinds, subs, divs)):
+        if k == 1:
+            got[:, c] = (raw[:, c] - np.float32(a)) / np.float32(b)
+        elif k == 2:
+            got[:, c] = torch.log10(raw[:, c])
+    assert torch.equal(got, want)
+    with pytest.raises(KeyError):                  # detector.py:70-76: no silent pass-through
+        det(raw, names[:-1] + ["not_a_feature"])
+    with pytest.raises(KeyError):
+        det.standardisation_table(["not_a_feature"])
