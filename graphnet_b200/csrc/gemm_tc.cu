@@ -787,6 +787,199 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     if (warp == 1) tc::tmem_dealloc_2cta<512>(tmem_base);
 }
 
+// =====================================================================================================================
+// Dual-group scattering kernel: the data-gradient GEMM of an EdgeConv layer whose hidden width needs TWO 256-channel
+// groups (336 = 256 + 80). gemm_tc_pair_kernel gives every group its own clusters, so dz is streamed twice and the launch
+// runs at the L2-slice cap. Here every cluster computes BOTH groups of its row tiles from ONE copy
+// of the dz tile: the tile's K blocks (this CTA's 126-row half, total_kb x 16 KiB <= 128 KiB) stay resident in shared
+// memory while the weight K blocks of group 0, then of group 1, stream through a ring of 16 KiB stages; the two
+// accumulators of a tile are the two TMEM buffers, so the epilogue of group 0 overlaps the MMAs of group 1 and the
+// epilogue of group 1 the MMAs of the next tile's group 0. An activation slot is released (aempty[kb]) by the commit
+// behind group 1's MMAs on it, so the next tile's K blocks roll in while the current tile is still being multiplied.
+// Per 252-row tile and cluster: 258 KiB of dz + 2 x 256 KiB of weights instead of 2 x (258 + 256) KiB.
+constexpr int DU_MAX_KB = 8;
+constexpr uint32_t DU_BAR_BYTES = 512;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PL_THREADS, 1)
+gemm_tc_pair_dual_scatter_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
+                                 int total_kb, int64_t rows, int n_out, int num_tiles, const ScatInfo sc, int nst_w,
+                                 uint32_t meta_stride, int dbg) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* act = smem;                                               // [total_kb] x 16 KiB: resident dz tile (own half)
+    uint8_t* wring = act + (uint32_t)total_kb * TC_TILE_BYTES;         // [nst_w] x 16 KiB: own 128 weight rows of one K block
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(wring + (uint32_t)nst_w * TC_TILE_BYTES);
+    uint64_t* wempty = wfull + PL_MAX_STAGES;
+    uint64_t* afull = wempty + PL_MAX_STAGES;        // [DU_MAX_KB] (leader's copy is waited on)
+    uint64_t* aempty = afull + DU_MAX_KB;            // [DU_MAX_KB] (multicast to both CTAs)
+    uint64_t* tmem_full = aempty + DU_MAX_KB;        // [2]
+    uint64_t* tmem_empty = tmem_full + 2;            // [2]
+    uint64_t* meta_full = tmem_empty + 2;            // [2]
+    uint64_t* meta_empty = meta_full + 2;            // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(meta_empty + 2);
+    uint8_t* meta = reinterpret_cast<uint8_t*>(wfull) + DU_BAR_BYTES;  // [2 buffers][2 sub-tiles] x meta_stride
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const int cluster_id = (int)(blockIdx.x >> 1), num_clusters = (int)(gridDim.x >> 1);
+
+    if (warp == 0 && lane == 0) { tc::tma_prefetch_desc(&tm_w); tc::tma_prefetch_desc(&tm_x); }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < PL_MAX_STAGES; ++s) { tc::mbar_init(&wfull[s], 1); tc::mbar_init(&wempty[s], 1); }
+            for (int k = 0; k < DU_MAX_KB; ++k) { tc::mbar_init(&afull[k], 1); tc::mbar_init(&aempty[k], 1); }
+            for (int b = 0; b < 2; ++b) {
+                tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], 16);
+                tc::mbar_init(&meta_full[b], 1); tc::mbar_init(&meta_empty[b], 8);
+            }
+            tc::fence_barrier_init();
+            tc::fence_proxy_async();
+        }
+        __syncwarp();
+        tc::tmem_alloc_2cta<512>(tmem_slot);
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---- TMA producer (both CTAs) -------------------------------------------------------------------------------
+        uint32_t itw = 0, vt_i = 0, ti = 0;
+        const uint32_t act_tx = 2u * (uint32_t)AGG_ROWS * TC_BK * 4, w_tx = 2u * TC_TILE_BYTES;       // both CTAs
+        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++ti) {
+            const int64_t row0 = (int64_t)t * (2 * AGG_ROWS) + (int64_t)rank * AGG_ROWS;
+            int offv[2][4];
+            unsigned lastv[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) scat_meta(sc, ((int64_t)t * 2 + h) * AGG_NPT, rows, lane, offv[h], lastv[h]);
+            for (int g = 0; g < 2; ++g, ++vt_i) {
+                for (int kb = 0; kb < total_kb; ++kb, ++itw) {
+                    if (g == 0) {                  // next tile's dz K block as soon as group 1 of the previous tile is done with the slot
+                        tc::mbar_wait_warp(&aempty[kb], (ti & 1) ^ 1);
+                        if (tc::elect_one()) {
+                            if (rank == 0) tc::mbar_arrive_expect_tx(&afull[kb], act_tx);
+                            tc::tma_load_2d_2sm(act + kb * TC_TILE_BYTES, &tm_x, &afull[kb], kb * TC_BK, (int)row0);
+                        }
+                        __syncwarp();
+                    }
+                    const uint32_t s = itw % (uint32_t)nst_w, ph = (itw / (uint32_t)nst_w) & 1;
+                    tc::mbar_wait_warp(&wempty[s], ph ^ 1);
+                    if (tc::elect_one()) {
+                        if (rank == 0) tc::mbar_arrive_expect_tx(&wfull[s], w_tx);
+                        tc::tma_load_2d_2sm(wring + s * TC_TILE_BYTES, &tm_w, &wfull[s], kb * TC_BK, g * 256 + (int)rank * 128);
+                    }
+                    __syncwarp();
+                }
+                // scatter metadata of this (tile, group): same mask rows / offsets for both groups, one block per TMEM buffer
+                const uint32_t buf = vt_i & 1;
+                tc::mbar_wait_warp(&meta_empty[buf], ((vt_i >> 1) & 1) ^ 1);
+                uint32_t bytes = 0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint8_t* mbh = meta + (buf * 2 + h) * meta_stride;
+                    int* so = reinterpret_cast<int*>(mbh + meta_stride - 512);
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) so[lane + 32 * q4] = offv[h][q4];
+                    if (lane == 0) *reinterpret_cast<unsigned*>(mbh + AGG_ROWS * sc.mask_ld * 4) = lastv[h];
+                    if (((int64_t)t * 2 + h) * AGG_NPT < sc.n_nodes) bytes += (uint32_t)(AGG_ROWS * sc.mask_ld * 4);
+                }
+                __syncwarp();
+                if (tc::elect_one()) {
+                    tc::mbar_arrive_expect_tx(&meta_full[buf], bytes);
+                    const uint32_t one = (uint32_t)(AGG_ROWS * sc.mask_ld * 4);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        if (((int64_t)t * 2 + h) * AGG_NPT < sc.n_nodes)
+                            tc::bulk_load(meta + (buf * 2 + h) * meta_stride, sc.hmask + ((int64_t)t * 2 + h) * AGG_ROWS * sc.mask_ld,
+                                          one, &meta_full[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ---- MMA issuer (leader): group 0 then group 1 of every tile against the resident dz K blocks ------------
+            constexpr uint32_t idesc = tc::umma_idesc_tf32(256, 256);
+            uint32_t itw = 0, vt_i = 0, ti = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters, ++ti) {
+                for (int g = 0; g < 2; ++g, ++vt_i) {
+                    const uint32_t buf = vt_i & 1;
+                    tc::mbar_wait_warp(&tmem_empty[buf], ((vt_i >> 1) & 1) ^ 1);
+                    tc::tcgen05_fence_after();
+                    const uint32_t acc = tmem_base + buf * 256;
+                    for (int kb = 0; kb < total_kb; ++kb, ++itw) {
+                        const uint32_t s = itw % (uint32_t)nst_w, ph = (itw / (uint32_t)nst_w) & 1;
+                        tc::mbar_wait_warp(&wfull[s], ph);
+                        if (g == 0) tc::mbar_wait_warp(&afull[kb], ti & 1);
+                        tc::tcgen05_fence_after();
+                        const uint64_t adesc = tc::umma_desc_sw128_kmajor(tc::smem_u32(wring + s * TC_TILE_BYTES));
+                        const uint64_t bdesc = tc::umma_desc_sw128_kmajor(tc::smem_u32(act + kb * TC_TILE_BYTES));
+                        if (tc::elect_one()) {
+                            if (!(dbg & 2)) {
+#pragma unroll
+                                for (int k = 0; k < TC_BK / 8; ++k)
+                                    tc::umma_tf32_2cta(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                            }
+                            tc::umma_commit_2cta(&wempty[s], 3);
+                            if (g == 1) tc::umma_commit_2cta(&aempty[kb], 3);
+                        }
+                        __syncwarp();
+                    }
+                    if (tc::elect_one()) tc::umma_commit_2cta(&tmem_full[buf], 3);
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ---- epilogue (each CTA: its own 128 channels of the group, all 256 columns) ------------------------------------
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        float colacc0 = 0.f, colacc1 = 0.f;
+        uint32_t vt_i = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g, ++vt_i) {
+                const uint32_t buf = vt_i & 1;
+                const int ch0 = g * 256 + (int)rank * 128;
+                const int ch = ch0 + q * 32 + lane;
+                const bool ch_ok = ch < n_out;
+                tc::mbar_wait<100>(&tmem_full[buf], (vt_i >> 1) & 1);
+                tc::tcgen05_fence_after();
+                tc::mbar_wait<100>(&meta_full[buf], (vt_i >> 1) & 1);
+                const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + half * 128);
+                const int64_t node0 = ((int64_t)t * 2 + half) * AGG_NPT;
+                if (node0 < sc.n_nodes && ch0 + q * 32 < n_out) {
+                    const uint32_t mb_a = tc::smem_u32(meta + (buf * 2 + half) * meta_stride);
+                    const uint32_t mword = 4u * (uint32_t)(ch0 >> 7) + (uint32_t)(lane & 3);
+                    float* dq = sc.dq + (ch_ok ? ch : ch % sc.hdim);
+                    float* dp = sc.dp + node0 * sc.lddp + ch;
+                    const unsigned lanebit = ch_ok ? (1u << (q * 8 + (lane >> 2))) : 0u;
+                    scat_tile_any(sc.mask_ld, tcol, mb_a, mb_a + meta_stride - 512u, mword, lanebit, dq, dp, sc.lddp,
+                                  sc.n_nodes - node0, ch_ok, (dbg & 64) != 0, sc.round_p != 0, g == 0 ? colacc0 : colacc1);
+                }
+                tc::tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    tc::mbar_arrive_cluster_relaxed(&tmem_empty[buf], 0);
+                    tc::mbar_arrive(&meta_empty[buf]);
+                }
+                __syncwarp();
+            }
+        }
+        if (sc.dbias != nullptr) {
+            const int c0 = (int)rank * 128 + q * 32 + lane, c1 = 256 + c0;
+            if (c0 < n_out) atomicAdd(sc.dbias + c0, colacc0);
+            if (c1 < n_out) atomicAdd(sc.dbias + c1, colacc1);
+        }
+    }
+    __syncwarp();
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();
+    if (warp == 1) tc::tmem_dealloc_2cta<512>(tmem_base);
+}
+
 // dst[r, c] = rna_tf32(src[r, c]) for c < cols, 0 for cols <= c < dst_cols
 __global__ void round_pad_tf32_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
                                       float* __restrict__ dst, int64_t ldd, int dst_cols) {
@@ -803,21 +996,38 @@ int g_linear_dbg = 0;   // tuning hook: see gnb_linear_set_debug
 int g_linear_variant = 0;   // 0 auto, 1 single-CTA kernel, 2 CTA-pair kernel
 int g_pair_resident = 0;    // 0: pair kernel streams the weights; n > 0: keep them resident when >= n activation stages fit
 
+cudaError_t init_tc_kernels() {
+    if (g_num_sms != 0) return cudaSuccess;
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_tc_pair_dual_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
+    if (e == cudaSuccess) g_num_sms = sms;
+    return e;
+}
+
+// Dual-group scattering launch (two 256-channel groups from one resident dz tile); false = shape not covered.
+bool dual_scatter_applicable(int hdim, int kblocks, int mask_ld, int* nst_w_out) {
+    if (hdim <= 256 || hdim > 512 || kblocks > DU_MAX_KB) return false;
+    const int64_t left = (int64_t)PL_MAX_DYN_SMEM - 1024 - DU_BAR_BYTES - 4 * (int64_t)sc_meta_stride(mask_ld) -
+                         (int64_t)kblocks * TC_TILE_BYTES;
+    int nst = left > 0 ? (int)(left / TC_TILE_BYTES) : 0;
+    if (nst > PL_MAX_STAGES) nst = PL_MAX_STAGES;
+    *nst_w_out = nst;
+    return nst >= 3;
+}
+
 // row_tiles = number of 128-row (plain) or 126-row (aggregating / scattering) tiles
 int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi, const float* bias, float* y, int64_t ldy,
                   int64_t rows, int n_out, int act, int round_out, int row_tiles, const AggInfo& agg, const ScatInfo& sc,
                   cudaStream_t stream) {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        GNB_CHECK(cudaGetDevice(&dev));
-        GNB_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-        GNB_CHECK(cudaFuncSetAttribute(gemm_tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)TC_SMEM_BYTES));
-        GNB_CHECK(cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM));
-    }
+    GNB_CHECK(init_tc_kernels());
     // measured (scripts/linear_probe.py): the pair kernel wins from two ch-tiles up; a single 128-channel tile is
     // faster on the single-CTA kernel (half of the pair's M = 256 would be padding)
-    const bool pair = (g_linear_variant == 2 || (g_linear_variant == 0 && row_tiles >= 2 * 148 && n_out > 128)) && n_out <= 1024;
+    const bool pair = (g_linear_variant >= 2 || (g_linear_variant == 0 && row_tiles >= 2 * 148 && n_out > 128)) && n_out <= 1024;
     if (pair) {
         const int tiles = (row_tiles + 1) / 2;
         const int groups = gnb_div_up(n_out, 256);
@@ -877,10 +1087,11 @@ int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi
 // Tuning hook (profiling only): bit0 epilogue skips its global stores, bit1 no MMAs, bit2 no weight loads, bit3 no
 // activation loads, bit6 no scatter epilogue math. Results are garbage with any bit set.
 GNB_EXPORT int gnb_linear_set_debug(int32_t flags) { g_linear_dbg = flags; return GNB_OK; }
-// Kernel selection for the tf32 Linear entry points: 0 auto (CTA-pair cta_group::2 kernel from 296 row tiles up),
-// 1 single-CTA kernel, 2 CTA-pair kernel.
+// Kernel selection for the tf32 Linear entry points: 0 auto (CTA-pair cta_group::2 kernel from 296 row tiles up, with the
+// dual-group scattering kernel where it applies), 1 single-CTA kernel, 2 CTA-pair kernel (one cluster set per channel group),
+// 3 CTA-pair kernel with the dual-group scattering kernel forced where it applies.
 GNB_EXPORT int gnb_linear_set_variant(int32_t v) {
-    if (v < 0 || v > 2) return GNB_ERR_ARG;
+    if (v < 0 || v > 3) return GNB_ERR_ARG;
     g_linear_variant = v;
     return GNB_OK;
 }
@@ -988,7 +1199,22 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_split_tf32(const float* dz, int64_t
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof};
     ScatInfo sc{nbr, hmask, mask_ld, dq, lddq, hdim, n, 1, dp, lddp, dbias, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0};
-    return launch_linear(tw, tx, pi, nullptr, nullptr, 0, rows, hdim, GNB_ACT_NONE, 0, gnb_div_up(n, AGG_NPT), agg, sc,
+    const int row_tiles = gnb_div_up(n, AGG_NPT);
+    int nst_w = 0;
+    if ((g_linear_variant == 3 || (g_linear_variant == 0 && row_tiles >= 2 * 148)) &&
+        dual_scatter_applicable(hdim, pi.kblocks[0], mask_ld, &nst_w)) {
+        GNB_CHECK(init_tc_kernels());
+        const int tiles = (row_tiles + 1) / 2;
+        int clusters = g_num_sms / 2;
+        if (clusters > tiles) clusters = tiles;
+        if (clusters < 1) clusters = 1;
+        const uint32_t mstride = sc_meta_stride(mask_ld);
+        const uint32_t smem = 1024 + (uint32_t)(pi.kblocks[0] + nst_w) * TC_TILE_BYTES + DU_BAR_BYTES + 4 * mstride;
+        gemm_tc_pair_dual_scatter_kernel<<<dim3((unsigned)(2 * clusters)), PL_THREADS, smem, (cudaStream_t)stream>>>(
+            tw, tx.m[0], pi.kblocks[0], rows, hdim, tiles, sc, nst_w, mstride, g_linear_dbg);
+        GNB_RETURN_LAUNCH();
+    }
+    return launch_linear(tw, tx, pi, nullptr, nullptr, 0, rows, hdim, GNB_ACT_NONE, 0, row_tiles, agg, sc,
                          (cudaStream_t)stream);
 }
 // Same with both halves in one [n, >= 2 hdim] tensor: dpq[:, 0:hdim] = dp (overwritten, unrounded), dpq[:, hdim:2 hdim] = dq

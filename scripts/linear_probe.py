@@ -120,7 +120,7 @@ def scatter_case(n, c_out, hdim, label, pitch=None):
 
 
 import sys as _s
-for variant, resident in (((1, 0), (2, 0)) if not (len(_s.argv) > 1 and _s.argv[1] in ("resident", "pitch")) else ()):
+for variant, resident in (((1, 0), (2, 0)) if not (len(_s.argv) > 1 and _s.argv[1] in ("resident", "pitch", "groups", "dual")) else ()):
     lib.gnb_linear_set_variant(variant)
     lib.gnb_linear_set_pair_resident(resident)
     print("== variant", variant, "(1 single-CTA, 2 CTA pair), resident weights from", resident, "stages", flush=True)
@@ -131,6 +131,20 @@ for variant, resident in (((1, 0), (2, 0)) if not (len(_s.argv) > 1 and _s.argv[
 lib.gnb_linear_set_variant(0)
 lib.gnb_linear_set_pair_resident(0)
 if len(_s.argv) > 1 and _s.argv[1] == "scatter":
+    _s.exit(0)
+if len(_s.argv) > 1 and _s.argv[1] == "dual":
+    for variant in (2, 3):
+        lib.gnb_linear_set_variant(variant)
+        print("== variant", variant, "(2 = one cluster set per channel group, 3 = dual-group kernel)", flush=True)
+        scatter_case(N, 256, 336, "dgrad + scatter epilogue")
+    lib.gnb_linear_set_variant(0)
+    _s.exit(0)
+if len(_s.argv) > 1 and _s.argv[1] == "groups":
+    # how much of the 336-channel launch is the second (80-channel) group's re-stream of dz?
+    lib.gnb_linear_set_variant(2)
+    for hd in (256, 336, 128, 80):
+        scatter_case(N, 256, hd, f"dgrad + scatter, hdim {hd}")
+    lib.gnb_linear_set_variant(0)
     _s.exit(0)
 if len(_s.argv) > 1 and _s.argv[1] == "pitch":
     lib.gnb_linear_set_variant(2)

@@ -23,7 +23,8 @@ def tf32_mode():
     ops.set_precision(old)
 
 
-@pytest.fixture(params=[(1, 0), (2, 0), (2, 2)], ids=["single_cta", "cta_pair", "cta_pair_resident_weights"])
+@pytest.fixture(params=[(1, 0), (2, 0), (2, 2), (3, 0)],
+                ids=["single_cta", "cta_pair", "cta_pair_resident_weights", "cta_pair_dual_group_scatter"])
 def linear_variant(request, built_library):
     """Run the tf32 Linear entry points on the single-CTA kernel and on the cta_group::2 CTA-pair kernel (weights
     streamed / resident in shared memory)."""
