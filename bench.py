@@ -354,10 +354,10 @@ def _time_launch(fn, reps=10):
 
 
 def roofline_top_kernel(trainer, db, pk):
-    """Dominant kernel of the training step (largest share of device time in profiles/r01): `gemm_tc_pair_kernel`, the
-    cta_group::2 tcgen05 (kind::tf32) GEMM over the padded edge list of a DynEdgeConv layer. Its heaviest launch is
-    the backward data-gradient GEMM with the scattering epilogue; the forward launch with the aggregating epilogue is
-    reported beside it. Algorithmic FLOPs per launch = 2 * E * 336 * 256 with E = actual edge count (SURVEY 8d:
+    """Dominant kernels of the training step (largest share of device time in profiles/r01): the cta_group::2 tcgen05
+    (kind::tf32) GEMMs over the padded edge list of a DynEdgeConv layer. The heaviest launch is the backward data-gradient
+    GEMM with the scattering epilogue (`gemm_tc_pair_dual_scatter_kernel`); the forward launch with the aggregating
+    epilogue (`gemm_tc_pair_kernel`) is reported beside it. Algorithmic FLOPs per launch = 2 * E * 336 * 256 with E = actual edge count (SURVEY 8d:
     deg * 2 * in * out per node). Timed alone with CUDA events on the launching stream (operands pre-rounded, so only
     the kernel runs); operands (> 0.7 GB per launch) exceed the 126 MB L2."""
     from graphnet_b200 import ops
@@ -400,8 +400,9 @@ def roofline_top_kernel(trainer, db, pk):
            "l2_view": l2_f}
     achieved = flops / sec_b / 1e12
     return {"bound": "tensor",
-            "kernel": "gemm_tc_pair_kernel (tcgen05 cta_group::2 kind::tf32 M256xN256xK8, TMA, TMEM double-buffered), scattering "
-                      "epilogue: dh = dz W2 (256 -> 336), ReLU mask, dP/dQ reduction over the padded edge list",
+            "kernel": "gemm_tc_pair_dual_scatter_kernel (tcgen05 cta_group::2 kind::tf32 M256xN256xK8, TMA, TMEM double-buffered; "
+                      "both 256-channel groups from one resident dz tile), scattering epilogue: dh = dz W2 (256 -> 336), ReLU mask, "
+                      "dP/dQ reduction over the padded edge list",
             "achieved": round(achieved, 3), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 5),
             "traffic": traffic, "peak_source": pk["source"] + " bf16 dense burst (tf32 tensor peak is half of it)",
             "launch_ms": round(sec_b * 1e3, 4), "rows": rows, "edges": e_real,

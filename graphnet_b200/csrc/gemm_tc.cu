@@ -830,7 +830,7 @@ gemm_tc_pair_dual_scatter_kernel(const __grid_constant__ CUtensorMap tm_w, const
             for (int k = 0; k < DU_MAX_KB; ++k) { tc::mbar_init(&afull[k], 1); tc::mbar_init(&aempty[k], 1); }
             for (int b = 0; b < 2; ++b) {
                 tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], 16);
-                tc::mbar_init(&meta_full[b], 1); tc::mbar_init(&meta_empty[b], 8);
+                tc::mbar_init(&meta_full[b], 1); tc::mbar_init(&meta_empty[b], 16);
             }
             tc::fence_barrier_init();
             tc::fence_proxy_async();
@@ -866,15 +866,21 @@ gemm_tc_pair_dual_scatter_kernel(const __grid_constant__ CUtensorMap tm_w, const
                     }
                     const uint32_t s = itw % (uint32_t)nst_w, ph = (itw / (uint32_t)nst_w) & 1;
                     tc::mbar_wait_warp(&wempty[s], ph ^ 1);
+                    // a CTA whose 128 weight rows of this group all lie beyond n_out (336 = 256 + 80: rank 1 of group 1) loads
+                    // nothing: its accumulator lanes are never read, and the zero-filled box would still cost 16 KiB of L2->SM
+                    const bool peer_rows = g * 256 + 128 < n_out;
                     if (tc::elect_one()) {
-                        if (rank == 0) tc::mbar_arrive_expect_tx(&wfull[s], w_tx);
-                        tc::tma_load_2d_2sm(wring + s * TC_TILE_BYTES, &tm_w, &wfull[s], kb * TC_BK, g * 256 + (int)rank * 128);
+                        if (rank == 0) tc::mbar_arrive_expect_tx(&wfull[s], peer_rows ? w_tx : w_tx / 2);
+                        if (rank == 0 || peer_rows)
+                            tc::tma_load_2d_2sm(wring + s * TC_TILE_BYTES, &tm_w, &wfull[s], kb * TC_BK, g * 256 + (int)rank * 128);
                     }
                     __syncwarp();
                 }
-                // scatter metadata of this (tile, group): same mask rows / offsets for both groups, one block per TMEM buffer
-                const uint32_t buf = vt_i & 1;
-                tc::mbar_wait_warp(&meta_empty[buf], ((vt_i >> 1) & 1) ^ 1);
+                if (g != 0) continue;
+                // scatter metadata of the tile (mask rows / offsets are the same for both groups): staged once, behind the
+                // loads of group 0, into the block of the tile's parity; released by the 16 epilogue passes (8 warps x 2 groups)
+                const uint32_t buf = ti & 1;
+                tc::mbar_wait_warp(&meta_empty[buf], ((ti >> 1) & 1) ^ 1);
                 uint32_t bytes = 0;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -936,8 +942,9 @@ gemm_tc_pair_dual_scatter_kernel(const __grid_constant__ CUtensorMap tm_w, const
         // ---- epilogue (each CTA: its own 128 channels of the group, all 256 columns) ------------------------------------
         const int q = warp & 3, half = (warp - 2) >> 2;
         float colacc0 = 0.f, colacc1 = 0.f;
-        uint32_t vt_i = 0;
-        for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        uint32_t vt_i = 0, ti = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++ti) {
+            const uint32_t mbuf = ti & 1;
 #pragma unroll
             for (int g = 0; g < 2; ++g, ++vt_i) {
                 const uint32_t buf = vt_i & 1;
@@ -946,11 +953,11 @@ gemm_tc_pair_dual_scatter_kernel(const __grid_constant__ CUtensorMap tm_w, const
                 const bool ch_ok = ch < n_out;
                 tc::mbar_wait<100>(&tmem_full[buf], (vt_i >> 1) & 1);
                 tc::tcgen05_fence_after();
-                tc::mbar_wait<100>(&meta_full[buf], (vt_i >> 1) & 1);
+                tc::mbar_wait<100>(&meta_full[mbuf], (ti >> 1) & 1);
                 const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + half * 128);
                 const int64_t node0 = ((int64_t)t * 2 + half) * AGG_NPT;
                 if (node0 < sc.n_nodes && ch0 + q * 32 < n_out) {
-                    const uint32_t mb_a = tc::smem_u32(meta + (buf * 2 + half) * meta_stride);
+                    const uint32_t mb_a = tc::smem_u32(meta + (mbuf * 2 + half) * meta_stride);
                     const uint32_t mword = 4u * (uint32_t)(ch0 >> 7) + (uint32_t)(lane & 3);
                     float* dq = sc.dq + (ch_ok ? ch : ch % sc.hdim);
                     float* dp = sc.dp + node0 * sc.lddp + ch;
@@ -962,7 +969,7 @@ gemm_tc_pair_dual_scatter_kernel(const __grid_constant__ CUtensorMap tm_w, const
                 __syncwarp();
                 if (lane == 0) {
                     tc::mbar_arrive_cluster_relaxed(&tmem_empty[buf], 0);
-                    tc::mbar_arrive(&meta_empty[buf]);
+                    tc::mbar_arrive(&meta_empty[mbuf]);
                 }
                 __syncwarp();
             }
