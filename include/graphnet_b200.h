@@ -79,8 +79,10 @@ int gnb_edgeconv_fused_fwd_tf32(const float* pq, int64_t ldpq, int32_t hdim, con
 /* Tuning aid for gnb_linear_fwd_tf32 / gnb_edge_linear_agg_fwd_tf32 (results are garbage with any bit set): bit0 the
  * epilogue skips its global stores, bit1 no MMAs, bit2 no weight loads, bit3 no activation loads. 0 = normal. */
 int gnb_linear_set_debug(int32_t flags);
-/* Kernel selection for gnb_linear_fwd_tf32 / gnb_edge_linear_agg_fwd_tf32 / gnb_edge_hidden_dgrad_scatter_tf32: 0 auto
- * (CTA-pair cta_group::2 kernel for >= 296 row tiles), 1 single-CTA kernel, 2 CTA-pair kernel. */
+/* Kernel selection for gnb_linear_fwd_tf32 / gnb_edge_linear_agg_fwd_tf32 / gnb_edge_hidden_dgrad_scatter(_split)_tf32:
+ * 0 auto (CTA-pair cta_group::2 kernel for >= 296 row tiles, dual-group scattering kernel where the hidden width needs two
+ * 256-channel groups), 1 single-CTA kernel, 2 CTA-pair kernel with one cluster set per channel group, 3 CTA-pair kernel
+ * with the dual-group scattering kernel forced wherever it applies. */
 int gnb_linear_set_variant(int32_t v);
 /* CTA-pair kernel shared-memory plan: 0 = stream the weight tiles with the activations; n >= 2 = keep the CTA's 128
  * weight rows resident whenever a single-part K leaves at least n activation stages (halves the L2->SM traffic). */
