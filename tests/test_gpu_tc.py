@@ -415,3 +415,60 @@ def test_tc_linear_accumulate_flag(built_library, tf32_mode, linear_variant, row
               rows, n_out, 0x200, 0, ops._stream())
     torch.cuda.synchronize()
     assert torch.equal(y.cpu().double(), ref)
+
+
+@pytest.mark.parametrize("variant", [2, 3], ids=["cta_pair", "dual_group"])
+@pytest.mark.parametrize("hdim,c_out,n", [(336, 256, 7013), (512, 96, 9001), (128, 256, 6500)])
+def test_edge_hidden_dgrad_scatter_many_tiles_per_cluster(built_library, tf32_mode, variant, hdim, c_out, n):
+    """The persistent pipelines with SEVERAL row tiles per cluster (barrier phase wrap-around, slot / metadata / TMEM buffer
+    reuse) -- the small bit-exact case above gives every cluster at most one tile. Random integer operands, random
+    activation bits, random in-event neighbours (some nodes with fewer than 8 and some with 9 neighbours); the fp64
+    reference is vectorised. Exact equality (products and order-independent sums are exact on these integers)."""
+    ops = tf32_mode
+    from graphnet_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(hdim + n)
+    rows = n * 9
+    nbr = torch.randint(0, n, (n, 9), generator=g)
+    base = torch.arange(n).unsqueeze(1)
+    nbr = (base + torch.randint(-40, 41, (n, 9), generator=g)).clamp_(0, n - 1)
+    deg = torch.full((n,), 8, dtype=torch.int64)
+    deg[torch.randint(0, n, (n // 20,), generator=g)] = 9                     # duplicate quirk: slot 8 holds an edge
+    few = torch.randint(0, n, (n // 15,), generator=g)
+    deg[few] = torch.randint(0, 8, (few.numel(),), generator=g)
+    valid = torch.arange(9).unsqueeze(0) < deg.unsqueeze(1)                   # [n, 9]
+    nbr = torch.where(valid, nbr, torch.full_like(nbr, -1))
+    dz = torch.randint(-2, 3, (rows, c_out), generator=g).float()
+    w2 = torch.randint(-1, 2, (c_out, hdim), generator=g).float()
+    bits = (torch.rand(rows, hdim, generator=g) < 0.5) & valid.reshape(-1, 1)  # padding slots carry no activation bits
+    mld = 4 * ((hdim + 127) // 128)
+    ntile = (n + 13) // 14
+    words = np.zeros((ntile * 126, mld), dtype=np.uint32)
+    words[rows:] = 0xFFFFFFFF                                                  # garbage behind the last node
+    bn = bits.numpy()
+    for c in range(hdim):      # layout of gnb_edge_hidden_fwd_mask
+        words[:rows, 4 * (c // 128) + c % 4] |= bn[:, c].astype(np.uint32) << np.uint32((c % 128) // 4)
+    dh = (dz.double() @ w2.double()) * bits.double()
+    dp_ref = dh.reshape(n, 9, hdim).sum(1)
+    dq_ref = torch.zeros(n, hdim, dtype=torch.float64)
+    flat_nbr = nbr.reshape(-1)
+    sel = flat_nbr >= 0
+    dq_ref.index_add_(0, flat_nbr[sel], dh[sel])
+    kpad = (c_out + 31) // 32 * 32
+    wt = torch.zeros(hdim, kpad)
+    wt[:, :c_out] = w2.t()
+    hmask = torch.from_numpy(words.view(np.int32)).cuda()
+    dzc, wtc, nbrc = dz.cuda(), wt.cuda(), nbr.int().cuda()
+    dq = torch.zeros(n, hdim, device="cuda")
+    dp = torch.full((n, hdim), 7.0, device="cuda")
+    dbias = torch.zeros(hdim, device="cuda")
+    assert lib.gnb_linear_set_variant(variant) == 0
+    try:
+        ops._call("gnb_edge_hidden_dgrad_scatter_split_tf32", ops._ptr(dzc), c_out, c_out, ops._ptr(wtc), kpad, ops._ptr(hmask), mld,
+                  hdim, ops._ptr(nbrc), n, ops._ptr(dq), hdim, ops._ptr(dp), hdim, ops._ptr(dbias), 0x100, ops._stream())
+        torch.cuda.synchronize()
+    finally:
+        lib.gnb_linear_set_variant(0)
+    assert torch.equal(dp.cpu().double(), dp_ref)
+    assert torch.equal(dq.cpu().double(), dq_ref)
+    assert torch.equal(dbias.cpu().double(), dp_ref.sum(0))
