@@ -41,6 +41,30 @@ def test_no_cpu_fallback():
         ops.knn_table(torch.rand(4, 3), [0, 1, 2], torch.tensor([0, 4]), 2)
 
 
+def test_optimizer_and_device_graph_definition_refuse_cpu_tensors():
+    """The pieces either side of the path (flat Adam, device-side graph definition) have no CPU fallback either, and the
+    device graph definition says which node definitions it covers."""
+    from graphnet_b200.distributed import FlatAdam, FlatGradAllReduce
+    from graphnet_b200.models.detector import IceCube86
+    from graphnet_b200.models.graphs import DeviceKNNGraph, KNNGraph
+    from graphnet_b200.models.graphs.nodes import NodeDefinition
+    lin = torch.nn.Linear(3, 2)
+    with pytest.raises(RuntimeError):
+        FlatAdam(FlatGradAllReduce(lin.parameters()))
+    names = ["dom_x", "dom_y", "dom_z", "dom_time", "charge", "rde", "pmt_area"]
+    definition = KNNGraph(detector=IceCube86(), input_feature_names=names)
+    builder = DeviceKNNGraph(definition)
+    with pytest.raises(RuntimeError):
+        builder(torch.rand(5, 7), torch.tensor([5], dtype=torch.int32))
+
+    class Other(NodeDefinition):
+        def _define_output_feature_names(self, input_feature_names):
+            return input_feature_names
+
+    with pytest.raises(NotImplementedError):
+        DeviceKNNGraph(KNNGraph(detector=IceCube86(), node_definition=Other(), input_feature_names=names))
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "graphnet_b200")
     for dirpath, _, files in os.walk(pkg):
