@@ -28,8 +28,7 @@ constexpr int TC_MAX_PARTS = 6;
 constexpr uint32_t TC_TILE_BYTES = TC_BM * TC_BK * 4;                           // 16 KiB: one 128 x 32 fp32 tile
 constexpr uint32_t TC_STAGE_BYTES = (TC_MT + 1) * TC_TILE_BYTES;                // 2 weight tiles + 1 activation tile
 constexpr int SC_MAX_MASK_LD = 16;                                              // mask words per row (hdim <= 512)
-constexpr uint32_t SC_META_MASK_BYTES = 126 * SC_MAX_MASK_LD * 4;               // 8064: one tile of activation mask rows
-constexpr uint32_t SC_META_BYTES = 8192 + 512;                                  // mask rows + 128 scatter offsets
+constexpr uint32_t SC_META_BYTES = 8192 + 512;         // single-CTA kernel: mask rows (<= 8064 B) + lastv | 128 scatter offsets
 constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * SC_META_BYTES;
 constexpr uint32_t TC_TMEM_COLS = 2 * TC_MT * TC_BN;                            // 512: two accumulator buffers
 
@@ -42,10 +41,10 @@ struct AggInfo { const int* deg; int64_t n_nodes; unsigned* maskbits; int enable
 constexpr int AGG_W = 9, AGG_NPT = 14, AGG_ROWS = AGG_W * AGG_NPT;   // k = 8 neighbour tables
 // Scattering epilogue (backward of the hoisted EdgeConv hidden layer fused into the data-gradient GEMM): rows are padded
 // edge slots as above, output channel c of row (i, s) is dh = (dz W2)[(i,s), c]; the epilogue applies the ReLU mask
-// (bit mask of h > 0 written by the forward hidden-layer kernel), sums the slots of a node into dPQ[i, c] (P half) and
-// adds each slot into dPQ[nbr[i,s], hdim + c] (Q half, fp32 `red.global.add`, 32 consecutive channels per warp
-// instruction). dh [E, hdim] is never stored. Per tile the producer warp stages the 126 mask rows (one bulk copy) and
-// the 126 scatter offsets nbr * ldpq in shared memory, so the epilogue touches no global metadata.
+// (bit mask of h > 0 written by the forward hidden-layer kernel), sums the slots of a node into dp[i, c] (the P half of
+// dPQ) and adds each slot into dq[nbr[i,s], c] (the Q half; fp32 `red.global.add`, 32 consecutive channels per warp
+// instruction). dh [E, hdim] is never stored. Per tile the producer warp stages the 126 mask rows (one bulk copy), the
+// 126 scatter offsets nbr * lddq and the "slot 8 is real" bits in shared memory: the epilogue touches no global metadata.
 // dq: [n, >= hdim] rows of pitch lddq (fp32 reductions; zero on entry); dp: [n, >= hdim] rows of pitch lddp (overwritten,
 // rounded to tf32 when round_p); dbias (optional): [hdim] += column sums of dp (the bias gradient of the hoisted Linear).
 struct ScatInfo { const int* nbr; const unsigned* hmask; int mask_ld; float* dq; int64_t lddq; int hdim; int64_t n_nodes; int enabled;
