@@ -1,1 +1,1 @@
-from .nodes import NodeDefinition, NodesAsPulses  # noqa: F401
+from .nodes import NodeDefinition, NodesAsPulses, PercentileClusters  # noqa: F401

@@ -74,3 +74,28 @@ def test_detector_standardisation_pinned_on_reference_icecube86():
         det(raw, names[:-1] + ["not_a_feature"])
     with pytest.raises(KeyError):
         det.standardisation_table(["not_a_feature"])
+
+
+def test_percentile_clusters_pinned_on_reference_utils():
+    """`PercentileClusters` (host-side node definition of BASELINE config #4) reproduces the reference's own
+    `cluster_summarize_with_percentiles` bit for bit in float64 (tests/golden/make_golden_nodes.py), keeps its output
+    feature names, and flows through `KNNGraph` (float32 nodes, n_pulses = raw pulse count, edges deferred on the CPU)."""
+    from graphnet_b200.models.detector import IdentityDetector
+    from graphnet_b200.models.graphs import KNNGraph
+    from graphnet_b200.models.graphs.nodes import PercentileClusters
+    gold = torch.load(os.path.join(GOLDEN_DIR, "nodes_percentile_clusters.pt"))
+    names, cluster_on, pcts = gold["features"], gold["cluster_on"], gold["percentiles"]
+    for case in gold["cases"]:
+        node_def = PercentileClusters(cluster_on=cluster_on, percentiles=pcts, add_counts=case["add_counts"],
+                                      input_feature_names=names)
+        data, out_names = node_def(case["x"])
+        assert data.x.dtype == torch.float64 and torch.equal(data.x, case["nodes"])
+        assert len(out_names) == case["nodes"].shape[1] == 3 + 4 * 3 + int(case["add_counts"])
+        assert out_names[:4] == ["dom_x", "dom_y", "dom_z", "dom_time_pct10"] and (out_names[-1] == "counts") == case["add_counts"]
+    case = gold["cases"][-2]
+    definition = KNNGraph(detector=IdentityDetector(), node_definition=PercentileClusters(cluster_on, pcts),
+                          input_feature_names=names)
+    graph = definition(case["x"].numpy(), names)
+    assert definition.nb_outputs == 16 and graph.x.dtype == torch.float32
+    assert torch.equal(graph.x, case["nodes"].float()) and int(graph.n_pulses) == case["x"].shape[0]
+    assert torch.equal(graph["counts"], graph.x[:, -1])
