@@ -209,3 +209,50 @@ def test_high_multiplicity_event_and_layer_sweep(built_library):
             conv = DynEdgeConv(copy.deepcopy(nn), aggr="add", nb_neighbors=k, features_subset=slice(0, 3)).cuda()
             out, _ = conv.forward_table(x.cuda(), graph, ptr2.cuda())
             assert rel_err(out, ref_out) < 1e-5, (k, width)
+
+
+def test_config4_percentile_cluster_nodes_end_to_end(built_library):
+    """BASELINE config #4: `PercentileClusters` nodes (F = 3 + 4*3 + 1 = 16) built per event on the host like the reference's
+    dataloader workers, collated, edges built on the device batch, DynEdge with [min, max, mean, sum] pooling, forward and
+    backward against the oracle (fp32 mode, rel 1e-3; latent graphs teacher-forced)."""
+    from graphnet_b200.data import Batch
+    from graphnet_b200.models.detector import IdentityDetector
+    from graphnet_b200.models.gnn import DynEdge
+    from graphnet_b200.models.graphs import KNNGraph
+    from graphnet_b200.models.graphs.nodes import PercentileClusters
+    names = ["dom_x", "dom_y", "dom_z", "dom_time", "charge", "rde", "pmt_area"]
+    definition = KNNGraph(detector=IdentityDetector(), input_feature_names=names, nb_nearest_neighbours=8,
+                          node_definition=PercentileClusters(["dom_x", "dom_y", "dom_z"], [10, 50, 90]))
+    rng = np.random.default_rng(4)
+    graphs = []
+    for n, n_doms in [(3000, 700), (40, 12), (900, 300), (5, 5), (400, 9)]:
+        doms = np.round(rng.uniform(-1.0, 1.0, size=(n_doms, 3)), 2).astype(np.float32)
+        x = np.concatenate([doms[rng.integers(0, n_doms, size=n)], rng.normal(size=(n, 4)).astype(np.float32)], axis=1)
+        graphs.append(definition(x, names))
+    host = Batch.from_data_list(graphs)
+    assert host.x.shape[1] == 16 and host.edge_index is None                 # edges deferred on the CPU
+    dev = definition.build_edges(host.to("cuda"))
+    x, batch, n_pulses = host.x, host.batch, host.n_pulses
+    ptr = batch_to_ptr(batch)
+    ei0 = knn_graph_ref(x[:, :3], 8, ptr=ptr)
+    assert torch.equal(dev.edge_index.cpu(), ei0)
+    kwargs = dict(global_pooling_schemes=["min", "max", "mean", "sum"])
+    torch.manual_seed(0)
+    ref = DynEdgeRef(16, **kwargs)
+    model = DynEdge(16, **kwargs)
+    model.load_state_dict(ref.state_dict())
+    model = model.cuda()
+    model._debug_record = True
+    y = model(dev)
+    y.square().sum().backward()
+    forced = [None]
+    for li in range(1, 4):
+        feats = model._debug["skips"][li].detach().cpu()
+        ei_k = model._debug["graphs"][li].edge_index().cpu()
+        assert torch.equal(ei_k, knn_graph_ref(feats[:, :3], 8, ptr=ptr)), f"latent graph {li}"
+        forced.append(ei_k)
+    y_ref = ref(namespace(x=x, edge_index=ei0, batch=batch, n_pulses=n_pulses), forced_graphs=forced)
+    y_ref.square().sum().backward()
+    assert rel_err(y, y_ref) < REL_TOL
+    for (key, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+        assert rel_err(p.grad, q.grad) < REL_TOL, key
