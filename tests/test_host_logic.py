@@ -30,6 +30,32 @@ def test_header_symbols_are_exported(built_library):
         assert hasattr(lib, name), f"{name} declared in include/graphnet_b200.h but not exported"
 
 
+def test_ctypes_signatures_match_header_prototypes():
+    """Every prototype in include/graphnet_b200.h and its ctypes signature agree argument by argument on the C type class
+    (pointer / int32 / int64 / float): a drifted binding would pass garbage to a kernel launcher."""
+    header = open(os.path.join(ROOT, "include", "graphnet_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = re.findall(r"\b(?:int|int64_t)\s+(gnb_\w+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) == len(_lib.SIGNATURES)
+
+    def kind(arg: str):
+        arg = " ".join(arg.split())
+        if "*" in arg:
+            return ctypes.c_void_p
+        if arg.startswith("int64_t"):
+            return ctypes.c_int64
+        if arg.startswith(("int32_t", "int ")):
+            return ctypes.c_int32
+        if arg.startswith("float"):
+            return ctypes.c_float
+        raise AssertionError(f"unparsed argument {arg!r}")
+
+    for name, args in protos:
+        args = args.strip()
+        want = [] if args in ("", "void") else [kind(a) for a in args.split(",")]
+        assert want == list(_lib.SIGNATURES[name]), name
+
+
 def test_no_cpu_fallback():
     model = DynEdge(7, global_pooling_schemes=["max"])
     data = Data(x=torch.rand(5, 7), edge_index=torch.tensor([[1, 0], [0, 1]]), batch=torch.zeros(5, dtype=torch.int64),
