@@ -37,8 +37,7 @@ for hid in (336, 128):
     print(f"hidden fwd (mask) hid={hid}: {t:.0f} us, {4.0 * n * 9 * hid / t / 1e6:.2f} TB/s written", flush=True)
 x = db["x"]
 ptr = data.ptr if hasattr(data, "ptr") else None
-from oracle.dynedge_oracle import batch_to_ptr  # noqa: E402  (probe script only)
-ptr = batch_to_ptr(db["batch"].cpu()).to(dev)
+ptr = ops.batch_to_ptr(db["batch"], 512)
 for variant in (0, 1):
     lib.gnb_knn_set_variant(variant)
     t = timed(lambda: ops.knn_table(x, [0, 1, 2], ptr, 8))

@@ -4,13 +4,12 @@ import sys, torch
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 from graphnet_b200 import ops
 from helpers import tie_heavy_events
-from oracle.dynedge_oracle import batch_to_ptr
 ops.set_precision('tf32')
 seq = [int(v) for v in sys.argv[1].split(',')]
 sizes = [1, 2, 5, 9, 10, 64, 130, 12, 300]
 x, batch, _ = tie_heavy_events(sizes, 5, seed=3)
-ptr = batch_to_ptr(batch)
-graph = ops.knn_table(x.cuda(), [0, 1, 2], ptr.cuda(), 8)
+ptr = ops.batch_to_ptr(batch.cuda(), len(sizes))
+graph = ops.knn_table(x.cuda(), [0, 1, 2], ptr, 8)
 n = x.shape[0]
 ops.set_edgeconv_variant(2)
 for hdim in seq:

@@ -5,7 +5,7 @@ kept in bf16 (as a `kind::f16` tcgen05 GEMM would need) instead of tf32-rounded 
 The oracle forward is run three times on the same synthetic events, weights and (fp64-forced) graphs: fp64 reference,
 tf32 storage (today's training route: h, dz, W2 rounded to 10 mantissa bits) and bf16 storage (7 mantissa bits), with
 fp32 arithmetic everywhere else. Errors are the per-tensor metric of the parity tests, |a - b|_inf / |b|_inf.
-Study script (imports oracle/): python scripts/bf16_storage_study.py
+Lives under tests/ because it drives the oracle (test infrastructure): python tests/studies/bf16_storage_study.py
 """
 import sys
 
