@@ -27,12 +27,29 @@ def round_bf16(t):
     return t.bfloat16().float()
 
 
-def make_edgeconv(rounder):
+def trunc_tf32(t):
+    return (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def make_edgeconv(rounder, dq_mode=None):
+    """dq_mode: None = literal first Linear; "round" / "trunc" = hoisted first Linear (P = x (Wa - Wb)^T + b1, Q = x Wb^T,
+    h = relu(P_i + Q_j)) with the gradient of Q rounded (today's rounding pass) or truncated (what the tensor core would do
+    to an unrounded operand) to tf32 before the two GEMMs that consume it."""
     def edgeconv(x, edge_index, nn, aggr):
         lin1, _, lin2, _ = nn
         src, dst = edge_index[0], edge_index[1]
         x_i, x_j = x[dst], x[src]
-        h = torch.relu(lin1(torch.cat([x_i, x_j - x_i], dim=-1)))
+        if dq_mode is None:
+            h = torch.relu(lin1(torch.cat([x_i, x_j - x_i], dim=-1)))
+        else:
+            c = x.shape[1]
+            wa, wb = lin1.weight[:, :c], lin1.weight[:, c:]
+            pn = torch.nn.functional.linear(x, wa - wb, lin1.bias)
+            qn = torch.nn.functional.linear(x, wb)
+            if qn.requires_grad:
+                pn.register_hook(round_tf32)
+                qn.register_hook(round_tf32 if dq_mode == "round" else trunc_tf32)
+            h = torch.relu(pn[dst] + qn[src])
         if rounder is not None:
             h = h + (rounder(h) - h).detach()                       # stored h (consumed by the edge GEMM and both gradients)
             w2 = lin2.weight + (rounder(lin2.weight) - lin2.weight).detach()
@@ -46,9 +63,9 @@ def make_edgeconv(rounder):
     return edgeconv
 
 
-def run(model, data, forced, rounder, dtype):
+def run(model, data, forced, rounder, dtype, dq_mode=None):
     saved = orc.edgeconv_ref
-    orc.edgeconv_ref = make_edgeconv(rounder) if rounder is not None or dtype == torch.float32 else saved
+    orc.edgeconv_ref = make_edgeconv(rounder, dq_mode) if rounder is not None or dtype == torch.float32 else saved
     try:
         model = model.to(dtype)
         for p in model.parameters():
@@ -81,9 +98,12 @@ def main():
         p.grad = None
     y_ref, g_ref = run(m64, data, forced, None, torch.float64)
     print(f"events 24, pulses {x.shape[0]}, edges {ei0.shape[1]}")
-    for tag, rounder in (("fp32 arithmetic, exact storage", None), ("tf32 storage of h / dz / W2", round_tf32),
-                         ("bf16 storage of h / dz / W2", round_bf16)):
-        y, g = run(model, data, forced, rounder, torch.float32)
+    for tag, rounder, dq_mode in (("fp32 arithmetic, exact storage", None, None),
+                                  ("tf32 storage of h / dz / W2", round_tf32, None),
+                                  ("  + hoisted Linear, dP / dQ rounded", round_tf32, "round"),
+                                  ("  + hoisted Linear, dQ TRUNCATED", round_tf32, "trunc"),
+                                  ("bf16 storage of h / dz / W2", round_bf16, None)):
+        y, g = run(model, data, forced, rounder, torch.float32, dq_mode)
         errs = {k: rel(g[k], g_ref[k]) for k in g_ref}
         worst = max(errs, key=errs.get)
         print(f"{tag:34s}: output {rel(y, y_ref):.2e}   gradients max {errs[worst]:.2e} ({worst})  median "
