@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--events", type=int, default=512, help="training events per GPU (configs[2])")
     ap.add_argument("--infer-events", type=int, default=1024, help="inference events per GPU (configs[1])")
-    ap.add_argument("--precision", default=os.environ.get("GNB_PRECISION", "tf32"), choices=["tf32", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("GNB_PRECISION", "tf32"), choices=["tf32", "tf32x3", "fp32"])
     ap.add_argument("--cpu-events", type=int, default=48, help="events of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inference", action="store_true")
@@ -361,7 +361,7 @@ def roofline_top_kernel(trainer, db, pk):
     deg * 2 * in * out per node). Timed alone with CUDA events on the launching stream (operands pre-rounded, so only
     the kernel runs); operands (> 0.7 GB per launch) exceed the 126 MB L2."""
     from graphnet_b200 import ops
-    if ops.PRECISION != "tf32":
+    if ops.PRECISION not in ("tf32", "tf32x3"):
         return roofline_fp32_kernel(trainer, db, pk)
     d = dominant_launches(trainer, db)
     rows, n, e_real, hid, cout = d["rows"], d["n"], d["edges"], d["hid"], d["cout"]

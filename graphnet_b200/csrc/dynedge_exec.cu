@@ -47,6 +47,10 @@ int gnb_linear_fwd_tf32(const float* const*, const int64_t*, const int32_t*, int
                         float*, int64_t, int64_t, int32_t, int32_t, int32_t, void*);
 int gnb_linear_bwd_weight_tf32(const float*, int64_t, const float*, int64_t, float*, int64_t, int64_t, int32_t, int32_t,
                                int32_t, void*);
+int gnb_linear_fwd_tf32x3(const float* const*, const int64_t*, const int32_t*, int32_t, const float*, const float*, int64_t,
+                          const float*, float*, int64_t, int64_t, int32_t, int32_t, void*);
+int gnb_edge_linear_agg_fwd_tf32x3(const float*, int64_t, int32_t, const float*, const float*, int64_t, const float*,
+                                   const int32_t*, int64_t, int32_t, float*, int64_t, uint32_t*, void*);
 int gnb_linear_fwd_f32(const float*, int64_t, const float*, int64_t, const float*, float*, int64_t, int64_t, int64_t,
                        int64_t, int32_t, int32_t, void*);
 int gnb_linear_bwd_data_f32(const float*, int64_t, const float*, int64_t, float*, int64_t, int64_t, int64_t, int64_t,
@@ -59,7 +63,8 @@ int gnb_linear_bwd_weight_f32(const float*, int64_t, const float*, int64_t, floa
 #define GNB_MAX_KNN_COLS 16
 
 struct gnb_dynedge_config {
-    int32_t nb_inputs, k, precision;               // precision: 0 = fp32 SIMT, 1 = tf32 tcgen05
+    int32_t nb_inputs, k, precision;               // precision: 0 = fp32 SIMT, 1 = tf32 tcgen05, 2 = tf32x3 (split-operand
+                                                   // forward GEMMs = fp32 grade, single-pass tf32 backward GEMMs)
     int32_t n_conv, conv_hidden[GNB_MAX_LAYERS], conv_out[GNB_MAX_LAYERS];
     int32_t n_post, post_out[GNB_MAX_LAYERS];
     int32_t n_readout, readout_out[GNB_MAX_LAYERS];
@@ -78,14 +83,17 @@ inline int64_t up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 // ---- small kernels private to the executor ---------------------------------------------------------
 // dst[r, c] = (c < cols ? maybe_round(src[r, c]) : 0)        (strided copy / pad / tf32 rounding)
+// lo != nullptr (tf32x3 weights): dst = rna_tf32(v), lo = rna_tf32(v - dst)
 __global__ void copy_pad_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
-                                float* __restrict__ dst, int64_t ldd, int dst_cols, int rnd) {
+                                float* __restrict__ dst, int64_t ldd, int dst_cols, int rnd, float* __restrict__ lo) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rows * dst_cols) return;
     const int64_t r = t / dst_cols;
     const int c = (int)(t - r * dst_cols);
     float v = c < cols ? src[r * lds + c] : 0.f;
-    dst[r * ldd + c] = rnd ? gnb_round_tf32(v) : v;
+    const float hi = rnd ? gnb_round_tf32(v) : v;
+    dst[r * ldd + c] = hi;
+    if (lo != nullptr) lo[r * ldd + c] = gnb_round_tf32(v - hi);
 }
 // dst[r, c] += src[r, c]
 __global__ void add2d_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
@@ -109,14 +117,16 @@ __global__ void transpose_pad_kernel(const float* __restrict__ src, int64_t lds,
 // First Linear of an EdgeConv MLP hoisted to nodes: W1 = [Wa | Wb] ([H, 2C]) -> Wcat = [Wa - Wb ; Wb] ([2H, ld]),
 // bcat = [b1 ; 0]
 __global__ void pack_conv_kernel(const float* __restrict__ w1, const float* __restrict__ b1, int h, int c,
-                                 float* __restrict__ wcat, int64_t ld, float* __restrict__ bcat, int rnd) {
+                                 float* __restrict__ wcat, int64_t ld, float* __restrict__ bcat, int rnd, float* __restrict__ wlo) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 2 * (int64_t)h * ld) return;
     const int r = (int)(t / ld);
     const int col = (int)(t - (int64_t)r * ld);
     float v = 0.f;
     if (col < c) v = r < h ? w1[(int64_t)r * 2 * c + col] - w1[(int64_t)r * 2 * c + c + col] : w1[(int64_t)(r - h) * 2 * c + c + col];
-    wcat[(int64_t)r * ld + col] = rnd ? gnb_round_tf32(v) : v;
+    const float hi = rnd ? gnb_round_tf32(v) : v;
+    wcat[(int64_t)r * ld + col] = hi;
+    if (wlo != nullptr) wlo[(int64_t)r * ld + col] = gnb_round_tf32(v - hi);
     if (col == 0) bcat[r] = r < h ? b1[r] : 0.f;
 }
 // dW1[r, col] += dWcat[r, col];  dW1[r, C + col] += dWcat[H + r, col] - dWcat[r, col];  db1 += dbcat[0:H]
@@ -155,8 +165,8 @@ struct Arena {
     }
 };
 
-struct ConvBuf { float *wcat, *bcat, *w2p, *pq, *h, *m, *y; int32_t *nbr, *deg; uint32_t *mask, *hmask; int cin, cin_ld, kld, hid, hld, cout, mld; };
-struct DenseBuf { float *wp, *z; int k_total, kld, n_out; };
+struct ConvBuf { float *wcat, *wcat_lo, *w2p_lo, *bcat, *w2p, *pq, *h, *m, *y; int32_t *nbr, *deg; uint32_t *mask, *hmask; int cin, cin_ld, kld, hid, hld, cout, mld; };
+struct DenseBuf { float *wp, *wp_lo, *z; int k_total, kld, n_out; };
 
 struct Plan {
     int64_t n, nseg;
@@ -183,7 +193,9 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
     if (c.globals_after_pooling && c.n_pool == 0) return GNB_ERR_ARG;
     Arena a(ws, cap);
     p.n = n; p.nseg = nseg; p.w0 = w0; p.width = c.k + 1;
-    p.agg = c.precision == 1 && c.k == 8 && w0 == 9 && !(c.flags & 1) && (training || (c.flags & 2));
+    const bool split = c.precision == 2;      // pre-split weight operands: a lo buffer behind every packed forward weight
+    if (c.precision < 0 || c.precision > 2) return GNB_ERR_ARG;
+    p.agg = c.precision >= 1 && c.k == 8 && w0 == 9 && !(c.flags & 1) && (training || (c.flags & 2) || split);
     const int f = c.nb_inputs, ng = f + 5;
     const bool distribute = !c.globals_after_pooling;
     p.node_width = f + (distribute ? ng : 0);
@@ -211,8 +223,10 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
         b.kld = (int)up(b.cin_ld, 32);
         b.hid = c.conv_hidden[l]; b.hld = (int)up(b.hid, 32); b.cout = c.conv_out[l];
         b.wcat = a.get<float>((int64_t)2 * b.hid * b.kld);
+        b.wcat_lo = split ? a.get<float>((int64_t)2 * b.hid * b.kld) : nullptr;
         b.bcat = a.get<float>(2 * b.hid);
         b.w2p = a.get<float>((int64_t)b.cout * b.hld);
+        b.w2p_lo = split ? a.get<float>((int64_t)b.cout * b.hld) : nullptr;
         b.pq = training ? a.get<float>(n * 2 * b.hid) : pq_shared;
         b.h = training ? a.get<float>(n * wl * b.hid) : h_shared;
         b.m = training ? (p.agg ? nullptr : a.get<float>(n * wl * b.cout)) : m_shared;
@@ -241,6 +255,7 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
         d.k_total = j == 0 ? off : prev;
         d.kld = (int)up(d.k_total, 32);
         d.wp = a.get<float>((int64_t)d.n_out * d.kld);
+        d.wp_lo = split ? a.get<float>((int64_t)d.n_out * d.kld) : nullptr;
         d.z = a.get<float>(n * d.n_out);
         prev = d.n_out;
     }
@@ -264,6 +279,7 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
             d.k_total = rprev;
             d.kld = (int)up(rprev, 32);
             d.wp = a.get<float>((int64_t)d.n_out * d.kld);
+            d.wp_lo = split ? a.get<float>((int64_t)d.n_out * d.kld) : nullptr;
             d.z = a.get<float>(p.out_rows * d.n_out);
             rprev = d.n_out;
         }
@@ -296,7 +312,7 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
             }
         p.dwp = a.get<float>(max_wp);
         p.wt = a.get<float>(max_wp);
-        p.dbtmp = a.get<float>(4096);
+        p.dbtmp = a.get<float>(2 * max_h > 4096 ? 2 * max_h : 4096);
         p.gro_a = a.get<float>(max_dense);
         p.gro_b = a.get<float>(max_dense);
     }
@@ -308,13 +324,19 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
 struct Exec {
     const gnb_dynedge_config& c;
     cudaStream_t st;
-    bool tf32;
-    int rnd;
-    Exec(const gnb_dynedge_config& cfg, void* s) : c(cfg), st((cudaStream_t)s), tf32(cfg.precision == 1), rnd(cfg.precision == 1 ? GNB_FLAG_ROUND_TF32 : 0) {}
+    bool tf32;        // tensor-core GEMMs (precision 1 and 2)
+    bool split;       // precision 2: forward GEMMs on split operands (activations stay plain fp32, weights come as hi + lo)
+    bool fround;      // forward activations are stored rounded to tf32 (precision 1 only)
+    int rnd;          // backward: gradients that feed a tensor-core GEMM are stored rounded
+    int frnd;         // forward flag for the producers of GEMM operands
+    Exec(const gnb_dynedge_config& cfg, void* s)
+        : c(cfg), st((cudaStream_t)s), tf32(cfg.precision >= 1), split(cfg.precision == 2), fround(cfg.precision == 1),
+          rnd(cfg.precision >= 1 ? GNB_FLAG_ROUND_TF32 : 0), frnd(cfg.precision == 1 ? GNB_FLAG_ROUND_TF32 : 0) {}
 
-    int copy_pad(const float* src, int64_t lds, int64_t rows, int cols, float* dst, int64_t ldd, int dst_cols, bool round) {
+    int copy_pad(const float* src, int64_t lds, int64_t rows, int cols, float* dst, int64_t ldd, int dst_cols, bool round,
+                 float* lo = nullptr) {
         if (rows * dst_cols == 0) return 0;
-        copy_pad_kernel<<<gnb_div_up(rows * dst_cols, 256), 256, 0, st>>>(src, lds, rows, cols, dst, ldd, dst_cols, round ? 1 : 0);
+        copy_pad_kernel<<<gnb_div_up(rows * dst_cols, 256), 256, 0, st>>>(src, lds, rows, cols, dst, ldd, dst_cols, round ? 1 : 0, lo);
         EXL(); return 0;
     }
     int add2d(const float* src, int64_t lds, int64_t rows, int cols, float* dst, int64_t ldd) {
@@ -329,8 +351,10 @@ struct Exec {
     // y = act(sum_p x_p wp[:, off_p : off_p + k_p]^T + b)
     // round_out: round y to tf32 -- only needed when y itself feeds a tensor-core GEMM
     int lin_fwd(int nparts, const float* const* xs, const int64_t* lds, const int32_t* ks, const int* offs, const float* wp,
-                int64_t ldw, const float* bias, float* y, int64_t rows, int n_out, int act, int round_out = 1) {
+                int64_t ldw, const float* bias, float* y, int64_t rows, int n_out, int act, int round_out = 1,
+                const float* wp_lo = nullptr) {
         if (rows == 0) return 0;
+        if (split) return gnb_linear_fwd_tf32x3(xs, lds, ks, nparts, wp, wp_lo, ldw, bias, y, n_out, rows, n_out, act, st);
         if (tf32) return gnb_linear_fwd_tf32(xs, lds, ks, nparts, wp, ldw, bias, y, n_out, rows, n_out, act, round_out, st);
         for (int q = 0; q < nparts; ++q)
             EX(gnb_linear_fwd_f32(xs[q], lds[q], wp + offs[q], ldw, q == nparts - 1 ? bias : nullptr, y, n_out, rows, n_out,
@@ -397,8 +421,8 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
     training &= 1;
     // global variables (+ x0 = [x | g[batch] | 0])
     EX(gnb_global_vars(x, ldx, f, nbr0, deg0, w0, ptr, nseg, n_pulses, p.g, distribute ? p.x0 : nullptr, p.x0_ld, stream));
-    if (!distribute) EX(e.copy_pad(x, ldx, n, f, p.x0, p.x0_ld, p.x0_ld, e.tf32));
-    else if (e.tf32) EX(e.copy_pad(p.x0, p.x0_ld, n, p.x0_ld, p.x0, p.x0_ld, p.x0_ld, true));
+    if (!distribute) EX(e.copy_pad(x, ldx, n, f, p.x0, p.x0_ld, p.x0_ld, e.fround));
+    else if (e.fround) EX(e.copy_pad(p.x0, p.x0_ld, n, p.x0_ld, p.x0, p.x0_ld, p.x0_ld, true));
     // DynEdgeConv layers
     const float* xin = p.x0;
     const int32_t *nbr = nbr0, *deg = deg0;
@@ -408,33 +432,38 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
         ConvBuf& b = p.conv[l];
         const float *w1 = params[pi], *b1 = params[pi + 1], *w2 = params[pi + 2], *b2 = params[pi + 3];
         pi += 4;
-        pack_conv_kernel<<<gnb_div_up(2 * (int64_t)b.hid * b.kld, 256), 256, 0, e.st>>>(w1, b1, b.hid, b.cin, b.wcat, b.kld, b.bcat, e.tf32 ? 1 : 0);
+        pack_conv_kernel<<<gnb_div_up(2 * (int64_t)b.hid * b.kld, 256), 256, 0, e.st>>>(w1, b1, b.hid, b.cin, b.wcat, b.kld, b.bcat, e.tf32 ? 1 : 0, b.wcat_lo);
         EXL();
-        EX(e.copy_pad(w2, b.hid, b.cout, b.hid, b.w2p, b.hld, b.hld, e.tf32));
+        EX(e.copy_pad(w2, b.hid, b.cout, b.hid, b.w2p, b.hld, b.hld, e.tf32, b.w2p_lo));
         {   // PQ = xin Wcat^T + bcat
             const float* xs[1] = {xin}; const int64_t lds[1] = {b.cin_ld}; const int32_t ks[1] = {b.cin_ld}; const int offs[1] = {0};
-            EX(e.lin_fwd(1, xs, lds, ks, offs, b.wcat, b.kld, b.bcat, b.pq, n, 2 * b.hid, GNB_ACT_NONE, 0));   // P+Q is added in fp32
+            EX(e.lin_fwd(1, xs, lds, ks, offs, b.wcat, b.kld, b.bcat, b.pq, n, 2 * b.hid, GNB_ACT_NONE, 0, b.wcat_lo));   // P+Q is added in fp32
         }
-        if (!training && e.tf32 && fused_edge && !p.agg && b.hid <= 352 && wl <= 32) {
+        if (!training && e.tf32 && !e.split && fused_edge && !p.agg && b.hid <= 352 && wl <= 32) {
             // inference: gather + hidden ReLU + E x H x C contraction + bias/ReLU + aggregation in one tcgen05 kernel
             EX(gnb_edgeconv_fused_fwd_tf32(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, b.w2p, b.hld, b2, b.cout, GNB_AGGR_ADD, 1,
                                            b.y, b.cout, stream));
         } else if (p.agg) {
             // training (and inference with flags bit 1): the second Linear, ReLU and the k-sum run in one tcgen05 kernel; h is kept for the backward pass;
             // whose epilogue writes y and one ReLU bit per (slot, channel) -- the [E, C] message tensor is never stored
+            // (tf32x3: h, y stay plain fp32 -- the split happens inside the GEMMs; the weight gradient later truncates h)
             if (b.hmask != nullptr)
-                EX(gnb_edge_hidden_fwd_mask(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, GNB_ACT_RELU | e.rnd, b.h, b.hid, b.hmask,
+                EX(gnb_edge_hidden_fwd_mask(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, GNB_ACT_RELU | e.frnd, b.h, b.hid, b.hmask,
                                             b.mld, stream));
             else
-                EX(gnb_edge_hidden_fwd(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, GNB_ACT_RELU | e.rnd, b.h, b.hid, stream));
-            EX(gnb_edge_linear_agg_fwd_tf32(b.h, b.hid, b.hid, b.w2p, b.hld, b2, deg, n, b.cout, 1, b.y, b.cout, b.mask, stream));
+                EX(gnb_edge_hidden_fwd(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, GNB_ACT_RELU | e.frnd, b.h, b.hid, stream));
+            if (e.split)
+                EX(gnb_edge_linear_agg_fwd_tf32x3(b.h, b.hid, b.hid, b.w2p, b.w2p_lo, b.hld, b2, deg, n, b.cout, b.y, b.cout, b.mask,
+                                                  stream));
+            else
+                EX(gnb_edge_linear_agg_fwd_tf32(b.h, b.hid, b.hid, b.w2p, b.hld, b2, deg, n, b.cout, 1, b.y, b.cout, b.mask, stream));
         } else {
-            EX(gnb_edge_hidden_fwd(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, GNB_ACT_RELU | e.rnd, b.h, b.hid, stream));
+            EX(gnb_edge_hidden_fwd(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, GNB_ACT_RELU | e.frnd, b.h, b.hid, stream));
             {   // m = relu(h W2^T + b2)
                 const float* xs[1] = {b.h}; const int64_t lds[1] = {b.hid}; const int32_t ks[1] = {b.hid}; const int offs[1] = {0};
-                EX(e.lin_fwd(1, xs, lds, ks, offs, b.w2p, b.hld, b2, b.m, n * wl, b.cout, GNB_ACT_RELU, 0));   // summed in fp32
+                EX(e.lin_fwd(1, xs, lds, ks, offs, b.w2p, b.hld, b2, b.m, n * wl, b.cout, GNB_ACT_RELU, 0, b.w2p_lo));   // summed in fp32
             }
-            EX(gnb_edge_aggregate_fwd(b.m, b.cout, b.cout, deg, wl, n, GNB_AGGR_ADD | e.rnd, b.y, b.cout, nullptr, stream));
+            EX(gnb_edge_aggregate_fwd(b.m, b.cout, b.cout, deg, wl, n, GNB_AGGR_ADD | e.frnd, b.y, b.cout, nullptr, stream));
         }
         if (l + 1 < c.n_conv) {
             EX(gnb_knn_table(b.y, b.cout, knn_cols_dev, c.n_knn_cols, ptr, nseg, n, c.k, b.nbr, b.deg, stream));
@@ -454,15 +483,16 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
             const int64_t src_ld = p.node_width + [&] { int s = 0; for (int l = 0; l < c.n_conv; ++l) s += c.conv_out[l]; return s; }();
             for (int q = 0; q < p.post_parts; ++q) {
                 const int valid = q == 0 ? p.node_width : c.conv_out[q - 1];
-                EX(e.copy_pad(w + src_col, src_ld, d.n_out, valid, d.wp + p.part_off[q], d.kld, (int)up(p.part_k[q], 32), e.tf32));
+                EX(e.copy_pad(w + src_col, src_ld, d.n_out, valid, d.wp + p.part_off[q], d.kld, (int)up(p.part_k[q], 32), e.tf32,
+                              d.wp_lo ? d.wp_lo + p.part_off[q] : nullptr));
                 src_col += valid;
                 xs[q] = q == 0 ? p.x0 : p.conv[q - 1].y; lds[q] = p.part_k[q]; ks[q] = p.part_k[q];
             }
-            EX(e.lin_fwd(p.post_parts, xs, lds, ks, p.part_off, d.wp, d.kld, bias, d.z, n, d.n_out, GNB_ACT_RELU));
+            EX(e.lin_fwd(p.post_parts, xs, lds, ks, p.part_off, d.wp, d.kld, bias, d.z, n, d.n_out, GNB_ACT_RELU, 1, d.wp_lo));
         } else {
-            EX(e.copy_pad(w, d.k_total, d.n_out, d.k_total, d.wp, d.kld, d.kld, e.tf32));
+            EX(e.copy_pad(w, d.k_total, d.n_out, d.k_total, d.wp, d.kld, d.kld, e.tf32, d.wp_lo));
             const float* xs[1] = {zin}; const int64_t lds[1] = {d.k_total}; const int32_t ks[1] = {d.k_total}; const int offs[1] = {0};
-            EX(e.lin_fwd(1, xs, lds, ks, offs, d.wp, d.kld, bias, d.z, n, d.n_out, GNB_ACT_RELU));
+            EX(e.lin_fwd(1, xs, lds, ks, offs, d.wp, d.kld, bias, d.z, n, d.n_out, GNB_ACT_RELU, 1, d.wp_lo));
         }
         zin = d.z;
     }
@@ -474,18 +504,18 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
     if (c.n_pool > 0) {
         EX(gnb_segment_pool_fwd(zin, last_post, last_post, ptr, nseg, c.pool, c.n_pool, p.pooled, p.parg, stream));
         const int pc = c.n_pool * last_post;
-        EX(e.copy_pad(p.pooled, pc, nseg, pc, p.rin, p.rin_ld, c.globals_after_pooling ? pc : p.rin_ld, e.tf32));
+        EX(e.copy_pad(p.pooled, pc, nseg, pc, p.rin, p.rin_ld, c.globals_after_pooling ? pc : p.rin_ld, e.fround));
         if (c.globals_after_pooling)
-            EX(e.copy_pad(p.g, f + 5, nseg, f + 5, p.rin + pc, p.rin_ld, p.rin_ld - pc, e.tf32));
+            EX(e.copy_pad(p.g, f + 5, nseg, f + 5, p.rin + pc, p.rin_ld, p.rin_ld - pc, e.fround));
         rin = p.rin; rin_ld = p.rin_ld;
     }
     for (int j = 0; j < c.n_readout; ++j) {
         DenseBuf& d = p.ro[j];
         const float *w = params[pi], *bias = params[pi + 1];
         pi += 2;
-        EX(e.copy_pad(w, d.k_total, d.n_out, d.k_total, d.wp, d.kld, d.kld, e.tf32));
+        EX(e.copy_pad(w, d.k_total, d.n_out, d.k_total, d.wp, d.kld, d.kld, e.tf32, d.wp_lo));
         const float* xs[1] = {rin}; const int64_t lds[1] = {rin_ld}; const int32_t ks[1] = {d.k_total}; const int offs[1] = {0};
-        EX(e.lin_fwd(1, xs, lds, ks, offs, d.wp, d.kld, bias, d.z, p.out_rows, d.n_out, GNB_ACT_RELU));
+        EX(e.lin_fwd(1, xs, lds, ks, offs, d.wp, d.kld, bias, d.z, p.out_rows, d.n_out, GNB_ACT_RELU, 1, d.wp_lo));
         rin = d.z; rin_ld = d.n_out;
     }
     const int last = p.ro[c.n_readout - 1].n_out;

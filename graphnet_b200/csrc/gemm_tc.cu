@@ -454,9 +454,20 @@ struct GroupSplit { int ngroups; int start[5]; };
 // resident mode (single-part K that fits): the CTA's 128 weight rows stay in shared memory for the kernel's lifetime
 // (one TMA pass), a stage is the activation half only (16 KiB) and the L2->SM traffic per launch halves.
 struct PairCfg { int resident; int nstages; uint32_t meta_stride; };
+constexpr uint32_t PL_BAR_BYTES = 512;                // barrier block behind the ring
+// SPLIT = the fp32-grade "3xTF32" forward (precision mode tf32x3): the weight operand arrives pre-split from the pack
+// kernels (W = W_hi + W_lo, both tf32-exact, two tensor maps), the activation operand arrives as plain fp32 and is split
+// IN SHARED MEMORY by two extra warps (10, 11): X tile -> X_hi = rna_tf32(X) in place, X_lo = X - X_hi (exact) into a
+// fourth tile of the stage. Per 8-wide K step the issuer queues three MMAs: W_hi X_hi + W_lo X_hi + W_hi X_lo (the
+// W_lo X_lo term is below 2^-22 relative). Stage = {W_hi | W_lo | X | X_lo} = 64 KiB, 3 stages. Barriers of a stage:
+// full[s] (leader) collects the weight tiles of both CTAs, xfull[s] (LOCAL to each CTA: its splitter warps cannot wait on
+// a remote barrier) the CTA's own activation half, sfull[s] (leader, count 2) the "split done" arrival of each CTA.
+constexpr int PL_SPLIT_THREADS = 384, PL_SPLIT_STAGES = 3;
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PL_THREADS, 1)
-gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ TmapArray tm_x,
+template <bool SPLIT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SPLIT ? PL_SPLIT_THREADS : PL_THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_wlo,
+                    const __grid_constant__ TmapArray tm_x,
                     const PartInfo parts, const float* __restrict__ bias, float* __restrict__ y, int64_t ldy,
                     int64_t rows, int n_out, int act, int round_out, int num_tiles, const AggInfo agg, const ScatInfo sc,
                     const GroupSplit gs, const PairCfg pc) {
@@ -465,9 +476,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     int total_kb = 0;
     for (int p = 0; p < parts.nparts; ++p) total_kb += parts.kblocks[p];
     const int nstages = pc.nstages;
-    const uint32_t stage_bytes = pc.resident ? TC_TILE_BYTES : 2 * TC_TILE_BYTES;
+    const uint32_t stage_bytes = SPLIT ? 4 * TC_TILE_BYTES : (pc.resident ? TC_TILE_BYTES : 2 * TC_TILE_BYTES);
     uint8_t* s_a = smem;                                                     // resident weights (resident mode)
-    uint8_t* ring = smem + (pc.resident ? (uint32_t)total_kb * TC_TILE_BYTES : 0u);
+    uint8_t* ring = smem + ((pc.resident && !SPLIT) ? (uint32_t)total_kb * TC_TILE_BYTES : 0u);
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + nstages * stage_bytes);
     uint64_t* empty = full + PL_MAX_STAGES;
     uint64_t* tmem_full = empty + PL_MAX_STAGES;      // [2]
@@ -475,8 +486,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     uint64_t* meta_full = tmem_empty + 2;         // [2]
     uint64_t* meta_empty = meta_full + 2;         // [2]
     uint64_t* a_full = meta_empty + 2;            // [1] resident weights landed (leader's copy is waited on)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
-    uint8_t* meta = ring + nstages * stage_bytes + 256;           // [2 buffers][2 sub-tiles] x pc.meta_stride
+    uint64_t* xfull = a_full + 1;                 // [PL_MAX_STAGES] SPLIT: own activation half landed (local)
+    uint64_t* sfull = xfull + PL_MAX_STAGES;      // [PL_MAX_STAGES] SPLIT: both CTAs split their half (leader's copy)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfull + PL_MAX_STAGES);
+    uint8_t* meta = ring + nstages * stage_bytes + PL_BAR_BYTES;  // [2 buffers][2 sub-tiles] x pc.meta_stride
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = tc::cluster_ctarank();
@@ -494,7 +507,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < PL_MAX_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+            for (int s = 0; s < PL_MAX_STAGES; ++s) {
+                tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1);
+                tc::mbar_init(&xfull[s], 1); tc::mbar_init(&sfull[s], 2);
+            }
             tc::mbar_init(a_full, 1);
             for (int b = 0; b < 2; ++b) {
                 tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], 16);
@@ -519,8 +535,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     if (warp == 0) {
         // ---- TMA producer (both CTAs): own weight rows + own half of the activation rows ------------------------
         uint32_t it = 0, tile_i = 0;
-        const uint32_t stage_tx = 2u * ((pc.resident ? 0u : TC_TILE_BYTES) + (uint32_t)half_rows * TC_BK * 4);   // both CTAs
-        if (pc.resident && tc::elect_one()) {      // the CTA's 128 weight rows, all K blocks, once
+        const uint32_t stage_tx = SPLIT ? 4u * TC_TILE_BYTES      // W_hi + W_lo of both CTAs (activations: xfull, per CTA)
+                                        : 2u * ((pc.resident ? 0u : TC_TILE_BYTES) + (uint32_t)half_rows * TC_BK * 4);   // both CTAs
+        if (!SPLIT && pc.resident && tc::elect_one()) {      // the CTA's 128 weight rows, all K blocks, once
             if (rank == 0) tc::mbar_arrive_expect_tx(a_full, 2u * (uint32_t)total_kb * TC_TILE_BYTES);
             for (int kb = 0; kb < total_kb; ++kb) tc::tma_load_2d_2sm(s_a + kb * TC_TILE_BYTES, &tm_w, a_full, kb * TC_BK, ch0);
         }
@@ -541,7 +558,15 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                     tc::mbar_wait_warp(&empty[s], ph ^ 1);
                     if (prof_on) pw0 += clock64() - c0;
                     uint8_t* st = ring + s * stage_bytes;
-                    if (tc::elect_one()) {
+                    if (SPLIT) {
+                        if (tc::elect_one()) {
+                            if (rank == 0) tc::mbar_arrive_expect_tx(&full[s], stage_tx);
+                            tc::tma_load_2d_2sm(st, &tm_w, &full[s], kb_w * TC_BK, ch0);
+                            tc::tma_load_2d_2sm(st + TC_TILE_BYTES, &tm_wlo, &full[s], kb_w * TC_BK, ch0);
+                            tc::mbar_arrive_expect_tx(&xfull[s], (uint32_t)half_rows * TC_BK * 4);
+                            tc::tma_load_2d(st + 2 * TC_TILE_BYTES, &tm_x.m[p], &xfull[s], kb * TC_BK, (int)row0);
+                        }
+                    } else if (tc::elect_one()) {
                         if (rank == 0) tc::mbar_arrive_expect_tx(&full[s], stage_tx);
                         if (!pc.resident) tc::tma_load_2d_2sm(st, &tm_w, &full[s], kb_w * TC_BK, ch0);
                         tc::tma_load_2d_2sm(st + (pc.resident ? 0u : TC_TILE_BYTES), &tm_x.m[p], &full[s], kb * TC_BK, (int)row0);
@@ -592,9 +617,28 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                     const uint32_t s = it % (uint32_t)nstages, ph = (it / (uint32_t)nstages) & 1;
                     const long long c0 = prof_on ? clock64() : 0;
                     tc::mbar_wait_warp(&full[s], ph);
+                    if (SPLIT) tc::mbar_wait_warp<true>(&sfull[s], ph);      // both halves of X split into hi / lo (peer's arrival: cluster-scope acquire)
                     if (prof_on) pw0 += clock64() - c0;
                     tc::tcgen05_fence_after();
                     const uint32_t st = tc::smem_u32(ring + s * stage_bytes);
+                    if (SPLIT) {
+                        const uint64_t ahi = tc::umma_desc_sw128_kmajor(st), alo = tc::umma_desc_sw128_kmajor(st + TC_TILE_BYTES);
+                        const uint64_t bhi = tc::umma_desc_sw128_kmajor(st + 2 * TC_TILE_BYTES);
+                        const uint64_t blo = tc::umma_desc_sw128_kmajor(st + 3 * TC_TILE_BYTES);
+                        if (tc::elect_one()) {
+                            if (!(agg.dbg & 2)) {
+#pragma unroll
+                                for (int k = 0; k < TC_BK / 8; ++k) {
+                                    tc::umma_tf32_2cta(acc, alo + 2 * k, bhi + 2 * k, idesc, (kbi | k) != 0 ? 1u : 0u);
+                                    tc::umma_tf32_2cta(acc, ahi + 2 * k, blo + 2 * k, idesc, 1u);
+                                    tc::umma_tf32_2cta(acc, ahi + 2 * k, bhi + 2 * k, idesc, 1u);
+                                }
+                            }
+                            tc::umma_commit_2cta(&empty[s], 3);
+                        }
+                        __syncwarp();
+                        continue;
+                    }
                     const uint64_t adesc = tc::umma_desc_sw128_kmajor(pc.resident ? tc::smem_u32(s_a + kbi * TC_TILE_BYTES) : st);
                     const uint64_t bdesc = tc::umma_desc_sw128_kmajor(pc.resident ? st : st + TC_TILE_BYTES);
                     if (tc::elect_one()) {          // one election per K block (see the single-CTA kernel)
@@ -608,6 +652,42 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                     __syncwarp();
                 }
                 if (tc::elect_one()) tc::umma_commit_2cta(&tmem_full[buf], 3);
+                __syncwarp();
+            }
+        }
+    } else if (SPLIT && warp >= 10) {
+        // ---- operand splitter (both CTAs, warps 10 / 11 take alternate stages): X -> (X_hi in place, X_lo) -----------
+        // Elementwise, so the 128-byte swizzle of the tile is irrelevant: lane l of step i owns the 16-byte chunk 32 i + l.
+        uint32_t it = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+            for (int kbi = 0; kbi < total_kb; ++kbi, ++it) {
+                if ((int)(it & 1u) != warp - 10) continue;
+                const uint32_t s = it % (uint32_t)nstages, ph = (it / (uint32_t)nstages) & 1;
+                tc::mbar_wait<20>(&xfull[s], ph);
+                const uint32_t xa = tc::smem_u32(ring + s * stage_bytes + 2 * TC_TILE_BYTES) + (uint32_t)lane * 16u;
+#pragma unroll 1
+                for (int i0 = 0; i0 < (int)(TC_TILE_BYTES / 512); i0 += 8) {
+                    uint32_t v[8][4];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)             // 8 independent 16-byte loads in flight
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(v[i][0]), "=r"(v[i][1]), "=r"(v[i][2]), "=r"(v[i][3]) : "r"(xa + 512u * (uint32_t)(i0 + i)));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float hi[4], lo[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            hi[e] = tc::round_tf32(__uint_as_float(v[i][e]));
+                            lo[e] = __uint_as_float(v[i][e]) - hi[e];        // exact: fits the 13 dropped mantissa bits
+                        }
+                        const uint32_t a = xa + 512u * (uint32_t)(i0 + i);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(hi[3]) : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + TC_TILE_BYTES), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(lo[3]) : "memory");
+                    }
+                }
+                tc::fence_proxy_async();            // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive_cluster(&sfull[s], 0);
                 __syncwarp();
             }
         }
@@ -1002,13 +1082,16 @@ int g_linear_dbg = 0;   // tuning hook: see gnb_linear_set_debug
 int g_linear_variant = 0;   // 0 auto, 1 single-CTA kernel, 2 CTA-pair kernel
 int g_pair_resident = 0;    // 0: pair kernel streams the weights; n > 0: keep them resident when >= n activation stages fit
 
+unsigned long long g_tc_attr_devs = 0ull;      // shared-memory attributes are per device: one bit per device ordinal
 cudaError_t init_tc_kernels() {
-    if (g_num_sms != 0) return cudaSuccess;
     int dev = 0, sms = 0;
     cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess && dev < 64 && ((g_tc_attr_devs >> dev) & 1ull) && g_num_sms != 0) return cudaSuccess;
+    if (e == cudaSuccess && dev < 64) g_tc_attr_devs |= 1ull << dev;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_tc_pair_dual_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
     if (e == cudaSuccess) g_num_sms = sms;
@@ -1027,13 +1110,16 @@ bool dual_scatter_applicable(int hdim, int kblocks, int mask_ld, int* nst_w_out)
 }
 
 // row_tiles = number of 128-row (plain) or 126-row (aggregating / scattering) tiles
+// twlo != nullptr: split-operand (3xTF32) forward -- always the CTA-pair kernel (the only one with splitter warps).
 int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi, const float* bias, float* y, int64_t ldy,
                   int64_t rows, int n_out, int act, int round_out, int row_tiles, const AggInfo& agg, const ScatInfo& sc,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, const CUtensorMap* twlo = nullptr) {
     GNB_CHECK(init_tc_kernels());
+    const bool split = twlo != nullptr;
+    if (split && (n_out > 1024 || sc.enabled)) return GNB_ERR_UNSUPPORTED;
     // measured (scripts/linear_probe.py): the pair kernel wins from two ch-tiles up; a single 128-channel tile is
     // faster on the single-CTA kernel (half of the pair's M = 256 would be padding)
-    const bool pair = (g_linear_variant >= 2 || (g_linear_variant == 0 && row_tiles >= 2 * 148 && n_out > 128)) && n_out <= 1024;
+    const bool pair = split || ((g_linear_variant >= 2 || (g_linear_variant == 0 && row_tiles >= 2 * 148 && n_out > 128)) && n_out <= 1024);
     if (pair) {
         const int tiles = (row_tiles + 1) / 2;
         const int groups = gnb_div_up(n_out, 256);
@@ -1061,7 +1147,7 @@ int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi
         for (int p = 0; p < pi.nparts; ++p) total_kb += pi.kblocks[p];
         PairCfg pc;
         pc.meta_stride = sc.enabled ? sc_meta_stride(sc.mask_ld) : 0u;
-        const uint32_t fixed = 1024 + 256 + 4 * pc.meta_stride;
+        const uint32_t fixed = 1024 + PL_BAR_BYTES + 4 * pc.meta_stride;
         const int64_t res_left = (int64_t)PL_MAX_DYN_SMEM - fixed - (int64_t)total_kb * TC_TILE_BYTES;
         int res_stages = res_left > 0 ? (int)(res_left / TC_TILE_BYTES) : 0;
         if (res_stages > PL_MAX_STAGES) res_stages = PL_MAX_STAGES;
@@ -1072,10 +1158,18 @@ int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi
             pc.nstages = (int)((PL_MAX_DYN_SMEM - fixed) / (2 * TC_TILE_BYTES));
             if (pc.nstages > 6) pc.nstages = 6;
         }
+        if (split) {
+            pc.resident = 0;
+            pc.nstages = PL_SPLIT_STAGES;
+            const uint32_t smem_split = fixed + PL_SPLIT_STAGES * 4 * TC_TILE_BYTES;
+            gemm_tc_pair_kernel<true><<<grid, PL_SPLIT_THREADS, smem_split, stream>>>(tw, *twlo, tx, pi, bias, y, ldy, rows, n_out,
+                                                                                      act, round_out, tiles, agg, sc, gs, pc);
+            GNB_RETURN_LAUNCH();
+        }
         const uint32_t smem = fixed + (pc.resident ? (uint32_t)total_kb * TC_TILE_BYTES + pc.nstages * TC_TILE_BYTES
                                                    : pc.nstages * 2 * TC_TILE_BYTES);
-        gemm_tc_pair_kernel<<<grid, PL_THREADS, smem, stream>>>(tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out, tiles,
-                                                               agg, sc, gs, pc);
+        gemm_tc_pair_kernel<false><<<grid, PL_THREADS, smem, stream>>>(tw, tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out,
+                                                                      tiles, agg, sc, gs, pc);
         GNB_RETURN_LAUNCH();
     }
     const int groups = gnb_div_up(n_out, TC_MT * TC_BM);
@@ -1116,9 +1210,9 @@ GNB_EXPORT int gnb_linear_set_profile_buffer(void* buf) { g_linear_prof = (unsig
 // xs / ldxs / ks: HOST arrays with one entry per part (device pointer, row pitch, width).
 // w: [n_out, sum_p ceil(k_p/32)*32] fp32, part p's columns start at the 32-aligned running offset and are
 // zero padded; weights and activations pre-rounded to tf32.
-GNB_EXPORT int gnb_linear_fwd_tf32(const float* const* xs, const int64_t* ldxs, const int32_t* ks, int32_t nparts,
-                                   const float* w, int64_t ldw, const float* bias, float* y, int64_t ldy, int64_t rows,
-                                   int32_t n_out, int32_t act, int32_t round_out, void* stream) {
+static int linear_fwd_impl(const float* const* xs, const int64_t* ldxs, const int32_t* ks, int32_t nparts,
+                           const float* w, const float* w_lo, int64_t ldw, const float* bias, float* y, int64_t ldy, int64_t rows,
+                           int32_t n_out, int32_t act, int32_t round_out, void* stream) {
     if (nparts < 1 || nparts > TC_MAX_PARTS || rows < 0 || n_out < 1) return GNB_ERR_ARG;
     if (rows == 0) return GNB_OK;
     if (rows >= (int64_t)1 << 31) return GNB_ERR_ARG;
@@ -1138,18 +1232,38 @@ GNB_EXPORT int gnb_linear_fwd_tf32(const float* const* xs, const int64_t* ldxs, 
     CUtensorMap tw;
     int rc = gnb_make_tmap_f32(&tw, w, n_out, ktot, ldw, TC_BM);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    CUtensorMap twlo;
+    if (w_lo != nullptr) {
+        rc = gnb_make_tmap_f32(&twlo, w_lo, n_out, ktot, ldw, TC_BM);
+        if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    }
     AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof};
     ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0};
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out, gnb_div_up(rows, TC_BN), agg, sc,
-                         (cudaStream_t)stream);
+                         (cudaStream_t)stream, w_lo != nullptr ? &twlo : nullptr);
+}
+GNB_EXPORT int gnb_linear_fwd_tf32(const float* const* xs, const int64_t* ldxs, const int32_t* ks, int32_t nparts,
+                                   const float* w, int64_t ldw, const float* bias, float* y, int64_t ldy, int64_t rows,
+                                   int32_t n_out, int32_t act, int32_t round_out, void* stream) {
+    return linear_fwd_impl(xs, ldxs, ks, nparts, w, nullptr, ldw, bias, y, ldy, rows, n_out, act, round_out, stream);
+}
+// fp32-grade forward Linear on the tensor cores ("3xTF32"): w_hi = rna_tf32(W), w_lo = rna_tf32(W - w_hi) in the packed
+// layout of gnb_linear_fwd_tf32 (same pitch ldw), activations plain fp32 (split into hi / lo inside the kernel):
+//   y = act(sum_p x_p (w_hi + w_lo)^T + bias), three tf32 products per K step, fp32 accumulation in TMEM.
+// Always the CTA-pair kernel; n_out <= 1024. The output is not rounded.
+GNB_EXPORT int gnb_linear_fwd_tf32x3(const float* const* xs, const int64_t* ldxs, const int32_t* ks, int32_t nparts,
+                                     const float* w_hi, const float* w_lo, int64_t ldw, const float* bias, float* y,
+                                     int64_t ldy, int64_t rows, int32_t n_out, int32_t act, void* stream) {
+    if (w_hi == nullptr || w_lo == nullptr) return GNB_ERR_ARG;
+    return linear_fwd_impl(xs, ldxs, ks, nparts, w_hi, w_lo, ldw, bias, y, ldy, rows, n_out, act, 0, stream);
 }
 
 // Second Linear of the EdgeConv MLP fused with ReLU and the k-neighbour SUM (k = 8 tables, width 9):
 //   y[i, :] = sum_{s < deg[i]} relu(h[i*9 + s, :] w^T + bias),   maskbits[tile = i / 14][ch][4 x u32] = (pre-activation > 0)
 // h: [n*9, k] tf32-rounded padded edge list, w: [n_out, ceil(k/32)*32] packed. n_out <= 512. maskbits may be NULL.
-GNB_EXPORT int gnb_edge_linear_agg_fwd_tf32(const float* h, int64_t ldh, int32_t k, const float* w, int64_t ldw,
-                                            const float* bias, const int32_t* deg, int64_t n, int32_t n_out,
-                                            int32_t round_out, float* y, int64_t ldy, uint32_t* maskbits, void* stream) {
+static int edge_linear_agg_impl(const float* h, int64_t ldh, int32_t k, const float* w, const float* w_lo, int64_t ldw,
+                                const float* bias, const int32_t* deg, int64_t n, int32_t n_out,
+                                int32_t round_out, float* y, int64_t ldy, uint32_t* maskbits, void* stream) {
     if (n < 0 || n_out < 1 || k < 1) return GNB_ERR_ARG;
     if (n == 0) return GNB_OK;
     const int64_t rows = n * AGG_W;
@@ -1166,10 +1280,28 @@ GNB_EXPORT int gnb_edge_linear_agg_fwd_tf32(const float* h, int64_t ldh, int32_t
     CUtensorMap tw;
     rc = gnb_make_tmap_f32(&tw, w, n_out, ktot, ldw, TC_BM);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    CUtensorMap twlo;
+    if (w_lo != nullptr) {
+        rc = gnb_make_tmap_f32(&twlo, w_lo, n_out, ktot, ldw, TC_BM);
+        if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    }
     AggInfo agg{deg, n, maskbits, 1, g_linear_dbg, g_linear_prof};
     ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0};
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, GNB_ACT_RELU, round_out, gnb_div_up(n, AGG_NPT), agg, sc,
-                         (cudaStream_t)stream);
+                         (cudaStream_t)stream, w_lo != nullptr ? &twlo : nullptr);
+}
+GNB_EXPORT int gnb_edge_linear_agg_fwd_tf32(const float* h, int64_t ldh, int32_t k, const float* w, int64_t ldw,
+                                            const float* bias, const int32_t* deg, int64_t n, int32_t n_out,
+                                            int32_t round_out, float* y, int64_t ldy, uint32_t* maskbits, void* stream) {
+    return edge_linear_agg_impl(h, ldh, k, w, nullptr, ldw, bias, deg, n, n_out, round_out, y, ldy, maskbits, stream);
+}
+// The same with split operands ("3xTF32", see gnb_linear_fwd_tf32x3): h plain fp32 (not rounded), w_hi / w_lo packed
+// like w; y is written unrounded.
+GNB_EXPORT int gnb_edge_linear_agg_fwd_tf32x3(const float* h, int64_t ldh, int32_t k, const float* w_hi, const float* w_lo,
+                                              int64_t ldw, const float* bias, const int32_t* deg, int64_t n, int32_t n_out,
+                                              float* y, int64_t ldy, uint32_t* maskbits, void* stream) {
+    if (w_hi == nullptr || w_lo == nullptr) return GNB_ERR_ARG;
+    return edge_linear_agg_impl(h, ldh, k, w_hi, w_lo, ldw, bias, deg, n, n_out, 0, y, ldy, maskbits, stream);
 }
 
 // Data gradient of the EdgeConv second Linear fused with the backward of the hoisted hidden layer (k = 8 tables, width 9):
@@ -1233,6 +1365,27 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_tf32(const float* dz, int64_t lddz,
                                                     ldpq, nullptr, 0, stream);
 }
 
+// hi[r, c] = rna_tf32(src[r, c]), lo[r, c] = rna_tf32(src[r, c] - hi[r, c]) (zero padded to dst_cols): the pre-split weight
+// operand of the tf32x3 GEMMs.
+static __global__ void split_pad_tf32_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
+                                      float* __restrict__ hi, float* __restrict__ lo, int64_t ldd, int dst_cols) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * dst_cols) return;
+    const int64_t r = t / dst_cols;
+    const int c = (int)(t - r * dst_cols);
+    const float v = c < cols ? src[r * lds + c] : 0.f;
+    const float h = tc::round_tf32(v);
+    hi[r * ldd + c] = h;
+    lo[r * ldd + c] = tc::round_tf32(v - h);
+}
+GNB_EXPORT int gnb_split_pad_tf32(const float* src, int64_t lds, int64_t rows, int32_t cols, float* hi, float* lo, int64_t ldd,
+                                  int32_t dst_cols, void* stream) {
+    if (dst_cols < cols || rows < 0 || hi == nullptr || lo == nullptr) return GNB_ERR_ARG;
+    if (rows == 0) return GNB_OK;
+    split_pad_tf32_kernel<<<gnb_div_up(rows * dst_cols, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, rows, cols, hi, lo, ldd,
+                                                                                              dst_cols);
+    GNB_RETURN_LAUNCH();
+}
 // dst[rows, dst_cols] = [rna_tf32(src[rows, cols]) | 0]; used to pack weights / round activations.
 GNB_EXPORT int gnb_round_pad_tf32(const float* src, int64_t lds, int64_t rows, int32_t cols, float* dst, int64_t ldd,
                                   int32_t dst_cols, void* stream) {

@@ -171,11 +171,13 @@ GNB_EXPORT int gnb_linear_bwd_weight_tf32(const float* dz, int64_t lddz, const f
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     rc = make_tmap_box32(&tz, dz, rows, n_out, lddz);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_devs = 0ull;     // the attribute is per device: one bit per device ordinal
+    int dev = 0;
+    GNB_CHECK(cudaGetDevice(&dev));
+    if (dev >= 64 || !((attr_devs >> dev) & 1ull)) {
         GNB_CHECK(cudaFuncSetAttribute(gemm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)WG_SMEM_BYTES));
-        attr_set = true;
+        if (dev < 64) attr_devs |= 1ull << dev;
     }
     const int tiles_m = gnb_div_up(k_in, WG_BM), tiles_n = gnb_div_up(n_out, WG_BN);
     const int tiles = tiles_m * tiles_n;

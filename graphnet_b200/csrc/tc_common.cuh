@@ -88,11 +88,25 @@ __device__ __forceinline__ bool elect_one() {
 // Wait executed by a CONVERGED warp with a warp-uniform exit (vote): unlike the per-thread spin of mbar_wait, the
 // compiler can prove that control flow stays convergent, so loop counters / descriptors computed afterwards live in
 // uniform registers and the tcgen05.mma / TMA operands need no R2UR broadcasts.
+// Same test with acquire semantics at CLUSTER scope: for barriers whose arrival comes from the peer CTA and orders that
+// CTA's shared-memory writes (the operand splitter of the tf32x3 GEMM) before this warp's tcgen05.mma.
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t addr, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return done;
+}
+template <bool CLUSTER_ACQUIRE = false>
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     long long t0 = 0;
     for (uint32_t it = 1;; ++it) {
-        if (__all_sync(0xffffffffu, mbar_try_wait(addr, parity))) return;
+        if (__all_sync(0xffffffffu, CLUSTER_ACQUIRE ? mbar_try_wait_cluster(addr, parity) : mbar_try_wait(addr, parity))) return;
         if ((it & 4095u) == 0u) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;

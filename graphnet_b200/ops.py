@@ -25,17 +25,32 @@ POOL = {"min": 0, "max": 1, "sum": 2, "mean": 3}
 # Precision of the dense contractions:
 #   "fp32": fp32 SIMT GEMMs (exact fp32 products, ~1e-6 from the oracle)
 #   "tf32": tcgen05 kind::tf32 GEMMs (operands rounded to tf32 with cvt.rna, fp32 accumulation in TMEM)
+#   "tf32x3": fp32-grade tensor-core mode -- every FORWARD GEMM runs on split operands (x = x_hi + x_lo, W = W_hi + W_lo,
+#             three kind::tf32 products per K step, activations stay plain fp32); the backward GEMMs are single-pass tf32.
+#             Outputs ~1e-6, gradients ~5e-4 from the fp64 oracle (tests/studies/split_precision_study.py: the forward's
+#             rounding, not the backward's, is what moved the tf32 gradients to 2e-3).
 PRECISION = os.environ.get("GNB_PRECISION", "fp32")
+PRECISIONS = ("fp32", "tf32", "tf32x3")
 
 
 def set_precision(mode: str) -> None:
     global PRECISION
-    if mode not in ("fp32", "tf32"):
+    if mode not in PRECISIONS:
         raise ValueError(f"unknown precision {mode!r}")
     PRECISION = mode
 
 
 def _tf32() -> bool:
+    """Tensor-core GEMMs (both tf32 modes)."""
+    return PRECISION in ("tf32", "tf32x3")
+
+
+def _split() -> bool:
+    return PRECISION == "tf32x3"
+
+
+def _fround() -> bool:
+    """Forward activations that feed a tensor-core GEMM are stored rounded to tf32 (single-pass mode only)."""
     return PRECISION == "tf32"
 
 
@@ -274,6 +289,41 @@ def _tc_operand(t: Tensor) -> Tensor:
     return _round_pad(t)
 
 
+def _tma_operand(t: Tensor) -> Tensor:
+    """TMA-addressable plain-fp32 version of an activation matrix (tf32x3: the GEMM splits it, or truncates it)."""
+    if _tma_ok(t):
+        return t
+    cols = t.shape[1]
+    padded = torch.zeros(t.shape[0], (cols + 3) // 4 * 4, dtype=torch.float32, device=t.device)
+    padded[:, :cols] = t
+    return padded[:, :cols]
+
+
+def _tc_pack_weight_split(w: Tensor, offsets: Sequence[int], ks: Sequence[int]) -> Tuple[Tensor, Tensor]:
+    """(hi, lo) in the packed layout of `_tc_pack_weight`: hi = rna_tf32(w), lo = rna_tf32(w - hi)."""
+    kbs = [(k + 31) // 32 * 32 for k in ks]
+    hi = torch.empty(w.shape[0], sum(kbs), dtype=torch.float32, device=w.device)
+    lo = torch.empty_like(hi)
+    ldp, koff = hi.shape[1], 0
+    for off, k, kb in zip(offsets, ks, kbs):
+        src = w[:, off:off + k]
+        _call("gnb_split_pad_tf32", _ptr(src), _ld(w), w.shape[0], k, ctypes.c_void_p(hi.data_ptr() + 4 * koff),
+              ctypes.c_void_p(lo.data_ptr() + 4 * koff), ldp, kb, _stream())
+        koff += kb
+    return hi, lo
+
+
+def _tc_linear_x3(parts: Sequence[Tensor], w_hi: Tensor, w_lo: Tensor, bias: Optional[Tensor], n_out: int, act: int) -> Tensor:
+    rows, nparts = parts[0].shape[0], len(parts)
+    y = torch.empty(rows, n_out, dtype=torch.float32, device=w_hi.device)
+    xs = (ctypes.c_void_p * nparts)(*[p.data_ptr() for p in parts])
+    lds = (ctypes.c_int64 * nparts)(*[_ld(p) for p in parts])
+    ks = (ctypes.c_int32 * nparts)(*[p.shape[1] for p in parts])
+    _call("gnb_linear_fwd_tf32x3", xs, lds, ks, nparts, _ptr(w_hi), _ptr(w_lo), w_hi.shape[1], _ptr(bias), _ptr(y), n_out,
+          rows, n_out, act, _stream())
+    return y
+
+
 def _tc_pack_weight(w: Tensor, offsets: Sequence[int], ks: Sequence[int]) -> Tensor:
     """[n_out, sum ceil(k_p/32)*32]: part p's columns, rounded to tf32, at the 32-aligned running offset."""
     kbs = [(k + 31) // 32 * 32 for k in ks]
@@ -311,7 +361,11 @@ def _dense_forward(parts: Sequence[Tensor], w: Tensor, b: Optional[Tensor], offs
     round_out: round y to tf32 (only needed when y itself feeds a tensor-core GEMM)."""
     rows, n_out = parts[0].shape[0], w.shape[0]
     tc = _tf32() and len(parts) <= 6 and rows > 0
-    if tc:
+    if tc and _split() and n_out <= 1024:
+        parts = tuple(_tma_operand(p) for p in parts)
+        w_hi, w_lo = _tc_pack_weight_split(w, offsets, [p.shape[1] for p in parts])
+        y = _tc_linear_x3(parts, w_hi, w_lo, b, n_out, act)
+    elif tc:
         parts = tuple(_tc_operand(p) for p in parts)
         packed = _tc_pack_weight(w, offsets, [p.shape[1] for p in parts])
         y = _tc_linear(parts, packed, b, n_out, act, round_out=round_out)
@@ -333,8 +387,8 @@ def _dense_backward(dz: Tensor, w: Tensor, parts: Sequence[Tensor], offsets: Seq
     for p, off, need in zip(parts, offsets, need_dparts):
         kp = p.shape[1]
         if dw is not None:
-            if tc and WGRAD_TC:
-                _gemm_bwd_weight_tc(dzr, _tc_operand(p), dw[:, off:], kp)
+            if tc and WGRAD_TC:       # tf32x3: the saved activation is plain fp32, the tensor core truncates it
+                _gemm_bwd_weight_tc(dzr, _tma_operand(p) if _split() else _tc_operand(p), dw[:, off:], kp)
             else:
                 _gemm_bwd_weight(dz, p, dw[:, off:], kp)
         if not need:
@@ -376,13 +430,13 @@ class _MultiLinearAct(torch.autograd.Function):
 def linear_act(x: Tensor, w: Tensor, b: Optional[Tensor], act: int = ACT_NONE, round_out: bool = True) -> Tensor:
     """act(x @ w^T + b) (torch.nn.Linear + activation of dynedge.py:200-247)."""
     y = _MultiLinearAct.apply(w, b, act, (0,), round_out, x)
-    return _mark_rounded(y) if (_tf32() and round_out) else y
+    return _mark_rounded(y) if (_fround() and round_out) else y
 
 
 def multi_linear_act(parts: Sequence[Tensor], w: Tensor, b: Optional[Tensor], offsets: Sequence[int],
                      act: int = ACT_NONE) -> Tensor:
     y = _MultiLinearAct.apply(w, b, act, tuple(int(o) for o in offsets), True, *parts)
-    return _mark_rounded(y) if _tf32() else y
+    return _mark_rounded(y) if _fround() else y
 
 
 # --------------------------------------------------------------------------- #
@@ -399,10 +453,10 @@ class _EdgeHidden(torch.autograd.Function):
         hdim = pq.shape[1] // 2
         h = torch.empty(graph.n * graph.width, hdim, dtype=torch.float32, device=pq.device)
         _call("gnb_edge_hidden_fwd", _ptr(pq), _ld(pq), hdim, _ptr(graph.nbr), _ptr(graph.deg), graph.width, graph.n,
-              act | (FLAG_ROUND_TF32 if _tf32() else 0), _ptr(h), _ld(h), _stream())
+              act | (FLAG_ROUND_TF32 if _fround() else 0), _ptr(h), _ld(h), _stream())
         ctx.graph, ctx.act = graph, act
         ctx.save_for_backward(h)
-        return _mark_rounded(h) if _tf32() else h
+        return _mark_rounded(h) if _fround() else h
 
     @staticmethod
     def backward(ctx, gh: Tensor):
@@ -418,7 +472,7 @@ class _EdgeHidden(torch.autograd.Function):
 
 def edge_hidden(pq: Tensor, graph: KnnGraph, act: int = ACT_RELU) -> Tensor:
     h = _EdgeHidden.apply(pq, graph, act)
-    return _mark_rounded(h) if _tf32() else h
+    return _mark_rounded(h) if _fround() else h
 
 
 class _EdgeCat(torch.autograd.Function):
@@ -460,10 +514,10 @@ class _EdgeAggregate(torch.autograd.Function):
         y = torch.empty(graph.n, c, dtype=torch.float32, device=m.device)
         arg = torch.empty(graph.n, c, dtype=torch.int8, device=m.device) if aggr == 2 else None
         _call("gnb_edge_aggregate_fwd", _ptr(m), _ld(m), c, _ptr(graph.deg), graph.width, graph.n,
-              aggr | (FLAG_ROUND_TF32 if _tf32() else 0), _ptr(y), _ld(y), _ptr(arg), _stream())
+              aggr | (FLAG_ROUND_TF32 if _fround() else 0), _ptr(y), _ld(y), _ptr(arg), _stream())
         ctx.graph, ctx.aggr, ctx.c = graph, aggr, c
         ctx.save_for_backward(arg) if arg is not None else None
-        return _mark_rounded(y) if _tf32() else y
+        return _mark_rounded(y) if _fround() else y
 
     @staticmethod
     def backward(ctx, gy: Tensor):
@@ -478,7 +532,7 @@ class _EdgeAggregate(torch.autograd.Function):
 
 def edge_aggregate(m: Tensor, graph: KnnGraph, aggr: str = "add") -> Tensor:
     y = _EdgeAggregate.apply(m, graph, AGGR[aggr])
-    return _mark_rounded(y) if _tf32() else y
+    return _mark_rounded(y) if _fround() else y
 
 
 class _EdgeConvHoisted(torch.autograd.Function):
@@ -491,11 +545,11 @@ class _EdgeConvHoisted(torch.autograd.Function):
         _cuda(pq, w2, b2)
         pq, w2 = _rowmajor(pq), _rowmajor(w2)
         hdim = pq.shape[1] // 2
-        rnd = FLAG_ROUND_TF32 if _tf32() else 0
+        rnd = FLAG_ROUND_TF32 if _fround() else 0
         h = torch.empty(graph.n * graph.width, hdim, dtype=torch.float32, device=pq.device)
         _call("gnb_edge_hidden_fwd", _ptr(pq), _ld(pq), hdim, _ptr(graph.nbr), _ptr(graph.deg), graph.width, graph.n,
               ACT_RELU | rnd, _ptr(h), _ld(h), _stream())
-        if _tf32():
+        if _fround():
             _mark_rounded(h)
         m, (h,), ctx.tc = _dense_forward((h,), w2, b2, (0,), ACT_RELU, round_out=False)    # summed in fp32
         c = m.shape[1]
@@ -551,10 +605,10 @@ def edgeconv_hoisted(pq: Tensor, w2: Tensor, b2: Optional[Tensor], graph: KnnGra
     """Per-edge half of EdgeConv for an MLP `Linear, ReLU, Linear, ReLU` whose first Linear was hoisted to nodes
     (pq = [P | Q]); aggr in add / mean. (max keeps the unfused route: it needs the arg-routed backward.)"""
     needs_grad = torch.is_grad_enabled() and (pq.requires_grad or w2.requires_grad or (b2 is not None and b2.requires_grad))
-    if _tf32() and FUSED_EDGECONV and not needs_grad and w2.shape[1] <= 352 and w2.shape[1] % 4 == 0 and graph.width <= 32:
+    if _fround() and FUSED_EDGECONV and not needs_grad and w2.shape[1] <= 352 and w2.shape[1] % 4 == 0 and graph.width <= 32:
         return edgeconv_fused_forward(pq, w2, b2, graph, aggr)
     y = _EdgeConvHoisted.apply(pq, w2, b2, graph, AGGR[aggr])
-    return _mark_rounded(y) if _tf32() else y
+    return _mark_rounded(y) if _fround() else y
 
 
 # --------------------------------------------------------------------------- #
@@ -629,6 +683,12 @@ def _ws_release(t: Tensor) -> None:
         pool.pop(0)
 
 
+def _copy_cfg(cfg):
+    dup = type(cfg)()
+    ctypes.memmove(ctypes.byref(dup), ctypes.byref(cfg), ctypes.sizeof(cfg))
+    return dup
+
+
 class _DynEdgeExec(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, graph: KnnGraph, ptr: Tensor, n_pulses: Tensor, x: Tensor, cols_dev: Tensor, out_cols: int,
@@ -637,7 +697,8 @@ class _DynEdgeExec(torch.autograd.Function):
         lib = _lib.load()
         x = _rowmajor(x.detach().float())
         n, nseg = x.shape[0], ptr.numel() - 1
-        cfg.precision = 1 if _tf32() else 0
+        cfg = _copy_cfg(cfg)      # the ctx keeps ITS OWN copy: a later set_precision() / flag change cannot alter the layout
+        cfg.precision = 2 if _split() else (1 if _tf32() else 0)
         cfg.flags = (0 if FUSED_EDGECONV else 1) | (2 if INFERENCE_ROUTE == "split" else 0)
         nbytes = lib.gnb_dynedge_workspace_bytes(ctypes.byref(cfg), n, nseg, graph.width, training)
         if nbytes < 0:
@@ -680,6 +741,10 @@ class _DynEdgeExec(torch.autograd.Function):
     def backward(ctx, gout: Tensor):
         if not ctx.training:
             raise RuntimeError("DynEdge executor: backward requested after an inference-mode forward")
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("DynEdge executor: the workspace of this forward was already consumed by a backward pass "
+                               "(retain_graph / double backward are not supported on the executor route)")
+        ctx.consumed = True
         ws, ptr, *params = ctx.saved_tensors
         gout = gout.contiguous().float()
         direct = ACCUMULATE_INTO_GRAD and all(

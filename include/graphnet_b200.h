@@ -146,6 +146,17 @@ int gnb_colsum(const float* a, int64_t lda, int64_t rows, int32_t cols, float* o
 int gnb_linear_fwd_tf32(const float* const* xs, const int64_t* ldxs, const int32_t* ks, int32_t nparts, const float* w,
                         int64_t ldw, const float* bias, float* y, int64_t ldy, int64_t rows, int32_t n_out, int32_t act,
                         int32_t round_out, void* stream);
+/* The same Linear at fp32 grade on the tensor cores (precision mode "tf32x3", the forward pass of training): split
+ * operands, W = w_hi + w_lo (both tf32-exact, from gnb_split_pad_tf32; same packed layout and pitch) and x = x_hi + x_lo
+ * (plain fp32 activations, split inside the kernel), three kind::tf32 products per K step (hi*hi + lo*hi + hi*lo), fp32
+ * accumulation in TMEM; y is written unrounded. Replaces torch.nn.Linear's fp32 arithmetic (dynedge.py:200-203, 226-229,
+ * 246-247; the reference computes in fp32, graphs/graphs.py:21). Always the CTA-pair kernel; n_out <= 1024. */
+int gnb_linear_fwd_tf32x3(const float* const* xs, const int64_t* ldxs, const int32_t* ks, int32_t nparts,
+                          const float* w_hi, const float* w_lo, int64_t ldw, const float* bias, float* y, int64_t ldy,
+                          int64_t rows, int32_t n_out, int32_t act, void* stream);
+/* hi[rows, dst_cols] = [rna_tf32(src) | 0], lo = [rna_tf32(src - hi) | 0]: the pre-split weight operand of the tf32x3 GEMMs. */
+int gnb_split_pad_tf32(const float* src, int64_t lds, int64_t rows, int32_t cols, float* hi, float* lo, int64_t ldd,
+                       int32_t dst_cols, void* stream);
 /* dw[n_out, k_in] += dz[rows, n_out]^T x[rows, k_in] on tcgen05 (split over rows, fp32 red.add into dw).
  * TMA-fed MN-major operands; same alignment rules as gnb_linear_fwd_tf32. debug_swap: 0 in production. */
 int gnb_linear_bwd_weight_tf32(const float* dz, int64_t lddz, const float* x, int64_t ldx, float* dw, int64_t lddw,
@@ -156,6 +167,11 @@ int gnb_linear_bwd_weight_tf32(const float* dz, int64_t lddz, const float* x, in
 int gnb_edge_linear_agg_fwd_tf32(const float* h, int64_t ldh, int32_t k, const float* w, int64_t ldw, const float* bias,
                                  const int32_t* deg, int64_t n, int32_t n_out, int32_t round_out, float* y, int64_t ldy,
                                  uint32_t* maskbits, void* stream);
+/* gnb_edge_linear_agg_fwd_tf32 with split operands (see gnb_linear_fwd_tf32x3): h plain fp32, w_hi / w_lo packed like w;
+ * y unrounded. PyG EdgeConv's second Linear + aggr="add" (layers.py:55-62) at fp32 grade. */
+int gnb_edge_linear_agg_fwd_tf32x3(const float* h, int64_t ldh, int32_t k, const float* w_hi, const float* w_lo, int64_t ldw,
+                                   const float* bias, const int32_t* deg, int64_t n, int32_t n_out, float* y, int64_t ldy,
+                                   uint32_t* maskbits, void* stream);
 /* Backward of the above up to the pre-activation: dz[i*9+s] = g[i] * maskbit, db += colsum(dz); flags & 0x100 rounds dz. */
 int gnb_edge_mask_bwd_colsum(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols,
                              const int32_t* deg, float* dz, int64_t ldz, float* db, int32_t flags, void* stream);
@@ -205,7 +221,7 @@ int64_t gnb_launch_count(void);
 /* Mirrors the constructor arguments of DynEdge (src/graphnet/models/gnn/dynedge.py:24-38) for the fast-path
  * family: ReLU, no norm layers, 2-Linear conv MLPs with aggr=add, Linear-ReLU post-processing / read-out chains. */
 typedef struct {
-    int32_t nb_inputs, k, precision;                 /* precision: 0 fp32 SIMT GEMMs, 1 tf32 tcgen05 GEMMs */
+    int32_t nb_inputs, k, precision;                 /* precision: 0 fp32 SIMT GEMMs, 1 tf32 tcgen05 GEMMs, 2 tf32x3: forward GEMMs split-operand (fp32 grade), backward GEMMs tf32 */
     int32_t n_conv, conv_hidden[GNB_MAX_LAYERS], conv_out[GNB_MAX_LAYERS];
     int32_t n_post, post_out[GNB_MAX_LAYERS];
     int32_t n_readout, readout_out[GNB_MAX_LAYERS];
