@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """Benchmark of the B200 DynEdge hot path (BASELINE.json metric: DynEdge events/sec, fwd+bwd and inference).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU cores
+    python bench.py --gpus N --steps K --warmup W             # this repo's CUDA path (headline workload train512)
+    python bench.py --impl reference --gpus N --steps K ...    # the reference algorithm on the host CPU cores
+    python bench.py --workload {infer1024,highmult20k,percentile16,prometheus50,microbench}   # the other BASELINE configs
 
 One "step" = one pass of the hot path over one batch of synthetic IceCube-like events:
   headline `value`  : training step of BASELINE configs[2] -- device-resident x/batch/n_pulses (no edge_index)
                       -> kNN graph -> DynEdge fwd -> direction(vMF)+energy(LogCosh) heads and loss -> bwd ->
-                      (NCCL mean all-reduce of the flat gradient buffer when N > 1) -> Adam step (one launch on the flat buffers);
-                      512 events per GPU (weak scaling), events/s summed over all ranks.
-  `inference`       : BASELINE configs[1] -- forward + energy head on 1024 events per GPU, no collective.
+                      (NCCL sum all-reduce of the flat gradient buffer when N > 1, its tail overlapped with the backward of
+                      the early layers; 1 / world folded into the optimizer) -> Adam step (one launch on the flat buffers);
+                      512 events per GPU (weak scaling), events/s summed over all ranks. Precision mode tf32x3 (split-operand
+                      forward GEMMs, single-pass tf32 backward GEMMs: outputs ~1e-6, gradients < 1e-3 from the oracle); the
+                      single-pass tf32 mode (gradients 2.3e-3) is reported beside it under `alt_precision`.
+  `inference`       : BASELINE configs[1] -- forward + energy head on 1024 events per GPU, no collective; own e2e + roofline.
   `e2e`             : the training step driven from pinned HOST buffers through the public API
                       (H2D copy of the batch and D2H read of the loss inside the timed region).
+  `kernels`         : every kernel >= 1 % of the step -- us per step, algorithmic FLOP / bytes, fraction of its roofline.
 Rank 0 prints ONE JSON line.
 """
 
@@ -20,9 +25,9 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -36,6 +41,9 @@ import torch.distributed as dist
 METRIC = "dynedge_train_events_per_sec"
 UNIT = "events/s"
 POOLS = ["min", "max", "mean", "sum"]
+TOLERANCE = {"tf32x3": "out 2e-5 / grad 1e-3 vs the fp64 oracle (tests/test_gpu_tf32x3.py)",
+             "tf32": "out 1e-3 / grad 3e-3 (single-pass tf32, measured 8e-4 / 2.3e-3, tests/test_gpu_tc.py)",
+             "fp32": "out 1e-3 / grad 1e-3 (SIMT fp32, measured 4e-7 / 8e-7)"}
 
 
 def parse_args():
@@ -44,13 +52,18 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="train512",
+                    choices=["train512", "infer1024", "highmult20k", "percentile16", "prometheus50", "microbench"])
     ap.add_argument("--events", type=int, default=512, help="training events per GPU (configs[2])")
     ap.add_argument("--infer-events", type=int, default=1024, help="inference events per GPU (configs[1])")
-    ap.add_argument("--precision", default=os.environ.get("GNB_PRECISION", "tf32"), choices=["tf32", "tf32x3", "fp32"])
-    ap.add_argument("--cpu-events", type=int, default=48, help="events of the bounded CPU-baseline sample")
+    ap.add_argument("--precision", default=os.environ.get("GNB_PRECISION", "tf32x3"), choices=["tf32x3", "tf32", "fp32"])
+    ap.add_argument("--cpu-events", type=int, default=128, help="events of the bounded CPU-baseline sample (BASELINE.md 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inference", action="store_true")
-    ap.add_argument("--repeats", type=int, default=3, help="repetitions of the K timed steps; the fastest is reported")
+    ap.add_argument("--no-kernel-table", action="store_true")
+    ap.add_argument("--no-alt-precision", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="one all-reduce behind the backward instead of the overlapped pair")
+    ap.add_argument("--repeats", type=int, default=3, help="repetitions of the K timed steps; the MEDIAN repetition is reported")
     return ap.parse_args()
 
 
@@ -62,6 +75,51 @@ def peaks():
                 "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
                 "sm_max_mhz": p.get("sm_max_mhz", 1965.0), "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+
+
+def measure_tf32_peak(dev, sustained_s: float = 2.0):
+    """TF32 dense peak measured the way MEASURED_PEAKS.json measures bf16: torch.matmul 8192^3 with
+    allow_tf32, best of 10 with CUDA events (burst) and back to back for `sustained_s` seconds (sustained). cuBLAS is only
+    the measuring stick for the roofline denominator; it is not on the product path."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        c = torch.empty(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        flops = 2.0 * n ** 3
+        best = 0.0
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, flops / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        reps = max(10, int(sustained_s * best * 1e12 / flops))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        sustained = reps * flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
+        del a, b, c
+        return {"tf32_tflops": round(best, 1), "tf32_tflops_sustained": round(sustained, 1),
+                "how": f"torch.matmul fp32 with allow_tf32, 8192^3: best of 10 (burst), {reps} back to back (sustained)"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def full_peaks(dev, measure=True):
+    pk = peaks()
+    tf = measure_tf32_peak(dev) if measure else {"tf32_tflops": 0.0, "tf32_tflops_sustained": 0.0, "how": ""}
+    pk.update({"tf32_tflops": tf["tf32_tflops"], "tf32_tflops_sustained": tf["tf32_tflops_sustained"], "tf32_how": tf["how"]})
+    return pk
 
 
 # --------------------------------------------------------------------------------------------- #
@@ -121,29 +179,39 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------- #
 # workload
 # --------------------------------------------------------------------------------------------- #
-def host_batches(num_events: int, count: int, seed0: int, rank: int = 0, world: int = 1):
+def _pin(t):
+    return t.pin_memory() if torch.cuda.is_available() else t
+
+
+def host_batches(num_events: int, count: int, seed0: int, rank: int = 0, world: int = 1, **gen):
     """`count` pinned host batches. With world > 1 every rank builds the same GLOBAL batch of num_events * world events
-    and keeps its contiguous event range from `shard_events` (ranges balanced by pulse count): the global
-    batch is exactly num_events * world events per step, the per-rank event counts differ by a few events."""
-    from graphnet_b200.distributed import shard_events
+    and keeps the events `assign_events` gives it (balanced on the cost model n + beta n^2, largest events spread first,
+    SURVEY 8e): the global batch is exactly num_events * world events per step, the per-rank event counts differ slightly.
+    `event_index` = the global indices of the rank's events (ascending)."""
+    from graphnet_b200.distributed import assign_events
     from graphnet_b200.synthetic import make_batch
     out = []
     for i in range(count):
-        raw = make_batch(num_events * world, seed=seed0 + i)
+        raw = make_batch(num_events * world, seed=seed0 + i, **gen)
+        index = np.arange(num_events * world)
         if world > 1:
-            lo, hi = shard_events(raw["n_pulses"], world)[rank]
-            starts = np.concatenate([[0], np.cumsum(raw["n_pulses"].astype(np.int64))])
-            n0, n1 = int(starts[lo]), int(starts[hi])
-            raw = {"x": raw["x"][n0:n1], "batch": raw["batch"][n0:n1] - lo, "n_pulses": raw["n_pulses"][lo:hi],
-                   "energy": raw["energy"][lo:hi], "direction": raw["direction"][lo:hi]}
-        out.append({k: torch.from_numpy(np.ascontiguousarray(raw[k])).pin_memory() if torch.cuda.is_available()
-                    else torch.from_numpy(np.ascontiguousarray(raw[k]))
-                    for k in ("x", "batch", "n_pulses", "energy", "direction")})
+            index = assign_events(raw["n_pulses"], world)[rank]
+            sizes = raw["n_pulses"].astype(np.int64)
+            starts = np.concatenate([[0], np.cumsum(sizes)])
+            rows = np.concatenate([np.arange(starts[e], starts[e + 1]) for e in index])
+            raw = {"x": raw["x"][rows], "batch": np.repeat(np.arange(len(index), dtype=np.int64), sizes[index]),
+                   "n_pulses": raw["n_pulses"][index], "energy": raw["energy"][index], "direction": raw["direction"][index]}
+        hb = {k: _pin(torch.from_numpy(np.ascontiguousarray(raw[k]))) for k in ("x", "batch", "n_pulses", "energy", "direction")}
+        hb["event_index"] = torch.from_numpy(np.ascontiguousarray(index))
+        out.append(hb)
     return out
 
 
+DEVICE_KEYS = ("x", "batch", "n_pulses", "energy", "direction")
+
+
 def to_device(hb, dev):
-    return {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+    return {k: hb[k].to(dev, non_blocking=True) for k in DEVICE_KEYS if k in hb}
 
 
 class DeviceStager:
@@ -151,17 +219,17 @@ class DeviceStager:
     into the same preallocated device memory (what an input pipeline does), so the H2D copies are inside the timed
     region but no allocator traffic is."""
 
-    def __init__(self, host_batches_list, dev):
-        self.bufs = {}
-        for k in host_batches_list[0]:
+    def __init__(self, host_batches_list, dev, keys=DEVICE_KEYS):
+        self.bufs, self.keys = {}, [k for k in keys if k in host_batches_list[0]]
+        for k in self.keys:
             biggest = max(host_batches_list, key=lambda hb: hb[k].shape[0])[k]
             self.bufs[k] = torch.empty_like(biggest, device=dev)
 
     def load(self, hb):
         out = {}
-        for k, v in hb.items():
-            dst = self.bufs[k][: v.shape[0]]
-            dst.copy_(v, non_blocking=True)
+        for k in self.keys:
+            dst = self.bufs[k][: hb[k].shape[0]]
+            dst.copy_(hb[k], non_blocking=True)
             out[k] = dst
         return out
 
@@ -169,37 +237,43 @@ class DeviceStager:
 class Trainer:
     """The public-API training step: KNNEdges -> DynEdge -> heads/loss -> backward -> all-reduce -> Adam."""
 
-    def __init__(self, dev, world: int):
-        from graphnet_b200.distributed import FlatGradAllReduce
+    def __init__(self, dev, world: int, nb_inputs: int = 7, overlap: bool = True):
+        from graphnet_b200 import ops as _ops
+        from graphnet_b200.distributed import FlatAdam, FlatGradAllReduce
         from graphnet_b200.models.gnn import DynEdge
         from graphnet_b200.models.graphs.edges import KNNEdges
         from graphnet_b200.tasks import FusedEnergyDirectionTask
         torch.manual_seed(0)
-        self.backbone = DynEdge(7, global_pooling_schemes=POOLS).to(dev)
+        self.backbone = DynEdge(nb_inputs, global_pooling_schemes=POOLS).to(dev)
         self.tasks = FusedEnergyDirectionTask(128).to(dev)      # both heads + both losses in two CUDA kernels
         self.energy, self.direction = self.tasks.energy, self.tasks.direction
         self.edges = KNNEdges(8)
         self.params = list(self.backbone.parameters()) + list(self.energy.parameters()) + \
             list(self.direction.parameters())
         self.reducer = FlatGradAllReduce(self.params)
-        from graphnet_b200 import ops as _ops
         _ops.ACCUMULATE_INTO_GRAD = True      # gradients land directly in the flat all-reduce buffer
-        from graphnet_b200.distributed import FlatAdam
         self.opt = FlatAdam(self.reducer, lr=1e-3, eps=1e-3)     # torch.optim.Adam semantics, one launch on the flat buffers
         self.world = world
+        self.overlap = overlap and world > 1
+        n_conv = len(self.backbone._conv_layers)
+        self.tail_param, self.tail_layer = 4 * (n_conv - 1), n_conv - 1   # last conv layer onward: final once its backward ran
 
     def make_data(self, db):
         from graphnet_b200 import Data
         return Data(x=db["x"], batch=db["batch"], n_pulses=db["n_pulses"])
 
-    def train_step(self, db):
+    def train_step(self, db, grad_probe=None):
         # the flat gradient buffer is zero here: allocated zeroed, then zeroed again by every Adam step behind its read
         data = self.edges(self.make_data(db))
         h = self.backbone(data)
         loss, _, _ = self.tasks(h, db["energy"], db["direction"])
+        if self.overlap:
+            self.reducer.arm_overlap(self.tail_param, self.tail_layer)
         loss.backward()
-        self.reducer.all_reduce_mean()
-        self.opt.step(zero_grad=True)
+        scale = self.reducer.all_reduce_sum_overlapped() if self.overlap else self.reducer.all_reduce_sum()
+        if grad_probe is not None:
+            grad_probe(self.reducer.flat, scale)          # test hook: the reduced gradient right before the optimizer
+        self.opt.step(zero_grad=True, grad_scale=scale)
         return loss
 
     @torch.no_grad()
@@ -208,8 +282,9 @@ class Trainer:
         return self.energy(self.backbone(data))
 
 
-def timed_loop(fn, batches, steps, warmup, flush, e2e_host=None, dev=None, sampler=None):
-    """Per-step CUDA-event timing with an (untimed) L2 flush between steps. Returns seconds."""
+def timed_loop(fn, batches, steps, warmup, flush, e2e_host=None, dev=None, sampler=None, d2h="scalar"):
+    """Per-step CUDA-event timing with an (untimed) L2 flush between steps. Returns seconds; the per-step device times
+    are left in `timed_loop.last_step_ms`."""
     # rotate only over batches that the warm-up has already seen: a first-seen shape costs one-off cudaMallocs
     # inside the caching allocator (measured: a 100-150 ms hiccup), which is not steady-state step time
     nb = max(1, min(warmup, len(batches if e2e_host is None else e2e_host)))
@@ -228,7 +303,8 @@ def timed_loop(fn, batches, steps, warmup, flush, e2e_host=None, dev=None, sampl
         dist.barrier()
     torch.cuda.synchronize()
     from graphnet_b200 import ops as _ops
-    total_ms, wall, host, launches0 = 0.0, 0.0, 0.0, _ops.kernel_launch_count()
+    total_ms, wall, host, launches0, per_step = 0.0, 0.0, 0.0, _ops.kernel_launch_count(), []
+    d2h_bytes = 0
     for i in range(steps):
         flush.fill_(float(i))                       # 256 MiB write: evicts L2 between timed steps
         torch.cuda.synchronize()
@@ -239,38 +315,46 @@ def timed_loop(fn, batches, steps, warmup, flush, e2e_host=None, dev=None, sampl
             out = fn(batches[i % len(batches)])
         else:
             out = fn(stager.load(e2e_host[i % len(e2e_host)]))
-            _ = float(out.detach().float().sum().item()) if out.numel() > 1 else float(out.item())   # D2H read
+            if d2h == "scalar" or out.numel() == 1:
+                _ = float(out.detach().float().sum().item()) if out.numel() > 1 else float(out.item())   # D2H read of the loss
+                d2h_bytes = 4
+            else:
+                _ = out.detach().cpu()                                                                  # D2H read of the predictions
+                d2h_bytes = int(out.numel() * out.element_size())
         end.record()
         host += time.perf_counter() - t0          # host time to enqueue the step (no sync)
         if sampler is not None:
             sampler.sample()                      # GPU is executing the step right now
         torch.cuda.synchronize()
         wall += time.perf_counter() - t0
-        total_ms += beg.elapsed_time(end)
-        if os.environ.get("GNB_BENCH_DEBUG"):
-            import gc as _gc
-            ms = torch.cuda.memory_stats()
-            print(f"step {i}: wall {1e3 * (time.perf_counter() - t0):.2f} ms, events {beg.elapsed_time(end):.2f} ms, e2e={e2e_host is not None} "
-                  f"device_allocs {ms['num_device_alloc']} reserved_MB {ms['reserved_bytes.all.current'] / 1e6:.0f} nodes {(batches[i % len(batches)] if e2e_host is None else e2e_host[i % len(e2e_host)])['x'].shape[0]} gc {_gc.get_count()} gcstats {[g['collections'] for g in _gc.get_stats()]}", file=sys.stderr)
+        per_step.append(beg.elapsed_time(end))
+        total_ms += per_step[-1]
     if dist.is_initialized():
         dist.barrier()
     torch.cuda.synchronize()
     timed_loop.last_launches = _ops.kernel_launch_count() - launches0      # over all `steps` timed steps
     timed_loop.last_host_ms = host / max(steps, 1) * 1e3
+    timed_loop.last_step_ms = per_step
+    timed_loop.last_d2h = d2h_bytes
     return (wall if e2e_host is not None else total_ms / 1e3)
 
 
-def best_of(repeats, *args, **kwargs):
-    """K timed steps, repeated; the fastest repetition is reported (like MEASURED_PEAKS.json's best-of-10): the GPU
-    hosts are shared and a descheduled Python thread or a stray cudaMalloc adds 30-150 ms to a single step now and
-    then. Launch / host-time side values are those of the reported repetition."""
-    best = None
-    for _ in range(repeats):
+def repeat_median(repeats, *args, **kwargs):
+    """K timed steps, repeated `repeats` times; the MEDIAN repetition is the reported one (BASELINE.md section 4 asks for
+    a median; round 1 reported the fastest repetition). Returns (seconds of the median repetition, stats) where stats
+    carries the fastest repetition and the median / min / max of all individual step times."""
+    runs = []
+    for _ in range(max(1, repeats)):
         sec = timed_loop(*args, **kwargs)
-        if best is None or sec < best[0]:
-            best = (sec, timed_loop.last_launches, timed_loop.last_host_ms)
-    timed_loop.last_launches, timed_loop.last_host_ms = best[1], best[2]
-    return best[0]
+        runs.append((sec, timed_loop.last_launches, timed_loop.last_host_ms, list(timed_loop.last_step_ms), timed_loop.last_d2h))
+    order = sorted(range(len(runs)), key=lambda i: runs[i][0])
+    med = runs[order[len(order) // 2]]
+    allsteps = [ms for r in runs for ms in r[3]]
+    timed_loop.last_launches, timed_loop.last_host_ms, timed_loop.last_d2h = med[1], med[2], med[4]
+    stats = {"best_repetition_s": runs[order[0]][0], "worst_repetition_s": runs[order[-1]][0],
+             "step_ms_median": round(float(np.median(allsteps)), 4), "step_ms_min": round(float(np.min(allsteps)), 4),
+             "step_ms_max": round(float(np.max(allsteps)), 4), "timed_steps_total": len(allsteps)}
+    return med[0], stats
 
 
 def max_over_ranks(seconds: float, dev) -> float:
@@ -281,27 +365,28 @@ def max_over_ranks(seconds: float, dev) -> float:
     return float(t.item())
 
 
-def sum_over_ranks(value: float, dev) -> float:
+def gather_ranks(value: float, dev):
     if not dist.is_initialized():
-        return value
+        return [value]
     t = torch.tensor([value], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return float(t.item())
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [float(o.item()) for o in out]
 
 
 # --------------------------------------------------------------------------------------------- #
-# roofline of the dominant kernel, timed live with CUDA events on the launching stream
+# roofline of the dominant kernels, timed live with CUDA events on the launching stream
 # --------------------------------------------------------------------------------------------- #
 def dominant_launches(trainer, db):
-    """The two heaviest launches of the training step (profiles/r01 launch lists), set up on real graph metadata of
-    one batch with random operand values, each as a zero-argument callable through the C-ABI:
+    """The heaviest launches of the step (profiles/ launch lists), set up on real graph metadata of one batch with random
+    operand values, each as a zero-argument callable through the C-ABI:
 
-      dgrad_scatter: gemm_tc_pair_kernel, backward of an EdgeConv layer: dh = dz W2 (rows = N*9 padded edge slots,
-                     K = 256, 336 output channels) with the ReLU-mask + dP/dQ scatter epilogue (dh never stored)
-      agg_fwd:       gemm_tc_pair_kernel, forward m = relu(h W2^T + b2) (K = 336, 256 channels) with the k-sum
-                     + mask-bit epilogue (m never stored)
+      dgrad_scatter: gemm_tc_pair_dual_scatter_kernel, backward of an EdgeConv layer: dh = dz W2 (rows = N*9 padded edge
+                     slots, K = 256, 336 output channels) with the ReLU-mask + dP/dQ scatter epilogue (dh never stored)
+      agg_fwd:       gemm_tc_pair_kernel<false>, forward m = relu(h W2^T + b2) (K = 336, 256 channels) with the k-sum
+                     + mask-bit epilogue (m never stored), single-pass tf32
+      agg_fwd_x3:    gemm_tc_pair_kernel<true>, the same launch on split operands (3 tf32 products per K step)
     """
-    import ctypes
     from graphnet_b200 import ops
     dev = db["x"].device
     data = trainer.edges(trainer.make_data(db))
@@ -313,13 +398,13 @@ def dominant_launches(trainer, db):
     hid, cout = lin.in_features, lin.out_features
     ntile = (n + 13) // 14
     w2 = lin.weight.detach()
-    # forward operands
-    h = ops._round_pad(torch.rand(rows, hid, device=dev))
+    h_raw = torch.rand(rows, hid, device=dev)
+    h = ops._round_pad(h_raw)
     w2p = ops._tc_pack_weight(w2, (0,), (hid,))
+    w_hi, w_lo = ops._tc_pack_weight_split(w2, (0,), (hid,))
     b2 = lin.bias.detach()
     y = torch.empty(n, cout, device=dev)
     maskbits = torch.empty(ntile * cout * 4, dtype=torch.int32, device=dev)
-    # backward operands
     dz = ops._round_pad(torch.randn(rows, cout, device=dev))
     wt = ops._tc_pack_weight(w2.t().contiguous(), (0,), (cout,))
     mld = 4 * ((hid + 127) // 128)
@@ -330,14 +415,18 @@ def dominant_launches(trainer, db):
         ops._call("gnb_edge_linear_agg_fwd_tf32", ops._ptr(h), hid, hid, ops._ptr(w2p), w2p.shape[1], ops._ptr(b2),
                   ops._ptr(graph.deg), n, cout, 1, ops._ptr(y), cout, ops._ptr(maskbits), ops._stream())
 
+    def agg_fwd_x3():
+        ops._call("gnb_edge_linear_agg_fwd_tf32x3", ops._ptr(h_raw), hid, hid, ops._ptr(w_hi), ops._ptr(w_lo), w_hi.shape[1],
+                  ops._ptr(b2), ops._ptr(graph.deg), n, cout, ops._ptr(y), cout, ops._ptr(maskbits), ops._stream())
+
     def dgrad_scatter():
         ops._call("gnb_edge_hidden_dgrad_scatter_tf32", ops._ptr(dz), cout, cout, ops._ptr(wt), wt.shape[1], ops._ptr(hmask),
                   mld, hid, ops._ptr(graph.nbr), n, ops._ptr(dpq), 2 * hid, ops._stream())
 
-    keep = (h, w2p, b2, y, maskbits, dz, wt, hmask, dpq, graph)
+    keep = (h, h_raw, w2p, w_hi, w_lo, b2, y, maskbits, dz, wt, hmask, dpq, graph)
     e_real = int(graph.deg.sum().item())
-    return {"agg_fwd": agg_fwd, "dgrad_scatter": dgrad_scatter, "rows": rows, "n": n, "edges": e_real, "hid": hid,
-            "cout": cout, "mld": mld, "keep": keep}
+    return {"agg_fwd": agg_fwd, "agg_fwd_x3": agg_fwd_x3, "dgrad_scatter": dgrad_scatter, "rows": rows, "n": n,
+            "edges": e_real, "hid": hid, "cout": cout, "mld": mld, "keep": keep}
 
 
 def _time_launch(fn, reps=10):
@@ -353,63 +442,66 @@ def _time_launch(fn, reps=10):
     return beg.elapsed_time(end) / 1e3 / reps
 
 
-def roofline_top_kernel(trainer, db, pk):
-    """Dominant kernels of the training step (largest share of device time in profiles/r01): the cta_group::2 tcgen05
-    (kind::tf32) GEMMs over the padded edge list of a DynEdgeConv layer. The heaviest launch is the backward data-gradient
-    GEMM with the scattering epilogue (`gemm_tc_pair_dual_scatter_kernel`); the forward launch with the aggregating
-    epilogue (`gemm_tc_pair_kernel`) is reported beside it. Algorithmic FLOPs per launch = 2 * E * 336 * 256 with E = actual edge count (SURVEY 8d:
-    deg * 2 * in * out per node). Timed alone with CUDA events on the launching stream (operands pre-rounded, so only
-    the kernel runs); operands (> 0.7 GB per launch) exceed the 126 MB L2."""
-    from graphnet_b200 import ops
-    if ops.PRECISION not in ("tf32", "tf32x3"):
+def _traffic(name):
+    """ncu --set full DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the committed captures."""
+    for rnd in ("r02", "r01"):
+        path = os.path.join(ROOT, "profiles", rnd, "roofline_traffic.json")
+        if os.path.exists(path):
+            t = json.load(open(path))
+            if name in t:
+                return dict(t[name], source=f"profiles/{rnd}/roofline_traffic.json")
+            if name == "dgrad_scatter" and "dram_bytes_per_launch" in t:
+                return {"dram_bytes_per_launch": t["dram_bytes_per_launch"], "rows": t.get("rows"), "source": t.get("source")}
+    return None
+
+
+def roofline_top_kernel(trainer, db, pk, precision, inference=False):
+    """Dominant kernel of the step in `precision`, timed alone with CUDA events on the launching stream (operands > 0.7 GB
+    per launch exceed the 126 MB L2). Algorithmic FLOPs per launch = 2 * E * 336 * 256 with E = the real edge count
+    (deg * 2 * in * out per node; the split kernel EXECUTES three tf32 products per algorithmic product and is
+    charged the algorithmic count only). peak = the TF32 dense peak measured in this run (burst: the kernel is timed alone).
+    Training: the forward aggregating launch in tf32x3 (gemm_tc_pair_kernel<true>, the step's heaviest family) with the
+    backward scattering launch beside it; inference / single-pass: the single-pass aggregating launch."""
+    if precision == "fp32":
         return roofline_fp32_kernel(trainer, db, pk)
     d = dominant_launches(trainer, db)
     rows, n, e_real, hid, cout = d["rows"], d["n"], d["edges"], d["hid"], d["cout"]
     flops = 2.0 * e_real * hid * cout
-    peak = pk["bf16_tflops"]            # kernel timed alone -> burst figure
-    sec_b = _time_launch(d["dgrad_scatter"])
-    sec_f = _time_launch(d["agg_fwd"])
-    tpath = os.path.join(ROOT, "profiles", "r01", "roofline_traffic.json")
-    traffic, l2_b, l2_f = None, None, None
-    if os.path.exists(tpath):
-        t = json.load(open(tpath))
-        traffic = {"dram_bytes_per_launch": t.get("dram_bytes_per_launch"), "rows": t.get("rows"), "source": t.get("source")}
-        # L2 <-> SM view (what actually bounds these launches, DESIGN.md section 4): bytes that crossed the L2 slices per
-        # launch (ncu: l1tex__m_xbar2l1tex_read_bytes + l1tex__m_l1tex2xbar_write_bytes of the committed capture, same
-        # shapes) / the launch time measured here, against the full-chip LTS cap of ~6300 B/clk (B300_MICROARCH.md) at
-        # the maximum SM clock (an upper bound: under tensor load the clock sits near 1.75 GHz)
-        cap = 6300.0 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e9          # GB/s
-        if t.get("rows") == rows and t.get("l2_to_sm_bytes"):
-            by = float(t["l2_to_sm_bytes"]) + float(t.get("sm_to_l2_write_bytes", 0))
-            l2_b = {"l2_bytes_per_launch": by, "achieved_gbs": round(by / sec_b / 1e9, 1), "cap_gbs": round(cap, 1),
-                    "frac": round(by / sec_b / 1e9 / cap, 4)}
-            ff = t.get("forward_launch", {})
-            if ff.get("l2_to_sm_bytes"):
-                byf = float(ff["l2_to_sm_bytes"]) + float(ff.get("sm_to_l2_write_bytes", 0))
-                l2_f = {"l2_bytes_per_launch": byf, "achieved_gbs": round(byf / sec_f / 1e9, 1), "cap_gbs": round(cap, 1),
-                        "frac": round(byf / sec_f / 1e9 / cap, 4)}
-    # HBM view. backward: reads dz [rows, 256] + mask rows, reduces into dPQ [n, 672] (one fp32 per (edge slot, channel)
-    # through L2 atomics, counted once as written bytes); forward: reads h [rows, 336], writes y [n, 256] + mask bits
-    bytes_b = 4.0 * rows * cout + 4.0 * rows * d["mld"] + 4.0 * n * 2 * hid
+    peak = pk["tf32_tflops"]
     bytes_f = 4.0 * rows * hid + 4.0 * n * cout + 16.0 * ((n + 13) // 14) * cout
-    fwd = {"kernel": "gemm_tc_pair_kernel, aggregating epilogue: m = relu(h W2^T + b2) summed over the k slots, 336 -> 256",
-           "launch_ms": round(sec_f * 1e3, 4), "achieved": round(flops / sec_f / 1e12, 3), "unit": "TFLOP/s",
-           "frac": round(flops / sec_f / 1e12 / peak, 5),
-           "hbm_view": {"algorithmic_bytes": bytes_f, "achieved_gbs": round(bytes_f / sec_f / 1e9, 1),
-                        "frac": round(bytes_f / sec_f / 1e9 / pk["hbm_gbs"], 4)},
-           "l2_view": l2_f}
-    achieved = flops / sec_b / 1e12
-    return {"bound": "tensor",
-            "kernel": "gemm_tc_pair_dual_scatter_kernel (tcgen05 cta_group::2 kind::tf32 M256xN256xK8, TMA, TMEM double-buffered; "
-                      "both 256-channel groups from one resident dz tile), scattering epilogue: dh = dz W2 (256 -> 336), ReLU mask, "
-                      "dP/dQ reduction over the padded edge list",
-            "achieved": round(achieved, 3), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 5),
-            "traffic": traffic, "peak_source": pk["source"] + " bf16 dense burst (tf32 tensor peak is half of it)",
-            "launch_ms": round(sec_b * 1e3, 4), "rows": rows, "edges": e_real,
-            "hbm_view": {"algorithmic_bytes": bytes_b, "achieved_gbs": round(bytes_b / sec_b / 1e9, 1),
-                         "peak_gbs": pk["hbm_gbs"], "frac": round(bytes_b / sec_b / 1e9 / pk["hbm_gbs"], 4),
-                         "note": "plus one fp32 L2 reduction per (edge slot, channel): 4 * rows * 336 bytes of atomic traffic"},
-            "l2_view": l2_b, "forward_launch": fwd}
+    bytes_b = 4.0 * rows * cout + 4.0 * rows * d["mld"] + 4.0 * n * 2 * hid
+
+    def entry(kernel, sec, by, executed=1.0, traffic=None):
+        ach = flops / sec / 1e12
+        return {"kernel": kernel, "launch_ms": round(sec * 1e3, 4), "achieved": round(ach, 3), "unit": "TFLOP/s",
+                "frac": round(ach / peak, 5), "executed_tflops": round(ach * executed, 3),
+                "executed_frac": round(ach * executed / peak, 5),
+                "hbm_view": {"algorithmic_bytes": by, "achieved_gbs": round(by / sec / 1e9, 1),
+                             "frac": round(by / sec / 1e9 / pk["hbm_gbs"], 4)}, "traffic": traffic}
+    sec_f = _time_launch(d["agg_fwd"])
+    sec_b = _time_launch(d["dgrad_scatter"])
+    fwd1 = entry("gemm_tc_pair_kernel<false>, aggregating epilogue (single-pass tf32): m = relu(h W2^T + b2) summed over the "
+                 "k slots, 336 -> 256", sec_f, bytes_f, 1.0, _traffic("agg_fwd"))
+    bwd = entry("gemm_tc_pair_dual_scatter_kernel: dh = dz W2 (256 -> 336), ReLU mask, dP/dQ reduction over the padded edge "
+                "list (single-pass tf32; both 256-channel groups from one resident dz tile)", sec_b, bytes_b, 1.0,
+                _traffic("dgrad_scatter"))
+    if precision == "tf32x3" and not inference:
+        sec_x = _time_launch(d["agg_fwd_x3"])
+        top = entry("gemm_tc_pair_kernel<true> (tcgen05 cta_group::2 kind::tf32 M256xN256xK8, split operands: 3 MMAs per K step, "
+                    "TMA 4 x 48 KiB stages + in-kernel hi/lo splitter, TMEM double-buffered), aggregating epilogue: "
+                    "m = relu(h W2^T + b2) summed over the k slots, 336 -> 256", sec_x, bytes_f, 3.0, _traffic("agg_fwd_x3"))
+        others = {"backward_launch": bwd, "single_pass_forward_launch": fwd1}
+    elif inference:
+        top, others = fwd1, {}
+    else:
+        top, others = bwd, {"forward_launch": fwd1}
+    out = {"bound": "tensor", "achieved": top["achieved"], "peak": peak, "unit": "TFLOP/s", "frac": top["frac"],
+           "traffic": top["traffic"], "kernel": top["kernel"], "launch_ms": top["launch_ms"],
+           "peak_source": "tf32 dense burst peak measured in this run (" + pk["tf32_how"] + ")",
+           "executed_tflops": top["executed_tflops"], "executed_frac": top["executed_frac"], "hbm_view": top["hbm_view"],
+           "rows": rows, "edges": e_real, "algorithmic_flops_per_launch": flops}
+    out.update(others)
+    return out
 
 
 def roofline_fp32_kernel(trainer, db, pk):
@@ -425,14 +517,160 @@ def roofline_fp32_kernel(trainer, db, pk):
     sec = _time_launch(lambda: ops.linear_act(h, w, b, ops.ACT_RELU))
     flops = 2.0 * e_real * lin.in_features * lin.out_features
     achieved = flops / sec / 1e12
-    peak = pk["bf16_tflops"]
+    peak = pk["tf32_tflops"]
     hbm_bytes = 4.0 * rows * (lin.in_features + lin.out_features)
     return {"bound": "tensor", "kernel": "gemm_f32_kernel<0,0,1> (fp32 SIMT): edge MLP Linear 336->256 + ReLU over the padded edge list",
             "achieved": round(achieved, 3), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 5),
-            "traffic": None, "peak_source": pk["source"] + " bf16 dense burst", "launch_ms": round(sec * 1e3, 4),
+            "traffic": None, "peak_source": "tf32 dense burst peak measured in this run", "launch_ms": round(sec * 1e3, 4),
             "rows": rows, "edges": e_real,
             "hbm_view": {"algorithmic_bytes": hbm_bytes, "achieved_gbs": round(hbm_bytes / sec / 1e9, 1),
                          "peak_gbs": pk["hbm_gbs"], "frac": round(hbm_bytes / sec / 1e9 / pk["hbm_gbs"], 4)}}
+
+
+# --------------------------------------------------------------------------------------------- #
+# per-kernel table: device time per kernel family from one CUPTI pass (explanatory only -- every headline number is
+# CUDA-event timed without a profiler), algorithmic work from the model's shapes
+# --------------------------------------------------------------------------------------------- #
+def _family(name: str) -> str:
+    name = re.sub(r"^void\s+", "", name)
+    name = name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+    m = re.match(r"([A-Za-z0-9_:]+)(<[^(]*>)?", name)
+    fam = m.group(1) if m else name
+    if fam.startswith("gemm_tc_pair_kernel"):
+        split = bool(re.search(r"gemm_tc_pair_kernel<\s*(\(bool\))?\s*(1|true)\s*>", name))
+        fam = "gemm_tc_pair_kernel<split>" if split else "gemm_tc_pair_kernel<single>"
+    return fam
+
+
+def algorithmic_work(cfg, n, rows, e_real, nseg, precision, train=True):
+    """Algorithmic FLOPs (literal GEMM shapes, real edge count) and minimum HBM bytes per kernel family for one step of the
+    default-shaped DynEdge described by `cfg` (conv hidden / out widths, post, read-out), following the dispatch rules of
+    csrc/gemm_tc.cu::launch_linear (CTA-pair kernel for > 128 output channels and >= 296 row tiles)."""
+    work = {}
+
+    def add(fam, flops=0.0, by=0.0, bound="tensor"):
+        w = work.setdefault(fam, {"flops": 0.0, "bytes": 0.0, "bound": bound, "launches": 0})
+        w["flops"] += flops
+        w["bytes"] += by
+        w["launches"] += 1
+
+    def dense_fam(m_rows, n_out, fwd):
+        if precision == "fp32":
+            return "gemm_f32_kernel"
+        if fwd and precision == "tf32x3":
+            return "gemm_tc_pair_kernel<split>"
+        tiles = (m_rows + 127) // 128
+        return "gemm_tc_pair_kernel<single>" if (tiles >= 296 and n_out > 128) else "gemm_tc_linear_kernel"
+    tc = precision != "fp32"
+    cin = cfg["x0_width"]
+    skip_w = cin
+    for hid, cout in cfg["conv"]:
+        add(dense_fam(n, 2 * hid, True), 2.0 * n * cin * 2 * hid, 4.0 * n * (cin + 2 * hid))
+        add("edge_hidden_fwd_node_kernel", 0.0, 4.0 * rows * hid + 4.0 * n * 2 * hid, "hbm")
+        add(dense_fam(rows, cout, True), 2.0 * e_real * hid * cout, 4.0 * rows * hid + 4.0 * n * cout)
+        add("knn_table_split_kernel", 0.0, n * (12.0 + 40.0), "hbm")
+        if train:
+            add("edge_mask_bwd_kernel", 0.0, 4.0 * rows * cout + 4.0 * n * cout, "hbm")
+            add("gemm_tc_wgrad_kernel" if tc else "gemm_f32_kernel", 2.0 * e_real * hid * cout, 4.0 * rows * (hid + cout))
+            fam = "gemm_tc_pair_dual_scatter_kernel" if (tc and hid > 256) else dense_fam(rows, hid, False)
+            add(fam, 2.0 * e_real * hid * cout, 4.0 * rows * cout + 4.0 * n * 2 * hid)
+            add("round_move_zero_kernel", 0.0, 12.0 * n * hid, "hbm")
+            add("gemm_tc_wgrad_kernel" if tc else "gemm_f32_kernel", 2.0 * n * cin * 2 * hid, 4.0 * n * (cin + 2 * hid))
+            if cin != cfg["x0_width"]:
+                add(dense_fam(n, cin, False), 2.0 * n * cin * 2 * hid, 4.0 * n * (2 * cin + 2 * hid))
+        cin = cout
+        skip_w += cout
+    k_in = skip_w
+    for j, width in enumerate(cfg["post"]):
+        add(dense_fam(n, width, True), 2.0 * n * k_in * width, 4.0 * n * (k_in + width))
+        if train:
+            add("act_bwd_colsum_kernel", 0.0, 12.0 * n * width, "hbm")
+            add("gemm_tc_wgrad_kernel" if tc else "gemm_f32_kernel", 2.0 * n * k_in * width, 4.0 * n * (k_in + width))
+            dg_in = k_in - cfg["x0_width"] if j == 0 else k_in
+            add(dense_fam(n, 256, False), 2.0 * n * dg_in * width, 4.0 * n * (dg_in + width))
+        k_in = width
+    pooled = len(POOLS) * k_in
+    add("segment_pool_fwd_kernel", 0.0, 4.0 * n * k_in + 8.0 * nseg * pooled, "hbm")
+    add("global_vars_kernel", 0.0, 4.0 * n * (cfg["nb_inputs"] + 9 + cfg["x0_ld"]), "hbm")
+    if train:
+        add("segment_pool_bwd_kernel", 0.0, 4.0 * n * k_in + 8.0 * nseg * pooled, "hbm")
+    return work
+
+
+def kernel_table(step_fn, db, cfg, n, rows, e_real, nseg, precision, pk, train=True, steps=2):
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        step_fn(db)
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(steps):
+                step_fn(db)
+            torch.cuda.synchronize()
+        fam_us, fam_n = {}, {}
+        for ev in prof.key_averages():
+            us = float(getattr(ev, "device_time_total", 0.0) or getattr(ev, "cuda_time_total", 0.0) or 0.0)
+            if us <= 0.0:
+                continue
+            fam = _family(ev.key)
+            fam_us[fam] = fam_us.get(fam, 0.0) + us / steps
+            fam_n[fam] = fam_n.get(fam, 0) + ev.count / steps
+    except Exception as exc:            # CUPTI unavailable: the table is explanatory, the bench line stays valid without it
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+    total = sum(fam_us.values())
+    if total <= 0.0:
+        return {"unavailable": "the profiler returned no device activity"}
+    work = algorithmic_work(cfg, n, rows, e_real, nseg, precision, train)
+    rows_out = []
+    alg_flops_total = sum(w["flops"] for w in work.values())
+    for fam, us in sorted(fam_us.items(), key=lambda kv: -kv[1]):
+        if us < 0.01 * total:
+            continue
+        w = work.get(fam)
+        row = {"kernel": fam, "us_per_step": round(us, 1), "share": round(us / total, 4), "launches_per_step": round(fam_n[fam], 1)}
+        if w is not None:
+            if w["bound"] == "tensor":
+                ach = w["flops"] / (us * 1e-6) / 1e12
+                row.update({"bound": "tensor", "algorithmic_gflop": round(w["flops"] / 1e9, 2), "achieved_tflops": round(ach, 1),
+                            "frac": round(ach / pk["tf32_tflops_sustained"], 4),
+                            "hbm_frac": round(w["bytes"] / (us * 1e-6) / 1e9 / pk["hbm_gbs"], 4)})
+            else:
+                ach = w["bytes"] / (us * 1e-6) / 1e9
+                row.update({"bound": "hbm", "algorithmic_mb": round(w["bytes"] / 1e6, 2), "achieved_gbs": round(ach, 1),
+                            "frac": round(ach / pk["hbm_gbs"], 4)})
+        rows_out.append(row)
+    return {"source": f"one CUPTI pass over {steps} steps after the timed loops (explanatory; headline numbers are CUDA-event "
+                      "timed without a profiler); tensor fractions against the tf32 SUSTAINED peak measured in this run, "
+                      "HBM fractions against MEASURED_PEAKS.json",
+            "device_us_per_step": round(total, 1), "algorithmic_gflop_per_step": round(alg_flops_total / 1e9, 1),
+            "kernels": rows_out}
+
+
+def model_shape(trainer):
+    bb = trainer.backbone
+    conv = [(c.nn[0].out_features, c.nn[2].out_features) for c in bb._conv_layers]
+    post = [m.out_features for m in bb._post_processing if isinstance(m, torch.nn.Linear)]
+    nbi = bb._nb_inputs
+    x0w = nbi + nbi + 5
+    return {"conv": conv, "post": post, "nb_inputs": nbi, "x0_width": x0w, "x0_ld": (x0w + 31) // 32 * 32}
+
+
+def literal_flops(cfg, n, e_real, nseg, train):
+    """the reference's literal algorithm -- per edge 2 (2 C_in H + H C_out), per node the post-processing, per
+    event the read-out; backward = 2 x forward GEMM FLOPs minus the first layer's dX."""
+    cin = cfg["x0_width"]
+    fwd, first_dx = 0.0, 0.0
+    for i, (hid, cout) in enumerate(cfg["conv"]):
+        f = 2.0 * e_real * (2 * cin * hid + hid * cout)
+        fwd += f
+        if i == 0:
+            first_dx = 2.0 * e_real * 2 * cin * hid
+        cin = cout
+    k_in = cfg["x0_width"] + sum(c for _, c in cfg["conv"])
+    for width in cfg["post"]:
+        fwd += 2.0 * n * k_in * width
+        k_in = width
+    fwd += 2.0 * nseg * len(POOLS) * k_in * 128
+    return fwd + (2.0 * fwd - first_dx if train else 0.0)
 
 
 # --------------------------------------------------------------------------------------------- #
@@ -469,10 +707,12 @@ def cpu_reference_events_per_sec(num_events: int, steps: int, warmup: int, train
 
     for _ in range(warmup):
         step()
-    t0 = time.perf_counter()
+    times = []
     for _ in range(steps):
+        t0 = time.perf_counter()
         step()
-    sec = (time.perf_counter() - t0) / steps
+        times.append(time.perf_counter() - t0)
+    sec = float(np.median(times))
     return num_events / sec, sec, cores, int(x.shape[0])
 
 
@@ -483,7 +723,7 @@ def run_reference(args):
     steps = max(1, min(args.steps, 3))
     warm = 1 if args.warmup > 0 else 0
     evs, sec, cores, nodes = cpu_reference_events_per_sec(args.cpu_events, steps, warm, train=True)
-    sample = (f"{args.cpu_events} synthetic events ({nodes} pulses), {warm} warm-up + {steps} timed training steps of "
+    sample = (f"{args.cpu_events} synthetic events ({nodes} pulses), {warm} warm-up + {steps} timed training steps (median) of "
               "the pure-torch oracle (reference's own PyG stack is not installable here)")
     line = {"impl": "reference", "metric": METRIC, "value": round(evs, 3), "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True,
@@ -499,11 +739,14 @@ def workload_config(args, world):
                         "(LogCosh) training step fwd+bwd+Adam, 512 events/GPU, synthetic IceCube86 pulse maps "
                         "(lognormal pulses/event, median 100, max 5000); configs[1] inference B=1024 under 'inference'",
             "events_per_gpu": args.events, "global_events": args.events * world, "parallelism": f"dp{world}",
-            "sharding": "global batch cut into contiguous event ranges balanced by pulse count (shard_events); no data-path collective",
-            "precision": args.precision, "inputs": "x/batch/n_pulses resident in HBM; kNN graph built inside the step",
+            "sharding": "global batch spread over the ranks by assign_events (cost n + 1.1e-4 n^2 per event, largest first); "
+                        "no data-path collective",
+            "precision": f"{args.precision}: {TOLERANCE[args.precision]}",
+            "inputs": "x/batch/n_pulses resident in HBM; kNN graph built inside the step",
             "l2": "256 MiB buffer rewritten between timed steps; min(4, warmup) rotating batches",
             "warmup_executed": "max(W, 2 x rotating batches) untimed steps per timed loop",
-            "repeats": f"{args.repeats} repetitions of the K timed steps, fastest reported"}
+            "repeats": f"{args.repeats} repetitions of the K timed steps, the MEDIAN repetition reported (fastest and per-step "
+                       "median under 'timing')"}
 
 
 def _emit(line):
@@ -521,6 +764,134 @@ def _quiet_stdout():
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
+
+
+def graph_stats(trainer, db):
+    data = trainer.edges(trainer.make_data(db))
+    g = data.knn_graph()
+    return int(g.n), int(g.n * g.width), int(g.deg.sum().item()), int(db["n_pulses"].numel())
+
+
+def run_train512(args, dev, world, rank, local):
+    from graphnet_b200 import ops
+    ops.set_precision(args.precision)
+    pk = full_peaks(dev, measure=rank == 0)
+    trainer = Trainer(dev, world, overlap=not args.no_overlap)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+
+    train_host = host_batches(args.events, 4, seed0=20240607, rank=rank, world=world)
+    train_dev = [to_device(hb, dev) for hb in train_host]
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    sec_local, tstats = repeat_median(args.repeats, trainer.train_step, train_dev, args.steps, args.warmup, flush,
+                                      sampler=sampler if rank == 0 else None)
+    launches = timed_loop.last_launches        # kernels of libgraphnet_b200.so launched inside the timed steps
+    host_ms = timed_loop.last_host_ms
+    rank_ms = gather_ranks(tstats["step_ms_median"], dev)
+    sec = max_over_ranks(sec_local, dev)
+    events_total = float(args.events * world * args.steps)      # every step processes the whole global batch
+    value = events_total / sec
+    timing = dict(tstats, value_best_repetition=round(events_total / max_over_ranks(tstats["best_repetition_s"], dev), 2),
+                  per_rank_step_ms_median=[round(v, 4) for v in rank_ms],
+                  per_rank_spread=round((max(rank_ms) - min(rank_ms)) / max(float(np.mean(rank_ms)), 1e-9), 4))
+
+    # end-to-end through the public API from pinned host buffers
+    sec_e2e, _ = repeat_median(args.repeats, trainer.train_step, None, args.steps, args.warmup, flush, e2e_host=train_host, dev=dev)
+    sec_e2e = max_over_ranks(sec_e2e, dev)
+    h2d = sum(int(train_host[0][k].numel() * train_host[0][k].element_size()) for k in DEVICE_KEYS)
+    e2e = {"value": round(events_total / sec_e2e, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+    clocks = sampler.stop() if rank == 0 else None
+
+    alt = None
+    if not args.no_alt_precision and args.precision == "tf32x3":
+        ops.set_precision("tf32")
+        sec_a, st_a = repeat_median(args.repeats, trainer.train_step, train_dev, args.steps, args.warmup, flush)
+        sec_a = max_over_ranks(sec_a, dev)
+        alt = {"precision": "tf32: " + TOLERANCE["tf32"], "value": round(events_total / sec_a, 2), "unit": UNIT,
+               "ms_per_step": round(sec_a / args.steps * 1e3, 3), "step_ms_median": st_a["step_ms_median"]}
+        ops.set_precision(args.precision)
+
+    inference = None
+    if not args.no_inference:
+        inference = run_inference(args, trainer, dev, world, rank, flush, pk)
+
+    roof, table, whole = None, None, None
+    if rank == 0:
+        roof = roofline_top_kernel(trainer, train_dev[0], pk, args.precision)
+        n, rows, e_real, nseg = graph_stats(trainer, train_dev[0])
+        cfg = model_shape(trainer)
+        if not args.no_kernel_table and world == 1:      # (its steps contain collectives: one rank cannot run them alone)
+            table = kernel_table(trainer.train_step, train_dev[0], cfg, n, rows, e_real, nseg, args.precision, pk, train=True)
+        lit = literal_flops(cfg, n, e_real, nseg, True)
+        alg = sum(w["flops"] for w in algorithmic_work(cfg, n, rows, e_real, nseg, args.precision, True).values())
+        step_s = tstats["step_ms_median"] * 1e-3
+        whole = {"literal_gflop_per_step": round(lit / 1e9, 1), "hoisted_gflop_per_step": round(alg / 1e9, 1),
+                 "literal_tflops": round(lit / step_s / 1e12, 1), "hoisted_tflops": round(alg / step_s / 1e12, 1),
+                 "frac_literal_vs_tf32_sustained": round(lit / step_s / 1e12 / max(pk["tf32_tflops_sustained"], 1e-9), 4),
+                 "frac_hoisted_vs_tf32_sustained": round(alg / step_s / 1e12 / max(pk["tf32_tflops_sustained"], 1e-9), 4),
+                 "note": "literal = the reference's per-edge MLP (SURVEY 8d); hoisted = the GEMMs this path runs (first Linear of "
+                         "every EdgeConv moved from edges to nodes), algorithmic count (a split product counted once)"}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        evs, csec, cores, nodes = cpu_reference_events_per_sec(args.cpu_events, 2, 1, train=True)
+        cpu = {"value": round(evs, 3), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_events} of the same synthetic events ({nodes} pulses), 1 warm-up + 2 timed "
+                         f"training steps of the pure-torch oracle on {cores} host threads"}
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(sec / args.steps * 1e3, 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32",
+                "data": "synthetic", "config": workload_config(args, world), "e2e": e2e, "gpu_launches": int(launches),
+                "gpu_launches_per_step": int(launches) // max(args.steps, 1),
+                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "inference": inference, "alt_precision": alt,
+                "timing": timing, "whole_step": whole, "kernels": table,
+                "peaks": {"hbm_gbs": pk["hbm_gbs"], "tf32_tflops": pk["tf32_tflops"],
+                          "tf32_tflops_sustained": pk["tf32_tflops_sustained"], "bf16_tflops": pk["bf16_tflops"],
+                          "source": pk["source"] + " (MEASURED_PEAKS.json) + tf32 measured in this run"},
+                "nodes_per_step_rank0": int(train_host[0]["x"].shape[0]),
+                "host_enqueue_ms_per_step": round(host_ms, 3)}
+        _emit(line)
+
+
+def run_inference(args, trainer, dev, world, rank, flush, pk):
+    """BASELINE configs[1]: energy-regression inference, 1024 events per GPU, in the single-pass tf32 mode (predictions within
+    rel 1e-3: tests/test_gpu_tc.py) and, beside it, in the mode of the training run. Device-resident `value`, `e2e` from
+    pinned host buffers (H2D of the batch, D2H of the [B, 1] predictions inside the timed region), own roofline."""
+    from graphnet_b200 import ops
+    inf_host = host_batches(args.infer_events, 2, seed0=777, rank=rank, world=world)
+    inf_dev = [to_device(hb, dev) for hb in inf_host]
+    events_total = float(args.infer_events * world * args.steps)
+    keep = ops.PRECISION
+    out = {"workload": "BASELINE configs[1]: energy-regression inference, 1024 events/GPU, no collective", "unit": UNIT}
+    try:
+        for mode in (["tf32", keep] if keep == "tf32x3" else ["tf32"]):
+            ops.set_precision(mode)
+            sec, st = repeat_median(args.repeats, trainer.infer_step, inf_dev, args.steps, args.warmup, flush)
+            sec = max_over_ranks(sec, dev)
+            entry = {"precision": f"{mode}: {TOLERANCE[mode].split(' / ')[0]}", "value": round(events_total / sec, 2),
+                     "ms_per_step": round(sec / args.steps * 1e3, 3), "step_ms_median": st["step_ms_median"]}
+            if mode == "tf32":
+                sec_e, _ = repeat_median(args.repeats, trainer.infer_step, None, args.steps, args.warmup, flush, e2e_host=inf_host,
+                                         dev=dev, d2h="tensor")
+                sec_e = max_over_ranks(sec_e, dev)
+                h2d = sum(int(inf_host[0][k].numel() * inf_host[0][k].element_size()) for k in ("x", "batch", "n_pulses"))
+                entry["e2e"] = {"value": round(events_total / sec_e, 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                                "d2h_bytes_per_step": int(timed_loop.last_d2h)}
+                out.update(entry)
+                if rank == 0:
+                    out["roofline"] = roofline_top_kernel(trainer, inf_dev[0], pk, "tf32", inference=True)
+                    if not args.no_kernel_table:
+                        n, rows, e_real, nseg = graph_stats(trainer, inf_dev[0])
+                        out["kernels"] = kernel_table(trainer.infer_step, inf_dev[0], model_shape(trainer), n, rows, e_real, nseg,
+                                                      "tf32", pk, train=False)
+            else:
+                out["alt_precision"] = entry
+    finally:
+        ops.set_precision(keep)
+    return out
 
 
 def main():
@@ -543,58 +914,24 @@ def main():
         entry.build()
     if world > 1:
         dist.barrier()
-    from graphnet_b200 import ops
-    ops.set_precision(args.precision)
-    pk = peaks()
-    trainer = Trainer(dev, world)
-    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
-
-    train_host = host_batches(args.events, 4, seed0=20240607, rank=rank, world=world)
-    train_dev = [to_device(hb, dev) for hb in train_host]
-    torch.cuda.synchronize()
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    sec = best_of(args.repeats, trainer.train_step, train_dev, args.steps, args.warmup, flush, sampler=sampler if rank == 0 else None)
-    launches = timed_loop.last_launches        # kernels of libgraphnet_b200.so launched inside the timed steps
-    host_ms = timed_loop.last_host_ms
-    sec = max_over_ranks(sec, dev)
-    events_total = float(args.events * world * args.steps)      # every step processes the whole global batch
-    value = events_total / sec
-
-    # end-to-end through the public API from pinned host buffers
-    sec_e2e = best_of(args.repeats, trainer.train_step, None, args.steps, args.warmup, flush, e2e_host=train_host, dev=dev)
-    sec_e2e = max_over_ranks(sec_e2e, dev)
-    h2d = sum(int(v.numel() * v.element_size()) for v in train_host[0].values())
-    e2e = {"value": round(events_total / sec_e2e, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
-
-    inference = None
-    if not args.no_inference:
-        inf_host = host_batches(args.infer_events, 2, seed0=777, rank=rank, world=world)
-        inf_dev = [to_device(hb, dev) for hb in inf_host]
-        sec_inf = max_over_ranks(best_of(args.repeats, trainer.infer_step, inf_dev, args.steps, args.warmup, flush), dev)
-        inference = {"value": round(float(args.infer_events * world * args.steps) / sec_inf, 2), "unit": UNIT,
-                     "workload": "BASELINE configs[1]: energy-regression inference, 1024 events/GPU, no collective",
-                     "ms_per_step": round(sec_inf / args.steps * 1e3, 3)}
-    clocks = sampler.stop() if rank == 0 else None
-
-    roof = roofline_top_kernel(trainer, train_dev[0], pk) if rank == 0 else None
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        evs, csec, cores, nodes = cpu_reference_events_per_sec(args.cpu_events, 2, 1, train=True)
-        cpu = {"value": round(evs, 3), "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_events} of the same synthetic events ({nodes} pulses), 1 warm-up + 2 timed "
-                         f"training steps of the pure-torch oracle on {cores} host threads"}
-    if rank == 0:
-        line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": round(sec / args.steps * 1e3, 3), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else args.precision,
-                "data": "synthetic", "config": workload_config(args, world), "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_per_step": int(launches) // max(args.steps, 1),
-                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "inference": inference,
-                "nodes_per_step_rank0": int(train_host[0]["x"].shape[0]),
-                "host_enqueue_ms_per_step": round(host_ms, 3)}
-        _emit(line)
+    if args.workload == "train512":
+        run_train512(args, dev, world, rank, local)
+    elif args.workload == "infer1024":
+        from graphnet_b200 import ops
+        ops.set_precision(args.precision)
+        pk = full_peaks(dev)
+        trainer = Trainer(dev, world)
+        flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+        inf = run_inference(args, trainer, dev, world, rank, flush, pk)
+        if rank == 0:
+            _emit({"metric": "dynedge_inference_events_per_sec", "value": inf["value"], "unit": UNIT, "n_gpus": world,
+                   "steps": args.steps, "warmup": args.warmup, "ms_per_step": inf["ms_per_step"], "higher_is_better": True,
+                   "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+                   "config": {"workload": inf["workload"]}, "e2e": inf.get("e2e"), "roofline": inf.get("roofline"),
+                   "kernels": inf.get("kernels"), "alt_precision": inf.get("alt_precision")})
+    else:
+        import bench_workloads
+        bench_workloads.run(args, dev, world, rank)
     if world > 1:
         dist.destroy_process_group()
 

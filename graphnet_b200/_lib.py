@@ -34,7 +34,7 @@ SIGNATURES: Dict[str, list] = {
     "gnb_knn_set_variant": [_i32],
     "gnb_standardize": [_p, _i64, _i64, _i32, _p, _p, _p, _p, _i64, _p],
     "gnb_ptr_to_batch": [_p, _i64, _i64, _p, _p],
-    "gnb_adam_flat": [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _i32, _p],
+    "gnb_adam_flat": [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _i32, _p],
     "gnb_task_heads_fwd": [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p],
     "gnb_task_heads_bwd": [_p, _i64, _i32, _p, _p, _p, _p, _i64, _p, _i64, _p, _p, _p, _p, _p],
     "gnb_linear_set_profile_buffer": [_p],
@@ -84,6 +84,7 @@ SIGNATURES.update({
     "gnb_dynedge_layout": [_p, _i64, _i64, _i32, _i32, _p],
     "gnb_dynedge_forward": [_p, _p, _p, _i64, _p, _p, _p, _p, _i32, _p, _i64, _i64, _p, _i64, _p, _i32, _p],
     "gnb_dynedge_backward": [_p, _p, _p, _p, _p, _i32, _i64, _i64, _p, _i64, _p, _p],
+    "gnb_dynedge_set_backward_event": [_p, _i32],
 })
 RESTYPES = {"gnb_dynedge_workspace_bytes": ctypes.c_int64, "gnb_launch_count": ctypes.c_int64}
 

@@ -75,6 +75,16 @@ struct gnb_dynedge_config {
 };
 
 extern "C" __attribute__((visibility("default"))) long long gnb_launch_counter = 0;
+// Optional marker inside the backward pass (multi-GPU overlap): once the backward of conv layer `g_bwd_event_layer` has been
+// enqueued, the gradients of that layer, of the post-processing and of the read-out are final -- the event lets a side
+// stream start their all-reduce while the earlier layers' backward still runs.
+static cudaEvent_t g_bwd_event = nullptr;
+static int g_bwd_event_layer = -1;
+GNB_EXPORT int gnb_dynedge_set_backward_event(void* event, int32_t after_conv_layer) {
+    g_bwd_event = (cudaEvent_t)event;
+    g_bwd_event_layer = event != nullptr ? after_conv_layer : -1;
+    return GNB_OK;
+}
 GNB_EXPORT int64_t gnb_launch_count(void) { return (int64_t)gnb_launch_counter; }
 
 namespace {
@@ -643,6 +653,7 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
         EXL();
         if (l > 0)   // gradient into the previous layer's output: accumulate onto the post-processing part
             EX(e.lin_bwd_data(dzq, 2 * b.hid, b.wcat, b.kld, 0, b.cin_ld, 2 * b.hid, p.gnode[l], b.cin_ld, n, true, p.wt, p.dh_big));
+        if (g_bwd_event != nullptr && l == g_bwd_event_layer) GNB_CHECK(cudaEventRecord(g_bwd_event, e.st));
     }
     return GNB_OK;
 }

@@ -459,10 +459,14 @@ constexpr uint32_t PL_BAR_BYTES = 512;                // barrier block behind th
 // kernels (W = W_hi + W_lo, both tf32-exact, two tensor maps), the activation operand arrives as plain fp32 and is split
 // IN SHARED MEMORY by two extra warps (10, 11): X tile -> X_hi = rna_tf32(X) in place, X_lo = X - X_hi (exact) into a
 // fourth tile of the stage. Per 8-wide K step the issuer queues three MMAs: W_hi X_hi + W_lo X_hi + W_hi X_lo (the
-// W_lo X_lo term is below 2^-22 relative). Stage = {W_hi | W_lo | X | X_lo} = 64 KiB, 3 stages. Barriers of a stage:
-// full[s] (leader) collects the weight tiles of both CTAs, xfull[s] (LOCAL to each CTA: its splitter warps cannot wait on
-// a remote barrier) the CTA's own activation half, sfull[s] (leader, count 2) the "split done" arrival of each CTA.
-constexpr int PL_SPLIT_THREADS = 384, PL_SPLIT_STAGES = 3;
+// W_lo X_lo term is below 2^-22 relative). TMA stage = {W_hi | W_lo | X} = 48 KiB, 4 stages (the depth that covers the
+// L2 latency); X_lo lives in its own ring of 2 x 16 KiB (one slot per splitter warp: it is produced locally, a few hundred
+// cycles before its MMAs, so it needs no latency-covering depth -- with X_lo inside the stages only 3 stages fit and the
+// aggregating launch ran at 624 us against a 370 us tensor floor). Barriers of a stage: full[s] (leader) collects the weight
+// tiles of both CTAs, xfull[s] (LOCAL to each CTA: its splitter warps cannot wait on a remote barrier) the CTA's own
+// activation half, sfull[s] (leader, count 2) the "split done" arrival of each CTA; lo_empty[j] (local, multicast commit)
+// returns X_lo slot j to its splitter warp.
+constexpr int PL_SPLIT_THREADS = 384, PL_SPLIT_STAGES = 4, PL_SPLIT_LO_SLOTS = 2;
 
 template <bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SPLIT ? PL_SPLIT_THREADS : PL_THREADS, 1)
@@ -476,10 +480,12 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     int total_kb = 0;
     for (int p = 0; p < parts.nparts; ++p) total_kb += parts.kblocks[p];
     const int nstages = pc.nstages;
-    const uint32_t stage_bytes = SPLIT ? 4 * TC_TILE_BYTES : (pc.resident ? TC_TILE_BYTES : 2 * TC_TILE_BYTES);
+    const uint32_t stage_bytes = SPLIT ? 3 * TC_TILE_BYTES : (pc.resident ? TC_TILE_BYTES : 2 * TC_TILE_BYTES);
     uint8_t* s_a = smem;                                                     // resident weights (resident mode)
     uint8_t* ring = smem + ((pc.resident && !SPLIT) ? (uint32_t)total_kb * TC_TILE_BYTES : 0u);
-    uint64_t* full = reinterpret_cast<uint64_t*>(ring + nstages * stage_bytes);
+    uint8_t* lo_ring = ring + nstages * stage_bytes;                         // SPLIT: [PL_SPLIT_LO_SLOTS] x 16 KiB of X_lo
+    uint8_t* bar_base = lo_ring + (SPLIT ? PL_SPLIT_LO_SLOTS * TC_TILE_BYTES : 0u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(bar_base);
     uint64_t* empty = full + PL_MAX_STAGES;
     uint64_t* tmem_full = empty + PL_MAX_STAGES;      // [2]
     uint64_t* tmem_empty = tmem_full + 2;         // [2] (leader's copy is the one waited on)
@@ -488,8 +494,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     uint64_t* a_full = meta_empty + 2;            // [1] resident weights landed (leader's copy is waited on)
     uint64_t* xfull = a_full + 1;                 // [PL_MAX_STAGES] SPLIT: own activation half landed (local)
     uint64_t* sfull = xfull + PL_MAX_STAGES;      // [PL_MAX_STAGES] SPLIT: both CTAs split their half (leader's copy)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfull + PL_MAX_STAGES);
-    uint8_t* meta = ring + nstages * stage_bytes + PL_BAR_BYTES;  // [2 buffers][2 sub-tiles] x pc.meta_stride
+    uint64_t* lo_empty = sfull + PL_MAX_STAGES;   // [PL_SPLIT_LO_SLOTS] SPLIT: the MMAs reading X_lo slot j completed (local)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lo_empty + PL_SPLIT_LO_SLOTS);
+    uint8_t* meta = bar_base + PL_BAR_BYTES;      // [2 buffers][2 sub-tiles] x pc.meta_stride
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = tc::cluster_ctarank();
@@ -512,6 +519,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                 tc::mbar_init(&xfull[s], 1); tc::mbar_init(&sfull[s], 2);
             }
             tc::mbar_init(a_full, 1);
+            for (int j = 0; j < PL_SPLIT_LO_SLOTS; ++j) tc::mbar_init(&lo_empty[j], 1);
             for (int b = 0; b < 2; ++b) {
                 tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], 16);
                 tc::mbar_init(&meta_full[b], 1); tc::mbar_init(&meta_empty[b], 8);
@@ -624,7 +632,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                     if (SPLIT) {
                         const uint64_t ahi = tc::umma_desc_sw128_kmajor(st), alo = tc::umma_desc_sw128_kmajor(st + TC_TILE_BYTES);
                         const uint64_t bhi = tc::umma_desc_sw128_kmajor(st + 2 * TC_TILE_BYTES);
-                        const uint64_t blo = tc::umma_desc_sw128_kmajor(st + 3 * TC_TILE_BYTES);
+                        const uint64_t blo = tc::umma_desc_sw128_kmajor(tc::smem_u32(lo_ring + (it & 1u) * TC_TILE_BYTES));
                         if (tc::elect_one()) {
                             if (!(agg.dbg & 2)) {
 #pragma unroll
@@ -635,6 +643,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                                 }
                             }
                             tc::umma_commit_2cta(&empty[s], 3);
+                            tc::umma_commit_2cta(&lo_empty[it & 1u], 3);
                         }
                         __syncwarp();
                         continue;
@@ -664,7 +673,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                 if ((int)(it & 1u) != warp - 10) continue;
                 const uint32_t s = it % (uint32_t)nstages, ph = (it / (uint32_t)nstages) & 1;
                 tc::mbar_wait<20>(&xfull[s], ph);
+                tc::mbar_wait<20>(&lo_empty[warp - 10], ((it >> 1) & 1u) ^ 1u);     // this warp's X_lo slot: MMAs of its previous use done
                 const uint32_t xa = tc::smem_u32(ring + s * stage_bytes + 2 * TC_TILE_BYTES) + (uint32_t)lane * 16u;
+                const uint32_t la = tc::smem_u32(lo_ring + (uint32_t)(warp - 10) * TC_TILE_BYTES) + (uint32_t)lane * 16u;
 #pragma unroll 1
                 for (int i0 = 0; i0 < (int)(TC_TILE_BYTES / 512); i0 += 8) {
                     uint32_t v[8][4];
@@ -682,12 +693,15 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                         }
                         const uint32_t a = xa + 512u * (uint32_t)(i0 + i);
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(hi[3]) : "memory");
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + TC_TILE_BYTES), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(lo[3]) : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(la + 512u * (uint32_t)(i0 + i)), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(lo[3]) : "memory");
                     }
                 }
-                tc::fence_proxy_async();            // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                // generic-proxy writes -> visible to the tensor core's async-proxy reads. The notification itself is relaxed: a
+                // cluster-scope release costs ~1300 cycles (tc_common.cuh) on the TMA -> split -> MMA chain of every stage, and
+                // every lane's stores are complete once its proxy fence retires, before lane 0 signals
+                tc::fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive_cluster(&sfull[s], 0);
+                if (lane == 0) tc::mbar_arrive_cluster_relaxed(&sfull[s], 0);
                 __syncwarp();
             }
         }
@@ -1161,7 +1175,7 @@ int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi
         if (split) {
             pc.resident = 0;
             pc.nstages = PL_SPLIT_STAGES;
-            const uint32_t smem_split = fixed + PL_SPLIT_STAGES * 4 * TC_TILE_BYTES;
+            const uint32_t smem_split = fixed + (PL_SPLIT_STAGES * 3 + PL_SPLIT_LO_SLOTS) * TC_TILE_BYTES;
             gemm_tc_pair_kernel<true><<<grid, PL_SPLIT_THREADS, smem_split, stream>>>(tw, *twlo, tx, pi, bias, y, ldy, rows, n_out,
                                                                                       act, round_out, tiles, agg, sc, gs, pc);
             GNB_RETURN_LAUNCH();

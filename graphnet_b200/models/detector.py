@@ -63,6 +63,22 @@ class IceCube86(Detector):
         }
 
 
+class ORCA150SuperDense(Detector):
+    """Prometheus ORCA150SuperDense: xy/100, (z+350)/100, t/1.05e4 (reference detector/prometheus.py:11-39)."""
+
+    def affine_map(self) -> Dict[str, Tuple[int, float, float]]:
+        return {"sensor_pos_x": (STD_AFFINE, 0.0, 100.0), "sensor_pos_y": (STD_AFFINE, 0.0, 100.0),
+                "sensor_pos_z": (STD_AFFINE, -350.0, 100.0), "t": (STD_AFFINE, 0.0, 1.05e04)}
+
+    def feature_map(self) -> Dict[str, Callable]:
+        return {"sensor_pos_x": lambda v: v / 100, "sensor_pos_y": lambda v: v / 100,
+                "sensor_pos_z": lambda v: (v + 350) / 100, "t": lambda v: v / 1.05e04}
+
+
+class Prometheus(ORCA150SuperDense):
+    """Reference to ORCA150SuperDense (detector/prometheus.py:365-366): the detector of BASELINE configs[0]."""
+
+
 class IdentityDetector(Detector):
     """No standardisation at all (inputs are already standardised; not a reference class)."""
 

@@ -21,8 +21,20 @@ from graphnet_b200.models.model import Model
 class GraphDefinition(Model):
     def __init__(self, detector, node_definition=None, edge_definition=None,
                  input_feature_names: Optional[List[str]] = None, dtype: Optional[torch.dtype] = torch.float,
-                 perturbation_dict: Optional[Dict[str, float]] = None, seed: Any = None, **kwargs: Any):
+                 perturbation_dict: Optional[Dict[str, float]] = None, seed: Any = None,
+                 add_inactive_sensors: bool = False, sensor_mask: Optional[List[int]] = None,
+                 string_mask: Optional[List[int]] = None, sort_by: Optional[str] = None, repeat_labels: bool = False,
+                 **kwargs: Any):
         super().__init__()
+        # Reference options that belong to the dataloader side of the graph definition (graph_definition.py:33-37,
+        # 184-207) and are NOT implemented here: refuse them instead of silently building a different graph.
+        dropped = {"add_inactive_sensors": add_inactive_sensors, "sensor_mask": sensor_mask, "string_mask": string_mask,
+                   "sort_by": sort_by, "repeat_labels": repeat_labels}
+        used = [k for k, v in dropped.items() if v not in (None, False)]
+        if used:
+            raise NotImplementedError(
+                f"graphnet_b200.GraphDefinition does not implement {used} (outside the DynEdge hot path); "
+                "apply them in the dataloader before the graph definition")
         from graphnet_b200.models.graphs.nodes import NodesAsPulses
         self._detector = detector
         self._node_definition = node_definition or NodesAsPulses()

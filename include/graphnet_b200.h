@@ -250,6 +250,11 @@ int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* const* param
 int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const* grads, const int64_t* ptr, const int32_t* nbr0,
                          const int32_t* deg0, int32_t w0, int64_t n, int64_t nseg, void* workspace,
                          int64_t workspace_bytes, const float* gout, void* stream);
+/* Multi-GPU overlap hook: `event` (a cudaEvent_t, NULL to clear) is recorded on the backward's stream right after the
+ * backward of conv layer `after_conv_layer` has been enqueued; from then on the gradients of that layer, of every later conv
+ * layer, of the post-processing and of the read-out are final, so their slice of the flat gradient buffer can be all-reduced
+ * on a side stream while the earlier layers' backward runs (DDP's bucketed overlap, easy_model.py:90-110). Process-wide. */
+int gnb_dynedge_set_backward_event(void* event, int32_t after_conv_layer);
 
 /* Device-side graph definition (raw pulses -> DynEdge input). gnb_standardize replaces Detector._standardize
  * (models/detector/detector.py:63-77; IceCube86 table at detector/icecube.py:21-48): out[r, c] = x (kind 0),
@@ -261,9 +266,10 @@ int gnb_ptr_to_batch(const int64_t* ptr, int64_t nseg, int64_t n, int64_t* batch
 /* Adam step over one flat fp32 parameter buffer (torch.optim.Adam semantics as configured by the reference:
  * easy_model.py:215-219, examples/04_training/01_train_dynedge.py:128-129): g' = g + weight_decay p, m += (1-beta1)(g'-m),
  * v = beta2 v + (1-beta2) g'^2, p -= step_size m / (sqrt(v) inv_sqrt_bc2 + eps) with step_size = lr / (1 - beta1^t) and
- * inv_sqrt_bc2 = 1 / sqrt(1 - beta2^t) computed by the caller. p, g, m, v: [n], 16-byte aligned; zero_grad != 0 leaves g = 0. */
+ * inv_sqrt_bc2 = 1 / sqrt(1 - beta2^t) computed by the caller. p, g, m, v: [n], 16-byte aligned; zero_grad != 0 leaves g = 0.
+ * g is multiplied by grad_scale on the way in (1 / world_size = the mean of DDP, easy_model.py:90-110, after a SUM all-reduce). */
 int gnb_adam_flat(float* p, float* g, float* m, float* v, int64_t n, float step_size, float beta1, float beta2, float eps,
-                  float inv_sqrt_bc2, float weight_decay, int32_t zero_grad, void* stream);
+                  float inv_sqrt_bc2, float weight_decay, float grad_scale, int32_t zero_grad, void* stream);
 /* ---- task heads + losses (the O(B) step right after the path) -------------------------------------
  * EnergyReconstruction (task/reconstruction.py:101-112) + LogCoshLoss on log10 (training/loss_functions.py:93-112) and
  * DirectionReconstructionWithKappa (reconstruction.py:49-70) + VonMisesFisher3DLoss (loss_functions.py:281-353, 424-447;

@@ -1,0 +1,81 @@
+"""BASELINE configs[0]: the reference's own example data -- `data/examples/sqlite/prometheus/prometheus-events.db`, 50 events,
+1 872 pulses (19 % duplicate-xyz pulses, 8 events with fewer than 9 pulses: the k + 1 duplicate quirk and the short-event
+cases of the kNN contract), F = 4, batch 16 (examples/04_training/01_train_dynedge.py:85,113-142,195,223) -- through
+KNNGraph(Prometheus) -> collate -> device KNNEdges -> DynEdge(4) forward + backward against the oracle, in every precision mode.
+The pulse table travels as tests/golden/prometheus_events.npz (written by tests/golden/make_prometheus_fixture.py from the
+reference's data base and its own, unmodified detector/prometheus.py)."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN_DIR, namespace, rel_err
+from oracle.dynedge_oracle import DynEdgeRef, batch_to_ptr, knn_graph_ref
+
+pytestmark = pytest.mark.gpu
+GRAD_TOL = {"fp32": 1e-3, "tf32x3": 1e-3, "tf32": 3e-3}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "tf32"])
+def test_prometheus_example_epoch_vs_oracle(built_library, precision):
+    import sys
+    sys.path.insert(0, os.path.dirname(GOLDEN_DIR[:-len("/golden")]))
+    import bench_workloads
+    from graphnet_b200 import ops
+    from graphnet_b200.models.gnn import DynEdge
+    from graphnet_b200.tasks import EnergyReconstruction
+    fx = np.load(os.path.join(GOLDEN_DIR, "prometheus_events.npz"))
+    batches, definition = bench_workloads.prometheus_batches(16)
+    assert [int(b.n_pulses.numel()) for b in batches] == [16, 16, 16, 2] and definition.nb_outputs == 4
+    # the host-side detector reproduces the reference's own standardisation bit for bit
+    assert torch.equal(torch.cat([b.x for b in batches]), torch.from_numpy(fx["standardized"]))
+    kwargs = dict(global_pooling_schemes=["min", "max", "mean", "sum"])
+    torch.manual_seed(0)
+    ref = DynEdgeRef(4, **kwargs)
+    head_ref = EnergyReconstruction(128)
+    model = DynEdge(4, **kwargs)
+    model.load_state_dict(ref.state_dict())
+    model = model.cuda()
+    head = EnergyReconstruction(128)
+    head.load_state_dict(head_ref.state_dict())
+    head = head.cuda()
+    model._debug_record = True
+    ref, head_ref = ref.double(), head_ref.double()
+    old = ops.PRECISION
+    ops.set_precision(precision)
+    try:
+        worst_out, worst_grad = 0.0, 0.0
+        for hb in batches:
+            assert hb.edge_index is None                                    # edges deferred on the CPU (dataloader workers)
+            dev = definition.build_edges(hb.to("cuda"))
+            x, batch, n_pulses = hb.x, hb.batch, hb.n_pulses
+            ptr = batch_to_ptr(batch)
+            ei0 = knn_graph_ref(x[:, :3], 8, ptr=ptr)
+            assert torch.equal(dev.edge_index.cpu(), ei0)                   # initial graph: bit-exact (duplicates, short events)
+            model.zero_grad(set_to_none=True)
+            head.zero_grad(set_to_none=True)
+            pred = head(model(dev))
+            loss = head.compute_loss(pred, hb.total_energy.float().cuda())
+            loss.backward()
+            forced = [None]
+            for li in range(1, 4):                                          # all four graphs torch.equal
+                feats = model._debug["skips"][li].detach().cpu()
+                ei_k = model._debug["graphs"][li].edge_index().cpu()
+                assert torch.equal(ei_k, knn_graph_ref(feats[:, :3], 8, ptr=ptr)), f"latent graph {li}"
+                forced.append(ei_k)
+            for p in list(ref.parameters()) + list(head_ref.parameters()):
+                p.grad = None
+            pred_ref = head_ref(ref(namespace(x=x.double(), edge_index=ei0, batch=batch, n_pulses=n_pulses), forced_graphs=forced))
+            loss_ref = head_ref.compute_loss(pred_ref, hb.total_energy.double())
+            loss_ref.backward()
+            worst_out = max(worst_out, rel_err(pred, pred_ref), rel_err(loss, loss_ref))
+            gerr = {k: rel_err(p.grad, q.grad) for (k, p), (_, q) in zip(list(model.named_parameters()) + list(head.named_parameters()),
+                                                                        list(ref.named_parameters()) + list(head_ref.named_parameters()))}
+            worst_grad = max(worst_grad, max(gerr.values()))
+        print(f"prometheus50 {precision}: predictions / loss {worst_out:.2e}, max grad {worst_grad:.2e}")
+        assert worst_out < 1e-3
+        assert worst_grad < GRAD_TOL[precision]
+    finally:
+        ops.set_precision(old)

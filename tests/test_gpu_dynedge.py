@@ -11,6 +11,22 @@ from oracle.dynedge_oracle import DynEdgeRef, batch_to_ptr, knn_graph_ref
 
 pytestmark = pytest.mark.gpu
 REL_TOL = 1e-3
+# (precision, executor route): the golden / default-config / config-#4 tests run on EVERY route bench.py can time.
+# Stated gradient tolerance per precision (outputs: 1e-3 everywhere): fp32 and tf32x3 meet north_star's rel 1e-3; the
+# single-pass tf32 mode is the stated looser mode (3e-3; measured 2.3e-3: its forward rounding flips ReLU decisions).
+MODES = [("fp32", True), ("tf32", True), ("tf32x3", True), ("tf32x3", False)]
+GRAD_TOL = {"fp32": 1e-3, "tf32x3": 1e-3, "tf32": 3e-3}
+
+
+@pytest.fixture(params=MODES, ids=lambda m: f"{m[0]}-{'executor' if m[1] else 'per_operator'}")
+def mode(request, built_library):
+    from graphnet_b200 import ops
+    old_p, old_e = ops.PRECISION, ops.USE_EXECUTOR
+    ops.set_precision(request.param[0])
+    ops.USE_EXECUTOR = request.param[1]
+    yield request.param[0]
+    ops.set_precision(old_p)
+    ops.USE_EXECUTOR = old_e
 
 
 def _run_kernel_model(fx_kwargs, nb_inputs, state_dict, x, batch, n_pulses, edge_index=None, k=8):
@@ -31,7 +47,7 @@ def _run_kernel_model(fx_kwargs, nb_inputs, state_dict, x, batch, n_pulses, edge
 
 
 @pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1][:-3])
-def test_dynedge_matches_reference_golden(built_library, path):
+def test_dynedge_matches_reference_golden(mode, path):
     fx = load_golden(path)
     ref = DynEdgeRef(fx["nb_inputs"], **fx["kwargs"])
     sd = fx.get("state_dict") or seeded_state_dict(ref, fx["weight_seed"])
@@ -47,19 +63,33 @@ def test_dynedge_matches_reference_golden(built_library, path):
     for li in range(1, len(model._debug["graphs"])):
         feats = model._debug["skips"][li].detach().cpu()
         assert torch.equal(model._debug["graphs"][li].edge_index().cpu(), knn_graph_ref(feats[:, cols], k, ptr=ptr))
-    assert rel_err(y, fx["out_f64"]) < REL_TOL
-    for key, p in model.named_parameters():
-        if key not in fx["grads_f64"]:
-            continue
-        g = fx["grads_f64"][key]
-        if g.shape == p.grad.shape:
-            assert rel_err(p.grad, g) < REL_TOL, key
-        else:
-            mine = torch.stack([p.grad.norm(), p.grad.abs().max()]).cpu()
-            assert rel_err(mine, g[:2]) < REL_TOL, key
+    if mode == "fp32":      # the golden run's own numbers (its latent graphs are those of fp32-accurate features)
+        assert rel_err(y, fx["out_f64"]) < REL_TOL
+        for key, p in model.named_parameters():
+            if key not in fx["grads_f64"]:
+                continue
+            g = fx["grads_f64"][key]
+            if g.shape == p.grad.shape:
+                assert rel_err(p.grad, g) < REL_TOL, key
+            else:
+                mine = torch.stack([p.grad.norm(), p.grad.abs().max()]).cpu()
+                assert rel_err(mine, g[:2]) < REL_TOL, key
+        return
+    # tensor-core modes: a latent near-tie may legitimately resolve differently from the golden run, so the oracle (pinned
+    # bit for bit on these golden files by tests/test_oracle_golden.py) is run in fp64 on the kernel's own graphs
+    ref = ref.double()
+    ref.load_state_dict({k_: v.double() for k_, v in sd.items()})
+    forced = [None] + [model._debug["graphs"][li].edge_index().cpu() for li in range(1, len(model._debug["graphs"]))]
+    y_ref = ref(namespace(x=fx["x"].double(), edge_index=fx["edge_index"], batch=fx["batch"], n_pulses=fx["n_pulses"]),
+                forced_graphs=forced)
+    (y_ref * w.cpu().double()).sum().backward()
+    assert rel_err(y, y_ref) < REL_TOL
+    gerr = {key: rel_err(p.grad, q.grad) for (key, p), (_, q) in zip(model.named_parameters(), ref.named_parameters())}
+    print(f"{mode} golden {path.split('/')[-1]}: out {rel_err(y, y_ref):.2e} max grad {max(gerr.values()):.2e}")
+    assert max(gerr.values()) < GRAD_TOL[mode], gerr
 
 
-def test_dynedge_default_config_vs_oracle_teacher_forced(built_library):
+def test_dynedge_default_config_vs_oracle_teacher_forced(mode):
     """BASELINE config: F=7, k=8, default layer sizes, 4 poolings; 24 synthetic IceCube-like events."""
     from graphnet_b200.synthetic import make_batch
     raw = make_batch(24, seed=5, n_max=400)
@@ -78,15 +108,19 @@ def test_dynedge_default_config_vs_oracle_teacher_forced(built_library):
         ei_k = model._debug["graphs"][li].edge_index().cpu()
         assert torch.equal(ei_k, knn_graph_ref(feats[:, :3], 8, ptr=ptr)), f"latent graph {li}"
         forced.append(ei_k)
-    d_ref = namespace(x=x, edge_index=ei0, batch=batch, n_pulses=n_pulses)
+    ref = ref.double()
+    d_ref = namespace(x=x.double(), edge_index=ei0, batch=batch, n_pulses=n_pulses)
     y_ref, inter = ref(d_ref, forced_graphs=forced, return_intermediates=True)
     y_ref.square().sum().backward()
     assert rel_err(model._debug["global_variables"], inter["global_variables"]) < 1e-5
+    # single-pass tf32 keeps the round-1 statement for the deep latent features (1.9e-3 measured on skip 4)
+    skip_tol = 2.5e-3 if mode == "tf32" else REL_TOL
     for li in range(5):
-        assert rel_err(model._debug["skips"][li], inter["skips"][li]) < REL_TOL, f"skip {li}"
+        assert rel_err(model._debug["skips"][li], inter["skips"][li]) < skip_tol, f"skip {li}"
     assert rel_err(y, y_ref) < REL_TOL
-    for (key, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
-        assert rel_err(p.grad, q.grad) < REL_TOL, key
+    gerr = {key: rel_err(p.grad, q.grad) for (key, p), (_, q) in zip(model.named_parameters(), ref.named_parameters())}
+    print(f"{mode} default config: out {rel_err(y, y_ref):.2e} max grad {max(gerr.values()):.2e}")
+    assert max(gerr.values()) < GRAD_TOL[mode], gerr
 
 
 def test_dynedge_accepts_foreign_edge_index_and_pulse_level_output(built_library):
@@ -111,7 +145,7 @@ def test_smoke_entry(built_library):
     entry.smoke()
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "tf32x3"])
 def test_executor_matches_per_operator_route(built_library, precision):
     """The native step executor (one C call) and the per-operator autograd route run the same kernels: outputs and
     all gradients must agree to fp32 round-off (atomics change summation order only)."""
@@ -211,7 +245,7 @@ def test_high_multiplicity_event_and_layer_sweep(built_library):
             assert rel_err(out, ref_out) < 1e-5, (k, width)
 
 
-def test_config4_percentile_cluster_nodes_end_to_end(built_library):
+def test_config4_percentile_cluster_nodes_end_to_end(mode):
     """BASELINE config #4: `PercentileClusters` nodes (F = 3 + 4*3 + 1 = 16) built per event on the host like the reference's
     dataloader workers, collated, edges built on the device batch, DynEdge with [min, max, mean, sum] pooling, forward and
     backward against the oracle (fp32 mode, rel 1e-3; latent graphs teacher-forced)."""
@@ -251,8 +285,10 @@ def test_config4_percentile_cluster_nodes_end_to_end(built_library):
         ei_k = model._debug["graphs"][li].edge_index().cpu()
         assert torch.equal(ei_k, knn_graph_ref(feats[:, :3], 8, ptr=ptr)), f"latent graph {li}"
         forced.append(ei_k)
-    y_ref = ref(namespace(x=x, edge_index=ei0, batch=batch, n_pulses=n_pulses), forced_graphs=forced)
+    ref = ref.double()
+    y_ref = ref(namespace(x=x.double(), edge_index=ei0, batch=batch, n_pulses=n_pulses), forced_graphs=forced)
     y_ref.square().sum().backward()
     assert rel_err(y, y_ref) < REL_TOL
-    for (key, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
-        assert rel_err(p.grad, q.grad) < REL_TOL, key
+    gerr = {key: rel_err(p.grad, q.grad) for (key, p), (_, q) in zip(model.named_parameters(), ref.named_parameters())}
+    print(f"{mode} config #4: out {rel_err(y, y_ref):.2e} max grad {max(gerr.values()):.2e}")
+    assert max(gerr.values()) < GRAD_TOL[mode], gerr

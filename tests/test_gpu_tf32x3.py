@@ -2,7 +2,8 @@
 
 The reference computes in fp32 throughout (graphs/graphs.py:21, dynedge.py:200-203); north_star asks for rel 1e-3 on
 predictions AND gradients. Stated tolerances of this mode (tests/studies/split_precision_study.py predicts 5e-7 / 6e-4):
-  * a single split GEMM against fp64:                 rel 5e-6
+  * a single split GEMM against fp64:                 rel 1e-5 (measured 1.4e-6 at K = 256 ... 6e-6 at K = 1056: the
+                                                      tensor core's fp32 accumulation, not the operand split)
   * DynEdge outputs against the oracle:               rel 2e-5
   * all 22 parameter gradients against the oracle:    rel 1e-3
 Integer operands have an all-zero lo part, so the split kernels must also be BIT-EXACT there (pins the 4-tile stage
@@ -59,7 +60,7 @@ def test_x3_linear_bit_exact_on_integers(x3_mode, rows, n_out, widths):
 @pytest.mark.parametrize("rows,n_out,widths", [(300, 336, [256]), (515, 256, [336]), (777, 336, [32, 256, 256, 256, 256]),
                                                (4099, 128, [1024]), (80000, 672, [256])])
 def test_x3_linear_is_fp32_grade(x3_mode, rows, n_out, widths):
-    """Real-valued operands against fp64: 5e-6 (a single-pass tf32 GEMM sits at ~3e-4 on the same data, so a kernel that
+    """Real-valued operands against fp64: 1e-5 (a single-pass tf32 GEMM sits at ~3e-4 on the same data, so a kernel that
     dropped one of the two lo products cannot pass). Backward GEMMs stay single-pass: 2e-3 per GEMM as in tf32 mode."""
     ops = x3_mode
     torch.manual_seed(rows)
@@ -76,7 +77,7 @@ def test_x3_linear_is_fp32_grade(x3_mode, rows, n_out, widths):
     (out * gout.cuda()).sum().backward()
     err = rel_err(out, ref)
     print(f"tf32x3 linear {rows}x{k}->{n_out}: rel {err:.2e}")
-    assert err < 5e-6
+    assert err < 1e-5
     dz = gout.double() * (out.detach().cpu() > 0)
     gx = torch.cat([p.grad for p in xparts], dim=1)
     assert rel_err(gx, dz @ w.double()) < 2e-3
@@ -150,7 +151,7 @@ def test_x3_edge_linear_agg_is_fp32_grade(x3_mode, k, n_out, nev):
     y, y_ref, _, _, _, _ = _agg_case(ops, k, n_out, sizes, integer=False)
     err = rel_err(y, y_ref)
     print(f"tf32x3 aggregating GEMM k={k} n_out={n_out} nodes={y.shape[0]}: rel {err:.2e}")
-    assert err < 5e-6
+    assert err < 1e-5
 
 
 @pytest.mark.parametrize("executor", [True, False], ids=["executor", "per_operator"])
@@ -223,3 +224,34 @@ def test_x3_inference_predictions(x3_mode):
     err = rel_err(y, y_ref)
     print("tf32x3 inference rel error:", f"{err:.2e}")
     assert err < 2e-5
+
+
+def test_tensor_core_tf32_operand_conversion_probe(built_library):
+    """What does tcgen05 kind::tf32 do with the 13 low mantissa bits of an fp32 operand? x W^T with W = identity reads the
+    converted operand back: it must equal either the truncated or the rna-rounded value (the kernels never rely on which:
+    single-pass operands are pre-rounded, the splitter writes tf32-exact hi parts). Printed for DESIGN.md."""
+    from graphnet_b200 import ops
+    old = ops.PRECISION
+    ops.set_precision("tf32")
+    try:
+        rows, k = 256, 32
+        g = torch.Generator().manual_seed(1)
+        bits = torch.randint(0x3F800000, 0x40000000, (rows, k), generator=g, dtype=torch.int32)     # [1, 2) with random low bits
+        x = bits.view(torch.float32)
+        xc = x.cuda()
+        w = torch.eye(k, device="cuda")
+        y = torch.empty(rows, k, device="cuda")
+        xs = (ctypes.c_void_p * 1)(xc.data_ptr())
+        lds = (ctypes.c_int64 * 1)(k)
+        ks = (ctypes.c_int32 * 1)(k)
+        ops._call("gnb_linear_fwd_tf32", xs, lds, ks, 1, ops._ptr(w), k, ops._ptr(None), ops._ptr(y), k, rows, k, 0, 0, ops._stream())
+        torch.cuda.synchronize()
+        got = y.cpu().numpy().view(np.uint32)
+        b = bits.numpy().view(np.uint32)
+        trunc = b & np.uint32(0xFFFFE000)
+        rna = (b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)
+        is_trunc, is_rna = bool(np.array_equal(got, trunc)), bool(np.array_equal(got, rna))
+        print(f"tcgen05 kind::tf32 operand conversion: truncation={is_trunc} round-to-nearest-away={is_rna}")
+        assert is_trunc or is_rna or bool(np.all((got == trunc) | (got == rna)))
+    finally:
+        ops.set_precision(old)
