@@ -20,8 +20,16 @@ __device__ __forceinline__ float softplus1(float x) {    // torch softplus(beta 
     return x > 20.f ? x : log1pf(expf(x));
 }
 
+// VonMisesFisherLoss.log_cmk (loss_functions.py:307-326) for m = 3: exact below kappa_switch = 100, from there on the
+// approximation -sqrt(4 + k^2) shifted by approx(100) - exact(100) for continuity.
+constexpr float TH_KAPPA_SWITCH = 100.f, TH_LOG_C3_OFFSET = -2.78729248046875f;   // the reference's float32 offset
+__device__ __forceinline__ float log_c3(float k) {
+    if (k >= TH_KAPPA_SWITCH) return -sqrtf(4.f + k * k) - TH_LOG_C3_OFFSET;
+    return logf(k) - TH_LOG_2PI - k - logf(-expm1f(-2.f * k));
+}
 // d/dk log C_3(k) = 1/k - coth(k); series below 0.1 (the closed form cancels catastrophically there)
 __device__ __forceinline__ float dlog_c3(float k) {
+    if (k >= TH_KAPPA_SWITCH) return -k / sqrtf(4.f + k * k);
     if (k < 0.1f) { const float k2 = k * k; return k * (-1.f / 3.f + k2 * (1.f / 45.f - k2 * (2.f / 945.f))); }
     const float e = expf(-2.f * k);
     return 1.f / k - (1.f + e) / (1.f - e);
@@ -63,7 +71,7 @@ task_heads_fwd_kernel(const float* __restrict__ feat, int64_t ldf, int hdim, con
             const float px = kappa * ux, py = kappa * uy, pz = kappa * uz;       // what the loss rebuilds from the prediction
             const float kn = sqrtf(px * px + py * py + pz * pz);
             const float tx = direction[ev * 3], ty = direction[ev * 3 + 1], tz = direction[ev * 3 + 2];
-            const float logc = logf(kn) - TH_LOG_2PI - kn - log1pf(-expf(-2.f * kn));
+            const float logc = log_c3(kn);
             ld = -logc - (px * tx + py * ty + pz * tz);
             const float s = kn > 1e-30f ? -dlog_c3(kn) / kn : 0.f;
             pred_e[ev] = pe;

@@ -4,9 +4,10 @@ after the hot path. Plain torch ops on the device -- listed as a "next" row in S
 Reference: `EnergyReconstruction` (src/graphnet/models/task/reconstruction.py:101-112) with
 `LogCoshLoss` (src/graphnet/training/loss_functions.py:93-112) on log10(energy) as in
 examples/04_training/01_train_dynedge.py:113-124; `DirectionReconstructionWithKappa`
-(reconstruction.py:49-70) with `VonMisesFisher3DLoss` (loss_functions.py:281-353, 424-447). log C_3(kappa)
-is evaluated in closed form (kappa / (4 pi sinh kappa)), which is what the reference's scipy-Bessel
-`LogCMK` computes for m = 3 (tests/training/test_loss_functions.py:81-83) without the host round trip.
+(reconstruction.py:49-70) with `VonMisesFisher3DLoss` (loss_functions.py:281-353, 424-447). Below the reference's
+kappa_switch = 100 log C_3(kappa) is evaluated in closed form (kappa / (4 pi sinh kappa)), which is what the reference's
+scipy-Bessel `LogCMK` computes for m = 3 (tests/training/test_loss_functions.py:81-83) without the host round trip; from
+100 on it follows the reference's shifted approximation (loss_functions.py:307-326).
 """
 
 from __future__ import annotations
@@ -45,10 +46,21 @@ class DirectionReconstructionWithKappa(torch.nn.Module):
         kappa = torch.linalg.vector_norm(z, dim=1) + _eps_like(z)
         return torch.cat([z / kappa.unsqueeze(1), kappa.unsqueeze(1)], dim=1)
 
-    @staticmethod
-    def log_c3(kappa: Tensor) -> Tensor:
-        # log(kappa / (4 pi sinh kappa)) = log k - log(2 pi) - k - log(1 - exp(-2k))
-        return torch.log(kappa) - math.log(2.0 * math.pi) - kappa - torch.log1p(-torch.exp(-2.0 * kappa))
+    # VonMisesFisherLoss.log_cmk (loss_functions.py:307-326): exact form below kappa_switch = 100, the approximation of
+    # arXiv:1812.04616 sec. 8.2 above it, shifted by `offset = approx(100) - exact(100)` for continuity. For m = 3 the
+    # approximation is -sqrt(4 + kappa^2) (its log term has the factor m / 2 - 1.5 = 0).
+    # The reference evaluates the offset on a float32 `kappa_switch` tensor (loss_functions.py:318-323), whatever the dtype
+    # of kappa: -2.78729248046875 (the float64 value would be -2.787291119978647); kept bit for bit.
+    KAPPA_SWITCH = 100.0
+    LOG_C3_OFFSET = -2.78729248046875
+
+    @classmethod
+    def log_c3(cls, kappa: Tensor) -> Tensor:
+        # exact: log(kappa / (4 pi sinh kappa)) = log k - log(2 pi) - k - log(1 - exp(-2k)); -expm1 keeps the last term
+        # accurate for tiny kappa in fp32
+        exact = torch.log(kappa) - math.log(2.0 * math.pi) - kappa - torch.log(-torch.expm1(-2.0 * kappa))
+        approx = -torch.sqrt(4.0 + kappa * kappa) - cls.LOG_C3_OFFSET
+        return torch.where(kappa < cls.KAPPA_SWITCH, exact, approx)
 
     def compute_loss(self, pred: Tensor, direction: Tensor) -> Tensor:
         kappa = pred[:, 3]

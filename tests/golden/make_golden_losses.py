@@ -57,7 +57,18 @@ def main() -> None:
     k = torch.tensor([1e-4, 1e-3, 1e-2, 0.1, 1.0, 3.0, 10.0, 30.0, 100.0], dtype=torch.float64, requires_grad=True)
     c3 = lf.VonMisesFisherLoss.log_cmk_exact(3, k)
     (gk,) = torch.autograd.grad(c3.sum(), k)
-    out = {"logcosh": {"pred_log10": pl.detach(), "true_log10": torch.log10(true_e), "elements": el.detach(),
+    # --- the full log_cmk (exact below kappa_switch = 100, shifted approximation above), through the vMF loss itself
+    kb = torch.tensor([50.0, 99.0, 99.999, 100.0, 100.001, 150.0, 200.0, 1000.0], dtype=torch.float64, requires_grad=True)
+    cb = lf.VonMisesFisherLoss.log_cmk(3, kb)
+    (gkb,) = torch.autograd.grad(cb.sum(), kb)
+    zb = torch.stack([kb.detach(), torch.zeros_like(kb.detach()), torch.zeros_like(kb.detach())], dim=1).requires_grad_(True)
+    kap = torch.linalg.vector_norm(zb, dim=1) + torch.finfo(torch.float64).eps
+    tb = torch.tensor([[0.6, 0.0, 0.8]], dtype=torch.float64).expand(len(kb), 3)
+    evb = vmf(torch.cat([zb / kap.unsqueeze(1), kap.unsqueeze(1)], dim=1), tb, return_elements=True)
+    (gzb,) = torch.autograd.grad(evb.mean(), zb)
+    out = {"log_cmk_switch": {"kappa": kb.detach(), "value": cb.detach(), "grad": gkb, "z": zb.detach(), "target": tb.clone(),
+                              "elements": evb.detach(), "grad_z": gzb},
+           "logcosh": {"pred_log10": pl.detach(), "true_log10": torch.log10(true_e), "elements": el.detach(),
                        "loss": loss.detach(), "grad_pred_log10": gl},
            "vmf3d": {"z": z.detach(), "target": t, "elements": ev.detach(), "loss": lv.detach(), "grad_z": gz},
            "log_c3": {"kappa": k.detach(), "value": c3.detach(), "grad": gk}}

@@ -68,6 +68,8 @@ def test_vmf3d_matches_reference_loss_function():
 def test_log_c3_known_answers():
     """Reference test_von_mises_fisher_exact_m3: log k - k - log(2 pi (1 - exp(-2k))), values and gradients."""
     g = GOLD["log_c3"]
+    below = g["kappa"] < 100.0                 # from kappa_switch = 100 on the reference uses its approximation (next test)
+    g = {key: v[below] for key, v in g.items()}
     k = g["kappa"].clone().requires_grad_(True)
     val = DirectionReconstructionWithKappa.log_c3(k)
     (grad,) = torch.autograd.grad(val.sum(), k)
@@ -79,3 +81,27 @@ def test_log_c3_known_answers():
     assert torch.allclose(val, g["value"], rtol=1e-8, atol=1e-10)
     assert torch.allclose(grad, g["grad"], rtol=1e-6, atol=1e-8)
     assert math.isfinite(float(DirectionReconstructionWithKappa.log_c3(torch.tensor(1e-4))))
+
+
+def test_log_c3_follows_the_reference_kappa_switch():
+    """loss_functions.py:307-326: above kappa_switch = 100 the reference uses the shifted approximation -- values, gradients
+    and the vMF loss itself on predictions with |z| up to 1000 (golden vectors from the reference's own log_cmk)."""
+    g = GOLD["log_cmk_switch"]
+    k = g["kappa"].clone().requires_grad_(True)
+    val = DirectionReconstructionWithKappa.log_c3(k)
+    (grad,) = torch.autograd.grad(val.sum(), k)
+    assert torch.allclose(val, g["value"], rtol=1e-10, atol=1e-9)
+    assert torch.allclose(grad, g["grad"], rtol=1e-7, atol=1e-9)
+    head = _identity_head(DirectionReconstructionWithKappa, 3)
+    z = g["z"].clone().requires_grad_(True)
+    pred = head(z)
+    kap = pred[:, 3]
+    p = kap.unsqueeze(1) * pred[:, :3]
+    el = -DirectionReconstructionWithKappa.log_c3(torch.norm(p, dim=1)) - torch.sum(p * g["target"], dim=1)
+    (gz,) = torch.autograd.grad(el.mean(), z)
+    assert torch.allclose(el, g["elements"], rtol=1e-10, atol=1e-9)
+    assert torch.allclose(gz, g["grad_z"], rtol=1e-7, atol=1e-9)
+    # fp32: -expm1 keeps log(1 - exp(-2k)) finite and accurate for tiny kappa
+    tiny = torch.tensor([1e-6, 1e-5], dtype=torch.float32)
+    ref = (torch.log(tiny.double()) - math.log(2 * math.pi) - tiny.double() - torch.log(-torch.expm1(-2 * tiny.double())))
+    assert torch.allclose(DirectionReconstructionWithKappa.log_c3(tiny).double(), ref, rtol=1e-5)
