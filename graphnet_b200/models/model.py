@@ -46,11 +46,18 @@ class Model(torch.nn.Module, metaclass=_ConfigSaver):
     @classmethod
     def from_config(cls, source: Dict[str, Any], **_: Any) -> "Model":
         """Rebuild from `{class_name, arguments}` (cf. model.py:81-108)."""
+        # the reference's YAML files nest every model as {"ModelConfig": {class_name, arguments}} (configs/models/*.yml,
+        # utilities/config/model_config.py:317-346); both forms are accepted
+        if isinstance(source, dict) and set(source) == {"ModelConfig"}:
+            source = source["ModelConfig"]
         registry = {c.__name__: c for c in _all_subclasses(Model)}
+        if source["class_name"] not in registry:
+            raise KeyError(f"Model.from_config: class {source['class_name']!r} is not part of the DynEdge hot path "
+                           f"(known: {sorted(registry)})")
         klass = registry[source["class_name"]]
         args = {}
         for key, val in source["arguments"].items():
-            if isinstance(val, dict) and "class_name" in val and "arguments" in val:
+            if isinstance(val, dict) and (set(val) == {"ModelConfig"} or ("class_name" in val and "arguments" in val)):
                 val = Model.from_config(val)
             args[key] = val
         return klass(**args)

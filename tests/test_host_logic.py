@@ -179,3 +179,72 @@ def test_library_missing_is_loud(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _lib.load()
+
+
+def test_reference_import_paths_and_yaml_model_config_load_unchanged():
+    """The `graphnet` shim package serves the reference's import paths for the hot path's classes, and the backbone /
+    graph-definition sections of the reference's model configs (configs/models/example_energy_reconstruction_model.yml:1-33,
+    nested `ModelConfig: {class_name, arguments}` as written by utilities/config/model_config.py:317-346) rebuild the same
+    objects -- the round trip of tests/utilities/test_model_config.py:20-42."""
+    import yaml
+    from graphnet.models import Model as RefPathModel
+    from graphnet.models.components.layers import DynEdgeConv as RefPathConv
+    from graphnet.models.detector.icecube import IceCube86 as RefPathIC86
+    from graphnet.models.detector.prometheus import Prometheus as RefPathPrometheus
+    from graphnet.models.gnn import DynEdge as RefPathDynEdge
+    from graphnet.models.gnn.dynedge import DynEdge as RefPathDynEdge2
+    from graphnet.models.graphs import KNNGraph as RefPathKNNGraph
+    from graphnet.models.graphs.edges import KNNEdges as RefPathKNNEdges
+    from graphnet.models.graphs.nodes import NodesAsPulses as RefPathNodes
+    from graphnet_b200.models.components.layers import DynEdgeConv
+    from graphnet_b200.models.detector import Prometheus
+    assert RefPathDynEdge is DynEdge and RefPathDynEdge2 is DynEdge and RefPathConv is DynEdgeConv
+    assert RefPathKNNGraph is KNNGraph and RefPathPrometheus is Prometheus and RefPathIC86 is IceCube86
+    assert RefPathModel is Model and RefPathKNNEdges.__name__ == "KNNEdges" and RefPathNodes.__name__ == "NodesAsPulses"
+    snippet = """
+backbone:
+  ModelConfig:
+    arguments:
+      add_global_variables_after_pooling: false
+      dynedge_layer_sizes: null
+      features_subset: null
+      global_pooling_schemes: [min, max, mean, sum]
+      nb_inputs: 4
+      nb_neighbours: 8
+      post_processing_layer_sizes: null
+      readout_layer_sizes: null
+    class_name: DynEdge
+graph_definition:
+  ModelConfig:
+    arguments:
+      columns: [0, 1, 2]
+      detector:
+        ModelConfig:
+          arguments: {}
+          class_name: Prometheus
+      dtype: null
+      nb_nearest_neighbours: 8
+      node_definition:
+        ModelConfig:
+          arguments: {}
+          class_name: NodesAsPulses
+      input_feature_names: [sensor_pos_x, sensor_pos_y, sensor_pos_z, t]
+    class_name: KNNGraph
+"""
+    cfg = yaml.safe_load(snippet)
+    backbone = RefPathModel.from_config(cfg["backbone"])
+    assert isinstance(backbone, DynEdge) and backbone.nb_inputs == 4 and backbone.nb_outputs == 128
+    assert "_conv_layers.3.nn.2.weight" in backbone.state_dict() and backbone.state_dict()["_readout.0.weight"].shape == (128, 1024)
+    definition = RefPathModel.from_config(cfg["graph_definition"])
+    assert isinstance(definition, KNNGraph) and isinstance(definition._detector, Prometheus) and definition.nb_outputs == 4
+    rebuilt = RefPathModel.from_config(backbone.config)
+    assert repr(rebuilt) == repr(backbone)
+    with pytest.raises(KeyError, match="not part of the DynEdge hot path"):
+        RefPathModel.from_config({"class_name": "StandardModel", "arguments": {}})
+
+
+def test_graph_definition_refuses_reference_options_it_does_not_implement():
+    for kw in ({"add_inactive_sensors": True}, {"sensor_mask": [1, 2]}, {"string_mask": [3]}, {"sort_by": "dom_time"},
+               {"repeat_labels": True}):
+        with pytest.raises(NotImplementedError):
+            KNNGraph(detector=IceCube86(), input_feature_names=FEATURES_ICECUBE86, **kw)
