@@ -173,7 +173,9 @@ def global_variables_ref(x: Tensor, edge_index: Tensor, batch: Tensor,
     means = segment_pool_ref(x, ptr, "mean")
     hs = [homophily_ref(edge_index, x[:, c].detach(), batch, nseg).reshape(-1, 1).to(x.dtype)
           for c in range(4)]
-    logn = torch.log10(n_pulses.to(x.dtype) if not n_pulses.is_floating_point() else n_pulses)
+    # dynedge.py:287 takes log10 of the int32 `n_pulses` tensor itself: torch evaluates that in float32 whatever the dtype of
+    # x (visible only in fp64 runs, at 6e-8)
+    logn = torch.log10(n_pulses.to(torch.float32) if not n_pulses.is_floating_point() else n_pulses)
     return torch.cat([means] + hs + [logn.to(x.dtype).unsqueeze(1)], dim=1)
 
 

@@ -16,7 +16,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def golden_files() -> List[str]:
     # DynEdge cases only (losses.pt holds the task-loss vectors of tests/test_tasks.py, detector_*.pt the standardisation)
     return sorted(f for f in glob.glob(os.path.join(GOLDEN_DIR, "*.pt"))
-                  if os.path.basename(f) != "losses.pt" and not os.path.basename(f).startswith(("detector_", "nodes_")))
+                  if os.path.basename(f) != "losses.pt" and not os.path.basename(f).startswith(("detector_", "nodes_", "users_")))
 
 
 def load_golden(path: str) -> Dict:

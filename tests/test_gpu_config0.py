@@ -74,6 +74,9 @@ def test_prometheus_example_epoch_vs_oracle(built_library, precision):
             gerr = {k: rel_err(p.grad, q.grad) for (k, p), (_, q) in zip(list(model.named_parameters()) + list(head.named_parameters()),
                                                                         list(ref.named_parameters()) + list(head_ref.named_parameters()))}
             worst_grad = max(worst_grad, max(gerr.values()))
+            wk = max(gerr, key=gerr.get)
+            print(f"  batch of {int(n_pulses.numel())} events / {x.shape[0]} pulses: worst grad {wk} {gerr[wk]:.2e}; "
+                  + ", ".join(f"{k_.split('.', 1)[-1]}={v:.1e}" for k_, v in gerr.items() if v > 1e-3))
         print(f"prometheus50 {precision}: predictions / loss {worst_out:.2e}, max grad {worst_grad:.2e}")
         assert worst_out < 1e-3
         assert worst_grad < GRAD_TOL[precision]

@@ -1,0 +1,70 @@
+"""The other users of `DynEdgeConv` on the CUDA kernels against the oracle restatements that are pinned
+on the reference's own dynedge_jinst.py / particlenet.py / dynedge.py (tests/test_oracle_golden.py): `DynEdgeJINST`
+(LeakyReLU MLPs, add), `ParticleNeT` (3-Linear MLPs with BatchNorm1d in training and eval mode, mean aggregation, static
+graph with GELU) and DeepIce's DynEdge block (k = 9, GELU, LayerNorm, pulse-level output; icemix.py:100-118).
+rel 1e-3 on outputs and every parameter gradient; kNN graphs bit-exact on the kernel's own features."""
+
+import os
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from helpers import GOLDEN_DIR, rel_err
+from oracle.dynedge_oracle import DynEdgeRef, batch_to_ptr, knn_graph_ref
+from oracle.users_oracle import DynEdgeJINSTRef, ParticleNeTRef
+
+pytestmark = pytest.mark.gpu
+CASES = ["jinst", "particlenet_train", "particlenet_eval", "particlenet_static_gelu", "deepice_dynedge"]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("case", CASES)
+def test_dynedgeconv_users_vs_oracle(built_library, case, precision):
+    from graphnet_b200 import Data, ops
+    from graphnet_b200.models.gnn import DynEdge, DynEdgeJINST, ParticleNeT
+    from graphnet_b200.models.graphs.edges import KNNEdges
+    g = torch.load(os.path.join(GOLDEN_DIR, "users_dynedgeconv.pt"))[case]
+    if case == "jinst":
+        model, ref, k, cols = DynEdgeJINST(**g["kwargs"]), DynEdgeJINSTRef(**g["kwargs"]), 8, slice(0, 3)
+    elif case == "deepice_dynedge":
+        model, ref, k, cols = DynEdge(g["nb_inputs"], **g["kwargs"]), DynEdgeRef(g["nb_inputs"], **g["kwargs"]), 9, slice(0, 3)
+    else:
+        model, ref = ParticleNeT(g["nb_inputs"], **g["kwargs"]), ParticleNeTRef(g["nb_inputs"], **g["kwargs"])
+        k, cols = g["kwargs"]["nb_neighbours"], slice(0, 3)
+    assert list(model.state_dict().keys()) == list(ref.state_dict().keys())            # drop-in: same state_dict keys
+    model.load_state_dict(g["state_dict"])
+    ref = ref.double()
+    ref.load_state_dict({k_: (v.double() if v.is_floating_point() else v) for k_, v in g["state_dict"].items()})
+    train = case in ("jinst", "particlenet_train", "deepice_dynedge")
+    model = model.cuda().train(train)
+    ref.train(train)
+    model._debug_record = True
+    old = ops.PRECISION
+    ops.set_precision(precision)
+    try:
+        x, batch, n_pulses = g["x"], g["batch"], g["n_pulses"]
+        data = KNNEdges(k)(Data(x=x.cuda(), batch=batch.cuda(), n_pulses=n_pulses.cuda()))
+        assert torch.equal(data.edge_index.cpu(), g["edge_index"])                     # the reference run's own initial graph
+        y = model(data)
+        w = torch.linspace(0.5, 1.5, y.numel()).reshape(y.shape)
+        (y * w.cuda()).sum().backward()
+        ptr = batch_to_ptr(batch)
+        graphs = model._debug["graphs"]
+        forced = [None]
+        for li in range(1, len(graphs)):
+            ei_k = graphs[li].edge_index().cpu()
+            if case != "particlenet_static_gelu":                                       # static graph: nothing recomputed
+                feats = model._debug["skips"][li].detach().cpu()
+                assert torch.equal(ei_k, knn_graph_ref(feats[:, cols], k, ptr=ptr)), f"latent graph {li}"
+            forced.append(ei_k)
+        y_ref = ref(SimpleNamespace(x=x.double(), edge_index=g["edge_index"], batch=batch, n_pulses=n_pulses), forced_graphs=forced)
+        (y_ref * w.double()).sum().backward()
+        err = rel_err(y, y_ref)
+        gerr = {k_: rel_err(p.grad, q.grad) for (k_, p), (_, q) in zip(model.named_parameters(), ref.named_parameters())
+                if q.grad is not None}
+        print(f"{case} {precision}: out {err:.2e}, max grad {max(gerr.values()):.2e} ({max(gerr, key=gerr.get)})")
+        assert err < 1e-3
+        assert max(gerr.values()) < 1e-3, gerr
+    finally:
+        ops.set_precision(old)

@@ -99,3 +99,35 @@ def test_percentile_clusters_pinned_on_reference_utils():
     assert definition.nb_outputs == 16 and graph.x.dtype == torch.float32
     assert torch.equal(graph.x, case["nodes"].float()) and int(graph.n_pulses) == case["x"].shape[0]
     assert torch.equal(graph["counts"], graph.x[:, -1])
+
+
+def _users_gold():
+    return torch.load(os.path.join(GOLDEN_DIR, "users_dynedgeconv.pt"))
+
+
+@pytest.mark.parametrize("case", ["jinst", "particlenet_train", "particlenet_eval", "particlenet_static_gelu", "deepice_dynedge"])
+def test_users_oracle_reproduces_the_reference_models(case):
+    """oracle/users_oracle.py (DynEdgeJINST, ParticleNeT) and DynEdgeRef with DeepIce's arguments against golden vectors from
+    the reference's own dynedge_jinst.py / particlenet.py / dynedge.py (tests/golden/make_golden_users.py): fp64, 1e-10."""
+    from types import SimpleNamespace
+    from oracle.dynedge_oracle import DynEdgeRef
+    from oracle.users_oracle import DynEdgeJINSTRef, ParticleNeTRef
+    g = _users_gold()[case]
+    if case == "jinst":
+        model = DynEdgeJINSTRef(**g["kwargs"])
+    elif case == "deepice_dynedge":
+        model = DynEdgeRef(g["nb_inputs"], **g["kwargs"])
+    else:
+        model = ParticleNeTRef(g["nb_inputs"], **g["kwargs"])
+    model = model.double()
+    model.load_state_dict({k: (v.double() if v.is_floating_point() else v) for k, v in g["state_dict"].items()})
+    model.train(case in ("jinst", "particlenet_train", "deepice_dynedge"))
+    data = SimpleNamespace(x=g["x"].double(), edge_index=g["edge_index"], batch=g["batch"], n_pulses=g["n_pulses"])
+    y = model(data)
+    w = torch.linspace(0.5, 1.5, y.numel(), dtype=torch.float64).reshape(y.shape)
+    (y * w).sum().backward()
+    assert torch.allclose(y, g["out_f64"], rtol=1e-10, atol=1e-12)
+    grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    assert set(grads) == set(g["grads_f64"])
+    for k, v in g["grads_f64"].items():
+        assert torch.allclose(grads[k].float(), v, rtol=2e-5, atol=1e-7), k
