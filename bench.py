@@ -266,6 +266,7 @@ class Trainer:
         # the flat gradient buffer is zero here: allocated zeroed, then zeroed again by every Adam step behind its read
         data = self.edges(self.make_data(db))
         h = self.backbone(data)
+        self.last_backbone_out = h.detach()               # (a view, no copy: parity tests read the read-out decisions from it)
         loss, _, _ = self.tasks(h, db["energy"], db["direction"])
         if self.overlap:
             self.reducer.arm_overlap(self.tail_param, self.tail_layer)

@@ -302,11 +302,24 @@ class DynEdgeRef(torch.nn.Module):
             layers.append(act)
         self._readout = torch.nn.Sequential(*layers)
 
+    @staticmethod
+    def _apply_forcing_last_relu(seq: torch.nn.Sequential, x: Tensor, mask: Optional[Tensor]):
+        """seq(x), with the ReLU decisions of the LAST activation taken from `mask` when given: y = z * mask."""
+        if mask is None or len(seq) == 0 or not isinstance(seq[-1], torch.nn.ReLU):
+            return seq(x), None
+        z = seq[:-1](x)
+        return z * mask.to(z.dtype), z
+
     def forward(self, data, forced_graphs: Optional[List[Tensor]] = None,
-                return_intermediates: bool = False):
+                return_intermediates: bool = False, forced_output_mask: Optional[Tensor] = None):
         """dynedge.py:295-349. `forced_graphs[l]` (optional) replaces the graph
         used as INPUT of conv layer l (l>=1) -- used to compare against a kernel
-        run whose latent features (and thus kNN graphs) differ by rounding."""
+        run whose latent features (and thus kNN graphs) differ by rounding.
+        `forced_output_mask` (optional, bool, shape of the output) replaces the ReLU decisions of the model's LAST
+        activation (read-out, or post-processing with skip_readout): the gradient of a ReLU network is discontinuous where a
+        pre-activation crosses zero, and with B x 128 read-out units a single unit within rounding of zero moves a whole
+        bias-gradient entry by 1 / B -- the same teacher-forcing as for the graphs; callers assert that the forced decisions
+        differ from the oracle's own only within rounding of zero (`final_pre` in the intermediates)."""
         x, edge_index, batch = data.x, data.edge_index, data.batch
         nseg = int(batch.max().item()) + 1
         ptr = batch_to_ptr(batch, nseg)
@@ -329,16 +342,20 @@ class DynEdgeRef(torch.nn.Module):
             graphs.append(edge_index)
             skips.append(x)
         x = torch.cat(skips, dim=1)                                          # :328
-        x = self._post_processing(x)                                         # :331
+        final_pre = None
+        if self._skip_readout:
+            x, final_pre = self._apply_forcing_last_relu(self._post_processing, x, forced_output_mask)   # :331
+        else:
+            x = self._post_processing(x)                                     # :331
         post = x
         if not self._skip_readout:
             if self._schemes:
                 x = torch.cat([segment_pool_ref(x, ptr, s) for s in self._schemes], dim=1)  # :251-264
                 if self._after:
                     x = torch.cat([x, g], dim=1)                             # :337-344
-            x = self._readout(x)                                             # :347
+            x, final_pre = self._apply_forcing_last_relu(self._readout, x, forced_output_mask)            # :347
         if return_intermediates:
-            return x, {"global_variables": g, "skips": skips, "graphs": graphs, "post": post}
+            return x, {"global_variables": g, "skips": skips, "graphs": graphs, "post": post, "final_pre": final_pre}
         return x
 
 

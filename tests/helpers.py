@@ -60,3 +60,27 @@ def tie_heavy_events(sizes, nb_inputs: int, seed: int):
 
 def namespace(**kw) -> SimpleNamespace:
     return SimpleNamespace(**kw)
+
+
+# Largest |pre-activation| (relative to the largest one of the tensor) at which the kernel's read-out ReLU decision may
+# differ from the oracle's: the forward error of the mode with a safety factor.
+FLIP_TOL = {"fp32": 2e-5, "tf32x3": 2e-4, "tf32": 5e-3}
+
+
+def oracle_on_kernel_decisions(ref, data, forced_graphs, y_kernel, mode: str):
+    """Oracle forward teacher-forced with the kernel's latent graphs AND the kernel's ReLU decisions of the LAST activation
+    (y_kernel > 0). The gradient of a ReLU network jumps where a pre-activation crosses zero; at the read-out ([B, 128]
+    units) one unit within rounding of zero moves a bias-gradient entry by 1 / B, so gradients can only be compared on the
+    same side of every such kink. Asserts that the two sides disagree ONLY within the forward error of `mode` (FLIP_TOL,
+    relative to the largest pre-activation). Returns (y_ref, intermediates, number of forced decisions)."""
+    mask = (y_kernel.detach().cpu() > 0)
+    y_ref, inter = ref(data, forced_graphs=forced_graphs, return_intermediates=True, forced_output_mask=mask)
+    z = inter["final_pre"]
+    forced = 0
+    if z is not None:
+        differ = mask != (z.detach() > 0)
+        forced = int(differ.sum())
+        if forced:
+            worst = float(z.detach()[differ].abs().max() / z.detach().abs().max())
+            assert worst <= FLIP_TOL[mode], f"read-out ReLU decision differs at |z| = {worst:.2e} of max (mode {mode})"
+    return y_ref, inter, forced

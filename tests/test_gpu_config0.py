@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN_DIR, namespace, rel_err
+from helpers import GOLDEN_DIR, namespace, oracle_on_kernel_decisions, rel_err
 from oracle.dynedge_oracle import DynEdgeRef, batch_to_ptr, knn_graph_ref
 
 pytestmark = pytest.mark.gpu
@@ -46,7 +46,7 @@ def test_prometheus_example_epoch_vs_oracle(built_library, precision):
     old = ops.PRECISION
     ops.set_precision(precision)
     try:
-        worst_out, worst_grad = 0.0, 0.0
+        worst_out, worst_grad, forced_total = 0.0, 0.0, 0
         for hb in batches:
             assert hb.edge_index is None                                    # edges deferred on the CPU (dataloader workers)
             dev = definition.build_edges(hb.to("cuda"))
@@ -56,7 +56,8 @@ def test_prometheus_example_epoch_vs_oracle(built_library, precision):
             assert torch.equal(dev.edge_index.cpu(), ei0)                   # initial graph: bit-exact (duplicates, short events)
             model.zero_grad(set_to_none=True)
             head.zero_grad(set_to_none=True)
-            pred = head(model(dev))
+            feat = model(dev)
+            pred = head(feat)
             loss = head.compute_loss(pred, hb.total_energy.float().cuda())
             loss.backward()
             forced = [None]
@@ -67,7 +68,10 @@ def test_prometheus_example_epoch_vs_oracle(built_library, precision):
                 forced.append(ei_k)
             for p in list(ref.parameters()) + list(head_ref.parameters()):
                 p.grad = None
-            pred_ref = head_ref(ref(namespace(x=x.double(), edge_index=ei0, batch=batch, n_pulses=n_pulses), forced_graphs=forced))
+            feat_ref, _, nforced = oracle_on_kernel_decisions(ref, namespace(x=x.double(), edge_index=ei0, batch=batch,
+                                                                             n_pulses=n_pulses), forced, feat, precision)
+            forced_total += nforced
+            pred_ref = head_ref(feat_ref)
             loss_ref = head_ref.compute_loss(pred_ref, hb.total_energy.double())
             loss_ref.backward()
             worst_out = max(worst_out, rel_err(pred, pred_ref), rel_err(loss, loss_ref))
@@ -77,7 +81,8 @@ def test_prometheus_example_epoch_vs_oracle(built_library, precision):
             wk = max(gerr, key=gerr.get)
             print(f"  batch of {int(n_pulses.numel())} events / {x.shape[0]} pulses: worst grad {wk} {gerr[wk]:.2e}; "
                   + ", ".join(f"{k_.split('.', 1)[-1]}={v:.1e}" for k_, v in gerr.items() if v > 1e-3))
-        print(f"prometheus50 {precision}: predictions / loss {worst_out:.2e}, max grad {worst_grad:.2e}")
+        print(f"prometheus50 {precision}: predictions / loss {worst_out:.2e}, max grad {worst_grad:.2e}, "
+              f"read-out ReLU decisions taken from the kernel: {forced_total}")
         assert worst_out < 1e-3
         assert worst_grad < GRAD_TOL[precision]
     finally:

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import namespace, rel_err
+from helpers import namespace, oracle_on_kernel_decisions, rel_err
 from oracle.dynedge_oracle import DynEdgeRef, batch_to_ptr, knn_graph_ref
 
 pytestmark = pytest.mark.gpu
@@ -117,8 +117,7 @@ def test_dynedge_tf32_mode_vs_oracle(built_library, tf32_mode):
         ei_k = model._debug["graphs"][li].edge_index().cpu()
         assert torch.equal(ei_k, knn_graph_ref(feats[:, :3], 8, ptr=ptr)), f"latent graph {li}"
         forced.append(ei_k)
-    y_ref, inter = ref(namespace(x=x, edge_index=ei0, batch=batch, n_pulses=n_pulses), forced_graphs=forced,
-                       return_intermediates=True)
+    y_ref, inter, _ = oracle_on_kernel_decisions(ref, namespace(x=x, edge_index=ei0, batch=batch, n_pulses=n_pulses), forced, y, "tf32")
     y_ref.square().sum().backward()
     errs = {f"skip{li}": rel_err(model._debug["skips"][li], inter["skips"][li]) for li in range(5)}
     errs["out"] = rel_err(y, y_ref)

@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import namespace, rel_err
+from helpers import namespace, oracle_on_kernel_decisions, rel_err
 from oracle.dynedge_oracle import DynEdgeRef, batch_to_ptr, knn_graph_ref
 
 pytestmark = pytest.mark.gpu
@@ -186,8 +186,8 @@ def test_dynedge_tf32x3_vs_oracle(x3_mode, executor, monkeypatch):
         assert torch.equal(ei_k, knn_graph_ref(feats[:, :3], 8, ptr=ptr)), f"latent graph {li}"
         forced.append(ei_k)
     ref = ref.double()
-    y_ref, inter = ref(namespace(x=x.double(), edge_index=ei0, batch=batch, n_pulses=n_pulses), forced_graphs=forced,
-                       return_intermediates=True)
+    y_ref, inter, _ = oracle_on_kernel_decisions(ref, namespace(x=x.double(), edge_index=ei0, batch=batch, n_pulses=n_pulses),
+                                                 forced, y, "tf32x3")
     y_ref.square().sum().backward()
     errs = {f"skip{li}": rel_err(model._debug["skips"][li], inter["skips"][li]) for li in range(5)}
     errs["out"] = rel_err(y, y_ref)

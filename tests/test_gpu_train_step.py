@@ -3,8 +3,8 @@ ACCUMULATE_INTO_GRAD into the flat buffer, fused task heads, FlatAdam) -- agains
 torch.optim.Adam on the SAME 512 events: loss, the flat gradient (per parameter tensor) and the post-step weights.
 
 Stated tolerances: loss rel 1e-4; gradients per tensor rel 1e-3 in tf32x3 (the headline mode) and 3e-3 in single-pass tf32;
-the Adam update dW = W_after - W_before per tensor within 2x the gradient tolerance (first step: dW = lr g / (|g| + eps), whose
-relative sensitivity to g is eps / (|g| + eps) <= 1)."""
+post-step weights = torch.optim.Adam applied to the kernel's own flat gradient, to 2e-7 absolute (lr = 1e-3). The oracle is
+teacher-forced with the kernel's latent graphs and read-out ReLU decisions (tests/helpers.py::oracle_on_kernel_decisions)."""
 
 import os
 import sys
@@ -12,7 +12,7 @@ import sys
 import pytest
 import torch
 
-from helpers import namespace, rel_err
+from helpers import namespace, oracle_on_kernel_decisions, rel_err
 from oracle.dynedge_oracle import DynEdgeRef, batch_to_ptr, knn_graph_ref
 
 pytestmark = pytest.mark.gpu
@@ -65,7 +65,8 @@ def test_bench_train_step_vs_oracle_and_torch_adam(built_library, precision, gra
         direction.load_state_dict({k.split(".", 1)[1]: v for k, v in heads_before.items() if k.startswith("direction.")})
         params = list(ref.parameters()) + list(energy.parameters()) + list(direction.parameters())
         opt = torch.optim.Adam(params, lr=1e-3, eps=1e-3)
-        h = ref(namespace(x=x, edge_index=ei0, batch=batch, n_pulses=n_pulses), forced_graphs=forced)
+        h, _, nforced = oracle_on_kernel_decisions(ref, namespace(x=x, edge_index=ei0, batch=batch, n_pulses=n_pulses), forced,
+                                                   trainer.last_backbone_out, precision)
         loss_ref = energy.compute_loss(energy(h), hb["energy"]) + direction.compute_loss(direction(h), hb["direction"])
         loss_ref.backward()
         assert rel_err(loss, loss_ref) < 1e-4, (float(loss), float(loss_ref))
@@ -76,14 +77,19 @@ def test_bench_train_step_vs_oracle_and_torch_adam(built_library, precision, gra
             gerr[name] = rel_err(probe["flat"][off:off + p.numel()].view_as(p), p.grad)
             off += p.numel()
         assert off == probe["flat"].numel()
-        old_w = [p.detach().clone() for p in params]
+        # the optimizer: torch.optim.Adam fed the KERNEL's gradient must land on FlatAdam's weights (Adam's first step is
+        # lr g / (|g| + eps): sign-like, so comparing updates computed from two slightly different gradients says nothing)
+        off = 0
+        for p in params:
+            p.grad = probe["flat"][off:off + p.numel()].view_as(p).clone()
+            off += p.numel()
         opt.step()
         mine = list(trainer.backbone.parameters()) + list(trainer.energy.parameters()) + list(trainer.direction.parameters())
-        uerr = {name: rel_err(m.detach().cpu() - w0, p.detach() - w0) for name, m, p, w0 in zip(names, mine, params, old_w)}
+        werr = max(float((m.detach().cpu() - p.detach()).abs().max()) for m, p in zip(mine, params))
         print(f"train_step {precision}: loss {float(loss):.6f} vs {float(loss_ref):.6f}, max grad err {max(gerr.values()):.2e} "
-              f"({max(gerr, key=gerr.get)}), max update err {max(uerr.values()):.2e}")
+              f"({max(gerr, key=gerr.get)}), post-step weights vs torch Adam {werr:.2e}, forced read-out decisions {nforced}")
         assert max(gerr.values()) < grad_tol, gerr
-        assert max(uerr.values()) < 2 * grad_tol, uerr
+        assert werr < 2e-7                               # lr = 1e-3: a 2e-4 relative agreement of every update
     finally:
         ops.set_precision(old_p)
         ops.ACCUMULATE_INTO_GRAD = old_acc

@@ -61,8 +61,16 @@ def test_dynedgeconv_users_vs_oracle(built_library, case, precision):
         y_ref = ref(SimpleNamespace(x=x.double(), edge_index=g["edge_index"], batch=batch, n_pulses=n_pulses), forced_graphs=forced)
         (y_ref * w.double()).sum().backward()
         err = rel_err(y, y_ref)
-        gerr = {k_: rel_err(p.grad, q.grad) for (k_, p), (_, q) in zip(model.named_parameters(), ref.named_parameters())
-                if q.grad is not None}
+        gerr = {}
+        for (k_, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+            if q.grad is None:
+                continue
+            if float(q.grad.abs().max()) < 1e-9:
+                # a Linear bias in front of a training-mode BatchNorm1d: its gradient is identically zero (the batch mean is
+                # subtracted); fp32 leaves rounding noise there, which has no relative scale
+                assert float(p.grad.abs().max()) < 1e-5, k_
+                continue
+            gerr[k_] = rel_err(p.grad, q.grad)
         print(f"{case} {precision}: out {err:.2e}, max grad {max(gerr.values()):.2e} ({max(gerr, key=gerr.get)})")
         assert err < 1e-3
         assert max(gerr.values()) < 1e-3, gerr
