@@ -11,6 +11,7 @@
 // (or none), global variables before or after pooling, skip_readout. Everything else stays on the
 // per-operator route in graphnet_b200/models (generic `nn`, LayerNorm, GELU, max/mean aggregation).
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <stdint.h>
 
 // ---- launchers of the other translation units (C ABI, include/graphnet_b200.h) -----------------------
@@ -93,7 +94,14 @@ inline int64_t up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 // ---- small kernels private to the executor ---------------------------------------------------------
 // dst[r, c] = (c < cols ? maybe_round(src[r, c]) : 0)        (strided copy / pad / tf32 rounding)
-// lo != nullptr (tf32x3 weights): dst = rna_tf32(v), lo = rna_tf32(v - dst)
+// bf16 correction operand of the split GEMM (csrc/gemm_tc.cu::split_pad_tf32_kernel): row `crow` viewed as bf16, per 32-wide K
+// block [bf16(v - hi) x 32 | bf16(hi) x 32]
+__device__ __forceinline__ void store_corr(float* crow, int c, float v, float hi) {
+    __nv_bfloat16* b = reinterpret_cast<__nv_bfloat16*>(crow);
+    b[(c >> 5) * 64 + (c & 31)] = __float2bfloat16_rn(v - hi);
+    b[(c >> 5) * 64 + 32 + (c & 31)] = __float2bfloat16_rn(hi);
+}
+// lo != nullptr (tf32x3 weights; dst_cols % 32 == 0): dst = rna_tf32(v), lo = the bf16 correction operand
 __global__ void copy_pad_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
                                 float* __restrict__ dst, int64_t ldd, int dst_cols, int rnd, float* __restrict__ lo) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -103,7 +111,7 @@ __global__ void copy_pad_kernel(const float* __restrict__ src, int64_t lds, int6
     float v = c < cols ? src[r * lds + c] : 0.f;
     const float hi = rnd ? gnb_round_tf32(v) : v;
     dst[r * ldd + c] = hi;
-    if (lo != nullptr) lo[r * ldd + c] = gnb_round_tf32(v - hi);
+    if (lo != nullptr) store_corr(lo + r * ldd, c, v, hi);
 }
 // dst[r, c] += src[r, c]
 __global__ void add2d_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
@@ -136,7 +144,7 @@ __global__ void pack_conv_kernel(const float* __restrict__ w1, const float* __re
     if (col < c) v = r < h ? w1[(int64_t)r * 2 * c + col] - w1[(int64_t)r * 2 * c + c + col] : w1[(int64_t)(r - h) * 2 * c + c + col];
     const float hi = rnd ? gnb_round_tf32(v) : v;
     wcat[(int64_t)r * ld + col] = hi;
-    if (wlo != nullptr) wlo[(int64_t)r * ld + col] = gnb_round_tf32(v - hi);
+    if (wlo != nullptr) store_corr(wlo + (int64_t)r * ld, col, v, hi);
     if (col == 0) bcat[r] = r < h ? b1[r] : 0.f;
 }
 // dW1[r, col] += dWcat[r, col];  dW1[r, C + col] += dWcat[H + r, col] - dWcat[r, col];  db1 += dbcat[0:H]

@@ -20,6 +20,7 @@
 // producers so that the tensor core's truncation is exact (unbiased rounding overall).
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -455,17 +456,20 @@ struct GroupSplit { int ngroups; int start[5]; };
 // (one TMA pass), a stage is the activation half only (16 KiB) and the L2->SM traffic per launch halves.
 struct PairCfg { int resident; int nstages; uint32_t meta_stride; };
 constexpr uint32_t PL_BAR_BYTES = 512;                // barrier block behind the ring
-// SPLIT = the fp32-grade "3xTF32" forward (precision mode tf32x3): the weight operand arrives pre-split from the pack
-// kernels (W = W_hi + W_lo, both tf32-exact, two tensor maps), the activation operand arrives as plain fp32 and is split
-// IN SHARED MEMORY by two extra warps (10, 11): X tile -> X_hi = rna_tf32(X) in place, X_lo = X - X_hi (exact) into a
-// fourth tile of the stage. Per 8-wide K step the issuer queues three MMAs: W_hi X_hi + W_lo X_hi + W_hi X_lo (the
-// W_lo X_lo term is below 2^-22 relative). TMA stage = {W_hi | W_lo | X} = 48 KiB, 4 stages (the depth that covers the
-// L2 latency); X_lo lives in its own ring of 2 x 16 KiB (one slot per splitter warp: it is produced locally, a few hundred
-// cycles before its MMAs, so it needs no latency-covering depth -- with X_lo inside the stages only 3 stages fit and the
-// aggregating launch ran at 624 us against a 370 us tensor floor). Barriers of a stage: full[s] (leader) collects the weight
-// tiles of both CTAs, xfull[s] (LOCAL to each CTA: its splitter warps cannot wait on a remote barrier) the CTA's own
-// activation half, sfull[s] (leader, count 2) the "split done" arrival of each CTA; lo_empty[j] (local, multicast commit)
-// returns X_lo slot j to its splitter warp.
+// SPLIT = the fp32-grade split-operand forward (precision mode tf32x3): W = W_hi + W_lo, X = X_hi + X_lo with the hi parts
+// tf32-exact; the product is W_hi X_hi (kind::tf32) + the two correction products W_lo X_hi + W_hi X_lo, whose operands need
+// only ~8 significant bits (they are 2^-11 of the main term) and therefore run as ONE bf16 contraction (kind::f16, twice the
+// MMA rate) over the concatenated K axis: A_corr = [bf16(W_lo) | bf16(W_hi)] (64 bf16 = one 128-byte swizzle row per 32-wide K
+// block, packed by gnb_split_pad_tf32), B_corr = [bf16(X_hi) | bf16(X_lo)]. Per K block: 4 tf32 + 4 bf16 MMAs of 256 x 256
+// (8 x 128 tensor cycles) instead of 12 tf32 MMAs; error of the dropped bits ~2^-19 (W_lo X_lo is below 2^-22).
+// The weight operands arrive from the pack kernels (two tensor maps); the activation operand arrives as plain fp32 and is
+// split IN SHARED MEMORY by two extra warps (10, 11): X tile -> X_hi = rna_tf32(X) in place, B_corr into its own ring.
+// TMA stage = {W_hi | A_corr | X} = 48 KiB, 4 stages (the depth that covers the L2 latency); B_corr lives in a ring of
+// 2 x 16 KiB (one slot per splitter warp: it is produced locally, a few hundred cycles before its MMAs, so it needs no
+// latency-covering depth -- with it inside the stages only 3 stages fit and the aggregating launch ran at 624 us).
+// Barriers of a stage: full[s] (leader) collects the weight tiles of both CTAs, xfull[s] (LOCAL to each CTA: its splitter
+// warps cannot wait on a remote barrier) the CTA's own activation half, sfull[s] (leader, count 2) the "split done" arrival
+// of each CTA; lo_empty[j] (local, multicast commit) returns B_corr slot j to its splitter warp.
 constexpr int PL_SPLIT_THREADS = 384, PL_SPLIT_STAGES = 4, PL_SPLIT_LO_SLOTS = 2;
 
 template <bool SPLIT>
@@ -570,7 +574,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                         if (tc::elect_one()) {
                             if (rank == 0) tc::mbar_arrive_expect_tx(&full[s], stage_tx);
                             tc::tma_load_2d_2sm(st, &tm_w, &full[s], kb_w * TC_BK, ch0);
-                            tc::tma_load_2d_2sm(st + TC_TILE_BYTES, &tm_wlo, &full[s], kb_w * TC_BK, ch0);
+                            tc::tma_load_2d_2sm(st + TC_TILE_BYTES, &tm_wlo, &full[s], kb_w * 2 * TC_BK, ch0);   // bf16 map: 64 per K block
                             tc::mbar_arrive_expect_tx(&xfull[s], (uint32_t)half_rows * TC_BK * 4);
                             tc::tma_load_2d(st + 2 * TC_TILE_BYTES, &tm_x.m[p], &xfull[s], kb * TC_BK, (int)row0);
                         }
@@ -635,12 +639,13 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                         const uint64_t blo = tc::umma_desc_sw128_kmajor(tc::smem_u32(lo_ring + (it & 1u) * TC_TILE_BYTES));
                         if (tc::elect_one()) {
                             if (!(agg.dbg & 2)) {
+                                constexpr uint32_t idesc_bf16 = tc::umma_idesc_bf16(256, 256);
 #pragma unroll
-                                for (int k = 0; k < TC_BK / 8; ++k) {
-                                    tc::umma_tf32_2cta(acc, alo + 2 * k, bhi + 2 * k, idesc, (kbi | k) != 0 ? 1u : 0u);
-                                    tc::umma_tf32_2cta(acc, ahi + 2 * k, blo + 2 * k, idesc, 1u);
+                                for (int k = 0; k < TC_BK / 8; ++k)      // corrections first (small terms), 16 bf16 = 32 B per MMA
+                                    tc::umma_bf16_2cta(acc, alo + 2 * k, blo + 2 * k, idesc_bf16, (kbi | k) != 0 ? 1u : 0u);
+#pragma unroll
+                                for (int k = 0; k < TC_BK / 8; ++k)
                                     tc::umma_tf32_2cta(acc, ahi + 2 * k, bhi + 2 * k, idesc, 1u);
-                                }
                             }
                             tc::umma_commit_2cta(&empty[s], 3);
                             tc::umma_commit_2cta(&lo_empty[it & 1u], 3);
@@ -665,8 +670,11 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
             }
         }
     } else if (SPLIT && warp >= 10) {
-        // ---- operand splitter (both CTAs, warps 10 / 11 take alternate stages): X -> (X_hi in place, X_lo) -----------
-        // Elementwise, so the 128-byte swizzle of the tile is irrelevant: lane l of step i owns the 16-byte chunk 32 i + l.
+        // ---- operand splitter (both CTAs, warps 10 / 11 take alternate stages): X -> (X_hi in place, B_corr) ----------
+        // Lane l of step i owns the 16-byte chunk q = 32 i + l of the X tile: row r = q / 8, physical chunk p = q % 8 holding
+        // the logical chunk c = p ^ (r % 8) (128-byte swizzle) = k 4c .. 4c + 3. B_corr row r = [bf16(x_hi) k 0..31 |
+        // bf16(x_lo) k 0..31] in the same swizzle: the 4 hi values are half (c & 1) of logical chunk c / 2, the 4 lo values
+        // of logical chunk 4 + c / 2.
         uint32_t it = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
             for (int kbi = 0; kbi < total_kb; ++kbi, ++it) {
@@ -675,7 +683,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                 tc::mbar_wait<20>(&xfull[s], ph);
                 tc::mbar_wait<20>(&lo_empty[warp - 10], ((it >> 1) & 1u) ^ 1u);     // this warp's X_lo slot: MMAs of its previous use done
                 const uint32_t xa = tc::smem_u32(ring + s * stage_bytes + 2 * TC_TILE_BYTES) + (uint32_t)lane * 16u;
-                const uint32_t la = tc::smem_u32(lo_ring + (uint32_t)(warp - 10) * TC_TILE_BYTES) + (uint32_t)lane * 16u;
+                // B_corr slot of this warp; row base of lane's chunk in step 0: (lane / 8) * 128 B (+ 4 rows = 512 B per step)
+                const uint32_t la_row = tc::smem_u32(lo_ring + (uint32_t)(warp - 10) * TC_TILE_BYTES) + ((uint32_t)lane >> 3) * 128u;
 #pragma unroll 1
                 for (int i0 = 0; i0 < (int)(TC_TILE_BYTES / 512); i0 += 8) {
                     uint32_t v[8][4];
@@ -693,7 +702,18 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                         }
                         const uint32_t a = xa + 512u * (uint32_t)(i0 + i);
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(hi[3]) : "memory");
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(la + 512u * (uint32_t)(i0 + i)), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(lo[3]) : "memory");
+                        // row of this chunk: q / 8 = 4 (i0 + i) + lane / 8; r % 8 = (4 (i0 + i) + lane / 8) % 8
+                        const uint32_t r7 = ((uint32_t)(4 * (i0 + i)) + ((uint32_t)lane >> 3)) & 7u;
+                        const uint32_t c = ((uint32_t)lane & 7u) ^ r7;                        // logical 16-byte chunk of the X row
+                        const uint32_t row_a = la_row + 512u * (uint32_t)(i0 + i);            // B_corr row base (128 B per row)
+                        const uint32_t a_hi = row_a + ((((c >> 1)) ^ r7) << 4) + ((c & 1u) << 3);
+                        const uint32_t a_lo = row_a + (((4u + (c >> 1)) ^ r7) << 4) + ((c & 1u) << 3);
+                        const __nv_bfloat162 h01 = __floats2bfloat162_rn(hi[0], hi[1]), h23 = __floats2bfloat162_rn(hi[2], hi[3]);
+                        const __nv_bfloat162 l01 = __floats2bfloat162_rn(lo[0], lo[1]), l23 = __floats2bfloat162_rn(lo[2], lo[3]);
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
+                                     "r"(*reinterpret_cast<const uint32_t*>(&h23)) : "memory");
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_lo), "r"(*reinterpret_cast<const uint32_t*>(&l01)),
+                                     "r"(*reinterpret_cast<const uint32_t*>(&l23)) : "memory");
                     }
                 }
                 // generic-proxy writes -> visible to the tensor core's async-proxy reads. The notification itself is relaxed: a
@@ -1247,8 +1267,8 @@ static int linear_fwd_impl(const float* const* xs, const int64_t* ldxs, const in
     int rc = gnb_make_tmap_f32(&tw, w, n_out, ktot, ldw, TC_BM);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     CUtensorMap twlo;
-    if (w_lo != nullptr) {
-        rc = gnb_make_tmap_f32(&twlo, w_lo, n_out, ktot, ldw, TC_BM);
+    if (w_lo != nullptr) {        // the bf16 correction operand: [n_out, 2 ktot] bf16 in the bytes of a [n_out, ktot] fp32 matrix
+        rc = gnb_make_tmap_bf16(&twlo, w_lo, n_out, 2 * ktot, ldw * 4, TC_BM);
         if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     }
     AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof};
@@ -1295,8 +1315,8 @@ static int edge_linear_agg_impl(const float* h, int64_t ldh, int32_t k, const fl
     rc = gnb_make_tmap_f32(&tw, w, n_out, ktot, ldw, TC_BM);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     CUtensorMap twlo;
-    if (w_lo != nullptr) {
-        rc = gnb_make_tmap_f32(&twlo, w_lo, n_out, ktot, ldw, TC_BM);
+    if (w_lo != nullptr) {        // the bf16 correction operand: [n_out, 2 ktot] bf16 in the bytes of a [n_out, ktot] fp32 matrix
+        rc = gnb_make_tmap_bf16(&twlo, w_lo, n_out, 2 * ktot, ldw * 4, TC_BM);
         if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     }
     AggInfo agg{deg, n, maskbits, 1, g_linear_dbg, g_linear_prof};
@@ -1379,10 +1399,11 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_tf32(const float* dz, int64_t lddz,
                                                     ldpq, nullptr, 0, stream);
 }
 
-// hi[r, c] = rna_tf32(src[r, c]), lo[r, c] = rna_tf32(src[r, c] - hi[r, c]) (zero padded to dst_cols): the pre-split weight
-// operand of the tf32x3 GEMMs.
+// hi[r, c] = rna_tf32(src[r, c]) (zero padded to dst_cols) and the bf16 correction operand of the split GEMM in the same
+// number of bytes: row r of `corr` (viewed as bf16[2 * ldd]) holds, per 32-wide K block kb, [bf16(v - hi) x 32 | bf16(hi) x 32]
+// at bf16 index 64 kb -- one 128-byte swizzle row of A_corr per K block.
 static __global__ void split_pad_tf32_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
-                                      float* __restrict__ hi, float* __restrict__ lo, int64_t ldd, int dst_cols) {
+                                      float* __restrict__ hi, float* __restrict__ corr, int64_t ldd, int dst_cols) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rows * dst_cols) return;
     const int64_t r = t / dst_cols;
@@ -1390,11 +1411,13 @@ static __global__ void split_pad_tf32_kernel(const float* __restrict__ src, int6
     const float v = c < cols ? src[r * lds + c] : 0.f;
     const float h = tc::round_tf32(v);
     hi[r * ldd + c] = h;
-    lo[r * ldd + c] = tc::round_tf32(v - h);
+    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(corr + r * ldd);
+    crow[(c >> 5) * 64 + (c & 31)] = __float2bfloat16_rn(v - h);
+    crow[(c >> 5) * 64 + 32 + (c & 31)] = __float2bfloat16_rn(h);
 }
 GNB_EXPORT int gnb_split_pad_tf32(const float* src, int64_t lds, int64_t rows, int32_t cols, float* hi, float* lo, int64_t ldd,
                                   int32_t dst_cols, void* stream) {
-    if (dst_cols < cols || rows < 0 || hi == nullptr || lo == nullptr) return GNB_ERR_ARG;
+    if (dst_cols < cols || (dst_cols & 31) || rows < 0 || hi == nullptr || lo == nullptr) return GNB_ERR_ARG;
     if (rows == 0) return GNB_OK;
     split_pad_tf32_kernel<<<gnb_div_up(rows * dst_cols, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, rows, cols, hi, lo, ldd,
                                                                                               dst_cols);

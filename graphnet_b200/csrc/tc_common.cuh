@@ -256,6 +256,20 @@ __device__ __forceinline__ void umma_tf32_2cta(uint32_t d_tmem, uint64_t a_desc,
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// kind::f16 with bf16 operands (UMMA_K = 16 = 32 bytes per instruction), fp32 accumulate, both operands K-major: the
+// correction products of the split-operand GEMM. a / b format code 1 = BF16 (0 = F16, 2 = TF32 in the same field).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive (once all prior MMAs of this thread completed) on the barrier at this offset in every CTA of `mask`
 __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -310,6 +324,21 @@ static inline int gnb_make_tmap_f32(CUtensorMap* map, const float* base, int64_t
     cuuint32_t estr[2] = {1u, 1u};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -1;
+}
+// bf16 row-major matrix [rows, cols] with row pitch ld_bytes: box = [64 cols (= 128 B), box_rows], 128-byte swizzle.
+static inline int gnb_make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld_bytes,
+                                     uint32_t box_rows) {
+    gnb_encode_tiled_fn enc = gnb_get_encode_tiled();
+    if (enc == nullptr) return -2;
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) || (ld_bytes & 15)) return -1;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld_bytes)};
+    cuuint32_t box[2] = {64u, box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -1;
 }

@@ -147,14 +147,16 @@ int gnb_linear_fwd_tf32(const float* const* xs, const int64_t* ldxs, const int32
                         int64_t ldw, const float* bias, float* y, int64_t ldy, int64_t rows, int32_t n_out, int32_t act,
                         int32_t round_out, void* stream);
 /* The same Linear at fp32 grade on the tensor cores (precision mode "tf32x3", the forward pass of training): split
- * operands, W = w_hi + w_lo (both tf32-exact, from gnb_split_pad_tf32; same packed layout and pitch) and x = x_hi + x_lo
- * (plain fp32 activations, split inside the kernel), three kind::tf32 products per K step (hi*hi + lo*hi + hi*lo), fp32
- * accumulation in TMEM; y is written unrounded. Replaces torch.nn.Linear's fp32 arithmetic (dynedge.py:200-203, 226-229,
+ * operands, W = w_hi + w_lo and x = x_hi + x_lo (hi parts tf32-exact; plain fp32 activations, split inside the kernel):
+ * w_hi x_hi as kind::tf32 plus the two correction products w_lo x_hi + w_hi x_lo as ONE bf16 contraction (kind::f16) over
+ * the concatenated K axis -- w_lo here is that bf16 operand as written by gnb_split_pad_tf32 (same bytes and pitch as a
+ * [n_out, ldw] fp32 matrix) --, fp32 accumulation in TMEM; y is written unrounded. Replaces torch.nn.Linear's fp32 arithmetic (dynedge.py:200-203, 226-229,
  * 246-247; the reference computes in fp32, graphs/graphs.py:21). Always the CTA-pair kernel; n_out <= 1024. */
 int gnb_linear_fwd_tf32x3(const float* const* xs, const int64_t* ldxs, const int32_t* ks, int32_t nparts,
                           const float* w_hi, const float* w_lo, int64_t ldw, const float* bias, float* y, int64_t ldy,
                           int64_t rows, int32_t n_out, int32_t act, void* stream);
-/* hi[rows, dst_cols] = [rna_tf32(src) | 0], lo = [rna_tf32(src - hi) | 0]: the pre-split weight operand of the tf32x3 GEMMs. */
+/* hi[rows, dst_cols] = [rna_tf32(src) | 0] and the bf16 correction operand of the tf32x3 GEMMs in `lo`: row r viewed as
+ * bf16[2 ldd] holds per 32-wide K block kb, at bf16 index 64 kb, [bf16(src - hi) x 32 | bf16(hi) x 32]. dst_cols % 32 == 0. */
 int gnb_split_pad_tf32(const float* src, int64_t lds, int64_t rows, int32_t cols, float* hi, float* lo, int64_t ldd,
                        int32_t dst_cols, void* stream);
 /* dw[n_out, k_in] += dz[rows, n_out]^T x[rows, k_in] on tcgen05 (split over rows, fp32 red.add into dw).

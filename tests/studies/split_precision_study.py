@@ -46,6 +46,11 @@ def mm(a, b, mode):
         ah, bh = rna(a), rna(b)
         al, bl = rna(a - ah), rna(b - bh)
         return ah @ bh + (ah @ bl + al @ bh)
+    if mode == "3b":                                   # hi*hi in tf32, the two correction products with bf16 operands
+        ah, bh = rna(a), rna(b)
+        al, bl = a - ah, b - bh
+        bf = lambda t: t.bfloat16().float()
+        return ah @ bh + (bf(ah) @ bf(bl) + bf(al) @ bf(bh))
     if mode == "2a":                                   # only the first operand split
         ah = trunc(a)
         al = trunc(a - ah)
@@ -149,11 +154,8 @@ def main():
     print(f"events {nev}, pulses {x.shape[0]}, edges {ei0.shape[1]}")
     cases = [
         ("all 1x (round-1 tf32 route)", ("1", "1", "1"), ("1", "1", "1")),
-        ("all 3x", ("3", "3", "3"), ("3", "3", "3")),
-        ("fwd 3x, dgrad 1x, wgrad 1x", ("3", "1", "1"), ("3", "1", "1")),
         ("fwd 3x (rna split), dgrad 1x, wgrad 1x x-truncated", ("3r", "1", "1t"), ("3r", "1", "1t")),
-        ("fwd 3x, dgrad 3x, wgrad 1x", ("3", "3", "1"), ("3", "3", "1")),
-        ("fwd 3x, dgrad 1x, wgrad 3x", ("3", "1", "3"), ("3", "1", "3")),
+        ("fwd hi*hi tf32 + bf16 corrections, bwd as above", ("3b", "1", "1t"), ("3b", "1", "1t")),
     ]
     for tag, node, edge in cases:
         MODES["node"], MODES["edge"] = node, edge

@@ -118,11 +118,14 @@ def _agg_case(ops, k, n_out, sizes, integer):
     ops._call("gnb_edge_linear_agg_fwd_tf32x3", ops._ptr(hc), k, k, ops._ptr(hi), ops._ptr(lo), kpad, ops._ptr(bc),
               ops._ptr(graph.deg), n, n_out, ops._ptr(y), n_out, ops._ptr(mask), ops._stream())
     torch.cuda.synchronize()
-    # the split itself: hi + lo reproduces w to 2^-22, both parts tf32-exact
-    assert rel_err(hi[:, :k].double() + lo[:, :k].double(), w.double()) < 3e-7
-    for part in (hi, lo):
-        bits = part.cpu().numpy().view(np.uint32)
-        assert not (bits & np.uint32(0x1FFF)).any()
+    # the split itself: hi is tf32-exact; the correction operand holds, per 32-wide K block, [bf16(w - hi) | bf16(hi)]
+    assert not (hi.cpu().numpy().view(np.uint32) & np.uint32(0x1FFF)).any()
+    corr = lo.view(torch.bfloat16).reshape(n_out, kpad // 32, 2, 32).float().cpu()
+    wp = torch.zeros(n_out, kpad)
+    wp[:, :k] = w
+    hic = hi.cpu()
+    assert rel_err(hic.double() + corr[:, :, 0].reshape(n_out, kpad).double(), wp.double()) < 2e-6      # bf16 lo: 2^-11 * 2^-9
+    assert torch.equal(corr[:, :, 1].reshape(n_out, kpad), hic.bfloat16().float())
     return y, y_ref, mask, on, graph, n
 
 
