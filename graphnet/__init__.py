@@ -18,6 +18,8 @@ import sys
 _ALIASES = {
     "models": "models", "models.model": "models.model", "models.utils": "models.utils",
     "models.gnn": "models.gnn", "models.gnn.gnn": "models.gnn.gnn", "models.gnn.dynedge": "models.gnn.dynedge",
+    "models.gnn.dynedge_jinst": "models.gnn.dynedge_jinst", "models.gnn.particlenet": "models.gnn.particlenet",
+    "models.gnn.dynedge_kaggle_tito": "models.gnn.dynedge_kaggle_tito",
     "models.components": "models.components", "models.components.layers": "models.components.layers",
     "models.graphs": "models.graphs", "models.graphs.graphs": "models.graphs.graphs",
     "models.graphs.graph_definition": "models.graphs.graph_definition",

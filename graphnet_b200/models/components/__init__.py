@@ -1,1 +1,1 @@
-from .layers import DynEdgeConv  # noqa: F401
+from .layers import DynEdgeConv, DynTrans, EdgeConvTito  # noqa: F401

@@ -115,3 +115,98 @@ class DynEdgeConv(Model):
             ptr = ops.batch_to_ptr(batch, int(batch.max().item()) + 1)
         x, new_graph = self.forward_table(x, graph, ptr)
         return x, new_graph.edge_index()
+
+
+class EdgeConvTito(Model):
+    """EdgeConv of the TITO solution: out_i = AGG_j nn([x_i, x_j - x_i, x_j]) (reference: layers.py:72-114, a PyG
+    `MessagePassing` with `aggr="max"` by default).
+
+    B200 design: when `nn` starts with a Linear over the 3C message (it always does in `DynTrans`), that Linear is hoisted
+    from edges to nodes exactly like DynEdge's -- W1 [x_i; x_j - x_i; x_j] + b1 = (W1a - W1b) x_i + b1 + (W1b + W1c) x_j --
+    so the [E, 3C] message is never built: one [N, C] x [C, 2H] GEMM, the gather-add kernel (`edge_hidden`, no activation),
+    the rest of `nn` on the [E, H] rows and the arg-routed max-aggregation kernel. Other `nn`s take the generic route."""
+
+    def __init__(self, nn: Callable, aggr: str = "max", **kwargs: Any):
+        assert aggr in ops.AGGR, f"aggr={aggr!r} not supported"
+        super().__init__()
+        self.nn = nn
+        self.aggr = aggr
+
+    def edge_conv(self, x: Tensor, graph: ops.KnnGraph) -> Tensor:
+        c = x.shape[1]
+        seq = self.nn if isinstance(self.nn, torch.nn.Sequential) else None
+        first = seq[0] if seq is not None and len(seq) and isinstance(seq[0], torch.nn.Linear) else None
+        if first is not None and first.in_features == 3 * c and first.out_features % 4 == 0:
+            w = first.weight
+            wa, wb, wc = w[:, :c], w[:, c:2 * c], w[:, 2 * c:]
+            wcat = pad_columns(torch.cat([wa - wb, wb + wc], dim=0), 4)                  # [2H, c]
+            xp = pad_columns(x, 4)
+            bcat = None if first.bias is None else torch.cat([first.bias, torch.zeros_like(first.bias)])
+            pq = ops.linear_act(xp, wcat, bcat, ops.ACT_NONE, round_out=False)           # [N, 2H] = [P | Q]
+            a1 = ops.edge_hidden(pq, graph, ops.ACT_NONE)                                # [N*W, H]: W1 msg + b1 per edge slot
+            m = a1
+            for layer in list(seq)[1:]:
+                m = layer(m)
+        else:
+            u = ops.edge_cat(x, graph)                                                   # [x_i | x_j - x_i]
+            m = self.nn(torch.cat([u, u[:, c:] + u[:, :c]], dim=1))
+        return ops.edge_aggregate(m.float(), graph, self.aggr)
+
+    def forward(self, x: Tensor, edge_index) -> Tensor:
+        graph = edge_index if isinstance(edge_index, ops.KnnGraph) else ops.KnnGraph.from_edge_index(edge_index, x.shape[0])
+        return self.edge_conv(x, graph)
+
+
+def to_dense_events(x: Tensor, ptr: Tensor) -> Tuple[Tensor, Tensor]:
+    """`torch_geometric.utils.to_dense_batch` for sorted events given as `ptr`: ([B, L_max, C] zero padded, mask [B, L_max])."""
+    sizes = ptr[1:] - ptr[:-1]
+    nseg, lmax = int(sizes.numel()), int(sizes.max().item()) if sizes.numel() else 0
+    batch = torch.repeat_interleave(torch.arange(nseg, device=x.device), sizes)
+    pos = torch.arange(x.shape[0], device=x.device) - ptr[:-1][batch]
+    dense = x.new_zeros(nseg, lmax, x.shape[1])
+    dense[batch, pos] = x
+    mask = torch.zeros(nseg, lmax, dtype=torch.bool, device=x.device)
+    mask[batch, pos] = True
+    return dense, mask
+
+
+class DynTrans(EdgeConvTito):
+    """`dynTrans1` layer of the TITO solution (reference: layers.py:117-197): EdgeConvTito with a LeakyReLU MLP, residual
+    connection when the widths agree, LayerNorm, and one TransformerEncoder layer applied per event (padded dense batch with
+    a key-padding mask, like the reference's `to_dense_batch`). Same attribute names (`nn`, `norm1`,
+    `_transformer_encoder`) and therefore `state_dict` keys. The graph is static: this fork never recomputes kNN here."""
+
+    def __init__(self, layer_sizes: Optional[List[int]] = None, aggr: str = "max",
+                 features_subset: Optional[Union[Sequence[int], slice]] = None, n_head: int = 8, **kwargs: Any):
+        if features_subset is None:
+            features_subset = slice(None)
+        assert isinstance(features_subset, (list, slice))
+        if layer_sizes is None:
+            layer_sizes = [256, 256, 256]
+        layers: List[torch.nn.Module] = []
+        for ix, (nb_in, nb_out) in enumerate(zip(layer_sizes[:-1], layer_sizes[1:])):
+            layers.append(torch.nn.Linear(3 * nb_in if ix == 0 else nb_in, nb_out))
+            layers.append(torch.nn.LeakyReLU())
+        d_model = layer_sizes[-1]
+        super().__init__(nn=torch.nn.Sequential(*layers), aggr=aggr, **kwargs)
+        self.features_subset = features_subset
+        self.norm1 = torch.nn.LayerNorm(d_model, eps=1e-5)
+        encoder_layer = torch.nn.TransformerEncoderLayer(d_model=d_model, nhead=n_head, batch_first=True, norm_first=False)
+        self._transformer_encoder = torch.nn.TransformerEncoder(encoder_layer, num_layers=1)
+
+    def forward_table(self, x: Tensor, graph: ops.KnnGraph, ptr: Tensor) -> Tensor:
+        x_out = self.edge_conv(x, graph)
+        x = x + x_out if x_out.shape[-1] == x.shape[-1] else x_out
+        x = self.norm1(x)
+        dense, mask = to_dense_events(x, ptr)
+        dense = self._transformer_encoder(dense, src_key_padding_mask=~mask)
+        return dense[mask]
+
+    def forward(self, x: Tensor, edge_index, batch: Optional[Tensor] = None) -> Tensor:
+        n = x.shape[0]
+        graph = edge_index if isinstance(edge_index, ops.KnnGraph) else ops.KnnGraph.from_edge_index(edge_index, n)
+        if batch is None:
+            ptr = torch.tensor([0, n], dtype=torch.int64, device=x.device)
+        else:
+            ptr = ops.batch_to_ptr(batch, int(batch.max().item()) + 1)
+        return self.forward_table(x, graph, ptr)

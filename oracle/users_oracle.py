@@ -118,3 +118,97 @@ class ParticleNeTRef(torch.nn.Module):
                 x = torch.cat([segment_pool_ref(x, ptr, s) for s in self._schemes], dim=1)
             x = self._readout(x)
         return (x, graphs) if return_graphs else x
+
+
+# --------------------------------------------------------------------------------------------------------------------- #
+# TITO family: EdgeConvTito / DynTrans (/root/reference/src/graphnet/models/components/layers.py:72-197)
+# and DynEdgeTITO (/root/reference/src/graphnet/models/gnn/dynedge_kaggle_tito.py:31-278). Pinned like the classes above.
+# --------------------------------------------------------------------------------------------------------------------- #
+def edgeconv_tito_ref(x, edge_index, nn, aggr: str = "max"):
+    """out_i = AGG_j nn([x_i, x_j - x_i, x_j]) (layers.py:100-112); empty neighbourhood -> 0; max routes its gradient to one
+    arg-max edge (first occurrence in the target-grouped edge list) [EXT torch_scatter / PyG]."""
+    from oracle.dynedge_oracle import _SegmentExtreme
+    src, dst = edge_index[0], edge_index[1]
+    n = x.shape[0]
+    x_i, x_j = x[dst], x[src]
+    msg = nn(torch.cat([x_i, x_j - x_i, x_j], dim=-1))
+    if aggr in ("add", "sum"):
+        return msg.new_zeros(n, msg.shape[1]).index_add_(0, dst, msg)
+    order = torch.argsort(dst, stable=True)
+    rowptr = torch.searchsorted(dst[order].contiguous(), torch.arange(n + 1))
+    return _SegmentExtreme.apply(msg[order], rowptr, aggr == "max")[0]
+
+
+class DynTransRef(torch.nn.Module):
+    def __init__(self, layer_sizes, aggr: str = "max", n_head: int = 8):
+        super().__init__()
+        layers = []
+        for ix, (a, b) in enumerate(zip(layer_sizes[:-1], layer_sizes[1:])):                                # layers.py:151-159
+            layers += [torch.nn.Linear(3 * a if ix == 0 else a, b), torch.nn.LeakyReLU()]
+        self.nn = torch.nn.Sequential(*layers)
+        self.aggr = aggr
+        d_model = layer_sizes[-1]
+        self.norm1 = torch.nn.LayerNorm(d_model, eps=1e-5)                                                  # :167
+        enc = torch.nn.TransformerEncoderLayer(d_model=d_model, nhead=n_head, batch_first=True, norm_first=False)   # :170-175
+        self._transformer_encoder = torch.nn.TransformerEncoder(enc, num_layers=1)
+
+    def forward(self, x, edge_index, batch):
+        x_out = edgeconv_tito_ref(x, edge_index, self.nn, self.aggr)                                        # :183
+        x = x + x_out if x_out.shape[-1] == x.shape[-1] else x_out                                          # :185-188
+        x = self.norm1(x)                                                                                   # :190
+        # to_dense_batch + key-padding mask (:193-195), event by event: padding never influences a valid position
+        counts = torch.bincount(batch)
+        outs, lo = [], 0
+        for c in counts.tolist():
+            outs.append(self._transformer_encoder(x[lo:lo + c].unsqueeze(0)).squeeze(0))
+            lo += c
+        return torch.cat(outs, dim=0)
+
+
+class DynEdgeTITORef(torch.nn.Module):
+    def __init__(self, nb_inputs: int, features_subset=None, dyntrans_layer_sizes=None, global_pooling_schemes=("max",),
+                 use_global_features: bool = True, use_post_processing_layers: bool = True, post_processing_layer_sizes=None,
+                 readout_layer_sizes=None, n_head: int = 8, nb_neighbours: int = 8):
+        super().__init__()
+        if dyntrans_layer_sizes is None:
+            dyntrans_layer_sizes = [(256, 256)] * 4
+        if post_processing_layer_sizes is None:
+            post_processing_layer_sizes = [336, 256]
+        if readout_layer_sizes is None:
+            readout_layer_sizes = [256, 128]
+        if isinstance(global_pooling_schemes, str):
+            global_pooling_schemes = [global_pooling_schemes]
+        self._schemes = list(global_pooling_schemes)
+        self._use_globals, self._use_post = use_global_features, use_post_processing_layers
+        act = torch.nn.LeakyReLU()
+        self._conv_layers = torch.nn.ModuleList()
+        width = nb_inputs
+        for sizes in dyntrans_layer_sizes:                                                                  # tito.py:161-170
+            self._conv_layers.append(DynTransRef([width] + list(sizes), "max", n_head))
+            width = sizes[-1]
+        if use_post_processing_layers:                                                                      # :172-186
+            dims, layers = [width] + list(post_processing_layer_sizes), []
+            for a, b in zip(dims[:-1], dims[1:]):
+                layers += [torch.nn.Linear(a, b), act]
+            self._post_processing = torch.nn.Sequential(*layers)
+            width = dims[-1]
+        width = width * len(self._schemes) + ((5 + nb_inputs) if use_global_features else 0)                 # :190-198
+        dims, layers = [width] + list(readout_layer_sizes), []
+        for a, b in zip(dims[:-1], dims[1:]):
+            layers += [torch.nn.Linear(a, b), act]
+        self._readout = torch.nn.Sequential(*layers)
+
+    def forward(self, data):
+        from oracle.dynedge_oracle import global_variables_ref
+        x, edge_index, batch = data.x, data.edge_index, data.batch
+        nseg = int(batch.max().item()) + 1
+        ptr = batch_to_ptr(batch, nseg)
+        g = global_variables_ref(x, edge_index, batch, data.n_pulses, ptr) if self._use_globals else None   # :229-262
+        for conv in self._conv_layers:                                                                      # :264-265 (static graph)
+            x = conv(x, edge_index, batch)
+        if self._use_post:
+            x = self._post_processing(x)
+        x = torch.cat([segment_pool_ref(x, ptr, s) for s in self._schemes], dim=1)                          # :270
+        if self._use_globals:
+            x = torch.cat([x, g], dim=1)
+        return self._readout(x)

@@ -83,6 +83,32 @@ class _MessagePassing(torch.nn.Module):
         super().__init__()
         self.aggr = aggr
 
+    def propagate(self, edge_index, x, size=None):
+        """PyG MessagePassing.propagate for flow='source_to_target': message(x_i = x[1][dst], x_j = x[0][src]) reduced over
+        the edges of every target node; nodes without in-edges get 0 (used by the reference's EdgeConvTito, layers.py:100-106)."""
+        src, dst = edge_index[0], edge_index[1]
+        msg = self.message(x_i=x[1][dst], x_j=x[0][src])
+        n = x[1].shape[0]
+        idx = dst.unsqueeze(1).expand_as(msg)
+        reduce = {"add": "sum", "sum": "sum", "mean": "mean", "max": "amax", "min": "amin"}[self.aggr]
+        return torch.zeros(n, msg.shape[1], dtype=msg.dtype).scatter_reduce(0, idx, msg, reduce, include_self=reduce == "sum")
+
+
+def _to_dense_batch(x, batch=None):
+    """torch_geometric.utils.to_dense_batch: [B, L_max, C] zero padded + bool mask."""
+    if batch is None:
+        return x.unsqueeze(0), torch.ones(1, x.shape[0], dtype=torch.bool)
+    nb = int(batch.max()) + 1
+    counts = torch.bincount(batch, minlength=nb)
+    lmax = int(counts.max())
+    start = torch.cumsum(counts, 0) - counts
+    pos = torch.arange(x.shape[0]) - start[batch]
+    dense = torch.zeros(nb, lmax, x.shape[1], dtype=x.dtype)
+    dense[batch, pos] = x
+    mask = torch.zeros(nb, lmax, dtype=torch.bool)
+    mask[batch, pos] = True
+    return dense, mask
+
 
 class _EdgeConv(_MessagePassing):
     """PyG EdgeConv: out_i = aggr_j nn(cat[x_i, x_j - x_i])."""
@@ -161,7 +187,7 @@ def install_shims() -> None:
     _mod("torch_geometric.nn.inits", reset=lambda *_: None)
     _mod("torch_geometric.typing", Adj=torch.Tensor, PairTensor=tuple)
     _mod("torch_geometric.data", Data=_Data, Batch=_Data)
-    _mod("torch_geometric.utils", homophily=_homophily, to_dense_batch=None)
+    _mod("torch_geometric.utils", homophily=_homophily, to_dense_batch=_to_dense_batch)
     _mod("torch_scatter", scatter_max=_scatter("amax"), scatter_min=_scatter("amin"),
          scatter_sum=_scatter("sum"), scatter_mean=_scatter("mean"))
     _mod("pytorch_lightning", LightningModule=_LightningModule)

@@ -63,6 +63,18 @@ def main() -> None:
     x, batch, n_pulses = mg.make_events([4, 13, 28, 10], 9, seed=23)
     torch.manual_seed(0)
     out["deepice_dynedge"] = dict(run(dynedge(9, **kw3), x, batch, n_pulses, 9), kwargs=kw3, nb_inputs=9)
+    # DynEdgeTITO (dynedge_kaggle_tito.py + the reference's own EdgeConvTito / DynTrans in layers.py) at reduced widths, eval
+    # mode (the TransformerEncoderLayer's dropout is random in training mode)
+    tito = importlib.import_module("graphnet.models.gnn.dynedge_kaggle_tito").DynEdgeTITO
+    kw4 = dict(dyntrans_layer_sizes=[(32, 32), (32, 32), (48, 48)], global_pooling_schemes=["max", "mean"], n_head=4,
+               post_processing_layer_sizes=[40, 24], readout_layer_sizes=[24, 8])
+    x, batch, n_pulses = mg.make_events([3, 12, 30, 9, 17], 6, seed=24)
+    torch.manual_seed(0)
+    out["tito"] = dict(run(tito(6, **kw4), x, batch, n_pulses, 8, train=False), kwargs=kw4, nb_inputs=6)
+    kw5 = dict(dyntrans_layer_sizes=[(6, 6)], global_pooling_schemes=["max"], n_head=2, use_global_features=False,
+               use_post_processing_layers=False, readout_layer_sizes=[8])
+    torch.manual_seed(0)
+    out["tito_residual_no_globals"] = dict(run(tito(6, **kw5), x, batch, n_pulses, 8, train=False), kwargs=kw5, nb_inputs=6)
     torch.save(out, os.path.join(HERE, "users_dynedgeconv.pt"))
     for k_, v in out.items():
         print(k_, tuple(v["out_f64"].shape), float(v["out_f64"].abs().max()))

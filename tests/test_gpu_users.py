@@ -12,23 +12,26 @@ import torch
 
 from helpers import GOLDEN_DIR, rel_err
 from oracle.dynedge_oracle import DynEdgeRef, batch_to_ptr, knn_graph_ref
-from oracle.users_oracle import DynEdgeJINSTRef, ParticleNeTRef
+from oracle.users_oracle import DynEdgeJINSTRef, DynEdgeTITORef, ParticleNeTRef
 
 pytestmark = pytest.mark.gpu
-CASES = ["jinst", "particlenet_train", "particlenet_eval", "particlenet_static_gelu", "deepice_dynedge"]
+CASES = ["jinst", "particlenet_train", "particlenet_eval", "particlenet_static_gelu", "deepice_dynedge", "tito",
+         "tito_residual_no_globals"]
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("case", CASES)
 def test_dynedgeconv_users_vs_oracle(built_library, case, precision):
     from graphnet_b200 import Data, ops
-    from graphnet_b200.models.gnn import DynEdge, DynEdgeJINST, ParticleNeT
+    from graphnet_b200.models.gnn import DynEdge, DynEdgeJINST, DynEdgeTITO, ParticleNeT
     from graphnet_b200.models.graphs.edges import KNNEdges
     g = torch.load(os.path.join(GOLDEN_DIR, "users_dynedgeconv.pt"))[case]
     if case == "jinst":
         model, ref, k, cols = DynEdgeJINST(**g["kwargs"]), DynEdgeJINSTRef(**g["kwargs"]), 8, slice(0, 3)
     elif case == "deepice_dynedge":
         model, ref, k, cols = DynEdge(g["nb_inputs"], **g["kwargs"]), DynEdgeRef(g["nb_inputs"], **g["kwargs"]), 9, slice(0, 3)
+    elif case.startswith("tito"):       # static graph; EdgeConvTito with max aggregation + per-event transformer (eval mode)
+        model, ref, k, cols = DynEdgeTITO(g["nb_inputs"], **g["kwargs"]), DynEdgeTITORef(g["nb_inputs"], **g["kwargs"]), 8, None
     else:
         model, ref = ParticleNeT(g["nb_inputs"], **g["kwargs"]), ParticleNeTRef(g["nb_inputs"], **g["kwargs"])
         k, cols = g["kwargs"]["nb_neighbours"], slice(0, 3)
@@ -50,7 +53,7 @@ def test_dynedgeconv_users_vs_oracle(built_library, case, precision):
         w = torch.linspace(0.5, 1.5, y.numel()).reshape(y.shape)
         (y * w.cuda()).sum().backward()
         ptr = batch_to_ptr(batch)
-        graphs = model._debug["graphs"]
+        graphs = model._debug["graphs"] if hasattr(model, "_debug") else []
         forced = [None]
         for li in range(1, len(graphs)):
             ei_k = graphs[li].edge_index().cpu()
@@ -58,7 +61,8 @@ def test_dynedgeconv_users_vs_oracle(built_library, case, precision):
                 feats = model._debug["skips"][li].detach().cpu()
                 assert torch.equal(ei_k, knn_graph_ref(feats[:, cols], k, ptr=ptr)), f"latent graph {li}"
             forced.append(ei_k)
-        y_ref = ref(SimpleNamespace(x=x.double(), edge_index=g["edge_index"], batch=batch, n_pulses=n_pulses), forced_graphs=forced)
+        d_ref = SimpleNamespace(x=x.double(), edge_index=g["edge_index"], batch=batch, n_pulses=n_pulses)
+        y_ref = ref(d_ref) if case.startswith("tito") else ref(d_ref, forced_graphs=forced)
         (y_ref * w.double()).sum().backward()
         err = rel_err(y, y_ref)
         gerr = {}

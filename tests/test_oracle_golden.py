@@ -105,16 +105,19 @@ def _users_gold():
     return torch.load(os.path.join(GOLDEN_DIR, "users_dynedgeconv.pt"))
 
 
-@pytest.mark.parametrize("case", ["jinst", "particlenet_train", "particlenet_eval", "particlenet_static_gelu", "deepice_dynedge"])
+@pytest.mark.parametrize("case", ["jinst", "particlenet_train", "particlenet_eval", "particlenet_static_gelu", "deepice_dynedge",
+                                  "tito", "tito_residual_no_globals"])
 def test_users_oracle_reproduces_the_reference_models(case):
     """oracle/users_oracle.py (DynEdgeJINST, ParticleNeT) and DynEdgeRef with DeepIce's arguments against golden vectors from
     the reference's own dynedge_jinst.py / particlenet.py / dynedge.py (tests/golden/make_golden_users.py): fp64, 1e-10."""
     from types import SimpleNamespace
     from oracle.dynedge_oracle import DynEdgeRef
-    from oracle.users_oracle import DynEdgeJINSTRef, ParticleNeTRef
+    from oracle.users_oracle import DynEdgeJINSTRef, DynEdgeTITORef, ParticleNeTRef
     g = _users_gold()[case]
     if case == "jinst":
         model = DynEdgeJINSTRef(**g["kwargs"])
+    elif case.startswith("tito"):
+        model = DynEdgeTITORef(g["nb_inputs"], **g["kwargs"])
     elif case == "deepice_dynedge":
         model = DynEdgeRef(g["nb_inputs"], **g["kwargs"])
     else:
@@ -126,7 +129,8 @@ def test_users_oracle_reproduces_the_reference_models(case):
     y = model(data)
     w = torch.linspace(0.5, 1.5, y.numel(), dtype=torch.float64).reshape(y.shape)
     (y * w).sum().backward()
-    assert torch.allclose(y, g["out_f64"], rtol=1e-10, atol=1e-12)
+    # TITO: the reference pads events into one dense batch (masked attention), the oracle runs event by event: 1e-9
+    assert torch.allclose(y, g["out_f64"], rtol=1e-9 if case.startswith("tito") else 1e-10, atol=1e-12)
     grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
     assert set(grads) == set(g["grads_f64"])
     for k, v in g["grads_f64"].items():
