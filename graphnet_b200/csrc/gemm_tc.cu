@@ -463,7 +463,8 @@ constexpr uint32_t PL_BAR_BYTES = 512;                // barrier block behind th
 // block, packed by gnb_split_pad_tf32), B_corr = [bf16(X_hi) | bf16(X_lo)]. Per K block: 4 tf32 + 4 bf16 MMAs of 256 x 256
 // (8 x 128 tensor cycles) instead of 12 tf32 MMAs; error of the dropped bits ~2^-19 (W_lo X_lo is below 2^-22).
 // The weight operands arrive from the pack kernels (two tensor maps); the activation operand arrives as plain fp32 and is
-// split IN SHARED MEMORY by two extra warps (10, 11): X tile -> X_hi = rna_tf32(X) in place, B_corr into its own ring.
+// split IN SHARED MEMORY by two extra warps (10, 11): X tile (left as it is: kind::tf32 reads its truncation = X_hi) ->
+// B_corr into its own ring.
 // TMA stage = {W_hi | A_corr | X} = 48 KiB, 4 stages (the depth that covers the L2 latency); B_corr lives in a ring of
 // 2 x 16 KiB (one slot per splitter warp: it is produced locally, a few hundred cycles before its MMAs, so it needs no
 // latency-covering depth -- with it inside the stages only 3 stages fit and the aggregating launch ran at 624 us).
@@ -670,18 +671,32 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
             }
         }
     } else if (SPLIT && warp >= 10) {
-        // ---- operand splitter (both CTAs, warps 10 / 11 take alternate stages): X -> (X_hi in place, B_corr) ----------
+        // ---- operand splitter (both CTAs, warps 10 / 11 take alternate stages): X tile -> B_corr ---------------------------
+        // X_hi = the fp32 value with its 13 low mantissa bits dropped, which is exactly what kind::tf32 reads from the raw X
+        // tile (tests/test_gpu_tf32x3.py::test_tensor_core_tf32_operand_conversion_probe pins that conversion), so the tile
+        // is NOT rewritten; X_lo = X - X_hi is exact. B_corr row r = [bf16(x_hi) k 0..31 | bf16(x_lo) k 0..31]: the high
+        // halves of the fp32 words (x_hi: truncation, unbiased against the symmetric W_lo; x_lo: + 0x8000 = rounded).
         // Lane l of step i owns the 16-byte chunk q = 32 i + l of the X tile: row r = q / 8, physical chunk p = q % 8 holding
-        // the logical chunk c = p ^ (r % 8) (128-byte swizzle) = k 4c .. 4c + 3. B_corr row r = [bf16(x_hi) k 0..31 |
-        // bf16(x_lo) k 0..31] in the same swizzle: the 4 hi values are half (c & 1) of logical chunk c / 2, the 4 lo values
-        // of logical chunk 4 + c / 2.
+        // the logical chunk c = p ^ (r % 8) (128-byte swizzle) = k 4c .. 4c + 3; its 4 hi values are half (c & 1) of logical
+        // chunk c / 2 of the B_corr row, its 4 lo values of logical chunk 4 + c / 2. r % 8 = (4 i + l / 8) % 8 depends on i
+        // only through its parity: two constant offset pairs per lane, everything else folds into store immediates.
+        // (Integer ops only: the first version converted with cvt.rna.tf32 / cvt.rn.bf16x2 -- quarter-rate pipes, ~3000
+        // cycles per 16 KiB tile and warp -- and made the splitter, not the tensor pipe, the kernel's bound: 494 us.)
+        uint32_t off_hi[2], off_lo[2];
+#pragma unroll
+        for (int par = 0; par < 2; ++par) {
+            const uint32_t r7 = ((uint32_t)(4 * par) + ((uint32_t)lane >> 3)) & 7u;
+            const uint32_t c = ((uint32_t)lane & 7u) ^ r7;
+            off_hi[par] = (((c >> 1) ^ r7) << 4) + ((c & 1u) << 3);
+            off_lo[par] = (((4u + (c >> 1)) ^ r7) << 4) + ((c & 1u) << 3);
+        }
         uint32_t it = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
             for (int kbi = 0; kbi < total_kb; ++kbi, ++it) {
                 if ((int)(it & 1u) != warp - 10) continue;
                 const uint32_t s = it % (uint32_t)nstages, ph = (it / (uint32_t)nstages) & 1;
                 tc::mbar_wait<20>(&xfull[s], ph);
-                tc::mbar_wait<20>(&lo_empty[warp - 10], ((it >> 1) & 1u) ^ 1u);     // this warp's X_lo slot: MMAs of its previous use done
+                tc::mbar_wait<20>(&lo_empty[warp - 10], ((it >> 1) & 1u) ^ 1u);     // this warp's B_corr slot: MMAs of its previous use done
                 const uint32_t xa = tc::smem_u32(ring + s * stage_bytes + 2 * TC_TILE_BYTES) + (uint32_t)lane * 16u;
                 // B_corr slot of this warp; row base of lane's chunk in step 0: (lane / 8) * 128 B (+ 4 rows = 512 B per step)
                 const uint32_t la_row = tc::smem_u32(lo_ring + (uint32_t)(warp - 10) * TC_TILE_BYTES) + ((uint32_t)lane >> 3) * 128u;
@@ -692,28 +707,18 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                     for (int i = 0; i < 8; ++i)             // 8 independent 16-byte loads in flight
                         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                                      : "=r"(v[i][0]), "=r"(v[i][1]), "=r"(v[i][2]), "=r"(v[i][3]) : "r"(xa + 512u * (uint32_t)(i0 + i)));
+                    const uint32_t blk = la_row + 512u * (uint32_t)i0;
+                    const uint32_t bh[2] = {blk + off_hi[0], blk + off_hi[1]}, bl[2] = {blk + off_lo[0], blk + off_lo[1]};
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        float hi[4], lo[4];
+                        uint32_t lo[4];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            hi[e] = tc::round_tf32(__uint_as_float(v[i][e]));
-                            lo[e] = __uint_as_float(v[i][e]) - hi[e];        // exact: fits the 13 dropped mantissa bits
-                        }
-                        const uint32_t a = xa + 512u * (uint32_t)(i0 + i);
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(hi[3]) : "memory");
-                        // row of this chunk: q / 8 = 4 (i0 + i) + lane / 8; r % 8 = (4 (i0 + i) + lane / 8) % 8
-                        const uint32_t r7 = ((uint32_t)(4 * (i0 + i)) + ((uint32_t)lane >> 3)) & 7u;
-                        const uint32_t c = ((uint32_t)lane & 7u) ^ r7;                        // logical 16-byte chunk of the X row
-                        const uint32_t row_a = la_row + 512u * (uint32_t)(i0 + i);            // B_corr row base (128 B per row)
-                        const uint32_t a_hi = row_a + ((((c >> 1)) ^ r7) << 4) + ((c & 1u) << 3);
-                        const uint32_t a_lo = row_a + (((4u + (c >> 1)) ^ r7) << 4) + ((c & 1u) << 3);
-                        const __nv_bfloat162 h01 = __floats2bfloat162_rn(hi[0], hi[1]), h23 = __floats2bfloat162_rn(hi[2], hi[3]);
-                        const __nv_bfloat162 l01 = __floats2bfloat162_rn(lo[0], lo[1]), l23 = __floats2bfloat162_rn(lo[2], lo[3]);
-                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
-                                     "r"(*reinterpret_cast<const uint32_t*>(&h23)) : "memory");
-                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_lo), "r"(*reinterpret_cast<const uint32_t*>(&l01)),
-                                     "r"(*reinterpret_cast<const uint32_t*>(&l23)) : "memory");
+                        for (int e = 0; e < 4; ++e)          // x - trunc_tf32(x), exact; + 0x8000: rounded by the high-half pick below
+                            lo[e] = __float_as_uint(__uint_as_float(v[i][e]) - __uint_as_float(v[i][e] & 0xFFFFE000u)) + 0x8000u;
+                        const uint32_t h01 = __byte_perm(v[i][0], v[i][1], 0x7632), h23 = __byte_perm(v[i][2], v[i][3], 0x7632);
+                        const uint32_t l01 = __byte_perm(lo[0], lo[1], 0x7632), l23 = __byte_perm(lo[2], lo[3], 0x7632);
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(bh[i & 1] + 512u * (uint32_t)i), "r"(h01), "r"(h23) : "memory");
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(bl[i & 1] + 512u * (uint32_t)i), "r"(l01), "r"(l23) : "memory");
                     }
                 }
                 // generic-proxy writes -> visible to the tensor core's async-proxy reads. The notification itself is relaxed: a

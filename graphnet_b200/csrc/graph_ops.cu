@@ -40,10 +40,27 @@ global_vars_kernel(const float* __restrict__ x, int64_t ldx, int nf, const int* 
         for (int f = 0; f < GV_MAX_F; ++f)
             if (f < nf) acc[f] += xi[f];
         const int dg = deg[i];
-        for (int s = 0; s < dg; ++s) {
-            const float* xj = x + (int64_t)nbr[i * width + s] * ldx;
+        const float xi0 = xi[0], xi1 = xi[1], xi2 = xi[2], xi3 = xi[3];
+        // the neighbour indices first, then all gathers: 4 slots at a time are independent loads in flight (one slot
+        // per iteration made every gather wait for the previous compare: the largest event set the kernel's time)
+        for (int s0 = 0; s0 < dg; s0 += 4) {
+            int nb[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) same[c] += (xj[c] == xi[c]) ? 1.f : 0.f;
+            for (int u = 0; u < 4; ++u) nb[u] = s0 + u < dg ? nbr[i * width + s0 + u] : -1;
+            float v[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float* xj = x + (int64_t)(nb[u] < 0 ? i : nb[u]) * ldx;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[u][c] = xj[c];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (nb[u] >= 0) {
+                    same[0] += (v[u][0] == xi0) ? 1.f : 0.f; same[1] += (v[u][1] == xi1) ? 1.f : 0.f;
+                    same[2] += (v[u][2] == xi2) ? 1.f : 0.f; same[3] += (v[u][3] == xi3) ? 1.f : 0.f;
+                }
+            }
         }
         edges += (float)dg;
     }
@@ -81,7 +98,22 @@ global_vars_kernel(const float* __restrict__ x, int64_t ldx, int nf, const int* 
     }
     __syncthreads();
     if (tid < ng) g[(int64_t)b * ng + tid] = s_g[tid];
-    if (x0 != nullptr) {
+    if (x0 != nullptr && !(ld0 & 3) && ld0 <= 4 * GV_THREADS && !(reinterpret_cast<uintptr_t>(x0) & 15u)) {
+        // one float4 of a row per thread and step: no integer division in the loop, 16-byte coalesced stores
+        const int chunks = (int)(ld0 >> 2), rows_per_step = GV_THREADS / chunks;
+        const int ch = tid % chunks, r0 = tid / chunks;
+        if (r0 < rows_per_step) {
+            for (int64_t i = lo + r0; i < hi; i += rows_per_step) {
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = 4 * ch + e;
+                    v[e] = c < nf ? x[i * ldx + c] : (c < x0_cols ? s_g[c - nf] : 0.f);
+                }
+                reinterpret_cast<float4*>(x0 + i * ld0)[ch] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+    } else if (x0 != nullptr) {
         const int64_t total = (hi - lo) * ld0;
         for (int64_t t = tid; t < total; t += GV_THREADS) {
             const int64_t i = lo + t / ld0;
@@ -397,11 +429,21 @@ segment_pool_fwd_kernel(const float* __restrict__ x, int64_t ldx, int c_tot, con
     float vmin = FLT_MAX, vmax = -FLT_MAX, vsum = 0.f;
     int amin = -1, amax = -1;
     if (c < c_tot) {
-        for (int64_t i = lo + ty; i < hi; i += POOL_RY) {
-            const float v = x[i * ldx + c];
-            vsum += v;
-            if (amin < 0 || v < vmin) { vmin = v; amin = (int)i; }
-            if (amax < 0 || v > vmax) { vmax = v; amax = (int)i; }
+        // 4 rows per step: the loads are issued together, the (ordered) compare chain follows -- with one load per step
+        // every load waited for the previous row's compares and the largest event set the kernel's time
+        for (int64_t i = lo + ty; i < hi; i += 4 * POOL_RY) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = i + u * POOL_RY < hi ? x[(i + u * POOL_RY) * ldx + c] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i + u * POOL_RY < hi) {
+                    const int idx = (int)(i + u * POOL_RY);
+                    vsum += v[u];
+                    if (amin < 0 || v[u] < vmin) { vmin = v[u]; amin = idx; }
+                    if (amax < 0 || v[u] > vmax) { vmax = v[u]; amax = idx; }
+                }
+            }
         }
     }
     s_min[ty][threadIdx.x] = vmin; s_max[ty][threadIdx.x] = vmax; s_sum[ty][threadIdx.x] = vsum;
@@ -431,56 +473,64 @@ segment_pool_fwd_kernel(const float* __restrict__ x, int64_t ldx, int c_tot, con
     }
 }
 
-// backward: one warp per node (the event is found once per warp: binary search over ptr, all lanes on the same
-// cached addresses), lanes stride over the channels; the pooled gradients / arg tables (B x P x C) stay L2-resident
+// backward: one warp per PB_NODES consecutive nodes (the event of the first node is found by a binary search over ptr, all
+// lanes on the same cached addresses; the following nodes only compare against the event's end), lanes stride over the
+// channels; the pooled gradients / arg tables (B x P x C) stay L2-resident. (One node per warp spent most of its time in
+// the 9 dependent loads of the search: 79 us for 81 MB.)
+constexpr int PB_NODES = 8;
 __global__ void __launch_bounds__(256)
 segment_pool_bwd_kernel(const float* __restrict__ gout, int64_t ldg, const int* __restrict__ arg, int c_tot,
                         const int64_t* __restrict__ ptr, int nseg, int64_t n, int np, int s0,
                         int s1, int s2, int s3, float* __restrict__ gx, int64_t ldx, int vec4) {
-    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (i >= n) return;
+    const int64_t i0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PB_NODES;
+    if (i0 >= n) return;
     const int lane = threadIdx.x & 31;
     int lo = 0, hi = nseg;
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ptr[mid] <= i) lo = mid; else hi = mid; }
-    const int b = lo;
-    const float cnt = (float)(ptr[b + 1] - ptr[b]);
-    const float* gb = gout + (int64_t)b * ldg;
-    const int* ab = arg != nullptr ? arg + (int64_t)b * np * c_tot : nullptr;
-    const int ii = (int)i;
-    auto term = [&](int scheme, int p, int c) -> float {
-        if (p >= np) return 0.f;
-        const float g = gb[(int64_t)p * c_tot + c];
-        if (scheme == GNB_POOL_SUM) return g;
-        if (scheme == GNB_POOL_MEAN) return g / cnt;
-        return ab[(int64_t)p * c_tot + c] == ii ? g : 0.f;
-    };
-    if (vec4) {   // c_tot % 4 == 0, 16-byte aligned rows: four channels per lane, 512-byte warp stores
-        const int c4n = c_tot >> 2;
-        auto term4 = [&](int scheme, int p, int c4) -> float4 {
-            if (p >= np) return make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 g = reinterpret_cast<const float4*>(gb + (int64_t)p * c_tot)[c4];
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ptr[mid] <= i0) lo = mid; else hi = mid; }
+    int b = lo;
+    int64_t next = ptr[b + 1];
+    for (int k = 0; k < PB_NODES && i0 + k < n; ++k) {
+        const int64_t i = i0 + k;
+        while (i >= next && b + 1 < nseg) { ++b; next = ptr[b + 1]; }          // also steps over empty events
+        const float cnt = (float)(next - ptr[b]);
+        const float* gb = gout + (int64_t)b * ldg;
+        const int* ab = arg != nullptr ? arg + (int64_t)b * np * c_tot : nullptr;
+        const int ii = (int)i;
+        auto term = [&](int scheme, int p, int c) -> float {
+            if (p >= np) return 0.f;
+            const float g = gb[(int64_t)p * c_tot + c];
             if (scheme == GNB_POOL_SUM) return g;
-            if (scheme == GNB_POOL_MEAN) return make_float4(g.x / cnt, g.y / cnt, g.z / cnt, g.w / cnt);
-            const int4 a = reinterpret_cast<const int4*>(ab + (int64_t)p * c_tot)[c4];
-            return make_float4(a.x == ii ? g.x : 0.f, a.y == ii ? g.y : 0.f, a.z == ii ? g.z : 0.f, a.w == ii ? g.w : 0.f);
+            if (scheme == GNB_POOL_MEAN) return g / cnt;
+            return ab[(int64_t)p * c_tot + c] == ii ? g : 0.f;
         };
-        for (int c4 = lane; c4 < c4n; c4 += 32) {
-            float4 acc = term4(s0, 0, c4);
-            const float4 t1 = term4(s1, 1, c4), t2 = term4(s2, 2, c4), t3 = term4(s3, 3, c4);
-            acc.x += t1.x; acc.y += t1.y; acc.z += t1.z; acc.w += t1.w;
-            acc.x += t2.x; acc.y += t2.y; acc.z += t2.z; acc.w += t2.w;
-            acc.x += t3.x; acc.y += t3.y; acc.z += t3.z; acc.w += t3.w;
-            reinterpret_cast<float4*>(gx + i * ldx)[c4] = acc;
+        if (vec4) {   // c_tot % 4 == 0, 16-byte aligned rows: four channels per lane, 512-byte warp stores
+            const int c4n = c_tot >> 2;
+            auto term4 = [&](int scheme, int p, int c4) -> float4 {
+                if (p >= np) return make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 g = reinterpret_cast<const float4*>(gb + (int64_t)p * c_tot)[c4];
+                if (scheme == GNB_POOL_SUM) return g;
+                if (scheme == GNB_POOL_MEAN) return make_float4(g.x / cnt, g.y / cnt, g.z / cnt, g.w / cnt);
+                const int4 a = reinterpret_cast<const int4*>(ab + (int64_t)p * c_tot)[c4];
+                return make_float4(a.x == ii ? g.x : 0.f, a.y == ii ? g.y : 0.f, a.z == ii ? g.z : 0.f, a.w == ii ? g.w : 0.f);
+            };
+            for (int c4 = lane; c4 < c4n; c4 += 32) {
+                float4 acc = term4(s0, 0, c4);
+                const float4 t1 = term4(s1, 1, c4), t2 = term4(s2, 2, c4), t3 = term4(s3, 3, c4);
+                acc.x += t1.x; acc.y += t1.y; acc.z += t1.z; acc.w += t1.w;
+                acc.x += t2.x; acc.y += t2.y; acc.z += t2.z; acc.w += t2.w;
+                acc.x += t3.x; acc.y += t3.y; acc.z += t3.z; acc.w += t3.w;
+                reinterpret_cast<float4*>(gx + i * ldx)[c4] = acc;
+            }
+            continue;
         }
-        return;
-    }
-    for (int c = lane; c < c_tot; c += 32) {
-        // same summation order as the schemes are listed
-        float acc = term(s0, 0, c);
-        acc += term(s1, 1, c);
-        acc += term(s2, 2, c);
-        acc += term(s3, 3, c);
-        gx[i * ldx + c] = acc;
+        for (int c = lane; c < c_tot; c += 32) {
+            // same summation order as the schemes are listed
+            float acc = term(s0, 0, c);
+            acc += term(s1, 1, c);
+            acc += term(s2, 2, c);
+            acc += term(s3, 3, c);
+            gx[i * ldx + c] = acc;
+        }
     }
 }
 
@@ -795,7 +845,7 @@ GNB_EXPORT int gnb_segment_pool_bwd(const float* gout, int64_t ldg, const int32_
     int s[4] = {0, 0, 0, 0};
     for (int p = 0; p < np; ++p) s[p] = schemes[p];
     const int vec4 = !(c & 3) && !(ldg & 3) && !(ldx & 3) && aligned16(gout) && aligned16(gx) && (arg == nullptr || aligned16(arg));
-    segment_pool_bwd_kernel<<<gnb_div_up(n, 8), 256, 0, (cudaStream_t)stream>>>(gout, ldg, arg, c, ptr, (int)nseg, n, np,
+    segment_pool_bwd_kernel<<<gnb_div_up(n, 8 * PB_NODES), 256, 0, (cudaStream_t)stream>>>(gout, ldg, arg, c, ptr, (int)nseg, n, np,
                                                                                       s[0], s[1], s[2], s[3], gx, ldx, vec4);
     GNB_RETURN_LAUNCH();
 }
