@@ -611,7 +611,6 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
         }
     }
     // ---- DynEdgeConv layers, last to first -------------------------------------------------------
-    int dq_zeroed_hid = -1;     // width for which the Q half of p.dpq is known to be all zero
     for (int l = c.n_conv - 1; l >= 0; --l) {
         ConvBuf& b = p.conv[l];
         pi -= 4;
@@ -631,23 +630,19 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
         GNB_CHECK(cudaMemsetAsync(p.dbtmp, 0, (size_t)2 * b.hid * 4, e.st));
         const float* dzq = p.dzq;
         if (b.hmask != nullptr) {
-            // data gradient + ReLU mask + scatter in one kernel (dh [E, hid] is never materialised). The P half (slot sums,
-            // plain stores) goes straight into dzq, rounded for the tensor cores, with its column sums (bias gradient)
-            // accumulated by the epilogue; only the Q half (fp32 reductions from all over the event) needs the dPQ
-            // accumulation buffer and a rounding pass, which also leaves that half zeroed for the next layer of the same
-            // width (so it is memset only when the layout changes).
-            if (dq_zeroed_hid != b.hid)
-                GNB_CHECK(cudaMemset2DAsync(p.dpq + b.hid, (size_t)2 * b.hid * 4, 0, (size_t)b.hid * 4, (size_t)n, e.st));
+            // data gradient + ReLU mask + scatter in one kernel (dh [E, hid] is never materialised). Both halves land straight
+            // in dzq, the operand buffer of the two GEMMs that follow: the P half (slot sums, plain stores) rounded to tf32
+            // with its column sums (bias gradient) accumulated by the epilogue, the Q half by fp32 reductions from all over
+            // the event onto a zeroed half -- unrounded: the tensor core reads its truncation, which leaves the gradient
+            // error where it is (tests/studies/bf16_storage_study.py: 2.1e-3 / 7.0e-4 against 2.2e-3 / 7.6e-4 with the
+            // rounding pass this replaces: 12 B per value read + written + zeroed, ~55 us per layer, for a 4 B memset).
+            GNB_CHECK(cudaMemset2DAsync(p.dzq + b.hid, (size_t)2 * b.hid * 4, 0, (size_t)b.hid * 4, (size_t)n, e.st));
             const int nld = (int)up(b.cout, 32);
             EX(e.transpose_pad(b.w2p, b.hld, b.cout, b.hid, p.wt, nld, nld));
             EX(gnb_edge_hidden_dgrad_scatter_split_tf32(p.dz_big, b.cout, b.cout, p.wt, nld, b.hmask, b.mld, b.hid, nbr, n,
-                                                        p.dpq + b.hid, 2 * b.hid, p.dzq, 2 * b.hid, p.dbtmp, e.rnd, stream));
-            EX(gnb_act_bwd_colsum(p.dpq + b.hid, 2 * b.hid, nullptr, 0, n, b.hid, p.dzq + b.hid, 2 * b.hid, nullptr,
-                                  GNB_ACT_NONE | e.rnd | GNB_FLAG_ZERO_SRC, nullptr, 1, 0, stream));
-            dq_zeroed_hid = b.hid;
+                                                        p.dzq + b.hid, 2 * b.hid, p.dzq, 2 * b.hid, p.dbtmp, e.rnd, stream));
         } else {
             GNB_CHECK(cudaMemsetAsync(p.dpq, 0, (size_t)n * 2 * b.hid * 4, e.st));
-            dq_zeroed_hid = -1;
             EX(e.lin_bwd_data(p.dz_big, b.cout, b.w2p, b.hld, 0, b.hid, b.cout, p.dh_big, b.hid, rows, false, p.wt, nullptr));
             EX(gnb_edge_hidden_bwd(p.dh_big, b.hid, b.h, b.hid, b.hid, nbr, deg, wl, n, GNB_ACT_RELU, p.dpq, 2 * b.hid, stream));
             // PQ = xin Wcat^T + bcat: rounded copy for the tensor cores (tf32 mode) + bias gradient in the same pass

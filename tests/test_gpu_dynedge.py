@@ -198,7 +198,8 @@ def test_executor_matches_per_operator_route(built_library, precision):
             (y0, g0), (y1, g1) = results
             # tf32x3: the two routes sum the k messages in different places (TMEM epilogue vs aggregation kernel), so the
             # latent features differ at 1e-6 and a latent kNN near-tie may resolve differently: outputs 5e-4, gradients 2e-3
-            out_tol, grad_tol = (5e-4, 2e-3) if precision == "tf32x3" else (1e-5, 2e-4)
+            # tf32: the executor lets the tensor core truncate the Q half of dPQ where the per-operator route rounds it (5e-4)
+            out_tol, grad_tol = {"tf32x3": (5e-4, 2e-3), "tf32": (1e-5, 5e-4), "fp32": (1e-5, 2e-4)}[precision]
             assert y0.shape == y1.shape and rel_err(y1, y0) < out_tol, kwargs
             assert g0.keys() == g1.keys()
             for k in g0:
