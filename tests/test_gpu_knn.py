@@ -145,3 +145,42 @@ def test_device_graph_definition_from_raw_pulses(built_library):
             assert torch.equal(host.x[:, c], x[:, c])
     with pytest.raises(RuntimeError):                                   # no CPU fallback
         DeviceKNNGraph(definition)(raw, sizes)
+
+
+@pytest.mark.gpu
+def test_device_percentile_clusters_equal_the_host_node_definition(built_library):
+    """SURVEY 8f rank 3, second half: `PercentileClusters` nodes built for a whole raw batch on the device
+    (models/graphs/device.py::percentile_clusters: segmented lexsort, float64 percentile arithmetic of numpy) against the
+    host node definition, which is pinned bit for bit on the reference's own cluster_summarize_with_percentiles
+    (tests/test_oracle_golden.py). Nodes bit-exact (log10(count): 1 ulp of fp32), node ptr, raw n_pulses, kNN graph."""
+    from graphnet_b200.data import Batch
+    from graphnet_b200.models.detector import IceCube86
+    from graphnet_b200.models.graphs import DeviceKNNGraph, KNNGraph
+    from graphnet_b200.models.graphs.nodes import PercentileClusters
+    from graphnet_b200.synthetic import FEATURES_ICECUBE86
+    rng = np.random.default_rng(7)
+    sizes = [300, 1, 40, 7, 2500, 64]
+    raws = []
+    for n_ in sizes:
+        doms = np.round(rng.uniform(-500, 500, size=(max(1, n_ // 3), 3)), 0).astype(np.float32)
+        rest = np.stack([rng.normal(1e4, 1.5e3, n_), rng.lognormal(0.0, 0.7, n_), rng.choice([1.0, 1.35], n_),
+                         np.full(n_, 0.0444)], axis=1).astype(np.float32)
+        raws.append(np.concatenate([doms[rng.integers(0, len(doms), size=n_)], rest], axis=1))
+    definition = KNNGraph(detector=IceCube86(), input_feature_names=FEATURES_ICECUBE86, nb_nearest_neighbours=8,
+                          node_definition=PercentileClusters(["dom_x", "dom_y", "dom_z"], [10, 50, 90]))
+    host = Batch.from_data_list([definition(r, FEATURES_ICECUBE86) for r in raws])
+    raw = torch.from_numpy(np.concatenate(raws))
+    n_pulses = torch.tensor(sizes, dtype=torch.int32)
+    graph = DeviceKNNGraph(definition)(raw.cuda(), n_pulses.cuda())
+    x = graph.x.cpu()
+    assert x.shape == host.x.shape and x.shape[1] == 16
+    # the charge percentiles go through log10f on the device (2 ulp, see the NodesAsPulses test); everything else is exact
+    names = definition.output_feature_names
+    for c, name in enumerate(names):
+        if name.startswith("charge") or name == "counts":
+            assert torch.allclose(x[:, c], host.x[:, c], rtol=3e-7, atol=1e-9), name
+        else:
+            assert torch.equal(x[:, c], host.x[:, c]), name
+    assert torch.equal(graph.ptr.cpu(), host.ptr) and torch.equal(graph.batch.cpu(), host.batch)
+    assert torch.equal(graph.n_pulses.cpu(), n_pulses)                          # the RAW pulse counts (graph_definition.py:213)
+    assert torch.equal(graph.edge_index.cpu(), knn_graph_ref(x[:, :3], 8, ptr=host.ptr))
