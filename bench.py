@@ -183,16 +183,29 @@ def _pin(t):
     return t.pin_memory() if torch.cuda.is_available() else t
 
 
-def host_batches(num_events: int, count: int, seed0: int, rank: int = 0, world: int = 1, **gen):
+def _global_batch(num_events: int, world: int, seed: int, replicate: bool, **gen):
+    from graphnet_b200.synthetic import make_batch
+    if world == 1 or not replicate:
+        return make_batch(num_events * world, seed=seed, **gen)
+    one = make_batch(num_events, seed=seed, **gen)
+    sizes = np.tile(one["n_pulses"], world)
+    return {"x": np.tile(one["x"], (world, 1)), "n_pulses": sizes, "energy": np.tile(one["energy"], world),
+            "direction": np.tile(one["direction"], (world, 1)),
+            "batch": np.repeat(np.arange(len(sizes), dtype=np.int64), sizes.astype(np.int64))}
+
+
+def host_batches(num_events: int, count: int, seed0: int, rank: int = 0, world: int = 1, replicate: bool = False, **gen):
     """`count` pinned host batches. With world > 1 every rank builds the same GLOBAL batch of num_events * world events
     and keeps the events `assign_events` gives it (balanced on the cost model n + beta n^2, largest events spread first,
     SURVEY 8e): the global batch is exactly num_events * world events per step, the per-rank event counts differ slightly.
-    `event_index` = the global indices of the rank's events (ascending)."""
+    `event_index` = the global indices of the rank's events (ascending).
+    replicate=True (what the weak-scaling bench uses): the global batch is `world` replicas of the SAME num_events-event
+    draw, so the per-GPU work is exactly the 1-GPU work at every N (an independent draw of N x 512 events differs from the
+    1-GPU draw by a few percent in pulses -- 79.3 k vs 82.5 k per rank measured -- which would be read as scaling loss)."""
     from graphnet_b200.distributed import assign_events
-    from graphnet_b200.synthetic import make_batch
     out = []
     for i in range(count):
-        raw = make_batch(num_events * world, seed=seed0 + i, **gen)
+        raw = _global_batch(num_events, world, seed0 + i, replicate, **gen)
         index = np.arange(num_events * world)
         if world > 1:
             index = assign_events(raw["n_pulses"], world)[rank]
@@ -740,8 +753,8 @@ def workload_config(args, world):
                         "(LogCosh) training step fwd+bwd+Adam, 512 events/GPU, synthetic IceCube86 pulse maps "
                         "(lognormal pulses/event, median 100, max 5000); configs[1] inference B=1024 under 'inference'",
             "events_per_gpu": args.events, "global_events": args.events * world, "parallelism": f"dp{world}",
-            "sharding": "global batch spread over the ranks by assign_events (cost n + 1.1e-4 n^2 per event, largest first); "
-                        "no data-path collective",
+            "sharding": "global batch = N replicas of the 512-event draw (identical per-GPU work at every N), spread over the ranks "
+                        "by assign_events (cost n + 1.1e-4 n^2 per event, largest first); no data-path collective",
             "precision": f"{args.precision}: {TOLERANCE[args.precision]}",
             "inputs": "x/batch/n_pulses resident in HBM; kNN graph built inside the step",
             "l2": "256 MiB buffer rewritten between timed steps; min(4, warmup) rotating batches",
@@ -780,7 +793,7 @@ def run_train512(args, dev, world, rank, local):
     trainer = Trainer(dev, world, overlap=not args.no_overlap)
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
 
-    train_host = host_batches(args.events, 4, seed0=20240607, rank=rank, world=world)
+    train_host = host_batches(args.events, 4, seed0=20240607, rank=rank, world=world, replicate=True)
     train_dev = [to_device(hb, dev) for hb in train_host]
     torch.cuda.synchronize()
 
@@ -862,7 +875,7 @@ def run_inference(args, trainer, dev, world, rank, flush, pk):
     rel 1e-3: tests/test_gpu_tc.py) and, beside it, in the mode of the training run. Device-resident `value`, `e2e` from
     pinned host buffers (H2D of the batch, D2H of the [B, 1] predictions inside the timed region), own roofline."""
     from graphnet_b200 import ops
-    inf_host = host_batches(args.infer_events, 2, seed0=777, rank=rank, world=world)
+    inf_host = host_batches(args.infer_events, 2, seed0=777, rank=rank, world=world, replicate=True)
     inf_dev = [to_device(hb, dev) for hb in inf_host]
     events_total = float(args.infer_events * world * args.steps)
     keep = ops.PRECISION

@@ -174,11 +174,12 @@ def test_device_percentile_clusters_equal_the_host_node_definition(built_library
     graph = DeviceKNNGraph(definition)(raw.cuda(), n_pulses.cuda())
     x = graph.x.cpu()
     assert x.shape == host.x.shape and x.shape[1] == 16
-    # the charge percentiles go through log10f on the device (2 ulp, see the NodesAsPulses test); everything else is exact
+    # the charge percentiles go through log10f on the device (2 ulp of values up to ~1, see the NodesAsPulses test: 2.4e-7
+    # absolute, also where the interpolated percentile itself is near zero); everything else is exact
     names = definition.output_feature_names
     for c, name in enumerate(names):
         if name.startswith("charge") or name == "counts":
-            assert torch.allclose(x[:, c], host.x[:, c], rtol=3e-7, atol=1e-9), name
+            assert torch.allclose(x[:, c], host.x[:, c], rtol=3e-7, atol=5e-7), name
         else:
             assert torch.equal(x[:, c], host.x[:, c]), name
     assert torch.equal(graph.ptr.cpu(), host.ptr) and torch.equal(graph.batch.cpu(), host.batch)
