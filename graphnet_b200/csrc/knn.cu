@@ -225,45 +225,31 @@ knn_table_split_kernel(const float* __restrict__ x, int64_t ld, const int* __res
             const int a = (int)((lo > c0 ? lo : c0) - c0);
             const int b = (int)((hi < c0 + cnt ? hi : c0 + cnt) - c0);
             int jj = a + sub;
-            // Two phases per batch of KB candidates of this lane (ascending): (A) distances against the lane's CURRENT 9th
-            // best tau -- a bit per candidate that beats it; (B) the marked candidates are inserted in ascending order (the
-            // distance is recomputed: 11 instructions) until no lane of the warp has one left. Exactness: tau only ever
-            // decreases, so {d < tau at the start of the batch} contains every candidate the one-by-one scan would insert,
-            // and the insertion re-tests against the current list; order of insertion = ascending index = the reference
-            // scan, so ties keep the lower index. Why: a warp executes the 27-instruction insertion whenever ANY of its 32
-            // lanes needs it -- once the lists are full each lane needs it for ~9 / j of its candidates, but the warp paid
-            // it for 94 % of all steps (65 instructions per candidate, profiles/r01/p_knn_table_split.ncu-rep).
-            constexpr int KB = 16;
-            for (; jj < b; jj += KB * S) {
-                const float tau = bd[K1 - 1];
-                unsigned pass = 0u;
+            for (; jj + 3 * S < b; jj += 4 * S) {       // 4 independent distance evaluations, inserted in ascending order
+                float acc4[4];
 #pragma unroll
-                for (int u = 0; u < KB; ++u) {
-                    const int c = jj + u * S;
-                    if (c < b) {
-                        const float d0 = s_c[c] - qf[0];
-                        float acc = __fmul_rn(d0, d0);
-#pragma unroll
-                        for (int j = 1; j < D; ++j) {
-                            const float dj = s_c[j * chunk + c] - qf[j];
-                            acc = __fadd_rn(acc, __fmul_rn(dj, dj));
-                        }
-                        pass |= (tau > acc) ? (1u << u) : 0u;
-                    }
-                }
-                while (pass) {                              // (lanes without a marked candidate wait at the reconvergence point)
-                    const int u = __ffs(pass) - 1;
-                    pass &= pass - 1u;
-                    const int c = jj + u * S;
-                    const float d0 = s_c[c] - qf[0];
+                for (int u = 0; u < 4; ++u) {
+                    const float d0 = s_c[jj + u * S] - qf[0];
                     float acc = __fmul_rn(d0, d0);
 #pragma unroll
                     for (int j = 1; j < D; ++j) {
-                        const float dj = s_c[j * chunk + c] - qf[j];
+                        const float dj = s_c[j * chunk + jj + u * S] - qf[j];
                         acc = __fadd_rn(acc, __fmul_rn(dj, dj));
                     }
-                    insert_static<K1>(bd, bi, acc, (int)(c0 + c));
+                    acc4[u] = acc;
                 }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) insert_static<K1>(bd, bi, acc4[u], (int)(c0 + jj + u * S));
+            }
+            for (; jj < b; jj += S) {
+                const float d0 = s_c[jj] - qf[0];
+                float acc = __fmul_rn(d0, d0);
+#pragma unroll
+                for (int j = 1; j < D; ++j) {
+                    const float dj = s_c[j * chunk + jj] - qf[j];
+                    acc = __fadd_rn(acc, __fmul_rn(dj, dj));
+                }
+                insert_static<K1>(bd, bi, acc, (int)(c0 + jj));
             }
         }
     }
