@@ -15,12 +15,15 @@ Run through `python bench.py --workload NAME`.
 from __future__ import annotations
 
 import os
+import sys
 import time
 
 import numpy as np
 import torch
 
-import bench
+# bench.py runs as __main__ and has redirected fd 1 by the time this module is imported: a second copy of it (`import
+# bench`) would not know the real stdout and its `_emit` would write the result line to stderr
+bench = sys.modules["__main__"] if hasattr(sys.modules.get("__main__"), "_emit") else __import__("bench")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 
