@@ -63,6 +63,14 @@ SIGNATURES: Dict[str, list] = {
     "gnb_linear_fwd_f32": [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p],
     "gnb_linear_bwd_data_f32": [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i32, _p],
     "gnb_linear_bwd_weight_f32": [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _p],
+    "gnb_edge_hidden_fwd_bf16": [_p, _i64, _i32, _p, _p, _i32, _i64, _p, _p, _i64, _p, _i32, _p],
+    "gnb_edge_linear_agg_fwd_bf16": [_p, _p, _i64, _i32, _p, _p, _i64, _p, _p, _i64, _i32, _i32, _p, _i64, _p, _p],
+    "gnb_edge_mask_bwd_colsum_bf16": [_p, _i64, _p, _i64, _i32, _p, _p, _i64, _p, _p],
+    "gnb_linear_bwd_weight_bf16": [_p, _p, _i64, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _p],
+    "gnb_edge_hidden_dgrad_scatter_bf16": [_p, _p, _i64, _i32, _p, _p, _i64, _p, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _p,
+                                           _i32, _p],
+    "gnb_linear_fwd_bf16": [_p, _p, _i64, _i32, _p, _p, _i64, _p, _p, _i64, _i64, _i32, _i32, _i32, _p],
+    "gnb_to_bf16_planes": [_p, _i64, _i64, _i32, _p, _p, _i64, _i32, _i32, _p],
 }
 
 

@@ -52,6 +52,17 @@ int gnb_linear_fwd_tf32x3(const float* const*, const int64_t*, const int32_t*, i
                           const float*, float*, int64_t, int64_t, int32_t, int32_t, void*);
 int gnb_edge_linear_agg_fwd_tf32x3(const float*, int64_t, int32_t, const float*, const float*, int64_t, const float*,
                                    const int32_t*, int64_t, int32_t, float*, int64_t, uint32_t*, void*);
+int gnb_edge_hidden_fwd_bf16(const float*, int64_t, int32_t, const int32_t*, const int32_t*, int32_t, int64_t, void*, void*, int64_t,
+                             uint32_t*, int32_t, void*);
+int gnb_edge_linear_agg_fwd_bf16(const void*, const void*, int64_t, int32_t, const void*, const void*, int64_t, const float*,
+                                 const int32_t*, int64_t, int32_t, int32_t, float*, int64_t, uint32_t*, void*);
+int gnb_edge_mask_bwd_colsum_bf16(const float*, int64_t, const uint32_t*, int64_t, int32_t, void*, void*, int64_t, float*, void*);
+int gnb_linear_bwd_weight_bf16(const void*, const void*, int64_t, const void*, const void*, int64_t, float*, int64_t, int64_t, int32_t,
+                               int32_t, int32_t, void*);
+int gnb_edge_hidden_dgrad_scatter_bf16(const void*, const void*, int64_t, int32_t, const void*, const void*, int64_t, const uint32_t*,
+                                       int32_t, int32_t, const int32_t*, int64_t, float*, int64_t, float*, int64_t, float*, int32_t,
+                                       void*);
+int gnb_to_bf16_planes(const float*, int64_t, int64_t, int32_t, void*, void*, int64_t, int32_t, int32_t, void*);
 int gnb_linear_fwd_f32(const float*, int64_t, const float*, int64_t, const float*, float*, int64_t, int64_t, int64_t,
                        int64_t, int32_t, int32_t, void*);
 int gnb_linear_bwd_data_f32(const float*, int64_t, const float*, int64_t, float*, int64_t, int64_t, int64_t, int64_t,
@@ -65,7 +76,10 @@ int gnb_linear_bwd_weight_f32(const float*, int64_t, const float*, int64_t, floa
 
 struct gnb_dynedge_config {
     int32_t nb_inputs, k, precision;               // precision: 0 = fp32 SIMT, 1 = tf32 tcgen05, 2 = tf32x3 (split-operand
-                                                   // forward GEMMs = fp32 grade, single-pass tf32 backward GEMMs)
+                                                   // forward GEMMs = fp32 grade, single-pass tf32 backward GEMMs),
+                                                   // 3 = bf16 (per-edge tensors h / dz stored as ONE bf16 plane, per-edge GEMMs
+                                                   // kind::f16; node-level GEMMs as in 1), 4 = bf16x3 (per-edge tensors as TWO
+                                                   // bf16 planes, three products per per-edge GEMM; node-level GEMMs as in 2)
     int32_t n_conv, conv_hidden[GNB_MAX_LAYERS], conv_out[GNB_MAX_LAYERS];
     int32_t n_post, post_out[GNB_MAX_LAYERS];
     int32_t n_readout, readout_out[GNB_MAX_LAYERS];
@@ -183,7 +197,9 @@ struct Arena {
     }
 };
 
-struct ConvBuf { float *wcat, *wcat_lo, *w2p_lo, *bcat, *w2p, *pq, *h, *m, *y; int32_t *nbr, *deg; uint32_t *mask, *hmask; int cin, cin_ld, kld, hid, hld, cout, mld; };
+struct ConvBuf { float *wcat, *wcat_lo, *w2p_lo, *bcat, *w2p, *pq, *h, *m, *y; int32_t *nbr, *deg; uint32_t *mask, *hmask; int cin, cin_ld, kld, hid, hld, cout, mld;
+                 // bf16 modes: h planes [n * 9, hid], W2 planes [cout, hld64], W2^T planes [hid, cld64]
+                 __nv_bfloat16 *hb[2], *w2b[2], *w2tb[2]; int hld64, cld64; };
 struct DenseBuf { float *wp, *wp_lo, *z; int k_total, kld, n_out; };
 
 struct Plan {
@@ -198,6 +214,8 @@ struct Plan {
     float *pooled, *rin; int32_t* parg; int pool_c, rin_cols, rin_ld; int64_t out_rows;
     // backward scratch
     float *gnode[GNB_MAX_LAYERS + 1], *dz_big, *dh_big, *dpq, *dzq, *dwp, *wt, *dbtmp, *gro_a, *gro_b;
+    __nv_bfloat16* dzb[2];               // bf16 modes: dz planes [n * 9, max_c]
+    int bf;                              // bf16 planes per per-edge tensor (0: fp32 / tf32 tensors)
     int64_t bytes;
 };
 
@@ -211,9 +229,11 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
     if (c.globals_after_pooling && c.n_pool == 0) return GNB_ERR_ARG;
     Arena a(ws, cap);
     p.n = n; p.nseg = nseg; p.w0 = w0; p.width = c.k + 1;
-    const bool split = c.precision == 2;      // pre-split weight operands: a lo buffer behind every packed forward weight
-    if (c.precision < 0 || c.precision > 2) return GNB_ERR_ARG;
-    p.agg = c.precision >= 1 && c.k == 8 && w0 == 9 && !(c.flags & 1) && (training || (c.flags & 2) || split);
+    const bool split = c.precision == 2 || c.precision == 4;      // pre-split weight operands: a lo buffer behind every packed forward weight
+    if (c.precision < 0 || c.precision > 4) return GNB_ERR_ARG;
+    p.bf = c.precision >= 3 ? c.precision - 2 : 0;
+    p.agg = c.precision >= 1 && c.k == 8 && w0 == 9 && !(c.flags & 1) && (training || (c.flags & 2) || split || p.bf);
+    if (p.bf && !p.agg) return GNB_ERR_UNSUPPORTED;               // the bf16 modes exist on the k = 8 tensor-core route only
     const int f = c.nb_inputs, ng = f + 5;
     const bool distribute = !c.globals_after_pooling;
     p.node_width = f + (distribute ? ng : 0);
@@ -228,9 +248,13 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
         if (c.conv_out[l] > max_c) max_c = c.conv_out[l];
     }
     float *h_shared = nullptr, *m_shared = nullptr, *pq_shared = nullptr;
+    __nv_bfloat16* hb_shared[2] = {nullptr, nullptr};
     if (!training) {   // inference: per-edge tensors are transient, share them across layers
-        h_shared = a.get<float>(n * max_w * max_h);
-        m_shared = a.get<float>(n * max_w * max_c);
+        if (!p.bf) {
+            h_shared = a.get<float>(n * max_w * max_h);
+            m_shared = a.get<float>(n * max_w * max_c);
+        }
+        for (int pl = 0; pl < p.bf; ++pl) hb_shared[pl] = a.get<__nv_bfloat16>(n * max_w * max_h);
         pq_shared = a.get<float>(n * 2 * max_h);
     }
     for (int l = 0; l < c.n_conv; ++l) {
@@ -246,13 +270,22 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
         b.w2p = a.get<float>((int64_t)b.cout * b.hld);
         b.w2p_lo = split ? a.get<float>((int64_t)b.cout * b.hld) : nullptr;
         b.pq = training ? a.get<float>(n * 2 * b.hid) : pq_shared;
-        b.h = training ? a.get<float>(n * wl * b.hid) : h_shared;
+        b.hld64 = (int)up(b.hid, 64); b.cld64 = (int)up(b.cout, 64);
+        for (int pl = 0; pl < 2; ++pl) {
+            const bool on = pl < p.bf;
+            b.hb[pl] = on ? (training ? a.get<__nv_bfloat16>(n * wl * b.hid) : hb_shared[pl]) : nullptr;
+            b.w2b[pl] = on ? a.get<__nv_bfloat16>((int64_t)b.cout * b.hld64) : nullptr;
+            b.w2tb[pl] = (on && training) ? a.get<__nv_bfloat16>((int64_t)b.hid * b.cld64) : nullptr;
+        }
+        if (p.bf && ((b.hid & 7) || (b.cout & 7))) return GNB_ERR_UNSUPPORTED;
+        b.h = p.bf ? nullptr : (training ? a.get<float>(n * wl * b.hid) : h_shared);
         b.m = training ? (p.agg ? nullptr : a.get<float>(n * wl * b.cout)) : m_shared;
         b.mask = (p.agg && training) ? a.get<uint32_t>((n + 13) / 14 * (int64_t)b.cout * 4) : nullptr;
         // activation bits of h for the scattering data-gradient epilogue (whole 14-node tiles, mld words per slot row)
         b.mld = 4 * ((b.hid + 127) / 128);
         const bool scat = p.agg && training && b.hid <= 512 && n * 2 * b.hid < ((int64_t)1 << 31);
         b.hmask = scat ? a.get<uint32_t>((n + 13) / 14 * 126 * (int64_t)b.mld) : nullptr;
+        if (p.bf && training && !scat) return GNB_ERR_UNSUPPORTED;
         b.y = a.get<float>(n * b.cout);
         b.nbr = (l + 1 < c.n_conv) ? a.get<int32_t>(n * p.width) : nullptr;
         b.deg = (l + 1 < c.n_conv) ? a.get<int32_t>(n) : nullptr;
@@ -304,8 +337,9 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
     }
     if (training) {   // backward scratch
         for (int l = 0; l <= c.n_conv; ++l) p.gnode[l] = l == 0 ? nullptr : a.get<float>(n * c.conv_out[l - 1]);
-        p.dz_big = a.get<float>(n * max_w * max_c);
-        p.dh_big = a.get<float>(n * max_w * max_h);
+        p.dz_big = p.bf ? nullptr : a.get<float>(n * max_w * max_c);
+        p.dh_big = p.bf ? nullptr : a.get<float>(n * max_w * max_h);
+        for (int pl = 0; pl < 2; ++pl) p.dzb[pl] = pl < p.bf ? a.get<__nv_bfloat16>(n * max_w * max_c) : nullptr;
         p.dpq = a.get<float>(n * 2 * max_h);
         p.dzq = a.get<float>(n * 2 * max_h);
         int64_t max_wp = 0, max_dense = 0;
@@ -348,8 +382,9 @@ struct Exec {
     int rnd;          // backward: gradients that feed a tensor-core GEMM are stored rounded
     int frnd;         // forward flag for the producers of GEMM operands
     Exec(const gnb_dynedge_config& cfg, void* s)
-        : c(cfg), st((cudaStream_t)s), tf32(cfg.precision >= 1), split(cfg.precision == 2), fround(cfg.precision == 1),
-          rnd(cfg.precision >= 1 ? GNB_FLAG_ROUND_TF32 : 0), frnd(cfg.precision == 1 ? GNB_FLAG_ROUND_TF32 : 0) {}
+        : c(cfg), st((cudaStream_t)s), tf32(cfg.precision >= 1), split(cfg.precision == 2 || cfg.precision == 4),
+          fround(cfg.precision == 1 || cfg.precision == 3), rnd(cfg.precision >= 1 ? GNB_FLAG_ROUND_TF32 : 0),
+          frnd((cfg.precision == 1 || cfg.precision == 3) ? GNB_FLAG_ROUND_TF32 : 0) {}
 
     int copy_pad(const float* src, int64_t lds, int64_t rows, int cols, float* dst, int64_t ldd, int dst_cols, bool round,
                  float* lo = nullptr) {
@@ -461,6 +496,13 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
             // inference: gather + hidden ReLU + E x H x C contraction + bias/ReLU + aggregation in one tcgen05 kernel
             EX(gnb_edgeconv_fused_fwd_tf32(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, b.w2p, b.hld, b2, b.cout, GNB_AGGR_ADD, 1,
                                            b.y, b.cout, stream));
+        } else if (p.bf) {
+            // bf16 / bf16x3: h as bf16 plane(s) straight from the hidden-layer kernel, second Linear + ReLU + k-sum on kind::f16
+            EX(gnb_to_bf16_planes(w2, b.hid, b.cout, b.hid, b.w2b[0], b.w2b[1], b.hld64, b.hld64, 0, stream));
+            if (training) EX(gnb_to_bf16_planes(w2, b.hid, b.cout, b.hid, b.w2tb[0], b.w2tb[1], b.cld64, b.cld64, 1, stream));
+            EX(gnb_edge_hidden_fwd_bf16(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, b.hb[0], b.hb[1], b.hid, b.hmask, b.mld, stream));
+            EX(gnb_edge_linear_agg_fwd_bf16(b.hb[0], b.hb[1], b.hid, b.hid, b.w2b[0], b.w2b[1], b.hld64, b2, deg, n, b.cout,
+                                            e.fround ? 1 : 0, b.y, b.cout, b.mask, stream));
         } else if (p.agg) {
             // training (and inference with flags bit 1): the second Linear, ReLU and the k-sum run in one tcgen05 kernel; h is kept for the backward pass;
             // whose epilogue writes y and one ReLU bit per (slot, channel) -- the [E, C] message tensor is never stored
@@ -621,15 +663,22 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
         const int64_t rows = n * wl;
         const float* gy = p.gnode[l + 1];
         // (aggregate-bwd + ReLU-bwd + bias grad) in one pass
-        if (p.agg)
+        if (p.bf) {
+            EX(gnb_edge_mask_bwd_colsum_bf16(gy, b.cout, b.mask, n, b.cout, p.dzb[0], p.dzb[1], b.cout, gb2, stream));
+            EX(gnb_linear_bwd_weight_bf16(p.dzb[0], p.dzb[1], b.cout, b.hb[0], b.hb[1], b.hid, gw2, b.hid, rows, b.cout, b.hid, 0, stream));
+        } else if (p.agg)
             EX(gnb_edge_mask_bwd_colsum(gy, b.cout, b.mask, n, b.cout, deg, p.dz_big, b.cout, gb2, e.rnd, stream));
         else
             EX(gnb_act_bwd_colsum(gy, b.cout, b.m, b.cout, rows, b.cout, p.dz_big, b.cout, gb2, GNB_ACT_RELU | e.rnd, deg, wl,
                                   GNB_AGGR_ADD, stream));
-        EX(e.lin_bwd_weight(p.dz_big, b.cout, b.h, b.hid, gw2, b.hid, 0, b.hid, b.cout, rows));
+        if (!p.bf) EX(e.lin_bwd_weight(p.dz_big, b.cout, b.h, b.hid, gw2, b.hid, 0, b.hid, b.cout, rows));
         GNB_CHECK(cudaMemsetAsync(p.dbtmp, 0, (size_t)2 * b.hid * 4, e.st));
         const float* dzq = p.dzq;
-        if (b.hmask != nullptr) {
+        if (p.bf) {
+            GNB_CHECK(cudaMemset2DAsync(p.dzq + b.hid, (size_t)2 * b.hid * 4, 0, (size_t)b.hid * 4, (size_t)n, e.st));
+            EX(gnb_edge_hidden_dgrad_scatter_bf16(p.dzb[0], p.dzb[1], b.cout, b.cout, b.w2tb[0], b.w2tb[1], b.cld64, b.hmask, b.mld,
+                                                  b.hid, nbr, n, p.dzq + b.hid, 2 * b.hid, p.dzq, 2 * b.hid, p.dbtmp, e.rnd, stream));
+        } else if (b.hmask != nullptr) {
             // data gradient + ReLU mask + scatter in one kernel (dh [E, hid] is never materialised). Both halves land straight
             // in dzq, the operand buffer of the two GEMMs that follow: the P half (slot sums, plain stores) rounded to tf32
             // with its column sums (bias gradient) accumulated by the epilogue, the Q half by fp32 reductions from all over

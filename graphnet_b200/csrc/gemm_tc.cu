@@ -454,7 +454,7 @@ struct GroupSplit { int ngroups; int start[5]; };
 // [scatter metadata]. Streaming mode: a stage = this CTA's weight tile + its half of the activation rows (32 KiB);
 // resident mode (single-part K that fits): the CTA's 128 weight rows stay in shared memory for the kernel's lifetime
 // (one TMA pass), a stage is the activation half only (16 KiB) and the L2->SM traffic per launch halves.
-struct PairCfg { int resident; int nstages; uint32_t meta_stride; };
+struct PairCfg { int resident; int nstages; uint32_t meta_stride; int last_ksteps; };
 constexpr uint32_t PL_BAR_BYTES = 512;                // barrier block behind the ring
 // SPLIT = the fp32-grade split-operand forward (precision mode tf32x3): W = W_hi + W_lo, X = X_hi + X_lo with the hi parts
 // tf32-exact; the product is W_hi X_hi (kind::tf32) + the two correction products W_lo X_hi + W_hi X_lo, whose operands need
@@ -473,19 +473,30 @@ constexpr uint32_t PL_BAR_BYTES = 512;                // barrier block behind th
 // of each CTA; lo_empty[j] (local, multicast commit) returns B_corr slot j to its splitter warp.
 constexpr int PL_SPLIT_THREADS = 384, PL_SPLIT_STAGES = 4, PL_SPLIT_LO_SLOTS = 2;
 
-template <bool SPLIT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SPLIT ? PL_SPLIT_THREADS : PL_THREADS, 1)
+// MODE 0: single-pass tf32. MODE 1: the split-operand forward above. MODE 2 / 3: bf16 operands (kind::f16, UMMA_K = 16), the
+// "bf16" / "bf16x3" precision modes of the per-edge GEMMs: both operands arrive as NP = 1 / 2 bf16 PLANES (v ~ v0 + v1 with
+// v0 = bf16(v), v1 = bf16(v - v0); plane p of the weights in tm_w / tm_wlo, of the activations in tm_x.m[p]) written by
+// their producers, so there is no splitter; a K block is 64 bf16 = one 128-byte swizzle row, a stage {W planes | X planes} =
+// NP x 32 KiB. NP = 1: one product W0 X0 (bf16 grade, half the bytes and twice the MMA rate of tf32). NP = 2: W1 X0 + W0 X1 +
+// W0 X0 (dropped terms ~2^-17: fp32 grade for this path's tolerances at the bytes of the fp32 tensors, 3/4 of the split
+// mode's tensor time and no in-kernel operand conversion).
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == 1 ? PL_SPLIT_THREADS : PL_THREADS, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_wlo,
                     const __grid_constant__ TmapArray tm_x,
                     const PartInfo parts, const float* __restrict__ bias, float* __restrict__ y, int64_t ldy,
                     int64_t rows, int n_out, int act, int round_out, int num_tiles, const AggInfo agg, const ScatInfo sc,
                     const GroupSplit gs, const PairCfg pc) {
+    constexpr bool SPLIT = MODE == 1;
+    constexpr bool BF = MODE >= 2;
+    constexpr int NP = MODE == 3 ? 2 : 1;                 // bf16 planes per operand
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     int total_kb = 0;
     for (int p = 0; p < parts.nparts; ++p) total_kb += parts.kblocks[p];
     const int nstages = pc.nstages;
-    const uint32_t stage_bytes = SPLIT ? 3 * TC_TILE_BYTES : (pc.resident ? TC_TILE_BYTES : 2 * TC_TILE_BYTES);
+    const uint32_t stage_bytes = BF ? 2 * NP * TC_TILE_BYTES
+                                    : (SPLIT ? 3 * TC_TILE_BYTES : (pc.resident ? TC_TILE_BYTES : 2 * TC_TILE_BYTES));
     uint8_t* s_a = smem;                                                     // resident weights (resident mode)
     uint8_t* ring = smem + ((pc.resident && !SPLIT) ? (uint32_t)total_kb * TC_TILE_BYTES : 0u);
     uint8_t* lo_ring = ring + nstages * stage_bytes;                         // SPLIT: [PL_SPLIT_LO_SLOTS] x 16 KiB of X_lo
@@ -548,7 +559,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     if (warp == 0) {
         // ---- TMA producer (both CTAs): own weight rows + own half of the activation rows ------------------------
         uint32_t it = 0, tile_i = 0;
-        const uint32_t stage_tx = SPLIT ? 4u * TC_TILE_BYTES      // W_hi + W_lo of both CTAs (activations: xfull, per CTA)
+        const uint32_t stage_tx = BF ? 2u * NP * (TC_TILE_BYTES + (uint32_t)half_rows * 128u)     // every plane, both CTAs
+                                : SPLIT ? 4u * TC_TILE_BYTES      // W_hi + W_lo of both CTAs (activations: xfull, per CTA)
                                         : 2u * ((pc.resident ? 0u : TC_TILE_BYTES) + (uint32_t)half_rows * TC_BK * 4);   // both CTAs
         if (!SPLIT && pc.resident && tc::elect_one()) {      // the CTA's 128 weight rows, all K blocks, once
             if (rank == 0) tc::mbar_arrive_expect_tx(a_full, 2u * (uint32_t)total_kb * TC_TILE_BYTES);
@@ -571,7 +583,15 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                     tc::mbar_wait_warp(&empty[s], ph ^ 1);
                     if (prof_on) pw0 += clock64() - c0;
                     uint8_t* st = ring + s * stage_bytes;
-                    if (SPLIT) {
+                    if (BF) {            // K block = 64 bf16; single part
+                        if (tc::elect_one()) {
+                            if (rank == 0) tc::mbar_arrive_expect_tx(&full[s], stage_tx);
+                            tc::tma_load_2d_2sm(st, &tm_w, &full[s], kb_w * 64, ch0);
+                            if (NP == 2) tc::tma_load_2d_2sm(st + TC_TILE_BYTES, &tm_wlo, &full[s], kb_w * 64, ch0);
+                            tc::tma_load_2d_2sm(st + NP * TC_TILE_BYTES, &tm_x.m[0], &full[s], kb * 64, (int)row0);
+                            if (NP == 2) tc::tma_load_2d_2sm(st + (NP + 1) * TC_TILE_BYTES, &tm_x.m[1], &full[s], kb * 64, (int)row0);
+                        }
+                    } else if (SPLIT) {
                         if (tc::elect_one()) {
                             if (rank == 0) tc::mbar_arrive_expect_tx(&full[s], stage_tx);
                             tc::tma_load_2d_2sm(st, &tm_w, &full[s], kb_w * TC_BK, ch0);
@@ -634,6 +654,30 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                     if (prof_on) pw0 += clock64() - c0;
                     tc::tcgen05_fence_after();
                     const uint32_t st = tc::smem_u32(ring + s * stage_bytes);
+                    if (BF) {
+                        constexpr uint32_t idesc_bf16 = tc::umma_idesc_bf16(256, 256);
+                        const uint64_t a0 = tc::umma_desc_sw128_kmajor(st), a1 = tc::umma_desc_sw128_kmajor(st + TC_TILE_BYTES);
+                        const uint64_t b0 = tc::umma_desc_sw128_kmajor(st + NP * TC_TILE_BYTES);
+                        const uint64_t b1 = tc::umma_desc_sw128_kmajor(st + (NP + 1) * TC_TILE_BYTES);
+                        const int nk = kbi == total_kb - 1 ? pc.last_ksteps : 4;     // 16-wide K steps with data in this block
+                        if (tc::elect_one()) {
+                            if (!(agg.dbg & 2)) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    if (k < nk) {
+                                        if (NP == 2) {          // corrections first (small terms)
+                                            tc::umma_bf16_2cta(acc, a1 + 2 * k, b0 + 2 * k, idesc_bf16, (kbi | k) != 0 ? 1u : 0u);
+                                            tc::umma_bf16_2cta(acc, a0 + 2 * k, b1 + 2 * k, idesc_bf16, 1u);
+                                        }
+                                        tc::umma_bf16_2cta(acc, a0 + 2 * k, b0 + 2 * k, idesc_bf16, (NP == 2 || (kbi | k) != 0) ? 1u : 0u);
+                                    }
+                                }
+                            }
+                            tc::umma_commit_2cta(&empty[s], 3);
+                        }
+                        __syncwarp();
+                        continue;
+                    }
                     if (SPLIT) {
                         const uint64_t ahi = tc::umma_desc_sw128_kmajor(st), alo = tc::umma_desc_sw128_kmajor(st + TC_TILE_BYTES);
                         const uint64_t bhi = tc::umma_desc_sw128_kmajor(st + 2 * TC_TILE_BYTES);
@@ -1105,6 +1149,218 @@ gemm_tc_pair_dual_scatter_kernel(const __grid_constant__ CUtensorMap tm_w, const
     if (warp == 1) tc::tmem_dealloc_2cta<512>(tmem_base);
 }
 
+
+// The dual-group scattering kernel on bf16-plane operands (precision modes bf16 / bf16x3, see gemm_tc_pair_kernel MODE 2 / 3):
+// dz arrives as NP planes [rows, c_out] bf16, W2^T as NP planes [hdim, ceil(c_out / 64) * 64] bf16. The resident tile holds
+// every plane of the cluster's dz rows (total_kb K blocks of 64 x NP x 16 KiB); the weight ring streams 16 KiB tiles in the
+// order (group, K block, plane): behind plane 0 the issuer queues W0 X1 (NP = 2) and W0 X0, behind plane 1 W1 X0.
+template <int NP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PL_THREADS, 1)
+gemm_bf_pair_dual_scatter_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
+                                 const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
+                                 int total_kb, int last_ksteps, int64_t rows, int n_out, int num_tiles, const ScatInfo sc, int nst_w,
+                                 uint32_t meta_stride, int dbg) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* act = smem;                                               // [total_kb][NP] x 16 KiB: resident dz tile (own half)
+    uint8_t* wring = act + (uint32_t)(total_kb * NP) * TC_TILE_BYTES;  // [nst_w] x 16 KiB: own 128 weight rows, one K block, one plane
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(wring + (uint32_t)nst_w * TC_TILE_BYTES);
+    uint64_t* wempty = wfull + PL_MAX_STAGES;
+    uint64_t* afull = wempty + PL_MAX_STAGES;        // [DU_MAX_KB] (leader's copy is waited on)
+    uint64_t* aempty = afull + DU_MAX_KB;            // [DU_MAX_KB] (multicast to both CTAs)
+    uint64_t* tmem_full = aempty + DU_MAX_KB;        // [2]
+    uint64_t* tmem_empty = tmem_full + 2;            // [2]
+    uint64_t* meta_full = tmem_empty + 2;            // [2]
+    uint64_t* meta_empty = meta_full + 2;            // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(meta_empty + 2);
+    uint8_t* meta = reinterpret_cast<uint8_t*>(wfull) + DU_BAR_BYTES;  // [2 buffers][2 sub-tiles] x meta_stride
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const int cluster_id = (int)(blockIdx.x >> 1), num_clusters = (int)(gridDim.x >> 1);
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tm_w0); tc::tma_prefetch_desc(&tm_x0);
+        if (NP == 2) { tc::tma_prefetch_desc(&tm_w1); tc::tma_prefetch_desc(&tm_x1); }
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < PL_MAX_STAGES; ++s) { tc::mbar_init(&wfull[s], 1); tc::mbar_init(&wempty[s], 1); }
+            for (int k = 0; k < DU_MAX_KB; ++k) { tc::mbar_init(&afull[k], 1); tc::mbar_init(&aempty[k], 1); }
+            for (int b = 0; b < 2; ++b) {
+                tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], 16);
+                tc::mbar_init(&meta_full[b], 1); tc::mbar_init(&meta_empty[b], 16);
+            }
+            tc::fence_barrier_init();
+            tc::fence_proxy_async();
+        }
+        __syncwarp();
+        tc::tmem_alloc_2cta<512>(tmem_slot);
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---- TMA producer (both CTAs) -------------------------------------------------------------------------------
+        uint32_t itw = 0, ti = 0;
+        const uint32_t act_tx = 2u * NP * (uint32_t)AGG_ROWS * 128u, w_tx = 2u * TC_TILE_BYTES;       // both CTAs
+        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++ti) {
+            const int64_t row0 = (int64_t)t * (2 * AGG_ROWS) + (int64_t)rank * AGG_ROWS;
+            int offv[2][4];
+            unsigned lastv[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) scat_meta(sc, ((int64_t)t * 2 + h) * AGG_NPT, rows, lane, offv[h], lastv[h]);
+            for (int g = 0; g < 2; ++g) {
+                // a CTA whose 128 weight rows of this group all lie beyond n_out loads nothing (its accumulator lanes are never read)
+                const bool peer_rows = g * 256 + 128 < n_out;
+                for (int kb = 0; kb < total_kb; ++kb) {
+                    if (g == 0) {                  // next tile's dz K block as soon as group 1 of the previous tile is done with the slot
+                        tc::mbar_wait_warp(&aempty[kb], (ti & 1) ^ 1);
+                        if (tc::elect_one()) {
+                            if (rank == 0) tc::mbar_arrive_expect_tx(&afull[kb], act_tx);
+                            tc::tma_load_2d_2sm(act + (kb * NP) * TC_TILE_BYTES, &tm_x0, &afull[kb], kb * 64, (int)row0);
+                            if (NP == 2) tc::tma_load_2d_2sm(act + (kb * NP + 1) * TC_TILE_BYTES, &tm_x1, &afull[kb], kb * 64, (int)row0);
+                        }
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int pl = 0; pl < NP; ++pl, ++itw) {
+                        const uint32_t s = itw % (uint32_t)nst_w, ph = (itw / (uint32_t)nst_w) & 1;
+                        tc::mbar_wait_warp(&wempty[s], ph ^ 1);
+                        if (tc::elect_one()) {
+                            if (rank == 0) tc::mbar_arrive_expect_tx(&wfull[s], peer_rows ? w_tx : w_tx / 2);
+                            if (rank == 0 || peer_rows)
+                                tc::tma_load_2d_2sm(wring + s * TC_TILE_BYTES, pl == 0 ? &tm_w0 : &tm_w1, &wfull[s], kb * 64,
+                                                    g * 256 + (int)rank * 128);
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (g != 0) continue;
+                const uint32_t buf = ti & 1;
+                tc::mbar_wait_warp(&meta_empty[buf], ((ti >> 1) & 1) ^ 1);
+                uint32_t bytes = 0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint8_t* mbh = meta + (buf * 2 + h) * meta_stride;
+                    int* so = reinterpret_cast<int*>(mbh + meta_stride - 512);
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) so[lane + 32 * q4] = offv[h][q4];
+                    if (lane == 0) *reinterpret_cast<unsigned*>(mbh + AGG_ROWS * sc.mask_ld * 4) = lastv[h];
+                    if (((int64_t)t * 2 + h) * AGG_NPT < sc.n_nodes) bytes += (uint32_t)(AGG_ROWS * sc.mask_ld * 4);
+                }
+                __syncwarp();
+                if (tc::elect_one()) {
+                    tc::mbar_arrive_expect_tx(&meta_full[buf], bytes);
+                    const uint32_t one = (uint32_t)(AGG_ROWS * sc.mask_ld * 4);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        if (((int64_t)t * 2 + h) * AGG_NPT < sc.n_nodes)
+                            tc::bulk_load(meta + (buf * 2 + h) * meta_stride, sc.hmask + ((int64_t)t * 2 + h) * AGG_ROWS * sc.mask_ld,
+                                          one, &meta_full[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ---- MMA issuer (leader): group 0 then group 1 of every tile against the resident dz planes -----------------
+            constexpr uint32_t idesc = tc::umma_idesc_bf16(256, 256);
+            uint32_t itw = 0, vt_i = 0, ti = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters, ++ti) {
+                for (int g = 0; g < 2; ++g, ++vt_i) {
+                    const uint32_t buf = vt_i & 1;
+                    tc::mbar_wait_warp(&tmem_empty[buf], ((vt_i >> 1) & 1) ^ 1);
+                    tc::tcgen05_fence_after();
+                    const uint32_t acc = tmem_base + buf * 256;
+                    for (int kb = 0; kb < total_kb; ++kb) {
+                        const int nk = kb == total_kb - 1 ? last_ksteps : 4;
+                        const uint64_t x0 = tc::umma_desc_sw128_kmajor(tc::smem_u32(act + (kb * NP) * TC_TILE_BYTES));
+                        const uint64_t x1 = tc::umma_desc_sw128_kmajor(tc::smem_u32(act + (kb * NP + 1) * TC_TILE_BYTES));
+#pragma unroll
+                        for (int pl = 0; pl < NP; ++pl, ++itw) {
+                            const uint32_t s = itw % (uint32_t)nst_w, ph = (itw / (uint32_t)nst_w) & 1;
+                            tc::mbar_wait_warp(&wfull[s], ph);
+                            if (g == 0 && pl == 0) tc::mbar_wait_warp(&afull[kb], ti & 1);
+                            tc::tcgen05_fence_after();
+                            const uint64_t wd = tc::umma_desc_sw128_kmajor(tc::smem_u32(wring + s * TC_TILE_BYTES));
+                            if (tc::elect_one()) {
+                                if (!(dbg & 2)) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        if (k < nk) {
+                                            if (pl == 0) {
+                                                if (NP == 2) tc::umma_bf16_2cta(acc, wd + 2 * k, x1 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                                                tc::umma_bf16_2cta(acc, wd + 2 * k, x0 + 2 * k, idesc, (NP == 2 || (kb | k) != 0) ? 1u : 0u);
+                                            } else {
+                                                tc::umma_bf16_2cta(acc, wd + 2 * k, x0 + 2 * k, idesc, 1u);
+                                            }
+                                        }
+                                    }
+                                }
+                                tc::umma_commit_2cta(&wempty[s], 3);
+                                if (g == 1 && pl == NP - 1) tc::umma_commit_2cta(&aempty[kb], 3);
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    if (tc::elect_one()) tc::umma_commit_2cta(&tmem_full[buf], 3);
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ---- epilogue: identical to the tf32 kernel's (fp32 accumulators, same metadata blocks) -----------------------------
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        float colacc0 = 0.f, colacc1 = 0.f;
+        uint32_t vt_i = 0, ti = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++ti) {
+            const uint32_t mbuf = ti & 1;
+#pragma unroll
+            for (int g = 0; g < 2; ++g, ++vt_i) {
+                const uint32_t buf = vt_i & 1;
+                const int ch0 = g * 256 + (int)rank * 128;
+                const int ch = ch0 + q * 32 + lane;
+                const bool ch_ok = ch < n_out;
+                tc::mbar_wait<100>(&tmem_full[buf], (vt_i >> 1) & 1);
+                tc::tcgen05_fence_after();
+                tc::mbar_wait<100>(&meta_full[mbuf], (ti >> 1) & 1);
+                const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + half * 128);
+                const int64_t node0 = ((int64_t)t * 2 + half) * AGG_NPT;
+                if (node0 < sc.n_nodes && ch0 + q * 32 < n_out) {
+                    const uint32_t mb_a = tc::smem_u32(meta + (mbuf * 2 + half) * meta_stride);
+                    const uint32_t mword = 4u * (uint32_t)(ch0 >> 7) + (uint32_t)(lane & 3);
+                    float* dq = sc.dq + (ch_ok ? ch : ch % sc.hdim);
+                    float* dp = sc.dp + node0 * sc.lddp + ch;
+                    const unsigned lanebit = ch_ok ? (1u << (q * 8 + (lane >> 2))) : 0u;
+                    scat_tile_any(sc.mask_ld, tcol, mb_a, mb_a + meta_stride - 512u, mword, lanebit, dq, dp, sc.lddp,
+                                  sc.n_nodes - node0, ch_ok, (dbg & 64) != 0, sc.round_p != 0, g == 0 ? colacc0 : colacc1);
+                }
+                tc::tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    tc::mbar_arrive_cluster_relaxed(&tmem_empty[buf], 0);
+                    tc::mbar_arrive(&meta_empty[mbuf]);
+                }
+                __syncwarp();
+            }
+        }
+        if (sc.dbias != nullptr) {
+            const int c0 = (int)rank * 128 + q * 32 + lane, c1 = 256 + c0;
+            if (c0 < n_out) atomicAdd(sc.dbias + c0, colacc0);
+            if (c1 < n_out) atomicAdd(sc.dbias + c1, colacc1);
+        }
+    }
+    __syncwarp();
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();
+    if (warp == 1) tc::tmem_dealloc_2cta<512>(tmem_base);
+}
+
 // dst[r, c] = rna_tf32(src[r, c]) for c < cols, 0 for cols <= c < dst_cols
 __global__ void round_pad_tf32_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
                                       float* __restrict__ dst, int64_t ldd, int dst_cols) {
@@ -1129,8 +1385,14 @@ cudaError_t init_tc_kernels() {
     if (e == cudaSuccess && dev < 64) g_tc_attr_devs |= 1ull << dev;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_bf_pair_dual_scatter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_bf_pair_dual_scatter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_tc_pair_dual_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
     if (e == cudaSuccess) g_num_sms = sms;
@@ -1152,10 +1414,47 @@ bool dual_scatter_applicable(int hdim, int kblocks, int mask_ld, int* nst_w_out)
 // twlo != nullptr: split-operand (3xTF32) forward -- always the CTA-pair kernel (the only one with splitter warps).
 int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi, const float* bias, float* y, int64_t ldy,
                   int64_t rows, int n_out, int act, int round_out, int row_tiles, const AggInfo& agg, const ScatInfo& sc,
-                  cudaStream_t stream, const CUtensorMap* twlo = nullptr) {
+                  cudaStream_t stream, const CUtensorMap* twlo = nullptr, int bf_planes = 0, int bf_k = 0) {
     GNB_CHECK(init_tc_kernels());
-    const bool split = twlo != nullptr;
+    const bool split = twlo != nullptr && bf_planes == 0;
     if (split && (n_out > 1024 || sc.enabled)) return GNB_ERR_UNSUPPORTED;
+    if (bf_planes != 0) {
+        // bf16-plane operands: always the CTA-pair kernel; one K part of bf_k columns in 64-wide blocks (pi.kblocks[0] of them)
+        if (n_out > 1024 || pi.nparts != 1 || (bf_planes == 2 && twlo == nullptr)) return GNB_ERR_UNSUPPORTED;
+        const int tiles = (row_tiles + 1) / 2;
+        const int groups = gnb_div_up(n_out, 256);
+        GroupSplit gs;
+        gs.ngroups = groups;
+        int total = g_num_sms / 2, used = 0;
+        if (total < groups) total = groups;
+        gs.start[0] = 0;
+        for (int g = 0; g < groups; ++g) {
+            int c = g + 1 < groups ? (total + groups / 2) / groups : total - used;
+            if (c < 1) c = 1;
+            if (c > tiles) c = tiles;
+            used += c;
+            gs.start[g + 1] = used;
+        }
+        for (int g = groups + 1; g < 5; ++g) gs.start[g] = used;
+        PairCfg pc;
+        pc.meta_stride = sc.enabled ? sc_meta_stride(sc.mask_ld) : 0u;
+        pc.resident = 0;
+        const uint32_t fixed = 1024 + PL_BAR_BYTES + 4 * pc.meta_stride;
+        const uint32_t stage = 2u * (uint32_t)bf_planes * TC_TILE_BYTES;
+        pc.nstages = (int)((PL_MAX_DYN_SMEM - fixed) / stage);
+        if (pc.nstages > 6) pc.nstages = 6;
+        if (pc.nstages < 2) return GNB_ERR_UNSUPPORTED;
+        pc.last_ksteps = (bf_k - 64 * (pi.kblocks[0] - 1) + 15) / 16;
+        const uint32_t smem = fixed + (uint32_t)pc.nstages * stage;
+        dim3 grid((unsigned)(2 * used));
+        if (bf_planes == 2)
+            gemm_tc_pair_kernel<3><<<grid, PL_THREADS, smem, stream>>>(tw, *twlo, tx, pi, bias, y, ldy, rows, n_out, act, round_out,
+                                                                     tiles, agg, sc, gs, pc);
+        else
+            gemm_tc_pair_kernel<2><<<grid, PL_THREADS, smem, stream>>>(tw, tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out,
+                                                                     tiles, agg, sc, gs, pc);
+        GNB_RETURN_LAUNCH();
+    }
     // measured (scripts/linear_probe.py): the pair kernel wins from two ch-tiles up; a single 128-channel tile is
     // faster on the single-CTA kernel (half of the pair's M = 256 would be padding)
     const bool pair = split || ((g_linear_variant >= 2 || (g_linear_variant == 0 && row_tiles >= 2 * 148 && n_out > 128)) && n_out <= 1024);
@@ -1185,6 +1484,7 @@ int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi
         int total_kb = 0;
         for (int p = 0; p < pi.nparts; ++p) total_kb += pi.kblocks[p];
         PairCfg pc;
+        pc.last_ksteps = 4;
         pc.meta_stride = sc.enabled ? sc_meta_stride(sc.mask_ld) : 0u;
         const uint32_t fixed = 1024 + PL_BAR_BYTES + 4 * pc.meta_stride;
         const int64_t res_left = (int64_t)PL_MAX_DYN_SMEM - fixed - (int64_t)total_kb * TC_TILE_BYTES;
@@ -1201,13 +1501,13 @@ int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi
             pc.resident = 0;
             pc.nstages = PL_SPLIT_STAGES;
             const uint32_t smem_split = fixed + (PL_SPLIT_STAGES * 3 + PL_SPLIT_LO_SLOTS) * TC_TILE_BYTES;
-            gemm_tc_pair_kernel<true><<<grid, PL_SPLIT_THREADS, smem_split, stream>>>(tw, *twlo, tx, pi, bias, y, ldy, rows, n_out,
+            gemm_tc_pair_kernel<1><<<grid, PL_SPLIT_THREADS, smem_split, stream>>>(tw, *twlo, tx, pi, bias, y, ldy, rows, n_out,
                                                                                       act, round_out, tiles, agg, sc, gs, pc);
             GNB_RETURN_LAUNCH();
         }
         const uint32_t smem = fixed + (pc.resident ? (uint32_t)total_kb * TC_TILE_BYTES + pc.nstages * TC_TILE_BYTES
                                                    : pc.nstages * 2 * TC_TILE_BYTES);
-        gemm_tc_pair_kernel<false><<<grid, PL_THREADS, smem, stream>>>(tw, tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out,
+        gemm_tc_pair_kernel<0><<<grid, PL_THREADS, smem, stream>>>(tw, tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out,
                                                                       tiles, agg, sc, gs, pc);
         GNB_RETURN_LAUNCH();
     }
@@ -1435,5 +1735,154 @@ GNB_EXPORT int gnb_round_pad_tf32(const float* src, int64_t lds, int64_t rows, i
     if (rows == 0) return GNB_OK;
     round_pad_tf32_kernel<<<gnb_div_up(rows * dst_cols, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, rows, cols, dst,
                                                                                               ldd, dst_cols);
+    GNB_RETURN_LAUNCH();
+}
+
+// ---- bf16-plane entry points (precision modes "bf16": one plane, "bf16x3": two planes v ~ v0 + v1) ---------------------------
+// Operand planes are bf16 matrices (pitches in ELEMENTS, multiples of 8); plane 1 pointers NULL = one plane.
+// Second Linear of the EdgeConv MLP fused with ReLU and the k-neighbour SUM, like gnb_edge_linear_agg_fwd_tf32:
+//   y[i, :] = sum_{s < deg[i]} relu(h[i*9 + s, :] w^T + bias); h planes [n*9, k], w planes [n_out, >= k] (zero beyond k);
+// y rounded to tf32 with round_out.
+GNB_EXPORT int gnb_edge_linear_agg_fwd_bf16(const void* h0, const void* h1, int64_t ldh, int32_t k, const void* w0, const void* w1,
+                                            int64_t ldw, const float* bias, const int32_t* deg, int64_t n, int32_t n_out,
+                                            int32_t round_out, float* y, int64_t ldy, uint32_t* maskbits, void* stream) {
+    if (n < 0 || n_out < 1 || k < 1 || h0 == nullptr || w0 == nullptr || ((h1 == nullptr) != (w1 == nullptr))) return GNB_ERR_ARG;
+    if ((ldh & 7) || (ldw & 7) || ldh < k || ldw < k) return GNB_ERR_ARG;
+    if (n == 0) return GNB_OK;
+    const int64_t rows = n * AGG_W;
+    if (rows >= (int64_t)1 << 31) return GNB_ERR_ARG;
+    const int planes = h1 != nullptr ? 2 : 1;
+    PartInfo pi;
+    TmapArray tx;
+    pi.nparts = 1;
+    pi.kblocks[0] = (k + 63) / 64;
+    for (int p = 1; p < TC_MAX_PARTS; ++p) pi.kblocks[p] = 0;
+    int rc = gnb_make_tmap_bf16(&tx.m[0], h0, rows, k, ldh * 2, AGG_ROWS);
+    if (rc == 0 && planes == 2) rc = gnb_make_tmap_bf16(&tx.m[1], h1, rows, k, ldh * 2, AGG_ROWS);
+    if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    for (int p = planes; p < TC_MAX_PARTS; ++p) tx.m[p] = tx.m[0];
+    CUtensorMap tw, tw1;
+    rc = gnb_make_tmap_bf16(&tw, w0, n_out, k, ldw * 2, TC_BM);
+    if (rc == 0 && planes == 2) rc = gnb_make_tmap_bf16(&tw1, w1, n_out, k, ldw * 2, TC_BM);
+    if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    AggInfo agg{deg, n, maskbits, 1, g_linear_dbg, g_linear_prof};
+    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0};
+    return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, GNB_ACT_RELU, round_out, gnb_div_up(n, AGG_NPT), agg, sc,
+                         (cudaStream_t)stream, planes == 2 ? &tw1 : nullptr, planes, k);
+}
+
+// Data gradient of the EdgeConv second Linear fused with the backward of the hoisted hidden layer, like
+// gnb_edge_hidden_dgrad_scatter_split_tf32, on bf16 planes: dz planes [n*9, c_out], wt planes (W2^T) [hdim, >= c_out].
+// dq / dp / dbias / hmask / nbr / flags as in the tf32 entry point.
+GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_bf16(const void* dz0, const void* dz1, int64_t lddz, int32_t c_out, const void* wt0,
+                                                  const void* wt1, int64_t ldw, const uint32_t* hmask, int32_t mask_ld,
+                                                  int32_t hdim, const int32_t* nbr, int64_t n, float* dq, int64_t lddq, float* dp,
+                                                  int64_t lddp, float* dbias, int32_t flags, void* stream) {
+    if (n < 0 || hdim < 1 || hdim > 512 || c_out < 1 || lddq < hdim || lddp < hdim || dq == nullptr || dp == nullptr)
+        return GNB_ERR_ARG;
+    if (dz0 == nullptr || wt0 == nullptr || ((dz1 == nullptr) != (wt1 == nullptr))) return GNB_ERR_ARG;
+    if ((lddz & 7) || (ldw & 7) || lddz < c_out || ldw < c_out) return GNB_ERR_ARG;
+    if ((mask_ld & 3) || mask_ld > SC_MAX_MASK_LD || mask_ld < 4 * ((hdim + 127) / 128)) return GNB_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(hmask) & 15u) || n * lddq >= ((int64_t)1 << 31)) return GNB_ERR_ARG;
+    if (n == 0) return GNB_OK;
+    const int64_t rows = n * AGG_W;
+    if (rows >= (int64_t)1 << 31) return GNB_ERR_ARG;
+    const int planes = dz1 != nullptr ? 2 : 1;
+    PartInfo pi;
+    TmapArray tx;
+    pi.nparts = 1;
+    pi.kblocks[0] = (c_out + 63) / 64;
+    for (int p = 1; p < TC_MAX_PARTS; ++p) pi.kblocks[p] = 0;
+    int rc = gnb_make_tmap_bf16(&tx.m[0], dz0, rows, c_out, lddz * 2, AGG_ROWS);
+    if (rc == 0 && planes == 2) rc = gnb_make_tmap_bf16(&tx.m[1], dz1, rows, c_out, lddz * 2, AGG_ROWS);
+    if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    for (int p = planes; p < TC_MAX_PARTS; ++p) tx.m[p] = tx.m[0];
+    CUtensorMap tw, tw1;
+    rc = gnb_make_tmap_bf16(&tw, wt0, hdim, c_out, ldw * 2, TC_BM);
+    if (rc == 0 && planes == 2) rc = gnb_make_tmap_bf16(&tw1, wt1, hdim, c_out, ldw * 2, TC_BM);
+    if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof};
+    ScatInfo sc{nbr, hmask, mask_ld, dq, lddq, hdim, n, 1, dp, lddp, dbias, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0};
+    const int row_tiles = gnb_div_up(n, AGG_NPT);
+    const int last_ksteps = (c_out - 64 * (pi.kblocks[0] - 1) + 15) / 16;
+    if (hdim > 256 && g_linear_variant != 2) {          // two 256-channel groups from one resident dz tile
+        const uint32_t mstride = sc_meta_stride(mask_ld);
+        const int64_t left = (int64_t)PL_MAX_DYN_SMEM - 1024 - DU_BAR_BYTES - 4 * (int64_t)mstride -
+                             (int64_t)pi.kblocks[0] * planes * TC_TILE_BYTES;
+        int nst_w = left > 0 ? (int)(left / TC_TILE_BYTES) : 0;
+        if (nst_w > PL_MAX_STAGES) nst_w = PL_MAX_STAGES;
+        if (pi.kblocks[0] <= DU_MAX_KB && nst_w >= 3) {
+            GNB_CHECK(init_tc_kernels());
+            const int tiles = (row_tiles + 1) / 2;
+            int clusters = g_num_sms / 2;
+            if (clusters > tiles) clusters = tiles;
+            if (clusters < 1) clusters = 1;
+            const uint32_t smem = 1024 + (uint32_t)(pi.kblocks[0] * planes + nst_w) * TC_TILE_BYTES + DU_BAR_BYTES + 4 * mstride;
+            if (planes == 2)
+                gemm_bf_pair_dual_scatter_kernel<2><<<dim3((unsigned)(2 * clusters)), PL_THREADS, smem, (cudaStream_t)stream>>>(
+                    tw, tw1, tx.m[0], tx.m[1], pi.kblocks[0], last_ksteps, rows, hdim, tiles, sc, nst_w, mstride, g_linear_dbg);
+            else
+                gemm_bf_pair_dual_scatter_kernel<1><<<dim3((unsigned)(2 * clusters)), PL_THREADS, smem, (cudaStream_t)stream>>>(
+                    tw, tw, tx.m[0], tx.m[0], pi.kblocks[0], last_ksteps, rows, hdim, tiles, sc, nst_w, mstride, g_linear_dbg);
+            GNB_RETURN_LAUNCH();
+        }
+    }
+    return launch_linear(tw, tx, pi, nullptr, nullptr, 0, rows, hdim, GNB_ACT_NONE, 0, row_tiles, agg, sc, (cudaStream_t)stream,
+                         planes == 2 ? &tw1 : nullptr, planes, c_out);
+}
+
+// Plain Linear on bf16 planes (the CTA-pair kernel's plain epilogue): y = act(x w^T + bias), x planes [rows, k], w planes
+// [n_out, >= k]; fp32 output (rounded to tf32 with round_out).
+GNB_EXPORT int gnb_linear_fwd_bf16(const void* x0, const void* x1, int64_t ldx, int32_t k, const void* w0, const void* w1,
+                                   int64_t ldw, const float* bias, float* y, int64_t ldy, int64_t rows, int32_t n_out,
+                                   int32_t act, int32_t round_out, void* stream) {
+    if (rows < 0 || n_out < 1 || k < 1 || x0 == nullptr || w0 == nullptr || ((x1 == nullptr) != (w1 == nullptr))) return GNB_ERR_ARG;
+    if ((ldx & 7) || (ldw & 7) || ldx < k || ldw < k) return GNB_ERR_ARG;
+    if (rows == 0) return GNB_OK;
+    if (rows >= (int64_t)1 << 31) return GNB_ERR_ARG;
+    const int planes = x1 != nullptr ? 2 : 1;
+    PartInfo pi;
+    TmapArray tx;
+    pi.nparts = 1;
+    pi.kblocks[0] = (k + 63) / 64;
+    for (int p = 1; p < TC_MAX_PARTS; ++p) pi.kblocks[p] = 0;
+    int rc = gnb_make_tmap_bf16(&tx.m[0], x0, rows, k, ldx * 2, TC_BN);
+    if (rc == 0 && planes == 2) rc = gnb_make_tmap_bf16(&tx.m[1], x1, rows, k, ldx * 2, TC_BN);
+    if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    for (int p = planes; p < TC_MAX_PARTS; ++p) tx.m[p] = tx.m[0];
+    CUtensorMap tw, tw1;
+    rc = gnb_make_tmap_bf16(&tw, w0, n_out, k, ldw * 2, TC_BM);
+    if (rc == 0 && planes == 2) rc = gnb_make_tmap_bf16(&tw1, w1, n_out, k, ldw * 2, TC_BM);
+    if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof};
+    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0};
+    return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out, gnb_div_up(rows, TC_BN), agg, sc,
+                         (cudaStream_t)stream, planes == 2 ? &tw1 : nullptr, planes, k);
+}
+
+// fp32 [rows, cols] (pitch lds) -> bf16 planes [rows, dst_cols] (pitch ldd elements): p0 = bf16(v), p1 = bf16(v - p0) (p1 may
+// be NULL); columns beyond cols are zero. transpose != 0: dst[c, r] planes of src[r, c] (dst has `cols` rows of dst_cols >= rows).
+static __global__ void to_bf16_planes_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
+                                             __nv_bfloat16* __restrict__ p0, __nv_bfloat16* __restrict__ p1, int64_t ldd, int dst_cols,
+                                             int transpose) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t drows = transpose ? cols : rows;
+    if (t >= drows * dst_cols) return;
+    const int64_t r = t / dst_cols;
+    const int c = (int)(t - r * dst_cols);
+    float v = 0.f;
+    if (transpose) { if (c < rows) v = src[(int64_t)c * lds + r]; }
+    else if (c < cols) v = src[r * lds + c];
+    const __nv_bfloat16 b0 = __float2bfloat16_rn(v);
+    p0[r * ldd + c] = b0;
+    if (p1 != nullptr) p1[r * ldd + c] = __float2bfloat16_rn(v - __bfloat162float(b0));
+}
+GNB_EXPORT int gnb_to_bf16_planes(const float* src, int64_t lds, int64_t rows, int32_t cols, void* p0, void* p1, int64_t ldd,
+                                  int32_t dst_cols, int32_t transpose, void* stream) {
+    if (rows < 0 || cols < 0 || p0 == nullptr || ldd < dst_cols || dst_cols < (transpose ? rows : cols)) return GNB_ERR_ARG;
+    const int64_t total = (transpose ? (int64_t)cols : rows) * dst_cols;
+    if (total == 0) return GNB_OK;
+    to_bf16_planes_kernel<<<gnb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, rows, cols, (__nv_bfloat16*)p0,
+                                                                                      (__nv_bfloat16*)p1, ldd, dst_cols, transpose);
     GNB_RETURN_LAUNCH();
 }

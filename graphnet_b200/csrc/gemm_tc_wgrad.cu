@@ -151,6 +151,159 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     if (warp == 1) tc::tmem_dealloc<WG_BN>(tmem_base);
 }
 
+
+// ---- bf16-plane variant (precision modes bf16 / bf16x3) ----------------------------------------------------------------------
+// Operands are NP bf16 planes per tensor (v ~ v0 + v1). 16-bit MN-major operands use the plain 128-byte swizzle: atom = 8 rows x
+// 128 B (64 bf16 of the MN index), SBO = 1024 B between 8-row groups of the K (row) index, LBO = one TMA box between 64-column
+// blocks; a kind::f16 MMA consumes 16 rows = 2 atoms. Stage = 64 / NP rows of every plane (48 KiB), products x0 dz0
+// (+ x1 dz0 + x0 dz1 for NP = 2).
+constexpr int WB_STAGES = 4;
+constexpr uint32_t WB_STAGE_BYTES = 48 * 1024;
+constexpr uint32_t WB_SMEM_BYTES = WB_STAGES * WB_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor16(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32;
+    d |= static_cast<uint64_t>(1) << 46;          // descriptor version (sm_100)
+    d |= static_cast<uint64_t>(2) << 61;          // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int NP>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+gemm_bf_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
+                     const __grid_constant__ CUtensorMap tm_z0, const __grid_constant__ CUtensorMap tm_z1,
+                     float* __restrict__ dw, int64_t lddw, int64_t rows, int n_out, int k_in, int n_tiles_n,
+                     int64_t rows_per_split, int dbg) {
+    constexpr int BK = 64 / NP;                                  // rows per stage
+    constexpr uint32_t BOX = BK * 128;                           // one [BK rows x 64 columns] bf16 box
+    constexpr uint32_t A_BYTES = 2 * BOX, B_BYTES = 4 * BOX;     // per plane: 128 k_in columns, 256 n_out columns
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + WB_STAGES * WB_STAGE_BYTES);
+    uint64_t* empty = full + WB_STAGES;
+    uint64_t* tmem_full = empty + WB_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_m = blockIdx.x / n_tiles_n, tile_n = blockIdx.x % n_tiles_n;
+    const int kin0 = tile_m * WG_BM;
+    const int out0 = tile_n * WG_BN;
+    int n_cols = n_out - out0;
+    if (n_cols > WG_BN) n_cols = WG_BN;
+    const int n_mma = (n_cols + 15) & ~15;
+    const int n_boxes_b = (n_cols + 63) >> 6;
+    const int64_t r_lo = (int64_t)blockIdx.y * rows_per_split;
+    int64_t r_hi = r_lo + rows_per_split;
+    if (r_hi > rows) r_hi = rows;
+    const int num_kb = r_hi > r_lo ? (int)((r_hi - r_lo + BK - 1) / BK) : 0;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tm_x0); tc::tma_prefetch_desc(&tm_z0);
+        if (NP == 2) { tc::tma_prefetch_desc(&tm_x1); tc::tma_prefetch_desc(&tm_z1); }
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < WB_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+            tc::mbar_init(tmem_full, 1);
+            tc::fence_barrier_init();
+            tc::fence_proxy_async();
+        }
+        __syncwarp();
+        tc::tmem_alloc<WG_BN>(tmem_slot);
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (num_kb > 0) {
+        if (warp == 0) {
+            for (int it = 0; it < num_kb; ++it) {
+                const int s = it % WB_STAGES;
+                const uint32_t ph = (it / WB_STAGES) & 1;
+                tc::mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* st = smem + s * WB_STAGE_BYTES;          // [A plane 0 | A plane 1 | B plane 0 | B plane 1]
+                const int r = (int)(r_lo + (int64_t)it * BK);
+                if (tc::elect_one()) {
+                    tc::mbar_arrive_expect_tx(&full[s], (uint32_t)NP * (2 + n_boxes_b) * BOX);
+#pragma unroll
+                    for (int pl = 0; pl < NP; ++pl) {
+#pragma unroll
+                        for (int b = 0; b < 2; ++b)
+                            tc::tma_load_2d(st + pl * A_BYTES + b * BOX, pl == 0 ? &tm_x0 : &tm_x1, &full[s], kin0 + 64 * b, r);
+                        for (int b = 0; b < n_boxes_b; ++b)
+                            tc::tma_load_2d(st + NP * A_BYTES + pl * B_BYTES + b * BOX, pl == 0 ? &tm_z0 : &tm_z1, &full[s], out0 + 64 * b, r);
+                    }
+                }
+                __syncwarp();
+            }
+        } else if (warp == 1) {
+            // kind::f16 (bf16), fp32 accumulate, A and B MN-major (bits 15, 16)
+            const uint32_t idesc = tc::umma_idesc_bf16(WG_BM, (uint32_t)n_mma) | (1u << 15) | (1u << 16);
+            // bring-up variants (production: 0): bit0 swaps LBO / SBO
+            const uint32_t lbo = (dbg & 1) ? 1024u : BOX;
+            const uint32_t sbo = (dbg & 1) ? BOX : 1024u;
+            for (int it = 0; it < num_kb; ++it) {
+                const int s = it % WB_STAGES;
+                const uint32_t ph = (it / WB_STAGES) & 1;
+                tc::mbar_wait(&full[s], ph);
+                tc::tcgen05_fence_after();
+                const uint32_t sa = tc::smem_u32(smem + s * WB_STAGE_BYTES);
+                const uint64_t a0 = umma_desc_sw128_mnmajor16(sa, lbo, sbo), a1 = umma_desc_sw128_mnmajor16(sa + A_BYTES, lbo, sbo);
+                const uint64_t b0 = umma_desc_sw128_mnmajor16(sa + NP * A_BYTES, lbo, sbo);
+                const uint64_t b1 = umma_desc_sw128_mnmajor16(sa + NP * A_BYTES + B_BYTES, lbo, sbo);
+                if (tc::elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {          // 16 rows = two 1024-byte atoms per 64-column block
+                        const uint64_t adv = (uint64_t)(k * (2048 >> 4));
+                        if (NP == 2) {
+                            umma_bf16(tmem_base, a1 + adv, b0 + adv, idesc, (it | k) != 0 ? 1u : 0u);
+                            umma_bf16(tmem_base, a0 + adv, b1 + adv, idesc, 1u);
+                        }
+                        umma_bf16(tmem_base, a0 + adv, b0 + adv, idesc, (NP == 2 || (it | k) != 0) ? 1u : 0u);
+                    }
+                    tc::umma_commit(&empty[s]);
+                }
+                __syncwarp();
+            }
+            if (tc::elect_one()) tc::umma_commit(tmem_full);
+            __syncwarp();
+        } else {
+            tc::mbar_wait<200>(tmem_full, 0);
+            tc::tcgen05_fence_after();
+            const int q = warp & 3;
+            const int kin = kin0 + q * 32 + lane;
+            const bool ok = kin < k_in;
+            for (int c = 0; c * 32 < n_cols; ++c) {
+                uint32_t r[32];
+                tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+                tc::tmem_ld_wait();
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int o = out0 + c * 32 + j;
+                        if (o < n_out) atomicAdd(dw + (int64_t)o * lddw + kin, __uint_as_float(r[j]));
+                    }
+                }
+            }
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<WG_BN>(tmem_base);
+}
+
 // [rows, cols] fp32 row-major, box = 32 columns x 32 rows, 128-byte swizzle with 32-byte atoms, OOB -> 0
 static int make_tmap_box32(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld) {
     return gnb_make_tmap_f32(map, base, rows, cols, ld, 32u, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
@@ -191,5 +344,49 @@ GNB_EXPORT int gnb_linear_bwd_weight_tf32(const float* dz, int64_t lddz, const f
     dim3 grid((unsigned)tiles, (unsigned)splits);
     gemm_tc_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, (cudaStream_t)stream>>>(tx, tz, dw, lddw, rows, n_out, k_in,
                                                                                     tiles_n, rps, debug_swap);
+    GNB_RETURN_LAUNCH();
+}
+
+// dw[n_out, k_in] += dz^T x on bf16 planes: dz planes [rows, n_out] (pitch lddz elements), x planes [rows, k_in] (pitch ldx);
+// plane 1 pointers NULL (both) = one plane. Pitches multiples of 8 elements. debug bit 0 swaps the descriptor's LBO / SBO.
+GNB_EXPORT int gnb_linear_bwd_weight_bf16(const void* dz0, const void* dz1, int64_t lddz, const void* x0, const void* x1,
+                                          int64_t ldx, float* dw, int64_t lddw, int64_t rows, int32_t n_out, int32_t k_in,
+                                          int32_t debug, void* stream) {
+    if (rows < 0 || n_out < 1 || k_in < 1 || dz0 == nullptr || x0 == nullptr || ((dz1 == nullptr) != (x1 == nullptr))) return GNB_ERR_ARG;
+    if ((lddz & 7) || (ldx & 7) || lddz < n_out || ldx < k_in) return GNB_ERR_ARG;
+    if (rows == 0) return GNB_OK;
+    if (rows >= (int64_t)1 << 31) return GNB_ERR_ARG;
+    const int planes = dz1 != nullptr ? 2 : 1;
+    const int bk = 64 / planes;
+    CUtensorMap tx0, tx1, tz0, tz1;
+    int rc = gnb_make_tmap_bf16(&tx0, x0, rows, k_in, ldx * 2, (uint32_t)bk);
+    if (rc == 0) rc = gnb_make_tmap_bf16(&tz0, dz0, rows, n_out, lddz * 2, (uint32_t)bk);
+    if (rc == 0 && planes == 2) rc = gnb_make_tmap_bf16(&tx1, x1, rows, k_in, ldx * 2, (uint32_t)bk);
+    if (rc == 0 && planes == 2) rc = gnb_make_tmap_bf16(&tz1, dz1, rows, n_out, lddz * 2, (uint32_t)bk);
+    if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    static unsigned long long attr_devs = 0ull;
+    int dev = 0;
+    GNB_CHECK(cudaGetDevice(&dev));
+    if (dev >= 64 || !((attr_devs >> dev) & 1ull)) {
+        GNB_CHECK(cudaFuncSetAttribute(gemm_bf_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WB_SMEM_BYTES));
+        GNB_CHECK(cudaFuncSetAttribute(gemm_bf_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WB_SMEM_BYTES));
+        if (dev < 64) attr_devs |= 1ull << dev;
+    }
+    const int tiles_m = gnb_div_up(k_in, WG_BM), tiles_n = gnb_div_up(n_out, WG_BN);
+    const int tiles = tiles_m * tiles_n;
+    int splits = (2 * 148) / tiles;
+    const int64_t max_splits = (rows + 8 * bk - 1) / (8 * bk);
+    if (splits > max_splits) splits = (int)max_splits;
+    if (splits < 1) splits = 1;
+    int64_t rps = (rows + splits - 1) / splits;
+    rps = ((rps + bk - 1) / bk) * bk;
+    splits = (int)((rows + rps - 1) / rps);
+    dim3 grid((unsigned)tiles, (unsigned)splits);
+    if (planes == 2)
+        gemm_bf_wgrad_kernel<2><<<grid, WG_THREADS, WB_SMEM_BYTES, (cudaStream_t)stream>>>(tx0, tx1, tz0, tz1, dw, lddw, rows, n_out, k_in,
+                                                                                         tiles_n, rps, debug);
+    else
+        gemm_bf_wgrad_kernel<1><<<grid, WG_THREADS, WB_SMEM_BYTES, (cudaStream_t)stream>>>(tx0, tx0, tz0, tz0, dw, lddw, rows, n_out, k_in,
+                                                                                         tiles_n, rps, debug);
     GNB_RETURN_LAUNCH();
 }

@@ -8,6 +8,7 @@
 //   EdgeConv gather / aggregate  models/components/layers.py:60 (PyG EdgeConv.propagate)
 //   global pooling    src/graphnet/models/gnn/dynedge.py:251-264 (torch_scatter.scatter_*)
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <float.h>
 
 namespace {
@@ -282,6 +283,96 @@ static void launch_hidden_node(int nit, dim3 grid, cudaStream_t st, const float*
         case 2: edge_hidden_fwd_node_kernel<2, MASK><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, act, h, ldh, hmask, mask_ld); break;
         case 3: edge_hidden_fwd_node_kernel<3, MASK><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, act, h, ldh, hmask, mask_ld); break;
         default: edge_hidden_fwd_node_kernel<4, MASK><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, act, h, ldh, hmask, mask_ld); break;
+    }
+}
+
+
+// The same hidden layer written as bf16 PLANES for the bf16 / bf16x3 precision modes (csrc/gemm_tc.cu, MODE 2 / 3):
+// h0 = bf16(h), h1 = bf16(h - h0) (NP = 2), each [n * width, ldh] bf16. The activation bits are taken from the fp32 value.
+__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    return make_uint2(*reinterpret_cast<const unsigned*>(&lo), *reinterpret_cast<const unsigned*>(&hi));
+}
+__device__ __forceinline__ float bf16_lo_f(unsigned w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi_f(unsigned w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+template <int NIT, int NP>
+__global__ void __launch_bounds__(256)
+edge_hidden_fwd_node_bf16_kernel(const float* __restrict__ pq, int64_t ldpq, int hdim, const int* __restrict__ nbr,
+                                 const int* __restrict__ deg, int width, int64_t n, __nv_bfloat16* __restrict__ h0,
+                                 __nv_bfloat16* __restrict__ h1, int64_t ldh, unsigned* __restrict__ hmask, int mask_ld) {
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int lane = threadIdx.x & 31;
+    const int h4 = hdim >> 2;
+    const int dg = deg[i];
+    const int nb = lane < width ? nbr[i * width + lane] : -1;
+    const float4* p = reinterpret_cast<const float4*>(pq + i * ldpq);
+    float4 pa[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int c = it * 32 + lane;
+        pa[it] = c < h4 ? p[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int s0 = 0; s0 < width; s0 += 3) {
+        float4 qv[3][NIT];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int s = s0 + u;
+            const int j = __shfl_sync(0xffffffffu, nb, s < 32 ? s : 0);
+            const bool valid = s < width && s < dg && j >= 0;
+            const float4* q = reinterpret_cast<const float4*>(pq + (int64_t)(valid ? j : 0) * ldpq + hdim);
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int c = it * 32 + lane;
+                qv[u][it] = (valid && c < h4) ? q[c] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int s = s0 + u;
+            if (s < width) {                                  // warp-uniform
+                const int64_t r = i * width + s;
+                uint2* o0 = reinterpret_cast<uint2*>(h0 + r * ldh);
+                uint2* o1 = NP == 2 ? reinterpret_cast<uint2*>(h1 + r * ldh) : nullptr;
+                const bool valid = s < dg && __shfl_sync(0xffffffffu, nb, s < 32 ? s : 0) >= 0;
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    const int c = it * 32 + lane;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid)
+                        v = make_float4(fmaxf(pa[it].x + qv[u][it].x, 0.f), fmaxf(pa[it].y + qv[u][it].y, 0.f),
+                                        fmaxf(pa[it].z + qv[u][it].z, 0.f), fmaxf(pa[it].w + qv[u][it].w, 0.f));
+                    const uint2 b0 = pack_bf16x4(v.x, v.y, v.z, v.w);
+                    if (c < h4) {
+                        o0[c] = b0;
+                        if (NP == 2)
+                            o1[c] = pack_bf16x4(v.x - bf16_lo_f(b0.x), v.y - bf16_hi_f(b0.x), v.z - bf16_lo_f(b0.y), v.w - bf16_hi_f(b0.y));
+                    }
+                    if (hmask != nullptr) {
+                        const bool in = c < h4;
+                        const unsigned bx = __ballot_sync(0xffffffffu, in && v.x > 0.f), by = __ballot_sync(0xffffffffu, in && v.y > 0.f);
+                        const unsigned bz = __ballot_sync(0xffffffffu, in && v.z > 0.f), bw = __ballot_sync(0xffffffffu, in && v.w > 0.f);
+                        if (lane == 0 && it * 4 < mask_ld)
+                            *reinterpret_cast<uint4*>(hmask + r * mask_ld + it * 4) = make_uint4(bx, by, bz, bw);
+                    }
+                }
+                if (hmask != nullptr)
+                    for (int w = 4 * NIT + lane; w < mask_ld; w += 32) hmask[r * mask_ld + w] = 0u;
+            }
+        }
+    }
+}
+
+template <int NP>
+static void launch_hidden_node_bf16(int nit, dim3 grid, cudaStream_t st, const float* pq, int64_t ldpq, int hdim, const int* nbr,
+                                    const int* deg, int width, int64_t n, __nv_bfloat16* h0, __nv_bfloat16* h1, int64_t ldh,
+                                    unsigned* hmask, int mask_ld) {
+    switch (nit) {
+        case 1: edge_hidden_fwd_node_bf16_kernel<1, NP><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld); break;
+        case 2: edge_hidden_fwd_node_bf16_kernel<2, NP><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld); break;
+        case 3: edge_hidden_fwd_node_bf16_kernel<3, NP><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld); break;
+        default: edge_hidden_fwd_node_bf16_kernel<4, NP><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld); break;
     }
 }
 
@@ -715,6 +806,69 @@ edge_mask_bwd_kernel(const float* __restrict__ g, int64_t ldg, const uint4* __re
     }
 }
 
+
+// The mask backward written as bf16 planes (precision modes bf16 / bf16x3): dz0 = bf16(dz), dz1 = bf16(dz - dz0) (NP = 2);
+// the bias gradient db sums the fp32 values.
+template <int NP>
+__global__ void __launch_bounds__(256)
+edge_mask_bwd_bf16_kernel(const float* __restrict__ g, int64_t ldg, const uint4* __restrict__ mask4, int64_t n, int cols,
+                          __nv_bfloat16* __restrict__ dz0, __nv_bfloat16* __restrict__ dz1, int64_t ldz, float* __restrict__ db,
+                          int64_t n_tiles) {
+    __shared__ float4 s_g[EM_NPT][64];
+    __shared__ __align__(16) unsigned s_m[4][256];
+    __shared__ float4 s_acc[4][64];
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 64 + tx;
+    const int cols4 = cols >> 2;
+    const int c4 = blockIdx.y * 64 + tx;
+    const bool col_ok = c4 < cols4;
+    const int64_t rows = n * EM_W;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        __syncthreads();
+        for (int e = tid; e < EM_NPT * 64; e += 256) {
+            const int f = e >> 6, cc = blockIdx.y * 64 + (e & 63);
+            const int64_t node = tile * EM_NPT + f;
+            s_g[f][e & 63] = (node < n && cc < cols4) ? reinterpret_cast<const float4*>(g + node * ldg)[cc]
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        {
+            const int ch = blockIdx.y * 256 + tid;
+            const uint4 m = ch < cols ? mask4[tile * cols + ch] : make_uint4(0u, 0u, 0u, 0u);
+            s_m[0][tid] = m.x; s_m[1][tid] = m.y; s_m[2][tid] = m.z; s_m[3][tid] = m.w;
+        }
+        __syncthreads();
+        if (col_ok) {
+            const int64_t row_base = tile * EM_ROWS;
+            const int r_end = rows - row_base < EM_ROWS ? (int)(rows - row_base) : EM_ROWS;
+#pragma unroll 4
+            for (int r = ty; r < r_end; r += 4) {
+                float4 gv = s_g[r / EM_W][tx];
+                const uint4 w = reinterpret_cast<const uint4*>(s_m[r >> 5])[tx];
+                const unsigned sh = r & 31;
+                gv.x = ((w.x >> sh) & 1u) ? gv.x : 0.f; gv.y = ((w.y >> sh) & 1u) ? gv.y : 0.f;
+                gv.z = ((w.z >> sh) & 1u) ? gv.z : 0.f; gv.w = ((w.w >> sh) & 1u) ? gv.w : 0.f;
+                const uint2 b0 = pack_bf16x4(gv.x, gv.y, gv.z, gv.w);
+                reinterpret_cast<uint2*>(dz0 + (row_base + r) * ldz)[c4] = b0;
+                if (NP == 2)
+                    reinterpret_cast<uint2*>(dz1 + (row_base + r) * ldz)[c4] =
+                        pack_bf16x4(gv.x - bf16_lo_f(b0.x), gv.y - bf16_hi_f(b0.x), gv.z - bf16_lo_f(b0.y), gv.w - bf16_hi_f(b0.y));
+                acc.x += gv.x; acc.y += gv.y; acc.z += gv.z; acc.w += gv.w;
+            }
+        }
+    }
+    if (db == nullptr) return;
+    s_acc[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && col_ok) {
+        for (int t = 1; t < 4; ++t) {
+            const float4 o = s_acc[t][tx];
+            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        atomicAdd(db + 4 * c4 + 0, acc.x); atomicAdd(db + 4 * c4 + 1, acc.y);
+        atomicAdd(db + 4 * c4 + 2, acc.z); atomicAdd(db + 4 * c4 + 3, acc.w);
+    }
+}
+
 // out[c] += sum_r a[r, c]; out must be zero on entry. CTA = 32 x 8, 256 rows per CTA.
 __global__ void colsum_kernel(const float* __restrict__ a, int64_t lda, int64_t rows, int cols,
                               float* __restrict__ out) {
@@ -948,5 +1102,45 @@ GNB_EXPORT int gnb_ptr_to_batch(const int64_t* ptr, int64_t nseg, int64_t n, int
     if (n < 0 || nseg < 1 || nseg >= ((int64_t)1 << 31)) return GNB_ERR_ARG;
     if (n == 0) return GNB_OK;
     ptr_to_batch_kernel<<<gnb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(ptr, (int)nseg, n, batch);
+    GNB_RETURN_LAUNCH();
+}
+
+// ---- bf16-plane producers (precision modes bf16 / bf16x3; pitches in bf16 ELEMENTS, multiples of 8) -----------------------------
+// h planes of the hoisted EdgeConv hidden layer: h0 = bf16(relu(P_i + Q_j)), h1 = bf16(h - h0) (h1 may be NULL), plus the
+// activation bits of gnb_edge_hidden_fwd_mask (hmask may be NULL: inference). hdim <= 512, width <= 32.
+GNB_EXPORT int gnb_edge_hidden_fwd_bf16(const float* pq, int64_t ldpq, int32_t hdim, const int32_t* nbr, const int32_t* deg,
+                                        int32_t width, int64_t n, void* h0, void* h1, int64_t ldh, uint32_t* hmask,
+                                        int32_t mask_ld, void* stream) {
+    if ((hdim & 7) || (ldpq & 3) || (ldh & 7) || ldh < hdim || !aligned16(pq) || !aligned16(h0) || !aligned16(h1) || h0 == nullptr)
+        return GNB_ERR_ARG;
+    if (hdim > 512 || width > 32 || width < 1) return GNB_ERR_UNSUPPORTED;
+    if (hmask != nullptr && (mask_ld != 4 * ((hdim + 127) / 128) || !aligned16(hmask))) return GNB_ERR_ARG;
+    if (n == 0) return GNB_OK;
+    const dim3 grid((unsigned)gnb_div_up(n, 8));
+    if (h1 != nullptr)
+        launch_hidden_node_bf16<2>((hdim + 127) / 128, grid, (cudaStream_t)stream, pq, ldpq, hdim, nbr, deg, width, n,
+                                   (__nv_bfloat16*)h0, (__nv_bfloat16*)h1, ldh, hmask, mask_ld);
+    else
+        launch_hidden_node_bf16<1>((hdim + 127) / 128, grid, (cudaStream_t)stream, pq, ldpq, hdim, nbr, deg, width, n,
+                                   (__nv_bfloat16*)h0, nullptr, ldh, hmask, mask_ld);
+    GNB_RETURN_LAUNCH();
+}
+// dz planes of the "ReLU + k-sum" backward from the aggregating epilogue's bit mask (see gnb_edge_mask_bwd_colsum):
+// dz0 = bf16(dz), dz1 = bf16(dz - dz0) (may be NULL); db[c] += column sums of the fp32 values.
+GNB_EXPORT int gnb_edge_mask_bwd_colsum_bf16(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols,
+                                             void* dz0, void* dz1, int64_t ldz, float* db, void* stream) {
+    if (maskbits == nullptr || dz0 == nullptr) return GNB_ERR_ARG;
+    if ((cols & 7) || (ldg & 3) || (ldz & 7) || ldz < cols || !aligned16(g) || !aligned16(dz0) || !aligned16(dz1) || !aligned16(maskbits))
+        return GNB_ERR_ARG;
+    if (n == 0) return GNB_OK;
+    const int64_t n_tiles = (n + EM_NPT - 1) / EM_NPT;
+    const int64_t max_ctas = 148 * 8;
+    dim3 grid((unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas), (unsigned)gnb_div_up(cols >> 2, 64)), block(64, 4);
+    if (dz1 != nullptr)
+        edge_mask_bwd_bf16_kernel<2><<<grid, block, 0, (cudaStream_t)stream>>>(g, ldg, reinterpret_cast<const uint4*>(maskbits), n, cols,
+                                                                             (__nv_bfloat16*)dz0, (__nv_bfloat16*)dz1, ldz, db, n_tiles);
+    else
+        edge_mask_bwd_bf16_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(g, ldg, reinterpret_cast<const uint4*>(maskbits), n, cols,
+                                                                             (__nv_bfloat16*)dz0, nullptr, ldz, db, n_tiles);
     GNB_RETURN_LAUNCH();
 }

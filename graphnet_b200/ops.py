@@ -29,8 +29,14 @@ POOL = {"min": 0, "max": 1, "sum": 2, "mean": 3}
 #             three kind::tf32 products per K step, activations stay plain fp32); the backward GEMMs are single-pass tf32.
 #             Outputs ~1e-6, gradients ~5e-4 from the fp64 oracle (tests/studies/split_precision_study.py: the forward's
 #             rounding, not the backward's, is what moved the tf32 gradients to 2e-3).
+#   "bf16": north_star's looser mode -- the per-edge tensors of the executor route (h, dz: the [N k, C] tensors that dominate
+#             the bytes) are stored as ONE bf16 plane and the three per-edge GEMMs run as kind::f16; node-level GEMMs as "tf32".
+#             Stated tolerance: outputs 5e-3, gradients 1.5e-2 (tests/test_gpu_bf16.py).
+#   "bf16x3": the per-edge tensors as TWO bf16 planes (v ~ bf16(v) + bf16(v - bf16(v))), three products per per-edge GEMM in the
+#             forward AND the backward pass; node-level forward GEMMs as "tf32x3". fp32 grade like "tf32x3".
+#             Both bf16 modes exist on the executor route (k = 8 graphs); elsewhere they behave like "tf32" / "tf32x3".
 PRECISION = os.environ.get("GNB_PRECISION", "fp32")
-PRECISIONS = ("fp32", "tf32", "tf32x3")
+PRECISIONS = ("fp32", "tf32", "tf32x3", "bf16", "bf16x3")
 
 
 def set_precision(mode: str) -> None:
@@ -41,17 +47,17 @@ def set_precision(mode: str) -> None:
 
 
 def _tf32() -> bool:
-    """Tensor-core GEMMs (both tf32 modes)."""
-    return PRECISION in ("tf32", "tf32x3")
+    """Tensor-core GEMMs (every mode but fp32)."""
+    return PRECISION != "fp32"
 
 
 def _split() -> bool:
-    return PRECISION == "tf32x3"
+    return PRECISION in ("tf32x3", "bf16x3")
 
 
 def _fround() -> bool:
     """Forward activations that feed a tensor-core GEMM are stored rounded to tf32 (single-pass mode only)."""
-    return PRECISION == "tf32"
+    return PRECISION in ("tf32", "bf16")
 
 
 def _mark_rounded(t: Tensor) -> Tensor:
@@ -700,7 +706,15 @@ class _DynEdgeExec(torch.autograd.Function):
         cfg = _copy_cfg(cfg)      # the ctx keeps ITS OWN copy: a later set_precision() / flag change cannot alter the layout
         cfg.precision = 2 if _split() else (1 if _tf32() else 0)
         cfg.flags = (0 if FUSED_EDGECONV else 1) | (2 if INFERENCE_ROUTE == "split" else 0)
-        nbytes = lib.gnb_dynedge_workspace_bytes(ctypes.byref(cfg), n, nseg, graph.width, training)
+        nbytes = -2
+        if PRECISION in ("bf16", "bf16x3"):     # per-edge tensors as bf16 planes where the configuration has the k = 8 route
+            base = cfg.precision
+            cfg.precision = 3 if PRECISION == "bf16" else 4
+            nbytes = lib.gnb_dynedge_workspace_bytes(ctypes.byref(cfg), n, nseg, graph.width, training)
+            if nbytes == -2:
+                cfg.precision = base
+        if nbytes == -2:
+            nbytes = lib.gnb_dynedge_workspace_bytes(ctypes.byref(cfg), n, nseg, graph.width, training)
         if nbytes < 0:
             raise RuntimeError(f"gnb_dynedge_workspace_bytes: unsupported configuration [{nbytes}]")
         ws = _ws_acquire(int(nbytes), x.device)

@@ -203,6 +203,40 @@ int gnb_edge_hidden_fwd_mask(const float* pq, int64_t ldpq, int32_t hdim, const 
 int gnb_round_pad_tf32(const float* src, int64_t lds, int64_t rows, int32_t cols, float* dst, int64_t ldd,
                        int32_t dst_cols, void* stream);
 
+/* ---- bf16-plane per-edge GEMMs: precision modes "bf16" (one plane, north_star's looser mode) and "bf16x3" (two planes) ----
+ * A per-edge tensor v is stored as bf16 planes v0 = bf16(v), v1 = bf16(v - v0) written by its producer; plane-1 pointers
+ * NULL (for every operand of a call) = one plane. Pitches are in bf16 ELEMENTS, multiples of 8; pointers 16-byte aligned.
+ * One plane: a single kind::f16 product (half the bytes, twice the MMA rate of tf32). Two planes: v0 w0 + v1 w0 + v0 w1
+ * (dropped terms ~2^-17) -- the bytes of the fp32 tensors, no in-kernel operand split. Same reference arithmetic as the tf32
+ * entry points they mirror (torch.nn.Linear / PyG EdgeConv in fp32: layers.py:55-62, dynedge.py:200-203). */
+/* hidden layer of the hoisted EdgeConv MLP as planes: h = relu(P_i + Q_j) (gnb_edge_hidden_fwd_mask), hmask may be NULL. */
+int gnb_edge_hidden_fwd_bf16(const float* pq, int64_t ldpq, int32_t hdim, const int32_t* nbr, const int32_t* deg,
+                             int32_t width, int64_t n, void* h0, void* h1, int64_t ldh, uint32_t* hmask, int32_t mask_ld,
+                             void* stream);
+/* gnb_edge_linear_agg_fwd_tf32 on planes: h planes [n*9, k], w planes [n_out, ldw >= k] (zero beyond k). */
+int gnb_edge_linear_agg_fwd_bf16(const void* h0, const void* h1, int64_t ldh, int32_t k, const void* w0, const void* w1,
+                                 int64_t ldw, const float* bias, const int32_t* deg, int64_t n, int32_t n_out,
+                                 int32_t round_out, float* y, int64_t ldy, uint32_t* maskbits, void* stream);
+/* gnb_edge_mask_bwd_colsum writing dz as planes [n*9, ldz >= cols]; db sums the fp32 values. */
+int gnb_edge_mask_bwd_colsum_bf16(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols, void* dz0,
+                                  void* dz1, int64_t ldz, float* db, void* stream);
+/* gnb_linear_bwd_weight_tf32 on planes: dw[n_out, k_in] += dz^T x (fp32 red.add); debug: 0 in production. */
+int gnb_linear_bwd_weight_bf16(const void* dz0, const void* dz1, int64_t lddz, const void* x0, const void* x1, int64_t ldx,
+                               float* dw, int64_t lddw, int64_t rows, int32_t n_out, int32_t k_in, int32_t debug,
+                               void* stream);
+/* gnb_edge_hidden_dgrad_scatter_split_tf32 on planes: dz planes [n*9, c_out], wt planes = W2^T [hdim, ldw >= c_out]. */
+int gnb_edge_hidden_dgrad_scatter_bf16(const void* dz0, const void* dz1, int64_t lddz, int32_t c_out, const void* wt0,
+                                       const void* wt1, int64_t ldw, const uint32_t* hmask, int32_t mask_ld, int32_t hdim,
+                                       const int32_t* nbr, int64_t n, float* dq, int64_t lddq, float* dp, int64_t lddp,
+                                       float* dbias, int32_t flags, void* stream);
+/* Plain Linear on planes (CTA-pair kernel): y = act(x w^T + bias), fp32 output. */
+int gnb_linear_fwd_bf16(const void* x0, const void* x1, int64_t ldx, int32_t k, const void* w0, const void* w1, int64_t ldw,
+                        const float* bias, float* y, int64_t ldy, int64_t rows, int32_t n_out, int32_t act,
+                        int32_t round_out, void* stream);
+/* fp32 [rows, cols] -> planes [rows, dst_cols] (zero beyond cols); transpose != 0: planes of src^T ([cols, dst_cols >= rows]). */
+int gnb_to_bf16_planes(const float* src, int64_t lds, int64_t rows, int32_t cols, void* p0, void* p1, int64_t ldd,
+                       int32_t dst_cols, int32_t transpose, void* stream);
+
 /* fp32 SIMT backend: y[m,n] = act(x[m,k] w[n,k]^T + bias (+ y if accumulate)); act: 0 none, 1 relu. */
 int gnb_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,
                        int64_t ldy, int64_t m, int64_t n, int64_t k, int32_t act, int32_t accumulate, void* stream);
@@ -223,7 +257,9 @@ int64_t gnb_launch_count(void);
 /* Mirrors the constructor arguments of DynEdge (src/graphnet/models/gnn/dynedge.py:24-38) for the fast-path
  * family: ReLU, no norm layers, 2-Linear conv MLPs with aggr=add, Linear-ReLU post-processing / read-out chains. */
 typedef struct {
-    int32_t nb_inputs, k, precision;                 /* precision: 0 fp32 SIMT GEMMs, 1 tf32 tcgen05 GEMMs, 2 tf32x3: forward GEMMs split-operand (fp32 grade), backward GEMMs tf32 */
+    int32_t nb_inputs, k, precision;                 /* precision: 0 fp32 SIMT GEMMs, 1 tf32 tcgen05 GEMMs, 2 tf32x3: forward GEMMs split-operand (fp32 grade), backward GEMMs tf32,
+                                                        3 bf16: per-edge tensors as one bf16 plane (kind::f16), node-level GEMMs as 1,
+                                                        4 bf16x3: per-edge tensors as two bf16 planes, node-level GEMMs as 2 */
     int32_t n_conv, conv_hidden[GNB_MAX_LAYERS], conv_out[GNB_MAX_LAYERS];
     int32_t n_post, post_out[GNB_MAX_LAYERS];
     int32_t n_readout, readout_out[GNB_MAX_LAYERS];
