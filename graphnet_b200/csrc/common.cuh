@@ -52,3 +52,23 @@ enum : int { GNB_AGGR_ADD = 0, GNB_AGGR_MEAN = 1, GNB_AGGR_MAX = 2 };
 
 // pooling scheme codes
 enum : int { GNB_POOL_MIN = 0, GNB_POOL_MAX = 1, GNB_POOL_SUM = 2, GNB_POOL_MEAN = 3 };
+
+// Power-of-two scaling of a gradient tensor stored as ONE fp16 plane (precision mode mixed16): `maxbits` = fp32 bits of
+// max|g| (gnb_absmax_bits). Returns {scale, 1 / scale} with scale = 2^(14 - floor(log2 max)), so that max * scale lies in
+// [2^14, 2^15) (fp16's largest finite value is 65504) and elements down to 2^-29 of the maximum keep a normal fp16 encoding.
+// Exact in both directions (powers of two); 1 for an all-zero tensor.
+__host__ __device__ __forceinline__ float2 gnb_pow2_scale(unsigned maxbits) {
+    const int e = (int)((maxbits >> 23) & 0xffu);
+    if (e == 0 || e == 255) return float2{1.f, 1.f};
+    int se = 268 - e;                        // biased exponent of the scale: 127 + 14 - (e - 127)
+    se = se < 2 ? 2 : (se > 252 ? 252 : se);
+    const unsigned sb = (unsigned)se << 23, ib = (unsigned)(254 - se) << 23;
+#ifdef __CUDA_ARCH__
+    return float2{__uint_as_float(sb), __uint_as_float(ib)};
+#else
+    float s, i;
+    __builtin_memcpy(&s, &sb, 4);
+    __builtin_memcpy(&i, &ib, 4);
+    return float2{s, i};
+#endif
+}

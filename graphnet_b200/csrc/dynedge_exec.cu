@@ -63,6 +63,19 @@ int gnb_edge_hidden_dgrad_scatter_bf16(const void*, const void*, int64_t, int32_
                                        int32_t, int32_t, const int32_t*, int64_t, float*, int64_t, float*, int64_t, float*, int32_t,
                                        void*);
 int gnb_to_bf16_planes(const float*, int64_t, int64_t, int32_t, void*, void*, int64_t, int32_t, int32_t, void*);
+int gnb_zero_block(float*, int64_t, int64_t, int32_t, void*);
+int gnb_to_f16_planes(const float*, int64_t, int64_t, int32_t, void*, void*, int64_t, int32_t, int32_t, void*);
+int gnb_absmax_bits(const float*, int64_t, int64_t, int32_t, int32_t, uint32_t*, void*);
+int gnb_edge_hidden_fwd_f16(const float*, int64_t, int32_t, const int32_t*, const int32_t*, int32_t, int64_t, void*, void*, int64_t,
+                            uint32_t*, int32_t, const uint32_t*, void*);
+int gnb_edge_linear_agg_fwd_f16(const void*, const void*, int64_t, int32_t, const void*, const void*, int64_t, const float*,
+                                const int32_t*, int64_t, int32_t, int32_t, float*, int64_t, uint32_t*, const uint32_t*, void*);
+int gnb_edge_mask_bwd_colsum_f16(const float*, int64_t, const uint32_t*, int64_t, int32_t, void*, int64_t, float*, const uint32_t*, void*);
+int gnb_linear_bwd_weight_f16(const void*, int64_t, const void*, const void*, int64_t, float*, int64_t, int64_t, int32_t, int32_t,
+                              const uint32_t*, const uint32_t*, void*);
+int gnb_edge_hidden_dgrad_scatter_f16(const void*, int64_t, int32_t, const void*, int64_t, const uint32_t*, int32_t, int32_t,
+                                          const int32_t*, int64_t, float*, int64_t, float*, int64_t, float*, int32_t, const uint32_t*,
+                                          void*);
 int gnb_linear_fwd_f32(const float*, int64_t, const float*, int64_t, const float*, float*, int64_t, int64_t, int64_t,
                        int64_t, int32_t, int32_t, void*);
 int gnb_linear_bwd_data_f32(const float*, int64_t, const float*, int64_t, float*, int64_t, int64_t, int64_t, int64_t,
@@ -79,7 +92,11 @@ struct gnb_dynedge_config {
                                                    // forward GEMMs = fp32 grade, single-pass tf32 backward GEMMs),
                                                    // 3 = bf16 (per-edge tensors h / dz stored as ONE bf16 plane, per-edge GEMMs
                                                    // kind::f16; node-level GEMMs as in 1), 4 = bf16x3 (per-edge tensors as TWO
-                                                   // bf16 planes, three products per per-edge GEMM; node-level GEMMs as in 2)
+                                                   // bf16 planes, three products per per-edge GEMM; node-level GEMMs as in 2),
+                                                   // 5 = mixed16: per-edge tensors as fp16 planes scaled per layer by a power of
+                                                   // two (fp16 = tf32's significand in half the bytes): forward on two planes of
+                                                   // h and W2 (three products, fp32 grade), backward on ONE plane of dz, h, W2^T
+                                                   // (tf32 grade); node-level GEMMs as in 2
     int32_t n_conv, conv_hidden[GNB_MAX_LAYERS], conv_out[GNB_MAX_LAYERS];
     int32_t n_post, post_out[GNB_MAX_LAYERS];
     int32_t n_readout, readout_out[GNB_MAX_LAYERS];
@@ -216,6 +233,8 @@ struct Plan {
     float *gnode[GNB_MAX_LAYERS + 1], *dz_big, *dh_big, *dpq, *dzq, *dwp, *wt, *dbtmp, *gro_a, *gro_b;
     __nv_bfloat16* dzb[2];               // bf16 modes: dz planes [n * 9, max_c]
     int bf;                              // bf16 planes per per-edge tensor (0: fp32 / tf32 tensors)
+    bool mixed;                          // mode 5: dz / W2^T as one fp16 plane in the backward pass
+    uint32_t* scale_bits;                // mixed16: [2][GNB_MAX_LAYERS] fp32 bits of 2 max|PQ| (>= max h) and of max|g_y| per layer
     int64_t bytes;
 };
 
@@ -229,9 +248,10 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
     if (c.globals_after_pooling && c.n_pool == 0) return GNB_ERR_ARG;
     Arena a(ws, cap);
     p.n = n; p.nseg = nseg; p.w0 = w0; p.width = c.k + 1;
-    const bool split = c.precision == 2 || c.precision == 4;      // pre-split weight operands: a lo buffer behind every packed forward weight
-    if (c.precision < 0 || c.precision > 4) return GNB_ERR_ARG;
-    p.bf = c.precision >= 3 ? c.precision - 2 : 0;
+    const bool split = c.precision == 2 || c.precision >= 4;      // pre-split weight operands: a lo buffer behind every packed forward weight
+    if (c.precision < 0 || c.precision > 5) return GNB_ERR_ARG;
+    p.bf = c.precision >= 3 ? (c.precision == 3 ? 1 : 2) : 0;
+    p.mixed = c.precision == 5;
     p.agg = c.precision >= 1 && c.k == 8 && w0 == 9 && !(c.flags & 1) && (training || (c.flags & 2) || split || p.bf);
     if (p.bf && !p.agg) return GNB_ERR_UNSUPPORTED;               // the bf16 modes exist on the k = 8 tensor-core route only
     const int f = c.nb_inputs, ng = f + 5;
@@ -240,6 +260,7 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
     p.x0_ld = (int)up(p.node_width, 32);
     p.g = a.get<float>(nseg * ng);
     p.x0 = a.get<float>(n * p.x0_ld);
+    p.scale_bits = p.mixed ? a.get<uint32_t>(2 * GNB_MAX_LAYERS) : nullptr;
     const int64_t max_w = w0 > p.width ? w0 : p.width;
     int max_h = 0, max_c = 0;
     for (int l = 0; l < c.n_conv; ++l) {
@@ -275,7 +296,7 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
             const bool on = pl < p.bf;
             b.hb[pl] = on ? (training ? a.get<__nv_bfloat16>(n * wl * b.hid) : hb_shared[pl]) : nullptr;
             b.w2b[pl] = on ? a.get<__nv_bfloat16>((int64_t)b.cout * b.hld64) : nullptr;
-            b.w2tb[pl] = (on && training) ? a.get<__nv_bfloat16>((int64_t)b.hid * b.cld64) : nullptr;
+            b.w2tb[pl] = (on && training && !(p.mixed && pl == 1)) ? a.get<__nv_bfloat16>((int64_t)b.hid * b.cld64) : nullptr;
         }
         if (p.bf && ((b.hid & 7) || (b.cout & 7))) return GNB_ERR_UNSUPPORTED;
         b.h = p.bf ? nullptr : (training ? a.get<float>(n * wl * b.hid) : h_shared);
@@ -339,7 +360,7 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
         for (int l = 0; l <= c.n_conv; ++l) p.gnode[l] = l == 0 ? nullptr : a.get<float>(n * c.conv_out[l - 1]);
         p.dz_big = p.bf ? nullptr : a.get<float>(n * max_w * max_c);
         p.dh_big = p.bf ? nullptr : a.get<float>(n * max_w * max_h);
-        for (int pl = 0; pl < 2; ++pl) p.dzb[pl] = pl < p.bf ? a.get<__nv_bfloat16>(n * max_w * max_c) : nullptr;
+        for (int pl = 0; pl < 2; ++pl) p.dzb[pl] = (pl < p.bf && !(p.mixed && pl == 1)) ? a.get<__nv_bfloat16>(n * max_w * max_c) : nullptr;
         p.dpq = a.get<float>(n * 2 * max_h);
         p.dzq = a.get<float>(n * 2 * max_h);
         int64_t max_wp = 0, max_dense = 0;
@@ -382,7 +403,7 @@ struct Exec {
     int rnd;          // backward: gradients that feed a tensor-core GEMM are stored rounded
     int frnd;         // forward flag for the producers of GEMM operands
     Exec(const gnb_dynedge_config& cfg, void* s)
-        : c(cfg), st((cudaStream_t)s), tf32(cfg.precision >= 1), split(cfg.precision == 2 || cfg.precision == 4),
+        : c(cfg), st((cudaStream_t)s), tf32(cfg.precision >= 1), split(cfg.precision == 2 || cfg.precision >= 4),
           fround(cfg.precision == 1 || cfg.precision == 3), rnd(cfg.precision >= 1 ? GNB_FLAG_ROUND_TF32 : 0),
           frnd((cfg.precision == 1 || cfg.precision == 3) ? GNB_FLAG_ROUND_TF32 : 0) {}
 
@@ -498,11 +519,22 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
                                            b.y, b.cout, stream));
         } else if (p.bf) {
             // bf16 / bf16x3: h as bf16 plane(s) straight from the hidden-layer kernel, second Linear + ReLU + k-sum on kind::f16
-            EX(gnb_to_bf16_planes(w2, b.hid, b.cout, b.hid, b.w2b[0], b.w2b[1], b.hld64, b.hld64, 0, stream));
-            if (training) EX(gnb_to_bf16_planes(w2, b.hid, b.cout, b.hid, b.w2tb[0], b.w2tb[1], b.cld64, b.cld64, 1, stream));
-            EX(gnb_edge_hidden_fwd_bf16(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, b.hb[0], b.hb[1], b.hid, b.hmask, b.mld, stream));
-            EX(gnb_edge_linear_agg_fwd_bf16(b.hb[0], b.hb[1], b.hid, b.hid, b.w2b[0], b.w2b[1], b.hld64, b2, deg, n, b.cout,
-                                            e.fround ? 1 : 0, b.y, b.cout, b.mask, stream));
+            if (p.mixed) {
+                uint32_t* hs = p.scale_bits + l;          // h = relu(P_i + Q_j) <= 2 max|PQ|
+                if (l == 0) GNB_CHECK(cudaMemsetAsync(p.scale_bits, 0, 2 * GNB_MAX_LAYERS * 4, e.st));
+                EX(gnb_absmax_bits(b.pq, 2 * b.hid, n, 2 * b.hid, 1, hs, stream));
+                EX(gnb_to_f16_planes(w2, b.hid, b.cout, b.hid, b.w2b[0], b.w2b[1], b.hld64, b.hld64, 0, stream));
+                if (training) EX(gnb_to_f16_planes(w2, b.hid, b.cout, b.hid, b.w2tb[0], nullptr, b.cld64, b.cld64, 1, stream));
+                EX(gnb_edge_hidden_fwd_f16(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, b.hb[0], b.hb[1], b.hid, b.hmask, b.mld, hs, stream));
+                EX(gnb_edge_linear_agg_fwd_f16(b.hb[0], b.hb[1], b.hid, b.hid, b.w2b[0], b.w2b[1], b.hld64, b2, deg, n, b.cout, 0, b.y,
+                                               b.cout, b.mask, hs, stream));
+            } else {
+                EX(gnb_to_bf16_planes(w2, b.hid, b.cout, b.hid, b.w2b[0], b.w2b[1], b.hld64, b.hld64, 0, stream));
+                if (training) EX(gnb_to_bf16_planes(w2, b.hid, b.cout, b.hid, b.w2tb[0], b.w2tb[1], b.cld64, b.cld64, 1, stream));
+                EX(gnb_edge_hidden_fwd_bf16(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, b.hb[0], b.hb[1], b.hid, b.hmask, b.mld, stream));
+                EX(gnb_edge_linear_agg_fwd_bf16(b.hb[0], b.hb[1], b.hid, b.hid, b.w2b[0], b.w2b[1], b.hld64, b2, deg, n, b.cout,
+                                                e.fround ? 1 : 0, b.y, b.cout, b.mask, stream));
+            }
         } else if (p.agg) {
             // training (and inference with flags bit 1): the second Linear, ReLU and the k-sum run in one tcgen05 kernel; h is kept for the backward pass;
             // whose epilogue writes y and one ReLU bit per (slot, channel) -- the [E, C] message tensor is never stored
@@ -663,7 +695,12 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
         const int64_t rows = n * wl;
         const float* gy = p.gnode[l + 1];
         // (aggregate-bwd + ReLU-bwd + bias grad) in one pass
-        if (p.bf) {
+        if (p.mixed) {
+            uint32_t* gs = p.scale_bits + GNB_MAX_LAYERS + l;      // zeroed by the forward pass
+            EX(gnb_absmax_bits(gy, b.cout, n, b.cout, 0, gs, stream));
+            EX(gnb_edge_mask_bwd_colsum_f16(gy, b.cout, b.mask, n, b.cout, p.dzb[0], b.cout, gb2, gs, stream));
+            EX(gnb_linear_bwd_weight_f16(p.dzb[0], b.cout, b.hb[0], nullptr, b.hid, gw2, b.hid, rows, b.cout, b.hid, gs, p.scale_bits + l, stream));
+        } else if (p.bf) {
             EX(gnb_edge_mask_bwd_colsum_bf16(gy, b.cout, b.mask, n, b.cout, p.dzb[0], p.dzb[1], b.cout, gb2, stream));
             EX(gnb_linear_bwd_weight_bf16(p.dzb[0], p.dzb[1], b.cout, b.hb[0], b.hb[1], b.hid, gw2, b.hid, rows, b.cout, b.hid, 0, stream));
         } else if (p.agg)
@@ -675,9 +712,14 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
         GNB_CHECK(cudaMemsetAsync(p.dbtmp, 0, (size_t)2 * b.hid * 4, e.st));
         const float* dzq = p.dzq;
         if (p.bf) {
-            GNB_CHECK(cudaMemset2DAsync(p.dzq + b.hid, (size_t)2 * b.hid * 4, 0, (size_t)b.hid * 4, (size_t)n, e.st));
-            EX(gnb_edge_hidden_dgrad_scatter_bf16(p.dzb[0], p.dzb[1], b.cout, b.cout, b.w2tb[0], b.w2tb[1], b.cld64, b.hmask, b.mld,
-                                                  b.hid, nbr, n, p.dzq + b.hid, 2 * b.hid, p.dzq, 2 * b.hid, p.dbtmp, e.rnd, stream));
+            EX(gnb_zero_block(p.dzq + b.hid, 2 * b.hid, n, b.hid, stream));
+            if (p.mixed)
+                EX(gnb_edge_hidden_dgrad_scatter_f16(p.dzb[0], b.cout, b.cout, b.w2tb[0], b.cld64, b.hmask, b.mld, b.hid, nbr, n,
+                                                     p.dzq + b.hid, 2 * b.hid, p.dzq, 2 * b.hid, p.dbtmp, e.rnd,
+                                                     p.scale_bits + GNB_MAX_LAYERS + l, stream));
+            else
+                EX(gnb_edge_hidden_dgrad_scatter_bf16(p.dzb[0], p.dzb[1], b.cout, b.cout, b.w2tb[0], b.w2tb[1], b.cld64, b.hmask, b.mld,
+                                                      b.hid, nbr, n, p.dzq + b.hid, 2 * b.hid, p.dzq, 2 * b.hid, p.dbtmp, e.rnd, stream));
         } else if (b.hmask != nullptr) {
             // data gradient + ReLU mask + scatter in one kernel (dh [E, hid] is never materialised). Both halves land straight
             // in dzq, the operand buffer of the two GEMMs that follow: the P half (slot sums, plain stores) rounded to tf32
@@ -685,7 +727,7 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
             // the event onto a zeroed half -- unrounded: the tensor core reads its truncation, which leaves the gradient
             // error where it is (tests/studies/bf16_storage_study.py: 2.1e-3 / 7.0e-4 against 2.2e-3 / 7.6e-4 with the
             // rounding pass this replaces: 12 B per value read + written + zeroed, ~55 us per layer, for a 4 B memset).
-            GNB_CHECK(cudaMemset2DAsync(p.dzq + b.hid, (size_t)2 * b.hid * 4, 0, (size_t)b.hid * 4, (size_t)n, e.st));
+            EX(gnb_zero_block(p.dzq + b.hid, 2 * b.hid, n, b.hid, stream));
             const int nld = (int)up(b.cout, 32);
             EX(e.transpose_pad(b.w2p, b.hld, b.cout, b.hid, p.wt, nld, nld));
             EX(gnb_edge_hidden_dgrad_scatter_split_tf32(p.dz_big, b.cout, b.cout, p.wt, nld, b.hmask, b.mld, b.hid, nbr, n,

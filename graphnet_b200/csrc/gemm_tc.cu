@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -38,7 +39,8 @@ struct PartInfo { int nparts; int kblocks[TC_MAX_PARTS]; };
 // Aggregating epilogue (EdgeConv second Linear): rows are padded edge slots (node i, slot s) = i * 9 + s; a tile is
 // 14 nodes = 126 rows; the epilogue sums relu(acc + b) over the valid slots of every node, writes y[node, ch] and one
 // bit per (slot, channel) = "pre-activation > 0" for the backward pass. The [E, C] message tensor is never stored.
-struct AggInfo { const int* deg; int64_t n_nodes; unsigned* maskbits; int enabled; int dbg; unsigned long long* prof; };
+struct AggInfo { const int* deg; int64_t n_nodes; unsigned* maskbits; int enabled; int dbg; unsigned long long* prof;
+                 const unsigned* scale_bits; };   // mixed16: h arrives scaled by gnb_pow2_scale(*scale_bits).x (16-bit plane modes only)
 constexpr int AGG_W = 9, AGG_NPT = 14, AGG_ROWS = AGG_W * AGG_NPT;   // k = 8 neighbour tables
 // Scattering epilogue (backward of the hoisted EdgeConv hidden layer fused into the data-gradient GEMM): rows are padded
 // edge slots as above, output channel c of row (i, s) is dh = (dz W2)[(i,s), c]; the epilogue applies the ReLU mask
@@ -49,7 +51,8 @@ constexpr int AGG_W = 9, AGG_NPT = 14, AGG_ROWS = AGG_W * AGG_NPT;   // k = 8 ne
 // dq: [n, >= hdim] rows of pitch lddq (fp32 reductions; zero on entry); dp: [n, >= hdim] rows of pitch lddp (overwritten,
 // rounded to tf32 when round_p); dbias (optional): [hdim] += column sums of dp (the bias gradient of the hoisted Linear).
 struct ScatInfo { const int* nbr; const unsigned* hmask; int mask_ld; float* dq; int64_t lddq; int hdim; int64_t n_nodes; int enabled;
-                  float* dp; int64_t lddp; float* dbias; int round_p; };
+                  float* dp; int64_t lddp; float* dbias; int round_p;
+                  const unsigned* scale_bits; };   // mixed16: dz arrives scaled by gnb_pow2_scale(*scale_bits); NULL = unscaled
 
 // Producer side of the scattering epilogue: per 126-slot sub-tile (first node `node0`) every lane resolves 4 of the 128
 // offsets `nbr * lddq` (floats; padding slots and slots beyond the tensor are redirected to the Q row of the sub-tile's
@@ -88,10 +91,10 @@ __host__ __device__ constexpr uint32_t sc_meta_stride(int mask_ld) {
 // it is padding (1/9 of all reductions; a per-lane `v != 0` test would halve the reductions but costs a divergence
 // region per element: 461 -> 673 us). Per element: 2 LDS + LOP3 + FSEL + FADD + IMAD.WIDE + RED (the first version,
 // with generic-pointer metadata loads and offset selects, ran 17 and made the epilogue warps the kernel's bound).
-template <int NN, int J0, int MLD>
+template <int NN, int J0, int MLD, bool SCALED>
 __device__ __forceinline__ void scat_nodes(uint32_t taddr, uint32_t off_a, uint32_t msk_a, uint32_t mstride, unsigned lanebit,
                                            unsigned lastv, float* __restrict__ dq, float* __restrict__ dp, int64_t lddp,
-                                           int64_t nodes_left, bool ch_ok, bool skip, bool round_p, float& colacc) {
+                                           int64_t nodes_left, bool ch_ok, bool skip, bool round_p, float& colacc, float inv) {
     uint32_t r[32];
     tc::tmem_ld_32x32b_x32(taddr, r);
     int offr[NN * AGG_W];
@@ -111,7 +114,8 @@ __device__ __forceinline__ void scat_nodes(uint32_t taddr, uint32_t off_a, uint3
 #pragma unroll
         for (int sl = 0; sl < AGG_W; ++sl) {
             const int e = f * AGG_W + sl;
-            const float v = (mwr[e] & lanebit) ? __uint_as_float(r[J0 + e]) : 0.f;
+            float v = (mwr[e] & lanebit) ? __uint_as_float(r[J0 + e]) : 0.f;
+            if (SCALED) v *= inv;
             accp += v;
             if (sl < AGG_W - 1 || last_valid) tc::red_add_f32(dq + offr[e], v);
         }
@@ -120,29 +124,30 @@ __device__ __forceinline__ void scat_nodes(uint32_t taddr, uint32_t off_a, uint3
     }
 }
 // One 126-slot sub-tile = 14 nodes: columns [27 c, 27 c + 27) for c = 0..3, then [108, 126) out of a load at column 96.
-template <int MLD>
+template <int MLD, bool SCALED>
 __device__ __forceinline__ void scat_tile(uint32_t tcol, uint32_t mb_a, uint32_t off_a, uint32_t mword, uint32_t mstride,
                                           unsigned lanebit, float* dq, float* dp, int64_t ldpq, int64_t nodes_left, bool ch_ok,
-                                          bool skip, bool round_p, float& colacc) {
+                                          bool skip, bool round_p, float& colacc, float inv) {
     const uint32_t ms = MLD ? (uint32_t)MLD * 4u : mstride;
     const uint32_t msk_a = mb_a + 4u * mword;
     const unsigned lastv = tc::lds_u32(mb_a + (uint32_t)AGG_ROWS * ms);     // right behind the 126 mask rows
     asm volatile("" : "+l"(dq));      // keep the row base opaque: `dq + off` stays one IMAD.WIDE per reduction
 #pragma unroll 1
     for (int c = 0; c < 4; ++c)
-        scat_nodes<3, 0, MLD>(tcol + (uint32_t)(27 * c), off_a + 108u * c, msk_a + 27u * c * ms, ms, lanebit, lastv >> (3 * c), dq,
-                              dp + (int64_t)(3 * c) * ldpq, ldpq, nodes_left - 3 * c, ch_ok, skip, round_p, colacc);
-    scat_nodes<2, 12, MLD>(tcol + 96u, off_a + 432u, msk_a + 108u * ms, ms, lanebit, lastv >> 12, dq, dp + (int64_t)12 * ldpq, ldpq,
-                           nodes_left - 12, ch_ok, skip, round_p, colacc);
+        scat_nodes<3, 0, MLD, SCALED>(tcol + (uint32_t)(27 * c), off_a + 108u * c, msk_a + 27u * c * ms, ms, lanebit, lastv >> (3 * c), dq,
+                                      dp + (int64_t)(3 * c) * ldpq, ldpq, nodes_left - 3 * c, ch_ok, skip, round_p, colacc, inv);
+    scat_nodes<2, 12, MLD, SCALED>(tcol + 96u, off_a + 432u, msk_a + 108u * ms, ms, lanebit, lastv >> 12, dq, dp + (int64_t)12 * ldpq, ldpq,
+                                   nodes_left - 12, ch_ok, skip, round_p, colacc, inv);
 }
 // mb_a: shared address of the sub-tile's metadata block {126 mask rows | lastv | ... | 128 offsets at off_a}
+template <bool SCALED = false>
 __device__ __forceinline__ void scat_tile_any(int mask_ld, uint32_t tcol, uint32_t mb_a, uint32_t off_a, uint32_t mword,
                                               unsigned lanebit, float* dq, float* dp, int64_t ldpq, int64_t nodes_left, bool ch_ok,
-                                              bool skip, bool round_p, float& colacc) {
+                                              bool skip, bool round_p, float& colacc, float inv = 1.f) {
     // 4 / 12 words per row = hidden widths up to 128 / 257..384 (DynEdge: 128 and 336)
-    if (mask_ld == 12) scat_tile<12>(tcol, mb_a, off_a, mword, 48u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip, round_p, colacc);
-    else if (mask_ld == 4) scat_tile<4>(tcol, mb_a, off_a, mword, 16u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip, round_p, colacc);
-    else scat_tile<0>(tcol, mb_a, off_a, mword, (uint32_t)mask_ld * 4u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip, round_p, colacc);
+    if (mask_ld == 12) scat_tile<12, SCALED>(tcol, mb_a, off_a, mword, 48u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip, round_p, colacc, inv);
+    else if (mask_ld == 4) scat_tile<4, SCALED>(tcol, mb_a, off_a, mword, 16u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip, round_p, colacc, inv);
+    else scat_tile<0, SCALED>(tcol, mb_a, off_a, mword, (uint32_t)mask_ld * 4u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip, round_p, colacc, inv);
 }
 
 // Epilogue store of one 32-row chunk: lane = output channel, r[j] = row j. One coalesced 128-byte store per row; the
@@ -454,7 +459,7 @@ struct GroupSplit { int ngroups; int start[5]; };
 // [scatter metadata]. Streaming mode: a stage = this CTA's weight tile + its half of the activation rows (32 KiB);
 // resident mode (single-part K that fits): the CTA's 128 weight rows stay in shared memory for the kernel's lifetime
 // (one TMA pass), a stage is the activation half only (16 KiB) and the L2->SM traffic per launch halves.
-struct PairCfg { int resident; int nstages; uint32_t meta_stride; int last_ksteps; };
+struct PairCfg { int resident; int nstages; uint32_t meta_stride; int last_ksteps; uint32_t idesc16; };   // idesc16: kind::f16 descriptor (MODE 2 / 3)
 constexpr uint32_t PL_BAR_BYTES = 512;                // barrier block behind the ring
 // SPLIT = the fp32-grade split-operand forward (precision mode tf32x3): W = W_hi + W_lo, X = X_hi + X_lo with the hi parts
 // tf32-exact; the product is W_hi X_hi (kind::tf32) + the two correction products W_lo X_hi + W_hi X_lo, whose operands need
@@ -655,7 +660,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                     tc::tcgen05_fence_after();
                     const uint32_t st = tc::smem_u32(ring + s * stage_bytes);
                     if (BF) {
-                        constexpr uint32_t idesc_bf16 = tc::umma_idesc_bf16(256, 256);
+                        const uint32_t idesc_bf16 = pc.idesc16;
                         const uint64_t a0 = tc::umma_desc_sw128_kmajor(st), a1 = tc::umma_desc_sw128_kmajor(st + TC_TILE_BYTES);
                         const uint64_t b0 = tc::umma_desc_sw128_kmajor(st + NP * TC_TILE_BYTES);
                         const uint64_t b1 = tc::umma_desc_sw128_kmajor(st + (NP + 1) * TC_TILE_BYTES);
@@ -801,13 +806,20 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                     float* dq = sc.dq + (ch_ok ? ch : ch % sc.hdim);
                     float* dp = sc.dp + node0 * sc.lddp + ch;
                     const unsigned lanebit = ch_ok ? (1u << (q * 8 + (lane >> 2))) : 0u;
-                    scat_tile_any(sc.mask_ld, tcol, mb_a, mb_a + pc.meta_stride - 512u, mword, lanebit, dq, dp, sc.lddp,
-                                  sc.n_nodes - node0, ch_ok, (agg.dbg & 64) != 0, sc.round_p != 0, colacc);
+                    if (BF && sc.scale_bits != nullptr)
+                        scat_tile_any<true>(sc.mask_ld, tcol, mb_a, mb_a + pc.meta_stride - 512u, mword, lanebit, dq, dp, sc.lddp,
+                                            sc.n_nodes - node0, ch_ok, (agg.dbg & 64) != 0, sc.round_p != 0, colacc,
+                                            gnb_pow2_scale(*sc.scale_bits).y);
+                    else
+                        scat_tile_any(sc.mask_ld, tcol, mb_a, mb_a + pc.meta_stride - 512u, mword, lanebit, dq, dp, sc.lddp,
+                                      sc.n_nodes - node0, ch_ok, (agg.dbg & 64) != 0, sc.round_p != 0, colacc);
                 }
             } else if (agg.enabled) {
                 const int64_t st14 = (int64_t)t * 2 + half;            // 14-node tile index of the mask layout
                 const int64_t node0 = st14 * AGG_NPT;
                 if (node0 < agg.n_nodes) {
+                    // 16-bit plane modes: accumulators carry the producer's power-of-two scale of h; undone in the bias FMA
+                    const float ainv = (BF && agg.scale_bits != nullptr) ? gnb_pow2_scale(*agg.scale_bits).y : 1.f;
                     int dg[AGG_NPT];
                     const long long e0 = prof_on ? clock64() : 0;
 #pragma unroll
@@ -842,7 +854,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                             for (int j = 0; j < 32; ++j) {
                                 const int col = c * 32 + j;
                                 const bool slot_ok = col < AGG_ROWS && (col % AGG_W) < AGG_W - 1;     // compile-time
-                                const float pre = __uint_as_float(r[j]) + bv;
+                                const float pre = BF ? fmaf(__uint_as_float(r[j]), ainv, bv) : __uint_as_float(r[j]) + bv;
                                 rl[j] = slot_ok ? fmaxf(pre, 0.f) : 0.f;
                                 bt[j] = (slot_ok && pre > 0.f) ? (1u << j) : 0u;
                             }
@@ -884,7 +896,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                             const int col = c * 32 + j;
                             if (col < AGG_ROWS) {
                                 const int f = col / AGG_W, sl = col % AGG_W;       // compile-time after unrolling
-                                const float pre = __uint_as_float(r[j]) + bv;
+                                const float pre = BF ? fmaf(__uint_as_float(r[j]), ainv, bv) : __uint_as_float(r[j]) + bv;
                                 const bool on = (sl < dg[f]) && (pre > 0.f);
                                 acc += on ? pre : 0.f;
                                 w |= on ? (1u << j) : 0u;
@@ -1159,7 +1171,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PL_THREADS, 1)
 gemm_bf_pair_dual_scatter_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
                                  const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
                                  int total_kb, int last_ksteps, int64_t rows, int n_out, int num_tiles, const ScatInfo sc, int nst_w,
-                                 uint32_t meta_stride, int dbg) {
+                                 uint32_t meta_stride, int dbg, uint32_t idesc) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* act = smem;                                               // [total_kb][NP] x 16 KiB: resident dz tile (own half)
@@ -1268,7 +1280,6 @@ gemm_bf_pair_dual_scatter_kernel(const __grid_constant__ CUtensorMap tm_w0, cons
     } else if (warp == 1) {
         if (rank == 0) {
             // ---- MMA issuer (leader): group 0 then group 1 of every tile against the resident dz planes -----------------
-            constexpr uint32_t idesc = tc::umma_idesc_bf16(256, 256);
             uint32_t itw = 0, vt_i = 0, ti = 0;
             for (int t = cluster_id; t < num_tiles; t += num_clusters, ++ti) {
                 for (int g = 0; g < 2; ++g, ++vt_i) {
@@ -1315,6 +1326,7 @@ gemm_bf_pair_dual_scatter_kernel(const __grid_constant__ CUtensorMap tm_w0, cons
     } else {
         // ---- epilogue: identical to the tf32 kernel's (fp32 accumulators, same metadata blocks) -----------------------------
         const int q = warp & 3, half = (warp - 2) >> 2;
+        const float inv = sc.scale_bits != nullptr ? gnb_pow2_scale(*sc.scale_bits).y : 1.f;
         float colacc0 = 0.f, colacc1 = 0.f;
         uint32_t vt_i = 0, ti = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters, ++ti) {
@@ -1336,8 +1348,12 @@ gemm_bf_pair_dual_scatter_kernel(const __grid_constant__ CUtensorMap tm_w0, cons
                     float* dq = sc.dq + (ch_ok ? ch : ch % sc.hdim);
                     float* dp = sc.dp + node0 * sc.lddp + ch;
                     const unsigned lanebit = ch_ok ? (1u << (q * 8 + (lane >> 2))) : 0u;
-                    scat_tile_any(sc.mask_ld, tcol, mb_a, mb_a + meta_stride - 512u, mword, lanebit, dq, dp, sc.lddp,
-                                  sc.n_nodes - node0, ch_ok, (dbg & 64) != 0, sc.round_p != 0, g == 0 ? colacc0 : colacc1);
+                    if (NP == 1 && sc.scale_bits != nullptr)
+                        scat_tile_any<true>(sc.mask_ld, tcol, mb_a, mb_a + meta_stride - 512u, mword, lanebit, dq, dp, sc.lddp,
+                                            sc.n_nodes - node0, ch_ok, (dbg & 64) != 0, sc.round_p != 0, g == 0 ? colacc0 : colacc1, inv);
+                    else
+                        scat_tile_any(sc.mask_ld, tcol, mb_a, mb_a + meta_stride - 512u, mword, lanebit, dq, dp, sc.lddp,
+                                      sc.n_nodes - node0, ch_ok, (dbg & 64) != 0, sc.round_p != 0, g == 0 ? colacc0 : colacc1);
                 }
                 tc::tcgen05_fence_before();
                 __syncwarp();
@@ -1399,6 +1415,12 @@ cudaError_t init_tc_kernels() {
     return e;
 }
 
+// kind::f16 instruction descriptor of the CTA-pair MMAs (M 256 x N 256, fp32 accumulate, K-major); fmt bit 0: the weights (A) are
+// bf16 (else fp16), bit 1: the activations (B) are bf16 (else fp16)
+uint32_t idesc_f16_256(int fmt) {
+    return (1u << 4) | ((fmt & 1 ? 1u : 0u) << 7) | ((fmt & 2 ? 1u : 0u) << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+}
+
 // Dual-group scattering launch (two 256-channel groups from one resident dz tile); false = shape not covered.
 bool dual_scatter_applicable(int hdim, int kblocks, int mask_ld, int* nst_w_out) {
     if (hdim <= 256 || hdim > 512 || kblocks > DU_MAX_KB) return false;
@@ -1414,7 +1436,7 @@ bool dual_scatter_applicable(int hdim, int kblocks, int mask_ld, int* nst_w_out)
 // twlo != nullptr: split-operand (3xTF32) forward -- always the CTA-pair kernel (the only one with splitter warps).
 int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi, const float* bias, float* y, int64_t ldy,
                   int64_t rows, int n_out, int act, int round_out, int row_tiles, const AggInfo& agg, const ScatInfo& sc,
-                  cudaStream_t stream, const CUtensorMap* twlo = nullptr, int bf_planes = 0, int bf_k = 0) {
+                  cudaStream_t stream, const CUtensorMap* twlo = nullptr, int bf_planes = 0, int bf_k = 0, int fmt16 = 3) {
     GNB_CHECK(init_tc_kernels());
     const bool split = twlo != nullptr && bf_planes == 0;
     if (split && (n_out > 1024 || sc.enabled)) return GNB_ERR_UNSUPPORTED;
@@ -1445,6 +1467,7 @@ int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi
         if (pc.nstages > 6) pc.nstages = 6;
         if (pc.nstages < 2) return GNB_ERR_UNSUPPORTED;
         pc.last_ksteps = (bf_k - 64 * (pi.kblocks[0] - 1) + 15) / 16;
+        pc.idesc16 = idesc_f16_256(fmt16);
         const uint32_t smem = fixed + (uint32_t)pc.nstages * stage;
         dim3 grid((unsigned)(2 * used));
         if (bf_planes == 2)
@@ -1485,6 +1508,7 @@ int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi
         for (int p = 0; p < pi.nparts; ++p) total_kb += pi.kblocks[p];
         PairCfg pc;
         pc.last_ksteps = 4;
+        pc.idesc16 = 0;
         pc.meta_stride = sc.enabled ? sc_meta_stride(sc.mask_ld) : 0u;
         const uint32_t fixed = 1024 + PL_BAR_BYTES + 4 * pc.meta_stride;
         const int64_t res_left = (int64_t)PL_MAX_DYN_SMEM - fixed - (int64_t)total_kb * TC_TILE_BYTES;
@@ -1576,8 +1600,8 @@ static int linear_fwd_impl(const float* const* xs, const int64_t* ldxs, const in
         rc = gnb_make_tmap_bf16(&twlo, w_lo, n_out, 2 * ktot, ldw * 4, TC_BM);
         if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     }
-    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof};
-    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0};
+    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr};
+    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, nullptr};
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out, gnb_div_up(rows, TC_BN), agg, sc,
                          (cudaStream_t)stream, w_lo != nullptr ? &twlo : nullptr);
 }
@@ -1624,8 +1648,8 @@ static int edge_linear_agg_impl(const float* h, int64_t ldh, int32_t k, const fl
         rc = gnb_make_tmap_bf16(&twlo, w_lo, n_out, 2 * ktot, ldw * 4, TC_BM);
         if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     }
-    AggInfo agg{deg, n, maskbits, 1, g_linear_dbg, g_linear_prof};
-    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0};
+    AggInfo agg{deg, n, maskbits, 1, g_linear_dbg, g_linear_prof, nullptr};
+    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, nullptr};
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, GNB_ACT_RELU, round_out, gnb_div_up(n, AGG_NPT), agg, sc,
                          (cudaStream_t)stream, w_lo != nullptr ? &twlo : nullptr);
 }
@@ -1674,8 +1698,8 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_split_tf32(const float* dz, int64_t
     CUtensorMap tw;
     rc = gnb_make_tmap_f32(&tw, wt, hdim, ktot, ldw, TC_BM);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
-    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof};
-    ScatInfo sc{nbr, hmask, mask_ld, dq, lddq, hdim, n, 1, dp, lddp, dbias, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0};
+    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr};
+    ScatInfo sc{nbr, hmask, mask_ld, dq, lddq, hdim, n, 1, dp, lddp, dbias, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0, nullptr};
     const int row_tiles = gnb_div_up(n, AGG_NPT);
     int nst_w = 0;
     if ((g_linear_variant == 3 || (g_linear_variant == 0 && row_tiles >= 2 * 148)) &&
@@ -1743,9 +1767,11 @@ GNB_EXPORT int gnb_round_pad_tf32(const float* src, int64_t lds, int64_t rows, i
 // Second Linear of the EdgeConv MLP fused with ReLU and the k-neighbour SUM, like gnb_edge_linear_agg_fwd_tf32:
 //   y[i, :] = sum_{s < deg[i]} relu(h[i*9 + s, :] w^T + bias); h planes [n*9, k], w planes [n_out, >= k] (zero beyond k);
 // y rounded to tf32 with round_out.
-GNB_EXPORT int gnb_edge_linear_agg_fwd_bf16(const void* h0, const void* h1, int64_t ldh, int32_t k, const void* w0, const void* w1,
-                                            int64_t ldw, const float* bias, const int32_t* deg, int64_t n, int32_t n_out,
-                                            int32_t round_out, float* y, int64_t ldy, uint32_t* maskbits, void* stream) {
+static int edge_linear_agg16_impl(const void* h0, const void* h1, int64_t ldh, int32_t k, const void* w0, const void* w1,
+                                  int64_t ldw, const float* bias, const int32_t* deg, int64_t n, int32_t n_out,
+                                  int32_t round_out, float* y, int64_t ldy, uint32_t* maskbits, int fmt16,
+                                  const uint32_t* scale_bits, void* stream) {
+    const CUtensorMapDataType dt = fmt16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     if (n < 0 || n_out < 1 || k < 1 || h0 == nullptr || w0 == nullptr || ((h1 == nullptr) != (w1 == nullptr))) return GNB_ERR_ARG;
     if ((ldh & 7) || (ldw & 7) || ldh < k || ldw < k) return GNB_ERR_ARG;
     if (n == 0) return GNB_OK;
@@ -1757,27 +1783,43 @@ GNB_EXPORT int gnb_edge_linear_agg_fwd_bf16(const void* h0, const void* h1, int6
     pi.nparts = 1;
     pi.kblocks[0] = (k + 63) / 64;
     for (int p = 1; p < TC_MAX_PARTS; ++p) pi.kblocks[p] = 0;
-    int rc = gnb_make_tmap_bf16(&tx.m[0], h0, rows, k, ldh * 2, AGG_ROWS);
-    if (rc == 0 && planes == 2) rc = gnb_make_tmap_bf16(&tx.m[1], h1, rows, k, ldh * 2, AGG_ROWS);
+    int rc = gnb_make_tmap_16(&tx.m[0], h0, rows, k, ldh * 2, AGG_ROWS, dt);
+    if (rc == 0 && planes == 2) rc = gnb_make_tmap_16(&tx.m[1], h1, rows, k, ldh * 2, AGG_ROWS, dt);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     for (int p = planes; p < TC_MAX_PARTS; ++p) tx.m[p] = tx.m[0];
     CUtensorMap tw, tw1;
-    rc = gnb_make_tmap_bf16(&tw, w0, n_out, k, ldw * 2, TC_BM);
-    if (rc == 0 && planes == 2) rc = gnb_make_tmap_bf16(&tw1, w1, n_out, k, ldw * 2, TC_BM);
+    rc = gnb_make_tmap_16(&tw, w0, n_out, k, ldw * 2, TC_BM, dt);
+    if (rc == 0 && planes == 2) rc = gnb_make_tmap_16(&tw1, w1, n_out, k, ldw * 2, TC_BM, dt);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
-    AggInfo agg{deg, n, maskbits, 1, g_linear_dbg, g_linear_prof};
-    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0};
+    AggInfo agg{deg, n, maskbits, 1, g_linear_dbg, g_linear_prof, scale_bits};
+    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, nullptr};
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, GNB_ACT_RELU, round_out, gnb_div_up(n, AGG_NPT), agg, sc,
-                         (cudaStream_t)stream, planes == 2 ? &tw1 : nullptr, planes, k);
+                         (cudaStream_t)stream, planes == 2 ? &tw1 : nullptr, planes, k, fmt16 ? 3 : 0);
 }
+GNB_EXPORT int gnb_edge_linear_agg_fwd_bf16(const void* h0, const void* h1, int64_t ldh, int32_t k, const void* w0, const void* w1,
+                                            int64_t ldw, const float* bias, const int32_t* deg, int64_t n, int32_t n_out,
+                                            int32_t round_out, float* y, int64_t ldy, uint32_t* maskbits, void* stream) {
+    return edge_linear_agg16_impl(h0, h1, ldh, k, w0, w1, ldw, bias, deg, n, n_out, round_out, y, ldy, maskbits, 1, nullptr, stream);
+}
+// The same on fp16 planes (mode mixed16): h planes hold h * 2^s, 2^s = gnb_pow2_scale(*scale_bits).x (gnb_edge_hidden_fwd_f16);
+// the epilogue folds 2^-s into its bias FMA. w planes: fp16 of the unscaled weights (gnb_to_f16_planes).
+GNB_EXPORT int gnb_edge_linear_agg_fwd_f16(const void* h0, const void* h1, int64_t ldh, int32_t k, const void* w0, const void* w1,
+                                           int64_t ldw, const float* bias, const int32_t* deg, int64_t n, int32_t n_out,
+                                           int32_t round_out, float* y, int64_t ldy, uint32_t* maskbits,
+                                           const uint32_t* scale_bits, void* stream) {
+    return edge_linear_agg16_impl(h0, h1, ldh, k, w0, w1, ldw, bias, deg, n, n_out, round_out, y, ldy, maskbits, 0, scale_bits, stream);
+}
+
 
 // Data gradient of the EdgeConv second Linear fused with the backward of the hoisted hidden layer, like
 // gnb_edge_hidden_dgrad_scatter_split_tf32, on bf16 planes: dz planes [n*9, c_out], wt planes (W2^T) [hdim, >= c_out].
 // dq / dp / dbias / hmask / nbr / flags as in the tf32 entry point.
-GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_bf16(const void* dz0, const void* dz1, int64_t lddz, int32_t c_out, const void* wt0,
-                                                  const void* wt1, int64_t ldw, const uint32_t* hmask, int32_t mask_ld,
-                                                  int32_t hdim, const int32_t* nbr, int64_t n, float* dq, int64_t lddq, float* dp,
-                                                  int64_t lddp, float* dbias, int32_t flags, void* stream) {
+static int dgrad_scatter16_impl(const void* dz0, const void* dz1, int64_t lddz, int32_t c_out, const void* wt0,
+                                const void* wt1, int64_t ldw, const uint32_t* hmask, int32_t mask_ld,
+                                int32_t hdim, const int32_t* nbr, int64_t n, float* dq, int64_t lddq, float* dp,
+                                int64_t lddp, float* dbias, int32_t flags, int fmt16, const uint32_t* scale_bits, void* stream) {
+    const CUtensorMapDataType tw_t = (fmt16 & 1) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const CUtensorMapDataType tx_t = (fmt16 & 2) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     if (n < 0 || hdim < 1 || hdim > 512 || c_out < 1 || lddq < hdim || lddp < hdim || dq == nullptr || dp == nullptr)
         return GNB_ERR_ARG;
     if (dz0 == nullptr || wt0 == nullptr || ((dz1 == nullptr) != (wt1 == nullptr))) return GNB_ERR_ARG;
@@ -1793,16 +1835,16 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_bf16(const void* dz0, const void* d
     pi.nparts = 1;
     pi.kblocks[0] = (c_out + 63) / 64;
     for (int p = 1; p < TC_MAX_PARTS; ++p) pi.kblocks[p] = 0;
-    int rc = gnb_make_tmap_bf16(&tx.m[0], dz0, rows, c_out, lddz * 2, AGG_ROWS);
-    if (rc == 0 && planes == 2) rc = gnb_make_tmap_bf16(&tx.m[1], dz1, rows, c_out, lddz * 2, AGG_ROWS);
+    int rc = gnb_make_tmap_16(&tx.m[0], dz0, rows, c_out, lddz * 2, AGG_ROWS, tx_t);
+    if (rc == 0 && planes == 2) rc = gnb_make_tmap_16(&tx.m[1], dz1, rows, c_out, lddz * 2, AGG_ROWS, tx_t);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     for (int p = planes; p < TC_MAX_PARTS; ++p) tx.m[p] = tx.m[0];
     CUtensorMap tw, tw1;
-    rc = gnb_make_tmap_bf16(&tw, wt0, hdim, c_out, ldw * 2, TC_BM);
-    if (rc == 0 && planes == 2) rc = gnb_make_tmap_bf16(&tw1, wt1, hdim, c_out, ldw * 2, TC_BM);
+    rc = gnb_make_tmap_16(&tw, wt0, hdim, c_out, ldw * 2, TC_BM, tw_t);
+    if (rc == 0 && planes == 2) rc = gnb_make_tmap_16(&tw1, wt1, hdim, c_out, ldw * 2, TC_BM, tw_t);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
-    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof};
-    ScatInfo sc{nbr, hmask, mask_ld, dq, lddq, hdim, n, 1, dp, lddp, dbias, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0};
+    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr};
+    ScatInfo sc{nbr, hmask, mask_ld, dq, lddq, hdim, n, 1, dp, lddp, dbias, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0, scale_bits};
     const int row_tiles = gnb_div_up(n, AGG_NPT);
     const int last_ksteps = (c_out - 64 * (pi.kblocks[0] - 1) + 15) / 16;
     if (hdim > 256 && g_linear_variant != 2) {          // two 256-channel groups from one resident dz tile
@@ -1820,16 +1862,33 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_bf16(const void* dz0, const void* d
             const uint32_t smem = 1024 + (uint32_t)(pi.kblocks[0] * planes + nst_w) * TC_TILE_BYTES + DU_BAR_BYTES + 4 * mstride;
             if (planes == 2)
                 gemm_bf_pair_dual_scatter_kernel<2><<<dim3((unsigned)(2 * clusters)), PL_THREADS, smem, (cudaStream_t)stream>>>(
-                    tw, tw1, tx.m[0], tx.m[1], pi.kblocks[0], last_ksteps, rows, hdim, tiles, sc, nst_w, mstride, g_linear_dbg);
+                    tw, tw1, tx.m[0], tx.m[1], pi.kblocks[0], last_ksteps, rows, hdim, tiles, sc, nst_w, mstride, g_linear_dbg, idesc_f16_256(fmt16));
             else
                 gemm_bf_pair_dual_scatter_kernel<1><<<dim3((unsigned)(2 * clusters)), PL_THREADS, smem, (cudaStream_t)stream>>>(
-                    tw, tw, tx.m[0], tx.m[0], pi.kblocks[0], last_ksteps, rows, hdim, tiles, sc, nst_w, mstride, g_linear_dbg);
+                    tw, tw, tx.m[0], tx.m[0], pi.kblocks[0], last_ksteps, rows, hdim, tiles, sc, nst_w, mstride, g_linear_dbg, idesc_f16_256(fmt16));
             GNB_RETURN_LAUNCH();
         }
     }
     return launch_linear(tw, tx, pi, nullptr, nullptr, 0, rows, hdim, GNB_ACT_NONE, 0, row_tiles, agg, sc, (cudaStream_t)stream,
-                         planes == 2 ? &tw1 : nullptr, planes, c_out);
+                         planes == 2 ? &tw1 : nullptr, planes, c_out, fmt16);
 }
+GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_bf16(const void* dz0, const void* dz1, int64_t lddz, int32_t c_out, const void* wt0,
+                                                  const void* wt1, int64_t ldw, const uint32_t* hmask, int32_t mask_ld,
+                                                  int32_t hdim, const int32_t* nbr, int64_t n, float* dq, int64_t lddq, float* dp,
+                                                  int64_t lddp, float* dbias, int32_t flags, void* stream) {
+    return dgrad_scatter16_impl(dz0, dz1, lddz, c_out, wt0, wt1, ldw, hmask, mask_ld, hdim, nbr, n, dq, lddq, dp, lddp, dbias, flags,
+                                3, nullptr, stream);
+}
+// mixed16: dz as ONE fp16 plane scaled by gnb_pow2_scale(*scale_bits).x (gnb_edge_mask_bwd_colsum_f16), wt = W2^T as ONE fp16
+// plane (gnb_to_f16_planes); the epilogue multiplies by the inverse power of two. fp16 = the significand of tf32 at half the bytes.
+GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_f16(const void* dz, int64_t lddz, int32_t c_out, const void* wt, int64_t ldw,
+                                                     const uint32_t* hmask, int32_t mask_ld, int32_t hdim, const int32_t* nbr,
+                                                     int64_t n, float* dq, int64_t lddq, float* dp, int64_t lddp, float* dbias,
+                                                     int32_t flags, const uint32_t* scale_bits, void* stream) {
+    return dgrad_scatter16_impl(dz, nullptr, lddz, c_out, wt, nullptr, ldw, hmask, mask_ld, hdim, nbr, n, dq, lddq, dp, lddp, dbias,
+                                flags, 0, scale_bits, stream);
+}
+
 
 // Plain Linear on bf16 planes (the CTA-pair kernel's plain epilogue): y = act(x w^T + bias), x planes [rows, k], w planes
 // [n_out, >= k]; fp32 output (rounded to tf32 with round_out).
@@ -1854,8 +1913,8 @@ GNB_EXPORT int gnb_linear_fwd_bf16(const void* x0, const void* x1, int64_t ldx, 
     rc = gnb_make_tmap_bf16(&tw, w0, n_out, k, ldw * 2, TC_BM);
     if (rc == 0 && planes == 2) rc = gnb_make_tmap_bf16(&tw1, w1, n_out, k, ldw * 2, TC_BM);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
-    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof};
-    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0};
+    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr};
+    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, nullptr};
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out, gnb_div_up(rows, TC_BN), agg, sc,
                          (cudaStream_t)stream, planes == 2 ? &tw1 : nullptr, planes, k);
 }
@@ -1884,5 +1943,31 @@ GNB_EXPORT int gnb_to_bf16_planes(const float* src, int64_t lds, int64_t rows, i
     if (total == 0) return GNB_OK;
     to_bf16_planes_kernel<<<gnb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, rows, cols, (__nv_bfloat16*)p0,
                                                                                       (__nv_bfloat16*)p1, ldd, dst_cols, transpose);
+    GNB_RETURN_LAUNCH();
+}
+
+// fp32 [rows, cols] -> fp16 planes [rows or cols, dst_cols] (zero padded; transpose != 0: of src^T): p0 = fp16(v), p1 =
+// fp16(v - p0) (may be NULL), round to nearest.
+static __global__ void to_f16_planes_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols, __half* __restrict__ p0,
+                                            __half* __restrict__ p1, int64_t ldd, int dst_cols, int transpose) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t drows = transpose ? cols : rows;
+    if (t >= drows * dst_cols) return;
+    const int64_t r = t / dst_cols;
+    const int c = (int)(t - r * dst_cols);
+    float v = 0.f;
+    if (transpose) { if (c < rows) v = src[(int64_t)c * lds + r]; }
+    else if (c < cols) v = src[r * lds + c];
+    const __half b0 = __float2half_rn(v);
+    p0[r * ldd + c] = b0;
+    if (p1 != nullptr) p1[r * ldd + c] = __float2half_rn(v - __half2float(b0));
+}
+GNB_EXPORT int gnb_to_f16_planes(const float* src, int64_t lds, int64_t rows, int32_t cols, void* p0, void* p1, int64_t ldd,
+                                 int32_t dst_cols, int32_t transpose, void* stream) {
+    if (rows < 0 || cols < 0 || p0 == nullptr || ldd < dst_cols || dst_cols < (transpose ? rows : cols)) return GNB_ERR_ARG;
+    const int64_t total = (transpose ? (int64_t)cols : rows) * dst_cols;
+    if (total == 0) return GNB_OK;
+    to_f16_planes_kernel<<<gnb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, rows, cols, (__half*)p0, (__half*)p1, ldd,
+                                                                                     dst_cols, transpose);
     GNB_RETURN_LAUNCH();
 }

@@ -152,14 +152,15 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 }
 
 
-// ---- bf16-plane variant (precision modes bf16 / bf16x3) ----------------------------------------------------------------------
-// Operands are NP bf16 planes per tensor (v ~ v0 + v1). 16-bit MN-major operands use the plain 128-byte swizzle: atom = 8 rows x
-// 128 B (64 bf16 of the MN index), SBO = 1024 B between 8-row groups of the K (row) index, LBO = one TMA box between 64-column
-// blocks; a kind::f16 MMA consumes 16 rows = 2 atoms. Stage = 64 / NP rows of every plane (48 KiB), products x0 dz0
-// (+ x1 dz0 + x0 dz1 for NP = 2).
-constexpr int WB_STAGES = 4;
-constexpr uint32_t WB_STAGE_BYTES = 48 * 1024;
-constexpr uint32_t WB_SMEM_BYTES = WB_STAGES * WB_STAGE_BYTES + 1024 + 256;
+// ---- 16-bit plane variant (precision modes bf16 / bf16x3 / mixed16) ------------------------------------------------------------
+// Operands are 16-bit planes (v ~ v0 + v1): NPA planes of x (the A operand), NPB planes of dz (B). 16-bit MN-major operands
+// use the plain 128-byte swizzle: atom = 8 rows x 128 B (64 elements of the MN index), SBO = 1024 B between 8-row groups of
+// the K (row) index, LBO = one TMA box between 64-column blocks; a kind::f16 MMA consumes 16 rows = 2 atoms. A stage holds BK
+// rows of every plane. Products: x0 dz0 (1, 1); x1 dz0 + x0 dz0 (2, 1: dz as ONE scaled fp16 plane, mode mixed16);
+// x1 dz0 + x0 dz1 + x0 dz0 (2, 2). Element formats (bf16 / fp16, independently for A and B) come with the instruction
+// descriptor; out_scale_bits (optional) = device word holding the fp32 bits of max|g| the dz producer scaled by (see
+// gnb_absmax_bits): the epilogue multiplies by the inverse power of two.
+constexpr uint32_t WB_SMEM_BYTES = 192 * 1024 + 1024 + 256;
 
 __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor16(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
     uint64_t d = 0;
@@ -170,7 +171,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor16(uint32_t smem_addr
     d |= static_cast<uint64_t>(2) << 61;          // SWIZZLE_128B
     return d;
 }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -179,20 +180,22 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         : "memory");
 }
 
-template <int NP>
+template <int NPA, int NPB, int BK>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 gemm_bf_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
                      const __grid_constant__ CUtensorMap tm_z0, const __grid_constant__ CUtensorMap tm_z1,
                      float* __restrict__ dw, int64_t lddw, int64_t rows, int n_out, int k_in, int n_tiles_n,
-                     int64_t rows_per_split, int dbg) {
-    constexpr int BK = 64 / NP;                                  // rows per stage
-    constexpr uint32_t BOX = BK * 128;                           // one [BK rows x 64 columns] bf16 box
+                     int64_t rows_per_split, int dbg, uint32_t fmt_a, uint32_t fmt_b, const unsigned* __restrict__ out_scale_bits,
+                     const unsigned* __restrict__ out_scale_bits2) {
+    constexpr uint32_t BOX = BK * 128;                           // one [BK rows x 64 columns] 16-bit box
     constexpr uint32_t A_BYTES = 2 * BOX, B_BYTES = 4 * BOX;     // per plane: 128 k_in columns, 256 n_out columns
+    constexpr uint32_t STAGE = NPA * A_BYTES + NPB * B_BYTES;
+    constexpr int STAGES = (192 * 1024) / STAGE;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + WB_STAGES * WB_STAGE_BYTES);
-    uint64_t* empty = full + WB_STAGES;
-    uint64_t* tmem_full = empty + WB_STAGES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -210,11 +213,12 @@ gemm_bf_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_con
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tm_x0); tc::tma_prefetch_desc(&tm_z0);
-        if (NP == 2) { tc::tma_prefetch_desc(&tm_x1); tc::tma_prefetch_desc(&tm_z1); }
+        if (NPA == 2) tc::tma_prefetch_desc(&tm_x1);
+        if (NPB == 2) tc::tma_prefetch_desc(&tm_z1);
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < WB_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+            for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
             tc::mbar_init(tmem_full, 1);
             tc::fence_barrier_init();
             tc::fence_proxy_async();
@@ -230,48 +234,48 @@ gemm_bf_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_con
     if (num_kb > 0) {
         if (warp == 0) {
             for (int it = 0; it < num_kb; ++it) {
-                const int s = it % WB_STAGES;
-                const uint32_t ph = (it / WB_STAGES) & 1;
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
                 tc::mbar_wait(&empty[s], ph ^ 1);
-                uint8_t* st = smem + s * WB_STAGE_BYTES;          // [A plane 0 | A plane 1 | B plane 0 | B plane 1]
+                uint8_t* st = smem + s * STAGE;          // [A plane 0 | A plane 1 | B plane 0 | B plane 1]
                 const int r = (int)(r_lo + (int64_t)it * BK);
                 if (tc::elect_one()) {
-                    tc::mbar_arrive_expect_tx(&full[s], (uint32_t)NP * (2 + n_boxes_b) * BOX);
+                    tc::mbar_arrive_expect_tx(&full[s], (uint32_t)(NPA * 2 + NPB * n_boxes_b) * BOX);
 #pragma unroll
-                    for (int pl = 0; pl < NP; ++pl) {
+                    for (int pl = 0; pl < NPA; ++pl)
 #pragma unroll
                         for (int b = 0; b < 2; ++b)
                             tc::tma_load_2d(st + pl * A_BYTES + b * BOX, pl == 0 ? &tm_x0 : &tm_x1, &full[s], kin0 + 64 * b, r);
+#pragma unroll
+                    for (int pl = 0; pl < NPB; ++pl)
                         for (int b = 0; b < n_boxes_b; ++b)
-                            tc::tma_load_2d(st + NP * A_BYTES + pl * B_BYTES + b * BOX, pl == 0 ? &tm_z0 : &tm_z1, &full[s], out0 + 64 * b, r);
-                    }
+                            tc::tma_load_2d(st + NPA * A_BYTES + pl * B_BYTES + b * BOX, pl == 0 ? &tm_z0 : &tm_z1, &full[s], out0 + 64 * b, r);
                 }
                 __syncwarp();
             }
         } else if (warp == 1) {
-            // kind::f16 (bf16), fp32 accumulate, A and B MN-major (bits 15, 16)
-            const uint32_t idesc = tc::umma_idesc_bf16(WG_BM, (uint32_t)n_mma) | (1u << 15) | (1u << 16);
+            // kind::f16, fp32 accumulate, A and B MN-major (bits 15, 16); formats: 0 = fp16, 1 = bf16
+            const uint32_t idesc = (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | (((uint32_t)n_mma >> 3) << 17) | ((WG_BM >> 4) << 24) |
+                                   (1u << 15) | (1u << 16);
             // bring-up variants (production: 0): bit0 swaps LBO / SBO
             const uint32_t lbo = (dbg & 1) ? 1024u : BOX;
             const uint32_t sbo = (dbg & 1) ? BOX : 1024u;
             for (int it = 0; it < num_kb; ++it) {
-                const int s = it % WB_STAGES;
-                const uint32_t ph = (it / WB_STAGES) & 1;
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
                 tc::mbar_wait(&full[s], ph);
                 tc::tcgen05_fence_after();
-                const uint32_t sa = tc::smem_u32(smem + s * WB_STAGE_BYTES);
+                const uint32_t sa = tc::smem_u32(smem + s * STAGE);
                 const uint64_t a0 = umma_desc_sw128_mnmajor16(sa, lbo, sbo), a1 = umma_desc_sw128_mnmajor16(sa + A_BYTES, lbo, sbo);
-                const uint64_t b0 = umma_desc_sw128_mnmajor16(sa + NP * A_BYTES, lbo, sbo);
-                const uint64_t b1 = umma_desc_sw128_mnmajor16(sa + NP * A_BYTES + B_BYTES, lbo, sbo);
+                const uint64_t b0 = umma_desc_sw128_mnmajor16(sa + NPA * A_BYTES, lbo, sbo);
+                const uint64_t b1 = umma_desc_sw128_mnmajor16(sa + NPA * A_BYTES + B_BYTES, lbo, sbo);
                 if (tc::elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {          // 16 rows = two 1024-byte atoms per 64-column block
                         const uint64_t adv = (uint64_t)(k * (2048 >> 4));
-                        if (NP == 2) {
-                            umma_bf16(tmem_base, a1 + adv, b0 + adv, idesc, (it | k) != 0 ? 1u : 0u);
-                            umma_bf16(tmem_base, a0 + adv, b1 + adv, idesc, 1u);
-                        }
-                        umma_bf16(tmem_base, a0 + adv, b0 + adv, idesc, (NP == 2 || (it | k) != 0) ? 1u : 0u);
+                        if (NPA == 2) umma_f16(tmem_base, a1 + adv, b0 + adv, idesc, (it | k) != 0 ? 1u : 0u);
+                        if (NPB == 2) umma_f16(tmem_base, a0 + adv, b1 + adv, idesc, 1u);
+                        umma_f16(tmem_base, a0 + adv, b0 + adv, idesc, (NPA == 2 || (it | k) != 0) ? 1u : 0u);
                     }
                     tc::umma_commit(&empty[s]);
                 }
@@ -280,6 +284,9 @@ gemm_bf_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_con
             if (tc::elect_one()) tc::umma_commit(tmem_full);
             __syncwarp();
         } else {
+            float inv = 1.f;
+            if (out_scale_bits != nullptr) inv = gnb_pow2_scale(*out_scale_bits).y;
+            if (out_scale_bits2 != nullptr) inv *= gnb_pow2_scale(*out_scale_bits2).y;
             tc::mbar_wait<200>(tmem_full, 0);
             tc::tcgen05_fence_after();
             const int q = warp & 3;
@@ -293,7 +300,7 @@ gemm_bf_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_con
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int o = out0 + c * 32 + j;
-                        if (o < n_out) atomicAdd(dw + (int64_t)o * lddw + kin, __uint_as_float(r[j]));
+                        if (o < n_out) atomicAdd(dw + (int64_t)o * lddw + kin, __uint_as_float(r[j]) * inv);
                     }
                 }
             }
@@ -347,29 +354,34 @@ GNB_EXPORT int gnb_linear_bwd_weight_tf32(const float* dz, int64_t lddz, const f
     GNB_RETURN_LAUNCH();
 }
 
-// dw[n_out, k_in] += dz^T x on bf16 planes: dz planes [rows, n_out] (pitch lddz elements), x planes [rows, k_in] (pitch ldx);
-// plane 1 pointers NULL (both) = one plane. Pitches multiples of 8 elements. debug bit 0 swaps the descriptor's LBO / SBO.
-GNB_EXPORT int gnb_linear_bwd_weight_bf16(const void* dz0, const void* dz1, int64_t lddz, const void* x0, const void* x1,
-                                          int64_t ldx, float* dw, int64_t lddw, int64_t rows, int32_t n_out, int32_t k_in,
-                                          int32_t debug, void* stream) {
-    if (rows < 0 || n_out < 1 || k_in < 1 || dz0 == nullptr || x0 == nullptr || ((dz1 == nullptr) != (x1 == nullptr))) return GNB_ERR_ARG;
+// dw[n_out, k_in] += dz^T x on 16-bit planes: dz planes [rows, n_out] (pitch lddz elements), x planes [rows, k_in] (pitch ldx);
+// x1 / dz1 may be NULL (dz1 non-NULL requires x1). fmt bit 0: x is bf16 (else fp16), bit 1: dz is bf16 (else fp16).
+// out_scale_bits (may be NULL): device word with the fp32 bits of the max|g| the dz producer scaled by -- the result is
+// multiplied by the inverse power of two (gnb_absmax_bits). Pitches multiples of 8 elements. debug bit 0 swaps LBO / SBO.
+static int wgrad16_impl(const void* dz0, const void* dz1, int64_t lddz, const void* x0, const void* x1, int64_t ldx, float* dw,
+                        int64_t lddw, int64_t rows, int32_t n_out, int32_t k_in, int32_t debug, int32_t fmt,
+                        const uint32_t* out_scale_bits, const uint32_t* out_scale_bits2, void* stream) {
+    if (rows < 0 || n_out < 1 || k_in < 1 || dz0 == nullptr || x0 == nullptr || (dz1 != nullptr && x1 == nullptr)) return GNB_ERR_ARG;
     if ((lddz & 7) || (ldx & 7) || lddz < n_out || ldx < k_in) return GNB_ERR_ARG;
     if (rows == 0) return GNB_OK;
     if (rows >= (int64_t)1 << 31) return GNB_ERR_ARG;
-    const int planes = dz1 != nullptr ? 2 : 1;
-    const int bk = 64 / planes;
+    const int npa = x1 != nullptr ? 2 : 1, npb = dz1 != nullptr ? 2 : 1;
+    const int bk = npa == 1 ? 64 : 32;
+    const CUtensorMapDataType ta = (fmt & 1) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const CUtensorMapDataType tb = (fmt & 2) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     CUtensorMap tx0, tx1, tz0, tz1;
-    int rc = gnb_make_tmap_bf16(&tx0, x0, rows, k_in, ldx * 2, (uint32_t)bk);
-    if (rc == 0) rc = gnb_make_tmap_bf16(&tz0, dz0, rows, n_out, lddz * 2, (uint32_t)bk);
-    if (rc == 0 && planes == 2) rc = gnb_make_tmap_bf16(&tx1, x1, rows, k_in, ldx * 2, (uint32_t)bk);
-    if (rc == 0 && planes == 2) rc = gnb_make_tmap_bf16(&tz1, dz1, rows, n_out, lddz * 2, (uint32_t)bk);
+    int rc = gnb_make_tmap_16(&tx0, x0, rows, k_in, ldx * 2, (uint32_t)bk, ta);
+    if (rc == 0) rc = gnb_make_tmap_16(&tz0, dz0, rows, n_out, lddz * 2, (uint32_t)bk, tb);
+    if (rc == 0 && npa == 2) rc = gnb_make_tmap_16(&tx1, x1, rows, k_in, ldx * 2, (uint32_t)bk, ta);
+    if (rc == 0 && npb == 2) rc = gnb_make_tmap_16(&tz1, dz1, rows, n_out, lddz * 2, (uint32_t)bk, tb);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     static unsigned long long attr_devs = 0ull;
     int dev = 0;
     GNB_CHECK(cudaGetDevice(&dev));
     if (dev >= 64 || !((attr_devs >> dev) & 1ull)) {
-        GNB_CHECK(cudaFuncSetAttribute(gemm_bf_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WB_SMEM_BYTES));
-        GNB_CHECK(cudaFuncSetAttribute(gemm_bf_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WB_SMEM_BYTES));
+        GNB_CHECK(cudaFuncSetAttribute(gemm_bf_wgrad_kernel<1, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WB_SMEM_BYTES));
+        GNB_CHECK(cudaFuncSetAttribute(gemm_bf_wgrad_kernel<2, 1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WB_SMEM_BYTES));
+        GNB_CHECK(cudaFuncSetAttribute(gemm_bf_wgrad_kernel<2, 2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WB_SMEM_BYTES));
         if (dev < 64) attr_devs |= 1ull << dev;
     }
     const int tiles_m = gnb_div_up(k_in, WG_BM), tiles_n = gnb_div_up(n_out, WG_BN);
@@ -382,11 +394,30 @@ GNB_EXPORT int gnb_linear_bwd_weight_bf16(const void* dz0, const void* dz1, int6
     rps = ((rps + bk - 1) / bk) * bk;
     splits = (int)((rows + rps - 1) / rps);
     dim3 grid((unsigned)tiles, (unsigned)splits);
-    if (planes == 2)
-        gemm_bf_wgrad_kernel<2><<<grid, WG_THREADS, WB_SMEM_BYTES, (cudaStream_t)stream>>>(tx0, tx1, tz0, tz1, dw, lddw, rows, n_out, k_in,
-                                                                                         tiles_n, rps, debug);
+    const uint32_t fa = (fmt & 1) ? 1u : 0u, fb = (fmt & 2) ? 1u : 0u;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (npa == 2 && npb == 2)
+        gemm_bf_wgrad_kernel<2, 2, 32><<<grid, WG_THREADS, WB_SMEM_BYTES, st>>>(tx0, tx1, tz0, tz1, dw, lddw, rows, n_out, k_in, tiles_n,
+                                                                              rps, debug, fa, fb, out_scale_bits, out_scale_bits2);
+    else if (npa == 2)
+        gemm_bf_wgrad_kernel<2, 1, 32><<<grid, WG_THREADS, WB_SMEM_BYTES, st>>>(tx0, tx1, tz0, tz0, dw, lddw, rows, n_out, k_in, tiles_n,
+                                                                              rps, debug, fa, fb, out_scale_bits, out_scale_bits2);
     else
-        gemm_bf_wgrad_kernel<1><<<grid, WG_THREADS, WB_SMEM_BYTES, (cudaStream_t)stream>>>(tx0, tx0, tz0, tz0, dw, lddw, rows, n_out, k_in,
-                                                                                         tiles_n, rps, debug);
+        gemm_bf_wgrad_kernel<1, 1, 64><<<grid, WG_THREADS, WB_SMEM_BYTES, st>>>(tx0, tx0, tz0, tz0, dw, lddw, rows, n_out, k_in, tiles_n,
+                                                                              rps, debug, fa, fb, out_scale_bits, out_scale_bits2);
     GNB_RETURN_LAUNCH();
+}
+GNB_EXPORT int gnb_linear_bwd_weight_bf16(const void* dz0, const void* dz1, int64_t lddz, const void* x0, const void* x1,
+                                          int64_t ldx, float* dw, int64_t lddw, int64_t rows, int32_t n_out, int32_t k_in,
+                                          int32_t debug, void* stream) {
+    if ((dz1 == nullptr) != (x1 == nullptr)) return GNB_ERR_ARG;
+    return wgrad16_impl(dz0, dz1, lddz, x0, x1, ldx, dw, lddw, rows, n_out, k_in, debug, 3, nullptr, nullptr, stream);
+}
+// mixed16: dz as ONE fp16 plane scaled by gnb_pow2_scale(*dz_scale_bits).x, x as fp16 plane(s) of x * gnb_pow2_scale(
+// *x_scale_bits).x (x1 may be NULL: fp16 = tf32's significand); the epilogue undoes both powers of two. A kind::f16 MMA takes
+// ONE element format for both operands (bf16 against fp16 traps as an illegal instruction on sm_100a).
+GNB_EXPORT int gnb_linear_bwd_weight_f16(const void* dz, int64_t lddz, const void* x0, const void* x1, int64_t ldx, float* dw,
+                                         int64_t lddw, int64_t rows, int32_t n_out, int32_t k_in, const uint32_t* dz_scale_bits,
+                                         const uint32_t* x_scale_bits, void* stream) {
+    return wgrad16_impl(dz, nullptr, lddz, x0, x1, ldx, dw, lddw, rows, n_out, k_in, 0, 0, dz_scale_bits, x_scale_bits, stream);
 }

@@ -9,6 +9,7 @@
 //   global pooling    src/graphnet/models/gnn/dynedge.py:251-264 (torch_scatter.scatter_*)
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <float.h>
 
 namespace {
@@ -296,11 +297,21 @@ __device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d)
 __device__ __forceinline__ float bf16_lo_f(unsigned w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi_f(unsigned w) { return __uint_as_float(w & 0xFFFF0000u); }
 
-template <int NIT, int NP>
+// fp16 planes of four scaled values and of their remainders (mode mixed16): p0 = fp16(v s), p1 = fp16(v s - p0)
+__device__ __forceinline__ uint2 pack_f16x4(float a, float b, float c, float d) {
+    const __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+    return make_uint2(*reinterpret_cast<const unsigned*>(&lo), *reinterpret_cast<const unsigned*>(&hi));
+}
+__device__ __forceinline__ float2 unpack_f16x2(unsigned w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+
+// F16: the planes are fp16 of h * scale, scale = gnb_pow2_scale(*scale_bits).x with *scale_bits >= fp32 bits of max h.
+template <int NIT, int NP, bool F16>
 __global__ void __launch_bounds__(256)
 edge_hidden_fwd_node_bf16_kernel(const float* __restrict__ pq, int64_t ldpq, int hdim, const int* __restrict__ nbr,
                                  const int* __restrict__ deg, int width, int64_t n, __nv_bfloat16* __restrict__ h0,
-                                 __nv_bfloat16* __restrict__ h1, int64_t ldh, unsigned* __restrict__ hmask, int mask_ld) {
+                                 __nv_bfloat16* __restrict__ h1, int64_t ldh, unsigned* __restrict__ hmask, int mask_ld,
+                                 const unsigned* __restrict__ scale_bits) {
+    const float scale = F16 ? gnb_pow2_scale(*scale_bits).x : 1.f;
     const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
     const int lane = threadIdx.x & 31;
@@ -343,11 +354,23 @@ edge_hidden_fwd_node_bf16_kernel(const float* __restrict__ pq, int64_t ldpq, int
                     if (valid)
                         v = make_float4(fmaxf(pa[it].x + qv[u][it].x, 0.f), fmaxf(pa[it].y + qv[u][it].y, 0.f),
                                         fmaxf(pa[it].z + qv[u][it].z, 0.f), fmaxf(pa[it].w + qv[u][it].w, 0.f));
-                    const uint2 b0 = pack_bf16x4(v.x, v.y, v.z, v.w);
-                    if (c < h4) {
-                        o0[c] = b0;
-                        if (NP == 2)
-                            o1[c] = pack_bf16x4(v.x - bf16_lo_f(b0.x), v.y - bf16_hi_f(b0.x), v.z - bf16_lo_f(b0.y), v.w - bf16_hi_f(b0.y));
+                    if (F16) {
+                        const float4 sv = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+                        const uint2 b0 = pack_f16x4(sv.x, sv.y, sv.z, sv.w);
+                        if (c < h4) {
+                            o0[c] = b0;
+                            if (NP == 2) {
+                                const float2 f01 = unpack_f16x2(b0.x), f23 = unpack_f16x2(b0.y);
+                                o1[c] = pack_f16x4(sv.x - f01.x, sv.y - f01.y, sv.z - f23.x, sv.w - f23.y);
+                            }
+                        }
+                    } else {
+                        const uint2 b0 = pack_bf16x4(v.x, v.y, v.z, v.w);
+                        if (c < h4) {
+                            o0[c] = b0;
+                            if (NP == 2)
+                                o1[c] = pack_bf16x4(v.x - bf16_lo_f(b0.x), v.y - bf16_hi_f(b0.x), v.z - bf16_lo_f(b0.y), v.w - bf16_hi_f(b0.y));
+                        }
                     }
                     if (hmask != nullptr) {
                         const bool in = c < h4;
@@ -364,15 +387,15 @@ edge_hidden_fwd_node_bf16_kernel(const float* __restrict__ pq, int64_t ldpq, int
     }
 }
 
-template <int NP>
+template <int NP, bool F16>
 static void launch_hidden_node_bf16(int nit, dim3 grid, cudaStream_t st, const float* pq, int64_t ldpq, int hdim, const int* nbr,
                                     const int* deg, int width, int64_t n, __nv_bfloat16* h0, __nv_bfloat16* h1, int64_t ldh,
-                                    unsigned* hmask, int mask_ld) {
+                                    unsigned* hmask, int mask_ld, const unsigned* sb) {
     switch (nit) {
-        case 1: edge_hidden_fwd_node_bf16_kernel<1, NP><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld); break;
-        case 2: edge_hidden_fwd_node_bf16_kernel<2, NP><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld); break;
-        case 3: edge_hidden_fwd_node_bf16_kernel<3, NP><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld); break;
-        default: edge_hidden_fwd_node_bf16_kernel<4, NP><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld); break;
+        case 1: edge_hidden_fwd_node_bf16_kernel<1, NP, F16><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld, sb); break;
+        case 2: edge_hidden_fwd_node_bf16_kernel<2, NP, F16><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld, sb); break;
+        case 3: edge_hidden_fwd_node_bf16_kernel<3, NP, F16><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld, sb); break;
+        default: edge_hidden_fwd_node_bf16_kernel<4, NP, F16><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld, sb); break;
     }
 }
 
@@ -809,11 +832,13 @@ edge_mask_bwd_kernel(const float* __restrict__ g, int64_t ldg, const uint4* __re
 
 // The mask backward written as bf16 planes (precision modes bf16 / bf16x3): dz0 = bf16(dz), dz1 = bf16(dz - dz0) (NP = 2);
 // the bias gradient db sums the fp32 values.
+// NP = 0: ONE fp16 plane of dz * scale, scale = gnb_pow2_scale(*scale_bits).x (mode mixed16).
 template <int NP>
 __global__ void __launch_bounds__(256)
 edge_mask_bwd_bf16_kernel(const float* __restrict__ g, int64_t ldg, const uint4* __restrict__ mask4, int64_t n, int cols,
                           __nv_bfloat16* __restrict__ dz0, __nv_bfloat16* __restrict__ dz1, int64_t ldz, float* __restrict__ db,
-                          int64_t n_tiles) {
+                          int64_t n_tiles, const unsigned* __restrict__ scale_bits) {
+    const float scale = (NP == 0) ? gnb_pow2_scale(*scale_bits).x : 1.f;
     __shared__ float4 s_g[EM_NPT][64];
     __shared__ __align__(16) unsigned s_m[4][256];
     __shared__ float4 s_acc[4][64];
@@ -847,7 +872,13 @@ edge_mask_bwd_bf16_kernel(const float* __restrict__ g, int64_t ldg, const uint4*
                 const unsigned sh = r & 31;
                 gv.x = ((w.x >> sh) & 1u) ? gv.x : 0.f; gv.y = ((w.y >> sh) & 1u) ? gv.y : 0.f;
                 gv.z = ((w.z >> sh) & 1u) ? gv.z : 0.f; gv.w = ((w.w >> sh) & 1u) ? gv.w : 0.f;
-                const uint2 b0 = pack_bf16x4(gv.x, gv.y, gv.z, gv.w);
+                uint2 b0;
+                if (NP == 0) {
+                    const __half2 lo = __floats2half2_rn(gv.x * scale, gv.y * scale), hi = __floats2half2_rn(gv.z * scale, gv.w * scale);
+                    b0 = make_uint2(*reinterpret_cast<const unsigned*>(&lo), *reinterpret_cast<const unsigned*>(&hi));
+                } else {
+                    b0 = pack_bf16x4(gv.x, gv.y, gv.z, gv.w);
+                }
                 reinterpret_cast<uint2*>(dz0 + (row_base + r) * ldz)[c4] = b0;
                 if (NP == 2)
                     reinterpret_cast<uint2*>(dz1 + (row_base + r) * ldz)[c4] =
@@ -1108,22 +1139,39 @@ GNB_EXPORT int gnb_ptr_to_batch(const int64_t* ptr, int64_t nseg, int64_t n, int
 // ---- bf16-plane producers (precision modes bf16 / bf16x3; pitches in bf16 ELEMENTS, multiples of 8) -----------------------------
 // h planes of the hoisted EdgeConv hidden layer: h0 = bf16(relu(P_i + Q_j)), h1 = bf16(h - h0) (h1 may be NULL), plus the
 // activation bits of gnb_edge_hidden_fwd_mask (hmask may be NULL: inference). hdim <= 512, width <= 32.
-GNB_EXPORT int gnb_edge_hidden_fwd_bf16(const float* pq, int64_t ldpq, int32_t hdim, const int32_t* nbr, const int32_t* deg,
-                                        int32_t width, int64_t n, void* h0, void* h1, int64_t ldh, uint32_t* hmask,
-                                        int32_t mask_ld, void* stream) {
+static int hidden_fwd16_impl(const float* pq, int64_t ldpq, int32_t hdim, const int32_t* nbr, const int32_t* deg,
+                             int32_t width, int64_t n, void* h0, void* h1, int64_t ldh, uint32_t* hmask,
+                             int32_t mask_ld, const uint32_t* scale_bits, void* stream) {
     if ((hdim & 7) || (ldpq & 3) || (ldh & 7) || ldh < hdim || !aligned16(pq) || !aligned16(h0) || !aligned16(h1) || h0 == nullptr)
         return GNB_ERR_ARG;
     if (hdim > 512 || width > 32 || width < 1) return GNB_ERR_UNSUPPORTED;
     if (hmask != nullptr && (mask_ld != 4 * ((hdim + 127) / 128) || !aligned16(hmask))) return GNB_ERR_ARG;
     if (n == 0) return GNB_OK;
     const dim3 grid((unsigned)gnb_div_up(n, 8));
-    if (h1 != nullptr)
-        launch_hidden_node_bf16<2>((hdim + 127) / 128, grid, (cudaStream_t)stream, pq, ldpq, hdim, nbr, deg, width, n,
-                                   (__nv_bfloat16*)h0, (__nv_bfloat16*)h1, ldh, hmask, mask_ld);
-    else
-        launch_hidden_node_bf16<1>((hdim + 127) / 128, grid, (cudaStream_t)stream, pq, ldpq, hdim, nbr, deg, width, n,
-                                   (__nv_bfloat16*)h0, nullptr, ldh, hmask, mask_ld);
+    const int nit = (hdim + 127) / 128;
+    cudaStream_t st = (cudaStream_t)stream;
+    __nv_bfloat16 *a = (__nv_bfloat16*)h0, *b = (__nv_bfloat16*)h1;
+    if (scale_bits != nullptr) {
+        if (h1 != nullptr) launch_hidden_node_bf16<2, true>(nit, grid, st, pq, ldpq, hdim, nbr, deg, width, n, a, b, ldh, hmask, mask_ld, scale_bits);
+        else launch_hidden_node_bf16<1, true>(nit, grid, st, pq, ldpq, hdim, nbr, deg, width, n, a, nullptr, ldh, hmask, mask_ld, scale_bits);
+    } else {
+        if (h1 != nullptr) launch_hidden_node_bf16<2, false>(nit, grid, st, pq, ldpq, hdim, nbr, deg, width, n, a, b, ldh, hmask, mask_ld, nullptr);
+        else launch_hidden_node_bf16<1, false>(nit, grid, st, pq, ldpq, hdim, nbr, deg, width, n, a, nullptr, ldh, hmask, mask_ld, nullptr);
+    }
     GNB_RETURN_LAUNCH();
+}
+GNB_EXPORT int gnb_edge_hidden_fwd_bf16(const float* pq, int64_t ldpq, int32_t hdim, const int32_t* nbr, const int32_t* deg,
+                                        int32_t width, int64_t n, void* h0, void* h1, int64_t ldh, uint32_t* hmask,
+                                        int32_t mask_ld, void* stream) {
+    return hidden_fwd16_impl(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld, nullptr, stream);
+}
+// The same as fp16 planes of h * 2^s (mode mixed16): 2^s = gnb_pow2_scale(*scale_bits).x, *scale_bits >= fp32 bits of max h
+// (gnb_absmax_bits over PQ with shift = 1: h = relu(P_i + Q_j) <= 2 max|PQ|).
+GNB_EXPORT int gnb_edge_hidden_fwd_f16(const float* pq, int64_t ldpq, int32_t hdim, const int32_t* nbr, const int32_t* deg,
+                                       int32_t width, int64_t n, void* h0, void* h1, int64_t ldh, uint32_t* hmask,
+                                       int32_t mask_ld, const uint32_t* scale_bits, void* stream) {
+    if (scale_bits == nullptr) return GNB_ERR_ARG;
+    return hidden_fwd16_impl(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld, scale_bits, stream);
 }
 // dz planes of the "ReLU + k-sum" backward from the aggregating epilogue's bit mask (see gnb_edge_mask_bwd_colsum):
 // dz0 = bf16(dz), dz1 = bf16(dz - dz0) (may be NULL); db[c] += column sums of the fp32 values.
@@ -1138,9 +1186,90 @@ GNB_EXPORT int gnb_edge_mask_bwd_colsum_bf16(const float* g, int64_t ldg, const 
     dim3 grid((unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas), (unsigned)gnb_div_up(cols >> 2, 64)), block(64, 4);
     if (dz1 != nullptr)
         edge_mask_bwd_bf16_kernel<2><<<grid, block, 0, (cudaStream_t)stream>>>(g, ldg, reinterpret_cast<const uint4*>(maskbits), n, cols,
-                                                                             (__nv_bfloat16*)dz0, (__nv_bfloat16*)dz1, ldz, db, n_tiles);
+                                                                             (__nv_bfloat16*)dz0, (__nv_bfloat16*)dz1, ldz, db, n_tiles, nullptr);
     else
         edge_mask_bwd_bf16_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(g, ldg, reinterpret_cast<const uint4*>(maskbits), n, cols,
-                                                                             (__nv_bfloat16*)dz0, nullptr, ldz, db, n_tiles);
+                                                                             (__nv_bfloat16*)dz0, nullptr, ldz, db, n_tiles, nullptr);
+    GNB_RETURN_LAUNCH();
+}
+// The same as ONE fp16 plane of dz * 2^s, 2^s = gnb_pow2_scale(*scale_bits).x with *scale_bits = fp32 bits of max|g|
+// (gnb_absmax_bits on g): fp16 carries tf32's significand in half the bytes once the tensor's range is centred.
+GNB_EXPORT int gnb_edge_mask_bwd_colsum_f16(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols,
+                                            void* dz, int64_t ldz, float* db, const uint32_t* scale_bits, void* stream) {
+    if (maskbits == nullptr || dz == nullptr || scale_bits == nullptr) return GNB_ERR_ARG;
+    if ((cols & 7) || (ldg & 3) || (ldz & 7) || ldz < cols || !aligned16(g) || !aligned16(dz) || !aligned16(maskbits)) return GNB_ERR_ARG;
+    if (n == 0) return GNB_OK;
+    const int64_t n_tiles = (n + EM_NPT - 1) / EM_NPT;
+    const int64_t max_ctas = 148 * 8;
+    dim3 grid((unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas), (unsigned)gnb_div_up(cols >> 2, 64)), block(64, 4);
+    edge_mask_bwd_bf16_kernel<0><<<grid, block, 0, (cudaStream_t)stream>>>(g, ldg, reinterpret_cast<const uint4*>(maskbits), n, cols,
+                                                                         (__nv_bfloat16*)dz, nullptr, ldz, db, n_tiles, scale_bits);
+    GNB_RETURN_LAUNCH();
+}
+
+// *out_bits = max(*out_bits, fp32 bits of 2^shift max |a[r, c]|) over a [rows, cols] matrix (cols % 4 == 0); *out_bits must be
+// initialised (0) by the caller. Non-negative floats order like their bit patterns, so one atomicMax per CTA suffices.
+__global__ void __launch_bounds__(256) absmax_bits_kernel(const float* __restrict__ a, int64_t lda, int64_t rows, int cols4,
+                                                           unsigned* __restrict__ out_bits, unsigned shift) {
+    unsigned m = 0u;
+    const int64_t total = rows * cols4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    auto upd = [&](const float4 v) {
+        m = max(max(m, __float_as_uint(fabsf(v.x))), max(__float_as_uint(fabsf(v.y)), max(__float_as_uint(fabsf(v.z)), __float_as_uint(fabsf(v.w)))));
+    };
+    if (lda == 4 * (int64_t)cols4) {              // contiguous: flat float4 stream, four independent loads in flight per thread
+        const float4* p = reinterpret_cast<const float4*>(a);
+        int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; t + 3 * stride < total; t += 4 * stride) {
+            const float4 v0 = p[t], v1 = p[t + stride], v2 = p[t + 2 * stride], v3 = p[t + 3 * stride];
+            upd(v0); upd(v1); upd(v2); upd(v3);
+        }
+        for (; t < total; t += stride) upd(p[t]);
+    } else {
+        for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+            const int64_t r = t / cols4;
+            const int c = (int)(t - r * cols4);
+            upd(reinterpret_cast<const float4*>(a + r * lda)[c]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ unsigned s_m[8];
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = max(m, s_m[w]);
+        if (m < 0x7f800000u && m != 0u) atomicMax(out_bits, min(m + (shift << 23), 0x7f000000u));   // NaN / Inf do not set the scale
+    }
+}
+GNB_EXPORT int gnb_absmax_bits(const float* a, int64_t lda, int64_t rows, int32_t cols, int32_t shift, uint32_t* out_bits,
+                               void* stream) {
+    if ((cols & 3) || (lda & 3) || !aligned16(a) || out_bits == nullptr || rows < 0 || shift < 0 || shift > 8) return GNB_ERR_ARG;
+    if (rows == 0 || cols == 0) return GNB_OK;
+    const int64_t total = rows * (cols >> 2);
+    int64_t ctas = (total + 256 * 8 - 1) / (256 * 8);
+    if (ctas > 148 * 8) ctas = 148 * 8;
+    absmax_bits_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(a, lda, rows, cols >> 2, out_bits, (unsigned)shift);
+    GNB_RETURN_LAUNCH();
+}
+
+
+// a[r, 0:cols] = 0 for a [rows, cols] block of pitch lda (cols % 4 == 0, 16-byte aligned): the scatter target of the fused
+// data-gradient kernels (the Q half of dPQ). cudaMemset2DAsync moves this block at ~2 TB/s; plain float4 stores at HBM speed.
+__global__ void __launch_bounds__(256) zero_block_kernel(float* __restrict__ a, int64_t lda, int64_t rows, int cols4) {
+    const int64_t total = rows * cols4;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / cols4;
+        const int c = (int)(t - r * cols4);
+        reinterpret_cast<float4*>(a + r * lda)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+GNB_EXPORT int gnb_zero_block(float* a, int64_t lda, int64_t rows, int32_t cols, void* stream) {
+    if ((cols & 3) || (lda & 3) || !aligned16(a) || rows < 0 || cols < 0) return GNB_ERR_ARG;
+    if (rows == 0 || cols == 0) return GNB_OK;
+    const int64_t total = rows * (cols >> 2);
+    int64_t ctas = (total + 255) / 256;
+    if (ctas > 148 * 16) ctas = 148 * 16;
+    zero_block_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(a, lda, rows, cols >> 2);
     GNB_RETURN_LAUNCH();
 }

@@ -327,9 +327,9 @@ static inline int gnb_make_tmap_f32(CUtensorMap* map, const float* base, int64_t
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -1;
 }
-// bf16 row-major matrix [rows, cols] with row pitch ld_bytes: box = [64 cols (= 128 B), box_rows], 128-byte swizzle.
-static inline int gnb_make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld_bytes,
-                                     uint32_t box_rows) {
+// 16-bit (bf16 / fp16) row-major matrix [rows, cols] with row pitch ld_bytes: box = [64 cols (= 128 B), box_rows], 128-byte swizzle.
+static inline int gnb_make_tmap_16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld_bytes,
+                                   uint32_t box_rows, CUtensorMapDataType dtype) {
     gnb_encode_tiled_fn enc = gnb_get_encode_tiled();
     if (enc == nullptr) return -2;
     if ((reinterpret_cast<uintptr_t>(base) & 15u) || (ld_bytes & 15)) return -1;
@@ -337,8 +337,12 @@ static inline int gnb_make_tmap_bf16(CUtensorMap* map, const void* base, int64_t
     cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld_bytes)};
     cuuint32_t box[2] = {64u, box_rows};
     cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+    CUresult r = enc(map, dtype, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -1;
+}
+static inline int gnb_make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld_bytes,
+                                     uint32_t box_rows) {
+    return gnb_make_tmap_16(map, base, rows, cols, ld_bytes, box_rows, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
 }

@@ -233,9 +233,44 @@ int gnb_edge_hidden_dgrad_scatter_bf16(const void* dz0, const void* dz1, int64_t
 int gnb_linear_fwd_bf16(const void* x0, const void* x1, int64_t ldx, int32_t k, const void* w0, const void* w1, int64_t ldw,
                         const float* bias, float* y, int64_t ldy, int64_t rows, int32_t n_out, int32_t act,
                         int32_t round_out, void* stream);
+/* ---- precision mode "mixed16": the per-edge tensors as fp16 planes -- fp16 carries tf32's 11-bit significand in half the
+ * bytes -- scaled per layer by a power of two so that they sit inside fp16's range. A scale word (device uint32) holds the
+ * fp32 bits of (a bound on) max|v|: gnb_absmax_bits over the producer's input; scale 2^s = 2^(14 - floor(log2 max)), applied by
+ * the producer and undone exactly (power of two) in the consuming epilogues. Forward: two planes of h and W2, three products
+ * (fp32 grade); backward: ONE plane of dz, h, W2^T (tf32 grade). (bf16 against fp16 operands in one MMA is an illegal
+ * instruction on sm_100a, so every operand of these GEMMs is fp16.) */
+/* *out_bits = max(*out_bits, fp32 bits of 2^shift * max|a|); *out_bits zero before the first call. */
+int gnb_absmax_bits(const float* a, int64_t lda, int64_t rows, int32_t cols, int32_t shift, uint32_t* out_bits, void* stream);
+/* gnb_edge_hidden_fwd_bf16 with fp16 planes of h * 2^s; *scale_bits >= bits of max h (absmax of PQ with shift 1). */
+int gnb_edge_hidden_fwd_f16(const float* pq, int64_t ldpq, int32_t hdim, const int32_t* nbr, const int32_t* deg,
+                            int32_t width, int64_t n, void* h0, void* h1, int64_t ldh, uint32_t* hmask, int32_t mask_ld,
+                            const uint32_t* scale_bits, void* stream);
+/* gnb_edge_linear_agg_fwd_bf16 on fp16 planes; the epilogue folds 2^-s of h into its bias FMA. */
+int gnb_edge_linear_agg_fwd_f16(const void* h0, const void* h1, int64_t ldh, int32_t k, const void* w0, const void* w1,
+                                int64_t ldw, const float* bias, const int32_t* deg, int64_t n, int32_t n_out,
+                                int32_t round_out, float* y, int64_t ldy, uint32_t* maskbits, const uint32_t* scale_bits,
+                                void* stream);
+/* gnb_edge_mask_bwd_colsum with dz as ONE fp16 plane of dz * 2^s (*scale_bits = bits of max|g|). */
+int gnb_edge_mask_bwd_colsum_f16(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols, void* dz,
+                                 int64_t ldz, float* db, const uint32_t* scale_bits, void* stream);
+/* dw += dz^T x: dz the scaled fp16 plane, x fp16 plane(s) of the scaled x (x1 may be NULL); both scales undone. */
+int gnb_linear_bwd_weight_f16(const void* dz, int64_t lddz, const void* x0, const void* x1, int64_t ldx, float* dw,
+                              int64_t lddw, int64_t rows, int32_t n_out, int32_t k_in, const uint32_t* dz_scale_bits,
+                              const uint32_t* x_scale_bits, void* stream);
+/* gnb_edge_hidden_dgrad_scatter_split_tf32 with dz (scaled) and wt = W2^T as single fp16 planes. */
+int gnb_edge_hidden_dgrad_scatter_f16(const void* dz, int64_t lddz, int32_t c_out, const void* wt, int64_t ldw,
+                                      const uint32_t* hmask, int32_t mask_ld, int32_t hdim, const int32_t* nbr, int64_t n,
+                                      float* dq, int64_t lddq, float* dp, int64_t lddp, float* dbias, int32_t flags,
+                                      const uint32_t* scale_bits, void* stream);
+/* fp32 [rows, cols] -> fp16 planes (round to nearest; zero padded to dst_cols; p1 may be NULL); transpose != 0: of src^T. */
+int gnb_to_f16_planes(const float* src, int64_t lds, int64_t rows, int32_t cols, void* p0, void* p1, int64_t ldd,
+                      int32_t dst_cols, int32_t transpose, void* stream);
 /* fp32 [rows, cols] -> planes [rows, dst_cols] (zero beyond cols); transpose != 0: planes of src^T ([cols, dst_cols >= rows]). */
 int gnb_to_bf16_planes(const float* src, int64_t lds, int64_t rows, int32_t cols, void* p0, void* p1, int64_t ldd,
                        int32_t dst_cols, int32_t transpose, void* stream);
+
+/* a[r, 0:cols] = 0 over a [rows, cols] block of pitch lda (the zero-on-entry scatter target dq of the fused data-gradient kernels). */
+int gnb_zero_block(float* a, int64_t lda, int64_t rows, int32_t cols, void* stream);
 
 /* fp32 SIMT backend: y[m,n] = act(x[m,k] w[n,k]^T + bias (+ y if accumulate)); act: 0 none, 1 relu. */
 int gnb_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,
@@ -259,7 +294,8 @@ int64_t gnb_launch_count(void);
 typedef struct {
     int32_t nb_inputs, k, precision;                 /* precision: 0 fp32 SIMT GEMMs, 1 tf32 tcgen05 GEMMs, 2 tf32x3: forward GEMMs split-operand (fp32 grade), backward GEMMs tf32,
                                                         3 bf16: per-edge tensors as one bf16 plane (kind::f16), node-level GEMMs as 1,
-                                                        4 bf16x3: per-edge tensors as two bf16 planes, node-level GEMMs as 2 */
+                                                        4 bf16x3: per-edge tensors as two bf16 planes, node-level GEMMs as 2,
+                                                        5 mixed16: per-edge tensors as scaled fp16 planes (two forward, one backward), node-level GEMMs as 2 */
     int32_t n_conv, conv_hidden[GNB_MAX_LAYERS], conv_out[GNB_MAX_LAYERS];
     int32_t n_post, post_out[GNB_MAX_LAYERS];
     int32_t n_readout, readout_out[GNB_MAX_LAYERS];

@@ -265,10 +265,206 @@ def test_linear_fwd_bf16_grade(ops, np_, rows, k, n_out):
     assert err < (8e-3 if np_ == 1 else 2e-5)
 
 
-MODE_TOL = {"bf16": (5e-3, 1.5e-2), "bf16x3": (2e-5, 1e-3)}
+def _scale_word(maxval):
+    """Device word with the fp32 bits of `maxval` and the power-of-two scale gnb_pow2_scale derives from it."""
+    bits = int(np.float32(maxval).view(np.uint32))
+    e = (bits >> 23) & 0xFF
+    scale = 2.0 ** (14 - (e - 127))
+    return torch.tensor([bits], dtype=torch.int64).int().cuda(), scale
 
 
-@pytest.mark.parametrize("mode", ["bf16", "bf16x3"])
+def test_absmax_bits(ops):
+    g = torch.Generator().manual_seed(11)
+    a = torch.randn(1000, 256, generator=g) * 3e-4
+    a[977, 13] = -0.0421
+    word = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ac = a.cuda()
+    ops._call("gnb_absmax_bits", ops._ptr(ac), 256, 1000, 256, 0, ops._ptr(word), ops._stream())
+    torch.cuda.synchronize()
+    assert int(word.item()) == int(np.float32(0.0421).view(np.uint32))
+    ops._call("gnb_absmax_bits", ops._ptr(ac), 256, 1000, 256, 1, ops._ptr(word), ops._stream())      # max with 2 x the maximum
+    torch.cuda.synchronize()
+    assert int(word.item()) == int(np.float32(0.0842).view(np.uint32))
+
+
+@pytest.mark.parametrize("maxval", [0.0421, 3.7e-6, 900.0])
+def test_edge_mask_bwd_f16_is_the_scaled_fp32_kernel(ops, maxval):
+    graph, n = _graph(ops, [3, 14, 15, 200, 41], seed=1)
+    n_out = 256
+    g = torch.Generator().manual_seed(7)
+    mask = torch.randint(-2 ** 31, 2 ** 31 - 1, ((n + 13) // 14 * n_out * 4,), generator=g, dtype=torch.int64).int().cuda()
+    gy = (torch.rand(n, n_out, generator=g) * 2 - 1) * maxval
+    gy[0, 0] = maxval
+    gy = gy.cuda()
+    word = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops._call("gnb_absmax_bits", ops._ptr(gy), n_out, n, n_out, 0, ops._ptr(word), ops._stream())
+    _, scale = _scale_word(maxval)
+    assert 2 ** 14 <= maxval * scale < 2 ** 15
+    dz = torch.empty(n * 9, n_out, device="cuda")
+    db_ref = torch.zeros(n_out, device="cuda")
+    ops._call("gnb_edge_mask_bwd_colsum", ops._ptr(gy), n_out, ops._ptr(mask), n, n_out, ops._ptr(graph.deg), ops._ptr(dz),
+              n_out, ops._ptr(db_ref), 0, ops._stream())
+    dz16 = torch.empty(n * 9, n_out, dtype=torch.float16, device="cuda")
+    db = torch.zeros(n_out, device="cuda")
+    ops._call("gnb_edge_mask_bwd_colsum_f16", ops._ptr(gy), n_out, ops._ptr(mask), n, n_out, ops._ptr(dz16), n_out, ops._ptr(db),
+              ops._ptr(word), ops._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(dz16, (dz * scale).half())
+    assert rel_err(dz16.float() / scale, dz) < 2.0 ** -11          # fp16 = tf32's significand
+    assert rel_err(db, db_ref) < 1e-5
+
+
+def f16_planes(ops, t, np_, dst_cols=None, transpose=False):
+    t = t.contiguous()
+    rows, cols = t.shape
+    drows = cols if transpose else rows
+    dst_cols = dst_cols or ((rows if transpose else cols) + 7) // 8 * 8
+    p0 = torch.full((drows, dst_cols), 7.0, dtype=torch.float16, device="cuda")
+    p1 = torch.full((drows, dst_cols), 7.0, dtype=torch.float16, device="cuda") if np_ == 2 else None
+    ops._call("gnb_to_f16_planes", ops._ptr(t), cols, rows, cols, ops._ptr(p0), ops._ptr(p1), dst_cols, dst_cols,
+              1 if transpose else 0, ops._stream())
+    return p0, p1
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_to_f16_planes(ops, np_):
+    g = torch.Generator().manual_seed(3)
+    t = torch.randn(37, 52, generator=g) * 0.05
+    p0, p1 = f16_planes(ops, t.cuda(), np_, dst_cols=64)
+    assert torch.equal(p0.cpu()[:, :52], t.half()) and not p0.cpu()[:, 52:].float().abs().any()
+    if np_ == 2:
+        assert torch.equal(p1.cpu()[:, :52], (t - t.half().float()).half())
+        assert rel_err(p0.float()[:, :52] + p1.float()[:, :52], t) < 2.0 ** -19
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+@pytest.mark.parametrize("hdim", [128, 336])
+def test_hidden_fwd_f16_planes_are_the_scaled_fp32_kernel(ops, np_, hdim):
+    graph, n = _graph(ops, [1, 2, 5, 9, 10, 64, 130, 12, 300, 3], seed=hdim)
+    g = torch.Generator().manual_seed(hdim)
+    pq = (torch.randn(n, 2 * hdim, generator=g) * 37.0).cuda()
+    word = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops._call("gnb_absmax_bits", ops._ptr(pq), 2 * hdim, n, 2 * hdim, 1, ops._ptr(word), ops._stream())
+    bound = 2 * float(pq.abs().max())
+    _, scale = _scale_word(bound)
+    mld = 4 * ((hdim + 127) // 128)
+    rows = (n + 13) // 14 * 126
+    h_ref = torch.zeros(n * 9, hdim, device="cuda")
+    m_ref = torch.zeros(rows, mld, dtype=torch.int32, device="cuda")
+    ops._call("gnb_edge_hidden_fwd_mask", ops._ptr(pq), 2 * hdim, hdim, ops._ptr(graph.nbr), ops._ptr(graph.deg), 9, n,
+              ops.ACT_RELU, ops._ptr(h_ref), hdim, ops._ptr(m_ref), mld, ops._stream())
+    h0 = torch.full((n * 9, hdim), 3.0, dtype=torch.float16, device="cuda")
+    h1 = torch.full((n * 9, hdim), 3.0, dtype=torch.float16, device="cuda") if np_ == 2 else None
+    m = torch.zeros(rows, mld, dtype=torch.int32, device="cuda")
+    ops._call("gnb_edge_hidden_fwd_f16", ops._ptr(pq), 2 * hdim, hdim, ops._ptr(graph.nbr), ops._ptr(graph.deg), 9, n,
+              ops._ptr(h0), ops._ptr(h1), hdim, ops._ptr(m), mld, ops._ptr(word), ops._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(m.cpu()[: n * 9], m_ref.cpu()[: n * 9])
+    assert float(h_ref.max()) * scale < 2 ** 15 and not torch.isinf(h0.float()).any()
+    want0 = (h_ref * scale).half()
+    assert torch.equal(h0, want0)
+    if np_ == 2:
+        assert torch.equal(h1, (h_ref * scale - want0.float()).half())
+        assert rel_err((h0.float() + h1.float()) / scale, h_ref) < 2.0 ** -20
+
+
+@pytest.mark.parametrize("np_,which", [(1, "int"), (2, "int"), (2, "h"), (2, "w")])
+@pytest.mark.parametrize("k,n_out", [(336, 256), (128, 256), (40, 104)])
+def test_edge_linear_agg_f16_bit_exact(ops, np_, which, k, n_out):
+    """fp16 planes with a power-of-two scale on h: same exact cases as the bf16 planes (fp16 holds 11-bit significands, so the
+    two-plane values fit as well), the epilogue's 2^-s is exact."""
+    graph, n = _graph(ops, [1, 2, 5, 9, 10, 64, 130, 12, 300, 3, 700], seed=k)
+    deg = graph.deg.cpu()
+    g = torch.Generator().manual_seed(n_out + k)
+    h, w, b = _agg_inputs(k, n_out, np_, which, g, n)
+    if which == "h":
+        h = two_plane_values((n * 9, k), g, scale_bits=4, mag_bits=15).abs()        # 15-bit significands: two fp16 planes
+    pre = h.double() @ w.double().t() + b.double()
+    valid = (torch.arange(9).unsqueeze(0) < deg.unsqueeze(1)).reshape(-1)
+    on = (pre > 0) & valid.unsqueeze(1)
+    y_ref = (pre * on).reshape(n, 9, n_out).sum(1)
+    word, scale = _scale_word(float(h.max()))
+    h0, h1 = f16_planes(ops, (h * scale).cuda(), np_)
+    kw = (k + 63) // 64 * 64
+    w0, w1 = f16_planes(ops, w.cuda(), np_, dst_cols=kw)
+    if np_ == 2:
+        assert torch.equal((h0.float().cpu() + h1.float().cpu()) / scale, h) and torch.equal((w0.float() + w1.float()).cpu()[:, :k], w)
+    y = torch.empty(n, n_out, device="cuda")
+    mask = torch.zeros((n + 13) // 14 * n_out * 4, dtype=torch.int32, device="cuda")
+    bc = b.cuda()
+    ops._call("gnb_edge_linear_agg_fwd_f16", ops._ptr(h0), ops._ptr(h1), h0.shape[1], k, ops._ptr(w0), ops._ptr(w1), kw,
+              ops._ptr(bc), ops._ptr(graph.deg), n, n_out, 0, ops._ptr(y), n_out, ops._ptr(mask), ops._ptr(word), ops._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(y.cpu().double(), y_ref)
+
+
+@pytest.mark.parametrize("planes_x", [1, 2])
+@pytest.mark.parametrize("rows,n_out,k_in", [(126 * 5, 256, 336), (4000, 256, 128), (20000, 256, 336), (513, 104, 344)])
+def test_wgrad_f16_bit_exact(ops, planes_x, rows, n_out, k_in):
+    """x as scaled fp16 plane(s), dz as one scaled fp16 plane: the epilogue's two inverse powers of two are exact."""
+    g = torch.Generator().manual_seed(rows + k_in)
+    x = two_plane_values((rows, k_in), g, scale_bits=4, mag_bits=13) if planes_x == 2 else torch.randint(-2, 3, (rows, k_in), generator=g).float()
+    dz = torch.randint(-3, 4, (rows, n_out), generator=g).float() * 2.0 ** -9
+    if planes_x == 2:
+        dz = torch.randint(-1, 2, (rows, n_out), generator=g).float() * 2.0 ** -9
+    wz, sz = _scale_word(3 * 2.0 ** -9)
+    wx, sx = _scale_word(float(x.abs().max()))
+    ref = dz.double().t() @ x.double()
+    x0, x1 = f16_planes(ops, (x * sx).cuda(), planes_x)
+    dz16 = (dz * sz).half().cuda()
+    dw = torch.zeros(n_out, k_in, device="cuda")
+    ops._call("gnb_linear_bwd_weight_f16", ops._ptr(dz16), n_out, ops._ptr(x0), ops._ptr(x1), x0.shape[1], ops._ptr(dw), k_in,
+              rows, n_out, k_in, ops._ptr(wz), ops._ptr(wx), ops._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(dw.cpu().double(), ref)
+
+
+@pytest.mark.parametrize("hdim,c_out,variant", [(336, 256, 0), (128, 256, 0), (336, 256, 2), (40, 104, 0)])
+def test_dgrad_scatter_f16_bit_exact(ops, hdim, c_out, variant):
+    graph, n = _graph(ops, [1, 2, 5, 9, 10, 64, 130, 12, 300, 3, 500], seed=hdim + c_out)
+    g = torch.Generator().manual_seed(hdim)
+    dz = torch.randint(-1, 2, (n * 9, c_out), generator=g).float() * 2.0 ** -20
+    w2 = torch.randint(-8, 9, (c_out, hdim), generator=g).float() / 8          # exact in fp16
+    word, scale = _scale_word(2.0 ** -20)
+    nbr, deg = graph.nbr.cpu().long(), graph.deg.cpu()
+    valid = ((torch.arange(9).unsqueeze(0) < deg.unsqueeze(1)) & (nbr >= 0)).reshape(-1)
+    dz = dz * valid.unsqueeze(1)
+    hbits = torch.rand(n * 9, hdim, generator=g) < 0.6
+    mld = 4 * ((hdim + 127) // 128)
+    rows_m = (n + 13) // 14 * 126
+    c = torch.arange(hdim)
+    word_i, bit = 4 * (c // 128) + c % 4, (c % 128) // 4
+    hm = torch.zeros(rows_m, mld, dtype=torch.int64)
+    hm[: n * 9].index_put_((torch.arange(n * 9).unsqueeze(1).expand(-1, hdim), word_i.unsqueeze(0).expand(n * 9, -1)),
+                           hbits.long() << bit.unsqueeze(0), accumulate=True)
+    hm = torch.where(hm >= 2 ** 31, hm - 2 ** 32, hm).int().cuda()
+    da = (dz.double() @ w2.double()) * hbits
+    dp_ref = da.reshape(n, 9, hdim).sum(1)
+    dq_ref = torch.zeros(n, hdim, dtype=torch.float64)
+    dq_ref.index_add_(0, nbr.reshape(-1).clamp(min=0)[valid], da[valid])
+    dz16 = (dz * scale).half().cuda()
+    cw = (c_out + 63) // 64 * 64
+    wt16, _ = f16_planes(ops, w2.cuda(), 1, dst_cols=cw, transpose=True)
+    assert torch.equal(wt16.cpu()[:, :c_out].float(), w2.t()) and not wt16.cpu()[:, c_out:].float().abs().any()
+    dq = torch.zeros(n, hdim, device="cuda")
+    dp = torch.full((n, hdim), 9.0, device="cuda")
+    dbias = torch.zeros(hdim, device="cuda")
+    ops._call("gnb_linear_set_variant", variant)
+    try:
+        ops._call("gnb_edge_hidden_dgrad_scatter_f16", ops._ptr(dz16), c_out, c_out, ops._ptr(wt16), cw, ops._ptr(hm), mld, hdim,
+                  ops._ptr(graph.nbr), n, ops._ptr(dq), hdim, ops._ptr(dp), hdim, ops._ptr(dbias), 0, ops._ptr(word), ops._stream())
+        torch.cuda.synchronize()
+    finally:
+        ops._call("gnb_linear_set_variant", 0)
+    assert torch.equal(dp.cpu().double(), dp_ref)
+    assert torch.equal(dq.cpu().double(), dq_ref)
+    assert torch.equal(dbias.cpu().double(), dp_ref.sum(0))
+
+
+MODE_TOL = {"bf16": (5e-3, 1.5e-2), "bf16x3": (2e-5, 1e-3), "mixed16": (2e-5, 1e-3)}
+
+
+@pytest.mark.parametrize("mode", ["bf16", "bf16x3", "mixed16"])
 def test_dynedge_bf16_modes_vs_oracle(ops, mode):
     """Default DynEdge (4 pooling schemes) on the executor route against the fp64 oracle fed the kernel's own graphs and
     read-out decisions: outputs and EVERY parameter gradient within the mode's stated tolerance; latent kNN graphs bit-exact
@@ -313,7 +509,7 @@ def test_dynedge_bf16_modes_vs_oracle(ops, mode):
     assert max(gerr.values()) < grad_tol, gerr
 
 
-@pytest.mark.parametrize("mode", ["bf16", "bf16x3"])
+@pytest.mark.parametrize("mode", ["bf16", "bf16x3", "mixed16"])
 def test_dynedge_bf16_inference_matches_training_forward(ops, mode):
     """The inference route (shared per-edge buffers, no masks) computes the same numbers as the training forward."""
     ops.set_precision(mode)
