@@ -38,10 +38,18 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+# arithmetic type of the path's dominant contractions (not a precision claim: config.precision states the tolerance)
+DTYPE = {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32", "bf16": "bf16", "bf16x3": "bf16", "mixed16": "f16"}
 METRIC = "dynedge_train_events_per_sec"
 UNIT = "events/s"
 POOLS = ["min", "max", "mean", "sum"]
-TOLERANCE = {"tf32x3": "out 2e-5 / grad 1e-3 vs the fp64 oracle (tests/test_gpu_tf32x3.py)",
+TOLERANCE = {"mixed16": "out 2e-5 / grad 1e-3 vs the fp64 oracle (tests/test_gpu_bf16.py, tests/test_gpu_train_step.py; measured "
+                        "9e-6 / 5.5e-4): per-edge tensors as power-of-two scaled fp16 planes, forward 3 products (fp32 grade), "
+                        "backward 1 product (tf32 grade); node-level GEMMs as tf32x3",
+             "bf16x3": "out 2e-5 / grad 1e-3 (per-edge tensors as two bf16 planes, 3 products forward and backward; measured 9e-6 / 5.5e-4)",
+             "bf16": "out 5e-3 / grad 1.5e-2 (north_star's looser mode: per-edge tensors as ONE bf16 plane; measured 2.3e-3 / 5.7e-3, "
+                     "tests/test_gpu_bf16.py)",
+             "tf32x3": "out 2e-5 / grad 1e-3 vs the fp64 oracle (tests/test_gpu_tf32x3.py)",
              "tf32": "out 1e-3 / grad 3e-3 (single-pass tf32, measured 8e-4 / 2.3e-3, tests/test_gpu_tc.py)",
              "fp32": "out 1e-3 / grad 1e-3 (SIMT fp32, measured 4e-7 / 8e-7)"}
 
@@ -56,7 +64,8 @@ def parse_args():
                     choices=["train512", "infer1024", "highmult20k", "percentile16", "prometheus50", "microbench"])
     ap.add_argument("--events", type=int, default=512, help="training events per GPU (configs[2])")
     ap.add_argument("--infer-events", type=int, default=1024, help="inference events per GPU (configs[1])")
-    ap.add_argument("--precision", default=os.environ.get("GNB_PRECISION", "tf32x3"), choices=["tf32x3", "tf32", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("GNB_PRECISION", "mixed16"),
+                    choices=["mixed16", "bf16x3", "bf16", "tf32x3", "tf32", "fp32"])
     ap.add_argument("--cpu-events", type=int, default=128, help="events of the bounded CPU-baseline sample (BASELINE.md 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inference", action="store_true")
@@ -437,9 +446,45 @@ def dominant_launches(trainer, db):
         ops._call("gnb_edge_hidden_dgrad_scatter_tf32", ops._ptr(dz), cout, cout, ops._ptr(wt), wt.shape[1], ops._ptr(hmask),
                   mld, hid, ops._ptr(graph.nbr), n, ops._ptr(dpq), 2 * hid, ops._stream())
 
-    keep = (h, h_raw, w2p, w_hi, w_lo, b2, y, maskbits, dz, wt, hmask, dpq, graph)
+    # mixed16: fp16 planes (power-of-two scaled) of the same operands
+    def f16_planes(t, two, dst_cols=None, transpose=False):
+        r, c = t.shape
+        dr, dc = (c, dst_cols or r) if transpose else (r, dst_cols or c)
+        p0 = torch.empty(dr, dc, dtype=torch.float16, device=dev)
+        p1 = torch.empty(dr, dc, dtype=torch.float16, device=dev) if two else None
+        ops._call("gnb_to_f16_planes", ops._ptr(t), c, r, c, ops._ptr(p0), ops._ptr(p1), dc, dc, 1 if transpose else 0, ops._stream())
+        return p0, p1
+    hw = torch.zeros(1, dtype=torch.int32, device=dev)
+    zw = torch.zeros(1, dtype=torch.int32, device=dev)
+    ops._call("gnb_absmax_bits", ops._ptr(h_raw), hid, rows, hid, 0, ops._ptr(hw), ops._stream())
+    ops._call("gnb_absmax_bits", ops._ptr(dz), cout, rows, cout, 0, ops._ptr(zw), ops._stream())
+    hscale = 2.0 ** (14 - (((int(hw.item()) >> 23) & 0xFF) - 127))
+    zscale = 2.0 ** (14 - (((int(zw.item()) >> 23) & 0xFF) - 127))
+    h16 = f16_planes(h_raw * hscale, True)
+    hld64, cld64 = (hid + 63) // 64 * 64, (cout + 63) // 64 * 64
+    w16 = f16_planes(w2.contiguous(), True, dst_cols=hld64)
+    wt16 = f16_planes(w2.contiguous(), False, dst_cols=cld64, transpose=True)
+    dz16 = (dz * zscale).half()
+    dwg = torch.zeros(cout, hid, device=dev)
+
+    def agg_fwd_f16x3():
+        ops._call("gnb_edge_linear_agg_fwd_f16", ops._ptr(h16[0]), ops._ptr(h16[1]), hid, hid, ops._ptr(w16[0]), ops._ptr(w16[1]),
+                  hld64, ops._ptr(b2), ops._ptr(graph.deg), n, cout, 0, ops._ptr(y), cout, ops._ptr(maskbits), ops._ptr(hw),
+                  ops._stream())
+
+    def dgrad_scatter_f16():
+        ops._call("gnb_edge_hidden_dgrad_scatter_f16", ops._ptr(dz16), cout, cout, ops._ptr(wt16[0]), cld64, ops._ptr(hmask), mld,
+                  hid, ops._ptr(graph.nbr), n, ops._ptr(dpq[:, hid:]), 2 * hid, ops._ptr(dpq), 2 * hid, ops._ptr(None), 0,
+                  ops._ptr(zw), ops._stream())
+
+    def wgrad_f16():
+        ops._call("gnb_linear_bwd_weight_f16", ops._ptr(dz16), cout, ops._ptr(h16[0]), ops._ptr(None), hid, ops._ptr(dwg), hid, rows,
+                  cout, hid, ops._ptr(zw), ops._ptr(hw), ops._stream())
+
+    keep = (h, h_raw, w2p, w_hi, w_lo, b2, y, maskbits, dz, wt, hmask, dpq, graph, hw, zw, h16, w16, wt16, dz16, dwg)
     e_real = int(graph.deg.sum().item())
-    return {"agg_fwd": agg_fwd, "agg_fwd_x3": agg_fwd_x3, "dgrad_scatter": dgrad_scatter, "rows": rows, "n": n,
+    return {"agg_fwd": agg_fwd, "agg_fwd_x3": agg_fwd_x3, "dgrad_scatter": dgrad_scatter, "agg_fwd_f16x3": agg_fwd_f16x3,
+            "dgrad_scatter_f16": dgrad_scatter_f16, "wgrad_f16": wgrad_f16, "rows": rows, "n": n,
             "edges": e_real, "hid": hid, "cout": cout, "mld": mld, "keep": keep}
 
 
@@ -485,10 +530,10 @@ def roofline_top_kernel(trainer, db, pk, precision, inference=False):
     bytes_f = 4.0 * rows * hid + 4.0 * n * cout + 16.0 * ((n + 13) // 14) * cout
     bytes_b = 4.0 * rows * cout + 4.0 * rows * d["mld"] + 4.0 * n * 2 * hid
 
-    def entry(kernel, sec, by, executed=1.0, traffic=None):
+    def entry(kernel, sec, by, executed=1.0, traffic=None, peak=peak):
         ach = flops / sec / 1e12
         return {"kernel": kernel, "launch_ms": round(sec * 1e3, 4), "achieved": round(ach, 3), "unit": "TFLOP/s",
-                "frac": round(ach / peak, 5), "executed_tflops": round(ach * executed, 3),
+                "frac": round(ach / peak, 5), "peak": peak, "executed_tflops": round(ach * executed, 3),
                 "executed_frac": round(ach * executed / peak, 5),
                 "hbm_view": {"algorithmic_bytes": by, "achieved_gbs": round(by / sec / 1e9, 1),
                              "frac": round(by / sec / 1e9 / pk["hbm_gbs"], 4)}, "traffic": traffic}
@@ -499,6 +544,29 @@ def roofline_top_kernel(trainer, db, pk, precision, inference=False):
     bwd = entry("gemm_tc_pair_dual_scatter_kernel: dh = dz W2 (256 -> 336), ReLU mask, dP/dQ reduction over the padded edge "
                 "list (single-pass tf32; both 256-channel groups from one resident dz tile)", sec_b, bytes_b, 1.0,
                 _traffic("dgrad_scatter"))
+    if precision == "mixed16" and not inference:
+        # kind::f16 kernels: the denominator is the measured dense bf16 / fp16 burst peak of MEASURED_PEAKS.json
+        p16 = pk["bf16_tflops"]
+        by_f = 4.0 * rows * hid + 4.0 * n * cout + 16.0 * ((n + 13) // 14) * cout            # two fp16 planes of h
+        by_b = 2.0 * rows * cout + 4.0 * rows * d["mld"] + 4.0 * n * 2 * hid               # one fp16 plane of dz
+        by_w = 2.0 * rows * (hid + cout)
+        top = entry("gemm_bf_pair_dual_scatter_kernel<1> (tcgen05 cta_group::2 kind::f16 M256xN256xK16, fp16 operands): dh = dz W2 "
+                    "(256 -> 336) on the power-of-two scaled fp16 plane of dz, ReLU mask + dP slot sums + dQ fp32 reductions in the "
+                    "epilogue (dh never stored); both 256-channel groups from one resident dz tile. Bound by the L2 slices (213 M "
+                    "fp32 reductions + the TMA stream), not by the tensor pipe", _time_launch(d["dgrad_scatter_f16"]), by_b, 1.0,
+                    _traffic("dgrad_scatter_f16"), p16)
+        fwd = entry("gemm_tc_pair_kernel<3> (kind::f16, two fp16 planes per operand, 3 products per K step, 3 x 64 KiB TMA stages): "
+                    "m = relu(h W2^T + b2) summed over the k slots, 336 -> 256; executes 3 MMAs per algorithmic product",
+                    _time_launch(d["agg_fwd_f16x3"]), by_f, 3.0, _traffic("agg_fwd_f16x3"), p16)
+        wg = entry("gemm_bf_wgrad_kernel<1,1,64> (kind::f16, MN-major TMA operands): dW2 = dz^T h on one fp16 plane each; HBM-bound",
+                   _time_launch(d["wgrad_f16"]), by_w, 1.0, _traffic("wgrad_f16"), p16)
+        out = {"bound": "tensor", "achieved": top["achieved"], "peak": p16, "unit": "TFLOP/s", "frac": top["frac"],
+               "traffic": top["traffic"], "kernel": top["kernel"], "launch_ms": top["launch_ms"],
+               "peak_source": "dense bf16 burst peak of MEASURED_PEAKS.json (kind::f16 runs fp16 and bf16 at the same rate)",
+               "executed_tflops": top["executed_tflops"], "executed_frac": top["executed_frac"], "hbm_view": top["hbm_view"],
+               "rows": rows, "edges": e_real, "algorithmic_flops_per_launch": flops,
+               "forward_launch": fwd, "weight_gradient_launch": wg}
+        return out
     if precision == "tf32x3" and not inference:
         sec_x = _time_launch(d["agg_fwd_x3"])
         top = entry("gemm_tc_pair_kernel<true> (tcgen05 cta_group::2 kind::tf32 M256xN256xK8, split operands: 3 MMAs per K step, "
@@ -551,8 +619,8 @@ def _family(name: str) -> str:
     m = re.match(r"([A-Za-z0-9_:]+)(<[^(]*>)?", name)
     fam = m.group(1) if m else name
     if fam.startswith("gemm_tc_pair_kernel"):
-        split = bool(re.search(r"gemm_tc_pair_kernel<\s*(\(bool\))?\s*(1|true)\s*>", name))
-        fam = "gemm_tc_pair_kernel<split>" if split else "gemm_tc_pair_kernel<single>"
+        m2 = re.search(r"gemm_tc_pair_kernel<\s*(\(int\))?\s*(\d)\s*>", name)
+        fam = "gemm_tc_pair_kernel<" + {"0": "single", "1": "split", "2": "f16", "3": "f16x3"}.get(m2.group(2) if m2 else "0", "single") + ">"
     return fam
 
 
@@ -568,10 +636,14 @@ def algorithmic_work(cfg, n, rows, e_real, nseg, precision, train=True):
         w["bytes"] += by
         w["launches"] += 1
 
+    # 16-bit plane modes (per-edge tensors): planes forward / backward and bytes per stored element
+    planes = {"bf16": (1, 1), "bf16x3": (2, 2), "mixed16": (2, 1)}.get(precision)
+    node_split = precision in ("tf32x3", "bf16x3", "mixed16")       # node-level forward GEMMs on split operands
+
     def dense_fam(m_rows, n_out, fwd):
         if precision == "fp32":
             return "gemm_f32_kernel"
-        if fwd and precision == "tf32x3":
+        if fwd and node_split:
             return "gemm_tc_pair_kernel<split>"
         tiles = (m_rows + 127) // 128
         return "gemm_tc_pair_kernel<single>" if (tiles >= 296 and n_out > 128) else "gemm_tc_linear_kernel"
@@ -580,15 +652,34 @@ def algorithmic_work(cfg, n, rows, e_real, nseg, precision, train=True):
     skip_w = cin
     for hid, cout in cfg["conv"]:
         add(dense_fam(n, 2 * hid, True), 2.0 * n * cin * 2 * hid, 4.0 * n * (cin + 2 * hid))
-        add("edge_hidden_fwd_node_kernel", 0.0, 4.0 * rows * hid + 4.0 * n * 2 * hid, "hbm")
-        add(dense_fam(rows, cout, True), 2.0 * e_real * hid * cout, 4.0 * rows * hid + 4.0 * n * cout)
         add("knn_table_split_kernel", 0.0, n * (12.0 + 40.0), "hbm")
+        if planes is not None:
+            pf, pb = planes
+            hb, zb = 2.0 * pf, 2.0 * pb                    # bytes per element of h / dz as stored
+            add("edge_hidden_fwd_node_bf16_kernel", 0.0, hb * rows * hid + 4.0 * n * 2 * hid, "hbm")
+            add("gemm_tc_pair_kernel<f16x3>" if pf == 2 else "gemm_tc_pair_kernel<f16>", 2.0 * e_real * hid * cout,
+                hb * rows * hid + 4.0 * n * cout)
+            if precision == "mixed16":
+                add("absmax_bits_kernel", 0.0, 4.0 * n * 2 * hid, "hbm")
+            if train:
+                add("edge_mask_bwd_bf16_kernel", 0.0, zb * rows * cout + 4.0 * n * cout, "hbm")
+                if precision == "mixed16":
+                    add("absmax_bits_kernel", 0.0, 4.0 * n * cout, "hbm")
+                # the weight gradient reads one plane of h in mixed16 (fp16 = tf32's significand), every plane otherwise
+                add("gemm_bf_wgrad_kernel", 2.0 * e_real * hid * cout, rows * (zb * cout + (2.0 if precision == "mixed16" else hb) * hid))
+                fam = "gemm_bf_pair_dual_scatter_kernel" if hid > 256 else ("gemm_tc_pair_kernel<f16x3>" if pb == 2 else "gemm_tc_pair_kernel<f16>")
+                add(fam, 2.0 * e_real * hid * cout, zb * rows * cout + 4.0 * n * 2 * hid)
+                add("zero_block_kernel", 0.0, 4.0 * n * hid, "hbm")
+        else:
+            add("edge_hidden_fwd_node_kernel", 0.0, 4.0 * rows * hid + 4.0 * n * 2 * hid, "hbm")
+            add(dense_fam(rows, cout, True), 2.0 * e_real * hid * cout, 4.0 * rows * hid + 4.0 * n * cout)
         if train:
-            add("edge_mask_bwd_kernel", 0.0, 4.0 * rows * cout + 4.0 * n * cout, "hbm")
-            add("gemm_tc_wgrad_kernel" if tc else "gemm_f32_kernel", 2.0 * e_real * hid * cout, 4.0 * rows * (hid + cout))
-            fam = "gemm_tc_pair_dual_scatter_kernel" if (tc and hid > 256) else dense_fam(rows, hid, False)
-            add(fam, 2.0 * e_real * hid * cout, 4.0 * rows * cout + 4.0 * n * 2 * hid)
-            add("round_move_zero_kernel", 0.0, 12.0 * n * hid, "hbm")
+            if planes is None:
+                add("edge_mask_bwd_kernel", 0.0, 4.0 * rows * cout + 4.0 * n * cout, "hbm")
+                add("gemm_tc_wgrad_kernel" if tc else "gemm_f32_kernel", 2.0 * e_real * hid * cout, 4.0 * rows * (hid + cout))
+                fam = "gemm_tc_pair_dual_scatter_kernel" if (tc and hid > 256) else dense_fam(rows, hid, False)
+                add(fam, 2.0 * e_real * hid * cout, 4.0 * rows * cout + 4.0 * n * 2 * hid)
+                add("zero_block_kernel", 0.0, 4.0 * n * hid, "hbm")
             add("gemm_tc_wgrad_kernel" if tc else "gemm_f32_kernel", 2.0 * n * cin * 2 * hid, 4.0 * n * (cin + 2 * hid))
             if cin != cfg["x0_width"]:
                 add(dense_fam(n, cin, False), 2.0 * n * cin * 2 * hid, 4.0 * n * (2 * cin + 2 * hid))
@@ -644,8 +735,10 @@ def kernel_table(step_fn, db, cfg, n, rows, e_real, nseg, precision, pk, train=T
         if w is not None:
             if w["bound"] == "tensor":
                 ach = w["flops"] / (us * 1e-6) / 1e12
+                f16 = fam.startswith("gemm_bf_") or fam.endswith(("<f16>", "<f16x3>"))      # kind::f16 kernels: bf16 / fp16 dense peak
                 row.update({"bound": "tensor", "algorithmic_gflop": round(w["flops"] / 1e9, 2), "achieved_tflops": round(ach, 1),
-                            "frac": round(ach / pk["tf32_tflops_sustained"], 4),
+                            "frac": round(ach / (pk["bf16_tflops_sustained"] if f16 else pk["tf32_tflops_sustained"]), 4),
+                            "peak": "bf16_tflops_sustained" if f16 else "tf32_tflops_sustained",
                             "hbm_frac": round(w["bytes"] / (us * 1e-6) / 1e9 / pk["hbm_gbs"], 4)})
             else:
                 ach = w["bytes"] / (us * 1e-6) / 1e9
@@ -653,8 +746,9 @@ def kernel_table(step_fn, db, cfg, n, rows, e_real, nseg, precision, pk, train=T
                             "frac": round(ach / pk["hbm_gbs"], 4)})
         rows_out.append(row)
     return {"source": f"one CUPTI pass over {steps} steps after the timed loops (explanatory; headline numbers are CUDA-event "
-                      "timed without a profiler); tensor fractions against the tf32 SUSTAINED peak measured in this run, "
-                      "HBM fractions against MEASURED_PEAKS.json",
+                      "timed without a profiler); tensor fractions against the SUSTAINED dense peak of the kernel's operand type (tf32: "
+                      "measured in this run; kind::f16 kernels: MEASURED_PEAKS.json bf16_tflops_sustained), HBM fractions against "
+                      "MEASURED_PEAKS.json",
             "device_us_per_step": round(total, 1), "algorithmic_gflop_per_step": round(alg_flops_total / 1e9, 1),
             "kernels": rows_out}
 
@@ -820,12 +914,14 @@ def run_train512(args, dev, world, rank, local):
     clocks = sampler.stop() if rank == 0 else None
 
     alt = None
-    if not args.no_alt_precision and args.precision == "tf32x3":
-        ops.set_precision("tf32")
-        sec_a, st_a = repeat_median(args.repeats, trainer.train_step, train_dev, args.steps, args.warmup, flush)
-        sec_a = max_over_ranks(sec_a, dev)
-        alt = {"precision": "tf32: " + TOLERANCE["tf32"], "value": round(events_total / sec_a, 2), "unit": UNIT,
-               "ms_per_step": round(sec_a / args.steps * 1e3, 3), "step_ms_median": st_a["step_ms_median"]}
+    if not args.no_alt_precision and args.precision in ("tf32x3", "mixed16"):
+        alt = []          # the same step in the other precision modes (bf16 = north_star's looser, stated mode)
+        for mode in (["bf16", "tf32x3", "tf32"] if args.precision == "mixed16" else ["tf32"]):
+            ops.set_precision(mode)
+            sec_a, st_a = repeat_median(args.repeats, trainer.train_step, train_dev, args.steps, args.warmup, flush)
+            sec_a = max_over_ranks(sec_a, dev)
+            alt.append({"precision": f"{mode}: " + TOLERANCE[mode], "value": round(events_total / sec_a, 2), "unit": UNIT,
+                        "ms_per_step": round(sec_a / args.steps * 1e3, 3), "step_ms_median": st_a["step_ms_median"]})
         ops.set_precision(args.precision)
 
     inference = None
@@ -857,7 +953,7 @@ def run_train512(args, dev, world, rank, local):
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(sec / args.steps * 1e3, 3), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32",
+                "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[args.precision],
                 "data": "synthetic", "config": workload_config(args, world), "e2e": e2e, "gpu_launches": int(launches),
                 "gpu_launches_per_step": int(launches) // max(args.steps, 1),
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "inference": inference, "alt_precision": alt,
@@ -881,7 +977,7 @@ def run_inference(args, trainer, dev, world, rank, flush, pk):
     keep = ops.PRECISION
     out = {"workload": "BASELINE configs[1]: energy-regression inference, 1024 events/GPU, no collective", "unit": UNIT}
     try:
-        for mode in (["tf32", keep] if keep == "tf32x3" else ["tf32"]):
+        for mode in (["tf32", "bf16", keep] if keep in ("tf32x3", "mixed16") else ["tf32"]):
             ops.set_precision(mode)
             sec, st = repeat_median(args.repeats, trainer.infer_step, inf_dev, args.steps, args.warmup, flush)
             sec = max_over_ranks(sec, dev)
@@ -902,7 +998,7 @@ def run_inference(args, trainer, dev, world, rank, flush, pk):
                         out["kernels"] = kernel_table(trainer.infer_step, inf_dev[0], model_shape(trainer), n, rows, e_real, nseg,
                                                       "tf32", pk, train=False)
             else:
-                out["alt_precision"] = entry
+                out.setdefault("alt_precision", []).append(entry)
     finally:
         ops.set_precision(keep)
     return out

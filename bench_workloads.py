@@ -83,7 +83,7 @@ class EnergyTrainer:
 def _line(args, metric, value, sec, config, extra):
     line = {"metric": metric, "value": round(value, 2), "unit": bench.UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(sec * 1e3, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "tf32", "data": config.pop("data", "synthetic"), "config": config}
+            "dtype": bench.DTYPE[args.precision], "data": config.pop("data", "synthetic"), "config": config}
     line.update(extra)
     bench._emit(line)
 

@@ -18,10 +18,10 @@ pytestmark = pytest.mark.gpu
 # Batches of 16 events / ~600 pulses (and one of 2 events / 61 pulses): fp32 meets rel 1e-3; tf32x3 (single-pass tf32 backward
 # GEMMs) is stated at 2e-3 on batches this small (measured 1.4e-3; 7.5e-4 on the 512-event training batch). The single-pass
 # tf32 mode is not run here: its forward rounding flips ReLU decisions all over a 600-pulse network (measured 2e-2).
-GRAD_TOL = {"fp32": 1e-3, "tf32x3": 2e-3}
+GRAD_TOL = {"fp32": 1e-3, "tf32x3": 2e-3, "mixed16": 2e-3}
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "mixed16"])
 def test_prometheus_example_epoch_vs_oracle(built_library, precision):
     import sys
     sys.path.insert(0, os.path.dirname(GOLDEN_DIR[:-len("/golden")]))
