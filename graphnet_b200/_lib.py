@@ -79,6 +79,7 @@ SIGNATURES: Dict[str, list] = {
     "gnb_edge_hidden_dgrad_scatter_f16": [_p, _i64, _i32, _p, _i64, _p, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _i32,
                                           _p, _p],
     "gnb_zero_block": [_p, _i64, _i64, _i32, _p],
+    "gnb_linear_next_absmax": [_p, _i32],
     "gnb_to_f16_planes": [_p, _i64, _i64, _i32, _p, _p, _i64, _i32, _i32, _p],
 }
 

@@ -64,6 +64,7 @@ int gnb_edge_hidden_dgrad_scatter_bf16(const void*, const void*, int64_t, int32_
                                        void*);
 int gnb_to_bf16_planes(const float*, int64_t, int64_t, int32_t, void*, void*, int64_t, int32_t, int32_t, void*);
 int gnb_zero_block(float*, int64_t, int64_t, int32_t, void*);
+int gnb_linear_next_absmax(uint32_t*, int32_t);
 int gnb_to_f16_planes(const float*, int64_t, int64_t, int32_t, void*, void*, int64_t, int32_t, int32_t, void*);
 int gnb_absmax_bits(const float*, int64_t, int64_t, int32_t, int32_t, uint32_t*, void*);
 int gnb_edge_hidden_fwd_f16(const float*, int64_t, int32_t, const int32_t*, const int32_t*, int32_t, int64_t, void*, void*, int64_t,
@@ -96,7 +97,9 @@ struct gnb_dynedge_config {
                                                    // 5 = mixed16: per-edge tensors as fp16 planes scaled per layer by a power of
                                                    // two (fp16 = tf32's significand in half the bytes): forward on two planes of
                                                    // h and W2 (three products, fp32 grade), backward on ONE plane of dz, h, W2^T
-                                                   // (tf32 grade); node-level GEMMs as in 2
+                                                   // (tf32 grade); node-level GEMMs as in 2;
+                                                   // 6 = f16: ONE scaled fp16 plane forward and backward (tf32 grade at half the
+                                                   // per-edge bytes); node-level GEMMs as in 1
     int32_t n_conv, conv_hidden[GNB_MAX_LAYERS], conv_out[GNB_MAX_LAYERS];
     int32_t n_post, post_out[GNB_MAX_LAYERS];
     int32_t n_readout, readout_out[GNB_MAX_LAYERS];
@@ -248,10 +251,10 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
     if (c.globals_after_pooling && c.n_pool == 0) return GNB_ERR_ARG;
     Arena a(ws, cap);
     p.n = n; p.nseg = nseg; p.w0 = w0; p.width = c.k + 1;
-    const bool split = c.precision == 2 || c.precision >= 4;      // pre-split weight operands: a lo buffer behind every packed forward weight
-    if (c.precision < 0 || c.precision > 5) return GNB_ERR_ARG;
-    p.bf = c.precision >= 3 ? (c.precision == 3 ? 1 : 2) : 0;
-    p.mixed = c.precision == 5;
+    const bool split = c.precision == 2 || c.precision == 4 || c.precision == 5;   // pre-split weight operands: a lo buffer behind every packed forward weight
+    if (c.precision < 0 || c.precision > 6) return GNB_ERR_ARG;
+    p.bf = c.precision >= 3 ? ((c.precision == 3 || c.precision == 6) ? 1 : 2) : 0;
+    p.mixed = c.precision >= 5;           // fp16 planes with power-of-two scale words
     p.agg = c.precision >= 1 && c.k == 8 && w0 == 9 && !(c.flags & 1) && (training || (c.flags & 2) || split || p.bf);
     if (p.bf && !p.agg) return GNB_ERR_UNSUPPORTED;               // the bf16 modes exist on the k = 8 tensor-core route only
     const int f = c.nb_inputs, ng = f + 5;
@@ -403,9 +406,9 @@ struct Exec {
     int rnd;          // backward: gradients that feed a tensor-core GEMM are stored rounded
     int frnd;         // forward flag for the producers of GEMM operands
     Exec(const gnb_dynedge_config& cfg, void* s)
-        : c(cfg), st((cudaStream_t)s), tf32(cfg.precision >= 1), split(cfg.precision == 2 || cfg.precision >= 4),
-          fround(cfg.precision == 1 || cfg.precision == 3), rnd(cfg.precision >= 1 ? GNB_FLAG_ROUND_TF32 : 0),
-          frnd((cfg.precision == 1 || cfg.precision == 3) ? GNB_FLAG_ROUND_TF32 : 0) {}
+        : c(cfg), st((cudaStream_t)s), tf32(cfg.precision >= 1), split(cfg.precision == 2 || cfg.precision == 4 || cfg.precision == 5),
+          fround(cfg.precision == 1 || cfg.precision == 3 || cfg.precision == 6), rnd(cfg.precision >= 1 ? GNB_FLAG_ROUND_TF32 : 0),
+          frnd((cfg.precision == 1 || cfg.precision == 3 || cfg.precision == 6) ? GNB_FLAG_ROUND_TF32 : 0) {}
 
     int copy_pad(const float* src, int64_t lds, int64_t rows, int cols, float* dst, int64_t ldd, int dst_cols, bool round,
                  float* lo = nullptr) {
@@ -510,6 +513,10 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
         EXL();
         EX(e.copy_pad(w2, b.hid, b.cout, b.hid, b.w2p, b.hld, b.hld, e.tf32, b.w2p_lo));
         {   // PQ = xin Wcat^T + bcat
+            if (p.mixed) {      // fp16-plane modes: the GEMM epilogue also yields the scale word of h = relu(P_i + Q_j) <= 2 max|PQ|
+                if (l == 0) GNB_CHECK(cudaMemsetAsync(p.scale_bits, 0, 2 * GNB_MAX_LAYERS * 4, e.st));
+                EX(gnb_linear_next_absmax(p.scale_bits + l, 1));
+            }
             const float* xs[1] = {xin}; const int64_t lds[1] = {b.cin_ld}; const int32_t ks[1] = {b.cin_ld}; const int offs[1] = {0};
             EX(e.lin_fwd(1, xs, lds, ks, offs, b.wcat, b.kld, b.bcat, b.pq, n, 2 * b.hid, GNB_ACT_NONE, 0, b.wcat_lo));   // P+Q is added in fp32
         }
@@ -520,14 +527,12 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
         } else if (p.bf) {
             // bf16 / bf16x3: h as bf16 plane(s) straight from the hidden-layer kernel, second Linear + ReLU + k-sum on kind::f16
             if (p.mixed) {
-                uint32_t* hs = p.scale_bits + l;          // h = relu(P_i + Q_j) <= 2 max|PQ|
-                if (l == 0) GNB_CHECK(cudaMemsetAsync(p.scale_bits, 0, 2 * GNB_MAX_LAYERS * 4, e.st));
-                EX(gnb_absmax_bits(b.pq, 2 * b.hid, n, 2 * b.hid, 1, hs, stream));
+                uint32_t* hs = p.scale_bits + l;          // written by the PQ GEMM's epilogue (gnb_linear_next_absmax above)
                 EX(gnb_to_f16_planes(w2, b.hid, b.cout, b.hid, b.w2b[0], b.w2b[1], b.hld64, b.hld64, 0, stream));
                 if (training) EX(gnb_to_f16_planes(w2, b.hid, b.cout, b.hid, b.w2tb[0], nullptr, b.cld64, b.cld64, 1, stream));
                 EX(gnb_edge_hidden_fwd_f16(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, b.hb[0], b.hb[1], b.hid, b.hmask, b.mld, hs, stream));
-                EX(gnb_edge_linear_agg_fwd_f16(b.hb[0], b.hb[1], b.hid, b.hid, b.w2b[0], b.w2b[1], b.hld64, b2, deg, n, b.cout, 0, b.y,
-                                               b.cout, b.mask, hs, stream));
+                EX(gnb_edge_linear_agg_fwd_f16(b.hb[0], b.hb[1], b.hid, b.hid, b.w2b[0], b.w2b[1], b.hld64, b2, deg, n, b.cout,
+                                               e.fround ? 1 : 0, b.y, b.cout, b.mask, hs, stream));
             } else {
                 EX(gnb_to_bf16_planes(w2, b.hid, b.cout, b.hid, b.w2b[0], b.w2b[1], b.hld64, b.hld64, 0, stream));
                 if (training) EX(gnb_to_bf16_planes(w2, b.hid, b.cout, b.hid, b.w2tb[0], b.w2tb[1], b.cld64, b.cld64, 1, stream));

@@ -40,7 +40,8 @@ struct PartInfo { int nparts; int kblocks[TC_MAX_PARTS]; };
 // 14 nodes = 126 rows; the epilogue sums relu(acc + b) over the valid slots of every node, writes y[node, ch] and one
 // bit per (slot, channel) = "pre-activation > 0" for the backward pass. The [E, C] message tensor is never stored.
 struct AggInfo { const int* deg; int64_t n_nodes; unsigned* maskbits; int enabled; int dbg; unsigned long long* prof;
-                 const unsigned* scale_bits; };   // mixed16: h arrives scaled by gnb_pow2_scale(*scale_bits).x (16-bit plane modes only)
+                 const unsigned* scale_bits;      // mixed16: h arrives scaled by gnb_pow2_scale(*scale_bits).x (16-bit plane modes only)
+                 unsigned* absmax_bits; int absmax_shift; };   // plain epilogue: *absmax_bits = max(., bits of 2^shift max|y|) (gnb_linear_next_absmax)
 constexpr int AGG_W = 9, AGG_NPT = 14, AGG_ROWS = AGG_W * AGG_NPT;   // k = 8 neighbour tables
 // Scattering epilogue (backward of the hoisted EdgeConv hidden layer fused into the data-gradient GEMM): rows are padded
 // edge slots as above, output channel c of row (i, s) is dh = (dz W2)[(i,s), c]; the epilogue applies the ReLU mask
@@ -153,15 +154,26 @@ __device__ __forceinline__ void scat_tile_any(int mask_ld, uint32_t tcol, uint32
 // Epilogue store of one 32-row chunk: lane = output channel, r[j] = row j. One coalesced 128-byte store per row; the
 // address is a running pointer and activation / rounding are resolved outside the unrolled loop (the naive per-element
 // form compiled to ~30 instructions per store and made the epilogue warps the bottleneck of the kernel).
+// returns max |stored value| of the lane (feeds gnb_linear_next_absmax: one FMNMX per element)
 template <bool ROUND>
-__device__ __forceinline__ void epi_store32(const uint32_t (&r)[32], float bv, float lo, float* __restrict__ yp, int64_t ldy) {
+__device__ __forceinline__ float epi_store32(const uint32_t (&r)[32], float bv, float lo, float* __restrict__ yp, int64_t ldy) {
+    float am = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         float v = fmaxf(__uint_as_float(r[j]) + bv, lo);
         if (ROUND) v = tc::round_tf32(v);
         *yp = v;
+        am = fmaxf(am, fabsf(v));
         yp += ldy;
     }
+    return am;
+}
+// epilogue warp: fold the lanes' maxima into *bits (non-negative floats order like their bit patterns; NaN / Inf are skipped)
+__device__ __forceinline__ void epi_absmax_commit(float am, unsigned* bits, int shift) {
+    unsigned m = __float_as_uint(am);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m != 0u && m < 0x7f800000u) atomicMax(bits, min(m + ((unsigned)shift << 23), 0x7f000000u));
 }
 // y += result (gradient accumulation onto an existing tensor): loads issued together, then the stores
 __device__ __forceinline__ void epi_accum32(const uint32_t (&r)[32], float bv, float lo, float* __restrict__ yp, int64_t ldy) {
@@ -171,8 +183,9 @@ __device__ __forceinline__ void epi_accum32(const uint32_t (&r)[32], float bv, f
 #pragma unroll
     for (int j = 0; j < 32; ++j) yp[(int64_t)j * ldy] = old[j] + fmaxf(__uint_as_float(r[j]) + bv, lo);
 }
-__device__ __noinline__ void epi_store_partial(const uint32_t (&r)[32], float bv, float lo, bool round, bool accum,
-                                               float* __restrict__ yp, int64_t ldy, int nvalid) {
+__device__ __noinline__ float epi_store_partial(const uint32_t (&r)[32], float bv, float lo, bool round, bool accum,
+                                                float* __restrict__ yp, int64_t ldy, int nvalid) {
+    float am = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         if (j < nvalid) {
@@ -180,9 +193,11 @@ __device__ __noinline__ void epi_store_partial(const uint32_t (&r)[32], float bv
             if (round) v = tc::round_tf32(v);
             if (accum) v += *yp;
             *yp = v;
+            am = fmaxf(am, fabsf(v));
             yp += ldy;
         }
     }
+    return am;
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -324,6 +339,7 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
         const float relu_lo = (act & 0xff) == GNB_ACT_RELU ? 0.f : -INFINITY;
         const bool accum = (act & GNB_FLAG_ACCUMULATE) != 0;
         float colacc = 0.f;                         // scattering epilogue: this lane's column sum of dP over all its tiles
+        float amax = 0.f;                           // plain epilogue: max |y| written by this lane
         uint32_t tile_i = 0;
         for (int t = blockIdx.x; t < num_row_tiles; t += gridDim.x, ++tile_i) {
             const uint32_t buf = tile_i & 1;
@@ -410,10 +426,10 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
                         float* yp = y + (row0 + col0) * ldy + ch;
                         if (left >= 32) {
                             if (accum) epi_accum32(r, bv, relu_lo, yp, ldy);
-                            else if (round_out) epi_store32<true>(r, bv, relu_lo, yp, ldy);
-                            else epi_store32<false>(r, bv, relu_lo, yp, ldy);
+                            else if (round_out) amax = fmaxf(amax, epi_store32<true>(r, bv, relu_lo, yp, ldy));
+                            else amax = fmaxf(amax, epi_store32<false>(r, bv, relu_lo, yp, ldy));
                         } else {
-                            epi_store_partial(r, bv, relu_lo, round_out != 0 && !accum, accum, yp, ldy, (int)left);
+                            amax = fmaxf(amax, epi_store_partial(r, bv, relu_lo, round_out != 0 && !accum, accum, yp, ldy, (int)left));
                         }
                     }
                 }
@@ -422,6 +438,7 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tmem_empty[buf]);
         }
+        if (agg.absmax_bits != nullptr) epi_absmax_commit(amax, agg.absmax_bits, agg.absmax_shift);
         if (sc.enabled && sc.dbias != nullptr) {
             const int chs = ch0 + half * TC_BM + q * 32 + lane;
             if (half < mt && chs < n_out) atomicAdd(sc.dbias + chs, colacc);
@@ -789,6 +806,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
         const float relu_lo = (act & 0xff) == GNB_ACT_RELU ? 0.f : -INFINITY;
         const bool accum = (act & GNB_FLAG_ACCUMULATE) != 0;
         float colacc = 0.f;                         // scattering epilogue: this lane's column sum of dP over all its tiles
+        float amax = 0.f;                           // plain epilogue: max |y| written by this lane
         uint32_t tile_i = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters, ++tile_i) {
             const uint32_t buf = tile_i & 1;
@@ -925,10 +943,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                         float* yp = y + (rbase + c * 32) * ldy + ch;
                         if (left >= 32) {
                             if (accum) epi_accum32(r, bv, relu_lo, yp, ldy);
-                            else if (round_out) epi_store32<true>(r, bv, relu_lo, yp, ldy);
-                            else epi_store32<false>(r, bv, relu_lo, yp, ldy);
+                            else if (round_out) amax = fmaxf(amax, epi_store32<true>(r, bv, relu_lo, yp, ldy));
+                            else amax = fmaxf(amax, epi_store32<false>(r, bv, relu_lo, yp, ldy));
                         } else {
-                            epi_store_partial(r, bv, relu_lo, round_out != 0 && !accum, accum, yp, ldy, (int)left);
+                            amax = fmaxf(amax, epi_store_partial(r, bv, relu_lo, round_out != 0 && !accum, accum, yp, ldy, (int)left));
                         }
                     }
                 }
@@ -947,6 +965,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
             if (prof_on) pw1 += clock64() - c1;
         }
         if (sc.enabled && sc.dbias != nullptr && ch_ok) atomicAdd(sc.dbias + ch, colacc);
+        if (agg.absmax_bits != nullptr) epi_absmax_commit(amax, agg.absmax_bits, agg.absmax_shift);
     }
     __syncwarp();
     if (prof_on && lane == 0 && warp <= 2) {
@@ -1392,6 +1411,8 @@ unsigned long long* g_linear_prof = nullptr;
 int g_linear_dbg = 0;   // tuning hook: see gnb_linear_set_debug
 int g_linear_variant = 0;   // 0 auto, 1 single-CTA kernel, 2 CTA-pair kernel
 int g_pair_resident = 0;    // 0: pair kernel streams the weights; n > 0: keep them resident when >= n activation stages fit
+unsigned* g_next_absmax = nullptr;   // gnb_linear_next_absmax: consumed by the next gnb_linear_fwd_tf32 / _tf32x3 launch
+int g_next_absmax_shift = 0;
 
 unsigned long long g_tc_attr_devs = 0ull;      // shared-memory attributes are per device: one bit per device ordinal
 cudaError_t init_tc_kernels() {
@@ -1600,10 +1621,20 @@ static int linear_fwd_impl(const float* const* xs, const int64_t* ldxs, const in
         rc = gnb_make_tmap_bf16(&twlo, w_lo, n_out, 2 * ktot, ldw * 4, TC_BM);
         if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     }
-    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr};
+    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr, g_next_absmax, g_next_absmax_shift};
+    g_next_absmax = nullptr;
     ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, nullptr};
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out, gnb_div_up(rows, TC_BN), agg, sc,
                          (cudaStream_t)stream, w_lo != nullptr ? &twlo : nullptr);
+}
+// One-shot hook: the NEXT gnb_linear_fwd_tf32 / gnb_linear_fwd_tf32x3 launch (without the accumulate flag) also folds
+// max|y| of everything it stores into *bits as gnb_absmax_bits would (bits of 2^shift max|y|; *bits zero-initialised by the
+// caller). Saves the separate absmax pass over PQ in the fp16-plane modes (one FMNMX per stored element in the epilogue).
+GNB_EXPORT int gnb_linear_next_absmax(uint32_t* bits, int32_t shift) {
+    if (shift < 0 || shift > 8) return GNB_ERR_ARG;
+    g_next_absmax = bits;
+    g_next_absmax_shift = shift;
+    return GNB_OK;
 }
 GNB_EXPORT int gnb_linear_fwd_tf32(const float* const* xs, const int64_t* ldxs, const int32_t* ks, int32_t nparts,
                                    const float* w, int64_t ldw, const float* bias, float* y, int64_t ldy, int64_t rows,
@@ -1648,7 +1679,7 @@ static int edge_linear_agg_impl(const float* h, int64_t ldh, int32_t k, const fl
         rc = gnb_make_tmap_bf16(&twlo, w_lo, n_out, 2 * ktot, ldw * 4, TC_BM);
         if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     }
-    AggInfo agg{deg, n, maskbits, 1, g_linear_dbg, g_linear_prof, nullptr};
+    AggInfo agg{deg, n, maskbits, 1, g_linear_dbg, g_linear_prof, nullptr, nullptr, 0};
     ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, nullptr};
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, GNB_ACT_RELU, round_out, gnb_div_up(n, AGG_NPT), agg, sc,
                          (cudaStream_t)stream, w_lo != nullptr ? &twlo : nullptr);
@@ -1698,7 +1729,7 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_split_tf32(const float* dz, int64_t
     CUtensorMap tw;
     rc = gnb_make_tmap_f32(&tw, wt, hdim, ktot, ldw, TC_BM);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
-    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr};
+    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr, nullptr, 0};
     ScatInfo sc{nbr, hmask, mask_ld, dq, lddq, hdim, n, 1, dp, lddp, dbias, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0, nullptr};
     const int row_tiles = gnb_div_up(n, AGG_NPT);
     int nst_w = 0;
@@ -1791,7 +1822,7 @@ static int edge_linear_agg16_impl(const void* h0, const void* h1, int64_t ldh, i
     rc = gnb_make_tmap_16(&tw, w0, n_out, k, ldw * 2, TC_BM, dt);
     if (rc == 0 && planes == 2) rc = gnb_make_tmap_16(&tw1, w1, n_out, k, ldw * 2, TC_BM, dt);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
-    AggInfo agg{deg, n, maskbits, 1, g_linear_dbg, g_linear_prof, scale_bits};
+    AggInfo agg{deg, n, maskbits, 1, g_linear_dbg, g_linear_prof, scale_bits, nullptr, 0};
     ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, nullptr};
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, GNB_ACT_RELU, round_out, gnb_div_up(n, AGG_NPT), agg, sc,
                          (cudaStream_t)stream, planes == 2 ? &tw1 : nullptr, planes, k, fmt16 ? 3 : 0);
@@ -1843,7 +1874,7 @@ static int dgrad_scatter16_impl(const void* dz0, const void* dz1, int64_t lddz, 
     rc = gnb_make_tmap_16(&tw, wt0, hdim, c_out, ldw * 2, TC_BM, tw_t);
     if (rc == 0 && planes == 2) rc = gnb_make_tmap_16(&tw1, wt1, hdim, c_out, ldw * 2, TC_BM, tw_t);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
-    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr};
+    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr, nullptr, 0};
     ScatInfo sc{nbr, hmask, mask_ld, dq, lddq, hdim, n, 1, dp, lddp, dbias, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0, scale_bits};
     const int row_tiles = gnb_div_up(n, AGG_NPT);
     const int last_ksteps = (c_out - 64 * (pi.kblocks[0] - 1) + 15) / 16;
@@ -1913,7 +1944,7 @@ GNB_EXPORT int gnb_linear_fwd_bf16(const void* x0, const void* x1, int64_t ldx, 
     rc = gnb_make_tmap_bf16(&tw, w0, n_out, k, ldw * 2, TC_BM);
     if (rc == 0 && planes == 2) rc = gnb_make_tmap_bf16(&tw1, w1, n_out, k, ldw * 2, TC_BM);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
-    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr};
+    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr, nullptr, 0};
     ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, nullptr};
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out, gnb_div_up(rows, TC_BN), agg, sc,
                          (cudaStream_t)stream, planes == 2 ? &tw1 : nullptr, planes, k);

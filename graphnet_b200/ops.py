@@ -36,10 +36,13 @@ POOL = {"min": 0, "max": 1, "sum": 2, "mean": 3}
 #             forward AND the backward pass; node-level forward GEMMs as "tf32x3". fp32 grade like "tf32x3".
 #             Both bf16 modes exist on the executor route (k = 8 graphs); elsewhere they behave like "tf32" / "tf32x3".
 PRECISION = os.environ.get("GNB_PRECISION", "fp32")
-#   "mixed16": forward as "bf16x3"; in the backward pass dz and W2^T travel as ONE fp16 plane (fp16 = tf32's 11-bit significand
-#             in half the bytes; dz scaled per layer by a power of two so that it sits inside fp16's range) and the weight
-#             gradient runs against both bf16 planes of h. Same grade as "tf32x3" (fp32-grade forward, tf32-grade backward).
-PRECISIONS = ("fp32", "tf32", "tf32x3", "bf16", "bf16x3", "mixed16")
+#   "mixed16": the per-edge tensors as fp16 planes scaled per layer by a power of two (fp16 = tf32's 11-bit significand in half
+#             the bytes; the scale word comes from an absmax pass and is undone exactly in the consuming epilogues): forward on TWO
+#             planes of h and W2 (three products, fp32 grade), backward on ONE plane of dz, h and W2^T (tf32 grade); node-level
+#             forward GEMMs as "tf32x3". Same grade as "tf32x3" (fp32-grade forward, tf32-grade backward). bench.py's headline.
+#   "f16": ONE scaled fp16 plane per per-edge tensor, forward and backward: the grade of "tf32" (same 11-bit significand) at half
+#             the per-edge bytes and twice the MMA rate; node-level GEMMs as "tf32". The inference mode of bench.py.
+PRECISIONS = ("fp32", "tf32", "tf32x3", "bf16", "bf16x3", "mixed16", "f16")
 
 
 def set_precision(mode: str) -> None:
@@ -60,7 +63,7 @@ def _split() -> bool:
 
 def _fround() -> bool:
     """Forward activations that feed a tensor-core GEMM are stored rounded to tf32 (single-pass mode only)."""
-    return PRECISION in ("tf32", "bf16")
+    return PRECISION in ("tf32", "bf16", "f16")
 
 
 def _mark_rounded(t: Tensor) -> Tensor:
@@ -710,9 +713,9 @@ class _DynEdgeExec(torch.autograd.Function):
         cfg.precision = 2 if _split() else (1 if _tf32() else 0)
         cfg.flags = (0 if FUSED_EDGECONV else 1) | (2 if INFERENCE_ROUTE == "split" else 0)
         nbytes = -2
-        if PRECISION in ("bf16", "bf16x3", "mixed16"):     # per-edge tensors as 16-bit planes where the configuration has the k = 8 route
+        if PRECISION in ("bf16", "bf16x3", "mixed16", "f16"):     # per-edge tensors as 16-bit planes where the configuration has the k = 8 route
             base = cfg.precision
-            cfg.precision = {"bf16": 3, "bf16x3": 4, "mixed16": 5}[PRECISION]
+            cfg.precision = {"bf16": 3, "bf16x3": 4, "mixed16": 5, "f16": 6}[PRECISION]
             nbytes = lib.gnb_dynedge_workspace_bytes(ctypes.byref(cfg), n, nseg, graph.width, training)
             if nbytes == -2:
                 cfg.precision = base

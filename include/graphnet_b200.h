@@ -241,6 +241,8 @@ int gnb_linear_fwd_bf16(const void* x0, const void* x1, int64_t ldx, int32_t k, 
  * instruction on sm_100a, so every operand of these GEMMs is fp16.) */
 /* *out_bits = max(*out_bits, fp32 bits of 2^shift * max|a|); *out_bits zero before the first call. */
 int gnb_absmax_bits(const float* a, int64_t lda, int64_t rows, int32_t cols, int32_t shift, uint32_t* out_bits, void* stream);
+/* One-shot: the next gnb_linear_fwd_tf32 / _tf32x3 launch also folds bits of 2^shift max|y| into *bits (as gnb_absmax_bits). */
+int gnb_linear_next_absmax(uint32_t* bits, int32_t shift);
 /* gnb_edge_hidden_fwd_bf16 with fp16 planes of h * 2^s; *scale_bits >= bits of max h (absmax of PQ with shift 1). */
 int gnb_edge_hidden_fwd_f16(const float* pq, int64_t ldpq, int32_t hdim, const int32_t* nbr, const int32_t* deg,
                             int32_t width, int64_t n, void* h0, void* h1, int64_t ldh, uint32_t* hmask, int32_t mask_ld,
@@ -295,7 +297,8 @@ typedef struct {
     int32_t nb_inputs, k, precision;                 /* precision: 0 fp32 SIMT GEMMs, 1 tf32 tcgen05 GEMMs, 2 tf32x3: forward GEMMs split-operand (fp32 grade), backward GEMMs tf32,
                                                         3 bf16: per-edge tensors as one bf16 plane (kind::f16), node-level GEMMs as 1,
                                                         4 bf16x3: per-edge tensors as two bf16 planes, node-level GEMMs as 2,
-                                                        5 mixed16: per-edge tensors as scaled fp16 planes (two forward, one backward), node-level GEMMs as 2 */
+                                                        5 mixed16: per-edge tensors as scaled fp16 planes (two forward, one backward), node-level GEMMs as 2,
+                                                        6 f16: one scaled fp16 plane forward and backward (tf32 grade), node-level GEMMs as 1 */
     int32_t n_conv, conv_hidden[GNB_MAX_LAYERS], conv_out[GNB_MAX_LAYERS];
     int32_t n_post, post_out[GNB_MAX_LAYERS];
     int32_t n_readout, readout_out[GNB_MAX_LAYERS];

@@ -64,7 +64,7 @@ def namespace(**kw) -> SimpleNamespace:
 
 # Largest |pre-activation| (relative to the largest one of the tensor) at which the kernel's read-out ReLU decision may
 # differ from the oracle's: the forward error of the mode with a safety factor.
-FLIP_TOL = {"fp32": 2e-5, "tf32x3": 2e-4, "tf32": 5e-3, "bf16x3": 2e-4, "mixed16": 2e-4, "bf16": 3e-2}
+FLIP_TOL = {"fp32": 2e-5, "tf32x3": 2e-4, "tf32": 5e-3, "bf16x3": 2e-4, "mixed16": 2e-4, "f16": 5e-3, "bf16": 3e-2}
 
 
 def oracle_on_kernel_decisions(ref, data, forced_graphs, y_kernel, mode: str):
