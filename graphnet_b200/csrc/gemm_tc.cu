@@ -1396,6 +1396,269 @@ gemm_bf_pair_dual_scatter_kernel(const __grid_constant__ CUtensorMap tm_w0, cons
     if (warp == 1) tc::tmem_dealloc_2cta<512>(tmem_base);
 }
 
+
+// The fp16 scattering kernel WITHOUT a stored dz: the B operand (the cluster's dz rows) is expanded in shared memory by four
+// builder warps per CTA from the node-level gradient and the ReLU bits of the aggregating epilogue -- dz[(i, s), c] =
+// g[i, c] * bit(i, s, c) is a 9-fold redundant function of those two. Inputs as prepared by gnb_edge_dz_prep: g16 [n, c_out] =
+// fp16(g * 2^s) and the ROW-major bits rowmask[(i * 9 + s) * (c_out / 32) + c / 32]. Per tile the producer warp stages this
+// CTA's 14 g16 rows (one bulk copy, 7 KiB) and its 126 rows of mask words (one bulk copy, 4 KiB) in a double-buffered staging
+// area; builder lane (chunk column j of a 64-channel K block, node f) reads the node's 8 fp16 values once and one byte of
+// channel bits per slot and writes the node's 9 rows of the K-major 128-byte-swizzled tile (row r at r * 128 B, chunk j at
+// j ^ (r & 7)) as 16-byte stores; per K block: fence.proxy.async, then one relaxed cluster arrive per builder warp on the
+// leader's afull[kb] (count 8), the hand-off of the split-operand kernel. K blocks are rebuilt as soon as the last group of the
+// previous tile released them (aempty[kb]). c_out <= 256, c_out % 64 == 0; ngroups = 1 (hdim <= 256) or 2.
+constexpr int DB_THREADS = PL_THREADS + 128;
+struct DzBuild { const __half* g16; const unsigned* rowmask; int c_out; };
+// kind::f16 instruction descriptor of the CTA-pair MMAs (M 256 x N 256, fp32 accumulate, K-major), fp16 x fp16
+__host__ __device__ constexpr uint32_t idesc_f16_256_dev() { return (1u << 4) | ((256u >> 3) << 17) | ((256u >> 4) << 24); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DB_THREADS, 1)
+gemm_f16_pair_scatter_build_kernel(const __grid_constant__ CUtensorMap tm_w0, const DzBuild zb, int total_kb, int last_ksteps,
+                                   int64_t rows, int n_out, int num_tiles, const ScatInfo sc, int nst_w, uint32_t meta_stride,
+                                   int dbg, int ngroups) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* act = smem;                                               // [total_kb] x 16 KiB: dz tile built here (own half)
+    uint8_t* wring = act + (uint32_t)total_kb * TC_TILE_BYTES;         // [nst_w] x 16 KiB
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(wring + (uint32_t)nst_w * TC_TILE_BYTES);
+    uint64_t* wempty = wfull + PL_MAX_STAGES;
+    uint64_t* afull = wempty + PL_MAX_STAGES;        // [DU_MAX_KB] (leader's copy: 8 builder-warp arrivals of the pair)
+    uint64_t* aempty = afull + DU_MAX_KB;            // [DU_MAX_KB] (multicast to both CTAs)
+    uint64_t* tmem_full = aempty + DU_MAX_KB;        // [2]
+    uint64_t* tmem_empty = tmem_full + 2;            // [2]
+    uint64_t* meta_full = tmem_empty + 2;            // [2]
+    uint64_t* meta_empty = meta_full + 2;            // [2]
+    uint64_t* gfull = meta_empty + 2;                // [2] staging block landed (local)
+    uint64_t* gempty = gfull + 2;                    // [2] the 4 builder warps are done with the staging block (local)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gempty + 2);
+    uint8_t* meta = reinterpret_cast<uint8_t*>(wfull) + DU_BAR_BYTES;  // [2 buffers][2 sub-tiles] x meta_stride
+    const uint32_t cw = (uint32_t)zb.c_out >> 5;                       // mask words per edge-slot row
+    const uint32_t gbytes = (uint32_t)AGG_NPT * (uint32_t)zb.c_out * 2u, mbytes = (uint32_t)AGG_ROWS * cw * 4u;
+    const uint32_t stg_stride = gbytes + mbytes;                       // {14 g16 rows | 126 rows x cw mask words}
+    uint8_t* stg = meta + 4 * meta_stride;                             // [2] x stg_stride (16-byte aligned: all parts are)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const int cluster_id = (int)(blockIdx.x >> 1), num_clusters = (int)(gridDim.x >> 1);
+    const int64_t ntile14 = (sc.n_nodes + AGG_NPT - 1) / AGG_NPT;
+
+    if (warp == 0 && lane == 0) tc::tma_prefetch_desc(&tm_w0);
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < PL_MAX_STAGES; ++s) { tc::mbar_init(&wfull[s], 1); tc::mbar_init(&wempty[s], 1); }
+            for (int k = 0; k < DU_MAX_KB; ++k) { tc::mbar_init(&afull[k], 8); tc::mbar_init(&aempty[k], 1); }
+            for (int b = 0; b < 2; ++b) {
+                tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], 16);
+                tc::mbar_init(&meta_full[b], 1); tc::mbar_init(&meta_empty[b], 8 * ngroups);
+                tc::mbar_init(&gfull[b], 1); tc::mbar_init(&gempty[b], 4);
+            }
+            tc::fence_barrier_init();
+            tc::fence_proxy_async();
+        }
+        __syncwarp();
+        tc::tmem_alloc_2cta<512>(tmem_slot);
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---- producer (both CTAs): staging block of the tile, weight tiles, scatter metadata ------------------------------
+        uint32_t itw = 0, ti = 0;
+        const uint32_t w_tx = 2u * TC_TILE_BYTES;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++ti) {
+            const uint32_t buf = ti & 1;
+            const int64_t st14 = (int64_t)t * 2 + rank, node0 = st14 * AGG_NPT;
+            {   // this CTA's 14 g16 rows + mask rows
+                tc::mbar_wait_warp(&gempty[buf], ((ti >> 1) & 1) ^ 1);
+                int64_t nv = sc.n_nodes - node0;
+                nv = nv < 0 ? 0 : (nv > AGG_NPT ? AGG_NPT : nv);
+                const uint32_t gb = (uint32_t)nv * (uint32_t)zb.c_out * 2u;
+                if (tc::elect_one()) {
+                    tc::mbar_arrive_expect_tx(&gfull[buf], gb + (st14 < ntile14 ? mbytes : 0u));
+                    if (nv > 0) tc::bulk_load(stg + buf * stg_stride, zb.g16 + node0 * zb.c_out, gb, &gfull[buf]);
+                    if (st14 < ntile14) tc::bulk_load(stg + buf * stg_stride + gbytes, zb.rowmask + st14 * AGG_ROWS * cw, mbytes, &gfull[buf]);
+                }
+                __syncwarp();
+            }
+            int offv[2][4];
+            unsigned lastv[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) scat_meta(sc, ((int64_t)t * 2 + h) * AGG_NPT, rows, lane, offv[h], lastv[h]);
+            for (int g = 0; g < ngroups; ++g) {
+                const bool peer_rows = g * 256 + 128 < n_out;
+                for (int kb = 0; kb < total_kb; ++kb, ++itw) {
+                    const uint32_t s = itw % (uint32_t)nst_w, ph = (itw / (uint32_t)nst_w) & 1;
+                    tc::mbar_wait_warp(&wempty[s], ph ^ 1);
+                    if (tc::elect_one()) {
+                        if (rank == 0) tc::mbar_arrive_expect_tx(&wfull[s], peer_rows ? w_tx : w_tx / 2);
+                        if (rank == 0 || peer_rows)
+                            tc::tma_load_2d_2sm(wring + s * TC_TILE_BYTES, &tm_w0, &wfull[s], kb * 64, g * 256 + (int)rank * 128);
+                    }
+                    __syncwarp();
+                }
+                if (g != 0) continue;
+                tc::mbar_wait_warp(&meta_empty[buf], ((ti >> 1) & 1) ^ 1);
+                uint32_t bytes = 0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint8_t* mbh = meta + (buf * 2 + h) * meta_stride;
+                    int* so = reinterpret_cast<int*>(mbh + meta_stride - 512);
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) so[lane + 32 * q4] = offv[h][q4];
+                    if (lane == 0) *reinterpret_cast<unsigned*>(mbh + AGG_ROWS * sc.mask_ld * 4) = lastv[h];
+                    if (((int64_t)t * 2 + h) * AGG_NPT < sc.n_nodes) bytes += (uint32_t)(AGG_ROWS * sc.mask_ld * 4);
+                }
+                __syncwarp();
+                if (tc::elect_one()) {
+                    tc::mbar_arrive_expect_tx(&meta_full[buf], bytes);
+                    const uint32_t one = (uint32_t)(AGG_ROWS * sc.mask_ld * 4);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        if (((int64_t)t * 2 + h) * AGG_NPT < sc.n_nodes)
+                            tc::bulk_load(meta + (buf * 2 + h) * meta_stride, sc.hmask + ((int64_t)t * 2 + h) * AGG_ROWS * sc.mask_ld,
+                                          one, &meta_full[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ---- MMA issuer (leader) ------------------------------------------------------------------------------------
+            constexpr uint32_t idesc = idesc_f16_256_dev();
+            uint32_t itw = 0, vt_i = 0, ti = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters, ++ti) {
+                for (int g = 0; g < ngroups; ++g, ++vt_i) {
+                    const uint32_t buf = vt_i & 1;
+                    tc::mbar_wait_warp(&tmem_empty[buf], ((vt_i >> 1) & 1) ^ 1);
+                    tc::tcgen05_fence_after();
+                    const uint32_t acc = tmem_base + buf * 256;
+                    for (int kb = 0; kb < total_kb; ++kb, ++itw) {
+                        const int nk = kb == total_kb - 1 ? last_ksteps : 4;
+                        const uint32_t s = itw % (uint32_t)nst_w, ph = (itw / (uint32_t)nst_w) & 1;
+                        tc::mbar_wait_warp(&wfull[s], ph);
+                        if (g == 0) tc::mbar_wait_warp<true>(&afull[kb], ti & 1);      // both CTAs' builders (cluster-scope acquire)
+                        tc::tcgen05_fence_after();
+                        const uint64_t wd = tc::umma_desc_sw128_kmajor(tc::smem_u32(wring + s * TC_TILE_BYTES));
+                        const uint64_t x0 = tc::umma_desc_sw128_kmajor(tc::smem_u32(act + kb * TC_TILE_BYTES));
+                        if (tc::elect_one()) {
+                            if (!(dbg & 2)) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (k < nk) tc::umma_bf16_2cta(acc, wd + 2 * k, x0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                            }
+                            tc::umma_commit_2cta(&wempty[s], 3);
+                            if (g == ngroups - 1) tc::umma_commit_2cta(&aempty[kb], 3);
+                        }
+                        __syncwarp();
+                    }
+                    if (tc::elect_one()) tc::umma_commit_2cta(&tmem_full[buf], 3);
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp >= 10) {
+        // ---- dz builders (both CTAs, warps 10..13): lane -> (chunk column j, node f) of a 64-channel K block ------------------
+        const int gl = (warp - 10) * 32 + lane;              // 0..127
+        const int j = gl & 7, f = gl >> 3;                   // f < 14 active
+        const bool node_on = f < AGG_NPT;
+        uint32_t ti = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++ti) {
+            const uint32_t buf = ti & 1;
+            tc::mbar_wait<20>(&gfull[buf], (ti >> 1) & 1);
+            const uint32_t ga = tc::smem_u32(stg + buf * stg_stride), ma = ga + gbytes;
+            const int64_t node0 = ((int64_t)t * 2 + rank) * AGG_NPT;
+            const bool have = node_on && node0 + f < sc.n_nodes;
+            for (int kb = 0; kb < total_kb; ++kb) {
+                tc::mbar_wait<20>(&aempty[kb], (ti & 1) ^ 1);
+                const int c0 = kb * 64 + j * 8;
+                if (node_on) {
+                    uint32_t gh[4] = {0u, 0u, 0u, 0u};
+                    unsigned rb[AGG_W];                       // per slot: the byte of channel bits c0 .. c0 + 7 of row 9 f + sl
+#pragma unroll
+                    for (int sl = 0; sl < AGG_W; ++sl) rb[sl] = 0u;
+                    if (have && c0 < zb.c_out) {
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(gh[0]), "=r"(gh[1]), "=r"(gh[2]), "=r"(gh[3])
+                                     : "r"(ga + ((uint32_t)f * (uint32_t)zb.c_out + (uint32_t)c0) * 2u));
+                        const uint32_t mrow = ma + (9u * (uint32_t)f * cw + (uint32_t)(c0 >> 5)) * 4u;
+                        const unsigned bsh = (unsigned)(c0 & 31);            // 0, 8, 16, 24
+#pragma unroll
+                        for (int sl = 0; sl < AGG_W; ++sl) rb[sl] = (tc::lds_u32(mrow + (uint32_t)sl * cw * 4u) >> bsh) & 0xFFu;
+                    }
+                    const uint32_t kbase = tc::smem_u32(act + kb * TC_TILE_BYTES);
+#pragma unroll
+                    for (int sl = 0; sl < AGG_W; ++sl) {
+                        const uint32_t r = 9u * (uint32_t)f + (uint32_t)sl;
+                        uint32_t o[4];
+#pragma unroll
+                        for (int p2 = 0; p2 < 4; ++p2) {
+                            const uint32_t t2 = (rb[sl] >> (2 * p2)) & 3u;           // bits of channels 2 p2, 2 p2 + 1 -> low / high half
+                            o[p2] = gh[p2] & (((t2 * 0x8001u) & 0x00010001u) * 0xFFFFu);
+                        }
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(kbase + r * 128u + (((uint32_t)j ^ (r & 7u)) << 4)),
+                                     "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                    }
+                }
+                tc::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive_cluster_relaxed(&afull[kb], 0);
+                __syncwarp();
+            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&gempty[buf]);
+            __syncwarp();
+        }
+    } else {
+        // ---- epilogue ---------------------------------------------------------------------------------------------------
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const float inv = sc.scale_bits != nullptr ? gnb_pow2_scale(*sc.scale_bits).y : 1.f;
+        float colacc0 = 0.f, colacc1 = 0.f;
+        uint32_t vt_i = 0, ti = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++ti) {
+            const uint32_t mbuf = ti & 1;
+            for (int g = 0; g < ngroups; ++g, ++vt_i) {
+                const uint32_t buf = vt_i & 1;
+                const int ch0 = g * 256 + (int)rank * 128;
+                const int ch = ch0 + q * 32 + lane;
+                const bool ch_ok = ch < n_out;
+                tc::mbar_wait<100>(&tmem_full[buf], (vt_i >> 1) & 1);
+                tc::tcgen05_fence_after();
+                tc::mbar_wait<100>(&meta_full[mbuf], (ti >> 1) & 1);
+                const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + half * 128);
+                const int64_t node0 = ((int64_t)t * 2 + half) * AGG_NPT;
+                if (node0 < sc.n_nodes && ch0 + q * 32 < n_out) {
+                    const uint32_t mb_a = tc::smem_u32(meta + (mbuf * 2 + half) * meta_stride);
+                    const uint32_t mword = 4u * (uint32_t)(ch0 >> 7) + (uint32_t)(lane & 3);
+                    float* dq = sc.dq + (ch_ok ? ch : ch % sc.hdim);
+                    float* dp = sc.dp + node0 * sc.lddp + ch;
+                    const unsigned lanebit = ch_ok ? (1u << (q * 8 + (lane >> 2))) : 0u;
+                    scat_tile_any<true>(sc.mask_ld, tcol, mb_a, mb_a + meta_stride - 512u, mword, lanebit, dq, dp, sc.lddp,
+                                        sc.n_nodes - node0, ch_ok, (dbg & 64) != 0, sc.round_p != 0, g == 0 ? colacc0 : colacc1, inv);
+                }
+                tc::tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    tc::mbar_arrive_cluster_relaxed(&tmem_empty[buf], 0);
+                    tc::mbar_arrive(&meta_empty[mbuf]);
+                }
+                __syncwarp();
+            }
+        }
+        if (sc.dbias != nullptr) {
+            const int c0 = (int)rank * 128 + q * 32 + lane, c1 = 256 + c0;
+            if (c0 < n_out) atomicAdd(sc.dbias + c0, colacc0);
+            if (c1 < n_out && ngroups > 1) atomicAdd(sc.dbias + c1, colacc1);
+        }
+    }
+    __syncwarp();
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();
+    if (warp == 1) tc::tmem_dealloc_2cta<512>(tmem_base);
+}
+
 // dst[r, c] = rna_tf32(src[r, c]) for c < cols, 0 for cols <= c < dst_cols
 __global__ void round_pad_tf32_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
                                       float* __restrict__ dst, int64_t ldd, int dst_cols) {
@@ -1432,6 +1695,8 @@ cudaError_t init_tc_kernels() {
         e = cudaFuncSetAttribute(gemm_bf_pair_dual_scatter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_tc_pair_dual_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_f16_pair_scatter_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
     if (e == cudaSuccess) g_num_sms = sms;
     return e;
 }
@@ -2000,5 +2265,48 @@ GNB_EXPORT int gnb_to_f16_planes(const float* src, int64_t lds, int64_t rows, in
     if (total == 0) return GNB_OK;
     to_f16_planes_kernel<<<gnb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, rows, cols, (__half*)p0, (__half*)p1, ldd,
                                                                                      dst_cols, transpose);
+    GNB_RETURN_LAUNCH();
+}
+
+// gnb_edge_hidden_dgrad_scatter_f16 WITHOUT a stored dz: the kernel expands dz[(i, s), :] = g16[i, :] * bit(i, s, :) itself from
+// the outputs of gnb_edge_dz_prep: g16 [n, c_out] = fp16(g * 2^s) (contiguous rows) and the row-major ReLU bits
+// rowmask[(i * 9 + s) * (c_out / 32) + c / 32] (rows padded to whole 14-node tiles). wt = W2^T as one fp16 plane
+// [hdim, ldw >= c_out]; *scale_bits as given to gnb_edge_dz_prep. c_out <= 256, c_out % 64 == 0.
+GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_f16_masked(const void* g16, const uint32_t* rowmask, int32_t c_out, const void* wt,
+                                                        int64_t ldw, const uint32_t* hmask, int32_t mask_ld, int32_t hdim,
+                                                        const int32_t* nbr, int64_t n, float* dq, int64_t lddq, float* dp,
+                                                        int64_t lddp, float* dbias, int32_t flags, const uint32_t* scale_bits,
+                                                        void* stream) {
+    if (n < 0 || hdim < 1 || hdim > 512 || c_out < 64 || c_out > 256 || (c_out & 63) || lddq < hdim || lddp < hdim || dq == nullptr ||
+        dp == nullptr || g16 == nullptr || rowmask == nullptr || wt == nullptr || scale_bits == nullptr)
+        return GNB_ERR_ARG;
+    if ((ldw & 7) || ldw < c_out || (reinterpret_cast<uintptr_t>(g16) & 15u) || (reinterpret_cast<uintptr_t>(rowmask) & 15u))
+        return GNB_ERR_ARG;
+    if ((mask_ld & 3) || mask_ld > SC_MAX_MASK_LD || mask_ld < 4 * ((hdim + 127) / 128)) return GNB_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(hmask) & 15u) || n * lddq >= ((int64_t)1 << 31)) return GNB_ERR_ARG;
+    if (n == 0) return GNB_OK;
+    const int64_t rows = n * AGG_W;
+    if (rows >= (int64_t)1 << 31) return GNB_ERR_ARG;
+    const int kblocks = (c_out + 63) / 64;
+    CUtensorMap tw;
+    int rc = gnb_make_tmap_16(&tw, wt, hdim, c_out, ldw * 2, TC_BM, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    GNB_CHECK(init_tc_kernels());
+    ScatInfo sc{nbr, hmask, mask_ld, dq, lddq, hdim, n, 1, dp, lddp, dbias, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0, scale_bits};
+    const uint32_t mstride = sc_meta_stride(mask_ld);
+    const uint32_t stg = 2u * ((uint32_t)AGG_NPT * (uint32_t)c_out * 2u + (uint32_t)AGG_ROWS * (uint32_t)(c_out >> 5) * 4u);
+    const int64_t left = (int64_t)PL_MAX_DYN_SMEM - 1024 - DU_BAR_BYTES - 4 * (int64_t)mstride - stg - (int64_t)kblocks * TC_TILE_BYTES;
+    int nst_w = left > 0 ? (int)(left / TC_TILE_BYTES) : 0;
+    if (nst_w > PL_MAX_STAGES) nst_w = PL_MAX_STAGES;
+    if (nst_w < 3) return GNB_ERR_UNSUPPORTED;
+    const int tiles = (gnb_div_up(n, AGG_NPT) + 1) / 2;
+    int clusters = g_num_sms / 2;
+    if (clusters > tiles) clusters = tiles;
+    if (clusters < 1) clusters = 1;
+    const uint32_t smem = 1024 + (uint32_t)(kblocks + nst_w) * TC_TILE_BYTES + DU_BAR_BYTES + 4 * mstride + stg;
+    DzBuild zb{(const __half*)g16, rowmask, c_out};
+    const int last_ksteps = (c_out - 64 * (kblocks - 1) + 15) / 16;
+    gemm_f16_pair_scatter_build_kernel<<<dim3((unsigned)(2 * clusters)), DB_THREADS, smem, (cudaStream_t)stream>>>(
+        tw, zb, kblocks, last_ksteps, rows, hdim, tiles, sc, nst_w, mstride, g_linear_dbg, hdim > 256 ? 2 : 1);
     GNB_RETURN_LAUNCH();
 }

@@ -1273,3 +1273,41 @@ GNB_EXPORT int gnb_zero_block(float* a, int64_t lda, int64_t rows, int32_t cols,
     zero_block_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(a, lda, rows, cols >> 2);
     GNB_RETURN_LAUNCH();
 }
+
+
+// Bias gradient of the aggregating Linear without a stored dz: db[c] += sum_i g[i, c] * popcount(bits 9 (i % 14) .. + 9 of
+// maskbits[(i / 14), c]) -- column sums of dz = g * bit, from [n, cols] + the mask words only. CTA = 256 channels x tiles.
+__global__ void __launch_bounds__(256) edge_mask_colsum_kernel(const float* __restrict__ g, int64_t ldg, const uint4* __restrict__ mask4,
+                                                                int64_t n, int cols, float* __restrict__ db, int64_t n_tiles) {
+    const int c = blockIdx.y * 256 + threadIdx.x;
+    if (c >= cols) return;
+    float acc = 0.f;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t node0 = tile * EM_NPT;
+        float gv[EM_NPT];
+#pragma unroll
+        for (int f = 0; f < EM_NPT; ++f) {            // 15 independent loads in flight (clamped rows: masked out below)
+            const int64_t nd = node0 + f < n ? node0 + f : n - 1;
+            gv[f] = g[nd * ldg + c];
+        }
+        const uint4 m = mask4[tile * cols + c];
+        const unsigned w[5] = {m.x, m.y, m.z, m.w, 0u};
+#pragma unroll
+        for (int f = 0; f < EM_NPT; ++f) {
+            const int bp = 9 * f;                                                   // compile-time after unrolling
+            const unsigned b9 = __funnelshift_r(w[bp >> 5], w[(bp >> 5) + 1], bp & 31) & 0x1FFu;
+            acc += (node0 + f < n) ? gv[f] * (float)__popc(b9) : 0.f;
+        }
+    }
+    atomicAdd(db + c, acc);
+}
+GNB_EXPORT int gnb_edge_mask_colsum(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols, float* db,
+                                    void* stream) {
+    if (maskbits == nullptr || g == nullptr || db == nullptr || cols < 1 || !aligned16(maskbits)) return GNB_ERR_ARG;
+    if (n == 0) return GNB_OK;
+    const int64_t n_tiles = (n + EM_NPT - 1) / EM_NPT;
+    const int64_t max_ctas = 148 * 8;
+    dim3 grid((unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas), (unsigned)gnb_div_up(cols, 256));
+    edge_mask_colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, ldg, reinterpret_cast<const uint4*>(maskbits), n, cols, db, n_tiles);
+    GNB_RETURN_LAUNCH();
+}

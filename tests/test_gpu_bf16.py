@@ -392,10 +392,16 @@ def test_edge_linear_agg_f16_bit_exact(ops, np_, which, k, n_out):
     y = torch.empty(n, n_out, device="cuda")
     mask = torch.zeros((n + 13) // 14 * n_out * 4, dtype=torch.int32, device="cuda")
     bc = b.cuda()
+    rowmask = torch.full(((n + 13) // 14 * 126, n_out // 32), -1, dtype=torch.int32, device="cuda") if n_out % 32 == 0 else None
     ops._call("gnb_edge_linear_agg_fwd_f16", ops._ptr(h0), ops._ptr(h1), h0.shape[1], k, ops._ptr(w0), ops._ptr(w1), kw,
-              ops._ptr(bc), ops._ptr(graph.deg), n, n_out, 0, ops._ptr(y), n_out, ops._ptr(mask), ops._ptr(word), ops._stream())
+              ops._ptr(bc), ops._ptr(graph.deg), n, n_out, 0, ops._ptr(y), n_out, ops._ptr(mask), ops._ptr(word), ops._ptr(rowmask),
+              ops._stream())
     torch.cuda.synchronize()
     assert torch.equal(y.cpu().double(), y_ref)
+    if rowmask is not None:        # the row-major copy of the ReLU bits: bit c % 32 of word c / 32 of row (i, s)
+        rm = rowmask.cpu()[: n * 9].long() & 0xFFFFFFFF
+        got = ((rm.unsqueeze(2) >> torch.arange(32).view(1, 1, 32)) & 1).reshape(n * 9, n_out).bool()
+        assert torch.equal(got, on)
 
 
 @pytest.mark.parametrize("planes_x", [1, 2])
@@ -459,6 +465,119 @@ def test_dgrad_scatter_f16_bit_exact(ops, hdim, c_out, variant):
     assert torch.equal(dp.cpu().double(), dp_ref)
     assert torch.equal(dq.cpu().double(), dq_ref)
     assert torch.equal(dbias.cpu().double(), dp_ref.sum(0))
+
+
+def _mask_case(ops, sizes, n_out, seed, gmax):
+    """Random ReLU bit masks in the aggregating epilogue's layout (bits of padding slots zero), a gradient g, and the dz they
+    imply: dz[(i, s), c] = g[i, c] * bit."""
+    graph, n = _graph(ops, sizes, seed=seed)
+    gen = torch.Generator().manual_seed(seed)
+    deg = graph.deg.cpu()
+    valid = (torch.arange(9).unsqueeze(0) < deg.unsqueeze(1))                       # [n, 9]
+    bits = (torch.rand(n, 9, n_out, generator=gen) < 0.55) & valid.unsqueeze(2)     # [n, 9, C]
+    ntile = (n + 13) // 14
+    full = torch.zeros(ntile * 14, 9, n_out, dtype=torch.bool)
+    full[:n] = bits
+    cols = full.reshape(ntile, 126, n_out)                                           # bit index 9 f + s
+    words = torch.zeros(ntile, n_out, 4, dtype=torch.int64)
+    for w in range(4):
+        chunk = cols[:, 32 * w: min(126, 32 * w + 32)]                               # [ntile, <=32, C]
+        sh = torch.arange(chunk.shape[1]).view(1, -1, 1)
+        words[:, :, w] = (chunk.long() << sh).sum(1)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).int().reshape(-1).cuda()
+    # the row-major copy: word c / 32 of row (i, s), bit c % 32 (rows padded to whole tiles)
+    rowm = None
+    if n_out % 32 == 0:
+        rb = full.reshape(ntile * 126, n_out // 32, 32).long()
+        rowm = (rb << torch.arange(32).view(1, 1, 32)).sum(2)
+        rowm = torch.where(rowm >= 2 ** 31, rowm - 2 ** 32, rowm).int().cuda()
+    g = torch.randint(-4, 5, (n, n_out), generator=gen).float() * (gmax / 4)
+    dz = (g.unsqueeze(1) * bits).reshape(n * 9, n_out)
+    return graph, n, words, g, dz, rowm
+
+
+@pytest.mark.parametrize("n_out,k_in,sizes", [(256, 336, [1, 2, 5, 9, 10, 64, 130, 12, 300, 3, 700]), (256, 128, [400, 900, 14, 15]),
+                                              (96, 344, [77, 5, 230]), (256, 336, [3000, 2500])])
+def test_wgrad_f16_masked_bit_exact(ops, n_out, k_in, sizes):
+    """dW2 with dz expanded inside the kernel from g and the mask words == the same product on a stored dz (fp64 reference)."""
+    graph, n, words, g, dz, rowm = _mask_case(ops, sizes, n_out, seed=n_out + k_in, gmax=2.0 ** -9)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randint(-2, 3, (n * 9, k_in), generator=gen).float()
+    wz, _ = _scale_word(2.0 ** -9)
+    wx, sx = _scale_word(2.0)
+    ref = dz.double().t() @ x.double()
+    x16 = (x * sx).half().cuda()
+    gc = g.cuda()
+    dw = torch.zeros(n_out, k_in, device="cuda")
+    ops._call("gnb_linear_bwd_weight_f16_masked", ops._ptr(gc), n_out, ops._ptr(rowm), ops._ptr(x16), k_in, ops._ptr(dw), k_in, n,
+              n_out, k_in, ops._ptr(wz), ops._ptr(wx), ops._stream())
+    db = torch.zeros(n_out, device="cuda")
+    ops._call("gnb_edge_mask_colsum", ops._ptr(gc), n_out, ops._ptr(words), n, n_out, ops._ptr(db), ops._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(dw.cpu().double(), ref)
+    assert torch.equal(db.cpu().double(), dz.double().sum(0))
+
+
+@pytest.mark.parametrize("hdim,c_out,sizes", [(336, 256, [1, 2, 5, 9, 10, 64, 130, 12, 300, 3, 500]), (128, 256, [400, 900, 14, 15]),
+                                              (40, 128, [77, 5, 230]), (336, 256, [3000, 2500]), (512, 64, [100, 37])])
+def test_dgrad_scatter_f16_masked_bit_exact(ops, hdim, c_out, sizes):
+    graph, n, words, g, dz, rowm = _mask_case(ops, sizes, c_out, seed=hdim + c_out, gmax=2.0 ** -20)
+    gen = torch.Generator().manual_seed(hdim)
+    w2 = torch.randint(-8, 9, (c_out, hdim), generator=gen).float() / 8
+    word, _ = _scale_word(2.0 ** -20)
+    nbr, deg = graph.nbr.cpu().long(), graph.deg.cpu()
+    valid = ((torch.arange(9).unsqueeze(0) < deg.unsqueeze(1)) & (nbr >= 0)).reshape(-1)
+    hbits = torch.rand(n * 9, hdim, generator=gen) < 0.6
+    mld = 4 * ((hdim + 127) // 128)
+    rows_m = (n + 13) // 14 * 126
+    c = torch.arange(hdim)
+    word_i, bit = 4 * (c // 128) + c % 4, (c % 128) // 4
+    hm = torch.zeros(rows_m, mld, dtype=torch.int64)
+    hm[: n * 9].index_put_((torch.arange(n * 9).unsqueeze(1).expand(-1, hdim), word_i.unsqueeze(0).expand(n * 9, -1)),
+                           hbits.long() << bit.unsqueeze(0), accumulate=True)
+    hm = torch.where(hm >= 2 ** 31, hm - 2 ** 32, hm).int().cuda()
+    da = (dz.double() @ w2.double()) * hbits
+    dp_ref = da.reshape(n, 9, hdim).sum(1)
+    dq_ref = torch.zeros(n, hdim, dtype=torch.float64)
+    dq_ref.index_add_(0, nbr.reshape(-1).clamp(min=0)[valid], da[valid])
+    cw = (c_out + 63) // 64 * 64
+    wt16, _ = f16_planes(ops, w2.cuda(), 1, dst_cols=cw, transpose=True)
+    dq = torch.zeros(n, hdim, device="cuda")
+    dp = torch.full((n, hdim), 9.0, device="cuda")
+    dbias = torch.zeros(hdim, device="cuda")
+    gc = g.cuda()
+    ops._call("gnb_edge_hidden_dgrad_scatter_f16_masked", ops._ptr(gc), c_out, ops._ptr(rowm), c_out, ops._ptr(wt16), cw, ops._ptr(hm),
+              mld, hdim, ops._ptr(graph.nbr), n, ops._ptr(dq), hdim, ops._ptr(dp), hdim, ops._ptr(dbias), 0, ops._ptr(word),
+              ops._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(dp.cpu().double(), dp_ref)
+    assert torch.equal(dq.cpu().double(), dq_ref)
+    assert torch.equal(dbias.cpu().double(), dp_ref.sum(0))
+
+
+def test_mixed16_stored_dz_route_matches_the_masked_route(ops):
+    """Executor flag bit 2 (ops.STORE_DZ): the stored-dz backward and the in-kernel expansion compute the same gradients."""
+    from graphnet_b200 import Data
+    from graphnet_b200.models.gnn import DynEdge
+    from graphnet_b200.models.graphs.edges import KNNEdges
+    from graphnet_b200.synthetic import make_batch
+    ops.set_precision("mixed16")
+    raw = make_batch(24, seed=11, n_max=500)
+    x, batch, n_pulses = (torch.from_numpy(raw[k]) for k in ("x", "batch", "n_pulses"))
+    torch.manual_seed(3)
+    model = DynEdge(7, global_pooling_schemes=["min", "max", "mean", "sum"]).cuda()
+    data = KNNEdges(8)(Data(x=x.cuda(), batch=batch.cuda(), n_pulses=n_pulses.cuda()))
+    grads = []
+    for store in (False, True):
+        ops.STORE_DZ = store
+        try:
+            model.zero_grad(set_to_none=True)
+            model(data).square().sum().backward()
+            grads.append([p.grad.clone() for p in model.parameters()])
+        finally:
+            ops.STORE_DZ = False
+    for a, b in zip(*grads):
+        assert rel_err(a, b) < 2e-5
 
 
 MODE_TOL = {"bf16": (5e-3, 1.5e-2), "bf16x3": (2e-5, 1e-3), "mixed16": (2e-5, 1e-3), "f16": (1e-3, 3e-3)}
