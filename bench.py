@@ -467,12 +467,12 @@ def dominant_launches(trainer, db):
     dz16 = (dz * zscale).half()
     dwg = torch.zeros(cout, hid, device=dev)
     rowmask = torch.randint(-2 ** 31, 2 ** 31 - 1, (ntile * 126, cout // 32), dtype=torch.int32, device=dev)
-    gy = torch.randn(n, cout, device=dev)
+    g16 = torch.randn(n, cout, device=dev).half()
 
     def agg_fwd_f16x3():
         ops._call("gnb_edge_linear_agg_fwd_f16", ops._ptr(h16[0]), ops._ptr(h16[1]), hid, hid, ops._ptr(w16[0]), ops._ptr(w16[1]),
                   hld64, ops._ptr(b2), ops._ptr(graph.deg), n, cout, 0, ops._ptr(y), cout, ops._ptr(maskbits), ops._ptr(hw),
-                  ops._ptr(rowmask), ops._stream())
+                  ops._stream())
 
     def dgrad_scatter_f16():
         ops._call("gnb_edge_hidden_dgrad_scatter_f16", ops._ptr(dz16), cout, cout, ops._ptr(wt16[0]), cld64, ops._ptr(hmask), mld,
@@ -484,15 +484,15 @@ def dominant_launches(trainer, db):
                   cout, hid, ops._ptr(zw), ops._ptr(hw), ops._stream())
 
     def wgrad_f16_masked():
-        ops._call("gnb_linear_bwd_weight_f16_masked", ops._ptr(gy), cout, ops._ptr(rowmask), ops._ptr(h16[0]), hid, ops._ptr(dwg), hid, n,
+        ops._call("gnb_linear_bwd_weight_f16_masked", ops._ptr(g16), ops._ptr(rowmask), ops._ptr(h16[0]), hid, ops._ptr(dwg), hid, n,
                   cout, hid, ops._ptr(zw), ops._ptr(hw), ops._stream())
 
     def dgrad_scatter_f16_masked():
-        ops._call("gnb_edge_hidden_dgrad_scatter_f16_masked", ops._ptr(gy), cout, ops._ptr(rowmask), cout, ops._ptr(wt16[0]), cld64,
+        ops._call("gnb_edge_hidden_dgrad_scatter_f16_masked", ops._ptr(g16), ops._ptr(rowmask), cout, ops._ptr(wt16[0]), cld64,
                   ops._ptr(hmask), mld, hid, ops._ptr(graph.nbr), n, ops._ptr(dpq[:, hid:]), 2 * hid, ops._ptr(dpq), 2 * hid,
                   ops._ptr(None), 0, ops._ptr(zw), ops._stream())
 
-    keep = (h, h_raw, w2p, w_hi, w_lo, b2, y, maskbits, dz, wt, hmask, dpq, graph, hw, zw, h16, w16, wt16, dz16, dwg, rowmask, gy)
+    keep = (h, h_raw, w2p, w_hi, w_lo, b2, y, maskbits, dz, wt, hmask, dpq, graph, hw, zw, h16, w16, wt16, dz16, dwg, rowmask, g16)
     e_real = int(graph.deg.sum().item())
     return {"agg_fwd": agg_fwd, "agg_fwd_x3": agg_fwd_x3, "dgrad_scatter": dgrad_scatter, "agg_fwd_f16x3": agg_fwd_f16x3,
             "dgrad_scatter_f16": dgrad_scatter_f16, "wgrad_f16": wgrad_f16, "wgrad_f16_masked": wgrad_f16_masked,

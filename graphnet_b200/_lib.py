@@ -73,16 +73,16 @@ SIGNATURES: Dict[str, list] = {
     "gnb_to_bf16_planes": [_p, _i64, _i64, _i32, _p, _p, _i64, _i32, _i32, _p],
     "gnb_absmax_bits": [_p, _i64, _i64, _i32, _i32, _p, _p],
     "gnb_edge_hidden_fwd_f16": [_p, _i64, _i32, _p, _p, _i32, _i64, _p, _p, _i64, _p, _i32, _p, _p],
-    "gnb_edge_linear_agg_fwd_f16": [_p, _p, _i64, _i32, _p, _p, _i64, _p, _p, _i64, _i32, _i32, _p, _i64, _p, _p, _p, _p],
+    "gnb_edge_linear_agg_fwd_f16": [_p, _p, _i64, _i32, _p, _p, _i64, _p, _p, _i64, _i32, _i32, _p, _i64, _p, _p, _p],
     "gnb_edge_mask_bwd_colsum_f16": [_p, _i64, _p, _i64, _i32, _p, _i64, _p, _p, _p],
     "gnb_linear_bwd_weight_f16": [_p, _i64, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _p, _p, _p],
     "gnb_edge_hidden_dgrad_scatter_f16": [_p, _i64, _i32, _p, _i64, _p, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _i32,
                                           _p, _p],
     "gnb_zero_block": [_p, _i64, _i64, _i32, _p],
-    "gnb_linear_bwd_weight_f16_masked": [_p, _i64, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _p, _p, _p],
-    "gnb_edge_hidden_dgrad_scatter_f16_masked": [_p, _i64, _p, _i32, _p, _i64, _p, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _p,
+    "gnb_edge_dz_prep": [_p, _i64, _p, _i64, _i32, _p, _p, _p, _p, _p],
+    "gnb_linear_bwd_weight_f16_masked": [_p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _p, _p, _p],
+    "gnb_edge_hidden_dgrad_scatter_f16_masked": [_p, _p, _i32, _p, _i64, _p, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _p,
                                                  _i32, _p, _p],
-    "gnb_edge_mask_colsum": [_p, _i64, _p, _i64, _i32, _p, _p],
     "gnb_linear_next_absmax": [_p, _i32],
     "gnb_to_f16_planes": [_p, _i64, _i64, _i32, _p, _p, _i64, _i32, _i32, _p],
 }

@@ -65,18 +65,18 @@ int gnb_edge_hidden_dgrad_scatter_bf16(const void*, const void*, int64_t, int32_
 int gnb_to_bf16_planes(const float*, int64_t, int64_t, int32_t, void*, void*, int64_t, int32_t, int32_t, void*);
 int gnb_zero_block(float*, int64_t, int64_t, int32_t, void*);
 int gnb_linear_next_absmax(uint32_t*, int32_t);
-int gnb_linear_bwd_weight_f16_masked(const float*, int64_t, const uint32_t*, const void*, int64_t, float*, int64_t, int64_t, int32_t,
-                                     int32_t, const uint32_t*, const uint32_t*, void*);
-int gnb_edge_hidden_dgrad_scatter_f16_masked(const float*, int64_t, const uint32_t*, int32_t, const void*, int64_t, const uint32_t*,
-                                             int32_t, int32_t, const int32_t*, int64_t, float*, int64_t, float*, int64_t, float*,
-                                             int32_t, const uint32_t*, void*);
-int gnb_edge_mask_colsum(const float*, int64_t, const uint32_t*, int64_t, int32_t, float*, void*);
+int gnb_linear_bwd_weight_f16_masked(const void*, const uint32_t*, const void*, int64_t, float*, int64_t, int64_t, int32_t, int32_t,
+                                     const uint32_t*, const uint32_t*, void*);
+int gnb_edge_hidden_dgrad_scatter_f16_masked(const void*, const uint32_t*, int32_t, const void*, int64_t, const uint32_t*, int32_t,
+                                             int32_t, const int32_t*, int64_t, float*, int64_t, float*, int64_t, float*, int32_t,
+                                             const uint32_t*, void*);
+int gnb_edge_dz_prep(const float*, int64_t, const uint32_t*, int64_t, int32_t, const uint32_t*, void*, uint32_t*, float*, void*);
 int gnb_to_f16_planes(const float*, int64_t, int64_t, int32_t, void*, void*, int64_t, int32_t, int32_t, void*);
 int gnb_absmax_bits(const float*, int64_t, int64_t, int32_t, int32_t, uint32_t*, void*);
 int gnb_edge_hidden_fwd_f16(const float*, int64_t, int32_t, const int32_t*, const int32_t*, int32_t, int64_t, void*, void*, int64_t,
                             uint32_t*, int32_t, const uint32_t*, void*);
 int gnb_edge_linear_agg_fwd_f16(const void*, const void*, int64_t, int32_t, const void*, const void*, int64_t, const float*,
-                                const int32_t*, int64_t, int32_t, int32_t, float*, int64_t, uint32_t*, const uint32_t*, uint32_t*, void*);
+                                const int32_t*, int64_t, int32_t, int32_t, float*, int64_t, uint32_t*, const uint32_t*, void*);
 int gnb_edge_mask_bwd_colsum_f16(const float*, int64_t, const uint32_t*, int64_t, int32_t, void*, int64_t, float*, const uint32_t*, void*);
 int gnb_linear_bwd_weight_f16(const void*, int64_t, const void*, const void*, int64_t, float*, int64_t, int64_t, int32_t, int32_t,
                               const uint32_t*, const uint32_t*, void*);
@@ -223,7 +223,7 @@ struct Arena {
     }
 };
 
-struct ConvBuf { float *wcat, *wcat_lo, *w2p_lo, *bcat, *w2p, *pq, *h, *m, *y; int32_t *nbr, *deg; uint32_t *mask, *hmask, *rowmask; int cin, cin_ld, kld, hid, hld, cout, mld;
+struct ConvBuf { float *wcat, *wcat_lo, *w2p_lo, *bcat, *w2p, *pq, *h, *m, *y; int32_t *nbr, *deg; uint32_t *mask, *hmask; bool nodz; int cin, cin_ld, kld, hid, hld, cout, mld;
                  // bf16 modes: h planes [n * 9, hid], W2 planes [cout, hld64], W2^T planes [hid, cld64]
                  __nv_bfloat16 *hb[2], *w2b[2], *w2tb[2]; int hld64, cld64; };
 struct DenseBuf { float *wp, *wp_lo, *z; int k_total, kld, n_out; };
@@ -243,6 +243,7 @@ struct Plan {
     __nv_bfloat16* dzb[2];               // bf16 modes: dz planes [n * 9, max_c]
     int bf;                              // bf16 planes per per-edge tensor (0: fp32 / tf32 tensors)
     bool mixed;                          // mode 5: dz / W2^T as one fp16 plane in the backward pass
+    __nv_bfloat16* g16; uint32_t* rowmask;   // dz-free backward: fp16(g_y 2^s) [n, max_c] and row-major ReLU bits [tiles * 126, max_c / 32]
     uint32_t* scale_bits;                // mixed16: [2][GNB_MAX_LAYERS] fp32 bits of 2 max|PQ| (>= max h) and of max|g_y| per layer
     int64_t bytes;
 };
@@ -311,9 +312,8 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
         b.h = p.bf ? nullptr : (training ? a.get<float>(n * wl * b.hid) : h_shared);
         b.m = training ? (p.agg ? nullptr : a.get<float>(n * wl * b.cout)) : m_shared;
         b.mask = (p.agg && training) ? a.get<uint32_t>((n + 13) / 14 * (int64_t)b.cout * 4) : nullptr;
-        // fp16-plane modes: row-major copy of the same bits for the backward GEMMs that expand dz themselves (no stored dz)
-        b.rowmask = (p.mixed && training && !(c.flags & 4) && b.cout <= 256 && (b.cout & 63) == 0 && wl == 9)
-                        ? a.get<uint32_t>((n + 13) / 14 * 126 * (int64_t)(b.cout / 32)) : nullptr;
+        // fp16-plane modes: the backward GEMMs expand dz themselves (no stored dz) where the shapes allow it
+        b.nodz = p.mixed && training && !(c.flags & 4) && b.cout <= 256 && (b.cout & 63) == 0 && wl == 9;
         // activation bits of h for the scattering data-gradient epilogue (whole 14-node tiles, mld words per slot row)
         b.mld = 4 * ((b.hid + 127) / 128);
         const bool scat = p.agg && training && b.hid <= 512 && n * 2 * b.hid < ((int64_t)1 << 31);
@@ -372,7 +372,12 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
         for (int l = 0; l <= c.n_conv; ++l) p.gnode[l] = l == 0 ? nullptr : a.get<float>(n * c.conv_out[l - 1]);
         p.dz_big = p.bf ? nullptr : a.get<float>(n * max_w * max_c);
         p.dh_big = p.bf ? nullptr : a.get<float>(n * max_w * max_h);
-        for (int pl = 0; pl < 2; ++pl) p.dzb[pl] = (pl < p.bf && !(p.mixed && pl == 1)) ? a.get<__nv_bfloat16>(n * max_w * max_c) : nullptr;
+        bool any_dz = false, any_nodz = false;
+        for (int l = 0; l < c.n_conv; ++l) { any_dz = any_dz || !p.conv[l].nodz; any_nodz = any_nodz || p.conv[l].nodz; }
+        for (int pl = 0; pl < 2; ++pl)
+            p.dzb[pl] = (pl < p.bf && !(p.mixed && pl == 1) && any_dz) ? a.get<__nv_bfloat16>(n * max_w * max_c) : nullptr;
+        p.g16 = any_nodz ? a.get<__nv_bfloat16>(n * (int64_t)max_c) : nullptr;
+        p.rowmask = any_nodz ? a.get<uint32_t>((n + 13) / 14 * 126 * (int64_t)(max_c / 32)) : nullptr;
         p.dpq = a.get<float>(n * 2 * max_h);
         p.dzq = a.get<float>(n * 2 * max_h);
         int64_t max_wp = 0, max_dense = 0;
@@ -541,7 +546,7 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
                 if (training) EX(gnb_to_f16_planes(w2, b.hid, b.cout, b.hid, b.w2tb[0], nullptr, b.cld64, b.cld64, 1, stream));
                 EX(gnb_edge_hidden_fwd_f16(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, b.hb[0], b.hb[1], b.hid, b.hmask, b.mld, hs, stream));
                 EX(gnb_edge_linear_agg_fwd_f16(b.hb[0], b.hb[1], b.hid, b.hid, b.w2b[0], b.w2b[1], b.hld64, b2, deg, n, b.cout,
-                                               e.fround ? 1 : 0, b.y, b.cout, b.mask, hs, b.rowmask, stream));
+                                               e.fround ? 1 : 0, b.y, b.cout, b.mask, hs, stream));
             } else {
                 EX(gnb_to_bf16_planes(w2, b.hid, b.cout, b.hid, b.w2b[0], b.w2b[1], b.hld64, b.hld64, 0, stream));
                 if (training) EX(gnb_to_bf16_planes(w2, b.hid, b.cout, b.hid, b.w2tb[0], b.w2tb[1], b.cld64, b.cld64, 1, stream));
@@ -709,15 +714,16 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
         const int64_t rows = n * wl;
         const float* gy = p.gnode[l + 1];
         // fp16-plane modes: dz is expanded inside the two GEMMs instead of being stored (flags bit 2 keeps the stored-dz route)
-        const bool nodz = b.rowmask != nullptr;
+        const bool nodz = b.nodz;
         // (aggregate-bwd + ReLU-bwd + bias grad) in one pass
         if (p.mixed) {
             uint32_t* gs = p.scale_bits + GNB_MAX_LAYERS + l;      // zeroed by the forward pass
             EX(gnb_absmax_bits(gy, b.cout, n, b.cout, 0, gs, stream));
             if (nodz) {
                 // dz = g * mask bit is never stored: both GEMMs expand it in shared memory from g_y and the mask words
-                EX(gnb_edge_mask_colsum(gy, b.cout, b.mask, n, b.cout, gb2, stream));
-                EX(gnb_linear_bwd_weight_f16_masked(gy, b.cout, b.rowmask, b.hb[0], b.hid, gw2, b.hid, n, b.cout, b.hid, gs, p.scale_bits + l, stream));
+                // (one small pass writes fp16(g_y 2^s), the row-major bits and the bias gradient)
+                EX(gnb_edge_dz_prep(gy, b.cout, b.mask, n, b.cout, gs, p.g16, p.rowmask, gb2, stream));
+                EX(gnb_linear_bwd_weight_f16_masked(p.g16, p.rowmask, b.hb[0], b.hid, gw2, b.hid, n, b.cout, b.hid, gs, p.scale_bits + l, stream));
             } else {
                 EX(gnb_edge_mask_bwd_colsum_f16(gy, b.cout, b.mask, n, b.cout, p.dzb[0], b.cout, gb2, gs, stream));
                 EX(gnb_linear_bwd_weight_f16(p.dzb[0], b.cout, b.hb[0], nullptr, b.hid, gw2, b.hid, rows, b.cout, b.hid, gs, p.scale_bits + l, stream));
@@ -736,7 +742,7 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
         if (p.bf) {
             EX(gnb_zero_block(p.dzq + b.hid, 2 * b.hid, n, b.hid, stream));
             if (p.mixed && nodz)
-                EX(gnb_edge_hidden_dgrad_scatter_f16_masked(gy, b.cout, b.rowmask, b.cout, b.w2tb[0], b.cld64, b.hmask, b.mld, b.hid, nbr, n,
+                EX(gnb_edge_hidden_dgrad_scatter_f16_masked(p.g16, p.rowmask, b.cout, b.w2tb[0], b.cld64, b.hmask, b.mld, b.hid, nbr, n,
                                                             p.dzq + b.hid, 2 * b.hid, p.dzq, 2 * b.hid, p.dbtmp, e.rnd,
                                                             p.scale_bits + GNB_MAX_LAYERS + l, stream));
             else if (p.mixed)

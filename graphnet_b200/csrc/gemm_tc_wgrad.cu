@@ -314,33 +314,37 @@ gemm_bf_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_con
 
 
 // ---- weight gradient of the aggregating Linear WITHOUT a stored dz (fp16-plane modes) ------------------------------------------
-// dz[(i, s), c] = g[i, c] * bit(i, s, c) is a 9-fold redundant function of the node-level gradient g [n, n_out] and of the
-// ReLU bits the aggregating epilogue wrote in ROW-major form (rowmask[(i * 9 + s) * (n_out / 32) + c / 32], csrc/gemm_tc.cu). Four
-// builder warps expand, per 64-row stage, the rows' g values (scaled by the layer's power of two, rounded to fp16 once per
-// node) and mask bits straight into the MN-major 128-byte-swizzled B tile (row rr at rr * 128 B of its 64-channel box, 16-byte
-// chunk j at j ^ (rr & 7)): the kernel reads h (one fp16 plane, TMA) + g + mask words instead of h + dz, the HBM traffic that
-// bounds it drops from 0.85 to 0.5 GB per 713 k-row launch, and the mask-backward kernel no longer writes dz at all.
-// Warps: 0 TMA (A = h), 1 MMA, 2..5 epilogue, 6..9 builders. full[s] collects the TMA transaction + the 4 builder warps.
-constexpr int WGB_THREADS = 320, WGB_BK = 64, WGB_STAGES = 4;
+// dz[(i, s), c] = g[i, c] * bit(i, s, c) is a 9-fold redundant function of the node-level gradient and the ReLU bits of the
+// aggregating epilogue. Inputs as prepared by gnb_edge_dz_prep: g16 [n, n_out] = fp16(g * 2^s) and the row-major bits
+// rowmask[(i * 9 + s) * (n_out / 32) + c / 32]. Per 64-row stage the TMA warp also stages the <= 9 g16 rows the stage's nodes
+// need (one bulk copy); eight builder warps (8 rows each; lane = 8 consecutive channels) read the row's node values with one
+// 16-byte shared load, expand the row's byte of channel bits into two half-word masks per register and write the MN-major
+// 128-byte-swizzled B tile (row rr at rr * 128 B of its 64-channel box, chunk j at j ^ (rr & 7)) with one 16-byte store: the
+// kernel reads h (one fp16 plane) + 0.06 GB instead of h + dz, i.e. 0.54 instead of 0.85 GB per 713 k-row launch.
+// Warps: 0 TMA (A = h, g16 rows), 1 MMA, 2..5 epilogue, 6..13 builders. full[s] collects the TMA transaction + the 8 builder warps.
+constexpr int WGB_THREADS = 448, WGB_BK = 64, WGB_STAGES = 4, WGB_NB = 8;
 constexpr uint32_t WGB_BOX = WGB_BK * 128, WGB_A_BYTES = 2 * WGB_BOX, WGB_B_BYTES = 4 * WGB_BOX;
-constexpr uint32_t WGB_STAGE = WGB_A_BYTES + WGB_B_BYTES;
+constexpr uint32_t WGB_G_BYTES = 9 * 512;                               // <= 9 nodes x 256 channels x 2 B
+constexpr uint32_t WGB_STAGE = WGB_A_BYTES + WGB_B_BYTES + 5 * 1024;    // g16 rows behind the operand tiles (1 KiB-aligned stages)
 constexpr uint32_t WGB_SMEM_BYTES = WGB_STAGES * WGB_STAGE + 1024 + 256;
 
 __global__ void __launch_bounds__(WGB_THREADS, 1)
-gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ g, int64_t ldg,
-                            const unsigned* __restrict__ maskw, float* __restrict__ dw, int64_t lddw, int64_t rows, int n_out,
+gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __half* __restrict__ g16,
+                            const unsigned* __restrict__ rowmask, float* __restrict__ dw, int64_t lddw, int64_t rows, int n_out,
                             int k_in, int64_t rows_per_split, const unsigned* __restrict__ dz_scale_bits,
                             const unsigned* __restrict__ x_scale_bits) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + WGB_STAGES * WGB_STAGE);
     uint64_t* empty = full + WGB_STAGES;
-    uint64_t* tmem_full = empty + WGB_STAGES;
+    uint64_t* gfull = empty + WGB_STAGES;             // the stage's g16 rows landed
+    uint64_t* tmem_full = gfull + WGB_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kin0 = blockIdx.x * WG_BM;
     const int n_mma = (n_out + 15) & ~15;
+    const int64_t n_nodes = rows / 9;
     const int64_t r_lo = (int64_t)blockIdx.y * rows_per_split;
     int64_t r_hi = r_lo + rows_per_split;
     if (r_hi > rows) r_hi = rows;
@@ -349,7 +353,9 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const floa
     if (warp == 0 && lane == 0) tc::tma_prefetch_desc(&tm_x);
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < WGB_STAGES; ++s) { tc::mbar_init(&full[s], 5); tc::mbar_init(&empty[s], 1); }
+            for (int s = 0; s < WGB_STAGES; ++s) {
+                tc::mbar_init(&full[s], 1 + WGB_NB); tc::mbar_init(&empty[s], 1); tc::mbar_init(&gfull[s], 1);
+            }
             tc::mbar_init(tmem_full, 1);
             tc::fence_barrier_init();
             tc::fence_proxy_async();
@@ -369,11 +375,17 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const floa
                 const uint32_t ph = (it / WGB_STAGES) & 1;
                 tc::mbar_wait(&empty[s], ph ^ 1);
                 uint8_t* st = smem + s * WGB_STAGE;
-                const int r = (int)(r_lo + (int64_t)it * WGB_BK);
+                const int64_t r = r_lo + (int64_t)it * WGB_BK;
+                const int64_t nd0 = r / 9;
+                int64_t nd1 = (r + WGB_BK - 1) / 9 + 1;                 // one past the last node of the stage
+                nd1 = nd1 < n_nodes ? nd1 : n_nodes;
+                const uint32_t gb = nd1 > nd0 ? (uint32_t)(nd1 - nd0) * (uint32_t)n_out * 2u : 0u;
                 if (tc::elect_one()) {
+                    tc::mbar_arrive_expect_tx(&gfull[s], gb);
+                    if (gb) tc::bulk_load(st + WGB_A_BYTES + WGB_B_BYTES, g16 + nd0 * n_out, gb, &gfull[s]);
                     tc::mbar_arrive_expect_tx(&full[s], WGB_A_BYTES);
-                    tc::tma_load_2d(st, &tm_x, &full[s], kin0, r);
-                    tc::tma_load_2d(st + WGB_BOX, &tm_x, &full[s], kin0 + 64, r);
+                    tc::tma_load_2d(st, &tm_x, &full[s], kin0, (int)r);
+                    tc::tma_load_2d(st + WGB_BOX, &tm_x, &full[s], kin0 + 64, (int)r);
                 }
                 __syncwarp();
             }
@@ -400,74 +412,48 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const floa
             if (tc::elect_one()) tc::umma_commit(tmem_full);
             __syncwarp();
         } else if (warp >= 6) {
-            // ---- dz builders: lane = 8 consecutive channels, warp bw = rows [16 bw, 16 bw + 16) of the 64-row stage --------------
-            // 16 consecutive rows touch <= 3 nodes and <= 2 mask words per channel ((tile, w) and its successor: (tile, w + 1) or,
-            // across a tile boundary, (tile + 1, 0)). Everything a stage needs (6 float4 of g, 16 mask words) is loaded ONE STAGE
-            // AHEAD, so the global-load latency hides behind the previous stage's build instead of serialising every row.
+            // ---- dz builders: lane = 8 consecutive channels, warp bw = rows [8 bw, 8 bw + 8) of the 64-row stage ----------------
             const int bw = warp - 6;
-            const int c0 = 8 * lane;
-            const bool ch_on = c0 < n_out;
-            const float scale = gnb_pow2_scale(*dz_scale_bits).x;
-            const uint32_t boxoff = (uint32_t)(lane >> 3) * WGB_BOX, jj = (uint32_t)(lane & 7);
-            const int64_t n_nodes = rows / 9;
-            float4 gq[6];
-            unsigned mrow[16];                                           // the 16 rows' mask words of this lane's 32-channel group
             const int cw = n_out >> 5;
-            const unsigned bsh = 8u * ((unsigned)lane & 3u);             // this lane's 8 channels = byte (lane % 4) of that word
+            const bool ch_on = 8 * lane < n_out;
+            const unsigned bsh = 8u * ((unsigned)lane & 3u);             // this lane's 8 channels = byte (lane % 4) of word lane / 4
+            const uint32_t boxoff = (uint32_t)(lane >> 3) * WGB_BOX, jj = (uint32_t)(lane & 7);
+            unsigned mrow[8];                                            // the 8 rows' mask words, loaded one stage ahead
             auto prefetch = [&](int it) {
-                const int64_t R0 = r_lo + (int64_t)it * WGB_BK + 16 * bw;
-                const int64_t nd0 = R0 / 9;
-                const bool on = ch_on && R0 < rows;
+                const int64_t R0 = r_lo + (int64_t)it * WGB_BK + 8 * bw;
+                const unsigned* mp = rowmask + R0 * cw + (lane >> 2);
 #pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    int64_t nd = nd0 + u;
-                    nd = nd < n_nodes ? nd : n_nodes - 1;
-                    const float4* gp = reinterpret_cast<const float4*>(g + nd * ldg + c0);
-                    gq[2 * u] = on ? __ldg(gp) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    gq[2 * u + 1] = on ? __ldg(gp + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                const unsigned* mp = maskw + R0 * cw + (lane >> 2);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) mrow[i] = (on && R0 + i < rows) ? __ldg(mp + (int64_t)i * cw) : 0u;
+                for (int i = 0; i < 8; ++i) mrow[i] = (ch_on && R0 + i < rows) ? __ldg(mp + (int64_t)i * cw) : 0u;
             };
             prefetch(0);
             for (int it = 0; it < num_kb; ++it) {
                 const int s = it % WGB_STAGES;
                 const uint32_t ph = (it / WGB_STAGES) & 1;
-                // consume the registers loaded one stage ahead: fp16 pairs of the 3 nodes, one byte of channel bits per row
-                const int64_t R0 = r_lo + (int64_t)it * WGB_BK + 16 * bw;
-                const int64_t nd0 = R0 / 9;
-                uint32_t gh[3][4];
+                unsigned rb[8];
 #pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    const __half2 h0 = __floats2half2_rn(gq[2 * u].x * scale, gq[2 * u].y * scale), h1 = __floats2half2_rn(gq[2 * u].z * scale, gq[2 * u].w * scale);
-                    const __half2 h2 = __floats2half2_rn(gq[2 * u + 1].x * scale, gq[2 * u + 1].y * scale), h3 = __floats2half2_rn(gq[2 * u + 1].z * scale, gq[2 * u + 1].w * scale);
-                    gh[u][0] = *reinterpret_cast<const uint32_t*>(&h0); gh[u][1] = *reinterpret_cast<const uint32_t*>(&h1);
-                    gh[u][2] = *reinterpret_cast<const uint32_t*>(&h2); gh[u][3] = *reinterpret_cast<const uint32_t*>(&h3);
-                }
-                unsigned rb[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) rb[i] = (mrow[i] >> bsh) & 0xFFu;
+                for (int i = 0; i < 8; ++i) rb[i] = (mrow[i] >> bsh) & 0xFFu;
                 if (it + 1 < num_kb) prefetch(it + 1);
-                tc::mbar_wait<20>(&empty[s], ph ^ 1);
+                const int64_t Rs = r_lo + (int64_t)it * WGB_BK;          // first row of the stage
+                const int64_t R0 = Rs + 8 * bw;
+                const int nd_first = (int)(Rs / 9);
+                tc::mbar_wait<20>(&gfull[s], ph);                        // (the TMA warp issued it after empty[s]: the stage is free)
+                const uint32_t sg = tc::smem_u32(smem + s * WGB_STAGE + WGB_A_BYTES + WGB_B_BYTES) + (uint32_t)lane * 16u;
                 const uint32_t sb = tc::smem_u32(smem + s * WGB_STAGE + WGB_A_BYTES) + boxoff;
-                int nrel = 0;                                               // node of row i relative to nd0
-                int64_t next_node_row = (nd0 + 1) * 9;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int rr = 16 * bw + i;
-                    const int64_t R = R0 + i;
-                    if (R >= next_node_row) { ++nrel; next_node_row += 9; }
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = 8 * bw + i;
+                    const int nrel = (int)((R0 + i) / 9) - nd_first;     // warp-uniform; rows beyond `rows` carry zero bits
+                    uint32_t gv[4];
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(gv[0]), "=r"(gv[1]), "=r"(gv[2]), "=r"(gv[3])
+                                 : "r"(sg + (uint32_t)nrel * (uint32_t)n_out * 2u));
                     uint32_t o[4];
 #pragma unroll
                     for (int p2 = 0; p2 < 4; ++p2) {
-                        const uint32_t gv = nrel == 0 ? gh[0][p2] : (nrel == 1 ? gh[1][p2] : gh[2][p2]);
-                        const uint32_t t2 = (rb[i] >> (2 * p2)) & 3u;                       // bits of channels 2 p2, 2 p2 + 1 (0 beyond rows)
-                        o[p2] = gv & ((((t2 * 0x8001u) & 0x00010001u)) * 0xFFFFu);
+                        const uint32_t t2 = (rb[i] >> (2 * p2)) & 3u;
+                        o[p2] = gv[p2] & (((t2 * 0x8001u) & 0x00010001u) * 0xFFFFu);
                     }
-                    if (ch_on)
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + (uint32_t)rr * 128u + ((jj ^ ((uint32_t)rr & 7u)) << 4)),
-                                     "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + (uint32_t)rr * 128u + ((jj ^ ((uint32_t)rr & 7u)) << 4)),
+                                 "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
                 }
                 tc::fence_proxy_async();
                 __syncwarp();
@@ -612,18 +598,17 @@ GNB_EXPORT int gnb_linear_bwd_weight_f16(const void* dz, int64_t lddz, const voi
     return wgrad16_impl(dz, nullptr, lddz, x0, x1, ldx, dw, lddw, rows, n_out, k_in, 0, 0, dz_scale_bits, x_scale_bits, stream);
 }
 
-// The same weight gradient with dz EXPANDED IN THE KERNEL from the node-level gradient g [n, n_out] (fp32) and the row-major
-// ReLU bits of the aggregating epilogue (gnb_edge_linear_agg_fwd_f16: rowmask[(i * 9 + s) * (n_out / 32) + c / 32], bit c % 32):
-//   dw[n_out, k_in] += sum_{i, s} (g[i, :] * bit(i, s, :))^T x[(i, s), :]        rows = 9 n (k = 8 tables)
-// x = ONE fp16 plane of h * 2^sx [9 n, k_in]; g is rounded to fp16 after the power-of-two scale of *dz_scale_bits (max|g|), like
-// gnb_edge_mask_bwd_colsum_f16 would store it. n_out <= 256, n_out % 32 == 0.
-GNB_EXPORT int gnb_linear_bwd_weight_f16_masked(const float* g, int64_t ldg, const uint32_t* maskbits, const void* x, int64_t ldx,
-                                                float* dw, int64_t lddw, int64_t n, int32_t n_out, int32_t k_in,
+// The same weight gradient with dz EXPANDED IN THE KERNEL from the outputs of gnb_edge_dz_prep: g16 [n, n_out] = fp16(g * 2^s)
+// (contiguous rows) and the row-major ReLU bits rowmask[(i * 9 + s) * (n_out / 32) + c / 32] (bit c % 32):
+//   dw[n_out, k_in] += sum_{i, s} (g16[i, :] * bit(i, s, :))^T x[(i, s), :] * 2^-s * 2^-sx        rows = 9 n (k = 8 tables)
+// x = ONE fp16 plane of h * 2^sx [9 n, k_in]. n_out <= 256, n_out % 32 == 0.
+GNB_EXPORT int gnb_linear_bwd_weight_f16_masked(const void* g16, const uint32_t* rowmask, const void* x, int64_t ldx, float* dw,
+                                                int64_t lddw, int64_t n, int32_t n_out, int32_t k_in,
                                                 const uint32_t* dz_scale_bits, const uint32_t* x_scale_bits, void* stream) {
-    if (n < 0 || n_out < 32 || n_out > 256 || (n_out & 31) || k_in < 1 || g == nullptr || maskbits == nullptr || x == nullptr ||
+    if (n < 0 || n_out < 32 || n_out > 256 || (n_out & 31) || k_in < 1 || g16 == nullptr || rowmask == nullptr || x == nullptr ||
         dz_scale_bits == nullptr)
         return GNB_ERR_ARG;
-    if ((ldx & 7) || ldx < k_in || (ldg & 3) || ldg < n_out || (reinterpret_cast<uintptr_t>(g) & 15u)) return GNB_ERR_ARG;
+    if ((ldx & 7) || ldx < k_in || (reinterpret_cast<uintptr_t>(g16) & 15u)) return GNB_ERR_ARG;
     if (n == 0) return GNB_OK;
     const int64_t rows = n * 9;
     if (rows >= (int64_t)1 << 31) return GNB_ERR_ARG;
@@ -646,6 +631,6 @@ GNB_EXPORT int gnb_linear_bwd_weight_f16_masked(const float* g, int64_t ldg, con
     rps = ((rps + WGB_BK - 1) / WGB_BK) * WGB_BK;
     splits = (int)((rows + rps - 1) / rps);
     gemm_f16_wgrad_build_kernel<<<dim3((unsigned)tiles, (unsigned)splits), WGB_THREADS, WGB_SMEM_BYTES, (cudaStream_t)stream>>>(
-        tx, g, ldg, maskbits, dw, lddw, rows, n_out, k_in, rps, dz_scale_bits, x_scale_bits);
+        tx, (const __half*)g16, rowmask, dw, lddw, rows, n_out, k_in, rps, dz_scale_bits, x_scale_bits);
     GNB_RETURN_LAUNCH();
 }

@@ -247,13 +247,11 @@ int gnb_linear_next_absmax(uint32_t* bits, int32_t shift);
 int gnb_edge_hidden_fwd_f16(const float* pq, int64_t ldpq, int32_t hdim, const int32_t* nbr, const int32_t* deg,
                             int32_t width, int64_t n, void* h0, void* h1, int64_t ldh, uint32_t* hmask, int32_t mask_ld,
                             const uint32_t* scale_bits, void* stream);
-/* gnb_edge_linear_agg_fwd_bf16 on fp16 planes; the epilogue folds 2^-s of h into its bias FMA. rowmask (may be NULL; needs
- * n_out % 32 == 0): a second, ROW-major copy of the ReLU bits -- rowmask[(i * 9 + s) * (n_out / 32) + c / 32] bit c % 32, buffer of
- * ceil(n / 14) * 126 rows -- read by the *_masked backward kernels. */
+/* gnb_edge_linear_agg_fwd_bf16 on fp16 planes; the epilogue folds 2^-s of h into its bias FMA. */
 int gnb_edge_linear_agg_fwd_f16(const void* h0, const void* h1, int64_t ldh, int32_t k, const void* w0, const void* w1,
                                 int64_t ldw, const float* bias, const int32_t* deg, int64_t n, int32_t n_out,
                                 int32_t round_out, float* y, int64_t ldy, uint32_t* maskbits, const uint32_t* scale_bits,
-                                uint32_t* rowmask, void* stream);
+                                void* stream);
 /* gnb_edge_mask_bwd_colsum with dz as ONE fp16 plane of dz * 2^s (*scale_bits = bits of max|g|). */
 int gnb_edge_mask_bwd_colsum_f16(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols, void* dz,
                                  int64_t ldz, float* db, const uint32_t* scale_bits, void* stream);
@@ -266,20 +264,24 @@ int gnb_edge_hidden_dgrad_scatter_f16(const void* dz, int64_t lddz, int32_t c_ou
                                       const uint32_t* hmask, int32_t mask_ld, int32_t hdim, const int32_t* nbr, int64_t n,
                                       float* dq, int64_t lddq, float* dp, int64_t lddp, float* dbias, int32_t flags,
                                       const uint32_t* scale_bits, void* stream);
-/* The two backward GEMMs of the aggregating Linear WITHOUT a stored dz: dz[(i, s), :] = g[i, :] * bit(i, s, :) is expanded inside
- * the kernels (builder warps write the tensor-core operand tile in shared memory) from the node-level gradient g [n, c_out] and
- * the row-major ReLU bits of gnb_edge_linear_agg_fwd_f16 (rowmask); values as gnb_edge_mask_bwd_colsum_f16 would store them
- * (fp16 of g * 2^s). c_out <= 256, c_out % 32 == 0 (weight gradient) / % 64 == 0 (scatter), k = 8 tables. */
-int gnb_linear_bwd_weight_f16_masked(const float* g, int64_t ldg, const uint32_t* rowmask, const void* x, int64_t ldx, float* dw,
-                                     int64_t lddw, int64_t n, int32_t n_out, int32_t k_in, const uint32_t* dz_scale_bits,
+/* The backward of the aggregating Linear WITHOUT a stored dz (fp16-plane modes): dz[(i, s), :] = g[i, :] * bit(i, s, :) is a
+ * 9-fold redundant function of the node-level gradient and the ReLU bits, so the two GEMMs expand it in shared memory (builder
+ * warps write the tensor-core operand tile) instead of reading a stored [9 n, c_out] tensor (autograd of PyG EdgeConv's
+ * aggr="add" + ReLU, layers.py:55-62). gnb_edge_dz_prep makes their inputs in one pass over g [n, cols] and the tile-major
+ * maskbits of gnb_edge_linear_agg_fwd_*: g16 [n, cols] = fp16(g * 2^s) (2^s from *scale_bits = bits of max|g|), rowmask =
+ * the same bits ROW-major ([ceil(n / 14) * 126, cols / 32] words: bit c % 32 of word c / 32 of row i * 9 + s), and db[c] +=
+ * column sums of dz (the bias gradient). cols % 32 == 0 (scatter: % 64), cols <= 256, k = 8 tables. */
+int gnb_edge_dz_prep(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols, const uint32_t* scale_bits,
+                     void* g16, uint32_t* rowmask, float* db, void* stream);
+/* dw[n_out, k_in] += dz^T x with x = one fp16 plane of h * 2^sx [9 n, k_in]; both scales undone in the epilogue. */
+int gnb_linear_bwd_weight_f16_masked(const void* g16, const uint32_t* rowmask, const void* x, int64_t ldx, float* dw, int64_t lddw,
+                                     int64_t n, int32_t n_out, int32_t k_in, const uint32_t* dz_scale_bits,
                                      const uint32_t* x_scale_bits, void* stream);
-int gnb_edge_hidden_dgrad_scatter_f16_masked(const float* g, int64_t ldg, const uint32_t* rowmask, int32_t c_out, const void* wt,
-                                             int64_t ldw, const uint32_t* hmask, int32_t mask_ld, int32_t hdim,
-                                             const int32_t* nbr, int64_t n, float* dq, int64_t lddq, float* dp, int64_t lddp,
-                                             float* dbias, int32_t flags, const uint32_t* scale_bits, void* stream);
-/* db[c] += sum_i g[i, c] * (number of set mask bits of node i, channel c): the bias gradient that goes with them (reads the
- * tile-major maskbits of the aggregating epilogue). */
-int gnb_edge_mask_colsum(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols, float* db, void* stream);
+/* gnb_edge_hidden_dgrad_scatter_f16 on the expanded dz; wt = W2^T as one fp16 plane [hdim, ldw >= c_out]. */
+int gnb_edge_hidden_dgrad_scatter_f16_masked(const void* g16, const uint32_t* rowmask, int32_t c_out, const void* wt, int64_t ldw,
+                                             const uint32_t* hmask, int32_t mask_ld, int32_t hdim, const int32_t* nbr, int64_t n,
+                                             float* dq, int64_t lddq, float* dp, int64_t lddp, float* dbias, int32_t flags,
+                                             const uint32_t* scale_bits, void* stream);
 /* fp32 [rows, cols] -> fp16 planes (round to nearest; zero padded to dst_cols; p1 may be NULL); transpose != 0: of src^T. */
 int gnb_to_f16_planes(const float* src, int64_t lds, int64_t rows, int32_t cols, void* p0, void* p1, int64_t ldd,
                       int32_t dst_cols, int32_t transpose, void* stream);

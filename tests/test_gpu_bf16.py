@@ -392,16 +392,10 @@ def test_edge_linear_agg_f16_bit_exact(ops, np_, which, k, n_out):
     y = torch.empty(n, n_out, device="cuda")
     mask = torch.zeros((n + 13) // 14 * n_out * 4, dtype=torch.int32, device="cuda")
     bc = b.cuda()
-    rowmask = torch.full(((n + 13) // 14 * 126, n_out // 32), -1, dtype=torch.int32, device="cuda") if n_out % 32 == 0 else None
     ops._call("gnb_edge_linear_agg_fwd_f16", ops._ptr(h0), ops._ptr(h1), h0.shape[1], k, ops._ptr(w0), ops._ptr(w1), kw,
-              ops._ptr(bc), ops._ptr(graph.deg), n, n_out, 0, ops._ptr(y), n_out, ops._ptr(mask), ops._ptr(word), ops._ptr(rowmask),
-              ops._stream())
+              ops._ptr(bc), ops._ptr(graph.deg), n, n_out, 0, ops._ptr(y), n_out, ops._ptr(mask), ops._ptr(word), ops._stream())
     torch.cuda.synchronize()
     assert torch.equal(y.cpu().double(), y_ref)
-    if rowmask is not None:        # the row-major copy of the ReLU bits: bit c % 32 of word c / 32 of row (i, s)
-        rm = rowmask.cpu()[: n * 9].long() & 0xFFFFFFFF
-        got = ((rm.unsqueeze(2) >> torch.arange(32).view(1, 1, 32)) & 1).reshape(n * 9, n_out).bool()
-        assert torch.equal(got, on)
 
 
 @pytest.mark.parametrize("planes_x", [1, 2])
@@ -493,38 +487,45 @@ def _mask_case(ops, sizes, n_out, seed, gmax):
         rowm = torch.where(rowm >= 2 ** 31, rowm - 2 ** 32, rowm).int().cuda()
     g = torch.randint(-4, 5, (n, n_out), generator=gen).float() * (gmax / 4)
     dz = (g.unsqueeze(1) * bits).reshape(n * 9, n_out)
-    return graph, n, words, g, dz, rowm
+    # the kernels' inputs come from gnb_edge_dz_prep: fp16(g 2^s), row-major bits, bias gradient
+    wz, sz = _scale_word(gmax)
+    gc = g.cuda()
+    g16 = torch.full((n, n_out), 7.0, dtype=torch.float16, device="cuda")
+    rowmask = torch.full((ntile * 126, max(n_out // 32, 1)), -1, dtype=torch.int32, device="cuda")
+    db = torch.zeros(n_out, device="cuda")
+    if n_out % 32 == 0:
+        ops._call("gnb_edge_dz_prep", ops._ptr(gc), n_out, ops._ptr(words), n, n_out, ops._ptr(wz), ops._ptr(g16), ops._ptr(rowmask),
+                  ops._ptr(db), ops._stream())
+        torch.cuda.synchronize()
+        assert torch.equal(g16.cpu(), (g * sz).half())
+        assert torch.equal(rowmask.cpu(), rowm.cpu())
+        assert torch.equal(db.cpu().double(), dz.double().sum(0))
+    return graph, n, wz, g16, dz, rowmask
 
 
 @pytest.mark.parametrize("n_out,k_in,sizes", [(256, 336, [1, 2, 5, 9, 10, 64, 130, 12, 300, 3, 700]), (256, 128, [400, 900, 14, 15]),
                                               (96, 344, [77, 5, 230]), (256, 336, [3000, 2500])])
 def test_wgrad_f16_masked_bit_exact(ops, n_out, k_in, sizes):
     """dW2 with dz expanded inside the kernel from g and the mask words == the same product on a stored dz (fp64 reference)."""
-    graph, n, words, g, dz, rowm = _mask_case(ops, sizes, n_out, seed=n_out + k_in, gmax=2.0 ** -9)
+    graph, n, wz, g16, dz, rowm = _mask_case(ops, sizes, n_out, seed=n_out + k_in, gmax=2.0 ** -9)
     gen = torch.Generator().manual_seed(5)
     x = torch.randint(-2, 3, (n * 9, k_in), generator=gen).float()
-    wz, _ = _scale_word(2.0 ** -9)
     wx, sx = _scale_word(2.0)
     ref = dz.double().t() @ x.double()
     x16 = (x * sx).half().cuda()
-    gc = g.cuda()
     dw = torch.zeros(n_out, k_in, device="cuda")
-    ops._call("gnb_linear_bwd_weight_f16_masked", ops._ptr(gc), n_out, ops._ptr(rowm), ops._ptr(x16), k_in, ops._ptr(dw), k_in, n,
+    ops._call("gnb_linear_bwd_weight_f16_masked", ops._ptr(g16), ops._ptr(rowm), ops._ptr(x16), k_in, ops._ptr(dw), k_in, n,
               n_out, k_in, ops._ptr(wz), ops._ptr(wx), ops._stream())
-    db = torch.zeros(n_out, device="cuda")
-    ops._call("gnb_edge_mask_colsum", ops._ptr(gc), n_out, ops._ptr(words), n, n_out, ops._ptr(db), ops._stream())
     torch.cuda.synchronize()
     assert torch.equal(dw.cpu().double(), ref)
-    assert torch.equal(db.cpu().double(), dz.double().sum(0))
 
 
 @pytest.mark.parametrize("hdim,c_out,sizes", [(336, 256, [1, 2, 5, 9, 10, 64, 130, 12, 300, 3, 500]), (128, 256, [400, 900, 14, 15]),
                                               (40, 128, [77, 5, 230]), (336, 256, [3000, 2500]), (512, 64, [100, 37])])
 def test_dgrad_scatter_f16_masked_bit_exact(ops, hdim, c_out, sizes):
-    graph, n, words, g, dz, rowm = _mask_case(ops, sizes, c_out, seed=hdim + c_out, gmax=2.0 ** -20)
+    graph, n, word, g16, dz, rowm = _mask_case(ops, sizes, c_out, seed=hdim + c_out, gmax=2.0 ** -20)
     gen = torch.Generator().manual_seed(hdim)
     w2 = torch.randint(-8, 9, (c_out, hdim), generator=gen).float() / 8
-    word, _ = _scale_word(2.0 ** -20)
     nbr, deg = graph.nbr.cpu().long(), graph.deg.cpu()
     valid = ((torch.arange(9).unsqueeze(0) < deg.unsqueeze(1)) & (nbr >= 0)).reshape(-1)
     hbits = torch.rand(n * 9, hdim, generator=gen) < 0.6
@@ -545,8 +546,7 @@ def test_dgrad_scatter_f16_masked_bit_exact(ops, hdim, c_out, sizes):
     dq = torch.zeros(n, hdim, device="cuda")
     dp = torch.full((n, hdim), 9.0, device="cuda")
     dbias = torch.zeros(hdim, device="cuda")
-    gc = g.cuda()
-    ops._call("gnb_edge_hidden_dgrad_scatter_f16_masked", ops._ptr(gc), c_out, ops._ptr(rowm), c_out, ops._ptr(wt16), cw, ops._ptr(hm),
+    ops._call("gnb_edge_hidden_dgrad_scatter_f16_masked", ops._ptr(g16), ops._ptr(rowm), c_out, ops._ptr(wt16), cw, ops._ptr(hm),
               mld, hdim, ops._ptr(graph.nbr), n, ops._ptr(dq), hdim, ops._ptr(dp), hdim, ops._ptr(dbias), 0, ops._ptr(word),
               ops._stream())
     torch.cuda.synchronize()
