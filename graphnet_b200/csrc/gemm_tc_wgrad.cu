@@ -322,23 +322,28 @@ gemm_bf_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_con
 // 128-byte-swizzled B tile (row rr at rr * 128 B of its 64-channel box, chunk j at j ^ (rr & 7)) with one 16-byte store: the
 // kernel reads h (one fp16 plane) + 0.06 GB instead of h + dz, i.e. 0.54 instead of 0.85 GB per 713 k-row launch.
 // Warps: 0 TMA (A = h, g16 rows), 1 MMA, 2..5 epilogue, 6..13 builders. full[s] collects the TMA transaction + the 8 builder warps.
-constexpr int WGB_THREADS = 448, WGB_BK = 64, WGB_STAGES = 4, WGB_NB = 8;
+// Two rings: the TMA ring {A = h box pair 16 KiB | the stage's g16 rows <= 4.5 KiB} is WGB_NA = 7 stages deep -- with nothing
+// but 20 KiB per stage arriving from memory, the 4-stage ring of the stored-dz kernel left too few bytes in flight (155 us
+// floor measured with builders and MMAs switched off) --, the locally built B tile (32 KiB) is double-buffered.
+constexpr int WGB_THREADS = 448, WGB_BK = 64, WGB_NA = 7, WGB_NBUF = 2, WGB_NB = 8;
 constexpr uint32_t WGB_BOX = WGB_BK * 128, WGB_A_BYTES = 2 * WGB_BOX, WGB_B_BYTES = 4 * WGB_BOX;
-constexpr uint32_t WGB_G_BYTES = 9 * 512;                               // <= 9 nodes x 256 channels x 2 B
-constexpr uint32_t WGB_STAGE = WGB_A_BYTES + WGB_B_BYTES + 5 * 1024;    // g16 rows behind the operand tiles (1 KiB-aligned stages)
-constexpr uint32_t WGB_SMEM_BYTES = WGB_STAGES * WGB_STAGE + 1024 + 256;
+constexpr uint32_t WGB_ASTAGE = WGB_A_BYTES + 5 * 1024;                 // g16 rows (<= 9 x 512 B) behind the A tile; 1 KiB-aligned
+constexpr uint32_t WGB_DATA_BYTES = WGB_NA * WGB_ASTAGE + WGB_NBUF * WGB_B_BYTES;
+constexpr uint32_t WGB_SMEM_BYTES = WGB_DATA_BYTES + 1024 + 256;
 
 __global__ void __launch_bounds__(WGB_THREADS, 1)
 gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __half* __restrict__ g16,
                             const unsigned* __restrict__ rowmask, float* __restrict__ dw, int64_t lddw, int64_t rows, int n_out,
                             int k_in, int64_t rows_per_split, const unsigned* __restrict__ dz_scale_bits,
-                            const unsigned* __restrict__ x_scale_bits) {
+                            const unsigned* __restrict__ x_scale_bits, int dbg) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + WGB_STAGES * WGB_STAGE);
-    uint64_t* empty = full + WGB_STAGES;
-    uint64_t* gfull = empty + WGB_STAGES;             // the stage's g16 rows landed
-    uint64_t* tmem_full = gfull + WGB_STAGES;
+    uint8_t* bring = smem + WGB_NA * WGB_ASTAGE;                       // [WGB_NBUF] x 32 KiB
+    uint64_t* afull = reinterpret_cast<uint64_t*>(smem + WGB_DATA_BYTES);
+    uint64_t* aempty = afull + WGB_NA;
+    uint64_t* bfull = aempty + WGB_NA;                // the 8 builder warps wrote the B tile
+    uint64_t* bempty = bfull + WGB_NBUF;              // the MMAs that read it completed
+    uint64_t* tmem_full = bempty + WGB_NBUF;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -353,9 +358,8 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
     if (warp == 0 && lane == 0) tc::tma_prefetch_desc(&tm_x);
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < WGB_STAGES; ++s) {
-                tc::mbar_init(&full[s], 1 + WGB_NB); tc::mbar_init(&empty[s], 1); tc::mbar_init(&gfull[s], 1);
-            }
+            for (int s = 0; s < WGB_NA; ++s) { tc::mbar_init(&afull[s], 1); tc::mbar_init(&aempty[s], 1); }
+            for (int s = 0; s < WGB_NBUF; ++s) { tc::mbar_init(&bfull[s], WGB_NB); tc::mbar_init(&bempty[s], 1); }
             tc::mbar_init(tmem_full, 1);
             tc::fence_barrier_init();
             tc::fence_proxy_async();
@@ -371,41 +375,40 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
     if (num_kb > 0) {
         if (warp == 0) {
             for (int it = 0; it < num_kb; ++it) {
-                const int s = it % WGB_STAGES;
-                const uint32_t ph = (it / WGB_STAGES) & 1;
-                tc::mbar_wait(&empty[s], ph ^ 1);
-                uint8_t* st = smem + s * WGB_STAGE;
+                const int s = it % WGB_NA;
+                const uint32_t ph = (it / WGB_NA) & 1;
+                tc::mbar_wait(&aempty[s], ph ^ 1);
+                uint8_t* st = smem + s * WGB_ASTAGE;
                 const int64_t r = r_lo + (int64_t)it * WGB_BK;
                 const int64_t nd0 = r / 9;
                 int64_t nd1 = (r + WGB_BK - 1) / 9 + 1;                 // one past the last node of the stage
                 nd1 = nd1 < n_nodes ? nd1 : n_nodes;
                 const uint32_t gb = nd1 > nd0 ? (uint32_t)(nd1 - nd0) * (uint32_t)n_out * 2u : 0u;
                 if (tc::elect_one()) {
-                    tc::mbar_arrive_expect_tx(&gfull[s], gb);
-                    if (gb) tc::bulk_load(st + WGB_A_BYTES + WGB_B_BYTES, g16 + nd0 * n_out, gb, &gfull[s]);
-                    tc::mbar_arrive_expect_tx(&full[s], WGB_A_BYTES);
-                    tc::tma_load_2d(st, &tm_x, &full[s], kin0, (int)r);
-                    tc::tma_load_2d(st + WGB_BOX, &tm_x, &full[s], kin0 + 64, (int)r);
+                    tc::mbar_arrive_expect_tx(&afull[s], WGB_A_BYTES + gb);
+                    if (gb) tc::bulk_load(st + WGB_A_BYTES, g16 + nd0 * n_out, gb, &afull[s]);
+                    tc::tma_load_2d(st, &tm_x, &afull[s], kin0, (int)r);
+                    tc::tma_load_2d(st + WGB_BOX, &tm_x, &afull[s], kin0 + 64, (int)r);
                 }
                 __syncwarp();
             }
         } else if (warp == 1) {
             const uint32_t idesc = (1u << 4) | (((uint32_t)n_mma >> 3) << 17) | ((WG_BM >> 4) << 24) | (1u << 15) | (1u << 16);   // fp16 x fp16
             for (int it = 0; it < num_kb; ++it) {
-                const int s = it % WGB_STAGES;
-                const uint32_t ph = (it / WGB_STAGES) & 1;
-                tc::mbar_wait(&full[s], ph);
+                const int s = it % WGB_NA, sb = it % WGB_NBUF;
+                tc::mbar_wait(&afull[s], (it / WGB_NA) & 1);
+                tc::mbar_wait(&bfull[sb], (it / WGB_NBUF) & 1);
                 tc::tcgen05_fence_after();
-                const uint32_t sa = tc::smem_u32(smem + s * WGB_STAGE);
-                const uint64_t a0 = umma_desc_sw128_mnmajor16(sa, WGB_BOX, 1024u);
-                const uint64_t b0 = umma_desc_sw128_mnmajor16(sa + WGB_A_BYTES, WGB_BOX, 1024u);
+                const uint64_t a0 = umma_desc_sw128_mnmajor16(tc::smem_u32(smem + s * WGB_ASTAGE), WGB_BOX, 1024u);
+                const uint64_t b0 = umma_desc_sw128_mnmajor16(tc::smem_u32(bring + sb * WGB_B_BYTES), WGB_BOX, 1024u);
                 if (tc::elect_one()) {
 #pragma unroll
                     for (int k = 0; k < WGB_BK / 16; ++k) {
                         const uint64_t adv = (uint64_t)(k * (2048 >> 4));
-                        umma_f16(tmem_base, a0 + adv, b0 + adv, idesc, (it | k) != 0 ? 1u : 0u);
+                        if (!(dbg & 2)) umma_f16(tmem_base, a0 + adv, b0 + adv, idesc, (it | k) != 0 ? 1u : 0u);
                     }
-                    tc::umma_commit(&empty[s]);
+                    tc::umma_commit(&aempty[s]);
+                    tc::umma_commit(&bempty[sb]);
                 }
                 __syncwarp();
             }
@@ -419,45 +422,52 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
             const unsigned bsh = 8u * ((unsigned)lane & 3u);             // this lane's 8 channels = byte (lane % 4) of word lane / 4
             const uint32_t boxoff = (uint32_t)(lane >> 3) * WGB_BOX, jj = (uint32_t)(lane & 7);
             unsigned mrow[8];                                            // the 8 rows' mask words, loaded one stage ahead
+            const uint32_t r_lo32 = (uint32_t)r_lo, rows32 = (uint32_t)rows;      // rows < 2^31 (checked by the launcher)
             auto prefetch = [&](int it) {
-                const int64_t R0 = r_lo + (int64_t)it * WGB_BK + 8 * bw;
-                const unsigned* mp = rowmask + R0 * cw + (lane >> 2);
+                const uint32_t R0 = r_lo32 + (uint32_t)it * WGB_BK + 8u * (uint32_t)bw;
+                const unsigned* mp = rowmask + (int64_t)R0 * cw + (lane >> 2);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) mrow[i] = (ch_on && R0 + i < rows) ? __ldg(mp + (int64_t)i * cw) : 0u;
+                for (int i = 0; i < 8; ++i) mrow[i] = (ch_on && R0 + i < rows32) ? __ldg(mp + i * cw) : 0u;
             };
             prefetch(0);
             for (int it = 0; it < num_kb; ++it) {
-                const int s = it % WGB_STAGES;
-                const uint32_t ph = (it / WGB_STAGES) & 1;
-                unsigned rb[8];
+                const int s = it % WGB_NA, sbuf = it % WGB_NBUF;
+                unsigned rb[8];                                          // the rows' bytes of channel bits (0 beyond `rows`)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) rb[i] = (mrow[i] >> bsh) & 0xFFu;
                 if (it + 1 < num_kb) prefetch(it + 1);
-                const int64_t Rs = r_lo + (int64_t)it * WGB_BK;          // first row of the stage
-                const int64_t R0 = Rs + 8 * bw;
-                const int nd_first = (int)(Rs / 9);
-                tc::mbar_wait<20>(&gfull[s], ph);                        // (the TMA warp issued it after empty[s]: the stage is free)
-                const uint32_t sg = tc::smem_u32(smem + s * WGB_STAGE + WGB_A_BYTES + WGB_B_BYTES) + (uint32_t)lane * 16u;
-                const uint32_t sb = tc::smem_u32(smem + s * WGB_STAGE + WGB_A_BYTES) + boxoff;
+                const uint32_t Rs = r_lo32 + (uint32_t)it * WGB_BK;      // first row of the stage
+                const uint32_t R0 = Rs + 8u * (uint32_t)bw;
+                const uint32_t q0 = __umulhi(R0, 0x38E38E39u) >> 1;      // R0 / 9
+                const uint32_t rem0 = R0 - 9u * q0;
+                const uint32_t nrel0 = q0 - (__umulhi(Rs, 0x38E38E39u) >> 1);
+                tc::mbar_wait(&afull[s], (it / WGB_NA) & 1);             // the stage's g16 rows (and A) landed
+                tc::mbar_wait(&bempty[sbuf], ((it / WGB_NBUF) & 1) ^ 1); // the MMAs of the B slot's previous use completed
+                const uint32_t sg = tc::smem_u32(smem + s * WGB_ASTAGE + WGB_A_BYTES) + (uint32_t)lane * 16u + nrel0 * (uint32_t)n_out * 2u;
+                const uint32_t sb = tc::smem_u32(bring + sbuf * WGB_B_BYTES) + boxoff + (uint32_t)(8 * bw) * 128u;
+                // 8 rows touch at most 2 nodes: their fp16 values are read ONCE each (shared-memory bandwidth, not issue slots, is
+                // what a stage is short of: B written 32 KiB + read by the MMAs 48 KiB + the TMA's 20 KiB per ~900 cycles)
+                uint32_t ga[4], gb2[4];
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ga[0]), "=r"(ga[1]), "=r"(ga[2]), "=r"(ga[3]) : "r"(sg));
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(gb2[0]), "=r"(gb2[1]), "=r"(gb2[2]), "=r"(gb2[3])
+                             : "r"(sg + (uint32_t)n_out * 2u));
+                if (!(dbg & 1))
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int rr = 8 * bw + i;
-                    const int nrel = (int)((R0 + i) / 9) - nd_first;     // warp-uniform; rows beyond `rows` carry zero bits
-                    uint32_t gv[4];
-                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(gv[0]), "=r"(gv[1]), "=r"(gv[2]), "=r"(gv[3])
-                                 : "r"(sg + (uint32_t)nrel * (uint32_t)n_out * 2u));
+                    const bool second = rem0 + (uint32_t)i >= 9u;        // warp-uniform
                     uint32_t o[4];
 #pragma unroll
                     for (int p2 = 0; p2 < 4; ++p2) {
-                        const uint32_t t2 = (rb[i] >> (2 * p2)) & 3u;
-                        o[p2] = gv[p2] & (((t2 * 0x8001u) & 0x00010001u) * 0xFFFFu);
+                        const uint32_t t2 = (rb[i] >> (2 * p2)) & 3u;    // bits of channels 2 p2, 2 p2 + 1 -> low / high half-word mask
+                        o[p2] = (second ? gb2[p2] : ga[p2]) & (((t2 * 0x8001u) & 0x00010001u) * 0xFFFFu);
                     }
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + (uint32_t)rr * 128u + ((jj ^ ((uint32_t)rr & 7u)) << 4)),
+                    // row rr = 8 bw + i: chunk position jj ^ (rr & 7) = jj ^ i
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + (uint32_t)i * 128u + ((jj ^ (uint32_t)i) << 4)),
                                  "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
                 }
                 tc::fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&full[s]);
+                if (lane == 0) tc::mbar_arrive(&bfull[sbuf]);
                 __syncwarp();
             }
         } else {
@@ -598,6 +608,9 @@ GNB_EXPORT int gnb_linear_bwd_weight_f16(const void* dz, int64_t lddz, const voi
     return wgrad16_impl(dz, nullptr, lddz, x0, x1, ldx, dw, lddw, rows, n_out, k_in, 0, 0, dz_scale_bits, x_scale_bits, stream);
 }
 
+static int g_wgrad_dbg = 0;     // profiling hook (results are garbage with any bit set): bit 0 builders store nothing, bit 1 no MMAs
+GNB_EXPORT int gnb_wgrad_set_debug(int32_t flags) { g_wgrad_dbg = flags; return GNB_OK; }
+
 // The same weight gradient with dz EXPANDED IN THE KERNEL from the outputs of gnb_edge_dz_prep: g16 [n, n_out] = fp16(g * 2^s)
 // (contiguous rows) and the row-major ReLU bits rowmask[(i * 9 + s) * (n_out / 32) + c / 32] (bit c % 32):
 //   dw[n_out, k_in] += sum_{i, s} (g16[i, :] * bit(i, s, :))^T x[(i, s), :] * 2^-s * 2^-sx        rows = 9 n (k = 8 tables)
@@ -631,6 +644,6 @@ GNB_EXPORT int gnb_linear_bwd_weight_f16_masked(const void* g16, const uint32_t*
     rps = ((rps + WGB_BK - 1) / WGB_BK) * WGB_BK;
     splits = (int)((rows + rps - 1) / rps);
     gemm_f16_wgrad_build_kernel<<<dim3((unsigned)tiles, (unsigned)splits), WGB_THREADS, WGB_SMEM_BYTES, (cudaStream_t)stream>>>(
-        tx, (const __half*)g16, rowmask, dw, lddw, rows, n_out, k_in, rps, dz_scale_bits, x_scale_bits);
+        tx, (const __half*)g16, rowmask, dw, lddw, rows, n_out, k_in, rps, dz_scale_bits, x_scale_bits, g_wgrad_dbg);
     GNB_RETURN_LAUNCH();
 }

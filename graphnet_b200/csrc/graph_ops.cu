@@ -1312,19 +1312,20 @@ __global__ void __launch_bounds__(256) edge_dz_prep_kernel(const float* __restri
                 g16[(node0 + f) * cols + c] = __float2half_rn(gv[f] * scale);
             }
         }
-        // row-major words: bit r of this lane's word k -> bit `lane` of row 32 k + r's word; lane r keeps and stores it
+        // row-major words: 32 x 32 bit transposes across the warp (lane = channel, bit = row  ->  lane = row, bit = channel) by
+        // five rounds of block swaps with the lane's partner (recursive transpose: 5 shuffles instead of 32 ballots per word)
         unsigned* rm = rowmask + tile * EM_ROWS * cw + (c >> 5);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            unsigned mine = 0u;
+            unsigned a = w[k];
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-                if (32 * k + r < EM_ROWS) {                                         // compile-time
-                    const unsigned bal = __ballot_sync(0xffffffffu, (w[k] >> r) & 1u);
-                    if (lane == r) mine = bal;
-                }
+            for (int jb = 16; jb > 0; jb >>= 1) {
+                const unsigned msk = jb == 16 ? 0x0000FFFFu : jb == 8 ? 0x00FF00FFu : jb == 4 ? 0x0F0F0F0Fu : jb == 2 ? 0x33333333u : 0x55555555u;
+                const unsigned p = __shfl_xor_sync(0xffffffffu, a, jb);
+                // lanes with bit jb clear keep their low blocks and take the partner's low blocks into their high blocks
+                a = (lane & jb) ? ((a & ~msk) | ((p >> jb) & msk)) : ((a & msk) | ((p << jb) & ~msk));
             }
-            if (32 * k + lane < EM_ROWS) rm[(int64_t)(32 * k + lane) * cw] = mine;
+            if (32 * k + lane < EM_ROWS) rm[(int64_t)(32 * k + lane) * cw] = a;
         }
     }
     atomicAdd(db + c, acc);

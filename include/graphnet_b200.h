@@ -273,6 +273,8 @@ int gnb_edge_hidden_dgrad_scatter_f16(const void* dz, int64_t lddz, int32_t c_ou
  * column sums of dz (the bias gradient). cols % 32 == 0 (scatter: % 64), cols <= 256, k = 8 tables. */
 int gnb_edge_dz_prep(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols, const uint32_t* scale_bits,
                      void* g16, uint32_t* rowmask, float* db, void* stream);
+/* profiling hook of gnb_linear_bwd_weight_f16_masked (0 in production; results are garbage otherwise) */
+int gnb_wgrad_set_debug(int32_t flags);
 /* dw[n_out, k_in] += dz^T x with x = one fp16 plane of h * 2^sx [9 n, k_in]; both scales undone in the epilogue. */
 int gnb_linear_bwd_weight_f16_masked(const void* g16, const uint32_t* rowmask, const void* x, int64_t ldx, float* dw, int64_t lddw,
                                      int64_t n, int32_t n_out, int32_t k_in, const uint32_t* dz_scale_bits,
