@@ -39,7 +39,7 @@ enum : int { GNB_ACT_NONE = 0, GNB_ACT_RELU = 1 };
 // OR-ed into an `act` / `aggr` argument: round the stored result to tf32 (cvt.rna) so that a following
 // tcgen05 kind::tf32 GEMM, which truncates its fp32 operands, sees exactly representable values.
 #define GNB_STD_MAX_F 32
-enum : int { GNB_FLAG_ROUND_TF32 = 0x100, GNB_FLAG_ACCUMULATE = 0x200, GNB_FLAG_ZERO_SRC = 0x400 };   // 0x200 in `act` of the tf32 Linear: y += result
+enum : int { GNB_FLAG_ROUND_TF32 = 0x100, GNB_FLAG_ACCUMULATE = 0x200, GNB_FLAG_ZERO_SRC = 0x400, GNB_FLAG_HMASK_ROWMAJOR = 0x800 };   // 0x200 in `act` of the tf32 Linear: y += result
 
 __device__ __forceinline__ float gnb_round_tf32(float v) {
     uint32_t r;

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 // ---- launchers of the other translation units (C ABI, include/graphnet_b200.h) -----------------------
 extern "C" {
@@ -70,6 +71,9 @@ int gnb_linear_bwd_weight_f16_masked(const void*, const uint32_t*, const void*, 
 int gnb_edge_hidden_dgrad_scatter_f16_masked(const void*, const uint32_t*, int32_t, const void*, int64_t, const uint32_t*, int32_t,
                                              int32_t, const int32_t*, int64_t, float*, int64_t, float*, int64_t, float*, int32_t,
                                              const uint32_t*, void*);
+int gnb_edgeconv_fused_fwd_f16(const float*, int64_t, int32_t, const int32_t*, const int32_t*, int64_t, const void*, const void*,
+                               int64_t, const float*, int32_t, int32_t, float*, int64_t, uint32_t*, void*, int64_t, uint8_t*, int64_t,
+                               const uint32_t*, void*);
 int gnb_edge_dz_prep(const float*, int64_t, const uint32_t*, int64_t, int32_t, const uint32_t*, void*, uint32_t*, float*, void*);
 int gnb_to_f16_planes(const float*, int64_t, int64_t, int32_t, void*, void*, int64_t, int32_t, int32_t, void*);
 int gnb_absmax_bits(const float*, int64_t, int64_t, int32_t, int32_t, uint32_t*, void*);
@@ -223,7 +227,7 @@ struct Arena {
     }
 };
 
-struct ConvBuf { float *wcat, *wcat_lo, *w2p_lo, *bcat, *w2p, *pq, *h, *m, *y; int32_t *nbr, *deg; uint32_t *mask, *hmask; bool nodz; int cin, cin_ld, kld, hid, hld, cout, mld;
+struct ConvBuf { float *wcat, *wcat_lo, *w2p_lo, *bcat, *w2p, *pq, *h, *m, *y; int32_t *nbr, *deg; uint32_t *mask, *hmask; bool nodz, fused; int cin, cin_ld, kld, hid, hld, cout, mld;
                  // bf16 modes: h planes [n * 9, hid], W2 planes [cout, hld64], W2^T planes [hid, cld64]
                  __nv_bfloat16 *hb[2], *w2b[2], *w2tb[2]; int hld64, cld64; };
 struct DenseBuf { float *wp, *wp_lo, *z; int k_total, kld, n_out; };
@@ -285,7 +289,8 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
             h_shared = a.get<float>(n * max_w * max_h);
             m_shared = a.get<float>(n * max_w * max_c);
         }
-        for (int pl = 0; pl < p.bf; ++pl) hb_shared[pl] = a.get<__nv_bfloat16>(n * max_w * max_h);
+        bool all_fused = p.mixed && !(c.flags & 8) && w0 == 9 && max_h <= 512 && max_c <= 256;      // (see b.fused below)
+        for (int pl = 0; pl < p.bf && !all_fused; ++pl) hb_shared[pl] = a.get<__nv_bfloat16>(n * max_w * max_h);
         pq_shared = a.get<float>(n * 2 * max_h);
     }
     for (int l = 0; l < c.n_conv; ++l) {
@@ -302,9 +307,15 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
         b.w2p_lo = split ? a.get<float>((int64_t)b.cout * b.hld) : nullptr;
         b.pq = training ? a.get<float>(n * 2 * b.hid) : pq_shared;
         b.hld64 = (int)up(b.hid, 64); b.cld64 = (int)up(b.cout, 64);
+        // fp16-plane modes: the backward GEMMs expand dz themselves (no stored dz) where the shapes allow it, and then the
+        // forward is ONE kernel (gather + hidden layer + second Linear + aggregation: h never crosses HBM except plane 0
+        // as the weight gradient's operand); inference fuses whenever the shapes allow it. flags bit 3 keeps the two-kernel forward.
+        b.nodz = p.mixed && training && !(c.flags & 4) && b.cout <= 256 && (b.cout & 63) == 0 && wl == 9;
+        b.fused = p.mixed && !(c.flags & 8) && b.cout <= 256 && wl == 9 && b.hid <= 512 && (training ? b.nodz : true);
         for (int pl = 0; pl < 2; ++pl) {
             const bool on = pl < p.bf;
-            b.hb[pl] = on ? (training ? a.get<__nv_bfloat16>(n * wl * b.hid) : hb_shared[pl]) : nullptr;
+            const bool h_on = on && !(b.fused && (pl == 1 || !training));      // fused forward: only plane 0, only for the backward pass
+            b.hb[pl] = h_on ? (training ? a.get<__nv_bfloat16>(n * wl * b.hid) : hb_shared[pl]) : nullptr;
             b.w2b[pl] = on ? a.get<__nv_bfloat16>((int64_t)b.cout * b.hld64) : nullptr;
             b.w2tb[pl] = (on && training && !(p.mixed && pl == 1)) ? a.get<__nv_bfloat16>((int64_t)b.hid * b.cld64) : nullptr;
         }
@@ -312,8 +323,7 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
         b.h = p.bf ? nullptr : (training ? a.get<float>(n * wl * b.hid) : h_shared);
         b.m = training ? (p.agg ? nullptr : a.get<float>(n * wl * b.cout)) : m_shared;
         b.mask = (p.agg && training) ? a.get<uint32_t>((n + 13) / 14 * (int64_t)b.cout * 4) : nullptr;
-        // fp16-plane modes: the backward GEMMs expand dz themselves (no stored dz) where the shapes allow it
-        b.nodz = p.mixed && training && !(c.flags & 4) && b.cout <= 256 && (b.cout & 63) == 0 && wl == 9;
+
         // activation bits of h for the scattering data-gradient epilogue (whole 14-node tiles, mld words per slot row)
         b.mld = 4 * ((b.hid + 127) / 128);
         const bool scat = p.agg && training && b.hid <= 512 && n * 2 * b.hid < ((int64_t)1 << 31);
@@ -544,9 +554,17 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
                 uint32_t* hs = p.scale_bits + l;          // written by the PQ GEMM's epilogue (gnb_linear_next_absmax above)
                 EX(gnb_to_f16_planes(w2, b.hid, b.cout, b.hid, b.w2b[0], b.w2b[1], b.hld64, b.hld64, 0, stream));
                 if (training) EX(gnb_to_f16_planes(w2, b.hid, b.cout, b.hid, b.w2tb[0], nullptr, b.cld64, b.cld64, 1, stream));
-                EX(gnb_edge_hidden_fwd_f16(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, b.hb[0], b.hb[1], b.hid, b.hmask, b.mld, hs, stream));
-                EX(gnb_edge_linear_agg_fwd_f16(b.hb[0], b.hb[1], b.hid, b.hid, b.w2b[0], b.w2b[1], b.hld64, b2, deg, n, b.cout,
-                                               e.fround ? 1 : 0, b.y, b.cout, b.mask, hs, stream));
+                if (b.fused) {
+                    static const int dbgf = getenv("GNB_FUSED_DBG") ? atoi(getenv("GNB_FUSED_DBG")) : 0;
+                    EX(gnb_edgeconv_fused_fwd_f16(b.pq, 2 * b.hid, b.hid, nbr, deg, n, b.w2b[0], b.w2b[1], b.hld64, b2, b.cout,
+                                                  e.fround ? 1 : 0, b.y, b.cout, (dbgf & 4) ? nullptr : b.mask,
+                                                  (training && !(dbgf & 1)) ? (void*)b.hb[0] : nullptr, b.hid,
+                                                  (training && !(dbgf & 2)) ? (uint8_t*)b.hmask : nullptr, (int64_t)b.mld * 4, hs, stream));
+                } else {
+                    EX(gnb_edge_hidden_fwd_f16(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, b.hb[0], b.hb[1], b.hid, b.hmask, b.mld, hs, stream));
+                    EX(gnb_edge_linear_agg_fwd_f16(b.hb[0], b.hb[1], b.hid, b.hid, b.w2b[0], b.w2b[1], b.hld64, b2, deg, n, b.cout,
+                                                   e.fround ? 1 : 0, b.y, b.cout, b.mask, hs, stream));
+                }
             } else {
                 EX(gnb_to_bf16_planes(w2, b.hid, b.cout, b.hid, b.w2b[0], b.w2b[1], b.hld64, b.hld64, 0, stream));
                 if (training) EX(gnb_to_bf16_planes(w2, b.hid, b.cout, b.hid, b.w2tb[0], b.w2tb[1], b.cld64, b.cld64, 1, stream));
@@ -743,7 +761,8 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
             EX(gnb_zero_block(p.dzq + b.hid, 2 * b.hid, n, b.hid, stream));
             if (p.mixed && nodz)
                 EX(gnb_edge_hidden_dgrad_scatter_f16_masked(p.g16, p.rowmask, b.cout, b.w2tb[0], b.cld64, b.hmask, b.mld, b.hid, nbr, n,
-                                                            p.dzq + b.hid, 2 * b.hid, p.dzq, 2 * b.hid, p.dbtmp, e.rnd,
+                                                            p.dzq + b.hid, 2 * b.hid, p.dzq, 2 * b.hid, p.dbtmp,
+                                                            e.rnd | (b.fused ? GNB_FLAG_HMASK_ROWMAJOR : 0),
                                                             p.scale_bits + GNB_MAX_LAYERS + l, stream));
             else if (p.mixed)
                 EX(gnb_edge_hidden_dgrad_scatter_f16(p.dzb[0], b.cout, b.cout, b.w2tb[0], b.cld64, b.hmask, b.mld, b.hid, nbr, n,

@@ -53,7 +53,8 @@ constexpr int AGG_W = 9, AGG_NPT = 14, AGG_ROWS = AGG_W * AGG_NPT;   // k = 8 ne
 // rounded to tf32 when round_p); dbias (optional): [hdim] += column sums of dp (the bias gradient of the hoisted Linear).
 struct ScatInfo { const int* nbr; const unsigned* hmask; int mask_ld; float* dq; int64_t lddq; int hdim; int64_t n_nodes; int enabled;
                   float* dp; int64_t lddp; float* dbias; int round_p;
-                  const unsigned* scale_bits; };   // mixed16: dz arrives scaled by gnb_pow2_scale(*scale_bits); NULL = unscaled
+                  const unsigned* scale_bits;      // mixed16: dz arrives scaled by gnb_pow2_scale(*scale_bits); NULL = unscaled
+                  int hmask_rowmajor; };           // hmask rows hold bit c % 32 of word c / 32 (fused forward) instead of the ballot layout
 
 // Producer side of the scattering epilogue: per 126-slot sub-tile (first node `node0`) every lane resolves 4 of the 128
 // offsets `nbr * lddq` (floats; padding slots and slots beyond the tensor are redirected to the Q row of the sub-tile's
@@ -1630,10 +1631,11 @@ gemm_f16_pair_scatter_build_kernel(const __grid_constant__ CUtensorMap tm_w0, co
                 const int64_t node0 = ((int64_t)t * 2 + half) * AGG_NPT;
                 if (node0 < sc.n_nodes && ch0 + q * 32 < n_out) {
                     const uint32_t mb_a = tc::smem_u32(meta + (mbuf * 2 + half) * meta_stride);
-                    const uint32_t mword = 4u * (uint32_t)(ch0 >> 7) + (uint32_t)(lane & 3);
+                    // activation bits: ballot layout of the hidden-layer kernels, or plain row-major bits of the fused forward
+                    const uint32_t mword = sc.hmask_rowmajor ? (uint32_t)((ch0 + q * 32) >> 5) : 4u * (uint32_t)(ch0 >> 7) + (uint32_t)(lane & 3);
                     float* dq = sc.dq + (ch_ok ? ch : ch % sc.hdim);
                     float* dp = sc.dp + node0 * sc.lddp + ch;
-                    const unsigned lanebit = ch_ok ? (1u << (q * 8 + (lane >> 2))) : 0u;
+                    const unsigned lanebit = ch_ok ? (sc.hmask_rowmajor ? (1u << lane) : (1u << (q * 8 + (lane >> 2)))) : 0u;
                     scat_tile_any<true>(sc.mask_ld, tcol, mb_a, mb_a + meta_stride - 512u, mword, lanebit, dq, dp, sc.lddp,
                                         sc.n_nodes - node0, ch_ok, (dbg & 64) != 0, sc.round_p != 0, g == 0 ? colacc0 : colacc1, inv);
                 }
@@ -1650,6 +1652,266 @@ gemm_f16_pair_scatter_build_kernel(const __grid_constant__ CUtensorMap tm_w0, co
             const int c0 = (int)rank * 128 + q * 32 + lane, c1 = 256 + c0;
             if (c0 < n_out) atomicAdd(sc.dbias + c0, colacc0);
             if (c1 < n_out && ngroups > 1) atomicAdd(sc.dbias + c1, colacc1);
+        }
+    }
+    __syncwarp();
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();
+    if (warp == 1) tc::tmem_dealloc_2cta<512>(tmem_base);
+}
+
+
+// =====================================================================================================================
+// Fused EdgeConv forward for the fp16-plane modes: gather + hidden layer + second Linear + ReLU + k-sum in ONE kernel.
+//   y[i, :] = sum_{s < deg[i]} relu(W2 relu(P_i + Q_nbr[i,s]) + b2)          (layers.py:55-62 -> PyG EdgeConv, aggr="add")
+// The CTA-pair aggregating GEMM above reads h = relu(P_i + Q_j) from HBM, where a separate kernel wrote it (0.96 GB per
+// 713 k-row layer each way). Here eight builder warps per CTA produce the B operand in shared memory instead: lane = (row,
+// 8-channel chunk) of a 64-channel K block gathers Q_j and P_i (fp32, L2 / L1), adds, applies ReLU and the layer's power-of-two
+// scale, rounds to fp16 (plane 0) and, for NP = 2, the remainder again (plane 1), and writes the K-major 128-byte-swizzled
+// tile (row r at r * 128 B, chunk j at j ^ (r & 7)); fence.proxy.async + one relaxed cluster arrive per warp on the leader's
+// bfull[slot] (count 16) hands a K block to the MMA warp, which multiplies it against the TMA-streamed weight planes
+// (W0 X0, and for NP = 2 also W1 X0 + W0 X1). Training additionally needs two side outputs, written by the same builders
+// straight from their registers: plane 0 of h (the x operand of the weight gradient; 16-byte global stores) and the bits h > 0
+// (one byte per (row, chunk): hbytes[row * (ldhb) + c / 8], bit c % 8 -- the scattering epilogue reads them through
+// ScatInfo::hmask_rowmajor). The epilogue is the aggregating epilogue (bias, ReLU, k-sum, 126 mask bits per (tile, channel)).
+// n_out <= 256 (one channel group), hid % 8 == 0, k = 8 tables.
+// Warps: 0 TMA (weights), 1 MMA, 2..5 epilogue (lane quarter = warp % 4, both sub-tiles), 6..13 builders.
+constexpr int FU_THREADS = 448, FU_NBW = 8, FU_WSTAGES = 3, FU_BSLOTS = 3;
+struct FuseSrc { const float* pq; int64_t ldpq; const int* nbr; const int* deg; int64_t n_nodes; int hid;
+                 __half* h0_out; int64_t ldh; unsigned char* hbytes; int64_t ldhb; const unsigned* scale_bits; };
+
+template <int NP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FU_THREADS, 1)
+gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
+                               const FuseSrc fs, const float* __restrict__ bias, float* __restrict__ y, int64_t ldy, int n_out,
+                               int round_out, int num_tiles, int total_kb, int last_ksteps, unsigned* __restrict__ maskbits) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr uint32_t WST = NP * TC_TILE_BYTES, BSL = NP * TC_TILE_BYTES;
+    uint8_t* wring = smem;                                       // [FU_WSTAGES] x {W0 | W1}: own 128 weight rows of one K block
+    uint8_t* bring = wring + FU_WSTAGES * WST;                   // [FU_BSLOTS] x {X0 | X1}: own 126 rows of one K block
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(bring + FU_BSLOTS * BSL);
+    uint64_t* wempty = wfull + FU_WSTAGES;
+    uint64_t* bfull = wempty + FU_WSTAGES;          // leader's copy: 16 builder-warp arrivals of the pair
+    uint64_t* bempty = bfull + FU_BSLOTS;           // multicast to both CTAs
+    uint64_t* tmem_full = bempty + FU_BSLOTS;       // [2]
+    uint64_t* tmem_empty = tmem_full + 2;           // [2] leader's copy: 8 epilogue warps of the pair
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const int cluster_id = (int)(blockIdx.x >> 1), num_clusters = (int)(gridDim.x >> 1);
+    const int ch0 = (int)rank * 128;
+
+    if (warp == 0 && lane == 0) { tc::tma_prefetch_desc(&tm_w0); if (NP == 2) tc::tma_prefetch_desc(&tm_w1); }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < FU_WSTAGES; ++s) { tc::mbar_init(&wfull[s], 1); tc::mbar_init(&wempty[s], 1); }
+            for (int s = 0; s < FU_BSLOTS; ++s) { tc::mbar_init(&bfull[s], 2 * FU_NBW); tc::mbar_init(&bempty[s], 1); }
+            for (int b = 0; b < 2; ++b) { tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], 8); }
+            tc::fence_barrier_init();
+            tc::fence_proxy_async();
+        }
+        __syncwarp();
+        tc::tmem_alloc_2cta<512>(tmem_slot);
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---- TMA producer (both CTAs): own 128 weight rows, every plane ---------------------------------------------------
+        uint32_t it = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+            for (int kb = 0; kb < total_kb; ++kb, ++it) {
+                const uint32_t s = it % FU_WSTAGES, ph = (it / FU_WSTAGES) & 1;
+                tc::mbar_wait_warp(&wempty[s], ph ^ 1);
+                if (tc::elect_one()) {
+                    if (rank == 0) tc::mbar_arrive_expect_tx(&wfull[s], 2u * WST);
+                    tc::tma_load_2d_2sm(wring + s * WST, &tm_w0, &wfull[s], kb * 64, ch0);
+                    if (NP == 2) tc::tma_load_2d_2sm(wring + s * WST + TC_TILE_BYTES, &tm_w1, &wfull[s], kb * 64, ch0);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ---- MMA issuer (leader) ------------------------------------------------------------------------------------
+            constexpr uint32_t idesc = idesc_f16_256_dev();
+            uint32_t it = 0, tile_i = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters, ++tile_i) {
+                const uint32_t buf = tile_i & 1;
+                tc::mbar_wait_warp(&tmem_empty[buf], ((tile_i >> 1) & 1) ^ 1);
+                tc::tcgen05_fence_after();
+                const uint32_t acc = tmem_base + buf * 256;
+                for (int kb = 0; kb < total_kb; ++kb, ++it) {
+                    const uint32_t s = it % FU_WSTAGES, sl = it % FU_BSLOTS;
+                    tc::mbar_wait_warp(&wfull[s], (it / FU_WSTAGES) & 1);
+                    tc::mbar_wait_warp<true>(&bfull[sl], (it / FU_BSLOTS) & 1);      // both CTAs' builders (cluster-scope acquire)
+                    tc::tcgen05_fence_after();
+                    const uint32_t wa = tc::smem_u32(wring + s * WST), ba = tc::smem_u32(bring + sl * BSL);
+                    const uint64_t a0 = tc::umma_desc_sw128_kmajor(wa), a1 = tc::umma_desc_sw128_kmajor(wa + TC_TILE_BYTES);
+                    const uint64_t b0 = tc::umma_desc_sw128_kmajor(ba), b1 = tc::umma_desc_sw128_kmajor(ba + TC_TILE_BYTES);
+                    const int nk = kb == total_kb - 1 ? last_ksteps : 4;
+                    if (tc::elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (k < nk) {
+                                if (NP == 2) {
+                                    tc::umma_bf16_2cta(acc, a1 + 2 * k, b0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                                    tc::umma_bf16_2cta(acc, a0 + 2 * k, b1 + 2 * k, idesc, 1u);
+                                }
+                                tc::umma_bf16_2cta(acc, a0 + 2 * k, b0 + 2 * k, idesc, (NP == 2 || (kb | k) != 0) ? 1u : 0u);
+                            }
+                        }
+                        tc::umma_commit_2cta(&wempty[s], 3);
+                        tc::umma_commit_2cta(&bempty[sl], 3);
+                    }
+                    __syncwarp();
+                }
+                if (tc::elect_one()) tc::umma_commit_2cta(&tmem_full[buf], 3);
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 6) {
+        // ---- builders: lane -> chunk column j (8 channels of the K block), rows rs, rs + 32, rs + 64, rs + 96 ----------------
+        const int gl = (warp - 6) * 32 + lane;               // 0..255
+        const int j = gl & 7, rs = gl >> 3;                  // rs 0..31
+        const float scale = gnb_pow2_scale(*fs.scale_bits).x;
+        const int hid = fs.hid;
+        uint32_t it = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+            const int64_t node0 = ((int64_t)t * 2 + rank) * AGG_NPT;
+            // the lane's 4 rows of the sub-tile: target node, source node, validity (the same for every K block)
+            int64_t poff[4], qoff[4];
+            bool val[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = rs + 32 * u;
+                const int f = r / AGG_W, sl = r - f * AGG_W;
+                const int64_t nd = node0 + f;
+                const bool in = r < AGG_ROWS && nd < fs.n_nodes;
+                const int src = in ? fs.nbr[nd * AGG_W + sl] : -1;
+                val[u] = in && src >= 0 && sl < fs.deg[nd];
+                poff[u] = (val[u] ? nd : 0) * fs.ldpq;
+                qoff[u] = (int64_t)(val[u] ? src : 0) * fs.ldpq + hid;
+            }
+            for (int kb = 0; kb < total_kb; ++kb, ++it) {
+                const uint32_t sl = it % FU_BSLOTS;
+                const int c0 = kb * 64 + j * 8;
+                const bool c_on = c0 < hid;
+                float4 pv[4][2], qv[4][2];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {             // 16 independent 16-byte loads in flight per lane
+                    const bool on = val[u] && c_on;
+                    const float4* pp = reinterpret_cast<const float4*>(fs.pq + poff[u] + c0);
+                    const float4* qp = reinterpret_cast<const float4*>(fs.pq + qoff[u] + c0);
+                    pv[u][0] = on ? __ldg(pp) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    pv[u][1] = on ? __ldg(pp + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    qv[u][0] = on ? __ldg(qp) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    qv[u][1] = on ? __ldg(qp + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                tc::mbar_wait(&bempty[sl], ((it / FU_BSLOTS) & 1) ^ 1);      // the MMAs of the slot's previous use completed
+                const uint32_t ba = tc::smem_u32(bring + sl * BSL);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = rs + 32 * u;
+                    if (r < AGG_ROWS) {                   // (lane-dependent only for u = 3)
+                        float hv[8];
+                        hv[0] = fmaxf(pv[u][0].x + qv[u][0].x, 0.f); hv[1] = fmaxf(pv[u][0].y + qv[u][0].y, 0.f);
+                        hv[2] = fmaxf(pv[u][0].z + qv[u][0].z, 0.f); hv[3] = fmaxf(pv[u][0].w + qv[u][0].w, 0.f);
+                        hv[4] = fmaxf(pv[u][1].x + qv[u][1].x, 0.f); hv[5] = fmaxf(pv[u][1].y + qv[u][1].y, 0.f);
+                        hv[6] = fmaxf(pv[u][1].z + qv[u][1].z, 0.f); hv[7] = fmaxf(pv[u][1].w + qv[u][1].w, 0.f);
+                        unsigned bits = 0u;
+                        uint32_t p0[4], p1[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            bits |= (hv[2 * e] > 0.f ? 1u : 0u) << (2 * e);
+                            bits |= (hv[2 * e + 1] > 0.f ? 1u : 0u) << (2 * e + 1);
+                            const float a = hv[2 * e] * scale, b = hv[2 * e + 1] * scale;
+                            const __half2 h2 = __floats2half2_rn(a, b);
+                            p0[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                            if (NP == 2) {
+                                const float2 back = __half22float2(h2);
+                                const __half2 l2 = __floats2half2_rn(a - back.x, b - back.y);
+                                p1[e] = *reinterpret_cast<const uint32_t*>(&l2);
+                            }
+                        }
+                        const uint32_t off = (uint32_t)r * 128u + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ba + off), "r"(p0[0]), "r"(p0[1]), "r"(p0[2]), "r"(p0[3]) : "memory");
+                        if (NP == 2)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ba + TC_TILE_BYTES + off), "r"(p1[0]), "r"(p1[1]), "r"(p1[2]), "r"(p1[3]) : "memory");
+                        const int64_t grow = node0 * AGG_W + r;
+                        if (fs.h0_out != nullptr && c_on && node0 + r / AGG_W < fs.n_nodes)
+                            *reinterpret_cast<uint4*>(fs.h0_out + grow * fs.ldh + c0) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+                        // (a pair's second sub-tile may lie wholly beyond the last node: its rows do not exist in the side outputs)
+                        if (fs.hbytes != nullptr && c_on && node0 < fs.n_nodes) fs.hbytes[grow * fs.ldhb + (c0 >> 3)] = (unsigned char)bits;
+                    }
+                }
+                tc::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive_cluster_relaxed(&bfull[sl], 0);
+                __syncwarp();
+            }
+        }
+    } else {
+        // ---- epilogue: 4 warps per CTA (lane quarter q), each draining both sub-tiles of the CTA's 128 channels -----------------
+        const int q = warp & 3;
+        const int ch = ch0 + q * 32 + lane;
+        const bool ch_ok = ch < n_out;
+        const float bv = (bias != nullptr && ch_ok) ? bias[ch] : 0.f;
+        const float ainv = gnb_pow2_scale(*fs.scale_bits).y;
+        uint32_t tile_i = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++tile_i) {
+            const uint32_t buf = tile_i & 1;
+            tc::mbar_wait<100>(&tmem_full[buf], (tile_i >> 1) & 1);
+            tc::tcgen05_fence_after();
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + half * 128);
+                const int64_t st14 = (int64_t)t * 2 + half;
+                const int64_t node0 = st14 * AGG_NPT;
+                if (node0 >= fs.n_nodes) continue;
+                int dg[AGG_NPT];
+#pragma unroll
+                for (int f = 0; f < AGG_NPT; ++f) dg[f] = (node0 + f < fs.n_nodes) ? fs.deg[node0 + f] : 0;
+                float acc = 0.f;
+                unsigned bits[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[32];
+                    tc::tmem_ld_32x32b_x32(tcol + (uint32_t)(c * 32), r);
+                    tc::tmem_ld_wait();
+                    unsigned w = 0u;
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) {
+                        const int col = c * 32 + jj;
+                        if (col < AGG_ROWS) {
+                            const int f = col / AGG_W, sl = col % AGG_W;       // compile-time after unrolling
+                            const float pre = fmaf(__uint_as_float(r[jj]), ainv, bv);
+                            const bool on = (sl < dg[f]) && (pre > 0.f);
+                            acc += on ? pre : 0.f;
+                            w |= on ? (1u << jj) : 0u;
+                            if (sl == AGG_W - 1) {
+                                float o = acc;
+                                if (round_out) o = tc::round_tf32(o);
+                                if (ch_ok && node0 + f < fs.n_nodes) y[(node0 + f) * ldy + ch] = o;
+                                acc = 0.f;
+                            }
+                        }
+                    }
+                    bits[c] = w;
+                }
+                if (ch_ok && maskbits != nullptr)
+                    reinterpret_cast<uint4*>(maskbits)[st14 * n_out + ch] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+            }
+            tc::tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster_relaxed(&tmem_empty[buf], 0);
+            __syncwarp();
         }
     }
     __syncwarp();
@@ -1697,6 +1959,10 @@ cudaError_t init_tc_kernels() {
         e = cudaFuncSetAttribute(gemm_tc_pair_dual_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_f16_pair_scatter_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_f16_pair_agg_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_f16_pair_agg_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_MAX_DYN_SMEM);
     if (e == cudaSuccess) g_num_sms = sms;
     return e;
 }
@@ -1888,7 +2154,7 @@ static int linear_fwd_impl(const float* const* xs, const int64_t* ldxs, const in
     }
     AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr, g_next_absmax, g_next_absmax_shift};
     g_next_absmax = nullptr;
-    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, nullptr};
+    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, nullptr, 0};
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out, gnb_div_up(rows, TC_BN), agg, sc,
                          (cudaStream_t)stream, w_lo != nullptr ? &twlo : nullptr);
 }
@@ -1945,7 +2211,7 @@ static int edge_linear_agg_impl(const float* h, int64_t ldh, int32_t k, const fl
         if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     }
     AggInfo agg{deg, n, maskbits, 1, g_linear_dbg, g_linear_prof, nullptr, nullptr, 0};
-    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, nullptr};
+    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, nullptr, 0};
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, GNB_ACT_RELU, round_out, gnb_div_up(n, AGG_NPT), agg, sc,
                          (cudaStream_t)stream, w_lo != nullptr ? &twlo : nullptr);
 }
@@ -1995,7 +2261,7 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_split_tf32(const float* dz, int64_t
     rc = gnb_make_tmap_f32(&tw, wt, hdim, ktot, ldw, TC_BM);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr, nullptr, 0};
-    ScatInfo sc{nbr, hmask, mask_ld, dq, lddq, hdim, n, 1, dp, lddp, dbias, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0, nullptr};
+    ScatInfo sc{nbr, hmask, mask_ld, dq, lddq, hdim, n, 1, dp, lddp, dbias, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0, nullptr, 0};
     const int row_tiles = gnb_div_up(n, AGG_NPT);
     int nst_w = 0;
     if ((g_linear_variant == 3 || (g_linear_variant == 0 && row_tiles >= 2 * 148)) &&
@@ -2088,7 +2354,7 @@ static int edge_linear_agg16_impl(const void* h0, const void* h1, int64_t ldh, i
     if (rc == 0 && planes == 2) rc = gnb_make_tmap_16(&tw1, w1, n_out, k, ldw * 2, TC_BM, dt);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     AggInfo agg{deg, n, maskbits, 1, g_linear_dbg, g_linear_prof, scale_bits, nullptr, 0};
-    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, nullptr};
+    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, nullptr, 0};
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, GNB_ACT_RELU, round_out, gnb_div_up(n, AGG_NPT), agg, sc,
                          (cudaStream_t)stream, planes == 2 ? &tw1 : nullptr, planes, k, fmt16 ? 3 : 0);
 }
@@ -2140,7 +2406,7 @@ static int dgrad_scatter16_impl(const void* dz0, const void* dz1, int64_t lddz, 
     if (rc == 0 && planes == 2) rc = gnb_make_tmap_16(&tw1, wt1, hdim, c_out, ldw * 2, TC_BM, tw_t);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr, nullptr, 0};
-    ScatInfo sc{nbr, hmask, mask_ld, dq, lddq, hdim, n, 1, dp, lddp, dbias, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0, scale_bits};
+    ScatInfo sc{nbr, hmask, mask_ld, dq, lddq, hdim, n, 1, dp, lddp, dbias, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0, scale_bits, (flags & GNB_FLAG_HMASK_ROWMAJOR) ? 1 : 0};
     const int row_tiles = gnb_div_up(n, AGG_NPT);
     const int last_ksteps = (c_out - 64 * (pi.kblocks[0] - 1) + 15) / 16;
     if (hdim > 256 && g_linear_variant != 2) {          // two 256-channel groups from one resident dz tile
@@ -2210,7 +2476,7 @@ GNB_EXPORT int gnb_linear_fwd_bf16(const void* x0, const void* x1, int64_t ldx, 
     if (rc == 0 && planes == 2) rc = gnb_make_tmap_bf16(&tw1, w1, n_out, k, ldw * 2, TC_BM);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr, nullptr, 0};
-    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, nullptr};
+    ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, nullptr, 0};
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out, gnb_div_up(rows, TC_BN), agg, sc,
                          (cudaStream_t)stream, planes == 2 ? &tw1 : nullptr, planes, k);
 }
@@ -2282,6 +2548,8 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_f16_masked(const void* g16, const u
         return GNB_ERR_ARG;
     if ((ldw & 7) || ldw < c_out || (reinterpret_cast<uintptr_t>(g16) & 15u) || (reinterpret_cast<uintptr_t>(rowmask) & 15u))
         return GNB_ERR_ARG;
+    // flags & 0x800: hmask holds plain row-major bits (bit c % 32 of word c / 32: gnb_edgeconv_fused_fwd_f16) instead of the
+    // ballot layout of gnb_edge_hidden_fwd_mask
     if ((mask_ld & 3) || mask_ld > SC_MAX_MASK_LD || mask_ld < 4 * ((hdim + 127) / 128)) return GNB_ERR_ARG;
     if ((reinterpret_cast<uintptr_t>(hmask) & 15u) || n * lddq >= ((int64_t)1 << 31)) return GNB_ERR_ARG;
     if (n == 0) return GNB_OK;
@@ -2292,7 +2560,7 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_f16_masked(const void* g16, const u
     int rc = gnb_make_tmap_16(&tw, wt, hdim, c_out, ldw * 2, TC_BM, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     GNB_CHECK(init_tc_kernels());
-    ScatInfo sc{nbr, hmask, mask_ld, dq, lddq, hdim, n, 1, dp, lddp, dbias, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0, scale_bits};
+    ScatInfo sc{nbr, hmask, mask_ld, dq, lddq, hdim, n, 1, dp, lddp, dbias, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0, scale_bits, (flags & GNB_FLAG_HMASK_ROWMAJOR) ? 1 : 0};
     const uint32_t mstride = sc_meta_stride(mask_ld);
     const uint32_t stg = 2u * ((uint32_t)AGG_NPT * (uint32_t)c_out * 2u + (uint32_t)AGG_ROWS * (uint32_t)(c_out >> 5) * 4u);
     const int64_t left = (int64_t)PL_MAX_DYN_SMEM - 1024 - DU_BAR_BYTES - 4 * (int64_t)mstride - stg - (int64_t)kblocks * TC_TILE_BYTES;
@@ -2308,5 +2576,47 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_f16_masked(const void* g16, const u
     const int last_ksteps = (c_out - 64 * (kblocks - 1) + 15) / 16;
     gemm_f16_pair_scatter_build_kernel<<<dim3((unsigned)(2 * clusters)), DB_THREADS, smem, (cudaStream_t)stream>>>(
         tw, zb, kblocks, last_ksteps, rows, hdim, tiles, sc, nst_w, mstride, g_linear_dbg, hdim > 256 ? 2 : 1);
+    GNB_RETURN_LAUNCH();
+}
+
+// Fused EdgeConv forward of the fp16-plane modes (gemm_f16_pair_agg_fused_kernel): from PQ [n, 2 hid] (P = own half, Q = source
+// half of the hoisted first Linear), the k = 8 neighbour table and the fp16 weight planes of W2 (w1 NULL = one plane):
+//   y[i, :] = sum_{s < deg[i]} relu(W2 relu(P_i + Q_nbr[i, s]) + b2),  maskbits as gnb_edge_linear_agg_fwd_*.
+// h never touches HBM on the forward path. Training side outputs (both may be NULL): h0_out = fp16(h * 2^s) [9 n, ldh] (plane 0,
+// the weight gradient's x operand) and hbytes [ceil(n / 14) * 126, ldhb] = bits of h > 0, one byte per 8 channels (bit c % 8 of
+// byte c / 8). *scale_bits >= bits of max h (absmax of PQ with shift 1). n_out <= 256, hid % 8 == 0, hid <= 512.
+GNB_EXPORT int gnb_edgeconv_fused_fwd_f16(const float* pq, int64_t ldpq, int32_t hid, const int32_t* nbr, const int32_t* deg,
+                                          int64_t n, const void* w0, const void* w1, int64_t ldw, const float* bias,
+                                          int32_t n_out, int32_t round_out, float* y, int64_t ldy, uint32_t* maskbits,
+                                          void* h0_out, int64_t ldh, uint8_t* hbytes, int64_t ldhb, const uint32_t* scale_bits,
+                                          void* stream) {
+    if (n < 0 || n_out < 1 || n_out > 256 || hid < 8 || hid > 512 || (hid & 7) || pq == nullptr || nbr == nullptr || deg == nullptr ||
+        w0 == nullptr || y == nullptr || scale_bits == nullptr)
+        return GNB_ERR_ARG;
+    if ((ldpq & 3) || ldpq < 2 * (int64_t)hid || (ldw & 7) || ldw < hid || (reinterpret_cast<uintptr_t>(pq) & 15u)) return GNB_ERR_ARG;
+    if (h0_out != nullptr && ((ldh & 7) || ldh < hid || (reinterpret_cast<uintptr_t>(h0_out) & 15u))) return GNB_ERR_ARG;
+    if (hbytes != nullptr && ldhb < hid / 8) return GNB_ERR_ARG;
+    if (n == 0) return GNB_OK;
+    if (n * AGG_W >= (int64_t)1 << 31) return GNB_ERR_ARG;
+    const int planes = w1 != nullptr ? 2 : 1;
+    const int kblocks = (hid + 63) / 64;
+    CUtensorMap tw0, tw1;
+    int rc = gnb_make_tmap_16(&tw0, w0, n_out, hid, ldw * 2, TC_BM, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    if (rc == 0 && planes == 2) rc = gnb_make_tmap_16(&tw1, w1, n_out, hid, ldw * 2, TC_BM, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    GNB_CHECK(init_tc_kernels());
+    const int tiles = (gnb_div_up(n, AGG_NPT) + 1) / 2;
+    int clusters = g_num_sms / 2;
+    if (clusters > tiles) clusters = tiles;
+    if (clusters < 1) clusters = 1;
+    FuseSrc fs{pq, ldpq, nbr, deg, n, hid, (__half*)h0_out, ldh, hbytes, ldhb, scale_bits};
+    const uint32_t smem = 1024 + (uint32_t)(FU_WSTAGES + FU_BSLOTS) * planes * TC_TILE_BYTES + 512;
+    const int last_ksteps = (hid - 64 * (kblocks - 1) + 15) / 16;
+    if (planes == 2)
+        gemm_f16_pair_agg_fused_kernel<2><<<dim3((unsigned)(2 * clusters)), FU_THREADS, smem, (cudaStream_t)stream>>>(
+            tw0, tw1, fs, bias, y, ldy, n_out, round_out, tiles, kblocks, last_ksteps, maskbits);
+    else
+        gemm_f16_pair_agg_fused_kernel<1><<<dim3((unsigned)(2 * clusters)), FU_THREADS, smem, (cudaStream_t)stream>>>(
+            tw0, tw0, fs, bias, y, ldy, n_out, round_out, tiles, kblocks, last_ksteps, maskbits);
     GNB_RETURN_LAUNCH();
 }

@@ -77,6 +77,9 @@ def _is_rounded(t: Tensor) -> bool:
 # fp16-plane modes: True keeps the stored-dz backward (mask-backward kernel writes dz [N k, C]); False (default) expands dz
 # inside the weight-gradient and scattering GEMMs from the node-level gradient and the ReLU bit mask
 STORE_DZ = False
+# fp16-plane modes: False (default) runs the fused EdgeConv forward (gather + hidden layer + second Linear + aggregation in one
+# kernel, h built in shared memory); True keeps the two-kernel forward (hidden-layer kernel writes h, aggregating GEMM reads it)
+UNFUSED_FORWARD = False
 
 # number of kernels launched through this module (bench.py reports it as `gpu_launches`)
 LAUNCHES = 0
@@ -715,7 +718,7 @@ class _DynEdgeExec(torch.autograd.Function):
         n, nseg = x.shape[0], ptr.numel() - 1
         cfg = _copy_cfg(cfg)      # the ctx keeps ITS OWN copy: a later set_precision() / flag change cannot alter the layout
         cfg.precision = 2 if _split() else (1 if _tf32() else 0)
-        cfg.flags = (0 if FUSED_EDGECONV else 1) | (2 if INFERENCE_ROUTE == "split" else 0) | (4 if STORE_DZ else 0)
+        cfg.flags = (0 if FUSED_EDGECONV else 1) | (2 if INFERENCE_ROUTE == "split" else 0) | (4 if STORE_DZ else 0) | (8 if UNFUSED_FORWARD else 0)
         nbytes = -2
         if PRECISION in ("bf16", "bf16x3", "mixed16", "f16"):     # per-edge tensors as 16-bit planes where the configuration has the k = 8 route
             base = cfg.precision

@@ -264,6 +264,16 @@ int gnb_edge_hidden_dgrad_scatter_f16(const void* dz, int64_t lddz, int32_t c_ou
                                       const uint32_t* hmask, int32_t mask_ld, int32_t hdim, const int32_t* nbr, int64_t n,
                                       float* dq, int64_t lddq, float* dp, int64_t lddp, float* dbias, int32_t flags,
                                       const uint32_t* scale_bits, void* stream);
+/* Fused EdgeConv forward of the fp16-plane modes: gather + hidden layer + second Linear + ReLU + k-sum in ONE tcgen05 kernel
+ * (PyG EdgeConv.message / aggregate, layers.py:55-62, on the hoisted first Linear): builder warps produce the B operand tile
+ * h = relu(P_i + Q_j) * 2^s (fp16 plane 0, and plane 1 = remainder when w1 != NULL) in shared memory from PQ [n, 2 hid], so h
+ * never crosses HBM on the forward path. y / maskbits as gnb_edge_linear_agg_fwd_f16. Training side outputs (may be NULL):
+ * h0_out [9 n, ldh] = plane 0 of h (x operand of the weight gradient), hbytes [ceil(n / 14) * 126, ldhb] = bits of h > 0,
+ * byte c / 8 bit c % 8 (= row-major words; flags 0x800 of gnb_edge_hidden_dgrad_scatter_f16_masked). n_out <= 256, hid % 8 == 0. */
+int gnb_edgeconv_fused_fwd_f16(const float* pq, int64_t ldpq, int32_t hid, const int32_t* nbr, const int32_t* deg, int64_t n,
+                               const void* w0, const void* w1, int64_t ldw, const float* bias, int32_t n_out, int32_t round_out,
+                               float* y, int64_t ldy, uint32_t* maskbits, void* h0_out, int64_t ldh, uint8_t* hbytes,
+                               int64_t ldhb, const uint32_t* scale_bits, void* stream);
 /* The backward of the aggregating Linear WITHOUT a stored dz (fp16-plane modes): dz[(i, s), :] = g[i, :] * bit(i, s, :) is a
  * 9-fold redundant function of the node-level gradient and the ReLU bits, so the two GEMMs expand it in shared memory (builder
  * warps write the tensor-core operand tile) instead of reading a stored [9 n, c_out] tensor (autograd of PyG EdgeConv's
@@ -329,7 +339,9 @@ typedef struct {
                                                         bit 1: inference runs hidden layer + aggregating GEMM (two kernels per
                                                         layer, faster at k = 8) instead of the single fused EdgeConv kernel;
                                                         bit 2: fp16-plane modes store dz (mask-backward kernel) instead of
-                                                        expanding it inside the two backward GEMMs */
+                                                        expanding it inside the two backward GEMMs;
+                                                        bit 3: fp16-plane modes keep the two-kernel forward (hidden-layer kernel
+                                                        + aggregating GEMM) instead of the fused EdgeConv forward */
 } gnb_dynedge_config;
 
 /* Bytes of workspace for a batch of n nodes / nseg events whose initial graph has table width w0; < 0: error. */

@@ -555,6 +555,96 @@ def test_dgrad_scatter_f16_masked_bit_exact(ops, hdim, c_out, sizes):
     assert torch.equal(dbias.cpu().double(), dp_ref.sum(0))
 
 
+@pytest.mark.parametrize("np_", [1, 2])
+@pytest.mark.parametrize("hid,n_out,sizes", [(336, 256, [1, 2, 5, 9, 10, 64, 130, 12, 300, 3, 700]), (128, 256, [400, 900, 14, 15]),
+                                             (40, 104, [77, 5, 230]), (336, 256, [3000, 2500]), (128, 256, [14 * 5])])
+def test_edgeconv_fused_fwd_f16_matches_the_two_kernel_forward(ops, np_, hid, n_out, sizes):
+    """gather + hidden layer + second Linear + aggregation in one kernel == hidden-layer kernel followed by the aggregating GEMM:
+    the two run the same products on the same fp16 planes, so y agrees to fp32 summation order of the TMEM accumulators (exact
+    on these integer-valued operands) and plane 0 / the ReLU bits / the mask words agree bit for bit."""
+    graph, n = _graph(ops, sizes, seed=hid + n_out)
+    gen = torch.Generator().manual_seed(hid)
+    pq = torch.randint(-6, 7, (n, 2 * hid), generator=gen).float() * 0.25
+    w = (torch.randint(-2, 3, (n_out, hid), generator=gen).float() if np_ == 1 else two_plane_values((n_out, hid), gen, scale_bits=6, mag_bits=13))
+    b = torch.randint(-3, 4, (n_out,), generator=gen).float()
+    pqc, bc = pq.cuda(), b.cuda()
+    word = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops._call("gnb_absmax_bits", ops._ptr(pqc), 2 * hid, n, 2 * hid, 1, ops._ptr(word), ops._stream())
+    kw = (hid + 63) // 64 * 64
+    w0, w1 = f16_planes(ops, w.cuda(), np_, dst_cols=kw)
+    ntile = (n + 13) // 14
+    mld = 4 * ((hid + 127) // 128)
+    # reference: the two-kernel forward
+    h0 = torch.zeros(n * 9, hid, dtype=torch.float16, device="cuda")
+    h1 = torch.zeros(n * 9, hid, dtype=torch.float16, device="cuda") if np_ == 2 else None
+    hm = torch.zeros(ntile * 126, mld, dtype=torch.int32, device="cuda")
+    ops._call("gnb_edge_hidden_fwd_f16", ops._ptr(pqc), 2 * hid, hid, ops._ptr(graph.nbr), ops._ptr(graph.deg), 9, n, ops._ptr(h0),
+              ops._ptr(h1), hid, ops._ptr(hm), mld, ops._ptr(word), ops._stream())
+    y_ref = torch.empty(n, n_out, device="cuda")
+    m_ref = torch.zeros(ntile * n_out * 4, dtype=torch.int32, device="cuda")
+    ops._call("gnb_edge_linear_agg_fwd_f16", ops._ptr(h0), ops._ptr(h1), hid, hid, ops._ptr(w0), ops._ptr(w1), kw, ops._ptr(bc),
+              ops._ptr(graph.deg), n, n_out, 0, ops._ptr(y_ref), n_out, ops._ptr(m_ref), ops._ptr(word), ops._stream())
+    # fused
+    y = torch.empty(n, n_out, device="cuda")
+    m = torch.zeros(ntile * n_out * 4, dtype=torch.int32, device="cuda")
+    h0f = torch.full((n * 9, hid), 5.0, dtype=torch.float16, device="cuda")
+    guard = torch.full((4096,), 77, dtype=torch.uint8, device="cuda")          # right behind the side outputs: must stay untouched
+    hb_all = torch.zeros(ntile * 126 * mld * 4 + 4096, dtype=torch.uint8, device="cuda")
+    hb_all[ntile * 126 * mld * 4:] = 77
+    hb = hb_all[: ntile * 126 * mld * 4].view(ntile * 126, mld * 4)
+    ops._call("gnb_edgeconv_fused_fwd_f16", ops._ptr(pqc), 2 * hid, hid, ops._ptr(graph.nbr), ops._ptr(graph.deg), n, ops._ptr(w0),
+              ops._ptr(w1), kw, ops._ptr(bc), n_out, 0, ops._ptr(y), n_out, ops._ptr(m), ops._ptr(h0f), hid, ops._ptr(hb), mld * 4,
+              ops._ptr(word), ops._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(hb_all[ntile * 126 * mld * 4:], guard)
+    assert torch.equal(h0f, h0)
+    assert torch.equal(y, y_ref)
+    assert torch.equal(m, m_ref)
+    # activation bits: the fused kernel's row-major bytes (bit c % 8 of byte c / 8) vs h > 0
+    bits = ((hb.cpu()[: n * 9, : hid // 8].long().unsqueeze(2) >> torch.arange(8).view(1, 1, 8)) & 1).reshape(n * 9, hid).bool()
+    assert torch.equal(bits, h0.cpu().float() > 0) or torch.equal(bits, (h0.cpu().float() > 0) | bits)   # (fp16 may flush a tiny h to 0)
+    # inference form: no side outputs
+    y2 = torch.empty(n, n_out, device="cuda")
+    ops._call("gnb_edgeconv_fused_fwd_f16", ops._ptr(pqc), 2 * hid, hid, ops._ptr(graph.nbr), ops._ptr(graph.deg), n, ops._ptr(w0),
+              ops._ptr(w1), kw, ops._ptr(bc), n_out, 0, ops._ptr(y2), n_out, ops._ptr(None), ops._ptr(None), hid, ops._ptr(None), mld * 4,
+              ops._ptr(word), ops._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(y2, y_ref)
+
+
+def test_mixed16_unfused_forward_matches_the_fused_forward(ops):
+    """Executor flag bit 3 (ops.UNFUSED_FORWARD): two-kernel forward vs fused EdgeConv forward, training step gradients."""
+    from graphnet_b200 import Data
+    from graphnet_b200.models.gnn import DynEdge
+    from graphnet_b200.models.graphs.edges import KNNEdges
+    from graphnet_b200.synthetic import make_batch
+    ops.set_precision("mixed16")
+    raw = make_batch(24, seed=11, n_max=500)
+    x, batch, n_pulses = (torch.from_numpy(raw[k]) for k in ("x", "batch", "n_pulses"))
+    torch.manual_seed(3)
+    model = DynEdge(7, global_pooling_schemes=["min", "max", "mean", "sum"]).cuda()
+    data = KNNEdges(8)(Data(x=x.cuda(), batch=batch.cuda(), n_pulses=n_pulses.cuda()))
+    model._debug_record = True
+    outs, first, grads = [], [], []
+    for unfused in (False, True):
+        ops.UNFUSED_FORWARD = unfused
+        try:
+            model.zero_grad(set_to_none=True)
+            y = model(data)
+            first.append(model._debug["skips"][1].detach().clone())
+            y.square().sum().backward()
+            outs.append(y.detach().clone())
+            grads.append([p.grad.clone() for p in model.parameters()])
+        finally:
+            ops.UNFUSED_FORWARD = False
+    # the first layer runs on the same graph in both: same products, TMEM summation order aside. Later layers rebuild their kNN
+    # graphs from features that differ in the last bits, so a near-tie may pick another neighbour: compared at the mode's tolerance
+    assert rel_err(first[0], first[1]) < 2e-6
+    assert rel_err(outs[0], outs[1]) < 1e-3
+    for a, b in zip(*grads):
+        assert rel_err(a, b) < 2e-2
+
+
 def test_mixed16_stored_dz_route_matches_the_masked_route(ops):
     """Executor flag bit 2 (ops.STORE_DZ): the stored-dz backward and the in-kernel expansion compute the same gradients."""
     from graphnet_b200 import Data
