@@ -1778,65 +1778,90 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
         }
     } else if (warp >= 6) {
         // ---- builders: lane -> chunk column j (8 channels of the K block), rows rs, rs + 32, rs + 64, rs + 96 ----------------
+        // What the first version measured (ncu, profiles/r02/r_fused_fwd.ncu-rep): 612 SASS instructions per lane and K block
+        // -- a third of them 64-bit address arithmetic and zero fills recomputed every K block -- and a third of the builders'
+        // time waiting for the gathers right behind their issue. Hence: row offsets as 32-bit counts of 16-byte units, fixed
+        // per tile (one IMAD.WIDE per load); padding rows gather row 0 and are zeroed by a per-row scale of 0 (no predicated
+        // loads, no zero fills); the K block is built in two halves (rows u = 0, 1 / u = 2, 3) whose gathers are issued half
+        // a K block ahead of their use; the next tile's neighbour-table entries are fetched under the current tile's K loop.
         const int gl = (warp - 6) * 32 + lane;               // 0..255
         const int j = gl & 7, rs = gl >> 3;                  // rs 0..31
         const float scale = gnb_pow2_scale(*fs.scale_bits).x;
         const int hid = fs.hid;
+        const uint32_t ld16 = (uint32_t)(fs.ldpq >> 2);                         // PQ row pitch in 16-byte units
+        const uint32_t p16 = 2u * (uint32_t)j, q16 = (uint32_t)(hid >> 2) + 2u * (uint32_t)j;
+        const float4* pq4 = reinterpret_cast<const float4*>(fs.pq);
+        uint4* h0v = reinterpret_cast<uint4*>(fs.h0_out);
+        const uint32_t ldh16 = (uint32_t)(fs.ldh >> 3), ldhb = (uint32_t)fs.ldhb;
+        int fr[4], sr[4];                                    // (node, slot) of the lane's rows inside a 14-node sub-tile
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int r = rs + 32 * u; fr[u] = r / AGG_W; sr[u] = r - fr[u] * AGG_W; }
+        int src_n[4], dg_n[4];
+        auto fetch_rows = [&](int t) {
+            const int64_t node0 = ((int64_t)t * 2 + rank) * AGG_NPT;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t nd = node0 + fr[u];
+                const bool in = rs + 32 * u < AGG_ROWS && nd < fs.n_nodes;
+                src_n[u] = in ? __ldg(fs.nbr + nd * AGG_W + sr[u]) : -1;
+                dg_n[u] = in ? __ldg(fs.deg + nd) : 0;
+            }
+        };
+        if (cluster_id < num_tiles) fetch_rows(cluster_id);
         uint32_t it = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
             const int64_t node0 = ((int64_t)t * 2 + rank) * AGG_NPT;
-            // the lane's 4 rows of the sub-tile: target node, source node, validity (the same for every K block)
-            int64_t poff[4], qoff[4];
-            bool val[4];
+            uint32_t po[4], qo[4], ho[4], bo[4];
+            float sc[4];
+            bool hok[4];
+            const bool bok = node0 < fs.n_nodes;     // (a pair's second sub-tile may lie wholly beyond the last node: no side outputs)
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int r = rs + 32 * u;
-                const int f = r / AGG_W, sl = r - f * AGG_W;
-                const int64_t nd = node0 + f;
-                const bool in = r < AGG_ROWS && nd < fs.n_nodes;
-                const int src = in ? fs.nbr[nd * AGG_W + sl] : -1;
-                val[u] = in && src >= 0 && sl < fs.deg[nd];
-                poff[u] = (val[u] ? nd : 0) * fs.ldpq;
-                qoff[u] = (int64_t)(val[u] ? src : 0) * fs.ldpq + hid;
+                const bool v = src_n[u] >= 0 && sr[u] < dg_n[u];
+                po[u] = (v ? (uint32_t)(node0 + fr[u]) : 0u) * ld16 + p16;
+                qo[u] = (v ? (uint32_t)src_n[u] : 0u) * ld16 + q16;
+                sc[u] = v ? scale : 0.f;
+                const uint32_t grow = (uint32_t)(node0 * AGG_W) + (uint32_t)(rs + 32 * u);
+                ho[u] = grow * ldh16 + (uint32_t)j;
+                bo[u] = grow * ldhb + (uint32_t)j;
+                hok[u] = node0 + fr[u] < fs.n_nodes;
             }
-            for (int kb = 0; kb < total_kb; ++kb, ++it) {
-                const uint32_t sl = it % FU_BSLOTS;
-                const int c0 = kb * 64 + j * 8;
-                const bool c_on = c0 < hid;
-                float4 pv[4][2], qv[4][2];
+            if (t + num_clusters < num_tiles) fetch_rows(t + num_clusters);
+            float4 pa[2][2], qa[2][2], pb[2][2], qb[2][2];
+            // (chunks beyond hid -- only in the last K block -- gather the K block 0 columns instead and are zeroed by the scale)
+            auto gather = [&](int kb, int u0, float4 (&pv)[2][2], float4 (&qv)[2][2]) {
+                const uint32_t koff = (kb * 64 + j * 8 < hid) ? (uint32_t)kb * 16u : 0u;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {             // 16 independent 16-byte loads in flight per lane
-                    const bool on = val[u] && c_on;
-                    const float4* pp = reinterpret_cast<const float4*>(fs.pq + poff[u] + c0);
-                    const float4* qp = reinterpret_cast<const float4*>(fs.pq + qoff[u] + c0);
-                    pv[u][0] = on ? __ldg(pp) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    pv[u][1] = on ? __ldg(pp + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    qv[u][0] = on ? __ldg(qp) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    qv[u][1] = on ? __ldg(qp + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int uu = 0; uu < 2; ++uu) {
+                    const float4* pp = pq4 + (po[u0 + uu] + koff);
+                    const float4* qp = pq4 + (qo[u0 + uu] + koff);
+                    pv[uu][0] = __ldg(pp); pv[uu][1] = __ldg(pp + 1);
+                    qv[uu][0] = __ldg(qp); qv[uu][1] = __ldg(qp + 1);
                 }
-                tc::mbar_wait(&bempty[sl], ((it / FU_BSLOTS) & 1) ^ 1);      // the MMAs of the slot's previous use completed
-                const uint32_t ba = tc::smem_u32(bring + sl * BSL);
+            };
+            auto build = [&](int kb, int u0, const float4 (&pv)[2][2], const float4 (&qv)[2][2], uint32_t ba) {
+                const bool on = kb * 64 + j * 8 < hid;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int r = rs + 32 * u;
+                for (int uu = 0; uu < 2; ++uu) {
+                    const int u = u0 + uu, r = rs + 32 * u;
                     if (r < AGG_ROWS) {                   // (lane-dependent only for u = 3)
-                        float hv[8];
-                        hv[0] = fmaxf(pv[u][0].x + qv[u][0].x, 0.f); hv[1] = fmaxf(pv[u][0].y + qv[u][0].y, 0.f);
-                        hv[2] = fmaxf(pv[u][0].z + qv[u][0].z, 0.f); hv[3] = fmaxf(pv[u][0].w + qv[u][0].w, 0.f);
-                        hv[4] = fmaxf(pv[u][1].x + qv[u][1].x, 0.f); hv[5] = fmaxf(pv[u][1].y + qv[u][1].y, 0.f);
-                        hv[6] = fmaxf(pv[u][1].z + qv[u][1].z, 0.f); hv[7] = fmaxf(pv[u][1].w + qv[u][1].w, 0.f);
+                        const float s = on ? sc[u] : 0.f;
+                        float a[8];
+                        a[0] = fmaxf(pv[uu][0].x + qv[uu][0].x, 0.f) * s; a[1] = fmaxf(pv[uu][0].y + qv[uu][0].y, 0.f) * s;
+                        a[2] = fmaxf(pv[uu][0].z + qv[uu][0].z, 0.f) * s; a[3] = fmaxf(pv[uu][0].w + qv[uu][0].w, 0.f) * s;
+                        a[4] = fmaxf(pv[uu][1].x + qv[uu][1].x, 0.f) * s; a[5] = fmaxf(pv[uu][1].y + qv[uu][1].y, 0.f) * s;
+                        a[6] = fmaxf(pv[uu][1].z + qv[uu][1].z, 0.f) * s; a[7] = fmaxf(pv[uu][1].w + qv[uu][1].w, 0.f) * s;
                         unsigned bits = 0u;
                         uint32_t p0[4], p1[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            bits |= (hv[2 * e] > 0.f ? 1u : 0u) << (2 * e);
-                            bits |= (hv[2 * e + 1] > 0.f ? 1u : 0u) << (2 * e + 1);
-                            const float a = hv[2 * e] * scale, b = hv[2 * e + 1] * scale;
-                            const __half2 h2 = __floats2half2_rn(a, b);
+                            bits |= (a[2 * e] > 0.f ? 1u : 0u) << (2 * e);
+                            bits |= (a[2 * e + 1] > 0.f ? 1u : 0u) << (2 * e + 1);
+                            const __half2 h2 = __floats2half2_rn(a[2 * e], a[2 * e + 1]);
                             p0[e] = *reinterpret_cast<const uint32_t*>(&h2);
                             if (NP == 2) {
                                 const float2 back = __half22float2(h2);
-                                const __half2 l2 = __floats2half2_rn(a - back.x, b - back.y);
+                                const __half2 l2 = __floats2half2_rn(a[2 * e] - back.x, a[2 * e + 1] - back.y);
                                 p1[e] = *reinterpret_cast<const uint32_t*>(&l2);
                             }
                         }
@@ -1844,13 +1869,20 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ba + off), "r"(p0[0]), "r"(p0[1]), "r"(p0[2]), "r"(p0[3]) : "memory");
                         if (NP == 2)
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ba + TC_TILE_BYTES + off), "r"(p1[0]), "r"(p1[1]), "r"(p1[2]), "r"(p1[3]) : "memory");
-                        const int64_t grow = node0 * AGG_W + r;
-                        if (fs.h0_out != nullptr && c_on && node0 + r / AGG_W < fs.n_nodes)
-                            *reinterpret_cast<uint4*>(fs.h0_out + grow * fs.ldh + c0) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
-                        // (a pair's second sub-tile may lie wholly beyond the last node: its rows do not exist in the side outputs)
-                        if (fs.hbytes != nullptr && c_on && node0 < fs.n_nodes) fs.hbytes[grow * fs.ldhb + (c0 >> 3)] = (unsigned char)bits;
+                        if (h0v != nullptr && on && hok[u]) h0v[ho[u] + (uint32_t)kb * 8u] = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+                        if (fs.hbytes != nullptr && on && bok) fs.hbytes[bo[u] + (uint32_t)kb * 8u] = (unsigned char)bits;
                     }
                 }
+            };
+            gather(0, 0, pa, qa);
+            for (int kb = 0; kb < total_kb; ++kb, ++it) {
+                const uint32_t sl = it % FU_BSLOTS;
+                gather(kb, 2, pb, qb);
+                tc::mbar_wait(&bempty[sl], ((it / FU_BSLOTS) & 1) ^ 1);      // the MMAs of the slot's previous use completed
+                const uint32_t ba = tc::smem_u32(bring + sl * BSL);
+                build(kb, 0, pa, qa, ba);
+                if (kb + 1 < total_kb) gather(kb + 1, 0, pa, qa);
+                build(kb, 2, pb, qb, ba);
                 tc::fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive_cluster_relaxed(&bfull[sl], 0);
@@ -1878,32 +1910,79 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
                 int dg[AGG_NPT];
 #pragma unroll
                 for (int f = 0; f < AGG_NPT; ++f) dg[f] = (node0 + f < fs.n_nodes) ? fs.deg[node0 + f] : 0;
-                float acc = 0.f;
                 unsigned bits[4];
+                bool regular = true;                       // every node of the sub-tile has exactly k = 8 neighbours
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t r[32];
-                    tc::tmem_ld_32x32b_x32(tcol + (uint32_t)(c * 32), r);
-                    tc::tmem_ld_wait();
-                    unsigned w = 0u;
+                for (int f = 0; f < AGG_NPT; ++f) regular = regular && dg[f] == AGG_W - 1;
+                if (regular) {
+                    // fast path (as in gemm_tc_pair_kernel): slot validity is compile-time, relu = fmaxf, mask word by an OR tree
+                    float nodeacc[AGG_NPT];
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) {
-                        const int col = c * 32 + jj;
-                        if (col < AGG_ROWS) {
-                            const int f = col / AGG_W, sl = col % AGG_W;       // compile-time after unrolling
+                    for (int f = 0; f < AGG_NPT; ++f) nodeacc[f] = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t r[32];
+                        tc::tmem_ld_32x32b_x32(tcol + (uint32_t)(c * 32), r);
+                        tc::tmem_ld_wait();
+                        float rl[32];
+                        unsigned bt[32];
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) {
+                            const int col = c * 32 + jj;
+                            const bool slot_ok = col < AGG_ROWS && (col % AGG_W) < AGG_W - 1;     // compile-time
                             const float pre = fmaf(__uint_as_float(r[jj]), ainv, bv);
-                            const bool on = (sl < dg[f]) && (pre > 0.f);
-                            acc += on ? pre : 0.f;
-                            w |= on ? (1u << jj) : 0u;
-                            if (sl == AGG_W - 1) {
-                                float o = acc;
-                                if (round_out) o = tc::round_tf32(o);
-                                if (ch_ok && node0 + f < fs.n_nodes) y[(node0 + f) * ldy + ch] = o;
-                                acc = 0.f;
+                            rl[jj] = slot_ok ? fmaxf(pre, 0.f) : 0.f;
+                            bt[jj] = (slot_ok && pre > 0.f) ? (1u << jj) : 0u;
+                        }
+#pragma unroll
+                        for (int st = 16; st > 0; st >>= 1)
+#pragma unroll
+                            for (int jj = 0; jj < st; ++jj) bt[jj] |= bt[jj + st];
+                        bits[c] = bt[0];
+#pragma unroll
+                        for (int f = 0; f < AGG_NPT; ++f) {
+                            const int c_lo = c * 32, c_hi = c * 32 + 32;
+                            const int n_lo = f * AGG_W, n_hi = f * AGG_W + AGG_W - 1;            // valid slots [n_lo, n_hi)
+                            if (n_lo < c_hi && n_hi > c_lo) {                                     // compile-time
+                                auto g = [&](int col) -> float { return (col >= c_lo && col < c_hi) ? rl[col - c_lo] : 0.f; };
+                                const float s8 = ((g(n_lo) + g(n_lo + 1)) + (g(n_lo + 2) + g(n_lo + 3))) +
+                                                 ((g(n_lo + 4) + g(n_lo + 5)) + (g(n_lo + 6) + g(n_lo + 7)));
+                                nodeacc[f] += s8;
+                                if (n_hi <= c_hi) {                                               // node complete in this chunk
+                                    float o = nodeacc[f];
+                                    if (round_out) o = tc::round_tf32(o);
+                                    if (ch_ok) y[(node0 + f) * ldy + ch] = o;
+                                }
                             }
                         }
                     }
-                    bits[c] = w;
+                } else {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t r[32];
+                        tc::tmem_ld_32x32b_x32(tcol + (uint32_t)(c * 32), r);
+                        tc::tmem_ld_wait();
+                        unsigned w = 0u;
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) {
+                            const int col = c * 32 + jj;
+                            if (col < AGG_ROWS) {
+                                const int f = col / AGG_W, sl = col % AGG_W;       // compile-time after unrolling
+                                const float pre = fmaf(__uint_as_float(r[jj]), ainv, bv);
+                                const bool on = (sl < dg[f]) && (pre > 0.f);
+                                acc += on ? pre : 0.f;
+                                w |= on ? (1u << jj) : 0u;
+                                if (sl == AGG_W - 1) {
+                                    float o = acc;
+                                    if (round_out) o = tc::round_tf32(o);
+                                    if (ch_ok && node0 + f < fs.n_nodes) y[(node0 + f) * ldy + ch] = o;
+                                    acc = 0.f;
+                                }
+                            }
+                        }
+                        bits[c] = w;
+                    }
                 }
                 if (ch_ok && maskbits != nullptr)
                     reinterpret_cast<uint4*>(maskbits)[st14 * n_out + ch] = make_uint4(bits[0], bits[1], bits[2], bits[3]);

@@ -170,17 +170,48 @@ knn_table_kernel(const float* __restrict__ x, int64_t ld, const int* __restrict_
     }
 }
 
-// Split variant for the k = 8, 3-column graphs of DynEdge: S consecutive lanes share one query, lane s scans the
-// candidates a + s, a + s + S, ... of the query's event (ascending, strict '>' insertion: every partial list is the
-// exact top-9 of its subset under the total order (distance, index)), then the S sorted lists are merged with S-lane
-// shuffle minima under the same total order. The kernel's time is set by the largest event of the batch (one thread
-// used to walk all of its 5 000 pulses); with S = 8 that tail is 8 x shorter. Result is identical bit for bit.
+// Split variant for the k = 8, 3-column graphs of DynEdge: S consecutive lanes share one query and scan disjoint subsets of
+// the query's event in ascending index order; every lane keeps a sorted list that contains every member of the global top-9
+// that lies in its subset (strict '>' insertion under ascending indices = the total order (distance, index)), then the S
+// sorted lists are merged with S-lane shuffle minima under the same total order. Result is identical bit for bit.
+//
+// The scan is built around what the first version measured (ncu, profiles/r01/p_knn_table_split.ncu-rep: issue-bound, 65 SASS
+// instructions per candidate, 27..45 of them the 9-entry insertion that a warp pays whenever ANY of its 32 lanes accepts a
+// candidate -- and sum n^2 is dominated by the events with thousands of pulses, where a lane accepts a few per cent):
+//   * a lane takes groups of 4 consecutive candidates (lane s: groups s, s + S, ...), so the coordinates arrive as three
+//     16-byte shared-memory loads per group instead of twelve 4-byte loads, with 32-bit index arithmetic only;
+//   * accepted candidates (distance below the lane's current 9th best) are only APPENDED to a per-lane FIFO in shared memory
+//     (predicated stores, no branch); the warp runs the insertion loop when some lane's FIFO could overflow on the next
+//     group, so its cost is shared by every pending entry of the warp instead of being paid per accepting lane. The FIFO
+//     keeps ascending candidate order per lane, and a stale 9th best only lets extra candidates through (the insertion
+//     re-checks), so the lists are the same as with immediate insertion;
+//   * the S lanes of a query share a cut: the smallest of their 9th-best distances (refreshed by three shuffles after every
+//     insertion round). Some lane already holds 9 candidates at or below the cut, so a candidate strictly above it cannot
+//     be among the query's 9 best and is dropped without touching any list (a tie with the cut is kept: it may win on its
+//     index). With 8 young lists per query a lane accepted 13 .. 60 % of its candidates; against the shared cut the accept
+//     rate is that of one list over the whole event (2 .. 14 %). A lane's list is then no longer the exact top-9 of its
+//     subset, but it still contains every member of the query's top-9 that lies in the subset, which is all the merge needs.
+constexpr int KNN_CH = 1024;      // candidates per shared-memory chunk
+constexpr int KNN_QC = 8;         // FIFO entries per lane (a group appends at most 4)
+
+template <int K1>
+__device__ __forceinline__ void knn_flush(float (&bd)[K1], int (&bi)[K1], const float (*s_qd)[KNN_THREADS],
+                                          const int (*s_qi)[KNN_THREADS], int tid, int& qn) {
+    const int m = __reduce_max_sync(0xffffffffu, qn);
+    for (int e = 0; e < m; ++e)
+        if (e < qn) insert_static<K1>(bd, bi, s_qd[e][tid], s_qi[e][tid]);
+    qn = 0;
+}
+
 template <int K1, int D, int S>
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_table_split_kernel(const float* __restrict__ x, int64_t ld, const int* __restrict__ cols,
-                       const int64_t* __restrict__ ptr, int nseg, int64_t n, int chunk,
+                       const int64_t* __restrict__ ptr, int nseg, int64_t n,
                        int* __restrict__ nbr, int* __restrict__ deg) {
-    extern __shared__ float s_c[];            // [D][chunk]
+    static_assert(D == 3 && S == 8, "scan is written for 3 coordinates and 8 lanes per query");
+    __shared__ __align__(16) float s_c[D][KNN_CH];
+    __shared__ float s_qd[KNN_QC][KNN_THREADS];
+    __shared__ int s_qi[KNN_QC][KNN_THREADS];
     __shared__ int s_cols[D];
     __shared__ long long s_range[2];
     constexpr int QPC = KNN_THREADS / S;      // queries per CTA
@@ -211,48 +242,59 @@ knn_table_split_kernel(const float* __restrict__ x, int64_t ld, const int* __res
     int bi[K1];
 #pragma unroll
     for (int e = 0; e < K1; ++e) { bd[e] = 1e10f; bi[e] = -1; }
+    int qn = 0;
+    float cut = 1e10f;        // smallest 9th best of the query's S lanes (as of the last flush)
 
-    for (int64_t c0 = r_lo; c0 < r_hi; c0 += chunk) {
-        const int cnt = (int)((r_hi - c0) < chunk ? (r_hi - c0) : chunk);
+    for (int64_t c0 = r_lo; c0 < r_hi; c0 += KNN_CH) {
+        const int cnt = (int)((r_hi - c0) < KNN_CH ? (r_hi - c0) : KNN_CH);
         __syncthreads();   // previous chunk fully consumed
         for (int c = tid; c < cnt; c += KNN_THREADS) {       // one node per thread: its D coordinates share a sector
             const float* row = x + (c0 + c) * ld;
 #pragma unroll
-            for (int j = 0; j < D; ++j) s_c[j * chunk + c] = row[s_cols[j]];
+            for (int j = 0; j < D; ++j) s_c[j][c] = row[s_cols[j]];
         }
         __syncthreads();
+        // the lane's part of the chunk, as positions relative to c0: [a, b) (empty when the event does not touch the chunk)
+        int a = 0, b = 0;
         if (active) {
-            const int a = (int)((lo > c0 ? lo : c0) - c0);
-            const int b = (int)((hi < c0 + cnt ? hi : c0 + cnt) - c0);
-            int jj = a + sub;
-            for (; jj + 3 * S < b; jj += 4 * S) {       // 4 independent distance evaluations, inserted in ascending order
-                float acc4[4];
+            a = (int)((lo > c0 ? lo : c0) - c0);
+            b = (int)((hi < c0 + cnt ? hi : c0 + cnt) - c0);
+            if (b <= a) a = b = 0;     // the event does not touch this chunk (positions beyond the chunk must never be formed)
+        }
+        const unsigned span = (unsigned)(b - a);
+        const int gb = (b + 3) >> 2;                       // groups [a >> 2, gb)
+        int g = (a >> 2) + sub;
+        const int mine = gb > g ? (gb - g + S - 1) / S : 0;
+        const int steps = __reduce_max_sync(0xffffffffu, mine);      // warp-uniform trip count: the flush votes with all lanes
+        const int base = (int)c0;
+        for (int t = 0; t < steps; ++t, g += S) {
+            const bool gin = g < gb;
+            const int p0 = gin ? (g << 2) : 0;
+            const float4 cx = *reinterpret_cast<const float4*>(&s_c[0][p0]);
+            const float4 cy = *reinterpret_cast<const float4*>(&s_c[1][p0]);
+            const float4 cz = *reinterpret_cast<const float4*>(&s_c[2][p0]);
+            const float vx[4] = {cx.x, cx.y, cx.z, cx.w}, vy[4] = {cy.x, cy.y, cy.z, cy.w}, vz[4] = {cz.x, cz.y, cz.z, cz.w};
+            const float lim = bd[K1 - 1];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float d0 = s_c[jj + u * S] - qf[0];
-                    float acc = __fmul_rn(d0, d0);
-#pragma unroll
-                    for (int j = 1; j < D; ++j) {
-                        const float dj = s_c[j * chunk + jj + u * S] - qf[j];
-                        acc = __fadd_rn(acc, __fmul_rn(dj, dj));
-                    }
-                    acc4[u] = acc;
+            for (int u = 0; u < 4; ++u) {
+                const float d0 = vx[u] - qf[0], d1 = vy[u] - qf[1], d2 = vz[u] - qf[2];
+                const float acc = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+                const bool hit = gin && (unsigned)(p0 + u - a) < span && lim > acc && acc <= cut;
+                if (hit) {
+                    s_qd[qn][tid] = acc;
+                    s_qi[qn][tid] = base + p0 + u;
+                    ++qn;
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) insert_static<K1>(bd, bi, acc4[u], (int)(c0 + jj + u * S));
             }
-            for (; jj < b; jj += S) {
-                const float d0 = s_c[jj] - qf[0];
-                float acc = __fmul_rn(d0, d0);
+            if (__any_sync(0xffffffffu, qn > KNN_QC - 4)) {
+                knn_flush<K1>(bd, bi, s_qd, s_qi, tid, qn);
+                cut = bd[K1 - 1];
 #pragma unroll
-                for (int j = 1; j < D; ++j) {
-                    const float dj = s_c[j * chunk + jj] - qf[j];
-                    acc = __fadd_rn(acc, __fmul_rn(dj, dj));
-                }
-                insert_static<K1>(bd, bi, acc, (int)(c0 + jj));
+                for (int off = 1; off < S; off <<= 1) cut = fminf(cut, __shfl_xor_sync(0xffffffffu, cut, off));
             }
         }
     }
+    knn_flush<K1>(bd, bi, s_qd, s_qi, tid, qn);
     // merge the S sorted partial lists: K1 rounds of "smallest head under (distance, index)"; the owner pops its head
     int res[K1];
 #pragma unroll
@@ -324,10 +366,7 @@ int launch_knn(const float* x, int64_t ld, const int* cols, int d, const int64_t
 template <int K1, int D, int S>
 int launch_knn_split(const float* x, int64_t ld, const int* cols, const int64_t* ptr, int nseg, int64_t n, int* nbr, int* deg,
                      cudaStream_t st) {
-    const int chunk = 1024;
-    const size_t smem = (size_t)chunk * D * sizeof(float);
-    knn_table_split_kernel<K1, D, S><<<gnb_div_up(n, KNN_THREADS / S), KNN_THREADS, smem, st>>>(x, ld, cols, ptr, nseg, n, chunk,
-                                                                                                  nbr, deg);
+    knn_table_split_kernel<K1, D, S><<<gnb_div_up(n, KNN_THREADS / S), KNN_THREADS, 0, st>>>(x, ld, cols, ptr, nseg, n, nbr, deg);
     GNB_RETURN_LAUNCH();
 }
 

@@ -41,14 +41,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the thread may stay suspended in hardware (no issue slots used) until the phase
+// completes or the hint (ns) expires, instead of returning to a software polling loop after the default, short limit --
+// ncu (profiles/r02/r_bwd_builders.ncu-rep) showed 36 .. 47 % of the builder kernels' executed instructions in these loops.
+#ifndef GNB_MBAR_HINT_NS
+#define GNB_MBAR_HINT_NS 20000
+#endif
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"((uint32_t)GNB_MBAR_HINT_NS)
         : "memory");
     return done;
 }
@@ -94,10 +100,10 @@ __device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t addr, uint32_
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"((uint32_t)GNB_MBAR_HINT_NS)
         : "memory");
     return done;
 }

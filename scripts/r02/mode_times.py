@@ -19,8 +19,10 @@ dbs = [bench.to_device(hb, dev) for hb in bench.host_batches(nev, 2, 20240607 if
 step = tr.train_step if what == "train" else tr.infer_step
 flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
 for mode in modes:
-    ops.STORE_DZ = mode.endswith("+dz")
-    mode = mode.replace("+dz", "")
+    tag = mode
+    ops.STORE_DZ = "+dz" in mode
+    ops.UNFUSED_FORWARD = "+unf" in mode
+    mode = mode.replace("+dz", "").replace("+unf", "")
     ops.set_precision(mode)
     for i in range(6):
         step(dbs[i & 1])
@@ -36,7 +38,7 @@ for mode in modes:
         ts.append(e0.elapsed_time(e1))
     ts.sort()
     med = ts[len(ts) // 2]
-    print(f"== {mode}{'+dz' if ops.STORE_DZ else ''} {what}: median {med:.3f} ms / step = {nev / med * 1e3:.0f} events/s (min {ts[0]:.3f})", flush=True)
+    print(f"== {tag} {what}: median {med:.3f} ms / step = {nev / med * 1e3:.0f} events/s (min {ts[0]:.3f})", flush=True)
     with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
         for i in range(2):
             step(dbs[i & 1])

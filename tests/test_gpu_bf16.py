@@ -658,14 +658,18 @@ def test_mixed16_stored_dz_route_matches_the_masked_route(ops):
     model = DynEdge(7, global_pooling_schemes=["min", "max", "mean", "sum"]).cuda()
     data = KNNEdges(8)(Data(x=x.cuda(), batch=batch.cuda(), n_pulses=n_pulses.cuda()))
     grads = []
-    for store in (False, True):
-        ops.STORE_DZ = store
-        try:
+    # both runs on the two-kernel forward: the stored-dz route cannot use the fused forward kernel (the executor fuses the
+    # forward only where the backward expands dz itself), and a different forward kernel means a different TMEM summation order
+    ops.UNFUSED_FORWARD = True
+    try:
+        for store in (False, True):
+            ops.STORE_DZ = store
             model.zero_grad(set_to_none=True)
             model(data).square().sum().backward()
             grads.append([p.grad.clone() for p in model.parameters()])
-        finally:
-            ops.STORE_DZ = False
+    finally:
+        ops.STORE_DZ = False
+        ops.UNFUSED_FORWARD = False
     for a, b in zip(*grads):
         assert rel_err(a, b) < 2e-5
 
