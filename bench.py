@@ -492,11 +492,27 @@ def dominant_launches(trainer, db):
                   ops._ptr(hmask), mld, hid, ops._ptr(graph.nbr), n, ops._ptr(dpq[:, hid:]), 2 * hid, ops._ptr(dpq), 2 * hid,
                   ops._ptr(None), 0, ops._ptr(zw), ops._stream())
 
-    keep = (h, h_raw, w2p, w_hi, w_lo, b2, y, maskbits, dz, wt, hmask, dpq, graph, hw, zw, h16, w16, wt16, dz16, dwg, rowmask, g16)
+    # the fused EdgeConv forward of the fp16-plane modes: PQ (hoisted first Linear) + neighbour table in, y + bit masks out,
+    # training side outputs = plane 0 of h and the row-major ReLU bits
+    pq = torch.randn(n, 2 * hid, device=dev)
+    pqw = torch.zeros(1, dtype=torch.int32, device=dev)
+    ops._call("gnb_absmax_bits", ops._ptr(pq), 2 * hid, n, 2 * hid, 1, ops._ptr(pqw), ops._stream())
+    h0f = torch.empty(rows, hid, dtype=torch.float16, device=dev)
+    hbytes = torch.empty(ntile * 126, mld * 4, dtype=torch.uint8, device=dev)
+
+    def fused_fwd_f16(planes=2, side=True):
+        ops._call("gnb_edgeconv_fused_fwd_f16", ops._ptr(pq), 2 * hid, hid, ops._ptr(graph.nbr), ops._ptr(graph.deg), n,
+                  ops._ptr(w16[0]), ops._ptr(w16[1] if planes == 2 else None), hld64, ops._ptr(b2), cout, 0, ops._ptr(y), cout,
+                  ops._ptr(maskbits if side else None), ops._ptr(h0f if side else None), hid, ops._ptr(hbytes if side else None),
+                  mld * 4, ops._ptr(pqw), ops._stream())
+
+    keep = (h, h_raw, w2p, w_hi, w_lo, b2, y, maskbits, dz, wt, hmask, dpq, graph, hw, zw, h16, w16, wt16, dz16, dwg, rowmask, g16,
+            pq, pqw, h0f, hbytes)
     e_real = int(graph.deg.sum().item())
     return {"agg_fwd": agg_fwd, "agg_fwd_x3": agg_fwd_x3, "dgrad_scatter": dgrad_scatter, "agg_fwd_f16x3": agg_fwd_f16x3,
             "dgrad_scatter_f16": dgrad_scatter_f16, "wgrad_f16": wgrad_f16, "wgrad_f16_masked": wgrad_f16_masked,
-            "dgrad_scatter_f16_masked": dgrad_scatter_f16_masked, "rows": rows, "n": n,
+            "dgrad_scatter_f16_masked": dgrad_scatter_f16_masked, "fused_fwd_f16x3": fused_fwd_f16,
+            "fused_fwd_f16x3_inference": lambda: fused_fwd_f16(2, False), "rows": rows, "n": n,
             "edges": e_real, "hid": hid, "cout": cout, "mld": mld, "keep": keep}
 
 
@@ -557,27 +573,32 @@ def roofline_top_kernel(trainer, db, pk, precision, inference=False):
                 "list (single-pass tf32; both 256-channel groups from one resident dz tile)", sec_b, bytes_b, 1.0,
                 _traffic("dgrad_scatter"))
     if precision == "mixed16" and not inference:
-        # kind::f16 kernels: the denominator is the measured dense bf16 / fp16 burst peak of MEASURED_PEAKS.json
+        # kind::f16 kernels: the denominator is the measured dense bf16 / fp16 burst peak of MEASURED_PEAKS.json.
+        # The three per-edge launches of a layer in this mode, none of which reads or writes a [N k, .] fp32 tensor:
         p16 = pk["bf16_tflops"]
-        by_f = 4.0 * rows * hid + 4.0 * n * cout + 16.0 * ((n + 13) // 14) * cout            # two fp16 planes of h
-        by_b = 2.0 * rows * cout + 4.0 * rows * d["mld"] + 4.0 * n * 2 * hid               # one fp16 plane of dz
-        by_w = 2.0 * rows * (hid + cout)
-        top = entry("gemm_bf_pair_dual_scatter_kernel<1> (tcgen05 cta_group::2 kind::f16 M256xN256xK16, fp16 operands): dh = dz W2 "
-                    "(256 -> 336) on the power-of-two scaled fp16 plane of dz, ReLU mask + dP slot sums + dQ fp32 reductions in the "
-                    "epilogue (dh never stored); both 256-channel groups from one resident dz tile. Bound by the L2 slices (213 M "
-                    "fp32 reductions + the TMA stream), not by the tensor pipe", _time_launch(d["dgrad_scatter_f16"]), by_b, 1.0,
-                    _traffic("dgrad_scatter_f16"), p16)
-        fwd = entry("gemm_tc_pair_kernel<3> (kind::f16, two fp16 planes per operand, 3 products per K step, 3 x 64 KiB TMA stages): "
-                    "m = relu(h W2^T + b2) summed over the k slots, 336 -> 256; executes 3 MMAs per algorithmic product",
-                    _time_launch(d["agg_fwd_f16x3"]), by_f, 3.0, _traffic("agg_fwd_f16x3"), p16)
-        wg = entry("gemm_bf_wgrad_kernel<1,1,64> (kind::f16, MN-major TMA operands): dW2 = dz^T h on one fp16 plane each; HBM-bound",
-                   _time_launch(d["wgrad_f16"]), by_w, 1.0, _traffic("wgrad_f16"), p16)
+        ntile = (n + 13) // 14
+        by_f = 4.0 * n * 2 * hid + 4.0 * 10 * n + 4.0 * n * cout + 16.0 * ntile * cout + 2.0 * rows * hid + 4.0 * rows * d["mld"]
+        by_b = 2.0 * n * cout + 4.0 * rows * (cout // 32) + 4.0 * rows * d["mld"] + 4.0 * rows + 4.0 * n * 2 * hid
+        by_w = 2.0 * rows * hid + 2.0 * n * cout + 4.0 * rows * (cout // 32)
+        top = entry("gemm_f16_pair_agg_fused_kernel<2> (tcgen05 cta_group::2 kind::f16 M256xN256xK16; fused EdgeConv forward): "
+                    "builder warps gather P_i + Q_j (fp32), ReLU, scale, split into two fp16 planes straight into the swizzled B tile; "
+                    "3 MMAs per algorithmic product against the TMA-streamed W2 planes; epilogue = bias + ReLU + k-sum + 126 mask "
+                    "bits per (tile, channel); side outputs plane 0 of h + ReLU bits for the backward pass. h [N k, 336] never "
+                    "crosses HBM in fp32. Bound by the builders (gather latency + issue slots), not by the tensor pipe",
+                    _time_launch(d["fused_fwd_f16x3"]), by_f, 3.0, _traffic("fused_fwd_f16x3"), p16)
+        bwd16 = entry("gemm_f16_pair_scatter_build_kernel (kind::f16): dh = dz W2 (256 -> 336) with dz expanded in shared memory from "
+                      "fp16(g) [N, 256] and the row-major ReLU bits (dz never stored); ReLU mask + dP slot sums + dQ fp32 reductions "
+                      "in the epilogue (dh never stored). Bound by the epilogue's 213 M L2 reductions",
+                      _time_launch(d["dgrad_scatter_f16_masked"]), by_b, 1.0, _traffic("dgrad_scatter_f16_masked"), p16)
+        wg = entry("gemm_f16_wgrad_build_kernel (kind::f16, MN-major operands): dW2 = dz^T h with dz expanded in shared memory from "
+                   "fp16(g) and the ReLU bits; reads plane 0 of h only", _time_launch(d["wgrad_f16_masked"]), by_w, 1.0,
+                   _traffic("wgrad_f16_masked"), p16)
         out = {"bound": "tensor", "achieved": top["achieved"], "peak": p16, "unit": "TFLOP/s", "frac": top["frac"],
                "traffic": top["traffic"], "kernel": top["kernel"], "launch_ms": top["launch_ms"],
                "peak_source": "dense bf16 burst peak of MEASURED_PEAKS.json (kind::f16 runs fp16 and bf16 at the same rate)",
                "executed_tflops": top["executed_tflops"], "executed_frac": top["executed_frac"], "hbm_view": top["hbm_view"],
                "rows": rows, "edges": e_real, "algorithmic_flops_per_launch": flops,
-               "forward_launch": fwd, "weight_gradient_launch": wg}
+               "backward_launch": bwd16, "weight_gradient_launch": wg}
         return out
     if precision == "tf32x3" and not inference:
         sec_x = _time_launch(d["agg_fwd_x3"])

@@ -289,7 +289,7 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
             h_shared = a.get<float>(n * max_w * max_h);
             m_shared = a.get<float>(n * max_w * max_c);
         }
-        bool all_fused = p.mixed && !(c.flags & 8) && w0 == 9 && max_h <= 512 && max_c <= 256;      // (see b.fused below)
+        bool all_fused = c.precision == 5 && !(c.flags & 8) && w0 == 9 && max_h <= 512 && max_c <= 256;      // (see b.fused below)
         for (int pl = 0; pl < p.bf && !all_fused; ++pl) hb_shared[pl] = a.get<__nv_bfloat16>(n * max_w * max_h);
         pq_shared = a.get<float>(n * 2 * max_h);
     }
@@ -311,7 +311,9 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
         // forward is ONE kernel (gather + hidden layer + second Linear + aggregation: h never crosses HBM except plane 0
         // as the weight gradient's operand); inference fuses whenever the shapes allow it. flags bit 3 keeps the two-kernel forward.
         b.nodz = p.mixed && training && !(c.flags & 4) && b.cout <= 256 && (b.cout & 63) == 0 && wl == 9;
-        b.fused = p.mixed && !(c.flags & 8) && b.cout <= 256 && wl == 9 && b.hid <= 512 && (training ? b.nodz : true);
+        // (inference: the fused kernel wins with two planes -- 5.55 against 6.27 ms per 1024 events -- and loses with one, where
+        // the two-kernel forward moves half the bytes: 4.67 against 4.31 ms)
+        b.fused = p.mixed && !(c.flags & 8) && b.cout <= 256 && wl == 9 && b.hid <= 512 && (training ? b.nodz : c.precision == 5);
         for (int pl = 0; pl < 2; ++pl) {
             const bool on = pl < p.bf;
             const bool h_on = on && !(b.fused && (pl == 1 || !training));      // fused forward: only plane 0, only for the backward pass

@@ -1577,27 +1577,33 @@ gemm_f16_pair_scatter_build_kernel(const __grid_constant__ CUtensorMap tm_w0, co
                 const int c0 = kb * 64 + j * 8;
                 if (node_on) {
                     uint32_t gh[4] = {0u, 0u, 0u, 0u};
-                    unsigned rb[AGG_W];                       // per slot: the byte of channel bits c0 .. c0 + 7 of row 9 f + sl
+                    unsigned nlo[AGG_W], nhi[AGG_W];          // per slot: the channel bits c0 .. c0 + 7 of row 9 f + sl as two nibbles
 #pragma unroll
-                    for (int sl = 0; sl < AGG_W; ++sl) rb[sl] = 0u;
+                    for (int sl = 0; sl < AGG_W; ++sl) nlo[sl] = nhi[sl] = 0u;
                     if (have && c0 < zb.c_out) {
                         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(gh[0]), "=r"(gh[1]), "=r"(gh[2]), "=r"(gh[3])
                                      : "r"(ga + ((uint32_t)f * (uint32_t)zb.c_out + (uint32_t)c0) * 2u));
                         const uint32_t mrow = ma + (9u * (uint32_t)f * cw + (uint32_t)(c0 >> 5)) * 4u;
                         const unsigned bsh = (unsigned)(c0 & 31);            // 0, 8, 16, 24
 #pragma unroll
-                        for (int sl = 0; sl < AGG_W; ++sl) rb[sl] = (tc::lds_u32(mrow + (uint32_t)sl * cw * 4u) >> bsh) & 0xFFu;
+                        for (int sl = 0; sl < AGG_W; ++sl) {
+                            const unsigned mw = tc::lds_u32(mrow + (uint32_t)sl * cw * 4u);
+                            nlo[sl] = (mw >> bsh) & 15u;
+                            nhi[sl] = (mw >> (bsh + 4u)) & 15u;
+                        }
                     }
                     const uint32_t kbase = tc::smem_u32(act + kb * TC_TILE_BYTES);
 #pragma unroll
                     for (int sl = 0; sl < AGG_W; ++sl) {
                         const uint32_t r = 9u * (uint32_t)f + (uint32_t)sl;
+                        // 4 channel bits -> sign bits of 4 bytes (bit m lands on bit 8 m + 7), byte permute with sign replication
+                        // -> the two half-word masks of each fp16x2 register (see gemm_f16_wgrad_build_kernel)
+                        const uint32_t ylo = nlo[sl] * 0x10204080u, yhi = nhi[sl] * 0x10204080u;
                         uint32_t o[4];
-#pragma unroll
-                        for (int p2 = 0; p2 < 4; ++p2) {
-                            const uint32_t t2 = (rb[sl] >> (2 * p2)) & 3u;           // bits of channels 2 p2, 2 p2 + 1 -> low / high half
-                            o[p2] = gh[p2] & (((t2 * 0x8001u) & 0x00010001u) * 0xFFFFu);
-                        }
+                        o[0] = gh[0] & tc::prmt(ylo, 0u, 0x9988u);
+                        o[1] = gh[1] & tc::prmt(ylo, 0u, 0xBBAAu);
+                        o[2] = gh[2] & tc::prmt(yhi, 0u, 0x9988u);
+                        o[3] = gh[3] & tc::prmt(yhi, 0u, 0xBBAAu);
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(kbase + r * 128u + (((uint32_t)j ^ (r & 7u)) << 4)),
                                      "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
                     }
@@ -1882,6 +1888,8 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
                 const uint32_t ba = tc::smem_u32(bring + sl * BSL);
                 build(kb, 0, pa, qa, ba);
                 if (kb + 1 < total_kb) gather(kb + 1, 0, pa, qa);
+                // (an L2 prefetch of the NEXT tile's P / Q rows from here -- PQ is 213 MB per 79 k-node layer, larger than L2, so
+                // about half of a tile's first touches are DRAM reads -- made the launch 30 % slower: 1501 -> 1967 us per step)
                 build(kb, 2, pb, qb, ba);
                 tc::fence_proxy_async();
                 __syncwarp();

@@ -377,7 +377,7 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
             for (int it = 0; it < num_kb; ++it) {
                 const int s = it % WGB_NA;
                 const uint32_t ph = (it / WGB_NA) & 1;
-                tc::mbar_wait(&aempty[s], ph ^ 1);
+                tc::mbar_wait<0, true>(&aempty[s], ph ^ 1);
                 uint8_t* st = smem + s * WGB_ASTAGE;
                 const int64_t r = r_lo + (int64_t)it * WGB_BK;
                 const int64_t nd0 = r / 9;
@@ -396,8 +396,8 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
             const uint32_t idesc = (1u << 4) | (((uint32_t)n_mma >> 3) << 17) | ((WG_BM >> 4) << 24) | (1u << 15) | (1u << 16);   // fp16 x fp16
             for (int it = 0; it < num_kb; ++it) {
                 const int s = it % WGB_NA, sb = it % WGB_NBUF;
-                tc::mbar_wait(&afull[s], (it / WGB_NA) & 1);
-                tc::mbar_wait(&bfull[sb], (it / WGB_NBUF) & 1);
+                tc::mbar_wait<0, true>(&afull[s], (it / WGB_NA) & 1);
+                tc::mbar_wait<0, true>(&bfull[sb], (it / WGB_NBUF) & 1);
                 tc::tcgen05_fence_after();
                 const uint64_t a0 = umma_desc_sw128_mnmajor16(tc::smem_u32(smem + s * WGB_ASTAGE), WGB_BOX, 1024u);
                 const uint64_t b0 = umma_desc_sw128_mnmajor16(tc::smem_u32(bring + sb * WGB_B_BYTES), WGB_BOX, 1024u);
@@ -423,26 +423,33 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
             const uint32_t boxoff = (uint32_t)(lane >> 3) * WGB_BOX, jj = (uint32_t)(lane & 7);
             unsigned mrow[8];                                            // the 8 rows' mask words, loaded one stage ahead
             const uint32_t r_lo32 = (uint32_t)r_lo, rows32 = (uint32_t)rows;      // rows < 2^31 (checked by the launcher)
+            const unsigned* mp0 = rowmask + ((int64_t)r_lo32 + 8 * bw) * cw + (lane >> 2);     // row 8 bw of stage 0
             auto prefetch = [&](int it) {
                 const uint32_t R0 = r_lo32 + (uint32_t)it * WGB_BK + 8u * (uint32_t)bw;
-                const unsigned* mp = rowmask + (int64_t)R0 * cw + (lane >> 2);
+                const unsigned* mp = mp0 + (int64_t)it * (WGB_BK * cw);
+                if (ch_on && R0 + 8u <= rows32) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) mrow[i] = (ch_on && R0 + i < rows32) ? __ldg(mp + i * cw) : 0u;
+                    for (int i = 0; i < 8; ++i) mrow[i] = __ldg(mp + i * cw);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) mrow[i] = (ch_on && R0 + i < rows32) ? __ldg(mp + i * cw) : 0u;
+                }
             };
             prefetch(0);
             for (int it = 0; it < num_kb; ++it) {
                 const int s = it % WGB_NA, sbuf = it % WGB_NBUF;
-                unsigned rb[8];                                          // the rows' bytes of channel bits (0 beyond `rows`)
+                // the lane's 8 channel bits of every row as two nibbles (0 beyond `rows`)
+                unsigned nlo[8], nhi[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) rb[i] = (mrow[i] >> bsh) & 0xFFu;
+                for (int i = 0; i < 8; ++i) { nlo[i] = (mrow[i] >> bsh) & 15u; nhi[i] = (mrow[i] >> (bsh + 4u)) & 15u; }
                 if (it + 1 < num_kb) prefetch(it + 1);
                 const uint32_t Rs = r_lo32 + (uint32_t)it * WGB_BK;      // first row of the stage
                 const uint32_t R0 = Rs + 8u * (uint32_t)bw;
                 const uint32_t q0 = __umulhi(R0, 0x38E38E39u) >> 1;      // R0 / 9
                 const uint32_t rem0 = R0 - 9u * q0;
                 const uint32_t nrel0 = q0 - (__umulhi(Rs, 0x38E38E39u) >> 1);
-                tc::mbar_wait(&afull[s], (it / WGB_NA) & 1);             // the stage's g16 rows (and A) landed
-                tc::mbar_wait(&bempty[sbuf], ((it / WGB_NBUF) & 1) ^ 1); // the MMAs of the B slot's previous use completed
+                tc::mbar_wait<0, true>(&afull[s], (it / WGB_NA) & 1);             // the stage's g16 rows (and A) landed
+                tc::mbar_wait<0, true>(&bempty[sbuf], ((it / WGB_NBUF) & 1) ^ 1); // the MMAs of the B slot's previous use completed
                 const uint32_t sg = tc::smem_u32(smem + s * WGB_ASTAGE + WGB_A_BYTES) + (uint32_t)lane * 16u + nrel0 * (uint32_t)n_out * 2u;
                 const uint32_t sb = tc::smem_u32(bring + sbuf * WGB_B_BYTES) + boxoff + (uint32_t)(8 * bw) * 128u;
                 // 8 rows touch at most 2 nodes: their fp16 values are read ONCE each (shared-memory bandwidth, not issue slots, is
@@ -455,12 +462,15 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const bool second = rem0 + (uint32_t)i >= 9u;        // warp-uniform
+                    // 4 channel bits -> the sign bits of 4 bytes (one multiply: bit m lands on bit 8 m + 7, no two partial
+                    // products share a position), then one byte permute with sign replication per pair of channels gives the
+                    // two half-word masks of an fp16x2 register
+                    const uint32_t ylo = nlo[i] * 0x10204080u, yhi = nhi[i] * 0x10204080u;
                     uint32_t o[4];
-#pragma unroll
-                    for (int p2 = 0; p2 < 4; ++p2) {
-                        const uint32_t t2 = (rb[i] >> (2 * p2)) & 3u;    // bits of channels 2 p2, 2 p2 + 1 -> low / high half-word mask
-                        o[p2] = (second ? gb2[p2] : ga[p2]) & (((t2 * 0x8001u) & 0x00010001u) * 0xFFFFu);
-                    }
+                    o[0] = (second ? gb2[0] : ga[0]) & tc::prmt(ylo, 0u, 0x9988u);
+                    o[1] = (second ? gb2[1] : ga[1]) & tc::prmt(ylo, 0u, 0xBBAAu);
+                    o[2] = (second ? gb2[2] : ga[2]) & tc::prmt(yhi, 0u, 0x9988u);
+                    o[3] = (second ? gb2[3] : ga[3]) & tc::prmt(yhi, 0u, 0xBBAAu);
                     // row rr = 8 bw + i: chunk position jj ^ (rr & 7) = jj ^ i
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + (uint32_t)i * 128u + ((jj ^ (uint32_t)i) << 4)),
                                  "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
@@ -473,7 +483,7 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
         } else {
             float inv = gnb_pow2_scale(*dz_scale_bits).y;
             if (x_scale_bits != nullptr) inv *= gnb_pow2_scale(*x_scale_bits).y;
-            tc::mbar_wait<200>(tmem_full, 0);
+            tc::mbar_wait<200, true>(tmem_full, 0);
             tc::tcgen05_fence_after();
             const int q = warp & 3;
             const int kin = kin0 + q * 32 + lane;

@@ -105,14 +105,24 @@ global_vars_kernel(const float* __restrict__ x, int64_t ldx, int nf, const int* 
         const int chunks = (int)(ld0 >> 2), rows_per_step = GV_THREADS / chunks;
         const int ch = tid % chunks, r0 = tid / chunks;
         if (r0 < rows_per_step) {
-            for (int64_t i = lo + r0; i < hi; i += rows_per_step) {
-                float v[4];
+            // 4 rows per thread and step: the loads of x are in flight together (one row per step made the largest event's
+            // load -> store chain the kernel's time)
+            for (int64_t ib = lo + r0; ib < hi; ib += 4 * rows_per_step) {
+                float v[4][4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int c = 4 * ch + e;
-                    v[e] = c < nf ? x[i * ldx + c] : (c < x0_cols ? s_g[c - nf] : 0.f);
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t i = ib + (int64_t)u * rows_per_step;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = 4 * ch + e;
+                        v[u][e] = c < nf ? (i < hi ? x[i * ldx + c] : 0.f) : (c < x0_cols ? s_g[c - nf] : 0.f);
+                    }
                 }
-                reinterpret_cast<float4*>(x0 + i * ld0)[ch] = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t i = ib + (int64_t)u * rows_per_step;
+                    if (i < hi) reinterpret_cast<float4*>(x0 + i * ld0)[ch] = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+                }
             }
         }
     } else if (x0 != nullptr) {
@@ -705,59 +715,75 @@ __global__ void relu_bwd_kernel(const float* __restrict__ g, int64_t ldg, const 
 // with g_row(r) = g[r] (plain) or, when deg != nullptr, the broadcast of the aggregated gradient
 // g[i] (add) / g[i]/deg[i] (mean) to the valid slots of node i = r / width (zero for padding slots).
 // One pass over the E x C tensors instead of three (aggregate-bwd, relu-bwd, colsum).
-// CTA = 64 float4 columns x 4 rows, ACT_ROWS rows per CTA, grid.y over 256-column chunks.
+// CTA = bx float4 columns x by row lanes (bx = the row's float4 count rounded up to a warp when that is <= 128, else 64 with
+// grid.y over 256-column chunks); `rpc` rows per CTA, chosen by the launcher so that small tensors still fill the GPU (the
+// read-out's 512 x 128 tensor used to run on 2 CTAs of 64 dependent steps: 33 us); 4 rows per thread and step in flight.
 constexpr int ACT_ROWS = 256;
 
 __global__ void __launch_bounds__(256)
 act_bwd_colsum_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ y, int64_t ldy,
                       int64_t rows, int cols4, float* __restrict__ dz, int64_t ldz, float* __restrict__ db, int flags,
-                      const int* __restrict__ deg, int width, int aggr) {
-    const int c4 = blockIdx.y * 64 + threadIdx.x;
+                      const int* __restrict__ deg, int width, int aggr, int rpc) {
+    const int bx = blockDim.x, by = blockDim.y;
+    const int c4 = blockIdx.y * bx + threadIdx.x;
     const int ty = threadIdx.y;
     const bool col_ok = c4 < cols4;
     const bool relu = (flags & 0xff) == GNB_ACT_RELU, rnd = (flags & GNB_FLAG_ROUND_TF32) != 0;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int64_t r0 = (int64_t)blockIdx.x * ACT_ROWS;
-    const int64_t r1 = r0 + ACT_ROWS < rows ? r0 + ACT_ROWS : rows;
+    const int64_t r0 = (int64_t)blockIdx.x * rpc;
+    const int64_t r1 = r0 + rpc < rows ? r0 + rpc : rows;
     if (col_ok) {
-        for (int64_t r = r0 + ty; r < r1; r += 4) {
-            float4 gv;
-            if (deg != nullptr) {
-                const int64_t i = r / width;
-                const int s = (int)(r - i * width);
-                const int dg = deg[i];
-                if (s < dg) {
-                    gv = reinterpret_cast<const float4*>(g + i * ldg)[c4];
-                    if (aggr == GNB_AGGR_MEAN) {
-                        const float sc = 1.f / (float)dg;
-                        gv.x *= sc; gv.y *= sc; gv.z *= sc; gv.w *= sc;
+        for (int64_t rb = r0 + ty; rb < r1; rb += 4 * by) {
+            float4 gv[4], yv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t r = rb + (int64_t)u * by;
+                gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                yv[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (r < r1) {
+                    if (deg != nullptr) {
+                        const int64_t i = r / width;
+                        const int s = (int)(r - i * width);
+                        const int dg = deg[i];
+                        if (s < dg) {
+                            gv[u] = reinterpret_cast<const float4*>(g + i * ldg)[c4];
+                            if (aggr == GNB_AGGR_MEAN) {
+                                const float sc = 1.f / (float)dg;
+                                gv[u].x *= sc; gv[u].y *= sc; gv[u].z *= sc; gv[u].w *= sc;
+                            }
+                        }
+                    } else {
+                        gv[u] = reinterpret_cast<const float4*>(g + r * ldg)[c4];
                     }
-                } else {
-                    gv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (relu) yv[u] = reinterpret_cast<const float4*>(y + r * ldy)[c4];
                 }
-            } else {
-                gv = reinterpret_cast<const float4*>(g + r * ldg)[c4];
             }
-            if (relu) {
-                const float4 yv = reinterpret_cast<const float4*>(y + r * ldy)[c4];
-                gv.x = yv.x > 0.f ? gv.x : 0.f; gv.y = yv.y > 0.f ? gv.y : 0.f;
-                gv.z = yv.z > 0.f ? gv.z : 0.f; gv.w = yv.w > 0.f ? gv.w : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t r = rb + (int64_t)u * by;
+                if (r < r1) {
+                    float4 v = gv[u];
+                    if (relu) {
+                        v.x = yv[u].x > 0.f ? v.x : 0.f; v.y = yv[u].y > 0.f ? v.y : 0.f;
+                        v.z = yv[u].z > 0.f ? v.z : 0.f; v.w = yv[u].w > 0.f ? v.w : 0.f;
+                    }
+                    if (rnd) {
+                        v.x = gnb_round_tf32(v.x); v.y = gnb_round_tf32(v.y);
+                        v.z = gnb_round_tf32(v.z); v.w = gnb_round_tf32(v.w);
+                    }
+                    reinterpret_cast<float4*>(dz + r * ldz)[c4] = v;
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
             }
-            if (rnd) {
-                gv.x = gnb_round_tf32(gv.x); gv.y = gnb_round_tf32(gv.y);
-                gv.z = gnb_round_tf32(gv.z); gv.w = gnb_round_tf32(gv.w);
-            }
-            reinterpret_cast<float4*>(dz + r * ldz)[c4] = gv;
-            acc.x += gv.x; acc.y += gv.y; acc.z += gv.z; acc.w += gv.w;
         }
     }
     if (db == nullptr) return;
-    __shared__ float4 s_acc[4][64];
-    s_acc[ty][threadIdx.x] = acc;
+    __shared__ float4 s_acc[256];
+    s_acc[ty * bx + threadIdx.x] = acc;
     __syncthreads();
     if (ty == 0 && col_ok) {
-        for (int t = 1; t < 4; ++t) {
-            const float4 o = s_acc[t][threadIdx.x];
+        for (int t = 1; t < by; ++t) {
+            const float4 o = s_acc[t * bx + threadIdx.x];
             acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
         }
         atomicAdd(db + 4 * c4 + 0, acc.x); atomicAdd(db + 4 * c4 + 1, acc.y);
@@ -1085,8 +1111,16 @@ GNB_EXPORT int gnb_act_bwd_colsum(const float* g, int64_t ldg, const float* y, i
                                                                          (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0);
         GNB_RETURN_LAUNCH();
     }
-    act_bwd_colsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(g, ldg, y, ldy, rows, cols >> 2, dz, ldz, db, flags,
-                                                                    deg, width, aggr);
+    {
+        const int cols4 = cols >> 2;
+        const int bx = cols4 <= 128 ? (cols4 + 31) / 32 * 32 : 64, by = 256 / bx < 1 ? 1 : 256 / bx;
+        int64_t rpc = gnb_div_up(rows, 4 * 148);                      // ~4 CTAs per SM
+        rpc = rpc > ACT_ROWS ? ACT_ROWS : rpc;
+        rpc = gnb_div_up(rpc, by) * by;
+        dim3 grid2((unsigned)gnb_div_up(rows, rpc), (unsigned)gnb_div_up(cols4, bx)), block2(bx, by);
+        act_bwd_colsum_kernel<<<grid2, block2, 0, (cudaStream_t)stream>>>(g, ldg, y, ldy, rows, cols4, dz, ldz, db, flags,
+                                                                          deg, width, aggr, (int)rpc);
+    }
     GNB_RETURN_LAUNCH();
 }
 

@@ -206,9 +206,9 @@ __device__ __forceinline__ void knn_flush(float (&bd)[K1], int (&bi)[K1], const 
 template <int K1, int D, int S>
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_table_split_kernel(const float* __restrict__ x, int64_t ld, const int* __restrict__ cols,
-                       const int64_t* __restrict__ ptr, int nseg, int64_t n,
+                       const int64_t* __restrict__ ptr, int nseg, int64_t n, int64_t size_lo, int64_t size_hi,
                        int* __restrict__ nbr, int* __restrict__ deg) {
-    static_assert(D == 3 && S == 8, "scan is written for 3 coordinates and 8 lanes per query");
+    static_assert(D == 3 && (S & (S - 1)) == 0 && S <= 32, "scan is written for 3 coordinates; lanes per query a power of two");
     __shared__ __align__(16) float s_c[D][KNN_CH];
     __shared__ float s_qd[KNN_QC][KNN_THREADS];
     __shared__ int s_qi[KNN_QC][KNN_THREADS];
@@ -219,20 +219,26 @@ knn_table_split_kernel(const float* __restrict__ x, int64_t ld, const int* __res
     const int sub = tid % S;
     const int64_t q0 = (int64_t)blockIdx.x * QPC;
     const int64_t q = q0 + tid / S;
-    const bool active = q < n;
+    bool active = q < n;
     if (tid < D) s_cols[tid] = cols[tid];
+    if (tid == 0) { s_range[0] = 0x7fffffffffffffffLL; s_range[1] = 0; }
+    __syncthreads();
 
+    // this launch handles the queries whose event has size_lo <= pulses < size_hi (the other size class runs with another S)
     int64_t lo = 0, hi = 0;
     if (active) {
         const int b = find_segment(ptr, nseg, q);
         lo = ptr[b];
         hi = ptr[b + 1];
+        active = hi - lo >= size_lo && hi - lo < size_hi;
+        if (active && sub == 0) {
+            atomicMin(reinterpret_cast<unsigned long long*>(&s_range[0]), (unsigned long long)lo);
+            atomicMax(reinterpret_cast<unsigned long long*>(&s_range[1]), (unsigned long long)hi);
+        }
     }
-    if (tid == 0) s_range[0] = lo;
-    const int64_t q_last = (q0 + QPC < n ? q0 + QPC : n) - 1;
-    if (q == q_last && sub == 0) s_range[1] = hi;
     __syncthreads();
-    const int64_t r_lo = s_range[0], r_hi = s_range[1];
+    const int64_t r_lo = s_range[0], r_hi = s_range[1];     // union of the active queries' events (empty: r_lo > r_hi)
+    if (r_lo >= r_hi) return;
 
     float qf[D];
 #pragma unroll
@@ -363,10 +369,14 @@ int launch_knn(const float* x, int64_t ld, const int* cols, int d, const int64_t
     GNB_RETURN_LAUNCH();
 }
 
-template <int K1, int D, int S>
+// One launch with 8 lanes per query for every event. (Two size classes -- 2 lanes per query for events below 512 pulses, 8
+// above, each launch skipping the other's queries -- were measured at 162 + 226 us per step against 345 us: no gain; the
+// size window arguments stay for experiments.)
+template <int K1, int D>
 int launch_knn_split(const float* x, int64_t ld, const int* cols, const int64_t* ptr, int nseg, int64_t n, int* nbr, int* deg,
                      cudaStream_t st) {
-    knn_table_split_kernel<K1, D, S><<<gnb_div_up(n, KNN_THREADS / S), KNN_THREADS, 0, st>>>(x, ld, cols, ptr, nseg, n, nbr, deg);
+    knn_table_split_kernel<K1, D, 8><<<gnb_div_up(n, KNN_THREADS / 8), KNN_THREADS, 0, st>>>(x, ld, cols, ptr, nseg, n, 0,
+                                                                                              (int64_t)1 << 62, nbr, deg);
     GNB_RETURN_LAUNCH();
 }
 
@@ -395,7 +405,7 @@ GNB_EXPORT int gnb_knn_table(const float* x, int64_t ld, const int32_t* cols, in
     cudaStream_t st = (cudaStream_t)stream;
     const int k1 = k + 1;
     if (d == 3) {
-        if (k1 == 9 && g_knn_variant != 1) return launch_knn_split<9, 3, 8>(x, ld, cols, ptr, (int)nseg, n, nbr, deg, st);
+        if (k1 == 9 && g_knn_variant != 1) return launch_knn_split<9, 3>(x, ld, cols, ptr, (int)nseg, n, nbr, deg, st);
         if (k1 == 9) return launch_knn<9, 3>(x, ld, cols, d, ptr, (int)nseg, n, k1, nbr, deg, st);
         if (k1 == 5) return launch_knn<5, 3>(x, ld, cols, d, ptr, (int)nseg, n, k1, nbr, deg, st);
         if (k1 == 17) return launch_knn<17, 3>(x, ld, cols, d, ptr, (int)nseg, n, k1, nbr, deg, st);

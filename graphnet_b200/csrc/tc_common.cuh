@@ -16,6 +16,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // 32-bit shared-memory loads / fire-and-forget global reductions for the metadata-driven epilogues. A `const T*` into
 // dynamic shared memory that crossed a function boundary compiles to generic LD.E with 64-bit address arithmetic
 // (4 integer instructions per load); these take the 32-bit shared address, so constant offsets fold into the LDS.
+// byte permute; a selector nibble with bit 3 set replicates the sign bit of the selected byte over the result byte
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -41,34 +47,47 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// try_wait with a suspend-time hint: the thread may stay suspended in hardware (no issue slots used) until the phase
-// completes or the hint (ns) expires, instead of returning to a software polling loop after the default, short limit --
-// ncu (profiles/r02/r_bwd_builders.ncu-rep) showed 36 .. 47 % of the builder kernels' executed instructions in these loops.
+// try_wait, optionally with a suspend-time hint: with the hint the thread may stay suspended in hardware (no issue slots used)
+// until the phase completes or the hint (ns) expires, instead of returning to the software polling loop after the default,
+// short limit -- ncu (profiles/r02/r_bwd_builders.ncu-rep) showed 36 .. 47 % of the builder kernels' executed instructions in
+// these loops. Measured on the training step: only the weight-gradient builder kernel gains (701 -> 624 us per step); the split
+// forward GEMM, whose splitter warps wait for TMA data on the critical path, loses (817 -> 855 us: the wake-up is slower than
+// a poll); the other kernels do not move. Opt-in per wait (mbar_wait<SLEEP_NS, true>).
 #ifndef GNB_MBAR_HINT_NS
 #define GNB_MBAR_HINT_NS 20000
 #endif
+template <bool HINT = false>
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
     uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity), "r"((uint32_t)GNB_MBAR_HINT_NS)
-        : "memory");
+    if (HINT)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity), "r"((uint32_t)GNB_MBAR_HINT_NS)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
     return done;
 }
 // Bounded wait: a lost arrival traps (reported as a launch error) instead of hanging the GPU.
 // SLEEP_NS > 0 backs off between polls so that long waits (epilogue / metadata warps) do not steal issue slots
 // from the warps doing the work.
-template <int SLEEP_NS = 0>
+template <int SLEEP_NS = 0, bool HINT = false>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    if (mbar_try_wait(addr, parity)) return;
+    if (mbar_try_wait<HINT>(addr, parity)) return;
     long long t0 = 0;
     for (uint32_t it = 1;; ++it) {
         if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
-        if (mbar_try_wait(addr, parity)) return;
+        if (mbar_try_wait<HINT>(addr, parity)) return;
         if ((it & 4095u) == 0u) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
@@ -100,10 +119,10 @@ __device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t addr, uint32_
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity), "r"((uint32_t)GNB_MBAR_HINT_NS)
+        : "r"(addr), "r"(parity)
         : "memory");
     return done;
 }
