@@ -148,6 +148,7 @@ __device__ __forceinline__ void store_corr(float* crow, int c, float v, float hi
 // lo != nullptr (tf32x3 weights; dst_cols % 32 == 0): dst = rna_tf32(v), lo = the bf16 correction operand
 __global__ void copy_pad_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
                                 float* __restrict__ dst, int64_t ldd, int dst_cols, int rnd, float* __restrict__ lo) {
+    gnb_pdl_begin();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rows * dst_cols) return;
     const int64_t r = t / dst_cols;
@@ -160,6 +161,7 @@ __global__ void copy_pad_kernel(const float* __restrict__ src, int64_t lds, int6
 // dst[r, c] += src[r, c]
 __global__ void add2d_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
                              float* __restrict__ dst, int64_t ldd) {
+    gnb_pdl_begin();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rows * cols) return;
     const int64_t r = t / cols;
@@ -169,6 +171,7 @@ __global__ void add2d_kernel(const float* __restrict__ src, int64_t lds, int64_t
 // dst[c, r] = maybe_round(src[r, c]) (zero padded to dst_cols): W^T for the backward-data GEMM
 __global__ void transpose_pad_kernel(const float* __restrict__ src, int64_t lds, int rows, int cols,
                                      float* __restrict__ dst, int64_t ldd, int dst_cols, int rnd) {
+    gnb_pdl_begin();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)cols * dst_cols) return;
     const int c = (int)(t / dst_cols);          // dst row = src column
@@ -180,6 +183,7 @@ __global__ void transpose_pad_kernel(const float* __restrict__ src, int64_t lds,
 // bcat = [b1 ; 0]
 __global__ void pack_conv_kernel(const float* __restrict__ w1, const float* __restrict__ b1, int h, int c,
                                  float* __restrict__ wcat, int64_t ld, float* __restrict__ bcat, int rnd, float* __restrict__ wlo) {
+    gnb_pdl_begin();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 2 * (int64_t)h * ld) return;
     const int r = (int)(t / ld);
@@ -194,6 +198,7 @@ __global__ void pack_conv_kernel(const float* __restrict__ w1, const float* __re
 // dW1[r, col] += dWcat[r, col];  dW1[r, C + col] += dWcat[H + r, col] - dWcat[r, col];  db1 += dbcat[0:H]
 __global__ void unpack_conv_grad_kernel(const float* __restrict__ dwcat, int64_t ld, const float* __restrict__ dbcat,
                                         int h, int c, float* __restrict__ dw1, float* __restrict__ db1) {
+    gnb_pdl_begin();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)h * c) return;
     const int r = (int)(t / c);
@@ -439,16 +444,16 @@ struct Exec {
     int copy_pad(const float* src, int64_t lds, int64_t rows, int cols, float* dst, int64_t ldd, int dst_cols, bool round,
                  float* lo = nullptr) {
         if (rows * dst_cols == 0) return 0;
-        copy_pad_kernel<<<gnb_div_up(rows * dst_cols, 256), 256, 0, st>>>(src, lds, rows, cols, dst, ldd, dst_cols, round ? 1 : 0, lo);
+        gnb_launch(copy_pad_kernel, gnb_div_up(rows * dst_cols, 256), 256, 0, st)(src, lds, rows, cols, dst, ldd, dst_cols, round ? 1 : 0, lo);
         EXL(); return 0;
     }
     int add2d(const float* src, int64_t lds, int64_t rows, int cols, float* dst, int64_t ldd) {
         if (rows * cols == 0) return 0;
-        add2d_kernel<<<gnb_div_up(rows * cols, 256), 256, 0, st>>>(src, lds, rows, cols, dst, ldd);
+        gnb_launch(add2d_kernel, gnb_div_up(rows * cols, 256), 256, 0, st)(src, lds, rows, cols, dst, ldd);
         EXL(); return 0;
     }
     int transpose_pad(const float* src, int64_t lds, int rows, int cols, float* dst, int64_t ldd, int dst_cols) {
-        transpose_pad_kernel<<<gnb_div_up((int64_t)cols * dst_cols, 256), 256, 0, st>>>(src, lds, rows, cols, dst, ldd, dst_cols, tf32 ? 1 : 0);
+        gnb_launch(transpose_pad_kernel, gnb_div_up((int64_t)cols * dst_cols, 256), 256, 0, st)(src, lds, rows, cols, dst, ldd, dst_cols, tf32 ? 1 : 0);
         EXL(); return 0;
     }
     // y = act(sum_p x_p wp[:, off_p : off_p + k_p]^T + b)
@@ -535,7 +540,7 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
         ConvBuf& b = p.conv[l];
         const float *w1 = params[pi], *b1 = params[pi + 1], *w2 = params[pi + 2], *b2 = params[pi + 3];
         pi += 4;
-        pack_conv_kernel<<<gnb_div_up(2 * (int64_t)b.hid * b.kld, 256), 256, 0, e.st>>>(w1, b1, b.hid, b.cin, b.wcat, b.kld, b.bcat, e.tf32 ? 1 : 0, b.wcat_lo);
+        gnb_launch(pack_conv_kernel, gnb_div_up(2 * (int64_t)b.hid * b.kld, 256), 256, 0, e.st)(w1, b1, b.hid, b.cin, b.wcat, b.kld, b.bcat, e.tf32 ? 1 : 0, b.wcat_lo);
         EXL();
         EX(e.copy_pad(w2, b.hid, b.cout, b.hid, b.w2p, b.hld, b.hld, e.tf32, b.w2p_lo));
         {   // PQ = xin Wcat^T + bcat
@@ -796,7 +801,7 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
         const float* xin = l == 0 ? p.x0 : p.conv[l - 1].y;
         GNB_CHECK(cudaMemsetAsync(p.dwp, 0, (size_t)2 * b.hid * b.kld * 4, e.st));
         EX(e.lin_bwd_weight(dzq, 2 * b.hid, xin, b.cin_ld, p.dwp, b.kld, 0, b.cin_ld, 2 * b.hid, n));
-        unpack_conv_grad_kernel<<<gnb_div_up((int64_t)b.hid * b.cin, 256), 256, 0, e.st>>>(p.dwp, b.kld, p.dbtmp, b.hid, b.cin, gw1, gb1);
+        gnb_launch(unpack_conv_grad_kernel, gnb_div_up((int64_t)b.hid * b.cin, 256), 256, 0, e.st)(p.dwp, b.kld, p.dbtmp, b.hid, b.cin, gw1, gb1);
         EXL();
         if (l > 0)   // gradient into the previous layer's output: accumulate onto the post-processing part
             EX(e.lin_bwd_data(dzq, 2 * b.hid, b.wcat, b.kld, 0, b.cin_ld, 2 * b.hid, p.gnode[l], b.cin_ld, n, true, p.wt, p.dh_big));

@@ -113,6 +113,7 @@ __device__ __forceinline__ void ef_epilogue_tile(const TileMeta& m, uint32_t tad
 
 __global__ void __launch_bounds__(EF_THREADS, 1)
 edgeconv_fused_fwd_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfParams p) {
+    gnb_pdl_begin();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_a = smem;                                            // [kblocks][16 KiB] resident weights
@@ -363,6 +364,7 @@ constexpr uint32_t EP_BTILE_BYTES = 64 * 32 * 4;    // 8 KiB: 64 rows x 32 tf32 
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EP_THREADS, 1)
 edgeconv_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_w2, const EfParams p) {
+    gnb_pdl_begin();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_a = smem;                                            // [kblocks][16 KiB] resident weights (this CTA's half)
@@ -657,13 +659,13 @@ GNB_EXPORT int gnb_edgeconv_fused_fwd_tf32(const float* pq, int64_t ldpq, int32_
         }
         int clusters = g_ef_sms / 2;
         if (clusters > p.num_tiles) clusters = p.num_tiles;
-        edgeconv_fused_pair_kernel<<<dim3((unsigned)(2 * clusters)), EP_THREADS, EP_SMEM_BYTES, (cudaStream_t)stream>>>(tw, p);
+        gnb_launch(edgeconv_fused_pair_kernel, dim3((unsigned)(2 * clusters)), EP_THREADS, EP_SMEM_BYTES, (cudaStream_t)stream)(tw, p);
         GNB_RETURN_LAUNCH();
     }
     int ctas = g_ef_sms / halves;
     if (ctas < 1) ctas = 1;
     if (ctas > p.num_tiles) ctas = p.num_tiles;
     dim3 grid((unsigned)ctas, (unsigned)halves);
-    edgeconv_fused_fwd_kernel<<<grid, EF_THREADS, EF_SMEM_BYTES, (cudaStream_t)stream>>>(tw, p);
+    gnb_launch(edgeconv_fused_fwd_kernel, grid, EF_THREADS, EF_SMEM_BYTES, (cudaStream_t)stream)(tw, p);
     GNB_RETURN_LAUNCH();
 }

@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(NT)
 gemm_f32_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
                 float* __restrict__ C, int64_t ldc, int64_t M, int64_t N, int64_t K,
                 const float* __restrict__ bias, int act, int accumulate, int64_t k_per_split, int atomic_flag) {
+    gnb_pdl_begin();
     __shared__ __align__(16) float As[2][BK][BM + PADS];
     __shared__ __align__(16) float Bs[2][BK][BN + PADS];
     const int tid = threadIdx.x;
@@ -173,9 +174,9 @@ int launch(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, i
     if (grid.y > 65535u || grid.z > 65535u) return GNB_ERR_ARG;
     const bool vec = al16(A) && al16(B) && (lda % 4 == 0) && (ldb % 4 == 0);
     if (vec)
-        gemm_f32_kernel<TA, TB, true><<<grid, NT, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, act, accumulate, kps, atomic ? 1 : 0);
+        gnb_launch(gemm_f32_kernel<TA, TB, true>, grid, NT, 0, st)(A, lda, B, ldb, C, ldc, M, N, K, bias, act, accumulate, kps, atomic ? 1 : 0);
     else
-        gemm_f32_kernel<TA, TB, false><<<grid, NT, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, act, accumulate, kps, atomic ? 1 : 0);
+        gnb_launch(gemm_f32_kernel<TA, TB, false>, grid, NT, 0, st)(A, lda, B, ldb, C, ldc, M, N, K, bias, act, accumulate, kps, atomic ? 1 : 0);
     GNB_RETURN_LAUNCH();
 }
 

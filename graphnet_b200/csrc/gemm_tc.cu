@@ -206,6 +206,7 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
                       const PartInfo parts, const float* __restrict__ bias, float* __restrict__ y, int64_t ldy,
                       int64_t rows, int n_out, int act, int round_out, int num_row_tiles, const AggInfo agg,
                       const ScatInfo sc) {
+    gnb_pdl_begin();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
@@ -510,6 +511,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                     const PartInfo parts, const float* __restrict__ bias, float* __restrict__ y, int64_t ldy,
                     int64_t rows, int n_out, int act, int round_out, int num_tiles, const AggInfo agg, const ScatInfo sc,
                     const GroupSplit gs, const PairCfg pc) {
+    gnb_pdl_begin();
     constexpr bool SPLIT = MODE == 1;
     constexpr bool BF = MODE >= 2;
     constexpr int NP = MODE == 3 ? 2 : 1;                 // bf16 planes per operand
@@ -998,6 +1000,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PL_THREADS, 1)
 gemm_tc_pair_dual_scatter_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                                  int total_kb, int64_t rows, int n_out, int num_tiles, const ScatInfo sc, int nst_w,
                                  uint32_t meta_stride, int dbg) {
+    gnb_pdl_begin();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* act = smem;                                               // [total_kb] x 16 KiB: resident dz tile (own half)
@@ -1192,6 +1195,7 @@ gemm_bf_pair_dual_scatter_kernel(const __grid_constant__ CUtensorMap tm_w0, cons
                                  const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
                                  int total_kb, int last_ksteps, int64_t rows, int n_out, int num_tiles, const ScatInfo sc, int nst_w,
                                  uint32_t meta_stride, int dbg, uint32_t idesc) {
+    gnb_pdl_begin();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* act = smem;                                               // [total_kb][NP] x 16 KiB: resident dz tile (own half)
@@ -1417,6 +1421,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DB_THREADS, 1)
 gemm_f16_pair_scatter_build_kernel(const __grid_constant__ CUtensorMap tm_w0, const DzBuild zb, int total_kb, int last_ksteps,
                                    int64_t rows, int n_out, int num_tiles, const ScatInfo sc, int nst_w, uint32_t meta_stride,
                                    int dbg, int ngroups) {
+    gnb_pdl_begin();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* act = smem;                                               // [total_kb] x 16 KiB: dz tile built here (own half)
@@ -1692,6 +1697,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FU_THREADS, 1)
 gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
                                const FuseSrc fs, const float* __restrict__ bias, float* __restrict__ y, int64_t ldy, int n_out,
                                int round_out, int num_tiles, int total_kb, int last_ksteps, unsigned* __restrict__ maskbits) {
+    gnb_pdl_begin();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr uint32_t WST = NP * TC_TILE_BYTES, BSL = NP * TC_TILE_BYTES;
@@ -2011,6 +2017,7 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
 // dst[r, c] = rna_tf32(src[r, c]) for c < cols, 0 for cols <= c < dst_cols
 __global__ void round_pad_tf32_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
                                       float* __restrict__ dst, int64_t ldd, int dst_cols) {
+    gnb_pdl_begin();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rows * dst_cols) return;
     const int64_t r = t / dst_cols;
@@ -2110,10 +2117,10 @@ int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi
         const uint32_t smem = fixed + (uint32_t)pc.nstages * stage;
         dim3 grid((unsigned)(2 * used));
         if (bf_planes == 2)
-            gemm_tc_pair_kernel<3><<<grid, PL_THREADS, smem, stream>>>(tw, *twlo, tx, pi, bias, y, ldy, rows, n_out, act, round_out,
+            gnb_launch(gemm_tc_pair_kernel<3>, grid, PL_THREADS, smem, stream)(tw, *twlo, tx, pi, bias, y, ldy, rows, n_out, act, round_out,
                                                                      tiles, agg, sc, gs, pc);
         else
-            gemm_tc_pair_kernel<2><<<grid, PL_THREADS, smem, stream>>>(tw, tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out,
+            gnb_launch(gemm_tc_pair_kernel<2>, grid, PL_THREADS, smem, stream)(tw, tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out,
                                                                      tiles, agg, sc, gs, pc);
         GNB_RETURN_LAUNCH();
     }
@@ -2164,13 +2171,13 @@ int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi
             pc.resident = 0;
             pc.nstages = PL_SPLIT_STAGES;
             const uint32_t smem_split = fixed + (PL_SPLIT_STAGES * 3 + PL_SPLIT_LO_SLOTS) * TC_TILE_BYTES;
-            gemm_tc_pair_kernel<1><<<grid, PL_SPLIT_THREADS, smem_split, stream>>>(tw, *twlo, tx, pi, bias, y, ldy, rows, n_out,
+            gnb_launch(gemm_tc_pair_kernel<1>, grid, PL_SPLIT_THREADS, smem_split, stream)(tw, *twlo, tx, pi, bias, y, ldy, rows, n_out,
                                                                                       act, round_out, tiles, agg, sc, gs, pc);
             GNB_RETURN_LAUNCH();
         }
         const uint32_t smem = fixed + (pc.resident ? (uint32_t)total_kb * TC_TILE_BYTES + pc.nstages * TC_TILE_BYTES
                                                    : pc.nstages * 2 * TC_TILE_BYTES);
-        gemm_tc_pair_kernel<0><<<grid, PL_THREADS, smem, stream>>>(tw, tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out,
+        gnb_launch(gemm_tc_pair_kernel<0>, grid, PL_THREADS, smem, stream)(tw, tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out,
                                                                       tiles, agg, sc, gs, pc);
         GNB_RETURN_LAUNCH();
     }
@@ -2179,7 +2186,7 @@ int launch_linear(const CUtensorMap& tw, const TmapArray& tx, const PartInfo& pi
     if (ctas_x < 1) ctas_x = 1;
     if (ctas_x > row_tiles) ctas_x = row_tiles;
     dim3 grid((unsigned)ctas_x, (unsigned)groups);
-    gemm_tc_linear_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out,
+    gnb_launch(gemm_tc_linear_kernel, grid, TC_THREADS, TC_SMEM_BYTES, stream)(tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out,
                                                                        row_tiles, agg, sc);
     GNB_RETURN_LAUNCH();
 }
@@ -2360,7 +2367,7 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_split_tf32(const float* dz, int64_t
         if (clusters < 1) clusters = 1;
         const uint32_t mstride = sc_meta_stride(mask_ld);
         const uint32_t smem = 1024 + (uint32_t)(pi.kblocks[0] + nst_w) * TC_TILE_BYTES + DU_BAR_BYTES + 4 * mstride;
-        gemm_tc_pair_dual_scatter_kernel<<<dim3((unsigned)(2 * clusters)), PL_THREADS, smem, (cudaStream_t)stream>>>(
+        gnb_launch(gemm_tc_pair_dual_scatter_kernel, dim3((unsigned)(2 * clusters)), PL_THREADS, smem, (cudaStream_t)stream)(
             tw, tx.m[0], pi.kblocks[0], rows, hdim, tiles, sc, nst_w, mstride, g_linear_dbg);
         GNB_RETURN_LAUNCH();
     }
@@ -2382,6 +2389,7 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_tf32(const float* dz, int64_t lddz,
 // at bf16 index 64 kb -- one 128-byte swizzle row of A_corr per K block.
 static __global__ void split_pad_tf32_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
                                       float* __restrict__ hi, float* __restrict__ corr, int64_t ldd, int dst_cols) {
+    gnb_pdl_begin();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rows * dst_cols) return;
     const int64_t r = t / dst_cols;
@@ -2397,7 +2405,7 @@ GNB_EXPORT int gnb_split_pad_tf32(const float* src, int64_t lds, int64_t rows, i
                                   int32_t dst_cols, void* stream) {
     if (dst_cols < cols || (dst_cols & 31) || rows < 0 || hi == nullptr || lo == nullptr) return GNB_ERR_ARG;
     if (rows == 0) return GNB_OK;
-    split_pad_tf32_kernel<<<gnb_div_up(rows * dst_cols, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, rows, cols, hi, lo, ldd,
+    gnb_launch(split_pad_tf32_kernel, gnb_div_up(rows * dst_cols, 256), 256, 0, (cudaStream_t)stream)(src, lds, rows, cols, hi, lo, ldd,
                                                                                               dst_cols);
     GNB_RETURN_LAUNCH();
 }
@@ -2406,7 +2414,7 @@ GNB_EXPORT int gnb_round_pad_tf32(const float* src, int64_t lds, int64_t rows, i
                                   int32_t dst_cols, void* stream) {
     if (dst_cols < cols || rows < 0) return GNB_ERR_ARG;
     if (rows == 0) return GNB_OK;
-    round_pad_tf32_kernel<<<gnb_div_up(rows * dst_cols, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, rows, cols, dst,
+    gnb_launch(round_pad_tf32_kernel, gnb_div_up(rows * dst_cols, 256), 256, 0, (cudaStream_t)stream)(src, lds, rows, cols, dst,
                                                                                               ldd, dst_cols);
     GNB_RETURN_LAUNCH();
 }
@@ -2510,10 +2518,10 @@ static int dgrad_scatter16_impl(const void* dz0, const void* dz1, int64_t lddz, 
             if (clusters < 1) clusters = 1;
             const uint32_t smem = 1024 + (uint32_t)(pi.kblocks[0] * planes + nst_w) * TC_TILE_BYTES + DU_BAR_BYTES + 4 * mstride;
             if (planes == 2)
-                gemm_bf_pair_dual_scatter_kernel<2><<<dim3((unsigned)(2 * clusters)), PL_THREADS, smem, (cudaStream_t)stream>>>(
+                gnb_launch(gemm_bf_pair_dual_scatter_kernel<2>, dim3((unsigned)(2 * clusters)), PL_THREADS, smem, (cudaStream_t)stream)(
                     tw, tw1, tx.m[0], tx.m[1], pi.kblocks[0], last_ksteps, rows, hdim, tiles, sc, nst_w, mstride, g_linear_dbg, idesc_f16_256(fmt16));
             else
-                gemm_bf_pair_dual_scatter_kernel<1><<<dim3((unsigned)(2 * clusters)), PL_THREADS, smem, (cudaStream_t)stream>>>(
+                gnb_launch(gemm_bf_pair_dual_scatter_kernel<1>, dim3((unsigned)(2 * clusters)), PL_THREADS, smem, (cudaStream_t)stream)(
                     tw, tw, tx.m[0], tx.m[0], pi.kblocks[0], last_ksteps, rows, hdim, tiles, sc, nst_w, mstride, g_linear_dbg, idesc_f16_256(fmt16));
             GNB_RETURN_LAUNCH();
         }
@@ -2573,6 +2581,7 @@ GNB_EXPORT int gnb_linear_fwd_bf16(const void* x0, const void* x1, int64_t ldx, 
 static __global__ void to_bf16_planes_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
                                              __nv_bfloat16* __restrict__ p0, __nv_bfloat16* __restrict__ p1, int64_t ldd, int dst_cols,
                                              int transpose) {
+    gnb_pdl_begin();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t drows = transpose ? cols : rows;
     if (t >= drows * dst_cols) return;
@@ -2590,7 +2599,7 @@ GNB_EXPORT int gnb_to_bf16_planes(const float* src, int64_t lds, int64_t rows, i
     if (rows < 0 || cols < 0 || p0 == nullptr || ldd < dst_cols || dst_cols < (transpose ? rows : cols)) return GNB_ERR_ARG;
     const int64_t total = (transpose ? (int64_t)cols : rows) * dst_cols;
     if (total == 0) return GNB_OK;
-    to_bf16_planes_kernel<<<gnb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, rows, cols, (__nv_bfloat16*)p0,
+    gnb_launch(to_bf16_planes_kernel, gnb_div_up(total, 256), 256, 0, (cudaStream_t)stream)(src, lds, rows, cols, (__nv_bfloat16*)p0,
                                                                                       (__nv_bfloat16*)p1, ldd, dst_cols, transpose);
     GNB_RETURN_LAUNCH();
 }
@@ -2599,6 +2608,7 @@ GNB_EXPORT int gnb_to_bf16_planes(const float* src, int64_t lds, int64_t rows, i
 // fp16(v - p0) (may be NULL), round to nearest.
 static __global__ void to_f16_planes_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols, __half* __restrict__ p0,
                                             __half* __restrict__ p1, int64_t ldd, int dst_cols, int transpose) {
+    gnb_pdl_begin();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t drows = transpose ? cols : rows;
     if (t >= drows * dst_cols) return;
@@ -2616,7 +2626,7 @@ GNB_EXPORT int gnb_to_f16_planes(const float* src, int64_t lds, int64_t rows, in
     if (rows < 0 || cols < 0 || p0 == nullptr || ldd < dst_cols || dst_cols < (transpose ? rows : cols)) return GNB_ERR_ARG;
     const int64_t total = (transpose ? (int64_t)cols : rows) * dst_cols;
     if (total == 0) return GNB_OK;
-    to_f16_planes_kernel<<<gnb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, rows, cols, (__half*)p0, (__half*)p1, ldd,
+    gnb_launch(to_f16_planes_kernel, gnb_div_up(total, 256), 256, 0, (cudaStream_t)stream)(src, lds, rows, cols, (__half*)p0, (__half*)p1, ldd,
                                                                                      dst_cols, transpose);
     GNB_RETURN_LAUNCH();
 }
@@ -2661,7 +2671,7 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_f16_masked(const void* g16, const u
     const uint32_t smem = 1024 + (uint32_t)(kblocks + nst_w) * TC_TILE_BYTES + DU_BAR_BYTES + 4 * mstride + stg;
     DzBuild zb{(const __half*)g16, rowmask, c_out};
     const int last_ksteps = (c_out - 64 * (kblocks - 1) + 15) / 16;
-    gemm_f16_pair_scatter_build_kernel<<<dim3((unsigned)(2 * clusters)), DB_THREADS, smem, (cudaStream_t)stream>>>(
+    gnb_launch(gemm_f16_pair_scatter_build_kernel, dim3((unsigned)(2 * clusters)), DB_THREADS, smem, (cudaStream_t)stream)(
         tw, zb, kblocks, last_ksteps, rows, hdim, tiles, sc, nst_w, mstride, g_linear_dbg, hdim > 256 ? 2 : 1);
     GNB_RETURN_LAUNCH();
 }
@@ -2700,10 +2710,10 @@ GNB_EXPORT int gnb_edgeconv_fused_fwd_f16(const float* pq, int64_t ldpq, int32_t
     const uint32_t smem = 1024 + (uint32_t)(FU_WSTAGES + FU_BSLOTS) * planes * TC_TILE_BYTES + 512;
     const int last_ksteps = (hid - 64 * (kblocks - 1) + 15) / 16;
     if (planes == 2)
-        gemm_f16_pair_agg_fused_kernel<2><<<dim3((unsigned)(2 * clusters)), FU_THREADS, smem, (cudaStream_t)stream>>>(
+        gnb_launch(gemm_f16_pair_agg_fused_kernel<2>, dim3((unsigned)(2 * clusters)), FU_THREADS, smem, (cudaStream_t)stream)(
             tw0, tw1, fs, bias, y, ldy, n_out, round_out, tiles, kblocks, last_ksteps, maskbits);
     else
-        gemm_f16_pair_agg_fused_kernel<1><<<dim3((unsigned)(2 * clusters)), FU_THREADS, smem, (cudaStream_t)stream>>>(
+        gnb_launch(gemm_f16_pair_agg_fused_kernel<1>, dim3((unsigned)(2 * clusters)), FU_THREADS, smem, (cudaStream_t)stream)(
             tw0, tw0, fs, bias, y, ldy, n_out, round_out, tiles, kblocks, last_ksteps, maskbits);
     GNB_RETURN_LAUNCH();
 }

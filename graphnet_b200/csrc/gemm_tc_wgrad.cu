@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_z,
                      float* __restrict__ dw, int64_t lddw, int64_t rows, int n_out, int k_in, int n_tiles_n,
                      int64_t rows_per_split, int swap_lbo_sbo) {
+    gnb_pdl_begin();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
@@ -188,6 +189,7 @@ gemm_bf_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_con
                      float* __restrict__ dw, int64_t lddw, int64_t rows, int n_out, int k_in, int n_tiles_n,
                      int64_t rows_per_split, int dbg, uint32_t fmt_a, uint32_t fmt_b, const unsigned* __restrict__ out_scale_bits,
                      const unsigned* __restrict__ out_scale_bits2) {
+    gnb_pdl_begin();
     constexpr uint32_t BOX = BK * 128;                           // one [BK rows x 64 columns] 16-bit box
     constexpr uint32_t A_BYTES = 2 * BOX, B_BYTES = 4 * BOX;     // per plane: 128 k_in columns, 256 n_out columns
     constexpr uint32_t STAGE = NPA * A_BYTES + NPB * B_BYTES;
@@ -336,6 +338,7 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
                             const unsigned* __restrict__ rowmask, float* __restrict__ dw, int64_t lddw, int64_t rows, int n_out,
                             int k_in, int64_t rows_per_split, const unsigned* __restrict__ dz_scale_bits,
                             const unsigned* __restrict__ x_scale_bits, int dbg) {
+    gnb_pdl_begin();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* bring = smem + WGB_NA * WGB_ASTAGE;                       // [WGB_NBUF] x 32 KiB
@@ -545,7 +548,7 @@ GNB_EXPORT int gnb_linear_bwd_weight_tf32(const float* dz, int64_t lddz, const f
     rps = ((rps + WG_BK - 1) / WG_BK) * WG_BK;
     splits = (int)((rows + rps - 1) / rps);
     dim3 grid((unsigned)tiles, (unsigned)splits);
-    gemm_tc_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, (cudaStream_t)stream>>>(tx, tz, dw, lddw, rows, n_out, k_in,
+    gnb_launch(gemm_tc_wgrad_kernel, grid, WG_THREADS, WG_SMEM_BYTES, (cudaStream_t)stream)(tx, tz, dw, lddw, rows, n_out, k_in,
                                                                                     tiles_n, rps, debug_swap);
     GNB_RETURN_LAUNCH();
 }
@@ -593,13 +596,13 @@ static int wgrad16_impl(const void* dz0, const void* dz1, int64_t lddz, const vo
     const uint32_t fa = (fmt & 1) ? 1u : 0u, fb = (fmt & 2) ? 1u : 0u;
     cudaStream_t st = (cudaStream_t)stream;
     if (npa == 2 && npb == 2)
-        gemm_bf_wgrad_kernel<2, 2, 32><<<grid, WG_THREADS, WB_SMEM_BYTES, st>>>(tx0, tx1, tz0, tz1, dw, lddw, rows, n_out, k_in, tiles_n,
+        gnb_launch(gemm_bf_wgrad_kernel<2, 2, 32>, grid, WG_THREADS, WB_SMEM_BYTES, st)(tx0, tx1, tz0, tz1, dw, lddw, rows, n_out, k_in, tiles_n,
                                                                               rps, debug, fa, fb, out_scale_bits, out_scale_bits2);
     else if (npa == 2)
-        gemm_bf_wgrad_kernel<2, 1, 32><<<grid, WG_THREADS, WB_SMEM_BYTES, st>>>(tx0, tx1, tz0, tz0, dw, lddw, rows, n_out, k_in, tiles_n,
+        gnb_launch(gemm_bf_wgrad_kernel<2, 1, 32>, grid, WG_THREADS, WB_SMEM_BYTES, st)(tx0, tx1, tz0, tz0, dw, lddw, rows, n_out, k_in, tiles_n,
                                                                               rps, debug, fa, fb, out_scale_bits, out_scale_bits2);
     else
-        gemm_bf_wgrad_kernel<1, 1, 64><<<grid, WG_THREADS, WB_SMEM_BYTES, st>>>(tx0, tx0, tz0, tz0, dw, lddw, rows, n_out, k_in, tiles_n,
+        gnb_launch(gemm_bf_wgrad_kernel<1, 1, 64>, grid, WG_THREADS, WB_SMEM_BYTES, st)(tx0, tx0, tz0, tz0, dw, lddw, rows, n_out, k_in, tiles_n,
                                                                               rps, debug, fa, fb, out_scale_bits, out_scale_bits2);
     GNB_RETURN_LAUNCH();
 }
@@ -653,7 +656,7 @@ GNB_EXPORT int gnb_linear_bwd_weight_f16_masked(const void* g16, const uint32_t*
     int64_t rps = (rows + splits - 1) / splits;
     rps = ((rps + WGB_BK - 1) / WGB_BK) * WGB_BK;
     splits = (int)((rows + rps - 1) / rps);
-    gemm_f16_wgrad_build_kernel<<<dim3((unsigned)tiles, (unsigned)splits), WGB_THREADS, WGB_SMEM_BYTES, (cudaStream_t)stream>>>(
+    gnb_launch(gemm_f16_wgrad_build_kernel, dim3((unsigned)tiles, (unsigned)splits), WGB_THREADS, WGB_SMEM_BYTES, (cudaStream_t)stream)(
         tx, (const __half*)g16, rowmask, dw, lddw, rows, n_out, k_in, rps, dz_scale_bits, x_scale_bits, g_wgrad_dbg);
     GNB_RETURN_LAUNCH();
 }

@@ -25,6 +25,7 @@ global_vars_kernel(const float* __restrict__ x, int64_t ldx, int nf, const int* 
                    const int* __restrict__ deg, int width, const int64_t* __restrict__ ptr,
                    const float* __restrict__ n_pulses, float* __restrict__ g, float* __restrict__ x0,
                    int64_t ld0, int x0_cols) {
+    gnb_pdl_begin();
     const int b = blockIdx.x;
     const int64_t lo = ptr[b], hi = ptr[b + 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -147,6 +148,7 @@ __global__ void edge_hidden_fwd_kernel(const float* __restrict__ pq, int64_t ldp
                                        const int* __restrict__ nbr, const int* __restrict__ deg, int width,
                                        int64_t n, int act, float* __restrict__ h, int64_t ldh,
                                        unsigned* __restrict__ hmask, int mask_ld) {
+    gnb_pdl_begin();
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n * width) return;
     const int lane = threadIdx.x & 31;
@@ -219,6 +221,7 @@ __global__ void __launch_bounds__(256)
 edge_hidden_fwd_node_kernel(const float* __restrict__ pq, int64_t ldpq, int hdim, const int* __restrict__ nbr,
                             const int* __restrict__ deg, int width, int64_t n, int act, float* __restrict__ h, int64_t ldh,
                             unsigned* __restrict__ hmask, int mask_ld) {
+    gnb_pdl_begin();
     const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
     const int lane = threadIdx.x & 31;
@@ -290,10 +293,10 @@ static void launch_hidden_node(int nit, dim3 grid, cudaStream_t st, const float*
                                const int* deg, int width, int64_t n, int act, float* h, int64_t ldh, unsigned* hmask,
                                int mask_ld) {
     switch (nit) {
-        case 1: edge_hidden_fwd_node_kernel<1, MASK><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, act, h, ldh, hmask, mask_ld); break;
-        case 2: edge_hidden_fwd_node_kernel<2, MASK><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, act, h, ldh, hmask, mask_ld); break;
-        case 3: edge_hidden_fwd_node_kernel<3, MASK><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, act, h, ldh, hmask, mask_ld); break;
-        default: edge_hidden_fwd_node_kernel<4, MASK><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, act, h, ldh, hmask, mask_ld); break;
+        case 1: gnb_launch(edge_hidden_fwd_node_kernel<1, MASK>, grid, 256, 0, st)(pq, ldpq, hdim, nbr, deg, width, n, act, h, ldh, hmask, mask_ld); break;
+        case 2: gnb_launch(edge_hidden_fwd_node_kernel<2, MASK>, grid, 256, 0, st)(pq, ldpq, hdim, nbr, deg, width, n, act, h, ldh, hmask, mask_ld); break;
+        case 3: gnb_launch(edge_hidden_fwd_node_kernel<3, MASK>, grid, 256, 0, st)(pq, ldpq, hdim, nbr, deg, width, n, act, h, ldh, hmask, mask_ld); break;
+        default: gnb_launch(edge_hidden_fwd_node_kernel<4, MASK>, grid, 256, 0, st)(pq, ldpq, hdim, nbr, deg, width, n, act, h, ldh, hmask, mask_ld); break;
     }
 }
 
@@ -321,6 +324,7 @@ edge_hidden_fwd_node_bf16_kernel(const float* __restrict__ pq, int64_t ldpq, int
                                  const int* __restrict__ deg, int width, int64_t n, __nv_bfloat16* __restrict__ h0,
                                  __nv_bfloat16* __restrict__ h1, int64_t ldh, unsigned* __restrict__ hmask, int mask_ld,
                                  const unsigned* __restrict__ scale_bits) {
+    gnb_pdl_begin();
     const float scale = F16 ? gnb_pow2_scale(*scale_bits).x : 1.f;
     const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
@@ -402,10 +406,10 @@ static void launch_hidden_node_bf16(int nit, dim3 grid, cudaStream_t st, const f
                                     const int* deg, int width, int64_t n, __nv_bfloat16* h0, __nv_bfloat16* h1, int64_t ldh,
                                     unsigned* hmask, int mask_ld, const unsigned* sb) {
     switch (nit) {
-        case 1: edge_hidden_fwd_node_bf16_kernel<1, NP, F16><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld, sb); break;
-        case 2: edge_hidden_fwd_node_bf16_kernel<2, NP, F16><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld, sb); break;
-        case 3: edge_hidden_fwd_node_bf16_kernel<3, NP, F16><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld, sb); break;
-        default: edge_hidden_fwd_node_bf16_kernel<4, NP, F16><<<grid, 256, 0, st>>>(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld, sb); break;
+        case 1: gnb_launch(edge_hidden_fwd_node_bf16_kernel<1, NP, F16>, grid, 256, 0, st)(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld, sb); break;
+        case 2: gnb_launch(edge_hidden_fwd_node_bf16_kernel<2, NP, F16>, grid, 256, 0, st)(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld, sb); break;
+        case 3: gnb_launch(edge_hidden_fwd_node_bf16_kernel<3, NP, F16>, grid, 256, 0, st)(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld, sb); break;
+        default: gnb_launch(edge_hidden_fwd_node_bf16_kernel<4, NP, F16>, grid, 256, 0, st)(pq, ldpq, hdim, nbr, deg, width, n, h0, h1, ldh, hmask, mask_ld, sb); break;
     }
 }
 
@@ -416,6 +420,7 @@ __global__ void edge_hidden_bwd_kernel(const float* __restrict__ gh, int64_t ldg
                                        int64_t ldh, int hdim, const int* __restrict__ nbr,
                                        const int* __restrict__ deg, int width, int64_t n, int act,
                                        float* __restrict__ dpq, int64_t ldpq) {
+    gnb_pdl_begin();
     const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
     const int lane = threadIdx.x & 31;
@@ -445,6 +450,7 @@ __global__ void edge_hidden_bwd_kernel(const float* __restrict__ gh, int64_t ldg
 __global__ void edge_cat_fwd_kernel(const float* __restrict__ x, int64_t ldx, int c_in,
                                     const int* __restrict__ nbr, const int* __restrict__ deg, int width,
                                     int64_t n, float* __restrict__ u, int64_t ldu) {
+    gnb_pdl_begin();
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n * width) return;
     const int lane = threadIdx.x & 31;
@@ -467,6 +473,7 @@ __global__ void edge_cat_fwd_kernel(const float* __restrict__ x, int64_t ldx, in
 __global__ void edge_cat_bwd_kernel(const float* __restrict__ du, int64_t ldu, int c_in,
                                     const int* __restrict__ nbr, const int* __restrict__ deg, int width,
                                     int64_t n, float* __restrict__ dx, int64_t ldx) {
+    gnb_pdl_begin();
     const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
     const int lane = threadIdx.x & 31;
@@ -489,6 +496,7 @@ __global__ void edge_cat_bwd_kernel(const float* __restrict__ du, int64_t ldu, i
 __global__ void edge_aggregate_fwd_kernel(const float* __restrict__ m, int64_t ldm, int c_out,
                                           const int* __restrict__ deg, int width, int64_t n, int aggr,
                                           float* __restrict__ y, int64_t ldy, int8_t* __restrict__ arg) {
+    gnb_pdl_begin();
     const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
     const int lane = threadIdx.x & 31;
@@ -516,6 +524,7 @@ __global__ void edge_aggregate_fwd_kernel(const float* __restrict__ m, int64_t l
 __global__ void edge_aggregate_bwd_kernel(const float* __restrict__ gy, int64_t ldy, int c_out,
                                           const int* __restrict__ deg, int width, int64_t n, int aggr,
                                           const int8_t* __restrict__ arg, float* __restrict__ gm, int64_t ldm) {
+    gnb_pdl_begin();
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n * width) return;
     const int lane = threadIdx.x & 31;
@@ -544,6 +553,7 @@ __global__ void __launch_bounds__(POOL_CX * POOL_RY)
 segment_pool_fwd_kernel(const float* __restrict__ x, int64_t ldx, int c_tot, const int64_t* __restrict__ ptr,
                         int np, int s0, int s1, int s2, int s3, float* __restrict__ out,
                         int* __restrict__ arg) {
+    gnb_pdl_begin();
     const int b = blockIdx.x;
     const int c = blockIdx.y * POOL_CX + threadIdx.x;
     const int ty = threadIdx.y;
@@ -606,6 +616,7 @@ __global__ void __launch_bounds__(256)
 segment_pool_bwd_kernel(const float* __restrict__ gout, int64_t ldg, const int* __restrict__ arg, int c_tot,
                         const int64_t* __restrict__ ptr, int nseg, int64_t n, int np, int s0,
                         int s1, int s2, int s3, float* __restrict__ gx, int64_t ldx, int vec4) {
+    gnb_pdl_begin();
     const int64_t i0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PB_NODES;
     if (i0 >= n) return;
     const int lane = threadIdx.x & 31;
@@ -669,6 +680,7 @@ struct StdTable { int kind[GNB_STD_MAX_F]; float sub[GNB_STD_MAX_F]; float div[G
 
 __global__ void standardize_kernel(const float* __restrict__ x, int64_t ldx, int64_t n, int f, const StdTable t,
                                    float* __restrict__ out, int64_t ldo) {
+    gnb_pdl_begin();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * f) return;
     const int64_t r = i / f;
@@ -682,6 +694,7 @@ __global__ void standardize_kernel(const float* __restrict__ x, int64_t ldx, int
 
 // batch[i] = b for ptr[b] <= i < ptr[b+1] (the `batch` vector Batch.from_data_list builds, dataloader.py:12-18)
 __global__ void ptr_to_batch_kernel(const int64_t* __restrict__ ptr, int nseg, int64_t n, int64_t* __restrict__ batch) {
+    gnb_pdl_begin();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int lo = 0, hi = nseg;
@@ -693,6 +706,7 @@ __global__ void ptr_to_batch_kernel(const int64_t* __restrict__ ptr, int nseg, i
 // small dense helpers
 __global__ void relu_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ y, int64_t ldy,
                                 int64_t rows, int cols, float* __restrict__ dz, int64_t ldz, int flags) {
+    gnb_pdl_begin();
     const int c4 = cols >> 2;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rows * c4) return;
@@ -724,6 +738,7 @@ __global__ void __launch_bounds__(256)
 act_bwd_colsum_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ y, int64_t ldy,
                       int64_t rows, int cols4, float* __restrict__ dz, int64_t ldz, float* __restrict__ db, int flags,
                       const int* __restrict__ deg, int width, int aggr, int rpc) {
+    gnb_pdl_begin();
     const int bx = blockDim.x, by = blockDim.y;
     const int c4 = blockIdx.y * bx + threadIdx.x;
     const int ty = threadIdx.y;
@@ -800,6 +815,7 @@ constexpr int EM_W = 9, EM_NPT = 14, EM_ROWS = EM_W * EM_NPT;
 __global__ void __launch_bounds__(256)
 edge_mask_bwd_kernel(const float* __restrict__ g, int64_t ldg, const uint4* __restrict__ mask4, int64_t n, int cols,
                      float* __restrict__ dz, int64_t ldz, float* __restrict__ db, int rnd, int64_t n_tiles) {
+    gnb_pdl_begin();
     __shared__ float4 s_g[EM_NPT][64];
     __shared__ __align__(16) unsigned s_m[4][256];
     __shared__ float4 s_acc[4][64];
@@ -864,6 +880,7 @@ __global__ void __launch_bounds__(256)
 edge_mask_bwd_bf16_kernel(const float* __restrict__ g, int64_t ldg, const uint4* __restrict__ mask4, int64_t n, int cols,
                           __nv_bfloat16* __restrict__ dz0, __nv_bfloat16* __restrict__ dz1, int64_t ldz, float* __restrict__ db,
                           int64_t n_tiles, const unsigned* __restrict__ scale_bits) {
+    gnb_pdl_begin();
     const float scale = (NP == 0) ? gnb_pow2_scale(*scale_bits).x : 1.f;
     __shared__ float4 s_g[EM_NPT][64];
     __shared__ __align__(16) unsigned s_m[4][256];
@@ -929,6 +946,7 @@ edge_mask_bwd_bf16_kernel(const float* __restrict__ g, int64_t ldg, const uint4*
 // out[c] += sum_r a[r, c]; out must be zero on entry. CTA = 32 x 8, 256 rows per CTA.
 __global__ void colsum_kernel(const float* __restrict__ a, int64_t lda, int64_t rows, int cols,
                               float* __restrict__ out) {
+    gnb_pdl_begin();
     __shared__ float s[8][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
     const int64_t r0 = (int64_t)blockIdx.y * 256;
@@ -953,7 +971,7 @@ GNB_EXPORT int gnb_global_vars(const float* x, int64_t ldx, int32_t nf, const in
     if (nf < 4 || nf > GV_MAX_F || nseg < 0) return GNB_ERR_ARG;
     if (x0 != nullptr && ld0 < 2 * nf + 5) return GNB_ERR_ARG;
     if (nseg == 0) return GNB_OK;
-    global_vars_kernel<<<(unsigned)nseg, GV_THREADS, 0, (cudaStream_t)stream>>>(
+    gnb_launch(global_vars_kernel, (unsigned)nseg, GV_THREADS, 0, (cudaStream_t)stream)(
         x, ldx, nf, nbr, deg, width, ptr, n_pulses, g, x0, ld0, 2 * nf + 5);
     GNB_RETURN_LAUNCH();
 }
@@ -968,7 +986,7 @@ GNB_EXPORT int gnb_edge_hidden_fwd(const float* pq, int64_t ldpq, int32_t hdim, 
                                   deg, width, n, act, h, ldh, nullptr, 0);
         GNB_RETURN_LAUNCH();
     }
-    edge_hidden_fwd_kernel<<<gnb_div_up(n * width, 8), 256, 0, (cudaStream_t)stream>>>(pq, ldpq, hdim, nbr, deg, width,
+    gnb_launch(edge_hidden_fwd_kernel, gnb_div_up(n * width, 8), 256, 0, (cudaStream_t)stream)(pq, ldpq, hdim, nbr, deg, width,
                                                                                        n, act, h, ldh, nullptr, 0);
     GNB_RETURN_LAUNCH();
 }
@@ -986,7 +1004,7 @@ GNB_EXPORT int gnb_edge_hidden_fwd_mask(const float* pq, int64_t ldpq, int32_t h
                                  deg, width, n, act, h, ldh, hmask, mask_ld);
         GNB_RETURN_LAUNCH();
     }
-    edge_hidden_fwd_kernel<<<gnb_div_up(n * width, 8), 256, 0, (cudaStream_t)stream>>>(pq, ldpq, hdim, nbr, deg, width,
+    gnb_launch(edge_hidden_fwd_kernel, gnb_div_up(n * width, 8), 256, 0, (cudaStream_t)stream)(pq, ldpq, hdim, nbr, deg, width,
                                                                                        n, act, h, ldh, hmask, mask_ld);
     GNB_RETURN_LAUNCH();
 }
@@ -997,7 +1015,7 @@ GNB_EXPORT int gnb_edge_hidden_bwd(const float* gh, int64_t ldg, const float* h,
     if ((hdim & 3) || (ldpq & 3) || (ldh & 3) || (ldg & 3) || !aligned16(gh) || !aligned16(h) || !aligned16(dpq))
         return GNB_ERR_ARG;
     if (n == 0) return GNB_OK;
-    edge_hidden_bwd_kernel<<<gnb_div_up(n, 8), 256, 0, (cudaStream_t)stream>>>(gh, ldg, h, ldh, hdim, nbr, deg, width,
+    gnb_launch(edge_hidden_bwd_kernel, gnb_div_up(n, 8), 256, 0, (cudaStream_t)stream)(gh, ldg, h, ldh, hdim, nbr, deg, width,
                                                                                n, act, dpq, ldpq);
     GNB_RETURN_LAUNCH();
 }
@@ -1005,7 +1023,7 @@ GNB_EXPORT int gnb_edge_hidden_bwd(const float* gh, int64_t ldg, const float* h,
 GNB_EXPORT int gnb_edge_cat_fwd(const float* x, int64_t ldx, int32_t c_in, const int32_t* nbr, const int32_t* deg,
                                 int32_t width, int64_t n, float* u, int64_t ldu, void* stream) {
     if (n == 0) return GNB_OK;
-    edge_cat_fwd_kernel<<<gnb_div_up(n * width, 8), 256, 0, (cudaStream_t)stream>>>(x, ldx, c_in, nbr, deg, width, n, u,
+    gnb_launch(edge_cat_fwd_kernel, gnb_div_up(n * width, 8), 256, 0, (cudaStream_t)stream)(x, ldx, c_in, nbr, deg, width, n, u,
                                                                                     ldu);
     GNB_RETURN_LAUNCH();
 }
@@ -1013,7 +1031,7 @@ GNB_EXPORT int gnb_edge_cat_fwd(const float* x, int64_t ldx, int32_t c_in, const
 GNB_EXPORT int gnb_edge_cat_bwd(const float* du, int64_t ldu, int32_t c_in, const int32_t* nbr, const int32_t* deg,
                                 int32_t width, int64_t n, float* dx, int64_t ldx, void* stream) {
     if (n == 0) return GNB_OK;
-    edge_cat_bwd_kernel<<<gnb_div_up(n, 8), 256, 0, (cudaStream_t)stream>>>(du, ldu, c_in, nbr, deg, width, n, dx, ldx);
+    gnb_launch(edge_cat_bwd_kernel, gnb_div_up(n, 8), 256, 0, (cudaStream_t)stream)(du, ldu, c_in, nbr, deg, width, n, dx, ldx);
     GNB_RETURN_LAUNCH();
 }
 
@@ -1021,7 +1039,7 @@ GNB_EXPORT int gnb_edge_aggregate_fwd(const float* m, int64_t ldm, int32_t c_out
                                       int64_t n, int32_t aggr, float* y, int64_t ldy, int8_t* arg, void* stream) {
     if ((aggr & 0xff) > 2 || width > 127) return GNB_ERR_ARG;
     if (n == 0) return GNB_OK;
-    edge_aggregate_fwd_kernel<<<gnb_div_up(n, 8), 256, 0, (cudaStream_t)stream>>>(m, ldm, c_out, deg, width, n, aggr, y,
+    gnb_launch(edge_aggregate_fwd_kernel, gnb_div_up(n, 8), 256, 0, (cudaStream_t)stream)(m, ldm, c_out, deg, width, n, aggr, y,
                                                                                   ldy, arg);
     GNB_RETURN_LAUNCH();
 }
@@ -1030,7 +1048,7 @@ GNB_EXPORT int gnb_edge_aggregate_bwd(const float* gy, int64_t ldy, int32_t c_ou
                                       int64_t n, int32_t aggr, const int8_t* arg, float* gm, int64_t ldm, void* stream) {
     if (aggr < 0 || aggr > 2 || (aggr == GNB_AGGR_MAX && arg == nullptr)) return GNB_ERR_ARG;
     if (n == 0) return GNB_OK;
-    edge_aggregate_bwd_kernel<<<gnb_div_up(n * width, 8), 256, 0, (cudaStream_t)stream>>>(gy, ldy, c_out, deg, width, n,
+    gnb_launch(edge_aggregate_bwd_kernel, gnb_div_up(n * width, 8), 256, 0, (cudaStream_t)stream)(gy, ldy, c_out, deg, width, n,
                                                                                           aggr, arg, gm, ldm);
     GNB_RETURN_LAUNCH();
 }
@@ -1043,7 +1061,7 @@ GNB_EXPORT int gnb_segment_pool_fwd(const float* x, int64_t ldx, int32_t c, cons
     int s[4] = {0, 0, 0, 0};
     for (int p = 0; p < np; ++p) s[p] = schemes[p];
     dim3 grid((unsigned)nseg, (unsigned)gnb_div_up(c, POOL_CX)), block(POOL_CX, POOL_RY);
-    segment_pool_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, ldx, c, ptr, np, s[0], s[1], s[2], s[3], out,
+    gnb_launch(segment_pool_fwd_kernel, grid, block, 0, (cudaStream_t)stream)(x, ldx, c, ptr, np, s[0], s[1], s[2], s[3], out,
                                                                       arg);
     GNB_RETURN_LAUNCH();
 }
@@ -1056,7 +1074,7 @@ GNB_EXPORT int gnb_segment_pool_bwd(const float* gout, int64_t ldg, const int32_
     int s[4] = {0, 0, 0, 0};
     for (int p = 0; p < np; ++p) s[p] = schemes[p];
     const int vec4 = !(c & 3) && !(ldg & 3) && !(ldx & 3) && aligned16(gout) && aligned16(gx) && (arg == nullptr || aligned16(arg));
-    segment_pool_bwd_kernel<<<gnb_div_up(n, 8 * PB_NODES), 256, 0, (cudaStream_t)stream>>>(gout, ldg, arg, c, ptr, (int)nseg, n, np,
+    gnb_launch(segment_pool_bwd_kernel, gnb_div_up(n, 8 * PB_NODES), 256, 0, (cudaStream_t)stream)(gout, ldg, arg, c, ptr, (int)nseg, n, np,
                                                                                       s[0], s[1], s[2], s[3], gx, ldx, vec4);
     GNB_RETURN_LAUNCH();
 }
@@ -1066,7 +1084,7 @@ GNB_EXPORT int gnb_relu_bwd(const float* g, int64_t ldg, const float* y, int64_t
     if ((cols & 3) || (ldg & 3) || (ldy & 3) || (ldz & 3) || !aligned16(g) || !aligned16(y) || !aligned16(dz))
         return GNB_ERR_ARG;
     if (rows == 0) return GNB_OK;
-    relu_bwd_kernel<<<gnb_div_up(rows * (cols >> 2), 256), 256, 0, (cudaStream_t)stream>>>(g, ldg, y, ldy, rows, cols,
+    gnb_launch(relu_bwd_kernel, gnb_div_up(rows * (cols >> 2), 256), 256, 0, (cudaStream_t)stream)(g, ldg, y, ldy, rows, cols,
                                                                                            dz, ldz, flags);
     GNB_RETURN_LAUNCH();
 }
@@ -1077,6 +1095,7 @@ GNB_EXPORT int gnb_relu_bwd(const float* g, int64_t ldg, const float* y, int64_t
 // four independent rows per thread and step so that the loads still overlap.
 __global__ void __launch_bounds__(256)
 round_move_zero_kernel(float* g, int64_t ldg, int64_t rows, int cols4, float* __restrict__ dz, int64_t ldz, int rnd) {
+    gnb_pdl_begin();
     const int c4 = blockIdx.y * 64 + threadIdx.x;
     if (c4 >= cols4) return;
     const int64_t r0 = (int64_t)blockIdx.x * ACT_ROWS;
@@ -1107,7 +1126,7 @@ GNB_EXPORT int gnb_act_bwd_colsum(const float* g, int64_t ldg, const float* y, i
     dim3 grid((unsigned)gnb_div_up(rows, ACT_ROWS), (unsigned)gnb_div_up(cols >> 2, 64)), block(64, 4);
     if (flags & GNB_FLAG_ZERO_SRC) {
         if ((flags & 0xff) != GNB_ACT_NONE || deg != nullptr || db != nullptr) return GNB_ERR_ARG;
-        round_move_zero_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(const_cast<float*>(g), ldg, rows, cols >> 2, dz, ldz,
+        gnb_launch(round_move_zero_kernel, grid, block, 0, (cudaStream_t)stream)(const_cast<float*>(g), ldg, rows, cols >> 2, dz, ldz,
                                                                          (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0);
         GNB_RETURN_LAUNCH();
     }
@@ -1118,7 +1137,7 @@ GNB_EXPORT int gnb_act_bwd_colsum(const float* g, int64_t ldg, const float* y, i
         rpc = rpc > ACT_ROWS ? ACT_ROWS : rpc;
         rpc = gnb_div_up(rpc, by) * by;
         dim3 grid2((unsigned)gnb_div_up(rows, rpc), (unsigned)gnb_div_up(cols4, bx)), block2(bx, by);
-        act_bwd_colsum_kernel<<<grid2, block2, 0, (cudaStream_t)stream>>>(g, ldg, y, ldy, rows, cols4, dz, ldz, db, flags,
+        gnb_launch(act_bwd_colsum_kernel, grid2, block2, 0, (cudaStream_t)stream)(g, ldg, y, ldy, rows, cols4, dz, ldz, db, flags,
                                                                           deg, width, aggr, (int)rpc);
     }
     GNB_RETURN_LAUNCH();
@@ -1134,7 +1153,7 @@ GNB_EXPORT int gnb_edge_mask_bwd_colsum(const float* g, int64_t ldg, const uint3
     const int64_t n_tiles = (n + EM_NPT - 1) / EM_NPT;
     const int64_t max_ctas = 148 * 8;
     dim3 grid((unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas), (unsigned)gnb_div_up(cols >> 2, 64)), block(64, 4);
-    edge_mask_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(g, ldg, reinterpret_cast<const uint4*>(maskbits), n, cols,
+    gnb_launch(edge_mask_bwd_kernel, grid, block, 0, (cudaStream_t)stream)(g, ldg, reinterpret_cast<const uint4*>(maskbits), n, cols,
                                                                     dz, ldz, db, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0,
                                                                     n_tiles);
     GNB_RETURN_LAUNCH();
@@ -1143,7 +1162,7 @@ GNB_EXPORT int gnb_edge_mask_bwd_colsum(const float* g, int64_t ldg, const uint3
 GNB_EXPORT int gnb_colsum(const float* a, int64_t lda, int64_t rows, int32_t cols, float* out, void* stream) {
     if (rows == 0) return GNB_OK;
     dim3 grid((unsigned)gnb_div_up(cols, 32), (unsigned)gnb_div_up(rows, 256)), block(32, 8);
-    colsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a, lda, rows, cols, out);
+    gnb_launch(colsum_kernel, grid, block, 0, (cudaStream_t)stream)(a, lda, rows, cols, out);
     GNB_RETURN_LAUNCH();
 }
 
@@ -1159,14 +1178,14 @@ GNB_EXPORT int gnb_standardize(const float* x, int64_t ldx, int64_t n, int32_t f
         t.kind[c] = kind[c]; t.sub[c] = sub[c]; t.div[c] = div[c];
     }
     if (n == 0) return GNB_OK;
-    standardize_kernel<<<gnb_div_up(n * f, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, n, f, t, out, ldo);
+    gnb_launch(standardize_kernel, gnb_div_up(n * f, 256), 256, 0, (cudaStream_t)stream)(x, ldx, n, f, t, out, ldo);
     GNB_RETURN_LAUNCH();
 }
 
 GNB_EXPORT int gnb_ptr_to_batch(const int64_t* ptr, int64_t nseg, int64_t n, int64_t* batch, void* stream) {
     if (n < 0 || nseg < 1 || nseg >= ((int64_t)1 << 31)) return GNB_ERR_ARG;
     if (n == 0) return GNB_OK;
-    ptr_to_batch_kernel<<<gnb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(ptr, (int)nseg, n, batch);
+    gnb_launch(ptr_to_batch_kernel, gnb_div_up(n, 256), 256, 0, (cudaStream_t)stream)(ptr, (int)nseg, n, batch);
     GNB_RETURN_LAUNCH();
 }
 
@@ -1219,10 +1238,10 @@ GNB_EXPORT int gnb_edge_mask_bwd_colsum_bf16(const float* g, int64_t ldg, const 
     const int64_t max_ctas = 148 * 8;
     dim3 grid((unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas), (unsigned)gnb_div_up(cols >> 2, 64)), block(64, 4);
     if (dz1 != nullptr)
-        edge_mask_bwd_bf16_kernel<2><<<grid, block, 0, (cudaStream_t)stream>>>(g, ldg, reinterpret_cast<const uint4*>(maskbits), n, cols,
+        gnb_launch(edge_mask_bwd_bf16_kernel<2>, grid, block, 0, (cudaStream_t)stream)(g, ldg, reinterpret_cast<const uint4*>(maskbits), n, cols,
                                                                              (__nv_bfloat16*)dz0, (__nv_bfloat16*)dz1, ldz, db, n_tiles, nullptr);
     else
-        edge_mask_bwd_bf16_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(g, ldg, reinterpret_cast<const uint4*>(maskbits), n, cols,
+        gnb_launch(edge_mask_bwd_bf16_kernel<1>, grid, block, 0, (cudaStream_t)stream)(g, ldg, reinterpret_cast<const uint4*>(maskbits), n, cols,
                                                                              (__nv_bfloat16*)dz0, nullptr, ldz, db, n_tiles, nullptr);
     GNB_RETURN_LAUNCH();
 }
@@ -1236,7 +1255,7 @@ GNB_EXPORT int gnb_edge_mask_bwd_colsum_f16(const float* g, int64_t ldg, const u
     const int64_t n_tiles = (n + EM_NPT - 1) / EM_NPT;
     const int64_t max_ctas = 148 * 8;
     dim3 grid((unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas), (unsigned)gnb_div_up(cols >> 2, 64)), block(64, 4);
-    edge_mask_bwd_bf16_kernel<0><<<grid, block, 0, (cudaStream_t)stream>>>(g, ldg, reinterpret_cast<const uint4*>(maskbits), n, cols,
+    gnb_launch(edge_mask_bwd_bf16_kernel<0>, grid, block, 0, (cudaStream_t)stream)(g, ldg, reinterpret_cast<const uint4*>(maskbits), n, cols,
                                                                          (__nv_bfloat16*)dz, nullptr, ldz, db, n_tiles, scale_bits);
     GNB_RETURN_LAUNCH();
 }
@@ -1245,6 +1264,7 @@ GNB_EXPORT int gnb_edge_mask_bwd_colsum_f16(const float* g, int64_t ldg, const u
 // initialised (0) by the caller. Non-negative floats order like their bit patterns, so one atomicMax per CTA suffices.
 __global__ void __launch_bounds__(256) absmax_bits_kernel(const float* __restrict__ a, int64_t lda, int64_t rows, int cols4,
                                                            unsigned* __restrict__ out_bits, unsigned shift) {
+    gnb_pdl_begin();
     unsigned m = 0u;
     const int64_t total = rows * cols4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -1283,7 +1303,7 @@ GNB_EXPORT int gnb_absmax_bits(const float* a, int64_t lda, int64_t rows, int32_
     const int64_t total = rows * (cols >> 2);
     int64_t ctas = (total + 256 * 8 - 1) / (256 * 8);
     if (ctas > 148 * 8) ctas = 148 * 8;
-    absmax_bits_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(a, lda, rows, cols >> 2, out_bits, (unsigned)shift);
+    gnb_launch(absmax_bits_kernel, (unsigned)ctas, 256, 0, (cudaStream_t)stream)(a, lda, rows, cols >> 2, out_bits, (unsigned)shift);
     GNB_RETURN_LAUNCH();
 }
 
@@ -1291,6 +1311,7 @@ GNB_EXPORT int gnb_absmax_bits(const float* a, int64_t lda, int64_t rows, int32_
 // a[r, 0:cols] = 0 for a [rows, cols] block of pitch lda (cols % 4 == 0, 16-byte aligned): the scatter target of the fused
 // data-gradient kernels (the Q half of dPQ). cudaMemset2DAsync moves this block at ~2 TB/s; plain float4 stores at HBM speed.
 __global__ void __launch_bounds__(256) zero_block_kernel(float* __restrict__ a, int64_t lda, int64_t rows, int cols4) {
+    gnb_pdl_begin();
     const int64_t total = rows * cols4;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = t / cols4;
@@ -1304,7 +1325,7 @@ GNB_EXPORT int gnb_zero_block(float* a, int64_t lda, int64_t rows, int32_t cols,
     const int64_t total = rows * (cols >> 2);
     int64_t ctas = (total + 255) / 256;
     if (ctas > 148 * 16) ctas = 148 * 16;
-    zero_block_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(a, lda, rows, cols >> 2);
+    gnb_launch(zero_block_kernel, (unsigned)ctas, 256, 0, (cudaStream_t)stream)(a, lda, rows, cols >> 2);
     GNB_RETURN_LAUNCH();
 }
 
@@ -1320,6 +1341,7 @@ __global__ void __launch_bounds__(256) edge_dz_prep_kernel(const float* __restri
                                                             int64_t n, int cols, const unsigned* __restrict__ scale_bits,
                                                             __half* __restrict__ g16, unsigned* __restrict__ rowmask,
                                                             float* __restrict__ db, int64_t n_tiles) {
+    gnb_pdl_begin();
     const int c = blockIdx.y * 256 + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool c_on = c < cols;                               // warp-uniform (cols % 32 == 0)
@@ -1373,7 +1395,7 @@ GNB_EXPORT int gnb_edge_dz_prep(const float* g, int64_t ldg, const uint32_t* mas
     const int64_t n_tiles = (n + EM_NPT - 1) / EM_NPT;
     const int64_t max_ctas = 148 * 8;
     dim3 grid((unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas), (unsigned)gnb_div_up(cols, 256));
-    edge_dz_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, ldg, reinterpret_cast<const uint4*>(maskbits), n, cols, scale_bits,
+    gnb_launch(edge_dz_prep_kernel, grid, 256, 0, (cudaStream_t)stream)(g, ldg, reinterpret_cast<const uint4*>(maskbits), n, cols, scale_bits,
                                                                 (__half*)g16, rowmask, db, n_tiles);
     GNB_RETURN_LAUNCH();
 }

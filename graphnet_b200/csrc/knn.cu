@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(KNN_THREADS)
 knn_table_kernel(const float* __restrict__ x, int64_t ld, const int* __restrict__ cols, int d_rt,
                  const int64_t* __restrict__ ptr, int nseg, int64_t n, int k1_rt, int chunk,
                  int* __restrict__ nbr, int* __restrict__ deg) {
+    gnb_pdl_begin();
     extern __shared__ float s_c[];            // [d][chunk]
     __shared__ int s_cols[KNN_MAX_D];
     __shared__ long long s_range[2];
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(KNN_THREADS)
 knn_table_split_kernel(const float* __restrict__ x, int64_t ld, const int* __restrict__ cols,
                        const int64_t* __restrict__ ptr, int nseg, int64_t n, int64_t size_lo, int64_t size_hi,
                        int* __restrict__ nbr, int* __restrict__ deg) {
+    gnb_pdl_begin();
     static_assert(D == 3 && (S & (S - 1)) == 0 && S <= 32, "scan is written for 3 coordinates; lanes per query a power of two");
     __shared__ __align__(16) float s_c[D][KNN_CH];
     __shared__ float s_qd[KNN_QC][KNN_THREADS];
@@ -336,6 +338,7 @@ knn_table_split_kernel(const float* __restrict__ x, int64_t ld, const int* __res
 // ptr[b] = first i with batch[i] >= b  (batch sorted ascending; ptr has nseg+1 entries)
 __global__ void batch_to_ptr_kernel(const int64_t* __restrict__ batch, int64_t n, int64_t nseg,
                                     int64_t* __restrict__ ptr) {
+    gnb_pdl_begin();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i > n) return;
     const int64_t prev = (i == 0) ? -1 : batch[i - 1];
@@ -347,6 +350,7 @@ __global__ void batch_to_ptr_kernel(const int64_t* __restrict__ batch, int64_t n
 __global__ void table_to_edge_index_kernel(const int* __restrict__ nbr, const int* __restrict__ deg,
                                            const int64_t* __restrict__ rowptr, int64_t n, int width,
                                            int64_t n_edges, int64_t* __restrict__ edge_index) {
+    gnb_pdl_begin();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t q = t / width;
     const int s = (int)(t - q * width);
@@ -365,7 +369,7 @@ int launch_knn(const float* x, int64_t ld, const int* cols, int d, const int64_t
     const size_t smem = (size_t)chunk * d * sizeof(float);
     auto kern = knn_table_kernel<K1, D>;
     if (smem > 48 * 1024) GNB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<gnb_div_up(n, KNN_THREADS), KNN_THREADS, smem, st>>>(x, ld, cols, d, ptr, nseg, n, k1, chunk, nbr, deg);
+    gnb_launch(kern, gnb_div_up(n, KNN_THREADS), KNN_THREADS, smem, st)(x, ld, cols, d, ptr, nseg, n, k1, chunk, nbr, deg);
     GNB_RETURN_LAUNCH();
 }
 
@@ -375,7 +379,7 @@ int launch_knn(const float* x, int64_t ld, const int* cols, int d, const int64_t
 template <int K1, int D>
 int launch_knn_split(const float* x, int64_t ld, const int* cols, const int64_t* ptr, int nseg, int64_t n, int* nbr, int* deg,
                      cudaStream_t st) {
-    knn_table_split_kernel<K1, D, 8><<<gnb_div_up(n, KNN_THREADS / 8), KNN_THREADS, 0, st>>>(x, ld, cols, ptr, nseg, n, 0,
+    gnb_launch(knn_table_split_kernel<K1, D, 8>, gnb_div_up(n, KNN_THREADS / 8), KNN_THREADS, 0, st)(x, ld, cols, ptr, nseg, n, 0,
                                                                                               (int64_t)1 << 62, nbr, deg);
     GNB_RETURN_LAUNCH();
 }
@@ -393,7 +397,7 @@ GNB_EXPORT int gnb_knn_set_variant(int32_t v) {
 
 GNB_EXPORT int gnb_batch_to_ptr(const int64_t* batch, int64_t n, int64_t nseg, int64_t* ptr, void* stream) {
     if (n < 0 || nseg < 0) return GNB_ERR_ARG;
-    batch_to_ptr_kernel<<<gnb_div_up(n + 1, 256), 256, 0, (cudaStream_t)stream>>>(batch, n, nseg, ptr);
+    gnb_launch(batch_to_ptr_kernel, gnb_div_up(n + 1, 256), 256, 0, (cudaStream_t)stream)(batch, n, nseg, ptr);
     GNB_RETURN_LAUNCH();
 }
 
@@ -418,7 +422,7 @@ GNB_EXPORT int gnb_knn_table(const float* x, int64_t ld, const int32_t* cols, in
 GNB_EXPORT int gnb_table_to_edge_index(const int32_t* nbr, const int32_t* deg, const int64_t* rowptr, int64_t n,
                                        int32_t width, int64_t n_edges, int64_t* edge_index, void* stream) {
     if (n == 0 || n_edges == 0) return GNB_OK;
-    table_to_edge_index_kernel<<<gnb_div_up(n * width, 256), 256, 0, (cudaStream_t)stream>>>(
+    gnb_launch(table_to_edge_index_kernel, gnb_div_up(n * width, 256), 256, 0, (cudaStream_t)stream)(
         nbr, deg, rowptr, n, width, n_edges, edge_index);
     GNB_RETURN_LAUNCH();
 }

@@ -22,6 +22,7 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 __global__ void __launch_bounds__(256)
 adam_flat_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
                  float step_size, float b1, float b2, float eps, float inv_sqrt_bc2, float wd, float gs, int zero_grad) {
+    gnb_pdl_begin();
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= n) return;
     if (i + 4 <= n) {
@@ -56,7 +57,7 @@ GNB_EXPORT int gnb_adam_flat(float* p, float* g, float* m, float* v, int64_t n, 
           reinterpret_cast<uintptr_t>(v)) & 15u) != 0)
         return GNB_ERR_ARG;
     if (n == 0) return GNB_OK;
-    adam_flat_kernel<<<gnb_div_up(gnb_div_up(n, 4), 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, step_size, beta1, beta2, eps,
+    gnb_launch(adam_flat_kernel, gnb_div_up(gnb_div_up(n, 4), 256), 256, 0, (cudaStream_t)stream)(p, g, m, v, n, step_size, beta1, beta2, eps,
                                                                                            inv_sqrt_bc2, weight_decay, grad_scale, zero_grad);
     GNB_RETURN_LAUNCH();
 }

@@ -41,6 +41,7 @@ task_heads_fwd_kernel(const float* __restrict__ feat, int64_t ldf, int hdim, con
                       const float* __restrict__ energy, const float* __restrict__ direction, int64_t nev, float inv_n,
                       float* __restrict__ pred_e, float* __restrict__ pred_d, float* __restrict__ dz,
                       float* __restrict__ loss) {
+    gnb_pdl_begin();
     __shared__ float s_loss[TH_WARPS][2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ev = (int64_t)blockIdx.x * TH_WARPS + warp;
@@ -95,6 +96,7 @@ task_heads_bwd_kernel(const float* __restrict__ feat, int64_t ldf, int hdim, con
                       const float* __restrict__ wd, const float* __restrict__ dz, const float* __restrict__ gout,
                       int64_t nev, float* __restrict__ dfeat, int64_t lddf, float* __restrict__ dwe,
                       float* __restrict__ dbe, float* __restrict__ dwd, float* __restrict__ dbd) {
+    gnb_pdl_begin();
     extern __shared__ float s_acc[];            // [4][hdim] weight-gradient partial sums of this CTA + [4] bias sums
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float g = gout != nullptr ? gout[0] : 1.f;
@@ -136,7 +138,7 @@ GNB_EXPORT int gnb_task_heads_fwd(const float* feat, int64_t ldf, int32_t hdim, 
                                   int64_t nev, float* pred_e, float* pred_d, float* dz, float* loss, void* stream) {
     if (hdim < 1 || nev < 0 || ldf < hdim) return GNB_ERR_ARG;
     if (nev == 0) return GNB_OK;
-    task_heads_fwd_kernel<<<gnb_div_up(nev, TH_WARPS), TH_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    gnb_launch(task_heads_fwd_kernel, gnb_div_up(nev, TH_WARPS), TH_WARPS * 32, 0, (cudaStream_t)stream)(
         feat, ldf, hdim, we, be, wd, bd, energy, direction, nev, 1.f / (float)nev, pred_e, pred_d, dz, loss);
     GNB_RETURN_LAUNCH();
 }
@@ -149,7 +151,7 @@ GNB_EXPORT int gnb_task_heads_bwd(const float* feat, int64_t ldf, int32_t hdim, 
     if (hdim < 1 || hdim > 2048 || nev < 0 || ldf < hdim) return GNB_ERR_ARG;
     if (nev == 0) return GNB_OK;
     const size_t smem = (size_t)(4 * hdim + 4) * sizeof(float);
-    task_heads_bwd_kernel<<<gnb_div_up(nev, TH_WARPS), TH_WARPS * 32, smem, (cudaStream_t)stream>>>(
+    gnb_launch(task_heads_bwd_kernel, gnb_div_up(nev, TH_WARPS), TH_WARPS * 32, smem, (cudaStream_t)stream)(
         feat, ldf, hdim, we, wd, dz, gout, nev, dfeat, lddf, dwe, dbe, dwd, dbd);
     GNB_RETURN_LAUNCH();
 }
