@@ -1690,7 +1690,8 @@ gemm_f16_pair_scatter_build_kernel(const __grid_constant__ CUtensorMap tm_w0, co
 // Warps: 0 TMA (weights), 1 MMA, 2..5 epilogue (lane quarter = warp % 4, both sub-tiles), 6..13 builders.
 constexpr int FU_THREADS = 448, FU_NBW = 8, FU_WSTAGES = 3, FU_BSLOTS = 3;
 struct FuseSrc { const float* pq; int64_t ldpq; const int* nbr; const int* deg; int64_t n_nodes; int hid;
-                 __half* h0_out; int64_t ldh; unsigned char* hbytes; int64_t ldhb; const unsigned* scale_bits; };
+                 __half* h0_out; int64_t ldh; unsigned char* hbytes; int64_t ldhb; const unsigned* scale_bits;
+                 int dbg; };      // profiling hook (gnb_linear_set_debug; results are garbage): bit 3 no P gathers, bit 4 no Q gathers
 
 template <int NP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FU_THREADS, 1)
@@ -1847,8 +1848,9 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
                 for (int uu = 0; uu < 2; ++uu) {
                     const float4* pp = pq4 + (po[u0 + uu] + koff);
                     const float4* qp = pq4 + (qo[u0 + uu] + koff);
-                    pv[uu][0] = __ldg(pp); pv[uu][1] = __ldg(pp + 1);
-                    qv[uu][0] = __ldg(qp); qv[uu][1] = __ldg(qp + 1);
+                    const float4 z = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (fs.dbg & 8) { pv[uu][0] = z; pv[uu][1] = z; } else { pv[uu][0] = __ldg(pp); pv[uu][1] = __ldg(pp + 1); }
+                    if (fs.dbg & 16) { qv[uu][0] = z; qv[uu][1] = z; } else { qv[uu][0] = __ldg(qp); qv[uu][1] = __ldg(qp + 1); }
                 }
             };
             auto build = [&](int kb, int u0, const float4 (&pv)[2][2], const float4 (&qv)[2][2], uint32_t ba) {
@@ -2706,7 +2708,7 @@ GNB_EXPORT int gnb_edgeconv_fused_fwd_f16(const float* pq, int64_t ldpq, int32_t
     int clusters = g_num_sms / 2;
     if (clusters > tiles) clusters = tiles;
     if (clusters < 1) clusters = 1;
-    FuseSrc fs{pq, ldpq, nbr, deg, n, hid, (__half*)h0_out, ldh, hbytes, ldhb, scale_bits};
+    FuseSrc fs{pq, ldpq, nbr, deg, n, hid, (__half*)h0_out, ldh, hbytes, ldhb, scale_bits, g_linear_dbg};
     const uint32_t smem = 1024 + (uint32_t)(FU_WSTAGES + FU_BSLOTS) * planes * TC_TILE_BYTES + 512;
     const int last_ksteps = (hid - 64 * (kblocks - 1) + 15) / 16;
     if (planes == 2)

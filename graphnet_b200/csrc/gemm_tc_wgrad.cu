@@ -327,9 +327,12 @@ gemm_bf_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_con
 // Two rings: the TMA ring {A = h box pair 16 KiB | the stage's g16 rows <= 4.5 KiB} is WGB_NA = 7 stages deep -- with nothing
 // but 20 KiB per stage arriving from memory, the 4-stage ring of the stored-dz kernel left too few bytes in flight (155 us
 // floor measured with builders and MMAs switched off) --, the locally built B tile (32 KiB) is double-buffered.
-constexpr int WGB_THREADS = 448, WGB_BK = 64, WGB_NA = 7, WGB_NBUF = 2, WGB_NB = 8;
+// A CTA owns up to TWO 128-wide k_in tiles (two 256-column accumulators = all of TMEM): the dz tile is the expensive operand
+// here (built, not loaded), and it is the same for every k_in tile -- with one tile per CTA a 336-wide layer expanded dz three
+// times, with pairs twice (625 -> ... us per step). CTA x = k_in tiles {2 x, 2 x + 1}.
+constexpr int WGB_THREADS = 448, WGB_BK = 64, WGB_NA = 4, WGB_NBUF = 2, WGB_NB = 8;
 constexpr uint32_t WGB_BOX = WGB_BK * 128, WGB_A_BYTES = 2 * WGB_BOX, WGB_B_BYTES = 4 * WGB_BOX;
-constexpr uint32_t WGB_ASTAGE = WGB_A_BYTES + 5 * 1024;                 // g16 rows (<= 9 x 512 B) behind the A tile; 1 KiB-aligned
+constexpr uint32_t WGB_ASTAGE = 2 * WGB_A_BYTES + 5 * 1024;             // {A tile 0 | A tile 1 | g16 rows (<= 9 x 512 B)}; 1 KiB-aligned
 constexpr uint32_t WGB_DATA_BYTES = WGB_NA * WGB_ASTAGE + WGB_NBUF * WGB_B_BYTES;
 constexpr uint32_t WGB_SMEM_BYTES = WGB_DATA_BYTES + 1024 + 256;
 
@@ -350,7 +353,8 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kin0 = blockIdx.x * WG_BM;
+    const int kin0 = blockIdx.x * 2 * WG_BM;
+    const int nt = kin0 + WG_BM < k_in ? 2 : 1;                         // k_in tiles of this CTA
     const int n_mma = (n_out + 15) & ~15;
     const int64_t n_nodes = rows / 9;
     const int64_t r_lo = (int64_t)blockIdx.y * rows_per_split;
@@ -368,7 +372,7 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
             tc::fence_proxy_async();
         }
         __syncwarp();
-        tc::tmem_alloc<WG_BN>(tmem_slot);
+        tc::tmem_alloc<512>(tmem_slot);
     }
     tc::tcgen05_fence_before();
     __syncthreads();
@@ -388,10 +392,12 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
                 nd1 = nd1 < n_nodes ? nd1 : n_nodes;
                 const uint32_t gb = nd1 > nd0 ? (uint32_t)(nd1 - nd0) * (uint32_t)n_out * 2u : 0u;
                 if (tc::elect_one()) {
-                    tc::mbar_arrive_expect_tx(&afull[s], WGB_A_BYTES + gb);
-                    if (gb) tc::bulk_load(st + WGB_A_BYTES, g16 + nd0 * n_out, gb, &afull[s]);
-                    tc::tma_load_2d(st, &tm_x, &afull[s], kin0, (int)r);
-                    tc::tma_load_2d(st + WGB_BOX, &tm_x, &afull[s], kin0 + 64, (int)r);
+                    tc::mbar_arrive_expect_tx(&afull[s], (uint32_t)nt * WGB_A_BYTES + gb);
+                    if (gb) tc::bulk_load(st + 2 * WGB_A_BYTES, g16 + nd0 * n_out, gb, &afull[s]);
+                    for (int tt = 0; tt < nt; ++tt) {
+                        tc::tma_load_2d(st + tt * WGB_A_BYTES, &tm_x, &afull[s], kin0 + tt * WG_BM, (int)r);
+                        tc::tma_load_2d(st + tt * WGB_A_BYTES + WGB_BOX, &tm_x, &afull[s], kin0 + tt * WG_BM + 64, (int)r);
+                    }
                 }
                 __syncwarp();
             }
@@ -403,12 +409,20 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
                 tc::mbar_wait<0, true>(&bfull[sb], (it / WGB_NBUF) & 1);
                 tc::tcgen05_fence_after();
                 const uint64_t a0 = umma_desc_sw128_mnmajor16(tc::smem_u32(smem + s * WGB_ASTAGE), WGB_BOX, 1024u);
+                const uint64_t a1 = umma_desc_sw128_mnmajor16(tc::smem_u32(smem + s * WGB_ASTAGE + WGB_A_BYTES), WGB_BOX, 1024u);
                 const uint64_t b0 = umma_desc_sw128_mnmajor16(tc::smem_u32(bring + sb * WGB_B_BYTES), WGB_BOX, 1024u);
                 if (tc::elect_one()) {
 #pragma unroll
                     for (int k = 0; k < WGB_BK / 16; ++k) {
                         const uint64_t adv = (uint64_t)(k * (2048 >> 4));
                         if (!(dbg & 2)) umma_f16(tmem_base, a0 + adv, b0 + adv, idesc, (it | k) != 0 ? 1u : 0u);
+                    }
+                    if (nt == 2) {
+#pragma unroll
+                        for (int k = 0; k < WGB_BK / 16; ++k) {
+                            const uint64_t adv = (uint64_t)(k * (2048 >> 4));
+                            if (!(dbg & 2)) umma_f16(tmem_base + 256u, a1 + adv, b0 + adv, idesc, (it | k) != 0 ? 1u : 0u);
+                        }
                     }
                     tc::umma_commit(&aempty[s]);
                     tc::umma_commit(&bempty[sb]);
@@ -453,7 +467,7 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
                 const uint32_t nrel0 = q0 - (__umulhi(Rs, 0x38E38E39u) >> 1);
                 tc::mbar_wait<0, true>(&afull[s], (it / WGB_NA) & 1);             // the stage's g16 rows (and A) landed
                 tc::mbar_wait<0, true>(&bempty[sbuf], ((it / WGB_NBUF) & 1) ^ 1); // the MMAs of the B slot's previous use completed
-                const uint32_t sg = tc::smem_u32(smem + s * WGB_ASTAGE + WGB_A_BYTES) + (uint32_t)lane * 16u + nrel0 * (uint32_t)n_out * 2u;
+                const uint32_t sg = tc::smem_u32(smem + s * WGB_ASTAGE + 2 * WGB_A_BYTES) + (uint32_t)lane * 16u + nrel0 * (uint32_t)n_out * 2u;
                 const uint32_t sb = tc::smem_u32(bring + sbuf * WGB_B_BYTES) + boxoff + (uint32_t)(8 * bw) * 128u;
                 // 8 rows touch at most 2 nodes: their fp16 values are read ONCE each (shared-memory bandwidth, not issue slots, is
                 // what a stage is short of: B written 32 KiB + read by the MMAs 48 KiB + the TMA's 20 KiB per ~900 cycles)
@@ -489,17 +503,19 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
             tc::mbar_wait<200, true>(tmem_full, 0);
             tc::tcgen05_fence_after();
             const int q = warp & 3;
-            const int kin = kin0 + q * 32 + lane;
-            const bool ok = kin < k_in;
-            for (int c = 0; c * 32 < n_out; ++c) {
-                uint32_t r[32];
-                tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-                tc::tmem_ld_wait();
-                if (ok) {
+            for (int tt = 0; tt < nt; ++tt) {
+                const int kin = kin0 + tt * WG_BM + q * 32 + lane;
+                const bool ok = kin < k_in;
+                for (int c = 0; c * 32 < n_out; ++c) {
+                    uint32_t r[32];
+                    tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tt * 256 + c * 32), r);
+                    tc::tmem_ld_wait();
+                    if (ok) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int o = c * 32 + j;
-                        if (o < n_out) atomicAdd(dw + (int64_t)o * lddw + kin, __uint_as_float(r[j]) * inv);
+                        for (int j = 0; j < 32; ++j) {
+                            const int o = c * 32 + j;
+                            if (o < n_out) atomicAdd(dw + (int64_t)o * lddw + kin, __uint_as_float(r[j]) * inv);
+                        }
                     }
                 }
             }
@@ -507,7 +523,7 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
     }
     tc::tcgen05_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc<WG_BN>(tmem_base);
+    if (warp == 1) tc::tmem_dealloc<512>(tmem_base);
 }
 
 // [rows, cols] fp32 row-major, box = 32 columns x 32 rows, 128-byte swizzle with 32-byte atoms, OOB -> 0
@@ -648,7 +664,7 @@ GNB_EXPORT int gnb_linear_bwd_weight_f16_masked(const void* g16, const uint32_t*
         GNB_CHECK(cudaFuncSetAttribute(gemm_f16_wgrad_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WGB_SMEM_BYTES));
         if (dev < 64) attr_devs |= 1ull << dev;
     }
-    const int tiles = gnb_div_up(k_in, WG_BM);
+    const int tiles = gnb_div_up(gnb_div_up(k_in, WG_BM), 2);           // CTAs along k_in: pairs of 128-wide tiles
     int splits = (2 * 148) / tiles;
     const int64_t max_splits = (rows + 8 * WGB_BK - 1) / (8 * WGB_BK);
     if (splits > max_splits) splits = (int)max_splits;
