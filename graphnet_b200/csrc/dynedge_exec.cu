@@ -12,6 +12,7 @@
 // per-operator route in graphnet_b200/models (generic `nn`, LayerNorm, GELU, max/mean aggregation).
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdlib.h>
 
@@ -145,11 +146,26 @@ __device__ __forceinline__ void store_corr(float* crow, int c, float v, float hi
     b[(c >> 5) * 64 + (c & 31)] = __float2bfloat16_rn(v - hi);
     b[(c >> 5) * 64 + 32 + (c & 31)] = __float2bfloat16_rn(hi);
 }
+// ---- weight re-packing: every packed / transposed / split weight operand of a step in ONE launch ---------------------------
+// The GEMMs read weights re-packed per step (K padded to 32, tf32 rounding, the split operands' correction planes, fp16 / bf16
+// planes, W^T for the data-gradient GEMMs, Wcat = [W1a - W1b ; W1b]). These used to be ~35 launches of a few microseconds
+// each, interleaved with the layers and each followed by ~2 us of idle stream (scripts/r02/gaps.py): ~150 us of an 6.5 ms
+// step. The forward now collects them as jobs and runs them in one kernel before the first layer; the backward finds its
+// transposed operands in the workspace.
+enum : int { JOB_COPY_PAD = 0, JOB_TRANSPOSE_PAD = 1, JOB_PACK_CONV = 2, JOB_PLANES = 3 };
+struct PackJob {
+    const float* src; const float* src2;      // PACK_CONV: W1, b1
+    void* dst; void* dst2; void* dst3;        // COPY_PAD: dst, lo | TRANSPOSE_PAD: dst | PACK_CONV: Wcat, bcat, Wcat_lo | PLANES: p0, p1
+    int64_t lds, ldd;
+    int rows, cols, dst_cols, flags;          // flags: bit 0 round to tf32, bit 1 transpose (PLANES), bit 2 bf16 instead of fp16 (PLANES)
+    int kind; unsigned first_block;
+};
+constexpr int PACK_MAX_JOBS = 40;
+struct PackJobs { PackJob j[PACK_MAX_JOBS]; int n; unsigned total_blocks; };
+
 // lo != nullptr (tf32x3 weights; dst_cols % 32 == 0): dst = rna_tf32(v), lo = the bf16 correction operand
-__global__ void copy_pad_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
-                                float* __restrict__ dst, int64_t ldd, int dst_cols, int rnd, float* __restrict__ lo) {
-    gnb_pdl_begin();
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void copy_pad_elem(int64_t t, const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
+                                              float* __restrict__ dst, int64_t ldd, int dst_cols, int rnd, float* __restrict__ lo) {
     if (t >= rows * dst_cols) return;
     const int64_t r = t / dst_cols;
     const int c = (int)(t - r * dst_cols);
@@ -157,6 +173,77 @@ __global__ void copy_pad_kernel(const float* __restrict__ src, int64_t lds, int6
     const float hi = rnd ? gnb_round_tf32(v) : v;
     dst[r * ldd + c] = hi;
     if (lo != nullptr) store_corr(lo + r * ldd, c, v, hi);
+}
+// dst[c, r] = maybe_round(src[r, c]) (zero padded to dst_cols): W^T for the backward-data GEMM
+__device__ __forceinline__ void transpose_pad_elem(int64_t t, const float* __restrict__ src, int64_t lds, int rows, int cols,
+                                                   float* __restrict__ dst, int64_t ldd, int dst_cols, int rnd) {
+    if (t >= (int64_t)cols * dst_cols) return;
+    const int c = (int)(t / dst_cols);          // dst row = src column
+    const int r = (int)(t - (int64_t)c * dst_cols);
+    float v = r < rows ? src[(int64_t)r * lds + c] : 0.f;
+    dst[(int64_t)c * ldd + r] = rnd ? gnb_round_tf32(v) : v;
+}
+// First Linear of an EdgeConv MLP hoisted to nodes: W1 = [Wa | Wb] ([H, 2C]) -> Wcat = [Wa - Wb ; Wb] ([2H, ld]),
+// bcat = [b1 ; 0]
+__device__ __forceinline__ void pack_conv_elem(int64_t t, const float* __restrict__ w1, const float* __restrict__ b1, int h, int c,
+                                               float* __restrict__ wcat, int64_t ld, float* __restrict__ bcat, int rnd,
+                                               float* __restrict__ wlo) {
+    if (t >= 2 * (int64_t)h * ld) return;
+    const int r = (int)(t / ld);
+    const int col = (int)(t - (int64_t)r * ld);
+    float v = 0.f;
+    if (col < c) v = r < h ? w1[(int64_t)r * 2 * c + col] - w1[(int64_t)r * 2 * c + c + col] : w1[(int64_t)(r - h) * 2 * c + c + col];
+    const float hi = rnd ? gnb_round_tf32(v) : v;
+    wcat[(int64_t)r * ld + col] = hi;
+    if (wlo != nullptr) store_corr(wlo + (int64_t)r * ld, col, v, hi);
+    if (col == 0) bcat[r] = r < h ? b1[r] : 0.f;
+}
+// one or two 16-bit planes of a weight matrix (v ~ p0 + p1), optionally transposed, zero padded to dst_cols
+// (same arithmetic as gnb_to_f16_planes / gnb_to_bf16_planes in gemm_tc.cu)
+template <class T16>
+__device__ __forceinline__ void planes_elem(int64_t t, const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
+                                            T16* __restrict__ p0, T16* __restrict__ p1, int64_t ldd, int dst_cols, int transpose) {
+    const int64_t drows = transpose ? cols : rows;
+    if (t >= drows * dst_cols) return;
+    const int64_t r = t / dst_cols;
+    const int c = (int)(t - r * dst_cols);
+    float v = 0.f;
+    if (transpose) { if (c < rows) v = src[(int64_t)c * lds + r]; }
+    else if (c < cols) v = src[r * lds + c];
+    const T16 b0 = T16(v);
+    p0[r * ldd + c] = b0;
+    if (p1 != nullptr) p1[r * ldd + c] = T16(v - float(b0));
+}
+__global__ void copy_pad_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
+                                float* __restrict__ dst, int64_t ldd, int dst_cols, int rnd, float* __restrict__ lo) {
+    gnb_pdl_begin();
+    copy_pad_elem((int64_t)blockIdx.x * blockDim.x + threadIdx.x, src, lds, rows, cols, dst, ldd, dst_cols, rnd, lo);
+}
+__global__ void __launch_bounds__(256) pack_jobs_kernel(const __grid_constant__ PackJobs jobs) {
+    gnb_pdl_begin();
+    int k = 0;
+    while (k + 1 < jobs.n && blockIdx.x >= jobs.j[k + 1].first_block) ++k;
+    const PackJob& jb = jobs.j[k];
+    const int64_t t = (int64_t)(blockIdx.x - jb.first_block) * 256 + threadIdx.x;
+    switch (jb.kind) {
+        case JOB_COPY_PAD:
+            copy_pad_elem(t, jb.src, jb.lds, jb.rows, jb.cols, (float*)jb.dst, jb.ldd, jb.dst_cols, jb.flags & 1, (float*)jb.dst2);
+            break;
+        case JOB_TRANSPOSE_PAD:
+            transpose_pad_elem(t, jb.src, jb.lds, jb.rows, jb.cols, (float*)jb.dst, jb.ldd, jb.dst_cols, jb.flags & 1);
+            break;
+        case JOB_PACK_CONV:
+            pack_conv_elem(t, jb.src, jb.src2, jb.rows, jb.cols, (float*)jb.dst, jb.ldd, (float*)jb.dst2, jb.flags & 1, (float*)jb.dst3);
+            break;
+        default:
+            if (jb.flags & 4)
+                planes_elem<__nv_bfloat16>(t, jb.src, jb.lds, jb.rows, jb.cols, (__nv_bfloat16*)jb.dst, (__nv_bfloat16*)jb.dst2, jb.ldd,
+                                           jb.dst_cols, (jb.flags >> 1) & 1);
+            else
+                planes_elem<__half>(t, jb.src, jb.lds, jb.rows, jb.cols, (__half*)jb.dst, (__half*)jb.dst2, jb.ldd, jb.dst_cols,
+                                    (jb.flags >> 1) & 1);
+            break;
+    }
 }
 // dst[r, c] += src[r, c]
 __global__ void add2d_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
@@ -167,33 +254,6 @@ __global__ void add2d_kernel(const float* __restrict__ src, int64_t lds, int64_t
     const int64_t r = t / cols;
     const int c = (int)(t - r * cols);
     dst[r * ldd + c] += src[r * lds + c];
-}
-// dst[c, r] = maybe_round(src[r, c]) (zero padded to dst_cols): W^T for the backward-data GEMM
-__global__ void transpose_pad_kernel(const float* __restrict__ src, int64_t lds, int rows, int cols,
-                                     float* __restrict__ dst, int64_t ldd, int dst_cols, int rnd) {
-    gnb_pdl_begin();
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)cols * dst_cols) return;
-    const int c = (int)(t / dst_cols);          // dst row = src column
-    const int r = (int)(t - (int64_t)c * dst_cols);
-    float v = r < rows ? src[(int64_t)r * lds + c] : 0.f;
-    dst[(int64_t)c * ldd + r] = rnd ? gnb_round_tf32(v) : v;
-}
-// First Linear of an EdgeConv MLP hoisted to nodes: W1 = [Wa | Wb] ([H, 2C]) -> Wcat = [Wa - Wb ; Wb] ([2H, ld]),
-// bcat = [b1 ; 0]
-__global__ void pack_conv_kernel(const float* __restrict__ w1, const float* __restrict__ b1, int h, int c,
-                                 float* __restrict__ wcat, int64_t ld, float* __restrict__ bcat, int rnd, float* __restrict__ wlo) {
-    gnb_pdl_begin();
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * (int64_t)h * ld) return;
-    const int r = (int)(t / ld);
-    const int col = (int)(t - (int64_t)r * ld);
-    float v = 0.f;
-    if (col < c) v = r < h ? w1[(int64_t)r * 2 * c + col] - w1[(int64_t)r * 2 * c + c + col] : w1[(int64_t)(r - h) * 2 * c + c + col];
-    const float hi = rnd ? gnb_round_tf32(v) : v;
-    wcat[(int64_t)r * ld + col] = hi;
-    if (wlo != nullptr) store_corr(wlo + (int64_t)r * ld, col, v, hi);
-    if (col == 0) bcat[r] = r < h ? b1[r] : 0.f;
 }
 // dW1[r, col] += dWcat[r, col];  dW1[r, C + col] += dWcat[H + r, col] - dWcat[r, col];  db1 += dbcat[0:H]
 __global__ void unpack_conv_grad_kernel(const float* __restrict__ dwcat, int64_t ld, const float* __restrict__ dbcat,
@@ -232,10 +292,11 @@ struct Arena {
     }
 };
 
-struct ConvBuf { float *wcat, *wcat_lo, *w2p_lo, *bcat, *w2p, *pq, *h, *m, *y; int32_t *nbr, *deg; uint32_t *mask, *hmask; bool nodz, fused; int cin, cin_ld, kld, hid, hld, cout, mld;
+struct ConvBuf { float *wcat, *wcat_lo, *w2p_lo, *bcat, *w2p, *pq, *h, *m, *y; float *wcat_t, *w2t;   // (training, tensor-core modes: Wcat^T, W2^T for the data-gradient GEMMs)
+                 int32_t *nbr, *deg; uint32_t *mask, *hmask; bool nodz, fused; int cin, cin_ld, kld, hid, hld, cout, mld;
                  // bf16 modes: h planes [n * 9, hid], W2 planes [cout, hld64], W2^T planes [hid, cld64]
                  __nv_bfloat16 *hb[2], *w2b[2], *w2tb[2]; int hld64, cld64; };
-struct DenseBuf { float *wp, *wp_lo, *z; int k_total, kld, n_out; };
+struct DenseBuf { float *wp, *wp_lo, *z; int k_total, kld, n_out; float* wt; float* wt_part[GNB_MAX_LAYERS + 1]; };   // wt: W^T (per K-split part for the first post-processing layer)
 
 struct Plan {
     int64_t n, nseg;
@@ -310,6 +371,9 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
         b.bcat = a.get<float>(2 * b.hid);
         b.w2p = a.get<float>((int64_t)b.cout * b.hld);
         b.w2p_lo = split ? a.get<float>((int64_t)b.cout * b.hld) : nullptr;
+        const bool tcw = training && c.precision >= 1;          // transposed operands of the tensor-core data-gradient GEMMs
+        b.wcat_t = (tcw && l > 0) ? a.get<float>((int64_t)b.kld * up(2 * b.hid, 32)) : nullptr;
+        b.w2t = (tcw && c.precision <= 2) ? a.get<float>((int64_t)b.hld * up(b.cout, 32)) : nullptr;
         b.pq = training ? a.get<float>(n * 2 * b.hid) : pq_shared;
         b.hld64 = (int)up(b.hid, 64); b.cld64 = (int)up(b.cout, 64);
         // fp16-plane modes: the backward GEMMs expand dz themselves (no stored dz) where the shapes allow it, and then the
@@ -357,6 +421,12 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
         d.kld = (int)up(d.k_total, 32);
         d.wp = a.get<float>((int64_t)d.n_out * d.kld);
         d.wp_lo = split ? a.get<float>((int64_t)d.n_out * d.kld) : nullptr;
+        d.wt = nullptr;
+        for (int q = 0; q <= GNB_MAX_LAYERS; ++q) d.wt_part[q] = nullptr;
+        if (training && c.precision >= 1) {
+            if (j > 0) d.wt = a.get<float>((int64_t)d.kld * up(d.n_out, 32));
+            else for (int q = 1; q < p.post_parts; ++q) d.wt_part[q] = a.get<float>((int64_t)up(p.part_k[q], 32) * up(d.n_out, 32));
+        }
         d.z = a.get<float>(n * d.n_out);
         prev = d.n_out;
     }
@@ -381,6 +451,7 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
             d.kld = (int)up(rprev, 32);
             d.wp = a.get<float>((int64_t)d.n_out * d.kld);
             d.wp_lo = split ? a.get<float>((int64_t)d.n_out * d.kld) : nullptr;
+            d.wt = (training && c.precision >= 1) ? a.get<float>((int64_t)d.kld * up(d.n_out, 32)) : nullptr;
             d.z = a.get<float>(p.out_rows * d.n_out);
             rprev = d.n_out;
         }
@@ -439,7 +510,41 @@ struct Exec {
     Exec(const gnb_dynedge_config& cfg, void* s)
         : c(cfg), st((cudaStream_t)s), tf32(cfg.precision >= 1), split(cfg.precision == 2 || cfg.precision == 4 || cfg.precision == 5),
           fround(cfg.precision == 1 || cfg.precision == 3 || cfg.precision == 6), rnd(cfg.precision >= 1 ? GNB_FLAG_ROUND_TF32 : 0),
-          frnd((cfg.precision == 1 || cfg.precision == 3 || cfg.precision == 6) ? GNB_FLAG_ROUND_TF32 : 0) {}
+          frnd((cfg.precision == 1 || cfg.precision == 3 || cfg.precision == 6) ? GNB_FLAG_ROUND_TF32 : 0) {
+        jobs.n = 0; jobs.total_blocks = 0;
+    }
+
+    // ---- weight re-packing jobs (one launch per PACK_MAX_JOBS jobs) --------------------------------------------------------
+    PackJobs jobs;
+    void job_add(int kind, const float* src, const float* src2, void* dst, void* dst2, void* dst3, int64_t lds, int64_t ldd,
+                 int rows, int cols, int dst_cols, int flags, int64_t total, int* rc) {
+        if (total <= 0 || *rc != 0) return;
+        if (jobs.n == PACK_MAX_JOBS) *rc = job_flush();
+        PackJob& j = jobs.j[jobs.n++];
+        j.src = src; j.src2 = src2; j.dst = dst; j.dst2 = dst2; j.dst3 = dst3; j.lds = lds; j.ldd = ldd;
+        j.rows = rows; j.cols = cols; j.dst_cols = dst_cols; j.flags = flags; j.kind = kind; j.first_block = jobs.total_blocks;
+        jobs.total_blocks += (unsigned)gnb_div_up(total, 256);
+    }
+    int job_flush() {
+        if (jobs.n == 0) return 0;
+        gnb_launch(pack_jobs_kernel, jobs.total_blocks, 256, 0, st)(jobs);
+        jobs.n = 0; jobs.total_blocks = 0;
+        EXL(); return 0;
+    }
+    void job_copy_pad(const float* src, int64_t lds, int64_t rows, int cols, float* dst, int64_t ldd, int dst_cols, bool round,
+                      float* lo, int* rc) {
+        job_add(JOB_COPY_PAD, src, nullptr, dst, lo, nullptr, lds, ldd, (int)rows, cols, dst_cols, round ? 1 : 0, rows * dst_cols, rc);
+    }
+    // dst[k, nld] = (wp + off)[n_out, k]^T for lin_bwd_data
+    void job_transpose(const float* wp, int64_t ldw, int off, int k, int n_out, float* dst, int* rc) {
+        const int nld = (int)up(n_out, 32);
+        job_add(JOB_TRANSPOSE_PAD, wp + off, nullptr, dst, nullptr, nullptr, ldw, nld, n_out, k, nld, tf32 ? 1 : 0, (int64_t)k * nld, rc);
+    }
+    void job_planes(const float* src, int64_t lds, int rows, int cols, void* p0, void* p1, int64_t ldd, int dst_cols, bool transpose,
+                    bool bf16, int* rc) {
+        job_add(JOB_PLANES, src, nullptr, p0, p1, nullptr, lds, ldd, rows, cols, dst_cols, (transpose ? 2 : 0) | (bf16 ? 4 : 0),
+                (int64_t)(transpose ? cols : rows) * dst_cols, rc);
+    }
 
     int copy_pad(const float* src, int64_t lds, int64_t rows, int cols, float* dst, int64_t ldd, int dst_cols, bool round,
                  float* lo = nullptr) {
@@ -450,10 +555,6 @@ struct Exec {
     int add2d(const float* src, int64_t lds, int64_t rows, int cols, float* dst, int64_t ldd) {
         if (rows * cols == 0) return 0;
         gnb_launch(add2d_kernel, gnb_div_up(rows * cols, 256), 256, 0, st)(src, lds, rows, cols, dst, ldd);
-        EXL(); return 0;
-    }
-    int transpose_pad(const float* src, int64_t lds, int rows, int cols, float* dst, int64_t ldd, int dst_cols) {
-        gnb_launch(transpose_pad_kernel, gnb_div_up((int64_t)cols * dst_cols, 256), 256, 0, st)(src, lds, rows, cols, dst, ldd, dst_cols, tf32 ? 1 : 0);
         EXL(); return 0;
     }
     // y = act(sum_p x_p wp[:, off_p : off_p + k_p]^T + b)
@@ -469,15 +570,15 @@ struct Exec {
                                   ks[q], q == nparts - 1 ? act : GNB_ACT_NONE, q > 0 ? 1 : 0, st));
         return 0;
     }
-    // dx[rows, k] (+)= dz[rows, n_out] wp[:, off : off + k]     (wt = scratch for W^T in tf32 mode)
+    // dx[rows, k] (+)= dz[rows, n_out] wp[:, off : off + k]     (wt = W^T [k, up(n_out, 32)], packed by the forward pass, tensor-core modes)
     int lin_bwd_data(const float* dz, int64_t lddz, const float* wp, int64_t ldw, int off, int k, int n_out, float* dx,
-                     int64_t lddx, int64_t rows, bool accumulate, float* wt, float* tmp) {
+                     int64_t lddx, int64_t rows, bool accumulate, const float* wt) {
         if (rows == 0) return 0;
         if (!tf32) return gnb_linear_bwd_data_f32(dz, lddz, wp + off, ldw, dx, lddx, rows, n_out, k, accumulate ? 1 : 0, st);
+        if (wt == nullptr) return GNB_ERR_ARG;
         const int nld = (int)up(n_out, 32);
-        EX(transpose_pad(wp + off, ldw, n_out, k, wt, nld, nld));
         const float* xs[1] = {dz}; const int64_t l1[1] = {lddz}; const int32_t k1[1] = {n_out};
-        (void)tmp;   // dx += dz W is accumulated in the GEMM epilogue (flag 0x200), no temporary
+        // dx += dz W is accumulated in the GEMM epilogue (flag 0x200), no temporary
         return gnb_linear_fwd_tf32(xs, l1, k1, 1, wt, nld, nullptr, dx, lddx, rows, k,
                                    GNB_ACT_NONE | (accumulate ? GNB_FLAG_ACCUMULATE : 0), 0, st);
     }
@@ -527,6 +628,61 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
     const bool distribute = !c.globals_after_pooling;
     const bool fused_edge = (training & 2) == 0 && !(c.flags & 1);   // fused inference EdgeConv kernel
     training &= 1;
+    {   // every packed weight operand of the step (and, in training, of its backward pass): one launch
+        int rc = 0, pj = 0;
+        for (int l = 0; l < c.n_conv; ++l, pj += 4) {
+            ConvBuf& b = p.conv[l];
+            const float *w1 = params[pj], *b1 = params[pj + 1], *w2 = params[pj + 2];
+            e.job_add(JOB_PACK_CONV, w1, b1, b.wcat, b.bcat, b.wcat_lo, 0, b.kld, b.hid, b.cin, 0, e.tf32 ? 1 : 0, 2 * (int64_t)b.hid * b.kld, &rc);
+            if (!p.bf) e.job_copy_pad(w2, b.hid, b.cout, b.hid, b.w2p, b.hld, b.hld, e.tf32, b.w2p_lo, &rc);
+            if (p.bf) {
+                const bool bf16 = !p.mixed;
+                e.job_planes(w2, b.hid, b.cout, b.hid, b.w2b[0], b.w2b[1], b.hld64, b.hld64, false, bf16, &rc);
+                if (training & 1) e.job_planes(w2, b.hid, b.cout, b.hid, b.w2tb[0], b.w2tb[1], b.cld64, b.cld64, true, bf16, &rc);
+            }
+        }
+        {
+            DenseBuf& d = p.post[0];
+            const float* w = params[pj];
+            int src_col = 0;
+            int64_t src_ld = p.node_width;
+            for (int l = 0; l < c.n_conv; ++l) src_ld += c.conv_out[l];
+            for (int q = 0; q < p.post_parts; ++q) {
+                const int valid = q == 0 ? p.node_width : c.conv_out[q - 1];
+                e.job_copy_pad(w + src_col, src_ld, d.n_out, valid, d.wp + p.part_off[q], d.kld, (int)up(p.part_k[q], 32), e.tf32,
+                               d.wp_lo ? d.wp_lo + p.part_off[q] : nullptr, &rc);
+                src_col += valid;
+            }
+            pj += 2;
+        }
+        for (int j = 1; j < c.n_post; ++j, pj += 2) {
+            DenseBuf& d = p.post[j];
+            e.job_copy_pad(params[pj], d.k_total, d.n_out, d.k_total, d.wp, d.kld, d.kld, e.tf32, d.wp_lo, &rc);
+        }
+        if (!c.skip_readout)
+            for (int j = 0; j < c.n_readout; ++j, pj += 2) {
+                DenseBuf& d = p.ro[j];
+                e.job_copy_pad(params[pj], d.k_total, d.n_out, d.k_total, d.wp, d.kld, d.kld, e.tf32, d.wp_lo, &rc);
+            }
+        EX(rc);
+        EX(e.job_flush());      // (the transposes below read the packed buffers written above)
+        if ((training & 1) && e.tf32) {
+            for (int l = 0; l < c.n_conv; ++l) {
+                ConvBuf& b = p.conv[l];
+                if (b.wcat_t != nullptr) e.job_transpose(b.wcat, b.kld, 0, b.cin_ld, 2 * b.hid, b.wcat_t, &rc);
+                if (b.w2t != nullptr) e.job_transpose(b.w2p, b.hld, 0, b.hid, b.cout, b.w2t, &rc);
+            }
+            for (int q = 1; q < p.post_parts; ++q)
+                e.job_transpose(p.post[0].wp, p.post[0].kld, p.part_off[q], p.part_k[q], p.post[0].n_out, p.post[0].wt_part[q], &rc);
+            for (int j = 1; j < c.n_post; ++j)
+                e.job_transpose(p.post[j].wp, p.post[j].kld, 0, p.post[j].k_total, p.post[j].n_out, p.post[j].wt, &rc);
+            if (!c.skip_readout)
+                for (int j = 0; j < c.n_readout; ++j)
+                    e.job_transpose(p.ro[j].wp, p.ro[j].kld, 0, p.ro[j].k_total, p.ro[j].n_out, p.ro[j].wt, &rc);
+            EX(rc);
+            EX(e.job_flush());
+        }
+    }
     // global variables (+ x0 = [x | g[batch] | 0])
     EX(gnb_global_vars(x, ldx, f, nbr0, deg0, w0, ptr, nseg, n_pulses, p.g, distribute ? p.x0 : nullptr, p.x0_ld, stream));
     if (!distribute) EX(e.copy_pad(x, ldx, n, f, p.x0, p.x0_ld, p.x0_ld, e.fround));
@@ -538,11 +694,8 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
     int pi = 0;
     for (int l = 0; l < c.n_conv; ++l) {
         ConvBuf& b = p.conv[l];
-        const float *w1 = params[pi], *b1 = params[pi + 1], *w2 = params[pi + 2], *b2 = params[pi + 3];
+        const float* b2 = params[pi + 3];      // (W1, b1, W2 were packed by the job launch above)
         pi += 4;
-        gnb_launch(pack_conv_kernel, gnb_div_up(2 * (int64_t)b.hid * b.kld, 256), 256, 0, e.st)(w1, b1, b.hid, b.cin, b.wcat, b.kld, b.bcat, e.tf32 ? 1 : 0, b.wcat_lo);
-        EXL();
-        EX(e.copy_pad(w2, b.hid, b.cout, b.hid, b.w2p, b.hld, b.hld, e.tf32, b.w2p_lo));
         {   // PQ = xin Wcat^T + bcat
             if (p.mixed) {      // fp16-plane modes: the GEMM epilogue also yields the scale word of h = relu(P_i + Q_j) <= 2 max|PQ|
                 if (l == 0) GNB_CHECK(cudaMemsetAsync(p.scale_bits, 0, 2 * GNB_MAX_LAYERS * 4, e.st));
@@ -559,8 +712,6 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
             // bf16 / bf16x3: h as bf16 plane(s) straight from the hidden-layer kernel, second Linear + ReLU + k-sum on kind::f16
             if (p.mixed) {
                 uint32_t* hs = p.scale_bits + l;          // written by the PQ GEMM's epilogue (gnb_linear_next_absmax above)
-                EX(gnb_to_f16_planes(w2, b.hid, b.cout, b.hid, b.w2b[0], b.w2b[1], b.hld64, b.hld64, 0, stream));
-                if (training) EX(gnb_to_f16_planes(w2, b.hid, b.cout, b.hid, b.w2tb[0], nullptr, b.cld64, b.cld64, 1, stream));
                 if (b.fused) {
                     static const int dbgf = getenv("GNB_FUSED_DBG") ? atoi(getenv("GNB_FUSED_DBG")) : 0;
                     EX(gnb_edgeconv_fused_fwd_f16(b.pq, 2 * b.hid, b.hid, nbr, deg, n, b.w2b[0], b.w2b[1], b.hld64, b2, b.cout,
@@ -573,8 +724,6 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
                                                    e.fround ? 1 : 0, b.y, b.cout, b.mask, hs, stream));
                 }
             } else {
-                EX(gnb_to_bf16_planes(w2, b.hid, b.cout, b.hid, b.w2b[0], b.w2b[1], b.hld64, b.hld64, 0, stream));
-                if (training) EX(gnb_to_bf16_planes(w2, b.hid, b.cout, b.hid, b.w2tb[0], b.w2tb[1], b.cld64, b.cld64, 1, stream));
                 EX(gnb_edge_hidden_fwd_bf16(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, b.hb[0], b.hb[1], b.hid, b.hmask, b.mld, stream));
                 EX(gnb_edge_linear_agg_fwd_bf16(b.hb[0], b.hb[1], b.hid, b.hid, b.w2b[0], b.w2b[1], b.hld64, b2, deg, n, b.cout,
                                                 e.fround ? 1 : 0, b.y, b.cout, b.mask, stream));
@@ -611,22 +760,13 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
     const float* zin = nullptr;
     for (int j = 0; j < c.n_post; ++j) {
         DenseBuf& d = p.post[j];
-        const float *w = params[pi], *bias = params[pi + 1];
+        const float* bias = params[pi + 1];
         pi += 2;
         if (j == 0) {
             const float* xs[GNB_MAX_LAYERS + 1]; int64_t lds[GNB_MAX_LAYERS + 1]; int32_t ks[GNB_MAX_LAYERS + 1];
-            int src_col = 0;
-            const int64_t src_ld = p.node_width + [&] { int s = 0; for (int l = 0; l < c.n_conv; ++l) s += c.conv_out[l]; return s; }();
-            for (int q = 0; q < p.post_parts; ++q) {
-                const int valid = q == 0 ? p.node_width : c.conv_out[q - 1];
-                EX(e.copy_pad(w + src_col, src_ld, d.n_out, valid, d.wp + p.part_off[q], d.kld, (int)up(p.part_k[q], 32), e.tf32,
-                              d.wp_lo ? d.wp_lo + p.part_off[q] : nullptr));
-                src_col += valid;
-                xs[q] = q == 0 ? p.x0 : p.conv[q - 1].y; lds[q] = p.part_k[q]; ks[q] = p.part_k[q];
-            }
+            for (int q = 0; q < p.post_parts; ++q) { xs[q] = q == 0 ? p.x0 : p.conv[q - 1].y; lds[q] = p.part_k[q]; ks[q] = p.part_k[q]; }
             EX(e.lin_fwd(p.post_parts, xs, lds, ks, p.part_off, d.wp, d.kld, bias, d.z, n, d.n_out, GNB_ACT_RELU, 1, d.wp_lo));
         } else {
-            EX(e.copy_pad(w, d.k_total, d.n_out, d.k_total, d.wp, d.kld, d.kld, e.tf32, d.wp_lo));
             const float* xs[1] = {zin}; const int64_t lds[1] = {d.k_total}; const int32_t ks[1] = {d.k_total}; const int offs[1] = {0};
             EX(e.lin_fwd(1, xs, lds, ks, offs, d.wp, d.kld, bias, d.z, n, d.n_out, GNB_ACT_RELU, 1, d.wp_lo));
         }
@@ -647,9 +787,8 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
     }
     for (int j = 0; j < c.n_readout; ++j) {
         DenseBuf& d = p.ro[j];
-        const float *w = params[pi], *bias = params[pi + 1];
+        const float* bias = params[pi + 1];
         pi += 2;
-        EX(e.copy_pad(w, d.k_total, d.n_out, d.k_total, d.wp, d.kld, d.kld, e.tf32, d.wp_lo));
         const float* xs[1] = {rin}; const int64_t lds[1] = {rin_ld}; const int32_t ks[1] = {d.k_total}; const int offs[1] = {0};
         EX(e.lin_fwd(1, xs, lds, ks, offs, d.wp, d.kld, bias, d.z, p.out_rows, d.n_out, GNB_ACT_RELU, 1, d.wp_lo));
         rin = d.z; rin_ld = d.n_out;
@@ -690,7 +829,7 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
             // weight gradients accumulate straight into the caller's gradient buffer (both GEMM back ends add)
             EX(e.lin_bwd_weight(dz, d.n_out, xin, xin_ld, gw, d.k_total, 0, d.k_total, d.n_out, p.out_rows));
             const int64_t dx_ld = up(d.k_total, 4);
-            EX(e.lin_bwd_data(dz, d.n_out, d.wp, d.kld, 0, d.k_total, d.n_out, dx, dx_ld, p.out_rows, false, p.wt, nullptr));
+            EX(e.lin_bwd_data(dz, d.n_out, d.wp, d.kld, 0, d.k_total, d.n_out, dx, dx_ld, p.out_rows, false, d.wt));
             gcur = dx; gcur_ld = dx_ld;
         }
         if (c.n_pool > 0) {   // gradient of the pooled block -> nodes (the appended global variables carry no gradient)
@@ -711,7 +850,7 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
         if (j > 0) {
             EX(e.lin_bwd_weight(dz, d.n_out, p.post[j - 1].z, p.post[j - 1].n_out, gw, d.k_total, 0, d.k_total, d.n_out, n));
             float* dx = (dz == gz) ? gz2 : gz;
-            EX(e.lin_bwd_data(dz, d.n_out, d.wp, d.kld, 0, d.k_total, d.n_out, dx, d.k_total, n, false, p.wt, nullptr));
+            EX(e.lin_bwd_data(dz, d.n_out, d.wp, d.kld, 0, d.k_total, d.n_out, dx, d.k_total, n, false, d.wt));
             gcur = dx; gcur_ld = d.k_total;
         } else {
             int dst_col = 0;
@@ -722,9 +861,12 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
                 const float* xq = q == 0 ? p.x0 : p.conv[q - 1].y;
                 EX(e.lin_bwd_weight(dz, d.n_out, xq, p.part_k[q], gw, dst_ld, dst_col, valid, d.n_out, n));
                 dst_col += valid;
+                // fp16-plane modes: the GEMM that writes the FINAL value of a conv layer's output gradient also yields its
+                // max|g| (the scale word of dz): here for the last conv layer, in the conv loop below for the others
+                if (q == c.n_conv && p.mixed && e.tf32) EX(gnb_linear_next_absmax(p.scale_bits + GNB_MAX_LAYERS + (q - 1), 0));
                 if (q > 0)   // gradient w.r.t. the output of conv q-1 (x0 carries none)
                     EX(e.lin_bwd_data(dz, d.n_out, d.wp, d.kld, p.part_off[q], p.part_k[q], d.n_out, p.gnode[q], p.part_k[q], n,
-                                      false, p.wt, nullptr));
+                                      false, d.wt_part[q]));
             }
         }
     }
@@ -742,8 +884,9 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
         const bool nodz = b.nodz;
         // (aggregate-bwd + ReLU-bwd + bias grad) in one pass
         if (p.mixed) {
-            uint32_t* gs = p.scale_bits + GNB_MAX_LAYERS + l;      // zeroed by the forward pass
-            EX(gnb_absmax_bits(gy, b.cout, n, b.cout, 0, gs, stream));
+            uint32_t* gs = p.scale_bits + GNB_MAX_LAYERS + l;      // zeroed by the forward pass, filled by the epilogue of the GEMM
+                                                                   // that wrote the last contribution to gy (gnb_linear_next_absmax)
+            if (!e.tf32) EX(gnb_absmax_bits(gy, b.cout, n, b.cout, 0, gs, stream));
             if (nodz) {
                 // dz = g * mask bit is never stored: both GEMMs expand it in shared memory from g_y and the mask words
                 // (one small pass writes fp16(g_y 2^s), the row-major bits and the bias gradient)
@@ -787,12 +930,11 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
             // rounding pass this replaces: 12 B per value read + written + zeroed, ~55 us per layer, for a 4 B memset).
             EX(gnb_zero_block(p.dzq + b.hid, 2 * b.hid, n, b.hid, stream));
             const int nld = (int)up(b.cout, 32);
-            EX(e.transpose_pad(b.w2p, b.hld, b.cout, b.hid, p.wt, nld, nld));
-            EX(gnb_edge_hidden_dgrad_scatter_split_tf32(p.dz_big, b.cout, b.cout, p.wt, nld, b.hmask, b.mld, b.hid, nbr, n,
+            EX(gnb_edge_hidden_dgrad_scatter_split_tf32(p.dz_big, b.cout, b.cout, b.w2t, nld, b.hmask, b.mld, b.hid, nbr, n,
                                                         p.dzq + b.hid, 2 * b.hid, p.dzq, 2 * b.hid, p.dbtmp, e.rnd, stream));
         } else {
             GNB_CHECK(cudaMemsetAsync(p.dpq, 0, (size_t)n * 2 * b.hid * 4, e.st));
-            EX(e.lin_bwd_data(p.dz_big, b.cout, b.w2p, b.hld, 0, b.hid, b.cout, p.dh_big, b.hid, rows, false, p.wt, nullptr));
+            EX(e.lin_bwd_data(p.dz_big, b.cout, b.w2p, b.hld, 0, b.hid, b.cout, p.dh_big, b.hid, rows, false, b.w2t));
             EX(gnb_edge_hidden_bwd(p.dh_big, b.hid, b.h, b.hid, b.hid, nbr, deg, wl, n, GNB_ACT_RELU, p.dpq, 2 * b.hid, stream));
             // PQ = xin Wcat^T + bcat: rounded copy for the tensor cores (tf32 mode) + bias gradient in the same pass
             EX(gnb_act_bwd_colsum(p.dpq, 2 * b.hid, nullptr, 0, n, 2 * b.hid, p.dzq, 2 * b.hid, p.dbtmp, GNB_ACT_NONE | e.rnd,
@@ -803,8 +945,9 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
         EX(e.lin_bwd_weight(dzq, 2 * b.hid, xin, b.cin_ld, p.dwp, b.kld, 0, b.cin_ld, 2 * b.hid, n));
         gnb_launch(unpack_conv_grad_kernel, gnb_div_up((int64_t)b.hid * b.cin, 256), 256, 0, e.st)(p.dwp, b.kld, p.dbtmp, b.hid, b.cin, gw1, gb1);
         EXL();
+        if (l > 0 && p.mixed && e.tf32) EX(gnb_linear_next_absmax(p.scale_bits + GNB_MAX_LAYERS + (l - 1), 0));
         if (l > 0)   // gradient into the previous layer's output: accumulate onto the post-processing part
-            EX(e.lin_bwd_data(dzq, 2 * b.hid, b.wcat, b.kld, 0, b.cin_ld, 2 * b.hid, p.gnode[l], b.cin_ld, n, true, p.wt, p.dh_big));
+            EX(e.lin_bwd_data(dzq, 2 * b.hid, b.wcat, b.kld, 0, b.cin_ld, 2 * b.hid, p.gnode[l], b.cin_ld, n, true, b.wcat_t));
         if (g_bwd_event != nullptr && l == g_bwd_event_layer) GNB_CHECK(cudaEventRecord(g_bwd_event, e.st));
     }
     return GNB_OK;

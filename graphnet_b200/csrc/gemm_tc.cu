@@ -177,12 +177,19 @@ __device__ __forceinline__ void epi_absmax_commit(float am, unsigned* bits, int 
     if ((threadIdx.x & 31) == 0 && m != 0u && m < 0x7f800000u) atomicMax(bits, min(m + ((unsigned)shift << 23), 0x7f000000u));
 }
 // y += result (gradient accumulation onto an existing tensor): loads issued together, then the stores
-__device__ __forceinline__ void epi_accum32(const uint32_t (&r)[32], float bv, float lo, float* __restrict__ yp, int64_t ldy) {
+// y += act(acc + bias); returns max|y| of the 32 stored values (for gnb_linear_next_absmax)
+__device__ __forceinline__ float epi_accum32(const uint32_t (&r)[32], float bv, float lo, float* __restrict__ yp, int64_t ldy) {
     float old[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) old[j] = yp[(int64_t)j * ldy];
+    float am = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) yp[(int64_t)j * ldy] = old[j] + fmaxf(__uint_as_float(r[j]) + bv, lo);
+    for (int j = 0; j < 32; ++j) {
+        const float v = old[j] + fmaxf(__uint_as_float(r[j]) + bv, lo);
+        yp[(int64_t)j * ldy] = v;
+        am = fmaxf(am, fabsf(v));
+    }
+    return am;
 }
 __device__ __noinline__ float epi_store_partial(const uint32_t (&r)[32], float bv, float lo, bool round, bool accum,
                                                 float* __restrict__ yp, int64_t ldy, int nvalid) {
@@ -427,7 +434,7 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
                     if (ch_ok && left > 0 && !(agg.dbg & 1)) {
                         float* yp = y + (row0 + col0) * ldy + ch;
                         if (left >= 32) {
-                            if (accum) epi_accum32(r, bv, relu_lo, yp, ldy);
+                            if (accum) amax = fmaxf(amax, epi_accum32(r, bv, relu_lo, yp, ldy));
                             else if (round_out) amax = fmaxf(amax, epi_store32<true>(r, bv, relu_lo, yp, ldy));
                             else amax = fmaxf(amax, epi_store32<false>(r, bv, relu_lo, yp, ldy));
                         } else {
@@ -945,7 +952,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                     if (ch_ok && left > 0 && !(agg.dbg & 1)) {
                         float* yp = y + (rbase + c * 32) * ldy + ch;
                         if (left >= 32) {
-                            if (accum) epi_accum32(r, bv, relu_lo, yp, ldy);
+                            if (accum) amax = fmaxf(amax, epi_accum32(r, bv, relu_lo, yp, ldy));
                             else if (round_out) amax = fmaxf(amax, epi_store32<true>(r, bv, relu_lo, yp, ldy));
                             else amax = fmaxf(amax, epi_store32<false>(r, bv, relu_lo, yp, ldy));
                         } else {
@@ -1859,6 +1866,8 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
                 for (int uu = 0; uu < 2; ++uu) {
                     const int u = u0 + uu, r = rs + 32 * u;
                     if (r < AGG_ROWS) {                   // (lane-dependent only for u = 3)
+                        // (relu as (x + |x|) * (s / 2) -- FMA pipe instead of FMNMX on the half-rate ALU pipe -- was measured: the
+                        // launch alone 342 -> 336 us without gathers, but 1507 -> 1556 us inside the step; not kept)
                         const float s = on ? sc[u] : 0.f;
                         float a[8];
                         a[0] = fmaxf(pv[uu][0].x + qv[uu][0].x, 0.f) * s; a[1] = fmaxf(pv[uu][0].y + qv[uu][0].y, 0.f) * s;
@@ -2254,7 +2263,7 @@ static int linear_fwd_impl(const float* const* xs, const int64_t* ldxs, const in
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out, gnb_div_up(rows, TC_BN), agg, sc,
                          (cudaStream_t)stream, w_lo != nullptr ? &twlo : nullptr);
 }
-// One-shot hook: the NEXT gnb_linear_fwd_tf32 / gnb_linear_fwd_tf32x3 launch (without the accumulate flag) also folds
+// One-shot hook: the NEXT gnb_linear_fwd_tf32 / gnb_linear_fwd_tf32x3 launch (with or without the accumulate flag) also folds
 // max|y| of everything it stores into *bits as gnb_absmax_bits would (bits of 2^shift max|y|; *bits zero-initialised by the
 // caller). Saves the separate absmax pass over PQ in the fp16-plane modes (one FMNMX per stored element in the epilogue).
 GNB_EXPORT int gnb_linear_next_absmax(uint32_t* bits, int32_t shift) {

@@ -48,6 +48,10 @@ class KNNEdges(EdgeDefinition):
                 n_pulses = getattr(graph, "n_pulses", None)
                 nseg = int(n_pulses.numel()) if n_pulses is not None and n_pulses.dim() else int(batch.max().item()) + 1
                 ptr = ops.batch_to_ptr(batch, nseg)
+                try:                      # a collated Batch carries `ptr` (torch_geometric sets it): keep it for the model, which
+                    graph.ptr = ptr       # would otherwise rebuild it from `batch` with a second launch
+                except (AttributeError, TypeError):
+                    pass
         table = ops.knn_table(x, self._columns, ptr, self._nb_nearest_neighbours)
         if hasattr(graph, "set_knn_graph"):
             graph.set_knn_graph(table)
