@@ -39,13 +39,15 @@ import torch
 import torch.distributed as dist
 
 # arithmetic type of the path's dominant contractions (not a precision claim: config.precision states the tolerance)
-DTYPE = {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32", "bf16": "bf16", "bf16x3": "bf16", "mixed16": "f16"}
+DTYPE = {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32", "bf16": "bf16", "bf16x3": "bf16", "mixed16": "f16", "f16": "f16"}
 METRIC = "dynedge_train_events_per_sec"
 UNIT = "events/s"
 POOLS = ["min", "max", "mean", "sum"]
 TOLERANCE = {"mixed16": "out 2e-5 / grad 1e-3 vs the fp64 oracle (tests/test_gpu_bf16.py, tests/test_gpu_train_step.py; measured "
                         "9e-6 / 5.5e-4): per-edge tensors as power-of-two scaled fp16 planes, forward 3 products (fp32 grade), "
                         "backward 1 product (tf32 grade); node-level GEMMs as tf32x3",
+             "f16": "out 1e-3 / grad 3e-3 (per-edge tensors as ONE power-of-two scaled fp16 plane = tf32's 11-bit significand at half the "
+                    "bytes, node-level GEMMs single-pass tf32; measured 6e-4 / 2e-3, tests/test_gpu_bf16.py)",
              "bf16x3": "out 2e-5 / grad 1e-3 (per-edge tensors as two bf16 planes, 3 products forward and backward; measured 9e-6 / 5.5e-4)",
              "bf16": "out 5e-3 / grad 1.5e-2 (north_star's looser mode: per-edge tensors as ONE bf16 plane; measured 2.3e-3 / 5.7e-3, "
                      "tests/test_gpu_bf16.py)",
@@ -65,7 +67,7 @@ def parse_args():
     ap.add_argument("--events", type=int, default=512, help="training events per GPU (configs[2])")
     ap.add_argument("--infer-events", type=int, default=1024, help="inference events per GPU (configs[1])")
     ap.add_argument("--precision", default=os.environ.get("GNB_PRECISION", "mixed16"),
-                    choices=["mixed16", "bf16x3", "bf16", "tf32x3", "tf32", "fp32"])
+                    choices=["mixed16", "f16", "bf16x3", "bf16", "tf32x3", "tf32", "fp32"])
     ap.add_argument("--cpu-events", type=int, default=128, help="events of the bounded CPU-baseline sample (BASELINE.md 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inference", action="store_true")
@@ -474,6 +476,11 @@ def dominant_launches(trainer, db):
                   hld64, ops._ptr(b2), ops._ptr(graph.deg), n, cout, 0, ops._ptr(y), cout, ops._ptr(maskbits), ops._ptr(hw),
                   ops._stream())
 
+    def agg_fwd_f16x1():
+        ops._call("gnb_edge_linear_agg_fwd_f16", ops._ptr(h16[0]), ops._ptr(None), hid, hid, ops._ptr(w16[0]), ops._ptr(None),
+                  hld64, ops._ptr(b2), ops._ptr(graph.deg), n, cout, 1, ops._ptr(y), cout, ops._ptr(None), ops._ptr(hw),
+                  ops._stream())
+
     def dgrad_scatter_f16():
         ops._call("gnb_edge_hidden_dgrad_scatter_f16", ops._ptr(dz16), cout, cout, ops._ptr(wt16[0]), cld64, ops._ptr(hmask), mld,
                   hid, ops._ptr(graph.nbr), n, ops._ptr(dpq[:, hid:]), 2 * hid, ops._ptr(dpq), 2 * hid, ops._ptr(None), 0,
@@ -511,7 +518,7 @@ def dominant_launches(trainer, db):
     e_real = int(graph.deg.sum().item())
     return {"agg_fwd": agg_fwd, "agg_fwd_x3": agg_fwd_x3, "dgrad_scatter": dgrad_scatter, "agg_fwd_f16x3": agg_fwd_f16x3,
             "dgrad_scatter_f16": dgrad_scatter_f16, "wgrad_f16": wgrad_f16, "wgrad_f16_masked": wgrad_f16_masked,
-            "dgrad_scatter_f16_masked": dgrad_scatter_f16_masked, "fused_fwd_f16x3": fused_fwd_f16,
+            "dgrad_scatter_f16_masked": dgrad_scatter_f16_masked, "fused_fwd_f16x3": fused_fwd_f16, "agg_fwd_f16x1": agg_fwd_f16x1,
             "fused_fwd_f16x3_inference": lambda: fused_fwd_f16(2, False), "rows": rows, "n": n,
             "edges": e_real, "hid": hid, "cout": cout, "mld": mld, "keep": keep}
 
@@ -600,6 +607,16 @@ def roofline_top_kernel(trainer, db, pk, precision, inference=False):
                "rows": rows, "edges": e_real, "algorithmic_flops_per_launch": flops,
                "backward_launch": bwd16, "weight_gradient_launch": wg}
         return out
+    if precision == "f16" and inference:
+        p16 = pk["bf16_tflops"]
+        top = entry("gemm_tc_pair_kernel<2> (tcgen05 cta_group::2 kind::f16 M256xN256xK16, ONE power-of-two scaled fp16 plane per "
+                    "operand, TMA-fed), aggregating epilogue: m = relu(h W2^T + b2) summed over the k slots, 336 -> 256 (m never stored)",
+                    _time_launch(d["agg_fwd_f16x1"]), 2.0 * rows * hid + 4.0 * n * cout, 1.0, _traffic("agg_fwd_f16x1"), p16)
+        return {"bound": "tensor", "achieved": top["achieved"], "peak": p16, "unit": "TFLOP/s", "frac": top["frac"],
+                "traffic": top["traffic"], "kernel": top["kernel"], "launch_ms": top["launch_ms"],
+                "peak_source": "dense bf16 burst peak of MEASURED_PEAKS.json (kind::f16 runs fp16 and bf16 at the same rate)",
+                "executed_tflops": top["executed_tflops"], "executed_frac": top["executed_frac"], "hbm_view": top["hbm_view"],
+                "rows": rows, "edges": e_real, "algorithmic_flops_per_launch": flops}
     if precision == "tf32x3" and not inference:
         sec_x = _time_launch(d["agg_fwd_x3"])
         top = entry("gemm_tc_pair_kernel<true> (tcgen05 cta_group::2 kind::tf32 M256xN256xK8, split operands: 3 MMAs per K step, "
@@ -670,7 +687,9 @@ def algorithmic_work(cfg, n, rows, e_real, nseg, precision, train=True):
         w["launches"] += 1
 
     # 16-bit plane modes (per-edge tensors): planes forward / backward and bytes per stored element
-    planes = {"bf16": (1, 1), "bf16x3": (2, 2), "mixed16": (2, 1)}.get(precision)
+    planes = {"bf16": (1, 1), "bf16x3": (2, 2), "mixed16": (2, 1), "f16": (1, 1)}.get(precision)
+    scaled = precision in ("mixed16", "f16")                         # fp16 planes with a power-of-two scale word
+    fused_fwd = scaled and (train or precision == "mixed16")         # csrc/dynedge_exec.cu: ConvBuf::fused
     node_split = precision in ("tf32x3", "bf16x3", "mixed16")       # node-level forward GEMMs on split operands
 
     def dense_fam(m_rows, n_out, fwd):
@@ -689,17 +708,27 @@ def algorithmic_work(cfg, n, rows, e_real, nseg, precision, train=True):
         if planes is not None:
             pf, pb = planes
             hb, zb = 2.0 * pf, 2.0 * pb                    # bytes per element of h / dz as stored
-            add("edge_hidden_fwd_node_bf16_kernel", 0.0, hb * rows * hid + 4.0 * n * 2 * hid, "hbm")
-            add("gemm_tc_pair_kernel<f16x3>" if pf == 2 else "gemm_tc_pair_kernel<f16>", 2.0 * e_real * hid * cout,
-                hb * rows * hid + 4.0 * n * cout)
-            if precision == "mixed16":
-                add("absmax_bits_kernel", 0.0, 4.0 * n * 2 * hid, "hbm")
-            if train:
+            mld = 4 * ((hid + 127) // 128)
+            ntile = (n + 13) // 14
+            if fused_fwd:
+                # one kernel: PQ + neighbour table in, y (+ training: mask words, plane 0 of h, ReLU bits of h) out
+                side = (2.0 * rows * hid + 4.0 * rows * mld + 16.0 * ntile * cout) if train else 0.0
+                add("gemm_f16_pair_agg_fused_kernel", 2.0 * e_real * hid * cout, 4.0 * n * (2 * hid + cout) + 40.0 * n + side)
+            else:
+                add("edge_hidden_fwd_node_bf16_kernel", 0.0, hb * rows * hid + 4.0 * n * 2 * hid, "hbm")
+                add("gemm_tc_pair_kernel<f16x3>" if pf == 2 else "gemm_tc_pair_kernel<f16>", 2.0 * e_real * hid * cout,
+                    hb * rows * hid + 4.0 * n * cout)
+            if train and scaled:
+                # dz is never stored: both GEMMs expand it from fp16(g) [n, cout] and the row-major ReLU bits
+                rowmask = 4.0 * rows * (cout // 32)
+                add("edge_dz_prep_kernel", 0.0, 4.0 * n * cout + 2.0 * n * cout + rowmask + 16.0 * ntile * cout, "hbm")
+                add("gemm_f16_wgrad_build_kernel", 2.0 * e_real * hid * cout, 2.0 * rows * hid + 2.0 * n * cout + rowmask)
+                add("gemm_f16_pair_scatter_build_kernel", 2.0 * e_real * hid * cout,
+                    2.0 * n * cout + rowmask + 4.0 * rows * mld + 4.0 * rows + 4.0 * n * 2 * hid)
+                add("zero_block_kernel", 0.0, 4.0 * n * hid, "hbm")
+            elif train:
                 add("edge_mask_bwd_bf16_kernel", 0.0, zb * rows * cout + 4.0 * n * cout, "hbm")
-                if precision == "mixed16":
-                    add("absmax_bits_kernel", 0.0, 4.0 * n * cout, "hbm")
-                # the weight gradient reads one plane of h in mixed16 (fp16 = tf32's significand), every plane otherwise
-                add("gemm_bf_wgrad_kernel", 2.0 * e_real * hid * cout, rows * (zb * cout + (2.0 if precision == "mixed16" else hb) * hid))
+                add("gemm_bf_wgrad_kernel", 2.0 * e_real * hid * cout, rows * (zb * cout + hb * hid))
                 fam = "gemm_bf_pair_dual_scatter_kernel" if hid > 256 else ("gemm_tc_pair_kernel<f16x3>" if pb == 2 else "gemm_tc_pair_kernel<f16>")
                 add(fam, 2.0 * e_real * hid * cout, zb * rows * cout + 4.0 * n * 2 * hid)
                 add("zero_block_kernel", 0.0, 4.0 * n * hid, "hbm")
@@ -768,7 +797,7 @@ def kernel_table(step_fn, db, cfg, n, rows, e_real, nseg, precision, pk, train=T
         if w is not None:
             if w["bound"] == "tensor":
                 ach = w["flops"] / (us * 1e-6) / 1e12
-                f16 = fam.startswith("gemm_bf_") or fam.endswith(("<f16>", "<f16x3>"))      # kind::f16 kernels: bf16 / fp16 dense peak
+                f16 = fam.startswith(("gemm_bf_", "gemm_f16_")) or fam.endswith(("<f16>", "<f16x3>"))      # kind::f16 kernels: bf16 / fp16 dense peak
                 row.update({"bound": "tensor", "algorithmic_gflop": round(w["flops"] / 1e9, 2), "achieved_tflops": round(ach, 1),
                             "frac": round(ach / (pk["bf16_tflops_sustained"] if f16 else pk["tf32_tflops_sustained"]), 4),
                             "peak": "bf16_tflops_sustained" if f16 else "tf32_tflops_sustained",
@@ -1010,13 +1039,16 @@ def run_inference(args, trainer, dev, world, rank, flush, pk):
     keep = ops.PRECISION
     out = {"workload": "BASELINE configs[1]: energy-regression inference, 1024 events/GPU, no collective", "unit": UNIT}
     try:
-        for mode in (["tf32", "bf16", keep] if keep in ("tf32x3", "mixed16") else ["tf32"]):
+        # headline mode of the inference leg: "f16" (tf32 grade: out 1e-3) when the run's training mode is a tensor-core mode
+        head = "f16" if keep in ("mixed16", "f16", "tf32x3", "tf32", "bf16", "bf16x3") else keep
+        modes = [head] + [m for m in ("tf32", "bf16", keep) if m != head and keep in ("tf32x3", "mixed16")]
+        for mode in dict.fromkeys(modes):
             ops.set_precision(mode)
             sec, st = repeat_median(args.repeats, trainer.infer_step, inf_dev, args.steps, args.warmup, flush)
             sec = max_over_ranks(sec, dev)
             entry = {"precision": f"{mode}: {TOLERANCE[mode].split(' / ')[0]}", "value": round(events_total / sec, 2),
                      "ms_per_step": round(sec / args.steps * 1e3, 3), "step_ms_median": st["step_ms_median"]}
-            if mode == "tf32":
+            if mode == head:
                 sec_e, _ = repeat_median(args.repeats, trainer.infer_step, None, args.steps, args.warmup, flush, e2e_host=inf_host,
                                          dev=dev, d2h="tensor")
                 sec_e = max_over_ranks(sec_e, dev)
@@ -1025,11 +1057,11 @@ def run_inference(args, trainer, dev, world, rank, flush, pk):
                                 "d2h_bytes_per_step": int(timed_loop.last_d2h)}
                 out.update(entry)
                 if rank == 0:
-                    out["roofline"] = roofline_top_kernel(trainer, inf_dev[0], pk, "tf32", inference=True)
+                    out["roofline"] = roofline_top_kernel(trainer, inf_dev[0], pk, head, inference=True)
                     if not args.no_kernel_table:
                         n, rows, e_real, nseg = graph_stats(trainer, inf_dev[0])
                         out["kernels"] = kernel_table(trainer.infer_step, inf_dev[0], model_shape(trainer), n, rows, e_real, nseg,
-                                                      "tf32", pk, train=False)
+                                                      head, pk, train=False)
             else:
                 out.setdefault("alt_precision", []).append(entry)
     finally:
@@ -1069,8 +1101,8 @@ def main():
         if rank == 0:
             _emit({"metric": "dynedge_inference_events_per_sec", "value": inf["value"], "unit": UNIT, "n_gpus": world,
                    "steps": args.steps, "warmup": args.warmup, "ms_per_step": inf["ms_per_step"], "higher_is_better": True,
-                   "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
-                   "config": {"workload": inf["workload"]}, "e2e": inf.get("e2e"), "roofline": inf.get("roofline"),
+                   "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                   "config": {"workload": inf["workload"], "precision": inf.get("precision")}, "e2e": inf.get("e2e"), "roofline": inf.get("roofline"),
                    "kernels": inf.get("kernels"), "alt_precision": inf.get("alt_precision")})
     else:
         import bench_workloads

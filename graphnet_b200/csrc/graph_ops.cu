@@ -607,6 +607,100 @@ segment_pool_fwd_kernel(const float* __restrict__ x, int64_t ldx, int c_tot, con
     }
 }
 
+// Vectorised form for c % 4 == 0 and 16-byte aligned rows (every DynEdge configuration): thread = (4 channels, row lane),
+// CTA = 16 float4 lanes x 16 row lanes per (event, 64-channel block); 4 rows per thread and step in flight, pointer bumps
+// instead of 64-bit index arithmetic (the scalar kernel above spends 44 thread-instructions per element, ncu capture
+// profiles/r02/z_tail_kernels_knn_pool_globalvars_dzprep.ncu-rep).
+struct Pool4 { float mn[4], mx[4], sm[4]; int amn[4], amx[4]; };
+__device__ __forceinline__ void pool4_take(Pool4& p, const float4& v, int idx) {
+    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        p.sm[k] += e[k];
+        if (e[k] < p.mn[k]) { p.mn[k] = e[k]; p.amn[k] = idx; }       // strict: the first occurrence wins inside a thread
+        if (e[k] > p.mx[k]) { p.mx[k] = e[k]; p.amx[k] = idx; }
+    }
+}
+constexpr int POOL4_RY = 16;          // row lanes per CTA
+__device__ __forceinline__ void pool4_merge(Pool4& p, const Pool4& o) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        p.sm[k] += o.sm[k];
+        if (o.amn[k] >= 0 && (p.amn[k] < 0 || o.mn[k] < p.mn[k] || (o.mn[k] == p.mn[k] && o.amn[k] < p.amn[k]))) { p.mn[k] = o.mn[k]; p.amn[k] = o.amn[k]; }
+        if (o.amx[k] >= 0 && (p.amx[k] < 0 || o.mx[k] > p.mx[k] || (o.mx[k] == p.mx[k] && o.amx[k] < p.amx[k]))) { p.mx[k] = o.mx[k]; p.amx[k] = o.amx[k]; }
+    }
+}
+// The launch's time is its largest event (one CTA per (event, 64 channels)): with 16 row lanes and 4 rows in flight a
+// 2 566-pulse event was 40 dependent DRAM round trips = the 62 us both the scalar and the first float4 version took, whatever
+// their instruction counts. 8 rows in flight: 20 round trips (32 row lanes would halve that again but leave one CTA per SM
+// for the many small events).
+__global__ void __launch_bounds__(16 * POOL4_RY, 4)
+segment_pool_fwd4_kernel(const float* __restrict__ x, int64_t ldx, int c_tot, const int64_t* __restrict__ ptr,
+                         int np, int s0, int s1, int s2, int s3, float* __restrict__ out, int* __restrict__ arg) {
+    gnb_pdl_begin();
+    const int b = blockIdx.x;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;          // float4 lane, row lane
+    const int c4 = blockIdx.y * 16 + tx;
+    const bool col_ok = 4 * c4 < c_tot;
+    const int64_t lo = ptr[b], hi = ptr[b + 1];
+    Pool4 p;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { p.mn[k] = FLT_MAX; p.mx[k] = -FLT_MAX; p.sm[k] = 0.f; p.amn[k] = -1; p.amx[k] = -1; }
+    if (col_ok) {
+        const int cnt = (int)(hi - lo);
+        const float4* row = reinterpret_cast<const float4*>(x + (lo + ty) * ldx) + c4;
+        const int64_t step4 = POOL4_RY * (ldx >> 2);                   // POOL4_RY rows further, in float4 units
+        int r = ty;
+        for (; r + 7 * POOL4_RY < cnt; r += 8 * POOL4_RY) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = row[u * step4];
+            row += 8 * step4;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) pool4_take(p, v[u], (int)lo + r + u * POOL4_RY);
+        }
+        {   // tail: up to 7 rows, again all in flight together
+            float4 v[7];
+#pragma unroll
+            for (int u = 0; u < 7; ++u) v[u] = r + u * POOL4_RY < cnt ? row[u * step4] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 7; ++u) if (r + u * POOL4_RY < cnt) pool4_take(p, v[u], (int)lo + r + u * POOL4_RY);
+        }
+        // (all values of the lane equal to +-FLT_MAX: the strict compares above never fired; any seen row is a valid arg)
+        if (cnt > ty) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { if (p.amn[k] < 0) p.amn[k] = (int)lo + ty; if (p.amx[k] < 0) p.amx[k] = (int)lo + ty; }
+        }
+    }
+    __shared__ Pool4 s_p[POOL4_RY][16];
+    s_p[ty][tx] = p;
+    __syncthreads();
+#pragma unroll
+    for (int half = POOL4_RY / 2; half > 0; half >>= 1) {              // tree over the row lanes (lower lane = lower node indices first)
+        if (ty < half) { pool4_merge(p, s_p[ty + half][tx]); s_p[ty][tx] = p; }
+        __syncthreads();
+    }
+    if (ty != 0 || !col_ok) return;
+    const int schemes[4] = {s0, s1, s2, s3};
+    const float cntf = (float)(hi - lo);
+    for (int q = 0; q < np; ++q) {
+        float v[4]; int a[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            a[k] = -1;
+            switch (schemes[q]) {
+                case GNB_POOL_MIN: v[k] = p.amn[k] < 0 ? 0.f : p.mn[k]; a[k] = p.amn[k]; break;
+                case GNB_POOL_MAX: v[k] = p.amx[k] < 0 ? 0.f : p.mx[k]; a[k] = p.amx[k]; break;
+                case GNB_POOL_SUM: v[k] = p.sm[k]; break;
+                default: v[k] = p.sm[k] / (cntf < 1.f ? 1.f : cntf); break;
+            }
+        }
+        const int64_t o = (int64_t)b * np * c_tot + (int64_t)q * c_tot + 4 * c4;
+        *reinterpret_cast<float4*>(out + o) = make_float4(v[0], v[1], v[2], v[3]);
+        if (arg) *reinterpret_cast<int4*>(arg + o) = make_int4(a[0], a[1], a[2], a[3]);
+    }
+}
+
 // backward: one warp per PB_NODES consecutive nodes (the event of the first node is found by a binary search over ptr, all
 // lanes on the same cached addresses; the following nodes only compare against the event's end), lanes stride over the
 // channels; the pooled gradients / arg tables (B x P x C) stay L2-resident. (One node per warp spent most of its time in
@@ -1060,6 +1154,11 @@ GNB_EXPORT int gnb_segment_pool_fwd(const float* x, int64_t ldx, int32_t c, cons
     if (nseg == 0) return GNB_OK;
     int s[4] = {0, 0, 0, 0};
     for (int p = 0; p < np; ++p) s[p] = schemes[p];
+    if (!(c & 3) && !(ldx & 3) && aligned16(x) && aligned16(out) && (arg == nullptr || aligned16(arg))) {
+        gnb_launch(segment_pool_fwd4_kernel, dim3((unsigned)nseg, (unsigned)gnb_div_up(c, 64)), 16 * POOL4_RY, 0, (cudaStream_t)stream)(
+            x, ldx, c, ptr, np, s[0], s[1], s[2], s[3], out, arg);
+        GNB_RETURN_LAUNCH();
+    }
     dim3 grid((unsigned)nseg, (unsigned)gnb_div_up(c, POOL_CX)), block(POOL_CX, POOL_RY);
     gnb_launch(segment_pool_fwd_kernel, grid, block, 0, (cudaStream_t)stream)(x, ldx, c, ptr, np, s[0], s[1], s[2], s[3], out,
                                                                       arg);
