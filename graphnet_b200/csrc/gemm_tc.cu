@@ -1816,7 +1816,17 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
         int fr[4], sr[4];                                    // (node, slot) of the lane's rows inside a 14-node sub-tile
 #pragma unroll
         for (int u = 0; u < 4; ++u) { const int r = rs + 32 * u; fr[u] = r / AGG_W; sr[u] = r - fr[u] * AGG_W; }
-        int src_n[4], dg_n[4];
+        // A hidden width of 64 m + 16 (336: every wide layer of DynEdge) leaves a last K block of ONE MMA k step = two 8-channel
+        // chunks per row. Built with the (4 rows, chunk j) mapping it costs a full K block of builder time for a quarter of the
+        // work (lanes j >= 2 compute zeros the MMA never reads), a sixth of the builders' time per 336-wide tile. The tail is
+        // therefore built with its own mapping: lane = (row gl / 2, chunk gl % 2), one row per lane.
+        const bool tail = last_ksteps == 1;
+        const int nfull = tail ? total_kb - 1 : total_kb;
+        const int r2 = gl >> 1, j2 = gl & 1;
+        const int fr2 = r2 / AGG_W, sr2 = r2 - fr2 * AGG_W;
+        const bool on2 = (total_kb - 1) * 64 + j2 * 8 < hid;
+        const uint32_t koff2 = on2 ? (uint32_t)(total_kb - 1) * 16u + 2u * (uint32_t)j2 : 0u;
+        int src_n[4], dg_n[4], src_2 = -1, dg_2 = 0;
         auto fetch_rows = [&](int t) {
             const int64_t node0 = ((int64_t)t * 2 + rank) * AGG_NPT;
 #pragma unroll
@@ -1826,6 +1836,43 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
                 src_n[u] = in ? __ldg(fs.nbr + nd * AGG_W + sr[u]) : -1;
                 dg_n[u] = in ? __ldg(fs.deg + nd) : 0;
             }
+            if (tail) {
+                const int64_t nd = node0 + fr2;
+                const bool in = r2 < AGG_ROWS && nd < fs.n_nodes;
+                src_2 = in ? __ldg(fs.nbr + nd * AGG_W + sr2) : -1;
+                dg_2 = in ? __ldg(fs.deg + nd) : 0;
+            }
+        };
+        // One row of one chunk: 8 channels of relu(P_i + Q_j) * 2^s as one or two fp16 planes + the side outputs. The ReLU rides
+        // on the conversion (cvt.rn.relu.f16x2.f32); the bits h > 0 and the mask that clears the second plane where the first one
+        // was clamped come from ONE packed comparison per channel pair (the first version spent FMNMX + FSETP + SEL per channel on
+        // the half-rate ALU pipe). A positive value below fp16's smallest subnormal (2^-39 of the layer's maximum) counts as 0.
+        auto build_row = [&](const float4& pA, const float4& pB, const float4& qA, const float4& qB, float s, uint32_t saddr,
+                             uint32_t hoff, uint32_t boff, bool h_ok, bool b_ok) {
+            float x[8];
+            x[0] = (pA.x + qA.x) * s; x[1] = (pA.y + qA.y) * s; x[2] = (pA.z + qA.z) * s; x[3] = (pA.w + qA.w) * s;
+            x[4] = (pB.x + qB.x) * s; x[5] = (pB.y + qB.y) * s; x[6] = (pB.z + qB.z) * s; x[7] = (pB.w + qB.w) * s;
+            uint32_t p0[4], p1[4], acc = 0u;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                uint32_t h2;
+                asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(x[2 * e + 1]), "f"(x[2 * e]));
+                p0[e] = h2;
+                const __half2 hv = *reinterpret_cast<const __half2*>(&h2);
+                uint32_t m;                                                                     // 0xffff per half where h > 0
+                asm("set.gt.u32.f16x2 %0, %1, %2;" : "=r"(m) : "r"(h2), "r"(0u));
+                acc |= m & ((1u << (2 * e)) | (1u << (17 + 2 * e)));
+                if (NP == 2) {
+                    const float2 back = __half22float2(hv);
+                    const __half2 l2 = __floats2half2_rn(x[2 * e] - back.x, x[2 * e + 1] - back.y);
+                    p1[e] = *reinterpret_cast<const uint32_t*>(&l2) & m;
+                }
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(p0[0]), "r"(p0[1]), "r"(p0[2]), "r"(p0[3]) : "memory");
+            if (NP == 2)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr + TC_TILE_BYTES), "r"(p1[0]), "r"(p1[1]), "r"(p1[2]), "r"(p1[3]) : "memory");
+            if (h_ok) h0v[hoff] = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+            if (b_ok) fs.hbytes[boff] = (unsigned char)((acc | (acc >> 16)) & 0xffu);
         };
         if (cluster_id < num_tiles) fetch_rows(cluster_id);
         uint32_t it = 0;
@@ -1833,8 +1880,10 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
             const int64_t node0 = ((int64_t)t * 2 + rank) * AGG_NPT;
             uint32_t po[4], qo[4], ho[4], bo[4];
             float sc[4];
-            bool hok[4];
-            const bool bok = node0 < fs.n_nodes;     // (a pair's second sub-tile may lie wholly beyond the last node: no side outputs)
+            // side-output switches of the tile in one register: bit u = plane 0 of h for row u, bit 4 + u = the row's bits
+            // (a pair's second sub-tile may lie wholly beyond the last node: no side outputs), bits 8 / 9 = the tail row
+            uint32_t okm = 0u;
+            const bool bok = node0 < fs.n_nodes && fs.hbytes != nullptr;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const bool v = src_n[u] >= 0 && sr[u] < dg_n[u];
@@ -1844,7 +1893,22 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
                 const uint32_t grow = (uint32_t)(node0 * AGG_W) + (uint32_t)(rs + 32 * u);
                 ho[u] = grow * ldh16 + (uint32_t)j;
                 bo[u] = grow * ldhb + (uint32_t)j;
-                hok[u] = node0 + fr[u] < fs.n_nodes;
+                const bool rin = rs + 32 * u < AGG_ROWS;
+                if (rin && h0v != nullptr && node0 + fr[u] < fs.n_nodes) okm |= 1u << u;
+                if (rin && bok) okm |= 16u << u;
+            }
+            uint32_t po2 = 0u, qo2 = 0u, ho2 = 0u, bo2 = 0u;
+            float sc2 = 0.f;
+            if (tail) {
+                const bool v = src_2 >= 0 && sr2 < dg_2 && on2;
+                po2 = (v ? (uint32_t)(node0 + fr2) : 0u) * ld16 + koff2;
+                qo2 = (v ? (uint32_t)src_2 : 0u) * ld16 + (uint32_t)(hid >> 2) + koff2;
+                sc2 = v ? scale : 0.f;
+                const uint32_t grow = (uint32_t)(node0 * AGG_W) + (uint32_t)r2;
+                ho2 = grow * ldh16 + (uint32_t)(total_kb - 1) * 8u + (uint32_t)j2;
+                bo2 = grow * ldhb + (uint32_t)(total_kb - 1) * 8u + (uint32_t)j2;
+                if (r2 < AGG_ROWS && on2 && h0v != nullptr && node0 + fr2 < fs.n_nodes) okm |= 256u;
+                if (r2 < AGG_ROWS && on2 && bok) okm |= 512u;
             }
             if (t + num_clusters < num_tiles) fetch_rows(t + num_clusters);
             float4 pa[2][2], qa[2][2], pb[2][2], qb[2][2];
@@ -1855,63 +1919,63 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
                 for (int uu = 0; uu < 2; ++uu) {
                     const float4* pp = pq4 + (po[u0 + uu] + koff);
                     const float4* qp = pq4 + (qo[u0 + uu] + koff);
+#ifdef GNB_FUSED_ROLE_SWITCHES      // timing experiments (scripts/r02/fused_roles.py): bit 3 no P gathers, bit 4 no Q gathers
                     const float4 z = make_float4(1.f, 1.f, 1.f, 1.f);
                     if (fs.dbg & 8) { pv[uu][0] = z; pv[uu][1] = z; } else { pv[uu][0] = __ldg(pp); pv[uu][1] = __ldg(pp + 1); }
                     if (fs.dbg & 16) { qv[uu][0] = z; qv[uu][1] = z; } else { qv[uu][0] = __ldg(qp); qv[uu][1] = __ldg(qp + 1); }
+#else
+                    pv[uu][0] = __ldg(pp); pv[uu][1] = __ldg(pp + 1);
+                    qv[uu][0] = __ldg(qp); qv[uu][1] = __ldg(qp + 1);
+#endif
                 }
+            };
+            auto gather_tail = [&]() {
+                pa[0][0] = __ldg(pq4 + po2); pa[0][1] = __ldg(pq4 + po2 + 1);
+                qa[0][0] = __ldg(pq4 + qo2); qa[0][1] = __ldg(pq4 + qo2 + 1);
             };
             auto build = [&](int kb, int u0, const float4 (&pv)[2][2], const float4 (&qv)[2][2], uint32_t ba) {
                 const bool on = kb * 64 + j * 8 < hid;
+                const uint32_t okk = on ? okm : 0u;
 #pragma unroll
                 for (int uu = 0; uu < 2; ++uu) {
                     const int u = u0 + uu, r = rs + 32 * u;
                     if (r < AGG_ROWS) {                   // (lane-dependent only for u = 3)
-                        // (relu as (x + |x|) * (s / 2) -- FMA pipe instead of FMNMX on the half-rate ALU pipe -- was measured: the
-                        // launch alone 342 -> 336 us without gathers, but 1507 -> 1556 us inside the step; not kept)
-                        const float s = on ? sc[u] : 0.f;
-                        float a[8];
-                        a[0] = fmaxf(pv[uu][0].x + qv[uu][0].x, 0.f) * s; a[1] = fmaxf(pv[uu][0].y + qv[uu][0].y, 0.f) * s;
-                        a[2] = fmaxf(pv[uu][0].z + qv[uu][0].z, 0.f) * s; a[3] = fmaxf(pv[uu][0].w + qv[uu][0].w, 0.f) * s;
-                        a[4] = fmaxf(pv[uu][1].x + qv[uu][1].x, 0.f) * s; a[5] = fmaxf(pv[uu][1].y + qv[uu][1].y, 0.f) * s;
-                        a[6] = fmaxf(pv[uu][1].z + qv[uu][1].z, 0.f) * s; a[7] = fmaxf(pv[uu][1].w + qv[uu][1].w, 0.f) * s;
-                        unsigned bits = 0u;
-                        uint32_t p0[4], p1[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            bits |= (a[2 * e] > 0.f ? 1u : 0u) << (2 * e);
-                            bits |= (a[2 * e + 1] > 0.f ? 1u : 0u) << (2 * e + 1);
-                            const __half2 h2 = __floats2half2_rn(a[2 * e], a[2 * e + 1]);
-                            p0[e] = *reinterpret_cast<const uint32_t*>(&h2);
-                            if (NP == 2) {
-                                const float2 back = __half22float2(h2);
-                                const __half2 l2 = __floats2half2_rn(a[2 * e] - back.x, a[2 * e + 1] - back.y);
-                                p1[e] = *reinterpret_cast<const uint32_t*>(&l2);
-                            }
-                        }
                         const uint32_t off = (uint32_t)r * 128u + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ba + off), "r"(p0[0]), "r"(p0[1]), "r"(p0[2]), "r"(p0[3]) : "memory");
-                        if (NP == 2)
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ba + TC_TILE_BYTES + off), "r"(p1[0]), "r"(p1[1]), "r"(p1[2]), "r"(p1[3]) : "memory");
-                        if (h0v != nullptr && on && hok[u]) h0v[ho[u] + (uint32_t)kb * 8u] = make_uint4(p0[0], p0[1], p0[2], p0[3]);
-                        if (fs.hbytes != nullptr && on && bok) fs.hbytes[bo[u] + (uint32_t)kb * 8u] = (unsigned char)bits;
+                        build_row(pv[uu][0], pv[uu][1], qv[uu][0], qv[uu][1], on ? sc[u] : 0.f, ba + off, ho[u] + (uint32_t)kb * 8u,
+                                  bo[u] + (uint32_t)kb * 8u, (okk >> u) & 1u, (okk >> (4 + u)) & 1u);
                     }
                 }
             };
-            gather(0, 0, pa, qa);
-            for (int kb = 0; kb < total_kb; ++kb, ++it) {
+            auto publish = [&](uint32_t sl) {
+                tc::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive_cluster_relaxed(&bfull[sl], 0);
+                __syncwarp();
+            };
+            if (nfull > 0) gather(0, 0, pa, qa); else gather_tail();
+            for (int kb = 0; kb < nfull; ++kb, ++it) {
                 const uint32_t sl = it % FU_BSLOTS;
                 gather(kb, 2, pb, qb);
                 tc::mbar_wait(&bempty[sl], ((it / FU_BSLOTS) & 1) ^ 1);      // the MMAs of the slot's previous use completed
                 const uint32_t ba = tc::smem_u32(bring + sl * BSL);
                 build(kb, 0, pa, qa, ba);
-                if (kb + 1 < total_kb) gather(kb + 1, 0, pa, qa);
+                if (kb + 1 < nfull) gather(kb + 1, 0, pa, qa);
+                else if (tail) gather_tail();
                 // (an L2 prefetch of the NEXT tile's P / Q rows from here -- PQ is 213 MB per 79 k-node layer, larger than L2, so
                 // about half of a tile's first touches are DRAM reads -- made the launch 30 % slower: 1501 -> 1967 us per step)
                 build(kb, 2, pb, qb, ba);
-                tc::fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive_cluster_relaxed(&bfull[sl], 0);
-                __syncwarp();
+                publish(sl);
+            }
+            if (tail) {
+                const uint32_t sl = it % FU_BSLOTS;
+                tc::mbar_wait(&bempty[sl], ((it / FU_BSLOTS) & 1) ^ 1);
+                if (r2 < AGG_ROWS) {
+                    const uint32_t ba = tc::smem_u32(bring + sl * BSL);
+                    const uint32_t off = (uint32_t)r2 * 128u + (((uint32_t)j2 ^ ((uint32_t)r2 & 7u)) << 4);
+                    build_row(pa[0][0], pa[0][1], qa[0][0], qa[0][1], sc2, ba + off, ho2, bo2, (okm >> 8) & 1u, (okm >> 9) & 1u);
+                }
+                publish(sl);
+                ++it;
             }
         }
     } else {
