@@ -50,6 +50,9 @@ SIGNATURES: Dict[str, list] = {
     "gnb_linear_fwd_tf32x3": [_p, _p, _p, _i32, _p, _p, _i64, _p, _p, _i64, _i64, _i32, _i32, _p],
     "gnb_split_pad_tf32": [_p, _i64, _i64, _i32, _p, _p, _i64, _i32, _p],
     "gnb_edge_linear_agg_fwd_tf32x3": [_p, _i64, _i32, _p, _p, _i64, _p, _p, _i64, _i32, _p, _i64, _p, _p],
+    "gnb_edge_linear_aggmax_fwd_tf32": [_p, _i64, _i32, _p, _i64, _p, _p, _i64, _i32, _i32, _i32, _p, _i64, _p, _i64, _p],
+    "gnb_edge_linear_aggmax_fwd_tf32x3": [_p, _i64, _i32, _p, _p, _i64, _p, _p, _i64, _i32, _i32, _p, _i64, _p, _i64, _p],
+    "gnb_edge_argmax_bwd": [_p, _i64, _p, _i64, _i32, _i32, _i64, _i32, _i32, _p, _i64, _p, _p],
     "gnb_linear_bwd_weight_tf32": [_p, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _p],
     "gnb_edge_linear_agg_fwd_tf32": [_p, _i64, _i32, _p, _i64, _p, _p, _i64, _i32, _i32, _p, _i64, _p, _p],
     "gnb_edge_hidden_dgrad_scatter_tf32": [_p, _i64, _i32, _p, _i64, _p, _i32, _i32, _p, _i64, _p, _i64, _p],

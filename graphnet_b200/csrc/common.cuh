@@ -72,7 +72,8 @@ __device__ __forceinline__ float gnb_warp_sum(float v) {
 }
 
 // activation codes shared by every epilogue
-enum : int { GNB_ACT_NONE = 0, GNB_ACT_RELU = 1 };
+enum : int { GNB_ACT_NONE = 0, GNB_ACT_RELU = 1, GNB_ACT_LEAKY = 2 };      // LEAKY: torch.nn.LeakyReLU() default slope
+#define GNB_LEAKY_SLOPE 0.01f
 // OR-ed into an `act` / `aggr` argument: round the stored result to tf32 (cvt.rna) so that a following
 // tcgen05 kind::tf32 GEMM, which truncates its fp32 operands, sees exactly representable values.
 #define GNB_STD_MAX_F 32

@@ -41,8 +41,51 @@ struct PartInfo { int nparts; int kblocks[TC_MAX_PARTS]; };
 // bit per (slot, channel) = "pre-activation > 0" for the backward pass. The [E, C] message tensor is never stored.
 struct AggInfo { const int* deg; int64_t n_nodes; unsigned* maskbits; int enabled; int dbg; unsigned long long* prof;
                  const unsigned* scale_bits;      // mixed16: h arrives scaled by gnb_pow2_scale(*scale_bits).x (16-bit plane modes only)
-                 unsigned* absmax_bits; int absmax_shift; };   // plain epilogue: *absmax_bits = max(., bits of 2^shift max|y|) (gnb_linear_next_absmax)
+                 unsigned* absmax_bits; int absmax_shift;      // plain epilogue: *absmax_bits = max(., bits of 2^shift max|y|) (gnb_linear_next_absmax)
+                 // max-aggregating variant (EdgeConvTito, layers.py:72-114 with aggr="max"): y[i, ch] = max over the valid slots of
+                 // act(acc + b) (0 for a node without neighbours), arg[i * ldarg + ch] = winning slot | 0x40 if its pre-activation
+                 // was > 0 (-1: no neighbours); first slot on ties, like torch_scatter's scatter_max. slope: act(v) = v > 0 ? v : slope v
+                 signed char* arg; int64_t ldarg; float slope; };
 constexpr int AGG_W = 9, AGG_NPT = 14, AGG_ROWS = AGG_W * AGG_NPT;   // k = 8 neighbour tables
+// Max-aggregating epilogue of one 14-node sub-tile whose 126 slot columns start at TMEM address tcol (lane = channel).
+template <bool SCALED>
+__device__ __forceinline__ void aggmax_tile(uint32_t tcol, float bv, float ainv, const AggInfo& agg, int64_t node0, bool ch_ok, int ch,
+                                            float* __restrict__ y, int64_t ldy, int round_out) {
+    int dg[AGG_NPT];
+#pragma unroll
+    for (int f = 0; f < AGG_NPT; ++f) dg[f] = (node0 + f < agg.n_nodes) ? agg.deg[node0 + f] : 0;
+    float best = -INFINITY;
+    int barg = -1;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32b_x32(tcol + (uint32_t)(c * 32), r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int col = c * 32 + j;
+            if (col < AGG_ROWS) {
+                const int f = col / AGG_W, sl = col % AGG_W;       // compile-time after unrolling
+                const float pre = SCALED ? fmaf(__uint_as_float(r[j]), ainv, bv) : __uint_as_float(r[j]) + bv;
+                const float v = pre > 0.f ? pre : agg.slope * pre;
+                const bool take = sl < dg[f] && (barg < 0 || v > best);      // strict >: the first maximum wins
+                best = take ? v : best;
+                barg = take ? (sl | (pre > 0.f ? 0x40 : 0)) : barg;
+                if (sl == AGG_W - 1) {
+                    float o = barg >= 0 ? best : 0.f;
+                    if (round_out) o = tc::round_tf32(o);
+                    if (ch_ok && node0 + f < agg.n_nodes) {
+                        y[(node0 + f) * ldy + ch] = o;
+                        agg.arg[(node0 + f) * agg.ldarg + ch] = (signed char)barg;
+                    }
+                    best = -INFINITY;
+                    barg = -1;
+                }
+            }
+        }
+    }
+}
+
 // Scattering epilogue (backward of the hoisted EdgeConv hidden layer fused into the data-gradient GEMM): rows are padded
 // edge slots as above, output channel c of row (i, s) is dh = (dz W2)[(i,s), c]; the epilogue applies the ReLU mask
 // (bit mask of h > 0 written by the forward hidden-layer kernel), sums the slots of a node into dp[i, c] (the P half of
@@ -382,6 +425,10 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
                     const bool ch_ok = ch < n_out;
                     const float bv = (bias != nullptr && ch_ok) ? bias[ch] : 0.f;
                     const int64_t node0 = (int64_t)t * AGG_NPT;
+                    if (agg.arg != nullptr) {
+                        aggmax_tile<false>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * (TC_MT * TC_BN) + m * TC_BN), bv,
+                                           1.f, agg, node0, ch_ok, ch, y, ldy, round_out);
+                    } else {
                     int dg[AGG_NPT];
 #pragma unroll
                     for (int f = 0; f < AGG_NPT; ++f) dg[f] = (node0 + f < agg.n_nodes) ? agg.deg[node0 + f] : 0;
@@ -415,6 +462,7 @@ gemm_tc_linear_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
                     }
                     if (ch_ok && agg.maskbits != nullptr)
                         reinterpret_cast<uint4*>(agg.maskbits)[(int64_t)t * n_out + ch] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+                    }
                 }
             } else
             for (int m = 0; m < mt; ++m) {
@@ -845,7 +893,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
             } else if (agg.enabled) {
                 const int64_t st14 = (int64_t)t * 2 + half;            // 14-node tile index of the mask layout
                 const int64_t node0 = st14 * AGG_NPT;
-                if (node0 < agg.n_nodes) {
+                if (node0 < agg.n_nodes && agg.arg != nullptr) {
+                    const float ainv = (BF && agg.scale_bits != nullptr) ? gnb_pow2_scale(*agg.scale_bits).y : 1.f;
+                    aggmax_tile<BF>(tcol, bv, ainv, agg, node0, ch_ok, ch, y, ldy, round_out);
+                } else if (node0 < agg.n_nodes) {
                     // 16-bit plane modes: accumulators carry the producer's power-of-two scale of h; undone in the bias FMA
                     const float ainv = (BF && agg.scale_bits != nullptr) ? gnb_pow2_scale(*agg.scale_bits).y : 1.f;
                     int dg[AGG_NPT];
@@ -2321,7 +2372,7 @@ static int linear_fwd_impl(const float* const* xs, const int64_t* ldxs, const in
         rc = gnb_make_tmap_bf16(&twlo, w_lo, n_out, 2 * ktot, ldw * 4, TC_BM);
         if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     }
-    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr, g_next_absmax, g_next_absmax_shift};
+    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr, g_next_absmax, g_next_absmax_shift, nullptr, 0, 0.f};
     g_next_absmax = nullptr;
     ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, nullptr, 0};
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out, gnb_div_up(rows, TC_BN), agg, sc,
@@ -2357,7 +2408,8 @@ GNB_EXPORT int gnb_linear_fwd_tf32x3(const float* const* xs, const int64_t* ldxs
 // h: [n*9, k] tf32-rounded padded edge list, w: [n_out, ceil(k/32)*32] packed. n_out <= 512. maskbits may be NULL.
 static int edge_linear_agg_impl(const float* h, int64_t ldh, int32_t k, const float* w, const float* w_lo, int64_t ldw,
                                 const float* bias, const int32_t* deg, int64_t n, int32_t n_out,
-                                int32_t round_out, float* y, int64_t ldy, uint32_t* maskbits, void* stream) {
+                                int32_t round_out, float* y, int64_t ldy, uint32_t* maskbits, void* stream,
+                                int8_t* arg = nullptr, int64_t ldarg = 0, int32_t act = GNB_ACT_RELU) {
     if (n < 0 || n_out < 1 || k < 1) return GNB_ERR_ARG;
     if (n == 0) return GNB_OK;
     const int64_t rows = n * AGG_W;
@@ -2379,10 +2431,28 @@ static int edge_linear_agg_impl(const float* h, int64_t ldh, int32_t k, const fl
         rc = gnb_make_tmap_bf16(&twlo, w_lo, n_out, 2 * ktot, ldw * 4, TC_BM);
         if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     }
-    AggInfo agg{deg, n, maskbits, 1, g_linear_dbg, g_linear_prof, nullptr, nullptr, 0};
+    const float slope = act == GNB_ACT_RELU ? 0.f : (act == GNB_ACT_LEAKY ? GNB_LEAKY_SLOPE : 1.f);
+    AggInfo agg{deg, n, maskbits, 1, g_linear_dbg, g_linear_prof, nullptr, nullptr, 0, reinterpret_cast<signed char*>(arg), ldarg, slope};
     ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, nullptr, 0};
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, GNB_ACT_RELU, round_out, gnb_div_up(n, AGG_NPT), agg, sc,
                          (cudaStream_t)stream, w_lo != nullptr ? &twlo : nullptr);
+}
+// Second Linear of an EdgeConv MLP fused with its activation and the k-neighbour MAX (EdgeConvTito / any EdgeConv with
+// aggr = "max"; k = 8 tables, width 9): y[i, :] = max_{s < deg[i]} act(h[i*9 + s, :] w^T + bias), 0 for deg[i] = 0;
+// arg[i * ldarg + c] = winning slot | 0x40 if its pre-activation was > 0, -1 for deg[i] = 0 (what gnb_edge_argmax_bwd routes
+// the gradient by). act: GNB_ACT_NONE / RELU / LEAKY. The [E, C] message tensor is never stored.
+GNB_EXPORT int gnb_edge_linear_aggmax_fwd_tf32(const float* h, int64_t ldh, int32_t k, const float* w, int64_t ldw,
+                                               const float* bias, const int32_t* deg, int64_t n, int32_t n_out, int32_t act,
+                                               int32_t round_out, float* y, int64_t ldy, int8_t* arg, int64_t ldarg, void* stream) {
+    if (arg == nullptr || ldarg < n_out || act < 0 || act > 2) return GNB_ERR_ARG;
+    return edge_linear_agg_impl(h, ldh, k, w, nullptr, ldw, bias, deg, n, n_out, round_out, y, ldy, nullptr, stream, arg, ldarg, act);
+}
+// The same on split operands (fp32-grade forward, see gnb_linear_fwd_tf32x3): h plain fp32, y unrounded.
+GNB_EXPORT int gnb_edge_linear_aggmax_fwd_tf32x3(const float* h, int64_t ldh, int32_t k, const float* w_hi, const float* w_lo,
+                                                 int64_t ldw, const float* bias, const int32_t* deg, int64_t n, int32_t n_out,
+                                                 int32_t act, float* y, int64_t ldy, int8_t* arg, int64_t ldarg, void* stream) {
+    if (arg == nullptr || ldarg < n_out || act < 0 || act > 2 || w_hi == nullptr || w_lo == nullptr) return GNB_ERR_ARG;
+    return edge_linear_agg_impl(h, ldh, k, w_hi, w_lo, ldw, bias, deg, n, n_out, 0, y, ldy, nullptr, stream, arg, ldarg, act);
 }
 GNB_EXPORT int gnb_edge_linear_agg_fwd_tf32(const float* h, int64_t ldh, int32_t k, const float* w, int64_t ldw,
                                             const float* bias, const int32_t* deg, int64_t n, int32_t n_out,
@@ -2429,7 +2499,7 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_split_tf32(const float* dz, int64_t
     CUtensorMap tw;
     rc = gnb_make_tmap_f32(&tw, wt, hdim, ktot, ldw, TC_BM);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
-    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr, nullptr, 0};
+    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr, nullptr, 0, nullptr, 0, 0.f};
     ScatInfo sc{nbr, hmask, mask_ld, dq, lddq, hdim, n, 1, dp, lddp, dbias, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0, nullptr, 0};
     const int row_tiles = gnb_div_up(n, AGG_NPT);
     int nst_w = 0;
@@ -2523,7 +2593,7 @@ static int edge_linear_agg16_impl(const void* h0, const void* h1, int64_t ldh, i
     rc = gnb_make_tmap_16(&tw, w0, n_out, k, ldw * 2, TC_BM, dt);
     if (rc == 0 && planes == 2) rc = gnb_make_tmap_16(&tw1, w1, n_out, k, ldw * 2, TC_BM, dt);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
-    AggInfo agg{deg, n, maskbits, 1, g_linear_dbg, g_linear_prof, scale_bits, nullptr, 0};
+    AggInfo agg{deg, n, maskbits, 1, g_linear_dbg, g_linear_prof, scale_bits, nullptr, 0, nullptr, 0, 0.f};
     ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, nullptr, 0};
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, GNB_ACT_RELU, round_out, gnb_div_up(n, AGG_NPT), agg, sc,
                          (cudaStream_t)stream, planes == 2 ? &tw1 : nullptr, planes, k, fmt16 ? 3 : 0);
@@ -2575,7 +2645,7 @@ static int dgrad_scatter16_impl(const void* dz0, const void* dz1, int64_t lddz, 
     rc = gnb_make_tmap_16(&tw, wt0, hdim, c_out, ldw * 2, TC_BM, tw_t);
     if (rc == 0 && planes == 2) rc = gnb_make_tmap_16(&tw1, wt1, hdim, c_out, ldw * 2, TC_BM, tw_t);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
-    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr, nullptr, 0};
+    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr, nullptr, 0, nullptr, 0, 0.f};
     ScatInfo sc{nbr, hmask, mask_ld, dq, lddq, hdim, n, 1, dp, lddp, dbias, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0, scale_bits, (flags & GNB_FLAG_HMASK_ROWMAJOR) ? 1 : 0};
     const int row_tiles = gnb_div_up(n, AGG_NPT);
     const int last_ksteps = (c_out - 64 * (pi.kblocks[0] - 1) + 15) / 16;
@@ -2645,7 +2715,7 @@ GNB_EXPORT int gnb_linear_fwd_bf16(const void* x0, const void* x1, int64_t ldx, 
     rc = gnb_make_tmap_bf16(&tw, w0, n_out, k, ldw * 2, TC_BM);
     if (rc == 0 && planes == 2) rc = gnb_make_tmap_bf16(&tw1, w1, n_out, k, ldw * 2, TC_BM);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
-    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr, nullptr, 0};
+    AggInfo agg{nullptr, 0, nullptr, 0, g_linear_dbg, g_linear_prof, nullptr, nullptr, 0, nullptr, 0, 0.f};
     ScatInfo sc{nullptr, nullptr, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, nullptr, 0};
     return launch_linear(tw, tx, pi, bias, y, ldy, rows, n_out, act, round_out, gnb_div_up(rows, TC_BN), agg, sc,
                          (cudaStream_t)stream, planes == 2 ? &tw1 : nullptr, planes, k);

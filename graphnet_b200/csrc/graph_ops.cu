@@ -168,13 +168,17 @@ __global__ void edge_hidden_fwd_kernel(const float* __restrict__ pq, int64_t ldp
     const int64_t j = nbr[i * width + s];
     const float4* p = reinterpret_cast<const float4*>(pq + i * ldpq);
     const float4* q = reinterpret_cast<const float4*>(pq + j * ldpq + hdim);
-    const bool relu = (act & 0xff) == GNB_ACT_RELU, rnd = (act & GNB_FLAG_ROUND_TF32) != 0;
+    const bool relu = (act & 0xff) == GNB_ACT_RELU, leaky = (act & 0xff) == GNB_ACT_LEAKY, rnd = (act & GNB_FLAG_ROUND_TF32) != 0;
     if (mrow == nullptr) {
         for (int c = lane; c < h4; c += 32) {
             const float4 a = p[c], b = q[c];
             float4 v = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
             if (relu) {
                 v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+            if (leaky) {
+                v.x = v.x > 0.f ? v.x : GNB_LEAKY_SLOPE * v.x; v.y = v.y > 0.f ? v.y : GNB_LEAKY_SLOPE * v.y;
+                v.z = v.z > 0.f ? v.z : GNB_LEAKY_SLOPE * v.z; v.w = v.w > 0.f ? v.w : GNB_LEAKY_SLOPE * v.w;
             }
             if (rnd) {
                 v.x = gnb_round_tf32(v.x); v.y = gnb_round_tf32(v.y); v.z = gnb_round_tf32(v.z); v.w = gnb_round_tf32(v.w);
@@ -199,6 +203,10 @@ __global__ void edge_hidden_fwd_kernel(const float* __restrict__ pq, int64_t ldp
                 float4 v = make_float4(va[it].x + vb[it].x, va[it].y + vb[it].y, va[it].z + vb[it].z, va[it].w + vb[it].w);
                 if (relu) {
                     v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                }
+                if (leaky) {
+                    v.x = v.x > 0.f ? v.x : GNB_LEAKY_SLOPE * v.x; v.y = v.y > 0.f ? v.y : GNB_LEAKY_SLOPE * v.y;
+                    v.z = v.z > 0.f ? v.z : GNB_LEAKY_SLOPE * v.z; v.w = v.w > 0.f ? v.w : GNB_LEAKY_SLOPE * v.w;
                 }
                 if (rnd) {
                     v.x = gnb_round_tf32(v.x); v.y = gnb_round_tf32(v.y); v.z = gnb_round_tf32(v.z); v.w = gnb_round_tf32(v.w);
@@ -228,7 +236,7 @@ edge_hidden_fwd_node_kernel(const float* __restrict__ pq, int64_t ldpq, int hdim
     const int h4 = hdim >> 2;
     const int dg = deg[i];
     const int nb = lane < width ? nbr[i * width + lane] : -1;
-    const bool relu = (act & 0xff) == GNB_ACT_RELU, rnd = (act & GNB_FLAG_ROUND_TF32) != 0;
+    const bool relu = (act & 0xff) == GNB_ACT_RELU, leaky = (act & 0xff) == GNB_ACT_LEAKY, rnd = (act & GNB_FLAG_ROUND_TF32) != 0;
     const float4* p = reinterpret_cast<const float4*>(pq + i * ldpq);
     float4 pa[NIT];
 #pragma unroll
@@ -266,6 +274,10 @@ edge_hidden_fwd_node_kernel(const float* __restrict__ pq, int64_t ldpq, int hdim
                                         pa[it].w + qv[u][it].w);
                         if (relu) {
                             v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                        }
+                        if (leaky) {
+                            v.x = v.x > 0.f ? v.x : GNB_LEAKY_SLOPE * v.x; v.y = v.y > 0.f ? v.y : GNB_LEAKY_SLOPE * v.y;
+                            v.z = v.z > 0.f ? v.z : GNB_LEAKY_SLOPE * v.z; v.w = v.w > 0.f ? v.w : GNB_LEAKY_SLOPE * v.w;
                         }
                         if (rnd) {
                             v.x = gnb_round_tf32(v.x); v.y = gnb_round_tf32(v.y);
@@ -437,6 +449,11 @@ __global__ void edge_hidden_bwd_kernel(const float* __restrict__ gh, int64_t ldg
                 g.x = hv.x > 0.f ? g.x : 0.f; g.y = hv.y > 0.f ? g.y : 0.f;
                 g.z = hv.z > 0.f ? g.z : 0.f; g.w = hv.w > 0.f ? g.w : 0.f;
             }
+            if ((act & 0xff) == GNB_ACT_LEAKY) {       // h = leaky(a): h > 0 <=> a > 0
+                const float4 hv = reinterpret_cast<const float4*>(h + r * ldh)[c];
+                g.x = hv.x > 0.f ? g.x : GNB_LEAKY_SLOPE * g.x; g.y = hv.y > 0.f ? g.y : GNB_LEAKY_SLOPE * g.y;
+                g.z = hv.z > 0.f ? g.z : GNB_LEAKY_SLOPE * g.z; g.w = hv.w > 0.f ? g.w : GNB_LEAKY_SLOPE * g.w;
+            }
             acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
             const int64_t j = nbr[r];
             atomicAdd(reinterpret_cast<float4*>(dpq + j * ldpq + hdim) + c, g);
@@ -540,6 +557,46 @@ __global__ void edge_aggregate_bwd_kernel(const float* __restrict__ gy, int64_t 
             else v = (arg[i * c_out + c] == s) ? g : 0.f;
         }
         gm[r * ldm + c] = v;
+    }
+}
+
+// Backward of the max-aggregating GEMM epilogue (gnb_edge_linear_aggmax_fwd_*): y[i, c] = max_s act(pre[(i,s), c]) sends its
+// gradient to ONE slot, the arg-max (torch_scatter's scatter_max rule; first slot on ties), through the activation's slope
+// there: dz[(i,s), c] = (s == slot(arg[i, c])) ? gy[i, c] * (pos(arg[i, c]) ? 1 : slope) : 0, where arg = slot | 0x40 if the
+// winning pre-activation was > 0, -1 for a node without neighbours. db[c] += column sums of dz (may be NULL). One warp per
+// node; a CTA reduces its bias contributions in shared memory before the global atomics.
+constexpr int AMB_NODES = 8;      // nodes per warp
+__global__ void __launch_bounds__(256)
+edge_argmax_bwd_kernel(const float* __restrict__ gy, int64_t ldy, const int8_t* __restrict__ arg, int64_t ldarg, int c_out,
+                       int width, int64_t n, float slope, int rnd, float* __restrict__ dz, int64_t ldz, float* __restrict__ db) {
+    gnb_pdl_begin();
+    __shared__ float s_db[512];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (db != nullptr) {
+        for (int c = threadIdx.x; c < 512; c += 256) s_db[c] = 0.f;
+        __syncthreads();
+    }
+    const int64_t i0 = ((int64_t)blockIdx.x * 8 + warp) * AMB_NODES;
+    for (int c = lane; c < c_out; c += 32) {
+        float colacc = 0.f;
+        for (int f = 0; f < AMB_NODES; ++f) {
+            const int64_t i = i0 + f;
+            if (i >= n) break;
+            const int a = arg[i * ldarg + c];
+            float d = 0.f;
+            if (a >= 0) {
+                d = gy[i * ldy + c] * ((a & 0x40) ? 1.f : slope);
+                colacc += d;
+                if (rnd) d = gnb_round_tf32(d);
+            }
+            const int slot = a >= 0 ? (a & 0x3f) : -1;
+            for (int s = 0; s < width; ++s) dz[(i * width + s) * ldz + c] = s == slot ? d : 0.f;
+        }
+        if (db != nullptr) atomicAdd(&s_db[c & 511], colacc);
+    }
+    if (db != nullptr) {
+        __syncthreads();
+        for (int c = threadIdx.x; c < c_out && c < 512; c += 256) atomicAdd(db + c, s_db[c]);
     }
 }
 
@@ -1144,6 +1201,17 @@ GNB_EXPORT int gnb_edge_aggregate_bwd(const float* gy, int64_t ldy, int32_t c_ou
     if (n == 0) return GNB_OK;
     gnb_launch(edge_aggregate_bwd_kernel, gnb_div_up(n * width, 8), 256, 0, (cudaStream_t)stream)(gy, ldy, c_out, deg, width, n,
                                                                                           aggr, arg, gm, ldm);
+    GNB_RETURN_LAUNCH();
+}
+
+GNB_EXPORT int gnb_edge_argmax_bwd(const float* gy, int64_t ldy, const int8_t* arg, int64_t ldarg, int32_t c_out, int32_t width,
+                                   int64_t n, int32_t act, int32_t flags, float* dz, int64_t ldz, float* db, void* stream) {
+    if (gy == nullptr || arg == nullptr || dz == nullptr || c_out < 1 || c_out > 512 || width < 1 || width > 64 || act < 0 || act > 2)
+        return GNB_ERR_ARG;
+    if (n == 0) return GNB_OK;
+    const float slope = act == GNB_ACT_RELU ? 0.f : (act == GNB_ACT_LEAKY ? GNB_LEAKY_SLOPE : 1.f);
+    gnb_launch(edge_argmax_bwd_kernel, gnb_div_up(n, 8 * AMB_NODES), 256, 0, (cudaStream_t)stream)(
+        gy, ldy, arg, ldarg, c_out, width, n, slope, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0, dz, ldz, db);
     GNB_RETURN_LAUNCH();
 }
 

@@ -117,6 +117,17 @@ class DynEdgeConv(Model):
         return x, new_graph.edge_index()
 
 
+def _act_code(m: torch.nn.Module):
+    """ops.ACT_* of an activation module the kernels implement (None: something else)."""
+    if isinstance(m, torch.nn.ReLU):
+        return ops.ACT_RELU
+    if isinstance(m, torch.nn.LeakyReLU) and m.negative_slope == 0.01:
+        return ops.ACT_LEAKY
+    if isinstance(m, torch.nn.Identity):
+        return ops.ACT_NONE
+    return None
+
+
 class EdgeConvTito(Model):
     """EdgeConv of the TITO solution: out_i = AGG_j nn([x_i, x_j - x_i, x_j]) (reference: layers.py:72-114, a PyG
     `MessagePassing` with `aggr="max"` by default).
@@ -143,6 +154,12 @@ class EdgeConvTito(Model):
             xp = pad_columns(x, 4)
             bcat = None if first.bias is None else torch.cat([first.bias, torch.zeros_like(first.bias)])
             pq = ops.linear_act(xp, wcat, bcat, ops.ACT_NONE, round_out=False)           # [N, 2H] = [P | Q]
+            acts = [_act_code(m_) for m_ in list(seq)[1:]]
+            if (self.aggr == "max" and len(seq) == 4 and isinstance(seq[2], torch.nn.Linear) and acts[0] is not None
+                    and acts[2] is not None and ops.edgeconv_hoisted_max_ok(graph, first.out_features, seq[2].out_features)):
+                # Linear, act, Linear, act with max aggregation (every DynTrans layer of DynEdgeTITO): the second Linear, its
+                # activation and the maximum over the k slots run as ONE tcgen05 kernel, the backward is arg-routed
+                return ops.edgeconv_hoisted_max(pq, seq[2].weight, seq[2].bias, graph, acts[0], acts[2])
             a1 = ops.edge_hidden(pq, graph, ops.ACT_NONE)                                # [N*W, H]: W1 msg + b1 per edge slot
             m = a1
             for layer in list(seq)[1:]:

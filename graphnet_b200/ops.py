@@ -17,7 +17,7 @@ from torch import Tensor
 
 from . import _lib
 
-ACT_NONE, ACT_RELU = 0, 1
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2        # LEAKY: torch.nn.LeakyReLU() default slope 0.01
 FLAG_ROUND_TF32 = 0x100
 AGGR = {"add": 0, "sum": 0, "mean": 1, "max": 2}
 POOL = {"min": 0, "max": 1, "sum": 2, "mean": 3}
@@ -593,6 +593,73 @@ class _EdgeConvHoisted(torch.autograd.Function):
             _call("gnb_edge_hidden_bwd", _ptr(dh), _ld(dh), _ptr(h), _ld(h), hdim, _ptr(graph.nbr), _ptr(graph.deg),
                   graph.width, graph.n, ACT_RELU, _ptr(dpq), _ld(dpq), _stream())
         return dpq, dw2, db2, None, None
+
+
+class _EdgeConvHoistedMax(torch.autograd.Function):
+    """y_i = max_s act2(W2 act1(P_i + Q_{nbr[i,s]}) + b2): the per-edge part of an EdgeConv with max aggregation (EdgeConvTito,
+    reference layers.py:72-114 + dynedge_kaggle_tito.py:157-162) on the tensor cores. Forward: hidden-layer kernel ->
+    tcgen05 GEMM whose epilogue applies act2, takes the maximum over the k slots of every node and records the winning slot
+    (the [E, C] message tensor is never stored). Backward: the arg-routed kernel rebuilds dz [E, C] (one non-zero per node and
+    channel), dW2 and dh run on the tensor cores, the hidden-layer backward scatters dh to dPQ."""
+
+    @staticmethod
+    def forward(ctx, pq: Tensor, w2: Tensor, b2: Optional[Tensor], graph: KnnGraph, act1: int, act2: int):
+        _cuda(pq, w2, b2)
+        pq, w2 = _rowmajor(pq), _rowmajor(w2)
+        hdim, c_out = pq.shape[1] // 2, w2.shape[0]
+        rnd = FLAG_ROUND_TF32 if _fround() else 0
+        h = torch.empty(graph.n * graph.width, hdim, dtype=torch.float32, device=pq.device)
+        _call("gnb_edge_hidden_fwd", _ptr(pq), _ld(pq), hdim, _ptr(graph.nbr), _ptr(graph.deg), graph.width, graph.n,
+              act1 | rnd, _ptr(h), _ld(h), _stream())
+        y = torch.empty(graph.n, c_out, dtype=torch.float32, device=pq.device)
+        arg = torch.empty(graph.n, c_out, dtype=torch.int8, device=pq.device)
+        bias = None if b2 is None else b2.detach()
+        if _split():
+            w_hi, w_lo = _tc_pack_weight_split(w2.detach(), (0,), (hdim,))
+            _call("gnb_edge_linear_aggmax_fwd_tf32x3", _ptr(h), _ld(h), hdim, _ptr(w_hi), _ptr(w_lo), w_hi.shape[1], _ptr(bias),
+                  _ptr(graph.deg), graph.n, c_out, act2, _ptr(y), c_out, _ptr(arg), c_out, _stream())
+        else:
+            _mark_rounded(h)
+            w2p = _tc_pack_weight(w2.detach(), (0,), (hdim,))
+            _call("gnb_edge_linear_aggmax_fwd_tf32", _ptr(h), _ld(h), hdim, _ptr(w2p), w2p.shape[1], _ptr(bias),
+                  _ptr(graph.deg), graph.n, c_out, act2, 1, _ptr(y), c_out, _ptr(arg), c_out, _stream())
+            _mark_rounded(y)
+        ctx.graph, ctx.act1, ctx.act2, ctx.has_bias = graph, act1, act2, b2 is not None
+        ctx.save_for_backward(h, arg, w2)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy: Tensor):
+        h, arg, w2 = ctx.saved_tensors
+        graph = ctx.graph
+        gy = _rowmajor(gy.contiguous())
+        c_out = w2.shape[0]
+        dz = torch.empty(graph.n * graph.width, c_out, dtype=torch.float32, device=h.device)
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
+        db2 = torch.zeros(c_out, dtype=torch.float32, device=h.device) if want_db else None
+        _call("gnb_edge_argmax_bwd", _ptr(gy), _ld(gy), _ptr(arg), c_out, c_out, graph.width, graph.n, ctx.act2,
+              FLAG_ROUND_TF32, _ptr(dz), c_out, _ptr(db2), _stream())
+        _mark_rounded(dz)
+        dw2, (dh,) = _dense_backward(dz, w2, (h,), (0,), ctx.needs_input_grad[1], (ctx.needs_input_grad[0],), True)
+        dpq = None
+        if dh is not None:
+            hdim = h.shape[1]
+            dpq = torch.zeros(graph.n, 2 * hdim, dtype=torch.float32, device=h.device)
+            _call("gnb_edge_hidden_bwd", _ptr(dh), _ld(dh), _ptr(h), _ld(h), hdim, _ptr(graph.nbr), _ptr(graph.deg),
+                  graph.width, graph.n, ctx.act1, _ptr(dpq), _ld(dpq), _stream())
+        return dpq, dw2, db2, None, None, None
+
+
+def edgeconv_hoisted_max_ok(graph: KnnGraph, hdim: int, c_out: int) -> bool:
+    """The tensor-core max-aggregation route exists for k = 8 tables (width 9) in the tensor-core precision modes."""
+    return _tf32() and graph.width == 9 and hdim % 4 == 0 and 4 <= hdim <= 2048 and 1 <= c_out <= 512 and graph.n > 0
+
+
+def edgeconv_hoisted_max(pq: Tensor, w2: Tensor, b2: Optional[Tensor], graph: KnnGraph, act1: int, act2: int) -> Tensor:
+    """Per-edge half of an EdgeConv `Linear, act1, Linear, act2` with aggr = "max" whose first Linear was hoisted to nodes
+    (pq = [P | Q]); act in ACT_NONE / ACT_RELU / ACT_LEAKY."""
+    y = _EdgeConvHoistedMax.apply(pq, w2, b2, graph, act1, act2)
+    return _mark_rounded(y) if _fround() else y
 
 
 FUSED_EDGECONV = os.environ.get("GNB_FUSED_EDGECONV", "1") == "1"

@@ -174,6 +174,24 @@ int gnb_edge_linear_agg_fwd_tf32(const float* h, int64_t ldh, int32_t k, const f
 int gnb_edge_linear_agg_fwd_tf32x3(const float* h, int64_t ldh, int32_t k, const float* w_hi, const float* w_lo, int64_t ldw,
                                    const float* bias, const int32_t* deg, int64_t n, int32_t n_out, float* y, int64_t ldy,
                                    uint32_t* maskbits, void* stream);
+/* Second Linear of an EdgeConv MLP + activation + k-neighbour MAX in one tcgen05 kernel: replaces PyG MessagePassing
+ * (aggr="max") over EdgeConvTito.message (reference models/components/layers.py:72-114, instantiated with aggr="max" at
+ * models/gnn/dynedge_kaggle_tito.py:157-162): y[i] = max_{s<deg[i]} act(h[i*9+s] w^T + bias), 0 when deg[i] = 0;
+ * arg[i * ldarg + ch] = winning slot | 0x40 if its pre-activation was > 0, -1 when deg[i] = 0; the first slot wins ties
+ * (torch_scatter scatter_max). act = GNB_ACT_NONE (0) / RELU (1) / LEAKY (2: torch.nn.LeakyReLU() default slope 0.01).
+ * The [E, n_out] message tensor is never stored. h / w as for gnb_edge_linear_agg_fwd_tf32. */
+int gnb_edge_linear_aggmax_fwd_tf32(const float* h, int64_t ldh, int32_t k, const float* w, int64_t ldw, const float* bias,
+                                    const int32_t* deg, int64_t n, int32_t n_out, int32_t act, int32_t round_out, float* y,
+                                    int64_t ldy, int8_t* arg, int64_t ldarg, void* stream);
+/* The same on split operands (fp32-grade forward, see gnb_linear_fwd_tf32x3): h plain fp32, y unrounded. */
+int gnb_edge_linear_aggmax_fwd_tf32x3(const float* h, int64_t ldh, int32_t k, const float* w_hi, const float* w_lo, int64_t ldw,
+                                      const float* bias, const int32_t* deg, int64_t n, int32_t n_out, int32_t act, float* y,
+                                      int64_t ldy, int8_t* arg, int64_t ldarg, void* stream);
+/* Arg-routed backward of the max aggregation and its activation (autograd of scatter_max + LeakyReLU / ReLU in the reference):
+ * dz[i*width+s, c] = (s == slot(arg[i,c])) ? gy[i,c] * (arg[i,c] & 0x40 ? 1 : slope(act)) : 0; db[c] += column sums (db may
+ * be NULL); flags & 0x100 rounds dz to tf32. c_out <= 512. */
+int gnb_edge_argmax_bwd(const float* gy, int64_t ldy, const int8_t* arg, int64_t ldarg, int32_t c_out, int32_t width, int64_t n,
+                        int32_t act, int32_t flags, float* dz, int64_t ldz, float* db, void* stream);
 /* Backward of the above up to the pre-activation: dz[i*9+s] = g[i] * maskbit, db += colsum(dz); flags & 0x100 rounds dz. */
 int gnb_edge_mask_bwd_colsum(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols,
                              const int32_t* deg, float* dz, int64_t ldz, float* db, int32_t flags, void* stream);
