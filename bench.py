@@ -3,7 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W             # this repo's CUDA path (headline workload train512)
     python bench.py --impl reference --gpus N --steps K ...    # the reference algorithm on the host CPU cores
-    python bench.py --workload {infer1024,highmult20k,percentile16,prometheus50,microbench}   # the other BASELINE configs
+    python bench.py --workload {infer1024,highmult20k,percentile16,prometheus50,microbench,tito256}   # the other BASELINE configs
 
 One "step" = one pass of the hot path over one batch of synthetic IceCube-like events:
   headline `value`  : training step of BASELINE configs[2] -- device-resident x/batch/n_pulses (no edge_index)
@@ -63,7 +63,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train512",
-                    choices=["train512", "infer1024", "highmult20k", "percentile16", "prometheus50", "microbench"])
+                    choices=["train512", "infer1024", "highmult20k", "percentile16", "prometheus50", "microbench", "tito256"])
     ap.add_argument("--events", type=int, default=512, help="training events per GPU (configs[2])")
     ap.add_argument("--infer-events", type=int, default=1024, help="inference events per GPU (configs[1])")
     ap.add_argument("--precision", default=os.environ.get("GNB_PRECISION", "mixed16"),

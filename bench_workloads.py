@@ -4,6 +4,7 @@
                 01_train_dynedge.py:85,113-142,195,223) -- KNNGraph(Prometheus) -> DynEdge(4) -> energy head + LogCosh ->
                 backward -> Adam, one epoch = 4 steps (16 + 16 + 16 + 2 events)
   highmult20k   configs[3]: DynEdge with [min, max, mean, sum] pooling on high-multiplicity events (up to 20 000 pulses)
+  tito256       configs[3]: DynEdgeTITO (max aggregation in the GEMM epilogue) on 256 events of <= 256 pulses
   percentile16  configs[3]: the same events as `PercentileClusters` nodes (F = 16), nodes built on the host like the
                 reference's dataloader workers (untimed), DynEdge(16) on the device
   microbench    configs[4]: kNN graph build and one DynEdgeConv layer over pulses/event 16 ... 20 000, k = 4 / 8 / 16,
@@ -50,14 +51,14 @@ def _time_steps(fn, steps, warmup, flush=None):
 class EnergyTrainer:
     """KNNEdges -> DynEdge(F) -> EnergyReconstruction + LogCosh on log10 -> backward -> Adam (configs[0] / [3])."""
 
-    def __init__(self, dev, nb_inputs):
+    def __init__(self, dev, nb_inputs, backbone=None):
         from graphnet_b200 import ops
         from graphnet_b200.distributed import FlatAdam, FlatGradAllReduce
         from graphnet_b200.models.gnn import DynEdge
         from graphnet_b200.models.graphs.edges import KNNEdges
         from graphnet_b200.tasks import EnergyReconstruction
         torch.manual_seed(0)
-        self.backbone = DynEdge(nb_inputs, global_pooling_schemes=bench.POOLS).to(dev)
+        self.backbone = (DynEdge(nb_inputs, global_pooling_schemes=bench.POOLS) if backbone is None else backbone).to(dev)
         self.energy = EnergyReconstruction(128).to(dev)
         self.edges = KNNEdges(8)
         self.reducer = FlatGradAllReduce(list(self.backbone.parameters()) + list(self.energy.parameters()))
@@ -162,6 +163,44 @@ def run_highmult20k(args, dev):
            "initial_knn_ms": round(sec_knn * 1e3, 4), "knn_pairs_per_s": round(float((raw["n_pulses"].astype(np.float64) ** 2).sum()) / sec_knn, 1)})
 
 
+def run_tito256(args, dev):
+    """configs[3], the DynEdgeTITO half: 256 events clipped to 256 pulses (the TITO solution caps the pulses per event; its
+    per-event TransformerEncoder works on a padded dense [events, longest event, 256] batch)."""
+    from graphnet_b200 import ops
+    from graphnet_b200.models.gnn import DynEdgeTITO
+    from graphnet_b200.synthetic import event_sizes, make_batch
+    ops.set_precision(args.precision)
+    nev = 256
+    sizes = event_sizes(nev, np.random.default_rng(5), sigma=1.0, n_max=256)
+    raw = make_batch(nev, seed=5, sizes=sizes)
+    db = {k: torch.from_numpy(np.ascontiguousarray(raw[k])).to(dev) for k in ("x", "batch", "n_pulses", "energy")}
+    torch.manual_seed(0)
+    tr = EnergyTrainer(dev, 7, backbone=DynEdgeTITO(7, global_pooling_schemes=bench.POOLS))
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    res = {}
+    for name, on in (("max_epilogue", True), ("unfused_max", False)):
+        ops.MAX_EPILOGUE = on
+        sec, _ = _time_steps(lambda: tr.train_step(db), args.steps, args.warmup, flush)
+        sec_i, _ = _time_steps(lambda: tr.infer_step(db), args.steps, args.warmup, flush)
+        res[name] = (sec, sec_i)
+    ops.MAX_EPILOGUE = True
+    sec, sec_i = res["max_epilogue"]
+    n = int(db["x"].shape[0])
+    _line(args, "dynedge_train_events_per_sec", nev / sec, sec,
+          {"workload": "BASELINE configs[3]: DynEdgeTITO (4 DynTrans layers (256, 256), max aggregation, per-event TransformerEncoder, "
+                       "pooling min/max/mean/sum) on 256 events of <= 256 pulses, energy (LogCosh) fwd + bwd + Adam; the EdgeConvTito "
+                       "MLPs on the kernels (hoisted first Linear, max-aggregating tcgen05 epilogue, arg-routed backward), LayerNorm "
+                       "and the transformer as torch modules",
+           "precision": f"{args.precision}: {bench.TOLERANCE[args.precision]}", "events": nev, "pulses": n,
+           "l2": "256 MiB flush between timed steps"},
+          {"pulses_per_s": round(n / sec, 1),
+           "inference": {"value": round(nev / sec_i, 2), "unit": bench.UNIT, "ms_per_step": round(sec_i * 1e3, 4)},
+           "without_max_epilogue": {"train_ms_per_step": round(res["unfused_max"][0] * 1e3, 4),
+                                    "infer_ms_per_step": round(res["unfused_max"][1] * 1e3, 4),
+                                    "note": "the second Linear / LeakyReLU of every EdgeConvTito as torch modules on the [E, 256] "
+                                            "edge tensor + the SIMT max-aggregation kernel (the route before the fused epilogue)"}})
+
+
 def run_percentile16(args, dev):
     from graphnet_b200 import ops
     from graphnet_b200.data import Batch
@@ -248,4 +287,4 @@ def run(args, dev, world, rank):
     if rank != 0:
         return
     {"prometheus50": run_prometheus50, "highmult20k": run_highmult20k, "percentile16": run_percentile16,
-     "microbench": run_microbench}[args.workload](args, dev)
+     "microbench": run_microbench, "tito256": run_tito256}[args.workload](args, dev)

@@ -187,6 +187,49 @@ def to_dense_events(x: Tensor, ptr: Tensor) -> Tuple[Tensor, Tensor]:
     return dense, mask
 
 
+# The reference applies `TransformerEncoder` to a zero-padded dense batch [events, longest event, C] (layers.py:190-195). Every
+# part of an encoder layer except the attention itself is per token, so here the four Linear layers run on the packed token
+# list [N, C] through the tensor-core Linear kernels (no padding rows: 2.2 x fewer rows at <= 256 pulses per event; fp32-grade
+# tcgen05 instead of torch's fp32 SIMT GEMMs) and only q / k / v are padded for the per-event attention. False, or precision
+# mode "fp32" (the reference-arithmetic mode), = the literal module call on the padded batch.
+TRANSFORMER_ON_TOKENS = True
+
+
+def _encoder_layer_supported(layer: torch.nn.Module) -> bool:
+    return (isinstance(layer, torch.nn.TransformerEncoderLayer) and not layer.norm_first
+            and layer.activation in (torch.nn.functional.relu,) and layer.self_attn.in_proj_weight is not None
+            and layer.self_attn.batch_first and layer.self_attn.bias_k is None and not layer.self_attn.add_zero_attn)
+
+
+def _linear_tokens(x: Tensor, lin_w: Tensor, lin_b: Optional[Tensor], act: int) -> Tensor:
+    """act(x W^T + b) on the Linear kernels; wide layers in chunks of 1024 outputs (the split-operand GEMM's limit)."""
+    if lin_w.shape[0] <= 1024:
+        return ops.linear_act(x, lin_w, lin_b, act, round_out=False)
+    outs = [ops.linear_act(x, lin_w[o:o + 1024], None if lin_b is None else lin_b[o:o + 1024], act, round_out=False)
+            for o in range(0, lin_w.shape[0], 1024)]
+    return torch.cat(outs, dim=1)
+
+
+def encoder_layer_on_tokens(layer: torch.nn.TransformerEncoderLayer, x: Tensor, ptr: Tensor) -> Tensor:
+    """A post-norm `TransformerEncoderLayer` (ReLU feed-forward) applied per event to packed tokens x [N, C]: same parameters and
+    arithmetic as `layer(dense, src_key_padding_mask=~mask)[mask]`."""
+    attn = layer.self_attn
+    n, c = x.shape
+    heads = attn.num_heads
+    qkv = _linear_tokens(x, attn.in_proj_weight, attn.in_proj_bias, ops.ACT_NONE)                 # [N, 3C]
+    dense, mask = to_dense_events(qkv, ptr)                                                      # [B, L, 3C]
+    b, l = mask.shape
+    q, k, v = dense.view(b, l, 3, heads, c // heads).permute(2, 0, 3, 1, 4)                      # [B, heads, L, C / heads] each
+    o = torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=mask[:, None, None, :],
+                                                         dropout_p=attn.dropout if layer.training else 0.0)
+    o = o.permute(0, 2, 1, 3).reshape(b, l, c)[mask]                                             # back to tokens
+    o = _linear_tokens(o, attn.out_proj.weight, attn.out_proj.bias, ops.ACT_NONE)
+    x = layer.norm1(x + layer.dropout1(o))
+    ff = _linear_tokens(x, layer.linear1.weight, layer.linear1.bias, ops.ACT_RELU)
+    ff = _linear_tokens(layer.dropout(ff), layer.linear2.weight, layer.linear2.bias, ops.ACT_NONE)
+    return layer.norm2(x + layer.dropout2(ff))
+
+
 class DynTrans(EdgeConvTito):
     """`dynTrans1` layer of the TITO solution (reference: layers.py:117-197): EdgeConvTito with a LeakyReLU MLP, residual
     connection when the widths agree, LayerNorm, and one TransformerEncoder layer applied per event (padded dense batch with
@@ -215,8 +258,14 @@ class DynTrans(EdgeConvTito):
         x_out = self.edge_conv(x, graph)
         x = x + x_out if x_out.shape[-1] == x.shape[-1] else x_out
         x = self.norm1(x)
+        enc = self._transformer_encoder
+        if (TRANSFORMER_ON_TOKENS and ops.PRECISION != "fp32" and enc.norm is None
+                and all(_encoder_layer_supported(layer) for layer in enc.layers)):
+            for layer in enc.layers:
+                x = encoder_layer_on_tokens(layer, x, ptr)
+            return x
         dense, mask = to_dense_events(x, ptr)
-        dense = self._transformer_encoder(dense, src_key_padding_mask=~mask)
+        dense = enc(dense, src_key_padding_mask=~mask)
         return dense[mask]
 
     def forward(self, x: Tensor, edge_index, batch: Optional[Tensor] = None) -> Tensor:

@@ -650,9 +650,12 @@ class _EdgeConvHoistedMax(torch.autograd.Function):
         return dpq, dw2, db2, None, None, None
 
 
+MAX_EPILOGUE = True       # False: EdgeConv layers with aggr = "max" keep the unfused route (timing comparisons)
+
+
 def edgeconv_hoisted_max_ok(graph: KnnGraph, hdim: int, c_out: int) -> bool:
     """The tensor-core max-aggregation route exists for k = 8 tables (width 9) in the tensor-core precision modes."""
-    return _tf32() and graph.width == 9 and hdim % 4 == 0 and 4 <= hdim <= 2048 and 1 <= c_out <= 512 and graph.n > 0
+    return MAX_EPILOGUE and _tf32() and graph.width == 9 and hdim % 4 == 0 and 4 <= hdim <= 2048 and 1 <= c_out <= 512 and graph.n > 0
 
 
 def edgeconv_hoisted_max(pq: Tensor, w2: Tensor, b2: Optional[Tensor], graph: KnnGraph, act1: int, act2: int) -> Tensor:
