@@ -352,27 +352,63 @@ def timed_loop(fn, batches, steps, warmup, flush, e2e_host=None, dev=None, sampl
         per_step = [b.elapsed_time(e) for b, e in events]
         total_ms = sum(per_step)
     else:
+        # End to end: every step's inputs start in pinned host memory and every step's result is read back to the host, all
+        # inside ONE wall-clock region over the K steps -- pipelined the way an input pipeline + training loop are: the H2D
+        # copy of step i + 1 runs on a copy stream into the second staging buffer while step i computes, the result of step
+        # i is copied to pinned memory behind the step and read by the host one step later (a lagging loss read-out), so
+        # the host never drains the GPU between steps. The in-stream L2 flushes are part of the wall-clock time.
+        main = torch.cuda.current_stream()
+        copy_stream = torch.cuda.Stream()
+        stagers = [stager, DeviceStager(e2e_host, dev)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        free = [None, None]
+        res_host, res_evt, events = [None, None], [None, None], []
+
+        def stage(i):
+            hb = e2e_host[i % len(e2e_host)]
+            with torch.cuda.stream(copy_stream):
+                if free[i & 1] is not None:
+                    copy_stream.wait_event(free[i & 1])      # the step that last read this staging buffer has finished
+                dbs = stagers[i & 1].load(hb)
+                ready[i & 1].record(copy_stream)
+            return dbs
+
+        def read_result(i):
+            res_evt[i & 1].synchronize()
+            r = res_host[i & 1]
+            return float(r.sum()) if r.numel() > 1 and d2h == "scalar" else r
+
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        staged = stage(0)
         for i in range(steps):
-            flush.fill_(float(i))                       # 256 MiB write: evicts L2 between timed steps
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
+            flush.fill_(float(i))                   # 256 MiB write: evicts L2 between timed steps
+            main.wait_event(ready[i & 1])
             beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             beg.record()
-            out = fn(stager.load(e2e_host[i % len(e2e_host)]))
-            if d2h == "scalar" or out.numel() == 1:
-                _ = float(out.detach().float().sum().item()) if out.numel() > 1 else float(out.item())   # D2H read of the loss
-                d2h_bytes = 4
-            else:
-                _ = out.detach().cpu()                                                                  # D2H read of the predictions
-                d2h_bytes = int(out.numel() * out.element_size())
+            out = fn(staged).detach()
+            if d2h == "scalar" and out.numel() > 1:
+                out = out.float().sum()
+            if res_host[i & 1] is None or res_host[i & 1].shape != out.shape:
+                res_host[i & 1] = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+            res_host[i & 1].copy_(out, non_blocking=True)                     # D2H read of the loss / the predictions
+            d2h_bytes = int(out.numel() * out.element_size())
             end.record()
-            host += time.perf_counter() - t0          # host time to enqueue the step (no sync)
+            res_evt[i & 1] = end
+            free[i & 1] = end
+            events.append((beg, end))
+            if i + 1 < steps:
+                staged = stage(i + 1)
+            if i > 0:
+                _ = read_result(i - 1)
             if sampler is not None:
-                sampler.sample()                      # GPU is executing the step right now
-            torch.cuda.synchronize()
-            wall += time.perf_counter() - t0
-            per_step.append(beg.elapsed_time(end))
-            total_ms += per_step[-1]
+                sampler.sample()
+        _ = read_result(steps - 1)
+        host = time.perf_counter() - t0
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        per_step = [b.elapsed_time(e) for b, e in events]
+        total_ms = sum(per_step)
     if dist.is_initialized():
         dist.barrier()
     torch.cuda.synchronize()
@@ -935,8 +971,10 @@ def workload_config(args, world):
             "l2": "256 MiB buffer rewritten between timed steps; min(4, warmup) rotating batches",
             "timing": "value: the K steps enqueued back to back (no host synchronisation between steps, as in a training loop), "
                       "each step between its own pair of CUDA events, the L2 flush in the stream between two steps and outside "
-                      "both; barrier + synchronize before the first and after the last step. e2e: one synchronised step at a "
-                      "time (H2D of the batch and D2H of the loss inside each step)",
+                      "both; barrier + synchronize before the first and after the last step. e2e: wall clock over the K steps, "
+                      "pipelined like an input pipeline + training loop (H2D of step i + 1 on a copy stream into a second staging "
+                      "buffer under step i; the loss of step i copied to pinned memory behind the step and read by the host one "
+                      "step later); every H2D, D2H and L2 flush inside the wall-clock region",
             "warmup_executed": "max(W, 2 x rotating batches) untimed steps per timed loop",
             "repeats": f"{args.repeats} repetitions of the K timed steps, the MEDIAN repetition reported (fastest and per-step "
                        "median under 'timing')"}
