@@ -157,3 +157,39 @@ def test_aggmax_route_leaky_relu_vs_fp64(built_library, precision, tol_out, tol_
     print(precision, errs, "decisions that differ:", int(differ.sum()))
     assert errs["y"] < tol_out, errs
     assert max(errs["dpq"], errs["dw2"], errs["db2"]) < tol_grad, errs
+
+
+def test_encoder_layer_on_tokens_matches_the_padded_module_call(built_library):
+    """DynTrans' per-event TransformerEncoder layer applied to packed tokens (four Linear layers on the tensor-core kernels,
+    only q / k / v padded) against the literal `layer(dense, src_key_padding_mask=~mask)[mask]` of layers.py:190-195 in fp64."""
+    import copy
+
+    from graphnet_b200 import ops
+    from graphnet_b200.models.components.layers import encoder_layer_on_tokens, to_dense_events
+    torch.manual_seed(3)
+    d, sizes = 64, (5, 1, 17, 40, 2)
+    layer = torch.nn.TransformerEncoderLayer(d_model=d, nhead=4, dim_feedforward=2048, batch_first=True, norm_first=False).eval()
+    ref = copy.deepcopy(layer).double()
+    n = sum(sizes)
+    x = torch.randn(n, d)
+    w = torch.randn(n, d)
+    ptr = torch.tensor([0] + list(torch.tensor(sizes).cumsum(0)), dtype=torch.int64)
+    xr = x.double().requires_grad_(True)
+    dense, mask = to_dense_events(xr, ptr)
+    y_ref = ref(dense, src_key_padding_mask=~mask)[mask]
+    (y_ref * w.double()).sum().backward()
+    layer = layer.cuda()
+    old = ops.PRECISION
+    ops.set_precision("tf32x3")
+    try:
+        xd = x.cuda().requires_grad_(True)
+        y = encoder_layer_on_tokens(layer, xd, ptr.cuda())
+        (y * w.cuda()).sum().backward()
+    finally:
+        ops.set_precision(old)
+    assert rel_err(y, y_ref) < 2e-5
+    errs = {"x": rel_err(xd.grad, xr.grad)}
+    for (k, p), (_, q) in zip(layer.named_parameters(), ref.named_parameters()):
+        errs[k] = rel_err(p.grad, q.grad)
+    print(errs)
+    assert max(errs.values()) < 1e-3, errs
