@@ -566,7 +566,7 @@ def dominant_launches(trainer, db):
         ops._call("gnb_edgeconv_fused_fwd_f16", ops._ptr(pq), 2 * hid, hid, ops._ptr(graph.nbr), ops._ptr(graph.deg), n,
                   ops._ptr(w16[0]), ops._ptr(w16[1] if planes == 2 else None), hld64, ops._ptr(b2), cout, 0, ops._ptr(y), cout,
                   ops._ptr(maskbits if side else None), ops._ptr(h0f if side else None), hid, ops._ptr(hbytes if side else None),
-                  mld * 4, ops._ptr(pqw), ops._stream())
+                  mld * 4, ops._ptr(pqw), 1, ops._stream())         # (timing: random PQ, the layout the executor uses)
 
     keep = (h, h_raw, w2p, w_hi, w_lo, b2, y, maskbits, dz, wt, hmask, dpq, graph, hw, zw, h16, w16, wt16, dz16, dwg, rowmask, g16,
             pq, pqw, h0f, hbytes)
@@ -646,7 +646,7 @@ def roofline_top_kernel(trainer, db, pk, precision, inference=False):
                     "builder warps gather P_i + Q_j (fp32), ReLU, scale, split into two fp16 planes straight into the swizzled B tile; "
                     "3 MMAs per algorithmic product against the TMA-streamed W2 planes; epilogue = bias + ReLU + k-sum + 126 mask "
                     "bits per (tile, channel); side outputs plane 0 of h + ReLU bits for the backward pass. h [N k, 336] never "
-                    "crosses HBM in fp32. Bound by the builders (gather latency + issue slots), not by the tensor pipe",
+                    "crosses HBM in fp32. Inside the kernel the builder warps (L1 wavefronts, gather latency, issue slots) are the long pole, not the tensor pipe",
                     _time_launch(d["fused_fwd_f16x3"]), by_f, 3.0, _traffic("fused_fwd_f16x3"), p16)
         bwd16 = entry("gemm_f16_pair_scatter_build_kernel (kind::f16): dh = dz W2 (256 -> 336) with dz expanded in shared memory from "
                       "fp16(g) [N, 256] and the row-major ReLU bits (dz never stored); ReLU mask + dP slot sums + dQ fp32 reductions "
@@ -661,17 +661,18 @@ def roofline_top_kernel(trainer, db, pk, precision, inference=False):
                "executed_tflops": top["executed_tflops"], "executed_frac": top["executed_frac"], "hbm_view": top["hbm_view"],
                "rows": rows, "edges": e_real, "algorithmic_flops_per_launch": flops,
                "backward_launch": bwd16, "weight_gradient_launch": wg}
-        return out
+        return _roofline_by_intensity(out, flops, pk)
     if precision == "f16" and inference:
         p16 = pk["bf16_tflops"]
         top = entry("gemm_tc_pair_kernel<2> (tcgen05 cta_group::2 kind::f16 M256xN256xK16, ONE power-of-two scaled fp16 plane per "
                     "operand, TMA-fed), aggregating epilogue: m = relu(h W2^T + b2) summed over the k slots, 336 -> 256 (m never stored)",
                     _time_launch(d["agg_fwd_f16x1"]), 2.0 * rows * hid + 4.0 * n * cout, 1.0, _traffic("agg_fwd_f16x1"), p16)
-        return {"bound": "tensor", "achieved": top["achieved"], "peak": p16, "unit": "TFLOP/s", "frac": top["frac"],
-                "traffic": top["traffic"], "kernel": top["kernel"], "launch_ms": top["launch_ms"],
-                "peak_source": "dense bf16 burst peak of MEASURED_PEAKS.json (kind::f16 runs fp16 and bf16 at the same rate)",
-                "executed_tflops": top["executed_tflops"], "executed_frac": top["executed_frac"], "hbm_view": top["hbm_view"],
-                "rows": rows, "edges": e_real, "algorithmic_flops_per_launch": flops}
+        return _roofline_by_intensity(
+            {"bound": "tensor", "achieved": top["achieved"], "peak": p16, "unit": "TFLOP/s", "frac": top["frac"],
+             "traffic": top["traffic"], "kernel": top["kernel"], "launch_ms": top["launch_ms"],
+             "peak_source": "dense bf16 burst peak of MEASURED_PEAKS.json (kind::f16 runs fp16 and bf16 at the same rate)",
+             "executed_tflops": top["executed_tflops"], "executed_frac": top["executed_frac"], "hbm_view": top["hbm_view"],
+             "rows": rows, "edges": e_real, "algorithmic_flops_per_launch": flops}, flops, pk)
     if precision == "tf32x3" and not inference:
         sec_x = _time_launch(d["agg_fwd_x3"])
         top = entry("gemm_tc_pair_kernel<true> (tcgen05 cta_group::2 kind::tf32 M256xN256xK8, split operands: 3 MMAs per K step, "
@@ -688,6 +689,29 @@ def roofline_top_kernel(trainer, db, pk, precision, inference=False):
            "executed_tflops": top["executed_tflops"], "executed_frac": top["executed_frac"], "hbm_view": top["hbm_view"],
            "rows": rows, "edges": e_real, "algorithmic_flops_per_launch": flops}
     out.update(others)
+    return _roofline_by_intensity(out, flops, pk)
+
+
+def _roofline_by_intensity(out, flops, pk):
+    """Which roof bounds the launch is decided by the roofline model itself: algorithmic FLOP per algorithmic byte against the
+    ridge point (measured dense peak / measured HBM copy peak). Below the ridge the memory roof is the lower one and the line's
+    achieved / peak / frac are the HBM figures (the tensor figures stay under `tensor_view`); above it the tensor figures."""
+    hv = out.get("hbm_view") or {}
+    by = hv.get("algorithmic_bytes")
+    if not by:
+        return out
+    ai, ridge = flops / by, out["peak"] * 1e12 / (pk["hbm_gbs"] * 1e9)
+    out["arithmetic_intensity_flop_per_byte"] = round(ai, 1)
+    out["ridge_flop_per_byte"] = round(ridge, 1)
+    if ai < ridge:
+        out["tensor_view"] = {"achieved": out["achieved"], "peak": out["peak"], "unit": out["unit"], "frac": out["frac"],
+                              "executed_tflops": out.get("executed_tflops"), "executed_frac": out.get("executed_frac"),
+                              "peak_source": out.get("peak_source")}
+        out.update({"bound": "hbm", "achieved": hv["achieved_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hv["frac"],
+                    "peak_source": "HBM copy bandwidth of MEASURED_PEAKS.json (burst: the launch is timed alone)",
+                    "bound_rule": "arithmetic intensity below the ridge point: the memory roof is the lower roof"})
+    else:
+        out["bound_rule"] = "arithmetic intensity above the ridge point: the tensor roof is the lower roof"
     return out
 
 

@@ -84,7 +84,7 @@ SIGNATURES: Dict[str, list] = {
     "gnb_zero_block": [_p, _i64, _i64, _i32, _p],
     "gnb_wgrad_set_debug": [_i32],
     "gnb_edgeconv_fused_fwd_f16": [_p, _i64, _i32, _p, _p, _i64, _p, _p, _i64, _p, _i32, _i32, _p, _i64, _p, _p, _i64, _p, _i64,
-                                   _p, _p],
+                                   _p, _i32, _p],
     "gnb_edge_dz_prep": [_p, _i64, _p, _i64, _i32, _p, _p, _p, _p, _p],
     "gnb_linear_bwd_weight_f16_masked": [_p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _p, _p, _p],
     "gnb_edge_hidden_dgrad_scatter_f16_masked": [_p, _p, _i32, _p, _i64, _p, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _p,

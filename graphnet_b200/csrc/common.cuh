@@ -85,6 +85,17 @@ __device__ __forceinline__ float gnb_round_tf32(float v) {
     return __uint_as_float(r);
 }
 
+// Lane-interleaved order of a 64-column block of PQ for the fused EdgeConv forward (gnb_edgeconv_fused_fwd_f16, pq_layout 1):
+// stored 16-byte piece j (j < 8) holds hidden units 8 j .. 8 j + 3, piece 8 + j holds units 8 j + 4 .. 8 j + 7.
+__host__ __device__ __forceinline__ int gnb_pq_unit_of_stored(int s) { return s < 32 ? 8 * (s >> 2) + (s & 3) : 8 * ((s - 32) >> 2) + 4 + (s & 3); }
+__host__ __device__ __forceinline__ int gnb_pq_stored_of_unit(int q) { return 4 * (q >> 3) + (q & 3) + 32 * ((q >> 2) & 1); }
+// row r of [P half | Q half] (each hid rows): the same row with the permutation applied inside every FULL 64-row block of its half
+__host__ __device__ __forceinline__ int gnb_pq_map_row(int r, int hid, bool to_unit) {
+    const int half = r >= hid ? hid : 0, rr = r - half, blk = rr & ~63;
+    if (blk + 64 > hid) return r;
+    return half + blk + (to_unit ? gnb_pq_unit_of_stored(rr & 63) : gnb_pq_stored_of_unit(rr & 63));
+}
+
 // aggregation codes
 enum : int { GNB_AGGR_ADD = 0, GNB_AGGR_MEAN = 1, GNB_AGGR_MAX = 2 };
 

@@ -74,7 +74,7 @@ int gnb_edge_hidden_dgrad_scatter_f16_masked(const void*, const uint32_t*, int32
                                              const uint32_t*, void*);
 int gnb_edgeconv_fused_fwd_f16(const float*, int64_t, int32_t, const int32_t*, const int32_t*, int64_t, const void*, const void*,
                                int64_t, const float*, int32_t, int32_t, float*, int64_t, uint32_t*, void*, int64_t, uint8_t*, int64_t,
-                               const uint32_t*, void*);
+                               const uint32_t*, int32_t, void*);
 int gnb_edge_dz_prep(const float*, int64_t, const uint32_t*, int64_t, int32_t, const uint32_t*, void*, uint32_t*, float*, void*);
 int gnb_to_f16_planes(const float*, int64_t, int64_t, int32_t, void*, void*, int64_t, int32_t, int32_t, void*);
 int gnb_absmax_bits(const float*, int64_t, int64_t, int32_t, int32_t, uint32_t*, void*);
@@ -176,27 +176,31 @@ __device__ __forceinline__ void copy_pad_elem(int64_t t, const float* __restrict
 }
 // dst[c, r] = maybe_round(src[r, c]) (zero padded to dst_cols): W^T for the backward-data GEMM
 __device__ __forceinline__ void transpose_pad_elem(int64_t t, const float* __restrict__ src, int64_t lds, int rows, int cols,
-                                                   float* __restrict__ dst, int64_t ldd, int dst_cols, int rnd) {
+                                                   float* __restrict__ dst, int64_t ldd, int dst_cols, int rnd, int perm = 0) {
     if (t >= (int64_t)cols * dst_cols) return;
     const int c = (int)(t / dst_cols);          // dst row = src column
     const int r = (int)(t - (int64_t)c * dst_cols);
-    float v = r < rows ? src[(int64_t)r * lds + c] : 0.f;
+    // perm: the source rows (2 hid rows of a hoisted Linear's packed weight) are stored lane-interleaved; the transpose is natural
+    float v = r < rows ? src[(int64_t)(perm ? gnb_pq_map_row(r, rows / 2, false) : r) * lds + c] : 0.f;
     dst[(int64_t)c * ldd + r] = rnd ? gnb_round_tf32(v) : v;
 }
 // First Linear of an EdgeConv MLP hoisted to nodes: W1 = [Wa | Wb] ([H, 2C]) -> Wcat = [Wa - Wb ; Wb] ([2H, ld]),
 // bcat = [b1 ; 0]
 __device__ __forceinline__ void pack_conv_elem(int64_t t, const float* __restrict__ w1, const float* __restrict__ b1, int h, int c,
                                                float* __restrict__ wcat, int64_t ld, float* __restrict__ bcat, int rnd,
-                                               float* __restrict__ wlo) {
+                                               float* __restrict__ wlo, int perm = 0) {
     if (t >= 2 * (int64_t)h * ld) return;
-    const int r = (int)(t / ld);
-    const int col = (int)(t - (int64_t)r * ld);
+    const int rd = (int)(t / ld);               // row of Wcat as stored
+    const int col = (int)(t - (int64_t)rd * ld);
+    // perm: the output columns of PQ = x Wcat^T (= rows of Wcat) in the lane-interleaved order the fused EdgeConv forward
+    // gathers best (gnb_edgeconv_fused_fwd_f16, pq_layout 1); the hidden units of an MLP have no intrinsic order
+    const int r = perm ? gnb_pq_map_row(rd, h, true) : rd;        // the hidden unit (natural row) stored there
     float v = 0.f;
     if (col < c) v = r < h ? w1[(int64_t)r * 2 * c + col] - w1[(int64_t)r * 2 * c + c + col] : w1[(int64_t)(r - h) * 2 * c + c + col];
     const float hi = rnd ? gnb_round_tf32(v) : v;
-    wcat[(int64_t)r * ld + col] = hi;
-    if (wlo != nullptr) store_corr(wlo + (int64_t)r * ld, col, v, hi);
-    if (col == 0) bcat[r] = r < h ? b1[r] : 0.f;
+    wcat[(int64_t)rd * ld + col] = hi;
+    if (wlo != nullptr) store_corr(wlo + (int64_t)rd * ld, col, v, hi);
+    if (col == 0) bcat[rd] = r < h ? b1[r] : 0.f;
 }
 // one or two 16-bit planes of a weight matrix (v ~ p0 + p1), optionally transposed, zero padded to dst_cols
 // (same arithmetic as gnb_to_f16_planes / gnb_to_bf16_planes in gemm_tc.cu)
@@ -230,10 +234,10 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const __grid_constant__ 
             copy_pad_elem(t, jb.src, jb.lds, jb.rows, jb.cols, (float*)jb.dst, jb.ldd, jb.dst_cols, jb.flags & 1, (float*)jb.dst2);
             break;
         case JOB_TRANSPOSE_PAD:
-            transpose_pad_elem(t, jb.src, jb.lds, jb.rows, jb.cols, (float*)jb.dst, jb.ldd, jb.dst_cols, jb.flags & 1);
+            transpose_pad_elem(t, jb.src, jb.lds, jb.rows, jb.cols, (float*)jb.dst, jb.ldd, jb.dst_cols, jb.flags & 1, (jb.flags >> 3) & 1);
             break;
         case JOB_PACK_CONV:
-            pack_conv_elem(t, jb.src, jb.src2, jb.rows, jb.cols, (float*)jb.dst, jb.ldd, (float*)jb.dst2, jb.flags & 1, (float*)jb.dst3);
+            pack_conv_elem(t, jb.src, jb.src2, jb.rows, jb.cols, (float*)jb.dst, jb.ldd, (float*)jb.dst2, jb.flags & 1, (float*)jb.dst3, (jb.flags >> 3) & 1);
             break;
         default:
             if (jb.flags & 4)
@@ -293,7 +297,7 @@ struct Arena {
 };
 
 struct ConvBuf { float *wcat, *wcat_lo, *w2p_lo, *bcat, *w2p, *pq, *h, *m, *y; float *wcat_t, *w2t;   // (training, tensor-core modes: Wcat^T, W2^T for the data-gradient GEMMs)
-                 int32_t *nbr, *deg; uint32_t *mask, *hmask; bool nodz, fused; int cin, cin_ld, kld, hid, hld, cout, mld;
+                 int32_t *nbr, *deg; uint32_t *mask, *hmask; bool nodz, fused, pq_perm; int cin, cin_ld, kld, hid, hld, cout, mld;
                  // bf16 modes: h planes [n * 9, hid], W2 planes [cout, hld64], W2^T planes [hid, cld64]
                  __nv_bfloat16 *hb[2], *w2b[2], *w2tb[2]; int hld64, cld64; };
 struct DenseBuf { float *wp, *wp_lo, *z; int k_total, kld, n_out; float* wt; float* wt_part[GNB_MAX_LAYERS + 1]; };   // wt: W^T (per K-split part for the first post-processing layer)
@@ -383,6 +387,10 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
         // (inference: the fused kernel wins with two planes -- 5.55 against 6.27 ms per 1024 events -- and loses with one, where
         // the two-kernel forward moves half the bytes: 4.67 against 4.31 ms)
         b.fused = p.mixed && !(c.flags & 8) && b.cout <= 256 && wl == 9 && b.hid <= 512 && (training ? b.nodz : c.precision == 5);
+        // the fused forward is the only reader of this layer's PQ: its columns are stored in the order the builders gather best
+        // (GNB_PQ_NATURAL=1 keeps the natural order: timing comparisons)
+        static const bool pq_natural = getenv("GNB_PQ_NATURAL") != nullptr && atoi(getenv("GNB_PQ_NATURAL")) != 0;
+        b.pq_perm = b.fused && !pq_natural;
         for (int pl = 0; pl < 2; ++pl) {
             const bool on = pl < p.bf;
             const bool h_on = on && !(b.fused && (pl == 1 || !training));      // fused forward: only plane 0, only for the backward pass
@@ -536,9 +544,10 @@ struct Exec {
         job_add(JOB_COPY_PAD, src, nullptr, dst, lo, nullptr, lds, ldd, (int)rows, cols, dst_cols, round ? 1 : 0, rows * dst_cols, rc);
     }
     // dst[k, nld] = (wp + off)[n_out, k]^T for lin_bwd_data
-    void job_transpose(const float* wp, int64_t ldw, int off, int k, int n_out, float* dst, int* rc) {
+    void job_transpose(const float* wp, int64_t ldw, int off, int k, int n_out, float* dst, int* rc, bool perm = false) {
         const int nld = (int)up(n_out, 32);
-        job_add(JOB_TRANSPOSE_PAD, wp + off, nullptr, dst, nullptr, nullptr, ldw, nld, n_out, k, nld, tf32 ? 1 : 0, (int64_t)k * nld, rc);
+        job_add(JOB_TRANSPOSE_PAD, wp + off, nullptr, dst, nullptr, nullptr, ldw, nld, n_out, k, nld, (tf32 ? 1 : 0) | (perm ? 8 : 0),
+                (int64_t)k * nld, rc);
     }
     void job_planes(const float* src, int64_t lds, int rows, int cols, void* p0, void* p1, int64_t ldd, int dst_cols, bool transpose,
                     bool bf16, int* rc) {
@@ -633,7 +642,7 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
         for (int l = 0; l < c.n_conv; ++l, pj += 4) {
             ConvBuf& b = p.conv[l];
             const float *w1 = params[pj], *b1 = params[pj + 1], *w2 = params[pj + 2];
-            e.job_add(JOB_PACK_CONV, w1, b1, b.wcat, b.bcat, b.wcat_lo, 0, b.kld, b.hid, b.cin, 0, e.tf32 ? 1 : 0, 2 * (int64_t)b.hid * b.kld, &rc);
+            e.job_add(JOB_PACK_CONV, w1, b1, b.wcat, b.bcat, b.wcat_lo, 0, b.kld, b.hid, b.cin, 0, (e.tf32 ? 1 : 0) | (b.pq_perm ? 8 : 0), 2 * (int64_t)b.hid * b.kld, &rc);
             if (!p.bf) e.job_copy_pad(w2, b.hid, b.cout, b.hid, b.w2p, b.hld, b.hld, e.tf32, b.w2p_lo, &rc);
             if (p.bf) {
                 const bool bf16 = !p.mixed;
@@ -669,7 +678,7 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
         if ((training & 1) && e.tf32) {
             for (int l = 0; l < c.n_conv; ++l) {
                 ConvBuf& b = p.conv[l];
-                if (b.wcat_t != nullptr) e.job_transpose(b.wcat, b.kld, 0, b.cin_ld, 2 * b.hid, b.wcat_t, &rc);
+                if (b.wcat_t != nullptr) e.job_transpose(b.wcat, b.kld, 0, b.cin_ld, 2 * b.hid, b.wcat_t, &rc, b.pq_perm);
                 if (b.w2t != nullptr) e.job_transpose(b.w2p, b.hld, 0, b.hid, b.cout, b.w2t, &rc);
             }
             for (int q = 1; q < p.post_parts; ++q)
@@ -717,7 +726,8 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
                     EX(gnb_edgeconv_fused_fwd_f16(b.pq, 2 * b.hid, b.hid, nbr, deg, n, b.w2b[0], b.w2b[1], b.hld64, b2, b.cout,
                                                   e.fround ? 1 : 0, b.y, b.cout, (dbgf & 4) ? nullptr : b.mask,
                                                   (training && !(dbgf & 1)) ? (void*)b.hb[0] : nullptr, b.hid,
-                                                  (training && !(dbgf & 2)) ? (uint8_t*)b.hmask : nullptr, (int64_t)b.mld * 4, hs, stream));
+                                                  (training && !(dbgf & 2)) ? (uint8_t*)b.hmask : nullptr, (int64_t)b.mld * 4, hs,
+                                                  b.pq_perm ? 1 : 0, stream));
                 } else {
                     EX(gnb_edge_hidden_fwd_f16(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, b.hb[0], b.hb[1], b.hid, b.hmask, b.mld, hs, stream));
                     EX(gnb_edge_linear_agg_fwd_f16(b.hb[0], b.hb[1], b.hid, b.hid, b.w2b[0], b.w2b[1], b.hld64, b2, deg, n, b.cout,

@@ -1749,7 +1749,8 @@ gemm_f16_pair_scatter_build_kernel(const __grid_constant__ CUtensorMap tm_w0, co
 constexpr int FU_THREADS = 448, FU_NBW = 8, FU_WSTAGES = 3, FU_BSLOTS = 3;
 struct FuseSrc { const float* pq; int64_t ldpq; const int* nbr; const int* deg; int64_t n_nodes; int hid;
                  __half* h0_out; int64_t ldh; unsigned char* hbytes; int64_t ldhb; const unsigned* scale_bits;
-                 int dbg; };      // profiling hook (gnb_linear_set_debug; results are garbage): bit 3 no P gathers, bit 4 no Q gathers
+                 int dbg;         // profiling hook (gnb_linear_set_debug; results are garbage): bit 3 no P gathers, bit 4 no Q gathers
+                 int pq_perm; };  // 1: every full 64-column block of the P and of the Q half is stored lane-interleaved (below)
 
 template <int NP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FU_THREADS, 1)
@@ -1795,6 +1796,9 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
 
     if (warp == 0) {
         // ---- TMA producer (both CTAs): own 128 weight rows, every plane ---------------------------------------------------
+        // (Measured and not kept: this warp pulling the rows of the cluster's NEXT tile into L2 with one
+        // cp.async.bulk.prefetch.L2 per row, a whole tile time ahead of the builders' gathers: 1453 -> 1435 us per step, within
+        // the box-to-box spread -- first touches from DRAM are not what the builders wait for.)
         uint32_t it = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
             for (int kb = 0; kb < total_kb; ++kb, ++it) {
@@ -1860,7 +1864,14 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
         const float scale = gnb_pow2_scale(*fs.scale_bits).x;
         const int hid = fs.hid;
         const uint32_t ld16 = (uint32_t)(fs.ldpq >> 2);                         // PQ row pitch in 16-byte units
-        const uint32_t p16 = 2u * (uint32_t)j, q16 = (uint32_t)(hid >> 2) + 2u * (uint32_t)j;
+        const uint32_t q16 = (uint32_t)(hid >> 2);
+        // 16-byte pieces of the lane's 8 channels inside a K block's 256-byte row segment. Natural layout: pieces 2 j and 2 j + 1
+        // -- a warp-wide load then touches every other 16 bytes of 256, i.e. BOTH lines of every row it covers (and three for
+        // the Q half, which starts 64 bytes into a line when hid = 336), and the L1 data pipe is this kernel's busiest unit.
+        // Lane-interleaved layout (FuseSrc::pq_perm: the PQ GEMM's weight rows are packed in that order, the hidden units of an
+        // MLP have no intrinsic order): piece j holds channels 8 j .. 8 j + 3 and piece 8 + j channels 8 j + 4 .. 8 j + 7, so
+        // the eight lanes of a row read 128 contiguous bytes per load: 72 instead of 112 L1 wavefronts per warp and K block.
+        const uint32_t pcA_full = fs.pq_perm ? (uint32_t)j : 2u * (uint32_t)j, pcB_full = fs.pq_perm ? 8u + (uint32_t)j : 2u * (uint32_t)j + 1u;
         const float4* pq4 = reinterpret_cast<const float4*>(fs.pq);
         uint4* h0v = reinterpret_cast<uint4*>(fs.h0_out);
         const uint32_t ldh16 = (uint32_t)(fs.ldh >> 3), ldhb = (uint32_t)fs.ldhb;
@@ -1938,7 +1949,7 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const bool v = src_n[u] >= 0 && sr[u] < dg_n[u];
-                po[u] = (v ? (uint32_t)(node0 + fr[u]) : 0u) * ld16 + p16;
+                po[u] = (v ? (uint32_t)(node0 + fr[u]) : 0u) * ld16;
                 qo[u] = (v ? (uint32_t)src_n[u] : 0u) * ld16 + q16;
                 sc[u] = v ? scale : 0.f;
                 const uint32_t grow = (uint32_t)(node0 * AGG_W) + (uint32_t)(rs + 32 * u);
@@ -1965,18 +1976,20 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
             float4 pa[2][2], qa[2][2], pb[2][2], qb[2][2];
             // (chunks beyond hid -- only in the last K block -- gather the K block 0 columns instead and are zeroed by the scale)
             auto gather = [&](int kb, int u0, float4 (&pv)[2][2], float4 (&qv)[2][2]) {
-                const uint32_t koff = (kb * 64 + j * 8 < hid) ? (uint32_t)kb * 16u : 0u;
+                const bool on = kb * 64 + j * 8 < hid, full = kb * 64 + 64 <= hid;
+                const uint32_t koff = on ? (uint32_t)kb * 16u : 0u;
+                const uint32_t pcA = !on ? 0u : (full ? pcA_full : 2u * (uint32_t)j), pcB = !on ? 0u : (full ? pcB_full : 2u * (uint32_t)j + 1u);
 #pragma unroll
                 for (int uu = 0; uu < 2; ++uu) {
                     const float4* pp = pq4 + (po[u0 + uu] + koff);
                     const float4* qp = pq4 + (qo[u0 + uu] + koff);
 #ifdef GNB_FUSED_ROLE_SWITCHES      // timing experiments (scripts/r02/fused_roles.py): bit 3 no P gathers, bit 4 no Q gathers
                     const float4 z = make_float4(1.f, 1.f, 1.f, 1.f);
-                    if (fs.dbg & 8) { pv[uu][0] = z; pv[uu][1] = z; } else { pv[uu][0] = __ldg(pp); pv[uu][1] = __ldg(pp + 1); }
-                    if (fs.dbg & 16) { qv[uu][0] = z; qv[uu][1] = z; } else { qv[uu][0] = __ldg(qp); qv[uu][1] = __ldg(qp + 1); }
+                    if (fs.dbg & 8) { pv[uu][0] = z; pv[uu][1] = z; } else { pv[uu][0] = __ldg(pp + pcA); pv[uu][1] = __ldg(pp + pcB); }
+                    if (fs.dbg & 16) { qv[uu][0] = z; qv[uu][1] = z; } else { qv[uu][0] = __ldg(qp + pcA); qv[uu][1] = __ldg(qp + pcB); }
 #else
-                    pv[uu][0] = __ldg(pp); pv[uu][1] = __ldg(pp + 1);
-                    qv[uu][0] = __ldg(qp); qv[uu][1] = __ldg(qp + 1);
+                    pv[uu][0] = __ldg(pp + pcA); pv[uu][1] = __ldg(pp + pcB);
+                    qv[uu][0] = __ldg(qp + pcA); qv[uu][1] = __ldg(qp + pcB);
 #endif
                 }
             };
@@ -2827,11 +2840,15 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_f16_masked(const void* g16, const u
 // h never touches HBM on the forward path. Training side outputs (both may be NULL): h0_out = fp16(h * 2^s) [9 n, ldh] (plane 0,
 // the weight gradient's x operand) and hbytes [ceil(n / 14) * 126, ldhb] = bits of h > 0, one byte per 8 channels (bit c % 8 of
 // byte c / 8). *scale_bits >= bits of max h (absmax of PQ with shift 1). n_out <= 256, hid % 8 == 0, hid <= 512.
+// pq_layout 1: every full 64-column block of the P half and of the Q half of pq is stored lane-interleaved -- stored column s of
+// a block holds hidden unit gnb_pq_unit_of_stored(s) (common.cuh) -- which halves the L1 wavefronts of the builders' gathers;
+// the caller packs the rows of the hoisted Linear's weight in that order (dynedge_exec.cu). Outputs are in natural order.
 GNB_EXPORT int gnb_edgeconv_fused_fwd_f16(const float* pq, int64_t ldpq, int32_t hid, const int32_t* nbr, const int32_t* deg,
                                           int64_t n, const void* w0, const void* w1, int64_t ldw, const float* bias,
                                           int32_t n_out, int32_t round_out, float* y, int64_t ldy, uint32_t* maskbits,
                                           void* h0_out, int64_t ldh, uint8_t* hbytes, int64_t ldhb, const uint32_t* scale_bits,
-                                          void* stream) {
+                                          int32_t pq_layout, void* stream) {
+    if (pq_layout < 0 || pq_layout > 1) return GNB_ERR_ARG;
     if (n < 0 || n_out < 1 || n_out > 256 || hid < 8 || hid > 512 || (hid & 7) || pq == nullptr || nbr == nullptr || deg == nullptr ||
         w0 == nullptr || y == nullptr || scale_bits == nullptr)
         return GNB_ERR_ARG;
@@ -2851,7 +2868,7 @@ GNB_EXPORT int gnb_edgeconv_fused_fwd_f16(const float* pq, int64_t ldpq, int32_t
     int clusters = g_num_sms / 2;
     if (clusters > tiles) clusters = tiles;
     if (clusters < 1) clusters = 1;
-    FuseSrc fs{pq, ldpq, nbr, deg, n, hid, (__half*)h0_out, ldh, hbytes, ldhb, scale_bits, g_linear_dbg};
+    FuseSrc fs{pq, ldpq, nbr, deg, n, hid, (__half*)h0_out, ldh, hbytes, ldhb, scale_bits, g_linear_dbg, pq_layout};
     const uint32_t smem = 1024 + (uint32_t)(FU_WSTAGES + FU_BSLOTS) * planes * TC_TILE_BYTES + 512;
     const int last_ksteps = (hid - 64 * (kblocks - 1) + 15) / 16;
     if (planes == 2)

@@ -287,11 +287,14 @@ int gnb_edge_hidden_dgrad_scatter_f16(const void* dz, int64_t lddz, int32_t c_ou
  * h = relu(P_i + Q_j) * 2^s (fp16 plane 0, and plane 1 = remainder when w1 != NULL) in shared memory from PQ [n, 2 hid], so h
  * never crosses HBM on the forward path. y / maskbits as gnb_edge_linear_agg_fwd_f16. Training side outputs (may be NULL):
  * h0_out [9 n, ldh] = plane 0 of h (x operand of the weight gradient), hbytes [ceil(n / 14) * 126, ldhb] = bits of h > 0,
- * byte c / 8 bit c % 8 (= row-major words; flags 0x800 of gnb_edge_hidden_dgrad_scatter_f16_masked). n_out <= 256, hid % 8 == 0. */
+ * byte c / 8 bit c % 8 (= row-major words; flags 0x800 of gnb_edge_hidden_dgrad_scatter_f16_masked). n_out <= 256, hid % 8 == 0.
+ * pq_layout: 0 = natural column order of the P and Q halves; 1 = every full 64-column block of each half lane-interleaved
+ * (stored 16-byte piece j < 8 holds hidden units 8 j .. 8 j + 3, piece 8 + j units 8 j + 4 .. 8 j + 7: the eight lanes of a row
+ * then gather 128 contiguous bytes per load; the caller packs the hoisted Linear's weight rows in that order). Outputs natural. */
 int gnb_edgeconv_fused_fwd_f16(const float* pq, int64_t ldpq, int32_t hid, const int32_t* nbr, const int32_t* deg, int64_t n,
                                const void* w0, const void* w1, int64_t ldw, const float* bias, int32_t n_out, int32_t round_out,
                                float* y, int64_t ldy, uint32_t* maskbits, void* h0_out, int64_t ldh, uint8_t* hbytes,
-                               int64_t ldhb, const uint32_t* scale_bits, void* stream);
+                               int64_t ldhb, const uint32_t* scale_bits, int32_t pq_layout, void* stream);
 /* The backward of the aggregating Linear WITHOUT a stored dz (fp16-plane modes): dz[(i, s), :] = g[i, :] * bit(i, s, :) is a
  * 9-fold redundant function of the node-level gradient and the ReLU bits, so the two GEMMs expand it in shared memory (builder
  * warps write the tensor-core operand tile) instead of reading a stored [9 n, c_out] tensor (autograd of PyG EdgeConv's

@@ -555,10 +555,23 @@ def test_dgrad_scatter_f16_masked_bit_exact(ops, hdim, c_out, sizes):
     assert torch.equal(dbias.cpu().double(), dp_ref.sum(0))
 
 
+def _pq_lane_interleaved(pq, hid):
+    """pq_layout 1 of gnb_edgeconv_fused_fwd_f16: inside every full 64-column block of the P and of the Q half, stored column s
+    holds hidden unit 8 (s / 4) + s % 4 (s < 32) or 8 ((s - 32) / 4) + 4 + s % 4 (include/graphnet_b200.h)."""
+    idx = torch.arange(2 * hid)
+    s = torch.arange(64)
+    unit = torch.where(s < 32, 8 * (s // 4) + s % 4, 8 * ((s - 32) // 4) + 4 + s % 4)
+    for half in (0, hid):
+        for blk in range(0, hid - 63, 64):
+            idx[half + blk: half + blk + 64] = half + blk + unit
+    return pq[:, idx].contiguous()
+
+
+@pytest.mark.parametrize("layout", [0, 1])
 @pytest.mark.parametrize("np_", [1, 2])
 @pytest.mark.parametrize("hid,n_out,sizes", [(336, 256, [1, 2, 5, 9, 10, 64, 130, 12, 300, 3, 700]), (128, 256, [400, 900, 14, 15]),
                                              (40, 104, [77, 5, 230]), (336, 256, [3000, 2500]), (128, 256, [14 * 5])])
-def test_edgeconv_fused_fwd_f16_matches_the_two_kernel_forward(ops, np_, hid, n_out, sizes):
+def test_edgeconv_fused_fwd_f16_matches_the_two_kernel_forward(ops, np_, hid, n_out, sizes, layout):
     """gather + hidden layer + second Linear + aggregation in one kernel == hidden-layer kernel followed by the aggregating GEMM:
     the two run the same products on the same fp16 planes, so y agrees to fp32 summation order of the TMEM accumulators (exact
     on these integer-valued operands) and plane 0 / the ReLU bits / the mask words agree bit for bit."""
@@ -584,7 +597,9 @@ def test_edgeconv_fused_fwd_f16_matches_the_two_kernel_forward(ops, np_, hid, n_
     m_ref = torch.zeros(ntile * n_out * 4, dtype=torch.int32, device="cuda")
     ops._call("gnb_edge_linear_agg_fwd_f16", ops._ptr(h0), ops._ptr(h1), hid, hid, ops._ptr(w0), ops._ptr(w1), kw, ops._ptr(bc),
               ops._ptr(graph.deg), n, n_out, 0, ops._ptr(y_ref), n_out, ops._ptr(m_ref), ops._ptr(word), ops._stream())
-    # fused
+    # fused (layout 1: the same PQ with its columns stored lane-interleaved; every output stays in natural order)
+    if layout == 1:
+        pqc = _pq_lane_interleaved(pq, hid).cuda()
     y = torch.empty(n, n_out, device="cuda")
     m = torch.zeros(ntile * n_out * 4, dtype=torch.int32, device="cuda")
     h0f = torch.full((n * 9, hid), 5.0, dtype=torch.float16, device="cuda")
@@ -594,7 +609,7 @@ def test_edgeconv_fused_fwd_f16_matches_the_two_kernel_forward(ops, np_, hid, n_
     hb = hb_all[: ntile * 126 * mld * 4].view(ntile * 126, mld * 4)
     ops._call("gnb_edgeconv_fused_fwd_f16", ops._ptr(pqc), 2 * hid, hid, ops._ptr(graph.nbr), ops._ptr(graph.deg), n, ops._ptr(w0),
               ops._ptr(w1), kw, ops._ptr(bc), n_out, 0, ops._ptr(y), n_out, ops._ptr(m), ops._ptr(h0f), hid, ops._ptr(hb), mld * 4,
-              ops._ptr(word), ops._stream())
+              ops._ptr(word), layout, ops._stream())
     torch.cuda.synchronize()
     assert torch.equal(hb_all[ntile * 126 * mld * 4:], guard)
     assert torch.equal(h0f, h0)
@@ -607,7 +622,7 @@ def test_edgeconv_fused_fwd_f16_matches_the_two_kernel_forward(ops, np_, hid, n_
     y2 = torch.empty(n, n_out, device="cuda")
     ops._call("gnb_edgeconv_fused_fwd_f16", ops._ptr(pqc), 2 * hid, hid, ops._ptr(graph.nbr), ops._ptr(graph.deg), n, ops._ptr(w0),
               ops._ptr(w1), kw, ops._ptr(bc), n_out, 0, ops._ptr(y2), n_out, ops._ptr(None), ops._ptr(None), hid, ops._ptr(None), mld * 4,
-              ops._ptr(word), ops._stream())
+              ops._ptr(word), layout, ops._stream())
     torch.cuda.synchronize()
     assert torch.equal(y2, y_ref)
 
