@@ -1973,41 +1973,47 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
                 if (r2 < AGG_ROWS && on2 && bok) okm |= 512u;
             }
             if (t + num_clusters < num_tiles) fetch_rows(t + num_clusters);
-            float4 pa[2][2], qa[2][2], pb[2][2], qb[2][2];
+            // Gather registers: one (P, Q) pair of 32-byte pieces per row, each refilled for K block kb + 1 the moment its row of
+            // K block kb is built, so every load has three row builds + the hand-off of lead. (Until the last session the rows
+            // were refilled in pairs: the pair refilled at the top of the loop had half an iteration of lead, ~700 cycles against
+            // an L2 latency of ~1500 under load, and 34 % of the builders' time sat on its first use. Little's law on the numbers
+            // of profiles/r02/ak_gemm_f16_pair_agg_fused.ncu-rep: <= 64 KB of gathers in flight per SM / ~1500 cycles = the
+            // ~20 B per clock and SM the kernel moves -- the builders are bound by bytes in flight, not by L1 wavefronts (the
+            // lane-interleaved layout changed nothing) nor by first touches from DRAM (an L2 prefetch changed nothing).)
+            // (Measured and not kept: gathering K block 0 of the cluster's NEXT tile under the last K block of this one, with the
+            // tail row in registers of its own -- 8 more live registers across the K loop at the 128-register cap: 394 -> 487 us.)
+            float4 pr[4][2], qr[4][2];
             // (chunks beyond hid -- only in the last K block -- gather the K block 0 columns instead and are zeroed by the scale)
-            auto gather = [&](int kb, int u0, float4 (&pv)[2][2], float4 (&qv)[2][2]) {
+            // column offsets (16-byte units) of the lane's two pieces in K block kb: computed once per K block, not per row
+            auto piece_offsets = [&](int kb, uint32_t& cA, uint32_t& cB) {
                 const bool on = kb * 64 + j * 8 < hid, full = kb * 64 + 64 <= hid;
                 const uint32_t koff = on ? (uint32_t)kb * 16u : 0u;
-                const uint32_t pcA = !on ? 0u : (full ? pcA_full : 2u * (uint32_t)j), pcB = !on ? 0u : (full ? pcB_full : 2u * (uint32_t)j + 1u);
-#pragma unroll
-                for (int uu = 0; uu < 2; ++uu) {
-                    const float4* pp = pq4 + (po[u0 + uu] + koff);
-                    const float4* qp = pq4 + (qo[u0 + uu] + koff);
+                cA = koff + (!on ? 0u : (full ? pcA_full : 2u * (uint32_t)j));
+                cB = koff + (!on ? 0u : (full ? pcB_full : 2u * (uint32_t)j + 1u));
+            };
+            auto gather_row = [&](int u, uint32_t cA, uint32_t cB) {
+                // (32-bit sums first: one IMAD.WIDE per load; a 64-bit pointer + offset costs four instructions per load)
 #ifdef GNB_FUSED_ROLE_SWITCHES      // timing experiments (scripts/r02/fused_roles.py): bit 3 no P gathers, bit 4 no Q gathers
-                    const float4 z = make_float4(1.f, 1.f, 1.f, 1.f);
-                    if (fs.dbg & 8) { pv[uu][0] = z; pv[uu][1] = z; } else { pv[uu][0] = __ldg(pp + pcA); pv[uu][1] = __ldg(pp + pcB); }
-                    if (fs.dbg & 16) { qv[uu][0] = z; qv[uu][1] = z; } else { qv[uu][0] = __ldg(qp + pcA); qv[uu][1] = __ldg(qp + pcB); }
+                const float4 z = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (fs.dbg & 8) { pr[u][0] = z; pr[u][1] = z; } else { pr[u][0] = __ldg(pq4 + (po[u] + cA)); pr[u][1] = __ldg(pq4 + (po[u] + cB)); }
+                if (fs.dbg & 16) { qr[u][0] = z; qr[u][1] = z; } else { qr[u][0] = __ldg(pq4 + (qo[u] + cA)); qr[u][1] = __ldg(pq4 + (qo[u] + cB)); }
 #else
-                    pv[uu][0] = __ldg(pp + pcA); pv[uu][1] = __ldg(pp + pcB);
-                    qv[uu][0] = __ldg(qp + pcA); qv[uu][1] = __ldg(qp + pcB);
+                pr[u][0] = __ldg(pq4 + (po[u] + cA)); pr[u][1] = __ldg(pq4 + (po[u] + cB));
+                qr[u][0] = __ldg(pq4 + (qo[u] + cA)); qr[u][1] = __ldg(pq4 + (qo[u] + cB));
 #endif
-                }
             };
             auto gather_tail = [&]() {
-                pa[0][0] = __ldg(pq4 + po2); pa[0][1] = __ldg(pq4 + po2 + 1);
-                qa[0][0] = __ldg(pq4 + qo2); qa[0][1] = __ldg(pq4 + qo2 + 1);
+                pr[0][0] = __ldg(pq4 + po2); pr[0][1] = __ldg(pq4 + po2 + 1);
+                qr[0][0] = __ldg(pq4 + qo2); qr[0][1] = __ldg(pq4 + qo2 + 1);
             };
-            auto build = [&](int kb, int u0, const float4 (&pv)[2][2], const float4 (&qv)[2][2], uint32_t ba) {
-                const bool on = kb * 64 + j * 8 < hid;
+            auto build_one = [&](int kb, int u, uint32_t ba) {
+                const bool on = kb * 64 + j * 8 < hid;        // (loop-invariant per K block: hoisted by the compiler)
                 const uint32_t okk = on ? okm : 0u;
-#pragma unroll
-                for (int uu = 0; uu < 2; ++uu) {
-                    const int u = u0 + uu, r = rs + 32 * u;
-                    if (r < AGG_ROWS) {                   // (lane-dependent only for u = 3)
-                        const uint32_t off = (uint32_t)r * 128u + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4);
-                        build_row(pv[uu][0], pv[uu][1], qv[uu][0], qv[uu][1], on ? sc[u] : 0.f, ba + off, ho[u] + (uint32_t)kb * 8u,
-                                  bo[u] + (uint32_t)kb * 8u, (okk >> u) & 1u, (okk >> (4 + u)) & 1u);
-                    }
+                const int r = rs + 32 * u;
+                if (r < AGG_ROWS) {                   // (lane-dependent only for u = 3)
+                    const uint32_t off = (uint32_t)r * 128u + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4);
+                    build_row(pr[u][0], pr[u][1], qr[u][0], qr[u][1], on ? sc[u] : 0.f, ba + off, ho[u] + (uint32_t)kb * 8u,
+                              bo[u] + (uint32_t)kb * 8u, (okk >> u) & 1u, (okk >> (4 + u)) & 1u);
                 }
             };
             auto publish = [&](uint32_t sl) {
@@ -2016,18 +2022,29 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
                 if (lane == 0) tc::mbar_arrive_cluster_relaxed(&bfull[sl], 0);
                 __syncwarp();
             };
-            if (nfull > 0) gather(0, 0, pa, qa); else gather_tail();
+            if (nfull > 0) {
+                uint32_t cA, cB;
+                piece_offsets(0, cA, cB);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) gather_row(u, cA, cB);
+            } else {
+                gather_tail();
+            }
             for (int kb = 0; kb < nfull; ++kb, ++it) {
                 const uint32_t sl = it % FU_BSLOTS;
-                gather(kb, 2, pb, qb);
                 tc::mbar_wait(&bempty[sl], ((it / FU_BSLOTS) & 1) ^ 1);      // the MMAs of the slot's previous use completed
                 const uint32_t ba = tc::smem_u32(bring + sl * BSL);
-                build(kb, 0, pa, qa, ba);
-                if (kb + 1 < nfull) gather(kb + 1, 0, pa, qa);
-                else if (tail) gather_tail();
+                const bool more = kb + 1 < nfull;
+                uint32_t cA, cB;
+                piece_offsets(kb + 1, cA, cB);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    build_one(kb, u, ba);
+                    if (more) gather_row(u, cA, cB);
+                    else if (tail && u == 0) gather_tail();
+                }
                 // (an L2 prefetch of the NEXT tile's P / Q rows from here -- PQ is 213 MB per 79 k-node layer, larger than L2, so
                 // about half of a tile's first touches are DRAM reads -- made the launch 30 % slower: 1501 -> 1967 us per step)
-                build(kb, 2, pb, qb, ba);
                 publish(sl);
             }
             if (tail) {
@@ -2036,7 +2053,7 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
                 if (r2 < AGG_ROWS) {
                     const uint32_t ba = tc::smem_u32(bring + sl * BSL);
                     const uint32_t off = (uint32_t)r2 * 128u + (((uint32_t)j2 ^ ((uint32_t)r2 & 7u)) << 4);
-                    build_row(pa[0][0], pa[0][1], qa[0][0], qa[0][1], sc2, ba + off, ho2, bo2, (okm >> 8) & 1u, (okm >> 9) & 1u);
+                    build_row(pr[0][0], pr[0][1], qr[0][0], qr[0][1], sc2, ba + off, ho2, bo2, (okm >> 8) & 1u, (okm >> 9) & 1u);
                 }
                 publish(sl);
                 ++it;
