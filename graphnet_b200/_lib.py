@@ -89,6 +89,13 @@ SIGNATURES: Dict[str, list] = {
     "gnb_linear_bwd_weight_f16_masked": [_p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _p, _p, _p],
     "gnb_edge_hidden_dgrad_scatter_f16_masked": [_p, _p, _i32, _p, _i64, _p, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _p,
                                                  _i32, _p, _p],
+    "gnb_edge_slot_flag": [_p, _i64, _i32, _p, _p],
+    "gnb_edgeconv_fused_fwd_f16_w": [_p, _i64, _i32, _p, _p, _i64, _p, _p, _i64, _p, _i32, _i32, _p, _i64, _p, _p, _i64, _p, _i64,
+                                     _p, _i32, _p, _p],
+    "gnb_edge_dz_prep_w": [_p, _i64, _p, _i64, _i32, _p, _p, _p, _p, _p, _p],
+    "gnb_linear_bwd_weight_f16_masked_w": [_p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _p, _p, _p, _p],
+    "gnb_edge_hidden_dgrad_scatter_f16_masked_w": [_p, _p, _i32, _p, _i64, _p, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _p,
+                                                   _i32, _p, _p, _p],
     "gnb_linear_next_absmax": [_p, _i32],
     "gnb_to_f16_planes": [_p, _i64, _i64, _i32, _p, _p, _i64, _i32, _i32, _p],
 }

@@ -76,6 +76,18 @@ int gnb_edgeconv_fused_fwd_f16(const float*, int64_t, int32_t, const int32_t*, c
                                int64_t, const float*, int32_t, int32_t, float*, int64_t, uint32_t*, void*, int64_t, uint8_t*, int64_t,
                                const uint32_t*, int32_t, void*);
 int gnb_edge_dz_prep(const float*, int64_t, const uint32_t*, int64_t, int32_t, const uint32_t*, void*, uint32_t*, float*, void*);
+// the same four with the device-side layout switch (full9: *full9 == 0 selects the 8-slot layout; gnb_edge_slot_flag writes it)
+int gnb_edge_slot_flag(const int32_t*, int64_t, int32_t, int32_t*, void*);
+int gnb_linear_bwd_weight_f16_masked_w(const void*, const uint32_t*, const void*, int64_t, float*, int64_t, int64_t, int32_t, int32_t,
+                                       const uint32_t*, const uint32_t*, const int32_t*, void*);
+int gnb_edge_hidden_dgrad_scatter_f16_masked_w(const void*, const uint32_t*, int32_t, const void*, int64_t, const uint32_t*, int32_t,
+                                               int32_t, const int32_t*, int64_t, float*, int64_t, float*, int64_t, float*, int32_t,
+                                               const uint32_t*, const int32_t*, void*);
+int gnb_edgeconv_fused_fwd_f16_w(const float*, int64_t, int32_t, const int32_t*, const int32_t*, int64_t, const void*, const void*,
+                                 int64_t, const float*, int32_t, int32_t, float*, int64_t, uint32_t*, void*, int64_t, uint8_t*, int64_t,
+                                 const uint32_t*, int32_t, const int32_t*, void*);
+int gnb_edge_dz_prep_w(const float*, int64_t, const uint32_t*, int64_t, int32_t, const uint32_t*, void*, uint32_t*, float*,
+                       const int32_t*, void*);
 int gnb_to_f16_planes(const float*, int64_t, int64_t, int32_t, void*, void*, int64_t, int32_t, int32_t, void*);
 int gnb_absmax_bits(const float*, int64_t, int64_t, int32_t, int32_t, uint32_t*, void*);
 int gnb_edge_hidden_fwd_f16(const float*, int64_t, int32_t, const int32_t*, const int32_t*, int32_t, int64_t, void*, void*, int64_t,
@@ -297,7 +309,7 @@ struct Arena {
 };
 
 struct ConvBuf { float *wcat, *wcat_lo, *w2p_lo, *bcat, *w2p, *pq, *h, *m, *y; float *wcat_t, *w2t;   // (training, tensor-core modes: Wcat^T, W2^T for the data-gradient GEMMs)
-                 int32_t *nbr, *deg; uint32_t *mask, *hmask; bool nodz, fused, pq_perm; int cin, cin_ld, kld, hid, hld, cout, mld;
+                 int32_t *nbr, *deg; uint32_t *mask, *hmask; bool nodz, fused, pq_perm, slots8; int cin, cin_ld, kld, hid, hld, cout, mld;
                  // bf16 modes: h planes [n * 9, hid], W2 planes [cout, hld64], W2^T planes [hid, cld64]
                  __nv_bfloat16 *hb[2], *w2b[2], *w2tb[2]; int hld64, cld64; };
 struct DenseBuf { float *wp, *wp_lo, *z; int k_total, kld, n_out; float* wt; float* wt_part[GNB_MAX_LAYERS + 1]; };   // wt: W^T (per K-split part for the first post-processing layer)
@@ -319,6 +331,7 @@ struct Plan {
     bool mixed;                          // mode 5: dz / W2^T as one fp16 plane in the backward pass
     __nv_bfloat16* g16; uint32_t* rowmask;   // dz-free backward: fp16(g_y 2^s) [n, max_c] and row-major ReLU bits [tiles * 126, max_c / 32]
     uint32_t* scale_bits;                // mixed16: [2][GNB_MAX_LAYERS] fp32 bits of 2 max|PQ| (>= max h) and of max|g_y| per layer
+    int32_t* full9;                      // mixed16: [GNB_MAX_LAYERS] 1 = the layer's graph holds a node with k + 1 neighbours (9-slot layout), 0 = 8-slot layout
     int64_t bytes;
 };
 
@@ -345,6 +358,9 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
     p.g = a.get<float>(nseg * ng);
     p.x0 = a.get<float>(n * p.x0_ld);
     p.scale_bits = p.mixed ? a.get<uint32_t>(2 * GNB_MAX_LAYERS) : nullptr;
+    p.full9 = p.mixed ? a.get<int32_t>(GNB_MAX_LAYERS) : nullptr;
+    // edge-slot rows of a per-edge bit-mask buffer, whole tiles of either layout (14 x 9 or 16 x 8)
+    const int64_t tile_rows = ((n + 13) / 14 * 126 > (n + 15) / 16 * 128) ? (n + 13) / 14 * 126 : (n + 15) / 16 * 128;
     const int64_t max_w = w0 > p.width ? w0 : p.width;
     int max_h = 0, max_c = 0;
     for (int l = 0; l < c.n_conv; ++l) {
@@ -391,6 +407,10 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
         // (GNB_PQ_NATURAL=1 keeps the natural order: timing comparisons)
         static const bool pq_natural = getenv("GNB_PQ_NATURAL") != nullptr && atoi(getenv("GNB_PQ_NATURAL")) != 0;
         b.pq_perm = b.fused && !pq_natural;
+        // 8-slot layout of the layer's per-edge tensors when its graph holds no node with k + 1 neighbours (decided on the device per
+        // step: p.full9[l]); needs every per-edge kernel of the layer to know both layouts. flags bit 4 / GNB_SLOTS9=1: always 9 slots
+        static const bool slots9 = getenv("GNB_SLOTS9") != nullptr && atoi(getenv("GNB_SLOTS9")) != 0;
+        b.slots8 = b.fused && (!training || b.nodz) && !(c.flags & 16) && !slots9;
         for (int pl = 0; pl < 2; ++pl) {
             const bool on = pl < p.bf;
             const bool h_on = on && !(b.fused && (pl == 1 || !training));      // fused forward: only plane 0, only for the backward pass
@@ -406,7 +426,7 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
         // activation bits of h for the scattering data-gradient epilogue (whole 14-node tiles, mld words per slot row)
         b.mld = 4 * ((b.hid + 127) / 128);
         const bool scat = p.agg && training && b.hid <= 512 && n * 2 * b.hid < ((int64_t)1 << 31);
-        b.hmask = scat ? a.get<uint32_t>((n + 13) / 14 * 126 * (int64_t)b.mld) : nullptr;
+        b.hmask = scat ? a.get<uint32_t>(tile_rows * (int64_t)b.mld) : nullptr;
         if (p.bf && training && !scat) return GNB_ERR_UNSUPPORTED;
         b.y = a.get<float>(n * b.cout);
         b.nbr = (l + 1 < c.n_conv) ? a.get<int32_t>(n * p.width) : nullptr;
@@ -473,7 +493,7 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
         for (int pl = 0; pl < 2; ++pl)
             p.dzb[pl] = (pl < p.bf && !(p.mixed && pl == 1) && any_dz) ? a.get<__nv_bfloat16>(n * max_w * max_c) : nullptr;
         p.g16 = any_nodz ? a.get<__nv_bfloat16>(n * (int64_t)max_c) : nullptr;
-        p.rowmask = any_nodz ? a.get<uint32_t>((n + 13) / 14 * 126 * (int64_t)(max_c / 32)) : nullptr;
+        p.rowmask = any_nodz ? a.get<uint32_t>(tile_rows * (int64_t)(max_c / 32)) : nullptr;
         p.dpq = a.get<float>(n * 2 * max_h);
         p.dzq = a.get<float>(n * 2 * max_h);
         int64_t max_wp = 0, max_dense = 0;
@@ -723,11 +743,12 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
                 uint32_t* hs = p.scale_bits + l;          // written by the PQ GEMM's epilogue (gnb_linear_next_absmax above)
                 if (b.fused) {
                     static const int dbgf = getenv("GNB_FUSED_DBG") ? atoi(getenv("GNB_FUSED_DBG")) : 0;
-                    EX(gnb_edgeconv_fused_fwd_f16(b.pq, 2 * b.hid, b.hid, nbr, deg, n, b.w2b[0], b.w2b[1], b.hld64, b2, b.cout,
-                                                  e.fround ? 1 : 0, b.y, b.cout, (dbgf & 4) ? nullptr : b.mask,
-                                                  (training && !(dbgf & 1)) ? (void*)b.hb[0] : nullptr, b.hid,
-                                                  (training && !(dbgf & 2)) ? (uint8_t*)b.hmask : nullptr, (int64_t)b.mld * 4, hs,
-                                                  b.pq_perm ? 1 : 0, stream));
+                    if (b.slots8) EX(gnb_edge_slot_flag(deg, n, c.k, p.full9 + l, stream));
+                    EX(gnb_edgeconv_fused_fwd_f16_w(b.pq, 2 * b.hid, b.hid, nbr, deg, n, b.w2b[0], b.w2b[1], b.hld64, b2, b.cout,
+                                                    e.fround ? 1 : 0, b.y, b.cout, (dbgf & 4) ? nullptr : b.mask,
+                                                    (training && !(dbgf & 1)) ? (void*)b.hb[0] : nullptr, b.hid,
+                                                    (training && !(dbgf & 2)) ? (uint8_t*)b.hmask : nullptr, (int64_t)b.mld * 4, hs,
+                                                    b.pq_perm ? 1 : 0, b.slots8 ? p.full9 + l : nullptr, stream));
                 } else {
                     EX(gnb_edge_hidden_fwd_f16(b.pq, 2 * b.hid, b.hid, nbr, deg, wl, n, b.hb[0], b.hb[1], b.hid, b.hmask, b.mld, hs, stream));
                     EX(gnb_edge_linear_agg_fwd_f16(b.hb[0], b.hb[1], b.hid, b.hid, b.w2b[0], b.w2b[1], b.hld64, b2, deg, n, b.cout,
@@ -900,8 +921,9 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
             if (nodz) {
                 // dz = g * mask bit is never stored: both GEMMs expand it in shared memory from g_y and the mask words
                 // (one small pass writes fp16(g_y 2^s), the row-major bits and the bias gradient)
-                EX(gnb_edge_dz_prep(gy, b.cout, b.mask, n, b.cout, gs, p.g16, p.rowmask, gb2, stream));
-                EX(gnb_linear_bwd_weight_f16_masked(p.g16, p.rowmask, b.hb[0], b.hid, gw2, b.hid, n, b.cout, b.hid, gs, p.scale_bits + l, stream));
+                const int32_t* f9 = b.slots8 ? p.full9 + l : nullptr;          // written by the forward pass
+                EX(gnb_edge_dz_prep_w(gy, b.cout, b.mask, n, b.cout, gs, p.g16, p.rowmask, gb2, f9, stream));
+                EX(gnb_linear_bwd_weight_f16_masked_w(p.g16, p.rowmask, b.hb[0], b.hid, gw2, b.hid, n, b.cout, b.hid, gs, p.scale_bits + l, f9, stream));
             } else {
                 EX(gnb_edge_mask_bwd_colsum_f16(gy, b.cout, b.mask, n, b.cout, p.dzb[0], b.cout, gb2, gs, stream));
                 EX(gnb_linear_bwd_weight_f16(p.dzb[0], b.cout, b.hb[0], nullptr, b.hid, gw2, b.hid, rows, b.cout, b.hid, gs, p.scale_bits + l, stream));
@@ -920,10 +942,10 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
         if (p.bf) {
             EX(gnb_zero_block(p.dzq + b.hid, 2 * b.hid, n, b.hid, stream));
             if (p.mixed && nodz)
-                EX(gnb_edge_hidden_dgrad_scatter_f16_masked(p.g16, p.rowmask, b.cout, b.w2tb[0], b.cld64, b.hmask, b.mld, b.hid, nbr, n,
-                                                            p.dzq + b.hid, 2 * b.hid, p.dzq, 2 * b.hid, p.dbtmp,
-                                                            e.rnd | (b.fused ? GNB_FLAG_HMASK_ROWMAJOR : 0),
-                                                            p.scale_bits + GNB_MAX_LAYERS + l, stream));
+                EX(gnb_edge_hidden_dgrad_scatter_f16_masked_w(p.g16, p.rowmask, b.cout, b.w2tb[0], b.cld64, b.hmask, b.mld, b.hid, nbr, n,
+                                                              p.dzq + b.hid, 2 * b.hid, p.dzq, 2 * b.hid, p.dbtmp,
+                                                              e.rnd | (b.fused ? GNB_FLAG_HMASK_ROWMAJOR : 0),
+                                                              p.scale_bits + GNB_MAX_LAYERS + l, b.slots8 ? p.full9 + l : nullptr, stream));
             else if (p.mixed)
                 EX(gnb_edge_hidden_dgrad_scatter_f16(p.dzb[0], b.cout, b.cout, b.w2tb[0], b.cld64, b.hmask, b.mld, b.hid, nbr, n,
                                                      p.dzq + b.hid, 2 * b.hid, p.dzq, 2 * b.hid, p.dbtmp, e.rnd,

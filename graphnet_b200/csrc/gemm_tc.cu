@@ -103,28 +103,38 @@ struct ScatInfo { const int* nbr; const unsigned* hmask; int mask_ld; float* dq;
 // offsets `nbr * lddq` (floats; padding slots and slots beyond the tensor are redirected to the Q row of the sub-tile's
 // first node, where they add 0) and the warp builds `lastv`: bit f = "slot 8 of node f holds an edge" (the duplicate
 // quirk). The epilogue therefore runs no comparison / select on the offsets.
+// W = 8 (8-slot layout: 16 nodes x 8 slots per sub-tile, graphs without 9-neighbour nodes): the table keeps its pitch of 9, slot 8
+// is not part of the tile and lastv is 0. `rows` = 9 n in both layouts.
+template <int W = 9>
 __device__ __forceinline__ void scat_meta(const ScatInfo& sc, int64_t node0, int64_t rows, int lane, int (&offv)[4], unsigned& lastv) {
     unsigned vb[4];
     const int own_off = (int)node0 * (int)sc.lddq;
 #pragma unroll
     for (int q4 = 0; q4 < 4; ++q4) {
         const int col = lane + 32 * q4;
-        const int64_t r = node0 * AGG_W + col;
-        const int nb = (col < AGG_ROWS && r < rows) ? sc.nbr[r] : -1;
+        const int64_t r = W == 8 ? (node0 + (col >> 3)) * 9 + (col & 7) : node0 * AGG_W + col;
+        const int nb = (col < (W == 8 ? 128 : AGG_ROWS) && r < rows) ? sc.nbr[r] : -1;
         vb[q4] = __ballot_sync(0xffffffffu, nb >= 0);
         offv[q4] = nb >= 0 ? nb * (int)sc.lddq : own_off;
     }
     lastv = 0u;
+    if constexpr (W == 9) {
 #pragma unroll
-    for (int f = 0; f < AGG_NPT; ++f) {
-        const int col = f * AGG_W + AGG_W - 1;
-        lastv |= ((vb[col >> 5] >> (col & 31)) & 1u) << f;
+        for (int f = 0; f < AGG_NPT; ++f) {
+            const int col = f * AGG_W + AGG_W - 1;
+            lastv |= ((vb[col >> 5] >> (col & 31)) & 1u) << f;
+        }
     }
 }
 constexpr uint32_t SC_META_OFF = 8192;   // single-CTA kernel: byte offset of the 128 scatter offsets in a metadata block
 // metadata block of one sub-tile: {126 mask rows of mask_ld words | lastv (4 B) | pad to 16 | 128 offsets}
 __host__ __device__ constexpr uint32_t sc_meta_stride(int mask_ld) {
     return (((uint32_t)AGG_ROWS * (uint32_t)mask_ld * 4u + 4u + 15u) & ~15u) + 512u;
+}
+
+// (kernels that switch between the 9- and the 8-slot layout on the device: a block that holds either {126 rows | lastv} or 128 rows)
+__host__ __device__ constexpr uint32_t sc_meta_stride_w(int mask_ld) {
+    return ((128u * (uint32_t)mask_ld * 4u + 4u + 15u) & ~15u) + 512u;
 }
 
 // Scatter epilogue for NN consecutive nodes whose 9 slot columns sit in r[J0 ...] once the TMEM load issued here lands.
@@ -136,17 +146,17 @@ __host__ __device__ constexpr uint32_t sc_meta_stride(int mask_ld) {
 // it is padding (1/9 of all reductions; a per-lane `v != 0` test would halve the reductions but costs a divergence
 // region per element: 461 -> 673 us). Per element: 2 LDS + LOP3 + FSEL + FADD + IMAD.WIDE + RED (the first version,
 // with generic-pointer metadata loads and offset selects, ran 17 and made the epilogue warps the kernel's bound).
-template <int NN, int J0, int MLD, bool SCALED>
+template <int NN, int J0, int MLD, bool SCALED, int W = 9>
 __device__ __forceinline__ void scat_nodes(uint32_t taddr, uint32_t off_a, uint32_t msk_a, uint32_t mstride, unsigned lanebit,
                                            unsigned lastv, float* __restrict__ dq, float* __restrict__ dp, int64_t lddp,
                                            int64_t nodes_left, bool ch_ok, bool skip, bool round_p, float& colacc, float inv) {
     uint32_t r[32];
     tc::tmem_ld_32x32b_x32(taddr, r);
-    int offr[NN * AGG_W];
-    unsigned mwr[NN * AGG_W];
+    int offr[NN * W];
+    unsigned mwr[NN * W];
     const uint32_t ms = MLD ? (uint32_t)MLD * 4u : mstride;
 #pragma unroll
-    for (int e = 0; e < NN * AGG_W; ++e) {               // metadata loads overlap the TMEM load
+    for (int e = 0; e < NN * W; ++e) {               // metadata loads overlap the TMEM load
         offr[e] = (int)tc::lds_u32(off_a + 4u * e);
         mwr[e] = tc::lds_u32(msk_a + (uint32_t)e * ms);
     }
@@ -157,24 +167,33 @@ __device__ __forceinline__ void scat_nodes(uint32_t taddr, uint32_t off_a, uint3
         float accp = 0.f;
         const bool last_valid = (lastv >> f) & 1u;
 #pragma unroll
-        for (int sl = 0; sl < AGG_W; ++sl) {
-            const int e = f * AGG_W + sl;
+        for (int sl = 0; sl < W; ++sl) {
+            const int e = f * W + sl;
             float v = (mwr[e] & lanebit) ? __uint_as_float(r[J0 + e]) : 0.f;
             if (SCALED) v *= inv;
             accp += v;
-            if (sl < AGG_W - 1 || last_valid) tc::red_add_f32(dq + offr[e], v);
+            if (W == 8 || sl < W - 1 || last_valid) tc::red_add_f32(dq + offr[e], v);
         }
         colacc += accp;                                   // nodes beyond n / channels beyond hdim contribute exact zeros
         if (ch_ok && f < nodes_left) dp[(int64_t)f * lddp] = round_p ? tc::round_tf32(accp) : accp;
     }
 }
 // One 126-slot sub-tile = 14 nodes: columns [27 c, 27 c + 27) for c = 0..3, then [108, 126) out of a load at column 96.
-template <int MLD, bool SCALED>
+// (W = 8: one 128-slot sub-tile = 16 nodes, columns [32 c, 32 c + 32) = 4 nodes per load, every slot real)
+template <int MLD, bool SCALED, int W = 9>
 __device__ __forceinline__ void scat_tile(uint32_t tcol, uint32_t mb_a, uint32_t off_a, uint32_t mword, uint32_t mstride,
                                           unsigned lanebit, float* dq, float* dp, int64_t ldpq, int64_t nodes_left, bool ch_ok,
                                           bool skip, bool round_p, float& colacc, float inv) {
     const uint32_t ms = MLD ? (uint32_t)MLD * 4u : mstride;
     const uint32_t msk_a = mb_a + 4u * mword;
+    if (W == 8) {
+        asm volatile("" : "+l"(dq));
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c)
+            scat_nodes<4, 0, MLD, SCALED, 8>(tcol + (uint32_t)(32 * c), off_a + 128u * c, msk_a + 32u * c * ms, ms, lanebit, 0u, dq,
+                                             dp + (int64_t)(4 * c) * ldpq, ldpq, nodes_left - 4 * c, ch_ok, skip, round_p, colacc, inv);
+        return;
+    }
     const unsigned lastv = tc::lds_u32(mb_a + (uint32_t)AGG_ROWS * ms);     // right behind the 126 mask rows
     asm volatile("" : "+l"(dq));      // keep the row base opaque: `dq + off` stays one IMAD.WIDE per reduction
 #pragma unroll 1
@@ -185,14 +204,14 @@ __device__ __forceinline__ void scat_tile(uint32_t tcol, uint32_t mb_a, uint32_t
                                    nodes_left - 12, ch_ok, skip, round_p, colacc, inv);
 }
 // mb_a: shared address of the sub-tile's metadata block {126 mask rows | lastv | ... | 128 offsets at off_a}
-template <bool SCALED = false>
+template <bool SCALED = false, int W = 9>
 __device__ __forceinline__ void scat_tile_any(int mask_ld, uint32_t tcol, uint32_t mb_a, uint32_t off_a, uint32_t mword,
                                               unsigned lanebit, float* dq, float* dp, int64_t ldpq, int64_t nodes_left, bool ch_ok,
                                               bool skip, bool round_p, float& colacc, float inv = 1.f) {
     // 4 / 12 words per row = hidden widths up to 128 / 257..384 (DynEdge: 128 and 336)
-    if (mask_ld == 12) scat_tile<12, SCALED>(tcol, mb_a, off_a, mword, 48u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip, round_p, colacc, inv);
-    else if (mask_ld == 4) scat_tile<4, SCALED>(tcol, mb_a, off_a, mword, 16u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip, round_p, colacc, inv);
-    else scat_tile<0, SCALED>(tcol, mb_a, off_a, mword, (uint32_t)mask_ld * 4u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip, round_p, colacc, inv);
+    if (mask_ld == 12) scat_tile<12, SCALED, W>(tcol, mb_a, off_a, mword, 48u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip, round_p, colacc, inv);
+    else if (mask_ld == 4) scat_tile<4, SCALED, W>(tcol, mb_a, off_a, mword, 16u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip, round_p, colacc, inv);
+    else scat_tile<0, SCALED, W>(tcol, mb_a, off_a, mword, (uint32_t)mask_ld * 4u, lanebit, dq, dp, ldpq, nodes_left, ch_ok, skip, round_p, colacc, inv);
 }
 
 // Epilogue store of one 32-row chunk: lane = output channel, r[j] = row j. One coalesced 128-byte store per row; the
@@ -1475,11 +1494,13 @@ struct DzBuild { const __half* g16; const unsigned* rowmask; int c_out; };
 // kind::f16 instruction descriptor of the CTA-pair MMAs (M 256 x N 256, fp32 accumulate, K-major), fp16 x fp16
 __host__ __device__ constexpr uint32_t idesc_f16_256_dev() { return (1u << 4) | ((256u >> 3) << 17) | ((256u >> 4) << 24); }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DB_THREADS, 1)
-gemm_f16_pair_scatter_build_kernel(const __grid_constant__ CUtensorMap tm_w0, const DzBuild zb, int total_kb, int last_ksteps,
-                                   int64_t rows, int n_out, int num_tiles, const ScatInfo sc, int nst_w, uint32_t meta_stride,
-                                   int dbg, int ngroups) {
-    gnb_pdl_begin();
+template <int W>
+__device__ __forceinline__ void
+scatter_build_body(const CUtensorMap* tm_w0p, const DzBuild& zb, int total_kb, int last_ksteps,
+                   int64_t rows, int n_out, int num_tiles, const ScatInfo& sc, int nst_w, uint32_t meta_stride,
+                   int dbg, int ngroups) {
+    const CUtensorMap& tm_w0 = *tm_w0p;
+    constexpr int NPT = W == 8 ? 16 : AGG_NPT, ROWS = W * NPT;       // nodes / edge-slot rows of a CTA's sub-tile
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* act = smem;                                               // [total_kb] x 16 KiB: dz tile built here (own half)
@@ -1497,14 +1518,14 @@ gemm_f16_pair_scatter_build_kernel(const __grid_constant__ CUtensorMap tm_w0, co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gempty + 2);
     uint8_t* meta = reinterpret_cast<uint8_t*>(wfull) + DU_BAR_BYTES;  // [2 buffers][2 sub-tiles] x meta_stride
     const uint32_t cw = (uint32_t)zb.c_out >> 5;                       // mask words per edge-slot row
-    const uint32_t gbytes = (uint32_t)AGG_NPT * (uint32_t)zb.c_out * 2u, mbytes = (uint32_t)AGG_ROWS * cw * 4u;
+    const uint32_t gbytes = (uint32_t)NPT * (uint32_t)zb.c_out * 2u, mbytes = (uint32_t)ROWS * cw * 4u;
     const uint32_t stg_stride = gbytes + mbytes;                       // {14 g16 rows | 126 rows x cw mask words}
     uint8_t* stg = meta + 4 * meta_stride;                             // [2] x stg_stride (16-byte aligned: all parts are)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = tc::cluster_ctarank();
     const int cluster_id = (int)(blockIdx.x >> 1), num_clusters = (int)(gridDim.x >> 1);
-    const int64_t ntile14 = (sc.n_nodes + AGG_NPT - 1) / AGG_NPT;
+    const int64_t ntile14 = (sc.n_nodes + NPT - 1) / NPT;
 
     if (warp == 0 && lane == 0) tc::tma_prefetch_desc(&tm_w0);
     if (warp == 1) {
@@ -1534,23 +1555,23 @@ gemm_f16_pair_scatter_build_kernel(const __grid_constant__ CUtensorMap tm_w0, co
         const uint32_t w_tx = 2u * TC_TILE_BYTES;
         for (int t = cluster_id; t < num_tiles; t += num_clusters, ++ti) {
             const uint32_t buf = ti & 1;
-            const int64_t st14 = (int64_t)t * 2 + rank, node0 = st14 * AGG_NPT;
+            const int64_t st14 = (int64_t)t * 2 + rank, node0 = st14 * NPT;
             {   // this CTA's 14 g16 rows + mask rows
                 tc::mbar_wait_warp(&gempty[buf], ((ti >> 1) & 1) ^ 1);
                 int64_t nv = sc.n_nodes - node0;
-                nv = nv < 0 ? 0 : (nv > AGG_NPT ? AGG_NPT : nv);
+                nv = nv < 0 ? 0 : (nv > NPT ? NPT : nv);
                 const uint32_t gb = (uint32_t)nv * (uint32_t)zb.c_out * 2u;
                 if (tc::elect_one()) {
                     tc::mbar_arrive_expect_tx(&gfull[buf], gb + (st14 < ntile14 ? mbytes : 0u));
                     if (nv > 0) tc::bulk_load(stg + buf * stg_stride, zb.g16 + node0 * zb.c_out, gb, &gfull[buf]);
-                    if (st14 < ntile14) tc::bulk_load(stg + buf * stg_stride + gbytes, zb.rowmask + st14 * AGG_ROWS * cw, mbytes, &gfull[buf]);
+                    if (st14 < ntile14) tc::bulk_load(stg + buf * stg_stride + gbytes, zb.rowmask + st14 * ROWS * cw, mbytes, &gfull[buf]);
                 }
                 __syncwarp();
             }
             int offv[2][4];
             unsigned lastv[2];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) scat_meta(sc, ((int64_t)t * 2 + h) * AGG_NPT, rows, lane, offv[h], lastv[h]);
+            for (int h = 0; h < 2; ++h) scat_meta<W>(sc, ((int64_t)t * 2 + h) * NPT, rows, lane, offv[h], lastv[h]);
             for (int g = 0; g < ngroups; ++g) {
                 const bool peer_rows = g * 256 + 128 < n_out;
                 for (int kb = 0; kb < total_kb; ++kb, ++itw) {
@@ -1572,17 +1593,17 @@ gemm_f16_pair_scatter_build_kernel(const __grid_constant__ CUtensorMap tm_w0, co
                     int* so = reinterpret_cast<int*>(mbh + meta_stride - 512);
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) so[lane + 32 * q4] = offv[h][q4];
-                    if (lane == 0) *reinterpret_cast<unsigned*>(mbh + AGG_ROWS * sc.mask_ld * 4) = lastv[h];
-                    if (((int64_t)t * 2 + h) * AGG_NPT < sc.n_nodes) bytes += (uint32_t)(AGG_ROWS * sc.mask_ld * 4);
+                    if (W == 9 && lane == 0) *reinterpret_cast<unsigned*>(mbh + ROWS * sc.mask_ld * 4) = lastv[h];
+                    if (((int64_t)t * 2 + h) * NPT < sc.n_nodes) bytes += (uint32_t)(ROWS * sc.mask_ld * 4);
                 }
                 __syncwarp();
                 if (tc::elect_one()) {
                     tc::mbar_arrive_expect_tx(&meta_full[buf], bytes);
-                    const uint32_t one = (uint32_t)(AGG_ROWS * sc.mask_ld * 4);
+                    const uint32_t one = (uint32_t)(ROWS * sc.mask_ld * 4);
 #pragma unroll
                     for (int h = 0; h < 2; ++h)
-                        if (((int64_t)t * 2 + h) * AGG_NPT < sc.n_nodes)
-                            tc::bulk_load(meta + (buf * 2 + h) * meta_stride, sc.hmask + ((int64_t)t * 2 + h) * AGG_ROWS * sc.mask_ld,
+                        if (((int64_t)t * 2 + h) * NPT < sc.n_nodes)
+                            tc::bulk_load(meta + (buf * 2 + h) * meta_stride, sc.hmask + ((int64_t)t * 2 + h) * ROWS * sc.mask_ld,
                                           one, &meta_full[buf]);
                 }
                 __syncwarp();
@@ -1626,30 +1647,30 @@ gemm_f16_pair_scatter_build_kernel(const __grid_constant__ CUtensorMap tm_w0, co
     } else if (warp >= 10) {
         // ---- dz builders (both CTAs, warps 10..13): lane -> (chunk column j, node f) of a 64-channel K block ------------------
         const int gl = (warp - 10) * 32 + lane;              // 0..127
-        const int j = gl & 7, f = gl >> 3;                   // f < 14 active
-        const bool node_on = f < AGG_NPT;
+        const int j = gl & 7, f = gl >> 3;                   // f < NPT active
+        const bool node_on = f < NPT;
         uint32_t ti = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters, ++ti) {
             const uint32_t buf = ti & 1;
             tc::mbar_wait<20>(&gfull[buf], (ti >> 1) & 1);
             const uint32_t ga = tc::smem_u32(stg + buf * stg_stride), ma = ga + gbytes;
-            const int64_t node0 = ((int64_t)t * 2 + rank) * AGG_NPT;
+            const int64_t node0 = ((int64_t)t * 2 + rank) * NPT;
             const bool have = node_on && node0 + f < sc.n_nodes;
             for (int kb = 0; kb < total_kb; ++kb) {
                 tc::mbar_wait<20>(&aempty[kb], (ti & 1) ^ 1);
                 const int c0 = kb * 64 + j * 8;
                 if (node_on) {
                     uint32_t gh[4] = {0u, 0u, 0u, 0u};
-                    unsigned nlo[AGG_W], nhi[AGG_W];          // per slot: the channel bits c0 .. c0 + 7 of row 9 f + sl as two nibbles
+                    unsigned nlo[W], nhi[W];          // per slot: the channel bits c0 .. c0 + 7 of row 9 f + sl as two nibbles
 #pragma unroll
-                    for (int sl = 0; sl < AGG_W; ++sl) nlo[sl] = nhi[sl] = 0u;
+                    for (int sl = 0; sl < W; ++sl) nlo[sl] = nhi[sl] = 0u;
                     if (have && c0 < zb.c_out) {
                         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(gh[0]), "=r"(gh[1]), "=r"(gh[2]), "=r"(gh[3])
                                      : "r"(ga + ((uint32_t)f * (uint32_t)zb.c_out + (uint32_t)c0) * 2u));
-                        const uint32_t mrow = ma + (9u * (uint32_t)f * cw + (uint32_t)(c0 >> 5)) * 4u;
+                        const uint32_t mrow = ma + ((uint32_t)W * (uint32_t)f * cw + (uint32_t)(c0 >> 5)) * 4u;
                         const unsigned bsh = (unsigned)(c0 & 31);            // 0, 8, 16, 24
 #pragma unroll
-                        for (int sl = 0; sl < AGG_W; ++sl) {
+                        for (int sl = 0; sl < W; ++sl) {
                             const unsigned mw = tc::lds_u32(mrow + (uint32_t)sl * cw * 4u);
                             nlo[sl] = (mw >> bsh) & 15u;
                             nhi[sl] = (mw >> (bsh + 4u)) & 15u;
@@ -1657,8 +1678,8 @@ gemm_f16_pair_scatter_build_kernel(const __grid_constant__ CUtensorMap tm_w0, co
                     }
                     const uint32_t kbase = tc::smem_u32(act + kb * TC_TILE_BYTES);
 #pragma unroll
-                    for (int sl = 0; sl < AGG_W; ++sl) {
-                        const uint32_t r = 9u * (uint32_t)f + (uint32_t)sl;
+                    for (int sl = 0; sl < W; ++sl) {
+                        const uint32_t r = (uint32_t)W * (uint32_t)f + (uint32_t)sl;
                         // 4 channel bits -> sign bits of 4 bytes (bit m lands on bit 8 m + 7), byte permute with sign replication
                         // -> the two half-word masks of each fp16x2 register (see gemm_f16_wgrad_build_kernel)
                         const uint32_t ylo = nlo[sl] * 0x10204080u, yhi = nhi[sl] * 0x10204080u;
@@ -1697,7 +1718,7 @@ gemm_f16_pair_scatter_build_kernel(const __grid_constant__ CUtensorMap tm_w0, co
                 tc::tcgen05_fence_after();
                 tc::mbar_wait<100>(&meta_full[mbuf], (ti >> 1) & 1);
                 const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + half * 128);
-                const int64_t node0 = ((int64_t)t * 2 + half) * AGG_NPT;
+                const int64_t node0 = ((int64_t)t * 2 + half) * NPT;
                 if (node0 < sc.n_nodes && ch0 + q * 32 < n_out) {
                     const uint32_t mb_a = tc::smem_u32(meta + (mbuf * 2 + half) * meta_stride);
                     // activation bits: ballot layout of the hidden-layer kernels, or plain row-major bits of the fused forward
@@ -1705,7 +1726,7 @@ gemm_f16_pair_scatter_build_kernel(const __grid_constant__ CUtensorMap tm_w0, co
                     float* dq = sc.dq + (ch_ok ? ch : ch % sc.hdim);
                     float* dp = sc.dp + node0 * sc.lddp + ch;
                     const unsigned lanebit = ch_ok ? (sc.hmask_rowmajor ? (1u << lane) : (1u << (q * 8 + (lane >> 2)))) : 0u;
-                    scat_tile_any<true>(sc.mask_ld, tcol, mb_a, mb_a + meta_stride - 512u, mword, lanebit, dq, dp, sc.lddp,
+                    scat_tile_any<true, W>(sc.mask_ld, tcol, mb_a, mb_a + meta_stride - 512u, mword, lanebit, dq, dp, sc.lddp,
                                         sc.n_nodes - node0, ch_ok, (dbg & 64) != 0, sc.round_p != 0, g == 0 ? colacc0 : colacc1, inv);
                 }
                 tc::tcgen05_fence_before();
@@ -1730,6 +1751,18 @@ gemm_f16_pair_scatter_build_kernel(const __grid_constant__ CUtensorMap tm_w0, co
     if (warp == 1) tc::tmem_dealloc_2cta<512>(tmem_base);
 }
 
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DB_THREADS, 1)
+gemm_f16_pair_scatter_build_kernel(const __grid_constant__ CUtensorMap tm_w0, const DzBuild zb, int total_kb, int last_ksteps,
+                                   int64_t rows, int n_out, int num_tiles, const ScatInfo sc, int nst_w, uint32_t meta_stride,
+                                   int dbg, int ngroups, const int* __restrict__ full9) {
+    gnb_pdl_begin();
+    // (num_tiles counts pairs of 14-node sub-tiles; the 8-slot layout has 16-node sub-tiles)
+    if (full9 == nullptr || *full9 != 0)
+        scatter_build_body<9>(&tm_w0, zb, total_kb, last_ksteps, rows, n_out, num_tiles, sc, nst_w, meta_stride, dbg, ngroups);
+    else
+        scatter_build_body<8>(&tm_w0, zb, total_kb, last_ksteps, rows, n_out, (int)((sc.n_nodes + 31) / 32), sc, nst_w, meta_stride, dbg, ngroups);
+}
+
 
 // =====================================================================================================================
 // Fused EdgeConv forward for the fp16-plane modes: gather + hidden layer + second Linear + ReLU + k-sum in ONE kernel.
@@ -1752,12 +1785,16 @@ struct FuseSrc { const float* pq; int64_t ldpq; const int* nbr; const int* deg; 
                  int dbg;         // profiling hook (gnb_linear_set_debug; results are garbage): bit 3 no P gathers, bit 4 no Q gathers
                  int pq_perm; };  // 1: every full 64-column block of the P and of the Q half is stored lane-interleaved (below)
 
-template <int NP>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FU_THREADS, 1)
-gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
-                               const FuseSrc fs, const float* __restrict__ bias, float* __restrict__ y, int64_t ldy, int n_out,
-                               int round_out, int num_tiles, int total_kb, int last_ksteps, unsigned* __restrict__ maskbits) {
-    gnb_pdl_begin();
+// W = 9: 14 nodes x 9 slots per sub-tile (the table's width). W = 8: 16 nodes x 8 slots -- every row of the tile is a real edge slot of
+// a graph in which no node keeps 9 neighbours; side outputs and mask words in the 8-slot layout (rows i * 8 + s, bit 8 (i % 16) + s).
+template <int NP, int W>
+__device__ __forceinline__ void
+fused_fwd_body(const CUtensorMap* tm_w0p, const CUtensorMap* tm_w1p, const FuseSrc& fs, const float* __restrict__ bias,
+               float* __restrict__ y, int64_t ldy, int n_out, int round_out, int num_tiles, int total_kb, int last_ksteps,
+               unsigned* __restrict__ maskbits) {
+    const CUtensorMap& tm_w0 = *tm_w0p;
+    const CUtensorMap& tm_w1 = *tm_w1p;
+    constexpr int NPT = W == 8 ? 16 : AGG_NPT, ROWS = W * NPT, TBL_W = 9;      // TBL_W: pitch of the neighbour table (k + 1)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr uint32_t WST = NP * TC_TILE_BYTES, BSL = NP * TC_TILE_BYTES;
@@ -1877,7 +1914,7 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
         const uint32_t ldh16 = (uint32_t)(fs.ldh >> 3), ldhb = (uint32_t)fs.ldhb;
         int fr[4], sr[4];                                    // (node, slot) of the lane's rows inside a 14-node sub-tile
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { const int r = rs + 32 * u; fr[u] = r / AGG_W; sr[u] = r - fr[u] * AGG_W; }
+        for (int u = 0; u < 4; ++u) { const int r = rs + 32 * u; fr[u] = r / W; sr[u] = r - fr[u] * W; }
         // A hidden width of 64 m + 16 (336: every wide layer of DynEdge) leaves a last K block of ONE MMA k step = two 8-channel
         // chunks per row. Built with the (4 rows, chunk j) mapping it costs a full K block of builder time for a quarter of the
         // work (lanes j >= 2 compute zeros the MMA never reads), a sixth of the builders' time per 336-wide tile. The tail is
@@ -1885,23 +1922,23 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
         const bool tail = last_ksteps == 1;
         const int nfull = tail ? total_kb - 1 : total_kb;
         const int r2 = gl >> 1, j2 = gl & 1;
-        const int fr2 = r2 / AGG_W, sr2 = r2 - fr2 * AGG_W;
+        const int fr2 = r2 / W, sr2 = r2 - fr2 * W;
         const bool on2 = (total_kb - 1) * 64 + j2 * 8 < hid;
         const uint32_t koff2 = on2 ? (uint32_t)(total_kb - 1) * 16u + 2u * (uint32_t)j2 : 0u;
         int src_n[4], dg_n[4], src_2 = -1, dg_2 = 0;
         auto fetch_rows = [&](int t) {
-            const int64_t node0 = ((int64_t)t * 2 + rank) * AGG_NPT;
+            const int64_t node0 = ((int64_t)t * 2 + rank) * NPT;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int64_t nd = node0 + fr[u];
-                const bool in = rs + 32 * u < AGG_ROWS && nd < fs.n_nodes;
-                src_n[u] = in ? __ldg(fs.nbr + nd * AGG_W + sr[u]) : -1;
+                const bool in = rs + 32 * u < ROWS && nd < fs.n_nodes;
+                src_n[u] = in ? __ldg(fs.nbr + nd * TBL_W + sr[u]) : -1;
                 dg_n[u] = in ? __ldg(fs.deg + nd) : 0;
             }
             if (tail) {
                 const int64_t nd = node0 + fr2;
-                const bool in = r2 < AGG_ROWS && nd < fs.n_nodes;
-                src_2 = in ? __ldg(fs.nbr + nd * AGG_W + sr2) : -1;
+                const bool in = r2 < ROWS && nd < fs.n_nodes;
+                src_2 = in ? __ldg(fs.nbr + nd * TBL_W + sr2) : -1;
                 dg_2 = in ? __ldg(fs.deg + nd) : 0;
             }
         };
@@ -1939,7 +1976,7 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
         if (cluster_id < num_tiles) fetch_rows(cluster_id);
         uint32_t it = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-            const int64_t node0 = ((int64_t)t * 2 + rank) * AGG_NPT;
+            const int64_t node0 = ((int64_t)t * 2 + rank) * NPT;
             uint32_t po[4], qo[4], ho[4], bo[4];
             float sc[4];
             // side-output switches of the tile in one register: bit u = plane 0 of h for row u, bit 4 + u = the row's bits
@@ -1952,10 +1989,10 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
                 po[u] = (v ? (uint32_t)(node0 + fr[u]) : 0u) * ld16;
                 qo[u] = (v ? (uint32_t)src_n[u] : 0u) * ld16 + q16;
                 sc[u] = v ? scale : 0.f;
-                const uint32_t grow = (uint32_t)(node0 * AGG_W) + (uint32_t)(rs + 32 * u);
+                const uint32_t grow = (uint32_t)(node0 * W) + (uint32_t)(rs + 32 * u);
                 ho[u] = grow * ldh16 + (uint32_t)j;
                 bo[u] = grow * ldhb + (uint32_t)j;
-                const bool rin = rs + 32 * u < AGG_ROWS;
+                const bool rin = rs + 32 * u < ROWS;
                 if (rin && h0v != nullptr && node0 + fr[u] < fs.n_nodes) okm |= 1u << u;
                 if (rin && bok) okm |= 16u << u;
             }
@@ -1966,11 +2003,11 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
                 po2 = (v ? (uint32_t)(node0 + fr2) : 0u) * ld16 + koff2;
                 qo2 = (v ? (uint32_t)src_2 : 0u) * ld16 + (uint32_t)(hid >> 2) + koff2;
                 sc2 = v ? scale : 0.f;
-                const uint32_t grow = (uint32_t)(node0 * AGG_W) + (uint32_t)r2;
+                const uint32_t grow = (uint32_t)(node0 * W) + (uint32_t)r2;
                 ho2 = grow * ldh16 + (uint32_t)(total_kb - 1) * 8u + (uint32_t)j2;
                 bo2 = grow * ldhb + (uint32_t)(total_kb - 1) * 8u + (uint32_t)j2;
-                if (r2 < AGG_ROWS && on2 && h0v != nullptr && node0 + fr2 < fs.n_nodes) okm |= 256u;
-                if (r2 < AGG_ROWS && on2 && bok) okm |= 512u;
+                if (r2 < ROWS && on2 && h0v != nullptr && node0 + fr2 < fs.n_nodes) okm |= 256u;
+                if (r2 < ROWS && on2 && bok) okm |= 512u;
             }
             if (t + num_clusters < num_tiles) fetch_rows(t + num_clusters);
             // Gather registers: one (P, Q) pair of 32-byte pieces per row, each refilled for K block kb + 1 the moment its row of
@@ -2010,7 +2047,7 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
                 const bool on = kb * 64 + j * 8 < hid;        // (loop-invariant per K block: hoisted by the compiler)
                 const uint32_t okk = on ? okm : 0u;
                 const int r = rs + 32 * u;
-                if (r < AGG_ROWS) {                   // (lane-dependent only for u = 3)
+                if (r < ROWS) {                   // (lane-dependent only for u = 3)
                     const uint32_t off = (uint32_t)r * 128u + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4);
                     build_row(pr[u][0], pr[u][1], qr[u][0], qr[u][1], on ? sc[u] : 0.f, ba + off, ho[u] + (uint32_t)kb * 8u,
                               bo[u] + (uint32_t)kb * 8u, (okk >> u) & 1u, (okk >> (4 + u)) & 1u);
@@ -2050,7 +2087,7 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
             if (tail) {
                 const uint32_t sl = it % FU_BSLOTS;
                 tc::mbar_wait(&bempty[sl], ((it / FU_BSLOTS) & 1) ^ 1);
-                if (r2 < AGG_ROWS) {
+                if (r2 < ROWS) {
                     const uint32_t ba = tc::smem_u32(bring + sl * BSL);
                     const uint32_t off = (uint32_t)r2 * 128u + (((uint32_t)j2 ^ ((uint32_t)r2 & 7u)) << 4);
                     build_row(pr[0][0], pr[0][1], qr[0][0], qr[0][1], sc2, ba + off, ho2, bo2, (okm >> 8) & 1u, (okm >> 9) & 1u);
@@ -2075,20 +2112,20 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
             for (int half = 0; half < 2; ++half) {
                 const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + half * 128);
                 const int64_t st14 = (int64_t)t * 2 + half;
-                const int64_t node0 = st14 * AGG_NPT;
+                const int64_t node0 = st14 * NPT;
                 if (node0 >= fs.n_nodes) continue;
-                int dg[AGG_NPT];
+                int dg[NPT];
 #pragma unroll
-                for (int f = 0; f < AGG_NPT; ++f) dg[f] = (node0 + f < fs.n_nodes) ? fs.deg[node0 + f] : 0;
+                for (int f = 0; f < NPT; ++f) dg[f] = (node0 + f < fs.n_nodes) ? fs.deg[node0 + f] : 0;
                 unsigned bits[4];
                 bool regular = true;                       // every node of the sub-tile has exactly k = 8 neighbours
 #pragma unroll
-                for (int f = 0; f < AGG_NPT; ++f) regular = regular && dg[f] == AGG_W - 1;
+                for (int f = 0; f < NPT; ++f) regular = regular && dg[f] == 8;
                 if (regular) {
                     // fast path (as in gemm_tc_pair_kernel): slot validity is compile-time, relu = fmaxf, mask word by an OR tree
-                    float nodeacc[AGG_NPT];
+                    float nodeacc[NPT];
 #pragma unroll
-                    for (int f = 0; f < AGG_NPT; ++f) nodeacc[f] = 0.f;
+                    for (int f = 0; f < NPT; ++f) nodeacc[f] = 0.f;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         uint32_t r[32];
@@ -2099,7 +2136,7 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
 #pragma unroll
                         for (int jj = 0; jj < 32; ++jj) {
                             const int col = c * 32 + jj;
-                            const bool slot_ok = col < AGG_ROWS && (col % AGG_W) < AGG_W - 1;     // compile-time
+                            const bool slot_ok = col < ROWS && (W == 8 || (col % W) < W - 1);     // compile-time
                             const float pre = fmaf(__uint_as_float(r[jj]), ainv, bv);
                             rl[jj] = slot_ok ? fmaxf(pre, 0.f) : 0.f;
                             bt[jj] = (slot_ok && pre > 0.f) ? (1u << jj) : 0u;
@@ -2110,9 +2147,9 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
                             for (int jj = 0; jj < st; ++jj) bt[jj] |= bt[jj + st];
                         bits[c] = bt[0];
 #pragma unroll
-                        for (int f = 0; f < AGG_NPT; ++f) {
+                        for (int f = 0; f < NPT; ++f) {
                             const int c_lo = c * 32, c_hi = c * 32 + 32;
-                            const int n_lo = f * AGG_W, n_hi = f * AGG_W + AGG_W - 1;            // valid slots [n_lo, n_hi)
+                            const int n_lo = f * W, n_hi = f * W + 8;                             // valid slots [n_lo, n_hi)
                             if (n_lo < c_hi && n_hi > c_lo) {                                     // compile-time
                                 auto g = [&](int col) -> float { return (col >= c_lo && col < c_hi) ? rl[col - c_lo] : 0.f; };
                                 const float s8 = ((g(n_lo) + g(n_lo + 1)) + (g(n_lo + 2) + g(n_lo + 3))) +
@@ -2137,13 +2174,13 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
 #pragma unroll
                         for (int jj = 0; jj < 32; ++jj) {
                             const int col = c * 32 + jj;
-                            if (col < AGG_ROWS) {
-                                const int f = col / AGG_W, sl = col % AGG_W;       // compile-time after unrolling
+                            if (col < ROWS) {
+                                const int f = col / W, sl = col % W;       // compile-time after unrolling
                                 const float pre = fmaf(__uint_as_float(r[jj]), ainv, bv);
                                 const bool on = (sl < dg[f]) && (pre > 0.f);
                                 acc += on ? pre : 0.f;
                                 w |= on ? (1u << jj) : 0u;
-                                if (sl == AGG_W - 1) {
+                                if (sl == W - 1) {
                                     float o = acc;
                                     if (round_out) o = tc::round_tf32(o);
                                     if (ch_ok && node0 + f < fs.n_nodes) y[(node0 + f) * ldy + ch] = o;
@@ -2168,6 +2205,20 @@ gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const 
     __syncthreads();
     tc::cluster_sync_all();
     if (warp == 1) tc::tmem_dealloc_2cta<512>(tmem_base);
+}
+
+template <int NP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FU_THREADS, 1)
+gemm_f16_pair_agg_fused_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
+                               const FuseSrc fs, const float* __restrict__ bias, float* __restrict__ y, int64_t ldy, int n_out,
+                               int round_out, int num_tiles, int total_kb, int last_ksteps, unsigned* __restrict__ maskbits,
+                               const int* __restrict__ full9) {
+    gnb_pdl_begin();
+    // (num_tiles counts pairs of 14-node sub-tiles; the 8-slot layout has 16-node sub-tiles)
+    if (full9 == nullptr || *full9 != 0)
+        fused_fwd_body<NP, 9>(&tm_w0, &tm_w1, fs, bias, y, ldy, n_out, round_out, num_tiles, total_kb, last_ksteps, maskbits);
+    else
+        fused_fwd_body<NP, 8>(&tm_w0, &tm_w1, fs, bias, y, ldy, n_out, round_out, (int)((fs.n_nodes + 31) / 32), total_kb, last_ksteps, maskbits);
 }
 
 // dst[r, c] = rna_tf32(src[r, c]) for c < cols, 0 for cols <= c < dst_cols
@@ -2810,11 +2861,12 @@ GNB_EXPORT int gnb_to_f16_planes(const float* src, int64_t lds, int64_t rows, in
 // the outputs of gnb_edge_dz_prep: g16 [n, c_out] = fp16(g * 2^s) (contiguous rows) and the row-major ReLU bits
 // rowmask[(i * 9 + s) * (c_out / 32) + c / 32] (rows padded to whole 14-node tiles). wt = W2^T as one fp16 plane
 // [hdim, ldw >= c_out]; *scale_bits as given to gnb_edge_dz_prep. c_out <= 256, c_out % 64 == 0.
-GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_f16_masked(const void* g16, const uint32_t* rowmask, int32_t c_out, const void* wt,
-                                                        int64_t ldw, const uint32_t* hmask, int32_t mask_ld, int32_t hdim,
-                                                        const int32_t* nbr, int64_t n, float* dq, int64_t lddq, float* dp,
-                                                        int64_t lddp, float* dbias, int32_t flags, const uint32_t* scale_bits,
-                                                        void* stream) {
+// full9 (device, may be NULL = 9 slots): *full9 == 0 selects the 8-slot layout of rowmask and hmask (rows i * 8 + s, 16-node tiles).
+GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_f16_masked_w(const void* g16, const uint32_t* rowmask, int32_t c_out, const void* wt,
+                                                          int64_t ldw, const uint32_t* hmask, int32_t mask_ld, int32_t hdim,
+                                                          const int32_t* nbr, int64_t n, float* dq, int64_t lddq, float* dp,
+                                                          int64_t lddp, float* dbias, int32_t flags, const uint32_t* scale_bits,
+                                                          const int32_t* full9, void* stream) {
     if (n < 0 || hdim < 1 || hdim > 512 || c_out < 64 || c_out > 256 || (c_out & 63) || lddq < hdim || lddp < hdim || dq == nullptr ||
         dp == nullptr || g16 == nullptr || rowmask == nullptr || wt == nullptr || scale_bits == nullptr)
         return GNB_ERR_ARG;
@@ -2833,8 +2885,8 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_f16_masked(const void* g16, const u
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
     GNB_CHECK(init_tc_kernels());
     ScatInfo sc{nbr, hmask, mask_ld, dq, lddq, hdim, n, 1, dp, lddp, dbias, (flags & GNB_FLAG_ROUND_TF32) ? 1 : 0, scale_bits, (flags & GNB_FLAG_HMASK_ROWMAJOR) ? 1 : 0};
-    const uint32_t mstride = sc_meta_stride(mask_ld);
-    const uint32_t stg = 2u * ((uint32_t)AGG_NPT * (uint32_t)c_out * 2u + (uint32_t)AGG_ROWS * (uint32_t)(c_out >> 5) * 4u);
+    const uint32_t mstride = sc_meta_stride_w(mask_ld);
+    const uint32_t stg = 2u * (16u * (uint32_t)c_out * 2u + 128u * (uint32_t)(c_out >> 5) * 4u);       // sized for either layout
     const int64_t left = (int64_t)PL_MAX_DYN_SMEM - 1024 - DU_BAR_BYTES - 4 * (int64_t)mstride - stg - (int64_t)kblocks * TC_TILE_BYTES;
     int nst_w = left > 0 ? (int)(left / TC_TILE_BYTES) : 0;
     if (nst_w > PL_MAX_STAGES) nst_w = PL_MAX_STAGES;
@@ -2847,8 +2899,16 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_f16_masked(const void* g16, const u
     DzBuild zb{(const __half*)g16, rowmask, c_out};
     const int last_ksteps = (c_out - 64 * (kblocks - 1) + 15) / 16;
     gnb_launch(gemm_f16_pair_scatter_build_kernel, dim3((unsigned)(2 * clusters)), DB_THREADS, smem, (cudaStream_t)stream)(
-        tw, zb, kblocks, last_ksteps, rows, hdim, tiles, sc, nst_w, mstride, g_linear_dbg, hdim > 256 ? 2 : 1);
+        tw, zb, kblocks, last_ksteps, rows, hdim, tiles, sc, nst_w, mstride, g_linear_dbg, hdim > 256 ? 2 : 1, full9);
     GNB_RETURN_LAUNCH();
+}
+GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_f16_masked(const void* g16, const uint32_t* rowmask, int32_t c_out, const void* wt,
+                                                        int64_t ldw, const uint32_t* hmask, int32_t mask_ld, int32_t hdim,
+                                                        const int32_t* nbr, int64_t n, float* dq, int64_t lddq, float* dp,
+                                                        int64_t lddp, float* dbias, int32_t flags, const uint32_t* scale_bits,
+                                                        void* stream) {
+    return gnb_edge_hidden_dgrad_scatter_f16_masked_w(g16, rowmask, c_out, wt, ldw, hmask, mask_ld, hdim, nbr, n, dq, lddq, dp, lddp,
+                                                      dbias, flags, scale_bits, nullptr, stream);
 }
 
 // Fused EdgeConv forward of the fp16-plane modes (gemm_f16_pair_agg_fused_kernel): from PQ [n, 2 hid] (P = own half, Q = source
@@ -2860,11 +2920,13 @@ GNB_EXPORT int gnb_edge_hidden_dgrad_scatter_f16_masked(const void* g16, const u
 // pq_layout 1: every full 64-column block of the P half and of the Q half of pq is stored lane-interleaved -- stored column s of
 // a block holds hidden unit gnb_pq_unit_of_stored(s) (common.cuh) -- which halves the L1 wavefronts of the builders' gathers;
 // the caller packs the rows of the hoisted Linear's weight in that order (dynedge_exec.cu). Outputs are in natural order.
-GNB_EXPORT int gnb_edgeconv_fused_fwd_f16(const float* pq, int64_t ldpq, int32_t hid, const int32_t* nbr, const int32_t* deg,
-                                          int64_t n, const void* w0, const void* w1, int64_t ldw, const float* bias,
-                                          int32_t n_out, int32_t round_out, float* y, int64_t ldy, uint32_t* maskbits,
-                                          void* h0_out, int64_t ldh, uint8_t* hbytes, int64_t ldhb, const uint32_t* scale_bits,
-                                          int32_t pq_layout, void* stream) {
+// full9 (device, may be NULL = 9 slots): *full9 == 0 (no node keeps 9 neighbours: gnb_edge_slot_flag) selects the 8-slot layout of
+// every per-edge output: h0_out [8 n, ldh], hbytes [ceil(n / 16) * 128, ldhb], maskbits[(i / 16) * n_out + c] bit 8 (i % 16) + s.
+GNB_EXPORT int gnb_edgeconv_fused_fwd_f16_w(const float* pq, int64_t ldpq, int32_t hid, const int32_t* nbr, const int32_t* deg,
+                                            int64_t n, const void* w0, const void* w1, int64_t ldw, const float* bias,
+                                            int32_t n_out, int32_t round_out, float* y, int64_t ldy, uint32_t* maskbits,
+                                            void* h0_out, int64_t ldh, uint8_t* hbytes, int64_t ldhb, const uint32_t* scale_bits,
+                                            int32_t pq_layout, const int32_t* full9, void* stream) {
     if (pq_layout < 0 || pq_layout > 1) return GNB_ERR_ARG;
     if (n < 0 || n_out < 1 || n_out > 256 || hid < 8 || hid > 512 || (hid & 7) || pq == nullptr || nbr == nullptr || deg == nullptr ||
         w0 == nullptr || y == nullptr || scale_bits == nullptr)
@@ -2890,9 +2952,17 @@ GNB_EXPORT int gnb_edgeconv_fused_fwd_f16(const float* pq, int64_t ldpq, int32_t
     const int last_ksteps = (hid - 64 * (kblocks - 1) + 15) / 16;
     if (planes == 2)
         gnb_launch(gemm_f16_pair_agg_fused_kernel<2>, dim3((unsigned)(2 * clusters)), FU_THREADS, smem, (cudaStream_t)stream)(
-            tw0, tw1, fs, bias, y, ldy, n_out, round_out, tiles, kblocks, last_ksteps, maskbits);
+            tw0, tw1, fs, bias, y, ldy, n_out, round_out, tiles, kblocks, last_ksteps, maskbits, full9);
     else
         gnb_launch(gemm_f16_pair_agg_fused_kernel<1>, dim3((unsigned)(2 * clusters)), FU_THREADS, smem, (cudaStream_t)stream)(
-            tw0, tw0, fs, bias, y, ldy, n_out, round_out, tiles, kblocks, last_ksteps, maskbits);
+            tw0, tw0, fs, bias, y, ldy, n_out, round_out, tiles, kblocks, last_ksteps, maskbits, full9);
     GNB_RETURN_LAUNCH();
+}
+GNB_EXPORT int gnb_edgeconv_fused_fwd_f16(const float* pq, int64_t ldpq, int32_t hid, const int32_t* nbr, const int32_t* deg,
+                                          int64_t n, const void* w0, const void* w1, int64_t ldw, const float* bias,
+                                          int32_t n_out, int32_t round_out, float* y, int64_t ldy, uint32_t* maskbits,
+                                          void* h0_out, int64_t ldh, uint8_t* hbytes, int64_t ldhb, const uint32_t* scale_bits,
+                                          int32_t pq_layout, void* stream) {
+    return gnb_edgeconv_fused_fwd_f16_w(pq, ldpq, hid, nbr, deg, n, w0, w1, ldw, bias, n_out, round_out, y, ldy, maskbits, h0_out, ldh,
+                                        hbytes, ldhb, scale_bits, pq_layout, nullptr, stream);
 }

@@ -336,12 +336,14 @@ constexpr uint32_t WGB_ASTAGE = 2 * WGB_A_BYTES + 5 * 1024;             // {A ti
 constexpr uint32_t WGB_DATA_BYTES = WGB_NA * WGB_ASTAGE + WGB_NBUF * WGB_B_BYTES;
 constexpr uint32_t WGB_SMEM_BYTES = WGB_DATA_BYTES + 1024 + 256;
 
-__global__ void __launch_bounds__(WGB_THREADS, 1)
-gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __half* __restrict__ g16,
-                            const unsigned* __restrict__ rowmask, float* __restrict__ dw, int64_t lddw, int64_t rows, int n_out,
-                            int k_in, int64_t rows_per_split, const unsigned* __restrict__ dz_scale_bits,
-                            const unsigned* __restrict__ x_scale_bits, int dbg) {
-    gnb_pdl_begin();
+// W = 9 slots per node (rows = 9 n), or W = 8 for graphs without k + 1-neighbour nodes (rows = 8 n: a builder warp's 8 rows are one node).
+template <int W>
+__device__ __forceinline__ void
+wgrad_build_body(const CUtensorMap* tm_xp, const __half* __restrict__ g16,
+                 const unsigned* __restrict__ rowmask, float* __restrict__ dw, int64_t lddw, int64_t rows, int n_out,
+                 int k_in, int64_t rows_per_split, const unsigned* __restrict__ dz_scale_bits,
+                 const unsigned* __restrict__ x_scale_bits, int dbg) {
+    const CUtensorMap& tm_x = *tm_xp;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* bring = smem + WGB_NA * WGB_ASTAGE;                       // [WGB_NBUF] x 32 KiB
@@ -356,7 +358,7 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
     const int kin0 = blockIdx.x * 2 * WG_BM;
     const int nt = kin0 + WG_BM < k_in ? 2 : 1;                         // k_in tiles of this CTA
     const int n_mma = (n_out + 15) & ~15;
-    const int64_t n_nodes = rows / 9;
+    const int64_t n_nodes = rows / W;
     const int64_t r_lo = (int64_t)blockIdx.y * rows_per_split;
     int64_t r_hi = r_lo + rows_per_split;
     if (r_hi > rows) r_hi = rows;
@@ -387,8 +389,8 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
                 tc::mbar_wait<0, true>(&aempty[s], ph ^ 1);
                 uint8_t* st = smem + s * WGB_ASTAGE;
                 const int64_t r = r_lo + (int64_t)it * WGB_BK;
-                const int64_t nd0 = r / 9;
-                int64_t nd1 = (r + WGB_BK - 1) / 9 + 1;                 // one past the last node of the stage
+                const int64_t nd0 = r / W;
+                int64_t nd1 = (r + WGB_BK - 1) / W + 1;                 // one past the last node of the stage
                 nd1 = nd1 < n_nodes ? nd1 : n_nodes;
                 const uint32_t gb = nd1 > nd0 ? (uint32_t)(nd1 - nd0) * (uint32_t)n_out * 2u : 0u;
                 if (tc::elect_one()) {
@@ -462,9 +464,9 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
                 if (it + 1 < num_kb) prefetch(it + 1);
                 const uint32_t Rs = r_lo32 + (uint32_t)it * WGB_BK;      // first row of the stage
                 const uint32_t R0 = Rs + 8u * (uint32_t)bw;
-                const uint32_t q0 = __umulhi(R0, 0x38E38E39u) >> 1;      // R0 / 9
-                const uint32_t rem0 = R0 - 9u * q0;
-                const uint32_t nrel0 = q0 - (__umulhi(Rs, 0x38E38E39u) >> 1);
+                const uint32_t q0 = W == 8 ? R0 >> 3 : __umulhi(R0, 0x38E38E39u) >> 1;      // R0 / W
+                const uint32_t rem0 = R0 - (uint32_t)W * q0;
+                const uint32_t nrel0 = q0 - (W == 8 ? Rs >> 3 : __umulhi(Rs, 0x38E38E39u) >> 1);
                 tc::mbar_wait<0, true>(&afull[s], (it / WGB_NA) & 1);             // the stage's g16 rows (and A) landed
                 tc::mbar_wait<0, true>(&bempty[sbuf], ((it / WGB_NBUF) & 1) ^ 1); // the MMAs of the B slot's previous use completed
                 const uint32_t sg = tc::smem_u32(smem + s * WGB_ASTAGE + 2 * WGB_A_BYTES) + (uint32_t)lane * 16u + nrel0 * (uint32_t)n_out * 2u;
@@ -478,7 +480,7 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
                 if (!(dbg & 1))
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const bool second = rem0 + (uint32_t)i >= 9u;        // warp-uniform
+                    const bool second = rem0 + (uint32_t)i >= (uint32_t)W;        // warp-uniform
                     // 4 channel bits -> the sign bits of 4 bytes (one multiply: bit m lands on bit 8 m + 7, no two partial
                     // products share a position), then one byte permute with sign replication per pair of channels gives the
                     // two half-word masks of an fp16x2 register
@@ -524,6 +526,22 @@ gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __ha
     tc::tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) tc::tmem_dealloc<512>(tmem_base);
+}
+
+__global__ void __launch_bounds__(WGB_THREADS, 1)
+gemm_f16_wgrad_build_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_x8,
+                            const __half* __restrict__ g16, const unsigned* __restrict__ rowmask, float* __restrict__ dw,
+                            int64_t lddw, int64_t n_nodes, int n_out, int k_in, int64_t rows_per_split,
+                            const unsigned* __restrict__ dz_scale_bits, const unsigned* __restrict__ x_scale_bits, int dbg,
+                            const int* __restrict__ full9) {
+    gnb_pdl_begin();
+    if (full9 == nullptr || *full9 != 0)
+        wgrad_build_body<9>(&tm_x, g16, rowmask, dw, lddw, n_nodes * 9, n_out, k_in, rows_per_split, dz_scale_bits, x_scale_bits, dbg);
+    else {
+        const int64_t rows8 = n_nodes * 8;
+        const int64_t rps8 = ((rows8 + gridDim.y - 1) / gridDim.y + WGB_BK - 1) / WGB_BK * WGB_BK;
+        wgrad_build_body<8>(&tm_x8, g16, rowmask, dw, lddw, rows8, n_out, k_in, rps8, dz_scale_bits, x_scale_bits, dbg);
+    }
 }
 
 // [rows, cols] fp32 row-major, box = 32 columns x 32 rows, 128-byte swizzle with 32-byte atoms, OOB -> 0
@@ -644,9 +662,11 @@ GNB_EXPORT int gnb_wgrad_set_debug(int32_t flags) { g_wgrad_dbg = flags; return 
 // (contiguous rows) and the row-major ReLU bits rowmask[(i * 9 + s) * (n_out / 32) + c / 32] (bit c % 32):
 //   dw[n_out, k_in] += sum_{i, s} (g16[i, :] * bit(i, s, :))^T x[(i, s), :] * 2^-s * 2^-sx        rows = 9 n (k = 8 tables)
 // x = ONE fp16 plane of h * 2^sx [9 n, k_in]. n_out <= 256, n_out % 32 == 0.
-GNB_EXPORT int gnb_linear_bwd_weight_f16_masked(const void* g16, const uint32_t* rowmask, const void* x, int64_t ldx, float* dw,
-                                                int64_t lddw, int64_t n, int32_t n_out, int32_t k_in,
-                                                const uint32_t* dz_scale_bits, const uint32_t* x_scale_bits, void* stream) {
+// full9 (device, may be NULL = 9 slots): *full9 == 0 selects the 8-slot layout (rows i * 8 + s of x and rowmask, 8 n rows).
+GNB_EXPORT int gnb_linear_bwd_weight_f16_masked_w(const void* g16, const uint32_t* rowmask, const void* x, int64_t ldx, float* dw,
+                                                  int64_t lddw, int64_t n, int32_t n_out, int32_t k_in,
+                                                  const uint32_t* dz_scale_bits, const uint32_t* x_scale_bits, const int32_t* full9,
+                                                  void* stream) {
     if (n < 0 || n_out < 32 || n_out > 256 || (n_out & 31) || k_in < 1 || g16 == nullptr || rowmask == nullptr || x == nullptr ||
         dz_scale_bits == nullptr)
         return GNB_ERR_ARG;
@@ -657,6 +677,11 @@ GNB_EXPORT int gnb_linear_bwd_weight_f16_masked(const void* g16, const uint32_t*
     CUtensorMap tx;
     int rc = gnb_make_tmap_16(&tx, x, rows, k_in, ldx * 2, (uint32_t)WGB_BK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
     if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    CUtensorMap tx8 = tx;
+    if (full9 != nullptr) {
+        rc = gnb_make_tmap_16(&tx8, x, n * 8, k_in, ldx * 2, (uint32_t)WGB_BK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+        if (rc != 0) return rc == -2 ? GNB_ERR_UNSUPPORTED : GNB_ERR_ARG;
+    }
     static unsigned long long attr_devs = 0ull;
     int dev = 0;
     GNB_CHECK(cudaGetDevice(&dev));
@@ -665,7 +690,8 @@ GNB_EXPORT int gnb_linear_bwd_weight_f16_masked(const void* g16, const uint32_t*
         if (dev < 64) attr_devs |= 1ull << dev;
     }
     const int tiles = gnb_div_up(gnb_div_up(k_in, WG_BM), 2);           // CTAs along k_in: pairs of 128-wide tiles
-    int splits = (2 * 148) / tiles;
+    static const int waves = getenv("GNB_WGB_WAVES") ? atoi(getenv("GNB_WGB_WAVES")) : 1;      // one CTA per SM: 522 -> 458 us per step against two waves (epilogue atomics, prologues)
+    int splits = (waves * 148) / tiles;
     const int64_t max_splits = (rows + 8 * WGB_BK - 1) / (8 * WGB_BK);
     if (splits > max_splits) splits = (int)max_splits;
     if (splits < 1) splits = 1;
@@ -673,6 +699,11 @@ GNB_EXPORT int gnb_linear_bwd_weight_f16_masked(const void* g16, const uint32_t*
     rps = ((rps + WGB_BK - 1) / WGB_BK) * WGB_BK;
     splits = (int)((rows + rps - 1) / rps);
     gnb_launch(gemm_f16_wgrad_build_kernel, dim3((unsigned)tiles, (unsigned)splits), WGB_THREADS, WGB_SMEM_BYTES, (cudaStream_t)stream)(
-        tx, (const __half*)g16, rowmask, dw, lddw, rows, n_out, k_in, rps, dz_scale_bits, x_scale_bits, g_wgrad_dbg);
+        tx, tx8, (const __half*)g16, rowmask, dw, lddw, n, n_out, k_in, rps, dz_scale_bits, x_scale_bits, g_wgrad_dbg, full9);
     GNB_RETURN_LAUNCH();
+}
+GNB_EXPORT int gnb_linear_bwd_weight_f16_masked(const void* g16, const uint32_t* rowmask, const void* x, int64_t ldx, float* dw,
+                                                int64_t lddw, int64_t n, int32_t n_out, int32_t k_in,
+                                                const uint32_t* dz_scale_bits, const uint32_t* x_scale_bits, void* stream) {
+    return gnb_linear_bwd_weight_f16_masked_w(g16, rowmask, x, ldx, dw, lddw, n, n_out, k_in, dz_scale_bits, x_scale_bits, nullptr, stream);
 }

@@ -1504,11 +1504,14 @@ GNB_EXPORT int gnb_zero_block(float* a, int64_t lda, int64_t rows, int32_t cols,
 //   db[c]      += sum_i g[i, c] * popcount(bits of node i, channel c)                           (bias gradient = column sums of dz)
 // in one pass over 0.1 GB instead of the 0.37 GB write of a stored dz. CTA = 256 channels of one 14-node tile per iteration;
 // the 32 x 32 bit transposes are warp ballots. cols % 32 == 0.
-__global__ void __launch_bounds__(256) edge_dz_prep_kernel(const float* __restrict__ g, int64_t ldg, const uint4* __restrict__ mask4,
-                                                            int64_t n, int cols, const unsigned* __restrict__ scale_bits,
-                                                            __half* __restrict__ g16, unsigned* __restrict__ rowmask,
-                                                            float* __restrict__ db, int64_t n_tiles) {
-    gnb_pdl_begin();
+// W = 9: the layout above. W = 8 (graphs in which no node keeps k + 1 = 9 neighbours; the caller's device flag says so): 16 nodes per
+// tile, bit 8 (i % 16) + s of maskbits[(i / 16) * cols + c], rows (i * 8 + s) of rowmask -- 128 rows per tile, no padding rows.
+template <int W>
+__device__ __forceinline__ void edge_dz_prep_body(const float* __restrict__ g, int64_t ldg, const uint4* __restrict__ mask4,
+                                                  int64_t n, int cols, const unsigned* __restrict__ scale_bits,
+                                                  __half* __restrict__ g16, unsigned* __restrict__ rowmask, float* __restrict__ db) {
+    constexpr int NPT = W == 8 ? 16 : EM_NPT, ROWS = W * NPT;
+    const int64_t n_tiles = (n + NPT - 1) / NPT;
     const int c = blockIdx.y * 256 + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool c_on = c < cols;                               // warp-uniform (cols % 32 == 0)
@@ -1517,27 +1520,27 @@ __global__ void __launch_bounds__(256) edge_dz_prep_kernel(const float* __restri
     const int cw = cols >> 5;
     float acc = 0.f;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t node0 = tile * EM_NPT;
-        float gv[EM_NPT];
+        const int64_t node0 = tile * NPT;
+        float gv[NPT];
 #pragma unroll
-        for (int f = 0; f < EM_NPT; ++f) {
+        for (int f = 0; f < NPT; ++f) {
             const int64_t nd = node0 + f < n ? node0 + f : n - 1;
             gv[f] = g[nd * ldg + c];
         }
         const uint4 m = mask4[tile * cols + c];
         const unsigned w[5] = {m.x, m.y, m.z, m.w, 0u};
 #pragma unroll
-        for (int f = 0; f < EM_NPT; ++f) {
-            const int bp = 9 * f;                                                   // compile-time after unrolling
-            const unsigned b9 = __funnelshift_r(w[bp >> 5], w[(bp >> 5) + 1], bp & 31) & 0x1FFu;
+        for (int f = 0; f < NPT; ++f) {
+            const int bp = W * f;                                                   // compile-time after unrolling
+            const unsigned bw = __funnelshift_r(w[bp >> 5], w[(bp >> 5) + 1], bp & 31) & ((1u << W) - 1u);
             if (node0 + f < n) {
-                acc += gv[f] * (float)__popc(b9);
+                acc += gv[f] * (float)__popc(bw);
                 g16[(node0 + f) * cols + c] = __float2half_rn(gv[f] * scale);
             }
         }
         // row-major words: 32 x 32 bit transposes across the warp (lane = channel, bit = row  ->  lane = row, bit = channel) by
         // five rounds of block swaps with the lane's partner (recursive transpose: 5 shuffles instead of 32 ballots per word)
-        unsigned* rm = rowmask + tile * EM_ROWS * cw + (c >> 5);
+        unsigned* rm = rowmask + tile * ROWS * cw + (c >> 5);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             unsigned a = w[k];
@@ -1548,13 +1551,45 @@ __global__ void __launch_bounds__(256) edge_dz_prep_kernel(const float* __restri
                 // lanes with bit jb clear keep their low blocks and take the partner's low blocks into their high blocks
                 a = (lane & jb) ? ((a & ~msk) | ((p >> jb) & msk)) : ((a & msk) | ((p << jb) & ~msk));
             }
-            if (32 * k + lane < EM_ROWS) rm[(int64_t)(32 * k + lane) * cw] = a;
+            if (32 * k + lane < ROWS) rm[(int64_t)(32 * k + lane) * cw] = a;
         }
     }
     atomicAdd(db + c, acc);
 }
-GNB_EXPORT int gnb_edge_dz_prep(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols,
-                                const uint32_t* scale_bits, void* g16, uint32_t* rowmask, float* db, void* stream) {
+__global__ void __launch_bounds__(256) edge_dz_prep_kernel(const float* __restrict__ g, int64_t ldg, const uint4* __restrict__ mask4,
+                                                            int64_t n, int cols, const unsigned* __restrict__ scale_bits,
+                                                            __half* __restrict__ g16, unsigned* __restrict__ rowmask,
+                                                            float* __restrict__ db, const int* __restrict__ full9) {
+    gnb_pdl_begin();
+    if (full9 == nullptr || *full9 != 0) edge_dz_prep_body<9>(g, ldg, mask4, n, cols, scale_bits, g16, rowmask, db);
+    else edge_dz_prep_body<8>(g, ldg, mask4, n, cols, scale_bits, g16, rowmask, db);
+}
+// *flag = 1 when some node keeps more than k neighbours (the k + 1 duplicate quirk of the table, edges.py:72-80 -> torch_cluster), else
+// 0: the device-side switch between the 9-slot and the 8-slot layout of the per-edge kernels (no host synchronisation). One CTA.
+__global__ void __launch_bounds__(1024) edge_slot_flag_kernel(const int* __restrict__ deg, int64_t n, int k, int* __restrict__ flag) {
+    gnb_pdl_begin();
+    int any = 0;
+    const int64_t n4 = ((reinterpret_cast<uintptr_t>(deg) & 15u) == 0) ? n >> 2 : 0;       // 16-byte loads, four in flight per thread
+    const int4* d4 = reinterpret_cast<const int4*>(deg);
+    for (int64_t i = threadIdx.x; i < n4; i += 4096) {
+        int4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = i + 1024 * u < n4 ? __ldg(d4 + i + 1024 * u) : make_int4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) any |= (v[u].x > k) | (v[u].y > k) | (v[u].z > k) | (v[u].w > k);
+    }
+    for (int64_t i = 4 * n4 + threadIdx.x; i < n; i += 1024) any |= deg[i] > k;
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) *flag = any ? 1 : 0;
+}
+GNB_EXPORT int gnb_edge_slot_flag(const int32_t* deg, int64_t n, int32_t k, int32_t* flag, void* stream) {
+    if (deg == nullptr || flag == nullptr || n < 0) return GNB_ERR_ARG;
+    gnb_launch(edge_slot_flag_kernel, 1, 1024, 0, (cudaStream_t)stream)(deg, n, k, flag);
+    GNB_RETURN_LAUNCH();
+}
+GNB_EXPORT int gnb_edge_dz_prep_w(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols,
+                                  const uint32_t* scale_bits, void* g16, uint32_t* rowmask, float* db, const int32_t* full9,
+                                  void* stream) {
     if (maskbits == nullptr || g == nullptr || db == nullptr || g16 == nullptr || rowmask == nullptr || scale_bits == nullptr ||
         cols < 32 || (cols & 31) || !aligned16(maskbits))
         return GNB_ERR_ARG;
@@ -1563,6 +1598,10 @@ GNB_EXPORT int gnb_edge_dz_prep(const float* g, int64_t ldg, const uint32_t* mas
     const int64_t max_ctas = 148 * 8;
     dim3 grid((unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas), (unsigned)gnb_div_up(cols, 256));
     gnb_launch(edge_dz_prep_kernel, grid, 256, 0, (cudaStream_t)stream)(g, ldg, reinterpret_cast<const uint4*>(maskbits), n, cols, scale_bits,
-                                                                (__half*)g16, rowmask, db, n_tiles);
+                                                                (__half*)g16, rowmask, db, full9);
     GNB_RETURN_LAUNCH();
+}
+GNB_EXPORT int gnb_edge_dz_prep(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols,
+                                const uint32_t* scale_bits, void* g16, uint32_t* rowmask, float* db, void* stream) {
+    return gnb_edge_dz_prep_w(g, ldg, maskbits, n, cols, scale_bits, g16, rowmask, db, nullptr, stream);
 }

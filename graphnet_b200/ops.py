@@ -80,6 +80,9 @@ STORE_DZ = False
 # fp16-plane modes: False (default) runs the fused EdgeConv forward (gather + hidden layer + second Linear + aggregation in one
 # kernel, h built in shared memory); True keeps the two-kernel forward (hidden-layer kernel writes h, aggregating GEMM reads it)
 UNFUSED_FORWARD = False
+# fp16-plane modes: False (default) lets the device pick the 8-slot edge layout for every graph without a k + 1-neighbour node
+# (16 nodes x 8 slots per tile, -11 % rows in every per-edge kernel); True always uses the 9-slot layout
+SLOTS9 = False
 
 # number of kernels launched through this module (bench.py reports it as `gpu_launches`)
 LAUNCHES = 0
@@ -788,7 +791,7 @@ class _DynEdgeExec(torch.autograd.Function):
         n, nseg = x.shape[0], ptr.numel() - 1
         cfg = _copy_cfg(cfg)      # the ctx keeps ITS OWN copy: a later set_precision() / flag change cannot alter the layout
         cfg.precision = 2 if _split() else (1 if _tf32() else 0)
-        cfg.flags = (0 if FUSED_EDGECONV else 1) | (2 if INFERENCE_ROUTE == "split" else 0) | (4 if STORE_DZ else 0) | (8 if UNFUSED_FORWARD else 0)
+        cfg.flags = (0 if FUSED_EDGECONV else 1) | (2 if INFERENCE_ROUTE == "split" else 0) | (4 if STORE_DZ else 0) | (8 if UNFUSED_FORWARD else 0) | (16 if SLOTS9 else 0)
         nbytes = -2
         if PRECISION in ("bf16", "bf16x3", "mixed16", "f16"):     # per-edge tensors as 16-bit planes where the configuration has the k = 8 route
             base = cfg.precision

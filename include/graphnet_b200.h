@@ -315,6 +315,28 @@ int gnb_edge_hidden_dgrad_scatter_f16_masked(const void* g16, const uint32_t* ro
                                              const uint32_t* hmask, int32_t mask_ld, int32_t hdim, const int32_t* nbr, int64_t n,
                                              float* dq, int64_t lddq, float* dp, int64_t lddp, float* dbias, int32_t flags,
                                              const uint32_t* scale_bits, void* stream);
+/* The 8-slot edge layout (fp16-plane modes, k = 8). The neighbour table is k + 1 = 9 wide because a node with more than k exact
+ * duplicates at lower index keeps k + 1 edges (torch_cluster's knn_graph behind edges.py:72-80, layers.py:63-67); on graphs where
+ * no node does, slot 8 of every node is padding and costs 1/9 of every per-edge kernel. gnb_edge_slot_flag writes *flag = 1 when
+ * some deg[i] > k, else 0, on the device (no host synchronisation); the four _w entry points below take that word as `full9`
+ * (NULL or *full9 != 0: the 9-slot layout documented above) and, when *full9 == 0, run on 16-node x 8-slot tiles: per-edge rows
+ * i * 8 + s (h0_out / x [8 n, .], hbytes / hmask / rowmask [ceil(n / 16) * 128, .]), maskbits[(i / 16) * cols + c] bit
+ * 8 (i % 16) + s. A layer's four kernels must be given the same word. Results are identical in both layouts (the padding slot
+ * contributes exact zeros). Buffers sized for max(ceil(n / 14) * 126, ceil(n / 16) * 128) rows fit either layout. */
+int gnb_edge_slot_flag(const int32_t* deg, int64_t n, int32_t k, int32_t* flag, void* stream);
+int gnb_edgeconv_fused_fwd_f16_w(const float* pq, int64_t ldpq, int32_t hid, const int32_t* nbr, const int32_t* deg, int64_t n,
+                                 const void* w0, const void* w1, int64_t ldw, const float* bias, int32_t n_out, int32_t round_out,
+                                 float* y, int64_t ldy, uint32_t* maskbits, void* h0_out, int64_t ldh, uint8_t* hbytes,
+                                 int64_t ldhb, const uint32_t* scale_bits, int32_t pq_layout, const int32_t* full9, void* stream);
+int gnb_edge_dz_prep_w(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols, const uint32_t* scale_bits,
+                       void* g16, uint32_t* rowmask, float* db, const int32_t* full9, void* stream);
+int gnb_linear_bwd_weight_f16_masked_w(const void* g16, const uint32_t* rowmask, const void* x, int64_t ldx, float* dw,
+                                       int64_t lddw, int64_t n, int32_t n_out, int32_t k_in, const uint32_t* dz_scale_bits,
+                                       const uint32_t* x_scale_bits, const int32_t* full9, void* stream);
+int gnb_edge_hidden_dgrad_scatter_f16_masked_w(const void* g16, const uint32_t* rowmask, int32_t c_out, const void* wt, int64_t ldw,
+                                               const uint32_t* hmask, int32_t mask_ld, int32_t hdim, const int32_t* nbr, int64_t n,
+                                               float* dq, int64_t lddq, float* dp, int64_t lddp, float* dbias, int32_t flags,
+                                               const uint32_t* scale_bits, const int32_t* full9, void* stream);
 /* fp32 [rows, cols] -> fp16 planes (round to nearest; zero padded to dst_cols; p1 may be NULL); transpose != 0: of src^T. */
 int gnb_to_f16_planes(const float* src, int64_t lds, int64_t rows, int32_t cols, void* p0, void* p1, int64_t ldd,
                       int32_t dst_cols, int32_t transpose, void* stream);
@@ -362,7 +384,9 @@ typedef struct {
                                                         bit 2: fp16-plane modes store dz (mask-backward kernel) instead of
                                                         expanding it inside the two backward GEMMs;
                                                         bit 3: fp16-plane modes keep the two-kernel forward (hidden-layer kernel
-                                                        + aggregating GEMM) instead of the fused EdgeConv forward */
+                                                        + aggregating GEMM) instead of the fused EdgeConv forward;
+                                                        bit 4: fp16-plane modes always use the 9-slot edge layout (default: the
+                                                        8-slot layout for every graph without a k + 1-neighbour node) */
 } gnb_dynedge_config;
 
 /* Bytes of workspace for a batch of n nodes / nseg events whose initial graph has table width w0; < 0: error. */

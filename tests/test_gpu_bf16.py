@@ -753,4 +753,9 @@ def test_dynedge_bf16_inference_matches_training_forward(ops, mode):
     y_train = model(data)
     with torch.no_grad():
         y_inf = model(data)
-    assert torch.equal(y_train.detach(), y_inf)
+    if mode == "f16":
+        # f16 trains on the fused forward (8-slot tiles where the graph allows) and infers on the two-kernel forward (9-slot
+        # tiles): same products, but a node's eight messages are summed in a tile-position dependent order
+        assert rel_err(y_train, y_inf) < 1e-3
+    else:
+        assert torch.equal(y_train.detach(), y_inf)
