@@ -574,7 +574,8 @@ GNB_EXPORT int gnb_linear_bwd_weight_tf32(const float* dz, int64_t lddz, const f
     }
     const int tiles_m = gnb_div_up(k_in, WG_BM), tiles_n = gnb_div_up(n_out, WG_BN);
     const int tiles = tiles_m * tiles_n;
-    int splits = (2 * 148) / tiles;                                       // <= 2 full waves of 148 CTAs
+    static const int wg_waves = getenv("GNB_WG_WAVES") ? atoi(getenv("GNB_WG_WAVES")) : 1;      // one CTA per SM: 567 -> 482 us per step against two waves
+    int splits = (wg_waves * 148) / tiles;                                // one wave of 148 CTAs (every split-K slice ends in 32 k fp32 reductions into dw)
     const int64_t max_splits = (rows + 8 * WG_BK - 1) / (8 * WG_BK);     // at least 8 K-blocks per CTA
     if (splits > max_splits) splits = (int)max_splits;
     if (splits < 1) splits = 1;
