@@ -574,7 +574,8 @@ def dominant_launches(trainer, db):
     return {"agg_fwd": agg_fwd, "agg_fwd_x3": agg_fwd_x3, "dgrad_scatter": dgrad_scatter, "agg_fwd_f16x3": agg_fwd_f16x3,
             "dgrad_scatter_f16": dgrad_scatter_f16, "wgrad_f16": wgrad_f16, "wgrad_f16_masked": wgrad_f16_masked,
             "dgrad_scatter_f16_masked": dgrad_scatter_f16_masked, "fused_fwd_f16x3": fused_fwd_f16, "agg_fwd_f16x1": agg_fwd_f16x1,
-            "fused_fwd_f16x3_inference": lambda: fused_fwd_f16(2, False), "rows": rows, "n": n,
+            "fused_fwd_f16x3_inference": lambda: fused_fwd_f16(2, False), "fused_fwd_f16x1_inference": lambda: fused_fwd_f16(1, False),
+            "rows": rows, "n": n,
             "edges": e_real, "hid": hid, "cout": cout, "mld": mld, "keep": keep}
 
 
@@ -664,9 +665,11 @@ def roofline_top_kernel(trainer, db, pk, precision, inference=False):
         return _roofline_by_intensity(out, flops, pk)
     if precision == "f16" and inference:
         p16 = pk["bf16_tflops"]
-        top = entry("gemm_tc_pair_kernel<2> (tcgen05 cta_group::2 kind::f16 M256xN256xK16, ONE power-of-two scaled fp16 plane per "
-                    "operand, TMA-fed), aggregating epilogue: m = relu(h W2^T + b2) summed over the k slots, 336 -> 256 (m never stored)",
-                    _time_launch(d["agg_fwd_f16x1"]), 2.0 * rows * hid + 4.0 * n * cout, 1.0, _traffic("agg_fwd_f16x1"), p16)
+        top = entry("gemm_f16_pair_agg_fused_kernel<1> (tcgen05 cta_group::2 kind::f16 M256xN256xK16; fused EdgeConv forward on ONE "
+                    "power-of-two scaled fp16 plane): builder warps gather P_i + Q_j (fp32), ReLU, scale, fp16 into the swizzled B tile; "
+                    "W2's plane resident in shared memory (no weight streaming); epilogue = bias + ReLU + k-sum. Neither h [N k, 336] "
+                    "nor m [N k, 256] exists in HBM", _time_launch(d["fused_fwd_f16x1_inference"]),
+                    4.0 * n * 2 * hid + 4.0 * 10 * n + 4.0 * n * cout, 1.0, _traffic("fused_fwd_f16x1_inference"), p16)
         return _roofline_by_intensity(
             {"bound": "tensor", "achieved": top["achieved"], "peak": p16, "unit": "TFLOP/s", "frac": top["frac"],
              "traffic": top["traffic"], "kernel": top["kernel"], "launch_ms": top["launch_ms"],
@@ -768,7 +771,7 @@ def algorithmic_work(cfg, n, rows, e_real, nseg, precision, train=True):
     # 16-bit plane modes (per-edge tensors): planes forward / backward and bytes per stored element
     planes = {"bf16": (1, 1), "bf16x3": (2, 2), "mixed16": (2, 1), "f16": (1, 1)}.get(precision)
     scaled = precision in ("mixed16", "f16")                         # fp16 planes with a power-of-two scale word
-    fused_fwd = scaled and (train or precision == "mixed16")         # csrc/dynedge_exec.cu: ConvBuf::fused
+    fused_fwd = scaled                                               # csrc/dynedge_exec.cu: ConvBuf::fused
     node_split = precision in ("tf32x3", "bf16x3", "mixed16")       # node-level forward GEMMs on split operands
 
     def dense_fam(m_rows, n_out, fwd):

@@ -375,7 +375,8 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
             h_shared = a.get<float>(n * max_w * max_h);
             m_shared = a.get<float>(n * max_w * max_c);
         }
-        bool all_fused = c.precision == 5 && !(c.flags & 8) && w0 == 9 && max_h <= 512 && max_c <= 256;      // (see b.fused below)
+        static const bool f16_inf_fused0 = !(getenv("GNB_F16_INFER_FUSED") != nullptr && atoi(getenv("GNB_F16_INFER_FUSED")) == 0);
+        bool all_fused = (c.precision == 5 || (c.precision == 6 && f16_inf_fused0)) && !(c.flags & 8) && w0 == 9 && max_h <= 512 && max_c <= 256;      // (see b.fused below)
         for (int pl = 0; pl < p.bf && !all_fused; ++pl) hb_shared[pl] = a.get<__nv_bfloat16>(n * max_w * max_h);
         pq_shared = a.get<float>(n * 2 * max_h);
     }
@@ -400,9 +401,11 @@ int make_plan(const gnb_dynedge_config& c, int64_t n, int64_t nseg, int w0, bool
         // forward is ONE kernel (gather + hidden layer + second Linear + aggregation: h never crosses HBM except plane 0
         // as the weight gradient's operand); inference fuses whenever the shapes allow it. flags bit 3 keeps the two-kernel forward.
         b.nodz = p.mixed && training && !(c.flags & 4) && b.cout <= 256 && (b.cout & 63) == 0 && wl == 9;
-        // (inference: the fused kernel wins with two planes -- 5.55 against 6.27 ms per 1024 events -- and loses with one, where
-        // the two-kernel forward moves half the bytes: 4.67 against 4.31 ms)
-        b.fused = p.mixed && !(c.flags & 8) && b.cout <= 256 && wl == 9 && b.hid <= 512 && (training ? b.nodz : c.precision == 5);
+        // (inference: the fused kernel wins with two planes, 5.55 against 6.27 ms per 1024 events)
+        // (f16 inference, one plane: with W2's plane resident in shared memory the fused kernel moves no weights at all and wins,
+        // 3.88 against 4.00 ms per 1024 events; GNB_F16_INFER_FUSED=0 keeps the two-kernel forward there)
+        static const bool f16_inf_fused = !(getenv("GNB_F16_INFER_FUSED") != nullptr && atoi(getenv("GNB_F16_INFER_FUSED")) == 0);
+        b.fused = p.mixed && !(c.flags & 8) && b.cout <= 256 && wl == 9 && b.hid <= 512 && (training ? b.nodz : (c.precision == 5 || f16_inf_fused));
         // the fused forward is the only reader of this layer's PQ: its columns are stored in the order the builders gather best
         // (GNB_PQ_NATURAL=1 keeps the natural order: timing comparisons)
         static const bool pq_natural = getenv("GNB_PQ_NATURAL") != nullptr && atoi(getenv("GNB_PQ_NATURAL")) != 0;

@@ -1786,7 +1786,10 @@ constexpr int FU_THREADS = 448, FU_NBW = 8, FU_WSTAGES = 3, FU_BSLOTS = 3;
 struct FuseSrc { const float* pq; int64_t ldpq; const int* nbr; const int* deg; int64_t n_nodes; int hid;
                  __half* h0_out; int64_t ldh; unsigned char* hbytes; int64_t ldhb; const unsigned* scale_bits;
                  int dbg;         // profiling hook (gnb_linear_set_debug; results are garbage): bit 3 no P gathers, bit 4 no Q gathers
-                 int pq_perm; };  // 1: every full 64-column block of the P and of the Q half is stored lane-interleaved (below)
+                 int pq_perm;     // 1: every full 64-column block of the P and of the Q half is stored lane-interleaved (below)
+                 // wres = 1: plane 0 of the CTA's 128 weight rows (every K block) stays in shared memory for the kernel's lifetime and
+                 // only plane 1 streams through a ring of nwst stages of 16 KiB; wres = 0: both planes stream (nwst x NP x 16 KiB)
+                 int wres, nwst; };
 
 // W = 9: 14 nodes x 9 slots per sub-tile (the table's width). W = 8: 16 nodes x 8 slots -- every row of the tile is a real edge slot of
 // a graph in which no node keeps 9 neighbours; side outputs and mask words in the 8-slot layout (rows i * 8 + s, bit 8 (i % 16) + s).
@@ -1800,16 +1803,25 @@ fused_fwd_body(const CUtensorMap* tm_w0p, const CUtensorMap* tm_w1p, const FuseS
     constexpr int NPT = W == 8 ? 16 : AGG_NPT, ROWS = W * NPT, TBL_W = 9;      // TBL_W: pitch of the neighbour table (k + 1)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    constexpr uint32_t WST = NP * TC_TILE_BYTES, BSL = NP * TC_TILE_BYTES;
-    uint8_t* wring = smem;                                       // [FU_WSTAGES] x {W0 | W1}: own 128 weight rows of one K block
-    uint8_t* bring = wring + FU_WSTAGES * WST;                   // [FU_BSLOTS] x {X0 | X1}: own 126 rows of one K block
+    // Weight traffic: streamed whole, the planes of W2 cross L2 -> SM once per 28-node tile -- 393 KB per tile for a 336 / 256
+    // layer on two planes, 1.1 GB per 79 k-node launch, more than the gathers (0.9 GB). FuseSrc::wres keeps plane 0 (6 K blocks x
+    // 16 KiB = 96 KiB for hid <= 384) in shared memory for the kernel's lifetime; the launcher says when that pays.
+    constexpr uint32_t BSL = NP * TC_TILE_BYTES;
+    const bool wres = fs.wres != 0;
+    const uint32_t nwst = (uint32_t)fs.nwst;
+    const uint32_t WST = wres ? (NP - 1) * TC_TILE_BYTES : NP * TC_TILE_BYTES;      // bytes of a streamed stage
+    const bool wstream = WST != 0u;
+    uint8_t* w0res = smem;                                       // wres: [total_kb] x 16 KiB, plane 0 of the own 128 weight rows
+    uint8_t* wring = smem + (wres ? (uint32_t)total_kb * TC_TILE_BYTES : 0u);      // [nwst] x {W0 | W1} or {W1}: one K block
+    uint8_t* bring = wring + nwst * WST;                         // [FU_BSLOTS] x {X0 | X1}: own 126 rows of one K block
     uint64_t* wfull = reinterpret_cast<uint64_t*>(bring + FU_BSLOTS * BSL);
     uint64_t* wempty = wfull + FU_WSTAGES;
     uint64_t* bfull = wempty + FU_WSTAGES;          // leader's copy: 16 builder-warp arrivals of the pair
     uint64_t* bempty = bfull + FU_BSLOTS;           // multicast to both CTAs
     uint64_t* tmem_full = bempty + FU_BSLOTS;       // [2]
     uint64_t* tmem_empty = tmem_full + 2;           // [2] leader's copy: 8 epilogue warps of the pair
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* wres_full = tmem_empty + 2;           // [1] leader's copy: the resident plane of both CTAs landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = tc::cluster_ctarank();
@@ -1819,6 +1831,7 @@ fused_fwd_body(const CUtensorMap* tm_w0p, const CUtensorMap* tm_w1p, const FuseS
     if (warp == 0 && lane == 0) { tc::tma_prefetch_desc(&tm_w0); if (NP == 2) tc::tma_prefetch_desc(&tm_w1); }
     if (warp == 1) {
         if (lane == 0) {
+            tc::mbar_init(wres_full, 1);
             for (int s = 0; s < FU_WSTAGES; ++s) { tc::mbar_init(&wfull[s], 1); tc::mbar_init(&wempty[s], 1); }
             for (int s = 0; s < FU_BSLOTS; ++s) { tc::mbar_init(&bfull[s], 2 * FU_NBW); tc::mbar_init(&bempty[s], 1); }
             for (int b = 0; b < 2; ++b) { tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], 8); }
@@ -1840,14 +1853,21 @@ fused_fwd_body(const CUtensorMap* tm_w0p, const CUtensorMap* tm_w1p, const FuseS
         // cp.async.bulk.prefetch.L2 per row, a whole tile time ahead of the builders' gathers: 1453 -> 1435 us per step, within
         // the box-to-box spread -- first touches from DRAM are not what the builders wait for.)
         uint32_t it = 0;
-        for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        if (wres && cluster_id < num_tiles) {        // the resident plane: every K block of the own 128 weight rows, once
+            if (tc::elect_one()) {
+                if (rank == 0) tc::mbar_arrive_expect_tx(wres_full, 2u * (uint32_t)total_kb * TC_TILE_BYTES);
+                for (int kb = 0; kb < total_kb; ++kb) tc::tma_load_2d_2sm(w0res + kb * TC_TILE_BYTES, &tm_w0, wres_full, kb * 64, ch0);
+            }
+            __syncwarp();
+        }
+        for (int t = cluster_id; t < num_tiles && wstream; t += num_clusters) {
             for (int kb = 0; kb < total_kb; ++kb, ++it) {
-                const uint32_t s = it % FU_WSTAGES, ph = (it / FU_WSTAGES) & 1;
+                const uint32_t s = it % nwst, ph = (it / nwst) & 1;
                 tc::mbar_wait_warp(&wempty[s], ph ^ 1);
                 if (tc::elect_one()) {
                     if (rank == 0) tc::mbar_arrive_expect_tx(&wfull[s], 2u * WST);
-                    tc::tma_load_2d_2sm(wring + s * WST, &tm_w0, &wfull[s], kb * 64, ch0);
-                    if (NP == 2) tc::tma_load_2d_2sm(wring + s * WST + TC_TILE_BYTES, &tm_w1, &wfull[s], kb * 64, ch0);
+                    if (!wres) tc::tma_load_2d_2sm(wring + s * WST, &tm_w0, &wfull[s], kb * 64, ch0);
+                    if (NP == 2) tc::tma_load_2d_2sm(wring + s * WST + (wres ? 0u : TC_TILE_BYTES), &tm_w1, &wfull[s], kb * 64, ch0);
                 }
                 __syncwarp();
             }
@@ -1857,18 +1877,20 @@ fused_fwd_body(const CUtensorMap* tm_w0p, const CUtensorMap* tm_w1p, const FuseS
             // ---- MMA issuer (leader) ------------------------------------------------------------------------------------
             constexpr uint32_t idesc = idesc_f16_256_dev();
             uint32_t it = 0, tile_i = 0;
+            if (wres && cluster_id < num_tiles) { tc::mbar_wait_warp(wres_full, 0); tc::tcgen05_fence_after(); }
             for (int t = cluster_id; t < num_tiles; t += num_clusters, ++tile_i) {
                 const uint32_t buf = tile_i & 1;
                 tc::mbar_wait_warp(&tmem_empty[buf], ((tile_i >> 1) & 1) ^ 1);
                 tc::tcgen05_fence_after();
                 const uint32_t acc = tmem_base + buf * 256;
                 for (int kb = 0; kb < total_kb; ++kb, ++it) {
-                    const uint32_t s = it % FU_WSTAGES, sl = it % FU_BSLOTS;
-                    tc::mbar_wait_warp(&wfull[s], (it / FU_WSTAGES) & 1);
+                    const uint32_t s = it % nwst, sl = it % FU_BSLOTS;
+                    if (wstream) tc::mbar_wait_warp(&wfull[s], (it / nwst) & 1);
                     tc::mbar_wait_warp<true>(&bfull[sl], (it / FU_BSLOTS) & 1);      // both CTAs' builders (cluster-scope acquire)
                     tc::tcgen05_fence_after();
                     const uint32_t wa = tc::smem_u32(wring + s * WST), ba = tc::smem_u32(bring + sl * BSL);
-                    const uint64_t a0 = tc::umma_desc_sw128_kmajor(wa), a1 = tc::umma_desc_sw128_kmajor(wa + TC_TILE_BYTES);
+                    const uint64_t a0 = tc::umma_desc_sw128_kmajor(wres ? tc::smem_u32(w0res + kb * TC_TILE_BYTES) : wa);
+                    const uint64_t a1 = tc::umma_desc_sw128_kmajor(wres ? wa : wa + TC_TILE_BYTES);
                     const uint64_t b0 = tc::umma_desc_sw128_kmajor(ba), b1 = tc::umma_desc_sw128_kmajor(ba + TC_TILE_BYTES);
                     const int nk = kb == total_kb - 1 ? last_ksteps : 4;
                     if (tc::elect_one()) {
@@ -1882,7 +1904,7 @@ fused_fwd_body(const CUtensorMap* tm_w0p, const CUtensorMap* tm_w1p, const FuseS
                                 tc::umma_bf16_2cta(acc, a0 + 2 * k, b0 + 2 * k, idesc, (NP == 2 || (kb | k) != 0) ? 1u : 0u);
                             }
                         }
-                        tc::umma_commit_2cta(&wempty[s], 3);
+                        if (wstream) tc::umma_commit_2cta(&wempty[s], 3);
                         tc::umma_commit_2cta(&bempty[sl], 3);
                     }
                     __syncwarp();
@@ -2950,8 +2972,21 @@ GNB_EXPORT int gnb_edgeconv_fused_fwd_f16_w(const float* pq, int64_t ldpq, int32
     int clusters = g_num_sms / 2;
     if (clusters > tiles) clusters = tiles;
     if (clusters < 1) clusters = 1;
-    FuseSrc fs{pq, ldpq, nbr, deg, n, hid, (__half*)h0_out, ldh, hbytes, ldhb, scale_bits, g_linear_dbg, pq_layout};
-    const uint32_t smem = 1024 + (uint32_t)(FU_WSTAGES + FU_BSLOTS) * planes * TC_TILE_BYTES + 512;
+    // Plane 0 of W2 resident in shared memory when it fits beside the B ring (and, with two planes, at least two stages of plane 1:
+    // hid <= 384, 96 + 2 x 16 + 96 KiB). Measured: ONE plane (f16 inference: nothing streams at all) 4.00 -> 3.88 ms per 1024
+    // events; TWO planes (training) 1398 -> 1432 us per step although the launch's L2 -> SM bytes drop from 2.0 to 1.45 GB --
+    // the builder warps, not the crossbar, are this kernel's bound, and two stages of plane 1 are a shallower ring. So:
+    // resident for one plane, streamed for two; GNB_FUSED_WRES=0 / 2 = never / also with two planes (timing comparisons).
+    static const int wres_mode = getenv("GNB_FUSED_WRES") != nullptr ? atoi(getenv("GNB_FUSED_WRES")) : 1;
+    int wres = 0, nwst = FU_WSTAGES;
+    if (wres_mode == 2 || (wres_mode == 1 && planes == 1)) {
+        const int64_t left = (int64_t)PL_MAX_DYN_SMEM - 1024 - 512 - (int64_t)(kblocks + FU_BSLOTS * planes) * TC_TILE_BYTES;
+        const int fit = planes == 2 ? (int)(left / TC_TILE_BYTES) : FU_WSTAGES;
+        if (left >= 0 && fit >= 2) { wres = 1; nwst = fit < FU_WSTAGES ? fit : FU_WSTAGES; }
+    }
+    FuseSrc fs{pq, ldpq, nbr, deg, n, hid, (__half*)h0_out, ldh, hbytes, ldhb, scale_bits, g_linear_dbg, pq_layout, wres, nwst};
+    const uint32_t smem = 1024 + 512 + (wres ? (uint32_t)(kblocks + nwst * (planes - 1) + FU_BSLOTS * planes) * TC_TILE_BYTES
+                                             : (uint32_t)(FU_WSTAGES + FU_BSLOTS) * planes * TC_TILE_BYTES);
     const int last_ksteps = (hid - 64 * (kblocks - 1) + 15) / 16;
     if (planes == 2)
         gnb_launch(gemm_f16_pair_agg_fused_kernel<2>, dim3((unsigned)(2 * clusters)), FU_THREADS, smem, (cudaStream_t)stream)(
