@@ -1782,7 +1782,13 @@ gemm_f16_pair_scatter_build_kernel(const __grid_constant__ CUtensorMap tm_w0, co
 // ScatInfo::hmask_rowmajor). The epilogue is the aggregating epilogue (bias, ReLU, k-sum, 126 mask bits per (tile, channel)).
 // n_out <= 256 (one channel group), hid % 8 == 0, k = 8 tables.
 // Warps: 0 TMA (weights), 1 MMA, 2..5 epilogue (lane quarter = warp % 4, both sub-tiles), 6..13 builders.
-constexpr int FU_THREADS = 448, FU_NBW = 8, FU_WSTAGES = 3, FU_BSLOTS = 3;
+#ifndef GNB_FU_WSTAGES
+#define GNB_FU_WSTAGES 3
+#endif
+#ifndef GNB_FU_BSLOTS
+#define GNB_FU_BSLOTS 3
+#endif
+constexpr int FU_THREADS = 448, FU_NBW = 8, FU_WSTAGES = GNB_FU_WSTAGES, FU_BSLOTS = GNB_FU_BSLOTS;
 struct FuseSrc { const float* pq; int64_t ldpq; const int* nbr; const int* deg; int64_t n_nodes; int hid;
                  __half* h0_out; int64_t ldh; unsigned char* hbytes; int64_t ldhb; const unsigned* scale_bits;
                  int dbg;         // profiling hook (gnb_linear_set_debug; results are garbage): bit 3 no P gathers, bit 4 no Q gathers
