@@ -1795,7 +1795,8 @@ struct FuseSrc { const float* pq; int64_t ldpq; const int* nbr; const int* deg; 
                  int pq_perm;     // 1: every full 64-column block of the P and of the Q half is stored lane-interleaved (below)
                  // wres = 1: plane 0 of the CTA's 128 weight rows (every K block) stays in shared memory for the kernel's lifetime and
                  // only plane 1 streams through a ring of nwst stages of 16 KiB; wres = 0: both planes stream (nwst x NP x 16 KiB)
-                 int wres, nwst; };
+                 int wres, nwst;
+                 int rev; };      // 1: tiles in descending order (see the builders)
 
 // W = 9: 14 nodes x 9 slots per sub-tile (the table's width). W = 8: 16 nodes x 8 slots -- every row of the tile is a real edge slot of
 // a graph in which no node keeps 9 neighbours; side outputs and mask words in the 8-slot layout (rows i * 8 + s, bit 8 (i % 16) + s).
@@ -1957,7 +1958,11 @@ fused_fwd_body(const CUtensorMap* tm_w0p, const CUtensorMap* tm_w1p, const FuseS
         const bool on2 = (total_kb - 1) * 64 + j2 * 8 < hid;
         const uint32_t koff2 = on2 ? (uint32_t)(total_kb - 1) * 16u + 2u * (uint32_t)j2 : 0u;
         int src_n[4], dg_n[4], src_2 = -1, dg_2 = 0;
+        // tile order: fs.rev walks the tiles from the last one down -- the PQ GEMM has just written PQ front to back, so its tail is what
+        // the 126 MB L2 still holds when this kernel starts (PQ is 213 MB per 79 k-node layer)
+        const bool rev = fs.rev != 0;
         auto fetch_rows = [&](int t) {
+            if (rev) t = num_tiles - 1 - t;
             const int64_t node0 = ((int64_t)t * 2 + rank) * NPT;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -2007,7 +2012,7 @@ fused_fwd_body(const CUtensorMap* tm_w0p, const CUtensorMap* tm_w1p, const FuseS
         if (cluster_id < num_tiles) fetch_rows(cluster_id);
         uint32_t it = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-            const int64_t node0 = ((int64_t)t * 2 + rank) * NPT;
+            const int64_t node0 = ((int64_t)(rev ? num_tiles - 1 - t : t) * 2 + rank) * NPT;
             uint32_t po[4], qo[4], ho[4], bo[4];
             float sc[4];
             // side-output switches of the tile in one register: bit u = plane 0 of h for row u, bit 4 + u = the row's bits
@@ -2142,7 +2147,7 @@ fused_fwd_body(const CUtensorMap* tm_w0p, const CUtensorMap* tm_w1p, const FuseS
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
                 const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + half * 128);
-                const int64_t st14 = (int64_t)t * 2 + half;
+                const int64_t st14 = (int64_t)(fs.rev ? num_tiles - 1 - t : t) * 2 + half;
                 const int64_t node0 = st14 * NPT;
                 if (node0 >= fs.n_nodes) continue;
                 int dg[NPT];
@@ -2990,7 +2995,8 @@ GNB_EXPORT int gnb_edgeconv_fused_fwd_f16_w(const float* pq, int64_t ldpq, int32
         const int fit = planes == 2 ? (int)(left / TC_TILE_BYTES) : FU_WSTAGES;
         if (left >= 0 && fit >= 2) { wres = 1; nwst = fit < FU_WSTAGES ? fit : FU_WSTAGES; }
     }
-    FuseSrc fs{pq, ldpq, nbr, deg, n, hid, (__half*)h0_out, ldh, hbytes, ldhb, scale_bits, g_linear_dbg, pq_layout, wres, nwst};
+    static const int rev = getenv("GNB_FUSED_REV") != nullptr ? atoi(getenv("GNB_FUSED_REV")) : 0;
+    FuseSrc fs{pq, ldpq, nbr, deg, n, hid, (__half*)h0_out, ldh, hbytes, ldhb, scale_bits, g_linear_dbg, pq_layout, wres, nwst, rev};
     const uint32_t smem = 1024 + 512 + (wres ? (uint32_t)(kblocks + nwst * (planes - 1) + FU_BSLOTS * planes) * TC_TILE_BYTES
                                              : (uint32_t)(FU_WSTAGES + FU_BSLOTS) * planes * TC_TILE_BYTES);
     const int last_ksteps = (hid - 64 * (kblocks - 1) + 15) / 16;
