@@ -28,3 +28,13 @@ gs = sorted(g[0] for g in gaps)
 print("gap us: median", gs[len(gs) // 2], "p90", gs[int(0.9 * len(gs))], "max", gs[-1], "sum", sum(gs))
 for g in sorted(gaps, key=lambda g: -g[0])[:12]:
     print(f"  {g[0]:7.1f} us  {g[1]} -> {g[2]}")
+# where the idle time sits: gaps by the kernel that FOLLOWS them (launch ramp of that kernel), last step only
+import collections
+third = [g for g in gaps[2 * len(gaps) // 3:]]
+by = collections.defaultdict(lambda: [0, 0.0])
+for g in third:
+    by[g[2]][0] += 1
+    by[g[2]][1] += g[0]
+print("last step: gaps", len(third), "sum", round(sum(g[0] for g in third), 1), "us")
+for k, (c, t) in sorted(by.items(), key=lambda kv: -kv[1][1])[:16]:
+    print(f"  {t:7.1f} us over {c:3d} gaps (mean {t / c:5.2f})  before {k}")
