@@ -93,6 +93,7 @@ SIGNATURES: Dict[str, list] = {
     "gnb_edgeconv_fused_fwd_f16_w": [_p, _i64, _i32, _p, _p, _i64, _p, _p, _i64, _p, _i32, _i32, _p, _i64, _p, _p, _i64, _p, _i64,
                                      _p, _i32, _p, _p],
     "gnb_edge_dz_prep_w": [_p, _i64, _p, _i64, _i32, _p, _p, _p, _p, _p, _p],
+    "gnb_edge_dz_prep_wz": [_p, _i64, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _i32, _p],
     "gnb_linear_bwd_weight_f16_masked_w": [_p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _p, _p, _p, _p],
     "gnb_edge_hidden_dgrad_scatter_f16_masked_w": [_p, _p, _i32, _p, _i64, _p, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _p,
                                                    _i32, _p, _p, _p],

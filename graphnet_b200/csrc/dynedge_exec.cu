@@ -86,8 +86,8 @@ int gnb_edge_hidden_dgrad_scatter_f16_masked_w(const void*, const uint32_t*, int
 int gnb_edgeconv_fused_fwd_f16_w(const float*, int64_t, int32_t, const int32_t*, const int32_t*, int64_t, const void*, const void*,
                                  int64_t, const float*, int32_t, int32_t, float*, int64_t, uint32_t*, void*, int64_t, uint8_t*, int64_t,
                                  const uint32_t*, int32_t, const int32_t*, void*);
-int gnb_edge_dz_prep_w(const float*, int64_t, const uint32_t*, int64_t, int32_t, const uint32_t*, void*, uint32_t*, float*,
-                       const int32_t*, void*);
+int gnb_edge_dz_prep_wz(const float*, int64_t, const uint32_t*, int64_t, int32_t, const uint32_t*, void*, uint32_t*, float*,
+                        const int32_t*, float*, int64_t, int64_t, int32_t, float*, int32_t, void*);
 int gnb_to_f16_planes(const float*, int64_t, int64_t, int32_t, void*, void*, int64_t, int32_t, int32_t, void*);
 int gnb_absmax_bits(const float*, int64_t, int64_t, int32_t, int32_t, uint32_t*, void*);
 int gnb_edge_hidden_fwd_f16(const float*, int64_t, int32_t, const int32_t*, const int32_t*, int32_t, int64_t, void*, void*, int64_t,
@@ -925,7 +925,9 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
                 // dz = g * mask bit is never stored: both GEMMs expand it in shared memory from g_y and the mask words
                 // (one small pass writes fp16(g_y 2^s), the row-major bits and the bias gradient)
                 const int32_t* f9 = b.slots8 ? p.full9 + l : nullptr;          // written by the forward pass
-                EX(gnb_edge_dz_prep_w(gy, b.cout, b.mask, n, b.cout, gs, p.g16, p.rowmask, gb2, f9, stream));
+                // (the launch also zeroes the Q half of dPQ and the bias-gradient scratch for the scattering kernel below)
+                EX(gnb_edge_dz_prep_wz(gy, b.cout, b.mask, n, b.cout, gs, p.g16, p.rowmask, gb2, f9, p.dzq + b.hid, 2 * b.hid, n, b.hid,
+                                       p.dbtmp, 2 * b.hid, stream));
                 EX(gnb_linear_bwd_weight_f16_masked_w(p.g16, p.rowmask, b.hb[0], b.hid, gw2, b.hid, n, b.cout, b.hid, gs, p.scale_bits + l, f9, stream));
             } else {
                 EX(gnb_edge_mask_bwd_colsum_f16(gy, b.cout, b.mask, n, b.cout, p.dzb[0], b.cout, gb2, gs, stream));
@@ -940,10 +942,11 @@ GNB_EXPORT int gnb_dynedge_backward(const gnb_dynedge_config* cfg, float* const*
             EX(gnb_act_bwd_colsum(gy, b.cout, b.m, b.cout, rows, b.cout, p.dz_big, b.cout, gb2, GNB_ACT_RELU | e.rnd, deg, wl,
                                   GNB_AGGR_ADD, stream));
         if (!p.bf) EX(e.lin_bwd_weight(p.dz_big, b.cout, b.h, b.hid, gw2, b.hid, 0, b.hid, b.cout, rows));
-        GNB_CHECK(cudaMemsetAsync(p.dbtmp, 0, (size_t)2 * b.hid * 4, e.st));
+        const bool zeroed = p.mixed && nodz;          // by the dz prep launch above
+        if (!zeroed) GNB_CHECK(cudaMemsetAsync(p.dbtmp, 0, (size_t)2 * b.hid * 4, e.st));
         const float* dzq = p.dzq;
         if (p.bf) {
-            EX(gnb_zero_block(p.dzq + b.hid, 2 * b.hid, n, b.hid, stream));
+            if (!zeroed) EX(gnb_zero_block(p.dzq + b.hid, 2 * b.hid, n, b.hid, stream));
             if (p.mixed && nodz)
                 EX(gnb_edge_hidden_dgrad_scatter_f16_masked_w(p.g16, p.rowmask, b.cout, b.w2tb[0], b.cld64, b.hmask, b.mld, b.hid, nbr, n,
                                                               p.dzq + b.hid, 2 * b.hid, p.dzq, 2 * b.hid, p.dbtmp,

@@ -1556,11 +1556,28 @@ __device__ __forceinline__ void edge_dz_prep_body(const float* __restrict__ g, i
     }
     atomicAdd(db + c, acc);
 }
+// Zero job riding on the launch (the executor's backward pass): a [rows, 4 cols4] block of pitch lda (the Q half of dPQ, the scatter
+// target of the data-gradient kernel that follows) and nb floats at b (the bias-gradient scratch) -- a zero_block launch, a memset
+// and their two launch gaps (~24 us per layer) folded into a kernel that has store bandwidth to spare. a / b may be NULL.
+struct DzPrepZero { float* a; int64_t lda, rows; int cols4; float* b; int nb; };
 __global__ void __launch_bounds__(256) edge_dz_prep_kernel(const float* __restrict__ g, int64_t ldg, const uint4* __restrict__ mask4,
                                                             int64_t n, int cols, const unsigned* __restrict__ scale_bits,
                                                             __half* __restrict__ g16, unsigned* __restrict__ rowmask,
-                                                            float* __restrict__ db, const int* __restrict__ full9) {
+                                                            float* __restrict__ db, const int* __restrict__ full9, const DzPrepZero zj) {
     gnb_pdl_begin();
+    {
+        const int64_t nthreads = (int64_t)gridDim.x * gridDim.y * 256;
+        const int64_t t0 = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 256 + threadIdx.x;
+        if (zj.a != nullptr) {
+            const int64_t total = zj.rows * zj.cols4;
+            for (int64_t t = t0; t < total; t += nthreads) {
+                const int64_t r = t / zj.cols4;
+                reinterpret_cast<float4*>(zj.a + r * zj.lda)[(int)(t - r * zj.cols4)] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        if (zj.b != nullptr)
+            for (int64_t t = t0; t < zj.nb; t += nthreads) zj.b[t] = 0.f;
+    }
     if (full9 == nullptr || *full9 != 0) edge_dz_prep_body<9>(g, ldg, mask4, n, cols, scale_bits, g16, rowmask, db);
     else edge_dz_prep_body<8>(g, ldg, mask4, n, cols, scale_bits, g16, rowmask, db);
 }
@@ -1587,9 +1604,12 @@ GNB_EXPORT int gnb_edge_slot_flag(const int32_t* deg, int64_t n, int32_t k, int3
     gnb_launch(edge_slot_flag_kernel, 1, 1024, 0, (cudaStream_t)stream)(deg, n, k, flag);
     GNB_RETURN_LAUNCH();
 }
-GNB_EXPORT int gnb_edge_dz_prep_w(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols,
-                                  const uint32_t* scale_bits, void* g16, uint32_t* rowmask, float* db, const int32_t* full9,
-                                  void* stream) {
+GNB_EXPORT int gnb_edge_dz_prep_wz(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols,
+                                   const uint32_t* scale_bits, void* g16, uint32_t* rowmask, float* db, const int32_t* full9,
+                                   float* zero_a, int64_t lda, int64_t zrows, int32_t zcols, float* zero_b, int32_t zb_count,
+                                   void* stream) {
+    if (zero_a != nullptr && ((zcols & 3) || (lda & 3) || !aligned16(zero_a) || zrows < 0 || zcols < 0)) return GNB_ERR_ARG;
+    if (zero_b != nullptr && zb_count < 0) return GNB_ERR_ARG;
     if (maskbits == nullptr || g == nullptr || db == nullptr || g16 == nullptr || rowmask == nullptr || scale_bits == nullptr ||
         cols < 32 || (cols & 31) || !aligned16(maskbits))
         return GNB_ERR_ARG;
@@ -1598,8 +1618,14 @@ GNB_EXPORT int gnb_edge_dz_prep_w(const float* g, int64_t ldg, const uint32_t* m
     const int64_t max_ctas = 148 * 8;
     dim3 grid((unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas), (unsigned)gnb_div_up(cols, 256));
     gnb_launch(edge_dz_prep_kernel, grid, 256, 0, (cudaStream_t)stream)(g, ldg, reinterpret_cast<const uint4*>(maskbits), n, cols, scale_bits,
-                                                                (__half*)g16, rowmask, db, full9);
+                                                                (__half*)g16, rowmask, db, full9,
+                                                                DzPrepZero{zero_a, lda, zrows, zcols >> 2, zero_b, zb_count});
     GNB_RETURN_LAUNCH();
+}
+GNB_EXPORT int gnb_edge_dz_prep_w(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols,
+                                  const uint32_t* scale_bits, void* g16, uint32_t* rowmask, float* db, const int32_t* full9,
+                                  void* stream) {
+    return gnb_edge_dz_prep_wz(g, ldg, maskbits, n, cols, scale_bits, g16, rowmask, db, full9, nullptr, 0, 0, 0, nullptr, 0, stream);
 }
 GNB_EXPORT int gnb_edge_dz_prep(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols,
                                 const uint32_t* scale_bits, void* g16, uint32_t* rowmask, float* db, void* stream) {

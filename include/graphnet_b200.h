@@ -330,6 +330,11 @@ int gnb_edgeconv_fused_fwd_f16_w(const float* pq, int64_t ldpq, int32_t hid, con
                                  int64_t ldhb, const uint32_t* scale_bits, int32_t pq_layout, const int32_t* full9, void* stream);
 int gnb_edge_dz_prep_w(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols, const uint32_t* scale_bits,
                        void* g16, uint32_t* rowmask, float* db, const int32_t* full9, void* stream);
+/* gnb_edge_dz_prep_w with a zero job riding on the launch: zero_a[r, 0 : zcols] = 0 for r < zrows (pitch lda; the scatter target of
+ * the data-gradient kernel that follows) and zero_b[0 : zb_count] = 0; either pointer may be NULL. */
+int gnb_edge_dz_prep_wz(const float* g, int64_t ldg, const uint32_t* maskbits, int64_t n, int32_t cols, const uint32_t* scale_bits,
+                        void* g16, uint32_t* rowmask, float* db, const int32_t* full9, float* zero_a, int64_t lda, int64_t zrows,
+                        int32_t zcols, float* zero_b, int32_t zb_count, void* stream);
 int gnb_linear_bwd_weight_f16_masked_w(const void* g16, const uint32_t* rowmask, const void* x, int64_t ldx, float* dw,
                                        int64_t lddw, int64_t n, int32_t n_out, int32_t k_in, const uint32_t* dz_scale_bits,
                                        const uint32_t* x_scale_bits, const int32_t* full9, void* stream);

@@ -244,3 +244,32 @@ def test_mixed16_training_step_8slot_layout_matches_9slot_layout(ops, dup):
     assert rel_err(outs[0], outs[1]) < 1e-3
     for a, b in zip(*grads):
         assert rel_err(a, b) < 2e-2
+
+
+@pytest.mark.parametrize("slots8", [False, True])
+def test_dz_prep_zero_job(ops, slots8):
+    """gnb_edge_dz_prep_wz: the zero job riding on the launch clears exactly the [rows, cols] block of pitch lda and the scratch
+    vector, and the kernel's own outputs are those of the plain call."""
+    graph, n, flag, wz, g16_ref, dz, rowmask_ref = _mask_case8(ops, [300, 5, 77, 1000], 256, seed=3, gmax=2.0 ** -9)
+    gen = torch.Generator().manual_seed(3)
+    deg = graph.deg.cpu()
+    # the same inputs once more (the helper does not return them): rebuild g and the words from its outputs
+    g = (g16_ref.float().cpu() / _scale_word(2.0 ** -9)[1])
+    hid = 336
+    za = torch.full((n, 2 * hid), 3.0, device="cuda")
+    zb = torch.full((2 * hid + 64,), 5.0, device="cuda")
+    g16 = torch.empty_like(g16_ref)
+    rowmask = torch.full_like(rowmask_ref, -1)
+    db = torch.zeros(256, device="cuda")
+    # mask words in the layout the flag selects are not returned by the helper either: use all-zero words (dz = 0) -- the zero job
+    # and g16 do not depend on them
+    ntile = (n + 13) // 14
+    words = torch.zeros(ntile * 256 * 4, dtype=torch.int32, device="cuda")
+    fl = flag if slots8 else None
+    ops._call("gnb_edge_dz_prep_wz", ops._ptr(g.cuda()), 256, ops._ptr(words), n, 256, ops._ptr(wz), ops._ptr(g16), ops._ptr(rowmask),
+              ops._ptr(db), ops._ptr(fl), ops._ptr(za[:, hid:]), 2 * hid, n, hid, ops._ptr(zb), 2 * hid, ops._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(g16, g16_ref)
+    assert not db.any()
+    assert bool((za[:, :hid] == 3.0).all()) and not za[:, hid:].any()
+    assert not zb[: 2 * hid].any() and bool((zb[2 * hid:] == 5.0).all())
