@@ -803,11 +803,11 @@ def algorithmic_work(cfg, n, rows, e_real, nseg, precision, train=True):
             if train and scaled:
                 # dz is never stored: both GEMMs expand it from fp16(g) [n, cout] and the row-major ReLU bits
                 rowmask = 4.0 * rows * (cout // 32)
-                add("edge_dz_prep_kernel", 0.0, 4.0 * n * cout + 2.0 * n * cout + rowmask + 16.0 * ntile * cout, "hbm")
+                # (the launch also zeroes the Q half of dPQ for the scattering kernel: 4 n hid bytes, csrc/dynedge_exec.cu)
+                add("edge_dz_prep_kernel", 0.0, 4.0 * n * cout + 2.0 * n * cout + rowmask + 16.0 * ntile * cout + 4.0 * n * hid, "hbm")
                 add("gemm_f16_wgrad_build_kernel", 2.0 * e_real * hid * cout, 2.0 * rows * hid + 2.0 * n * cout + rowmask)
                 add("gemm_f16_pair_scatter_build_kernel", 2.0 * e_real * hid * cout,
                     2.0 * n * cout + rowmask + 4.0 * rows * mld + 4.0 * rows + 4.0 * n * 2 * hid)
-                add("zero_block_kernel", 0.0, 4.0 * n * hid, "hbm")
             elif train:
                 add("edge_mask_bwd_bf16_kernel", 0.0, zb * rows * cout + 4.0 * n * cout, "hbm")
                 add("gemm_bf_wgrad_kernel", 2.0 * e_real * hid * cout, rows * (zb * cout + hb * hid))
