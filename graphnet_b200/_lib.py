@@ -90,6 +90,7 @@ SIGNATURES: Dict[str, list] = {
     "gnb_edge_hidden_dgrad_scatter_f16_masked": [_p, _p, _i32, _p, _i64, _p, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _p,
                                                  _i32, _p, _p],
     "gnb_edge_slot_flag": [_p, _i64, _i32, _p, _p],
+    "gnb_edge_slot_flag_or": [_p, _i64, _i32, _p, _p],
     "gnb_edgeconv_fused_fwd_f16_w": [_p, _i64, _i32, _p, _p, _i64, _p, _p, _i64, _p, _i32, _i32, _p, _i64, _p, _p, _i64, _p, _i64,
                                      _p, _i32, _p, _p],
     "gnb_edge_dz_prep_w": [_p, _i64, _p, _i64, _i32, _p, _p, _p, _p, _p, _p],

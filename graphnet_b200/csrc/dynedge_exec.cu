@@ -77,7 +77,7 @@ int gnb_edgeconv_fused_fwd_f16(const float*, int64_t, int32_t, const int32_t*, c
                                const uint32_t*, int32_t, void*);
 int gnb_edge_dz_prep(const float*, int64_t, const uint32_t*, int64_t, int32_t, const uint32_t*, void*, uint32_t*, float*, void*);
 // the same four with the device-side layout switch (full9: *full9 == 0 selects the 8-slot layout; gnb_edge_slot_flag writes it)
-int gnb_edge_slot_flag(const int32_t*, int64_t, int32_t, int32_t*, void*);
+int gnb_edge_slot_flag_or(const int32_t*, int64_t, int32_t, int32_t*, void*);
 int gnb_linear_bwd_weight_f16_masked_w(const void*, const uint32_t*, const void*, int64_t, float*, int64_t, int64_t, int32_t, int32_t,
                                        const uint32_t*, const uint32_t*, const int32_t*, void*);
 int gnb_edge_hidden_dgrad_scatter_f16_masked_w(const void*, const uint32_t*, int32_t, const void*, int64_t, const uint32_t*, int32_t,
@@ -730,7 +730,8 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
         pi += 4;
         {   // PQ = xin Wcat^T + bcat
             if (p.mixed) {      // fp16-plane modes: the GEMM epilogue also yields the scale word of h = relu(P_i + Q_j) <= 2 max|PQ|
-                if (l == 0) GNB_CHECK(cudaMemsetAsync(p.scale_bits, 0, 2 * GNB_MAX_LAYERS * 4, e.st));
+                // (one memset: the scale words and, right behind them in the arena, the layers' edge-slot flag words)
+                if (l == 0) GNB_CHECK(cudaMemsetAsync(p.scale_bits, 0, (size_t)((char*)(p.full9 + GNB_MAX_LAYERS) - (char*)p.scale_bits), e.st));
                 EX(gnb_linear_next_absmax(p.scale_bits + l, 1));
             }
             const float* xs[1] = {xin}; const int64_t lds[1] = {b.cin_ld}; const int32_t ks[1] = {b.cin_ld}; const int offs[1] = {0};
@@ -746,7 +747,7 @@ GNB_EXPORT int gnb_dynedge_forward(const gnb_dynedge_config* cfg, const float* c
                 uint32_t* hs = p.scale_bits + l;          // written by the PQ GEMM's epilogue (gnb_linear_next_absmax above)
                 if (b.fused) {
                     static const int dbgf = getenv("GNB_FUSED_DBG") ? atoi(getenv("GNB_FUSED_DBG")) : 0;
-                    if (b.slots8) EX(gnb_edge_slot_flag(deg, n, c.k, p.full9 + l, stream));
+                    if (b.slots8) EX(gnb_edge_slot_flag_or(deg, n, c.k, p.full9 + l, stream));      // (the word was zeroed with the scale words)
                     EX(gnb_edgeconv_fused_fwd_f16_w(b.pq, 2 * b.hid, b.hid, nbr, deg, n, b.w2b[0], b.w2b[1], b.hld64, b2, b.cout,
                                                     e.fround ? 1 : 0, b.y, b.cout, (dbgf & 4) ? nullptr : b.mask,
                                                     (training && !(dbgf & 1)) ? (void*)b.hb[0] : nullptr, b.hid,

@@ -324,6 +324,8 @@ int gnb_edge_hidden_dgrad_scatter_f16_masked(const void* g16, const uint32_t* ro
  * 8 (i % 16) + s. A layer's four kernels must be given the same word. Results are identical in both layouts (the padding slot
  * contributes exact zeros). Buffers sized for max(ceil(n / 14) * 126, ceil(n / 16) * 128) rows fit either layout. */
 int gnb_edge_slot_flag(const int32_t* deg, int64_t n, int32_t k, int32_t* flag, void* stream);
+/* the same for a flag word the caller has zeroed (*flag = 1 is stored when some deg[i] > k, nothing otherwise): many CTAs */
+int gnb_edge_slot_flag_or(const int32_t* deg, int64_t n, int32_t k, int32_t* flag, void* stream);
 int gnb_edgeconv_fused_fwd_f16_w(const float* pq, int64_t ldpq, int32_t hid, const int32_t* nbr, const int32_t* deg, int64_t n,
                                  const void* w0, const void* w1, int64_t ldw, const float* bias, int32_t n_out, int32_t round_out,
                                  float* y, int64_t ldy, uint32_t* maskbits, void* h0_out, int64_t ldh, uint8_t* hbytes,

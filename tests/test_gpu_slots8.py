@@ -55,6 +55,13 @@ def test_slot_flag(ops):
     assert int(f) == 1
     ops._call("gnb_edge_slot_flag", ops._ptr(graph.deg), 0, 8, ops._ptr(f), ops._stream())          # empty graph: 8 slots
     assert int(f) == 0
+    # the many-CTA form ORs into a word the caller zeroed
+    ops._call("gnb_edge_slot_flag_or", ops._ptr(graph.deg), n, 8, ops._ptr(f), ops._stream())
+    assert int(f) == 0
+    ops._call("gnb_edge_slot_flag_or", ops._ptr(deg), n, 8, ops._ptr(f), ops._stream())
+    assert int(f) == 1
+    ops._call("gnb_edge_slot_flag_or", ops._ptr(graph.deg), n, 8, ops._ptr(f), ops._stream())        # never cleared by the kernel
+    assert int(f) == 1
 
 
 def _mask_case8(ops, sizes, n_out, seed, gmax):
